@@ -1,0 +1,1436 @@
+/*
+ * mrts_oracle.c -- CPU ORACLE (TEST INFRASTRUCTURE ONLY; see mrts_oracle.h).
+ *
+ * Restates, in plain C, the Java game rules of ConnAALL/MicroRTS.  Every function names the
+ * reference file:line it follows.  Data structures deliberately mirror the Java ones (ordered
+ * unit list with linear scans, insertion-ordered assignment map, heap "objects" that stay
+ * addressable after removal) so that the restatement can be audited line by line; this is the
+ * opposite of how the CUDA engine is organised, which keeps the two implementations independent.
+ */
+#include "mrts_oracle.h"
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------------------------------------
+ * java.util.Random (Java SE specification; JDK class, not in /root/reference -- see SURVEY 8c)
+ * ---------------------------------------------------------------------------------------------- */
+#define JR_MULT 0x5DEECE66DULL
+#define JR_ADD 0xBULL
+#define JR_MASK ((1ULL << 48) - 1)
+
+void o_jr_seed(OJRandom *r, int64_t seed) { r->s = ((uint64_t)seed ^ JR_MULT) & JR_MASK; }
+int32_t o_jr_next(OJRandom *r, int bits) {
+    r->s = (r->s * JR_MULT + JR_ADD) & JR_MASK;
+    return (int32_t)(int64_t)(r->s >> (48 - bits)); /* (int)(seed >>> (48-bits)) */
+}
+int32_t o_jr_next_int(OJRandom *r) { return o_jr_next(r, 32); }
+int32_t o_jr_next_int_bound(OJRandom *r, int32_t bound) {
+    int32_t v = o_jr_next(r, 31);
+    int32_t m = bound - 1;
+    if ((bound & m) == 0) {
+        v = (int32_t)(((int64_t)bound * (int64_t)v) >> 31);
+    } else {
+        int32_t u = v;
+        /* for (int u = r; u - (r = u % bound) + m < 0; u = next(31)); -- with Java int overflow */
+        for (;;) {
+            v = u % bound;
+            int32_t t = (int32_t)((uint32_t)u - (uint32_t)v + (uint32_t)m);
+            if (t >= 0) break;
+            u = o_jr_next(r, 31);
+        }
+    }
+    return v;
+}
+double o_jr_next_double(OJRandom *r) {
+    int64_t a = (int64_t)o_jr_next(r, 26);
+    int64_t b = (int64_t)o_jr_next(r, 27);
+    return (double)((a << 27) + b) * 0x1.0p-53;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * UnitTypeTable  (src/rts/units/UnitTypeTable.java:104-289, UnitType.java:23-110)
+ * ---------------------------------------------------------------------------------------------- */
+#define MAXT 16
+struct OUtt {
+    int n;
+    int conflict;
+    int16_t f[MAXT][OF_NFIELDS];
+    int flags[MAXT];
+    int nprod[MAXT];
+    uint8_t prod[MAXT][MAXT];
+};
+
+static void utt_defaults(OUtt *t, int id) {
+    /* UnitType.java:23-110 field initialisers */
+    int16_t *f = t->f[id];
+    f[OF_COST] = 1; f[OF_HP] = 1; f[OF_MINDMG] = 1; f[OF_MAXDMG] = 1; f[OF_RANGE] = 1;
+    f[OF_PRODUCE_T] = 10; f[OF_MOVE_T] = 10; f[OF_ATTACK_T] = 10; f[OF_HARVEST_T] = 10; f[OF_RETURN_T] = 10;
+    f[OF_HARVEST_AMT] = 1; f[OF_SIGHT] = 4;
+    t->flags[id] = OFL_MOVE | OFL_ATTACK;
+    t->nprod[id] = 0;
+}
+
+OUtt *o_utt_empty(int conflict) {
+    OUtt *t = (OUtt *)calloc(1, sizeof(OUtt));
+    t->conflict = conflict;
+    return t;
+}
+
+OUtt *o_utt_create(int version, int conflict) {
+    /* UnitTypeTable.setUnitTypeTable, UnitTypeTable.java:104-289; version 1 ORIGINAL, 2 FINETUNED, 3 NON_DETERMINISTIC */
+    OUtt *t = o_utt_empty(conflict);
+    t->n = 7;
+    for (int i = 0; i < 7; i++) utt_defaults(t, i);
+    int16_t *f;
+    /* Resource :108-117 */
+    f = t->f[0]; t->flags[0] = OFL_RESOURCE; f[OF_SIGHT] = 0;
+    /* Base :120-138 (v3 leaves produceTime at the default 10) */
+    f = t->f[1]; f[OF_COST] = 10; f[OF_HP] = 10;
+    if (version == 1) f[OF_PRODUCE_T] = 250; else if (version == 2) f[OF_PRODUCE_T] = 200;
+    t->flags[1] = OFL_STOCKPILE; f[OF_SIGHT] = 5;
+    /* Barracks :141-161 */
+    f = t->f[2]; f[OF_COST] = 5; f[OF_HP] = 4;
+    if (version == 1) f[OF_PRODUCE_T] = 200; else if (version == 2 || version == 3) f[OF_PRODUCE_T] = 100;
+    t->flags[2] = 0; f[OF_SIGHT] = 3;
+    /* Worker :164-190 */
+    f = t->f[3]; f[OF_COST] = 1; f[OF_HP] = 1;
+    if (version == 3) { f[OF_MINDMG] = 0; f[OF_MAXDMG] = 2; } else { f[OF_MINDMG] = f[OF_MAXDMG] = 1; }
+    f[OF_RANGE] = 1; f[OF_PRODUCE_T] = 50; f[OF_MOVE_T] = 10; f[OF_ATTACK_T] = 5; f[OF_HARVEST_T] = 20; f[OF_RETURN_T] = 10;
+    t->flags[3] = OFL_HARVEST | OFL_MOVE | OFL_ATTACK; f[OF_SIGHT] = 3;
+    /* Light :193-216 */
+    f = t->f[4]; f[OF_COST] = 2; f[OF_HP] = 4;
+    if (version == 3) { f[OF_MINDMG] = 1; f[OF_MAXDMG] = 3; } else { f[OF_MINDMG] = f[OF_MAXDMG] = 2; }
+    f[OF_RANGE] = 1; f[OF_PRODUCE_T] = 80; f[OF_MOVE_T] = 8; f[OF_ATTACK_T] = 5;
+    t->flags[4] = OFL_MOVE | OFL_ATTACK; f[OF_SIGHT] = 2;
+    /* Heavy :219-254 */
+    f = t->f[5];
+    if (version == 3) { f[OF_MINDMG] = 0; f[OF_MAXDMG] = 6; } else { f[OF_MINDMG] = f[OF_MAXDMG] = 4; }
+    f[OF_RANGE] = 1; f[OF_PRODUCE_T] = 120;
+    if (version == 1) { f[OF_MOVE_T] = 12; f[OF_HP] = 4; f[OF_COST] = 2; }
+    else if (version == 2 || version == 3) { f[OF_MOVE_T] = 10; f[OF_HP] = 8; f[OF_COST] = 3; }
+    f[OF_ATTACK_T] = 5; t->flags[5] = OFL_MOVE | OFL_ATTACK; f[OF_SIGHT] = 2;
+    /* Ranged :257-279 */
+    f = t->f[6]; f[OF_COST] = 2; f[OF_HP] = 1;
+    if (version == 3) { f[OF_MINDMG] = 1; f[OF_MAXDMG] = 2; } else { f[OF_MINDMG] = f[OF_MAXDMG] = 1; }
+    f[OF_RANGE] = 3; f[OF_PRODUCE_T] = 100; f[OF_MOVE_T] = 10; f[OF_ATTACK_T] = 5;
+    t->flags[6] = OFL_MOVE | OFL_ATTACK; f[OF_SIGHT] = 3;
+    /* produces :282-288 */
+    t->nprod[1] = 1; t->prod[1][0] = 3;
+    t->nprod[2] = 3; t->prod[2][0] = 4; t->prod[2][1] = 5; t->prod[2][2] = 6;
+    t->nprod[3] = 2; t->prod[3][0] = 1; t->prod[3][1] = 2;
+    return t;
+}
+
+void o_utt_set_type(OUtt *t, int id, const int16_t fields[OF_NFIELDS], int flags, int nprod, const uint8_t *prod) {
+    if (id >= t->n) t->n = id + 1;
+    memcpy(t->f[id], fields, sizeof(int16_t) * OF_NFIELDS);
+    t->flags[id] = flags;
+    t->nprod[id] = nprod;
+    for (int i = 0; i < nprod; i++) t->prod[id][i] = prod[i];
+}
+int o_utt_field(const OUtt *t, int id, int field) { return t->f[id][field]; }
+int o_utt_flags(const OUtt *t, int id) { return t->flags[id]; }
+int o_utt_produces(const OUtt *t, int id, uint8_t *out) {
+    for (int i = 0; i < t->nprod[id]; i++) out[i] = t->prod[id][i];
+    return t->nprod[id];
+}
+int o_utt_max_attack_range(const OUtt *t) {
+    /* UnitTypeTable.getMaxAttackRange */
+    int m = 0;
+    for (int i = 0; i < t->n; i++) if (t->f[i][OF_RANGE] > m) m = t->f[i][OF_RANGE];
+    return m;
+}
+void o_utt_free(OUtt *t) { free(t); }
+
+/* ------------------------------------------------------------------------------------------------
+ * State.  Units are "heap objects" in a pool (index = identity, never reused), the unit list holds pool
+ * indices in list order (PhysicalGameState.units, a LinkedList), assignments are kept in insertion
+ * order (GameState.unitActions, a LinkedHashMap).                      GameState.java:34-46
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct { int type, player, x, y, res, hp; int64_t id; } OUnit;
+
+typedef struct { int npos; int pos; int res[2]; } ORu1; /* ResourceUsage of ONE action: at most one position */
+
+typedef struct {
+    int type, param, x, y, utype;
+    ORu1 ru; /* r_cache (UnitAction.java:130,246-296), filled by act_ru() */
+    int ru_done;
+} OAct;
+
+typedef struct { int unit; OAct act; int time; } OAssign;
+
+/* merged ResourceUsage (ResourceUsage.java:12-13): list of positions + per-player resources */
+typedef struct { int npos; int cap; int *pos; int res[2]; } ORu;
+
+struct OGame {
+    const OUtt *utt;
+    int w, h;
+    uint8_t *terrain;
+    int res[2];
+    OUnit *pool; int pool_n, pool_cap;
+    int *list; int n, list_cap;
+    OAssign *asg; int na, asg_cap;
+    int time;
+    int cancel_ctr;
+    int64_t next_id;
+    OJRandom rng_policy;   /* util.Sampler.generator   (Sampler.java:17)  */
+    OJRandom rng_conflict; /* GameState.r               (GameState.java:37) */
+    OJRandom rng_damage;   /* UnitAction.r              (UnitAction.java:24) */
+    int errors;
+};
+
+enum { OE_ADD_OCCUPIED = 1, OE_MIXED_OWNERS = 2, OE_BAD_UNIT = 4, OE_INCONSISTENT_OLDER = 8, OE_FAILED_PRODUCE = 16,
+       OE_BAD_ACTION = 32 };
+
+static void ru_init(ORu *r) { r->npos = 0; r->cap = 0; r->pos = NULL; r->res[0] = r->res[1] = 0; }
+static void ru_free(ORu *r) { free(r->pos); r->pos = NULL; r->npos = r->cap = 0; }
+static void ru_add_pos(ORu *r, int p) {
+    if (r->npos == r->cap) { r->cap = r->cap ? r->cap * 2 : 16; r->pos = (int *)realloc(r->pos, sizeof(int) * r->cap); }
+    r->pos[r->npos++] = p;
+}
+static int ru_contains(const ORu *r, int p) {
+    for (int i = 0; i < r->npos; i++) if (r->pos[i] == p) return 1;
+    return 0;
+}
+/* ResourceUsage.merge, ResourceUsage.java:93-98 */
+static void ru_merge1(ORu *r, const ORu1 *o) {
+    if (o->npos) ru_add_pos(r, o->pos);
+    r->res[0] += o->res[0]; r->res[1] += o->res[1];
+}
+
+/* ResourceUsage.consistentWith(anotherUsage), ResourceUsage.java:31-50.  Four flavours by operand shape. */
+static int res_consistent(const int a[2], const int b[2], const OGame *g) {
+    for (int i = 0; i < 2; i++) {
+        if (b[i] == 0) continue;
+        if (a[i] + b[i] > 0 && a[i] + b[i] > g->res[i]) return 0;
+    }
+    return 1;
+}
+static int ru1_consistent_with_ru1(const ORu1 *self, const ORu1 *other, const OGame *g) {
+    if (other->npos && self->npos && self->pos == other->pos) return 0;
+    return res_consistent(self->res, other->res, g);
+}
+static int ru1_consistent_with_ru(const ORu1 *self, const ORu *other, const OGame *g) {
+    for (int i = 0; i < other->npos; i++) if (self->npos && self->pos == other->pos[i]) return 0;
+    return res_consistent(self->res, other->res, g);
+}
+static int ru_consistent_with_ru1(const ORu *self, const ORu1 *other, const OGame *g) {
+    if (other->npos && ru_contains(self, other->pos)) return 0;
+    return res_consistent(self->res, other->res, g);
+}
+
+static const int DX[4] = {0, 1, 0, -1}, DY[4] = {-1, 0, 1, 0}; /* UnitAction.java:94,100 */
+
+OGame *o_game_create(const OUtt *utt, int w, int h, const uint8_t *terrain, int res0, int res1) {
+    OGame *g = (OGame *)calloc(1, sizeof(OGame));
+    g->utt = utt; g->w = w; g->h = h;
+    g->terrain = (uint8_t *)malloc((size_t)w * h);
+    memcpy(g->terrain, terrain, (size_t)w * h);
+    g->res[0] = res0; g->res[1] = res1;
+    o_game_seed(g, 0);
+    return g;
+}
+
+static int pool_new(OGame *g) {
+    if (g->pool_n == g->pool_cap) { g->pool_cap = g->pool_cap ? g->pool_cap * 2 : 64; g->pool = (OUnit *)realloc(g->pool, sizeof(OUnit) * g->pool_cap); }
+    return g->pool_n++;
+}
+static void list_append(OGame *g, int u) {
+    if (g->n == g->list_cap) { g->list_cap = g->list_cap ? g->list_cap * 2 : 64; g->list = (int *)realloc(g->list, sizeof(int) * g->list_cap); }
+    g->list[g->n++] = u;
+}
+
+/* PhysicalGameState.getUnitAt, PhysicalGameState.java:263-270 (first match in list order) */
+static int unit_at(const OGame *g, int x, int y) {
+    for (int i = 0; i < g->n; i++) { const OUnit *u = &g->pool[g->list[i]]; if (u->x == x && u->y == y) return g->list[i]; }
+    return -1;
+}
+static int list_index_of(const OGame *g, int u) {
+    for (int i = 0; i < g->n; i++) if (g->list[i] == u) return i;
+    return -1;
+}
+
+/* PhysicalGameState.addUnit, PhysicalGameState.java:189-201 */
+static int add_unit(OGame *g, int u) {
+    const OUnit *nu = &g->pool[u];
+    for (int i = 0; i < g->n; i++) {
+        const OUnit *e = &g->pool[g->list[i]];
+        if (e->x == nu->x && e->y == nu->y) { g->errors |= OE_ADD_OCCUPIED; return 0; } /* Java throws */
+    }
+    list_append(g, u);
+    return 1;
+}
+
+void o_game_add_unit(OGame *g, int type, int64_t id, int player, int x, int y, int res, int hp) {
+    /* Unit(long ID,...) ctor, Unit.java:72-83 (hitpoints overridden by the XML value, Unit.fromXML) */
+    int u = pool_new(g);
+    OUnit *p = &g->pool[u];
+    p->type = type; p->player = player; p->x = x; p->y = y; p->res = res; p->hp = hp; p->id = id;
+    if (id >= g->next_id) g->next_id = id + 1;
+    add_unit(g, u);
+}
+
+OGame *o_game_clone(const OGame *s) {
+    /* GameState.clone, GameState.java:591-610: deep copy; assignment order preserved */
+    OGame *g = (OGame *)malloc(sizeof(OGame));
+    *g = *s;
+    g->terrain = (uint8_t *)malloc((size_t)s->w * s->h); memcpy(g->terrain, s->terrain, (size_t)s->w * s->h);
+    g->pool_cap = s->pool_n + 64; g->pool = (OUnit *)malloc(sizeof(OUnit) * g->pool_cap); memcpy(g->pool, s->pool, sizeof(OUnit) * s->pool_n);
+    g->list_cap = s->n + 64; g->list = (int *)malloc(sizeof(int) * g->list_cap); memcpy(g->list, s->list, sizeof(int) * s->n);
+    g->asg_cap = s->na + 64; g->asg = (OAssign *)malloc(sizeof(OAssign) * g->asg_cap); memcpy(g->asg, s->asg, sizeof(OAssign) * s->na);
+    return g;
+}
+void o_game_free(OGame *g) { if (!g) return; free(g->terrain); free(g->pool); free(g->list); free(g->asg); free(g); }
+void o_game_seed(OGame *g, int64_t seed) {
+    /* One stream per static Random of the reference.  The reference seeds none of them (parity unpinned);
+     * our convention: policy stream = Random(seed), conflict = Random(seed ^ 0x5851F42D4C957F2D),
+     * damage = Random(seed ^ 0x14057B7EF767814F). */
+    o_jr_seed(&g->rng_policy, seed);
+    o_jr_seed(&g->rng_conflict, seed ^ 0x5851F42D4C957F2DLL);
+    o_jr_seed(&g->rng_damage, seed ^ 0x14057B7EF767814FLL);
+}
+int o_game_time(const OGame *g) { return g->time; }
+int o_game_n_units(const OGame *g) { return g->n; }
+int o_game_resources(const OGame *g, int p) { return g->res[p]; }
+int o_game_errors(const OGame *g) { return g->errors; }
+
+int o_game_units(const OGame *g, int32_t *out) {
+    for (int i = 0; i < g->n; i++) {
+        const OUnit *u = &g->pool[g->list[i]];
+        int32_t *o = out + i * 8;
+        o[0] = u->type; o[1] = u->player; o[2] = u->x; o[3] = u->y; o[4] = u->res; o[5] = u->hp;
+        o[6] = (int32_t)(u->id & 0xffffffff); o[7] = (int32_t)(u->id >> 32);
+    }
+    return g->n;
+}
+
+static int find_assign(const OGame *g, int u) {
+    for (int i = 0; i < g->na; i++) if (g->asg[i].unit == u) return i;
+    return -1;
+}
+
+int o_game_assignments(const OGame *g, int32_t *out) {
+    for (int i = 0; i < g->n; i++) {
+        int32_t *o = out + i * 8;
+        int a = find_assign(g, g->list[i]);
+        memset(o, 0, sizeof(int32_t) * 8);
+        if (a >= 0) {
+            const OAssign *s = &g->asg[a];
+            o[0] = 1; o[1] = s->act.type; o[2] = s->act.param; o[3] = s->act.x; o[4] = s->act.y; o[5] = s->act.utype;
+            o[6] = s->time; o[7] = a;
+        }
+    }
+    return g->n;
+}
+
+/* PhysicalGameState.winner / gameover, PhysicalGameState.java:334-387 */
+int o_game_winner(const OGame *g) {
+    int cnt[2] = {0, 0};
+    for (int i = 0; i < g->n; i++) { int p = g->pool[g->list[i]].player; if (p >= 0) cnt[p]++; }
+    int winner = -1;
+    for (int i = 0; i < 2; i++) if (cnt[i] > 0) { if (winner == -1) winner = i; else return -1; }
+    return winner;
+}
+int o_game_gameover(const OGame *g) {
+    int cnt[2] = {0, 0}, total = 0;
+    for (int i = 0; i < g->n; i++) { int p = g->pool[g->list[i]].player; if (p >= 0) { cnt[p]++; total++; } }
+    if (total == 0) return 1;
+    int winner = -1;
+    for (int i = 0; i < 2; i++) if (cnt[i] > 0) { if (winner == -1) winner = i; else return 0; }
+    return winner != -1;
+}
+
+/* GameState.removeUnit, GameState.java:79-82 */
+static void remove_unit(OGame *g, int u) {
+    int i = list_index_of(g, u);
+    if (i >= 0) { memmove(&g->list[i], &g->list[i + 1], sizeof(int) * (g->n - i - 1)); g->n--; }
+    int a = find_assign(g, u);
+    if (a >= 0) { memmove(&g->asg[a], &g->asg[a + 1], sizeof(OAssign) * (g->na - a - 1)); g->na--; }
+}
+
+static OAct mk_act(int type, int param, int x, int y, int utype) {
+    OAct a; memset(&a, 0, sizeof a);
+    a.type = type; a.param = param; a.x = x; a.y = y; a.utype = utype;
+    return a;
+}
+static OAct act_none(int duration) { return mk_act(O_NONE, duration, 0, 0, -1); }
+static OAct act_from_v(const OActionV *v) { return mk_act(v->type, v->param, v->x, v->y, v->utype); }
+static OActionV act_to_v(const OAct *a) { OActionV v = {a->type, a->param, a->x, a->y, a->utype}; return v; }
+
+/* UnitAction.resourceUsage, UnitAction.java:246-296 (cached on first call) */
+static const ORu1 *act_ru(OAct *a, const OGame *g, int u) {
+    if (a->ru_done) return &a->ru;
+    a->ru_done = 1;
+    a->ru.npos = 0; a->ru.pos = 0; a->ru.res[0] = a->ru.res[1] = 0;
+    const OUnit *un = &g->pool[u];
+    if (a->type == O_MOVE || a->type == O_PRODUCE) {
+        if (a->type == O_PRODUCE) a->ru.res[un->player] += g->utt->f[a->utype][OF_COST];
+        int pos = un->x + un->y * g->w;
+        switch (a->param) {
+            case O_UP: pos -= g->w; break;
+            case O_RIGHT: pos++; break;
+            case O_DOWN: pos += g->w; break;
+            case O_LEFT: pos--; break;
+        }
+        a->ru.npos = 1; a->ru.pos = pos;
+    }
+    return &a->ru;
+}
+
+/* UnitAction.ETA, UnitAction.java:307-329 */
+static int act_eta(const OAct *a, const OGame *g, int u) {
+    const int16_t *f = g->utt->f[g->pool[u].type];
+    switch (a->type) {
+        case O_NONE: return a->param;
+        case O_MOVE: return f[OF_MOVE_T];
+        case O_ATTACK: return f[OF_ATTACK_T];
+        case O_HARVEST: return f[OF_HARVEST_T];
+        case O_RETURN: return f[OF_MOVE_T]; /* sic: moveTime */
+        case O_PRODUCE: return g->utt->f[a->utype][OF_PRODUCE_T];
+    }
+    return 0;
+}
+
+/* UnitAction.equals, UnitAction.java:192-208 */
+static int act_equals(const OAct *a, const OAct *b) {
+    if (a->type != b->type) return 0;
+    if (a->type == O_NONE || a->type == O_MOVE || a->type == O_HARVEST || a->type == O_RETURN) return a->param == b->param;
+    if (a->type == O_ATTACK) return a->x == b->x && a->y == b->y;
+    return a->param == b->param && a->utype == b->utype;
+}
+
+static int terrain_at(const OGame *g, int x, int y) { return g->terrain[x + y * g->w]; }
+
+/* Unit.getUnitActions(s, noneDuration), Unit.java:382-522 */
+static int unit_actions(const OGame *g, int u, int none_duration, OAct *l, int max) {
+    const OUnit *me = &g->pool[u];
+    const OUtt *t = g->utt;
+    int fl = t->flags[me->type];
+    int x = me->x, y = me->y, player = me->player;
+    int n = 0;
+#define PUSH(A) do { if (n < max) l[n] = (A); n++; } while (0)
+    int uup = -1, uright = -1, udown = -1, uleft = -1;
+    for (int i = 0; i < g->n; i++) {
+        const OUnit *o = &g->pool[g->list[i]];
+        if (o->x == x) {
+            if (o->y == y - 1) uup = g->list[i];
+            else if (o->y == y + 1) udown = g->list[i];
+        } else if (o->y == y) {
+            if (o->x == x - 1) uleft = g->list[i];
+            else if (o->x == x + 1) uright = g->list[i];
+        }
+    }
+    const OUnit *P = g->pool;
+    if (fl & OFL_ATTACK) {
+        if (t->f[me->type][OF_RANGE] == 1) {
+            if (y > 0 && uup >= 0 && P[uup].player != player && P[uup].player >= 0) PUSH(mk_act(O_ATTACK, -1, P[uup].x, P[uup].y, -1));
+            if (x < g->w - 1 && uright >= 0 && P[uright].player != player && P[uright].player >= 0) PUSH(mk_act(O_ATTACK, -1, P[uright].x, P[uright].y, -1));
+            if (y < g->h - 1 && udown >= 0 && P[udown].player != player && P[udown].player >= 0) PUSH(mk_act(O_ATTACK, -1, P[udown].x, P[udown].y, -1));
+            if (x > 0 && uleft >= 0 && P[uleft].player != player && P[uleft].player >= 0) PUSH(mk_act(O_ATTACK, -1, P[uleft].x, P[uleft].y, -1));
+        } else {
+            int sq = t->f[me->type][OF_RANGE] * t->f[me->type][OF_RANGE];
+            for (int i = 0; i < g->n; i++) {
+                const OUnit *o = &P[g->list[i]];
+                if (o->player < 0 || o->player == player) continue;
+                int sdx = (o->x - x) * (o->x - x), sdy = (o->y - y) * (o->y - y);
+                if (sdx + sdy <= sq) PUSH(mk_act(O_ATTACK, -1, o->x, o->y, -1));
+            }
+        }
+    }
+    if (fl & OFL_HARVEST) {
+        if (me->res == 0) {
+            if (y > 0 && uup >= 0 && (t->flags[P[uup].type] & OFL_RESOURCE)) PUSH(mk_act(O_HARVEST, O_UP, 0, 0, -1));
+            if (x < g->w - 1 && uright >= 0 && (t->flags[P[uright].type] & OFL_RESOURCE)) PUSH(mk_act(O_HARVEST, O_RIGHT, 0, 0, -1));
+            if (y < g->h - 1 && udown >= 0 && (t->flags[P[udown].type] & OFL_RESOURCE)) PUSH(mk_act(O_HARVEST, O_DOWN, 0, 0, -1));
+            if (x > 0 && uleft >= 0 && (t->flags[P[uleft].type] & OFL_RESOURCE)) PUSH(mk_act(O_HARVEST, O_LEFT, 0, 0, -1));
+        }
+        if (me->res > 0) {
+            if (y > 0 && uup >= 0 && (t->flags[P[uup].type] & OFL_STOCKPILE) && P[uup].player == player) PUSH(mk_act(O_RETURN, O_UP, 0, 0, -1));
+            if (x < g->w - 1 && uright >= 0 && (t->flags[P[uright].type] & OFL_STOCKPILE) && P[uright].player == player) PUSH(mk_act(O_RETURN, O_RIGHT, 0, 0, -1));
+            if (y < g->h - 1 && udown >= 0 && (t->flags[P[udown].type] & OFL_STOCKPILE) && P[udown].player == player) PUSH(mk_act(O_RETURN, O_DOWN, 0, 0, -1));
+            if (x > 0 && uleft >= 0 && (t->flags[P[uleft].type] & OFL_STOCKPILE) && P[uleft].player == player) PUSH(mk_act(O_RETURN, O_LEFT, 0, 0, -1));
+        }
+    }
+    int tup = (y > 0 ? terrain_at(g, x, y - 1) : 1);
+    int tright = (x < g->w - 1 ? terrain_at(g, x + 1, y) : 1);
+    int tdown = (y < g->h - 1 ? terrain_at(g, x, y + 1) : 1);
+    int tleft = (x > 0 ? terrain_at(g, x - 1, y) : 1);
+    for (int k = 0; k < t->nprod[me->type]; k++) {
+        int ut = t->prod[me->type][k];
+        if (player >= 0 && g->res[player] >= t->f[ut][OF_COST]) {
+            if (tup == 0 && unit_at(g, x, y - 1) < 0) PUSH(mk_act(O_PRODUCE, O_UP, 0, 0, ut));
+            if (tright == 0 && unit_at(g, x + 1, y) < 0) PUSH(mk_act(O_PRODUCE, O_RIGHT, 0, 0, ut));
+            if (tdown == 0 && unit_at(g, x, y + 1) < 0) PUSH(mk_act(O_PRODUCE, O_DOWN, 0, 0, ut));
+            if (tleft == 0 && unit_at(g, x - 1, y) < 0) PUSH(mk_act(O_PRODUCE, O_LEFT, 0, 0, ut));
+        }
+    }
+    if (fl & OFL_MOVE) {
+        if (tup == 0 && uup < 0) PUSH(mk_act(O_MOVE, O_UP, 0, 0, -1));
+        if (tright == 0 && uright < 0) PUSH(mk_act(O_MOVE, O_RIGHT, 0, 0, -1));
+        if (tdown == 0 && udown < 0) PUSH(mk_act(O_MOVE, O_DOWN, 0, 0, -1));
+        if (tleft == 0 && uleft < 0) PUSH(mk_act(O_MOVE, O_LEFT, 0, 0, -1));
+    }
+    PUSH(act_none(none_duration));
+#undef PUSH
+    return n;
+}
+
+#define MAX_UA 4200 /* ranged units can list one attack per enemy */
+
+int o_unit_actions(const OGame *g, int unit_idx, int none_duration, OActionV *out, int max_out) {
+    OAct *l = (OAct *)malloc(sizeof(OAct) * MAX_UA);
+    int n = unit_actions(g, g->list[unit_idx], none_duration, l, MAX_UA);
+    for (int i = 0; i < n && i < max_out; i++) out[i] = act_to_v(&l[i]);
+    free(l);
+    return n;
+}
+
+/* Unit.canExecuteAction, Unit.java:531-534 */
+static int can_execute(const OGame *g, int u, const OAct *a) {
+    if (a->type == O_PRODUCE && (a->utype < 0 || a->utype >= g->utt->n)) return 0; /* Java: NullPointerException */
+    if (a->type < 0 || a->type > O_ATTACK) return 0;
+    OAct *l = (OAct *)malloc(sizeof(OAct) * MAX_UA);
+    int n = unit_actions(g, u, act_eta(a, g, u), l, MAX_UA);
+    int ok = 0;
+    for (int i = 0; i < n && !ok; i++) ok = act_equals(&l[i], a);
+    free(l);
+    return ok;
+}
+
+/* GameState.free, GameState.java:191-207 */
+static int gs_free(const OGame *g, int x, int y) {
+    if (terrain_at(g, x, y) != 0) return 0;
+    for (int i = 0; i < g->n; i++) { const OUnit *u = &g->pool[g->list[i]]; if (u->x == x && u->y == y) return 0; }
+    for (int i = 0; i < g->na; i++) {
+        const OAssign *s = &g->asg[i];
+        if (s->act.type == O_MOVE || s->act.type == O_PRODUCE) {
+            const OUnit *u = &g->pool[s->unit];
+            int d = s->act.param;
+            if (d == O_UP && u->x == x && u->y == y + 1) return 0;
+            if (d == O_RIGHT && u->x == x - 1 && u->y == y) return 0;
+            if (d == O_DOWN && u->x == x && u->y == y - 1) return 0;
+            if (d == O_LEFT && u->x == x + 1 && u->y == y) return 0;
+        }
+    }
+    return 1;
+}
+int o_game_free_cell(const OGame *g, int x, int y) { return gs_free(g, x, y); }
+
+/* GameState.getResourceUsage, GameState.java:652-664 (units in list order) */
+static void gs_resource_usage(OGame *g, ORu *out) {
+    for (int i = 0; i < g->n; i++) {
+        int a = find_assign(g, g->list[i]);
+        if (a >= 0) ru_merge1(out, act_ru(&g->asg[a].act, g, g->asg[a].unit));
+    }
+}
+
+/* GameState.issue, GameState.java:249-328 */
+typedef struct { int unit; OAct act; } OPair;
+
+static int gs_issue(OGame *g, int n, OPair *pa) {
+    int ret = 0;
+    for (int k = 0; k < n; k++) {
+        int u = pa[k].unit;
+        OAct a = pa[k].act;
+        ORu1 ru = *act_ru(&a, g, u); /* :262, computed once */
+        for (int j = 0; j < g->na; j++) { /* :263 */
+            OAssign *e = &g->asg[j];
+            if (!ru1_consistent_with_ru1(act_ru(&e->act, g, e->unit), &ru, g)) {
+                if (e->time == g->time) {
+                    int cancel_old = 0, cancel_new = 0;
+                    switch (g->utt->conflict) {
+                        default:
+                        case 1: cancel_old = cancel_new = 1; break;
+                        case 2: if (o_jr_next_int_bound(&g->rng_conflict, 2) == 0) cancel_new = 1; else cancel_old = 1; break;
+                        case 3: if ((g->cancel_ctr % 2) == 0) cancel_new = 1; else cancel_old = 1; g->cancel_ctr++; break;
+                    }
+                    int d1 = act_eta(&e->act, g, e->unit);
+                    int d2 = act_eta(&a, g, u);
+                    int d = d1 < d2 ? d1 : d2;
+                    if (cancel_old) e->act = act_none(d);
+                    if (cancel_new) a = act_none(d);
+                } else {
+                    g->errors |= OE_INCONSISTENT_OLDER;
+                    a = mk_act(O_NONE, -1, 0, 0, -1); /* :316 new UnitAction(TYPE_NONE): parameter stays -1 */
+                }
+            }
+        }
+        pa[k].act = a;
+        /* :321-322 unitActions.put: existing key keeps its slot */
+        int s = find_assign(g, u);
+        if (s < 0) {
+            if (g->na == g->asg_cap) { g->asg_cap = g->asg_cap ? g->asg_cap * 2 : 64; g->asg = (OAssign *)realloc(g->asg, sizeof(OAssign) * g->asg_cap); }
+            s = g->na++;
+        }
+        g->asg[s].unit = u; g->asg[s].act = a; g->asg[s].time = g->time;
+        act_ru(&g->asg[s].act, g, u);
+        if (a.type != O_NONE) ret = 1;
+    }
+    return ret;
+}
+
+/* GameState.issueSafe, GameState.java:338-408 */
+static int gs_issue_safe(OGame *g, int n, OPair *pa) {
+    /* PlayerAction.integrityCheck, PlayerAction.java:244-259 */
+    int player = -1;
+    for (int k = 0; k < n; k++) {
+        int p = g->pool[pa[k].unit].player;
+        if (player == -1) player = p; else if (player != p) { g->errors |= OE_MIXED_OWNERS; return -1; }
+    }
+    for (int k = 0; k < n; k++) {
+        int u = pa[k].unit;
+        if (!can_execute(g, u, &pa[k].act)) { /* :347-354 */
+            int l = (pa[k].act.type == O_PRODUCE && (pa[k].act.utype < 0 || pa[k].act.utype >= g->utt->n)) ? 0 : act_eta(&pa[k].act, g, u);
+            pa[k].act = act_none(l);
+        }
+        const ORu1 *r = act_ru(&pa[k].act, g, u); /* :386-399 */
+        if (r->npos) {
+            int y = r->pos / g->w, x = r->pos % g->w;
+            if (terrain_at(g, x, y) != 0 || unit_at(g, x, y) >= 0) pa[k].act = act_none(act_eta(&pa[k].act, g, u));
+        }
+    }
+    return gs_issue(g, n, pa);
+}
+
+int o_game_issue(OGame *g, int n, const int32_t *unit_idx, const OActionV *acts, int safe) {
+    OPair *pa = (OPair *)malloc(sizeof(OPair) * (n > 0 ? n : 1));
+    for (int k = 0; k < n; k++) {
+        if (unit_idx[k] < 0 || unit_idx[k] >= g->n) { g->errors |= OE_BAD_UNIT; free(pa); return -1; }
+        pa[k].unit = g->list[unit_idx[k]];
+        pa[k].act = act_from_v(&acts[k]);
+    }
+    int r = safe ? gs_issue_safe(g, n, pa) : gs_issue(g, n, pa);
+    free(pa);
+    return r;
+}
+
+/* UnitAction.execute, UnitAction.java:338-465 */
+static int neighbour(const OGame *g, const OUnit *u, int dir) {
+    switch (dir) {
+        case O_UP: return unit_at(g, u->x, u->y - 1);
+        case O_RIGHT: return unit_at(g, u->x + 1, u->y);
+        case O_DOWN: return unit_at(g, u->x, u->y + 1);
+        case O_LEFT: return unit_at(g, u->x - 1, u->y);
+    }
+    return -1;
+}
+static void act_execute(OGame *g, const OAct *a, int ui) {
+    OUnit *u = &g->pool[ui];
+    const OUtt *t = g->utt;
+    switch (a->type) {
+        case O_NONE: break;
+        case O_MOVE:
+            switch (a->param) {
+                case O_UP: u->y--; break;
+                case O_RIGHT: u->x++; break;
+                case O_DOWN: u->y++; break;
+                case O_LEFT: u->x--; break;
+            }
+            break;
+        case O_ATTACK: {
+            int o = unit_at(g, a->x, a->y);
+            if (o >= 0) {
+                int mn = t->f[u->type][OF_MINDMG], mx = t->f[u->type][OF_MAXDMG];
+                int dmg = (mn == mx) ? mn : mn + o_jr_next_int_bound(&g->rng_damage, 1 + (mx - mn));
+                g->pool[o].hp -= dmg;
+                if (g->pool[o].hp <= 0) remove_unit(g, o);
+            }
+        } break;
+        case O_HARVEST: {
+            int r = neighbour(g, u, a->param);
+            if (r >= 0 && (t->flags[g->pool[r].type] & OFL_RESOURCE) && (t->flags[u->type] & OFL_HARVEST) && u->res == 0) {
+                int amt = t->f[u->type][OF_HARVEST_AMT];
+                g->pool[r].res -= amt;
+                if (g->pool[r].res <= 0) remove_unit(g, r);
+                u = &g->pool[ui];
+                u->res = amt;
+            }
+        } break;
+        case O_RETURN: {
+            int b = neighbour(g, u, a->param);
+            if (b >= 0 && (t->flags[g->pool[b].type] & OFL_STOCKPILE) && u->res > 0) {
+                g->res[u->player] += u->res;
+                u->res = 0;
+            }
+        } break;
+        case O_PRODUCE: {
+            int tx = u->x, ty = u->y;
+            switch (a->param) {
+                case O_UP: ty--; break;
+                case O_RIGHT: tx++; break;
+                case O_DOWN: ty++; break;
+                case O_LEFT: tx--; break;
+            }
+            int player = u->player, ut = a->utype;
+            /* new Unit(player,type,x,y,0): ID = next_ID++ even if the unit is then not added (Unit.java:95-103) */
+            int64_t id = g->next_id++;
+            int cost = t->f[ut][OF_COST];
+            if (g->res[player] - cost >= 0) {
+                int nu = pool_new(g);
+                OUnit *p = &g->pool[nu];
+                p->type = ut; p->player = player; p->x = tx; p->y = ty; p->res = 0; p->hp = t->f[ut][OF_HP]; p->id = id;
+                if (add_unit(g, nu)) g->res[player] -= cost;
+            } else {
+                g->errors |= OE_FAILED_PRODUCE;
+            }
+        } break;
+    }
+}
+
+/* GameState.cycle, GameState.java:553-571 */
+int o_game_cycle(OGame *g) {
+    g->time++;
+    int nr = 0;
+    OAssign *ready = (OAssign *)malloc(sizeof(OAssign) * (g->na > 0 ? g->na : 1));
+    for (int i = 0; i < g->na; i++)
+        if (act_eta(&g->asg[i].act, g, g->asg[i].unit) + g->asg[i].time <= g->time) ready[nr++] = g->asg[i];
+    for (int i = 0; i < nr; i++) {
+        int a = find_assign(g, ready[i].unit); /* unitActions.remove(uaa.unit) */
+        if (a >= 0) { memmove(&g->asg[a], &g->asg[a + 1], sizeof(OAssign) * (g->na - a - 1)); g->na--; }
+        act_execute(g, &ready[i].act, ready[i].unit); /* runs even if the unit died earlier in this loop */
+    }
+    free(ready);
+    return o_game_gameover(g);
+}
+
+/* GameState.isComplete, GameState.java:148-157 */
+int o_game_is_complete(const OGame *g) {
+    for (int i = 0; i < g->n; i++)
+        if (g->pool[g->list[i]].player != -1 && find_assign(g, g->list[i]) < 0) return 0;
+    return 1;
+}
+
+/* GameState.canExecuteAnyAction, GameState.java:416-423 */
+static int can_execute_any(const OGame *g, int p) {
+    for (int i = 0; i < g->n; i++)
+        if (g->pool[g->list[i]].player == p && find_assign(g, g->list[i]) < 0) return 1;
+    return 0;
+}
+
+/* GameState.getNextChangeTime, GameState.java:532-546 */
+int o_game_next_change_time(const OGame *g) {
+    int next = -1;
+    for (int p = 0; p < 2; p++) if (can_execute_any(g, p)) return g->time;
+    for (int i = 0; i < g->na; i++) {
+        int t = g->asg[i].time + act_eta(&g->asg[i].act, g, g->asg[i].unit);
+        if (next == -1 || t < next) next = t;
+    }
+    if (next == -1) return g->time;
+    return next;
+}
+
+/* GameState.isUnitActionAllowed, GameState.java:434-457 */
+static int is_unit_action_allowed(OGame *g, int u, OAct *ua) {
+    if (ua->type == O_MOVE) {
+        int x2 = g->pool[u].x + DX[ua->param], y2 = g->pool[u].y + DY[ua->param];
+        if (x2 < 0 || y2 < 0 || x2 >= g->w || y2 >= g->h || terrain_at(g, x2, y2) == 1 || unit_at(g, x2, y2) >= 0) return 0;
+    }
+    ORu r; ru_init(&r);
+    gs_resource_usage(g, &r);
+    int ok = ru1_consistent_with_ru(act_ru(ua, g, u), &r, g);
+    ru_free(&r);
+    return ok;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * RandomBiasedAI.getAction (ai/RandomBiasedAI.java:51-107) + Sampler.weighted (util/Sampler.java:116-137)
+ * ---------------------------------------------------------------------------------------------- */
+static int rb_get_action(OGame *g, int player, OPair *out) {
+    int n = 0;
+    if (!can_execute_any(g, player)) return 0;
+    ORu par; ru_init(&par);
+    gs_resource_usage(g, &par); /* :59-65, units in list order */
+    OAct *l = (OAct *)malloc(sizeof(OAct) * MAX_UA);
+    for (int i = 0; i < g->n; i++) {
+        int u = g->list[i];
+        if (g->pool[u].player != player || find_assign(g, u) >= 0) continue;
+        int na = unit_actions(g, u, 10, l, MAX_UA);
+        int none = -1;
+        double total = 0, accum = 0, tmp;
+        for (int k = 0; k < na; k++) {
+            if (l[k].type == O_NONE) none = k;
+            total += (l[k].type == O_ATTACK || l[k].type == O_HARVEST || l[k].type == O_RETURN) ? 5.0 : 1.0;
+        }
+        tmp = o_jr_next_double(&g->rng_policy) * total;
+        int pick = -1;
+        for (int k = 0; k < na; k++) {
+            accum += (l[k].type == O_ATTACK || l[k].type == O_HARVEST || l[k].type == O_RETURN) ? 5.0 : 1.0;
+            if (accum >= tmp) { pick = k; break; }
+        }
+        if (pick < 0) pick = none; /* Sampler throws -> catch -> none */
+        OAct ua = l[pick];
+        if (ru1_consistent_with_ru(act_ru(&ua, g, u), &par, g)) {
+            ru_merge1(&par, act_ru(&ua, g, u));
+            out[n].unit = u; out[n].act = ua; n++;
+        } else {
+            out[n].unit = u; out[n].act = l[none]; n++;
+        }
+    }
+    free(l);
+    ru_free(&par);
+    return n;
+}
+
+static int pairs_out(const OGame *g, int n, const OPair *pa, int32_t *unit_idx, OActionV *acts) {
+    for (int k = 0; k < n; k++) { unit_idx[k] = list_index_of(g, pa[k].unit); acts[k] = act_to_v(&pa[k].act); }
+    return n;
+}
+
+int o_ai_random_biased(OGame *g, int player, int32_t *unit_idx, OActionV *acts) {
+    OPair *pa = (OPair *)malloc(sizeof(OPair) * (g->n + 1));
+    int n = rb_get_action(g, player, pa);
+    pairs_out(g, n, pa, unit_idx, acts);
+    free(pa);
+    return n;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Pathfinding: AStarPathFinding.java:52-79,104-138,175-295 ; BFSPathFinding.java:41-147
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct { int n; int8_t *free_; int *closed, *open, *heur, *parents, *cost, *inoc; } OPf;
+
+static void pf_alloc(OPf *p, int n) {
+    p->n = n;
+    p->free_ = (int8_t *)malloc(n);
+    p->closed = (int *)malloc(sizeof(int) * n * 6);
+    p->open = p->closed + n; p->heur = p->open + n; p->parents = p->heur + n; p->cost = p->parents + n; p->inoc = p->cost + n;
+}
+static void pf_release(OPf *p) { free(p->free_); free(p->closed); }
+static int manh(int x, int y, int x2, int y2) { return abs(x - x2) + abs(y - y2); }
+
+static int pf_free(OPf *p, const OGame *g, int x, int y) {
+    int8_t *c = &p->free_[x + y * g->w];
+    if (*c < 0) *c = (int8_t)gs_free(g, x, y);
+    return *c;
+}
+
+/* AStarPathFinding.addToOpen :104-138; returns updated openinsert */
+static int astar_add(OPf *p, int openinsert, int newPos, int oldPos, int h) {
+    p->cost[newPos] = p->cost[oldPos] + 1;
+    int at = 0;
+    for (int i = openinsert - 1; i >= 0; i--) {
+        if (p->heur[i] + p->cost[p->open[i]] >= h + p->cost[newPos]) { at = i + 1; break; }
+    }
+    memmove(&p->open[at + 1], &p->open[at], sizeof(int) * (openinsert - at));
+    memmove(&p->heur[at + 1], &p->heur[at], sizeof(int) * (openinsert - at));
+    memmove(&p->parents[at + 1], &p->parents[at], sizeof(int) * (openinsert - at));
+    p->open[at] = newPos; p->heur[at] = h; p->parents[at] = oldPos;
+    p->inoc[newPos] = 1;
+    return openinsert + 1;
+}
+
+static int decode_first_step(const OPf *p, int pos, int parent, int w) {
+    int last = pos;
+    while (parent != pos) { last = pos; pos = parent; parent = p->closed[pos]; }
+    if (last == pos + w) return O_DOWN;
+    if (last == pos - 1) return O_LEFT;
+    if (last == pos - w) return O_UP;
+    if (last == pos + 1) return O_RIGHT;
+    return -1;
+}
+
+static int pf_find(const OGame *g, int kind, int start, int targetpos, int range, const ORu *ru) {
+    int w = g->w, h = g->h, n = w * h;
+    OPf p; pf_alloc(&p, n);
+    memset(p.free_, -1, n);
+    for (int i = 0; i < n; i++) { p.closed[i] = -1; p.inoc[i] = 0; }
+    if (ru) for (int i = 0; i < ru->npos; i++) { int q = ru->pos[i]; if (q >= 0 && q < n) p.free_[q] = 0; }
+    int tx = targetpos % w, ty = targetpos / w;
+    int sq = range * range;
+    const OUnit *s = &g->pool[start];
+    int startPos = s->y * w + s->x;
+    int result = -1;
+    if (kind == O_PF_ASTAR) {
+        int oi = 0;
+        p.open[0] = startPos; p.heur[0] = manh(s->x, s->y, tx, ty); p.parents[0] = startPos; p.inoc[startPos] = 1; p.cost[startPos] = 0; oi = 1;
+        while (oi > 0) {
+            oi--;
+            int pos = p.open[oi], parent = p.parents[oi];
+            if (p.closed[pos] != -1) continue;
+            p.closed[pos] = parent;
+            int x = pos % w, y = pos / w;
+            if ((x - tx) * (x - tx) + (y - ty) * (y - ty) <= sq) { result = decode_first_step(&p, pos, parent, w); break; }
+            if (y > 0 && p.inoc[pos - w] == 0 && pf_free(&p, g, x, y - 1)) oi = astar_add(&p, oi, pos - w, pos, manh(x, y - 1, tx, ty));
+            if (x < w - 1 && p.inoc[pos + 1] == 0 && pf_free(&p, g, x + 1, y)) oi = astar_add(&p, oi, pos + 1, pos, manh(x + 1, y, tx, ty));
+            if (y < h - 1 && p.inoc[pos + w] == 0 && pf_free(&p, g, x, y + 1)) oi = astar_add(&p, oi, pos + w, pos, manh(x, y + 1, tx, ty));
+            if (x > 0 && p.inoc[pos - 1] == 0 && pf_free(&p, g, x - 1, y)) oi = astar_add(&p, oi, pos - 1, pos, manh(x - 1, y, tx, ty));
+        }
+    } else {
+        int oi = 0, orm = 0;
+        p.open[0] = startPos; p.parents[0] = startPos; p.inoc[startPos] = 1; oi = 1;
+        while (oi != orm) {
+            int pos = p.open[orm], parent = p.parents[orm];
+            orm++; if (orm >= n) orm = 0;
+            if (p.closed[pos] != -1) continue;
+            p.closed[pos] = parent;
+            int x = pos % w, y = pos / w;
+            if ((x - tx) * (x - tx) + (y - ty) * (y - ty) <= sq) { result = decode_first_step(&p, pos, parent, w); break; }
+#define BFS_PUSH(NP) do { p.open[oi] = (NP); p.parents[oi] = pos; oi++; if (oi >= n) oi = 0; p.inoc[(NP)] = 1; } while (0)
+            if (y > 0 && p.inoc[pos - w] == 0 && pf_free(&p, g, x, y - 1)) BFS_PUSH(pos - w);
+            if (x < w - 1 && p.inoc[pos + 1] == 0 && pf_free(&p, g, x + 1, y)) BFS_PUSH(pos + 1);
+            if (y < h - 1 && p.inoc[pos + w] == 0 && pf_free(&p, g, x, y + 1)) BFS_PUSH(pos + w);
+            if (x > 0 && p.inoc[pos - 1] == 0 && pf_free(&p, g, x - 1, y)) BFS_PUSH(pos - 1);
+#undef BFS_PUSH
+        }
+    }
+    pf_release(&p);
+    return result;
+}
+
+int o_pathfind(const OGame *g, int kind, int unit_idx, int targetpos, int range, int n_ru, const int32_t *ru_pos) {
+    ORu r; ru_init(&r);
+    for (int i = 0; i < n_ru; i++) ru_add_pos(&r, ru_pos[i]);
+    int d = pf_find(g, kind, g->list[unit_idx], targetpos, range, &r);
+    ru_free(&r);
+    return d;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * AbstractionLayerAI + WorkerRush + LightRush
+ *   ai/abstraction/AbstractionLayerAI.java:58-113,143-245 ; WorkerRush.java:63-204 ; LightRush.java:77-258 ;
+ *   Attack.java:51 ; Harvest.java:72 ; Build.java:54 ; Train.java:48-128
+ * ---------------------------------------------------------------------------------------------- */
+enum { AA_TRAIN = 1, AA_BUILD, AA_HARVEST, AA_ATTACK };
+typedef struct {
+    int unit; int kind;
+    int type;          /* train / build */
+    int x, y;          /* build */
+    int target, base;  /* harvest (target may be -1 = null) / attack (target) */
+    int completed;     /* train */
+} OAbs;
+
+struct OAi { int kind; int pf; OAbs *a; int n, cap; };
+
+OAi *o_ai_create(int kind, int pathfinder) {
+    OAi *ai = (OAi *)calloc(1, sizeof(OAi));
+    ai->kind = kind; ai->pf = pathfinder;
+    return ai;
+}
+OAi *o_ai_clone(const OAi *s) { return o_ai_create(s->kind, s->pf); } /* AI.clone(): fresh instance, empty actions map */
+void o_ai_free(OAi *ai) { if (ai) { free(ai->a); free(ai); } }
+
+static OAbs *ai_get(OAi *ai, int u) { for (int i = 0; i < ai->n; i++) if (ai->a[i].unit == u) return &ai->a[i]; return NULL; }
+static void ai_put(OAi *ai, OAbs v) { /* LinkedHashMap.put: existing key keeps its slot */
+    OAbs *e = ai_get(ai, v.unit);
+    if (e) { *e = v; return; }
+    if (ai->n == ai->cap) { ai->cap = ai->cap ? ai->cap * 2 : 32; ai->a = (OAbs *)realloc(ai->a, sizeof(OAbs) * ai->cap); }
+    ai->a[ai->n++] = v;
+}
+static void ai_train(OAi *ai, int u, int type) { OAbs v = {u, AA_TRAIN, type, 0, 0, -1, -1, 0}; ai_put(ai, v); }
+static void ai_build(OAi *ai, int u, int type, int x, int y) { OAbs v = {u, AA_BUILD, type, x, y, -1, -1, 0}; ai_put(ai, v); }
+static void ai_harvest(OAi *ai, int u, int target, int base) { OAbs v = {u, AA_HARVEST, -1, 0, 0, target, base, 0}; ai_put(ai, v); }
+static void ai_attack(OAi *ai, int u, int target) { OAbs v = {u, AA_ATTACK, -1, 0, 0, target, -1, 0}; ai_put(ai, v); }
+
+static int in_list(const OGame *g, int u) { return u >= 0 && list_index_of(g, u) >= 0; }
+
+static int aa_completed(const OAbs *aa, const OGame *g) {
+    switch (aa->kind) {
+        case AA_TRAIN: return aa->completed;                                  /* Train.java:30 */
+        case AA_BUILD: return unit_at(g, aa->x, aa->y) >= 0;                  /* Build.java:33-37 */
+        case AA_HARVEST:                                                      /* Harvest.java:46-52 */
+            if (g->pool[aa->unit].res > 0) return !in_list(g, aa->base);
+            return !in_list(g, aa->target);
+        case AA_ATTACK: return !in_list(g, aa->target);                       /* Attack.java:30-33 */
+    }
+    return 1;
+}
+
+static int mk_move(OAct *out, int dir) { if (dir < 0) return 0; *out = mk_act(O_MOVE, dir, 0, 0, -1); return 1; }
+
+/* Train.score, Train.java:98-126 */
+static int train_score(const OGame *g, int x, int y, int type, int player) {
+    int distance = 0, first = 1;
+    for (int i = 0; i < g->n; i++) {
+        const OUnit *u = &g->pool[g->list[i]];
+        int ok = (g->utt->flags[type] & OFL_HARVEST) ? (g->utt->flags[u->type] & OFL_RESOURCE) != 0 : (u->player >= 0 && u->player != player);
+        if (ok) { int d = abs(u->x - x) + abs(u->y - y); if (first || d < distance) { distance = d; first = 0; } }
+    }
+    return -distance;
+}
+
+/* returns 1 and fills *out if the abstract action yields a unit action, 0 for null */
+static int aa_execute(OAi *ai, OAbs *aa, OGame *g, const ORu *ru, OAct *out) {
+    const OUnit *unit = &g->pool[aa->unit];
+    int w = g->w;
+    switch (aa->kind) {
+        case AA_ATTACK: { /* Attack.java:51-64 */
+            const OUnit *t = &g->pool[aa->target];
+            int dx = t->x - unit->x, dy = t->y - unit->y;
+            double d = sqrt((double)(dx * dx + dy * dy));
+            int range = g->utt->f[unit->type][OF_RANGE];
+            if (d <= range) { *out = mk_act(O_ATTACK, -1, t->x, t->y, -1); return 1; }
+            OAct mv;
+            if (mk_move(&mv, pf_find(g, ai->pf, aa->unit, t->x + t->y * w, range, ru)) && is_unit_action_allowed(g, aa->unit, &mv)) { *out = mv; return 1; }
+            return 0;
+        }
+        case AA_HARVEST: { /* Harvest.java:72-113 */
+            int other = (unit->res == 0) ? aa->target : aa->base;
+            int atype = (unit->res == 0) ? O_HARVEST : O_RETURN;
+            if (other < 0) return 0;
+            const OUnit *t = &g->pool[other];
+            OAct mv;
+            if (mk_move(&mv, pf_find(g, ai->pf, aa->unit, t->x + t->y * w, 1, ru))) {
+                if (is_unit_action_allowed(g, aa->unit, &mv)) { *out = mv; return 1; }
+                return 0;
+            }
+            if (t->x == unit->x && t->y == unit->y - 1) { *out = mk_act(atype, O_UP, 0, 0, -1); return 1; }
+            if (t->x == unit->x + 1 && t->y == unit->y) { *out = mk_act(atype, O_RIGHT, 0, 0, -1); return 1; }
+            if (t->x == unit->x && t->y == unit->y + 1) { *out = mk_act(atype, O_DOWN, 0, 0, -1); return 1; }
+            if (t->x == unit->x - 1 && t->y == unit->y) { *out = mk_act(atype, O_LEFT, 0, 0, -1); return 1; }
+            return 0;
+        }
+        case AA_BUILD: { /* Build.java:54-77 */
+            OAct mv;
+            if (mk_move(&mv, pf_find(g, ai->pf, aa->unit, aa->x + aa->y * w, 1, ru))) {
+                if (is_unit_action_allowed(g, aa->unit, &mv)) { *out = mv; return 1; }
+                return 0;
+            }
+            int dir = -1;
+            if (aa->x == unit->x && aa->y == unit->y - 1) dir = O_UP;
+            if (aa->x == unit->x + 1 && aa->y == unit->y) dir = O_RIGHT;
+            if (aa->x == unit->x && aa->y == unit->y + 1) dir = O_DOWN;
+            if (aa->x == unit->x - 1 && aa->y == unit->y) dir = O_LEFT;
+            if (dir >= 0) { OAct ua = mk_act(O_PRODUCE, dir, 0, 0, aa->type); if (is_unit_action_allowed(g, aa->unit, &ua)) { *out = ua; return 1; } }
+            return 0;
+        }
+        case AA_TRAIN: { /* Train.java:48-95 */
+            int x = unit->x, y = unit->y, best_dir = -1, best = -1;
+            if (y > 0 && gs_free(g, x, y - 1)) { int s = train_score(g, x, y - 1, aa->type, unit->player); if (s > best || best_dir == -1) { best = s; best_dir = O_UP; } }
+            if (x < g->w - 1 && gs_free(g, x + 1, y)) { int s = train_score(g, x + 1, y, aa->type, unit->player); if (s > best || best_dir == -1) { best = s; best_dir = O_RIGHT; } }
+            if (y < g->h - 1 && gs_free(g, x, y + 1)) { int s = train_score(g, x, y + 1, aa->type, unit->player); if (s > best || best_dir == -1) { best = s; best_dir = O_DOWN; } }
+            if (x > 0 && gs_free(g, x - 1, y)) { int s = train_score(g, x - 1, y, aa->type, unit->player); if (s > best || best_dir == -1) { best = s; best_dir = O_LEFT; } }
+            aa->completed = 1;
+            if (best_dir != -1) { OAct ua = mk_act(O_PRODUCE, best_dir, 0, 0, aa->type); if (is_unit_action_allowed(g, aa->unit, &ua)) { *out = ua; return 1; } }
+            return 0;
+        }
+    }
+    return 0;
+}
+
+/* AbstractionLayerAI.translateActions, AbstractionLayerAI.java:58-113 */
+static int ai_translate(OAi *ai, OGame *g, int player, OPair *out) {
+    int nd = 0;
+    OPair *desires = (OPair *)malloc(sizeof(OPair) * (ai->n + 1));
+    int *del = (int *)calloc(ai->n + 1, sizeof(int));
+    ORu ru; ru_init(&ru);
+    for (int i = 0; i < ai->n; i++) {
+        OAbs *aa = &ai->a[i];
+        if (!in_list(g, aa->unit)) { del[i] = 1; continue; }
+        if (aa_completed(aa, g)) { del[i] = 1; continue; }
+        if (find_assign(g, aa->unit) < 0) {
+            OAct ua;
+            if (aa_execute(ai, aa, g, &ru, &ua)) {
+                desires[nd].unit = aa->unit; desires[nd].act = ua; nd++;
+                ru_merge1(&ru, act_ru(&desires[nd - 1].act, g, aa->unit));
+            }
+        }
+    }
+    int k = 0;
+    for (int i = 0; i < ai->n; i++) if (!del[i]) ai->a[k++] = ai->a[i];
+    ai->n = k;
+    free(del); ru_free(&ru);
+    /* compose desires :93-101 */
+    ORu r; ru_init(&r);
+    gs_resource_usage(g, &r);
+    int n = 0;
+    for (int i = 0; i < nd; i++) {
+        const ORu1 *r2 = act_ru(&desires[i].act, g, desires[i].unit);
+        if (ru_consistent_with_ru1(&r, r2, g)) { out[n++] = desires[i]; ru_merge1(&r, r2); }
+    }
+    ru_free(&r); free(desires);
+    /* PlayerAction.fillWithNones(gs, player, 10), PlayerAction.java:217-235 */
+    for (int i = 0; i < g->n; i++) {
+        int u = g->list[i];
+        if (g->pool[u].player != player || find_assign(g, u) >= 0) continue;
+        int found = 0;
+        for (int j = 0; j < n; j++) if (out[j].unit == u) { found = 1; break; }
+        if (!found) { out[n].unit = u; out[n].act = act_none(10); n++; }
+    }
+    return n;
+}
+
+/* PhysicalGameState.getAllFree (PhysicalGameState.java:512-525) + AbstractionLayerAI.findBuildingPosition :143-229 */
+static int find_building_position(const OGame *g, const int *reserved, int nres, int dX, int dY) {
+    int w = g->w, h = g->h;
+    uint8_t *fr = (uint8_t *)malloc((size_t)w * h);
+    for (int i = 0; i < w * h; i++) fr[i] = g->terrain[i] == 0;
+    for (int i = 0; i < g->n; i++) { const OUnit *u = &g->pool[g->list[i]]; fr[u->x + u->y * w] = 0; }
+    int result = -1;
+    int maxl = h > w ? h : w;
+#define TRY(X, Y) do { int pos = (X) + (Y) * w; int rsv = 0; for (int q = 0; q < nres; q++) if (reserved[q] == pos) rsv = 1; \
+                       if (!rsv && fr[pos]) { result = pos; goto done; } } while (0)
+    for (int l = 1; l < maxl; l++) {
+        for (int side = 0; side < 4; side++) {
+            int x, y;
+            switch (side) {
+                case 0: y = dY - l; if (y < 0) continue;
+                    for (int dx = -l; dx <= l; dx++) { x = dX + dx; if (x < 0 || x >= w) continue; TRY(x, y); } break;
+                case 1: x = dX + l; if (x >= w) continue;
+                    for (int dy = -l; dy <= l; dy++) { y = dY + dy; if (y < 0 || y >= h) continue; TRY(x, y); } break;
+                case 2: y = dY + l; if (y >= h) continue;
+                    for (int dx = -l; dx <= l; dx++) { x = dX + dx; if (x < 0 || x >= w) continue; TRY(x, y); } break;
+                case 3: x = dX - l; if (x < 0) continue;
+                    for (int dy = -l; dy <= l; dy++) { y = dY + dy; if (y < 0 || y >= h) continue; TRY(x, y); } break;
+            }
+        }
+    }
+#undef TRY
+done:
+    free(fr);
+    return result;
+}
+
+/* AbstractionLayerAI.buildIfNotAlreadyBuilding :231-245 */
+static void build_if_not_already(OAi *ai, const OGame *g, int u, int type, int dX, int dY, int *reserved, int *nres) {
+    OAbs *a = ai_get(ai, u);
+    if (!(a && a->kind == AA_BUILD && a->type == type)) {
+        int pos = find_building_position(g, reserved, *nres, dX, dY);
+        ai_build(ai, u, type, pos % g->w, pos / g->w); /* Java % and / truncate like C for pos = -1 */
+        reserved[(*nres)++] = pos;
+    }
+}
+
+/* WorkerRush/LightRush.meleeUnitBehavior (WorkerRush.java:105-121, LightRush.java:141-159) */
+static void melee_behavior(OAi *ai, const OGame *g, int u, int player) {
+    int closest = -1, cd = 0;
+    const OUnit *me = &g->pool[u];
+    for (int i = 0; i < g->n; i++) {
+        const OUnit *o = &g->pool[g->list[i]];
+        if (o->player >= 0 && o->player != player) {
+            int d = abs(o->x - me->x) + abs(o->y - me->y);
+            if (closest < 0 || d < cd) { closest = g->list[i]; cd = d; }
+        }
+    }
+    if (closest >= 0) ai_attack(ai, u, closest);
+}
+
+/* harvest part shared by WorkerRush.workersBehavior :148-199 and LightRush.workersBehavior :203-252; returns 1 if still free */
+static int harvest_behavior(OAi *ai, const OGame *g, int u, int player) {
+    const OUnit *me = &g->pool[u];
+    int cbase = -1, cres = -1, cd = 0;
+    for (int i = 0; i < g->n; i++) {
+        const OUnit *o = &g->pool[g->list[i]];
+        if (g->utt->flags[o->type] & OFL_RESOURCE) { int d = abs(o->x - me->x) + abs(o->y - me->y); if (cres < 0 || d < cd) { cres = g->list[i]; cd = d; } }
+    }
+    cd = 0;
+    for (int i = 0; i < g->n; i++) {
+        const OUnit *o = &g->pool[g->list[i]];
+        if ((g->utt->flags[o->type] & OFL_STOCKPILE) && o->player == player) { int d = abs(o->x - me->x) + abs(o->y - me->y); if (cbase < 0 || d < cd) { cbase = g->list[i]; cd = d; } }
+    }
+    int still_free = 1;
+    OAbs *aa = ai_get(ai, u);
+    if (me->res > 0) {
+        if (cbase >= 0) {
+            if (aa && aa->kind == AA_HARVEST) { if (aa->base != cbase) ai_harvest(ai, u, -1, cbase); }
+            else ai_harvest(ai, u, -1, cbase);
+            still_free = 0;
+        }
+    } else {
+        if (cres >= 0 && cbase >= 0) {
+            if (aa && aa->kind == AA_HARVEST) { if (aa->target != cres || aa->base != cbase) ai_harvest(ai, u, cres, cbase); }
+            else ai_harvest(ai, u, cres, cbase);
+            still_free = 0;
+        }
+    }
+    return still_free;
+}
+
+static int type_by_role_base(void) { return 1; }
+static int type_by_role_barracks(void) { return 2; }
+static int type_by_role_worker(void) { return 3; }
+static int type_by_role_light(void) { return 4; }
+
+static int ai_get_action(OAi *ai, OGame *g, int player, OPair *out) {
+    const OUtt *t = g->utt;
+    int BASE = type_by_role_base(), BARRACKS = type_by_role_barracks(), WORKER = type_by_role_worker(), LIGHT = type_by_role_light();
+    int pres = g->res[player];
+    /* bases: WorkerRush.java:70-76,100-102 ; LightRush.java:83-89,123-133 */
+    for (int i = 0; i < g->n; i++) {
+        int u = g->list[i]; const OUnit *un = &g->pool[u];
+        if (un->type == BASE && un->player == player && find_assign(g, u) < 0) {
+            if (ai->kind == O_AI_WORKER_RUSH) {
+                if (pres >= t->f[WORKER][OF_COST]) ai_train(ai, u, WORKER);
+            } else {
+                int nworkers = 0;
+                for (int j = 0; j < g->n; j++) { const OUnit *o = &g->pool[g->list[j]]; if (o->type == WORKER && o->player == player) nworkers++; }
+                if (nworkers < 1 && pres >= t->f[WORKER][OF_COST]) ai_train(ai, u, WORKER);
+            }
+        }
+    }
+    /* barracks: LightRush.java:92-98,135-139 */
+    if (ai->kind == O_AI_LIGHT_RUSH) {
+        for (int i = 0; i < g->n; i++) {
+            int u = g->list[i]; const OUnit *un = &g->pool[u];
+            if (un->type == BARRACKS && un->player == player && find_assign(g, u) < 0) {
+                if (pres >= t->f[LIGHT][OF_COST]) ai_train(ai, u, LIGHT);
+            }
+        }
+    }
+    /* melee units */
+    for (int i = 0; i < g->n; i++) {
+        int u = g->list[i]; const OUnit *un = &g->pool[u];
+        if ((t->flags[un->type] & OFL_ATTACK) && !(t->flags[un->type] & OFL_HARVEST) && un->player == player && find_assign(g, u) < 0)
+            melee_behavior(ai, g, u, player);
+    }
+    /* workers (all own harvesters, busy ones included) */
+    int *workers = (int *)malloc(sizeof(int) * (g->n + 1)); int nw = 0;
+    for (int i = 0; i < g->n; i++) { int u = g->list[i]; const OUnit *un = &g->pool[u]; if ((t->flags[un->type] & OFL_HARVEST) && un->player == player) workers[nw++] = u; }
+    if (nw > 0) {
+        int nbases = 0, nbarracks = 0, resourcesUsed = 0;
+        for (int i = 0; i < g->n; i++) {
+            const OUnit *o = &g->pool[g->list[i]];
+            if (o->type == BASE && o->player == player) nbases++;
+            if (o->type == BARRACKS && o->player == player) nbarracks++;
+        }
+        int reserved[8]; int nres = 0;
+        int fw = 0; /* freeWorkers = workers[fw..nw) */
+        if (nbases == 0 && fw < nw) {
+            if (pres >= t->f[BASE][OF_COST] + resourcesUsed) {
+                int u = workers[fw++];
+                build_if_not_already(ai, g, u, BASE, g->pool[u].x, g->pool[u].y, reserved, &nres);
+                resourcesUsed += t->f[BASE][OF_COST];
+            }
+        }
+        if (ai->kind == O_AI_LIGHT_RUSH) {
+            if (nbarracks == 0) {
+                if (pres >= t->f[BARRACKS][OF_COST] + resourcesUsed && fw < nw) {
+                    int u = workers[fw++];
+                    build_if_not_already(ai, g, u, BARRACKS, g->pool[u].x, g->pool[u].y, reserved, &nres);
+                    resourcesUsed += t->f[BARRACKS][OF_COST];
+                }
+            }
+            int *still = (int *)malloc(sizeof(int) * (nw + 1)); int ns = 0;
+            for (int i = fw; i < nw; i++) if (harvest_behavior(ai, g, workers[i], player)) still[ns++] = workers[i];
+            for (int i = 0; i < ns; i++) melee_behavior(ai, g, still[i], player);
+            free(still);
+        } else {
+            /* WorkerRush.java:146-202: one harvest worker, the rest attack; a still-free harvester goes to the END of the list */
+            int *fl = (int *)malloc(sizeof(int) * (nw + 1)); int nf = 0;
+            int hw = -1;
+            if (fw < nw) hw = workers[fw++];
+            for (int i = fw; i < nw; i++) fl[nf++] = workers[i];
+            if (hw >= 0 && harvest_behavior(ai, g, hw, player)) fl[nf++] = hw;
+            for (int i = 0; i < nf; i++) melee_behavior(ai, g, fl[i], player);
+            free(fl);
+        }
+    }
+    free(workers);
+    return ai_translate(ai, g, player, out);
+}
+
+int o_ai_get_action(OAi *ai, OGame *g, int player, int32_t *unit_idx, OActionV *acts) {
+    OPair *pa = (OPair *)malloc(sizeof(OPair) * (g->n + 1));
+    int n = ai_get_action(ai, g, player, pa);
+    pairs_out(g, n, pa, unit_idx, acts);
+    free(pa);
+    return n;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Vector actions: PlayerAction.fromVectorAction (PlayerAction.java:384-417), UnitAction.fromVectorAction
+ * (UnitAction.java:675-709), JNIAI.getAction fill (ai/jni/JNIAI.java:51-55)
+ * ---------------------------------------------------------------------------------------------- */
+int o_from_vector_action(OGame *g, int player, int n, const int32_t *vec, int fill_none_duration, int32_t *unit_idx, OActionV *acts) {
+    ORu par; ru_init(&par);
+    gs_resource_usage(g, &par);
+    int R = o_utt_max_attack_range(g->utt) * 2 + 1, c = R / 2;
+    OPair *pa = (OPair *)malloc(sizeof(OPair) * (g->n + n + 1));
+    int m = 0;
+    for (int k = 0; k < n; k++) {
+        const int32_t *a = vec + k * 8;
+        int u = unit_at(g, a[0] % g->w, a[0] / g->w);
+        if (u >= 0 && g->pool[u].player == player && find_assign(g, u) < 0) {
+            OAct ua = mk_act(a[1], -1, 0, 0, -1);
+            switch (a[1]) {
+                case O_NONE: break;
+                case O_MOVE: ua.param = a[2]; break;
+                case O_HARVEST: ua.param = a[3]; break;
+                case O_RETURN: ua.param = a[4]; break;
+                case O_PRODUCE: ua.param = a[5]; ua.utype = a[6]; break;
+                case O_ATTACK: ua.x = g->pool[u].x + (a[7] % R - c); ua.y = g->pool[u].y + (a[7] / R - c); break;
+            }
+            if (ua.type == O_PRODUCE && (ua.utype < 0 || ua.utype >= g->utt->n)) { g->errors |= OE_BAD_ACTION; continue; }
+            if (ru1_consistent_with_ru(act_ru(&ua, g, u), &par, g)) {
+                ru_merge1(&par, act_ru(&ua, g, u));
+                pa[m].unit = u; pa[m].act = ua; m++;
+            }
+        }
+    }
+    ru_free(&par);
+    if (fill_none_duration != -9999) {
+        for (int i = 0; i < g->n; i++) {
+            int u = g->list[i];
+            if (g->pool[u].player != player || find_assign(g, u) >= 0) continue;
+            int found = 0;
+            for (int j = 0; j < m; j++) if (pa[j].unit == u) { found = 1; break; }
+            if (!found) { pa[m].unit = u; pa[m].act = act_none(fill_none_duration); m++; }
+        }
+    }
+    pairs_out(g, m, pa, unit_idx, acts);
+    free(pa);
+    return m;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Observations (GameState.java:922-968; PartiallyObservableGameState.java:35-179), masks
+ * (UnitAction.java:711-751, JNIGridnetClient.java:210-223)
+ * ---------------------------------------------------------------------------------------------- */
+static void observe_common(const OGame *g, int player, int32_t *out) {
+    int w = g->w, h = g->h, n = w * h;
+    for (int i = 0; i < g->n; i++) {
+        const OUnit *u = &g->pool[g->list[i]];
+        int c = u->y * w + u->x;
+        out[0 * n + c] = u->hp;
+        out[1 * n + c] = u->res;
+        if (u->player >= 0) out[2 * n + c] = ((u->player + player) % 2) + 1;
+        out[3 * n + c] = u->type + 1;
+        int a = find_assign(g, g->list[i]);
+        if (a >= 0) out[4 * n + c] = g->asg[a].act.type;
+    }
+    for (int i = 0; i < n; i++) out[5 * n + i] = g->terrain[i];
+    (void)h;
+}
+void o_observe(const OGame *g, int player, int32_t *out) {
+    memset(out, 0, sizeof(int32_t) * 6 * g->w * g->h);
+    observe_common(g, player, out);
+}
+void o_observe_po(const OGame *g, int player, int32_t *out) {
+    int w = g->w, h = g->h, n = w * h;
+    memset(out, 0, sizeof(int32_t) * 8 * n);
+    observe_common(g, player, out);
+    for (int i = 0; i < g->n; i++) { /* calculateVisibility :156-179 */
+        const OUnit *u = &g->pool[g->list[i]];
+        if (u->player < 0) continue;
+        int32_t *plane = out + (u->player == player ? 6 : 7) * n;
+        int sr = g->utt->f[u->type][OF_SIGHT];
+        for (int dy = -sr; dy <= sr; dy++) for (int dx = -sr; dx <= sr; dx++) {
+            int x = u->x + dx, y = u->y + dy;
+            if (x >= 0 && x < w && y >= 0 && y < h && dx * dx + dy * dy <= sr * sr) plane[y * w + x] = 1;
+        }
+    }
+}
+
+void o_masks(const OGame *g, int player, int32_t *out) {
+    int R = o_utt_max_attack_range(g->utt) * 2 + 1, c = R / 2, nt = g->utt->n;
+    int K = 1 + 6 + 16 + nt + R * R;
+    memset(out, 0, sizeof(int32_t) * (size_t)g->w * g->h * K);
+    OAct *l = (OAct *)malloc(sizeof(OAct) * MAX_UA);
+    for (int i = 0; i < g->n; i++) {
+        int u = g->list[i]; const OUnit *un = &g->pool[u];
+        if (un->player != player || find_assign(g, u) >= 0) continue;
+        int32_t *m = out + ((size_t)un->y * g->w + un->x) * K;
+        m[0] = 1;
+        int na = unit_actions(g, u, 10, l, MAX_UA);
+        for (int k = 0; k < na; k++) {
+            const OAct *ua = &l[k];
+            m[1 + ua->type] = 1;
+            switch (ua->type) {
+                case O_MOVE: m[1 + 6 + ua->param] = 1; break;
+                case O_HARVEST: m[1 + 6 + 4 + ua->param] = 1; break;
+                case O_RETURN: m[1 + 6 + 8 + ua->param] = 1; break;
+                case O_PRODUCE: m[1 + 6 + 12 + ua->param] = 1; m[1 + 6 + 16 + ua->utype] = 1; break;
+                case O_ATTACK: m[1 + 6 + 16 + nt + (c + (ua->y - un->y)) * R + (c + (ua->x - un->x))] = 1; break;
+            }
+        }
+    }
+    free(l);
+}
+
+/* PartiallyObservableGameState ctor :35-54 and observable :61-71 */
+OGame *o_po_view(const OGame *s, int observer) {
+    OGame *g = o_game_clone(s);
+    int *del = (int *)malloc(sizeof(int) * (g->n + 1)); int nd = 0;
+    for (int i = 0; i < g->n; i++) {
+        const OUnit *u = &g->pool[g->list[i]];
+        if (u->player == observer) continue;
+        int vis = 0;
+        for (int j = 0; j < g->n && !vis; j++) {
+            const OUnit *o = &g->pool[g->list[j]];
+            if (o->player == observer) {
+                int d = (o->x - u->x) * (o->x - u->x) + (o->y - u->y) * (o->y - u->y);
+                int sr = g->utt->f[o->type][OF_SIGHT];
+                if (d <= sr * sr) vis = 1;
+            }
+        }
+        if (!vis) del[nd++] = g->list[i];
+    }
+    for (int i = 0; i < nd; i++) remove_unit(g, del[i]);
+    free(del);
+    return g;
+}
+
+/* SimpleSqrtEvaluationFunction3.java:24-44 ; SimpleEvaluationFunction.java:21-36 */
+static float base_score(const OGame *g, int fn, int player) {
+    float score = g->res[player] * 20.0f;
+    int any = 0;
+    for (int i = 0; i < g->n; i++) {
+        const OUnit *u = &g->pool[g->list[i]];
+        if (u->player != player) continue;
+        any = 1;
+        score += u->res * 10.0f;
+        int cost = g->utt->f[u->type][OF_COST], mhp = g->utt->f[u->type][OF_HP];
+        if (fn == 0) {
+            /* score += 40f * cost * Math.sqrt(hp / maxhp)  -- int division, float*int -> float, * double -> double, += narrows */
+            double v = (double)(40.0f * (float)cost) * sqrt((double)(u->hp / mhp));
+            score = (float)((double)score + v);
+        } else {
+            score += (40.0f * (float)(cost * u->hp)) / (float)mhp;
+        }
+    }
+    if (fn == 0 && !any) return 0;
+    return score;
+}
+float o_evaluate(const OGame *g, int fn, int maxplayer, int minplayer) {
+    float s1 = base_score(g, fn, maxplayer), s2 = base_score(g, fn, minplayer);
+    if (fn == 0) {
+        if (s1 + s2 == 0) return 0.5f;
+        return (2 * s1 / (s1 + s2)) - 1;
+    }
+    return s1 - s2;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Loops: Game.start (rts/Game.java:126-140) and NaiveMCTS.simulate (NaiveMCTS.java:297-308)
+ * ---------------------------------------------------------------------------------------------- */
+static int policy(OGame *g, int kind, OAi *ai, int player, OPair *out) {
+    switch (kind) {
+        case O_AI_RANDOM_BIASED: return rb_get_action(g, player, out);
+        case O_AI_WORKER_RUSH:
+        case O_AI_LIGHT_RUSH: return ai_get_action(ai, g, player, out);
+        default: return 0; /* PassiveAI: empty PlayerAction */
+    }
+}
+
+int o_run_game(OGame *g, int kind0, OAi *ai0, int kind1, OAi *ai1, int n_cycles, int max_cycles, int64_t *stats) {
+    int gameover = o_game_gameover(g) && g->time > 0;
+    OPair *p0 = NULL, *p1 = NULL; int cap = 0;
+    for (int it = 0; it < n_cycles && !gameover && g->time < max_cycles; it++) {
+        if (g->n + 8 > cap) { cap = g->n * 2 + 64; p0 = (OPair *)realloc(p0, sizeof(OPair) * cap); p1 = (OPair *)realloc(p1, sizeof(OPair) * cap); }
+        int n0 = policy(g, kind0, ai0, 0, p0);
+        int n1 = policy(g, kind1, ai1, 1, p1);
+        gs_issue_safe(g, n0, p0);
+        gs_issue_safe(g, n1, p1);
+        gameover = o_game_cycle(g);
+        if (stats) { stats[0] += 1; stats[1] += n0 + n1; stats[2] += g->n; }
+    }
+    free(p0); free(p1);
+    return gameover;
+}
+
+int o_simulate(OGame *g, int time_limit) {
+    int gameover = 0;
+    OPair *pa = NULL; int cap = 0;
+    do {
+        if (o_game_is_complete(g)) {
+            gameover = o_game_cycle(g);
+        } else {
+            if (g->n + 8 > cap) { cap = g->n * 2 + 64; pa = (OPair *)realloc(pa, sizeof(OPair) * cap); }
+            int n = rb_get_action(g, 0, pa); gs_issue(g, n, pa);
+            n = rb_get_action(g, 1, pa); gs_issue(g, n, pa);
+        }
+    } while (!gameover && g->time < time_limit);
+    free(pa);
+    return gameover;
+}
