@@ -1,0 +1,202 @@
+/*
+ * microrts_cuda.h -- C ABI of libmicrorts_cuda.so, the B200-native batched microRTS simulator.
+ *
+ * The reference (ConnAALL/MicroRTS) has no FFI: its seam is the Java object API.  Each entry point below names
+ * the reference interface it replaces (file:line under the reference checkout).  A new Java class
+ * rts.cuda.BatchedGameState binds these symbols through Panama FFM or JNI; the Python
+ * package microrts_b200 binds them through ctypes.
+ *
+ * Conventions
+ *  - Every function returns 0 (MRTS_OK) or a negative MRTS_E_* code.  Nothing throws, nothing prints.
+ *    mrts_last_error() returns a human readable description of the last failure on the calling thread.
+ *  - Handles are opaque and library-owned; array arguments are caller-owned and never retained after return.
+ *  - A mrts_batch is bound to one CUDA device and one stream and is NOT thread-safe (one host thread per batch,
+ *    one batch per GPU; games shard across GPUs by contiguous index range, no data-path collective).
+ *  - "on_device" pointers are CUDA device pointers on the batch's device; otherwise host pointers.
+ *  - There is no CPU fallback: every compute entry point fails with MRTS_E_CUDA when no device is usable.
+ *  - Per-game anomalies (the reference's `throw new Error`, System.err chatter) set sticky bits in the game's
+ *    error word, readable through mrts_batch_export / mrts_batch_results.
+ */
+#ifndef MICRORTS_CUDA_H
+#define MICRORTS_CUDA_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRTS_ABI_VERSION 1
+
+enum {
+    MRTS_OK = 0,
+    MRTS_E_ARG = -1,      /* bad argument */
+    MRTS_E_IO = -2,       /* file not found / unreadable */
+    MRTS_E_PARSE = -3,    /* malformed XML / JSON */
+    MRTS_E_CUDA = -4,     /* CUDA runtime error (no device, launch failure, out of memory) */
+    MRTS_E_LIMIT = -5,    /* map or unit table exceeds an engine limit */
+    MRTS_E_STATE = -6     /* call not valid in the current state */
+};
+
+/* UnitAction.TYPE_*  (src/rts/UnitAction.java:29-59) */
+enum { MRTS_NONE = 0, MRTS_MOVE = 1, MRTS_HARVEST = 2, MRTS_RETURN = 3, MRTS_PRODUCE = 4, MRTS_ATTACK = 5 };
+/* UnitAction.DIRECTION_*  (src/rts/UnitAction.java:68-100) */
+enum { MRTS_DIR_NONE = -1, MRTS_UP = 0, MRTS_RIGHT = 1, MRTS_DOWN = 2, MRTS_LEFT = 3 };
+/* UnitTypeTable.VERSION_* / MOVE_CONFLICT_RESOLUTION_*  (src/rts/units/UnitTypeTable.java:28-60) */
+enum { MRTS_UTT_ORIGINAL = 1, MRTS_UTT_FINETUNED = 2, MRTS_UTT_NON_DETERMINISTIC = 3 };
+enum { MRTS_CANCEL_BOTH = 1, MRTS_CANCEL_RANDOM = 2, MRTS_CANCEL_ALTERNATING = 3 };
+
+/* Device-resident policies (the AI classes whose getAction() runs inside the step kernel). */
+enum {
+    MRTS_POLICY_EXTERNAL = 0,      /* actions staged with mrts_batch_set_actions (JNIAI, src/ai/jni/JNIAI.java:51-55) */
+    MRTS_POLICY_PASSIVE = 1,       /* ai.PassiveAI: never issues anything */
+    MRTS_POLICY_RANDOM_BIASED = 2, /* ai.RandomBiasedAI (src/ai/RandomBiasedAI.java:51-107) */
+    MRTS_POLICY_WORKER_RUSH = 3,   /* ai.abstraction.WorkerRush (src/ai/abstraction/WorkerRush.java:63-204) */
+    MRTS_POLICY_LIGHT_RUSH = 4     /* ai.abstraction.LightRush  (src/ai/abstraction/LightRush.java:77-258) */
+};
+enum { MRTS_PF_ASTAR = 0, MRTS_PF_BFS = 1 };
+
+/* Action row formats (8 int32 per row). */
+enum {
+    /* PlayerAction.fromVectorAction rows (src/rts/PlayerAction.java:384-417, src/rts/UnitAction.java:675-709):
+     * [cell = x + y*W, type, moveDir, harvestDir, returnDir, produceDir, produceType, attackRelIdx] */
+    MRTS_ACTIONS_VECTOR = 0,
+    /* a PlayerAction as (unit, UnitAction) pairs: [cell of the unit, type, parameter, x, y, unitType(-1 none), 0, 0] */
+    MRTS_ACTIONS_RAW = 1
+};
+
+enum { MRTS_DTYPE_U8 = 0, MRTS_DTYPE_I32 = 1 };
+enum { MRTS_FLAG_PARTIAL_OBS = 1u };
+enum { MRTS_EVAL_SIMPLE_SQRT3 = 0, MRTS_EVAL_SIMPLE = 1 };
+
+/* unit type fields for mrts_utt_get (order of the attributes in UnitType.toxml, src/rts/units/UnitType.java) */
+enum {
+    MRTS_UT_COST = 0, MRTS_UT_HP, MRTS_UT_MIN_DAMAGE, MRTS_UT_MAX_DAMAGE, MRTS_UT_ATTACK_RANGE, MRTS_UT_PRODUCE_TIME,
+    MRTS_UT_MOVE_TIME, MRTS_UT_ATTACK_TIME, MRTS_UT_HARVEST_TIME, MRTS_UT_RETURN_TIME, MRTS_UT_HARVEST_AMOUNT,
+    MRTS_UT_SIGHT_RADIUS, MRTS_UT_FLAGS /* isResource|isStockpile<<1|canHarvest<<2|canMove<<3|canAttack<<4 */,
+    MRTS_UT_N_PRODUCES, MRTS_UT_PRODUCES0 /* .. +k */
+};
+
+/* per-game error bits (sticky) */
+enum {
+    MRTS_GE_UNIT_OVERFLOW = 1,      /* unit table capacity exceeded (a produce was dropped) */
+    MRTS_GE_INCONSISTENT_OLDER = 2, /* GameState.issue "Inconsistent actions were executed!" branch (GameState.java:298-317) */
+    MRTS_GE_FAILED_PRODUCE = 4,     /* produce completed without resources (UnitAction.java:457-461) */
+    MRTS_GE_CELL_OCCUPIED = 8,      /* PhysicalGameState.addUnit would have thrown (PhysicalGameState.java:189-195) */
+    MRTS_GE_BAD_ACTION = 16         /* malformed external action row */
+};
+
+typedef struct mrts_utt mrts_utt;
+typedef struct mrts_map mrts_map;
+typedef struct mrts_batch mrts_batch;
+
+int mrts_abi_version(void);
+const char *mrts_last_error(void);
+
+/* ---- UnitTypeTable: new UnitTypeTable(version, crs), src/rts/units/UnitTypeTable.java:92-94,104-289 ---- */
+int mrts_utt_create(int version, int conflict_policy, mrts_utt **out);
+/* UnitTypeTable.fromJSON (src/rts/units/UnitTypeTable.java:393-411) */
+int mrts_utt_from_json(const char *json, mrts_utt **out);
+int mrts_utt_num_types(const mrts_utt *);
+int mrts_utt_get(const mrts_utt *, int type_id, int field);
+const char *mrts_utt_type_name(const mrts_utt *, int type_id);
+int mrts_utt_conflict_policy(const mrts_utt *);
+int mrts_utt_max_attack_range(const mrts_utt *);
+void mrts_utt_destroy(mrts_utt *);
+
+/* ---- PhysicalGameState.load(file, utt) / fromXML, src/rts/PhysicalGameState.java:65-76,700-726 ---- */
+int mrts_map_load_xml(const char *path, const mrts_utt *, mrts_map **out);
+int mrts_map_from_xml(const char *xml_text, const mrts_utt *, mrts_map **out);
+/* programmatic construction (MapGenerator-style); units rows = [type, id, player, x, y, resources, hitpoints] */
+int mrts_map_create(int width, int height, const uint8_t *terrain, int res0, int res1, int n_units,
+                    const int32_t *units, const mrts_utt *, mrts_map **out);
+int mrts_map_width(const mrts_map *);
+int mrts_map_height(const mrts_map *);
+int mrts_map_num_units(const mrts_map *);
+int mrts_map_get_units(const mrts_map *, int32_t *out /* [n][7] */);
+int mrts_map_get_terrain(const mrts_map *, uint8_t *out /* [h*w] */);
+int mrts_map_resources(const mrts_map *, int player);
+void mrts_map_destroy(mrts_map *);
+
+/* ---- batch of n_games GameState objects on one device: new GameState(pgs, utt), GameState.java:62-65 ----
+ * Game g starts from maps[g % n_maps]; all maps must share width and height. unit_capacity 0 = automatic
+ * (initial units + total resources, rounded up; at most 254). */
+int mrts_batch_create(const mrts_utt *, const mrts_map *const *maps, int n_maps, int64_t n_games, int device,
+                      uint32_t flags, int unit_capacity, mrts_batch **out);
+void mrts_batch_destroy(mrts_batch *);
+int64_t mrts_batch_num_games(const mrts_batch *);
+int mrts_batch_unit_capacity(const mrts_batch *);
+int mrts_batch_device(const mrts_batch *);
+/* the CUDA stream (cudaStream_t) all work of this batch is enqueued on */
+void *mrts_batch_stream(const mrts_batch *);
+int mrts_batch_sync(mrts_batch *);
+
+/* (Re)start every game from its map; seeds[g] seeds game g's java.util.Random streams (util/Sampler.java:17,
+ * rts/GameState.java:37, rts/UnitAction.java:24).  seeds may be NULL (seed = game index). */
+int mrts_batch_reset(mrts_batch *, const int64_t *seeds, int on_device);
+/* restart only games whose mask byte is non-zero (auto-reset of finished environments,
+ * src/tests/JNIGridnetVecClient.java:272-286) */
+int mrts_batch_reset_masked(mrts_batch *, const uint8_t *mask, const int64_t *seeds, int on_device);
+
+int mrts_batch_set_policy(mrts_batch *, int player, int policy, int pathfinder);
+
+/* Stage one PlayerAction per game for `player`, consumed by the next mrts_batch_step when that player's policy
+ * is EXTERNAL (decode of both players happens on the pre-issue state, as in JNIGridnetClientSelfPlay.gameStep).
+ * actions = [n_games][max_k][8], counts = [n_games].  fill_none_duration: JNIAI pads idle units with NONE(1);
+ * pass a negative value for no padding. */
+int mrts_batch_set_actions(mrts_batch *, int player, int format, const int32_t *actions, const int32_t *counts,
+                           int max_k, int fill_none_duration, int on_device);
+
+/* GameState.issueSafe(pa) / GameState.issue(pa) right now (GameState.java:338-408 / 249-328), no cycle. */
+int mrts_batch_issue(mrts_batch *, int player, int format, const int32_t *actions, const int32_t *counts,
+                     int max_k, int fill_none_duration, int safe, int on_device);
+
+/* Game.start loop body (src/rts/Game.java:126-140) for up to n_cycles cycles per game:
+ *   pa0 = policy0(gs); pa1 = policy1(gs); gs.issueSafe(pa0); gs.issueSafe(pa1); gameover = gs.cycle();
+ * A game stops at game over or when time >= max_cycles. */
+int mrts_batch_step(mrts_batch *, int n_cycles, int max_cycles);
+/* GameState.cycle() only (no policies): advance every unfinished game up to absolute time t_target[g]
+ * (or by n_cycles when t_target is NULL). TestTracesIntegrity.java:81-85 */
+int mrts_batch_cycle_to(mrts_batch *, const int32_t *t_target, int n_cycles, int on_device);
+
+/* NaiveMCTS.simulate + evaluate (src/ai/mcts/naivemcts/NaiveMCTS.java:195-223,297-308): for every game, clone
+ * its state (from observer's partially observable view if observer >= 0), play RandomBiasedAI vs itself with
+ * issue() for `depth` cycles, evaluate for maxplayer.  The batch itself is not modified.  seeds[g] seeds rollout g.
+ * out_eval[g] = ef.evaluate(maxplayer, 1-maxplayer, gs2) (float, undiscounted); out_time[g] = gs2.getTime()-start. */
+int mrts_batch_rollout(mrts_batch *, int depth, int eval_fn, int maxplayer, int observer, const int64_t *seeds,
+                       float *out_eval, int32_t *out_time, int on_device);
+
+/* GameState.getVectorObservation(player) (GameState.java:922-968; PartiallyObservableGameState.java:82-154 when the
+ * batch has MRTS_FLAG_PARTIAL_OBS): out = [n_games][C][H][W], C = 6 or 8.  player < 0: per-game player array
+ * not supported yet. */
+int mrts_batch_observe(mrts_batch *, int player, int dtype, void *out, int on_device);
+int mrts_batch_num_planes(const mrts_batch *);
+/* JNIGridnetClient.getMasks(player) (src/tests/JNIGridnetClient.java:210-223, UnitAction.java:711-751):
+ * out = [n_games][H][W][mask_width]. */
+int mrts_batch_masks(mrts_batch *, int player, int dtype, void *out, int on_device);
+int mrts_batch_mask_width(const mrts_batch *);
+
+/* Flat host copy of game states (parity checks, MCTS leaf import).  Arrays are sized by the caller:
+ *  header  [count][8]    : time, res0, res1, n_units, winner(-1 none), gameover(0/1), error bits, next unit id
+ *  units   [count][cap][8]: type, player, x, y, resources, hitpoints, id, has_action(0/1)   (list order)
+ *  actions [count][cap][8]: type, parameter, x, y, unitType, issue time, order (rank in assignment insertion order), 0
+ *  rng     [count][3]    : raw 48-bit states of the policy / conflict / damage streams                              */
+typedef struct {
+    int32_t *header;
+    int32_t *units;
+    int32_t *actions;
+    int64_t *rng;
+} mrts_state_host;
+int mrts_batch_export(mrts_batch *, int64_t first, int64_t count, mrts_state_host *out);
+int mrts_batch_import(mrts_batch *, int64_t first, int64_t count, const mrts_state_host *in);
+/* light per-game result: out[g] = {time, winner(-1 none), gameover, error bits} */
+int mrts_batch_results(mrts_batch *, int32_t *out /* [n_games][4] */, int on_device);
+
+/* counters since the last reset: {wins_p0, wins_p1, draws, games_finished, cycles, decisions, unit_cycles, errors} */
+int mrts_batch_stats(mrts_batch *, int64_t out[8]);
+/* number of kernels this batch has launched so far */
+int64_t mrts_batch_launch_count(const mrts_batch *);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MICRORTS_CUDA_H */

@@ -1,0 +1,12 @@
+"""microrts_b200 -- host-side mirror of the reference's simulation API over libmicrorts_cuda.so.
+
+Names follow the reference (rts.units.UnitTypeTable, rts.PhysicalGameState, rts.GameState, rts.UnitAction); the
+batched state is the new class the reference would gain as rts.cuda.BatchedGameState.
+"""
+from .api import (ACTIONS_RAW, ACTIONS_VECTOR, BatchedGameState, MicroRTSError, PhysicalGameState, UnitAction,
+                  UnitTypeTable, POLICY_EXTERNAL, POLICY_LIGHT_RUSH, POLICY_PASSIVE, POLICY_RANDOM_BIASED,
+                  POLICY_WORKER_RUSH)
+
+__all__ = ["UnitTypeTable", "PhysicalGameState", "BatchedGameState", "UnitAction", "MicroRTSError", "ACTIONS_RAW",
+           "ACTIONS_VECTOR", "POLICY_EXTERNAL", "POLICY_PASSIVE", "POLICY_RANDOM_BIASED", "POLICY_WORKER_RUSH",
+           "POLICY_LIGHT_RUSH"]

@@ -1,0 +1,323 @@
+"""Host-side mirror of the reference interface for the batched simulation path.
+
+  UnitTypeTable       <- src/rts/units/UnitTypeTable.java:92-94,104-289
+  PhysicalGameState   <- src/rts/PhysicalGameState.java:65-76,700-726 (load / fromXML)
+  UnitAction          <- src/rts/UnitAction.java:29-100 (constants)
+  BatchedGameState    <- the reference's GameState API (issueSafe/issue/cycle/winner/gameover/getVectorObservation,
+                         src/rts/GameState.java) applied to n games at once, plus the JNIGridnetVecClient-style
+                         reset/gameStep/getMasks surface (src/tests/JNIGridnetVecClient.java:179-316)
+
+All arrays are numpy (host) unless a torch CUDA tensor is passed as `out`/input, in which case its device pointer is
+handed to the C ABI directly (no copies).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+
+ACTIONS_VECTOR, ACTIONS_RAW = 0, 1
+POLICY_EXTERNAL, POLICY_PASSIVE, POLICY_RANDOM_BIASED, POLICY_WORKER_RUSH, POLICY_LIGHT_RUSH = range(5)
+PF_ASTAR, PF_BFS = 0, 1
+DTYPE_U8, DTYPE_I32 = 0, 1
+FLAG_PARTIAL_OBS = 1
+
+
+class MicroRTSError(RuntimeError):
+    pass
+
+
+def _check(rc):
+    if rc < 0:
+        raise MicroRTSError("libmicrorts_cuda error %d: %s" % (rc, _ffi.lib().mrts_last_error().decode()))
+    return rc
+
+
+class UnitAction:
+    TYPE_NONE, TYPE_MOVE, TYPE_HARVEST, TYPE_RETURN, TYPE_PRODUCE, TYPE_ATTACK_LOCATION = range(6)
+    NUMBER_OF_ACTION_TYPES = 6
+    DIRECTION_NONE, DIRECTION_UP, DIRECTION_RIGHT, DIRECTION_DOWN, DIRECTION_LEFT = -1, 0, 1, 2, 3
+    DIRECTION_OFFSET_X = (0, 1, 0, -1)
+    DIRECTION_OFFSET_Y = (-1, 0, 1, 0)
+
+
+class UnitType:
+    FIELDS = ["cost", "hp", "minDamage", "maxDamage", "attackRange", "produceTime", "moveTime", "attackTime",
+              "harvestTime", "returnTime", "harvestAmount", "sightRadius"]
+
+    def __init__(self, utt, tid):
+        L = _ffi.lib()
+        self.ID = tid
+        self.name = L.mrts_utt_type_name(utt._h, tid).decode()
+        for k, f in enumerate(self.FIELDS):
+            setattr(self, f, L.mrts_utt_get(utt._h, tid, k))
+        fl = L.mrts_utt_get(utt._h, tid, 12)
+        self.isResource, self.isStockpile, self.canHarvest, self.canMove, self.canAttack = [bool(fl >> b & 1) for b in range(5)]
+        n = L.mrts_utt_get(utt._h, tid, 13)
+        self.produces = [L.mrts_utt_get(utt._h, tid, 14 + k) for k in range(n)]
+
+
+class UnitTypeTable:
+    VERSION_ORIGINAL, VERSION_ORIGINAL_FINETUNED, VERSION_NON_DETERMINISTIC = 1, 2, 3
+    MOVE_CONFLICT_RESOLUTION_CANCEL_BOTH, MOVE_CONFLICT_RESOLUTION_CANCEL_RANDOM, MOVE_CONFLICT_RESOLUTION_CANCEL_ALTERNATING = 1, 2, 3
+
+    def __init__(self, version=1, conflict_policy=1, _handle=None):
+        if _handle is None:
+            h = C.c_void_p()
+            _check(_ffi.lib().mrts_utt_create(version, conflict_policy, C.byref(h)))
+            _handle = h
+        self._h = _handle
+        self._types = [UnitType(self, t) for t in range(_ffi.lib().mrts_utt_num_types(self._h))]
+
+    @classmethod
+    def fromJSON(cls, text):
+        h = C.c_void_p()
+        _check(_ffi.lib().mrts_utt_from_json(text.encode(), C.byref(h)))
+        return cls(_handle=h)
+
+    def __del__(self):
+        try:
+            _ffi.lib().mrts_utt_destroy(self._h)
+        except Exception:
+            pass
+
+    def getUnitTypes(self):
+        return list(self._types)
+
+    def getUnitType(self, key):
+        if isinstance(key, str):
+            for t in self._types:
+                if t.name == key:
+                    return t
+            return None
+        return self._types[key]
+
+    def getMoveConflictResolutionStrategy(self):
+        return _ffi.lib().mrts_utt_conflict_policy(self._h)
+
+    def getMaxAttackRange(self):
+        return _ffi.lib().mrts_utt_max_attack_range(self._h)
+
+
+class PhysicalGameState:
+    """A map / initial state.  Built by load(path, utt), fromXML(text, utt) or create(...)."""
+
+    def __init__(self, handle, utt):
+        self._h, self.utt = handle, utt
+
+    @classmethod
+    def load(cls, fileName, utt):
+        h = C.c_void_p()
+        _check(_ffi.lib().mrts_map_load_xml(str(fileName).encode(), utt._h, C.byref(h)))
+        return cls(h, utt)
+
+    @classmethod
+    def fromXML(cls, text, utt):
+        h = C.c_void_p()
+        _check(_ffi.lib().mrts_map_from_xml(text.encode(), utt._h, C.byref(h)))
+        return cls(h, utt)
+
+    @classmethod
+    def create(cls, width, height, terrain, resources, units, utt):
+        """units: rows [type, id, player, x, y, resources, hitpoints]."""
+        t = np.ascontiguousarray(terrain, dtype=np.uint8).reshape(-1)
+        u = np.ascontiguousarray(units, dtype=np.int32).reshape(-1, 7)
+        h = C.c_void_p()
+        _check(_ffi.lib().mrts_map_create(width, height, t.ctypes.data, resources[0], resources[1], len(u),
+                                          u.ctypes.data if len(u) else None, utt._h, C.byref(h)))
+        return cls(h, utt)
+
+    def __del__(self):
+        try:
+            _ffi.lib().mrts_map_destroy(self._h)
+        except Exception:
+            pass
+
+    def getWidth(self):
+        return _ffi.lib().mrts_map_width(self._h)
+
+    def getHeight(self):
+        return _ffi.lib().mrts_map_height(self._h)
+
+    def getUnits(self):
+        n = _ffi.lib().mrts_map_num_units(self._h)
+        out = np.zeros((max(n, 1), 7), dtype=np.int32)
+        _ffi.lib().mrts_map_get_units(self._h, out.ctypes.data)
+        return out[:n]
+
+    def getTerrain(self):
+        out = np.zeros(self.getWidth() * self.getHeight(), dtype=np.uint8)
+        _ffi.lib().mrts_map_get_terrain(self._h, out.ctypes.data)
+        return out.reshape(self.getHeight(), self.getWidth())
+
+    def getPlayerResources(self, p):
+        return _ffi.lib().mrts_map_resources(self._h, p)
+
+
+def _ptr(a):
+    """(pointer, on_device, keepalive) of a numpy array or torch tensor."""
+    if a is None:
+        return None, 0, None
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data, 0, a
+    # torch tensor
+    assert a.is_contiguous()
+    return a.data_ptr(), 1 if a.is_cuda else 0, a
+
+
+class BatchedGameState:
+    """n independent GameState objects stepped in lockstep on one GPU (rts.cuda.BatchedGameState)."""
+
+    def __init__(self, utt, pgs, n_games, device=0, partial_obs=False, unit_capacity=0):
+        maps = list(pgs) if isinstance(pgs, (list, tuple)) else [pgs]
+        self.utt, self.maps, self.n = utt, maps, int(n_games)
+        arr = (C.c_void_p * len(maps))(*[m._h for m in maps])
+        h = C.c_void_p()
+        _check(_ffi.lib().mrts_batch_create(utt._h, arr, len(maps), self.n, device, FLAG_PARTIAL_OBS if partial_obs else 0,
+                                            unit_capacity, C.byref(h)))
+        self._h = h
+        self.width, self.height = maps[0].getWidth(), maps[0].getHeight()
+        self.cap = _ffi.lib().mrts_batch_unit_capacity(h)
+        self.device = device
+        self.num_planes = _ffi.lib().mrts_batch_num_planes(h)
+        self.mask_width = _ffi.lib().mrts_batch_mask_width(h)
+
+    def close(self):
+        if self._h is not None:
+            _ffi.lib().mrts_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- lifecycle ---------------------------------------------------------------------------------------------------
+    def reset(self, seeds=None):
+        p, dev, _k = _ptr(None if seeds is None else (np.ascontiguousarray(seeds, dtype=np.int64) if isinstance(seeds, (list, np.ndarray)) else seeds))
+        _check(_ffi.lib().mrts_batch_reset(self._h, p, dev))
+
+    def reset_masked(self, mask, seeds=None):
+        m = np.ascontiguousarray(mask, dtype=np.uint8) if isinstance(mask, (list, np.ndarray)) else mask
+        s = None if seeds is None else (np.ascontiguousarray(seeds, dtype=np.int64) if isinstance(seeds, (list, np.ndarray)) else seeds)
+        pm, dm, _k1 = _ptr(m)
+        ps, ds, _k2 = _ptr(s)
+        assert s is None or dm == ds
+        _check(_ffi.lib().mrts_batch_reset_masked(self._h, pm, ps, dm))
+
+    def set_policy(self, player, policy, pathfinder=PF_ASTAR):
+        _check(_ffi.lib().mrts_batch_set_policy(self._h, player, policy, pathfinder))
+
+    def sync(self):
+        _check(_ffi.lib().mrts_batch_sync(self._h))
+
+    # -- actions -----------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _actions(actions, counts):
+        if isinstance(actions, (list, np.ndarray)):
+            actions = np.ascontiguousarray(actions, dtype=np.int32)
+        if isinstance(counts, (list, np.ndarray)):
+            counts = np.ascontiguousarray(counts, dtype=np.int32)
+        max_k = int(actions.shape[1]) if actions is not None and len(actions.shape) == 3 else 0
+        return actions, counts, max_k
+
+    def set_actions(self, player, actions, counts=None, fmt=ACTIONS_VECTOR, fill_none_duration=1):
+        """Stage one PlayerAction per game ([n][max_k][8] rows) for the next step() of an EXTERNAL player."""
+        a, c, k = self._actions(actions, counts)
+        pa, da, _k1 = _ptr(a)
+        pc, _dc, _k2 = _ptr(c)
+        _check(_ffi.lib().mrts_batch_set_actions(self._h, player, fmt, pa, pc, k, fill_none_duration, da))
+
+    def issue(self, player, actions, counts=None, fmt=ACTIONS_RAW, safe=False, fill_none_duration=-1):
+        """GameState.issue(pa) (GameState.java:249-328) for every game; issueSafe when safe=True."""
+        a, c, k = self._actions(actions, counts)
+        pa, da, _k1 = _ptr(a)
+        pc, _dc, _k2 = _ptr(c)
+        _check(_ffi.lib().mrts_batch_issue(self._h, player, fmt, pa, pc, k, fill_none_duration, 1 if safe else 0, da))
+
+    def issueSafe(self, player, actions, counts=None, fmt=ACTIONS_RAW, fill_none_duration=-1):
+        """GameState.issueSafe(pa) (GameState.java:338-408)."""
+        self.issue(player, actions, counts, fmt, True, fill_none_duration)
+
+    # -- time --------------------------------------------------------------------------------------------------------
+    def step(self, n_cycles=1, max_cycles=3000):
+        """Game.start loop body (Game.java:126-140) for n_cycles cycles per game."""
+        _check(_ffi.lib().mrts_batch_step(self._h, n_cycles, max_cycles))
+
+    def cycle(self, n_cycles=1):
+        """GameState.cycle() n times (no policies)."""
+        _check(_ffi.lib().mrts_batch_cycle_to(self._h, None, n_cycles, 0))
+
+    def cycle_to(self, t_target):
+        t = np.ascontiguousarray(t_target, dtype=np.int32) if isinstance(t_target, (list, np.ndarray)) else t_target
+        p, dev, _k = _ptr(t)
+        _check(_ffi.lib().mrts_batch_cycle_to(self._h, p, 0, dev))
+
+    # -- outputs -----------------------------------------------------------------------------------------------------
+    def observe(self, player, dtype=np.int32, out=None):
+        """GameState.getVectorObservation(player) for every game: [n][C][H][W]."""
+        code = DTYPE_U8 if np.dtype(dtype) == np.uint8 else DTYPE_I32
+        if out is None:
+            out = np.empty((self.n, self.num_planes, self.height, self.width), dtype=np.uint8 if code == DTYPE_U8 else np.int32)
+        p, dev, _k = _ptr(out)
+        _check(_ffi.lib().mrts_batch_observe(self._h, player, code, p, dev))
+        return out
+
+    def masks(self, player, dtype=np.int32, out=None):
+        """JNIGridnetClient.getMasks(player) for every game: [n][H][W][mask_width]."""
+        code = DTYPE_U8 if np.dtype(dtype) == np.uint8 else DTYPE_I32
+        if out is None:
+            out = np.empty((self.n, self.height, self.width, self.mask_width), dtype=np.uint8 if code == DTYPE_U8 else np.int32)
+        p, dev, _k = _ptr(out)
+        _check(_ffi.lib().mrts_batch_masks(self._h, player, code, p, dev))
+        return out
+
+    def results(self, out=None):
+        """[n][4] = time, winner (-1 none), gameover, error bits."""
+        if out is None:
+            out = np.empty((self.n, 4), dtype=np.int32)
+        p, dev, _k = _ptr(out)
+        _check(_ffi.lib().mrts_batch_results(self._h, p, dev))
+        return out
+
+    def stats(self):
+        out = np.zeros(8, dtype=np.int64)
+        _check(_ffi.lib().mrts_batch_stats(self._h, out.ctypes.data))
+        return dict(zip(["wins_p0", "wins_p1", "draws", "games_finished", "cycles", "decisions", "unit_cycles", "errors"], out.tolist()))
+
+    @property
+    def launch_count(self):
+        return _ffi.lib().mrts_batch_launch_count(self._h)
+
+    def export(self, first=0, count=None):
+        count = self.n - first if count is None else count
+        hdr = np.zeros((count, 8), dtype=np.int32)
+        units = np.zeros((count, self.cap, 8), dtype=np.int32)
+        acts = np.zeros((count, self.cap, 8), dtype=np.int32)
+        rng = np.zeros((count, 3), dtype=np.int64)
+        st = _ffi.StateHost(hdr.ctypes.data_as(C.POINTER(C.c_int32)), units.ctypes.data_as(C.POINTER(C.c_int32)),
+                            acts.ctypes.data_as(C.POINTER(C.c_int32)), rng.ctypes.data_as(C.POINTER(C.c_int64)))
+        _check(_ffi.lib().mrts_batch_export(self._h, first, count, C.byref(st)))
+        return dict(header=hdr, units=units, actions=acts, rng=rng)
+
+    def import_(self, state, first=0):
+        hdr = np.ascontiguousarray(state["header"], dtype=np.int32)
+        units = np.ascontiguousarray(state["units"], dtype=np.int32)
+        acts = np.ascontiguousarray(state["actions"], dtype=np.int32) if state.get("actions") is not None else None
+        rng = np.ascontiguousarray(state["rng"], dtype=np.int64) if state.get("rng") is not None else None
+        st = _ffi.StateHost(hdr.ctypes.data_as(C.POINTER(C.c_int32)), units.ctypes.data_as(C.POINTER(C.c_int32)),
+                            acts.ctypes.data_as(C.POINTER(C.c_int32)) if acts is not None else None,
+                            rng.ctypes.data_as(C.POINTER(C.c_int64)) if rng is not None else None)
+        _check(_ffi.lib().mrts_batch_import(self._h, first, len(hdr), C.byref(st)))
+
+    # reference-style accessors over an export
+    def getTime(self):
+        return self.results()[:, 0]
+
+    def winner(self):
+        return self.results()[:, 1]
+
+    def gameover(self):
+        return self.results()[:, 2].astype(bool)

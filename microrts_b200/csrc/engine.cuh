@@ -1,0 +1,1043 @@
+// engine.cuh -- warp-per-game microRTS rules engine for sm_100a (device code).
+//
+// One warp owns one game at a time.  The game's unit table (struct-of-arrays, slot order == the reference's unit list
+// order) and three byte maps over a wall-padded grid live in shared memory:
+//    grid [cell] : 0 empty, 0xFF wall/out of bounds, else unit slot + 1      -> getUnitAt / terrain in O(1)
+//    resv [cell] : slot + 1 of the unit whose in-flight MOVE/PRODUCE targets the cell  -> ResourceUsage.positionsUsed
+//    claim[cell] : bit p set while player p's policy has tentatively chosen the cell this cycle (PlayerAction.r)
+// Lanes work on different units (enumeration, sampling, legality) and arbitrate order-dependent effects with
+// ballot / shuffle / redux; effects that the reference applies sequentially are replayed in the same order.
+//
+// Each function cites the reference code it restates (paths under the reference checkout, src/...).
+// The file is also compiled for the host by tests/emu (MRTS_EMU) where warp primitives are emulated with
+// coroutines; that build is test tooling only and is never linked into libmicrorts_cuda.so.
+#pragma once
+#include "layout.h"
+
+#ifdef MRTS_EMU
+#define DEV static inline
+#define DEVN static
+#else
+#define DEV __device__ __forceinline__
+#define DEVN __device__ __noinline__
+#endif
+
+#define FULLM 0xffffffffu
+#define MASK48 ((1ULL << 48) - 1)
+#define A0_NOUT (0xFFu << 8) // "unitType == null"
+
+enum { ACT_NONE = 0, ACT_MOVE = 1, ACT_HARVEST = 2, ACT_RETURN = 3, ACT_PRODUCE = 4, ACT_ATTACK = 5 };
+enum { POL_EXTERNAL = 0, POL_PASSIVE = 1, POL_RANDOM_BIASED = 2, POL_WORKER_RUSH = 3, POL_LIGHT_RUSH = 4 };
+enum { FMT_VECTOR = 0, FMT_RAW = 1 };
+enum { MODE_GAME = 0, MODE_CYCLE_ONLY = 1, MODE_ISSUE_ONLY = 2, MODE_OBSERVE = 3, MODE_MASKS = 4 };
+enum { ST_OVER = 1, ST_COUNTED = 2 };
+enum { STAT_WINS0 = 0, STAT_WINS1, STAT_DRAWS, STAT_FINISHED, STAT_CYCLES, STAT_DECISIONS, STAT_UNIT_CYCLES, STAT_ERRORS };
+
+struct StepParams {
+    int32_t *hdr;              // [n_games][16]
+    uint32_t *units;           // [n_games][7][cap]
+    const uint32_t *maps;      // n_maps blobs (layout.h: mrts_map_blob_words)
+    const uint32_t *cst;       // MRTS_CONST_WORDS: unit type table + LCG jump table
+    unsigned long long *stats; // [8]
+    long long n_games;
+    int n_maps, map_words;
+    int W, H, cap;
+    int mode;
+    int n_cycles, max_cycles;
+    const int32_t *t_target;   // MODE_CYCLE_ONLY: absolute target time per game (or NULL)
+    int policy[2], pathfinder[2];
+    int conflict;              // UnitTypeTable.moveConflictResolutionStrategy
+    int safe;                  // issueSafe (1) or issue (0) for external actions
+    int issue_player;          // MODE_ISSUE_ONLY
+    const int32_t *ext_actions[2]; // [n_games][max_k][8]
+    const int32_t *ext_counts[2];  // [n_games]
+    int ext_maxk[2], ext_format[2], ext_fill[2];
+    int max_range;             // UnitTypeTable.getMaxAttackRange()
+    int n_types;               // utt.getUnitTypes().size()
+    // MODE_OBSERVE / MODE_MASKS
+    void *out;
+    int out_dtype;             // 0 = u8, 1 = i32
+    int out_player;
+    int partial_obs;
+};
+
+struct Game {
+    int lane;
+    int W, H, P, cap, pcw, conflict;
+    int32_t *hdr;
+    uint32_t *w0, *w1, *a0;
+    int32_t *a1, *tis;
+    uint32_t *seq, *uid;
+    uint32_t *pa0;
+    int32_t *pa1;
+    uint8_t *pslot, *grid, *resv, *claim, *list;
+    const uint32_t *utt;        // shared memory copy
+    const uint64_t *jump;       // shared memory copy
+    const uint32_t *grid_tmpl;  // global: wall-padded empty grid of this game's map
+};
+
+DEV void g_bind(Game &g, unsigned char *sm, const SmemLayout &L, int W, int H, int cap, int lane, const uint32_t *cst_sm,
+                int conflict) {
+    g.lane = lane; g.W = W; g.H = H; g.P = W + 2; g.cap = cap; g.pcw = L.pcw; g.conflict = conflict;
+    g.hdr = (int32_t *)(sm + L.hdr);
+    uint32_t *u = (uint32_t *)(sm + L.units);
+    g.w0 = u + UW_W0 * cap; g.w1 = u + UW_W1 * cap; g.a0 = u + UW_A0 * cap; g.a1 = (int32_t *)(u + UW_A1 * cap);
+    g.tis = (int32_t *)(u + UW_TIS * cap); g.seq = u + UW_SEQ * cap; g.uid = u + UW_ID * cap;
+    g.pa0 = (uint32_t *)(sm + L.pa0); g.pa1 = (int32_t *)(sm + L.pa1); g.pslot = sm + L.pslot;
+    g.grid = sm + L.grid; g.resv = sm + L.resv; g.claim = sm + L.claim; g.list = sm + L.list;
+    g.utt = cst_sm; g.jump = (const uint64_t *)(cst_sm + MRTS_MAX_TYPES * MRTS_UTT_WORDS);
+    g.grid_tmpl = nullptr;
+}
+
+// ---- small accessors -------------------------------------------------------------------------------------------------
+DEV int u_type(uint32_t w) { return w & 0xff; }
+DEV int u_pl(uint32_t w) { return (w >> 8) & 0xff; } // 0 neutral, 1 = player 0, 2 = player 1
+DEV int u_x(uint32_t w) { return (w >> 16) & 0xff; }
+DEV int u_y(uint32_t w) { return w >> 24; }
+DEV int cell_of(const Game &g, uint32_t w) { return (u_y(w) + 1) * g.P + u_x(w) + 1; }
+DEV int doff(const Game &g, int d) { return d == 0 ? -g.P : (d == 1 ? 1 : (d == 2 ? g.P : -1)); } // UnitAction.java:94,100
+DEV int ddx(int d) { return d == 1 ? 1 : (d == 3 ? -1 : 0); }
+DEV int ddy(int d) { return d == 0 ? -1 : (d == 2 ? 1 : 0); }
+DEV int ut_cost(const Game &g, int t) { return g.utt[t * 8] & 0xff; }
+DEV int ut_hp(const Game &g, int t) { return (g.utt[t * 8] >> 8) & 0xff; }
+DEV int ut_mind(const Game &g, int t) { return (g.utt[t * 8] >> 16) & 0xff; }
+DEV int ut_maxd(const Game &g, int t) { return g.utt[t * 8] >> 24; }
+DEV int ut_range(const Game &g, int t) { return g.utt[t * 8 + 1] & 0xff; }
+DEV int ut_sight(const Game &g, int t) { return (g.utt[t * 8 + 1] >> 8) & 0xff; }
+DEV int ut_hamt(const Game &g, int t) { return (g.utt[t * 8 + 1] >> 16) & 0xff; }
+DEV int ut_flags(const Game &g, int t) { return g.utt[t * 8 + 1] >> 24; }
+DEV int ut_nprod(const Game &g, int t) { return (g.utt[t * 8 + 4] >> 16) & 0xff; }
+DEV int ut_prod(const Game &g, int t, int k) { return (g.utt[t * 8 + 5 + (k >> 2)] >> ((k & 3) * 8)) & 0xff; }
+DEV int a_type(uint32_t A0) { return A0 & 0xF; }
+DEV int a_utype(uint32_t A0) { return (A0 >> 8) & 0xff; }
+DEV bool a_uses_cell(int at) { return at == ACT_MOVE || at == ACT_PRODUCE; }
+DEV int u_hp(uint32_t w1) { return (int)(int16_t)(w1 & 0xffff); }
+DEV int u_res(uint32_t w1) { return (int)(int16_t)(w1 >> 16); }
+DEV uint32_t mk_w1(int hp, int res) { return ((uint32_t)hp & 0xffffu) | ((uint32_t)res << 16); }
+DEV int nth4(int m, int n) { // index of the n-th set bit of a 4-bit mask
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+        if ((m >> d) & 1) { if (n == 0) return d; n--; }
+    }
+    return 0;
+}
+DEV int nth8(int m, int n) {
+    for (int d = 0; d < 8; d++) {
+        if ((m >> d) & 1) { if (n == 0) return d; n--; }
+    }
+    return 0;
+}
+
+// UnitAction.ETA, UnitAction.java:307-329 (RETURN uses moveTime)
+DEV int eta_of(const Game &g, int t, uint32_t A0, int A1) {
+    switch (a_type(A0)) {
+        case ACT_NONE: return A1;
+        case ACT_MOVE:
+        case ACT_RETURN: return (int)(g.utt[t * 8 + 2] >> 16);
+        case ACT_ATTACK: return (int)(g.utt[t * 8 + 3] & 0xffff);
+        case ACT_HARVEST: return (int)(g.utt[t * 8 + 3] >> 16);
+        case ACT_PRODUCE: { int ut = a_utype(A0); return ut < MRTS_MAX_TYPES ? (int)(g.utt[ut * 8 + 2] & 0xffff) : 0; }
+    }
+    return 0;
+}
+// target cell of a MOVE/PRODUCE (UnitAction.resourceUsage, UnitAction.java:254-291; an out-of-range direction leaves
+// `pos` at the unit's own cell)
+DEV int target_cell(const Game &g, int c, int A1) { return ((unsigned)A1 < 4u) ? c + doff(g, A1) : c; }
+
+// ---- java.util.Random (Java SE spec: 48-bit LCG) -----------------------------------------------------------------------
+DEV uint64_t lcg_next(uint64_t s) { return (s * 0x5DEECE66DULL + 0xBULL) & MASK48; }
+DEV uint64_t lcg_jump(const Game &g, uint64_t s, int draws) { // advance by `draws` nextDouble() calls (2 steps each)
+    while (draws > 64) { s = (s * g.jump[128] + g.jump[129]) & MASK48; draws -= 64; }
+    return (s * g.jump[2 * draws] + g.jump[2 * draws + 1]) & MASK48;
+}
+DEV double lcg_next_double(uint64_t &s) { // ((long)next(26) << 27) + next(27)) * 2^-53
+    s = lcg_next(s); long long a = (long long)(s >> 22);
+    s = lcg_next(s); long long b = (long long)(s >> 21);
+    return (double)((a << 27) + b) * 0x1.0p-53;
+}
+DEV int lcg_next_int_bound(uint64_t &s, int bound) { // Random.nextInt(bound)
+    s = lcg_next(s);
+    int r = (int)(s >> 17);
+    int m = bound - 1;
+    if ((bound & m) == 0) return (int)(((long long)bound * (long long)r) >> 31);
+    for (int u = r;;) {
+        r = u % bound;
+        if ((int)((unsigned)u - (unsigned)r + (unsigned)m) >= 0) break;
+        s = lcg_next(s); u = (int)(s >> 17);
+    }
+    return r;
+}
+DEV uint64_t hdr_rng(const Game &g, int lo) { return (uint64_t)(uint32_t)g.hdr[lo] | ((uint64_t)(uint32_t)g.hdr[lo + 1] << 32); }
+DEV void hdr_set_rng(Game &g, int lo, uint64_t s) { g.hdr[lo] = (int32_t)(uint32_t)s; g.hdr[lo + 1] = (int32_t)(uint32_t)(s >> 32); }
+
+// ---- load / store ------------------------------------------------------------------------------------------------------
+// scatter units into grid/resv (maps must hold only walls / zeros)
+DEV void g_scatter(Game &g) {
+    int n = g.hdr[H_NUNITS];
+    for (int i = g.lane; i < n; i += 32) {
+        uint32_t w = g.w0[i];
+        int c = cell_of(g, w);
+        g.grid[c] = (uint8_t)(i + 1);
+        uint32_t A0 = g.a0[i];
+        if (a_uses_cell(a_type(A0))) g.resv[target_cell(g, c, g.a1[i])] = (uint8_t)(i + 1);
+    }
+    __syncwarp();
+}
+DEV void g_reset_maps(Game &g) {
+    for (int i = g.lane; i < g.pcw; i += 32) {
+        ((uint32_t *)g.grid)[i] = g.grid_tmpl[i];
+        ((uint32_t *)g.resv)[i] = 0;
+        ((uint32_t *)g.claim)[i] = 0;
+    }
+    __syncwarp();
+}
+DEV void g_load(Game &g, const int32_t *ghdr, const uint32_t *gun) {
+    if (g.lane < MRTS_HDR_WORDS) g.hdr[g.lane] = ghdr[g.lane];
+    g_reset_maps(g);
+    int n = g.hdr[H_NUNITS];
+    uint32_t *su = g.w0;
+    for (int k = 0; k < MRTS_UNIT_WORDS; k++)
+        for (int i = g.lane; i < n; i += 32) su[k * g.cap + i] = gun[k * g.cap + i];
+    __syncwarp();
+    g_scatter(g);
+}
+DEV void g_store(Game &g, int32_t *ghdr, uint32_t *gun) {
+    __syncwarp();
+    if (g.lane < MRTS_HDR_WORDS) ghdr[g.lane] = g.hdr[g.lane];
+    int n = g.hdr[H_NUNITS];
+    const uint32_t *su = g.w0;
+    for (int k = 0; k < MRTS_UNIT_WORDS; k++)
+        for (int i = g.lane; i < n; i += 32) gun[k * g.cap + i] = su[k * g.cap + i];
+    __syncwarp();
+}
+
+// ---- Unit.getUnitActions (units/Unit.java:382-522) as category masks ----------------------------------------------------
+struct Enum {
+    uint32_t w;
+    int t, pl, c, fl, range;
+    int free_m, atk_m, harv_m, ret_m, aff_m;
+    int n_atk, nfree, n_aff, nb, total;
+};
+
+DEV bool enemy_in_range(const Game &g, uint32_t me, uint32_t ow, int sq) {
+    int opl = u_pl(ow);
+    if (opl == 0 || opl == u_pl(me)) return false;
+    int dx = u_x(ow) - u_x(me), dy = u_y(ow) - u_y(me);
+    return dx * dx + dy * dy <= sq;
+}
+
+DEV void enumerate(const Game &g, int s, Enum &e) {
+    uint32_t w = g.w0[s];
+    e.w = w; e.t = u_type(w); e.pl = u_pl(w); e.c = cell_of(g, w);
+    e.fl = ut_flags(g, e.t); e.range = ut_range(g, e.t);
+    int myres = u_res(g.w1[s]);
+    int free_m = 0, atk_m = 0, harv_m = 0, ret_m = 0;
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+        int gv = g.grid[e.c + doff(g, d)];
+        if (gv == 0) free_m |= 1 << d;
+        else if (gv != 0xFF) {
+            uint32_t nw = g.w0[gv - 1];
+            int npl = u_pl(nw), nfl = ut_flags(g, u_type(nw));
+            if (npl != 0 && npl != e.pl) atk_m |= 1 << d;
+            if (nfl & UF_RESOURCE) harv_m |= 1 << d;
+            if ((nfl & UF_STOCKPILE) && npl == e.pl) ret_m |= 1 << d;
+        }
+    }
+    if (!(e.fl & UF_ATTACK) || e.range != 1) atk_m = 0;
+    if (!(e.fl & UF_HARVEST)) { harv_m = 0; ret_m = 0; }
+    else { if (myres != 0) harv_m = 0; if (!(myres > 0)) ret_m = 0; }
+    int n_atk = __popc(atk_m);
+    if ((e.fl & UF_ATTACK) && e.range > 1) { // every enemy within range, in unit-list order (Unit.java:424-436)
+        int n = g.hdr[H_NUNITS], sq = e.range * e.range;
+        n_atk = 0;
+        for (int i = 0; i < n; i++) n_atk += enemy_in_range(g, w, g.w0[i], sq) ? 1 : 0;
+    }
+    int aff_m = 0;
+    if (e.pl != 0) {
+        int pres = g.hdr[H_RES0 + e.pl - 1], np = ut_nprod(g, e.t);
+        for (int k = 0; k < np; k++) if (pres >= ut_cost(g, ut_prod(g, e.t, k))) aff_m |= 1 << k;
+    }
+    e.free_m = free_m; e.atk_m = atk_m; e.harv_m = harv_m; e.ret_m = ret_m; e.aff_m = aff_m;
+    e.n_atk = n_atk; e.nfree = __popc(free_m); e.n_aff = __popc(aff_m);
+    e.nb = n_atk + __popc(harv_m) + __popc(ret_m);
+    e.total = 5 * e.nb + e.nfree * (e.n_aff + ((e.fl & UF_MOVE) ? 1 : 0)) + 1;
+}
+
+// the idx-th action of the list getUnitActions would return; out: packed action, its target cell (-1) and cost
+DEV void pick_action(const Game &g, const Enum &e, int idx, int none_duration, uint32_t &A0, int &A1, int &tcell, int &cost) {
+    tcell = -1; cost = 0;
+    int x = u_x(e.w), y = u_y(e.w);
+    if (idx < e.n_atk) {
+        int ax, ay;
+        if (e.range == 1) { int d = nth4(e.atk_m, idx); ax = x + ddx(d); ay = y + ddy(d); }
+        else {
+            int n = g.hdr[H_NUNITS], sq = e.range * e.range; ax = x; ay = y;
+            for (int i = 0; i < n; i++) {
+                uint32_t ow = g.w0[i];
+                if (enemy_in_range(g, e.w, ow, sq)) { if (idx == 0) { ax = u_x(ow); ay = u_y(ow); break; } idx--; }
+            }
+        }
+        A0 = ACT_ATTACK | A0_NOUT | ((uint32_t)ax << 16) | ((uint32_t)ay << 24); A1 = -1; return;
+    }
+    idx -= e.n_atk;
+    int nh = __popc(e.harv_m);
+    if (idx < nh) { A0 = ACT_HARVEST | A0_NOUT; A1 = nth4(e.harv_m, idx); return; }
+    idx -= nh;
+    int nr = __popc(e.ret_m);
+    if (idx < nr) { A0 = ACT_RETURN | A0_NOUT; A1 = nth4(e.ret_m, idx); return; }
+    idx -= nr;
+    int np = e.nfree * e.n_aff;
+    if (idx < np) {
+        int k = idx / e.nfree, d = nth4(e.free_m, idx - k * e.nfree);
+        int ut = ut_prod(g, e.t, nth8(e.aff_m, k));
+        A0 = ACT_PRODUCE | ((uint32_t)ut << 8); A1 = d; tcell = e.c + doff(g, d); cost = ut_cost(g, ut); return;
+    }
+    idx -= np;
+    if ((e.fl & UF_MOVE) && idx < e.nfree) { int d = nth4(e.free_m, idx); A0 = ACT_MOVE | A0_NOUT; A1 = d; tcell = e.c + doff(g, d); return; }
+    A0 = ACT_NONE | A0_NOUT; A1 = none_duration;
+}
+
+// Sampler.weighted (util/Sampler.java:116-137) over weights {5 x nb, 1 x rest}: first i with accum_i >= tmp.
+// accum_i are exact integers, so accum_i >= tmp  <=>  accum_i >= ceil(tmp).
+DEV int sample_index(double draw, int nb, int total) {
+    double tmp = __dmul_rn(draw, (double)total);
+    int c = (int)ceil(tmp);
+    if (5 * nb >= c) { int j = (c + 4) / 5; return j < 1 ? 0 : j - 1; }
+    return nb + (c - 5 * nb) - 1;
+}
+
+// Unit.canExecuteAction (units/Unit.java:531-534): is (A0,A1) in getUnitActions(u, ETA)?  NONE is always legal.
+DEV bool action_is_legal(const Game &g, int s, uint32_t A0, int A1) {
+    Enum e; enumerate(g, s, e);
+    int at = a_type(A0);
+    bool dir_ok = (unsigned)A1 < 4u;
+    switch (at) {
+        case ACT_NONE: return true;
+        case ACT_MOVE: return dir_ok && (e.fl & UF_MOVE) && ((e.free_m >> A1) & 1);
+        case ACT_HARVEST: return dir_ok && ((e.harv_m >> A1) & 1);
+        case ACT_RETURN: return dir_ok && ((e.ret_m >> A1) & 1);
+        case ACT_PRODUCE: {
+            if (!dir_ok || !((e.free_m >> A1) & 1)) return false;
+            int ut = a_utype(A0), np = ut_nprod(g, e.t);
+            for (int k = 0; k < np; k++) if (ut_prod(g, e.t, k) == ut && ((e.aff_m >> k) & 1)) return true;
+            return false;
+        }
+        case ACT_ATTACK: {
+            if (!(e.fl & UF_ATTACK)) return false;
+            int ax = (A0 >> 16) & 0xff, ay = A0 >> 24;
+            if (ax >= g.W || ay >= g.H) return false;
+            int gv = g.grid[(ay + 1) * g.P + ax + 1];
+            if (gv == 0 || gv == 0xFF) return false;
+            return enemy_in_range(g, e.w, g.w0[gv - 1], e.range * e.range);
+        }
+    }
+    return false;
+}
+
+// sum of in-flight PRODUCE costs per player == resourcesUsed of GameState.getResourceUsage (GameState.java:652-664)
+DEV void reserved_resources(const Game &g, int &r0, int &r1) {
+    int n = g.hdr[H_NUNITS], a = 0, b = 0;
+    for (int i = g.lane; i < n; i += 32) {
+        uint32_t A0 = g.a0[i];
+        if (a_type(A0) == ACT_PRODUCE) { int c = ut_cost(g, a_utype(A0)); if (u_pl(g.w0[i]) == 1) a += c; else b += c; }
+    }
+    r0 = __reduce_add_sync(FULLM, a); r1 = __reduce_add_sync(FULLM, b);
+}
+
+// ResourceUsage.consistentWith, resource half (ResourceUsage.java:40-47): self = the candidate action {cost for player pl},
+// other = the accumulated usage par[2]
+DEV bool res_consistent_cand_vs_acc(const Game &g, int pl, int cost, int par0, int par1) {
+    int s0 = (pl == 1 ? cost : 0) + par0, s1 = (pl == 2 ? cost : 0) + par1;
+    if (par0 != 0 && s0 > 0 && s0 > g.hdr[H_RES0]) return false;
+    if (par1 != 0 && s1 > 0 && s1 > g.hdr[H_RES1]) return false;
+    return true;
+}
+
+// Sequentially accept/reject the choices of up to 32 lanes in lane order against the accumulated PlayerAction usage
+// (RandomBiasedAI.java:92-99 / PlayerAction.fromVectorAction PlayerAction.java:407-411).  Returns this lane's verdict.
+DEV bool accept_in_order(Game &g, int player, int cnt, int tcell, int cost, bool candidate, int &par0, int &par1) {
+    bool mine = false;
+    int pl = player + 1;
+    for (int j = 0; j < cnt; j++) {
+        int c = __shfl_sync(FULLM, tcell, j), co = __shfl_sync(FULLM, cost, j);
+        bool cand = __shfl_sync(FULLM, candidate ? 1 : 0, j) != 0;
+        bool ok = cand;
+        if (ok && c >= 0 && (g.resv[c] != 0 || ((g.claim[c] >> player) & 1))) ok = false;
+        if (ok && !res_consistent_cand_vs_acc(g, pl, co, par0, par1)) ok = false;
+        __syncwarp(); // every lane has read claim[] before lane 0 updates it
+        if (ok) {
+            if (pl == 1) par0 += co; else par1 += co;
+            if (c >= 0 && g.lane == 0) g.claim[c] |= (uint8_t)(1 << player);
+        }
+        if (g.lane == j) mine = ok;
+        __syncwarp();
+    }
+    return mine;
+}
+
+// ---- RandomBiasedAI.getAction (ai/RandomBiasedAI.java:51-107) ------------------------------------------------------------
+// Appends (unit, action) pairs for `player` to the pending list starting at pn; returns the new count.
+DEVN int policy_random_biased(Game &g, int player, int pn) {
+    int n = g.hdr[H_NUNITS], n_idle = 0;
+    for (int base = 0; base < n; base += 32) {
+        int i = base + g.lane;
+        bool idle = i < n && u_pl(g.w0[i]) == player + 1 && a_type(g.a0[i]) == AT_IDLE;
+        unsigned m = __ballot_sync(FULLM, idle);
+        if (idle) g.list[n_idle + __popc(m & ((1u << g.lane) - 1))] = (uint8_t)i;
+        n_idle += __popc(m);
+    }
+    __syncwarp();
+    if (n_idle == 0) return pn; // canExecuteAnyAction false: no RNG draw
+    int par0, par1;
+    reserved_resources(g, par0, par1);
+    uint64_t s0 = hdr_rng(g, H_RNGP_LO);
+    for (int kb = 0; kb < n_idle; kb += 32) {
+        int k = kb + g.lane;
+        bool active = k < n_idle;
+        uint32_t A0 = ACT_NONE | A0_NOUT; int A1 = 10, tcell = -1, cost = 0, s = 0;
+        if (active) {
+            s = g.list[k];
+            Enum e; enumerate(g, s, e);
+            uint64_t st = lcg_jump(g, s0, k);
+            double dr = lcg_next_double(st);
+            pick_action(g, e, sample_index(dr, e.nb, e.total), 10, A0, A1, tcell, cost);
+        }
+        int cnt = n_idle - kb; if (cnt > 32) cnt = 32;
+        bool ok = accept_in_order(g, player, cnt, tcell, cost, active, par0, par1);
+        if (active) {
+            if (!ok) { A0 = ACT_NONE | A0_NOUT; A1 = 10; }
+            g.pslot[pn + k] = (uint8_t)s; g.pa0[pn + k] = A0; g.pa1[pn + k] = A1;
+        }
+    }
+    if (g.lane == 0) hdr_set_rng(g, H_RNGP_LO, lcg_jump(g, s0, n_idle));
+    __syncwarp();
+    return pn + n_idle;
+}
+
+// ---- external actions -----------------------------------------------------------------------------------------------------
+// FMT_VECTOR: PlayerAction.fromVectorAction (PlayerAction.java:384-417) + UnitAction.fromVectorAction (UnitAction.java:675-709)
+//             + JNIAI padding with NONE(fill) (ai/jni/JNIAI.java:51-55).   FMT_RAW: the pairs as given.
+DEVN int decode_external(Game &g, int player, int pn, const int32_t *rows, int count, int format, int fill, int maxR) {
+    int cells = g.W * g.H;
+    int start = pn;
+    if (format == FMT_RAW) {
+        for (int kb = 0; kb < count; kb += 32) {
+            int k = kb + g.lane;
+            bool ok = false; uint32_t A0 = 0; int A1 = 0, s = 0;
+            if (k < count) {
+                const int32_t *a = rows + (long long)k * 8;
+                int cell = a[0], at = a[1];
+                if (cell >= 0 && cell < cells && at >= 0 && at <= 5) {
+                    int gv = g.grid[(cell / g.W + 1) * g.P + cell % g.W + 1];
+                    if (gv != 0 && gv != 0xFF) {
+                        s = gv - 1; ok = true;
+                        int ut = (at == ACT_PRODUCE) ? a[5] : 0xFF;
+                        if (at == ACT_PRODUCE && (ut < 0 || ut >= MRTS_MAX_TYPES)) ok = false;
+                        A0 = (uint32_t)at | ((uint32_t)(ut & 0xff) << 8);
+                        if (at == ACT_ATTACK) A0 |= ((uint32_t)(a[3] & 0xff) << 16) | ((uint32_t)(a[4] & 0xff) << 24);
+                        A1 = a[2];
+                    }
+                }
+            }
+            unsigned m = __ballot_sync(FULLM, ok);
+            if (k < count && !ok) atomicOr(&g.hdr[H_ERR], GE_BAD_ACTION);
+            if (ok) { int q = pn + __popc(m & ((1u << g.lane) - 1)); g.pslot[q] = (uint8_t)s; g.pa0[q] = A0; g.pa1[q] = A1; }
+            pn += __popc(m);
+        }
+        __syncwarp();
+        return pn;
+    }
+    int par0, par1;
+    reserved_resources(g, par0, par1);
+    int R = maxR, ctr = R / 2;
+    for (int kb = 0; kb < count; kb += 32) {
+        int k = kb + g.lane;
+        bool cand = false; uint32_t A0 = 0; int A1 = -1, s = 0, tcell = -1, cost = 0;
+        if (k < count) {
+            const int32_t *a = rows + (long long)k * 8;
+            int cell = a[0], at = a[1];
+            if (cell >= 0 && cell < cells) {
+                int gv = g.grid[(cell / g.W + 1) * g.P + cell % g.W + 1];
+                if (gv != 0 && gv != 0xFF) {
+                    s = gv - 1;
+                    uint32_t w = g.w0[s];
+                    if (u_pl(w) == player + 1 && a_type(g.a0[s]) == AT_IDLE && at >= 0 && at <= 5) {
+                        cand = true;
+                        A0 = (uint32_t)at | A0_NOUT;
+                        switch (at) {
+                            case ACT_MOVE: A1 = a[2]; break;
+                            case ACT_HARVEST: A1 = a[3]; break;
+                            case ACT_RETURN: A1 = a[4]; break;
+                            case ACT_PRODUCE: A1 = a[5]; A0 = ACT_PRODUCE | ((uint32_t)(a[6] & 0xff) << 8);
+                                if (a[6] < 0 || a[6] >= MRTS_MAX_TYPES) cand = false; else cost = ut_cost(g, a[6]); break;
+                            case ACT_ATTACK: {
+                                int ax = u_x(w) + (a[7] % R - ctr), ay = u_y(w) + (a[7] / R - ctr);
+                                A0 |= ((uint32_t)(ax & 0xff) << 16) | ((uint32_t)(ay & 0xff) << 24);
+                                if (ax < 0 || ay < 0 || ax > 255 || ay > 255) A0 = ACT_ATTACK | A0_NOUT | (0xFFu << 16) | (0xFFu << 24);
+                            } break;
+                        }
+                        if (a_uses_cell(at)) tcell = target_cell(g, cell_of(g, w), A1);
+                        if (!cand) atomicOr(&g.hdr[H_ERR], GE_BAD_ACTION);
+                    }
+                }
+            }
+        }
+        int cnt = count - kb; if (cnt > 32) cnt = 32;
+        bool ok = accept_in_order(g, player, cnt, tcell, cost, cand, par0, par1);
+        unsigned m = __ballot_sync(FULLM, ok);
+        if (ok) { int q = pn + __popc(m & ((1u << g.lane) - 1)); g.pslot[q] = (uint8_t)s; g.pa0[q] = A0; g.pa1[q] = A1; }
+        pn += __popc(m);
+        __syncwarp();
+    }
+    if (fill >= 0) { // PlayerAction.fillWithNones (PlayerAction.java:217-235): idle own units not already in the action
+        int n = g.hdr[H_NUNITS];
+        for (int base = 0; base < n; base += 32) {
+            int i = base + g.lane;
+            bool idle = i < n && u_pl(g.w0[i]) == player + 1 && a_type(g.a0[i]) == AT_IDLE;
+            if (idle) for (int q = start; q < pn; q++) if (g.pslot[q] == i) { idle = false; break; }
+            unsigned m = __ballot_sync(FULLM, idle);
+            if (idle) { int q = pn + __popc(m & ((1u << g.lane) - 1)); g.pslot[q] = (uint8_t)i; g.pa0[q] = ACT_NONE | A0_NOUT; g.pa1[q] = fill; }
+            pn += __popc(m);
+            __syncwarp();
+        }
+    }
+    return pn;
+}
+
+// GameState.issueSafe legality pass (GameState.java:347-354,386-399): illegal actions become NONE(ETA(action)).
+DEV void legality_pass(Game &g, int from, int to) {
+    for (int k = from + g.lane; k < to; k += 32) {
+        int s = g.pslot[k];
+        uint32_t A0 = g.pa0[k]; int A1 = g.pa1[k];
+        if (!action_is_legal(g, s, A0, A1)) {
+            g.pa1[k] = eta_of(g, u_type(g.w0[s]), A0, A1);
+            g.pa0[k] = ACT_NONE | A0_NOUT;
+        }
+    }
+    __syncwarp();
+}
+
+// ---- GameState.issue (GameState.java:249-328) --------------------------------------------------------------------------
+// One conflicting pair (existing assignment of slot e, new action N of a unit of type t).  Uniform across lanes.
+DEV void resolve_conflict(Game &g, int e, int t, uint32_t &A0, int &A1, int time) {
+    uint32_t E0 = g.a0[e]; int E1 = g.a1[e]; uint32_t ew = g.w0[e];
+    bool same_cycle = g.tis[e] == time;
+    bool cancel_old = false, cancel_new = false;
+    if (same_cycle) {
+        switch (g.conflict) {
+            default: cancel_old = cancel_new = true; break;                         // CANCEL_BOTH
+            case 2: {                                                               // CANCEL_RANDOM: GameState.r.nextInt(2)
+                uint64_t s = hdr_rng(g, H_RNGC_LO);
+                int r = lcg_next_int_bound(s, 2);
+                __syncwarp();
+                if (g.lane == 0) hdr_set_rng(g, H_RNGC_LO, s);
+                if (r == 0) cancel_new = true; else cancel_old = true;
+            } break;
+            case 3: {                                                               // CANCEL_ALTERNATING
+                int ctr = g.hdr[H_CANCELCTR];
+                __syncwarp();
+                if (g.lane == 0) g.hdr[H_CANCELCTR] = ctr + 1;
+                if ((ctr % 2) == 0) cancel_new = true; else cancel_old = true;
+            } break;
+        }
+    }
+    int d1 = eta_of(g, u_type(ew), E0, E1), d2 = eta_of(g, t, A0, A1);
+    int d = d1 < d2 ? d1 : d2;
+    __syncwarp();
+    if (same_cycle) {
+        if (cancel_old && g.lane == 0) {
+            if (a_uses_cell(a_type(E0))) { int tc = target_cell(g, cell_of(g, ew), E1); if (g.resv[tc] == e + 1) g.resv[tc] = 0; }
+            g.a0[e] = (E0 & 0xF0u) | ACT_NONE | A0_NOUT; g.a1[e] = d;
+        }
+        if (cancel_new) { A0 = ACT_NONE | A0_NOUT; A1 = d; }
+    } else {
+        if (g.lane == 0) g.hdr[H_ERR] |= GE_INCONSISTENT_OLDER;
+        A0 = ACT_NONE | A0_NOUT; A1 = -1; // new UnitAction(TYPE_NONE): parameter stays -1 (GameState.java:316)
+    }
+    __syncwarp();
+}
+
+DEVN void issue_pending(Game &g, int from, int to) {
+    int time = g.hdr[H_TIME];
+    for (int k = from; k < to; k++) {
+        int s = g.pslot[k];
+        uint32_t A0 = g.pa0[k]; int A1 = g.pa1[k];
+        uint32_t w = g.w0[s];
+        int t = u_type(w), pl = u_pl(w), c = cell_of(g, w), at = a_type(A0);
+        int tc = -1, cost = 0;
+        if (a_uses_cell(at)) { tc = target_cell(g, c, A1); if (at == ACT_PRODUCE) cost = ut_cost(g, a_utype(A0)); }
+        __syncwarp();
+        if (tc >= 0 && g.lane == 0) g.claim[tc] = 0;
+        if (tc >= 0 && cost == 0) {
+            int e = g.resv[tc]; // at most one in-flight action can hold a cell
+            if (e != 0) resolve_conflict(g, e - 1, t, A0, A1, time);
+        } else if (cost != 0) {
+            // general pairwise check against every existing assignment, in insertion order (GameState.java:263-319)
+            int n = g.hdr[H_NUNITS], pres = pl ? g.hdr[H_RES0 + pl - 1] : 0;
+            unsigned cb = 0; // bit j: slot j*32+lane conflicts
+            for (int j = 0; j * 32 < n; j++) {
+                int i = j * 32 + g.lane;
+                if (i < n) {
+                    uint32_t E0 = g.a0[i]; int eat = a_type(E0);
+                    if (eat != AT_IDLE && !(E0 & A0_DEAD)) {
+                        uint32_t ew = g.w0[i];
+                        bool pos = a_uses_cell(eat) && target_cell(g, cell_of(g, ew), g.a1[i]) == tc;
+                        int ecost = (eat == ACT_PRODUCE && u_pl(ew) == pl) ? ut_cost(g, a_utype(E0)) : 0;
+                        bool res = (ecost + cost > 0) && (ecost + cost > pres);
+                        if (pos || res) cb |= 1u << j;
+                    }
+                }
+            }
+            for (;;) {
+                uint32_t best = 0xFFFFFFFFu; int bj = 0;
+                for (unsigned m = cb; m; m &= m - 1) { int j = __ffs(m) - 1; uint32_t q = g.seq[j * 32 + g.lane]; if (q < best) { best = q; bj = j; } }
+                uint32_t mn = __reduce_min_sync(FULLM, best);
+                if (mn == 0xFFFFFFFFu) break;
+                int owner = __ffs(__ballot_sync(FULLM, best == mn)) - 1;
+                int e = __shfl_sync(FULLM, bj * 32 + g.lane, owner);
+                if (g.lane == owner) cb &= ~(1u << bj);
+                resolve_conflict(g, e, t, A0, A1, time);
+            }
+        }
+        // unitActions.put(unit, new UnitActionAssignment(unit, action, time)): an existing key keeps its slot
+        __syncwarp(); // every lane has finished reading resv/a0 for this action
+        if (g.lane == 0) {
+            uint32_t prev = g.a0[s];
+            if (a_type(prev) == AT_IDLE) g.seq[s] = (uint32_t)g.hdr[H_NEXTSEQ]++;
+            else if (a_uses_cell(a_type(prev))) { int ptc = target_cell(g, c, g.a1[s]); if (g.resv[ptc] == s + 1) g.resv[ptc] = 0; }
+            g.a0[s] = (prev & 0xF0u) | (A0 & ~0xF0u); g.a1[s] = A1; g.tis[s] = time;
+            if (a_uses_cell(a_type(A0))) g.resv[tc] = (uint8_t)(s + 1);
+        }
+        __syncwarp();
+    }
+}
+
+// ---- GameState.cycle (GameState.java:553-571) + UnitAction.execute (UnitAction.java:338-465) ----------------------------
+DEV void kill_unit(Game &g, int v) { // GameState.removeUnit (GameState.java:79-82); lane 0 only
+    uint32_t vw = g.w0[v]; uint32_t V0 = g.a0[v];
+    int vc = cell_of(g, vw);
+    g.grid[vc] = 0;
+    if (a_uses_cell(a_type(V0))) { int tc = target_cell(g, vc, g.a1[v]); if (g.resv[tc] == v + 1) g.resv[tc] = 0; }
+    g.a0[v] = V0 | A0_DEAD; // keeps its action words: a ready action of a dead unit still executes this cycle
+}
+
+DEV int neighbour_slot(const Game &g, int c, int dir) { // getUnitAt of the adjacent cell, -1 if none
+    if ((unsigned)dir >= 4u) return -1;
+    int gv = g.grid[c + doff(g, dir)];
+    return (gv == 0 || gv == 0xFF) ? -1 : gv - 1;
+}
+
+// Execute the (already removed) assignment (A0,A1) of slot s.  Uniform across lanes; lane 0 writes.
+DEV void execute_action(Game &g, int s, uint32_t A0, int A1, bool dead, int &ndead) {
+    uint32_t w = g.w0[s];
+    int t = u_type(w), pl = u_pl(w), c = cell_of(g, w);
+    switch (a_type(A0)) {
+        case ACT_MOVE:
+            if (!dead && (unsigned)A1 < 4u) {
+                int nc = c + doff(g, A1);
+                int occ = g.grid[nc];
+                __syncwarp();
+                if (g.lane == 0) {
+                    if (occ != 0) g.hdr[H_ERR] |= GE_CELL_OCCUPIED;
+                    else {
+                        g.grid[c] = 0; g.grid[nc] = (uint8_t)(s + 1);
+                        g.w0[s] = (w & 0xffffu) | ((uint32_t)(u_x(w) + ddx(A1)) << 16) | ((uint32_t)(u_y(w) + ddy(A1)) << 24);
+                    }
+                }
+            }
+            break;
+        case ACT_ATTACK: {
+            int ax = (A0 >> 16) & 0xff, ay = A0 >> 24;
+            if (ax < g.W && ay < g.H) {
+                int gv = g.grid[(ay + 1) * g.P + ax + 1];
+                if (gv != 0 && gv != 0xFF) {
+                    int v = gv - 1;
+                    int mn = ut_mind(g, t), mx = ut_maxd(g, t), dmg = mn;
+                    if (mn != mx) { // UnitAction.r.nextInt(1 + max - min)
+                        uint64_t rs = hdr_rng(g, H_RNGD_LO);
+                        dmg = mn + lcg_next_int_bound(rs, 1 + (mx - mn));
+                        __syncwarp();
+                        if (g.lane == 0) hdr_set_rng(g, H_RNGD_LO, rs);
+                    }
+                    uint32_t vw1 = g.w1[v];
+                    int hp = u_hp(vw1) - dmg;
+                    __syncwarp();
+                    if (g.lane == 0) { g.w1[v] = mk_w1(hp, u_res(vw1)); if (hp <= 0) kill_unit(g, v); }
+                    if (hp <= 0) ndead++;
+                }
+            }
+        } break;
+        case ACT_HARVEST: {
+            int r = neighbour_slot(g, c, A1);
+            if (r >= 0) {
+                uint32_t rw = g.w0[r], rw1 = g.w1[r], mw1 = g.w1[s];
+                if ((ut_flags(g, u_type(rw)) & UF_RESOURCE) && (ut_flags(g, t) & UF_HARVEST) && u_res(mw1) == 0) {
+                    int amt = ut_hamt(g, t), left = u_res(rw1) - amt;
+                    __syncwarp();
+                    if (g.lane == 0) {
+                        g.w1[r] = mk_w1(u_hp(rw1), left);
+                        if (left <= 0) kill_unit(g, r);
+                        g.w1[s] = mk_w1(u_hp(mw1), amt);
+                    }
+                    if (left <= 0) ndead++;
+                }
+            }
+        } break;
+        case ACT_RETURN: {
+            int b = neighbour_slot(g, c, A1);
+            if (b >= 0 && pl != 0) {
+                uint32_t mw1 = g.w1[s];
+                if ((ut_flags(g, u_type(g.w0[b])) & UF_STOCKPILE) && u_res(mw1) > 0) {
+                    __syncwarp();
+                    if (g.lane == 0) { g.hdr[H_RES0 + pl - 1] += u_res(mw1); g.w1[s] = mk_w1(u_hp(mw1), 0); }
+                }
+            }
+        } break;
+        case ACT_PRODUCE: {
+            int ut = a_utype(A0);
+            int n = g.hdr[H_NUNITS];
+            int pres = pl ? g.hdr[H_RES0 + pl - 1] : 0;
+            __syncwarp();
+            if (g.lane == 0 && pl != 0 && ut < MRTS_MAX_TYPES) {
+                int id = g.hdr[H_NEXTID]++; // new Unit(...) takes an ID even when the unit is then not added
+                int cost = ut_cost(g, ut);
+                if (pres - cost >= 0) {
+                    int nc = target_cell(g, c, A1);
+                    if ((unsigned)A1 >= 4u || g.grid[nc] != 0) g.hdr[H_ERR] |= GE_CELL_OCCUPIED;
+                    else if (n >= g.cap) g.hdr[H_ERR] |= GE_UNIT_OVERFLOW;
+                    else {
+                        int nx = u_x(w) + ddx(A1), ny = u_y(w) + ddy(A1);
+                        g.w0[n] = (uint32_t)ut | ((uint32_t)pl << 8) | ((uint32_t)nx << 16) | ((uint32_t)ny << 24);
+                        g.w1[n] = mk_w1(ut_hp(g, ut), 0);
+                        g.a0[n] = AT_IDLE | A0_NOUT; g.a1[n] = 0; g.tis[n] = 0; g.seq[n] = 0; g.uid[n] = (uint32_t)id;
+                        g.grid[nc] = (uint8_t)(n + 1);
+                        g.hdr[H_NUNITS] = n + 1;
+                        g.hdr[H_RES0 + pl - 1] = pres - cost;
+                    }
+                } else g.hdr[H_ERR] |= GE_FAILED_PRODUCE;
+            }
+        } break;
+        default: break;
+    }
+    __syncwarp();
+}
+
+// remove dead slots, keeping order; rebuild the cell maps
+DEVN void compact_units(Game &g) {
+    int n = g.hdr[H_NUNITS], out = 0;
+    uint32_t *su = g.w0;
+    for (int base = 0; base < n; base += 32) {
+        int i = base + g.lane;
+        bool alive = i < n && !(g.a0[i] & A0_DEAD);
+        uint32_t r[MRTS_UNIT_WORDS];
+        if (alive) for (int k = 0; k < MRTS_UNIT_WORDS; k++) r[k] = su[k * g.cap + i];
+        unsigned m = __ballot_sync(FULLM, alive);
+        int pos = out + __popc(m & ((1u << g.lane) - 1));
+        __syncwarp();
+        if (alive) for (int k = 0; k < MRTS_UNIT_WORDS; k++) su[k * g.cap + pos] = r[k];
+        out += __popc(m);
+        __syncwarp();
+    }
+    if (g.lane == 0) g.hdr[H_NUNITS] = out;
+    __syncwarp();
+    g_reset_maps(g);
+    g_scatter(g);
+}
+
+// PhysicalGameState.gameover / winner (PhysicalGameState.java:334-387); returns gameover, sets winner (-1 none)
+DEV bool game_over(const Game &g, int &winner) {
+    int n = g.hdr[H_NUNITS], c0 = 0, c1 = 0;
+    for (int base = 0; base < n; base += 32) {
+        int i = base + g.lane;
+        int pl = i < n ? u_pl(g.w0[i]) : 0;
+        c0 += __popc(__ballot_sync(FULLM, pl == 1));
+        c1 += __popc(__ballot_sync(FULLM, pl == 2));
+    }
+    winner = (c0 > 0 && c1 == 0) ? 0 : ((c1 > 0 && c0 == 0) ? 1 : -1);
+    return c0 == 0 || c1 == 0;
+}
+
+// earliest completion time of any in-flight assignment (GameState.getNextChangeTime, GameState.java:539-542)
+DEV int min_ready_time(const Game &g) {
+    int n = g.hdr[H_NUNITS], best = 0x7fffffff;
+    for (int i = g.lane; i < n; i += 32) {
+        uint32_t A0 = g.a0[i];
+        if (a_type(A0) != AT_IDLE) { int rt = g.tis[i] + eta_of(g, u_type(g.w0[i]), A0, g.a1[i]); if (rt < best) best = rt; }
+    }
+    return (int)(__reduce_min_sync(FULLM, (unsigned)(best ^ 0x80000000)) ^ 0x80000000u);
+}
+
+// time := t_new, then execute every assignment with ETA + issueTime <= time in insertion order.  Returns gameover().
+DEVN bool cycle_execute(Game &g, int t_new, int &winner) {
+    __syncwarp();
+    if (g.lane == 0) g.hdr[H_TIME] = t_new;
+    int n = g.hdr[H_NUNITS];
+    unsigned rb = 0; // bit j: slot j*32+lane is in the ready snapshot
+    for (int j = 0; j * 32 < n; j++) {
+        int i = j * 32 + g.lane;
+        if (i < n) {
+            uint32_t A0 = g.a0[i];
+            if (a_type(A0) != AT_IDLE && g.tis[i] + eta_of(g, u_type(g.w0[i]), A0, g.a1[i]) <= t_new) rb |= 1u << j;
+        }
+    }
+    int ndead = 0;
+    for (;;) {
+        uint32_t best = 0xFFFFFFFFu; int bj = 0;
+        for (unsigned m = rb; m; m &= m - 1) { int j = __ffs(m) - 1; uint32_t q = g.seq[j * 32 + g.lane]; if (q < best) { best = q; bj = j; } }
+        uint32_t mn = __reduce_min_sync(FULLM, best);
+        if (mn == 0xFFFFFFFFu) break;
+        int owner = __ffs(__ballot_sync(FULLM, best == mn)) - 1;
+        int s = __shfl_sync(FULLM, bj * 32 + g.lane, owner);
+        if (g.lane == owner) rb &= ~(1u << bj);
+        // unitActions.remove(uaa.unit), then execute (even if the unit died earlier in this loop)
+        uint32_t A0 = g.a0[s]; int A1 = g.a1[s];
+        bool dead = (A0 & A0_DEAD) != 0;
+        int c = cell_of(g, g.w0[s]);
+        __syncwarp();
+        if (g.lane == 0) {
+            g.a0[s] = (A0 & 0xF0u) | AT_IDLE | A0_NOUT;
+            if (!dead && a_uses_cell(a_type(A0))) { int tc = target_cell(g, c, A1); if (g.resv[tc] == s + 1) g.resv[tc] = 0; }
+        }
+        __syncwarp();
+        execute_action(g, s, A0, A1, dead, ndead);
+    }
+    if (ndead > 0) compact_units(g);
+    return game_over(g, winner);
+}
+
+// ---- loops ---------------------------------------------------------------------------------------------------------------
+struct WarpStats { unsigned long long v[8]; };
+
+DEV int run_policy(Game &g, const StepParams &p, long long gi, int player, int pn, bool first_iter) {
+    switch (p.policy[player]) {
+        case POL_RANDOM_BIASED: return policy_random_biased(g, player, pn);
+        case POL_EXTERNAL:
+            if (first_iter && p.ext_actions[player]) {
+                int cnt = p.ext_counts[player] ? p.ext_counts[player][gi] : p.ext_maxk[player];
+                if (cnt > p.ext_maxk[player]) cnt = p.ext_maxk[player];
+                int n0 = pn;
+                pn = decode_external(g, player, pn, p.ext_actions[player] + gi * (long long)p.ext_maxk[player] * 8, cnt,
+                                     p.ext_format[player], p.ext_fill[player], 2 * p.max_range + 1);
+                if (p.safe) legality_pass(g, n0, pn);
+            }
+            return pn;
+        default: return pn; // PASSIVE (scripted policies are dispatched by the caller)
+    }
+}
+
+// Game.start loop body (rts/Game.java:126-140) with exact skipping of cycles in which nothing can happen.
+DEVN void run_game(Game &g, const StepParams &p, long long gi, WarpStats &ws) {
+    int status = g.hdr[H_STATUS];
+    if (status & ST_OVER) return;
+    int t0 = g.hdr[H_TIME];
+    int tlimit = t0 + p.n_cycles; if (tlimit > p.max_cycles) tlimit = p.max_cycles;
+    int winner;
+    bool force_next = game_over(g, winner); // a state that is already over ends at the very next cycle()
+    bool first = true;
+    unsigned long long decisions = 0, ucyc = 0;
+    for (;;) {
+        int time = g.hdr[H_TIME];
+        if (time >= tlimit) break;
+        int pn0 = run_policy(g, p, gi, 0, 0, first);
+        int pn1 = run_policy(g, p, gi, 1, pn0, first);
+        first = false;
+        issue_pending(g, 0, pn0);
+        issue_pending(g, pn0, pn1);
+        decisions += pn1;
+        int mrt = min_ready_time(g);
+        int tn = time + 1; if (!force_next && mrt > tn) tn = mrt;
+        int nu = g.hdr[H_NUNITS];
+        if (tn > tlimit) { ucyc += (unsigned long long)nu * (tlimit - time); __syncwarp(); if (g.lane == 0) g.hdr[H_TIME] = tlimit; __syncwarp(); break; }
+        ucyc += (unsigned long long)nu * (tn - time);
+        bool over = cycle_execute(g, tn, winner);
+        if (over) {
+            if (g.lane == 0) g.hdr[H_STATUS] = status | ST_OVER | ST_COUNTED | ((winner + 1) << 8);
+            __syncwarp();
+            ws.v[STAT_FINISHED]++; if (winner == 0) ws.v[STAT_WINS0]++; else if (winner == 1) ws.v[STAT_WINS1]++; else ws.v[STAT_DRAWS]++;
+            break;
+        }
+    }
+    int tend = g.hdr[H_TIME];
+    status = g.hdr[H_STATUS];
+    if (!(status & ST_COUNTED) && tend >= p.max_cycles) { // hit the cycle cap: a draw (winner() == -1)
+        __syncwarp();
+        if (g.lane == 0) g.hdr[H_STATUS] = status | ST_COUNTED;
+        __syncwarp();
+        ws.v[STAT_FINISHED]++; ws.v[STAT_DRAWS]++;
+    }
+    ws.v[STAT_CYCLES] += (unsigned long long)(tend - t0);
+    ws.v[STAT_DECISIONS] += decisions;
+    ws.v[STAT_UNIT_CYCLES] += ucyc;
+}
+
+// GameState.cycle() repeated until time == target (TestTracesIntegrity.java:81-85); no policies
+DEVN void run_cycles_only(Game &g, int target) {
+    int winner;
+    for (;;) {
+        int time = g.hdr[H_TIME];
+        if (time >= target) break;
+        int mrt = min_ready_time(g);
+        int tn = time + 1; if (mrt > tn) tn = mrt;
+        if (tn > target) { __syncwarp(); if (g.lane == 0) g.hdr[H_TIME] = target; __syncwarp(); break; }
+        bool over = cycle_execute(g, tn, winner);
+        __syncwarp();
+        if (g.lane == 0) { int st = g.hdr[H_STATUS] & ~(ST_OVER | 0x300); if (over) st |= ST_OVER | ((winner + 1) << 8); g.hdr[H_STATUS] = st; }
+        __syncwarp();
+    }
+}
+
+// issueSafe / issue of one staged PlayerAction, no cycle
+DEVN void run_issue_only(Game &g, const StepParams &p, long long gi) {
+    int pl = p.issue_player;
+    int cnt = p.ext_counts[pl] ? p.ext_counts[pl][gi] : p.ext_maxk[pl];
+    if (cnt > p.ext_maxk[pl]) cnt = p.ext_maxk[pl];
+    int pn = decode_external(g, pl, 0, p.ext_actions[pl] + gi * (long long)p.ext_maxk[pl] * 8, cnt, p.ext_format[pl],
+                             p.ext_fill[pl], 2 * p.max_range + 1);
+    if (p.safe) legality_pass(g, 0, pn);
+    issue_pending(g, 0, pn);
+}
+
+// ---- GameState.getVectorObservation (GameState.java:922-968) / PartiallyObservableGameState (:35-71,82-179) ------------
+// Planes: hp, resources, owner ((owner+player)%2+1), type+1, current action type, terrain [, my visibility, visible
+// enemies' visibility].  out = [n_games][C][H][W], u8 or i32.  resv/claim are reused as the two visibility maps.
+DEV void stamp_sight(Game &g, uint8_t *map, uint32_t w) {
+    int r = ut_sight(g, u_type(w)), d = 2 * r + 1, x0 = u_x(w) - r, y0 = u_y(w) - r;
+    for (int q = g.lane; q < d * d; q += 32) {
+        int dx = q % d - r, dy = q / d - r, x = x0 + q % d, y = y0 + q / d;
+        if (x >= 0 && x < g.W && y >= 0 && y < g.H && dx * dx + dy * dy <= r * r) map[(y + 1) * g.P + x + 1] = 1;
+    }
+}
+DEV void cell_planes(const Game &g, int cell, int player, bool po, int v[8]) {
+    int x = cell % g.W, y = cell / g.W, pc = (y + 1) * g.P + x + 1;
+    int gv = g.grid[pc];
+    for (int k = 0; k < 8; k++) v[k] = 0;
+    v[5] = g.grid_tmpl ? (int)(((const uint8_t *)g.grid_tmpl)[pc] == 0xFF) : 0;
+    if (po) { v[6] = g.resv[pc]; v[7] = g.claim[pc]; }
+    if (gv != 0 && gv != 0xFF) {
+        int s = gv - 1;
+        uint32_t w = g.w0[s], w1 = g.w1[s];
+        int pl = u_pl(w);
+        if (po && pl != player + 1 && !g.resv[pc]) return; // not observable: removed from the observer's view
+        v[0] = u_hp(w1); v[1] = u_res(w1);
+        if (pl != 0) v[2] = ((pl - 1 + player) % 2) + 1;
+        v[3] = u_type(w) + 1;
+        int at = a_type(g.a0[s]);
+        v[4] = at == (int)AT_IDLE ? 0 : at;
+    }
+}
+DEVN void observe_game(Game &g, const StepParams &p, long long gi) {
+    int cells = g.W * g.H, C = p.partial_obs ? 8 : 6, player = p.out_player;
+    bool po = p.partial_obs != 0;
+    if (po) {
+        int n = g.hdr[H_NUNITS];
+        for (int i = g.lane; i < g.pcw; i += 32) { ((uint32_t *)g.resv)[i] = 0; ((uint32_t *)g.claim)[i] = 0; }
+        __syncwarp();
+        for (int i = 0; i < n; i++) { uint32_t w = g.w0[i]; if (u_pl(w) == player + 1) stamp_sight(g, g.resv, w); }
+        __syncwarp();
+        for (int i = 0; i < n; i++) { // enemy units that survive the filter (PartiallyObservableGameState.java:44-53)
+            uint32_t w = g.w0[i];
+            if (u_pl(w) != 0 && u_pl(w) != player + 1 && g.resv[cell_of(g, w)]) stamp_sight(g, g.claim, w);
+        }
+        __syncwarp();
+    }
+    size_t base = (size_t)gi * C * cells;
+    if ((cells & 3) == 0) {
+        for (int q = g.lane; q < cells / 4; q += 32) {
+            int v[4][8];
+            for (int j = 0; j < 4; j++) cell_planes(g, q * 4 + j, player, po, v[j]);
+            for (int k = 0; k < C; k++) {
+                if (p.out_dtype == 0)
+                    ((uint32_t *)((uint8_t *)p.out + base + (size_t)k * cells))[q] =
+                        (uint32_t)(v[0][k] & 0xff) | ((uint32_t)(v[1][k] & 0xff) << 8) | ((uint32_t)(v[2][k] & 0xff) << 16) | ((uint32_t)(v[3][k] & 0xff) << 24);
+                else {
+                    int32_t *o = (int32_t *)p.out + base + (size_t)k * cells + q * 4;
+                    o[0] = v[0][k]; o[1] = v[1][k]; o[2] = v[2][k]; o[3] = v[3][k];
+                }
+            }
+        }
+    } else {
+        for (int cell = g.lane; cell < cells; cell += 32) {
+            int v[8];
+            cell_planes(g, cell, player, po, v);
+            for (int k = 0; k < C; k++) {
+                if (p.out_dtype == 0) ((uint8_t *)p.out)[base + (size_t)k * cells + cell] = (uint8_t)v[k];
+                else ((int32_t *)p.out)[base + (size_t)k * cells + cell] = v[k];
+            }
+        }
+    }
+}
+
+// ---- JNIGridnetClient.getMasks (tests/JNIGridnetClient.java:210-223) + UnitAction.getValidActionArray
+// (UnitAction.java:711-751).  The output must be zero-filled by the caller; only rows of idle own units are written.
+DEVN void masks_game(Game &g, const StepParams &p, long long gi) {
+    int n = g.hdr[H_NUNITS], player = p.out_player;
+    int R = 2 * p.max_range + 1, ctr = R / 2, nT = p.n_types, K = 1 + 6 + 16 + nT + R * R;
+    for (int s = 0; s < n; s++) {
+        uint32_t w = g.w0[s];
+        if (u_pl(w) != player + 1 || a_type(g.a0[s]) != AT_IDLE) continue; // uniform across lanes
+        Enum e; enumerate(g, s, e);
+        bool mv = (e.fl & UF_MOVE) != 0;
+        int pr_m = e.n_aff > 0 ? e.free_m : 0, mv_m = mv ? e.free_m : 0;
+        size_t row = ((size_t)gi * g.W * g.H + (size_t)u_y(w) * g.W + u_x(w)) * K;
+        for (int j = g.lane; j < K; j += 32) {
+            int v = 0;
+            if (j == 0) v = 1;
+            else if (j < 7) {
+                switch (j - 1) {
+                    case ACT_NONE: v = 1; break;
+                    case ACT_MOVE: v = mv_m != 0; break;
+                    case ACT_HARVEST: v = e.harv_m != 0; break;
+                    case ACT_RETURN: v = e.ret_m != 0; break;
+                    case ACT_PRODUCE: v = pr_m != 0; break;
+                    case ACT_ATTACK: v = e.n_atk > 0; break;
+                }
+            } else if (j < 11) v = (mv_m >> (j - 7)) & 1;
+            else if (j < 15) v = (e.harv_m >> (j - 11)) & 1;
+            else if (j < 19) v = (e.ret_m >> (j - 15)) & 1;
+            else if (j < 23) v = (pr_m >> (j - 19)) & 1;
+            else if (j < 23 + nT) {
+                int ut = j - 23, np = ut_nprod(g, e.t);
+                if (e.nfree > 0) for (int k = 0; k < np; k++) if (ut_prod(g, e.t, k) == ut && ((e.aff_m >> k) & 1)) v = 1;
+            } else if (e.fl & UF_ATTACK) {
+                int r = j - 23 - nT, ax = u_x(w) + r % R - ctr, ay = u_y(w) + r / R - ctr;
+                if (ax >= 0 && ay >= 0 && ax < g.W && ay < g.H) {
+                    int gv = g.grid[(ay + 1) * g.P + ax + 1];
+                    if (gv != 0 && gv != 0xFF) v = enemy_in_range(g, w, g.w0[gv - 1], e.range * e.range) ? 1 : 0;
+                }
+            }
+            if (p.out_dtype == 0) ((uint8_t *)p.out)[row + j] = (uint8_t)v;
+            else ((int32_t *)p.out)[row + j] = v;
+        }
+    }
+}
+
+// body of the step kernel for one thread; `smem` is the CTA's dynamic shared memory
+DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int nthreads, int bid, int nblocks) {
+    uint32_t *cst = (uint32_t *)smem;
+    for (int i = tid; i < MRTS_CONST_WORDS; i += nthreads) cst[i] = p.cst[i];
+    __syncthreads();
+    SmemLayout L = mrts_smem_layout(p.W, p.H, p.cap);
+    int warp = tid >> 5, lane = tid & 31, wpc = nthreads >> 5;
+    Game g;
+    g_bind(g, smem + MRTS_CONST_WORDS * 4 + (size_t)warp * L.total, L, p.W, p.H, p.cap, lane, cst, p.conflict);
+    WarpStats ws;
+    for (int i = 0; i < 8; i++) ws.v[i] = 0;
+    for (long long gi = (long long)bid * wpc + warp; gi < p.n_games; gi += (long long)nblocks * wpc) {
+        const uint32_t *blob = p.maps + (size_t)(gi % p.n_maps) * p.map_words;
+        g.grid_tmpl = blob;
+        int32_t *ghdr = p.hdr + gi * MRTS_HDR_WORDS;
+        uint32_t *gun = p.units + gi * (long long)MRTS_UNIT_WORDS * p.cap;
+        g_load(g, ghdr, gun);
+        int err0 = g.hdr[H_ERR];
+        if (p.mode == MODE_GAME) run_game(g, p, gi, ws);
+        else if (p.mode == MODE_CYCLE_ONLY) run_cycles_only(g, p.t_target ? p.t_target[gi] : g.hdr[H_TIME] + p.n_cycles);
+        else if (p.mode == MODE_ISSUE_ONLY) run_issue_only(g, p, gi);
+        else if (p.mode == MODE_OBSERVE) { observe_game(g, p, gi); continue; }
+        else { masks_game(g, p, gi); continue; }
+        if (g.hdr[H_ERR] != err0) ws.v[STAT_ERRORS]++;
+        g_store(g, ghdr, gun);
+    }
+    if (lane == 0 && p.stats)
+        for (int i = 0; i < 8; i++) if (ws.v[i]) atomicAdd(&p.stats[i], ws.v[i]);
+}

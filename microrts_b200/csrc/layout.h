@@ -1,0 +1,86 @@
+// layout.h -- data layout shared by the device engine and the host C-ABI.
+//
+// One game = a 16-word header + MRTS_UNIT_WORDS struct-of-arrays over `cap` unit slots, both in HBM and (while a
+// warp owns the game) in shared memory.  Unit slot order IS the reference's PhysicalGameState.units list order
+// (src/rts/PhysicalGameState.java:54); assignment (LinkedHashMap) order is carried by a per-unit sequence number.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define MRTS_HD __host__ __device__ inline
+#else
+#define MRTS_HD static inline
+#endif
+
+#define MRTS_HDR_WORDS 16
+enum {
+    H_TIME = 0,     // GameState.time
+    H_RES0 = 1,     // Player 0 resources
+    H_RES1 = 2,
+    H_NUNITS = 3,   // number of live unit slots
+    H_NEXTSEQ = 4,  // next assignment sequence number (insertion order of GameState.unitActions)
+    H_CANCELCTR = 5,// GameState.unitCancelationCounter
+    H_STATUS = 6,   // bit0: cycle() returned gameover; bits 8-9: winner+1
+    H_NEXTID = 7,   // next unit ID (Unit.next_ID, per game)
+    H_RNGP_LO = 8, H_RNGP_HI = 9,   // util.Sampler.generator   (policy draws)
+    H_RNGC_LO = 10, H_RNGC_HI = 11, // GameState.r               (CANCEL_RANDOM)
+    H_RNGD_LO = 12, H_RNGD_HI = 13, // UnitAction.r              (random damage)
+    H_ERR = 14,     // sticky MRTS_GE_* bits
+    H_SPARE = 15
+};
+
+// per-unit words
+enum { UW_W0 = 0, UW_W1, UW_A0, UW_A1, UW_TIS, UW_SEQ, UW_ID, MRTS_UNIT_WORDS };
+// W0: type | (player+1)<<8 | x<<16 | y<<24            W1: (uint16)hp | (uint16)res<<16
+// A0: atype(4) | flags(4) | utype<<8 | ax<<16 | ay<<24    A1: parameter (direction or NONE duration)
+// TIS: issue time (UnitActionAssignment.time)          SEQ: assignment sequence      ID: Unit.ID (low 32 bits)
+#define AT_IDLE 15u
+#define A0_DEAD 0x10u
+
+#define MRTS_MAX_TYPES 8
+#define MRTS_UTT_WORDS 8 // per type
+// U0: cost | hp<<8 | minDamage<<16 | maxDamage<<24
+// U1: attackRange | sightRadius<<8 | harvestAmount<<16 | flags<<24
+// U2: produceTime | moveTime<<16      U3: attackTime | harvestTime<<16     U4: returnTime | nProduces<<16
+// U5: produces[0..3] bytes            U6: produces[4..7] bytes             U7: pad
+enum { UF_RESOURCE = 1, UF_STOCKPILE = 2, UF_HARVEST = 4, UF_MOVE = 8, UF_ATTACK = 16 };
+
+#define MRTS_JUMP_ENTRIES 65 // LCG skip-ahead: entry d advances 2*d steps (d nextDouble() draws)
+#define MRTS_CONST_WORDS (MRTS_MAX_TYPES * MRTS_UTT_WORDS + MRTS_JUMP_ENTRIES * 4) // utt words + jump table (u64 pairs)
+
+#define MRTS_MAX_CAP 254
+#define MRTS_WARPS_PER_CTA 4
+
+// engine error bits == MRTS_GE_* of the public header
+enum { GE_UNIT_OVERFLOW = 1, GE_INCONSISTENT_OLDER = 2, GE_FAILED_PRODUCE = 4, GE_CELL_OCCUPIED = 8, GE_BAD_ACTION = 16 };
+
+struct SmemLayout {
+    int hdr, units, pa0, pa1, pslot, grid, resv, claim, list, total; // byte offsets inside one game's region
+    int pcw;                                                          // padded-grid size in 32-bit words
+};
+
+MRTS_HD SmemLayout mrts_smem_layout(int W, int H, int cap) {
+    SmemLayout L;
+    int pc = (W + 2) * (H + 2);
+    int pcb = (pc + 15) & ~15;
+    int capb = (cap + 15) & ~15;
+    int o = 0;
+    L.hdr = o; o += MRTS_HDR_WORDS * 4;
+    L.units = o; o += MRTS_UNIT_WORDS * cap * 4;
+    L.pa0 = o; o += cap * 4;
+    L.pa1 = o; o += cap * 4;
+    L.pslot = o; o += capb;
+    L.grid = o; o += pcb;
+    L.resv = o; o += pcb;
+    L.claim = o; o += pcb;
+    L.list = o; o += capb;
+    L.total = (o + 15) & ~15;
+    L.pcw = pcb / 4;
+    return L;
+}
+
+// per-map blob in HBM (32-bit words): [grid template pcw][init header 16][init units 7*cap]
+MRTS_HD int mrts_map_blob_words(int W, int H, int cap) {
+    int pcb = (((W + 2) * (H + 2)) + 15) & ~15;
+    return pcb / 4 + MRTS_HDR_WORDS + MRTS_UNIT_WORDS * cap;
+}

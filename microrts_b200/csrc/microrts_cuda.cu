@@ -1,0 +1,580 @@
+// microrts_cuda.cu -- libmicrorts_cuda.so: the C ABI of include/microrts_cuda.h over the sm_100a engine (engine.cuh).
+//
+// Build (see __graft_entry__.build): nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared ...
+// The same translation unit can be compiled for the host with -DMRTS_EMU by tests/emu/build.sh (test tooling that
+// emulates warps with coroutines); that build is never shipped and never loaded by the microrts_b200 package.
+#include "../../include/microrts_cuda.h"
+
+#include <algorithm>
+#include <memory>
+#include <string>
+#include <vector>
+
+#ifdef MRTS_EMU
+#include "cuda_shim.h"
+#else
+#include <cuda_runtime.h>
+#endif
+
+#include "engine.cuh"
+#include "host_model.hpp"
+
+using namespace mrts;
+
+// ------------------------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+// ------------------------------------------------------------------------------------------------------------------
+// device backend
+// ------------------------------------------------------------------------------------------------------------------
+#ifdef MRTS_EMU
+typedef void *stream_t;
+static int dev_select(int) { return 0; }
+static int dev_alloc(void **p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? 0 : -1; }
+static void dev_free(void *p) { free(p); }
+static int dev_h2d(void *d, const void *h, size_t n, stream_t) { memcpy(d, h, n); return 0; }
+static int dev_d2h(void *h, const void *d, size_t n, stream_t) { memcpy(h, d, n); return 0; }
+static int dev_d2d(void *d, const void *s, size_t n, stream_t) { memcpy(d, s, n); return 0; }
+static int dev_zero(void *d, size_t n, stream_t) { memset(d, 0, n); return 0; }
+static int dev_sync(stream_t) { return 0; }
+static const char *dev_errstr() { return "emulator"; }
+#else
+typedef cudaStream_t stream_t;
+static cudaError_t g_cuda_last = cudaSuccess;
+static int ck(cudaError_t e) { if (e != cudaSuccess) { g_cuda_last = e; return -1; } return 0; }
+static int dev_select(int d) { return ck(cudaSetDevice(d)); }
+static int dev_alloc(void **p, size_t n) { return ck(cudaMalloc(p, n ? n : 1)); }
+static void dev_free(void *p) { if (p) cudaFree(p); }
+static int dev_h2d(void *d, const void *h, size_t n, stream_t s) { return ck(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s)); }
+static int dev_d2h(void *h, const void *d, size_t n, stream_t s) { if (ck(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s))) return -1; return ck(cudaStreamSynchronize(s)); }
+static int dev_d2d(void *d, const void *s_, size_t n, stream_t s) { return ck(cudaMemcpyAsync(d, s_, n, cudaMemcpyDeviceToDevice, s)); }
+static int dev_zero(void *d, size_t n, stream_t s) { return ck(cudaMemsetAsync(d, 0, n, s)); }
+static int dev_sync(stream_t s) { return ck(cudaStreamSynchronize(s)); }
+static const char *dev_errstr() { return cudaGetErrorString(g_cuda_last); }
+#endif
+
+// ------------------------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------------------------
+struct ResetParams {
+    int32_t *hdr; uint32_t *units; const uint32_t *maps;
+    const long long *seeds; const uint8_t *mask;
+    long long n_games; int n_maps, map_words, cap, pcw;
+};
+
+// (re)initialise games from their map's initial state; one warp per game
+DEV void reset_kernel_body(const ResetParams &p, int tid, int nthreads, int bid, int nblocks) {
+    int warp = tid >> 5, lane = tid & 31, wpc = nthreads >> 5;
+    for (long long gi = (long long)bid * wpc + warp; gi < p.n_games; gi += (long long)nblocks * wpc) {
+        if (p.mask && !p.mask[gi]) continue;
+        const uint32_t *blob = p.maps + (size_t)(gi % p.n_maps) * p.map_words;
+        const int32_t *ih = (const int32_t *)(blob + p.pcw);
+        const uint32_t *iu = blob + p.pcw + MRTS_HDR_WORDS;
+        int32_t *gh = p.hdr + gi * MRTS_HDR_WORDS;
+        uint32_t *gu = p.units + gi * (long long)MRTS_UNIT_WORDS * p.cap;
+        int n = ih[H_NUNITS];
+        if (lane < MRTS_HDR_WORDS) {
+            int32_t v = ih[lane];
+            long long seed = p.seeds ? p.seeds[gi] : gi;
+            unsigned long long sp = ((unsigned long long)seed ^ 0x5DEECE66DULL) & MASK48;
+            unsigned long long sc = ((unsigned long long)(seed ^ 0x5851F42D4C957F2DLL) ^ 0x5DEECE66DULL) & MASK48;
+            unsigned long long sd = ((unsigned long long)(seed ^ 0x14057B7EF767814FLL) ^ 0x5DEECE66DULL) & MASK48;
+            if (lane == H_RNGP_LO) v = (int32_t)(uint32_t)sp;
+            if (lane == H_RNGP_HI) v = (int32_t)(uint32_t)(sp >> 32);
+            if (lane == H_RNGC_LO) v = (int32_t)(uint32_t)sc;
+            if (lane == H_RNGC_HI) v = (int32_t)(uint32_t)(sc >> 32);
+            if (lane == H_RNGD_LO) v = (int32_t)(uint32_t)sd;
+            if (lane == H_RNGD_HI) v = (int32_t)(uint32_t)(sd >> 32);
+            gh[lane] = v;
+        }
+        for (int k = 0; k < MRTS_UNIT_WORDS; k++)
+            for (int i = lane; i < n; i += 32) gu[k * p.cap + i] = iu[k * p.cap + i];
+    }
+}
+
+struct ResultParams { const int32_t *hdr; const uint32_t *units; int32_t *out; long long n_games; int cap; };
+// out[g] = {time, winner, gameover, error bits}; one thread per game (PhysicalGameState.winner/gameover :334-387)
+DEV void results_kernel_body(const ResultParams &p, long long gi) {
+    if (gi >= p.n_games) return;
+    const int32_t *h = p.hdr + gi * MRTS_HDR_WORDS;
+    const uint32_t *w0 = p.units + gi * (long long)MRTS_UNIT_WORDS * p.cap;
+    int n = h[H_NUNITS], c0 = 0, c1 = 0;
+    for (int i = 0; i < n; i++) { int pl = (w0[i] >> 8) & 0xff; c0 += pl == 1; c1 += pl == 2; }
+    int32_t *o = p.out + gi * 4;
+    o[0] = h[H_TIME];
+    o[1] = (c0 > 0 && c1 == 0) ? 0 : ((c1 > 0 && c0 == 0) ? 1 : -1);
+    o[2] = (c0 == 0 || c1 == 0) ? 1 : 0;
+    o[3] = h[H_ERR];
+}
+
+#ifndef MRTS_EMU
+__global__ void __launch_bounds__(MRTS_WARPS_PER_CTA * 32) k_step(StepParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    step_kernel_body(p, smem, threadIdx.x, blockDim.x, blockIdx.x, gridDim.x);
+}
+__global__ void __launch_bounds__(128) k_reset(ResetParams p) { reset_kernel_body(p, threadIdx.x, blockDim.x, blockIdx.x, gridDim.x); }
+__global__ void __launch_bounds__(128) k_results(ResultParams p) { results_kernel_body(p, (long long)blockIdx.x * blockDim.x + threadIdx.x); }
+#endif
+
+// ------------------------------------------------------------------------------------------------------------------
+// handles
+// ------------------------------------------------------------------------------------------------------------------
+struct mrts_utt { UttH h; };
+struct mrts_map { MapH h; };
+
+struct Staged { // external actions staged on the device
+    int32_t *actions = nullptr, *counts = nullptr;
+    size_t cap_rows = 0;
+    int max_k = 0, format = 0, fill = -1;
+    bool valid = false, own = true;
+};
+
+struct mrts_batch {
+    UttH utt;
+    int W = 0, H = 0, cap = 0, n_maps = 0, map_words = 0, device = 0;
+    long long n = 0;
+    uint32_t flags = 0;
+    int policy[2] = {MRTS_POLICY_PASSIVE, MRTS_POLICY_PASSIVE}, pathfinder[2] = {0, 0};
+    int32_t *d_hdr = nullptr; uint32_t *d_units = nullptr; uint32_t *d_maps = nullptr; uint32_t *d_cst = nullptr;
+    unsigned long long *d_stats = nullptr;
+    void *d_tmp = nullptr; size_t tmp_bytes = 0; // staging for host arguments
+    Staged staged[2];
+    stream_t stream = nullptr;
+    SmemLayout L;
+    size_t smem_bytes = 0;
+    int grid = 0, max_range = 0;
+    long long launches = 0;
+};
+
+static int ensure_tmp(mrts_batch *b, size_t bytes) {
+    if (bytes <= b->tmp_bytes) return 0;
+    dev_free(b->d_tmp); b->d_tmp = nullptr; b->tmp_bytes = 0;
+    if (dev_alloc(&b->d_tmp, bytes)) return -1;
+    b->tmp_bytes = bytes;
+    return 0;
+}
+
+static int launch_step(mrts_batch *b, StepParams &p) {
+    p.hdr = b->d_hdr; p.units = b->d_units; p.maps = b->d_maps; p.cst = b->d_cst; p.stats = b->d_stats;
+    p.n_games = b->n; p.n_maps = b->n_maps; p.map_words = b->map_words; p.W = b->W; p.H = b->H; p.cap = b->cap;
+    p.conflict = b->utt.conflict; p.max_range = b->max_range; p.n_types = (int)b->utt.types.size();
+    p.partial_obs = (b->flags & MRTS_FLAG_PARTIAL_OBS) ? 1 : 0;
+    int threads = MRTS_WARPS_PER_CTA * 32;
+    long long need = (b->n + MRTS_WARPS_PER_CTA - 1) / MRTS_WARPS_PER_CTA;
+    int grid = (int)std::min<long long>(b->grid, std::max<long long>(need, 1));
+    b->launches++;
+#ifdef MRTS_EMU
+    StepParams pc = p;
+    emu::launch(grid, threads, b->smem_bytes, [pc, threads, grid](unsigned char *sm, int tid, int bid) { step_kernel_body(pc, sm, tid, threads, bid, grid); });
+    return 0;
+#else
+    k_step<<<grid, threads, b->smem_bytes, b->stream>>>(p);
+    return ck(cudaGetLastError());
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int mrts_abi_version(void) { return MRTS_ABI_VERSION; }
+const char *mrts_last_error(void) { return g_err.c_str(); }
+
+int mrts_utt_create(int version, int conflict_policy, mrts_utt **out) {
+    if (!out || version < 1 || version > 3 || conflict_policy < 1 || conflict_policy > 3) return fail(MRTS_E_ARG, "mrts_utt_create: version must be 1..3 and conflict policy 1..3");
+    auto *u = new mrts_utt; u->h = make_utt(version, conflict_policy); *out = u; return MRTS_OK;
+}
+int mrts_utt_from_json(const char *json, mrts_utt **out) {
+    if (!json || !out) return fail(MRTS_E_ARG, "mrts_utt_from_json: null argument");
+    auto u = std::make_unique<mrts_utt>(); std::string err;
+    if (!utt_from_json(json, u->h, err)) return fail(MRTS_E_PARSE, err);
+    if (!utt_check_limits(u->h, err)) return fail(MRTS_E_LIMIT, err);
+    *out = u.release(); return MRTS_OK;
+}
+int mrts_utt_num_types(const mrts_utt *u) { return u ? (int)u->h.types.size() : MRTS_E_ARG; }
+int mrts_utt_get(const mrts_utt *u, int t, int f) {
+    if (!u || t < 0 || t >= (int)u->h.types.size()) return fail(MRTS_E_ARG, "mrts_utt_get: bad type id");
+    const UnitTypeH &x = u->h.types[t];
+    switch (f) {
+        case MRTS_UT_COST: return x.cost; case MRTS_UT_HP: return x.hp; case MRTS_UT_MIN_DAMAGE: return x.minDamage;
+        case MRTS_UT_MAX_DAMAGE: return x.maxDamage; case MRTS_UT_ATTACK_RANGE: return x.attackRange;
+        case MRTS_UT_PRODUCE_TIME: return x.produceTime; case MRTS_UT_MOVE_TIME: return x.moveTime;
+        case MRTS_UT_ATTACK_TIME: return x.attackTime; case MRTS_UT_HARVEST_TIME: return x.harvestTime;
+        case MRTS_UT_RETURN_TIME: return x.returnTime; case MRTS_UT_HARVEST_AMOUNT: return x.harvestAmount;
+        case MRTS_UT_SIGHT_RADIUS: return x.sightRadius; case MRTS_UT_FLAGS: return x.flags();
+        case MRTS_UT_N_PRODUCES: return (int)x.produces.size();
+    }
+    if (f >= MRTS_UT_PRODUCES0 && f < MRTS_UT_PRODUCES0 + (int)x.produces.size()) return x.produces[f - MRTS_UT_PRODUCES0];
+    return fail(MRTS_E_ARG, "mrts_utt_get: bad field");
+}
+const char *mrts_utt_type_name(const mrts_utt *u, int t) { return (u && t >= 0 && t < (int)u->h.types.size()) ? u->h.types[t].name.c_str() : nullptr; }
+int mrts_utt_conflict_policy(const mrts_utt *u) { return u ? u->h.conflict : MRTS_E_ARG; }
+int mrts_utt_max_attack_range(const mrts_utt *u) { return u ? u->h.maxAttackRange() : MRTS_E_ARG; }
+void mrts_utt_destroy(mrts_utt *u) { delete u; }
+
+int mrts_map_from_xml(const char *xml, const mrts_utt *u, mrts_map **out) {
+    if (!xml || !u || !out) return fail(MRTS_E_ARG, "mrts_map_from_xml: null argument");
+    auto m = std::make_unique<mrts_map>(); std::string err;
+    if (!map_from_xml(xml, u->h, m->h, err)) return fail(MRTS_E_PARSE, err);
+    if (!map_check(m->h, u->h, err)) return fail(MRTS_E_LIMIT, err);
+    *out = m.release(); return MRTS_OK;
+}
+int mrts_map_load_xml(const char *path, const mrts_utt *u, mrts_map **out) {
+    if (!path || !u || !out) return fail(MRTS_E_ARG, "mrts_map_load_xml: null argument");
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return fail(MRTS_E_IO, std::string("cannot open map file: ") + path);
+    std::stringstream ss; ss << f.rdbuf();
+    return mrts_map_from_xml(ss.str().c_str(), u, out);
+}
+int mrts_map_create(int w, int h, const uint8_t *terrain, int res0, int res1, int n_units, const int32_t *units, const mrts_utt *u, mrts_map **out) {
+    if (!u || !out || w <= 0 || h <= 0 || n_units < 0 || (n_units && !units)) return fail(MRTS_E_ARG, "mrts_map_create: bad argument");
+    auto m = std::make_unique<mrts_map>();
+    m->h.w = w; m->h.h = h; m->h.res[0] = res0; m->h.res[1] = res1;
+    m->h.terrain.assign((size_t)w * h, 0);
+    if (terrain) for (size_t i = 0; i < (size_t)w * h; i++) m->h.terrain[i] = terrain[i] ? 1 : 0;
+    for (int i = 0; i < n_units; i++) { const int32_t *r = units + i * 7; m->h.units.push_back(MapUnit{r[0], r[1], r[2], r[3], r[4], r[5], r[6]}); }
+    std::string err;
+    if (!map_check(m->h, u->h, err)) return fail(MRTS_E_LIMIT, err);
+    *out = m.release(); return MRTS_OK;
+}
+int mrts_map_width(const mrts_map *m) { return m ? m->h.w : MRTS_E_ARG; }
+int mrts_map_height(const mrts_map *m) { return m ? m->h.h : MRTS_E_ARG; }
+int mrts_map_num_units(const mrts_map *m) { return m ? (int)m->h.units.size() : MRTS_E_ARG; }
+int mrts_map_get_units(const mrts_map *m, int32_t *out) {
+    if (!m || !out) return fail(MRTS_E_ARG, "mrts_map_get_units: null argument");
+    for (size_t i = 0; i < m->h.units.size(); i++) { const MapUnit &u = m->h.units[i]; int32_t *r = out + i * 7; r[0] = u.type; r[1] = (int32_t)u.id; r[2] = u.player; r[3] = u.x; r[4] = u.y; r[5] = u.res; r[6] = u.hp; }
+    return (int)m->h.units.size();
+}
+int mrts_map_get_terrain(const mrts_map *m, uint8_t *out) { if (!m || !out) return fail(MRTS_E_ARG, "mrts_map_get_terrain: null argument"); memcpy(out, m->h.terrain.data(), m->h.terrain.size()); return MRTS_OK; }
+int mrts_map_resources(const mrts_map *m, int p) { return (m && p >= 0 && p < 2) ? m->h.res[p] : MRTS_E_ARG; }
+void mrts_map_destroy(mrts_map *m) { delete m; }
+
+void mrts_batch_destroy(mrts_batch *b) {
+    if (!b) return;
+    dev_select(b->device);
+    dev_free(b->d_hdr); dev_free(b->d_units); dev_free(b->d_maps); dev_free(b->d_cst); dev_free(b->d_stats); dev_free(b->d_tmp);
+    for (auto &s : b->staged) { dev_free(s.actions); dev_free(s.counts); }
+#ifndef MRTS_EMU
+    if (b->stream) cudaStreamDestroy(b->stream);
+#endif
+    delete b;
+}
+
+int mrts_batch_create(const mrts_utt *u, const mrts_map *const *maps, int n_maps, int64_t n_games, int device, uint32_t flags, int unit_capacity, mrts_batch **out) {
+    if (!u || !maps || n_maps < 1 || n_games < 1 || !out) return fail(MRTS_E_ARG, "mrts_batch_create: bad argument");
+    std::string err;
+    if (!utt_check_limits(u->h, err)) return fail(MRTS_E_LIMIT, err);
+    int W = maps[0]->h.w, H = maps[0]->h.h, bound = 0;
+    for (int i = 0; i < n_maps; i++) {
+        if (!maps[i] || maps[i]->h.w != W || maps[i]->h.h != H) return fail(MRTS_E_ARG, "mrts_batch_create: all maps of a batch must have the same size");
+        if (!map_check(maps[i]->h, u->h, err)) return fail(MRTS_E_LIMIT, err);
+        bound = std::max(bound, map_unit_bound(maps[i]->h));
+        bound = std::max(bound, (int)maps[i]->h.units.size());
+    }
+    int cap = unit_capacity > 0 ? unit_capacity : std::min(MRTS_MAX_CAP, (bound + 31) & ~31);
+    if (cap > MRTS_MAX_CAP) return fail(MRTS_E_LIMIT, "unit capacity above 254");
+    for (int i = 0; i < n_maps; i++) if ((int)maps[i]->h.units.size() > cap) return fail(MRTS_E_LIMIT, "map has more initial units than the unit capacity");
+    if (cap < 32) cap = 32;
+    auto b = std::unique_ptr<mrts_batch, void (*)(mrts_batch *)>(new mrts_batch, mrts_batch_destroy);
+    b->utt = u->h; b->W = W; b->H = H; b->cap = cap; b->n_maps = n_maps; b->n = n_games; b->flags = flags; b->device = device;
+    b->max_range = u->h.maxAttackRange();
+    b->L = mrts_smem_layout(W, H, cap);
+    b->map_words = mrts_map_blob_words(W, H, cap);
+    b->smem_bytes = MRTS_CONST_WORDS * 4 + (size_t)MRTS_WARPS_PER_CTA * b->L.total;
+    if (dev_select(device)) return fail(MRTS_E_CUDA, std::string("cannot select CUDA device: ") + dev_errstr());
+#ifndef MRTS_EMU
+    cudaDeviceProp prop;
+    if (ck(cudaGetDeviceProperties(&prop, device))) return fail(MRTS_E_CUDA, std::string("cudaGetDeviceProperties: ") + dev_errstr());
+    if (b->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) return fail(MRTS_E_LIMIT, "map too large for the shared-memory resident engine");
+    if (ck(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes))) return fail(MRTS_E_CUDA, std::string("cudaFuncSetAttribute: ") + dev_errstr());
+    int per_sm = 0;
+    if (ck(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step, MRTS_WARPS_PER_CTA * 32, b->smem_bytes))) return fail(MRTS_E_CUDA, std::string("occupancy query: ") + dev_errstr());
+    b->grid = std::max(1, per_sm) * prop.multiProcessorCount;
+    if (ck(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking))) return fail(MRTS_E_CUDA, std::string("cudaStreamCreate: ") + dev_errstr());
+#else
+    b->grid = 3;
+#endif
+    size_t hdr_bytes = (size_t)n_games * MRTS_HDR_WORDS * 4, unit_bytes = (size_t)n_games * MRTS_UNIT_WORDS * cap * 4;
+    if (dev_alloc((void **)&b->d_hdr, hdr_bytes) || dev_alloc((void **)&b->d_units, unit_bytes) ||
+        dev_alloc((void **)&b->d_maps, (size_t)n_maps * b->map_words * 4) || dev_alloc((void **)&b->d_cst, MRTS_CONST_WORDS * 4) ||
+        dev_alloc((void **)&b->d_stats, 8 * sizeof(unsigned long long)))
+        return fail(MRTS_E_CUDA, std::string("device allocation failed: ") + dev_errstr());
+    std::vector<uint32_t> blob, all;
+    for (int i = 0; i < n_maps; i++) { build_map_blob(maps[i]->h, cap, blob); all.insert(all.end(), blob.begin(), blob.end()); }
+    std::vector<uint32_t> cst; build_const_words(u->h, cst);
+    if (dev_h2d(b->d_maps, all.data(), all.size() * 4, b->stream) || dev_h2d(b->d_cst, cst.data(), cst.size() * 4, b->stream) ||
+        dev_zero(b->d_stats, 8 * sizeof(unsigned long long), b->stream) || dev_zero(b->d_units, unit_bytes, b->stream) || dev_sync(b->stream))
+        return fail(MRTS_E_CUDA, std::string("device upload failed: ") + dev_errstr());
+    mrts_batch *raw = b.release();
+    int rc = mrts_batch_reset(raw, nullptr, 0);
+    if (rc) { mrts_batch_destroy(raw); return rc; }
+    *out = raw;
+    return MRTS_OK;
+}
+
+int64_t mrts_batch_num_games(const mrts_batch *b) { return b ? b->n : MRTS_E_ARG; }
+int mrts_batch_unit_capacity(const mrts_batch *b) { return b ? b->cap : MRTS_E_ARG; }
+int mrts_batch_device(const mrts_batch *b) { return b ? b->device : MRTS_E_ARG; }
+void *mrts_batch_stream(const mrts_batch *b) { return b ? (void *)b->stream : nullptr; }
+int mrts_batch_sync(mrts_batch *b) { if (!b) return MRTS_E_ARG; if (dev_sync(b->stream)) return fail(MRTS_E_CUDA, std::string("stream sync: ") + dev_errstr()); return MRTS_OK; }
+int64_t mrts_batch_launch_count(const mrts_batch *b) { return b ? b->launches : 0; }
+int mrts_batch_num_planes(const mrts_batch *b) { return b ? ((b->flags & MRTS_FLAG_PARTIAL_OBS) ? 8 : 6) : MRTS_E_ARG; }
+int mrts_batch_mask_width(const mrts_batch *b) { if (!b) return MRTS_E_ARG; int R = 2 * b->max_range + 1; return 1 + 6 + 16 + (int)b->utt.types.size() + R * R; }
+
+static int do_reset(mrts_batch *b, const uint8_t *mask, const int64_t *seeds, int on_device) {
+    if (!b) return fail(MRTS_E_ARG, "null batch");
+    if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
+    const long long *d_seeds = (const long long *)seeds; const uint8_t *d_mask = mask;
+    if (!on_device && (seeds || mask)) {
+        size_t sb = seeds ? (size_t)b->n * 8 : 0, mb = mask ? (size_t)b->n : 0;
+        if (ensure_tmp(b, sb + mb)) return fail(MRTS_E_CUDA, std::string("staging allocation failed: ") + dev_errstr());
+        if (seeds) { if (dev_h2d(b->d_tmp, seeds, sb, b->stream)) return fail(MRTS_E_CUDA, dev_errstr()); d_seeds = (const long long *)b->d_tmp; }
+        if (mask) { if (dev_h2d((char *)b->d_tmp + sb, mask, mb, b->stream)) return fail(MRTS_E_CUDA, dev_errstr()); d_mask = (const uint8_t *)b->d_tmp + sb; }
+    }
+    ResetParams p{b->d_hdr, b->d_units, b->d_maps, d_seeds, d_mask, b->n, b->n_maps, b->map_words, b->cap, b->L.pcw};
+    b->launches++;
+    if (!mask) { if (dev_zero(b->d_stats, 8 * sizeof(unsigned long long), b->stream)) return fail(MRTS_E_CUDA, dev_errstr()); }
+    b->staged[0].valid = b->staged[1].valid = false;
+#ifdef MRTS_EMU
+    emu::launch(2, 128, 0, [p](unsigned char *, int tid, int bid) { reset_kernel_body(p, tid, 128, bid, 2); });
+#else
+    int grid = (int)std::min<long long>((b->n + 3) / 4, 148 * 16);
+    k_reset<<<grid, 128, 0, b->stream>>>(p);
+    if (ck(cudaGetLastError())) return fail(MRTS_E_CUDA, std::string("reset launch: ") + dev_errstr());
+    if (!on_device && (seeds || mask)) if (dev_sync(b->stream)) return fail(MRTS_E_CUDA, dev_errstr()); // staging buffer reuse
+#endif
+    return MRTS_OK;
+}
+int mrts_batch_reset(mrts_batch *b, const int64_t *seeds, int on_device) { return do_reset(b, nullptr, seeds, on_device); }
+int mrts_batch_reset_masked(mrts_batch *b, const uint8_t *mask, const int64_t *seeds, int on_device) {
+    if (!mask) return fail(MRTS_E_ARG, "mrts_batch_reset_masked: mask is required");
+    return do_reset(b, mask, seeds, on_device);
+}
+
+int mrts_batch_set_policy(mrts_batch *b, int player, int policy, int pathfinder) {
+    if (!b || player < 0 || player > 1) return fail(MRTS_E_ARG, "mrts_batch_set_policy: bad argument");
+    if (policy < MRTS_POLICY_EXTERNAL || policy > MRTS_POLICY_LIGHT_RUSH) return fail(MRTS_E_ARG, "mrts_batch_set_policy: unknown policy");
+    if (policy == MRTS_POLICY_WORKER_RUSH || policy == MRTS_POLICY_LIGHT_RUSH) return fail(MRTS_E_STATE, "scripted device policies are not available in this build");
+    b->policy[player] = policy; b->pathfinder[player] = pathfinder;
+    return MRTS_OK;
+}
+
+static int stage_actions(mrts_batch *b, int player, int format, const int32_t *actions, const int32_t *counts, int max_k, int fill, int on_device) {
+    if (!b || player < 0 || player > 1 || max_k < 0 || (max_k > 0 && !actions)) return fail(MRTS_E_ARG, "bad action arguments");
+    if (format != MRTS_ACTIONS_VECTOR && format != MRTS_ACTIONS_RAW) return fail(MRTS_E_ARG, "unknown action format");
+    if (max_k > b->cap) return fail(MRTS_E_ARG, "max_k exceeds the unit capacity of the batch");
+    if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
+    Staged &s = b->staged[player];
+    size_t rows = (size_t)b->n * (size_t)std::max(max_k, 1);
+    if (rows > s.cap_rows || !s.counts) {
+        dev_free(s.actions); dev_free(s.counts); s.actions = nullptr; s.counts = nullptr; s.cap_rows = 0;
+        if (dev_alloc((void **)&s.actions, rows * 8 * 4) || dev_alloc((void **)&s.counts, (size_t)b->n * 4)) return fail(MRTS_E_CUDA, std::string("staging allocation failed: ") + dev_errstr());
+        s.cap_rows = rows;
+    }
+    size_t ab = (size_t)b->n * max_k * 8 * 4;
+    if (ab) { if (on_device ? dev_d2d(s.actions, actions, ab, b->stream) : dev_h2d(s.actions, actions, ab, b->stream)) return fail(MRTS_E_CUDA, dev_errstr()); }
+    if (counts) { if (on_device ? dev_d2d(s.counts, counts, (size_t)b->n * 4, b->stream) : dev_h2d(s.counts, counts, (size_t)b->n * 4, b->stream)) return fail(MRTS_E_CUDA, dev_errstr()); }
+    else {
+        std::vector<int32_t> c((size_t)b->n, max_k);
+        if (dev_h2d(s.counts, c.data(), c.size() * 4, b->stream) || dev_sync(b->stream)) return fail(MRTS_E_CUDA, dev_errstr());
+    }
+    if (!on_device && dev_sync(b->stream)) return fail(MRTS_E_CUDA, dev_errstr()); // caller may reuse its host buffers
+    s.max_k = max_k; s.format = format; s.fill = fill; s.valid = true;
+    return MRTS_OK;
+}
+
+int mrts_batch_set_actions(mrts_batch *b, int player, int format, const int32_t *actions, const int32_t *counts, int max_k, int fill_none_duration, int on_device) {
+    return stage_actions(b, player, format, actions, counts, max_k, fill_none_duration, on_device);
+}
+
+static void fill_ext(mrts_batch *b, StepParams &p, int pl) {
+    Staged &s = b->staged[pl];
+    if (s.valid) { p.ext_actions[pl] = s.actions; p.ext_counts[pl] = s.counts; p.ext_maxk[pl] = s.max_k; p.ext_format[pl] = s.format; p.ext_fill[pl] = s.fill; }
+}
+
+int mrts_batch_issue(mrts_batch *b, int player, int format, const int32_t *actions, const int32_t *counts, int max_k, int fill_none_duration, int safe, int on_device) {
+    int rc = stage_actions(b, player, format, actions, counts, max_k, fill_none_duration, on_device);
+    if (rc) return rc;
+    StepParams p; memset(&p, 0, sizeof p);
+    p.mode = MODE_ISSUE_ONLY; p.issue_player = player; p.safe = safe ? 1 : 0;
+    fill_ext(b, p, player);
+    b->staged[player].valid = false;
+    if (launch_step(b, p)) return fail(MRTS_E_CUDA, std::string("issue launch: ") + dev_errstr());
+    return MRTS_OK;
+}
+
+int mrts_batch_step(mrts_batch *b, int n_cycles, int max_cycles) {
+    if (!b || n_cycles < 0) return fail(MRTS_E_ARG, "mrts_batch_step: bad argument");
+    if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
+    StepParams p; memset(&p, 0, sizeof p);
+    p.mode = MODE_GAME; p.n_cycles = n_cycles; p.max_cycles = max_cycles; p.safe = 1;
+    for (int pl = 0; pl < 2; pl++) { p.policy[pl] = b->policy[pl]; p.pathfinder[pl] = b->pathfinder[pl]; if (b->policy[pl] == MRTS_POLICY_EXTERNAL) fill_ext(b, p, pl); b->staged[pl].valid = false; }
+    if (launch_step(b, p)) return fail(MRTS_E_CUDA, std::string("step launch: ") + dev_errstr());
+    return MRTS_OK;
+}
+
+int mrts_batch_cycle_to(mrts_batch *b, const int32_t *t_target, int n_cycles, int on_device) {
+    if (!b) return fail(MRTS_E_ARG, "null batch");
+    if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
+    StepParams p; memset(&p, 0, sizeof p);
+    p.mode = MODE_CYCLE_ONLY; p.n_cycles = n_cycles;
+    if (t_target) {
+        if (on_device) p.t_target = t_target;
+        else {
+            if (ensure_tmp(b, (size_t)b->n * 4) || dev_h2d(b->d_tmp, t_target, (size_t)b->n * 4, b->stream)) return fail(MRTS_E_CUDA, dev_errstr());
+            p.t_target = (const int32_t *)b->d_tmp;
+        }
+    }
+    if (launch_step(b, p)) return fail(MRTS_E_CUDA, std::string("cycle launch: ") + dev_errstr());
+    if (t_target && !on_device && dev_sync(b->stream)) return fail(MRTS_E_CUDA, dev_errstr());
+    return MRTS_OK;
+}
+
+int mrts_batch_rollout(mrts_batch *, int, int, int, int, const int64_t *, float *, int32_t *, int) {
+    return fail(MRTS_E_STATE, "mrts_batch_rollout is not available in this build");
+}
+
+static int emit(mrts_batch *b, int mode, int player, int dtype, void *out, int on_device, size_t elems) {
+    if (!b || !out || player < 0 || player > 1 || (dtype != MRTS_DTYPE_U8 && dtype != MRTS_DTYPE_I32)) return fail(MRTS_E_ARG, "bad observation/mask argument");
+    if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
+    size_t bytes = elems * (dtype == MRTS_DTYPE_U8 ? 1 : 4);
+    void *d_out = out;
+    if (!on_device) { if (ensure_tmp(b, bytes)) return fail(MRTS_E_CUDA, std::string("staging allocation failed: ") + dev_errstr()); d_out = b->d_tmp; }
+    if (mode == MODE_MASKS && dev_zero(d_out, bytes, b->stream)) return fail(MRTS_E_CUDA, dev_errstr());
+    StepParams p; memset(&p, 0, sizeof p);
+    p.mode = mode; p.out = d_out; p.out_dtype = dtype; p.out_player = player;
+    if (launch_step(b, p)) return fail(MRTS_E_CUDA, std::string("launch: ") + dev_errstr());
+    if (!on_device && dev_d2h(out, d_out, bytes, b->stream)) return fail(MRTS_E_CUDA, dev_errstr());
+    return MRTS_OK;
+}
+int mrts_batch_observe(mrts_batch *b, int player, int dtype, void *out, int on_device) {
+    if (!b) return fail(MRTS_E_ARG, "null batch");
+    return emit(b, MODE_OBSERVE, player, dtype, out, on_device, (size_t)b->n * mrts_batch_num_planes(b) * b->W * b->H);
+}
+int mrts_batch_masks(mrts_batch *b, int player, int dtype, void *out, int on_device) {
+    if (!b) return fail(MRTS_E_ARG, "null batch");
+    return emit(b, MODE_MASKS, player, dtype, out, on_device, (size_t)b->n * b->W * b->H * mrts_batch_mask_width(b));
+}
+
+int mrts_batch_results(mrts_batch *b, int32_t *out, int on_device) {
+    if (!b || !out) return fail(MRTS_E_ARG, "mrts_batch_results: null argument");
+    if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
+    int32_t *d_out = out;
+    if (!on_device) { if (ensure_tmp(b, (size_t)b->n * 16)) return fail(MRTS_E_CUDA, dev_errstr()); d_out = (int32_t *)b->d_tmp; }
+    ResultParams p{b->d_hdr, b->d_units, d_out, b->n, b->cap};
+    b->launches++;
+#ifdef MRTS_EMU
+    for (long long g = 0; g < b->n; g++) results_kernel_body(p, g);
+#else
+    k_results<<<(unsigned)((b->n + 127) / 128), 128, 0, b->stream>>>(p);
+    if (ck(cudaGetLastError())) return fail(MRTS_E_CUDA, std::string("results launch: ") + dev_errstr());
+#endif
+    if (!on_device && dev_d2h(out, d_out, (size_t)b->n * 16, b->stream)) return fail(MRTS_E_CUDA, dev_errstr());
+    return MRTS_OK;
+}
+
+int mrts_batch_stats(mrts_batch *b, int64_t out[8]) {
+    if (!b || !out) return fail(MRTS_E_ARG, "mrts_batch_stats: null argument");
+    if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
+    if (dev_d2h(out, b->d_stats, 8 * sizeof(int64_t), b->stream)) return fail(MRTS_E_CUDA, dev_errstr());
+    return MRTS_OK;
+}
+
+// ---- export / import --------------------------------------------------------------------------------------------------
+int mrts_batch_export(mrts_batch *b, int64_t first, int64_t count, mrts_state_host *out) {
+    if (!b || !out || first < 0 || count < 0 || first + count > b->n) return fail(MRTS_E_ARG, "mrts_batch_export: bad range");
+    if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
+    int cap = b->cap;
+    std::vector<int32_t> hdr((size_t)count * MRTS_HDR_WORDS);
+    std::vector<uint32_t> un((size_t)count * MRTS_UNIT_WORDS * cap);
+    if (count && (dev_d2h(hdr.data(), b->d_hdr + first * MRTS_HDR_WORDS, hdr.size() * 4, b->stream) ||
+                  dev_d2h(un.data(), b->d_units + first * (long long)MRTS_UNIT_WORDS * cap, un.size() * 4, b->stream)))
+        return fail(MRTS_E_CUDA, dev_errstr());
+    for (int64_t g = 0; g < count; g++) {
+        const int32_t *h = &hdr[g * MRTS_HDR_WORDS];
+        const uint32_t *u = &un[g * (size_t)MRTS_UNIT_WORDS * cap];
+        int n = h[H_NUNITS], c0 = 0, c1 = 0;
+        for (int i = 0; i < n; i++) { int pl = (u[UW_W0 * cap + i] >> 8) & 0xff; c0 += pl == 1; c1 += pl == 2; }
+        if (out->header) {
+            int32_t *o = out->header + g * 8;
+            o[0] = h[H_TIME]; o[1] = h[H_RES0]; o[2] = h[H_RES1]; o[3] = n;
+            o[4] = (c0 > 0 && c1 == 0) ? 0 : ((c1 > 0 && c0 == 0) ? 1 : -1);
+            o[5] = (c0 == 0 || c1 == 0) ? 1 : 0; o[6] = h[H_ERR]; o[7] = h[H_NEXTID];
+        }
+        // rank of each assignment in insertion order
+        std::vector<std::pair<uint32_t, int>> order;
+        for (int i = 0; i < n; i++) if ((u[UW_A0 * cap + i] & 0xF) != AT_IDLE) order.emplace_back(u[UW_SEQ * cap + i], i);
+        std::sort(order.begin(), order.end());
+        std::vector<int> rank(n, 0);
+        for (size_t r = 0; r < order.size(); r++) rank[order[r].second] = (int)r;
+        for (int i = 0; i < cap; i++) {
+            int32_t *ou = out->units ? out->units + (g * cap + i) * 8 : nullptr;
+            int32_t *oa = out->actions ? out->actions + (g * cap + i) * 8 : nullptr;
+            if (ou) memset(ou, 0, 32);
+            if (oa) memset(oa, 0, 32);
+            if (i >= n) continue;
+            uint32_t w0 = u[UW_W0 * cap + i], w1 = u[UW_W1 * cap + i], a0 = u[UW_A0 * cap + i];
+            bool has = (a0 & 0xF) != AT_IDLE;
+            if (ou) { ou[0] = w0 & 0xff; ou[1] = (int)((w0 >> 8) & 0xff) - 1; ou[2] = (w0 >> 16) & 0xff; ou[3] = w0 >> 24; ou[4] = (int16_t)(w1 >> 16); ou[5] = (int16_t)(w1 & 0xffff); ou[6] = (int32_t)u[UW_ID * cap + i]; ou[7] = has; }
+            if (oa && has) {
+                int at = a0 & 0xF, ut = (a0 >> 8) & 0xff;
+                oa[0] = at; oa[1] = (int32_t)u[UW_A1 * cap + i];
+                oa[2] = at == MRTS_ATTACK ? (int)((a0 >> 16) & 0xff) : 0; oa[3] = at == MRTS_ATTACK ? (int)(a0 >> 24) : 0;
+                oa[4] = ut == 0xFF ? -1 : ut; oa[5] = (int32_t)u[UW_TIS * cap + i]; oa[6] = rank[i];
+            }
+        }
+        if (out->rng) for (int k = 0; k < 3; k++) out->rng[g * 3 + k] = (int64_t)((uint64_t)(uint32_t)h[H_RNGP_LO + 2 * k] | ((uint64_t)(uint32_t)h[H_RNGP_HI + 2 * k] << 32));
+    }
+    return MRTS_OK;
+}
+
+int mrts_batch_import(mrts_batch *b, int64_t first, int64_t count, const mrts_state_host *in) {
+    if (!b || !in || !in->header || !in->units || first < 0 || count < 0 || first + count > b->n) return fail(MRTS_E_ARG, "mrts_batch_import: bad argument");
+    if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
+    int cap = b->cap;
+    std::vector<int32_t> hdr((size_t)count * MRTS_HDR_WORDS, 0);
+    std::vector<uint32_t> un((size_t)count * MRTS_UNIT_WORDS * cap, 0);
+    for (int64_t g = 0; g < count; g++) {
+        int32_t *h = &hdr[g * MRTS_HDR_WORDS];
+        uint32_t *u = &un[g * (size_t)MRTS_UNIT_WORDS * cap];
+        const int32_t *ih = in->header + g * 8;
+        int n = ih[3];
+        if (n < 0 || n > cap) return fail(MRTS_E_LIMIT, "mrts_batch_import: more units than the batch capacity");
+        h[H_TIME] = ih[0]; h[H_RES0] = ih[1]; h[H_RES1] = ih[2]; h[H_NUNITS] = n; h[H_ERR] = ih[6]; h[H_NEXTID] = ih[7];
+        std::vector<std::pair<int, int>> order;
+        long long maxid = -1;
+        for (int i = 0; i < n; i++) {
+            const int32_t *iu = in->units + (g * cap + i) * 8;
+            u[UW_W0 * cap + i] = (uint32_t)(iu[0] & 0xff) | ((uint32_t)((iu[1] + 1) & 0xff) << 8) | ((uint32_t)(iu[2] & 0xff) << 16) | ((uint32_t)(iu[3] & 0xff) << 24);
+            u[UW_W1 * cap + i] = ((uint32_t)iu[5] & 0xffffu) | ((uint32_t)iu[4] << 16);
+            u[UW_ID * cap + i] = (uint32_t)iu[6];
+            maxid = std::max<long long>(maxid, iu[6]);
+            u[UW_A0 * cap + i] = AT_IDLE | (0xFFu << 8);
+            if (iu[7] && in->actions) {
+                const int32_t *ia = in->actions + (g * cap + i) * 8;
+                uint32_t a0 = (uint32_t)(ia[0] & 0xF) | ((uint32_t)((ia[4] < 0 ? 0xFF : ia[4]) & 0xff) << 8);
+                if (ia[0] == MRTS_ATTACK) a0 |= ((uint32_t)(ia[2] & 0xff) << 16) | ((uint32_t)(ia[3] & 0xff) << 24);
+                u[UW_A0 * cap + i] = a0; u[UW_A1 * cap + i] = (uint32_t)ia[1]; u[UW_TIS * cap + i] = (uint32_t)ia[5];
+                order.emplace_back(ia[6], i);
+            }
+        }
+        std::sort(order.begin(), order.end());
+        for (size_t r = 0; r < order.size(); r++) u[UW_SEQ * cap + order[r].second] = (uint32_t)r;
+        h[H_NEXTSEQ] = (int32_t)order.size();
+        if (h[H_NEXTID] <= maxid) h[H_NEXTID] = (int32_t)(maxid + 1);
+        for (int k = 0; k < 3; k++) {
+            uint64_t s = in->rng ? (uint64_t)in->rng[g * 3 + k] : jr_scramble((first + g) ^ (k == 1 ? SEED_XOR_CONFLICT : (k == 2 ? SEED_XOR_DAMAGE : 0)));
+            h[H_RNGP_LO + 2 * k] = (int32_t)(uint32_t)s; h[H_RNGP_HI + 2 * k] = (int32_t)(uint32_t)(s >> 32);
+        }
+    }
+    if (count && (dev_h2d(b->d_hdr + first * MRTS_HDR_WORDS, hdr.data(), hdr.size() * 4, b->stream) ||
+                  dev_h2d(b->d_units + first * (long long)MRTS_UNIT_WORDS * cap, un.data(), un.size() * 4, b->stream) || dev_sync(b->stream)))
+        return fail(MRTS_E_CUDA, dev_errstr());
+    return MRTS_OK;
+}
+
+} // extern "C"
