@@ -1,0 +1,328 @@
+#!/usr/bin/env python3
+"""bench.py -- game-cycles/sec of the batched microRTS hot path (BASELINE.json configs[1]).
+
+Workload (N=1): maps/16x16/basesWorkers16x16.xml, 65536 parallel games per GPU, RandomBiasedAI self-play,
+UnitTypeTable v1 + CANCEL_BOTH, 3000-cycle cap, fully observable.  One "step" advances every game by
+--cycles-per-step cycles (Game.start loop body: policy x2, issueSafe x2, cycle) in ONE launch of the step kernel;
+finished games restart on the device (auto-reset), so every timed window is a stationary mix of game phases.
+With the defaults (30 steps x 100 cycles) the timed window covers exactly one full 3000-cycle game per slot.
+
+  value     : game-cycles/s with the state resident in HBM (inputs larger than L2: 65536 x 3.6 KB = 239 MB).
+  e2e       : same metric through the public API with HOST buffers every step: H2D of the restart mask + seeds from
+              pinned memory, reset_masked + step, D2H of the per-game results -- all inside the timed region.
+  roofline  : algorithmic bytes = 2*(32+24*U) per game-cycle (SURVEY 8d, U = mean live units measured in the run)
+              x game-cycles per launch / mean launch time (CUDA events on the batch's stream) vs measured HBM peak.
+  cpu_baseline / --impl reference : the CPU restatement of the Java engine (oracle/, "port": no JVM in this image)
+              on the host cores, bounded sample.
+
+Multi-GPU (torchrun): games shard by rank (weak scaling, 65536 per GPU, seeds offset by rank), no data-path
+collective; one NCCL all-reduce of the win/draw counters at the end; time = max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+MAP_KEY = "16x16/basesWorkers16x16"
+MAX_CYCLES = 3000
+
+
+def workload_string(args):
+    return "maps/%s.xml x %d games/GPU, RandomBiasedAI self-play (Game.start loop), UTT v1 CANCEL_BOTH, %d-cycle cap" % (
+        args.map, args.games, MAX_CYCLES)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--games", type=int, default=65536, help="games per GPU")
+    ap.add_argument("--cycles-per-step", type=int, default=100)
+    ap.add_argument("--map", default=MAP_KEY)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port on the host cores (bench.py's cpu_baseline leg may execute oracle/)
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_baseline(map_key, seconds, threads=None):
+    import golden_io
+    from oracle import oracle as O
+    maps = golden_io.load_maps()
+    threads = threads or (os.cpu_count() or 1)
+    utt = O.Utt(1, 1)
+    cycles = [0] * threads
+    games_done = [0] * threads
+    deadline = time.time() + seconds
+
+    def work(i):
+        seed = 1000003 * i
+        while time.time() < deadline:
+            g = O.Game(utt, maps[map_key])
+            g.seed(seed)
+            seed += 1
+            while time.time() < deadline:
+                over, _ = g.run(O.AI_RANDOM_BIASED, None, O.AI_RANDOM_BIASED, None, 250, MAX_CYCLES)
+                if over or g.time >= MAX_CYCLES:
+                    break
+            cycles[i] += g.time
+            games_done[i] += 1
+
+    t0 = time.time()
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    dt = time.time() - t0
+    return dict(value=sum(cycles) / dt, unit="game-cycles/s", cores=threads, kind="port",
+                sample="%d RandomBiasedAI self-play games (%d game-cycles) of %s on %d host threads in %.1f s; C restatement of the Java "
+                       "engine (oracle/), not the JVM" % (sum(games_done), sum(cycles), map_key, threads, dt))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t_per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_baseline(args.map, min(1.0, t_per_step))
+    vals = []
+    t0 = time.time()
+    last = None
+    for _ in range(args.steps):
+        last = cpu_baseline(args.map, t_per_step)
+        vals.append(last["value"])
+    dt = time.time() - t0
+    v = sum(vals) / len(vals)
+    last["value"] = v
+    out = dict(metric="game_cycles_per_sec", value=v, unit="game-cycles/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+               ms_per_step=1000.0 * dt / max(1, args.steps), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="int32",
+               data="synthetic", impl="reference",
+               config=dict(workload=workload_string(args), games_per_gpu=args.games, cycles_per_step=args.cycles_per_step,
+                           max_cycles=MAX_CYCLES, note="CPU arm: each step is a bounded sample of the same workload on all host threads"),
+               cpu_baseline=last, e2e=dict(value=v, unit="game-cycles/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(out))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.p, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            out = ""
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx, samples=len(sm), reasons=sorted(reasons))
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import golden_io
+    import microrts_b200 as M
+    import parity as P
+    maps = golden_io.load_maps()
+    utt = M.UnitTypeTable(1, 1)
+    pgs = M.PhysicalGameState.fromXML(P.map_to_xml(maps[args.map]), utt)
+    n, C = args.games, args.cycles_per_step
+    b = M.BatchedGameState(utt, pgs, n, device=local)
+    from microrts_b200 import _ffi
+    stream = torch.cuda.ExternalStream(_ffi.lib().mrts_batch_stream(b._h), device=torch.device("cuda", local))
+    seeds = np.arange(n, dtype=np.int64) + rank * n
+    b.set_policy(0, M.POLICY_RANDOM_BIASED)
+    b.set_policy(1, M.POLICY_RANDOM_BIASED)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident run ("value") -------------------------------------------------------------------------------
+    b.reset(seeds)
+    b.set_auto_reset(True)
+    for _ in range(args.warmup):
+        b.step(C, MAX_CYCLES)
+    b.sync()
+    st0 = b.stats()
+    l0 = b.launch_count
+    clocks = ClockSampler(local)
+    clocks.start()
+    barrier()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t0 = time.perf_counter()
+    for a, z in evs:
+        a.record(stream)
+        b.step(C, MAX_CYCLES)
+        z.record(stream)
+    b.sync()
+    barrier()
+    wall = time.perf_counter() - t0
+    clk = clocks.stop()
+    launches = b.launch_count - l0
+    st1 = b.stats()
+    kernel_ms = [a.elapsed_time(z) for a, z in evs]
+    dev_s = sum(kernel_ms) / 1000.0
+    cycles = st1["cycles"] - st0["cycles"]
+    ucyc = st1["unit_cycles"] - st0["unit_cycles"]
+    decisions = st1["decisions"] - st0["decisions"]
+    res = b.results()
+    errors = int((res[:, 3] != 0).sum())
+
+    tmax = torch.tensor([wall, dev_s], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([cycles, ucyc, decisions, st1["wins_p0"], st1["wins_p1"], st1["draws"], st1["games_finished"], errors], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)  # the single NCCL reduce of win/score statistics
+    wall_max, dev_max = tmax.tolist()
+    cycles_all, ucyc_all, dec_all, w0, w1, dr, fin, err_all = tot.tolist()
+    value = cycles_all / wall_max
+    mean_units = ucyc_all / max(1, cycles_all)
+
+    # ---- end-to-end through the public API with host buffers ---------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        b.set_auto_reset(False)
+        b.reset(seeds)
+        mask = torch.zeros(n, dtype=torch.uint8).pin_memory()
+        hseeds = torch.from_numpy(seeds.copy()).pin_memory()
+        hres = torch.zeros((n, 4), dtype=torch.int32).pin_memory()
+        mask_np, seeds_np, res_np = mask.numpy(), hseeds.numpy(), hres.numpy()
+        episode = 0
+
+        def e2e_step():
+            nonlocal episode
+            b.reset_masked(mask_np, seeds_np)       # H2D: restart mask (n bytes) + seeds (8n bytes)
+            b.step(C, MAX_CYCLES)
+            b.results(res_np)                       # D2H: per-game {time, winner, gameover, errors} (16n bytes)
+            done = (res_np[:, 2] != 0) | (res_np[:, 0] >= MAX_CYCLES)
+            mask_np[:] = done
+            if done.any():
+                episode += 1
+                seeds_np[done] += world * n * episode
+            return int(res_np[:, 0].sum())
+
+        tprev = 0
+        for _ in range(args.warmup):
+            tprev = e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        adv = 0
+        for _ in range(args.steps):
+            before = np.where(mask_np != 0, 0, res_np[:, 0]).sum()
+            after = e2e_step()
+            adv += int(after - before)
+        b.sync()
+        barrier()
+        e_wall = time.perf_counter() - t0
+        et = torch.tensor([e_wall], dtype=torch.float64, device="cuda")
+        ea = torch.tensor([adv], dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(et, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ea, op=dist.ReduceOp.SUM)
+        e2e = dict(value=ea.item() / et.item(), unit="game-cycles/s", h2d_bytes_per_step=9 * n, d2h_bytes_per_step=16 * n,
+                   ms_per_step=1000.0 * et.item() / args.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (k_step) ---------------------------------------------------------------------
+    peaks, peak_src = None, "fallback"
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks["hbm_gbs"]) if peaks and "hbm_gbs" in peaks else 6650.0
+    if peaks:
+        peak_src = "measured (MEASURED_PEAKS.json)"
+    bytes_per_cycle = 2.0 * (32.0 + 24.0 * (ucyc / max(1, cycles)))
+    achieved = (cycles * bytes_per_cycle / max(1, len(kernel_ms))) / (dev_s / max(1, len(kernel_ms))) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_step_dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
+                    peak_source=peak_src, kernel="k_step", bytes_per_game_cycle=bytes_per_cycle,
+                    mean_launch_ms=sum(kernel_ms) / max(1, len(kernel_ms)),
+                    note="state-only stepping is issue/latency-bound, not HBM-bound (SURVEY 8d); frac is reported as the metric demands")
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = cpu_baseline(args.map, args.cpu_seconds)
+
+    out = dict(metric="game_cycles_per_sec", value=value, unit="game-cycles/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+               ms_per_step=1000.0 * wall_max / max(1, args.steps), higher_is_better=True, scaling="weak", vs_baseline=None,
+               dtype="int32", data="synthetic",
+               config=dict(workload=workload_string(args),
+                           games_per_gpu=n, cycles_per_step=C, max_cycles=MAX_CYCLES, auto_reset="on device",
+                           l2="state (%.0f MB/GPU) larger than L2, no flush" % (n * (64 + 7 * 4 * b.cap) / 1e6),
+                           mean_live_units=mean_units, decisions_per_cycle=dec_all / max(1, cycles_all), unit_capacity=b.cap),
+               clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu,
+               stats=dict(wins_p0=w0, wins_p1=w1, draws=dr, games_finished=fin, game_errors=err_all,
+                          device_time_s=dev_max, wall_time_s=wall_max))
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -138,6 +138,10 @@ int mrts_batch_reset(mrts_batch *, const int64_t *seeds, int on_device);
 int mrts_batch_reset_masked(mrts_batch *, const uint8_t *mask, const int64_t *seeds, int on_device);
 
 int mrts_batch_set_policy(mrts_batch *, int player, int policy, int pathfinder);
+/* When enabled, mrts_batch_step restarts a game from its map at the start of the step if the game ended (game over or
+ * time >= max_cycles) in an earlier step -- the auto-reset of src/tests/JNIGridnetVecClient.java:272-286, done on the
+ * device.  The game's RNG streams keep running across episodes, like the reference's static Random objects. */
+int mrts_batch_set_auto_reset(mrts_batch *, int enable);
 
 /* Stage one PlayerAction per game for `player`, consumed by the next mrts_batch_step when that player's policy
  * is EXTERNAL (decode of both players happens on the pre-issue state, as in JNIGridnetClientSelfPlay.gameStep).

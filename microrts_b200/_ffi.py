@@ -33,7 +33,7 @@ def bind(L):
         "mrts_batch_num_games": (i64, [vp]), "mrts_batch_unit_capacity": (i, [vp]), "mrts_batch_device": (i, [vp]),
         "mrts_batch_stream": (vp, [vp]), "mrts_batch_sync": (i, [vp]),
         "mrts_batch_reset": (i, [vp, vp, i]), "mrts_batch_reset_masked": (i, [vp, vp, vp, i]),
-        "mrts_batch_set_policy": (i, [vp, i, i, i]),
+        "mrts_batch_set_policy": (i, [vp, i, i, i]), "mrts_batch_set_auto_reset": (i, [vp, i]),
         "mrts_batch_set_actions": (i, [vp, i, i, vp, vp, i, i, i]),
         "mrts_batch_issue": (i, [vp, i, i, vp, vp, i, i, i, i]),
         "mrts_batch_step": (i, [vp, i, i]), "mrts_batch_cycle_to": (i, [vp, vp, i, i]),

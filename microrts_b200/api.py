@@ -210,6 +210,9 @@ class BatchedGameState:
     def set_policy(self, player, policy, pathfinder=PF_ASTAR):
         _check(_ffi.lib().mrts_batch_set_policy(self._h, player, policy, pathfinder))
 
+    def set_auto_reset(self, enable=True):
+        _check(_ffi.lib().mrts_batch_set_auto_reset(self._h, 1 if enable else 0))
+
     def sync(self):
         _check(_ffi.lib().mrts_batch_sync(self._h))
 

@@ -49,6 +49,7 @@ struct StepParams {
     int conflict;              // UnitTypeTable.moveConflictResolutionStrategy
     int safe;                  // issueSafe (1) or issue (0) for external actions
     int issue_player;          // MODE_ISSUE_ONLY
+    int auto_reset;            // MODE_GAME: restart finished games from their map at the start of the step
     const int32_t *ext_actions[2]; // [n_games][max_k][8]
     const int32_t *ext_counts[2];  // [n_games]
     int ext_maxk[2], ext_format[2], ext_fill[2];
@@ -198,6 +199,26 @@ DEV void g_load(Game &g, const int32_t *ghdr, const uint32_t *gun) {
     uint32_t *su = g.w0;
     for (int k = 0; k < MRTS_UNIT_WORDS; k++)
         for (int i = g.lane; i < n; i += 32) su[k * g.cap + i] = gun[k * g.cap + i];
+    __syncwarp();
+    g_scatter(g);
+}
+// restart from the map's initial state (the blob's init header/units); the three RNG streams keep running, as the
+// reference's static Random objects do across games.  H_SPARE counts episodes.
+DEV void g_restart(Game &g) {
+    const int32_t *ih = (const int32_t *)(g.grid_tmpl + g.pcw);
+    const uint32_t *iu = g.grid_tmpl + g.pcw + MRTS_HDR_WORDS;
+    __syncwarp();
+    if (g.lane < MRTS_HDR_WORDS) {
+        int32_t v = ih[g.lane];
+        if (g.lane >= H_RNGP_LO && g.lane <= H_RNGD_HI) v = g.hdr[g.lane];
+        if (g.lane == H_SPARE) v = g.hdr[H_SPARE] + 1;
+        g.hdr[g.lane] = v;
+    }
+    g_reset_maps(g);
+    int n = g.hdr[H_NUNITS];
+    uint32_t *su = g.w0;
+    for (int k = 0; k < MRTS_UNIT_WORDS; k++)
+        for (int i = g.lane; i < n; i += 32) su[k * g.cap + i] = iu[k * g.cap + i];
     __syncwarp();
     g_scatter(g);
 }
@@ -1030,7 +1051,10 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
         uint32_t *gun = p.units + gi * (long long)MRTS_UNIT_WORDS * p.cap;
         g_load(g, ghdr, gun);
         int err0 = g.hdr[H_ERR];
-        if (p.mode == MODE_GAME) run_game(g, p, gi, ws);
+        if (p.mode == MODE_GAME) {
+            if (p.auto_reset && ((g.hdr[H_STATUS] & ST_OVER) || g.hdr[H_TIME] >= p.max_cycles)) g_restart(g);
+            run_game(g, p, gi, ws);
+        }
         else if (p.mode == MODE_CYCLE_ONLY) run_cycles_only(g, p.t_target ? p.t_target[gi] : g.hdr[H_TIME] + p.n_cycles);
         else if (p.mode == MODE_ISSUE_ONLY) run_issue_only(g, p, gi);
         else if (p.mode == MODE_OBSERVE) { observe_game(g, p, gi); continue; }

@@ -145,7 +145,7 @@ struct mrts_batch {
     stream_t stream = nullptr;
     SmemLayout L;
     size_t smem_bytes = 0;
-    int grid = 0, max_range = 0;
+    int grid = 0, max_range = 0, auto_reset = 0;
     long long launches = 0;
 };
 
@@ -363,6 +363,8 @@ int mrts_batch_set_policy(mrts_batch *b, int player, int policy, int pathfinder)
     return MRTS_OK;
 }
 
+int mrts_batch_set_auto_reset(mrts_batch *b, int enable) { if (!b) return fail(MRTS_E_ARG, "null batch"); b->auto_reset = enable ? 1 : 0; return MRTS_OK; }
+
 static int stage_actions(mrts_batch *b, int player, int format, const int32_t *actions, const int32_t *counts, int max_k, int fill, int on_device) {
     if (!b || player < 0 || player > 1 || max_k < 0 || (max_k > 0 && !actions)) return fail(MRTS_E_ARG, "bad action arguments");
     if (format != MRTS_ACTIONS_VECTOR && format != MRTS_ACTIONS_RAW) return fail(MRTS_E_ARG, "unknown action format");
@@ -411,7 +413,7 @@ int mrts_batch_step(mrts_batch *b, int n_cycles, int max_cycles) {
     if (!b || n_cycles < 0) return fail(MRTS_E_ARG, "mrts_batch_step: bad argument");
     if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
     StepParams p; memset(&p, 0, sizeof p);
-    p.mode = MODE_GAME; p.n_cycles = n_cycles; p.max_cycles = max_cycles; p.safe = 1;
+    p.mode = MODE_GAME; p.n_cycles = n_cycles; p.max_cycles = max_cycles; p.safe = 1; p.auto_reset = b->auto_reset;
     for (int pl = 0; pl < 2; pl++) { p.policy[pl] = b->policy[pl]; p.pathfinder[pl] = b->pathfinder[pl]; if (b->policy[pl] == MRTS_POLICY_EXTERNAL) fill_ext(b, p, pl); b->staged[pl].valid = false; }
     if (launch_step(b, p)) return fail(MRTS_E_CUDA, std::string("step launch: ") + dev_errstr());
     return MRTS_OK;

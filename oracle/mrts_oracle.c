@@ -295,6 +295,8 @@ int o_game_time(const OGame *g) { return g->time; }
 int o_game_n_units(const OGame *g) { return g->n; }
 int o_game_resources(const OGame *g, int p) { return g->res[p]; }
 int o_game_errors(const OGame *g) { return g->errors; }
+void o_game_set_rng_state(OGame *g, int which, int64_t s) { OJRandom *r = which == 0 ? &g->rng_policy : (which == 1 ? &g->rng_conflict : &g->rng_damage); r->s = (uint64_t)s; }
+int64_t o_game_rng_state(const OGame *g, int which) { return (int64_t)(which == 0 ? g->rng_policy.s : (which == 1 ? g->rng_conflict.s : g->rng_damage.s)); }
 
 int o_game_units(const OGame *g, int32_t *out) {
     for (int i = 0; i < g->n; i++) {

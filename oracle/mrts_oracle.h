@@ -56,6 +56,9 @@ int o_game_resources(const OGame *, int player);
 int o_game_winner(const OGame *);
 int o_game_gameover(const OGame *);
 int o_game_errors(const OGame *);
+/* raw 48-bit LCG state: 0 policy, 1 conflict, 2 damage */
+int64_t o_game_rng_state(const OGame *, int which);
+void o_game_set_rng_state(OGame *, int which, int64_t state);
 /* out[i*8 .. ] = type, player, x, y, res, hp, id_lo, id_hi  (list order) */
 int o_game_units(const OGame *, int32_t *out);
 /* per unit in list order: has(0/1), type, param, x, y, utype, issue_time, order (rank in insertion order) */

@@ -49,7 +49,7 @@ def lib():
             "o_game_add_unit": (None, [vp, i, i64, i, i, i, i, i]),
             "o_game_clone": (vp, [vp]), "o_game_free": (None, [vp]), "o_game_seed": (None, [vp, i64]),
             "o_game_time": (i, [vp]), "o_game_n_units": (i, [vp]), "o_game_resources": (i, [vp, i]),
-            "o_game_winner": (i, [vp]), "o_game_gameover": (i, [vp]), "o_game_errors": (i, [vp]),
+            "o_game_rng_state": (i64, [vp, i]), "o_game_set_rng_state": (None, [vp, i, i64]), "o_game_winner": (i, [vp]), "o_game_gameover": (i, [vp]), "o_game_errors": (i, [vp]),
             "o_game_units": (i, [vp, pi32]), "o_game_assignments": (i, [vp, pi32]),
             "o_game_cycle": (i, [vp]), "o_game_is_complete": (i, [vp]), "o_game_next_change_time": (i, [vp]),
             "o_game_issue": (i, [vp, i, pi32, C.POINTER(ActionV), i]),
@@ -155,6 +155,12 @@ class Game:
     winner = property(lambda self: lib().o_game_winner(self.h))
     gameover = property(lambda self: bool(lib().o_game_gameover(self.h)))
     errors = property(lambda self: lib().o_game_errors(self.h))
+
+    def set_rng_state(self, which, state):
+        lib().o_game_set_rng_state(self.h, which, state)
+
+    def rng_state(self, which=0):
+        return lib().o_game_rng_state(self.h, which)
 
     def resources(self, p):
         return lib().o_game_resources(self.h, p)
