@@ -145,7 +145,7 @@ struct mrts_batch {
     stream_t stream = nullptr;
     SmemLayout L;
     size_t smem_bytes = 0;
-    int grid = 0, max_range = 0, auto_reset = 0;
+    int grid = 0, max_range = 0, auto_reset = 0, wpc = MRTS_WARPS_PER_CTA; // wpc: warps (games in flight) per CTA
     long long launches = 0;
 };
 
@@ -162,8 +162,8 @@ static int launch_step(mrts_batch *b, StepParams &p) {
     p.n_games = b->n; p.n_maps = b->n_maps; p.map_words = b->map_words; p.W = b->W; p.H = b->H; p.cap = b->cap;
     p.conflict = b->utt.conflict; p.max_range = b->max_range; p.n_types = (int)b->utt.types.size();
     p.partial_obs = (b->flags & MRTS_FLAG_PARTIAL_OBS) ? 1 : 0;
-    int threads = MRTS_WARPS_PER_CTA * 32;
-    long long need = (b->n + MRTS_WARPS_PER_CTA - 1) / MRTS_WARPS_PER_CTA;
+    int threads = b->wpc * 32;
+    long long need = (b->n + b->wpc - 1) / b->wpc;
     int grid = (int)std::min<long long>(b->grid, std::max<long long>(need, 1));
     b->launches++;
 #ifdef MRTS_EMU
@@ -284,18 +284,29 @@ int mrts_batch_create(const mrts_utt *u, const mrts_map *const *maps, int n_maps
     b->max_range = u->h.maxAttackRange();
     b->L = mrts_smem_layout(W, H, cap);
     b->map_words = mrts_map_blob_words(W, H, cap);
-    b->smem_bytes = MRTS_CONST_WORDS * 4 + (size_t)MRTS_WARPS_PER_CTA * b->L.total;
     if (dev_select(device)) return fail(MRTS_E_CUDA, std::string("cannot select CUDA device: ") + dev_errstr());
 #ifndef MRTS_EMU
     cudaDeviceProp prop;
     if (ck(cudaGetDeviceProperties(&prop, device))) return fail(MRTS_E_CUDA, std::string("cudaGetDeviceProperties: ") + dev_errstr());
-    if (b->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) return fail(MRTS_E_LIMIT, "map too large for the shared-memory resident engine");
-    if (ck(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes))) return fail(MRTS_E_CUDA, std::string("cudaFuncSetAttribute: ") + dev_errstr());
-    int per_sm = 0;
-    if (ck(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step, MRTS_WARPS_PER_CTA * 32, b->smem_bytes))) return fail(MRTS_E_CUDA, std::string("occupancy query: ") + dev_errstr());
-    b->grid = std::max(1, per_sm) * prop.multiProcessorCount;
+    // warps per CTA: as many games in flight per SM as shared memory allows (large maps need fewer, fatter CTAs)
+    int best_wpc = 0, best_warps = 0, best_blocks = 0;
+    for (int wpc = MRTS_WARPS_PER_CTA; wpc >= 1; wpc--) {
+        size_t sm = MRTS_CONST_WORDS * 4 + (size_t)wpc * b->L.total;
+        if (sm > (size_t)prop.sharedMemPerBlockOptin) continue;
+        if (ck(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm))) return fail(MRTS_E_CUDA, std::string("cudaFuncSetAttribute: ") + dev_errstr());
+        int per_sm = 0;
+        if (ck(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step, wpc * 32, sm))) return fail(MRTS_E_CUDA, std::string("occupancy query: ") + dev_errstr());
+        if (per_sm * wpc > best_warps) { best_warps = per_sm * wpc; best_wpc = wpc; best_blocks = per_sm; }
+    }
+    if (!best_wpc) return fail(MRTS_E_LIMIT, "map too large for the shared-memory resident engine");
+    b->wpc = best_wpc;
+    b->smem_bytes = MRTS_CONST_WORDS * 4 + (size_t)best_wpc * b->L.total;
+    if (ck(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin))) return fail(MRTS_E_CUDA, std::string("cudaFuncSetAttribute: ") + dev_errstr());
+    b->grid = best_blocks * prop.multiProcessorCount;
     if (ck(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking))) return fail(MRTS_E_CUDA, std::string("cudaStreamCreate: ") + dev_errstr());
 #else
+    b->wpc = 2;
+    b->smem_bytes = MRTS_CONST_WORDS * 4 + (size_t)b->wpc * b->L.total;
     b->grid = 3;
 #endif
     size_t hdr_bytes = (size_t)n_games * MRTS_HDR_WORDS * 4, unit_bytes = (size_t)n_games * MRTS_UNIT_WORDS * cap * 4;

@@ -135,3 +135,231 @@ def test_random_biased_selfplay(backend, maps, key, sizes, cycles, chunk):
 def test_utt_versions_and_conflict_policies(backend, maps, version, conflict):
     run_selfplay(backend, maps, "8x8/basesWorkers8x8", (4, 64), (2000, 3000), 11, version=version, conflict=conflict, check_every=10)
     run_selfplay(backend, maps, "16x16/TwoBasesBarracks16x16", (2, 32), (500, 2000), 40, version=version, conflict=conflict)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# observation planes and action masks (GameState.getVectorObservation / JNIGridnetClient.getMasks)
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("key", ["8x8/basesWorkers8x8", "16x16/basesWorkers16x16", "melee14x12Mixed18", "BWDistantResources32x32"])
+def test_observations_and_masks(backend, maps, key):
+    n = 3 if backend == "emu" else 24
+    chunks = 4 if backend == "emu" else 10
+    utt, outt = M.UnitTypeTable(1, 1), O.Utt(1, 1)
+    pgs = make_pgs(maps[key], utt)
+    b = M.BatchedGameState(utt, pgs, n)
+    bpo = M.BatchedGameState(utt, pgs, n, partial_obs=True)
+    seeds = np.arange(n, dtype=np.int64) + 5
+    games = []
+    for bb in (b, bpo):
+        bb.reset(seeds)
+        bb.set_policy(0, M.POLICY_RANDOM_BIASED)
+        bb.set_policy(1, M.POLICY_RANDOM_BIASED)
+    for g in range(n):
+        og = O.Game(outt, maps[key])
+        og.seed(int(seeds[g]))
+        games.append(og)
+    for c in range(chunks):
+        for player in (0, 1):
+            obs_i = b.observe(player, np.int32)
+            obs_b = b.observe(player, np.uint8)
+            po = bpo.observe(player, np.int32)
+            po_b = bpo.observe(player, np.uint8)
+            mk = b.masks(player, np.int32)
+            mk_b = b.masks(player, np.uint8)
+            assert obs_i.shape == (n, 6, maps[key]["h"], maps[key]["w"]) and po.shape[1] == 8
+            for g, og in enumerate(games):
+                ref = og.observe(player)
+                assert (obs_i[g] == ref).all(), (key, c, g, player)
+                assert (obs_b[g] == ref.astype(np.uint8)).all()
+                ref_po = og.po_view(player).observe(player, po=True)
+                assert (po[g] == ref_po).all(), "PO obs %s chunk %d game %d player %d\n%s\n%s" % (key, c, g, player, po[g], ref_po)
+                assert (po_b[g] == ref_po.astype(np.uint8)).all()
+                ref_m = og.masks(player)
+                assert (mk[g] == ref_m).all(), "masks %s chunk %d game %d player %d" % (key, c, g, player)
+                assert (mk_b[g] == ref_m.astype(np.uint8)).all()
+        for bb in (b, bpo):
+            bb.step(37, 3000)
+        for og in games:
+            og.run(O.AI_RANDOM_BIASED, None, O.AI_RANDOM_BIASED, None, 37, 3000)
+    b.close()
+    bpo.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# vector actions through the EXTERNAL policy (JNIGridnetClientSelfPlay.gameStep flow) against the oracle
+# ------------------------------------------------------------------------------------------------------------------
+def random_vector_actions(rng, og, player, w, h, max_k):
+    """A mix of sensible and nonsense rows: mostly rows addressing own idle units with a random legal-looking action."""
+    units = og.units()
+    asg = og.assignments()
+    rows = []
+    for i, u in enumerate(units):
+        if u[1] != player or asg[i][0]:
+            continue
+        if rng.random() < 0.15:
+            continue
+        acts = og.unit_actions(i)
+        if rng.random() < 0.8:
+            ty, par, x, y, ut = acts[rng.integers(len(acts))]
+        else:  # possibly illegal
+            ty, par, x, y, ut = int(rng.integers(6)), int(rng.integers(4)), int(u[2] + rng.integers(-2, 3)), int(u[3] + rng.integers(-2, 3)), int(rng.integers(1, 7))
+        row = [int(u[2] + u[3] * w), ty, 0, 0, 0, 0, 0, 0]
+        if ty == O.MOVE: row[2] = par
+        elif ty == O.HARVEST: row[3] = par
+        elif ty == O.RETURN: row[4] = par
+        elif ty == O.PRODUCE: row[5], row[6] = par, ut
+        elif ty == O.ATTACK: row[7] = int((y - u[3] + 3) * 7 + (x - u[2] + 3)) if abs(x - u[2]) <= 3 and abs(y - u[3]) <= 3 else 24
+        rows.append(row)
+    if rng.random() < 0.3:  # rows addressing empty cells / enemy units / busy units
+        rows.append([int(rng.integers(w * h)), int(rng.integers(6)), 1, 1, 1, 1, 3, 10])
+    rng.shuffle(rows)
+    return rows[:max_k]
+
+
+@pytest.mark.parametrize("key", ["8x8/basesWorkers8x8", "16x16/basesWorkers16x16"])
+def test_external_vector_actions(backend, maps, key):
+    n = 3 if backend == "emu" else 32
+    total = 250 if backend == "emu" else 1200
+    w, h = maps[key]["w"], maps[key]["h"]
+    utt, outt = M.UnitTypeTable(1, 1), O.Utt(1, 1)
+    b = M.BatchedGameState(utt, make_pgs(maps[key], utt), n)
+    b.set_policy(0, M.POLICY_EXTERNAL)
+    b.set_policy(1, M.POLICY_EXTERNAL)
+    games = [O.Game(outt, maps[key]) for _ in range(n)]
+    rng = np.random.default_rng(7)
+    max_k = 24
+    for t in range(total):
+        rows = [np.zeros((n, max_k, 8), dtype=np.int32) for _ in range(2)]
+        counts = [np.zeros(n, dtype=np.int32) for _ in range(2)]
+        pas = []
+        for g, og in enumerate(games):
+            pa = []
+            for player in (0, 1):
+                r = random_vector_actions(rng, og, player, w, h, max_k)
+                counts[player][g] = len(r)
+                if r:
+                    rows[player][g, :len(r)] = r
+                pa.append(og.from_vector_action(player, np.array(r, dtype=np.int32).reshape(-1, 8), fill_none=1))
+            pas.append(pa)
+        for player in (0, 1):
+            b.set_actions(player, rows[player], counts[player], M.ACTIONS_VECTOR, fill_none_duration=1)
+        b.step(1, 5000)
+        ex = b.export()
+        for g, og in enumerate(games):
+            if not (og.gameover and og.time > 0):
+                og.issue(pas[g][0], True)
+                og.issue(pas[g][1], True)
+                og.cycle()
+            P.assert_same_state(ex, g, og, "%s vector t=%d" % (key, t))
+    b.close()
+
+
+def test_auto_reset_and_masked_reset(backend, maps):
+    key = "8x8/basesWorkers8x8"
+    n = 4 if backend == "emu" else 64
+    cap = 400  # short cap so that episodes roll over
+    utt, outt = M.UnitTypeTable(1, 1), O.Utt(1, 1)
+    b = M.BatchedGameState(utt, make_pgs(maps[key], utt), n)
+    seeds = np.arange(n, dtype=np.int64) + 77
+    b.reset(seeds)
+    b.set_policy(0, M.POLICY_RANDOM_BIASED)
+    b.set_policy(1, M.POLICY_RANDOM_BIASED)
+    b.set_auto_reset(True)
+    games = []
+    for g in range(n):
+        og = O.Game(outt, maps[key])
+        og.seed(int(seeds[g]))
+        games.append(og)
+    for it in range(12):
+        b.step(150, cap)
+        for g in range(n):
+            og = games[g]
+            if (og.gameover and og.time > 0) or og.time >= cap:  # restart, RNG streams keep running
+                ng = O.Game(outt, maps[key])
+                for k in range(3):
+                    ng.set_rng_state(k, og.rng_state(k))
+                games[g] = og = ng
+            og.run(O.AI_RANDOM_BIASED, None, O.AI_RANDOM_BIASED, None, 150, cap)
+        ex = b.export()
+        for g in range(n):
+            P.assert_same_state(ex, g, games[g], "auto-reset it=%d" % it)
+    # masked reset with fresh seeds
+    b.set_auto_reset(False)
+    mask = np.zeros(n, dtype=np.uint8)
+    mask[::2] = 1
+    new_seeds = seeds + 1000
+    b.reset_masked(mask, new_seeds)
+    ex = b.export()
+    for g in range(n):
+        if mask[g]:
+            og = O.Game(outt, maps[key])
+            og.seed(int(new_seeds[g]))
+            games[g] = og
+        P.assert_same_state(ex, g, games[g], "masked reset")
+    b.close()
+
+
+def test_export_import_roundtrip(backend, maps):
+    key = "16x16/basesWorkers16x16"
+    n = 3 if backend == "emu" else 32
+    utt = M.UnitTypeTable(1, 1)
+    pgs = make_pgs(maps[key], utt)
+    a, c = M.BatchedGameState(utt, pgs, n), M.BatchedGameState(utt, pgs, n)
+    for bb in (a, c):
+        bb.set_policy(0, M.POLICY_RANDOM_BIASED)
+        bb.set_policy(1, M.POLICY_RANDOM_BIASED)
+    a.reset(np.arange(n, dtype=np.int64) + 9)
+    a.step(333, 3000)
+    st = a.export()
+    c.import_(st)
+    a.step(200, 3000)
+    c.step(200, 3000)
+    ea, ec = a.export(), c.export()
+    for k in ("header", "units", "actions", "rng"):
+        assert (ea[k] == ec[k]).all(), k
+    a.close()
+    c.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[1] at full size: properties that do not need the oracle at scale
+# ------------------------------------------------------------------------------------------------------------------
+def test_full_size_batch_properties(backend, maps):
+    if backend == "emu":
+        pytest.skip("full-size batch runs on the GPU only")
+    key, n = "16x16/basesWorkers16x16", 65536
+    utt, outt = M.UnitTypeTable(1, 1), O.Utt(1, 1)
+    pgs = make_pgs(maps[key], utt)
+    seeds = np.arange(n, dtype=np.int64)
+    b = M.BatchedGameState(utt, pgs, n)
+    b.set_policy(0, M.POLICY_RANDOM_BIASED)
+    b.set_policy(1, M.POLICY_RANDOM_BIASED)
+    b.reset(seeds)
+    for _ in range(6):
+        b.step(500, 3000)
+    res = b.results()
+    st = b.stats()
+    assert (res[:, 3] == 0).all(), "per-game error bits set"
+    over = res[:, 2] != 0
+    assert ((res[:, 0] == 3000) | over).all()
+    assert st["games_finished"] == n and st["cycles"] == int(res[:, 0].sum())
+    assert st["wins_p0"] == int(((res[:, 1] == 0) & over).sum()) and st["wins_p1"] == int(((res[:, 1] == 1) & over).sum())
+    full = b.export(0, 4096)
+    # determinism and independence of the batch partition: a sub-batch with the same seeds reproduces its games exactly
+    sub = M.BatchedGameState(utt, pgs, 4096)
+    sub.set_policy(0, M.POLICY_RANDOM_BIASED)
+    sub.set_policy(1, M.POLICY_RANDOM_BIASED)
+    sub.reset(seeds[:4096])
+    sub.step(3000, 3000)
+    es = sub.export()
+    for k in ("header", "units", "actions", "rng"):
+        assert (full[k] == es[k]).all(), k
+    # spot-check a sample of the full batch against the oracle (whole games)
+    for g in list(range(0, 64)) + [4095, 65535]:
+        og = O.Game(outt, maps[key])
+        og.seed(int(seeds[g]))
+        og.run(O.AI_RANDOM_BIASED, None, O.AI_RANDOM_BIASED, None, 3000, 3000)
+        ex = b.export(g, 1)
+        P.assert_same_state(ex, 0, og, "full-size game %d" % g)
+    b.close()
+    sub.close()
