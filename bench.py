@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--prewarm-seconds", type=float, default=1.5, help="untimed steps before the warm-up, until clocks have ramped")
     return ap.parse_args()
 
 
@@ -190,6 +191,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- clock ramp: untimed steps of the same kernel until the GPU has been busy for a while -------------------------
+    b.reset(seeds)
+    b.set_auto_reset(True)
+    t_pre = time.perf_counter()
+    while time.perf_counter() - t_pre < args.prewarm_seconds:
+        b.step(C, MAX_CYCLES)
+        b.sync()
+
     # ---- device-resident run ("value") -------------------------------------------------------------------------------
     b.reset(seeds)
     b.set_auto_reset(True)
@@ -314,7 +323,7 @@ def run_ours(args):
                            mean_live_units=mean_units, decisions_per_cycle=dec_all / max(1, cycles_all), unit_capacity=b.cap),
                clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu,
                stats=dict(wins_p0=w0, wins_p1=w1, draws=dr, games_finished=fin, game_errors=err_all,
-                          device_time_s=dev_max, wall_time_s=wall_max))
+                          device_time_s=dev_max, wall_time_s=wall_max, step_kernel_ms=[round(x, 3) for x in kernel_ms]))
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

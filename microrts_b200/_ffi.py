@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmicrorts_cuda.so")
+# MRTS_CUDA_LIB may point at another build of the same CUDA library (kernel tuning experiments); never a CPU path.
+LIB_PATH = os.environ.get("MRTS_CUDA_LIB") or os.path.join(_HERE, "libmicrorts_cuda.so")
 _lib = None
 
 

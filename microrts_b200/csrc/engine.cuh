@@ -19,7 +19,11 @@
 #define DEVN static
 #else
 #define DEV __device__ __forceinline__
+#ifdef MRTS_INLINE_ALL
+#define DEVN __device__ __forceinline__
+#else
 #define DEVN __device__ __noinline__
+#endif
 #endif
 
 #define FULLM 0xffffffffu
@@ -144,6 +148,16 @@ DEV int eta_of(const Game &g, int t, uint32_t A0, int A1) {
 // target cell of a MOVE/PRODUCE (UnitAction.resourceUsage, UnitAction.java:254-291; an out-of-range direction leaves
 // `pos` at the unit's own cell)
 DEV int target_cell(const Game &g, int c, int A1) { return ((unsigned)A1 < 4u) ? c + doff(g, A1) : c; }
+
+// The reference computes the used position with linear arithmetic, pos = x + y*W -/+ {W,1} (UnitAction.java:255-270), so
+// an (illegal) move off the left/right edge aliases the neighbouring row's end cell.  Returns the padded-grid index of
+// that linear position, or -1 when it falls outside the map.  Only external (possibly illegal) actions need this.
+DEV int linear_target_cell(const Game &g, uint32_t w, int A1) {
+    int lin = u_x(w) + u_y(w) * g.W;
+    if ((unsigned)A1 < 4u) lin += (A1 == 0 ? -g.W : (A1 == 1 ? 1 : (A1 == 2 ? g.W : -1)));
+    if (lin < 0 || lin >= g.W * g.H) return -1;
+    return (lin / g.W + 1) * g.P + lin % g.W + 1;
+}
 
 // ---- java.util.Random (Java SE spec: 48-bit LCG) -----------------------------------------------------------------------
 DEV uint64_t lcg_next(uint64_t s) { return (s * 0x5DEECE66DULL + 0xBULL) & MASK48; }
@@ -498,7 +512,7 @@ DEVN int decode_external(Game &g, int player, int pn, const int32_t *rows, int c
                                 if (ax < 0 || ay < 0 || ax > 255 || ay > 255) A0 = ACT_ATTACK | A0_NOUT | (0xFFu << 16) | (0xFFu << 24);
                             } break;
                         }
-                        if (a_uses_cell(at)) tcell = target_cell(g, cell_of(g, w), A1);
+                        if (a_uses_cell(at)) tcell = linear_target_cell(g, w, A1);
                         if (!cand) atomicOr(&g.hdr[H_ERR], GE_BAD_ACTION);
                     }
                 }
@@ -511,6 +525,16 @@ DEVN int decode_external(Game &g, int player, int pn, const int32_t *rows, int c
         pn += __popc(m);
         __syncwarp();
     }
+    // drop this player's tentative claims (they only model PlayerAction.r while the action list is being built)
+    for (int k = g.lane; k < count; k += 32) {
+        const int32_t *a = rows + (long long)k * 8;
+        int cell = a[0], at = a[1];
+        if (cell >= 0 && cell < cells && a_uses_cell(at)) {
+            int gv = g.grid[(cell / g.W + 1) * g.P + cell % g.W + 1];
+            if (gv != 0 && gv != 0xFF) { int tc = linear_target_cell(g, g.w0[gv - 1], at == ACT_MOVE ? a[2] : a[5]); if (tc >= 0) g.claim[tc] = 0; }
+        }
+    }
+    __syncwarp();
     if (fill >= 0) { // PlayerAction.fillWithNones (PlayerAction.java:217-235): idle own units not already in the action
         int n = g.hdr[H_NUNITS];
         for (int base = 0; base < n; base += 32) {

@@ -111,7 +111,10 @@ DEV void results_kernel_body(const ResultParams &p, long long gi) {
 }
 
 #ifndef MRTS_EMU
-__global__ void __launch_bounds__(MRTS_WARPS_PER_CTA * 32) k_step(StepParams p) {
+#ifndef MRTS_MIN_BLOCKS
+#define MRTS_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(MRTS_WARPS_PER_CTA * 32, MRTS_MIN_BLOCKS) k_step(StepParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     step_kernel_body(p, smem, threadIdx.x, blockDim.x, blockIdx.x, gridDim.x);
 }
