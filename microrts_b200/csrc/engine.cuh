@@ -267,8 +267,8 @@ DEV void enumerate(const Game &g, int s, Enum &e) {
     e.fl = ut_flags(g, e.t); e.range = ut_range(g, e.t);
     int myres = u_res(g.w1[s]);
     int free_m = 0, atk_m = 0, harv_m = 0, ret_m = 0;
-#pragma unroll
-    for (int d = 0; d < 4; d++) {
+#pragma unroll 1
+    for (int d = 0; d < 4; d++) { // kept rolled: the hot loop is instruction-fetch bound, code size matters more than ILP
         int gv = g.grid[e.c + doff(g, d)];
         if (gv == 0) free_m |= 1 << d;
         else if (gv != 0xFF) {
@@ -392,8 +392,25 @@ DEV bool res_consistent_cand_vs_acc(const Game &g, int pl, int cost, int par0, i
 // Sequentially accept/reject the choices of up to 32 lanes in lane order against the accumulated PlayerAction usage
 // (RandomBiasedAI.java:92-99 / PlayerAction.fromVectorAction PlayerAction.java:407-411).  Returns this lane's verdict.
 DEV bool accept_in_order(Game &g, int player, int cnt, int tcell, int cost, bool candidate, int &par0, int &par1) {
-    bool mine = false;
     int pl = player + 1;
+    // Parallel path: no candidate of this chunk costs resources.  Then `par` does not change, the resource half of
+    // consistentWith is the same for every lane, and verdicts only interact when two lanes want the same cell (the
+    // first in lane order wins; if the first is refused because the cell is taken, so are the others).
+    if (__ballot_sync(FULLM, candidate && cost != 0) == 0) {
+        bool over = (par0 > 0 && par0 > g.hdr[H_RES0]) || (par1 > 0 && par1 > g.hdr[H_RES1]);
+        bool ok = candidate && !over;
+        int key = (ok && tcell >= 0) ? tcell : -1 - g.lane;
+        unsigned same = __match_any_sync(FULLM, key);
+        if (ok && tcell >= 0) {
+            if (g.resv[tcell] != 0 || ((g.claim[tcell] >> player) & 1)) ok = false;
+            else if (same & ((1u << g.lane) - 1)) ok = false;
+        }
+        __syncwarp(); // all lanes have read claim[] before it is updated
+        if (ok && tcell >= 0) g.claim[tcell] |= (uint8_t)(1 << player);
+        __syncwarp();
+        return ok;
+    }
+    bool mine = false;
     for (int j = 0; j < cnt; j++) {
         int c = __shfl_sync(FULLM, tcell, j), co = __shfl_sync(FULLM, cost, j);
         bool cand = __shfl_sync(FULLM, candidate ? 1 : 0, j) != 0;
@@ -658,6 +675,53 @@ DEVN void issue_pending(Game &g, int from, int to) {
     }
 }
 
+// Parallel issue of the two action lists produced by device policies in one cycle, valid under CANCEL_BOTH.
+// Why it is exact (GameState.issue, GameState.java:249-328): a policy only emits actions that are consistent with the
+// in-flight usage and with its own earlier choices (RandomBiasedAI.java:92-99), and both policies looked at the same
+// pre-issue state (Game.java:134-137).  So the only inconsistencies issue() can find are between a player-1 action and a
+// player-0 action of this same cycle that target the same cell -- isolated pairs, each cancelled to
+// NONE(min(ETA_old, ETA_new)) -- and insertion order is simply list order.
+DEVN void issue_policy_lists(Game &g, int pn0, int pn1) {
+    int time = g.hdr[H_TIME];
+    uint32_t base_seq = (uint32_t)g.hdr[H_NEXTSEQ];
+    for (int k = g.lane; k < pn0; k += 32) {
+        int s = g.pslot[k];
+        uint32_t A0 = g.pa0[k]; int A1 = g.pa1[k];
+        if (a_uses_cell(a_type(A0))) { int tc = target_cell(g, cell_of(g, g.w0[s]), A1); g.resv[tc] = (uint8_t)(s + 1); g.claim[tc] = 0; }
+        g.a0[s] = (g.a0[s] & 0xF0u) | (A0 & ~0xF0u); g.a1[s] = A1; g.tis[s] = time; g.seq[s] = base_seq + k;
+    }
+    __syncwarp();
+    for (int k = pn0 + g.lane; k < pn1; k += 32) {
+        int s = g.pslot[k];
+        uint32_t A0 = g.pa0[k]; int A1 = g.pa1[k];
+        uint32_t w = g.w0[s];
+        if (a_uses_cell(a_type(A0))) {
+            int tc = target_cell(g, cell_of(g, w), A1);
+            g.claim[tc] = 0;
+            int e = g.resv[tc];
+            if (e == 0) g.resv[tc] = (uint8_t)(s + 1);
+            else {
+                e--;
+                if (g.tis[e] == time) {
+                    uint32_t E0 = g.a0[e];
+                    int d1 = eta_of(g, u_type(g.w0[e]), E0, g.a1[e]), d2 = eta_of(g, u_type(w), A0, A1);
+                    int d = d1 < d2 ? d1 : d2;
+                    g.a0[e] = (E0 & 0xF0u) | ACT_NONE | A0_NOUT; g.a1[e] = d;
+                    g.resv[tc] = 0;
+                    A0 = ACT_NONE | A0_NOUT; A1 = d;
+                } else {
+                    atomicOr(&g.hdr[H_ERR], GE_INCONSISTENT_OLDER);
+                    A0 = ACT_NONE | A0_NOUT; A1 = -1;
+                }
+            }
+        }
+        g.a0[s] = (g.a0[s] & 0xF0u) | (A0 & ~0xF0u); g.a1[s] = A1; g.tis[s] = time; g.seq[s] = base_seq + k;
+    }
+    __syncwarp();
+    if (g.lane == 0) g.hdr[H_NEXTSEQ] = (int32_t)(base_seq + pn1);
+    __syncwarp();
+}
+
 // ---- GameState.cycle (GameState.java:553-571) + UnitAction.execute (UnitAction.java:338-465) ----------------------------
 DEV void kill_unit(Game &g, int v) { // GameState.removeUnit (GameState.java:79-82); lane 0 only
     uint32_t vw = g.w0[v]; uint32_t V0 = g.a0[v];
@@ -673,22 +737,24 @@ DEV int neighbour_slot(const Game &g, int c, int dir) { // getUnitAt of the adja
     return (gv == 0 || gv == 0xFF) ? -1 : gv - 1;
 }
 
-// Execute the (already removed) assignment (A0,A1) of slot s.  Uniform across lanes; lane 0 writes.
-DEV void execute_action(Game &g, int s, uint32_t A0, int A1, bool dead, int &ndead) {
+// Execute the (already removed) assignment (A0,A1) of slot s.  Called by ONE lane (lane 0) for every ready assignment in
+// insertion order, so it is plain sequential code with no warp primitives.
+DEV void execute_serial(Game &g, int s, int &ndead) {
+    uint32_t A0 = g.a0[s]; int A1 = g.a1[s];
     uint32_t w = g.w0[s];
+    bool dead = (A0 & A0_DEAD) != 0;
     int t = u_type(w), pl = u_pl(w), c = cell_of(g, w);
+    // unitActions.remove(uaa.unit) (GameState.java:563); a dead unit lost its entry (and reservation) when it died
+    g.a0[s] = (A0 & 0xF0u) | AT_IDLE | A0_NOUT;
+    if (!dead && a_uses_cell(a_type(A0))) { int tc = target_cell(g, c, A1); if (g.resv[tc] == s + 1) g.resv[tc] = 0; }
     switch (a_type(A0)) {
         case ACT_MOVE:
             if (!dead && (unsigned)A1 < 4u) {
                 int nc = c + doff(g, A1);
-                int occ = g.grid[nc];
-                __syncwarp();
-                if (g.lane == 0) {
-                    if (occ != 0) g.hdr[H_ERR] |= GE_CELL_OCCUPIED;
-                    else {
-                        g.grid[c] = 0; g.grid[nc] = (uint8_t)(s + 1);
-                        g.w0[s] = (w & 0xffffu) | ((uint32_t)(u_x(w) + ddx(A1)) << 16) | ((uint32_t)(u_y(w) + ddy(A1)) << 24);
-                    }
+                if (g.grid[nc] != 0) g.hdr[H_ERR] |= GE_CELL_OCCUPIED;
+                else {
+                    g.grid[c] = 0; g.grid[nc] = (uint8_t)(s + 1);
+                    g.w0[s] = (w & 0xffffu) | ((uint32_t)(u_x(w) + ddx(A1)) << 16) | ((uint32_t)(u_y(w) + ddy(A1)) << 24);
                 }
             }
             break;
@@ -702,30 +768,24 @@ DEV void execute_action(Game &g, int s, uint32_t A0, int A1, bool dead, int &nde
                     if (mn != mx) { // UnitAction.r.nextInt(1 + max - min)
                         uint64_t rs = hdr_rng(g, H_RNGD_LO);
                         dmg = mn + lcg_next_int_bound(rs, 1 + (mx - mn));
-                        __syncwarp();
-                        if (g.lane == 0) hdr_set_rng(g, H_RNGD_LO, rs);
+                        hdr_set_rng(g, H_RNGD_LO, rs);
                     }
                     uint32_t vw1 = g.w1[v];
                     int hp = u_hp(vw1) - dmg;
-                    __syncwarp();
-                    if (g.lane == 0) { g.w1[v] = mk_w1(hp, u_res(vw1)); if (hp <= 0) kill_unit(g, v); }
-                    if (hp <= 0) ndead++;
+                    g.w1[v] = mk_w1(hp, u_res(vw1));
+                    if (hp <= 0) { kill_unit(g, v); ndead++; }
                 }
             }
         } break;
         case ACT_HARVEST: {
             int r = neighbour_slot(g, c, A1);
             if (r >= 0) {
-                uint32_t rw = g.w0[r], rw1 = g.w1[r], mw1 = g.w1[s];
-                if ((ut_flags(g, u_type(rw)) & UF_RESOURCE) && (ut_flags(g, t) & UF_HARVEST) && u_res(mw1) == 0) {
+                uint32_t rw1 = g.w1[r], mw1 = g.w1[s];
+                if ((ut_flags(g, u_type(g.w0[r])) & UF_RESOURCE) && (ut_flags(g, t) & UF_HARVEST) && u_res(mw1) == 0) {
                     int amt = ut_hamt(g, t), left = u_res(rw1) - amt;
-                    __syncwarp();
-                    if (g.lane == 0) {
-                        g.w1[r] = mk_w1(u_hp(rw1), left);
-                        if (left <= 0) kill_unit(g, r);
-                        g.w1[s] = mk_w1(u_hp(mw1), amt);
-                    }
-                    if (left <= 0) ndead++;
+                    g.w1[r] = mk_w1(u_hp(rw1), left);
+                    if (left <= 0) { kill_unit(g, r); ndead++; }
+                    g.w1[s] = mk_w1(u_hp(mw1), amt);
                 }
             }
         } break;
@@ -734,17 +794,15 @@ DEV void execute_action(Game &g, int s, uint32_t A0, int A1, bool dead, int &nde
             if (b >= 0 && pl != 0) {
                 uint32_t mw1 = g.w1[s];
                 if ((ut_flags(g, u_type(g.w0[b])) & UF_STOCKPILE) && u_res(mw1) > 0) {
-                    __syncwarp();
-                    if (g.lane == 0) { g.hdr[H_RES0 + pl - 1] += u_res(mw1); g.w1[s] = mk_w1(u_hp(mw1), 0); }
+                    g.hdr[H_RES0 + pl - 1] += u_res(mw1);
+                    g.w1[s] = mk_w1(u_hp(mw1), 0);
                 }
             }
         } break;
         case ACT_PRODUCE: {
             int ut = a_utype(A0);
-            int n = g.hdr[H_NUNITS];
-            int pres = pl ? g.hdr[H_RES0 + pl - 1] : 0;
-            __syncwarp();
-            if (g.lane == 0 && pl != 0 && ut < MRTS_MAX_TYPES) {
+            if (pl != 0 && ut < MRTS_MAX_TYPES) {
+                int n = g.hdr[H_NUNITS], pres = g.hdr[H_RES0 + pl - 1];
                 int id = g.hdr[H_NEXTID]++; // new Unit(...) takes an ID even when the unit is then not added
                 int cost = ut_cost(g, ut);
                 if (pres - cost >= 0) {
@@ -765,7 +823,6 @@ DEV void execute_action(Game &g, int s, uint32_t A0, int A1, bool dead, int &nde
         } break;
         default: break;
     }
-    __syncwarp();
 }
 
 // remove dead slots, keeping order; rebuild the cell maps
@@ -814,38 +871,44 @@ DEV int min_ready_time(const Game &g) {
 }
 
 // time := t_new, then execute every assignment with ETA + issueTime <= time in insertion order.  Returns gameover().
+// Ready assignments are found in parallel; NONE actions (no effect, so their position in the order is irrelevant) are
+// retired on the spot; the rest is ranked by insertion sequence and executed by one lane, because the reference's
+// effects are order dependent (kills, depletion, produce/return on the same player's resources).
 DEVN bool cycle_execute(Game &g, int t_new, int &winner) {
     __syncwarp();
     if (g.lane == 0) g.hdr[H_TIME] = t_new;
-    int n = g.hdr[H_NUNITS];
-    unsigned rb = 0; // bit j: slot j*32+lane is in the ready snapshot
-    for (int j = 0; j * 32 < n; j++) {
-        int i = j * 32 + g.lane;
+    int n = g.hdr[H_NUNITS], cnt = 0;
+    for (int base = 0; base < n; base += 32) {
+        int i = base + g.lane;
+        bool ready = false;
         if (i < n) {
             uint32_t A0 = g.a0[i];
-            if (a_type(A0) != AT_IDLE && g.tis[i] + eta_of(g, u_type(g.w0[i]), A0, g.a1[i]) <= t_new) rb |= 1u << j;
+            int at = a_type(A0);
+            if (at != (int)AT_IDLE && g.tis[i] + eta_of(g, u_type(g.w0[i]), A0, g.a1[i]) <= t_new) {
+                if (at == ACT_NONE) g.a0[i] = (A0 & 0xF0u) | AT_IDLE | A0_NOUT;
+                else ready = true;
+            }
         }
+        unsigned m = __ballot_sync(FULLM, ready);
+        if (ready) g.list[cnt + __popc(m & ((1u << g.lane) - 1))] = (uint8_t)i;
+        cnt += __popc(m);
     }
+    __syncwarp();
     int ndead = 0;
-    for (;;) {
-        uint32_t best = 0xFFFFFFFFu; int bj = 0;
-        for (unsigned m = rb; m; m &= m - 1) { int j = __ffs(m) - 1; uint32_t q = g.seq[j * 32 + g.lane]; if (q < best) { best = q; bj = j; } }
-        uint32_t mn = __reduce_min_sync(FULLM, best);
-        if (mn == 0xFFFFFFFFu) break;
-        int owner = __ffs(__ballot_sync(FULLM, best == mn)) - 1;
-        int s = __shfl_sync(FULLM, bj * 32 + g.lane, owner);
-        if (g.lane == owner) rb &= ~(1u << bj);
-        // unitActions.remove(uaa.unit), then execute (even if the unit died earlier in this loop)
-        uint32_t A0 = g.a0[s]; int A1 = g.a1[s];
-        bool dead = (A0 & A0_DEAD) != 0;
-        int c = cell_of(g, g.w0[s]);
-        __syncwarp();
-        if (g.lane == 0) {
-            g.a0[s] = (A0 & 0xF0u) | AT_IDLE | A0_NOUT;
-            if (!dead && a_uses_cell(a_type(A0))) { int tc = target_cell(g, c, A1); if (g.resv[tc] == s + 1) g.resv[tc] = 0; }
+    if (cnt > 0) {
+        uint8_t *order = g.pslot; // the pending list is empty at this point
+        for (int k = g.lane; k < cnt; k += 32) {
+            int s = g.list[k];
+            uint32_t my = g.seq[s];
+            int r = 0;
+            for (int j = 0; j < cnt; j++) r += g.seq[g.list[j]] < my ? 1 : 0;
+            order[r] = (uint8_t)s;
         }
         __syncwarp();
-        execute_action(g, s, A0, A1, dead, ndead);
+        if (g.lane == 0)
+            for (int r = 0; r < cnt; r++) execute_serial(g, order[r], ndead);
+        __syncwarp();
+        ndead = __shfl_sync(FULLM, ndead, 0);
     }
     if (ndead > 0) compact_units(g);
     return game_over(g, winner);
@@ -880,6 +943,8 @@ DEVN void run_game(Game &g, const StepParams &p, long long gi, WarpStats &ws) {
     int winner;
     bool force_next = game_over(g, winner); // a state that is already over ends at the very next cycle()
     bool first = true;
+    // device policies emit self-consistent lists; under CANCEL_BOTH they can be issued in parallel (issue_policy_lists)
+    bool fast_issue = p.conflict == 1 && p.policy[0] != POL_EXTERNAL && p.policy[1] != POL_EXTERNAL;
     unsigned long long decisions = 0, ucyc = 0;
     for (;;) {
         int time = g.hdr[H_TIME];
@@ -887,8 +952,8 @@ DEVN void run_game(Game &g, const StepParams &p, long long gi, WarpStats &ws) {
         int pn0 = run_policy(g, p, gi, 0, 0, first);
         int pn1 = run_policy(g, p, gi, 1, pn0, first);
         first = false;
-        issue_pending(g, 0, pn0);
-        issue_pending(g, pn0, pn1);
+        if (fast_issue) issue_policy_lists(g, pn0, pn1);
+        else { issue_pending(g, 0, pn0); issue_pending(g, pn0, pn1); }
         decisions += pn1;
         int mrt = min_ready_time(g);
         int tn = time + 1; if (!force_next && mrt > tn) tn = mrt;

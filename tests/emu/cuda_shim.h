@@ -147,6 +147,12 @@ inline int reduce_add_i(int v, int line) {
     for (int l = 0; l < 32; l++) a += (int)(uint32_t)s[l];
     return a;
 }
+inline unsigned match_any(long long v, int line) {
+    yield_wait(1, line, (uint64_t)v);
+    const uint64_t *s = warp_snap(); unsigned m = 0;
+    for (int l = 0; l < 32; l++) if (s[l] == (uint64_t)v) m |= 1u << l;
+    return m;
+}
 inline void syncwarp(int line) { yield_wait(1, line, 0); }
 inline void syncthreads(int line) { yield_wait(2, line, 0); }
 
@@ -155,6 +161,7 @@ inline void syncthreads(int line) { yield_wait(2, line, 0); }
 #define __shfl_sync(m, v, src) emu::shfl((v), (src), __LINE__)
 #define __ballot_sync(m, p) emu::ballot((p) ? 1 : 0, __LINE__)
 #define __reduce_min_sync(m, v) emu::reduce_min_u((unsigned)(v), __LINE__)
+#define __match_any_sync(m, v) emu::match_any((long long)(v), __LINE__)
 #define __reduce_add_sync(m, v) emu::reduce_add_i((int)(v), __LINE__)
 #define __syncwarp() emu::syncwarp(__LINE__)
 #define __syncthreads() emu::syncthreads(__LINE__)
