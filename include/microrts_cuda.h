@@ -162,12 +162,16 @@ int mrts_batch_step(mrts_batch *, int n_cycles, int max_cycles);
  * (or by n_cycles when t_target is NULL). TestTracesIntegrity.java:81-85 */
 int mrts_batch_cycle_to(mrts_batch *, const int32_t *t_target, int n_cycles, int on_device);
 
-/* NaiveMCTS.simulate + evaluate (src/ai/mcts/naivemcts/NaiveMCTS.java:195-223,297-308): for every game, clone
- * its state (from observer's partially observable view if observer >= 0), play RandomBiasedAI vs itself with
- * issue() for `depth` cycles, evaluate for maxplayer.  The batch itself is not modified.  seeds[g] seeds rollout g.
- * out_eval[g] = ef.evaluate(maxplayer, 1-maxplayer, gs2) (float, undiscounted); out_time[g] = gs2.getTime()-start. */
-int mrts_batch_rollout(mrts_batch *, int depth, int eval_fn, int maxplayer, int observer, const int64_t *seeds,
-                       float *out_eval, int32_t *out_time, int on_device);
+/* NaiveMCTS.simulate + evaluate (src/ai/mcts/naivemcts/NaiveMCTS.java:195-223,297-308): for every game g and every
+ * k < rollouts_per_game, clone the game's state (gs2 = leaf.gs.clone(), from observer's PartiallyObservableGameState
+ * when observer >= 0, src/rts/PartiallyObservableGameState.java:35-79), play RandomBiasedAI vs itself with issue() until
+ * game over or `depth` cycles, and evaluate for maxplayer.  The batch itself is not modified.
+ * Rollout r = g*rollouts_per_game + k is seeded with seeds[r] (r when seeds is NULL).
+ * out_eval[r] = ef.evaluate(maxplayer, 1-maxplayer, gs2) as float (SimpleSqrtEvaluationFunction3.java:24-44 or
+ * SimpleEvaluationFunction.java:21-36); out_time[r] = gs2.getTime() - start.  The caller applies the reference's
+ * discount evaluation * Math.pow(0.99, time/10.0) in double precision on the host (NaiveMCTS.java:205). */
+int mrts_batch_rollout(mrts_batch *, int rollouts_per_game, int depth, int eval_fn, int maxplayer, int observer,
+                       const int64_t *seeds, float *out_eval, int32_t *out_time, int on_device);
 
 /* GameState.getVectorObservation(player) (GameState.java:922-968; PartiallyObservableGameState.java:82-154 when the
  * batch has MRTS_FLAG_PARTIAL_OBS): out = [n_games][C][H][W], C = 6 or 8.  player < 0: per-game player array

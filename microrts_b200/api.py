@@ -258,6 +258,19 @@ class BatchedGameState:
         p, dev, _k = _ptr(t)
         _check(_ffi.lib().mrts_batch_cycle_to(self._h, p, 0, dev))
 
+    def rollout(self, depth=100, rollouts_per_game=1, eval_fn=0, maxplayer=0, observer=-1, seeds=None):
+        """NaiveMCTS.simulate + evaluation for every game (the batch is not modified).
+        Returns (evaluation[float32], simulated_cycles[int32]) of shape [n, rollouts_per_game]; the reference's discounted
+        value is evaluation * 0.99 ** (cycles / 10.0) (NaiveMCTS.java:205)."""
+        nr = self.n * rollouts_per_game
+        ev = np.zeros(nr, dtype=np.float32)
+        tm = np.zeros(nr, dtype=np.int32)
+        s = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.int64).reshape(-1)
+        assert s is None or len(s) == nr
+        _check(_ffi.lib().mrts_batch_rollout(self._h, rollouts_per_game, depth, eval_fn, maxplayer, observer,
+                                             None if s is None else s.ctypes.data, ev.ctypes.data, tm.ctypes.data, 0))
+        return ev.reshape(self.n, rollouts_per_game), tm.reshape(self.n, rollouts_per_game)
+
     # -- outputs -----------------------------------------------------------------------------------------------------
     def observe(self, player, dtype=np.int32, out=None):
         """GameState.getVectorObservation(player) for every game: [n][C][H][W]."""

@@ -33,7 +33,7 @@
 enum { ACT_NONE = 0, ACT_MOVE = 1, ACT_HARVEST = 2, ACT_RETURN = 3, ACT_PRODUCE = 4, ACT_ATTACK = 5 };
 enum { POL_EXTERNAL = 0, POL_PASSIVE = 1, POL_RANDOM_BIASED = 2, POL_WORKER_RUSH = 3, POL_LIGHT_RUSH = 4 };
 enum { FMT_VECTOR = 0, FMT_RAW = 1 };
-enum { MODE_GAME = 0, MODE_CYCLE_ONLY = 1, MODE_ISSUE_ONLY = 2, MODE_OBSERVE = 3, MODE_MASKS = 4 };
+enum { MODE_GAME = 0, MODE_CYCLE_ONLY = 1, MODE_ISSUE_ONLY = 2, MODE_OBSERVE = 3, MODE_MASKS = 4, MODE_ROLLOUT = 5 };
 enum { ST_OVER = 1, ST_COUNTED = 2 };
 enum { STAT_WINS0 = 0, STAT_WINS1, STAT_DRAWS, STAT_FINISHED, STAT_CYCLES, STAT_DECISIONS, STAT_UNIT_CYCLES, STAT_ERRORS };
 
@@ -64,6 +64,11 @@ struct StepParams {
     int out_dtype;             // 0 = u8, 1 = i32
     int out_player;
     int partial_obs;
+    // MODE_ROLLOUT: item r = game r / rollouts_per_game
+    int rollouts_per_game, depth, eval_fn, maxplayer, observer;
+    const long long *ro_seeds; // [n_games * rollouts_per_game] or NULL (seed = r)
+    float *ro_eval;            // [n_games * rollouts_per_game]
+    int32_t *ro_time;          // [n_games * rollouts_per_game] simulated cycles
 };
 
 struct Game {
@@ -127,6 +132,7 @@ DEV int nth4(int m, int n) { // index of the n-th set bit of a 4-bit mask
     return 0;
 }
 DEV int nth8(int m, int n) {
+    #pragma unroll 1
     for (int d = 0; d < 8; d++) {
         if ((m >> d) & 1) { if (n == 0) return d; n--; }
     }
@@ -162,6 +168,7 @@ DEV int linear_target_cell(const Game &g, uint32_t w, int A1) {
 // ---- java.util.Random (Java SE spec: 48-bit LCG) -----------------------------------------------------------------------
 DEV uint64_t lcg_next(uint64_t s) { return (s * 0x5DEECE66DULL + 0xBULL) & MASK48; }
 DEV uint64_t lcg_jump(const Game &g, uint64_t s, int draws) { // advance by `draws` nextDouble() calls (2 steps each)
+    #pragma unroll 1
     while (draws > 64) { s = (s * g.jump[128] + g.jump[129]) & MASK48; draws -= 64; }
     return (s * g.jump[2 * draws] + g.jump[2 * draws + 1]) & MASK48;
 }
@@ -175,6 +182,7 @@ DEV int lcg_next_int_bound(uint64_t &s, int bound) { // Random.nextInt(bound)
     int r = (int)(s >> 17);
     int m = bound - 1;
     if ((bound & m) == 0) return (int)(((long long)bound * (long long)r) >> 31);
+    #pragma unroll 1
     for (int u = r;;) {
         r = u % bound;
         if ((int)((unsigned)u - (unsigned)r + (unsigned)m) >= 0) break;
@@ -189,6 +197,7 @@ DEV void hdr_set_rng(Game &g, int lo, uint64_t s) { g.hdr[lo] = (int32_t)(uint32
 // scatter units into grid/resv (maps must hold only walls / zeros)
 DEV void g_scatter(Game &g) {
     int n = g.hdr[H_NUNITS];
+    #pragma unroll 1
     for (int i = g.lane; i < n; i += 32) {
         uint32_t w = g.w0[i];
         int c = cell_of(g, w);
@@ -199,6 +208,7 @@ DEV void g_scatter(Game &g) {
     __syncwarp();
 }
 DEV void g_reset_maps(Game &g) {
+    #pragma unroll 1
     for (int i = g.lane; i < g.pcw; i += 32) {
         ((uint32_t *)g.grid)[i] = g.grid_tmpl[i];
         ((uint32_t *)g.resv)[i] = 0;
@@ -211,7 +221,9 @@ DEV void g_load(Game &g, const int32_t *ghdr, const uint32_t *gun) {
     g_reset_maps(g);
     int n = g.hdr[H_NUNITS];
     uint32_t *su = g.w0;
+    #pragma unroll 1
     for (int k = 0; k < MRTS_UNIT_WORDS; k++)
+        #pragma unroll 1
         for (int i = g.lane; i < n; i += 32) su[k * g.cap + i] = gun[k * g.cap + i];
     __syncwarp();
     g_scatter(g);
@@ -231,7 +243,9 @@ DEV void g_restart(Game &g) {
     g_reset_maps(g);
     int n = g.hdr[H_NUNITS];
     uint32_t *su = g.w0;
+    #pragma unroll 1
     for (int k = 0; k < MRTS_UNIT_WORDS; k++)
+        #pragma unroll 1
         for (int i = g.lane; i < n; i += 32) su[k * g.cap + i] = iu[k * g.cap + i];
     __syncwarp();
     g_scatter(g);
@@ -241,7 +255,9 @@ DEV void g_store(Game &g, int32_t *ghdr, uint32_t *gun) {
     if (g.lane < MRTS_HDR_WORDS) ghdr[g.lane] = g.hdr[g.lane];
     int n = g.hdr[H_NUNITS];
     const uint32_t *su = g.w0;
+    #pragma unroll 1
     for (int k = 0; k < MRTS_UNIT_WORDS; k++)
+        #pragma unroll 1
         for (int i = g.lane; i < n; i += 32) gun[k * g.cap + i] = su[k * g.cap + i];
     __syncwarp();
 }
@@ -286,11 +302,13 @@ DEV void enumerate(const Game &g, int s, Enum &e) {
     if ((e.fl & UF_ATTACK) && e.range > 1) { // every enemy within range, in unit-list order (Unit.java:424-436)
         int n = g.hdr[H_NUNITS], sq = e.range * e.range;
         n_atk = 0;
+        #pragma unroll 1
         for (int i = 0; i < n; i++) n_atk += enemy_in_range(g, w, g.w0[i], sq) ? 1 : 0;
     }
     int aff_m = 0;
     if (e.pl != 0) {
         int pres = g.hdr[H_RES0 + e.pl - 1], np = ut_nprod(g, e.t);
+        #pragma unroll 1
         for (int k = 0; k < np; k++) if (pres >= ut_cost(g, ut_prod(g, e.t, k))) aff_m |= 1 << k;
     }
     e.free_m = free_m; e.atk_m = atk_m; e.harv_m = harv_m; e.ret_m = ret_m; e.aff_m = aff_m;
@@ -308,6 +326,7 @@ DEV void pick_action(const Game &g, const Enum &e, int idx, int none_duration, u
         if (e.range == 1) { int d = nth4(e.atk_m, idx); ax = x + ddx(d); ay = y + ddy(d); }
         else {
             int n = g.hdr[H_NUNITS], sq = e.range * e.range; ax = x; ay = y;
+            #pragma unroll 1
             for (int i = 0; i < n; i++) {
                 uint32_t ow = g.w0[i];
                 if (enemy_in_range(g, e.w, ow, sq)) { if (idx == 0) { ax = u_x(ow); ay = u_y(ow); break; } idx--; }
@@ -355,6 +374,7 @@ DEV bool action_is_legal(const Game &g, int s, uint32_t A0, int A1) {
         case ACT_PRODUCE: {
             if (!dir_ok || !((e.free_m >> A1) & 1)) return false;
             int ut = a_utype(A0), np = ut_nprod(g, e.t);
+            #pragma unroll 1
             for (int k = 0; k < np; k++) if (ut_prod(g, e.t, k) == ut && ((e.aff_m >> k) & 1)) return true;
             return false;
         }
@@ -373,6 +393,7 @@ DEV bool action_is_legal(const Game &g, int s, uint32_t A0, int A1) {
 // sum of in-flight PRODUCE costs per player == resourcesUsed of GameState.getResourceUsage (GameState.java:652-664)
 DEV void reserved_resources(const Game &g, int &r0, int &r1) {
     int n = g.hdr[H_NUNITS], a = 0, b = 0;
+    #pragma unroll 1
     for (int i = g.lane; i < n; i += 32) {
         uint32_t A0 = g.a0[i];
         if (a_type(A0) == ACT_PRODUCE) { int c = ut_cost(g, a_utype(A0)); if (u_pl(g.w0[i]) == 1) a += c; else b += c; }
@@ -411,6 +432,7 @@ DEV bool accept_in_order(Game &g, int player, int cnt, int tcell, int cost, bool
         return ok;
     }
     bool mine = false;
+    #pragma unroll 1
     for (int j = 0; j < cnt; j++) {
         int c = __shfl_sync(FULLM, tcell, j), co = __shfl_sync(FULLM, cost, j);
         bool cand = __shfl_sync(FULLM, candidate ? 1 : 0, j) != 0;
@@ -432,6 +454,7 @@ DEV bool accept_in_order(Game &g, int player, int cnt, int tcell, int cost, bool
 // Appends (unit, action) pairs for `player` to the pending list starting at pn; returns the new count.
 DEVN int policy_random_biased(Game &g, int player, int pn) {
     int n = g.hdr[H_NUNITS], n_idle = 0;
+    #pragma unroll 1
     for (int base = 0; base < n; base += 32) {
         int i = base + g.lane;
         bool idle = i < n && u_pl(g.w0[i]) == player + 1 && a_type(g.a0[i]) == AT_IDLE;
@@ -444,6 +467,7 @@ DEVN int policy_random_biased(Game &g, int player, int pn) {
     int par0, par1;
     reserved_resources(g, par0, par1);
     uint64_t s0 = hdr_rng(g, H_RNGP_LO);
+    #pragma unroll 1
     for (int kb = 0; kb < n_idle; kb += 32) {
         int k = kb + g.lane;
         bool active = k < n_idle;
@@ -474,6 +498,7 @@ DEVN int decode_external(Game &g, int player, int pn, const int32_t *rows, int c
     int cells = g.W * g.H;
     int start = pn;
     if (format == FMT_RAW) {
+        #pragma unroll 1
         for (int kb = 0; kb < count; kb += 32) {
             int k = kb + g.lane;
             bool ok = false; uint32_t A0 = 0; int A1 = 0, s = 0;
@@ -503,6 +528,7 @@ DEVN int decode_external(Game &g, int player, int pn, const int32_t *rows, int c
     int par0, par1;
     reserved_resources(g, par0, par1);
     int R = maxR, ctr = R / 2;
+    #pragma unroll 1
     for (int kb = 0; kb < count; kb += 32) {
         int k = kb + g.lane;
         bool cand = false; uint32_t A0 = 0; int A1 = -1, s = 0, tcell = -1, cost = 0;
@@ -543,6 +569,7 @@ DEVN int decode_external(Game &g, int player, int pn, const int32_t *rows, int c
         __syncwarp();
     }
     // drop this player's tentative claims (they only model PlayerAction.r while the action list is being built)
+    #pragma unroll 1
     for (int k = g.lane; k < count; k += 32) {
         const int32_t *a = rows + (long long)k * 8;
         int cell = a[0], at = a[1];
@@ -554,6 +581,7 @@ DEVN int decode_external(Game &g, int player, int pn, const int32_t *rows, int c
     __syncwarp();
     if (fill >= 0) { // PlayerAction.fillWithNones (PlayerAction.java:217-235): idle own units not already in the action
         int n = g.hdr[H_NUNITS];
+        #pragma unroll 1
         for (int base = 0; base < n; base += 32) {
             int i = base + g.lane;
             bool idle = i < n && u_pl(g.w0[i]) == player + 1 && a_type(g.a0[i]) == AT_IDLE;
@@ -569,6 +597,7 @@ DEVN int decode_external(Game &g, int player, int pn, const int32_t *rows, int c
 
 // GameState.issueSafe legality pass (GameState.java:347-354,386-399): illegal actions become NONE(ETA(action)).
 DEV void legality_pass(Game &g, int from, int to) {
+    #pragma unroll 1
     for (int k = from + g.lane; k < to; k += 32) {
         int s = g.pslot[k];
         uint32_t A0 = g.pa0[k]; int A1 = g.pa1[k];
@@ -622,6 +651,7 @@ DEV void resolve_conflict(Game &g, int e, int t, uint32_t &A0, int &A1, int time
 
 DEVN void issue_pending(Game &g, int from, int to) {
     int time = g.hdr[H_TIME];
+    #pragma unroll 1
     for (int k = from; k < to; k++) {
         int s = g.pslot[k];
         uint32_t A0 = g.pa0[k]; int A1 = g.pa1[k];
@@ -638,6 +668,7 @@ DEVN void issue_pending(Game &g, int from, int to) {
             // general pairwise check against every existing assignment, in insertion order (GameState.java:263-319)
             int n = g.hdr[H_NUNITS], pres = pl ? g.hdr[H_RES0 + pl - 1] : 0;
             unsigned cb = 0; // bit j: slot j*32+lane conflicts
+            #pragma unroll 1
             for (int j = 0; j * 32 < n; j++) {
                 int i = j * 32 + g.lane;
                 if (i < n) {
@@ -651,8 +682,10 @@ DEVN void issue_pending(Game &g, int from, int to) {
                     }
                 }
             }
+            #pragma unroll 1
             for (;;) {
                 uint32_t best = 0xFFFFFFFFu; int bj = 0;
+                #pragma unroll 1
                 for (unsigned m = cb; m; m &= m - 1) { int j = __ffs(m) - 1; uint32_t q = g.seq[j * 32 + g.lane]; if (q < best) { best = q; bj = j; } }
                 uint32_t mn = __reduce_min_sync(FULLM, best);
                 if (mn == 0xFFFFFFFFu) break;
@@ -684,6 +717,7 @@ DEVN void issue_pending(Game &g, int from, int to) {
 DEVN void issue_policy_lists(Game &g, int pn0, int pn1) {
     int time = g.hdr[H_TIME];
     uint32_t base_seq = (uint32_t)g.hdr[H_NEXTSEQ];
+    #pragma unroll 1
     for (int k = g.lane; k < pn0; k += 32) {
         int s = g.pslot[k];
         uint32_t A0 = g.pa0[k]; int A1 = g.pa1[k];
@@ -691,6 +725,7 @@ DEVN void issue_policy_lists(Game &g, int pn0, int pn1) {
         g.a0[s] = (g.a0[s] & 0xF0u) | (A0 & ~0xF0u); g.a1[s] = A1; g.tis[s] = time; g.seq[s] = base_seq + k;
     }
     __syncwarp();
+    #pragma unroll 1
     for (int k = pn0 + g.lane; k < pn1; k += 32) {
         int s = g.pslot[k];
         uint32_t A0 = g.pa0[k]; int A1 = g.pa1[k];
@@ -829,6 +864,7 @@ DEV void execute_serial(Game &g, int s, int &ndead) {
 DEVN void compact_units(Game &g) {
     int n = g.hdr[H_NUNITS], out = 0;
     uint32_t *su = g.w0;
+    #pragma unroll 1
     for (int base = 0; base < n; base += 32) {
         int i = base + g.lane;
         bool alive = i < n && !(g.a0[i] & A0_DEAD);
@@ -850,6 +886,7 @@ DEVN void compact_units(Game &g) {
 // PhysicalGameState.gameover / winner (PhysicalGameState.java:334-387); returns gameover, sets winner (-1 none)
 DEV bool game_over(const Game &g, int &winner) {
     int n = g.hdr[H_NUNITS], c0 = 0, c1 = 0;
+    #pragma unroll 1
     for (int base = 0; base < n; base += 32) {
         int i = base + g.lane;
         int pl = i < n ? u_pl(g.w0[i]) : 0;
@@ -863,6 +900,7 @@ DEV bool game_over(const Game &g, int &winner) {
 // earliest completion time of any in-flight assignment (GameState.getNextChangeTime, GameState.java:539-542)
 DEV int min_ready_time(const Game &g) {
     int n = g.hdr[H_NUNITS], best = 0x7fffffff;
+    #pragma unroll 1
     for (int i = g.lane; i < n; i += 32) {
         uint32_t A0 = g.a0[i];
         if (a_type(A0) != AT_IDLE) { int rt = g.tis[i] + eta_of(g, u_type(g.w0[i]), A0, g.a1[i]); if (rt < best) best = rt; }
@@ -878,6 +916,7 @@ DEVN bool cycle_execute(Game &g, int t_new, int &winner) {
     __syncwarp();
     if (g.lane == 0) g.hdr[H_TIME] = t_new;
     int n = g.hdr[H_NUNITS], cnt = 0;
+    #pragma unroll 1
     for (int base = 0; base < n; base += 32) {
         int i = base + g.lane;
         bool ready = false;
@@ -897,15 +936,18 @@ DEVN bool cycle_execute(Game &g, int t_new, int &winner) {
     int ndead = 0;
     if (cnt > 0) {
         uint8_t *order = g.pslot; // the pending list is empty at this point
+        #pragma unroll 1
         for (int k = g.lane; k < cnt; k += 32) {
             int s = g.list[k];
             uint32_t my = g.seq[s];
             int r = 0;
+            #pragma unroll 1
             for (int j = 0; j < cnt; j++) r += g.seq[g.list[j]] < my ? 1 : 0;
             order[r] = (uint8_t)s;
         }
         __syncwarp();
         if (g.lane == 0)
+            #pragma unroll 1
             for (int r = 0; r < cnt; r++) execute_serial(g, order[r], ndead);
         __syncwarp();
         ndead = __shfl_sync(FULLM, ndead, 0);
@@ -946,6 +988,7 @@ DEVN void run_game(Game &g, const StepParams &p, long long gi, WarpStats &ws) {
     // device policies emit self-consistent lists; under CANCEL_BOTH they can be issued in parallel (issue_policy_lists)
     bool fast_issue = p.conflict == 1 && p.policy[0] != POL_EXTERNAL && p.policy[1] != POL_EXTERNAL;
     unsigned long long decisions = 0, ucyc = 0;
+    #pragma unroll 1
     for (;;) {
         int time = g.hdr[H_TIME];
         if (time >= tlimit) break;
@@ -984,6 +1027,7 @@ DEVN void run_game(Game &g, const StepParams &p, long long gi, WarpStats &ws) {
 // GameState.cycle() repeated until time == target (TestTracesIntegrity.java:81-85); no policies
 DEVN void run_cycles_only(Game &g, int target) {
     int winner;
+    #pragma unroll 1
     for (;;) {
         int time = g.hdr[H_TIME];
         if (time >= target) break;
@@ -1013,6 +1057,7 @@ DEVN void run_issue_only(Game &g, const StepParams &p, long long gi) {
 // enemies' visibility].  out = [n_games][C][H][W], u8 or i32.  resv/claim are reused as the two visibility maps.
 DEV void stamp_sight(Game &g, uint8_t *map, uint32_t w) {
     int r = ut_sight(g, u_type(w)), d = 2 * r + 1, x0 = u_x(w) - r, y0 = u_y(w) - r;
+    #pragma unroll 1
     for (int q = g.lane; q < d * d; q += 32) {
         int dx = q % d - r, dy = q / d - r, x = x0 + q % d, y = y0 + q / d;
         if (x >= 0 && x < g.W && y >= 0 && y < g.H && dx * dx + dy * dy <= r * r) map[(y + 1) * g.P + x + 1] = 1;
@@ -1021,6 +1066,7 @@ DEV void stamp_sight(Game &g, uint8_t *map, uint32_t w) {
 DEV void cell_planes(const Game &g, int cell, int player, bool po, int v[8]) {
     int x = cell % g.W, y = cell / g.W, pc = (y + 1) * g.P + x + 1;
     int gv = g.grid[pc];
+    #pragma unroll 1
     for (int k = 0; k < 8; k++) v[k] = 0;
     v[5] = g.grid_tmpl ? (int)(((const uint8_t *)g.grid_tmpl)[pc] == 0xFF) : 0;
     if (po) { v[6] = g.resv[pc]; v[7] = g.claim[pc]; }
@@ -1041,10 +1087,13 @@ DEVN void observe_game(Game &g, const StepParams &p, long long gi) {
     bool po = p.partial_obs != 0;
     if (po) {
         int n = g.hdr[H_NUNITS];
+        #pragma unroll 1
         for (int i = g.lane; i < g.pcw; i += 32) { ((uint32_t *)g.resv)[i] = 0; ((uint32_t *)g.claim)[i] = 0; }
         __syncwarp();
+        #pragma unroll 1
         for (int i = 0; i < n; i++) { uint32_t w = g.w0[i]; if (u_pl(w) == player + 1) stamp_sight(g, g.resv, w); }
         __syncwarp();
+        #pragma unroll 1
         for (int i = 0; i < n; i++) { // enemy units that survive the filter (PartiallyObservableGameState.java:44-53)
             uint32_t w = g.w0[i];
             if (u_pl(w) != 0 && u_pl(w) != player + 1 && g.resv[cell_of(g, w)]) stamp_sight(g, g.claim, w);
@@ -1053,9 +1102,12 @@ DEVN void observe_game(Game &g, const StepParams &p, long long gi) {
     }
     size_t base = (size_t)gi * C * cells;
     if ((cells & 3) == 0) {
+        #pragma unroll 1
         for (int q = g.lane; q < cells / 4; q += 32) {
             int v[4][8];
+            #pragma unroll 1
             for (int j = 0; j < 4; j++) cell_planes(g, q * 4 + j, player, po, v[j]);
+            #pragma unroll 1
             for (int k = 0; k < C; k++) {
                 if (p.out_dtype == 0)
                     ((uint32_t *)((uint8_t *)p.out + base + (size_t)k * cells))[q] =
@@ -1067,9 +1119,11 @@ DEVN void observe_game(Game &g, const StepParams &p, long long gi) {
             }
         }
     } else {
+        #pragma unroll 1
         for (int cell = g.lane; cell < cells; cell += 32) {
             int v[8];
             cell_planes(g, cell, player, po, v);
+            #pragma unroll 1
             for (int k = 0; k < C; k++) {
                 if (p.out_dtype == 0) ((uint8_t *)p.out)[base + (size_t)k * cells + cell] = (uint8_t)v[k];
                 else ((int32_t *)p.out)[base + (size_t)k * cells + cell] = v[k];
@@ -1083,6 +1137,7 @@ DEVN void observe_game(Game &g, const StepParams &p, long long gi) {
 DEVN void masks_game(Game &g, const StepParams &p, long long gi) {
     int n = g.hdr[H_NUNITS], player = p.out_player;
     int R = 2 * p.max_range + 1, ctr = R / 2, nT = p.n_types, K = 1 + 6 + 16 + nT + R * R;
+    #pragma unroll 1
     for (int s = 0; s < n; s++) {
         uint32_t w = g.w0[s];
         if (u_pl(w) != player + 1 || a_type(g.a0[s]) != AT_IDLE) continue; // uniform across lanes
@@ -1090,6 +1145,7 @@ DEVN void masks_game(Game &g, const StepParams &p, long long gi) {
         bool mv = (e.fl & UF_MOVE) != 0;
         int pr_m = e.n_aff > 0 ? e.free_m : 0, mv_m = mv ? e.free_m : 0;
         size_t row = ((size_t)gi * g.W * g.H + (size_t)u_y(w) * g.W + u_x(w)) * K;
+        #pragma unroll 1
         for (int j = g.lane; j < K; j += 32) {
             int v = 0;
             if (j == 0) v = 1;
@@ -1122,9 +1178,116 @@ DEVN void masks_game(Game &g, const StepParams &p, long long gi) {
     }
 }
 
+// ---- NaiveMCTS playout (ai/mcts/naivemcts/NaiveMCTS.java:195-223,297-308) -----------------------------------------------
+// PartiallyObservableGameState(gs, observer) (rts/PartiallyObservableGameState.java:35-71): drop every unit that is not
+// the observer's and lies outside the sight radius of all observer units (with its assignment).
+DEVN void po_filter(Game &g, int observer) {
+    int n = g.hdr[H_NUNITS];
+#pragma unroll 1
+    for (int i = g.lane; i < g.pcw; i += 32) ((uint32_t *)g.claim)[i] = 0;
+    __syncwarp();
+#pragma unroll 1
+    for (int i = 0; i < n; i++) { uint32_t w = g.w0[i]; if (u_pl(w) == observer + 1) stamp_sight(g, g.claim, w); }
+    __syncwarp();
+    int removed = 0;
+#pragma unroll 1
+    for (int base = 0; base < n; base += 32) {
+        int i = base + g.lane;
+        bool drop = false;
+        if (i < n) { uint32_t w = g.w0[i]; drop = u_pl(w) != observer + 1 && !g.claim[cell_of(g, w)]; }
+        if (drop) g.a0[i] |= A0_DEAD;
+        removed += __popc(__ballot_sync(FULLM, drop));
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int i = g.lane; i < g.pcw; i += 32) ((uint32_t *)g.claim)[i] = 0;
+    __syncwarp();
+    if (removed) compact_units(g);
+}
+
+// SimpleSqrtEvaluationFunction3.base_score (ai/evaluation/SimpleSqrtEvaluationFunction3.java:32-44) and
+// SimpleEvaluationFunction.base_score (SimpleEvaluationFunction.java:27-36): float accumulation in unit-list order.
+DEV float base_score(const Game &g, int fn, int player) {
+    float score = __fmul_rn((float)g.hdr[H_RES0 + player], 20.0f);
+    bool any = false;
+    int n = g.hdr[H_NUNITS];
+#pragma unroll 1
+    for (int i = 0; i < n; i++) {
+        uint32_t w = g.w0[i];
+        if (u_pl(w) != player + 1) continue;
+        any = true;
+        uint32_t w1 = g.w1[i];
+        int t = u_type(w), cost = ut_cost(g, t), mhp = ut_hp(g, t), hp = u_hp(w1);
+        score = __fadd_rn(score, __fmul_rn((float)u_res(w1), 10.0f));
+        if (fn == 0) { // score += 40f * cost * Math.sqrt(hp / maxhp): int division, double product, narrowing +=
+            double v = __dmul_rn((double)__fmul_rn(40.0f, (float)cost), sqrt((double)(mhp ? hp / mhp : 0)));
+            score = (float)__dadd_rn((double)score, v);
+        } else score = __fadd_rn(score, __fdiv_rn(__fmul_rn(40.0f, (float)(cost * hp)), (float)mhp));
+    }
+    if (fn == 0 && !any) return 0.0f;
+    return score;
+}
+DEV float evaluate_state(const Game &g, int fn, int maxplayer) {
+    float s1 = base_score(g, fn, maxplayer), s2 = base_score(g, fn, 1 - maxplayer);
+    if (fn == 0) {
+        float sum = __fadd_rn(s1, s2);
+        if (sum == 0.0f) return 0.5f;
+        return __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, s1), sum), 1.0f);
+    }
+    return __fsub_rn(s1, s2);
+}
+
+// simulate(gs2, gs2.getTime() + depth):  do { if (gs.isComplete()) gameover = gs.cycle(); else { gs.issue(policy(0));
+// gs.issue(policy(1)); } } while (!gameover && time < limit) -- issue(), not issueSafe(); player 1 samples after
+// player 0's actions are in flight, so no same-cycle conflict can arise and both lists are inserted in parallel.
+DEVN void run_rollout(Game &g, const StepParams &p, long long r, WarpStats &ws) {
+    if (p.observer >= 0) po_filter(g, p.observer);
+    long long seed = p.ro_seeds ? p.ro_seeds[r] : r;
+    __syncwarp();
+    if (g.lane == 0) {
+        hdr_set_rng(g, H_RNGP_LO, ((unsigned long long)seed ^ 0x5DEECE66DULL) & MASK48);
+        hdr_set_rng(g, H_RNGC_LO, ((unsigned long long)(seed ^ 0x5851F42D4C957F2DLL) ^ 0x5DEECE66DULL) & MASK48);
+        hdr_set_rng(g, H_RNGD_LO, ((unsigned long long)(seed ^ 0x14057B7EF767814FLL) ^ 0x5DEECE66DULL) & MASK48);
+    }
+    __syncwarp();
+    int t0 = g.hdr[H_TIME], limit = t0 + p.depth, winner;
+    bool over_now = game_over(g, winner), gameover = false;
+    unsigned long long decisions = 0, ucyc = 0;
+    do {
+        int n = g.hdr[H_NUNITS];
+        bool idle = false;
+#pragma unroll 1
+        for (int i = g.lane; i < n; i += 32) idle |= u_pl(g.w0[i]) != 0 && a_type(g.a0[i]) == AT_IDLE;
+        if (__ballot_sync(FULLM, idle) == 0) { // isComplete()
+            int time = g.hdr[H_TIME];
+            int mrt = min_ready_time(g);
+            int tn = time + 1; if (!over_now && mrt > tn) tn = mrt;
+            if (tn > limit) { ucyc += (unsigned long long)n * (limit - time); __syncwarp(); if (g.lane == 0) g.hdr[H_TIME] = limit; __syncwarp(); break; }
+            ucyc += (unsigned long long)n * (tn - time);
+            gameover = cycle_execute(g, tn, winner);
+            over_now = gameover;
+        } else {
+            int pn = policy_random_biased(g, 0, 0);
+            issue_policy_lists(g, pn, pn);
+            decisions += pn;
+            pn = policy_random_biased(g, 1, 0);
+            issue_policy_lists(g, pn, pn);
+            decisions += pn;
+        }
+    } while (!gameover && g.hdr[H_TIME] < limit);
+    float ev = 0.0f;
+    if (g.lane == 0) ev = evaluate_state(g, p.eval_fn, p.maxplayer);
+    if (g.lane == 0) { if (p.ro_eval) p.ro_eval[r] = ev; if (p.ro_time) p.ro_time[r] = g.hdr[H_TIME] - t0; }
+    ws.v[STAT_CYCLES] += (unsigned long long)(g.hdr[H_TIME] - t0);
+    ws.v[STAT_DECISIONS] += decisions;
+    ws.v[STAT_UNIT_CYCLES] += ucyc;
+    ws.v[STAT_FINISHED]++;
+}
+
 // body of the step kernel for one thread; `smem` is the CTA's dynamic shared memory
 DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int nthreads, int bid, int nblocks) {
     uint32_t *cst = (uint32_t *)smem;
+    #pragma unroll 1
     for (int i = tid; i < MRTS_CONST_WORDS; i += nthreads) cst[i] = p.cst[i];
     __syncthreads();
     SmemLayout L = mrts_smem_layout(p.W, p.H, p.cap);
@@ -1132,8 +1295,13 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
     Game g;
     g_bind(g, smem + MRTS_CONST_WORDS * 4 + (size_t)warp * L.total, L, p.W, p.H, p.cap, lane, cst, p.conflict);
     WarpStats ws;
+    #pragma unroll 1
     for (int i = 0; i < 8; i++) ws.v[i] = 0;
-    for (long long gi = (long long)bid * wpc + warp; gi < p.n_games; gi += (long long)nblocks * wpc) {
+    #pragma unroll 1
+    long long n_items = p.mode == MODE_ROLLOUT ? p.n_games * p.rollouts_per_game : p.n_games;
+#pragma unroll 1
+    for (long long item = (long long)bid * wpc + warp; item < n_items; item += (long long)nblocks * wpc) {
+        long long gi = p.mode == MODE_ROLLOUT ? item / p.rollouts_per_game : item;
         const uint32_t *blob = p.maps + (size_t)(gi % p.n_maps) * p.map_words;
         g.grid_tmpl = blob;
         int32_t *ghdr = p.hdr + gi * MRTS_HDR_WORDS;
@@ -1147,10 +1315,12 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
         else if (p.mode == MODE_CYCLE_ONLY) run_cycles_only(g, p.t_target ? p.t_target[gi] : g.hdr[H_TIME] + p.n_cycles);
         else if (p.mode == MODE_ISSUE_ONLY) run_issue_only(g, p, gi);
         else if (p.mode == MODE_OBSERVE) { observe_game(g, p, gi); continue; }
+        else if (p.mode == MODE_ROLLOUT) { run_rollout(g, p, item, ws); continue; } // the batch itself is not modified
         else { masks_game(g, p, gi); continue; }
         if (g.hdr[H_ERR] != err0) ws.v[STAT_ERRORS]++;
         g_store(g, ghdr, gun);
     }
     if (lane == 0 && p.stats)
+        #pragma unroll 1
         for (int i = 0; i < 8; i++) if (ws.v[i]) atomicAdd(&p.stats[i], ws.v[i]);
 }

@@ -112,7 +112,7 @@ DEV void results_kernel_body(const ResultParams &p, long long gi) {
 
 #ifndef MRTS_EMU
 #ifndef MRTS_MIN_BLOCKS
-#define MRTS_MIN_BLOCKS 4
+#define MRTS_MIN_BLOCKS 6
 #endif
 __global__ void __launch_bounds__(MRTS_WARPS_PER_CTA * 32, MRTS_MIN_BLOCKS) k_step(StepParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -166,7 +166,8 @@ static int launch_step(mrts_batch *b, StepParams &p) {
     p.conflict = b->utt.conflict; p.max_range = b->max_range; p.n_types = (int)b->utt.types.size();
     p.partial_obs = (b->flags & MRTS_FLAG_PARTIAL_OBS) ? 1 : 0;
     int threads = b->wpc * 32;
-    long long need = (b->n + b->wpc - 1) / b->wpc;
+    long long items = p.mode == MODE_ROLLOUT ? b->n * p.rollouts_per_game : b->n;
+    long long need = (items + b->wpc - 1) / b->wpc;
     int grid = (int)std::min<long long>(b->grid, std::max<long long>(need, 1));
     b->launches++;
 #ifdef MRTS_EMU
@@ -450,8 +451,29 @@ int mrts_batch_cycle_to(mrts_batch *b, const int32_t *t_target, int n_cycles, in
     return MRTS_OK;
 }
 
-int mrts_batch_rollout(mrts_batch *, int, int, int, int, const int64_t *, float *, int32_t *, int) {
-    return fail(MRTS_E_STATE, "mrts_batch_rollout is not available in this build");
+int mrts_batch_rollout(mrts_batch *b, int rollouts_per_game, int depth, int eval_fn, int maxplayer, int observer, const int64_t *seeds,
+                       float *out_eval, int32_t *out_time, int on_device) {
+    if (!b || rollouts_per_game < 1 || depth < 0 || maxplayer < 0 || maxplayer > 1 || observer > 1 || (eval_fn != 0 && eval_fn != 1))
+        return fail(MRTS_E_ARG, "mrts_batch_rollout: bad argument");
+    if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
+    size_t nr = (size_t)b->n * rollouts_per_game;
+    StepParams p; memset(&p, 0, sizeof p);
+    p.mode = MODE_ROLLOUT; p.rollouts_per_game = rollouts_per_game; p.depth = depth; p.eval_fn = eval_fn; p.maxplayer = maxplayer;
+    p.observer = observer < 0 ? -1 : observer;
+    if (on_device) { p.ro_seeds = (const long long *)seeds; p.ro_eval = out_eval; p.ro_time = out_time; }
+    else {
+        if (ensure_tmp(b, nr * 16)) return fail(MRTS_E_CUDA, std::string("staging allocation failed: ") + dev_errstr());
+        char *t = (char *)b->d_tmp;
+        if (seeds) { if (dev_h2d(t, seeds, nr * 8, b->stream)) return fail(MRTS_E_CUDA, dev_errstr()); p.ro_seeds = (const long long *)t; }
+        p.ro_eval = (float *)(t + nr * 8); p.ro_time = (int32_t *)(t + nr * 12);
+    }
+    if (launch_step(b, p)) return fail(MRTS_E_CUDA, std::string("rollout launch: ") + dev_errstr());
+    if (!on_device) {
+        if (out_eval && dev_d2h(out_eval, p.ro_eval, nr * 4, b->stream)) return fail(MRTS_E_CUDA, dev_errstr());
+        if (out_time && dev_d2h(out_time, p.ro_time, nr * 4, b->stream)) return fail(MRTS_E_CUDA, dev_errstr());
+        if (dev_sync(b->stream)) return fail(MRTS_E_CUDA, dev_errstr());
+    }
+    return MRTS_OK;
 }
 
 static int emit(mrts_batch *b, int mode, int player, int dtype, void *out, int on_device, size_t elems) {

@@ -171,3 +171,9 @@ inline void syncthreads(int line) { yield_wait(2, line, 0); }
 template <typename T> static inline T atomicOr(T *p, T v) { T o = *p; *p = o | v; return o; }
 static inline int atomicOr(int *p, int v) { int o = *p; *p = o | v; return o; }
 template <typename T> static inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
+// IEEE single operations without contraction (the emulator is built with -ffp-contract=off)
+static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }

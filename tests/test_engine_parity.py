@@ -363,3 +363,47 @@ def test_full_size_batch_properties(backend, maps):
         P.assert_same_state(ex, 0, og, "full-size game %d" % g)
     b.close()
     sub.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# NaiveMCTS.simulate rollouts + evaluation functions (fully and partially observable roots)
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("key,observer", [("8x8/basesWorkers8x8", -1), ("8x8/basesWorkers8x8", 0), ("16x16/basesWorkers16x16", 1),
+                                          ("BWDistantResources32x32", 0), ("melee14x12Mixed18", -1)])
+def test_rollouts(backend, maps, key, observer):
+    n = 2 if backend == "emu" else 16
+    R = 2 if backend == "emu" else 6
+    depth = 100
+    utt, outt = M.UnitTypeTable(1, 1), O.Utt(1, 1)
+    b = M.BatchedGameState(utt, make_pgs(maps[key], utt), n)
+    seeds = np.arange(n, dtype=np.int64) + 3
+    b.reset(seeds)
+    b.set_policy(0, M.POLICY_RANDOM_BIASED)
+    b.set_policy(1, M.POLICY_RANDOM_BIASED)
+    games = []
+    for g in range(n):
+        og = O.Game(outt, maps[key])
+        og.seed(int(seeds[g]))
+        games.append(og)
+    for warm in (0, 230, 500):  # roots: the initial state and two mid-game states
+        if warm:
+            b.step(warm, 3000)
+            for og in games:
+                og.run(O.AI_RANDOM_BIASED, None, O.AI_RANDOM_BIASED, None, warm, 3000)
+        before = b.export()
+        rs = np.arange(n * R, dtype=np.int64) * 31 + 17 + warm
+        for fn in (0, 1):
+            ev, tm = b.rollout(depth=depth, rollouts_per_game=R, eval_fn=fn, maxplayer=1, observer=observer, seeds=rs)
+            for g, og in enumerate(games):
+                for k in range(R):
+                    c = og.po_view(observer) if observer >= 0 else og.clone()
+                    c.seed(int(rs[g * R + k]))
+                    start = c.time
+                    c.simulate(start + depth)
+                    ref = np.float32(c.evaluate(fn, 1, 0))
+                    assert tm[g, k] == c.time - start, (key, warm, g, k, tm[g, k], c.time - start)
+                    assert ev[g, k] == ref, (key, warm, fn, g, k, ev[g, k], ref)
+        after = b.export()
+        for kk in ("header", "units", "actions", "rng"):
+            assert (before[kk] == after[kk]).all(), "rollout modified the batch"
+    b.close()
