@@ -1,0 +1,204 @@
+package rts.cuda;
+
+import java.lang.foreign.Arena;
+import java.lang.foreign.FunctionDescriptor;
+import java.lang.foreign.Linker;
+import java.lang.foreign.MemorySegment;
+import java.lang.foreign.SymbolLookup;
+import java.lang.foreign.ValueLayout;
+import java.lang.invoke.MethodHandle;
+import java.nio.file.Path;
+
+import rts.units.UnitTypeTable;
+
+/**
+ * n independent microRTS games stepped in lockstep on one GPU through libmicrorts_cuda.so
+ * (include/microrts_cuda.h).  Mirrors the part of rts.GameState / tests.JNIGridnetVecClient that the batched
+ * simulation path needs: reset, issueSafe/issue, cycle, gameStep, getVectorObservation, getMasks, winner/gameover.
+ *
+ * Binding: Panama FFM (java.lang.foreign, JDK 22+).  NOT COMPILED in the build container of this repository (no JDK
+ * there); the signatures are written against include/microrts_cuda.h.  A JNI variant needs only a 1:1 C shim.
+ *
+ * Threading: like a GameState, an instance is confined to one thread.  One instance per GPU.
+ */
+public final class BatchedGameState implements AutoCloseable {
+    public static final int POLICY_EXTERNAL = 0, POLICY_PASSIVE = 1, POLICY_RANDOM_BIASED = 2, POLICY_WORKER_RUSH = 3, POLICY_LIGHT_RUSH = 4;
+    public static final int ACTIONS_VECTOR = 0, ACTIONS_RAW = 1;
+    public static final int DTYPE_U8 = 0, DTYPE_I32 = 1;
+
+    private static final Linker LINKER = Linker.nativeLinker();
+    private static final ValueLayout.OfInt I = ValueLayout.JAVA_INT;
+    private static final ValueLayout.OfLong L = ValueLayout.JAVA_LONG;
+    private static final java.lang.foreign.AddressLayout P = ValueLayout.ADDRESS;
+
+    private final Arena arena = Arena.ofConfined();
+    private final SymbolLookup lib;
+    private final MethodHandle lastError, uttCreate, uttDestroy, mapLoad, mapDestroy, batchCreate, batchDestroy, reset, resetMasked,
+            setPolicy, setAutoReset, setActions, issue, step, cycleTo, observe, masks, results, stats, rollout, numPlanes, maskWidth;
+
+    private MemorySegment utt, map, batch;
+    public final int numGames, width, height, planes, maskW;
+
+    private MethodHandle h(String name, FunctionDescriptor d) {
+        return LINKER.downcallHandle(lib.find(name).orElseThrow(() -> new UnsatisfiedLinkError(name)), d);
+    }
+
+    /**
+     * @param libraryPath path of libmicrorts_cuda.so
+     * @param uttVersion  UnitTypeTable.VERSION_* ; @param conflictPolicy UnitTypeTable.MOVE_CONFLICT_RESOLUTION_*
+     * @param mapPath     a map XML as accepted by PhysicalGameState.load
+     */
+    public BatchedGameState(Path libraryPath, int uttVersion, int conflictPolicy, String mapPath, int numGames, int device,
+                            boolean partialObs) {
+        lib = SymbolLookup.libraryLookup(libraryPath, arena);
+        lastError = h("mrts_last_error", FunctionDescriptor.of(P));
+        uttCreate = h("mrts_utt_create", FunctionDescriptor.of(I, I, I, P));
+        uttDestroy = h("mrts_utt_destroy", FunctionDescriptor.ofVoid(P));
+        mapLoad = h("mrts_map_load_xml", FunctionDescriptor.of(I, P, P, P));
+        mapDestroy = h("mrts_map_destroy", FunctionDescriptor.ofVoid(P));
+        batchCreate = h("mrts_batch_create", FunctionDescriptor.of(I, P, P, I, L, I, I, I, P));
+        batchDestroy = h("mrts_batch_destroy", FunctionDescriptor.ofVoid(P));
+        reset = h("mrts_batch_reset", FunctionDescriptor.of(I, P, P, I));
+        resetMasked = h("mrts_batch_reset_masked", FunctionDescriptor.of(I, P, P, P, I));
+        setPolicy = h("mrts_batch_set_policy", FunctionDescriptor.of(I, P, I, I, I));
+        setAutoReset = h("mrts_batch_set_auto_reset", FunctionDescriptor.of(I, P, I));
+        setActions = h("mrts_batch_set_actions", FunctionDescriptor.of(I, P, I, I, P, P, I, I, I));
+        issue = h("mrts_batch_issue", FunctionDescriptor.of(I, P, I, I, P, P, I, I, I, I));
+        step = h("mrts_batch_step", FunctionDescriptor.of(I, P, I, I));
+        cycleTo = h("mrts_batch_cycle_to", FunctionDescriptor.of(I, P, P, I, I));
+        observe = h("mrts_batch_observe", FunctionDescriptor.of(I, P, I, I, P, I));
+        masks = h("mrts_batch_masks", FunctionDescriptor.of(I, P, I, I, P, I));
+        results = h("mrts_batch_results", FunctionDescriptor.of(I, P, P, I));
+        stats = h("mrts_batch_stats", FunctionDescriptor.of(I, P, P));
+        rollout = h("mrts_batch_rollout", FunctionDescriptor.of(I, P, I, I, I, I, I, P, P, P, I));
+        numPlanes = h("mrts_batch_num_planes", FunctionDescriptor.of(I, P));
+        maskWidth = h("mrts_batch_mask_width", FunctionDescriptor.of(I, P));
+        try {
+            MemorySegment out = arena.allocate(P);
+            check((int) uttCreate.invoke(uttVersion, conflictPolicy, out));
+            utt = out.get(P, 0);
+            check((int) mapLoad.invoke(arena.allocateFrom(mapPath), utt, out));
+            map = out.get(P, 0);
+            MemorySegment maps = arena.allocate(P);
+            maps.set(P, 0, map);
+            check((int) batchCreate.invoke(utt, maps, 1, (long) numGames, device, partialObs ? 1 : 0, 0, out));
+            batch = out.get(P, 0);
+            this.numGames = numGames;
+            this.planes = (int) numPlanes.invoke(batch);
+            this.maskW = (int) maskWidth.invoke(batch);
+            // width/height come from the map: mrts_map_width / mrts_map_height (omitted handles for brevity)
+            this.width = (int) h("mrts_map_width", FunctionDescriptor.of(I, P)).invoke(map);
+            this.height = (int) h("mrts_map_height", FunctionDescriptor.of(I, P)).invoke(map);
+        } catch (Throwable t) {
+            throw new RuntimeException(t);
+        }
+    }
+
+    private void check(int rc) throws Throwable {
+        if (rc < 0) {
+            MemorySegment msg = ((MemorySegment) lastError.invoke()).reinterpret(4096);
+            throw new IllegalStateException("libmicrorts_cuda error " + rc + ": " + msg.getString(0));
+        }
+    }
+
+    /** new GameState(pgs, utt) for every game; seeds[g] seeds game g's java.util.Random streams (null: seed = g). */
+    public void reset(long[] seeds) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            check((int) reset.invoke(batch, seeds == null ? MemorySegment.NULL : a.allocateFrom(L, seeds), 0));
+        }
+    }
+
+    /** Which AI's getAction runs inside the step kernel for `player` (POLICY_*). */
+    public void setPolicy(int player, int policy) throws Throwable { check((int) setPolicy.invoke(batch, player, policy, 0)); }
+
+    /** JNIGridnetVecClient auto-reset (src/tests/JNIGridnetVecClient.java:272-286), done on the device. */
+    public void setAutoReset(boolean on) throws Throwable { check((int) setAutoReset.invoke(batch, on ? 1 : 0)); }
+
+    /** Stage vector actions [numGames][maxK][8] (PlayerAction.fromVectorAction rows) for an EXTERNAL player. */
+    public void setVectorActions(int player, int[] actions, int[] counts, int maxK) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            check((int) setActions.invoke(batch, player, ACTIONS_VECTOR, a.allocateFrom(I, actions), a.allocateFrom(I, counts), maxK, 1, 0));
+        }
+    }
+
+    /** gs.issueSafe(pa) for every game: rows [cell, type, parameter, x, y, unitType, 0, 0]. */
+    public void issueSafe(int player, int[] rawActions, int[] counts, int maxK) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            check((int) issue.invoke(batch, player, ACTIONS_RAW, a.allocateFrom(I, rawActions), a.allocateFrom(I, counts), maxK, -1, 1, 0));
+        }
+    }
+
+    /** Game.start loop body (src/rts/Game.java:126-140) nCycles times: policies, issueSafe x2, cycle. */
+    public void step(int nCycles, int maxCycles) throws Throwable { check((int) step.invoke(batch, nCycles, maxCycles)); }
+
+    /** gs.cycle() nCycles times, no policies. */
+    public void cycle(int nCycles) throws Throwable { check((int) cycleTo.invoke(batch, MemorySegment.NULL, nCycles, 0)); }
+
+    /** gs.getVectorObservation(player) of every game into out[numGames][planes][height][width]. */
+    public void getVectorObservation(int player, int[] out) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment seg = a.allocate(I, out.length);
+            check((int) observe.invoke(batch, player, DTYPE_I32, seg, 0));
+            MemorySegment.copy(seg, I, 0, out, 0, out.length);
+        }
+    }
+
+    /** JNIGridnetClient.getMasks(player) of every game into out[numGames][height][width][maskW]. */
+    public void getMasks(int player, int[] out) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment seg = a.allocate(I, out.length);
+            check((int) masks.invoke(batch, player, DTYPE_I32, seg, 0));
+            MemorySegment.copy(seg, I, 0, out, 0, out.length);
+        }
+    }
+
+    /** out[g] = {gs.getTime(), gs.winner(), gs.gameover() ? 1 : 0, error bits}. */
+    public int[] results() throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment seg = a.allocate(I, 4L * numGames);
+            check((int) results.invoke(batch, seg, 0));
+            return seg.toArray(I);
+        }
+    }
+
+    /** {wins_p0, wins_p1, draws, games_finished, cycles, decisions, unit_cycles, errors} since the last reset. */
+    public long[] stats() throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment seg = a.allocate(L, 8);
+            check((int) stats.invoke(batch, seg));
+            return seg.toArray(L);
+        }
+    }
+
+    /**
+     * NaiveMCTS.simulate + ef.evaluate for rolloutsPerGame clones of every game (src/ai/mcts/naivemcts/NaiveMCTS.java:195-223).
+     * Returns the undiscounted evaluations; multiply by Math.pow(0.99, time/10.0) with outTime as the reference does.
+     */
+    public float[] rollout(int rolloutsPerGame, int depth, int evalFn, int maxplayer, int observer, long[] seeds, int[] outTime) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            long n = (long) numGames * rolloutsPerGame;
+            MemorySegment ev = a.allocate(ValueLayout.JAVA_FLOAT, n), tm = a.allocate(I, n);
+            check((int) rollout.invoke(batch, rolloutsPerGame, depth, evalFn, maxplayer, observer,
+                    seeds == null ? MemorySegment.NULL : a.allocateFrom(L, seeds), ev, tm, 0));
+            if (outTime != null) MemorySegment.copy(tm, I, 0, outTime, 0, outTime.length);
+            return ev.toArray(ValueLayout.JAVA_FLOAT);
+        }
+    }
+
+    @Override
+    public void close() {
+        try {
+            if (batch != null) batchDestroy.invoke(batch);
+            if (map != null) mapDestroy.invoke(map);
+            if (utt != null) uttDestroy.invoke(utt);
+        } catch (Throwable ignored) {
+        }
+        arena.close();
+    }
+
+    /** Convenience: does `utt` (a reference UnitTypeTable) match the built-in table the native side was created with? */
+    public static boolean sameTable(UnitTypeTable utt, int version) {
+        UnitTypeTable ref = new UnitTypeTable(version, utt.getMoveConflictResolutionStrategy());
+        return ref.getUnitTypes().size() == utt.getUnitTypes().size();
+    }
+}

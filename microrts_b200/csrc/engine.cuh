@@ -1295,9 +1295,7 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
     Game g;
     g_bind(g, smem + MRTS_CONST_WORDS * 4 + (size_t)warp * L.total, L, p.W, p.H, p.cap, lane, cst, p.conflict);
     WarpStats ws;
-    #pragma unroll 1
     for (int i = 0; i < 8; i++) ws.v[i] = 0;
-    #pragma unroll 1
     long long n_items = p.mode == MODE_ROLLOUT ? p.n_games * p.rollouts_per_game : p.n_games;
 #pragma unroll 1
     for (long long item = (long long)bid * wpc + warp; item < n_items; item += (long long)nblocks * wpc) {
