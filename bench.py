@@ -181,7 +181,8 @@ def run_ours(args):
     b = M.BatchedGameState(utt, pgs, n, device=local)
     from microrts_b200 import _ffi
     stream = torch.cuda.ExternalStream(_ffi.lib().mrts_batch_stream(b._h), device=torch.device("cuda", local))
-    seeds = np.arange(n, dtype=np.int64) + rank * n
+    from microrts_b200 import sharding
+    seeds = sharding.global_seeds(0, rank * n, n)  # game g of the global batch always uses seed g
     b.set_policy(0, M.POLICY_RANDOM_BIASED)
     b.set_policy(1, M.POLICY_RANDOM_BIASED)
 
@@ -231,12 +232,13 @@ def run_ours(args):
     errors = int((res[:, 3] != 0).sum())
 
     tmax = torch.tensor([wall, dev_s], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([cycles, ucyc, decisions, st1["wins_p0"], st1["wins_p1"], st1["draws"], st1["games_finished"], errors], dtype=torch.int64, device="cuda")
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)  # the single NCCL reduce of win/score statistics
     wall_max, dev_max = tmax.tolist()
-    cycles_all, ucyc_all, dec_all, w0, w1, dr, fin, err_all = tot.tolist()
+    # the single NCCL reduce of win/score statistics (counters of the timed window; wins/draws since the reset)
+    red = sharding.reduce_stats(dict(st1, cycles=cycles, unit_cycles=ucyc, decisions=decisions, errors=errors), device="cuda")
+    cycles_all, ucyc_all, dec_all = red["cycles"], red["unit_cycles"], red["decisions"]
+    w0, w1, dr, fin, err_all = red["wins_p0"], red["wins_p1"], red["draws"], red["games_finished"], red["errors"]
     value = cycles_all / wall_max
     mean_units = ucyc_all / max(1, cycles_all)
 
