@@ -65,7 +65,10 @@ enum {
 };
 
 enum { MRTS_DTYPE_U8 = 0, MRTS_DTYPE_I32 = 1 };
-enum { MRTS_FLAG_PARTIAL_OBS = 1u };
+enum {
+    MRTS_FLAG_PARTIAL_OBS = 1u,
+    MRTS_FLAG_SCRIPTED_AI = 2u /* reserve pathfinding scratch so WORKER_RUSH / LIGHT_RUSH policies can be selected */
+};
 enum { MRTS_EVAL_SIMPLE_SQRT3 = 0, MRTS_EVAL_SIMPLE = 1 };
 
 /* unit type fields for mrts_utt_get (order of the attributes in UnitType.toxml, src/rts/units/UnitType.java) */

@@ -21,6 +21,7 @@ POLICY_EXTERNAL, POLICY_PASSIVE, POLICY_RANDOM_BIASED, POLICY_WORKER_RUSH, POLIC
 PF_ASTAR, PF_BFS = 0, 1
 DTYPE_U8, DTYPE_I32 = 0, 1
 FLAG_PARTIAL_OBS = 1
+FLAG_SCRIPTED_AI = 2
 
 
 class MicroRTSError(RuntimeError):
@@ -169,12 +170,13 @@ def _ptr(a):
 class BatchedGameState:
     """n independent GameState objects stepped in lockstep on one GPU (rts.cuda.BatchedGameState)."""
 
-    def __init__(self, utt, pgs, n_games, device=0, partial_obs=False, unit_capacity=0):
+    def __init__(self, utt, pgs, n_games, device=0, partial_obs=False, unit_capacity=0, scripted_ai=False):
         maps = list(pgs) if isinstance(pgs, (list, tuple)) else [pgs]
         self.utt, self.maps, self.n = utt, maps, int(n_games)
         arr = (C.c_void_p * len(maps))(*[m._h for m in maps])
         h = C.c_void_p()
-        _check(_ffi.lib().mrts_batch_create(utt._h, arr, len(maps), self.n, device, FLAG_PARTIAL_OBS if partial_obs else 0,
+        _check(_ffi.lib().mrts_batch_create(utt._h, arr, len(maps), self.n, device,
+                                            (FLAG_PARTIAL_OBS if partial_obs else 0) | (FLAG_SCRIPTED_AI if scripted_ai else 0),
                                             unit_capacity, C.byref(h)))
         self._h = h
         self.width, self.height = maps[0].getWidth(), maps[0].getHeight()

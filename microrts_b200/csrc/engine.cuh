@@ -53,6 +53,7 @@ struct StepParams {
     int conflict;              // UnitTypeTable.moveConflictResolutionStrategy
     int safe;                  // issueSafe (1) or issue (0) for external actions
     int issue_player;          // MODE_ISSUE_ONLY
+    int scripted;              // the batch reserves A* scratch (WORKER_RUSH / LIGHT_RUSH policies selectable)
     int auto_reset;            // MODE_GAME: restart finished games from their map at the start of the step
     const int32_t *ext_actions[2]; // [n_games][max_k][8]
     const int32_t *ext_counts[2];  // [n_games]
@@ -77,13 +78,15 @@ struct Game {
     int32_t *hdr;
     uint32_t *w0, *w1, *a0;
     int32_t *a1, *tis;
-    uint32_t *seq, *uid;
+    uint32_t *seq, *uid, *x0, *x1;
     uint32_t *pa0;
     int32_t *pa1;
     uint8_t *pslot, *grid, *resv, *claim, *list;
     const uint32_t *utt;        // shared memory copy
     const uint64_t *jump;       // shared memory copy
     const uint32_t *grid_tmpl;  // global: wall-padded empty grid of this game's map
+    uint16_t *as_closed, *as_cost, *as_opos, *as_opar, *as_of; // A* scratch over W*H cells (scripted batches only)
+    uint8_t *as_flags;
 };
 
 DEV void g_bind(Game &g, unsigned char *sm, const SmemLayout &L, int W, int H, int cap, int lane, const uint32_t *cst_sm,
@@ -93,6 +96,9 @@ DEV void g_bind(Game &g, unsigned char *sm, const SmemLayout &L, int W, int H, i
     uint32_t *u = (uint32_t *)(sm + L.units);
     g.w0 = u + UW_W0 * cap; g.w1 = u + UW_W1 * cap; g.a0 = u + UW_A0 * cap; g.a1 = (int32_t *)(u + UW_A1 * cap);
     g.tis = (int32_t *)(u + UW_TIS * cap); g.seq = u + UW_SEQ * cap; g.uid = u + UW_ID * cap;
+    g.x0 = u + UW_X0 * cap; g.x1 = u + UW_X1 * cap;
+    { int cells = W * H; g.as_closed = (uint16_t *)(sm + L.astar); g.as_cost = g.as_closed + cells; g.as_opos = g.as_cost + cells;
+      g.as_opar = g.as_opos + cells; g.as_of = g.as_opar + cells; g.as_flags = (uint8_t *)(g.as_of + cells); }
     g.pa0 = (uint32_t *)(sm + L.pa0); g.pa1 = (int32_t *)(sm + L.pa1); g.pslot = sm + L.pslot;
     g.grid = sm + L.grid; g.resv = sm + L.resv; g.claim = sm + L.claim; g.list = sm + L.list;
     g.utt = cst_sm; g.jump = (const uint64_t *)(cst_sm + MRTS_MAX_TYPES * MRTS_UTT_WORDS);
@@ -848,7 +854,7 @@ DEV void execute_serial(Game &g, int s, int &ndead) {
                         int nx = u_x(w) + ddx(A1), ny = u_y(w) + ddy(A1);
                         g.w0[n] = (uint32_t)ut | ((uint32_t)pl << 8) | ((uint32_t)nx << 16) | ((uint32_t)ny << 24);
                         g.w1[n] = mk_w1(ut_hp(g, ut), 0);
-                        g.a0[n] = AT_IDLE | A0_NOUT; g.a1[n] = 0; g.tis[n] = 0; g.seq[n] = 0; g.uid[n] = (uint32_t)id;
+                        g.a0[n] = AT_IDLE | A0_NOUT; g.a1[n] = 0; g.tis[n] = 0; g.seq[n] = 0; g.uid[n] = (uint32_t)id; g.x0[n] = 0; g.x1[n] = 0;
                         g.grid[nc] = (uint8_t)(n + 1);
                         g.hdr[H_NUNITS] = n + 1;
                         g.hdr[H_RES0 + pl - 1] = pres - cost;
@@ -872,12 +878,23 @@ DEVN void compact_units(Game &g) {
         if (alive) for (int k = 0; k < MRTS_UNIT_WORDS; k++) r[k] = su[k * g.cap + i];
         unsigned m = __ballot_sync(FULLM, alive);
         int pos = out + __popc(m & ((1u << g.lane) - 1));
+        if (i < n) g.list[i] = alive ? (uint8_t)(pos + 1) : 0; // old slot -> new slot + 1 (0: removed)
         __syncwarp();
         if (alive) for (int k = 0; k < MRTS_UNIT_WORDS; k++) su[k * g.cap + pos] = r[k];
         out += __popc(m);
         __syncwarp();
     }
     if (g.lane == 0) g.hdr[H_NUNITS] = out;
+    __syncwarp();
+    // unit references held by abstract actions (X1: attack/harvest target, base) follow their unit or become "dead object"
+#pragma unroll 1
+    for (int i = g.lane; i < out; i += 32) {
+        uint32_t X1 = g.x1[i];
+        uint32_t t = X1 & 0xff, b = (X1 >> 8) & 0xff;
+        if (t != 0 && t != 0xFF) { t = g.list[t - 1]; if (t == 0) t = 0xFF; }
+        if (b != 0 && b != 0xFF) { b = g.list[b - 1]; if (b == 0) b = 0xFF; }
+        g.x1[i] = (X1 & 0xffff0000u) | (b << 8) | t;
+    }
     __syncwarp();
     g_reset_maps(g);
     g_scatter(g);
@@ -956,6 +973,8 @@ DEVN bool cycle_execute(Game &g, int t_new, int &winner) {
     return game_over(g, winner);
 }
 
+#include "scripted.cuh"
+
 // ---- loops ---------------------------------------------------------------------------------------------------------------
 struct WarpStats { unsigned long long v[8]; };
 
@@ -972,7 +991,15 @@ DEV int run_policy(Game &g, const StepParams &p, long long gi, int player, int p
                 if (p.safe) legality_pass(g, n0, pn);
             }
             return pn;
-        default: return pn; // PASSIVE (scripted policies are dispatched by the caller)
+        case POL_WORKER_RUSH:
+        case POL_LIGHT_RUSH: {
+            if (!p.scripted) return pn;
+            int n0 = pn;
+            pn = policy_scripted(g, player, p.policy[player], p.pathfinder[player], pn);
+            legality_pass(g, n0, pn); // the list goes through issueSafe (Game.java:136-137), which may replace desires by NONE
+            return pn;
+        }
+        default: return pn; // PASSIVE
     }
 }
 
@@ -1000,6 +1027,15 @@ DEVN void run_game(Game &g, const StepParams &p, long long gi, WarpStats &ws) {
         decisions += pn1;
         int mrt = min_ready_time(g);
         int tn = time + 1; if (!force_next && mrt > tn) tn = mrt;
+        if (tn > time + 1 && p.scripted) {
+            // Cycles time+1 .. tn-1 are skipped because nothing can change in them, but the reference still calls getAction
+            // in each.  For the scripted AIs the FIRST of those calls is not a no-op: translateActions drops the entries that
+            // completed while being executed in this cycle (Train), which decides their position in the map when they are
+            // re-inserted later.  Replay that one call (it cannot emit actions: no own unit is idle); the rest are no-ops.
+#pragma unroll 1
+            for (int pl = 0; pl < 2; pl++)
+                if (p.policy[pl] == POL_WORKER_RUSH || p.policy[pl] == POL_LIGHT_RUSH) policy_scripted(g, pl, p.policy[pl], p.pathfinder[pl], 0);
+        }
         int nu = g.hdr[H_NUNITS];
         if (tn > tlimit) { ucyc += (unsigned long long)nu * (tlimit - time); __syncwarp(); if (g.lane == 0) g.hdr[H_TIME] = tlimit; __syncwarp(); break; }
         ucyc += (unsigned long long)nu * (tn - time);
@@ -1290,7 +1326,7 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
     #pragma unroll 1
     for (int i = tid; i < MRTS_CONST_WORDS; i += nthreads) cst[i] = p.cst[i];
     __syncthreads();
-    SmemLayout L = mrts_smem_layout(p.W, p.H, p.cap);
+    SmemLayout L = mrts_smem_layout(p.W, p.H, p.cap, p.scripted);
     int warp = tid >> 5, lane = tid & 31, wpc = nthreads >> 5;
     Game g;
     g_bind(g, smem + MRTS_CONST_WORDS * 4 + (size_t)warp * L.total, L, p.W, p.H, p.cap, lane, cst, p.conflict);

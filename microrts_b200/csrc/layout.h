@@ -12,7 +12,7 @@
 #define MRTS_HD static inline
 #endif
 
-#define MRTS_HDR_WORDS 16
+#define MRTS_HDR_WORDS 20
 enum {
     H_TIME = 0,     // GameState.time
     H_RES0 = 1,     // Player 0 resources
@@ -26,14 +26,20 @@ enum {
     H_RNGC_LO = 10, H_RNGC_HI = 11, // GameState.r               (CANCEL_RANDOM)
     H_RNGD_LO = 12, H_RNGD_HI = 13, // UnitAction.r              (random damage)
     H_ERR = 14,     // sticky MRTS_GE_* bits
-    H_SPARE = 15
+    H_SPARE = 15,   // episode counter (auto-reset)
+    H_ASEQ0 = 16,   // next insertion sequence of player 0's AbstractionLayerAI.actions map
+    H_ASEQ1 = 17,
+    H_RSV0 = 18, H_RSV1 = 19
 };
 
 // per-unit words
-enum { UW_W0 = 0, UW_W1, UW_A0, UW_A1, UW_TIS, UW_SEQ, UW_ID, MRTS_UNIT_WORDS };
+enum { UW_W0 = 0, UW_W1, UW_A0, UW_A1, UW_TIS, UW_SEQ, UW_ID, UW_X0, UW_X1, MRTS_UNIT_WORDS };
 // W0: type | (player+1)<<8 | x<<16 | y<<24            W1: (uint16)hp | (uint16)res<<16
 // A0: atype(4) | flags(4) | utype<<8 | ax<<16 | ay<<24    A1: parameter (direction or NONE duration)
 // TIS: issue time (UnitActionAssignment.time)          SEQ: assignment sequence      ID: Unit.ID (low 32 bits)
+// X0/X1: the unit's entry in its owner's AbstractionLayerAI.actions map (scripted policies):
+//   X0: kind(3: 0 none,1 train,2 build,3 harvest,4 attack) | completed<<3 | type<<4 | bx<<8 | by<<16 | bxNeg<<24 | aseqHi<<25
+//   X1: target slot+1 (0 null, 0xFF dead object) | base slot+1 <<8 | aseqLo<<16
 #define AT_IDLE 15u
 #define A0_DEAD 0x10u
 
@@ -55,11 +61,13 @@ enum { UF_RESOURCE = 1, UF_STOCKPILE = 2, UF_HARVEST = 4, UF_MOVE = 8, UF_ATTACK
 enum { GE_UNIT_OVERFLOW = 1, GE_INCONSISTENT_OLDER = 2, GE_FAILED_PRODUCE = 4, GE_CELL_OCCUPIED = 8, GE_BAD_ACTION = 16 };
 
 struct SmemLayout {
-    int hdr, units, pa0, pa1, pslot, grid, resv, claim, list, total; // byte offsets inside one game's region
+    int hdr, units, pa0, pa1, pslot, grid, resv, claim, list, astar, total; // byte offsets inside one game's region
     int pcw;                                                          // padded-grid size in 32-bit words
 };
 
-MRTS_HD SmemLayout mrts_smem_layout(int W, int H, int cap) {
+// A* / BFS scratch (scripted policies only): per cell closed u16, cost u16, flags u8, open list (pos u16, parent u16, f u16)
+#define MRTS_ASTAR_BYTES_PER_CELL 11
+MRTS_HD SmemLayout mrts_smem_layout(int W, int H, int cap, int scripted) {
     SmemLayout L;
     int pc = (W + 2) * (H + 2);
     int pcb = (pc + 15) & ~15;
@@ -74,6 +82,7 @@ MRTS_HD SmemLayout mrts_smem_layout(int W, int H, int cap) {
     L.resv = o; o += pcb;
     L.claim = o; o += pcb;
     L.list = o; o += capb;
+    L.astar = o; o += scripted ? ((W * H * MRTS_ASTAR_BYTES_PER_CELL + 15) & ~15) : 0;
     L.total = (o + 15) & ~15;
     L.pcw = pcb / 4;
     return L;

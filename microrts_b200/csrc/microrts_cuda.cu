@@ -148,7 +148,7 @@ struct mrts_batch {
     stream_t stream = nullptr;
     SmemLayout L;
     size_t smem_bytes = 0;
-    int grid = 0, max_range = 0, auto_reset = 0, wpc = MRTS_WARPS_PER_CTA; // wpc: warps (games in flight) per CTA
+    int grid = 0, max_range = 0, auto_reset = 0, scripted = 0, wpc = MRTS_WARPS_PER_CTA; // wpc: warps (games in flight) per CTA
     long long launches = 0;
 };
 
@@ -164,7 +164,7 @@ static int launch_step(mrts_batch *b, StepParams &p) {
     p.hdr = b->d_hdr; p.units = b->d_units; p.maps = b->d_maps; p.cst = b->d_cst; p.stats = b->d_stats;
     p.n_games = b->n; p.n_maps = b->n_maps; p.map_words = b->map_words; p.W = b->W; p.H = b->H; p.cap = b->cap;
     p.conflict = b->utt.conflict; p.max_range = b->max_range; p.n_types = (int)b->utt.types.size();
-    p.partial_obs = (b->flags & MRTS_FLAG_PARTIAL_OBS) ? 1 : 0;
+    p.partial_obs = (b->flags & MRTS_FLAG_PARTIAL_OBS) ? 1 : 0; p.scripted = b->scripted;
     int threads = b->wpc * 32;
     long long items = p.mode == MODE_ROLLOUT ? b->n * p.rollouts_per_game : b->n;
     long long need = (items + b->wpc - 1) / b->wpc;
@@ -286,7 +286,8 @@ int mrts_batch_create(const mrts_utt *u, const mrts_map *const *maps, int n_maps
     auto b = std::unique_ptr<mrts_batch, void (*)(mrts_batch *)>(new mrts_batch, mrts_batch_destroy);
     b->utt = u->h; b->W = W; b->H = H; b->cap = cap; b->n_maps = n_maps; b->n = n_games; b->flags = flags; b->device = device;
     b->max_range = u->h.maxAttackRange();
-    b->L = mrts_smem_layout(W, H, cap);
+    b->scripted = (flags & MRTS_FLAG_SCRIPTED_AI) ? 1 : 0;
+    b->L = mrts_smem_layout(W, H, cap, b->scripted);
     b->map_words = mrts_map_blob_words(W, H, cap);
     if (dev_select(device)) return fail(MRTS_E_CUDA, std::string("cannot select CUDA device: ") + dev_errstr());
 #ifndef MRTS_EMU
@@ -373,7 +374,9 @@ int mrts_batch_reset_masked(mrts_batch *b, const uint8_t *mask, const int64_t *s
 int mrts_batch_set_policy(mrts_batch *b, int player, int policy, int pathfinder) {
     if (!b || player < 0 || player > 1) return fail(MRTS_E_ARG, "mrts_batch_set_policy: bad argument");
     if (policy < MRTS_POLICY_EXTERNAL || policy > MRTS_POLICY_LIGHT_RUSH) return fail(MRTS_E_ARG, "mrts_batch_set_policy: unknown policy");
-    if (policy == MRTS_POLICY_WORKER_RUSH || policy == MRTS_POLICY_LIGHT_RUSH) return fail(MRTS_E_STATE, "scripted device policies are not available in this build");
+    if ((policy == MRTS_POLICY_WORKER_RUSH || policy == MRTS_POLICY_LIGHT_RUSH) && !b->scripted)
+        return fail(MRTS_E_STATE, "scripted policies need a batch created with MRTS_FLAG_SCRIPTED_AI");
+    if (pathfinder != MRTS_PF_ASTAR && pathfinder != MRTS_PF_BFS) return fail(MRTS_E_ARG, "unknown pathfinder");
     b->policy[player] = policy; b->pathfinder[player] = pathfinder;
     return MRTS_OK;
 }

@@ -407,3 +407,77 @@ def test_rollouts(backend, maps, key, observer):
         for kk in ("header", "units", "actions", "rng"):
             assert (before[kk] == after[kk]).all(), "rollout modified the batch"
     b.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# scripted policies on the device: LightRush / WorkerRush + AbstractionLayerAI + A* / BFS
+# ------------------------------------------------------------------------------------------------------------------
+def test_lightrush_traces_regenerated_on_device(backend, traces, maps):
+    """Pinned by golden data: LightRush(A*) vs LightRush(A*) on the device must end every one of the 140 recorded mirror
+    matches (src/tests/GenerateTestTraces.java:101-134, 500-cycle cap) in exactly the recorded final state."""
+    utt = M.UnitTypeTable(1, 1)
+    lr = [t for t in traces if "LightRush" in t["name"]]
+    groups = {}
+    for t in lr:
+        m = maps[t["mapkey"]]
+        groups.setdefault((m["w"], m["h"]), []).append(t)
+    if backend == "emu":
+        groups = {k: v for i, (k, v) in enumerate(sorted(groups.items())) if i % 5 == 0 and k[0] * k[1] <= 600}
+    checked = 0
+    for (w, h), ts in sorted(groups.items()):
+        b = M.BatchedGameState(utt, [make_pgs(maps[t["mapkey"]], utt) for t in ts], len(ts), scripted_ai=True)
+        b.set_policy(0, M.POLICY_LIGHT_RUSH)
+        b.set_policy(1, M.POLICY_LIGHT_RUSH)
+        b.step(500, 500)
+        ex = b.export()
+        for g, t in enumerate(ts):
+            last = t["entries"][-1]
+            hdr, units, _a = P.export_game(ex, g)
+            exp = np.array(last["units"], dtype=np.int32).reshape(-1, 6)
+            assert hdr[0] == last["time"], (t["name"], hdr[0], last["time"])
+            assert units[:, :6].shape == exp.shape and (units[:, :6] == exp).all(), "%s\ndev=\n%s\ntrace=\n%s" % (t["name"], units[:, :6], exp)
+            assert (hdr[1], hdr[2]) == tuple(last["res"]) and hdr[6] == 0, t["name"]
+            checked += 1
+        b.close()
+    assert checked == (140 if backend != "emu" else checked)
+
+
+SCRIPTED = [
+    # map, policy0, policy1, pathfinder
+    ("8x8/basesWorkers8x8", "LIGHT_RUSH", "WORKER_RUSH", 0),
+    ("16x16/basesWorkers16x16", "WORKER_RUSH", "LIGHT_RUSH", 0),
+    ("24x24/basesWorkers24x24", "WORKER_RUSH", "LIGHT_RUSH", 0),
+    ("24x24/basesWorkers24x24H", "LIGHT_RUSH", "WORKER_RUSH", 1),
+    ("16x16/TwoBasesBarracks16x16", "WORKER_RUSH", "WORKER_RUSH", 1),
+    ("8x8/FourBasesWorkers8x8", "LIGHT_RUSH", "RANDOM_BIASED", 0),
+    ("BWDistantResources32x32", "RANDOM_BIASED", "WORKER_RUSH", 0),
+]
+
+
+@pytest.mark.parametrize("key,p0,p1,pf", SCRIPTED)
+def test_scripted_policies_vs_oracle(backend, maps, key, p0, p1, pf):
+    n = 2 if backend == "emu" else 8
+    total = 600 if backend == "emu" else 3000
+    chunk = 25
+    utt, outt = M.UnitTypeTable(1, 1), O.Utt(1, 1)
+    b = M.BatchedGameState(utt, make_pgs(maps[key], utt), n, scripted_ai=True)
+    seeds = np.arange(n, dtype=np.int64) + 11
+    b.reset(seeds)
+    kinds = []
+    for pl, name in enumerate((p0, p1)):
+        b.set_policy(pl, getattr(M, "POLICY_" + name), pf)
+        kinds.append(getattr(O, "AI_" + name))
+    games, ais = [], []
+    for g in range(n):
+        og = O.Game(outt, maps[key])
+        og.seed(int(seeds[g]))
+        games.append(og)
+        ais.append([O.ScriptedAI(k, pf) if k in (O.AI_WORKER_RUSH, O.AI_LIGHT_RUSH) else None for k in kinds])
+    for t in range(0, total, chunk):
+        b.step(chunk, total)
+        ex = b.export()
+        for g, og in enumerate(games):
+            if not (og.gameover and og.time > 0):
+                og.run(kinds[0], ais[g][0], kinds[1], ais[g][1], chunk, total)
+            P.assert_same_state(ex, g, og, "%s %s/%s t=%d" % (key, p0, p1, t + chunk))
+    b.close()
