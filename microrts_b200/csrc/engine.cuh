@@ -53,7 +53,10 @@ struct StepParams {
     int conflict;              // UnitTypeTable.moveConflictResolutionStrategy
     int safe;                  // issueSafe (1) or issue (0) for external actions
     int issue_player;          // MODE_ISSUE_ONLY
-    int scripted;              // the batch reserves A* scratch (WORKER_RUSH / LIGHT_RUSH policies selectable)
+    int scripted;              // 0: no scripted policies; 1: A* scratch in shared memory; 2: A* scratch in global memory
+    int uw;                    // unit words per slot in HBM and shared memory: 7, or 9 (X0/X1) for scripted batches
+    unsigned char *astar_scratch; // scripted == 2: [grid * warps per CTA][astar_stride] bytes
+    long long astar_stride;
     int auto_reset;            // MODE_GAME: restart finished games from their map at the start of the step
     const int32_t *ext_actions[2]; // [n_games][max_k][8]
     const int32_t *ext_counts[2];  // [n_games]
@@ -74,7 +77,7 @@ struct StepParams {
 
 struct Game {
     int lane;
-    int W, H, P, cap, pcw, conflict;
+    int W, H, P, cap, pcw, conflict, uw; // uw: unit words resident in shared memory (7, or 9 with scripted policies)
     int32_t *hdr;
     uint32_t *w0, *w1, *a0;
     int32_t *a1, *tis;
@@ -90,14 +93,15 @@ struct Game {
 };
 
 DEV void g_bind(Game &g, unsigned char *sm, const SmemLayout &L, int W, int H, int cap, int lane, const uint32_t *cst_sm,
-                int conflict) {
+                int conflict, int scripted, unsigned char *astar_global) {
     g.lane = lane; g.W = W; g.H = H; g.P = W + 2; g.cap = cap; g.pcw = L.pcw; g.conflict = conflict;
+    g.uw = scripted ? MRTS_UNIT_WORDS : MRTS_UNIT_WORDS_CORE;
     g.hdr = (int32_t *)(sm + L.hdr);
     uint32_t *u = (uint32_t *)(sm + L.units);
     g.w0 = u + UW_W0 * cap; g.w1 = u + UW_W1 * cap; g.a0 = u + UW_A0 * cap; g.a1 = (int32_t *)(u + UW_A1 * cap);
     g.tis = (int32_t *)(u + UW_TIS * cap); g.seq = u + UW_SEQ * cap; g.uid = u + UW_ID * cap;
     g.x0 = u + UW_X0 * cap; g.x1 = u + UW_X1 * cap;
-    { int cells = W * H; g.as_closed = (uint16_t *)(sm + L.astar); g.as_cost = g.as_closed + cells; g.as_opos = g.as_cost + cells;
+    { int cells = W * H; g.as_closed = (uint16_t *)(astar_global ? astar_global : sm + L.astar); g.as_cost = g.as_closed + cells; g.as_opos = g.as_cost + cells;
       g.as_opar = g.as_opos + cells; g.as_of = g.as_opar + cells; g.as_flags = (uint8_t *)(g.as_of + cells); }
     g.pa0 = (uint32_t *)(sm + L.pa0); g.pa1 = (int32_t *)(sm + L.pa1); g.pslot = sm + L.pslot;
     g.grid = sm + L.grid; g.resv = sm + L.resv; g.claim = sm + L.claim; g.list = sm + L.list;
@@ -228,7 +232,7 @@ DEV void g_load(Game &g, const int32_t *ghdr, const uint32_t *gun) {
     int n = g.hdr[H_NUNITS];
     uint32_t *su = g.w0;
     #pragma unroll 1
-    for (int k = 0; k < MRTS_UNIT_WORDS; k++)
+    for (int k = 0; k < g.uw; k++)
         #pragma unroll 1
         for (int i = g.lane; i < n; i += 32) su[k * g.cap + i] = gun[k * g.cap + i];
     __syncwarp();
@@ -250,7 +254,7 @@ DEV void g_restart(Game &g) {
     int n = g.hdr[H_NUNITS];
     uint32_t *su = g.w0;
     #pragma unroll 1
-    for (int k = 0; k < MRTS_UNIT_WORDS; k++)
+    for (int k = 0; k < g.uw; k++)
         #pragma unroll 1
         for (int i = g.lane; i < n; i += 32) su[k * g.cap + i] = iu[k * g.cap + i];
     __syncwarp();
@@ -262,7 +266,7 @@ DEV void g_store(Game &g, int32_t *ghdr, uint32_t *gun) {
     int n = g.hdr[H_NUNITS];
     const uint32_t *su = g.w0;
     #pragma unroll 1
-    for (int k = 0; k < MRTS_UNIT_WORDS; k++)
+    for (int k = 0; k < g.uw; k++)
         #pragma unroll 1
         for (int i = g.lane; i < n; i += 32) gun[k * g.cap + i] = su[k * g.cap + i];
     __syncwarp();
@@ -854,7 +858,8 @@ DEV void execute_serial(Game &g, int s, int &ndead) {
                         int nx = u_x(w) + ddx(A1), ny = u_y(w) + ddy(A1);
                         g.w0[n] = (uint32_t)ut | ((uint32_t)pl << 8) | ((uint32_t)nx << 16) | ((uint32_t)ny << 24);
                         g.w1[n] = mk_w1(ut_hp(g, ut), 0);
-                        g.a0[n] = AT_IDLE | A0_NOUT; g.a1[n] = 0; g.tis[n] = 0; g.seq[n] = 0; g.uid[n] = (uint32_t)id; g.x0[n] = 0; g.x1[n] = 0;
+                        g.a0[n] = AT_IDLE | A0_NOUT; g.a1[n] = 0; g.tis[n] = 0; g.seq[n] = 0; g.uid[n] = (uint32_t)id;
+                        if (g.uw > MRTS_UNIT_WORDS_CORE) { g.x0[n] = 0; g.x1[n] = 0; }
                         g.grid[nc] = (uint8_t)(n + 1);
                         g.hdr[H_NUNITS] = n + 1;
                         g.hdr[H_RES0 + pl - 1] = pres - cost;
@@ -875,12 +880,12 @@ DEVN void compact_units(Game &g) {
         int i = base + g.lane;
         bool alive = i < n && !(g.a0[i] & A0_DEAD);
         uint32_t r[MRTS_UNIT_WORDS];
-        if (alive) for (int k = 0; k < MRTS_UNIT_WORDS; k++) r[k] = su[k * g.cap + i];
+        if (alive) for (int k = 0; k < MRTS_UNIT_WORDS; k++) if (k < g.uw) r[k] = su[k * g.cap + i];
         unsigned m = __ballot_sync(FULLM, alive);
         int pos = out + __popc(m & ((1u << g.lane) - 1));
         if (i < n) g.list[i] = alive ? (uint8_t)(pos + 1) : 0; // old slot -> new slot + 1 (0: removed)
         __syncwarp();
-        if (alive) for (int k = 0; k < MRTS_UNIT_WORDS; k++) su[k * g.cap + pos] = r[k];
+        if (alive) for (int k = 0; k < MRTS_UNIT_WORDS; k++) if (k < g.uw) su[k * g.cap + pos] = r[k];
         out += __popc(m);
         __syncwarp();
     }
@@ -888,7 +893,7 @@ DEVN void compact_units(Game &g) {
     __syncwarp();
     // unit references held by abstract actions (X1: attack/harvest target, base) follow their unit or become "dead object"
 #pragma unroll 1
-    for (int i = g.lane; i < out; i += 32) {
+    for (int i = g.lane; i < (g.uw > MRTS_UNIT_WORDS_CORE ? out : 0); i += 32) {
         uint32_t X1 = g.x1[i];
         uint32_t t = X1 & 0xff, b = (X1 >> 8) & 0xff;
         if (t != 0 && t != 0xFF) { t = g.list[t - 1]; if (t == 0) t = 0xFF; }
@@ -1329,7 +1334,8 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
     SmemLayout L = mrts_smem_layout(p.W, p.H, p.cap, p.scripted);
     int warp = tid >> 5, lane = tid & 31, wpc = nthreads >> 5;
     Game g;
-    g_bind(g, smem + MRTS_CONST_WORDS * 4 + (size_t)warp * L.total, L, p.W, p.H, p.cap, lane, cst, p.conflict);
+    g_bind(g, smem + MRTS_CONST_WORDS * 4 + (size_t)warp * L.total, L, p.W, p.H, p.cap, lane, cst, p.conflict, p.scripted,
+           p.scripted == 2 ? p.astar_scratch + ((long long)bid * wpc + warp) * p.astar_stride : nullptr);
     WarpStats ws;
     for (int i = 0; i < 8; i++) ws.v[i] = 0;
     long long n_items = p.mode == MODE_ROLLOUT ? p.n_games * p.rollouts_per_game : p.n_games;
@@ -1339,7 +1345,7 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
         const uint32_t *blob = p.maps + (size_t)(gi % p.n_maps) * p.map_words;
         g.grid_tmpl = blob;
         int32_t *ghdr = p.hdr + gi * MRTS_HDR_WORDS;
-        uint32_t *gun = p.units + gi * (long long)MRTS_UNIT_WORDS * p.cap;
+        uint32_t *gun = p.units + gi * (long long)p.uw * p.cap;
         g_load(g, ghdr, gun);
         int err0 = g.hdr[H_ERR];
         if (p.mode == MODE_GAME) {

@@ -34,6 +34,7 @@ enum {
 
 // per-unit words
 enum { UW_W0 = 0, UW_W1, UW_A0, UW_A1, UW_TIS, UW_SEQ, UW_ID, UW_X0, UW_X1, MRTS_UNIT_WORDS };
+#define MRTS_UNIT_WORDS_CORE 7 // words every kernel keeps in shared memory; X0/X1 only when scripted policies are enabled
 // W0: type | (player+1)<<8 | x<<16 | y<<24            W1: (uint16)hp | (uint16)res<<16
 // A0: atype(4) | flags(4) | utype<<8 | ax<<16 | ay<<24    A1: parameter (direction or NONE duration)
 // TIS: issue time (UnitActionAssignment.time)          SEQ: assignment sequence      ID: Unit.ID (low 32 bits)
@@ -74,7 +75,7 @@ MRTS_HD SmemLayout mrts_smem_layout(int W, int H, int cap, int scripted) {
     int capb = (cap + 15) & ~15;
     int o = 0;
     L.hdr = o; o += MRTS_HDR_WORDS * 4;
-    L.units = o; o += MRTS_UNIT_WORDS * cap * 4;
+    L.units = o; o += (scripted ? MRTS_UNIT_WORDS : MRTS_UNIT_WORDS_CORE) * cap * 4; // X0/X1 are resident only for scripted batches
     L.pa0 = o; o += cap * 4;
     L.pa1 = o; o += cap * 4;
     L.pslot = o; o += capb;
@@ -82,7 +83,7 @@ MRTS_HD SmemLayout mrts_smem_layout(int W, int H, int cap, int scripted) {
     L.resv = o; o += pcb;
     L.claim = o; o += pcb;
     L.list = o; o += capb;
-    L.astar = o; o += scripted ? ((W * H * MRTS_ASTAR_BYTES_PER_CELL + 15) & ~15) : 0;
+    L.astar = o; o += scripted == 1 ? ((W * H * MRTS_ASTAR_BYTES_PER_CELL + 15) & ~15) : 0; // scripted == 2: scratch in global memory
     L.total = (o + 15) & ~15;
     L.pcw = pcb / 4;
     return L;

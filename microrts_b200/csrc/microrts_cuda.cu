@@ -62,7 +62,7 @@ static const char *dev_errstr() { return cudaGetErrorString(g_cuda_last); }
 struct ResetParams {
     int32_t *hdr; uint32_t *units; const uint32_t *maps;
     const long long *seeds; const uint8_t *mask;
-    long long n_games; int n_maps, map_words, cap, pcw;
+    long long n_games; int n_maps, map_words, cap, pcw, uw;
 };
 
 // (re)initialise games from their map's initial state; one warp per game
@@ -74,7 +74,7 @@ DEV void reset_kernel_body(const ResetParams &p, int tid, int nthreads, int bid,
         const int32_t *ih = (const int32_t *)(blob + p.pcw);
         const uint32_t *iu = blob + p.pcw + MRTS_HDR_WORDS;
         int32_t *gh = p.hdr + gi * MRTS_HDR_WORDS;
-        uint32_t *gu = p.units + gi * (long long)MRTS_UNIT_WORDS * p.cap;
+        uint32_t *gu = p.units + gi * (long long)p.uw * p.cap;
         int n = ih[H_NUNITS];
         if (lane < MRTS_HDR_WORDS) {
             int32_t v = ih[lane];
@@ -90,17 +90,17 @@ DEV void reset_kernel_body(const ResetParams &p, int tid, int nthreads, int bid,
             if (lane == H_RNGD_HI) v = (int32_t)(uint32_t)(sd >> 32);
             gh[lane] = v;
         }
-        for (int k = 0; k < MRTS_UNIT_WORDS; k++)
+        for (int k = 0; k < p.uw; k++)
             for (int i = lane; i < n; i += 32) gu[k * p.cap + i] = iu[k * p.cap + i];
     }
 }
 
-struct ResultParams { const int32_t *hdr; const uint32_t *units; int32_t *out; long long n_games; int cap; };
+struct ResultParams { const int32_t *hdr; const uint32_t *units; int32_t *out; long long n_games; int cap, uw; };
 // out[g] = {time, winner, gameover, error bits}; one thread per game (PhysicalGameState.winner/gameover :334-387)
 DEV void results_kernel_body(const ResultParams &p, long long gi) {
     if (gi >= p.n_games) return;
     const int32_t *h = p.hdr + gi * MRTS_HDR_WORDS;
-    const uint32_t *w0 = p.units + gi * (long long)MRTS_UNIT_WORDS * p.cap;
+    const uint32_t *w0 = p.units + gi * (long long)p.uw * p.cap;
     int n = h[H_NUNITS], c0 = 0, c1 = 0;
     for (int i = 0; i < n; i++) { int pl = (w0[i] >> 8) & 0xff; c0 += pl == 1; c1 += pl == 2; }
     int32_t *o = p.out + gi * 4;
@@ -144,11 +144,12 @@ struct mrts_batch {
     int32_t *d_hdr = nullptr; uint32_t *d_units = nullptr; uint32_t *d_maps = nullptr; uint32_t *d_cst = nullptr;
     unsigned long long *d_stats = nullptr;
     void *d_tmp = nullptr; size_t tmp_bytes = 0; // staging for host arguments
+    unsigned char *d_astar = nullptr; long long astar_stride = 0; // pathfinding scratch of large-map scripted batches
     Staged staged[2];
     stream_t stream = nullptr;
     SmemLayout L;
     size_t smem_bytes = 0;
-    int grid = 0, max_range = 0, auto_reset = 0, scripted = 0, wpc = MRTS_WARPS_PER_CTA; // wpc: warps (games in flight) per CTA
+    int grid = 0, max_range = 0, auto_reset = 0, scripted = 0, uw = MRTS_UNIT_WORDS_CORE, wpc = MRTS_WARPS_PER_CTA; // wpc: warps (games in flight) per CTA
     long long launches = 0;
 };
 
@@ -164,7 +165,8 @@ static int launch_step(mrts_batch *b, StepParams &p) {
     p.hdr = b->d_hdr; p.units = b->d_units; p.maps = b->d_maps; p.cst = b->d_cst; p.stats = b->d_stats;
     p.n_games = b->n; p.n_maps = b->n_maps; p.map_words = b->map_words; p.W = b->W; p.H = b->H; p.cap = b->cap;
     p.conflict = b->utt.conflict; p.max_range = b->max_range; p.n_types = (int)b->utt.types.size();
-    p.partial_obs = (b->flags & MRTS_FLAG_PARTIAL_OBS) ? 1 : 0; p.scripted = b->scripted;
+    p.partial_obs = (b->flags & MRTS_FLAG_PARTIAL_OBS) ? 1 : 0; p.scripted = b->scripted; p.uw = b->uw;
+    p.astar_scratch = b->d_astar; p.astar_stride = b->astar_stride;
     int threads = b->wpc * 32;
     long long items = p.mode == MODE_ROLLOUT ? b->n * p.rollouts_per_game : b->n;
     long long need = (items + b->wpc - 1) / b->wpc;
@@ -260,7 +262,7 @@ void mrts_map_destroy(mrts_map *m) { delete m; }
 void mrts_batch_destroy(mrts_batch *b) {
     if (!b) return;
     dev_select(b->device);
-    dev_free(b->d_hdr); dev_free(b->d_units); dev_free(b->d_maps); dev_free(b->d_cst); dev_free(b->d_stats); dev_free(b->d_tmp);
+    dev_free(b->d_hdr); dev_free(b->d_units); dev_free(b->d_maps); dev_free(b->d_cst); dev_free(b->d_stats); dev_free(b->d_tmp); dev_free(b->d_astar);
     for (auto &s : b->staged) { dev_free(s.actions); dev_free(s.counts); }
 #ifndef MRTS_EMU
     if (b->stream) cudaStreamDestroy(b->stream);
@@ -286,7 +288,11 @@ int mrts_batch_create(const mrts_utt *u, const mrts_map *const *maps, int n_maps
     auto b = std::unique_ptr<mrts_batch, void (*)(mrts_batch *)>(new mrts_batch, mrts_batch_destroy);
     b->utt = u->h; b->W = W; b->H = H; b->cap = cap; b->n_maps = n_maps; b->n = n_games; b->flags = flags; b->device = device;
     b->max_range = u->h.maxAttackRange();
+    // scripted batches keep the pathfinding scratch in shared memory while a game's whole region stays small enough for
+    // several games per SM; larger maps move it to a per-warp global scratch (L1/L2 resident)
     b->scripted = (flags & MRTS_FLAG_SCRIPTED_AI) ? 1 : 0;
+    if (b->scripted && mrts_smem_layout(W, H, cap, 1).total > 48 * 1024) b->scripted = 2;
+    b->uw = b->scripted ? MRTS_UNIT_WORDS : MRTS_UNIT_WORDS_CORE;
     b->L = mrts_smem_layout(W, H, cap, b->scripted);
     b->map_words = mrts_map_blob_words(W, H, cap);
     if (dev_select(device)) return fail(MRTS_E_CUDA, std::string("cannot select CUDA device: ") + dev_errstr());
@@ -314,7 +320,11 @@ int mrts_batch_create(const mrts_utt *u, const mrts_map *const *maps, int n_maps
     b->smem_bytes = MRTS_CONST_WORDS * 4 + (size_t)b->wpc * b->L.total;
     b->grid = 3;
 #endif
-    size_t hdr_bytes = (size_t)n_games * MRTS_HDR_WORDS * 4, unit_bytes = (size_t)n_games * MRTS_UNIT_WORDS * cap * 4;
+    if (b->scripted == 2) {
+        b->astar_stride = ((long long)W * H * MRTS_ASTAR_BYTES_PER_CELL + 255) & ~255LL;
+        if (dev_alloc((void **)&b->d_astar, (size_t)b->grid * b->wpc * b->astar_stride)) return fail(MRTS_E_CUDA, std::string("device allocation failed: ") + dev_errstr());
+    }
+    size_t hdr_bytes = (size_t)n_games * MRTS_HDR_WORDS * 4, unit_bytes = (size_t)n_games * b->uw * cap * 4;
     if (dev_alloc((void **)&b->d_hdr, hdr_bytes) || dev_alloc((void **)&b->d_units, unit_bytes) ||
         dev_alloc((void **)&b->d_maps, (size_t)n_maps * b->map_words * 4) || dev_alloc((void **)&b->d_cst, MRTS_CONST_WORDS * 4) ||
         dev_alloc((void **)&b->d_stats, 8 * sizeof(unsigned long long)))
@@ -351,7 +361,7 @@ static int do_reset(mrts_batch *b, const uint8_t *mask, const int64_t *seeds, in
         if (seeds) { if (dev_h2d(b->d_tmp, seeds, sb, b->stream)) return fail(MRTS_E_CUDA, dev_errstr()); d_seeds = (const long long *)b->d_tmp; }
         if (mask) { if (dev_h2d((char *)b->d_tmp + sb, mask, mb, b->stream)) return fail(MRTS_E_CUDA, dev_errstr()); d_mask = (const uint8_t *)b->d_tmp + sb; }
     }
-    ResetParams p{b->d_hdr, b->d_units, b->d_maps, d_seeds, d_mask, b->n, b->n_maps, b->map_words, b->cap, b->L.pcw};
+    ResetParams p{b->d_hdr, b->d_units, b->d_maps, d_seeds, d_mask, b->n, b->n_maps, b->map_words, b->cap, b->L.pcw, b->uw};
     b->launches++;
     if (!mask) { if (dev_zero(b->d_stats, 8 * sizeof(unsigned long long), b->stream)) return fail(MRTS_E_CUDA, dev_errstr()); }
     b->staged[0].valid = b->staged[1].valid = false;
@@ -506,7 +516,7 @@ int mrts_batch_results(mrts_batch *b, int32_t *out, int on_device) {
     if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
     int32_t *d_out = out;
     if (!on_device) { if (ensure_tmp(b, (size_t)b->n * 16)) return fail(MRTS_E_CUDA, dev_errstr()); d_out = (int32_t *)b->d_tmp; }
-    ResultParams p{b->d_hdr, b->d_units, d_out, b->n, b->cap};
+    ResultParams p{b->d_hdr, b->d_units, d_out, b->n, b->cap, b->uw};
     b->launches++;
 #ifdef MRTS_EMU
     for (long long g = 0; g < b->n; g++) results_kernel_body(p, g);
@@ -531,13 +541,13 @@ int mrts_batch_export(mrts_batch *b, int64_t first, int64_t count, mrts_state_ho
     if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
     int cap = b->cap;
     std::vector<int32_t> hdr((size_t)count * MRTS_HDR_WORDS);
-    std::vector<uint32_t> un((size_t)count * MRTS_UNIT_WORDS * cap);
+    std::vector<uint32_t> un((size_t)count * b->uw * cap);
     if (count && (dev_d2h(hdr.data(), b->d_hdr + first * MRTS_HDR_WORDS, hdr.size() * 4, b->stream) ||
-                  dev_d2h(un.data(), b->d_units + first * (long long)MRTS_UNIT_WORDS * cap, un.size() * 4, b->stream)))
+                  dev_d2h(un.data(), b->d_units + first * (long long)b->uw * cap, un.size() * 4, b->stream)))
         return fail(MRTS_E_CUDA, dev_errstr());
     for (int64_t g = 0; g < count; g++) {
         const int32_t *h = &hdr[g * MRTS_HDR_WORDS];
-        const uint32_t *u = &un[g * (size_t)MRTS_UNIT_WORDS * cap];
+        const uint32_t *u = &un[g * (size_t)b->uw * cap];
         int n = h[H_NUNITS], c0 = 0, c1 = 0;
         for (int i = 0; i < n; i++) { int pl = (u[UW_W0 * cap + i] >> 8) & 0xff; c0 += pl == 1; c1 += pl == 2; }
         if (out->header) {
@@ -578,10 +588,10 @@ int mrts_batch_import(mrts_batch *b, int64_t first, int64_t count, const mrts_st
     if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
     int cap = b->cap;
     std::vector<int32_t> hdr((size_t)count * MRTS_HDR_WORDS, 0);
-    std::vector<uint32_t> un((size_t)count * MRTS_UNIT_WORDS * cap, 0);
+    std::vector<uint32_t> un((size_t)count * b->uw * cap, 0);
     for (int64_t g = 0; g < count; g++) {
         int32_t *h = &hdr[g * MRTS_HDR_WORDS];
-        uint32_t *u = &un[g * (size_t)MRTS_UNIT_WORDS * cap];
+        uint32_t *u = &un[g * (size_t)b->uw * cap];
         const int32_t *ih = in->header + g * 8;
         int n = ih[3];
         if (n < 0 || n > cap) return fail(MRTS_E_LIMIT, "mrts_batch_import: more units than the batch capacity");
@@ -613,7 +623,7 @@ int mrts_batch_import(mrts_batch *b, int64_t first, int64_t count, const mrts_st
         }
     }
     if (count && (dev_h2d(b->d_hdr + first * MRTS_HDR_WORDS, hdr.data(), hdr.size() * 4, b->stream) ||
-                  dev_h2d(b->d_units + first * (long long)MRTS_UNIT_WORDS * cap, un.data(), un.size() * 4, b->stream) || dev_sync(b->stream)))
+                  dev_h2d(b->d_units + first * (long long)b->uw * cap, un.data(), un.size() * 4, b->stream) || dev_sync(b->stream)))
         return fail(MRTS_E_CUDA, dev_errstr());
     return MRTS_OK;
 }
