@@ -5,7 +5,7 @@ Workload (N=1): maps/16x16/basesWorkers16x16.xml, 65536 parallel games per GPU, 
 UnitTypeTable v1 + CANCEL_BOTH, 3000-cycle cap, fully observable.  One "step" advances every game by
 --cycles-per-step cycles (Game.start loop body: policy x2, issueSafe x2, cycle) in ONE launch of the step kernel;
 finished games restart on the device (auto-reset), so every timed window is a stationary mix of game phases.
-With the defaults (30 steps x 100 cycles) the timed window covers exactly one full 3000-cycle game per slot.
+With the defaults (150 steps x 100 cycles) the timed window covers five full 3000-cycle games per slot.
 
   value     : game-cycles/s with the state resident in HBM (inputs larger than L2: 65536 x 3.6 KB = 239 MB).
   e2e       : same metric through the public API with HOST buffers every step: H2D of the restart mask + seeds from
@@ -42,7 +42,7 @@ def workload_string(args):
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=150)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--games", type=int, default=65536, help="games per GPU")
@@ -120,22 +120,62 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region: an NVML polling thread (10 ms period), with the
+    recipe's `nvidia-smi -lms` line as the fallback when NVML cannot be loaded."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.rows, self.p, self.index = [], None, index
+        self.index, self.p, self.thread, self.stop_flag = index, None, None, False
+        self.sm, self.mx, self.reasons = [], None, set()
+
+    def _visible_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
+
+    def _poll(self, nv, h):
+        bits = [(nv.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"), (nv.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"), (nv.nvmlClocksEventReasonSwPowerCap, "sw_power_cap")]
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for bit, name in bits:
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self._visible_index())
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self._visible_index()), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
 
     def stop(self):
+        if self.thread:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            sm = sorted(self.sm)
+            return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=self.mx, samples=len(sm), reasons=sorted(self.reasons), source="nvml")
         if not self.p:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+            return dict(sm_mhz=None, sm_max_mhz=None, samples=0, reasons=["nvidia-smi unavailable"])
         self.p.terminate()
         try:
             out = self.p.communicate(timeout=5)[0]
@@ -155,7 +195,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         sm.sort()
-        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx, samples=len(sm), reasons=sorted(reasons))
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx, samples=len(sm), reasons=sorted(reasons), source="nvidia-smi")
 
 
 def run_ours(args):

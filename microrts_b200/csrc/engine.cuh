@@ -17,8 +17,10 @@
 #ifdef MRTS_EMU
 #define DEV static inline
 #define DEVN static
+#define MDEV inline
 #else
 #define DEV __device__ __forceinline__
+#define MDEV __device__ __forceinline__
 #ifdef MRTS_INLINE_ALL
 #define DEVN __device__ __forceinline__
 #else
@@ -75,37 +77,58 @@ struct StepParams {
     int32_t *ro_time;          // [n_games * rollouts_per_game] simulated cycles
 };
 
+// The CTA's dynamic shared memory.  Every accessor below derives its address from this symbol, so the compiler knows the
+// address space (LDS/STS with 32-bit addressing) even inside functions that are not inlined.
+#ifdef MRTS_EMU
+static thread_local unsigned char *mrts_smem = nullptr;
+#else
+extern __shared__ __align__(16) unsigned char mrts_smem[];
+#endif
+
 struct Game {
     int lane;
-    int W, H, P, cap, pcw, conflict, uw; // uw: unit words resident in shared memory (7, or 9 with scripted policies)
-    int32_t *hdr;
-    uint32_t *w0, *w1, *a0;
-    int32_t *a1, *tis;
-    uint32_t *seq, *uid, *x0, *x1;
-    uint32_t *pa0;
-    int32_t *pa1;
-    uint8_t *pslot, *grid, *resv, *claim, *list;
-    const uint32_t *utt;        // shared memory copy
-    const uint64_t *jump;       // shared memory copy
-    const uint32_t *grid_tmpl;  // global: wall-padded empty grid of this game's map
+    int W, H, P, cap, pcw, conflict, uw; // uw: unit words mirrored in HBM (7, or 9 with scripted policies)
+    int sb;                               // byte offset of this game's region inside the CTA's shared memory
+    int o_pa0, o_pa1, o_pslot, o_grid, o_kind, o_resv, o_claim, o_list;
+    int pview;                            // window into the pending list (policy_scripted stages desires behind the final part)
+    const uint32_t *grid_tmpl;            // global: wall-padded empty grid of this game's map
     uint16_t *as_closed, *as_cost, *as_opos, *as_opar, *as_of; // A* scratch over W*H cells (scripted batches only)
     uint8_t *as_flags;
+
+    MDEV unsigned char *base() const { return mrts_smem + sb; }
+    MDEV int32_t *hdr() const { return (int32_t *)base(); }
+    MDEV uint32_t *uword(int k) const { return (uint32_t *)(base() + MRTS_HDR_WORDS * 4) + k * cap; }
+    MDEV uint32_t *w0() const { return uword(UW_W0); }
+    MDEV uint32_t *w1() const { return uword(UW_W1); }
+    MDEV uint32_t *a0() const { return uword(UW_A0); }
+    MDEV int32_t *a1() const { return (int32_t *)uword(UW_A1); }
+    MDEV int32_t *tis() const { return (int32_t *)uword(UW_TIS); }
+    MDEV uint32_t *seq() const { return uword(UW_SEQ); }
+    MDEV uint32_t *uid() const { return uword(UW_ID); }
+    MDEV uint32_t *x0() const { return uword(UW_X0); }
+    MDEV uint32_t *x1() const { return uword(UW_X1); }
+    MDEV int32_t *rdy() const { return (int32_t *)uword(uw); } // shared memory only: completion time, MRTS_NEVER when idle
+    MDEV uint32_t *pa0() const { return (uint32_t *)(base() + o_pa0) + pview; }
+    MDEV int32_t *pa1() const { return (int32_t *)(base() + o_pa1) + pview; }
+    MDEV uint8_t *pslot() const { return base() + o_pslot + pview; }
+    MDEV uint8_t *grid() const { return base() + o_grid; }
+    MDEV uint8_t *kind() const { return base() + o_kind; }
+    MDEV uint8_t *resv() const { return base() + o_resv; }
+    MDEV uint8_t *claim() const { return base() + o_claim; }
+    MDEV uint8_t *list() const { return base() + o_list; }
+    MDEV const uint32_t *utt() const { return (const uint32_t *)mrts_smem; }
+    MDEV const uint64_t *jump() const { return (const uint64_t *)(mrts_smem + MRTS_MAX_TYPES * MRTS_UTT_WORDS * 4); }
 };
 
-DEV void g_bind(Game &g, unsigned char *sm, const SmemLayout &L, int W, int H, int cap, int lane, const uint32_t *cst_sm,
-                int conflict, int scripted, unsigned char *astar_global) {
+DEV void g_bind(Game &g, int sb, const SmemLayout &L, int W, int H, int cap, int lane, int conflict, int scripted,
+                unsigned char *astar_global) {
     g.lane = lane; g.W = W; g.H = H; g.P = W + 2; g.cap = cap; g.pcw = L.pcw; g.conflict = conflict;
     g.uw = scripted ? MRTS_UNIT_WORDS : MRTS_UNIT_WORDS_CORE;
-    g.hdr = (int32_t *)(sm + L.hdr);
-    uint32_t *u = (uint32_t *)(sm + L.units);
-    g.w0 = u + UW_W0 * cap; g.w1 = u + UW_W1 * cap; g.a0 = u + UW_A0 * cap; g.a1 = (int32_t *)(u + UW_A1 * cap);
-    g.tis = (int32_t *)(u + UW_TIS * cap); g.seq = u + UW_SEQ * cap; g.uid = u + UW_ID * cap;
-    g.x0 = u + UW_X0 * cap; g.x1 = u + UW_X1 * cap;
-    { int cells = W * H; g.as_closed = (uint16_t *)(astar_global ? astar_global : sm + L.astar); g.as_cost = g.as_closed + cells; g.as_opos = g.as_cost + cells;
-      g.as_opar = g.as_opos + cells; g.as_of = g.as_opar + cells; g.as_flags = (uint8_t *)(g.as_of + cells); }
-    g.pa0 = (uint32_t *)(sm + L.pa0); g.pa1 = (int32_t *)(sm + L.pa1); g.pslot = sm + L.pslot;
-    g.grid = sm + L.grid; g.resv = sm + L.resv; g.claim = sm + L.claim; g.list = sm + L.list;
-    g.utt = cst_sm; g.jump = (const uint64_t *)(cst_sm + MRTS_MAX_TYPES * MRTS_UTT_WORDS);
+    g.sb = sb; g.pview = 0;
+    g.o_pa0 = L.pa0; g.o_pa1 = L.pa1; g.o_pslot = L.pslot; g.o_grid = L.grid; g.o_kind = L.kind; g.o_resv = L.resv;
+    g.o_claim = L.claim; g.o_list = L.list;
+    { int cells = W * H; g.as_closed = (uint16_t *)(astar_global ? astar_global : mrts_smem + sb + L.astar); g.as_cost = g.as_closed + cells;
+      g.as_opos = g.as_cost + cells; g.as_opar = g.as_opos + cells; g.as_of = g.as_opar + cells; g.as_flags = (uint8_t *)(g.as_of + cells); }
     g.grid_tmpl = nullptr;
 }
 
@@ -118,16 +141,16 @@ DEV int cell_of(const Game &g, uint32_t w) { return (u_y(w) + 1) * g.P + u_x(w) 
 DEV int doff(const Game &g, int d) { return d == 0 ? -g.P : (d == 1 ? 1 : (d == 2 ? g.P : -1)); } // UnitAction.java:94,100
 DEV int ddx(int d) { return d == 1 ? 1 : (d == 3 ? -1 : 0); }
 DEV int ddy(int d) { return d == 0 ? -1 : (d == 2 ? 1 : 0); }
-DEV int ut_cost(const Game &g, int t) { return g.utt[t * 8] & 0xff; }
-DEV int ut_hp(const Game &g, int t) { return (g.utt[t * 8] >> 8) & 0xff; }
-DEV int ut_mind(const Game &g, int t) { return (g.utt[t * 8] >> 16) & 0xff; }
-DEV int ut_maxd(const Game &g, int t) { return g.utt[t * 8] >> 24; }
-DEV int ut_range(const Game &g, int t) { return g.utt[t * 8 + 1] & 0xff; }
-DEV int ut_sight(const Game &g, int t) { return (g.utt[t * 8 + 1] >> 8) & 0xff; }
-DEV int ut_hamt(const Game &g, int t) { return (g.utt[t * 8 + 1] >> 16) & 0xff; }
-DEV int ut_flags(const Game &g, int t) { return g.utt[t * 8 + 1] >> 24; }
-DEV int ut_nprod(const Game &g, int t) { return (g.utt[t * 8 + 4] >> 16) & 0xff; }
-DEV int ut_prod(const Game &g, int t, int k) { return (g.utt[t * 8 + 5 + (k >> 2)] >> ((k & 3) * 8)) & 0xff; }
+DEV int ut_cost(const Game &g, int t) { return g.utt()[t * 8] & 0xff; }
+DEV int ut_hp(const Game &g, int t) { return (g.utt()[t * 8] >> 8) & 0xff; }
+DEV int ut_mind(const Game &g, int t) { return (g.utt()[t * 8] >> 16) & 0xff; }
+DEV int ut_maxd(const Game &g, int t) { return g.utt()[t * 8] >> 24; }
+DEV int ut_range(const Game &g, int t) { return g.utt()[t * 8 + 1] & 0xff; }
+DEV int ut_sight(const Game &g, int t) { return (g.utt()[t * 8 + 1] >> 8) & 0xff; }
+DEV int ut_hamt(const Game &g, int t) { return (g.utt()[t * 8 + 1] >> 16) & 0xff; }
+DEV int ut_flags(const Game &g, int t) { return g.utt()[t * 8 + 1] >> 24; }
+DEV int ut_nprod(const Game &g, int t) { return (g.utt()[t * 8 + 4] >> 16) & 0xff; }
+DEV int ut_prod(const Game &g, int t, int k) { return (g.utt()[t * 8 + 5 + (k >> 2)] >> ((k & 3) * 8)) & 0xff; }
 DEV int a_type(uint32_t A0) { return A0 & 0xF; }
 DEV int a_utype(uint32_t A0) { return (A0 >> 8) & 0xff; }
 DEV bool a_uses_cell(int at) { return at == ACT_MOVE || at == ACT_PRODUCE; }
@@ -154,10 +177,10 @@ DEV int eta_of(const Game &g, int t, uint32_t A0, int A1) {
     switch (a_type(A0)) {
         case ACT_NONE: return A1;
         case ACT_MOVE:
-        case ACT_RETURN: return (int)(g.utt[t * 8 + 2] >> 16);
-        case ACT_ATTACK: return (int)(g.utt[t * 8 + 3] & 0xffff);
-        case ACT_HARVEST: return (int)(g.utt[t * 8 + 3] >> 16);
-        case ACT_PRODUCE: { int ut = a_utype(A0); return ut < MRTS_MAX_TYPES ? (int)(g.utt[ut * 8 + 2] & 0xffff) : 0; }
+        case ACT_RETURN: return (int)(g.utt()[t * 8 + 2] >> 16);
+        case ACT_ATTACK: return (int)(g.utt()[t * 8 + 3] & 0xffff);
+        case ACT_HARVEST: return (int)(g.utt()[t * 8 + 3] >> 16);
+        case ACT_PRODUCE: { int ut = a_utype(A0); return ut < MRTS_MAX_TYPES ? (int)(g.utt()[ut * 8 + 2] & 0xffff) : 0; }
     }
     return 0;
 }
@@ -179,8 +202,8 @@ DEV int linear_target_cell(const Game &g, uint32_t w, int A1) {
 DEV uint64_t lcg_next(uint64_t s) { return (s * 0x5DEECE66DULL + 0xBULL) & MASK48; }
 DEV uint64_t lcg_jump(const Game &g, uint64_t s, int draws) { // advance by `draws` nextDouble() calls (2 steps each)
     #pragma unroll 1
-    while (draws > 64) { s = (s * g.jump[128] + g.jump[129]) & MASK48; draws -= 64; }
-    return (s * g.jump[2 * draws] + g.jump[2 * draws + 1]) & MASK48;
+    while (draws > 64) { s = (s * g.jump()[128] + g.jump()[129]) & MASK48; draws -= 64; }
+    return (s * g.jump()[2 * draws] + g.jump()[2 * draws + 1]) & MASK48;
 }
 DEV double lcg_next_double(uint64_t &s) { // ((long)next(26) << 27) + next(27)) * 2^-53
     s = lcg_next(s); long long a = (long long)(s >> 22);
@@ -200,71 +223,76 @@ DEV int lcg_next_int_bound(uint64_t &s, int bound) { // Random.nextInt(bound)
     }
     return r;
 }
-DEV uint64_t hdr_rng(const Game &g, int lo) { return (uint64_t)(uint32_t)g.hdr[lo] | ((uint64_t)(uint32_t)g.hdr[lo + 1] << 32); }
-DEV void hdr_set_rng(Game &g, int lo, uint64_t s) { g.hdr[lo] = (int32_t)(uint32_t)s; g.hdr[lo + 1] = (int32_t)(uint32_t)(s >> 32); }
+DEV uint64_t hdr_rng(const Game &g, int lo) { return (uint64_t)(uint32_t)g.hdr()[lo] | ((uint64_t)(uint32_t)g.hdr()[lo + 1] << 32); }
+DEV void hdr_set_rng(Game &g, int lo, uint64_t s) { g.hdr()[lo] = (int32_t)(uint32_t)s; g.hdr()[lo + 1] = (int32_t)(uint32_t)(s >> 32); }
 
 // ---- load / store ------------------------------------------------------------------------------------------------------
-// scatter units into grid/resv (maps must hold only walls / zeros)
-DEV void g_scatter(Game &g) {
-    int n = g.hdr[H_NUNITS];
-    #pragma unroll 1
-    for (int i = g.lane; i < n; i += 32) {
-        uint32_t w = g.w0[i];
-        int c = cell_of(g, w);
-        g.grid[c] = (uint8_t)(i + 1);
-        uint32_t A0 = g.a0[i];
-        if (a_uses_cell(a_type(A0))) g.resv[target_cell(g, c, g.a1[i])] = (uint8_t)(i + 1);
-    }
-    __syncwarp();
+DEV int kind_of(const Game &g, uint32_t w) { // the cell-kind byte of a unit (layout.h)
+    int fl = ut_flags(g, u_type(w));
+    return CK_UNIT | u_pl(w) | ((fl & UF_RESOURCE) ? 4 : 0) | ((fl & UF_STOCKPILE) ? 8 : 0);
 }
-DEV void g_reset_maps(Game &g) {
+// Rebuild the cell maps from the unit table: grid (slot+1), kind, resv (in-flight MOVE/PRODUCE targets); claim cleared.
+// with_rdy: also recompute the completion times (after a load; compaction carries them along instead).
+DEV void g_rebuild(Game &g, bool with_rdy) {
+    __syncwarp();
     #pragma unroll 1
     for (int i = g.lane; i < g.pcw; i += 32) {
-        ((uint32_t *)g.grid)[i] = g.grid_tmpl[i];
-        ((uint32_t *)g.resv)[i] = 0;
-        ((uint32_t *)g.claim)[i] = 0;
+        uint32_t t = g.grid_tmpl[i];
+        ((uint32_t *)g.grid())[i] = t;
+        ((uint32_t *)g.kind())[i] = t;
+        ((uint32_t *)g.resv())[i] = 0;
+        ((uint32_t *)g.claim())[i] = 0;
+    }
+    __syncwarp();
+    int n = g.hdr()[H_NUNITS];
+    #pragma unroll 1
+    for (int i = g.lane; i < n; i += 32) {
+        uint32_t w = g.w0()[i];
+        int c = cell_of(g, w);
+        g.grid()[c] = (uint8_t)(i + 1);
+        g.kind()[c] = (uint8_t)kind_of(g, w);
+        uint32_t A0 = g.a0()[i];
+        int A1 = g.a1()[i];
+        if (a_uses_cell(a_type(A0))) g.resv()[target_cell(g, c, A1)] = (uint8_t)(i + 1);
+        if (with_rdy) g.rdy()[i] = a_type(A0) == (int)AT_IDLE ? MRTS_NEVER : g.tis()[i] + eta_of(g, u_type(w), A0, A1);
     }
     __syncwarp();
 }
-DEV void g_load(Game &g, const int32_t *ghdr, const uint32_t *gun) {
-    if (g.lane < MRTS_HDR_WORDS) g.hdr[g.lane] = ghdr[g.lane];
-    g_reset_maps(g);
-    int n = g.hdr[H_NUNITS];
-    uint32_t *su = g.w0;
-    #pragma unroll 1
-    for (int k = 0; k < g.uw; k++)
-        #pragma unroll 1
-        for (int i = g.lane; i < n; i += 32) su[k * g.cap + i] = gun[k * g.cap + i];
+// Load the game from HBM; when `restart_if_over` and the game ended in an earlier step (game over, or time >= max_cycles),
+// start it again from the map's initial state instead (the blob's init header/units): the three RNG streams keep running,
+// as the reference's static Random objects do across games, and H_SPARE counts episodes.
+DEV void g_load(Game &g, const int32_t *ghdr, const uint32_t *gun, bool restart_if_over, int max_cycles) {
     __syncwarp();
-    g_scatter(g);
-}
-// restart from the map's initial state (the blob's init header/units); the three RNG streams keep running, as the
-// reference's static Random objects do across games.  H_SPARE counts episodes.
-DEV void g_restart(Game &g) {
-    const int32_t *ih = (const int32_t *)(g.grid_tmpl + g.pcw);
-    const uint32_t *iu = g.grid_tmpl + g.pcw + MRTS_HDR_WORDS;
-    __syncwarp();
-    if (g.lane < MRTS_HDR_WORDS) {
-        int32_t v = ih[g.lane];
-        if (g.lane >= H_RNGP_LO && g.lane <= H_RNGD_HI) v = g.hdr[g.lane];
-        if (g.lane == H_SPARE) v = g.hdr[H_SPARE] + 1;
-        g.hdr[g.lane] = v;
+    int32_t v = 0;
+    if (g.lane < MRTS_HDR_WORDS) v = ghdr[g.lane];
+    bool restart = false;
+    if (restart_if_over) {
+        int st = __shfl_sync(FULLM, v, H_STATUS), tm = __shfl_sync(FULLM, v, H_TIME);
+        restart = (st & ST_OVER) || tm >= max_cycles;
     }
-    g_reset_maps(g);
-    int n = g.hdr[H_NUNITS];
-    uint32_t *su = g.w0;
+    const uint32_t *src = gun;
+    if (restart) {
+        src = g.grid_tmpl + g.pcw + MRTS_HDR_WORDS;
+        if (g.lane < MRTS_HDR_WORDS) {
+            int32_t iv = ((const int32_t *)(g.grid_tmpl + g.pcw))[g.lane];
+            if (g.lane == H_SPARE) iv = v + 1;
+            if (!(g.lane >= H_RNGP_LO && g.lane <= H_RNGD_HI)) v = iv;
+        }
+    }
+    if (g.lane < MRTS_HDR_WORDS) g.hdr()[g.lane] = v;
+    int n = __shfl_sync(FULLM, v, H_NUNITS);
+    uint32_t *su = g.w0();
     #pragma unroll 1
     for (int k = 0; k < g.uw; k++)
         #pragma unroll 1
-        for (int i = g.lane; i < n; i += 32) su[k * g.cap + i] = iu[k * g.cap + i];
-    __syncwarp();
-    g_scatter(g);
+        for (int i = g.lane; i < n; i += 32) su[k * g.cap + i] = src[k * g.cap + i];
+    g_rebuild(g, true);
 }
 DEV void g_store(Game &g, int32_t *ghdr, uint32_t *gun) {
     __syncwarp();
-    if (g.lane < MRTS_HDR_WORDS) ghdr[g.lane] = g.hdr[g.lane];
-    int n = g.hdr[H_NUNITS];
-    const uint32_t *su = g.w0;
+    if (g.lane < MRTS_HDR_WORDS) ghdr[g.lane] = g.hdr()[g.lane];
+    int n = g.hdr()[H_NUNITS];
+    const uint32_t *su = g.w0();
     #pragma unroll 1
     for (int k = 0; k < g.uw; k++)
         #pragma unroll 1
@@ -288,21 +316,21 @@ DEV bool enemy_in_range(const Game &g, uint32_t me, uint32_t ow, int sq) {
 }
 
 DEV void enumerate(const Game &g, int s, Enum &e) {
-    uint32_t w = g.w0[s];
+    uint32_t w = g.w0()[s];
     e.w = w; e.t = u_type(w); e.pl = u_pl(w); e.c = cell_of(g, w);
     e.fl = ut_flags(g, e.t); e.range = ut_range(g, e.t);
-    int myres = u_res(g.w1[s]);
+    int myres = u_res(g.w1()[s]);
     int free_m = 0, atk_m = 0, harv_m = 0, ret_m = 0;
-#pragma unroll 1
-    for (int d = 0; d < 4; d++) { // kept rolled: the hot loop is instruction-fetch bound, code size matters more than ILP
-        int gv = g.grid[e.c + doff(g, d)];
-        if (gv == 0) free_m |= 1 << d;
-        else if (gv != 0xFF) {
-            uint32_t nw = g.w0[gv - 1];
-            int npl = u_pl(nw), nfl = ut_flags(g, u_type(nw));
+    const uint8_t *kind = g.kind() + e.c;
+#pragma unroll
+    for (int d = 0; d < 4; d++) { // four independent byte loads of the cell-kind map (no unit table access)
+        int kv = kind[doff(g, d)];
+        if (kv == 0) free_m |= 1 << d;
+        else if (kv != 0xFF) {
+            int npl = kv & 3;
             if (npl != 0 && npl != e.pl) atk_m |= 1 << d;
-            if (nfl & UF_RESOURCE) harv_m |= 1 << d;
-            if ((nfl & UF_STOCKPILE) && npl == e.pl) ret_m |= 1 << d;
+            if (kv & 4) harv_m |= 1 << d;
+            if ((kv & 8) && npl == e.pl) ret_m |= 1 << d;
         }
     }
     if (!(e.fl & UF_ATTACK) || e.range != 1) atk_m = 0;
@@ -310,14 +338,14 @@ DEV void enumerate(const Game &g, int s, Enum &e) {
     else { if (myres != 0) harv_m = 0; if (!(myres > 0)) ret_m = 0; }
     int n_atk = __popc(atk_m);
     if ((e.fl & UF_ATTACK) && e.range > 1) { // every enemy within range, in unit-list order (Unit.java:424-436)
-        int n = g.hdr[H_NUNITS], sq = e.range * e.range;
+        int n = g.hdr()[H_NUNITS], sq = e.range * e.range;
         n_atk = 0;
         #pragma unroll 1
-        for (int i = 0; i < n; i++) n_atk += enemy_in_range(g, w, g.w0[i], sq) ? 1 : 0;
+        for (int i = 0; i < n; i++) n_atk += enemy_in_range(g, w, g.w0()[i], sq) ? 1 : 0;
     }
     int aff_m = 0;
     if (e.pl != 0) {
-        int pres = g.hdr[H_RES0 + e.pl - 1], np = ut_nprod(g, e.t);
+        int pres = g.hdr()[H_RES0 + e.pl - 1], np = ut_nprod(g, e.t);
         #pragma unroll 1
         for (int k = 0; k < np; k++) if (pres >= ut_cost(g, ut_prod(g, e.t, k))) aff_m |= 1 << k;
     }
@@ -335,10 +363,10 @@ DEV void pick_action(const Game &g, const Enum &e, int idx, int none_duration, u
         int ax, ay;
         if (e.range == 1) { int d = nth4(e.atk_m, idx); ax = x + ddx(d); ay = y + ddy(d); }
         else {
-            int n = g.hdr[H_NUNITS], sq = e.range * e.range; ax = x; ay = y;
+            int n = g.hdr()[H_NUNITS], sq = e.range * e.range; ax = x; ay = y;
             #pragma unroll 1
             for (int i = 0; i < n; i++) {
-                uint32_t ow = g.w0[i];
+                uint32_t ow = g.w0()[i];
                 if (enemy_in_range(g, e.w, ow, sq)) { if (idx == 0) { ax = u_x(ow); ay = u_y(ow); break; } idx--; }
             }
         }
@@ -392,9 +420,9 @@ DEV bool action_is_legal(const Game &g, int s, uint32_t A0, int A1) {
             if (!(e.fl & UF_ATTACK)) return false;
             int ax = (A0 >> 16) & 0xff, ay = A0 >> 24;
             if (ax >= g.W || ay >= g.H) return false;
-            int gv = g.grid[(ay + 1) * g.P + ax + 1];
+            int gv = g.grid()[(ay + 1) * g.P + ax + 1];
             if (gv == 0 || gv == 0xFF) return false;
-            return enemy_in_range(g, e.w, g.w0[gv - 1], e.range * e.range);
+            return enemy_in_range(g, e.w, g.w0()[gv - 1], e.range * e.range);
         }
     }
     return false;
@@ -402,11 +430,11 @@ DEV bool action_is_legal(const Game &g, int s, uint32_t A0, int A1) {
 
 // sum of in-flight PRODUCE costs per player == resourcesUsed of GameState.getResourceUsage (GameState.java:652-664)
 DEV void reserved_resources(const Game &g, int &r0, int &r1) {
-    int n = g.hdr[H_NUNITS], a = 0, b = 0;
+    int n = g.hdr()[H_NUNITS], a = 0, b = 0;
     #pragma unroll 1
     for (int i = g.lane; i < n; i += 32) {
-        uint32_t A0 = g.a0[i];
-        if (a_type(A0) == ACT_PRODUCE) { int c = ut_cost(g, a_utype(A0)); if (u_pl(g.w0[i]) == 1) a += c; else b += c; }
+        uint32_t A0 = g.a0()[i];
+        if (a_type(A0) == ACT_PRODUCE) { int c = ut_cost(g, a_utype(A0)); if (u_pl(g.w0()[i]) == 1) a += c; else b += c; }
     }
     r0 = __reduce_add_sync(FULLM, a); r1 = __reduce_add_sync(FULLM, b);
 }
@@ -415,8 +443,8 @@ DEV void reserved_resources(const Game &g, int &r0, int &r1) {
 // other = the accumulated usage par[2]
 DEV bool res_consistent_cand_vs_acc(const Game &g, int pl, int cost, int par0, int par1) {
     int s0 = (pl == 1 ? cost : 0) + par0, s1 = (pl == 2 ? cost : 0) + par1;
-    if (par0 != 0 && s0 > 0 && s0 > g.hdr[H_RES0]) return false;
-    if (par1 != 0 && s1 > 0 && s1 > g.hdr[H_RES1]) return false;
+    if (par0 != 0 && s0 > 0 && s0 > g.hdr()[H_RES0]) return false;
+    if (par1 != 0 && s1 > 0 && s1 > g.hdr()[H_RES1]) return false;
     return true;
 }
 
@@ -428,16 +456,16 @@ DEV bool accept_in_order(Game &g, int player, int cnt, int tcell, int cost, bool
     // consistentWith is the same for every lane, and verdicts only interact when two lanes want the same cell (the
     // first in lane order wins; if the first is refused because the cell is taken, so are the others).
     if (__ballot_sync(FULLM, candidate && cost != 0) == 0) {
-        bool over = (par0 > 0 && par0 > g.hdr[H_RES0]) || (par1 > 0 && par1 > g.hdr[H_RES1]);
+        bool over = (par0 > 0 && par0 > g.hdr()[H_RES0]) || (par1 > 0 && par1 > g.hdr()[H_RES1]);
         bool ok = candidate && !over;
         int key = (ok && tcell >= 0) ? tcell : -1 - g.lane;
         unsigned same = __match_any_sync(FULLM, key);
         if (ok && tcell >= 0) {
-            if (g.resv[tcell] != 0 || ((g.claim[tcell] >> player) & 1)) ok = false;
+            if (g.resv()[tcell] != 0 || ((g.claim()[tcell] >> player) & 1)) ok = false;
             else if (same & ((1u << g.lane) - 1)) ok = false;
         }
         __syncwarp(); // all lanes have read claim[] before it is updated
-        if (ok && tcell >= 0) g.claim[tcell] |= (uint8_t)(1 << player);
+        if (ok && tcell >= 0) g.claim()[tcell] |= (uint8_t)(1 << player);
         __syncwarp();
         return ok;
     }
@@ -447,12 +475,12 @@ DEV bool accept_in_order(Game &g, int player, int cnt, int tcell, int cost, bool
         int c = __shfl_sync(FULLM, tcell, j), co = __shfl_sync(FULLM, cost, j);
         bool cand = __shfl_sync(FULLM, candidate ? 1 : 0, j) != 0;
         bool ok = cand;
-        if (ok && c >= 0 && (g.resv[c] != 0 || ((g.claim[c] >> player) & 1))) ok = false;
+        if (ok && c >= 0 && (g.resv()[c] != 0 || ((g.claim()[c] >> player) & 1))) ok = false;
         if (ok && !res_consistent_cand_vs_acc(g, pl, co, par0, par1)) ok = false;
         __syncwarp(); // every lane has read claim[] before lane 0 updates it
         if (ok) {
             if (pl == 1) par0 += co; else par1 += co;
-            if (c >= 0 && g.lane == 0) g.claim[c] |= (uint8_t)(1 << player);
+            if (c >= 0 && g.lane == 0) g.claim()[c] |= (uint8_t)(1 << player);
         }
         if (g.lane == j) mine = ok;
         __syncwarp();
@@ -463,13 +491,13 @@ DEV bool accept_in_order(Game &g, int player, int cnt, int tcell, int cost, bool
 // ---- RandomBiasedAI.getAction (ai/RandomBiasedAI.java:51-107) ------------------------------------------------------------
 // Appends (unit, action) pairs for `player` to the pending list starting at pn; returns the new count.
 DEVN int policy_random_biased(Game &g, int player, int pn) {
-    int n = g.hdr[H_NUNITS], n_idle = 0;
+    int n = g.hdr()[H_NUNITS], n_idle = 0;
     #pragma unroll 1
     for (int base = 0; base < n; base += 32) {
         int i = base + g.lane;
-        bool idle = i < n && u_pl(g.w0[i]) == player + 1 && a_type(g.a0[i]) == AT_IDLE;
+        bool idle = i < n && u_pl(g.w0()[i]) == player + 1 && a_type(g.a0()[i]) == AT_IDLE;
         unsigned m = __ballot_sync(FULLM, idle);
-        if (idle) g.list[n_idle + __popc(m & ((1u << g.lane) - 1))] = (uint8_t)i;
+        if (idle) g.list()[n_idle + __popc(m & ((1u << g.lane) - 1))] = (uint8_t)i;
         n_idle += __popc(m);
     }
     __syncwarp();
@@ -483,7 +511,7 @@ DEVN int policy_random_biased(Game &g, int player, int pn) {
         bool active = k < n_idle;
         uint32_t A0 = ACT_NONE | A0_NOUT; int A1 = 10, tcell = -1, cost = 0, s = 0;
         if (active) {
-            s = g.list[k];
+            s = g.list()[k];
             Enum e; enumerate(g, s, e);
             uint64_t st = lcg_jump(g, s0, k);
             double dr = lcg_next_double(st);
@@ -493,7 +521,7 @@ DEVN int policy_random_biased(Game &g, int player, int pn) {
         bool ok = accept_in_order(g, player, cnt, tcell, cost, active, par0, par1);
         if (active) {
             if (!ok) { A0 = ACT_NONE | A0_NOUT; A1 = 10; }
-            g.pslot[pn + k] = (uint8_t)s; g.pa0[pn + k] = A0; g.pa1[pn + k] = A1;
+            g.pslot()[pn + k] = (uint8_t)s; g.pa0()[pn + k] = A0; g.pa1()[pn + k] = A1;
         }
     }
     if (g.lane == 0) hdr_set_rng(g, H_RNGP_LO, lcg_jump(g, s0, n_idle));
@@ -516,7 +544,7 @@ DEVN int decode_external(Game &g, int player, int pn, const int32_t *rows, int c
                 const int32_t *a = rows + (long long)k * 8;
                 int cell = a[0], at = a[1];
                 if (cell >= 0 && cell < cells && at >= 0 && at <= 5) {
-                    int gv = g.grid[(cell / g.W + 1) * g.P + cell % g.W + 1];
+                    int gv = g.grid()[(cell / g.W + 1) * g.P + cell % g.W + 1];
                     if (gv != 0 && gv != 0xFF) {
                         s = gv - 1; ok = true;
                         int ut = (at == ACT_PRODUCE) ? a[5] : 0xFF;
@@ -528,8 +556,8 @@ DEVN int decode_external(Game &g, int player, int pn, const int32_t *rows, int c
                 }
             }
             unsigned m = __ballot_sync(FULLM, ok);
-            if (k < count && !ok) atomicOr(&g.hdr[H_ERR], GE_BAD_ACTION);
-            if (ok) { int q = pn + __popc(m & ((1u << g.lane) - 1)); g.pslot[q] = (uint8_t)s; g.pa0[q] = A0; g.pa1[q] = A1; }
+            if (k < count && !ok) atomicOr(&g.hdr()[H_ERR], GE_BAD_ACTION);
+            if (ok) { int q = pn + __popc(m & ((1u << g.lane) - 1)); g.pslot()[q] = (uint8_t)s; g.pa0()[q] = A0; g.pa1()[q] = A1; }
             pn += __popc(m);
         }
         __syncwarp();
@@ -546,11 +574,11 @@ DEVN int decode_external(Game &g, int player, int pn, const int32_t *rows, int c
             const int32_t *a = rows + (long long)k * 8;
             int cell = a[0], at = a[1];
             if (cell >= 0 && cell < cells) {
-                int gv = g.grid[(cell / g.W + 1) * g.P + cell % g.W + 1];
+                int gv = g.grid()[(cell / g.W + 1) * g.P + cell % g.W + 1];
                 if (gv != 0 && gv != 0xFF) {
                     s = gv - 1;
-                    uint32_t w = g.w0[s];
-                    if (u_pl(w) == player + 1 && a_type(g.a0[s]) == AT_IDLE && at >= 0 && at <= 5) {
+                    uint32_t w = g.w0()[s];
+                    if (u_pl(w) == player + 1 && a_type(g.a0()[s]) == AT_IDLE && at >= 0 && at <= 5) {
                         cand = true;
                         A0 = (uint32_t)at | A0_NOUT;
                         switch (at) {
@@ -566,7 +594,7 @@ DEVN int decode_external(Game &g, int player, int pn, const int32_t *rows, int c
                             } break;
                         }
                         if (a_uses_cell(at)) tcell = linear_target_cell(g, w, A1);
-                        if (!cand) atomicOr(&g.hdr[H_ERR], GE_BAD_ACTION);
+                        if (!cand) atomicOr(&g.hdr()[H_ERR], GE_BAD_ACTION);
                     }
                 }
             }
@@ -574,7 +602,7 @@ DEVN int decode_external(Game &g, int player, int pn, const int32_t *rows, int c
         int cnt = count - kb; if (cnt > 32) cnt = 32;
         bool ok = accept_in_order(g, player, cnt, tcell, cost, cand, par0, par1);
         unsigned m = __ballot_sync(FULLM, ok);
-        if (ok) { int q = pn + __popc(m & ((1u << g.lane) - 1)); g.pslot[q] = (uint8_t)s; g.pa0[q] = A0; g.pa1[q] = A1; }
+        if (ok) { int q = pn + __popc(m & ((1u << g.lane) - 1)); g.pslot()[q] = (uint8_t)s; g.pa0()[q] = A0; g.pa1()[q] = A1; }
         pn += __popc(m);
         __syncwarp();
     }
@@ -584,20 +612,20 @@ DEVN int decode_external(Game &g, int player, int pn, const int32_t *rows, int c
         const int32_t *a = rows + (long long)k * 8;
         int cell = a[0], at = a[1];
         if (cell >= 0 && cell < cells && a_uses_cell(at)) {
-            int gv = g.grid[(cell / g.W + 1) * g.P + cell % g.W + 1];
-            if (gv != 0 && gv != 0xFF) { int tc = linear_target_cell(g, g.w0[gv - 1], at == ACT_MOVE ? a[2] : a[5]); if (tc >= 0) g.claim[tc] = 0; }
+            int gv = g.grid()[(cell / g.W + 1) * g.P + cell % g.W + 1];
+            if (gv != 0 && gv != 0xFF) { int tc = linear_target_cell(g, g.w0()[gv - 1], at == ACT_MOVE ? a[2] : a[5]); if (tc >= 0) g.claim()[tc] = 0; }
         }
     }
     __syncwarp();
     if (fill >= 0) { // PlayerAction.fillWithNones (PlayerAction.java:217-235): idle own units not already in the action
-        int n = g.hdr[H_NUNITS];
+        int n = g.hdr()[H_NUNITS];
         #pragma unroll 1
         for (int base = 0; base < n; base += 32) {
             int i = base + g.lane;
-            bool idle = i < n && u_pl(g.w0[i]) == player + 1 && a_type(g.a0[i]) == AT_IDLE;
-            if (idle) for (int q = start; q < pn; q++) if (g.pslot[q] == i) { idle = false; break; }
+            bool idle = i < n && u_pl(g.w0()[i]) == player + 1 && a_type(g.a0()[i]) == AT_IDLE;
+            if (idle) for (int q = start; q < pn; q++) if (g.pslot()[q] == i) { idle = false; break; }
             unsigned m = __ballot_sync(FULLM, idle);
-            if (idle) { int q = pn + __popc(m & ((1u << g.lane) - 1)); g.pslot[q] = (uint8_t)i; g.pa0[q] = ACT_NONE | A0_NOUT; g.pa1[q] = fill; }
+            if (idle) { int q = pn + __popc(m & ((1u << g.lane) - 1)); g.pslot()[q] = (uint8_t)i; g.pa0()[q] = ACT_NONE | A0_NOUT; g.pa1()[q] = fill; }
             pn += __popc(m);
             __syncwarp();
         }
@@ -609,11 +637,11 @@ DEVN int decode_external(Game &g, int player, int pn, const int32_t *rows, int c
 DEV void legality_pass(Game &g, int from, int to) {
     #pragma unroll 1
     for (int k = from + g.lane; k < to; k += 32) {
-        int s = g.pslot[k];
-        uint32_t A0 = g.pa0[k]; int A1 = g.pa1[k];
+        int s = g.pslot()[k];
+        uint32_t A0 = g.pa0()[k]; int A1 = g.pa1()[k];
         if (!action_is_legal(g, s, A0, A1)) {
-            g.pa1[k] = eta_of(g, u_type(g.w0[s]), A0, A1);
-            g.pa0[k] = ACT_NONE | A0_NOUT;
+            g.pa1()[k] = eta_of(g, u_type(g.w0()[s]), A0, A1);
+            g.pa0()[k] = ACT_NONE | A0_NOUT;
         }
     }
     __syncwarp();
@@ -622,8 +650,8 @@ DEV void legality_pass(Game &g, int from, int to) {
 // ---- GameState.issue (GameState.java:249-328) --------------------------------------------------------------------------
 // One conflicting pair (existing assignment of slot e, new action N of a unit of type t).  Uniform across lanes.
 DEV void resolve_conflict(Game &g, int e, int t, uint32_t &A0, int &A1, int time) {
-    uint32_t E0 = g.a0[e]; int E1 = g.a1[e]; uint32_t ew = g.w0[e];
-    bool same_cycle = g.tis[e] == time;
+    uint32_t E0 = g.a0()[e]; int E1 = g.a1()[e]; uint32_t ew = g.w0()[e];
+    bool same_cycle = g.tis()[e] == time;
     bool cancel_old = false, cancel_new = false;
     if (same_cycle) {
         switch (g.conflict) {
@@ -636,9 +664,9 @@ DEV void resolve_conflict(Game &g, int e, int t, uint32_t &A0, int &A1, int time
                 if (r == 0) cancel_new = true; else cancel_old = true;
             } break;
             case 3: {                                                               // CANCEL_ALTERNATING
-                int ctr = g.hdr[H_CANCELCTR];
+                int ctr = g.hdr()[H_CANCELCTR];
                 __syncwarp();
-                if (g.lane == 0) g.hdr[H_CANCELCTR] = ctr + 1;
+                if (g.lane == 0) g.hdr()[H_CANCELCTR] = ctr + 1;
                 if ((ctr % 2) == 0) cancel_new = true; else cancel_old = true;
             } break;
         }
@@ -648,44 +676,44 @@ DEV void resolve_conflict(Game &g, int e, int t, uint32_t &A0, int &A1, int time
     __syncwarp();
     if (same_cycle) {
         if (cancel_old && g.lane == 0) {
-            if (a_uses_cell(a_type(E0))) { int tc = target_cell(g, cell_of(g, ew), E1); if (g.resv[tc] == e + 1) g.resv[tc] = 0; }
-            g.a0[e] = (E0 & 0xF0u) | ACT_NONE | A0_NOUT; g.a1[e] = d;
+            if (a_uses_cell(a_type(E0))) { int tc = target_cell(g, cell_of(g, ew), E1); if (g.resv()[tc] == e + 1) g.resv()[tc] = 0; }
+            g.a0()[e] = (E0 & 0xF0u) | ACT_NONE | A0_NOUT; g.a1()[e] = d; g.rdy()[e] = time + d;
         }
         if (cancel_new) { A0 = ACT_NONE | A0_NOUT; A1 = d; }
     } else {
-        if (g.lane == 0) g.hdr[H_ERR] |= GE_INCONSISTENT_OLDER;
+        if (g.lane == 0) g.hdr()[H_ERR] |= GE_INCONSISTENT_OLDER;
         A0 = ACT_NONE | A0_NOUT; A1 = -1; // new UnitAction(TYPE_NONE): parameter stays -1 (GameState.java:316)
     }
     __syncwarp();
 }
 
 DEVN void issue_pending(Game &g, int from, int to) {
-    int time = g.hdr[H_TIME];
+    int time = g.hdr()[H_TIME];
     #pragma unroll 1
     for (int k = from; k < to; k++) {
-        int s = g.pslot[k];
-        uint32_t A0 = g.pa0[k]; int A1 = g.pa1[k];
-        uint32_t w = g.w0[s];
+        int s = g.pslot()[k];
+        uint32_t A0 = g.pa0()[k]; int A1 = g.pa1()[k];
+        uint32_t w = g.w0()[s];
         int t = u_type(w), pl = u_pl(w), c = cell_of(g, w), at = a_type(A0);
         int tc = -1, cost = 0;
         if (a_uses_cell(at)) { tc = target_cell(g, c, A1); if (at == ACT_PRODUCE) cost = ut_cost(g, a_utype(A0)); }
         __syncwarp();
-        if (tc >= 0 && g.lane == 0) g.claim[tc] = 0;
+        if (tc >= 0 && g.lane == 0) g.claim()[tc] = 0;
         if (tc >= 0 && cost == 0) {
-            int e = g.resv[tc]; // at most one in-flight action can hold a cell
+            int e = g.resv()[tc]; // at most one in-flight action can hold a cell
             if (e != 0) resolve_conflict(g, e - 1, t, A0, A1, time);
         } else if (cost != 0) {
             // general pairwise check against every existing assignment, in insertion order (GameState.java:263-319)
-            int n = g.hdr[H_NUNITS], pres = pl ? g.hdr[H_RES0 + pl - 1] : 0;
+            int n = g.hdr()[H_NUNITS], pres = pl ? g.hdr()[H_RES0 + pl - 1] : 0;
             unsigned cb = 0; // bit j: slot j*32+lane conflicts
             #pragma unroll 1
             for (int j = 0; j * 32 < n; j++) {
                 int i = j * 32 + g.lane;
                 if (i < n) {
-                    uint32_t E0 = g.a0[i]; int eat = a_type(E0);
+                    uint32_t E0 = g.a0()[i]; int eat = a_type(E0);
                     if (eat != AT_IDLE && !(E0 & A0_DEAD)) {
-                        uint32_t ew = g.w0[i];
-                        bool pos = a_uses_cell(eat) && target_cell(g, cell_of(g, ew), g.a1[i]) == tc;
+                        uint32_t ew = g.w0()[i];
+                        bool pos = a_uses_cell(eat) && target_cell(g, cell_of(g, ew), g.a1()[i]) == tc;
                         int ecost = (eat == ACT_PRODUCE && u_pl(ew) == pl) ? ut_cost(g, a_utype(E0)) : 0;
                         bool res = (ecost + cost > 0) && (ecost + cost > pres);
                         if (pos || res) cb |= 1u << j;
@@ -696,7 +724,7 @@ DEVN void issue_pending(Game &g, int from, int to) {
             for (;;) {
                 uint32_t best = 0xFFFFFFFFu; int bj = 0;
                 #pragma unroll 1
-                for (unsigned m = cb; m; m &= m - 1) { int j = __ffs(m) - 1; uint32_t q = g.seq[j * 32 + g.lane]; if (q < best) { best = q; bj = j; } }
+                for (unsigned m = cb; m; m &= m - 1) { int j = __ffs(m) - 1; uint32_t q = g.seq()[j * 32 + g.lane]; if (q < best) { best = q; bj = j; } }
                 uint32_t mn = __reduce_min_sync(FULLM, best);
                 if (mn == 0xFFFFFFFFu) break;
                 int owner = __ffs(__ballot_sync(FULLM, best == mn)) - 1;
@@ -708,11 +736,11 @@ DEVN void issue_pending(Game &g, int from, int to) {
         // unitActions.put(unit, new UnitActionAssignment(unit, action, time)): an existing key keeps its slot
         __syncwarp(); // every lane has finished reading resv/a0 for this action
         if (g.lane == 0) {
-            uint32_t prev = g.a0[s];
-            if (a_type(prev) == AT_IDLE) g.seq[s] = (uint32_t)g.hdr[H_NEXTSEQ]++;
-            else if (a_uses_cell(a_type(prev))) { int ptc = target_cell(g, c, g.a1[s]); if (g.resv[ptc] == s + 1) g.resv[ptc] = 0; }
-            g.a0[s] = (prev & 0xF0u) | (A0 & ~0xF0u); g.a1[s] = A1; g.tis[s] = time;
-            if (a_uses_cell(a_type(A0))) g.resv[tc] = (uint8_t)(s + 1);
+            uint32_t prev = g.a0()[s];
+            if (a_type(prev) == AT_IDLE) g.seq()[s] = (uint32_t)g.hdr()[H_NEXTSEQ]++;
+            else if (a_uses_cell(a_type(prev))) { int ptc = target_cell(g, c, g.a1()[s]); if (g.resv()[ptc] == s + 1) g.resv()[ptc] = 0; }
+            g.a0()[s] = (prev & 0xF0u) | (A0 & ~0xF0u); g.a1()[s] = A1; g.tis()[s] = time; g.rdy()[s] = time + eta_of(g, t, A0, A1);
+            if (a_uses_cell(a_type(A0))) g.resv()[tc] = (uint8_t)(s + 1);
         }
         __syncwarp();
     }
@@ -725,88 +753,91 @@ DEVN void issue_pending(Game &g, int from, int to) {
 // player-0 action of this same cycle that target the same cell -- isolated pairs, each cancelled to
 // NONE(min(ETA_old, ETA_new)) -- and insertion order is simply list order.
 DEVN void issue_policy_lists(Game &g, int pn0, int pn1) {
-    int time = g.hdr[H_TIME];
-    uint32_t base_seq = (uint32_t)g.hdr[H_NEXTSEQ];
+    int time = g.hdr()[H_TIME];
+    uint32_t base_seq = (uint32_t)g.hdr()[H_NEXTSEQ];
     #pragma unroll 1
     for (int k = g.lane; k < pn0; k += 32) {
-        int s = g.pslot[k];
-        uint32_t A0 = g.pa0[k]; int A1 = g.pa1[k];
-        if (a_uses_cell(a_type(A0))) { int tc = target_cell(g, cell_of(g, g.w0[s]), A1); g.resv[tc] = (uint8_t)(s + 1); g.claim[tc] = 0; }
-        g.a0[s] = (g.a0[s] & 0xF0u) | (A0 & ~0xF0u); g.a1[s] = A1; g.tis[s] = time; g.seq[s] = base_seq + k;
+        int s = g.pslot()[k];
+        uint32_t A0 = g.pa0()[k]; int A1 = g.pa1()[k];
+        if (a_uses_cell(a_type(A0))) { int tc = target_cell(g, cell_of(g, g.w0()[s]), A1); g.resv()[tc] = (uint8_t)(s + 1); g.claim()[tc] = 0; }
+        g.a0()[s] = (g.a0()[s] & 0xF0u) | (A0 & ~0xF0u); g.a1()[s] = A1; g.tis()[s] = time; g.seq()[s] = base_seq + k;
+        g.rdy()[s] = time + eta_of(g, u_type(g.w0()[s]), A0, A1);
     }
     __syncwarp();
     #pragma unroll 1
     for (int k = pn0 + g.lane; k < pn1; k += 32) {
-        int s = g.pslot[k];
-        uint32_t A0 = g.pa0[k]; int A1 = g.pa1[k];
-        uint32_t w = g.w0[s];
+        int s = g.pslot()[k];
+        uint32_t A0 = g.pa0()[k]; int A1 = g.pa1()[k];
+        uint32_t w = g.w0()[s];
         if (a_uses_cell(a_type(A0))) {
             int tc = target_cell(g, cell_of(g, w), A1);
-            g.claim[tc] = 0;
-            int e = g.resv[tc];
-            if (e == 0) g.resv[tc] = (uint8_t)(s + 1);
+            g.claim()[tc] = 0;
+            int e = g.resv()[tc];
+            if (e == 0) g.resv()[tc] = (uint8_t)(s + 1);
             else {
                 e--;
-                if (g.tis[e] == time) {
-                    uint32_t E0 = g.a0[e];
-                    int d1 = eta_of(g, u_type(g.w0[e]), E0, g.a1[e]), d2 = eta_of(g, u_type(w), A0, A1);
+                if (g.tis()[e] == time) {
+                    uint32_t E0 = g.a0()[e];
+                    int d1 = eta_of(g, u_type(g.w0()[e]), E0, g.a1()[e]), d2 = eta_of(g, u_type(w), A0, A1);
                     int d = d1 < d2 ? d1 : d2;
-                    g.a0[e] = (E0 & 0xF0u) | ACT_NONE | A0_NOUT; g.a1[e] = d;
-                    g.resv[tc] = 0;
+                    g.a0()[e] = (E0 & 0xF0u) | ACT_NONE | A0_NOUT; g.a1()[e] = d; g.rdy()[e] = time + d;
+                    g.resv()[tc] = 0;
                     A0 = ACT_NONE | A0_NOUT; A1 = d;
                 } else {
-                    atomicOr(&g.hdr[H_ERR], GE_INCONSISTENT_OLDER);
+                    atomicOr(&g.hdr()[H_ERR], GE_INCONSISTENT_OLDER);
                     A0 = ACT_NONE | A0_NOUT; A1 = -1;
                 }
             }
         }
-        g.a0[s] = (g.a0[s] & 0xF0u) | (A0 & ~0xF0u); g.a1[s] = A1; g.tis[s] = time; g.seq[s] = base_seq + k;
+        g.a0()[s] = (g.a0()[s] & 0xF0u) | (A0 & ~0xF0u); g.a1()[s] = A1; g.tis()[s] = time; g.seq()[s] = base_seq + k;
+        g.rdy()[s] = time + eta_of(g, u_type(w), A0, A1);
     }
     __syncwarp();
-    if (g.lane == 0) g.hdr[H_NEXTSEQ] = (int32_t)(base_seq + pn1);
+    if (g.lane == 0) g.hdr()[H_NEXTSEQ] = (int32_t)(base_seq + pn1);
     __syncwarp();
 }
 
 // ---- GameState.cycle (GameState.java:553-571) + UnitAction.execute (UnitAction.java:338-465) ----------------------------
 DEV void kill_unit(Game &g, int v) { // GameState.removeUnit (GameState.java:79-82); lane 0 only
-    uint32_t vw = g.w0[v]; uint32_t V0 = g.a0[v];
+    uint32_t vw = g.w0()[v]; uint32_t V0 = g.a0()[v];
     int vc = cell_of(g, vw);
-    g.grid[vc] = 0;
-    if (a_uses_cell(a_type(V0))) { int tc = target_cell(g, vc, g.a1[v]); if (g.resv[tc] == v + 1) g.resv[tc] = 0; }
-    g.a0[v] = V0 | A0_DEAD; // keeps its action words: a ready action of a dead unit still executes this cycle
+    g.grid()[vc] = 0; g.kind()[vc] = 0;
+    if (a_uses_cell(a_type(V0))) { int tc = target_cell(g, vc, g.a1()[v]); if (g.resv()[tc] == v + 1) g.resv()[tc] = 0; }
+    g.a0()[v] = V0 | A0_DEAD; // keeps its action words: a ready action of a dead unit still executes this cycle
 }
 
 DEV int neighbour_slot(const Game &g, int c, int dir) { // getUnitAt of the adjacent cell, -1 if none
     if ((unsigned)dir >= 4u) return -1;
-    int gv = g.grid[c + doff(g, dir)];
+    int gv = g.grid()[c + doff(g, dir)];
     return (gv == 0 || gv == 0xFF) ? -1 : gv - 1;
 }
 
 // Execute the (already removed) assignment (A0,A1) of slot s.  Called by ONE lane (lane 0) for every ready assignment in
 // insertion order, so it is plain sequential code with no warp primitives.
 DEV void execute_serial(Game &g, int s, int &ndead) {
-    uint32_t A0 = g.a0[s]; int A1 = g.a1[s];
-    uint32_t w = g.w0[s];
+    uint32_t A0 = g.a0()[s]; int A1 = g.a1()[s];
+    uint32_t w = g.w0()[s];
     bool dead = (A0 & A0_DEAD) != 0;
     int t = u_type(w), pl = u_pl(w), c = cell_of(g, w);
     // unitActions.remove(uaa.unit) (GameState.java:563); a dead unit lost its entry (and reservation) when it died
-    g.a0[s] = (A0 & 0xF0u) | AT_IDLE | A0_NOUT;
-    if (!dead && a_uses_cell(a_type(A0))) { int tc = target_cell(g, c, A1); if (g.resv[tc] == s + 1) g.resv[tc] = 0; }
+    g.a0()[s] = (A0 & 0xF0u) | AT_IDLE | A0_NOUT; g.rdy()[s] = MRTS_NEVER;
+    if (!dead && a_uses_cell(a_type(A0))) { int tc = target_cell(g, c, A1); if (g.resv()[tc] == s + 1) g.resv()[tc] = 0; }
     switch (a_type(A0)) {
         case ACT_MOVE:
             if (!dead && (unsigned)A1 < 4u) {
                 int nc = c + doff(g, A1);
-                if (g.grid[nc] != 0) g.hdr[H_ERR] |= GE_CELL_OCCUPIED;
+                if (g.grid()[nc] != 0) g.hdr()[H_ERR] |= GE_CELL_OCCUPIED;
                 else {
-                    g.grid[c] = 0; g.grid[nc] = (uint8_t)(s + 1);
-                    g.w0[s] = (w & 0xffffu) | ((uint32_t)(u_x(w) + ddx(A1)) << 16) | ((uint32_t)(u_y(w) + ddy(A1)) << 24);
+                    g.grid()[c] = 0; g.grid()[nc] = (uint8_t)(s + 1);
+                    g.kind()[nc] = g.kind()[c]; g.kind()[c] = 0;
+                    g.w0()[s] = (w & 0xffffu) | ((uint32_t)(u_x(w) + ddx(A1)) << 16) | ((uint32_t)(u_y(w) + ddy(A1)) << 24);
                 }
             }
             break;
         case ACT_ATTACK: {
             int ax = (A0 >> 16) & 0xff, ay = A0 >> 24;
             if (ax < g.W && ay < g.H) {
-                int gv = g.grid[(ay + 1) * g.P + ax + 1];
+                int gv = g.grid()[(ay + 1) * g.P + ax + 1];
                 if (gv != 0 && gv != 0xFF) {
                     int v = gv - 1;
                     int mn = ut_mind(g, t), mx = ut_maxd(g, t), dmg = mn;
@@ -815,9 +846,9 @@ DEV void execute_serial(Game &g, int s, int &ndead) {
                         dmg = mn + lcg_next_int_bound(rs, 1 + (mx - mn));
                         hdr_set_rng(g, H_RNGD_LO, rs);
                     }
-                    uint32_t vw1 = g.w1[v];
+                    uint32_t vw1 = g.w1()[v];
                     int hp = u_hp(vw1) - dmg;
-                    g.w1[v] = mk_w1(hp, u_res(vw1));
+                    g.w1()[v] = mk_w1(hp, u_res(vw1));
                     if (hp <= 0) { kill_unit(g, v); ndead++; }
                 }
             }
@@ -825,46 +856,46 @@ DEV void execute_serial(Game &g, int s, int &ndead) {
         case ACT_HARVEST: {
             int r = neighbour_slot(g, c, A1);
             if (r >= 0) {
-                uint32_t rw1 = g.w1[r], mw1 = g.w1[s];
-                if ((ut_flags(g, u_type(g.w0[r])) & UF_RESOURCE) && (ut_flags(g, t) & UF_HARVEST) && u_res(mw1) == 0) {
+                uint32_t rw1 = g.w1()[r], mw1 = g.w1()[s];
+                if ((ut_flags(g, u_type(g.w0()[r])) & UF_RESOURCE) && (ut_flags(g, t) & UF_HARVEST) && u_res(mw1) == 0) {
                     int amt = ut_hamt(g, t), left = u_res(rw1) - amt;
-                    g.w1[r] = mk_w1(u_hp(rw1), left);
+                    g.w1()[r] = mk_w1(u_hp(rw1), left);
                     if (left <= 0) { kill_unit(g, r); ndead++; }
-                    g.w1[s] = mk_w1(u_hp(mw1), amt);
+                    g.w1()[s] = mk_w1(u_hp(mw1), amt);
                 }
             }
         } break;
         case ACT_RETURN: {
             int b = neighbour_slot(g, c, A1);
             if (b >= 0 && pl != 0) {
-                uint32_t mw1 = g.w1[s];
-                if ((ut_flags(g, u_type(g.w0[b])) & UF_STOCKPILE) && u_res(mw1) > 0) {
-                    g.hdr[H_RES0 + pl - 1] += u_res(mw1);
-                    g.w1[s] = mk_w1(u_hp(mw1), 0);
+                uint32_t mw1 = g.w1()[s];
+                if ((ut_flags(g, u_type(g.w0()[b])) & UF_STOCKPILE) && u_res(mw1) > 0) {
+                    g.hdr()[H_RES0 + pl - 1] += u_res(mw1);
+                    g.w1()[s] = mk_w1(u_hp(mw1), 0);
                 }
             }
         } break;
         case ACT_PRODUCE: {
             int ut = a_utype(A0);
             if (pl != 0 && ut < MRTS_MAX_TYPES) {
-                int n = g.hdr[H_NUNITS], pres = g.hdr[H_RES0 + pl - 1];
-                int id = g.hdr[H_NEXTID]++; // new Unit(...) takes an ID even when the unit is then not added
+                int n = g.hdr()[H_NUNITS], pres = g.hdr()[H_RES0 + pl - 1];
+                int id = g.hdr()[H_NEXTID]++; // new Unit(...) takes an ID even when the unit is then not added
                 int cost = ut_cost(g, ut);
                 if (pres - cost >= 0) {
                     int nc = target_cell(g, c, A1);
-                    if ((unsigned)A1 >= 4u || g.grid[nc] != 0) g.hdr[H_ERR] |= GE_CELL_OCCUPIED;
-                    else if (n >= g.cap) g.hdr[H_ERR] |= GE_UNIT_OVERFLOW;
+                    if ((unsigned)A1 >= 4u || g.grid()[nc] != 0) g.hdr()[H_ERR] |= GE_CELL_OCCUPIED;
+                    else if (n >= g.cap) g.hdr()[H_ERR] |= GE_UNIT_OVERFLOW;
                     else {
                         int nx = u_x(w) + ddx(A1), ny = u_y(w) + ddy(A1);
-                        g.w0[n] = (uint32_t)ut | ((uint32_t)pl << 8) | ((uint32_t)nx << 16) | ((uint32_t)ny << 24);
-                        g.w1[n] = mk_w1(ut_hp(g, ut), 0);
-                        g.a0[n] = AT_IDLE | A0_NOUT; g.a1[n] = 0; g.tis[n] = 0; g.seq[n] = 0; g.uid[n] = (uint32_t)id;
-                        if (g.uw > MRTS_UNIT_WORDS_CORE) { g.x0[n] = 0; g.x1[n] = 0; }
-                        g.grid[nc] = (uint8_t)(n + 1);
-                        g.hdr[H_NUNITS] = n + 1;
-                        g.hdr[H_RES0 + pl - 1] = pres - cost;
+                        g.w0()[n] = (uint32_t)ut | ((uint32_t)pl << 8) | ((uint32_t)nx << 16) | ((uint32_t)ny << 24);
+                        g.w1()[n] = mk_w1(ut_hp(g, ut), 0);
+                        g.a0()[n] = AT_IDLE | A0_NOUT; g.a1()[n] = 0; g.tis()[n] = 0; g.seq()[n] = 0; g.uid()[n] = (uint32_t)id;
+                        if (g.uw > MRTS_UNIT_WORDS_CORE) { g.x0()[n] = 0; g.x1()[n] = 0; }
+                        g.grid()[nc] = (uint8_t)(n + 1); g.kind()[nc] = (uint8_t)kind_of(g, g.w0()[n]); g.rdy()[n] = MRTS_NEVER;
+                        g.hdr()[H_NUNITS] = n + 1;
+                        g.hdr()[H_RES0 + pl - 1] = pres - cost;
                     }
-                } else g.hdr[H_ERR] |= GE_FAILED_PRODUCE;
+                } else g.hdr()[H_ERR] |= GE_FAILED_PRODUCE;
             }
         } break;
         default: break;
@@ -872,46 +903,44 @@ DEV void execute_serial(Game &g, int s, int &ndead) {
 }
 
 // remove dead slots, keeping order; rebuild the cell maps
-DEVN void compact_units(Game &g) {
-    int n = g.hdr[H_NUNITS], out = 0;
-    uint32_t *su = g.w0;
+DEV void compact_units(Game &g) {
+    int n = g.hdr()[H_NUNITS], out = 0;
+    uint32_t *su = g.w0();
     #pragma unroll 1
     for (int base = 0; base < n; base += 32) {
         int i = base + g.lane;
-        bool alive = i < n && !(g.a0[i] & A0_DEAD);
-        uint32_t r[MRTS_UNIT_WORDS];
-        if (alive) for (int k = 0; k < MRTS_UNIT_WORDS; k++) if (k < g.uw) r[k] = su[k * g.cap + i];
+        bool alive = i < n && !(g.a0()[i] & A0_DEAD);
+        uint32_t r[MRTS_UNIT_WORDS + 1]; // the words mirrored in HBM + RDY
+        if (alive) for (int k = 0; k <= MRTS_UNIT_WORDS; k++) if (k <= g.uw) r[k] = su[k * g.cap + i];
         unsigned m = __ballot_sync(FULLM, alive);
         int pos = out + __popc(m & ((1u << g.lane) - 1));
-        if (i < n) g.list[i] = alive ? (uint8_t)(pos + 1) : 0; // old slot -> new slot + 1 (0: removed)
+        if (i < n) g.list()[i] = alive ? (uint8_t)(pos + 1) : 0; // old slot -> new slot + 1 (0: removed)
         __syncwarp();
-        if (alive) for (int k = 0; k < MRTS_UNIT_WORDS; k++) if (k < g.uw) su[k * g.cap + pos] = r[k];
+        if (alive) for (int k = 0; k <= MRTS_UNIT_WORDS; k++) if (k <= g.uw) su[k * g.cap + pos] = r[k];
         out += __popc(m);
         __syncwarp();
     }
-    if (g.lane == 0) g.hdr[H_NUNITS] = out;
+    if (g.lane == 0) g.hdr()[H_NUNITS] = out;
     __syncwarp();
     // unit references held by abstract actions (X1: attack/harvest target, base) follow their unit or become "dead object"
 #pragma unroll 1
     for (int i = g.lane; i < (g.uw > MRTS_UNIT_WORDS_CORE ? out : 0); i += 32) {
-        uint32_t X1 = g.x1[i];
+        uint32_t X1 = g.x1()[i];
         uint32_t t = X1 & 0xff, b = (X1 >> 8) & 0xff;
-        if (t != 0 && t != 0xFF) { t = g.list[t - 1]; if (t == 0) t = 0xFF; }
-        if (b != 0 && b != 0xFF) { b = g.list[b - 1]; if (b == 0) b = 0xFF; }
-        g.x1[i] = (X1 & 0xffff0000u) | (b << 8) | t;
+        if (t != 0 && t != 0xFF) { t = g.list()[t - 1]; if (t == 0) t = 0xFF; }
+        if (b != 0 && b != 0xFF) { b = g.list()[b - 1]; if (b == 0) b = 0xFF; }
+        g.x1()[i] = (X1 & 0xffff0000u) | (b << 8) | t;
     }
-    __syncwarp();
-    g_reset_maps(g);
-    g_scatter(g);
+    g_rebuild(g, false);
 }
 
 // PhysicalGameState.gameover / winner (PhysicalGameState.java:334-387); returns gameover, sets winner (-1 none)
 DEV bool game_over(const Game &g, int &winner) {
-    int n = g.hdr[H_NUNITS], c0 = 0, c1 = 0;
+    int n = g.hdr()[H_NUNITS], c0 = 0, c1 = 0;
     #pragma unroll 1
     for (int base = 0; base < n; base += 32) {
         int i = base + g.lane;
-        int pl = i < n ? u_pl(g.w0[i]) : 0;
+        int pl = i < n ? u_pl(g.w0()[i]) : 0;
         c0 += __popc(__ballot_sync(FULLM, pl == 1));
         c1 += __popc(__ballot_sync(FULLM, pl == 2));
     }
@@ -920,51 +949,47 @@ DEV bool game_over(const Game &g, int &winner) {
 }
 
 // earliest completion time of any in-flight assignment (GameState.getNextChangeTime, GameState.java:539-542)
+DEV int warp_min_time(int best) { return (int)(__reduce_min_sync(FULLM, (unsigned)(best ^ 0x80000000)) ^ 0x80000000u); }
 DEV int min_ready_time(const Game &g) {
-    int n = g.hdr[H_NUNITS], best = 0x7fffffff;
+    int n = g.hdr()[H_NUNITS], best = MRTS_NEVER;
     #pragma unroll 1
-    for (int i = g.lane; i < n; i += 32) {
-        uint32_t A0 = g.a0[i];
-        if (a_type(A0) != AT_IDLE) { int rt = g.tis[i] + eta_of(g, u_type(g.w0[i]), A0, g.a1[i]); if (rt < best) best = rt; }
-    }
-    return (int)(__reduce_min_sync(FULLM, (unsigned)(best ^ 0x80000000)) ^ 0x80000000u);
+    for (int i = g.lane; i < n; i += 32) { int r = g.rdy()[i]; if (r < best) best = r; }
+    return warp_min_time(best);
 }
 
-// time := t_new, then execute every assignment with ETA + issueTime <= time in insertion order.  Returns gameover().
+// time := t_new, then execute every assignment with ETA + issueTime <= time in insertion order (GameState.cycle).
+// Returns the number of units removed; the caller re-evaluates gameover() only then (nothing else can end a game).
 // Ready assignments are found in parallel; NONE actions (no effect, so their position in the order is irrelevant) are
 // retired on the spot; the rest is ranked by insertion sequence and executed by one lane, because the reference's
 // effects are order dependent (kills, depletion, produce/return on the same player's resources).
-DEVN bool cycle_execute(Game &g, int t_new, int &winner) {
+DEV int cycle_execute(Game &g, int t_new) {
     __syncwarp();
-    if (g.lane == 0) g.hdr[H_TIME] = t_new;
-    int n = g.hdr[H_NUNITS], cnt = 0;
+    if (g.lane == 0) g.hdr()[H_TIME] = t_new;
+    int n = g.hdr()[H_NUNITS], cnt = 0;
     #pragma unroll 1
     for (int base = 0; base < n; base += 32) {
         int i = base + g.lane;
         bool ready = false;
-        if (i < n) {
-            uint32_t A0 = g.a0[i];
-            int at = a_type(A0);
-            if (at != (int)AT_IDLE && g.tis[i] + eta_of(g, u_type(g.w0[i]), A0, g.a1[i]) <= t_new) {
-                if (at == ACT_NONE) g.a0[i] = (A0 & 0xF0u) | AT_IDLE | A0_NOUT;
-                else ready = true;
-            }
+        if (i < n && g.rdy()[i] <= t_new) {
+            uint32_t A0 = g.a0()[i];
+            if (a_type(A0) == ACT_NONE) { g.a0()[i] = (A0 & 0xF0u) | AT_IDLE | A0_NOUT; g.rdy()[i] = MRTS_NEVER; }
+            else ready = true;
         }
         unsigned m = __ballot_sync(FULLM, ready);
-        if (ready) g.list[cnt + __popc(m & ((1u << g.lane) - 1))] = (uint8_t)i;
+        if (ready) g.list()[cnt + __popc(m & ((1u << g.lane) - 1))] = (uint8_t)i;
         cnt += __popc(m);
     }
     __syncwarp();
     int ndead = 0;
     if (cnt > 0) {
-        uint8_t *order = g.pslot; // the pending list is empty at this point
+        uint8_t *order = g.base() + g.o_pslot; // the pending list is empty at this point
         #pragma unroll 1
         for (int k = g.lane; k < cnt; k += 32) {
-            int s = g.list[k];
-            uint32_t my = g.seq[s];
+            int s = g.list()[k];
+            uint32_t my = g.seq()[s];
             int r = 0;
             #pragma unroll 1
-            for (int j = 0; j < cnt; j++) r += g.seq[g.list[j]] < my ? 1 : 0;
+            for (int j = 0; j < cnt; j++) r += g.seq()[g.list()[j]] < my ? 1 : 0;
             order[r] = (uint8_t)s;
         }
         __syncwarp();
@@ -973,9 +998,127 @@ DEVN bool cycle_execute(Game &g, int t_new, int &winner) {
             for (int r = 0; r < cnt; r++) execute_serial(g, order[r], ndead);
         __syncwarp();
         ndead = __shfl_sync(FULLM, ndead, 0);
+        if (ndead > 0) compact_units(g);
     }
-    if (ndead > 0) compact_units(g);
-    return game_over(g, winner);
+    return ndead;
+}
+DEVN int cycle_execute_ni(Game &g, int t_new) { return cycle_execute(g, t_new); } // one out-of-line copy for the generic kernel
+
+// ---- RandomBiasedAI.getAction for the players of one decision point, fused with issue (fast path) ----------------------
+// Lane i works on unit i (no list compaction, no pending list): a player's idle units enumerate, sample and arbitrate in
+// unit-list order, and the accepted actions go straight into the assignment words.
+struct RbCtx {
+    int time;          // GameState.time of the decision
+    uint32_t seq_base; // first insertion sequence number of this decision point
+    uint64_t s0;       // Sampler.generator state before the first draw
+    int k;             // draws (= actions issued) so far: player 0's idle units in list order, then player 1's
+    int par0, par1;    // PlayerAction.r resource usage while the current player's action is being built
+    int minr;          // lane-local min completion time of the assignments written by this lane
+    bool cancelled;    // lane-local: this lane's action was cancelled against the other player's (claim map needs clearing)
+};
+
+// Scan the unit table once: which players have an idle unit (bit 0 / bit 1), the in-flight PRODUCE costs per player
+// (GameState.getResourceUsage, GameState.java:652-664) and the lane-local minimum completion time of in-flight actions.
+DEV int rb_scan(const Game &g, int n, int &par0, int &par1, int &mr) {
+    int a = 0, b = 0;
+    bool i0 = false, i1 = false;
+    mr = MRTS_NEVER;
+    #pragma unroll 1
+    for (int i = g.lane; i < n; i += 32) {
+        uint32_t A0 = g.a0()[i];
+        int at = a_type(A0), pl = u_pl(g.w0()[i]), r = g.rdy()[i];
+        if (at == (int)AT_IDLE) { i0 |= pl == 1; i1 |= pl == 2; }
+        else {
+            if (r < mr) mr = r;
+            if (at == ACT_PRODUCE) { int c = ut_cost(g, a_utype(A0)); if (pl == 1) a += c; else b += c; }
+        }
+    }
+    int idle = (__ballot_sync(FULLM, i0) ? 1 : 0) | (__ballot_sync(FULLM, i1) ? 2 : 0);
+    if (idle) { par0 = __reduce_add_sync(FULLM, a); par1 = __reduce_add_sync(FULLM, b); }
+    return idle;
+}
+
+// Verdicts of one chunk of candidates (lanes in `m`, unit-list order) against the action being built: the chosen cell must
+// not be used (ResourceUsage.consistentWith, ResourceUsage.java:31-50) by an in-flight assignment or by an earlier choice
+// of this player, and the resources must suffice (RandomBiasedAI.java:92-99).  `simul`: a cell reserved by the OTHER
+// player's action of this same cycle does not block -- that player's list was built on the same state (Game.java:134-137)
+// and GameState.issue will find the pair inconsistent (handled by the caller).
+DEV bool rb_accept(const Game &g, int pl, unsigned m, bool cand, int tcell, int cost, bool simul, RbCtx &c) {
+    bool blocked = false;
+    if (cand && tcell >= 0) {
+        int ev = g.resv()[tcell];
+        if (ev != 0) blocked = !(simul && g.tis()[ev - 1] == c.time && u_pl(g.w0()[ev - 1]) != pl);
+        if (g.claim()[tcell] & pl) blocked = true; // this player's earlier choice of the cell was cancelled at issue (see rb_player)
+    }
+    unsigned same = __match_any_sync(FULLM, (cand && tcell >= 0) ? tcell : -1 - g.lane);
+    unsigned below = (1u << g.lane) - 1;
+    if (__ballot_sync(FULLM, cand && cost != 0) == 0) {
+        // No candidate costs resources: the resource half of consistentWith is the same for every lane, and verdicts only
+        // interact when two lanes want the same cell (the first in list order wins; if it is blocked, so are the others).
+        bool over = (c.par0 > 0 && c.par0 > g.hdr()[H_RES0]) || (c.par1 > 0 && c.par1 > g.hdr()[H_RES1]);
+        return cand && !over && !blocked && !(tcell >= 0 && (same & below));
+    }
+    bool mine = false;
+    unsigned acc = 0; // accepted lanes so far
+    #pragma unroll 1
+    for (unsigned mm = m; mm; mm &= mm - 1) {
+        int j = __ffs(mm) - 1;
+        int co = __shfl_sync(FULLM, cost, j);
+        unsigned sj = __shfl_sync(FULLM, same, j);
+        bool ok = __shfl_sync(FULLM, blocked ? 0 : 1, j) != 0;
+        if (ok && (sj & acc & ~(1u << j))) ok = false;
+        if (ok && !res_consistent_cand_vs_acc(g, pl, co, c.par0, c.par1)) ok = false;
+        if (ok) { if (pl == 1) c.par0 += co; else c.par1 += co; acc |= 1u << j; }
+        if (g.lane == j) mine = ok;
+    }
+    return mine;
+}
+
+// One player's getAction + issue.  pl = owner code (1 = player 0, 2 = player 1).
+DEV void rb_player(Game &g, int pl, int n, bool simul, RbCtx &c) {
+    #pragma unroll 1
+    for (int base = 0; base < n; base += 32) {
+        int i = base + g.lane;
+        bool idle = i < n && u_pl(g.w0()[i]) == pl && a_type(g.a0()[i]) == (int)AT_IDLE;
+        unsigned m = __ballot_sync(FULLM, idle);
+        if (m == 0) continue;
+        int k = c.k + __popc(m & ((1u << g.lane) - 1));
+        uint32_t A0 = ACT_NONE | A0_NOUT; int A1 = 10, tcell = -1, cost = 0, t = 0;
+        if (idle) {
+            Enum e; enumerate(g, i, e);
+            t = e.t;
+            uint64_t st = lcg_jump(g, c.s0, k);
+            double dr = lcg_next_double(st);
+            pick_action(g, e, sample_index(dr, e.nb, e.total), 10, A0, A1, tcell, cost);
+        }
+        bool ok = rb_accept(g, pl, m, idle, tcell, cost, simul, c);
+        __syncwarp(); // every lane has read resv[] before the accepted actions are written
+        if (idle) {
+            if (!ok) { A0 = ACT_NONE | A0_NOUT; A1 = 10; tcell = -1; }
+            int eta = eta_of(g, t, A0, A1);
+            if (tcell >= 0) {
+                int ev = g.resv()[tcell];
+                if (ev != 0) {
+                    // the other player's action of this same cycle targets the cell: GameState.issue cancels both to
+                    // NONE(min(ETA_old, ETA_new)) under CANCEL_BOTH (GameState.java:263-296)
+                    int es = ev - 1;
+                    uint32_t E0 = g.a0()[es];
+                    int d1 = eta_of(g, u_type(g.w0()[es]), E0, g.a1()[es]);
+                    if (d1 < eta) eta = d1;
+                    g.a0()[es] = (E0 & 0xF0u) | ACT_NONE | A0_NOUT; g.a1()[es] = eta; g.rdy()[es] = c.time + eta;
+                    g.resv()[tcell] = 0;
+                    // the cell stays part of this player's PlayerAction.r: a later unit of the same list must not choose it
+                    g.claim()[tcell] |= (uint8_t)pl; c.cancelled = true;
+                    A0 = ACT_NONE | A0_NOUT; A1 = eta;
+                } else g.resv()[tcell] = (uint8_t)(i + 1);
+            }
+            g.a0()[i] = (g.a0()[i] & 0xF0u) | (A0 & ~0xF0u); g.a1()[i] = A1; g.tis()[i] = c.time; g.seq()[i] = c.seq_base + k;
+            g.rdy()[i] = c.time + eta;
+            if (c.time + eta < c.minr) c.minr = c.time + eta;
+        }
+        c.k += __popc(m);
+        __syncwarp();
+    }
 }
 
 #include "scripted.cuh"
@@ -1008,21 +1151,95 @@ DEV int run_policy(Game &g, const StepParams &p, long long gi, int player, int p
     }
 }
 
+// One decision point of RandomBiasedAI players: scan, then each deciding player's pass.  Returns the earliest completion
+// time of any assignment afterwards.  simul: Game.start semantics (both lists built on the pre-issue state, issued p0 then
+// p1); otherwise NaiveMCTS.simulate semantics (player 1 decides on the state that already holds player 0's actions).
+DEV int rb_decide(Game &g, int n, int time, int polmask, bool simul, unsigned long long &decisions) {
+    int par0 = 0, par1 = 0, mr;
+    int idle = rb_scan(g, n, par0, par1, mr) & polmask;
+    if (idle) {
+        RbCtx c;
+        c.time = time; c.seq_base = (uint32_t)g.hdr()[H_NEXTSEQ]; c.s0 = hdr_rng(g, H_RNGP_LO); c.k = 0; c.minr = mr; c.cancelled = false;
+        #pragma unroll 1
+        for (int pl = 1; pl <= 2; pl++) {
+            if (!(idle & pl)) continue;
+            if (!simul && pl == 2 && (idle & 1)) { int mr2; rb_scan(g, n, par0, par1, mr2); } // player 0's new PRODUCEs are in flight now
+            c.par0 = par0; c.par1 = par1;
+            rb_player(g, pl, n, simul, c);
+        }
+        mr = c.minr;
+        if (__ballot_sync(FULLM, c.cancelled)) {
+            #pragma unroll 1
+            for (int i = g.lane; i < g.pcw; i += 32) ((uint32_t *)g.claim())[i] = 0;
+        }
+        if (g.lane == 0) { g.hdr()[H_NEXTSEQ] = (int32_t)(c.seq_base + c.k); hdr_set_rng(g, H_RNGP_LO, lcg_jump(g, c.s0, c.k)); }
+        __syncwarp();
+        decisions += c.k;
+    }
+    return warp_min_time(mr);
+}
+
+// The loop shared by Game.start (rts/Game.java:126-140, simul = true) and NaiveMCTS.simulate
+// (ai/mcts/naivemcts/NaiveMCTS.java:297-308, simul = false) for RandomBiasedAI / PassiveAI players under CANCEL_BOTH:
+// decide, then cycle.  Time jumps straight to the next completion time: while no unit is idle nothing can change
+// (GameState.getNextChangeTime, GameState.java:532-546).  Returns gameover; `time` ends at the last executed cycle or tlimit.
+DEV bool play_rb(Game &g, int polmask, bool simul, int tlimit, int &time, int &winner, unsigned long long &decisions, unsigned long long &ucyc) {
+    bool over = game_over(g, winner); // a state that is already over ends at the very next cycle()
+    int n = g.hdr()[H_NUNITS];
+    #pragma unroll 1
+    while (time < tlimit) {
+        int mrt = rb_decide(g, n, time, polmask, simul, decisions);
+        int tn = time + 1; if (!over && mrt > tn) tn = mrt;
+        if (tn > tlimit) { ucyc += (unsigned long long)n * (tlimit - time); time = tlimit; break; }
+        ucyc += (unsigned long long)n * (tn - time);
+        time = tn;
+        if (cycle_execute(g, tn) > 0) over = game_over(g, winner);
+        n = g.hdr()[H_NUNITS];
+        if (over) return true;
+    }
+    return false;
+}
+
+// Game.start loop body for device policies RandomBiasedAI / PassiveAI under CANCEL_BOTH (the fast path of run_game below)
+DEV void run_game_fast(Game &g, const StepParams &p, WarpStats &ws) {
+    int status = g.hdr()[H_STATUS];
+    if (status & ST_OVER) return;
+    int t0 = g.hdr()[H_TIME], time = t0;
+    int tlimit = t0 + p.n_cycles; if (tlimit > p.max_cycles) tlimit = p.max_cycles;
+    int polmask = (p.policy[0] == POL_RANDOM_BIASED ? 1 : 0) | (p.policy[1] == POL_RANDOM_BIASED ? 2 : 0);
+    int winner;
+    unsigned long long decisions = 0, ucyc = 0;
+    if (play_rb(g, polmask, true, tlimit, time, winner, decisions, ucyc)) {
+        status |= ST_OVER | ST_COUNTED | ((winner + 1) << 8);
+        ws.v[STAT_FINISHED]++; if (winner == 0) ws.v[STAT_WINS0]++; else if (winner == 1) ws.v[STAT_WINS1]++; else ws.v[STAT_DRAWS]++;
+    }
+    if (!(status & ST_COUNTED) && time >= p.max_cycles) { // hit the cycle cap: a draw (winner() == -1)
+        status |= ST_COUNTED;
+        ws.v[STAT_FINISHED]++; ws.v[STAT_DRAWS]++;
+    }
+    __syncwarp();
+    if (g.lane == 0) { g.hdr()[H_TIME] = time; g.hdr()[H_STATUS] = status; }
+    __syncwarp();
+    ws.v[STAT_CYCLES] += (unsigned long long)(time - t0);
+    ws.v[STAT_DECISIONS] += decisions;
+    ws.v[STAT_UNIT_CYCLES] += ucyc;
+}
+
 // Game.start loop body (rts/Game.java:126-140) with exact skipping of cycles in which nothing can happen.
 DEVN void run_game(Game &g, const StepParams &p, long long gi, WarpStats &ws) {
-    int status = g.hdr[H_STATUS];
+    int status = g.hdr()[H_STATUS];
     if (status & ST_OVER) return;
-    int t0 = g.hdr[H_TIME];
+    int t0 = g.hdr()[H_TIME];
     int tlimit = t0 + p.n_cycles; if (tlimit > p.max_cycles) tlimit = p.max_cycles;
     int winner;
-    bool force_next = game_over(g, winner); // a state that is already over ends at the very next cycle()
+    bool over = game_over(g, winner); // a state that is already over ends at the very next cycle()
     bool first = true;
     // device policies emit self-consistent lists; under CANCEL_BOTH they can be issued in parallel (issue_policy_lists)
     bool fast_issue = p.conflict == 1 && p.policy[0] != POL_EXTERNAL && p.policy[1] != POL_EXTERNAL;
     unsigned long long decisions = 0, ucyc = 0;
     #pragma unroll 1
     for (;;) {
-        int time = g.hdr[H_TIME];
+        int time = g.hdr()[H_TIME];
         if (time >= tlimit) break;
         int pn0 = run_policy(g, p, gi, 0, 0, first);
         int pn1 = run_policy(g, p, gi, 1, pn0, first);
@@ -1031,7 +1248,7 @@ DEVN void run_game(Game &g, const StepParams &p, long long gi, WarpStats &ws) {
         else { issue_pending(g, 0, pn0); issue_pending(g, pn0, pn1); }
         decisions += pn1;
         int mrt = min_ready_time(g);
-        int tn = time + 1; if (!force_next && mrt > tn) tn = mrt;
+        int tn = time + 1; if (!over && mrt > tn) tn = mrt;
         if (tn > time + 1 && p.scripted) {
             // Cycles time+1 .. tn-1 are skipped because nothing can change in them, but the reference still calls getAction
             // in each.  For the scripted AIs the FIRST of those calls is not a no-op: translateActions drops the entries that
@@ -1041,22 +1258,22 @@ DEVN void run_game(Game &g, const StepParams &p, long long gi, WarpStats &ws) {
             for (int pl = 0; pl < 2; pl++)
                 if (p.policy[pl] == POL_WORKER_RUSH || p.policy[pl] == POL_LIGHT_RUSH) policy_scripted(g, pl, p.policy[pl], p.pathfinder[pl], 0);
         }
-        int nu = g.hdr[H_NUNITS];
-        if (tn > tlimit) { ucyc += (unsigned long long)nu * (tlimit - time); __syncwarp(); if (g.lane == 0) g.hdr[H_TIME] = tlimit; __syncwarp(); break; }
+        int nu = g.hdr()[H_NUNITS];
+        if (tn > tlimit) { ucyc += (unsigned long long)nu * (tlimit - time); __syncwarp(); if (g.lane == 0) g.hdr()[H_TIME] = tlimit; __syncwarp(); break; }
         ucyc += (unsigned long long)nu * (tn - time);
-        bool over = cycle_execute(g, tn, winner);
+        if (cycle_execute_ni(g, tn) > 0) over = game_over(g, winner);
         if (over) {
-            if (g.lane == 0) g.hdr[H_STATUS] = status | ST_OVER | ST_COUNTED | ((winner + 1) << 8);
+            if (g.lane == 0) g.hdr()[H_STATUS] = status | ST_OVER | ST_COUNTED | ((winner + 1) << 8);
             __syncwarp();
             ws.v[STAT_FINISHED]++; if (winner == 0) ws.v[STAT_WINS0]++; else if (winner == 1) ws.v[STAT_WINS1]++; else ws.v[STAT_DRAWS]++;
             break;
         }
     }
-    int tend = g.hdr[H_TIME];
-    status = g.hdr[H_STATUS];
+    int tend = g.hdr()[H_TIME];
+    status = g.hdr()[H_STATUS];
     if (!(status & ST_COUNTED) && tend >= p.max_cycles) { // hit the cycle cap: a draw (winner() == -1)
         __syncwarp();
-        if (g.lane == 0) g.hdr[H_STATUS] = status | ST_COUNTED;
+        if (g.lane == 0) g.hdr()[H_STATUS] = status | ST_COUNTED;
         __syncwarp();
         ws.v[STAT_FINISHED]++; ws.v[STAT_DRAWS]++;
     }
@@ -1068,16 +1285,17 @@ DEVN void run_game(Game &g, const StepParams &p, long long gi, WarpStats &ws) {
 // GameState.cycle() repeated until time == target (TestTracesIntegrity.java:81-85); no policies
 DEVN void run_cycles_only(Game &g, int target) {
     int winner;
+    bool over = game_over(g, winner);
     #pragma unroll 1
     for (;;) {
-        int time = g.hdr[H_TIME];
+        int time = g.hdr()[H_TIME];
         if (time >= target) break;
         int mrt = min_ready_time(g);
-        int tn = time + 1; if (mrt > tn) tn = mrt;
-        if (tn > target) { __syncwarp(); if (g.lane == 0) g.hdr[H_TIME] = target; __syncwarp(); break; }
-        bool over = cycle_execute(g, tn, winner);
+        int tn = time + 1; if (!over && mrt > tn) tn = mrt;
+        if (tn > target) { __syncwarp(); if (g.lane == 0) g.hdr()[H_TIME] = target; __syncwarp(); break; }
+        if (cycle_execute_ni(g, tn) > 0) over = game_over(g, winner);
         __syncwarp();
-        if (g.lane == 0) { int st = g.hdr[H_STATUS] & ~(ST_OVER | 0x300); if (over) st |= ST_OVER | ((winner + 1) << 8); g.hdr[H_STATUS] = st; }
+        if (g.lane == 0) { int st = g.hdr()[H_STATUS] & ~(ST_OVER | 0x300); if (over) st |= ST_OVER | ((winner + 1) << 8); g.hdr()[H_STATUS] = st; }
         __syncwarp();
     }
 }
@@ -1106,20 +1324,20 @@ DEV void stamp_sight(Game &g, uint8_t *map, uint32_t w) {
 }
 DEV void cell_planes(const Game &g, int cell, int player, bool po, int v[8]) {
     int x = cell % g.W, y = cell / g.W, pc = (y + 1) * g.P + x + 1;
-    int gv = g.grid[pc];
+    int gv = g.grid()[pc];
     #pragma unroll 1
     for (int k = 0; k < 8; k++) v[k] = 0;
     v[5] = g.grid_tmpl ? (int)(((const uint8_t *)g.grid_tmpl)[pc] == 0xFF) : 0;
-    if (po) { v[6] = g.resv[pc]; v[7] = g.claim[pc]; }
+    if (po) { v[6] = g.resv()[pc]; v[7] = g.claim()[pc]; }
     if (gv != 0 && gv != 0xFF) {
         int s = gv - 1;
-        uint32_t w = g.w0[s], w1 = g.w1[s];
+        uint32_t w = g.w0()[s], w1 = g.w1()[s];
         int pl = u_pl(w);
-        if (po && pl != player + 1 && !g.resv[pc]) return; // not observable: removed from the observer's view
+        if (po && pl != player + 1 && !g.resv()[pc]) return; // not observable: removed from the observer's view
         v[0] = u_hp(w1); v[1] = u_res(w1);
         if (pl != 0) v[2] = ((pl - 1 + player) % 2) + 1;
         v[3] = u_type(w) + 1;
-        int at = a_type(g.a0[s]);
+        int at = a_type(g.a0()[s]);
         v[4] = at == (int)AT_IDLE ? 0 : at;
     }
 }
@@ -1127,17 +1345,17 @@ DEVN void observe_game(Game &g, const StepParams &p, long long gi) {
     int cells = g.W * g.H, C = p.partial_obs ? 8 : 6, player = p.out_player;
     bool po = p.partial_obs != 0;
     if (po) {
-        int n = g.hdr[H_NUNITS];
+        int n = g.hdr()[H_NUNITS];
         #pragma unroll 1
-        for (int i = g.lane; i < g.pcw; i += 32) { ((uint32_t *)g.resv)[i] = 0; ((uint32_t *)g.claim)[i] = 0; }
+        for (int i = g.lane; i < g.pcw; i += 32) { ((uint32_t *)g.resv())[i] = 0; ((uint32_t *)g.claim())[i] = 0; }
         __syncwarp();
         #pragma unroll 1
-        for (int i = 0; i < n; i++) { uint32_t w = g.w0[i]; if (u_pl(w) == player + 1) stamp_sight(g, g.resv, w); }
+        for (int i = 0; i < n; i++) { uint32_t w = g.w0()[i]; if (u_pl(w) == player + 1) stamp_sight(g, g.resv(), w); }
         __syncwarp();
         #pragma unroll 1
         for (int i = 0; i < n; i++) { // enemy units that survive the filter (PartiallyObservableGameState.java:44-53)
-            uint32_t w = g.w0[i];
-            if (u_pl(w) != 0 && u_pl(w) != player + 1 && g.resv[cell_of(g, w)]) stamp_sight(g, g.claim, w);
+            uint32_t w = g.w0()[i];
+            if (u_pl(w) != 0 && u_pl(w) != player + 1 && g.resv()[cell_of(g, w)]) stamp_sight(g, g.claim(), w);
         }
         __syncwarp();
     }
@@ -1176,12 +1394,12 @@ DEVN void observe_game(Game &g, const StepParams &p, long long gi) {
 // ---- JNIGridnetClient.getMasks (tests/JNIGridnetClient.java:210-223) + UnitAction.getValidActionArray
 // (UnitAction.java:711-751).  The output must be zero-filled by the caller; only rows of idle own units are written.
 DEVN void masks_game(Game &g, const StepParams &p, long long gi) {
-    int n = g.hdr[H_NUNITS], player = p.out_player;
+    int n = g.hdr()[H_NUNITS], player = p.out_player;
     int R = 2 * p.max_range + 1, ctr = R / 2, nT = p.n_types, K = 1 + 6 + 16 + nT + R * R;
     #pragma unroll 1
     for (int s = 0; s < n; s++) {
-        uint32_t w = g.w0[s];
-        if (u_pl(w) != player + 1 || a_type(g.a0[s]) != AT_IDLE) continue; // uniform across lanes
+        uint32_t w = g.w0()[s];
+        if (u_pl(w) != player + 1 || a_type(g.a0()[s]) != AT_IDLE) continue; // uniform across lanes
         Enum e; enumerate(g, s, e);
         bool mv = (e.fl & UF_MOVE) != 0;
         int pr_m = e.n_aff > 0 ? e.free_m : 0, mv_m = mv ? e.free_m : 0;
@@ -1209,8 +1427,8 @@ DEVN void masks_game(Game &g, const StepParams &p, long long gi) {
             } else if (e.fl & UF_ATTACK) {
                 int r = j - 23 - nT, ax = u_x(w) + r % R - ctr, ay = u_y(w) + r / R - ctr;
                 if (ax >= 0 && ay >= 0 && ax < g.W && ay < g.H) {
-                    int gv = g.grid[(ay + 1) * g.P + ax + 1];
-                    if (gv != 0 && gv != 0xFF) v = enemy_in_range(g, w, g.w0[gv - 1], e.range * e.range) ? 1 : 0;
+                    int gv = g.grid()[(ay + 1) * g.P + ax + 1];
+                    if (gv != 0 && gv != 0xFF) v = enemy_in_range(g, w, g.w0()[gv - 1], e.range * e.range) ? 1 : 0;
                 }
             }
             if (p.out_dtype == 0) ((uint8_t *)p.out)[row + j] = (uint8_t)v;
@@ -1222,26 +1440,26 @@ DEVN void masks_game(Game &g, const StepParams &p, long long gi) {
 // ---- NaiveMCTS playout (ai/mcts/naivemcts/NaiveMCTS.java:195-223,297-308) -----------------------------------------------
 // PartiallyObservableGameState(gs, observer) (rts/PartiallyObservableGameState.java:35-71): drop every unit that is not
 // the observer's and lies outside the sight radius of all observer units (with its assignment).
-DEVN void po_filter(Game &g, int observer) {
-    int n = g.hdr[H_NUNITS];
+DEV void po_filter(Game &g, int observer) {
+    int n = g.hdr()[H_NUNITS];
 #pragma unroll 1
-    for (int i = g.lane; i < g.pcw; i += 32) ((uint32_t *)g.claim)[i] = 0;
+    for (int i = g.lane; i < g.pcw; i += 32) ((uint32_t *)g.claim())[i] = 0;
     __syncwarp();
 #pragma unroll 1
-    for (int i = 0; i < n; i++) { uint32_t w = g.w0[i]; if (u_pl(w) == observer + 1) stamp_sight(g, g.claim, w); }
+    for (int i = 0; i < n; i++) { uint32_t w = g.w0()[i]; if (u_pl(w) == observer + 1) stamp_sight(g, g.claim(), w); }
     __syncwarp();
     int removed = 0;
 #pragma unroll 1
     for (int base = 0; base < n; base += 32) {
         int i = base + g.lane;
         bool drop = false;
-        if (i < n) { uint32_t w = g.w0[i]; drop = u_pl(w) != observer + 1 && !g.claim[cell_of(g, w)]; }
-        if (drop) g.a0[i] |= A0_DEAD;
+        if (i < n) { uint32_t w = g.w0()[i]; drop = u_pl(w) != observer + 1 && !g.claim()[cell_of(g, w)]; }
+        if (drop) g.a0()[i] |= A0_DEAD;
         removed += __popc(__ballot_sync(FULLM, drop));
     }
     __syncwarp();
 #pragma unroll 1
-    for (int i = g.lane; i < g.pcw; i += 32) ((uint32_t *)g.claim)[i] = 0;
+    for (int i = g.lane; i < g.pcw; i += 32) ((uint32_t *)g.claim())[i] = 0;
     __syncwarp();
     if (removed) compact_units(g);
 }
@@ -1249,15 +1467,15 @@ DEVN void po_filter(Game &g, int observer) {
 // SimpleSqrtEvaluationFunction3.base_score (ai/evaluation/SimpleSqrtEvaluationFunction3.java:32-44) and
 // SimpleEvaluationFunction.base_score (SimpleEvaluationFunction.java:27-36): float accumulation in unit-list order.
 DEV float base_score(const Game &g, int fn, int player) {
-    float score = __fmul_rn((float)g.hdr[H_RES0 + player], 20.0f);
+    float score = __fmul_rn((float)g.hdr()[H_RES0 + player], 20.0f);
     bool any = false;
-    int n = g.hdr[H_NUNITS];
+    int n = g.hdr()[H_NUNITS];
 #pragma unroll 1
     for (int i = 0; i < n; i++) {
-        uint32_t w = g.w0[i];
+        uint32_t w = g.w0()[i];
         if (u_pl(w) != player + 1) continue;
         any = true;
-        uint32_t w1 = g.w1[i];
+        uint32_t w1 = g.w1()[i];
         int t = u_type(w), cost = ut_cost(g, t), mhp = ut_hp(g, t), hp = u_hp(w1);
         score = __fadd_rn(score, __fmul_rn((float)u_res(w1), 10.0f));
         if (fn == 0) { // score += 40f * cost * Math.sqrt(hp / maxhp): int division, double product, narrowing +=
@@ -1281,7 +1499,7 @@ DEV float evaluate_state(const Game &g, int fn, int maxplayer) {
 // simulate(gs2, gs2.getTime() + depth):  do { if (gs.isComplete()) gameover = gs.cycle(); else { gs.issue(policy(0));
 // gs.issue(policy(1)); } } while (!gameover && time < limit) -- issue(), not issueSafe(); player 1 samples after
 // player 0's actions are in flight, so no same-cycle conflict can arise and both lists are inserted in parallel.
-DEVN void run_rollout(Game &g, const StepParams &p, long long r, WarpStats &ws) {
+DEV void run_rollout(Game &g, const StepParams &p, long long r, WarpStats &ws) {
     if (p.observer >= 0) po_filter(g, p.observer);
     long long seed = p.ro_seeds ? p.ro_seeds[r] : r;
     __syncwarp();
@@ -1291,73 +1509,64 @@ DEVN void run_rollout(Game &g, const StepParams &p, long long r, WarpStats &ws) 
         hdr_set_rng(g, H_RNGD_LO, ((unsigned long long)(seed ^ 0x14057B7EF767814FLL) ^ 0x5DEECE66DULL) & MASK48);
     }
     __syncwarp();
-    int t0 = g.hdr[H_TIME], limit = t0 + p.depth, winner;
-    bool over_now = game_over(g, winner), gameover = false;
+    int t0 = g.hdr()[H_TIME], time = t0, winner;
     unsigned long long decisions = 0, ucyc = 0;
-    do {
-        int n = g.hdr[H_NUNITS];
-        bool idle = false;
-#pragma unroll 1
-        for (int i = g.lane; i < n; i += 32) idle |= u_pl(g.w0[i]) != 0 && a_type(g.a0[i]) == AT_IDLE;
-        if (__ballot_sync(FULLM, idle) == 0) { // isComplete()
-            int time = g.hdr[H_TIME];
-            int mrt = min_ready_time(g);
-            int tn = time + 1; if (!over_now && mrt > tn) tn = mrt;
-            if (tn > limit) { ucyc += (unsigned long long)n * (limit - time); __syncwarp(); if (g.lane == 0) g.hdr[H_TIME] = limit; __syncwarp(); break; }
-            ucyc += (unsigned long long)n * (tn - time);
-            gameover = cycle_execute(g, tn, winner);
-            over_now = gameover;
-        } else {
-            int pn = policy_random_biased(g, 0, 0);
-            issue_policy_lists(g, pn, pn);
-            decisions += pn;
-            pn = policy_random_biased(g, 1, 0);
-            issue_policy_lists(g, pn, pn);
-            decisions += pn;
-        }
-    } while (!gameover && g.hdr[H_TIME] < limit);
-    float ev = 0.0f;
-    if (g.lane == 0) ev = evaluate_state(g, p.eval_fn, p.maxplayer);
-    if (g.lane == 0) { if (p.ro_eval) p.ro_eval[r] = ev; if (p.ro_time) p.ro_time[r] = g.hdr[H_TIME] - t0; }
-    ws.v[STAT_CYCLES] += (unsigned long long)(g.hdr[H_TIME] - t0);
+    play_rb(g, 3, false, t0 + p.depth, time, winner, decisions, ucyc);
+    __syncwarp();
+    if (g.lane == 0) {
+        g.hdr()[H_TIME] = time;
+        float ev = evaluate_state(g, p.eval_fn, p.maxplayer);
+        if (p.ro_eval) p.ro_eval[r] = ev;
+        if (p.ro_time) p.ro_time[r] = time - t0;
+    }
+    ws.v[STAT_CYCLES] += (unsigned long long)(time - t0);
     ws.v[STAT_DECISIONS] += decisions;
     ws.v[STAT_UNIT_CYCLES] += ucyc;
     ws.v[STAT_FINISHED]++;
 }
 
-// body of the step kernel for one thread; `smem` is the CTA's dynamic shared memory
+// Bodies of the step kernels for one thread.  Three kernels share the loop below; what differs is which entry points
+// are compiled in, so that the hot ones stay small enough for the instruction caches and fully inlined:
+//   KERNEL_FAST    MODE_GAME with RandomBiasedAI / PassiveAI players under CANCEL_BOTH
+//   KERNEL_ROLLOUT MODE_ROLLOUT
+//   KERNEL_GENERIC everything else (external actions, scripted policies, other conflict policies, cycle-only,
+//                  issue-only, observations, masks)
+enum { KERNEL_FAST = 0, KERNEL_ROLLOUT = 1, KERNEL_GENERIC = 2 };
+
+template <int KERNEL>
 DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int nthreads, int bid, int nblocks) {
-    uint32_t *cst = (uint32_t *)smem;
+#ifdef MRTS_EMU
+    mrts_smem = smem;
+#endif
+    uint32_t *cst = (uint32_t *)mrts_smem;
     #pragma unroll 1
     for (int i = tid; i < MRTS_CONST_WORDS; i += nthreads) cst[i] = p.cst[i];
     __syncthreads();
     SmemLayout L = mrts_smem_layout(p.W, p.H, p.cap, p.scripted);
     int warp = tid >> 5, lane = tid & 31, wpc = nthreads >> 5;
     Game g;
-    g_bind(g, smem + MRTS_CONST_WORDS * 4 + (size_t)warp * L.total, L, p.W, p.H, p.cap, lane, cst, p.conflict, p.scripted,
+    g_bind(g, MRTS_CONST_WORDS * 4 + warp * L.total, L, p.W, p.H, p.cap, lane, p.conflict, p.scripted,
            p.scripted == 2 ? p.astar_scratch + ((long long)bid * wpc + warp) * p.astar_stride : nullptr);
     WarpStats ws;
     for (int i = 0; i < 8; i++) ws.v[i] = 0;
-    long long n_items = p.mode == MODE_ROLLOUT ? p.n_games * p.rollouts_per_game : p.n_games;
+    long long n_items = KERNEL == KERNEL_ROLLOUT ? p.n_games * p.rollouts_per_game : p.n_games;
 #pragma unroll 1
     for (long long item = (long long)bid * wpc + warp; item < n_items; item += (long long)nblocks * wpc) {
-        long long gi = p.mode == MODE_ROLLOUT ? item / p.rollouts_per_game : item;
+        long long gi = KERNEL == KERNEL_ROLLOUT ? item / p.rollouts_per_game : item;
         const uint32_t *blob = p.maps + (size_t)(gi % p.n_maps) * p.map_words;
         g.grid_tmpl = blob;
         int32_t *ghdr = p.hdr + gi * MRTS_HDR_WORDS;
         uint32_t *gun = p.units + gi * (long long)p.uw * p.cap;
-        g_load(g, ghdr, gun);
-        int err0 = g.hdr[H_ERR];
-        if (p.mode == MODE_GAME) {
-            if (p.auto_reset && ((g.hdr[H_STATUS] & ST_OVER) || g.hdr[H_TIME] >= p.max_cycles)) g_restart(g);
-            run_game(g, p, gi, ws);
-        }
-        else if (p.mode == MODE_CYCLE_ONLY) run_cycles_only(g, p.t_target ? p.t_target[gi] : g.hdr[H_TIME] + p.n_cycles);
+        g_load(g, ghdr, gun, KERNEL != KERNEL_ROLLOUT && p.mode == MODE_GAME && p.auto_reset, p.max_cycles);
+        if (KERNEL == KERNEL_ROLLOUT) { run_rollout(g, p, item, ws); continue; } // the batch itself is not modified
+        int err0 = g.hdr()[H_ERR];
+        if (KERNEL == KERNEL_FAST) run_game_fast(g, p, ws);
+        else if (p.mode == MODE_GAME) run_game(g, p, gi, ws);
+        else if (p.mode == MODE_CYCLE_ONLY) run_cycles_only(g, p.t_target ? p.t_target[gi] : g.hdr()[H_TIME] + p.n_cycles);
         else if (p.mode == MODE_ISSUE_ONLY) run_issue_only(g, p, gi);
         else if (p.mode == MODE_OBSERVE) { observe_game(g, p, gi); continue; }
-        else if (p.mode == MODE_ROLLOUT) { run_rollout(g, p, item, ws); continue; } // the batch itself is not modified
         else { masks_game(g, p, gi); continue; }
-        if (g.hdr[H_ERR] != err0) ws.v[STAT_ERRORS]++;
+        if (g.hdr()[H_ERR] != err0) ws.v[STAT_ERRORS]++;
         g_store(g, ghdr, gun);
     }
     if (lane == 0 && p.stats)

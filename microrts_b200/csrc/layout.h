@@ -62,9 +62,18 @@ enum { UF_RESOURCE = 1, UF_STOCKPILE = 2, UF_HARVEST = 4, UF_MOVE = 8, UF_ATTACK
 enum { GE_UNIT_OVERFLOW = 1, GE_INCONSISTENT_OLDER = 2, GE_FAILED_PRODUCE = 4, GE_CELL_OCCUPIED = 8, GE_BAD_ACTION = 16 };
 
 struct SmemLayout {
-    int hdr, units, pa0, pa1, pslot, grid, resv, claim, list, astar, total; // byte offsets inside one game's region
-    int pcw;                                                          // padded-grid size in 32-bit words
+    int hdr, units, pa0, pa1, pslot, grid, kind, resv, claim, list, astar, total; // byte offsets inside one game's region
+    int pcw;                                                                     // padded-grid size in 32-bit words
+    int uws;                                                                     // unit words resident in shared memory
 };
+
+// Shared-memory-only per-unit word (index uw, after the words mirrored in HBM): RDY = completion time of the unit's
+// in-flight assignment (issue time + ETA), MRTS_NEVER when idle.  Rebuilt whenever a game is loaded.
+#define MRTS_NEVER 0x7fffffff
+
+// cell "kind" byte (kind map): 0 empty, 0xFF wall / out of bounds, else owner+1 (bits 0-1: 0 neutral) | isResource<<2 |
+// isStockpile<<3 | 0x10 -- what Unit.getUnitActions needs to know about a neighbouring cell, without touching the unit.
+#define CK_UNIT 0x10
 
 // A* / BFS scratch (scripted policies only): per cell closed u16, cost u16, flags u8, open list (pos u16, parent u16, f u16)
 #define MRTS_ASTAR_BYTES_PER_CELL 11
@@ -74,12 +83,14 @@ MRTS_HD SmemLayout mrts_smem_layout(int W, int H, int cap, int scripted) {
     int pcb = (pc + 15) & ~15;
     int capb = (cap + 15) & ~15;
     int o = 0;
+    L.uws = (scripted ? MRTS_UNIT_WORDS : MRTS_UNIT_WORDS_CORE) + 1; // X0/X1 are resident only for scripted batches; +1: RDY
     L.hdr = o; o += MRTS_HDR_WORDS * 4;
-    L.units = o; o += (scripted ? MRTS_UNIT_WORDS : MRTS_UNIT_WORDS_CORE) * cap * 4; // X0/X1 are resident only for scripted batches
+    L.units = o; o += L.uws * cap * 4;
     L.pa0 = o; o += cap * 4;
     L.pa1 = o; o += cap * 4;
     L.pslot = o; o += capb;
     L.grid = o; o += pcb;
+    L.kind = o; o += pcb;
     L.resv = o; o += pcb;
     L.claim = o; o += pcb;
     L.list = o; o += capb;

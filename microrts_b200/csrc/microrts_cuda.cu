@@ -112,11 +112,18 @@ DEV void results_kernel_body(const ResultParams &p, long long gi) {
 
 #ifndef MRTS_EMU
 #ifndef MRTS_MIN_BLOCKS
-#define MRTS_MIN_BLOCKS 6
+#define MRTS_MIN_BLOCKS 8
 #endif
-__global__ void __launch_bounds__(MRTS_WARPS_PER_CTA * 32, MRTS_MIN_BLOCKS) k_step(StepParams p) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    step_kernel_body(p, smem, threadIdx.x, blockDim.x, blockIdx.x, gridDim.x);
+// k_step_fast: Game.start loop with RandomBiasedAI / PassiveAI under CANCEL_BOTH (the benchmark path); k_rollout:
+// NaiveMCTS.simulate + evaluation; k_step: every other mode.  All three are persistent, one warp per game at a time.
+__global__ void __launch_bounds__(MRTS_WARPS_PER_CTA * 32, MRTS_MIN_BLOCKS) k_step_fast(StepParams p) {
+    step_kernel_body<KERNEL_FAST>(p, mrts_smem, threadIdx.x, blockDim.x, blockIdx.x, gridDim.x);
+}
+__global__ void __launch_bounds__(MRTS_WARPS_PER_CTA * 32, MRTS_MIN_BLOCKS) k_rollout(StepParams p) {
+    step_kernel_body<KERNEL_ROLLOUT>(p, mrts_smem, threadIdx.x, blockDim.x, blockIdx.x, gridDim.x);
+}
+__global__ void __launch_bounds__(MRTS_WARPS_PER_CTA * 32, 2) k_step(StepParams p) {
+    step_kernel_body<KERNEL_GENERIC>(p, mrts_smem, threadIdx.x, blockDim.x, blockIdx.x, gridDim.x);
 }
 __global__ void __launch_bounds__(128) k_reset(ResetParams p) { reset_kernel_body(p, threadIdx.x, blockDim.x, blockIdx.x, gridDim.x); }
 __global__ void __launch_bounds__(128) k_results(ResultParams p) { results_kernel_body(p, (long long)blockIdx.x * blockDim.x + threadIdx.x); }
@@ -148,8 +155,8 @@ struct mrts_batch {
     Staged staged[2];
     stream_t stream = nullptr;
     SmemLayout L;
-    size_t smem_bytes = 0;
-    int grid = 0, max_range = 0, auto_reset = 0, scripted = 0, uw = MRTS_UNIT_WORDS_CORE, wpc = MRTS_WARPS_PER_CTA; // wpc: warps (games in flight) per CTA
+    struct Plan { int wpc = 2, grid = 3; size_t smem = 0; } plan[3]; // per kernel: warps (games in flight) per CTA, CTAs, shared memory
+    int max_range = 0, auto_reset = 0, scripted = 0, uw = MRTS_UNIT_WORDS_CORE;
     long long launches = 0;
 };
 
@@ -167,17 +174,29 @@ static int launch_step(mrts_batch *b, StepParams &p) {
     p.conflict = b->utt.conflict; p.max_range = b->max_range; p.n_types = (int)b->utt.types.size();
     p.partial_obs = (b->flags & MRTS_FLAG_PARTIAL_OBS) ? 1 : 0; p.scripted = b->scripted; p.uw = b->uw;
     p.astar_scratch = b->d_astar; p.astar_stride = b->astar_stride;
-    int threads = b->wpc * 32;
+    // kernel selection: the specialised kernels cover exactly the cases their loops implement
+    int kernel = KERNEL_GENERIC;
+    auto rb_or_passive = [](int pol) { return pol == MRTS_POLICY_RANDOM_BIASED || pol == MRTS_POLICY_PASSIVE; };
+    if (p.mode == MODE_ROLLOUT) kernel = KERNEL_ROLLOUT;
+    else if (p.mode == MODE_GAME && p.conflict == MRTS_CANCEL_BOTH && rb_or_passive(p.policy[0]) && rb_or_passive(p.policy[1])) kernel = KERNEL_FAST;
+    const mrts_batch::Plan &pl = b->plan[kernel];
+    int threads = pl.wpc * 32;
     long long items = p.mode == MODE_ROLLOUT ? b->n * p.rollouts_per_game : b->n;
-    long long need = (items + b->wpc - 1) / b->wpc;
-    int grid = (int)std::min<long long>(b->grid, std::max<long long>(need, 1));
+    long long need = (items + pl.wpc - 1) / pl.wpc;
+    int grid = (int)std::min<long long>(pl.grid, std::max<long long>(need, 1));
     b->launches++;
 #ifdef MRTS_EMU
     StepParams pc = p;
-    emu::launch(grid, threads, b->smem_bytes, [pc, threads, grid](unsigned char *sm, int tid, int bid) { step_kernel_body(pc, sm, tid, threads, bid, grid); });
+    emu::launch(grid, threads, pl.smem, [pc, threads, grid, kernel](unsigned char *sm, int tid, int bid) {
+        if (kernel == KERNEL_FAST) step_kernel_body<KERNEL_FAST>(pc, sm, tid, threads, bid, grid);
+        else if (kernel == KERNEL_ROLLOUT) step_kernel_body<KERNEL_ROLLOUT>(pc, sm, tid, threads, bid, grid);
+        else step_kernel_body<KERNEL_GENERIC>(pc, sm, tid, threads, bid, grid);
+    });
     return 0;
 #else
-    k_step<<<grid, threads, b->smem_bytes, b->stream>>>(p);
+    if (kernel == KERNEL_FAST) k_step_fast<<<grid, threads, pl.smem, b->stream>>>(p);
+    else if (kernel == KERNEL_ROLLOUT) k_rollout<<<grid, threads, pl.smem, b->stream>>>(p);
+    else k_step<<<grid, threads, pl.smem, b->stream>>>(p);
     return ck(cudaGetLastError());
 #endif
 }
@@ -299,30 +318,33 @@ int mrts_batch_create(const mrts_utt *u, const mrts_map *const *maps, int n_maps
 #ifndef MRTS_EMU
     cudaDeviceProp prop;
     if (ck(cudaGetDeviceProperties(&prop, device))) return fail(MRTS_E_CUDA, std::string("cudaGetDeviceProperties: ") + dev_errstr());
-    // warps per CTA: as many games in flight per SM as shared memory allows (large maps need fewer, fatter CTAs)
-    int best_wpc = 0, best_warps = 0, best_blocks = 0;
-    for (int wpc = MRTS_WARPS_PER_CTA; wpc >= 1; wpc--) {
-        size_t sm = MRTS_CONST_WORDS * 4 + (size_t)wpc * b->L.total;
-        if (sm > (size_t)prop.sharedMemPerBlockOptin) continue;
-        if (ck(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm))) return fail(MRTS_E_CUDA, std::string("cudaFuncSetAttribute: ") + dev_errstr());
-        int per_sm = 0;
-        if (ck(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step, wpc * 32, sm))) return fail(MRTS_E_CUDA, std::string("occupancy query: ") + dev_errstr());
-        if (per_sm * wpc > best_warps) { best_warps = per_sm * wpc; best_wpc = wpc; best_blocks = per_sm; }
+    // Per kernel: as many games in flight per SM as shared memory and registers allow (large maps need fewer, fatter
+    // CTAs); grid = resident CTAs per SM x SMs (persistent kernel).
+    const void *kernels[3] = {(const void *)k_step_fast, (const void *)k_rollout, (const void *)k_step};
+    for (int kk = 0; kk < 3; kk++) {
+        int best_wpc = 0, best_warps = 0, best_blocks = 0;
+        if (ck(cudaFuncSetAttribute(kernels[kk], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin)) ||
+            ck(cudaFuncSetAttribute(kernels[kk], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)))
+            return fail(MRTS_E_CUDA, std::string("cudaFuncSetAttribute: ") + dev_errstr());
+        for (int wpc = MRTS_WARPS_PER_CTA; wpc >= 1; wpc--) {
+            size_t sm = MRTS_CONST_WORDS * 4 + (size_t)wpc * b->L.total;
+            if (sm > (size_t)prop.sharedMemPerBlockOptin) continue;
+            int per_sm = 0;
+            if (ck(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernels[kk], wpc * 32, sm))) return fail(MRTS_E_CUDA, std::string("occupancy query: ") + dev_errstr());
+            if (per_sm * wpc > best_warps) { best_warps = per_sm * wpc; best_wpc = wpc; best_blocks = per_sm; }
+        }
+        if (!best_wpc) return fail(MRTS_E_LIMIT, "map too large for the shared-memory resident engine");
+        b->plan[kk].wpc = best_wpc;
+        b->plan[kk].smem = MRTS_CONST_WORDS * 4 + (size_t)best_wpc * b->L.total;
+        b->plan[kk].grid = best_blocks * prop.multiProcessorCount;
     }
-    if (!best_wpc) return fail(MRTS_E_LIMIT, "map too large for the shared-memory resident engine");
-    b->wpc = best_wpc;
-    b->smem_bytes = MRTS_CONST_WORDS * 4 + (size_t)best_wpc * b->L.total;
-    if (ck(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin))) return fail(MRTS_E_CUDA, std::string("cudaFuncSetAttribute: ") + dev_errstr());
-    b->grid = best_blocks * prop.multiProcessorCount;
     if (ck(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking))) return fail(MRTS_E_CUDA, std::string("cudaStreamCreate: ") + dev_errstr());
 #else
-    b->wpc = 2;
-    b->smem_bytes = MRTS_CONST_WORDS * 4 + (size_t)b->wpc * b->L.total;
-    b->grid = 3;
+    for (int kk = 0; kk < 3; kk++) { b->plan[kk].wpc = 2; b->plan[kk].smem = MRTS_CONST_WORDS * 4 + (size_t)2 * b->L.total; b->plan[kk].grid = 3; }
 #endif
     if (b->scripted == 2) {
         b->astar_stride = ((long long)W * H * MRTS_ASTAR_BYTES_PER_CELL + 255) & ~255LL;
-        if (dev_alloc((void **)&b->d_astar, (size_t)b->grid * b->wpc * b->astar_stride)) return fail(MRTS_E_CUDA, std::string("device allocation failed: ") + dev_errstr());
+        if (dev_alloc((void **)&b->d_astar, (size_t)b->plan[KERNEL_GENERIC].grid * b->plan[KERNEL_GENERIC].wpc * b->astar_stride)) return fail(MRTS_E_CUDA, std::string("device allocation failed: ") + dev_errstr());
     }
     size_t hdr_bytes = (size_t)n_games * MRTS_HDR_WORDS * 4, unit_bytes = (size_t)n_games * b->uw * cap * 4;
     if (dev_alloc((void **)&b->d_hdr, hdr_bytes) || dev_alloc((void **)&b->d_units, unit_bytes) ||

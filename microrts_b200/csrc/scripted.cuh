@@ -27,14 +27,14 @@ DEV int aa_base(uint32_t X1) { return (X1 >> 8) & 0xff; }
 
 // actions.put(u, aa): an existing key keeps its position in the LinkedHashMap (lane 0 only)
 DEV void aa_put(Game &g, int s, int player, int kind, int type, int bx, int by, int target, int base) {
-    uint32_t oX0 = g.x0[s], oX1 = g.x1[s];
+    uint32_t oX0 = g.x0()[s], oX1 = g.x1()[s];
     uint32_t seq;
     if (aa_kind(oX0) != AA_NONE) seq = aa_seq(oX0, oX1);
-    else seq = (uint32_t)g.hdr[H_ASEQ0 + player]++;
+    else seq = (uint32_t)g.hdr()[H_ASEQ0 + player]++;
     uint32_t X0 = (uint32_t)kind | ((uint32_t)type << 4) | ((uint32_t)(bx & 0xff) << 8) | ((uint32_t)(by & 0xff) << 16) | (bx < 0 ? (1u << 24) : 0u) |
                   ((seq >> 16) << 25);
     uint32_t X1 = (uint32_t)target | ((uint32_t)base << 8) | ((seq & 0xffffu) << 16);
-    g.x0[s] = X0; g.x1[s] = X1;
+    g.x0()[s] = X0; g.x1()[s] = X1;
 }
 
 // ---- pathfinding ---------------------------------------------------------------------------------------------------------
@@ -44,7 +44,7 @@ DEV int pf_pc(const Game &g, int pos) { return (pos / g.W + 1) * g.P + pos % g.W
 DEV bool pf_free(const Game &g, int pos) {
     if (g.as_flags[pos] & PFF_BLOCKED) return false;
     int pc = pf_pc(g, pos);
-    return g.grid[pc] == 0 && g.resv[pc] == 0;
+    return g.grid()[pc] == 0 && g.resv()[pc] == 0;
 }
 DEV int pf_first_step(const Game &g, int pos, int parent) {
     int last = pos;
@@ -66,11 +66,11 @@ DEVN int pf_find(Game &g, int kind, int s, int targetpos, int range, int nd) {
     for (int i = 0; i < cells; i++) { g.as_closed[i] = 0xFFFF; g.as_flags[i] = 0; }
 #pragma unroll 1
     for (int k = 0; k < nd; k++) {
-        uint32_t A0 = g.pa0[k];
-        if (a_uses_cell(a_type(A0))) { int lin = linear_target_cell(g, g.w0[g.pslot[k]], g.pa1[k]); if (lin >= 0) { int pc = lin; int y = pc / g.P - 1, x = pc % g.P - 1; g.as_flags[x + y * W] |= PFF_BLOCKED; } }
+        uint32_t A0 = g.pa0()[k];
+        if (a_uses_cell(a_type(A0))) { int lin = linear_target_cell(g, g.w0()[g.pslot()[k]], g.pa1()[k]); if (lin >= 0) { int pc = lin; int y = pc / g.P - 1, x = pc % g.P - 1; g.as_flags[x + y * W] |= PFF_BLOCKED; } }
     }
     int tx = targetpos % W, ty = targetpos / W, sq = range * range;
-    uint32_t sw = g.w0[s];
+    uint32_t sw = g.w0()[s];
     int sx = u_x(sw), sy = u_y(sw), start = sy * W + sx;
     if (kind == 0) { // A*: open is sorted by descending f, newest first among equal f; pop from the end
         int oi = 0;
@@ -138,17 +138,17 @@ struct ScriptCtx { int player, pf, par0, par1, nd; };
 
 // GameState.isUnitActionAllowed (GameState.java:434-457)
 DEV bool unit_action_allowed(const Game &g, const ScriptCtx &c, int s, uint32_t A0, int A1) {
-    uint32_t w = g.w0[s];
+    uint32_t w = g.w0()[s];
     int at = a_type(A0), pc = cell_of(g, w), tc = -1, cost = 0;
     if (at == ACT_MOVE) {
         tc = pc + doff(g, A1);
-        if (g.grid[tc] != 0) return false; // out of bounds, wall or occupied
+        if (g.grid()[tc] != 0) return false; // out of bounds, wall or occupied
     } else if (at == ACT_PRODUCE) { tc = target_cell(g, pc, A1); cost = ut_cost(g, a_utype(A0)); }
-    if (tc >= 0 && g.resv[tc] != 0) return false;
+    if (tc >= 0 && g.resv()[tc] != 0) return false;
     int pl = u_pl(w);
     int s0 = (pl == 1 ? cost : 0) + c.par0, s1 = (pl == 2 ? cost : 0) + c.par1;
-    if (c.par0 != 0 && s0 > 0 && s0 > g.hdr[H_RES0]) return false;
-    if (c.par1 != 0 && s1 > 0 && s1 > g.hdr[H_RES1]) return false;
+    if (c.par0 != 0 && s0 > 0 && s0 > g.hdr()[H_RES0]) return false;
+    if (c.par1 != 0 && s1 > 0 && s1 > g.hdr()[H_RES1]) return false;
     return true;
 }
 
@@ -160,26 +160,26 @@ DEV bool mk_move(const Game &g, const ScriptCtx &c, int s, int dir, uint32_t &A0
 
 // Train.score (Train.java:98-126)
 DEV int train_score(const Game &g, int x, int y, int type, int pl) {
-    int n = g.hdr[H_NUNITS], distance = 0; bool first = true;
+    int n = g.hdr()[H_NUNITS], distance = 0; bool first = true;
     bool harvester = (ut_flags(g, type) & UF_HARVEST) != 0;
 #pragma unroll 1
     for (int i = 0; i < n; i++) {
-        uint32_t w = g.w0[i];
+        uint32_t w = g.w0()[i];
         bool ok = harvester ? (ut_flags(g, u_type(w)) & UF_RESOURCE) != 0 : (u_pl(w) != 0 && u_pl(w) != pl);
         if (ok) { int d = iabs(u_x(w) - x) + iabs(u_y(w) - y); if (first || d < distance) { distance = d; first = false; } }
     }
     return -distance;
 }
 
-DEV bool cell_gs_free(const Game &g, int pc) { return g.grid[pc] == 0 && g.resv[pc] == 0; }
+DEV bool cell_gs_free(const Game &g, int pc) { return g.grid()[pc] == 0 && g.resv()[pc] == 0; }
 
 // AbstractAction.execute for slot s; returns true and (A0, A1) if it yields a unit action
 DEVN bool aa_execute(Game &g, const ScriptCtx &c, int s, uint32_t &A0, int &A1) {
-    uint32_t X0 = g.x0[s], X1 = g.x1[s], w = g.w0[s];
+    uint32_t X0 = g.x0()[s], X1 = g.x1()[s], w = g.w0()[s];
     int x = u_x(w), y = u_y(w), t = u_type(w), W = g.W;
     switch (aa_kind(X0)) {
         case AA_ATTACK: { // Attack.java:51-64
-            uint32_t tw = g.w0[aa_target(X1) - 1];
+            uint32_t tw = g.w0()[aa_target(X1) - 1];
             int dx = u_x(tw) - x, dy = u_y(tw) - y, range = ut_range(g, t);
             if (dx * dx + dy * dy <= range * range) { A0 = ACT_ATTACK | A0_NOUT | ((uint32_t)u_x(tw) << 16) | ((uint32_t)u_y(tw) << 24); A1 = -1; return true; }
             int dir = pf_find(g, c.pf, s, u_x(tw) + u_y(tw) * W, range, c.nd);
@@ -187,10 +187,10 @@ DEVN bool aa_execute(Game &g, const ScriptCtx &c, int s, uint32_t &A0, int &A1) 
             return false;
         }
         case AA_HARVEST: { // Harvest.java:72-113
-            bool empty = u_res(g.w1[s]) == 0;
+            bool empty = u_res(g.w1()[s]) == 0;
             int other = empty ? aa_target(X1) : aa_base(X1);
             if (other == (int)REF_NULL) return false;
-            uint32_t ow = g.w0[other - 1];
+            uint32_t ow = g.w0()[other - 1];
             int dir = pf_find(g, c.pf, s, u_x(ow) + u_y(ow) * W, 1, c.nd);
             if (mk_move(g, c, s, dir, A0, A1)) return unit_action_allowed(g, c, s, A0, A1);
             int ox = u_x(ow), oy = u_y(ow), d = -1;
@@ -219,7 +219,7 @@ DEVN bool aa_execute(Game &g, const ScriptCtx &c, int s, uint32_t &A0, int &A1) 
                 int nc = pc + doff(g, d);
                 if (cell_gs_free(g, nc)) { int sc = train_score(g, x + ddx(d), y + ddy(d), type, pl); if (sc > best || best_dir == -1) { best = sc; best_dir = d; } }
             }
-            g.x0[s] = X0 | 8u; // completed = true
+            g.x0()[s] = X0 | 8u; // completed = true
             if (best_dir != -1) { A0 = ACT_PRODUCE | ((uint32_t)type << 8); A1 = best_dir; return unit_action_allowed(g, c, s, A0, A1); }
             return false;
         }
@@ -231,11 +231,11 @@ DEV bool ref_alive(int r) { return r != (int)REF_NULL && r != (int)REF_DEAD; }
 
 // AbstractAction.completed
 DEV bool aa_completed(const Game &g, int s) {
-    uint32_t X0 = g.x0[s], X1 = g.x1[s];
+    uint32_t X0 = g.x0()[s], X1 = g.x1()[s];
     switch (aa_kind(X0)) {
         case AA_TRAIN: return (X0 & 8u) != 0;
-        case AA_BUILD: { int bx = aa_bx(X0), by = aa_by(X0); if (bx < 0 || bx >= g.W || by >= g.H) return false; int gv = g.grid[(by + 1) * g.P + bx + 1]; return gv != 0 && gv != 0xFF; }
-        case AA_HARVEST: return u_res(g.w1[s]) > 0 ? !ref_alive(aa_base(X1)) : !ref_alive(aa_target(X1));
+        case AA_BUILD: { int bx = aa_bx(X0), by = aa_by(X0); if (bx < 0 || bx >= g.W || by >= g.H) return false; int gv = g.grid()[(by + 1) * g.P + bx + 1]; return gv != 0 && gv != 0xFF; }
+        case AA_HARVEST: return u_res(g.w1()[s]) > 0 ? !ref_alive(aa_base(X1)) : !ref_alive(aa_target(X1));
         case AA_ATTACK: return !ref_alive(aa_target(X1));
     }
     return true;
@@ -260,7 +260,7 @@ DEVN int find_building_position(const Game &g, const int *reserved, int nres, in
                 int pos = x + y * W;
                 bool rsv = false;
                 for (int q = 0; q < nres; q++) rsv |= reserved[q] == pos;
-                if (!rsv && g.grid[(y + 1) * g.P + x + 1] == 0) return pos;
+                if (!rsv && g.grid()[(y + 1) * g.P + x + 1] == 0) return pos;
             }
         }
     }
@@ -268,11 +268,11 @@ DEVN int find_building_position(const Game &g, const int *reserved, int nres, in
 }
 
 DEV void script_melee(Game &g, int s, int player) { // meleeUnitBehavior (WorkerRush.java:105-121, LightRush.java:141-159)
-    int n = g.hdr[H_NUNITS], closest = -1, cd = 0;
-    uint32_t w = g.w0[s];
+    int n = g.hdr()[H_NUNITS], closest = -1, cd = 0;
+    uint32_t w = g.w0()[s];
 #pragma unroll 1
     for (int i = 0; i < n; i++) {
-        uint32_t ow = g.w0[i];
+        uint32_t ow = g.w0()[i];
         if (u_pl(ow) != 0 && u_pl(ow) != player + 1) { int d = iabs(u_x(ow) - u_x(w)) + iabs(u_y(ow) - u_y(w)); if (closest < 0 || d < cd) { closest = i; cd = d; } }
     }
     if (closest >= 0) aa_put(g, s, player, AA_ATTACK, 0, 0, 0, closest + 1, REF_NULL);
@@ -280,22 +280,22 @@ DEV void script_melee(Game &g, int s, int player) { // meleeUnitBehavior (Worker
 
 // harvest part of workersBehavior (WorkerRush.java:148-199, LightRush.java:203-252); true if the worker is still free
 DEV bool script_harvest(Game &g, int s, int player) {
-    int n = g.hdr[H_NUNITS], cbase = -1, cres = -1, cd = 0;
-    uint32_t w = g.w0[s];
+    int n = g.hdr()[H_NUNITS], cbase = -1, cres = -1, cd = 0;
+    uint32_t w = g.w0()[s];
 #pragma unroll 1
     for (int i = 0; i < n; i++) {
-        uint32_t ow = g.w0[i];
+        uint32_t ow = g.w0()[i];
         if (ut_flags(g, u_type(ow)) & UF_RESOURCE) { int d = iabs(u_x(ow) - u_x(w)) + iabs(u_y(ow) - u_y(w)); if (cres < 0 || d < cd) { cres = i; cd = d; } }
     }
     cd = 0;
 #pragma unroll 1
     for (int i = 0; i < n; i++) {
-        uint32_t ow = g.w0[i];
+        uint32_t ow = g.w0()[i];
         if ((ut_flags(g, u_type(ow)) & UF_STOCKPILE) && u_pl(ow) == player + 1) { int d = iabs(u_x(ow) - u_x(w)) + iabs(u_y(ow) - u_y(w)); if (cbase < 0 || d < cd) { cbase = i; cd = d; } }
     }
-    uint32_t X0 = g.x0[s], X1 = g.x1[s];
+    uint32_t X0 = g.x0()[s], X1 = g.x1()[s];
     bool is_h = aa_kind(X0) == AA_HARVEST;
-    if (u_res(g.w1[s]) > 0) {
+    if (u_res(g.w1()[s]) > 0) {
         if (cbase >= 0) {
             if (!is_h || aa_base(X1) != cbase + 1) aa_put(g, s, player, AA_HARVEST, 0, 0, 0, REF_NULL, cbase + 1);
             return false;
@@ -308,9 +308,9 @@ DEV bool script_harvest(Game &g, int s, int player) {
 }
 
 DEV void script_build_if_not(Game &g, int s, int player, int type, int *reserved, int &nres) { // buildIfNotAlreadyBuilding :231-245
-    uint32_t X0 = g.x0[s];
+    uint32_t X0 = g.x0()[s];
     if (!(aa_kind(X0) == AA_BUILD && aa_type(X0) == type)) {
-        uint32_t w = g.w0[s];
+        uint32_t w = g.w0()[s];
         int pos = find_building_position(g, reserved, nres, u_x(w), u_y(w));
         int bx = pos < 0 ? -1 : pos % g.W, by = pos < 0 ? 0 : pos / g.W; // Java: -1 % w == -1, -1 / w == 0
         aa_put(g, s, player, AA_BUILD, type, bx, by, REF_NULL, REF_NULL);
@@ -331,36 +331,36 @@ DEVN int policy_scripted(Game &g, int player, int kind, int pathfinder, int pn) 
     reserved_resources(g, par0, par1);
     int out = pn;
     if (g.lane == 0) {
-        int n = g.hdr[H_NUNITS], pl = player + 1, pres = g.hdr[H_RES0 + player];
+        int n = g.hdr()[H_NUNITS], pl = player + 1, pres = g.hdr()[H_RES0 + player];
         bool light = kind == POL_LIGHT_RUSH;
         // bases (WorkerRush.java:70-76,100-102; LightRush.java:83-89,123-133)
 #pragma unroll 1
         for (int i = 0; i < n; i++) {
-            uint32_t w = g.w0[i];
-            if (u_type(w) == UT_BASE && u_pl(w) == pl && a_type(g.a0[i]) == AT_IDLE) {
+            uint32_t w = g.w0()[i];
+            if (u_type(w) == UT_BASE && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE) {
                 bool train = pres >= ut_cost(g, UT_WORKER);
-                if (light && train) { int nw = 0; for (int j = 0; j < n; j++) nw += (u_type(g.w0[j]) == UT_WORKER && u_pl(g.w0[j]) == pl) ? 1 : 0; train = nw < 1; }
+                if (light && train) { int nw = 0; for (int j = 0; j < n; j++) nw += (u_type(g.w0()[j]) == UT_WORKER && u_pl(g.w0()[j]) == pl) ? 1 : 0; train = nw < 1; }
                 if (train) aa_put(g, i, player, AA_TRAIN, UT_WORKER, 0, 0, REF_NULL, REF_NULL);
             }
         }
         if (light) { // barracks (LightRush.java:92-98,135-139)
 #pragma unroll 1
             for (int i = 0; i < n; i++) {
-                uint32_t w = g.w0[i];
-                if (u_type(w) == UT_BARRACKS && u_pl(w) == pl && a_type(g.a0[i]) == AT_IDLE && pres >= ut_cost(g, UT_LIGHT)) aa_put(g, i, player, AA_TRAIN, UT_LIGHT, 0, 0, REF_NULL, REF_NULL);
+                uint32_t w = g.w0()[i];
+                if (u_type(w) == UT_BARRACKS && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE && pres >= ut_cost(g, UT_LIGHT)) aa_put(g, i, player, AA_TRAIN, UT_LIGHT, 0, 0, REF_NULL, REF_NULL);
             }
         }
 #pragma unroll 1
         for (int i = 0; i < n; i++) { // melee units
-            uint32_t w = g.w0[i];
+            uint32_t w = g.w0()[i];
             int fl = ut_flags(g, u_type(w));
-            if ((fl & UF_ATTACK) && !(fl & UF_HARVEST) && u_pl(w) == pl && a_type(g.a0[i]) == AT_IDLE) script_melee(g, i, player);
+            if ((fl & UF_ATTACK) && !(fl & UF_HARVEST) && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE) script_melee(g, i, player);
         }
         // workers: all own harvesters, busy ones too, in list order
         int nbases = 0, nbarracks = 0, nworkers = 0;
 #pragma unroll 1
         for (int i = 0; i < n; i++) {
-            uint32_t w = g.w0[i];
+            uint32_t w = g.w0()[i];
             if (u_pl(w) != pl) continue;
             if (u_type(w) == UT_BASE) nbases++;
             if (u_type(w) == UT_BARRACKS) nbarracks++;
@@ -369,7 +369,7 @@ DEVN int policy_scripted(Game &g, int player, int kind, int pathfinder, int pn) 
         if (nworkers > 0) {
             int reserved[4], nres = 0, used = 0, taken = 0; // `taken` workers were removed from the front of freeWorkers
             int wi = -1;                                     // cursor over own harvesters in list order
-            auto next_worker = [&](int from) { for (int i = from + 1; i < n; i++) { uint32_t w = g.w0[i]; if (u_pl(w) == pl && (ut_flags(g, u_type(w)) & UF_HARVEST)) return i; } return -1; };
+            auto next_worker = [&](int from) { for (int i = from + 1; i < n; i++) { uint32_t w = g.w0()[i]; if (u_pl(w) == pl && (ut_flags(g, u_type(w)) & UF_HARVEST)) return i; } return -1; };
             if (nbases == 0 && taken < nworkers) {
                 if (pres >= ut_cost(g, UT_BASE) + used) { wi = next_worker(wi); taken++; script_build_if_not(g, wi, player, UT_BASE, reserved, nres); used += ut_cost(g, UT_BASE); }
             }
@@ -403,53 +403,53 @@ DEVN int policy_scripted(Game &g, int player, int kind, int pathfinder, int pn) 
             int best = -1; uint32_t bseq = 0xFFFFFFFFu;
 #pragma unroll 1
             for (int i = 0; i < n; i++) {
-                uint32_t X0 = g.x0[i];
-                if (aa_kind(X0) == AA_NONE || u_pl(g.w0[i]) != pl) continue;
-                uint32_t q = aa_seq(X0, g.x1[i]);
+                uint32_t X0 = g.x0()[i];
+                if (aa_kind(X0) == AA_NONE || u_pl(g.w0()[i]) != pl) continue;
+                uint32_t q = aa_seq(X0, g.x1()[i]);
                 if ((!have_last || q > last) && q < bseq) { bseq = q; best = i; }
             }
             if (best < 0) break;
             last = bseq; have_last = true;
-            if (aa_completed(g, best)) { g.x0[best] &= ~7u; continue; } // toDelete (a dead unit's entry vanished with its slot)
-            if (a_type(g.a0[best]) == AT_IDLE) {
+            if (aa_completed(g, best)) { g.x0()[best] &= ~7u; continue; } // toDelete (a dead unit's entry vanished with its slot)
+            if (a_type(g.a0()[best]) == AT_IDLE) {
                 uint32_t A0; int A1;
                 c.nd = nd;
                 // desires live in the tail of the pending arrays while they are collected: [cap - 1 - k] would collide with
                 // nothing, but pf_find wants them at [0, nd): policies run one after the other, so player 0's final list
                 // [0, pn) must stay intact -> stage at [pn, pn + nd) and give pf_find a window by temporarily viewing from pn
-                Game gv = g; gv.pa0 = g.pa0 + pn; gv.pa1 = g.pa1 + pn; gv.pslot = g.pslot + pn;
-                if (aa_execute(gv, c, best, A0, A1)) { g.pslot[pn + nd] = (uint8_t)best; g.pa0[pn + nd] = A0; g.pa1[pn + nd] = A1; nd++; }
+                Game gv = g; gv.pview = g.pview + pn;
+                if (aa_execute(gv, c, best, A0, A1)) { g.pslot()[pn + nd] = (uint8_t)best; g.pa0()[pn + nd] = A0; g.pa1()[pn + nd] = A1; nd++; }
             }
         }
         // compose desires against gs.getResourceUsage() (:93-101): pa.consistentWith(r2) with pa.r = in-flight + accepted
         int acc0 = par0, acc1 = par1, m = pn;
 #pragma unroll 1
         for (int k = 0; k < nd; k++) {
-            int s = g.pslot[pn + k]; uint32_t A0 = g.pa0[pn + k]; int A1 = g.pa1[pn + k];
-            uint32_t w = g.w0[s];
+            int s = g.pslot()[pn + k]; uint32_t A0 = g.pa0()[pn + k]; int A1 = g.pa1()[pn + k];
+            uint32_t w = g.w0()[s];
             int at = a_type(A0), tc = -1, cost = 0;
             if (a_uses_cell(at)) { tc = target_cell(g, cell_of(g, w), A1); if (at == ACT_PRODUCE) cost = ut_cost(g, a_utype(A0)); }
-            bool ok = !(tc >= 0 && (g.resv[tc] != 0 || ((g.claim[tc] >> player) & 1)));
+            bool ok = !(tc >= 0 && (g.resv()[tc] != 0 || ((g.claim()[tc] >> player) & 1)));
             if (ok && cost != 0) { int tot = (pl == 1 ? acc0 : acc1) + cost; if (tot > 0 && tot > pres) ok = false; }
             if (ok) {
-                if (tc >= 0) g.claim[tc] |= (uint8_t)(1 << player);
+                if (tc >= 0) g.claim()[tc] |= (uint8_t)(1 << player);
                 if (pl == 1) acc0 += cost; else acc1 += cost;
-                g.pslot[m] = (uint8_t)s; g.pa0[m] = A0; g.pa1[m] = A1; m++;
+                g.pslot()[m] = (uint8_t)s; g.pa0()[m] = A0; g.pa1()[m] = A1; m++;
             }
         }
         // the claims only modelled pa.r while composing; drop them (a desire may still be replaced by NONE in issueSafe)
 #pragma unroll 1
         for (int q = pn; q < m; q++) {
-            uint32_t A0 = g.pa0[q];
-            if (a_uses_cell(a_type(A0))) g.claim[target_cell(g, cell_of(g, g.w0[g.pslot[q]]), g.pa1[q])] = 0;
+            uint32_t A0 = g.pa0()[q];
+            if (a_uses_cell(a_type(A0))) g.claim()[target_cell(g, cell_of(g, g.w0()[g.pslot()[q]]), g.pa1()[q])] = 0;
         }
         // PlayerAction.fillWithNones(gs, player, 10) (PlayerAction.java:217-235)
 #pragma unroll 1
         for (int i = 0; i < n; i++) {
-            if (u_pl(g.w0[i]) != pl || a_type(g.a0[i]) != AT_IDLE) continue;
+            if (u_pl(g.w0()[i]) != pl || a_type(g.a0()[i]) != AT_IDLE) continue;
             bool found = false;
-            for (int q = pn; q < m; q++) found |= g.pslot[q] == i;
-            if (!found) { g.pslot[m] = (uint8_t)i; g.pa0[m] = ACT_NONE | A0_NOUT; g.pa1[m] = 10; m++; }
+            for (int q = pn; q < m; q++) found |= g.pslot()[q] == i;
+            if (!found) { g.pslot()[m] = (uint8_t)i; g.pa0()[m] = ACT_NONE | A0_NOUT; g.pa1()[m] = 10; m++; }
         }
         out = m;
     }
