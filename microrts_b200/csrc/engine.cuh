@@ -48,6 +48,7 @@ struct StepParams {
     long long n_games;
     int n_maps, map_words;
     int W, H, cap;
+    SmemLayout L;              // host-computed (mrts_smem_layout): offsets reach the kernels through the constant bank
     int mode;
     int n_cycles, max_cycles;
     const int32_t *t_target;   // MODE_CYCLE_ONLY: absolute target time per game (or NULL)
@@ -138,7 +139,7 @@ DEV int u_pl(uint32_t w) { return (w >> 8) & 0xff; } // 0 neutral, 1 = player 0,
 DEV int u_x(uint32_t w) { return (w >> 16) & 0xff; }
 DEV int u_y(uint32_t w) { return w >> 24; }
 DEV int cell_of(const Game &g, uint32_t w) { return (u_y(w) + 1) * g.P + u_x(w) + 1; }
-DEV int doff(const Game &g, int d) { return d == 0 ? -g.P : (d == 1 ? 1 : (d == 2 ? g.P : -1)); } // UnitAction.java:94,100
+DEV int doff(const Game &g, int d) { return (d & 1) ? 2 - d : (d - 1) * g.P; } // up -P, right +1, down +P, left -1 (UnitAction.java:94,100)
 DEV int ddx(int d) { return d == 1 ? 1 : (d == 3 ? -1 : 0); }
 DEV int ddy(int d) { return d == 0 ? -1 : (d == 2 ? 1 : 0); }
 DEV int ut_cost(const Game &g, int t) { return g.utt()[t * 8] & 0xff; }
@@ -157,12 +158,9 @@ DEV bool a_uses_cell(int at) { return at == ACT_MOVE || at == ACT_PRODUCE; }
 DEV int u_hp(uint32_t w1) { return (int)(int16_t)(w1 & 0xffff); }
 DEV int u_res(uint32_t w1) { return (int)(int16_t)(w1 >> 16); }
 DEV uint32_t mk_w1(int hp, int res) { return ((uint32_t)hp & 0xffffu) | ((uint32_t)res << 16); }
-DEV int nth4(int m, int n) { // index of the n-th set bit of a 4-bit mask
-#pragma unroll
-    for (int d = 0; d < 4; d++) {
-        if ((m >> d) & 1) { if (n == 0) return d; n--; }
-    }
-    return 0;
+DEV int nth4(int m, int n) { // index of the n-th set bit of a 4-bit mask: byte m of the table holds the positions, 2 bits each
+    unsigned long long T = (m & 8) ? 0xe439380e340d0c03ULL : 0x2409080204010000ULL;
+    return (int)(T >> ((m & 7) * 8 + 2 * n)) & 3;
 }
 DEV int nth8(int m, int n) {
     #pragma unroll 1
@@ -172,17 +170,14 @@ DEV int nth8(int m, int n) {
     return 0;
 }
 
-// UnitAction.ETA, UnitAction.java:307-329 (RETURN uses moveTime)
+// UnitAction.ETA, UnitAction.java:307-329 (RETURN uses moveTime; PRODUCE the produced type's produceTime): one lookup in
+// the u16 table eta[type][action type] behind the unit type table
 DEV int eta_of(const Game &g, int t, uint32_t A0, int A1) {
-    switch (a_type(A0)) {
-        case ACT_NONE: return A1;
-        case ACT_MOVE:
-        case ACT_RETURN: return (int)(g.utt()[t * 8 + 2] >> 16);
-        case ACT_ATTACK: return (int)(g.utt()[t * 8 + 3] & 0xffff);
-        case ACT_HARVEST: return (int)(g.utt()[t * 8 + 3] >> 16);
-        case ACT_PRODUCE: { int ut = a_utype(A0); return ut < MRTS_MAX_TYPES ? (int)(g.utt()[ut * 8 + 2] & 0xffff) : 0; }
-    }
-    return 0;
+    int at = a_type(A0);
+    if (at == ACT_NONE) return A1;
+    if (at > ACT_ATTACK) return 0;
+    if (at == ACT_PRODUCE) { t = a_utype(A0); if (t >= MRTS_MAX_TYPES) return 0; }
+    return ((const uint16_t *)(g.utt() + MRTS_ETA_OFFSET))[t * 8 + at];
 }
 // target cell of a MOVE/PRODUCE (UnitAction.resourceUsage, UnitAction.java:254-291; an out-of-range direction leaves
 // `pos` at the unit's own cell)
@@ -812,7 +807,7 @@ DEV int neighbour_slot(const Game &g, int c, int dir) { // getUnitAt of the adja
     return (gv == 0 || gv == 0xFF) ? -1 : gv - 1;
 }
 
-// Execute the (already removed) assignment (A0,A1) of slot s.  Called by ONE lane (lane 0) for every ready assignment in
+// Execute the (already removed) assignment (A0,A1) of slot s.  Called by ONE lane at a time, for every ready assignment in
 // insertion order, so it is plain sequential code with no warp primitives.
 DEV void execute_serial(Game &g, int s, int &ndead) {
     uint32_t A0 = g.a0()[s]; int A1 = g.a1()[s];
@@ -958,48 +953,41 @@ DEV int min_ready_time(const Game &g) {
 }
 
 // time := t_new, then execute every assignment with ETA + issueTime <= time in insertion order (GameState.cycle).
-// Returns the number of units removed; the caller re-evaluates gameover() only then (nothing else can end a game).
+// Returns non-zero when units were removed; the caller re-evaluates gameover() only then (nothing else can end a game).
 // Ready assignments are found in parallel; NONE actions (no effect, so their position in the order is irrelevant) are
-// retired on the spot; the rest is ranked by insertion sequence and executed by one lane, because the reference's
-// effects are order dependent (kills, depletion, produce/return on the same player's resources).
+// retired on the spot; the rest executes one at a time in insertion-sequence order (a warp-wide min picks the next
+// one), because the reference's effects are order dependent (kills, depletion, produce/return on a player's resources).
 DEV int cycle_execute(Game &g, int t_new) {
     __syncwarp();
     if (g.lane == 0) g.hdr()[H_TIME] = t_new;
-    int n = g.hdr()[H_NUNITS], cnt = 0;
+    int n = g.hdr()[H_NUNITS];
+    // this lane's ready assignment with the smallest insertion sequence (a lane owns units lane, lane + 32, ...)
+    uint32_t cs = 0xFFFFFFFFu; int ci = 0;
     #pragma unroll 1
-    for (int base = 0; base < n; base += 32) {
-        int i = base + g.lane;
-        bool ready = false;
-        if (i < n && g.rdy()[i] <= t_new) {
+    for (int i = g.lane; i < n; i += 32) {
+        if (g.rdy()[i] <= t_new) {
             uint32_t A0 = g.a0()[i];
             if (a_type(A0) == ACT_NONE) { g.a0()[i] = (A0 & 0xF0u) | AT_IDLE | A0_NOUT; g.rdy()[i] = MRTS_NEVER; }
-            else ready = true;
+            else { uint32_t q = g.seq()[i]; if (q < cs) { cs = q; ci = i; } }
         }
-        unsigned m = __ballot_sync(FULLM, ready);
-        if (ready) g.list()[cnt + __popc(m & ((1u << g.lane) - 1))] = (uint8_t)i;
-        cnt += __popc(m);
     }
     __syncwarp();
     int ndead = 0;
-    if (cnt > 0) {
-        uint8_t *order = g.base() + g.o_pslot; // the pending list is empty at this point
-        #pragma unroll 1
-        for (int k = g.lane; k < cnt; k += 32) {
-            int s = g.list()[k];
-            uint32_t my = g.seq()[s];
-            int r = 0;
+    #pragma unroll 1
+    for (;;) {
+        uint32_t mn = __reduce_min_sync(FULLM, cs);
+        if (mn == 0xFFFFFFFFu) break;
+        if (cs == mn) { // the owner of the oldest ready assignment executes it, then looks for its next one
+            execute_serial(g, ci, ndead);
+            cs = 0xFFFFFFFFu;
             #pragma unroll 1
-            for (int j = 0; j < cnt; j++) r += g.seq()[g.list()[j]] < my ? 1 : 0;
-            order[r] = (uint8_t)s;
+            for (int i = g.lane; i < n; i += 32)
+                if (g.rdy()[i] <= t_new) { uint32_t q = g.seq()[i]; if (q < cs) { cs = q; ci = i; } }
         }
-        __syncwarp();
-        if (g.lane == 0)
-            #pragma unroll 1
-            for (int r = 0; r < cnt; r++) execute_serial(g, order[r], ndead);
-        __syncwarp();
-        ndead = __shfl_sync(FULLM, ndead, 0);
-        if (ndead > 0) compact_units(g);
+        __syncwarp(); // its effects are visible to the lane that executes the next one
     }
+    ndead = __ballot_sync(FULLM, ndead > 0) ? 1 : 0;
+    if (ndead) compact_units(g);
     return ndead;
 }
 DEVN int cycle_execute_ni(Game &g, int t_new) { return cycle_execute(g, t_new); } // one out-of-line copy for the generic kernel
@@ -1542,7 +1530,7 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
     #pragma unroll 1
     for (int i = tid; i < MRTS_CONST_WORDS; i += nthreads) cst[i] = p.cst[i];
     __syncthreads();
-    SmemLayout L = mrts_smem_layout(p.W, p.H, p.cap, p.scripted);
+    const SmemLayout &L = p.L;
     int warp = tid >> 5, lane = tid & 31, wpc = nthreads >> 5;
     Game g;
     g_bind(g, MRTS_CONST_WORDS * 4 + warp * L.total, L, p.W, p.H, p.cap, lane, p.conflict, p.scripted,

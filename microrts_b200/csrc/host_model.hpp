@@ -161,6 +161,12 @@ inline void build_const_words(const UttH &u, std::vector<uint32_t> &w) {
         j[2 * d] = a; j[2 * d + 1] = c;
         for (int s = 0; s < 2; s++) { a = (a * A) & M; c = (c * A + C) & M; }
     }
+    uint16_t *eta = (uint16_t *)&w[MRTS_ETA_OFFSET];
+    for (size_t i = 0; i < u.types.size(); i++) {
+        const UnitTypeH &t = u.types[i];
+        eta[i * 8 + 1] = (uint16_t)t.moveTime; eta[i * 8 + 2] = (uint16_t)t.harvestTime; eta[i * 8 + 3] = (uint16_t)t.moveTime;
+        eta[i * 8 + 4] = (uint16_t)t.produceTime; eta[i * 8 + 5] = (uint16_t)t.attackTime;
+    }
 }
 
 struct MapUnit { int type; long long id; int player, x, y, res, hp; };

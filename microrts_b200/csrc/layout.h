@@ -53,7 +53,10 @@ enum { UW_W0 = 0, UW_W1, UW_A0, UW_A1, UW_TIS, UW_SEQ, UW_ID, UW_X0, UW_X1, MRTS
 enum { UF_RESOURCE = 1, UF_STOCKPILE = 2, UF_HARVEST = 4, UF_MOVE = 8, UF_ATTACK = 16 };
 
 #define MRTS_JUMP_ENTRIES 65 // LCG skip-ahead: entry d advances 2*d steps (d nextDouble() draws)
-#define MRTS_CONST_WORDS (MRTS_MAX_TYPES * MRTS_UTT_WORDS + MRTS_JUMP_ENTRIES * 4) // utt words + jump table (u64 pairs)
+#define MRTS_ETA_OFFSET (MRTS_MAX_TYPES * MRTS_UTT_WORDS + MRTS_JUMP_ENTRIES * 4) // word offset of the ETA table
+// ETA table: u16 eta[type][8], indexed by action type (1 MOVE, 2 HARVEST, 3 RETURN = moveTime, 4 PRODUCE = produceTime OF
+// THE ROW'S TYPE (look it up with the produced type), 5 ATTACK) -- UnitAction.ETA, UnitAction.java:307-329
+#define MRTS_CONST_WORDS (MRTS_ETA_OFFSET + MRTS_MAX_TYPES * 4) // utt words + jump table (u64 pairs) + ETA table
 
 #define MRTS_MAX_CAP 254
 #define MRTS_WARPS_PER_CTA 4

@@ -112,7 +112,7 @@ DEV void results_kernel_body(const ResultParams &p, long long gi) {
 
 #ifndef MRTS_EMU
 #ifndef MRTS_MIN_BLOCKS
-#define MRTS_MIN_BLOCKS 8
+#define MRTS_MIN_BLOCKS 6
 #endif
 // k_step_fast: Game.start loop with RandomBiasedAI / PassiveAI under CANCEL_BOTH (the benchmark path); k_rollout:
 // NaiveMCTS.simulate + evaluation; k_step: every other mode.  All three are persistent, one warp per game at a time.
@@ -170,7 +170,7 @@ static int ensure_tmp(mrts_batch *b, size_t bytes) {
 
 static int launch_step(mrts_batch *b, StepParams &p) {
     p.hdr = b->d_hdr; p.units = b->d_units; p.maps = b->d_maps; p.cst = b->d_cst; p.stats = b->d_stats;
-    p.n_games = b->n; p.n_maps = b->n_maps; p.map_words = b->map_words; p.W = b->W; p.H = b->H; p.cap = b->cap;
+    p.n_games = b->n; p.n_maps = b->n_maps; p.map_words = b->map_words; p.W = b->W; p.H = b->H; p.cap = b->cap; p.L = b->L;
     p.conflict = b->utt.conflict; p.max_range = b->max_range; p.n_types = (int)b->utt.types.size();
     p.partial_obs = (b->flags & MRTS_FLAG_PARTIAL_OBS) ? 1 : 0; p.scripted = b->scripted; p.uw = b->uw;
     p.astar_scratch = b->d_astar; p.astar_stride = b->astar_stride;

@@ -1,15 +1,16 @@
 #!/usr/bin/env python3
 """Join an `ncu --page source --print-source sass --csv` dump of k_step with nvdisasm line info and aggregate executed
 instructions / stall samples per source line and per enclosing function.
-usage: sass_by_line.py <ncu_sass.csv> <nvdisasm -g output> [engine.cuh]"""
+usage: sass_by_line.py <ncu_sass.csv> <nvdisasm -g output> [engine.cuh] [kernel symbol substring, default k_step_fast]"""
 import csv, re, sys, collections
 sass_csv, dis, src = sys.argv[1], sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None
+kern = sys.argv[4] if len(sys.argv) > 4 else 'k_step_fast'
 # instruction -> (file,line) from nvdisasm, for function k_step
 lines = []
 cur = None; infn = False
 for l in open(dis):
     if l.startswith('//---') and '.text.' in l:
-        infn = 'k_step' in l
+        infn = (kern + '10StepParams') in l or l.rstrip().endswith(kern)
         continue
     if not infn: continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', l)
