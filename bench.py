@@ -52,6 +52,12 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--prewarm-seconds", type=float, default=1.5, help="untimed steps before the warm-up, until clocks have ramped")
+    ap.add_argument("--workload", default="selfplay", choices=["selfplay", "obs", "scripted", "rollout"],
+                    help="selfplay: BASELINE configs[1] (the default, the headline line); the others are the secondary "
+                         "configurations of SURVEY 8(d): obs = cfg 5 (64x64 + fused observations every cycle), scripted = cfg 3 "
+                         "(24x24 WorkerRush vs LightRush, A*), rollout = cfg 4 (32x32 partially observable MCTS playouts)")
+    ap.add_argument("--rollouts-per-game", type=int, default=64)
+    ap.add_argument("--unit-capacity", type=int, default=0, help="unit slots per game (0 = automatic bound; a game that needs more sets its error flag)")
     return ap.parse_args()
 
 
@@ -371,9 +377,166 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# secondary workloads (SURVEY 8d cfg 3/4/5): same timing rules, one JSON line each, no CPU / e2e legs
+# ----------------------------------------------------------------------------------------------------------------------
+def run_secondary(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import golden_io
+    import microrts_b200 as M
+    import parity as P
+    from microrts_b200 import _ffi, sharding
+    maps = golden_io.load_maps()
+    utt = M.UnitTypeTable(1, 1)
+    n = args.games
+    seeds = sharding.global_seeds(0, rank * n, n)
+    wl = args.workload
+    obs = None
+    if wl == "obs":
+        key = "GardenOfWar64x64"
+        b = M.BatchedGameState(utt, M.PhysicalGameState.fromXML(P.map_to_xml(maps[key]), utt), n, device=local, unit_capacity=args.unit_capacity)
+        b.set_policy(0, M.POLICY_RANDOM_BIASED); b.set_policy(1, M.POLICY_RANDOM_BIASED)
+        obs = [torch.empty((n, 6, b.height, b.width), dtype=torch.uint8, device="cuda") for _ in range(2)]
+        b.set_observation_outputs(obs[0], obs[1])
+        C = args.cycles_per_step if args.cycles_per_step != 100 else 1
+        name = "maps/%s.xml x %d games/GPU, RandomBiasedAI self-play, %d cycle(s) per step, 6-plane uint8 observations of BOTH players written every step (fused)" % (key, n, C)
+    elif wl == "scripted":
+        keys = ["24x24/basesWorkers24x24"] + ["24x24/basesWorkers24x24" + c for c in "ABCDEFGHIJKL"]
+        pgs = [M.PhysicalGameState.fromXML(P.map_to_xml(maps[k]), utt) for k in keys]
+        b = M.BatchedGameState(utt, pgs, n, device=local, scripted_ai=True)
+        b.set_policy(0, M.POLICY_WORKER_RUSH, M.PF_ASTAR); b.set_policy(1, M.POLICY_LIGHT_RUSH, M.PF_ASTAR)
+        C = args.cycles_per_step
+        name = "maps/24x24/basesWorkers24x24{,A..L}.xml (13 variants round-robin) x %d games/GPU, WorkerRush vs LightRush with A*, %d-cycle cap (deterministic: 13 distinct games)" % (n, MAX_CYCLES)
+    else:
+        key = "BWDistantResources32x32"
+        b = M.BatchedGameState(utt, M.PhysicalGameState.fromXML(P.map_to_xml(maps[key]), utt), n, device=local)
+        b.set_policy(0, M.POLICY_RANDOM_BIASED); b.set_policy(1, M.POLICY_RANDOM_BIASED)
+        C = 100
+        name = "maps/%s.xml: %d root states/GPU (RandomBiased self-play advanced to t=0/500/1000 by thirds) x %d NaiveMCTS playouts (RandomBiasedAI both sides, depth 100) from player 0's partially observable view, SimpleSqrtEvaluationFunction3" % (key, n, args.rollouts_per_game)
+    stream = torch.cuda.ExternalStream(_ffi.lib().mrts_batch_stream(b._h), device=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    b.reset(seeds)
+    rollout_out = None
+    if wl == "rollout":
+        # roots: thirds of the batch advanced to t = 0 / 500 / 1000
+        third = n // 3
+        tgt = np.zeros(n, dtype=np.int64); tgt[third:2 * third] = 500; tgt[2 * third:] = 1000
+        for t in range(0, 1000, 100):
+            # games whose target is reached are frozen by exporting/importing nothing: step only advances unfinished games,
+            # so run the whole batch and restore the early roots afterwards
+            if t == 0:
+                snap0 = b.export(0, third)
+            if t == 500:
+                snap500 = b.export(third, third)
+            b.step(100, 3000)
+        b.import_(snap0, 0)
+        b.import_(snap500, third)
+        nr = n * args.rollouts_per_game
+        ev = torch.empty(nr, dtype=torch.float32, device="cuda"); tm = torch.empty(nr, dtype=torch.int32, device="cuda")
+        L = _ffi.lib()
+
+        def step():
+            rc = L.mrts_batch_rollout(b._h, args.rollouts_per_game, 100, 0, 0, 0, None, ev.data_ptr(), tm.data_ptr(), 1)
+            assert rc == 0, L.mrts_last_error()
+    else:
+        b.set_auto_reset(True)
+
+        def step():
+            b.step(C, MAX_CYCLES)
+
+    t_pre = time.perf_counter()
+    while time.perf_counter() - t_pre < args.prewarm_seconds:
+        step(); b.sync()
+    if wl != "rollout":
+        b.reset(seeds)
+        b.set_auto_reset(True)
+    for _ in range(args.warmup):
+        step()
+    b.sync()
+    st0, l0 = b.stats(), b.launch_count
+    clocks = ClockSampler(local); clocks.start()
+    barrier()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t0 = time.perf_counter()
+    for a, z in evs:
+        a.record(stream); step(); z.record(stream)
+    b.sync(); barrier()
+    wall = time.perf_counter() - t0
+    clk = clocks.stop()
+    st1 = b.stats()
+    launches = b.launch_count - l0
+    kernel_ms = [a.elapsed_time(z) for a, z in evs]
+    dev_s = sum(kernel_ms) / 1000.0
+    d = {k: st1[k] - st0[k] for k in st1}
+    tmax = torch.tensor([wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    red = sharding.reduce_stats(dict(st1, cycles=d["cycles"], unit_cycles=d["unit_cycles"], decisions=d["decisions"], errors=d["errors"]), device="cuda")
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cycles, ucyc = d["cycles"], d["unit_cycles"]
+    mean_units = ucyc / max(1, cycles)
+    peaks = None
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks["hbm_gbs"]) if peaks and "hbm_gbs" in peaks else 6650.0
+    state_bytes = 2.0 * (32.0 + 24.0 * mean_units)
+    extra = {}
+    if wl == "obs":
+        # B_state per game-cycle + B_obs = P*C*H*W bytes per emitted observation set (one per step)
+        bytes_total = cycles * state_bytes + args.steps * n * 2 * 6 * b.height * b.width
+        kern, form = "k_step_fast", "cycles*2*(32+24*U) + steps*games*2*6*H*W (uint8 planes of both players)"
+    elif wl == "scripted":
+        bytes_total = cycles * (state_bytes + 16.0 * mean_units)
+        kern, form = "k_step", "cycles*(2*(32+24*U) + 2*8*U)"
+    else:
+        rollouts = args.steps * n * args.rollouts_per_game
+        root_units = float(np.mean(b.export()["header"][:, 3]))
+        bytes_total = rollouts * (32.0 + 24.0 * root_units + 8.0)
+        kern, form = "k_rollout", "rollouts*(32+24*U0+8)"
+        extra = dict(rollouts_per_s=rollouts / tmax.item(), mean_rollout_cycles=cycles / max(1, rollouts), root_units=root_units)
+    achieved = bytes_total / dev_s / 1e9
+    out = dict(metric="game_cycles_per_sec", value=red["cycles"] / tmax.item(), unit="game-cycles/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+               ms_per_step=1000.0 * tmax.item() / max(1, args.steps), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="int32", data="synthetic",
+               config=dict(workload=name, games_per_gpu=n, cycles_per_step=C, max_cycles=MAX_CYCLES, mean_live_units=mean_units,
+                           l2="state + outputs larger than L2, no flush", unit_capacity=b.cap, **extra),
+               clocks=clk, e2e=None, gpu_launches=launches,
+               roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
+                             peak_source="measured (MEASURED_PEAKS.json)" if peaks else "fallback", kernel=kern, bytes_formula=form,
+                             mean_launch_ms=sum(kernel_ms) / max(1, len(kernel_ms))),
+               cpu_baseline=None,
+               stats=dict(wins_p0=red["wins_p0"], wins_p1=red["wins_p1"], draws=red["draws"], games_finished=red["games_finished"],
+                          game_errors=red["errors"], device_time_s=dev_s, wall_time_s=tmax.item()))
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload != "selfplay":
+        run_secondary(a)
     else:
         run_ours(a)

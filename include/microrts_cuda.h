@@ -181,6 +181,12 @@ int mrts_batch_rollout(mrts_batch *, int rollouts_per_game, int depth, int eval_
  * not supported yet. */
 int mrts_batch_observe(mrts_batch *, int player, int dtype, void *out, int on_device);
 int mrts_batch_num_planes(const mrts_batch *);
+/* Fused emission: while set (device pointers on the batch's device, 16-byte aligned; NULL disables a player), every
+ * mrts_batch_step also writes GameState.getVectorObservation(player) of the state it leaves behind into
+ * out_playerP = [n_games][C][H][W] -- what JNIGridnetVecClient.gameStep returns per environment
+ * (src/tests/JNIGridnetVecClient.java:213-297) -- from the state that is already in shared memory, without a second pass
+ * over the batch. */
+int mrts_batch_set_observation_outputs(mrts_batch *, int dtype, void *out_player0, void *out_player1);
 /* JNIGridnetClient.getMasks(player) (src/tests/JNIGridnetClient.java:210-223, UnitAction.java:711-751):
  * out = [n_games][H][W][mask_width]. */
 int mrts_batch_masks(mrts_batch *, int player, int dtype, void *out, int on_device);

@@ -5,8 +5,8 @@ batched state is the new class the reference would gain as rts.cuda.BatchedGameS
 """
 from .api import (ACTIONS_RAW, ACTIONS_VECTOR, BatchedGameState, MicroRTSError, PhysicalGameState, UnitAction,
                   UnitTypeTable, POLICY_EXTERNAL, POLICY_LIGHT_RUSH, POLICY_PASSIVE, POLICY_RANDOM_BIASED,
-                  POLICY_WORKER_RUSH)
+                  POLICY_WORKER_RUSH, PF_ASTAR, PF_BFS, DTYPE_U8, DTYPE_I32)
 
 __all__ = ["UnitTypeTable", "PhysicalGameState", "BatchedGameState", "UnitAction", "MicroRTSError", "ACTIONS_RAW",
            "ACTIONS_VECTOR", "POLICY_EXTERNAL", "POLICY_PASSIVE", "POLICY_RANDOM_BIASED", "POLICY_WORKER_RUSH",
-           "POLICY_LIGHT_RUSH"]
+           "POLICY_LIGHT_RUSH", "PF_ASTAR", "PF_BFS", "DTYPE_U8", "DTYPE_I32"]

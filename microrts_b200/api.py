@@ -283,6 +283,20 @@ class BatchedGameState:
         _check(_ffi.lib().mrts_batch_observe(self._h, player, code, p, dev))
         return out
 
+    def set_observation_outputs(self, out0=None, out1=None):
+        """Fused emission: every later step() also writes getVectorObservation(0) / (1) of the state it leaves behind into
+        out0 / out1 ([n][6][H][W], uint8 or int32 device tensors of the batch's device; None disables a player)."""
+        outs = [o for o in (out0, out1) if o is not None]
+        code = DTYPE_I32
+        if outs:
+            dt = str(outs[0].dtype)
+            code = DTYPE_U8 if "uint8" in dt else DTYPE_I32
+            for o in outs:
+                assert str(o.dtype) == dt and tuple(o.shape) == (self.n, self.num_planes, self.height, self.width)
+        ptrs = [_ptr(o)[0] if o is not None else None for o in (out0, out1)]
+        self._obs_keepalive = (out0, out1)
+        _check(_ffi.lib().mrts_batch_set_observation_outputs(self._h, code, ptrs[0], ptrs[1]))
+
     def masks(self, player, dtype=np.int32, out=None):
         """JNIGridnetClient.getMasks(player) for every game: [n][H][W][mask_width]."""
         code = DTYPE_U8 if np.dtype(dtype) == np.uint8 else DTYPE_I32

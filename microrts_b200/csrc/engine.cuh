@@ -71,6 +71,8 @@ struct StepParams {
     int out_dtype;             // 0 = u8, 1 = i32
     int out_player;
     int partial_obs;
+    void *obs_out[2];          // MODE_GAME: when set, the post-step observation of player 0 / 1 is written here ([n][6][H][W])
+    int obs_dtype;
     // MODE_ROLLOUT: item r = game r / rollouts_per_game
     int rollouts_per_game, depth, eval_fn, maxplayer, observer;
     const long long *ro_seeds; // [n_games * rollouts_per_game] or NULL (seed = r)
@@ -230,13 +232,17 @@ DEV int kind_of(const Game &g, uint32_t w) { // the cell-kind byte of a unit (la
 // with_rdy: also recompute the completion times (after a load; compaction carries them along instead).
 DEV void g_rebuild(Game &g, bool with_rdy) {
     __syncwarp();
-    #pragma unroll 1
-    for (int i = g.lane; i < g.pcw; i += 32) {
-        uint32_t t = g.grid_tmpl[i];
-        ((uint32_t *)g.grid())[i] = t;
-        ((uint32_t *)g.kind())[i] = t;
-        ((uint32_t *)g.resv())[i] = 0;
-        ((uint32_t *)g.claim())[i] = 0;
+    { // 16 bytes per lane and iteration; the template loads of several iterations are in flight together
+        uint4 z; z.x = z.y = z.z = z.w = 0;
+        int nq = g.pcw >> 2;
+        #pragma unroll 4
+        for (int i = g.lane; i < nq; i += 32) {
+            uint4 t = ((const uint4 *)g.grid_tmpl)[i];
+            ((uint4 *)g.grid())[i] = t;
+            ((uint4 *)g.kind())[i] = t;
+            ((uint4 *)g.resv())[i] = z;
+            ((uint4 *)g.claim())[i] = z;
+        }
     }
     __syncwarp();
     int n = g.hdr()[H_NUNITS];
@@ -1299,6 +1305,78 @@ DEVN void run_issue_only(Game &g, const StepParams &p, long long gi) {
     issue_pending(g, 0, pn);
 }
 
+// ---- GameState.getVectorObservation(player) (GameState.java:922-968), fully observable -----------------------------------
+// Planes: hp, resources, owner ((owner + player) % 2 + 1), type + 1, current action type, terrain; out = [C=6][H][W] of
+// this game, u8 or i32.  Almost every cell is empty, so the planes are first written in bulk with 16-byte stores (zeros;
+// the map's terrain plane for plane 5) and the units' five values are then scattered over them: the warp barrier orders
+// the two writes and the second one merges in L2, so DRAM sees each output byte once.  w0/w1/a0 point at the unit table
+// (shared memory inside the step kernels, HBM in k_observe).
+DEV void obs_emit(const uint32_t *w0, const uint32_t *w1, const uint32_t *a0, int n, int W, int H, const uint8_t *terrain, int player,
+                  int dtype, void *out, int lane) {
+    int cells = W * H;
+    if (dtype == 0) {
+        uint8_t *o = (uint8_t *)out;
+        if ((cells & 15) == 0) {
+            int nq = cells >> 4;
+            uint4 z; z.x = z.y = z.z = z.w = 0;
+            #pragma unroll 4
+            for (int q = lane; q < 5 * nq; q += 32) ((uint4 *)o)[q] = z;
+            #pragma unroll 2
+            for (int q = lane; q < nq; q += 32) ((uint4 *)(o + 5 * cells))[q] = ((const uint4 *)terrain)[q];
+        } else {
+            #pragma unroll 1
+            for (int q = lane; q < 5 * cells; q += 32) o[q] = 0;
+            #pragma unroll 1
+            for (int q = lane; q < cells; q += 32) o[5 * cells + q] = terrain[q];
+        }
+        __syncwarp();
+        #pragma unroll 1
+        for (int i = lane; i < n; i += 32) {
+            uint32_t w = w0[i], v1 = w1[i];
+            int at = a_type(a0[i]), pl = u_pl(w);
+            uint8_t *c = o + u_y(w) * W + u_x(w);
+            c[0] = (uint8_t)u_hp(v1); c[cells] = (uint8_t)u_res(v1);
+            c[2 * cells] = (uint8_t)(pl != 0 ? ((pl - 1 + player) % 2) + 1 : 0);
+            c[3 * cells] = (uint8_t)(u_type(w) + 1);
+            c[4 * cells] = (uint8_t)(at == (int)AT_IDLE ? 0 : at);
+        }
+    } else {
+        int32_t *o = (int32_t *)out;
+        if ((cells & 3) == 0) {
+            int nq = cells >> 2;
+            int4 z; z.x = z.y = z.z = z.w = 0;
+            #pragma unroll 4
+            for (int q = lane; q < 5 * nq; q += 32) ((int4 *)o)[q] = z;
+            #pragma unroll 2
+            for (int q = lane; q < nq; q += 32) {
+                uint32_t t = ((const uint32_t *)terrain)[q];
+                int4 v; v.x = t & 0xff; v.y = (t >> 8) & 0xff; v.z = (t >> 16) & 0xff; v.w = t >> 24;
+                ((int4 *)(o + 5 * cells))[q] = v;
+            }
+        } else {
+            #pragma unroll 1
+            for (int q = lane; q < 5 * cells; q += 32) o[q] = 0;
+            #pragma unroll 1
+            for (int q = lane; q < cells; q += 32) o[5 * cells + q] = terrain[q];
+        }
+        __syncwarp();
+        #pragma unroll 1
+        for (int i = lane; i < n; i += 32) {
+            uint32_t w = w0[i], v1 = w1[i];
+            int at = a_type(a0[i]), pl = u_pl(w);
+            int32_t *c = o + u_y(w) * W + u_x(w);
+            c[0] = u_hp(v1); c[cells] = u_res(v1);
+            c[2 * cells] = pl != 0 ? ((pl - 1 + player) % 2) + 1 : 0;
+            c[3 * cells] = u_type(w) + 1;
+            c[4 * cells] = at == (int)AT_IDLE ? 0 : at;
+        }
+    }
+    __syncwarp();
+}
+DEV size_t obs_bytes_per_game(int W, int H, int C, int dtype) { return (size_t)C * W * H * (dtype == 0 ? 1 : 4); }
+// the map blob's terrain plane (layout.h)
+DEV const uint8_t *map_terrain(const uint32_t *blob, int W, int H, int cap) { return (const uint8_t *)(blob + mrts_map_terrain_offset_words(W, H, cap)); }
+
 // ---- GameState.getVectorObservation (GameState.java:922-968) / PartiallyObservableGameState (:35-71,82-179) ------------
 // Planes: hp, resources, owner ((owner+player)%2+1), type+1, current action type, terrain [, my visibility, visible
 // enemies' visibility].  out = [n_games][C][H][W], u8 or i32.  resv/claim are reused as the two visibility maps.
@@ -1332,6 +1410,11 @@ DEV void cell_planes(const Game &g, int cell, int player, bool po, int v[8]) {
 DEVN void observe_game(Game &g, const StepParams &p, long long gi) {
     int cells = g.W * g.H, C = p.partial_obs ? 8 : 6, player = p.out_player;
     bool po = p.partial_obs != 0;
+    if (!po) {
+        obs_emit(g.w0(), g.w1(), g.a0(), g.hdr()[H_NUNITS], g.W, g.H, map_terrain(g.grid_tmpl, g.W, g.H, g.cap), player, p.out_dtype,
+                 (char *)p.out + (size_t)gi * obs_bytes_per_game(g.W, g.H, 6, p.out_dtype), g.lane);
+        return;
+    }
     if (po) {
         int n = g.hdr()[H_NUNITS];
         #pragma unroll 1
@@ -1517,9 +1600,10 @@ DEV void run_rollout(Game &g, const StepParams &p, long long r, WarpStats &ws) {
 // are compiled in, so that the hot ones stay small enough for the instruction caches and fully inlined:
 //   KERNEL_FAST    MODE_GAME with RandomBiasedAI / PassiveAI players under CANCEL_BOTH
 //   KERNEL_ROLLOUT MODE_ROLLOUT
+//   KERNEL_FAST_OBS KERNEL_FAST + the post-step observation planes of both players (mrts_batch_set_observation_outputs)
 //   KERNEL_GENERIC everything else (external actions, scripted policies, other conflict policies, cycle-only,
 //                  issue-only, observations, masks)
-enum { KERNEL_FAST = 0, KERNEL_ROLLOUT = 1, KERNEL_GENERIC = 2 };
+enum { KERNEL_FAST = 0, KERNEL_ROLLOUT = 1, KERNEL_GENERIC = 2, KERNEL_FAST_OBS = 3, N_KERNELS = 4 };
 
 template <int KERNEL>
 DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int nthreads, int bid, int nblocks) {
@@ -1548,7 +1632,7 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
         g_load(g, ghdr, gun, KERNEL != KERNEL_ROLLOUT && p.mode == MODE_GAME && p.auto_reset, p.max_cycles);
         if (KERNEL == KERNEL_ROLLOUT) { run_rollout(g, p, item, ws); continue; } // the batch itself is not modified
         int err0 = g.hdr()[H_ERR];
-        if (KERNEL == KERNEL_FAST) run_game_fast(g, p, ws);
+        if (KERNEL == KERNEL_FAST || KERNEL == KERNEL_FAST_OBS) run_game_fast(g, p, ws);
         else if (p.mode == MODE_GAME) run_game(g, p, gi, ws);
         else if (p.mode == MODE_CYCLE_ONLY) run_cycles_only(g, p.t_target ? p.t_target[gi] : g.hdr()[H_TIME] + p.n_cycles);
         else if (p.mode == MODE_ISSUE_ONLY) run_issue_only(g, p, gi);
@@ -1556,6 +1640,13 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
         else { masks_game(g, p, gi); continue; }
         if (g.hdr()[H_ERR] != err0) ws.v[STAT_ERRORS]++;
         g_store(g, ghdr, gun);
+        if (KERNEL == KERNEL_FAST_OBS || (KERNEL == KERNEL_GENERIC && p.mode == MODE_GAME)) {
+            #pragma unroll 1
+            for (int pl = 0; pl < 2; pl++)
+                if (p.obs_out[pl])
+                    obs_emit(g.w0(), g.w1(), g.a0(), g.hdr()[H_NUNITS], g.W, g.H, map_terrain(blob, g.W, g.H, g.cap), pl, p.obs_dtype,
+                             (char *)p.obs_out[pl] + (size_t)gi * obs_bytes_per_game(g.W, g.H, 6, p.obs_dtype), lane);
+        }
     }
     if (lane == 0 && p.stats)
         #pragma unroll 1

@@ -298,6 +298,8 @@ inline void build_map_blob(const MapH &m, int cap, std::vector<uint32_t> &blob) 
         n++;
     }
     hdr[H_RES0] = m.res[0]; hdr[H_RES1] = m.res[1]; hdr[H_NUNITS] = n; hdr[H_NEXTID] = (int32_t)next_id;
+    uint8_t *ter = (uint8_t *)(blob.data() + mrts_map_terrain_offset_words(W, H, cap));
+    for (int i = 0; i < W * H; i++) ter[i] = m.terrain[i] ? 1 : 0;
 }
 
 inline uint64_t jr_scramble(int64_t seed) { return ((uint64_t)seed ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1); }

@@ -88,9 +88,9 @@ MRTS_HD SmemLayout mrts_smem_layout(int W, int H, int cap, int scripted) {
     int o = 0;
     L.uws = (scripted ? MRTS_UNIT_WORDS : MRTS_UNIT_WORDS_CORE) + 1; // X0/X1 are resident only for scripted batches; +1: RDY
     L.hdr = o; o += MRTS_HDR_WORDS * 4;
-    L.units = o; o += L.uws * cap * 4;
-    L.pa0 = o; o += cap * 4;
-    L.pa1 = o; o += cap * 4;
+    L.units = o; o += (L.uws * cap * 4 + 15) & ~15; // every section starts 16-byte aligned (vector fills of the cell maps)
+    L.pa0 = o; o += (cap * 4 + 15) & ~15;
+    L.pa1 = o; o += (cap * 4 + 15) & ~15;
     L.pslot = o; o += capb;
     L.grid = o; o += pcb;
     L.kind = o; o += pcb;
@@ -103,8 +103,12 @@ MRTS_HD SmemLayout mrts_smem_layout(int W, int H, int cap, int scripted) {
     return L;
 }
 
-// per-map blob in HBM (32-bit words): [grid template pcw][init header 16][init units 7*cap]
-MRTS_HD int mrts_map_blob_words(int W, int H, int cap) {
+// per-map blob in HBM (32-bit words): [grid template pcw][init header][init units 9*cap][terrain plane, W*H bytes of 0/1,
+// 16-byte aligned: plane 5 of GameState.getVectorObservation]
+MRTS_HD int mrts_map_terrain_offset_words(int W, int H, int cap) {
     int pcb = (((W + 2) * (H + 2)) + 15) & ~15;
-    return pcb / 4 + MRTS_HDR_WORDS + MRTS_UNIT_WORDS * cap;
+    return (pcb / 4 + MRTS_HDR_WORDS + MRTS_UNIT_WORDS * cap + 3) & ~3;
+}
+MRTS_HD int mrts_map_blob_words(int W, int H, int cap) {
+    return mrts_map_terrain_offset_words(W, H, cap) + ((W * H + 15) & ~15) / 4;
 }

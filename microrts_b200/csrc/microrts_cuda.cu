@@ -110,6 +110,23 @@ DEV void results_kernel_body(const ResultParams &p, long long gi) {
     o[3] = h[H_ERR];
 }
 
+struct ObsParams {
+    const int32_t *hdr; const uint32_t *units; const uint32_t *maps; void *out;
+    long long n_games; int n_maps, map_words, W, H, cap, uw, player, dtype;
+};
+// GameState.getVectorObservation for every game straight from the state in HBM (fully observable batches): one warp per
+// game, no shared memory; reads 3 words per unit, writes the 6 planes (obs_emit)
+DEV void observe_kernel_body(const ObsParams &p, int tid, int nthreads, int bid, int nblocks) {
+    int warp = tid >> 5, lane = tid & 31, wpc = nthreads >> 5;
+    for (long long gi = (long long)bid * wpc + warp; gi < p.n_games; gi += (long long)nblocks * wpc) {
+        const uint32_t *blob = p.maps + (size_t)(gi % p.n_maps) * p.map_words;
+        const uint32_t *un = p.units + gi * (long long)p.uw * p.cap;
+        int n = p.hdr[gi * MRTS_HDR_WORDS + H_NUNITS];
+        obs_emit(un + UW_W0 * p.cap, un + UW_W1 * p.cap, un + UW_A0 * p.cap, n, p.W, p.H, map_terrain(blob, p.W, p.H, p.cap), p.player, p.dtype,
+                 (char *)p.out + (size_t)gi * obs_bytes_per_game(p.W, p.H, 6, p.dtype), lane);
+    }
+}
+
 #ifndef MRTS_EMU
 #ifndef MRTS_MIN_BLOCKS
 #define MRTS_MIN_BLOCKS 6
@@ -119,12 +136,16 @@ DEV void results_kernel_body(const ResultParams &p, long long gi) {
 __global__ void __launch_bounds__(MRTS_WARPS_PER_CTA * 32, MRTS_MIN_BLOCKS) k_step_fast(StepParams p) {
     step_kernel_body<KERNEL_FAST>(p, mrts_smem, threadIdx.x, blockDim.x, blockIdx.x, gridDim.x);
 }
+__global__ void __launch_bounds__(MRTS_WARPS_PER_CTA * 32, MRTS_MIN_BLOCKS) k_step_fast_obs(StepParams p) {
+    step_kernel_body<KERNEL_FAST_OBS>(p, mrts_smem, threadIdx.x, blockDim.x, blockIdx.x, gridDim.x);
+}
 __global__ void __launch_bounds__(MRTS_WARPS_PER_CTA * 32, MRTS_MIN_BLOCKS) k_rollout(StepParams p) {
     step_kernel_body<KERNEL_ROLLOUT>(p, mrts_smem, threadIdx.x, blockDim.x, blockIdx.x, gridDim.x);
 }
 __global__ void __launch_bounds__(MRTS_WARPS_PER_CTA * 32, 2) k_step(StepParams p) {
     step_kernel_body<KERNEL_GENERIC>(p, mrts_smem, threadIdx.x, blockDim.x, blockIdx.x, gridDim.x);
 }
+__global__ void __launch_bounds__(256) k_observe(ObsParams p) { observe_kernel_body(p, threadIdx.x, blockDim.x, blockIdx.x, gridDim.x); }
 __global__ void __launch_bounds__(128) k_reset(ResetParams p) { reset_kernel_body(p, threadIdx.x, blockDim.x, blockIdx.x, gridDim.x); }
 __global__ void __launch_bounds__(128) k_results(ResultParams p) { results_kernel_body(p, (long long)blockIdx.x * blockDim.x + threadIdx.x); }
 #endif
@@ -155,8 +176,9 @@ struct mrts_batch {
     Staged staged[2];
     stream_t stream = nullptr;
     SmemLayout L;
-    struct Plan { int wpc = 2, grid = 3; size_t smem = 0; } plan[3]; // per kernel: warps (games in flight) per CTA, CTAs, shared memory
+    struct Plan { int wpc = 2, grid = 3; size_t smem = 0; } plan[N_KERNELS]; // per kernel: warps (games in flight) per CTA, CTAs, shared memory
     int max_range = 0, auto_reset = 0, scripted = 0, uw = MRTS_UNIT_WORDS_CORE;
+    void *obs_out[2] = {nullptr, nullptr}; int obs_dtype = 0; // device buffers mrts_batch_step writes post-step observations to
     long long launches = 0;
 };
 
@@ -178,7 +200,8 @@ static int launch_step(mrts_batch *b, StepParams &p) {
     int kernel = KERNEL_GENERIC;
     auto rb_or_passive = [](int pol) { return pol == MRTS_POLICY_RANDOM_BIASED || pol == MRTS_POLICY_PASSIVE; };
     if (p.mode == MODE_ROLLOUT) kernel = KERNEL_ROLLOUT;
-    else if (p.mode == MODE_GAME && p.conflict == MRTS_CANCEL_BOTH && rb_or_passive(p.policy[0]) && rb_or_passive(p.policy[1])) kernel = KERNEL_FAST;
+    else if (p.mode == MODE_GAME && p.conflict == MRTS_CANCEL_BOTH && rb_or_passive(p.policy[0]) && rb_or_passive(p.policy[1]))
+        kernel = (p.obs_out[0] || p.obs_out[1]) ? KERNEL_FAST_OBS : KERNEL_FAST;
     const mrts_batch::Plan &pl = b->plan[kernel];
     int threads = pl.wpc * 32;
     long long items = p.mode == MODE_ROLLOUT ? b->n * p.rollouts_per_game : b->n;
@@ -189,14 +212,29 @@ static int launch_step(mrts_batch *b, StepParams &p) {
     StepParams pc = p;
     emu::launch(grid, threads, pl.smem, [pc, threads, grid, kernel](unsigned char *sm, int tid, int bid) {
         if (kernel == KERNEL_FAST) step_kernel_body<KERNEL_FAST>(pc, sm, tid, threads, bid, grid);
+        else if (kernel == KERNEL_FAST_OBS) step_kernel_body<KERNEL_FAST_OBS>(pc, sm, tid, threads, bid, grid);
         else if (kernel == KERNEL_ROLLOUT) step_kernel_body<KERNEL_ROLLOUT>(pc, sm, tid, threads, bid, grid);
         else step_kernel_body<KERNEL_GENERIC>(pc, sm, tid, threads, bid, grid);
     });
     return 0;
 #else
     if (kernel == KERNEL_FAST) k_step_fast<<<grid, threads, pl.smem, b->stream>>>(p);
+    else if (kernel == KERNEL_FAST_OBS) k_step_fast_obs<<<grid, threads, pl.smem, b->stream>>>(p);
     else if (kernel == KERNEL_ROLLOUT) k_rollout<<<grid, threads, pl.smem, b->stream>>>(p);
     else k_step<<<grid, threads, pl.smem, b->stream>>>(p);
+    return ck(cudaGetLastError());
+#endif
+}
+
+static int launch_observe(mrts_batch *b, int player, int dtype, void *d_out) {
+    ObsParams p{b->d_hdr, b->d_units, b->d_maps, d_out, b->n, b->n_maps, b->map_words, b->W, b->H, b->cap, b->uw, player, dtype};
+    b->launches++;
+#ifdef MRTS_EMU
+    emu::launch(2, 64, 0, [p](unsigned char *, int tid, int bid) { observe_kernel_body(p, tid, 64, bid, 2); });
+    return 0;
+#else
+    int grid = (int)std::min<long long>((b->n + 7) / 8, 148 * 8);
+    k_observe<<<grid, 256, 0, b->stream>>>(p);
     return ck(cudaGetLastError());
 #endif
 }
@@ -320,8 +358,8 @@ int mrts_batch_create(const mrts_utt *u, const mrts_map *const *maps, int n_maps
     if (ck(cudaGetDeviceProperties(&prop, device))) return fail(MRTS_E_CUDA, std::string("cudaGetDeviceProperties: ") + dev_errstr());
     // Per kernel: as many games in flight per SM as shared memory and registers allow (large maps need fewer, fatter
     // CTAs); grid = resident CTAs per SM x SMs (persistent kernel).
-    const void *kernels[3] = {(const void *)k_step_fast, (const void *)k_rollout, (const void *)k_step};
-    for (int kk = 0; kk < 3; kk++) {
+    const void *kernels[N_KERNELS] = {(const void *)k_step_fast, (const void *)k_rollout, (const void *)k_step, (const void *)k_step_fast_obs};
+    for (int kk = 0; kk < N_KERNELS; kk++) {
         int best_wpc = 0, best_warps = 0, best_blocks = 0;
         if (ck(cudaFuncSetAttribute(kernels[kk], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin)) ||
             ck(cudaFuncSetAttribute(kernels[kk], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)))
@@ -340,7 +378,7 @@ int mrts_batch_create(const mrts_utt *u, const mrts_map *const *maps, int n_maps
     }
     if (ck(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking))) return fail(MRTS_E_CUDA, std::string("cudaStreamCreate: ") + dev_errstr());
 #else
-    for (int kk = 0; kk < 3; kk++) { b->plan[kk].wpc = 2; b->plan[kk].smem = MRTS_CONST_WORDS * 4 + (size_t)2 * b->L.total; b->plan[kk].grid = 3; }
+    for (int kk = 0; kk < N_KERNELS; kk++) { b->plan[kk].wpc = 2; b->plan[kk].smem = MRTS_CONST_WORDS * 4 + (size_t)2 * b->L.total; b->plan[kk].grid = 3; }
 #endif
     if (b->scripted == 2) {
         b->astar_stride = ((long long)W * H * MRTS_ASTAR_BYTES_PER_CELL + 255) & ~255LL;
@@ -465,7 +503,19 @@ int mrts_batch_step(mrts_batch *b, int n_cycles, int max_cycles) {
     StepParams p; memset(&p, 0, sizeof p);
     p.mode = MODE_GAME; p.n_cycles = n_cycles; p.max_cycles = max_cycles; p.safe = 1; p.auto_reset = b->auto_reset;
     for (int pl = 0; pl < 2; pl++) { p.policy[pl] = b->policy[pl]; p.pathfinder[pl] = b->pathfinder[pl]; if (b->policy[pl] == MRTS_POLICY_EXTERNAL) fill_ext(b, p, pl); b->staged[pl].valid = false; }
+    bool fused = !(b->flags & MRTS_FLAG_PARTIAL_OBS); // partially observable batches observe in a second launch
+    if (fused) { p.obs_out[0] = b->obs_out[0]; p.obs_out[1] = b->obs_out[1]; p.obs_dtype = b->obs_dtype; }
     if (launch_step(b, p)) return fail(MRTS_E_CUDA, std::string("step launch: ") + dev_errstr());
+    if (!fused)
+        for (int pl = 0; pl < 2; pl++)
+            if (b->obs_out[pl]) { int rc = mrts_batch_observe(b, pl, b->obs_dtype, b->obs_out[pl], 1); if (rc) return rc; }
+    return MRTS_OK;
+}
+
+int mrts_batch_set_observation_outputs(mrts_batch *b, int dtype, void *out_player0, void *out_player1) {
+    if (!b || (dtype != MRTS_DTYPE_U8 && dtype != MRTS_DTYPE_I32)) return fail(MRTS_E_ARG, "mrts_batch_set_observation_outputs: bad argument");
+    if ((((uintptr_t)out_player0) | ((uintptr_t)out_player1)) & 15) return fail(MRTS_E_ARG, "observation buffers must be 16-byte aligned");
+    b->obs_out[0] = out_player0; b->obs_out[1] = out_player1; b->obs_dtype = dtype;
     return MRTS_OK;
 }
 
@@ -518,9 +568,13 @@ static int emit(mrts_batch *b, int mode, int player, int dtype, void *out, int o
     void *d_out = out;
     if (!on_device) { if (ensure_tmp(b, bytes)) return fail(MRTS_E_CUDA, std::string("staging allocation failed: ") + dev_errstr()); d_out = b->d_tmp; }
     if (mode == MODE_MASKS && dev_zero(d_out, bytes, b->stream)) return fail(MRTS_E_CUDA, dev_errstr());
-    StepParams p; memset(&p, 0, sizeof p);
-    p.mode = mode; p.out = d_out; p.out_dtype = dtype; p.out_player = player;
-    if (launch_step(b, p)) return fail(MRTS_E_CUDA, std::string("launch: ") + dev_errstr());
+    if (mode == MODE_OBSERVE && !(b->flags & MRTS_FLAG_PARTIAL_OBS)) {
+        if (launch_observe(b, player, dtype, d_out)) return fail(MRTS_E_CUDA, std::string("launch: ") + dev_errstr());
+    } else {
+        StepParams p; memset(&p, 0, sizeof p);
+        p.mode = mode; p.out = d_out; p.out_dtype = dtype; p.out_player = player;
+        if (launch_step(b, p)) return fail(MRTS_E_CUDA, std::string("launch: ") + dev_errstr());
+    }
     if (!on_device && dev_d2h(out, d_out, bytes, b->stream)) return fail(MRTS_E_CUDA, dev_errstr());
     return MRTS_OK;
 }

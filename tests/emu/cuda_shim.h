@@ -168,6 +168,8 @@ inline void syncthreads(int line) { yield_wait(2, line, 0); }
 #define __popc(x) __builtin_popcount((unsigned)(x))
 #define __ffs(x) __builtin_ffs((int)(x))
 #define __dmul_rn(a, b) ((double)(a) * (double)(b))
+struct uint4 { unsigned x, y, z, w; };
+struct int4 { int x, y, z, w; };
 template <typename T> static inline T atomicOr(T *p, T v) { T o = *p; *p = o | v; return o; }
 static inline int atomicOr(int *p, int v) { int o = *p; *p = o | v; return o; }
 template <typename T> static inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }

@@ -185,6 +185,58 @@ def test_observations_and_masks(backend, maps, key):
     bpo.close()
 
 
+def _device_buffer(backend, shape, dtype):
+    """A buffer the engine can write 'on device': a torch CUDA tensor, or plain host memory under the emulator."""
+    if backend == "emu":
+        return np.full(shape, 0x55, dtype=dtype)
+    import torch
+    return torch.full(shape, 0x55, dtype=torch.uint8 if dtype == np.uint8 else torch.int32, device="cuda")
+
+
+def _to_numpy(buf):
+    return buf if isinstance(buf, np.ndarray) else buf.cpu().numpy()
+
+
+@pytest.mark.parametrize("key,dtype,external", [("16x16/basesWorkers16x16", np.uint8, False), ("melee14x12Mixed18", np.int32, False),
+                                                ("NoWhereToRun9x8", np.uint8, True), ("8x8/basesWorkers8x8", np.int32, True)])
+def test_fused_step_observations(backend, maps, key, dtype, external):
+    """mrts_batch_set_observation_outputs: the planes written by the step kernel itself equal the oracle's
+    getVectorObservation of the post-step state for both players (fast RandomBiased kernel, and the generic kernel when a
+    player is EXTERNAL)."""
+    n = 3 if backend == "emu" else 40
+    utt, outt = M.UnitTypeTable(1, 1), O.Utt(1, 1)
+    m = maps[key]
+    b = M.BatchedGameState(utt, make_pgs(m, utt), n)
+    seeds = np.arange(n, dtype=np.int64) + 77
+    b.reset(seeds)
+    b.set_policy(0, M.POLICY_RANDOM_BIASED)
+    b.set_policy(1, M.POLICY_EXTERNAL if external else M.POLICY_RANDOM_BIASED)
+    shape = (n, 6, m["h"], m["w"])
+    o0, o1 = _device_buffer(backend, shape, dtype), _device_buffer(backend, shape, dtype)
+    b.set_observation_outputs(o0, o1)
+    games = []
+    for g in range(n):
+        og = O.Game(outt, m)
+        og.seed(int(seeds[g]))
+        games.append(og)
+    for it in range(6):
+        b.step(23, 3000)
+        b.sync()
+        a0, a1 = _to_numpy(o0), _to_numpy(o1)
+        for g, og in enumerate(games):
+            og.run(O.AI_RANDOM_BIASED, None, O.AI_PASSIVE if external else O.AI_RANDOM_BIASED, None, 23, 3000)
+            assert (a0[g] == og.observe(0).astype(dtype)).all(), (key, it, g)
+            assert (a1[g] == og.observe(1).astype(dtype)).all(), (key, it, g)
+    # player 1 only, then disabled: untouched buffers stay untouched
+    b.set_observation_outputs(None, o1)
+    before = _to_numpy(o0).copy()
+    b.step(5, 3000)
+    b.sync()
+    assert (_to_numpy(o0) == before).all()
+    b.set_observation_outputs(None, None)
+    b.close()
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # vector actions through the EXTERNAL policy (JNIGridnetClientSelfPlay.gameStep flow) against the oracle
 # ------------------------------------------------------------------------------------------------------------------
