@@ -95,8 +95,7 @@ struct Game {
     int o_pa0, o_pa1, o_pslot, o_grid, o_kind, o_resv, o_claim, o_list;
     int pview;                            // window into the pending list (policy_scripted stages desires behind the final part)
     const uint32_t *grid_tmpl;            // global: wall-padded empty grid of this game's map
-    uint16_t *as_closed, *as_cost, *as_opos, *as_opar, *as_of; // A* scratch over W*H cells (scripted batches only)
-    uint8_t *as_flags;
+    uint16_t *as_closed, *as_cost, *as_mark, *as_next, *as_head, *as_gen; // A*/BFS scratch of this warp (scripted batches only, layout.h)
 
     MDEV unsigned char *base() const { return mrts_smem + sb; }
     MDEV int32_t *hdr() const { return (int32_t *)base(); }
@@ -131,7 +130,7 @@ DEV void g_bind(Game &g, int sb, const SmemLayout &L, int W, int H, int cap, int
     g.o_pa0 = L.pa0; g.o_pa1 = L.pa1; g.o_pslot = L.pslot; g.o_grid = L.grid; g.o_kind = L.kind; g.o_resv = L.resv;
     g.o_claim = L.claim; g.o_list = L.list;
     { int cells = W * H; g.as_closed = (uint16_t *)(astar_global ? astar_global : mrts_smem + sb + L.astar); g.as_cost = g.as_closed + cells;
-      g.as_opos = g.as_cost + cells; g.as_opar = g.as_opos + cells; g.as_of = g.as_opar + cells; g.as_flags = (uint8_t *)(g.as_of + cells); }
+      g.as_mark = g.as_cost + cells; g.as_next = g.as_mark + cells; g.as_head = g.as_next + cells; g.as_gen = g.as_head + cells + W + H + 2; }
     g.grid_tmpl = nullptr;
 }
 
@@ -987,7 +986,7 @@ DEV int cycle_execute(Game &g, int t_new) {
             execute_serial(g, ci, ndead);
             cs = 0xFFFFFFFFu;
             #pragma unroll 1
-            for (int i = g.lane; i < n; i += 32)
+            for (int i = g.lane; n > 32 && i < n; i += 32) // only when lanes own several units
                 if (g.rdy()[i] <= t_new) { uint32_t q = g.seq()[i]; if (q < cs) { cs = q; ci = i; } }
         }
         __syncwarp(); // its effects are visible to the lane that executes the next one
@@ -1619,6 +1618,15 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
     Game g;
     g_bind(g, MRTS_CONST_WORDS * 4 + warp * L.total, L, p.W, p.H, p.cap, lane, p.conflict, p.scripted,
            p.scripted == 2 ? p.astar_scratch + ((long long)bid * wpc + warp) * p.astar_stride : nullptr);
+    if (KERNEL == KERNEL_GENERIC && p.scripted) { // pathfinding scratch: no stale marks, all buckets empty, generation 0
+        int cells = p.W * p.H;
+        #pragma unroll 1
+        for (int i = lane; i < cells; i += 32) g.as_mark[i] = 0;
+        #pragma unroll 1
+        for (int i = lane; i < cells + p.W + p.H + 2; i += 32) g.as_head[i] = 0xFFFF;
+        if (lane == 0) *g.as_gen = 0;
+        __syncwarp();
+    }
     WarpStats ws;
     for (int i = 0; i < 8; i++) ws.v[i] = 0;
     long long n_items = KERNEL == KERNEL_ROLLOUT ? p.n_games * p.rollouts_per_game : p.n_games;

@@ -78,8 +78,10 @@ struct SmemLayout {
 // isStockpile<<3 | 0x10 -- what Unit.getUnitActions needs to know about a neighbouring cell, without touching the unit.
 #define CK_UNIT 0x10
 
-// A* / BFS scratch (scripted policies only): per cell closed u16, cost u16, flags u8, open list (pos u16, parent u16, f u16)
-#define MRTS_ASTAR_BYTES_PER_CELL 11
+// A* / BFS scratch of one warp (scripted policies only), all u16: parent[cells], cost[cells], mark[cells] (query
+// generation << 3 | flags), next[cells] (bucket chains / BFS queue), head[cells + W + H + 2] (one LIFO bucket per f value),
+// generation counter.  Owned by the warp, not the game: it is initialised once per launch.
+#define MRTS_ASTAR_BYTES(W, H) ((10 * (W) * (H) + 2 * ((W) + (H) + 2) + 4 + 15) & ~15)
 MRTS_HD SmemLayout mrts_smem_layout(int W, int H, int cap, int scripted) {
     SmemLayout L;
     int pc = (W + 2) * (H + 2);
@@ -97,7 +99,7 @@ MRTS_HD SmemLayout mrts_smem_layout(int W, int H, int cap, int scripted) {
     L.resv = o; o += pcb;
     L.claim = o; o += pcb;
     L.list = o; o += capb;
-    L.astar = o; o += scripted == 1 ? ((W * H * MRTS_ASTAR_BYTES_PER_CELL + 15) & ~15) : 0; // scripted == 2: scratch in global memory
+    L.astar = o; o += scripted == 1 ? MRTS_ASTAR_BYTES(W, H) : 0; // scripted == 2: scratch in global memory
     L.total = (o + 15) & ~15;
     L.pcw = pcb / 4;
     return L;

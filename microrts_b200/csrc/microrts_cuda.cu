@@ -381,7 +381,7 @@ int mrts_batch_create(const mrts_utt *u, const mrts_map *const *maps, int n_maps
     for (int kk = 0; kk < N_KERNELS; kk++) { b->plan[kk].wpc = 2; b->plan[kk].smem = MRTS_CONST_WORDS * 4 + (size_t)2 * b->L.total; b->plan[kk].grid = 3; }
 #endif
     if (b->scripted == 2) {
-        b->astar_stride = ((long long)W * H * MRTS_ASTAR_BYTES_PER_CELL + 255) & ~255LL;
+        b->astar_stride = ((long long)MRTS_ASTAR_BYTES(W, H) + 255) & ~255LL;
         if (dev_alloc((void **)&b->d_astar, (size_t)b->plan[KERNEL_GENERIC].grid * b->plan[KERNEL_GENERIC].wpc * b->astar_stride)) return fail(MRTS_E_CUDA, std::string("device allocation failed: ") + dev_errstr());
     }
     size_t hdr_bytes = (size_t)n_games * MRTS_HDR_WORDS * 4, unit_bytes = (size_t)n_games * b->uw * cap * 4;

@@ -38,11 +38,20 @@ DEV void aa_put(Game &g, int s, int player, int kind, int type, int bx, int by, 
 }
 
 // ---- pathfinding ---------------------------------------------------------------------------------------------------------
-enum { PFF_INOC = 1, PFF_BLOCKED = 2 };
+// The reference keeps `open` as an array sorted by descending f = heuristic + cost with a new node inserted behind every
+// node of equal f, and pops from the end (AStarPathFinding.java:104-138,175-295): the node with the smallest f comes out
+// first and, among equal f, the NEWEST one.  That is exactly one LIFO stack per f value, so the open list here is a bucket
+// queue (head[f] -> chain through next[]): O(1) push and pop, same expansion order.  A node enters `open` at most once
+// (inOpenOrClosed), so its parent can be stored when it is pushed.  Per-cell state carries the query's generation number
+// instead of being cleared for every query.
+enum { PFF_INOC = 1, PFF_BLOCKED = 2, PFF_CLOSED = 4 };
+#define PF_NONE 0xFFFFu
 DEV int pf_pc(const Game &g, int pos) { return (pos / g.W + 1) * g.P + pos % g.W + 1; }
+DEV int pf_flags(const Game &g, int pos, int gen) { int m = g.as_mark[pos]; return (m >> 3) == gen ? (m & 7) : 0; }
+DEV void pf_set(const Game &g, int pos, int gen, int flags) { g.as_mark[pos] = (uint16_t)((gen << 3) | flags); }
 // GameState.free (GameState.java:191-207) unless the cell is used by a desire already chosen this cycle (ru)
-DEV bool pf_free(const Game &g, int pos) {
-    if (g.as_flags[pos] & PFF_BLOCKED) return false;
+DEV bool pf_free(const Game &g, int pos, int fl) {
+    if (fl & PFF_BLOCKED) return false;
     int pc = pf_pc(g, pos);
     return g.grid()[pc] == 0 && g.resv()[pc] == 0;
 }
@@ -59,79 +68,99 @@ DEV int pf_first_step(const Game &g, int pos, int parent) {
 DEV int iabs(int v) { return v < 0 ? -v : v; }
 
 // findPathToPositionInRange: direction of the first step of a shortest path from unit slot s to within `range` of
-// targetpos (linear), or -1 (null).  ru = target cells of the desires [0, nd) in the pending list.  Lane 0 only.
+// targetpos (linear), or -1 (null).  ru = target cells of the desires [0, nd) in the pending list.  One lane only.
 DEVN int pf_find(Game &g, int kind, int s, int targetpos, int range, int nd) {
     int W = g.W, H = g.H, cells = W * H;
+    int gen = *g.as_gen + 1;
+    if (gen >= 8191) { // generation numbers wrapped: forget every mark
 #pragma unroll 1
-    for (int i = 0; i < cells; i++) { g.as_closed[i] = 0xFFFF; g.as_flags[i] = 0; }
+        for (int i = 0; i < cells; i++) g.as_mark[i] = 0;
+        gen = 1;
+    }
+    *g.as_gen = (uint16_t)gen;
 #pragma unroll 1
     for (int k = 0; k < nd; k++) {
         uint32_t A0 = g.pa0()[k];
-        if (a_uses_cell(a_type(A0))) { int lin = linear_target_cell(g, g.w0()[g.pslot()[k]], g.pa1()[k]); if (lin >= 0) { int pc = lin; int y = pc / g.P - 1, x = pc % g.P - 1; g.as_flags[x + y * W] |= PFF_BLOCKED; } }
+        if (a_uses_cell(a_type(A0))) {
+            int pc = linear_target_cell(g, g.w0()[g.pslot()[k]], g.pa1()[k]);
+            if (pc >= 0) { int y = pc / g.P - 1, x = pc % g.P - 1; pf_set(g, x + y * W, gen, pf_flags(g, x + y * W, gen) | PFF_BLOCKED); }
+        }
     }
     int tx = targetpos % W, ty = targetpos / W, sq = range * range;
     uint32_t sw = g.w0()[s];
     int sx = u_x(sw), sy = u_y(sw), start = sy * W + sx;
-    if (kind == 0) { // A*: open is sorted by descending f, newest first among equal f; pop from the end
-        int oi = 0;
-        g.as_opos[0] = (uint16_t)start; g.as_of[0] = (uint16_t)(iabs(sx - tx) + iabs(sy - ty)); g.as_opar[0] = (uint16_t)start;
-        g.as_flags[start] |= PFF_INOC; g.as_cost[start] = 0; oi = 1;
+    int result = -1;
+    if (kind == 0) { // A*
+        int f0 = iabs(sx - tx) + iabs(sy - ty), flo = f0, fhi = f0, fcur = f0;
+        g.as_cost[start] = 0; g.as_closed[start] = (uint16_t)start;
+        pf_set(g, start, gen, pf_flags(g, start, gen) | PFF_INOC);
+        g.as_next[start] = PF_NONE; g.as_head[f0] = (uint16_t)start;
 #pragma unroll 1
-        while (oi > 0) {
-            oi--;
-            int pos = g.as_opos[oi], parent = g.as_opar[oi];
-            if (g.as_closed[pos] != 0xFFFF) continue;
-            g.as_closed[pos] = (uint16_t)parent;
+        for (;;) {
+#pragma unroll 1
+            while (fcur <= fhi && g.as_head[fcur] == PF_NONE) fcur++;
+            if (fcur > fhi) break;
+            int pos = g.as_head[fcur];
+            g.as_head[fcur] = g.as_next[pos];
+            int parent = g.as_closed[pos];
+            int fl = pf_flags(g, pos, gen);
+            if (fl & PFF_CLOSED) continue;
+            pf_set(g, pos, gen, fl | PFF_CLOSED);
             int x = pos % W, y = pos / W;
-            if ((x - tx) * (x - tx) + (y - ty) * (y - ty) <= sq) return pf_first_step(g, pos, parent);
+            if ((x - tx) * (x - tx) + (y - ty) * (y - ty) <= sq) { result = pf_first_step(g, pos, parent); break; }
+            int c = g.as_cost[pos] + 1;
 #pragma unroll 1
             for (int d = 0; d < 4; d++) { // up, right, down, left
                 int nx = x + ddx(d), ny = y + ddy(d);
                 if (nx < 0 || ny < 0 || nx >= W || ny >= H) continue;
                 int np = ny * W + nx;
-                if ((g.as_flags[np] & PFF_INOC) || !pf_free(g, np)) continue;
+                int nfl = pf_flags(g, np, gen);
+                if ((nfl & PFF_INOC) || !pf_free(g, np, nfl)) continue;
                 // addToOpen :104-138
-                int c = g.as_cost[pos] + 1;
                 g.as_cost[np] = (uint16_t)c;
-                int f = iabs(nx - tx) + iabs(ny - ty) + c, at = 0;
-#pragma unroll 1
-                for (int i = oi - 1; i >= 0; i--) if ((int)g.as_of[i] >= f) { at = i + 1; break; }
-#pragma unroll 1
-                for (int i = oi; i > at; i--) { g.as_opos[i] = g.as_opos[i - 1]; g.as_opar[i] = g.as_opar[i - 1]; g.as_of[i] = g.as_of[i - 1]; }
-                g.as_opos[at] = (uint16_t)np; g.as_opar[at] = (uint16_t)pos; g.as_of[at] = (uint16_t)f;
-                g.as_flags[np] |= PFF_INOC;
-                oi++;
+                g.as_closed[np] = (uint16_t)pos;
+                int f = iabs(nx - tx) + iabs(ny - ty) + c;
+                g.as_next[np] = g.as_head[f]; g.as_head[f] = (uint16_t)np;
+                if (f > fhi) fhi = f;
+                if (f < fcur) fcur = f;
+                if (f < flo) flo = f;
+                pf_set(g, np, gen, nfl | PFF_INOC);
             }
         }
-        return -1;
+#pragma unroll 1
+        for (int f = flo; f <= fhi; f++) g.as_head[f] = PF_NONE; // leave every bucket empty for the next query
+        return result;
     }
-    // BFS: FIFO ring of size W*H
+    // BFS: FIFO queue (positions in next[], parents in head[]); a cell is enqueued at most once, so it never wraps
+    uint16_t *qpos = g.as_next, *qpar = g.as_head;
     int oi = 0, orm = 0;
-    g.as_opos[0] = (uint16_t)start; g.as_opar[0] = (uint16_t)start; g.as_flags[start] |= PFF_INOC; oi = 1;
+    qpos[0] = (uint16_t)start; qpar[0] = (uint16_t)start; pf_set(g, start, gen, pf_flags(g, start, gen) | PFF_INOC); oi = 1;
 #pragma unroll 1
     while (oi != orm) {
-        int pos = g.as_opos[orm], parent = g.as_opar[orm];
-        orm++; if (orm >= cells) orm = 0;
-        if (g.as_closed[pos] != 0xFFFF) continue;
+        int pos = qpos[orm], parent = qpar[orm];
+        orm++;
+        int fl = pf_flags(g, pos, gen);
+        if (fl & PFF_CLOSED) continue;
+        pf_set(g, pos, gen, fl | PFF_CLOSED);
         g.as_closed[pos] = (uint16_t)parent;
         int x = pos % W, y = pos / W;
-        if ((x - tx) * (x - tx) + (y - ty) * (y - ty) <= sq) return pf_first_step(g, pos, parent);
+        if ((x - tx) * (x - tx) + (y - ty) * (y - ty) <= sq) { result = pf_first_step(g, pos, parent); break; }
 #pragma unroll 1
         for (int d = 0; d < 4; d++) {
             int nx = x + ddx(d), ny = y + ddy(d);
             if (nx < 0 || ny < 0 || nx >= W || ny >= H) continue;
             int np = ny * W + nx;
-            if ((g.as_flags[np] & PFF_INOC) || !pf_free(g, np)) continue;
-            g.as_opos[oi] = (uint16_t)np; g.as_opar[oi] = (uint16_t)pos;
-            oi++; if (oi >= cells) oi = 0;
-            g.as_flags[np] |= PFF_INOC;
+            int nfl = pf_flags(g, np, gen);
+            if ((nfl & PFF_INOC) || !pf_free(g, np, nfl)) continue;
+            qpos[oi] = (uint16_t)np; qpar[oi] = (uint16_t)pos;
+            oi++;
+            pf_set(g, np, gen, nfl | PFF_INOC);
         }
     }
-    return -1;
+#pragma unroll 1
+    for (int i = 0; i < oi; i++) qpar[i] = PF_NONE; // head[] doubles as the parent queue: restore the empty buckets
+    return result;
 }
-
-// In the A* above as_of holds f = heuristic + cost(node) at insertion; the reference compares heuristic[i] + cost[open[i]]
-// with h + cost[newPos], and a node's cost never changes after it is inserted, so the two are the same number.
 
 // ---- AbstractionLayerAI -------------------------------------------------------------------------------------------------
 struct ScriptCtx { int player, pf, par0, par1, nd; };
