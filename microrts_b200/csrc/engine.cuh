@@ -95,7 +95,7 @@ struct Game {
     int o_pa0, o_pa1, o_pslot, o_grid, o_kind, o_resv, o_claim, o_list;
     int pview;                            // window into the pending list (policy_scripted stages desires behind the final part)
     const uint32_t *grid_tmpl;            // global: wall-padded empty grid of this game's map
-    uint16_t *as_closed, *as_cost, *as_mark, *as_next, *as_head, *as_gen; // A*/BFS scratch of this warp (scripted batches only, layout.h)
+    uint16_t *as_closed, *as_xy, *as_mark, *as_next, *as_head, *as_gen; // A*/BFS scratch of this warp (scripted batches only, layout.h)
 
     MDEV unsigned char *base() const { return mrts_smem + sb; }
     MDEV int32_t *hdr() const { return (int32_t *)base(); }
@@ -129,8 +129,8 @@ DEV void g_bind(Game &g, int sb, const SmemLayout &L, int W, int H, int cap, int
     g.sb = sb; g.pview = 0;
     g.o_pa0 = L.pa0; g.o_pa1 = L.pa1; g.o_pslot = L.pslot; g.o_grid = L.grid; g.o_kind = L.kind; g.o_resv = L.resv;
     g.o_claim = L.claim; g.o_list = L.list;
-    { int cells = W * H; g.as_closed = (uint16_t *)(astar_global ? astar_global : mrts_smem + sb + L.astar); g.as_cost = g.as_closed + cells;
-      g.as_mark = g.as_cost + cells; g.as_next = g.as_mark + cells; g.as_head = g.as_next + cells; g.as_gen = g.as_head + cells + W + H + 2; }
+    { int pc = (W + 2) * (H + 2); g.as_closed = (uint16_t *)(astar_global ? astar_global : mrts_smem + sb + L.astar); g.as_xy = g.as_closed + pc;
+      g.as_mark = g.as_xy + pc; g.as_next = g.as_mark + pc; g.as_head = g.as_next + pc; g.as_gen = g.as_head + MRTS_ASTAR_HEADS(W, H); }
     g.grid_tmpl = nullptr;
 }
 
@@ -1619,11 +1619,10 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
     g_bind(g, MRTS_CONST_WORDS * 4 + warp * L.total, L, p.W, p.H, p.cap, lane, p.conflict, p.scripted,
            p.scripted == 2 ? p.astar_scratch + ((long long)bid * wpc + warp) * p.astar_stride : nullptr);
     if (KERNEL == KERNEL_GENERIC && p.scripted) { // pathfinding scratch: no stale marks, all buckets empty, generation 0
-        int cells = p.W * p.H;
         #pragma unroll 1
-        for (int i = lane; i < cells; i += 32) g.as_mark[i] = 0;
+        for (int i = lane; i < (p.W + 2) * (p.H + 2); i += 32) g.as_mark[i] = 0;
         #pragma unroll 1
-        for (int i = lane; i < cells + p.W + p.H + 2; i += 32) g.as_head[i] = 0xFFFF;
+        for (int i = lane; i < MRTS_ASTAR_HEADS(p.W, p.H); i += 32) g.as_head[i] = 0xFFFF;
         if (lane == 0) *g.as_gen = 0;
         __syncwarp();
     }

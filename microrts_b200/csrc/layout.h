@@ -78,10 +78,11 @@ struct SmemLayout {
 // isStockpile<<3 | 0x10 -- what Unit.getUnitActions needs to know about a neighbouring cell, without touching the unit.
 #define CK_UNIT 0x10
 
-// A* / BFS scratch of one warp (scripted policies only), all u16: parent[cells], cost[cells], mark[cells] (query
-// generation << 3 | flags), next[cells] (bucket chains / BFS queue), head[cells + W + H + 2] (one LIFO bucket per f value),
-// generation counter.  Owned by the warp, not the game: it is initialised once per launch.
-#define MRTS_ASTAR_BYTES(W, H) ((10 * (W) * (H) + 2 * ((W) + (H) + 2) + 4 + 15) & ~15)
+// A* / BFS scratch of one warp (scripted policies only), all u16; PC = padded cells (W+2)*(H+2): parent[PC], xy[PC]
+// (x | y << 8), mark[PC] (query generation << 3 | flags), next[PC] (bucket chains / BFS queue), head[W*H + W + H + 2] (one
+// LIFO bucket per f value), generation counter.  Owned by the warp, not the game: it is initialised once per launch.
+#define MRTS_ASTAR_HEADS(W, H) ((W) * (H) + (W) + (H) + 2)
+#define MRTS_ASTAR_BYTES(W, H) ((8 * ((W) + 2) * ((H) + 2) + 2 * MRTS_ASTAR_HEADS(W, H) + 4 + 15) & ~15)
 MRTS_HD SmemLayout mrts_smem_layout(int W, int H, int cap, int scripted) {
     SmemLayout L;
     int pc = (W + 2) * (H + 2);

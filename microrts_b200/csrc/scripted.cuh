@@ -46,35 +46,32 @@ DEV void aa_put(Game &g, int s, int player, int kind, int type, int bx, int by, 
 // instead of being cleared for every query.
 enum { PFF_INOC = 1, PFF_BLOCKED = 2, PFF_CLOSED = 4 };
 #define PF_NONE 0xFFFFu
-DEV int pf_pc(const Game &g, int pos) { return (pos / g.W + 1) * g.P + pos % g.W + 1; }
+// Positions are indices into the wall-padded grid: out of bounds looks like a wall, so there are no bounds checks, and a
+// node's coordinates are kept beside it (its cost is f - heuristic), so there are no divisions.
 DEV int pf_flags(const Game &g, int pos, int gen) { int m = g.as_mark[pos]; return (m >> 3) == gen ? (m & 7) : 0; }
 DEV void pf_set(const Game &g, int pos, int gen, int flags) { g.as_mark[pos] = (uint16_t)((gen << 3) | flags); }
 // GameState.free (GameState.java:191-207) unless the cell is used by a desire already chosen this cycle (ru)
-DEV bool pf_free(const Game &g, int pos, int fl) {
-    if (fl & PFF_BLOCKED) return false;
-    int pc = pf_pc(g, pos);
-    return g.grid()[pc] == 0 && g.resv()[pc] == 0;
-}
+DEV bool pf_free(const Game &g, int pc, int fl) { return !(fl & PFF_BLOCKED) && g.grid()[pc] == 0 && g.resv()[pc] == 0; }
 DEV int pf_first_step(const Game &g, int pos, int parent) {
     int last = pos;
 #pragma unroll 1
     while (parent != pos) { last = pos; pos = parent; parent = g.as_closed[pos]; }
-    if (last == pos + g.W) return 2;
+    if (last == pos + g.P) return 2;
     if (last == pos - 1) return 3;
-    if (last == pos - g.W) return 0;
+    if (last == pos - g.P) return 0;
     if (last == pos + 1) return 1;
     return -1;
 }
 DEV int iabs(int v) { return v < 0 ? -v : v; }
 
 // findPathToPositionInRange: direction of the first step of a shortest path from unit slot s to within `range` of
-// targetpos (linear), or -1 (null).  ru = target cells of the desires [0, nd) in the pending list.  One lane only.
-DEVN int pf_find(Game &g, int kind, int s, int targetpos, int range, int nd) {
-    int W = g.W, H = g.H, cells = W * H;
+// (tx, ty), or -1 (null).  ru = target cells of the desires [0, nd) in the pending list.  One lane only.
+DEVN int pf_find(Game &g, int kind, int s, int tx, int ty, int range, int nd) {
     int gen = *g.as_gen + 1;
     if (gen >= 8191) { // generation numbers wrapped: forget every mark
+        int pcells = g.P * (g.H + 2);
 #pragma unroll 1
-        for (int i = 0; i < cells; i++) g.as_mark[i] = 0;
+        for (int i = 0; i < pcells; i++) g.as_mark[i] = 0;
         gen = 1;
     }
     *g.as_gen = (uint16_t)gen;
@@ -83,16 +80,16 @@ DEVN int pf_find(Game &g, int kind, int s, int targetpos, int range, int nd) {
         uint32_t A0 = g.pa0()[k];
         if (a_uses_cell(a_type(A0))) {
             int pc = linear_target_cell(g, g.w0()[g.pslot()[k]], g.pa1()[k]);
-            if (pc >= 0) { int y = pc / g.P - 1, x = pc % g.P - 1; pf_set(g, x + y * W, gen, pf_flags(g, x + y * W, gen) | PFF_BLOCKED); }
+            if (pc >= 0) pf_set(g, pc, gen, pf_flags(g, pc, gen) | PFF_BLOCKED);
         }
     }
-    int tx = targetpos % W, ty = targetpos / W, sq = range * range;
+    int sq = range * range;
     uint32_t sw = g.w0()[s];
-    int sx = u_x(sw), sy = u_y(sw), start = sy * W + sx;
+    int sx = u_x(sw), sy = u_y(sw), start = cell_of(g, sw);
     int result = -1;
     if (kind == 0) { // A*
         int f0 = iabs(sx - tx) + iabs(sy - ty), flo = f0, fhi = f0, fcur = f0;
-        g.as_cost[start] = 0; g.as_closed[start] = (uint16_t)start;
+        g.as_xy[start] = (uint16_t)(sx | (sy << 8)); g.as_closed[start] = (uint16_t)start;
         pf_set(g, start, gen, pf_flags(g, start, gen) | PFF_INOC);
         g.as_next[start] = PF_NONE; g.as_head[f0] = (uint16_t)start;
 #pragma unroll 1
@@ -102,22 +99,21 @@ DEVN int pf_find(Game &g, int kind, int s, int targetpos, int range, int nd) {
             if (fcur > fhi) break;
             int pos = g.as_head[fcur];
             g.as_head[fcur] = g.as_next[pos];
-            int parent = g.as_closed[pos];
+            int parent = g.as_closed[pos], xy = g.as_xy[pos];
             int fl = pf_flags(g, pos, gen);
             if (fl & PFF_CLOSED) continue;
             pf_set(g, pos, gen, fl | PFF_CLOSED);
-            int x = pos % W, y = pos / W;
+            int x = xy & 0xff, y = xy >> 8;
             if ((x - tx) * (x - tx) + (y - ty) * (y - ty) <= sq) { result = pf_first_step(g, pos, parent); break; }
-            int c = g.as_cost[pos] + 1;
+            int c = fcur - (iabs(x - tx) + iabs(y - ty)) + 1; // cost of the neighbours: this node's f - heuristic + 1
 #pragma unroll 1
             for (int d = 0; d < 4; d++) { // up, right, down, left
-                int nx = x + ddx(d), ny = y + ddy(d);
-                if (nx < 0 || ny < 0 || nx >= W || ny >= H) continue;
-                int np = ny * W + nx;
+                int np = pos + doff(g, d);
                 int nfl = pf_flags(g, np, gen);
                 if ((nfl & PFF_INOC) || !pf_free(g, np, nfl)) continue;
                 // addToOpen :104-138
-                g.as_cost[np] = (uint16_t)c;
+                int nx = x + ddx(d), ny = y + ddy(d);
+                g.as_xy[np] = (uint16_t)(nx | (ny << 8));
                 g.as_closed[np] = (uint16_t)pos;
                 int f = iabs(nx - tx) + iabs(ny - ty) + c;
                 g.as_next[np] = g.as_head[f]; g.as_head[f] = (uint16_t)np;
@@ -134,7 +130,8 @@ DEVN int pf_find(Game &g, int kind, int s, int targetpos, int range, int nd) {
     // BFS: FIFO queue (positions in next[], parents in head[]); a cell is enqueued at most once, so it never wraps
     uint16_t *qpos = g.as_next, *qpar = g.as_head;
     int oi = 0, orm = 0;
-    qpos[0] = (uint16_t)start; qpar[0] = (uint16_t)start; pf_set(g, start, gen, pf_flags(g, start, gen) | PFF_INOC); oi = 1;
+    qpos[0] = (uint16_t)start; qpar[0] = (uint16_t)start; g.as_xy[start] = (uint16_t)(sx | (sy << 8));
+    pf_set(g, start, gen, pf_flags(g, start, gen) | PFF_INOC); oi = 1;
 #pragma unroll 1
     while (oi != orm) {
         int pos = qpos[orm], parent = qpar[orm];
@@ -143,15 +140,14 @@ DEVN int pf_find(Game &g, int kind, int s, int targetpos, int range, int nd) {
         if (fl & PFF_CLOSED) continue;
         pf_set(g, pos, gen, fl | PFF_CLOSED);
         g.as_closed[pos] = (uint16_t)parent;
-        int x = pos % W, y = pos / W;
+        int xy = g.as_xy[pos], x = xy & 0xff, y = xy >> 8;
         if ((x - tx) * (x - tx) + (y - ty) * (y - ty) <= sq) { result = pf_first_step(g, pos, parent); break; }
 #pragma unroll 1
         for (int d = 0; d < 4; d++) {
-            int nx = x + ddx(d), ny = y + ddy(d);
-            if (nx < 0 || ny < 0 || nx >= W || ny >= H) continue;
-            int np = ny * W + nx;
+            int np = pos + doff(g, d);
             int nfl = pf_flags(g, np, gen);
             if ((nfl & PFF_INOC) || !pf_free(g, np, nfl)) continue;
+            g.as_xy[np] = (uint16_t)((x + ddx(d)) | ((y + ddy(d)) << 8));
             qpos[oi] = (uint16_t)np; qpar[oi] = (uint16_t)pos;
             oi++;
             pf_set(g, np, gen, nfl | PFF_INOC);
@@ -205,13 +201,13 @@ DEV bool cell_gs_free(const Game &g, int pc) { return g.grid()[pc] == 0 && g.res
 // AbstractAction.execute for slot s; returns true and (A0, A1) if it yields a unit action
 DEVN bool aa_execute(Game &g, const ScriptCtx &c, int s, uint32_t &A0, int &A1) {
     uint32_t X0 = g.x0()[s], X1 = g.x1()[s], w = g.w0()[s];
-    int x = u_x(w), y = u_y(w), t = u_type(w), W = g.W;
+    int x = u_x(w), y = u_y(w), t = u_type(w);
     switch (aa_kind(X0)) {
         case AA_ATTACK: { // Attack.java:51-64
             uint32_t tw = g.w0()[aa_target(X1) - 1];
             int dx = u_x(tw) - x, dy = u_y(tw) - y, range = ut_range(g, t);
             if (dx * dx + dy * dy <= range * range) { A0 = ACT_ATTACK | A0_NOUT | ((uint32_t)u_x(tw) << 16) | ((uint32_t)u_y(tw) << 24); A1 = -1; return true; }
-            int dir = pf_find(g, c.pf, s, u_x(tw) + u_y(tw) * W, range, c.nd);
+            int dir = pf_find(g, c.pf, s, u_x(tw), u_y(tw), range, c.nd);
             if (mk_move(g, c, s, dir, A0, A1) && unit_action_allowed(g, c, s, A0, A1)) return true;
             return false;
         }
@@ -220,7 +216,7 @@ DEVN bool aa_execute(Game &g, const ScriptCtx &c, int s, uint32_t &A0, int &A1) 
             int other = empty ? aa_target(X1) : aa_base(X1);
             if (other == (int)REF_NULL) return false;
             uint32_t ow = g.w0()[other - 1];
-            int dir = pf_find(g, c.pf, s, u_x(ow) + u_y(ow) * W, 1, c.nd);
+            int dir = pf_find(g, c.pf, s, u_x(ow), u_y(ow), 1, c.nd);
             if (mk_move(g, c, s, dir, A0, A1)) return unit_action_allowed(g, c, s, A0, A1);
             int ox = u_x(ow), oy = u_y(ow), d = -1;
             if (ox == x && oy == y - 1) d = 0; else if (ox == x + 1 && oy == y) d = 1; else if (ox == x && oy == y + 1) d = 2; else if (ox == x - 1 && oy == y) d = 3;
@@ -230,7 +226,7 @@ DEVN bool aa_execute(Game &g, const ScriptCtx &c, int s, uint32_t &A0, int &A1) 
         }
         case AA_BUILD: { // Build.java:54-77
             int bx = aa_bx(X0), by = aa_by(X0);
-            int dir = pf_find(g, c.pf, s, bx + by * W, 1, c.nd);
+            int dir = pf_find(g, c.pf, s, bx, by, 1, c.nd);
             if (mk_move(g, c, s, dir, A0, A1)) return unit_action_allowed(g, c, s, A0, A1);
             int d = -1;
             if (bx == x && by == y - 1) d = 0;
@@ -425,20 +421,22 @@ DEVN int policy_scripted(Game &g, int player, int kind, int pathfinder, int pn) 
         // ---- translateActions (AbstractionLayerAI.java:58-113): abstract actions in insertion order --------------------
         ScriptCtx c; c.player = player; c.pf = pathfinder; c.par0 = par0; c.par1 = par1; c.nd = 0;
         int nd = 0;                 // desires are staged at pending[pn + ...]; pf_find reads ru from pending[0, nd) so stage at 0-based scratch
-        uint32_t last = 0; bool have_last = false;
+        // this player's map entries in insertion order: collect the slots, then an insertion sort by sequence number (slot
+        // order is nearly insertion order already)
+        int ne = 0;
 #pragma unroll 1
-        for (;;) {
-            // next entry of this player's map in insertion order
-            int best = -1; uint32_t bseq = 0xFFFFFFFFu;
+        for (int i = 0; i < n; i++) {
+            uint32_t X0 = g.x0()[i];
+            if (aa_kind(X0) == AA_NONE || u_pl(g.w0()[i]) != pl) continue;
+            uint32_t q = aa_seq(X0, g.x1()[i]);
+            int j = ne++;
 #pragma unroll 1
-            for (int i = 0; i < n; i++) {
-                uint32_t X0 = g.x0()[i];
-                if (aa_kind(X0) == AA_NONE || u_pl(g.w0()[i]) != pl) continue;
-                uint32_t q = aa_seq(X0, g.x1()[i]);
-                if ((!have_last || q > last) && q < bseq) { bseq = q; best = i; }
-            }
-            if (best < 0) break;
-            last = bseq; have_last = true;
+            while (j > 0) { int o = g.list()[j - 1]; if (aa_seq(g.x0()[o], g.x1()[o]) <= q) break; g.list()[j] = (uint8_t)o; j--; }
+            g.list()[j] = (uint8_t)i;
+        }
+#pragma unroll 1
+        for (int r = 0; r < ne; r++) {
+            int best = g.list()[r];
             if (aa_completed(g, best)) { g.x0()[best] &= ~7u; continue; } // toDelete (a dead unit's entry vanished with its slot)
             if (a_type(g.a0()[best]) == AT_IDLE) {
                 uint32_t A0; int A1;
