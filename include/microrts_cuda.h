@@ -140,7 +140,26 @@ int mrts_batch_reset(mrts_batch *, const int64_t *seeds, int on_device);
  * src/tests/JNIGridnetVecClient.java:272-286) */
 int mrts_batch_reset_masked(mrts_batch *, const uint8_t *mask, const int64_t *seeds, int on_device);
 
+/* restart the masked games from their map like mrts_batch_reset_masked, but keep their RNG streams running (the reference's
+ * Random objects are static and survive JNIGridnetVecClient's resets, src/tests/JNIGridnetVecClient.java:272-286) */
+int mrts_batch_restart_masked(mrts_batch *, const uint8_t *mask, int on_device);
+
 int mrts_batch_set_policy(mrts_batch *, int player, int policy, int pathfinder);
+/* Order of the two players inside one mrts_batch_step cycle.  0 (default): both PlayerActions are built on the pre-issue
+ * state, then issueSafe(p0), issueSafe(p1) -- Game.start / JNIGridnetClient.gameStep (src/rts/Game.java:134-137,
+ * src/tests/JNIGridnetClient.java:168-179).  1: player 1's PlayerAction is built on the state that already holds player
+ * 0's -- JNIGridnetClientSelfPlay.gameStep (src/tests/JNIGridnetClientSelfPlay.java:160-170). */
+int mrts_batch_set_issue_order(mrts_batch *, int sequential);
+/* Step facts for the reward functions (src/ai/reward, all classes), written by every later mrts_batch_step into
+ * out = [n_games][2 players][12] (device pointer; NULL disables), accumulated over the decision points of the step:
+ *   [0] HARVEST and [1] RETURN actions in the player's PlayerAction as issueSafe left it (ResourceGatherRewardFunction),
+ *   [2] ATTACKs on a cell held by the opponent, [3] on an own unit (AttackRewardFunction),
+ *   [4] PRODUCE Worker, [5] PRODUCE Barracks/Base, [6] PRODUCE Light/Heavy/Ranged (Produce*RewardFunction),
+ *   [7] the opponent had a Base before the cycle; [8]/[9] squared distance from it to the player's closest
+ *       Worker/Light/Heavy/Ranged before / after the cycle, -1 when there is none (CloserToEnemyBaseRewardFunction),
+ *   [10] some Resource unit still holds resources after the cycle, [11] internal.
+ * WinLossRewardFunction reads mrts_batch_results. */
+int mrts_batch_set_info_output(mrts_batch *, int32_t *out);
 /* When enabled, mrts_batch_step restarts a game from its map at the start of the step if the game ended (game over or
  * time >= max_cycles) in an earlier step -- the auto-reset of src/tests/JNIGridnetVecClient.java:272-286, done on the
  * device.  The game's RNG streams keep running across episodes, like the reference's static Random objects. */

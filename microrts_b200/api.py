@@ -212,6 +212,24 @@ class BatchedGameState:
     def set_policy(self, player, policy, pathfinder=PF_ASTAR):
         _check(_ffi.lib().mrts_batch_set_policy(self._h, player, policy, pathfinder))
 
+    def restart_masked(self, mask):
+        """Restart the masked games from their map; their RNG streams keep running (JNIGridnetVecClient auto-reset)."""
+        m = np.ascontiguousarray(mask, dtype=np.uint8) if isinstance(mask, (list, np.ndarray)) else mask
+        pm, dm, _k = _ptr(m)
+        _check(_ffi.lib().mrts_batch_restart_masked(self._h, pm, dm))
+
+    def set_issue_order(self, sequential):
+        """False: both players decide on the pre-issue state (Game.start); True: player 1 decides after player 0's actions
+        are issued (JNIGridnetClientSelfPlay.gameStep)."""
+        _check(_ffi.lib().mrts_batch_set_issue_order(self._h, 1 if sequential else 0))
+
+    def set_info_output(self, out):
+        """Device buffer int32 [n][2][12] that every later step() fills with the reward functions' step facts (None: off)."""
+        if out is not None:
+            assert tuple(out.shape) == (self.n, 2, 12) and "int32" in str(out.dtype)
+        self._info_keepalive = out
+        _check(_ffi.lib().mrts_batch_set_info_output(self._h, _ptr(out)[0] if out is not None else None))
+
     def set_auto_reset(self, enable=True):
         _check(_ffi.lib().mrts_batch_set_auto_reset(self._h, 1 if enable else 0))
 

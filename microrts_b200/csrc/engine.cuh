@@ -71,6 +71,10 @@ struct StepParams {
     int out_dtype;             // 0 = u8, 1 = i32
     int out_player;
     int partial_obs;
+    int sequential_issue;      // MODE_GAME: player 1 decides on the state that already holds player 0's actions
+                               // (JNIGridnetClientSelfPlay.gameStep) instead of both deciding on the pre-issue state (Game.start)
+    int32_t *info_out;         // MODE_GAME: [n_games][2][MRTS_INFO_WORDS] per-player step facts for the reward functions (or NULL)
+    uint32_t tm_worker, tm_building, tm_combat, tm_base, tm_mobile, tm_resource; // unit type id bit masks, resolved by name on the host
     void *obs_out[2];          // MODE_GAME: when set, the post-step observation of player 0 / 1 is written here ([n][6][H][W])
     int obs_dtype;
     // MODE_ROLLOUT: item r = game r / rollouts_per_game
@@ -1218,15 +1222,84 @@ DEV void run_game_fast(Game &g, const StepParams &p, WarpStats &ws) {
     ws.v[STAT_UNIT_CYCLES] += ucyc;
 }
 
+// ---- step facts for the reward functions (src/ai/reward/*.java) ----------------------------------------------------------
+// The reference computes rewards from the TraceEntry of the step: the PlayerActions as issueSafe left them (illegal actions
+// already replaced by NONE; conflicts NOT applied) and the PhysicalGameState before the cycle.  Counts per player:
+// [0] HARVEST, [1] RETURN (ResourceGatherRewardFunction), [2] ATTACKs on a cell held by the opponent, [3] on an own unit
+// (AttackRewardFunction), [4] PRODUCE Worker, [5] PRODUCE Barracks/Base, [6] PRODUCE Light/Heavy/Ranged
+// (Produce*RewardFunction).  Accumulated over the decision points of the step.
+DEVN void info_count(Game &g, const StepParams &p, int player, int from, int to, int32_t *o) {
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0;
+    #pragma unroll 1
+    for (int k = from + g.lane; k < to; k += 32) {
+        uint32_t A0 = g.pa0()[k];
+        int at = a_type(A0);
+        if (at == ACT_HARVEST) c0++;
+        else if (at == ACT_RETURN) c1++;
+        else if (at == ACT_ATTACK) {
+            int ax = (A0 >> 16) & 0xff, ay = A0 >> 24;
+            if (ax < g.W && ay < g.H) {
+                int gv = g.grid()[(ay + 1) * g.P + ax + 1];
+                if (gv != 0 && gv != 0xFF) { int opl = u_pl(g.w0()[gv - 1]); if (opl == 2 - player) c2++; else if (opl == player + 1) c3++; }
+            }
+        } else if (at == ACT_PRODUCE && a_utype(A0) < MRTS_MAX_TYPES) {
+            uint32_t bit = 1u << a_utype(A0);
+            if (p.tm_worker & bit) c4++;
+            if (p.tm_building & bit) c5++;
+            if (p.tm_combat & bit) c6++;
+        }
+    }
+    c0 = __reduce_add_sync(FULLM, c0); c1 = __reduce_add_sync(FULLM, c1); c2 = __reduce_add_sync(FULLM, c2); c3 = __reduce_add_sync(FULLM, c3);
+    c4 = __reduce_add_sync(FULLM, c4); c5 = __reduce_add_sync(FULLM, c5); c6 = __reduce_add_sync(FULLM, c6);
+    if (g.lane == 0) { o[0] += c0; o[1] += c1; o[2] += c2; o[3] += c3; o[4] += c4; o[5] += c5; o[6] += c6; }
+    __syncwarp();
+}
+// CloserToEnemyBaseRewardFunction: squared distance from the opponent's first Base (list order, position BEFORE the cycle)
+// to the player's closest Worker/Light/Heavy/Ranged.  before: find the base, o[7] = exists, o[11] = x | y << 8, o[8] = d2 or
+// -1; after: o[9] = d2 or -1 against the remembered base position.  Also o[10] = some Resource unit still holds resources
+// (ResourceGatherRewardFunction.isDone is its negation), evaluated on the state after the cycle.
+DEVN void info_distance(Game &g, const StepParams &p, int player, int32_t *o, bool before) {
+    int n = g.hdr()[H_NUNITS];
+    int bx = 0, by = 0, exists = 0;
+    if (before) {
+        #pragma unroll 1
+        for (int base = 0; base < n && !exists; base += 32) {
+            int i = base + g.lane;
+            uint32_t w = i < n ? g.w0()[i] : 0;
+            bool is = i < n && u_pl(w) == 2 - player && ((p.tm_base >> u_type(w)) & 1);
+            unsigned m = __ballot_sync(FULLM, is);
+            if (m) { int src = __ffs(m) - 1; uint32_t bw = __shfl_sync(FULLM, w, src); bx = u_x(bw); by = u_y(bw); exists = 1; }
+        }
+    } else { exists = o[7]; bx = o[11] & 0xff; by = (o[11] >> 8) & 0xff; }
+    int best = 0x7fffffff, resleft = 0;
+    #pragma unroll 1
+    for (int i = g.lane; i < n; i += 32) {
+        uint32_t w = g.w0()[i];
+        if (u_pl(w) == player + 1 && ((p.tm_mobile >> u_type(w)) & 1)) { int dx = bx - u_x(w), dy = by - u_y(w), d = dx * dx + dy * dy; if (d < best) best = d; }
+        if (((p.tm_resource >> u_type(w)) & 1) && u_res(g.w1()[i]) > 0) resleft = 1;
+    }
+    best = (int)__reduce_min_sync(FULLM, (unsigned)best);
+    resleft = __ballot_sync(FULLM, resleft) ? 1 : 0;
+    __syncwarp();
+    if (g.lane == 0) {
+        if (before) { o[7] = exists; o[11] = bx | (by << 8); o[8] = (exists && best != 0x7fffffff) ? best : -1; }
+        else { o[9] = (exists && best != 0x7fffffff) ? best : -1; o[10] = resleft; }
+    }
+    __syncwarp();
+}
+
 // Game.start loop body (rts/Game.java:126-140) with exact skipping of cycles in which nothing can happen.
 DEVN void run_game(Game &g, const StepParams &p, long long gi, WarpStats &ws) {
     int status = g.hdr()[H_STATUS];
+    int32_t *io = p.info_out ? p.info_out + gi * (2 * MRTS_INFO_WORDS) : nullptr;
+    if (io) { if (g.lane < 2 * MRTS_INFO_WORDS) io[g.lane] = 0; __syncwarp(); }
     if (status & ST_OVER) return;
     int t0 = g.hdr()[H_TIME];
     int tlimit = t0 + p.n_cycles; if (tlimit > p.max_cycles) tlimit = p.max_cycles;
     int winner;
     bool over = game_over(g, winner); // a state that is already over ends at the very next cycle()
     bool first = true;
+    if (io) { info_distance(g, p, 0, io, true); info_distance(g, p, 1, io + MRTS_INFO_WORDS, true); }
     // device policies emit self-consistent lists; under CANCEL_BOTH they can be issued in parallel (issue_policy_lists)
     bool fast_issue = p.conflict == 1 && p.policy[0] != POL_EXTERNAL && p.policy[1] != POL_EXTERNAL;
     unsigned long long decisions = 0, ucyc = 0;
@@ -1235,9 +1308,13 @@ DEVN void run_game(Game &g, const StepParams &p, long long gi, WarpStats &ws) {
         int time = g.hdr()[H_TIME];
         if (time >= tlimit) break;
         int pn0 = run_policy(g, p, gi, 0, 0, first);
+        if (io) info_count(g, p, 0, 0, pn0, io);
+        if (p.sequential_issue) issue_pending(g, 0, pn0);
         int pn1 = run_policy(g, p, gi, 1, pn0, first);
+        if (io) info_count(g, p, 1, pn0, pn1, io + MRTS_INFO_WORDS);
         first = false;
-        if (fast_issue) issue_policy_lists(g, pn0, pn1);
+        if (p.sequential_issue) issue_pending(g, pn0, pn1);
+        else if (fast_issue) issue_policy_lists(g, pn0, pn1);
         else { issue_pending(g, 0, pn0); issue_pending(g, pn0, pn1); }
         decisions += pn1;
         int mrt = min_ready_time(g);
@@ -1262,6 +1339,7 @@ DEVN void run_game(Game &g, const StepParams &p, long long gi, WarpStats &ws) {
             break;
         }
     }
+    if (io) { info_distance(g, p, 0, io, false); info_distance(g, p, 1, io + MRTS_INFO_WORDS, false); }
     int tend = g.hdr()[H_TIME];
     status = g.hdr()[H_STATUS];
     if (!(status & ST_COUNTED) && tend >= p.max_cycles) { // hit the cycle cap: a draw (winner() == -1)

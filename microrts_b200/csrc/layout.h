@@ -58,6 +58,7 @@ enum { UF_RESOURCE = 1, UF_STOCKPILE = 2, UF_HARVEST = 4, UF_MOVE = 8, UF_ATTACK
 // THE ROW'S TYPE (look it up with the produced type), 5 ATTACK) -- UnitAction.ETA, UnitAction.java:307-329
 #define MRTS_CONST_WORDS (MRTS_ETA_OFFSET + MRTS_MAX_TYPES * 4) // utt words + jump table (u64 pairs) + ETA table
 
+#define MRTS_INFO_WORDS 12 // per player and game: step facts for the reward functions (engine.cuh: info_count / info_distance)
 #define MRTS_MAX_CAP 254
 #define MRTS_WARPS_PER_CTA 4
 

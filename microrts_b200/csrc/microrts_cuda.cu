@@ -62,7 +62,7 @@ static const char *dev_errstr() { return cudaGetErrorString(g_cuda_last); }
 struct ResetParams {
     int32_t *hdr; uint32_t *units; const uint32_t *maps;
     const long long *seeds; const uint8_t *mask;
-    long long n_games; int n_maps, map_words, cap, pcw, uw;
+    long long n_games; int n_maps, map_words, cap, pcw, uw, keep_rng;
 };
 
 // (re)initialise games from their map's initial state; one warp per game
@@ -78,6 +78,11 @@ DEV void reset_kernel_body(const ResetParams &p, int tid, int nthreads, int bid,
         int n = ih[H_NUNITS];
         if (lane < MRTS_HDR_WORDS) {
             int32_t v = ih[lane];
+            if (p.keep_rng) { // restart: the RNG streams keep running and the episode counter advances (JNIGridnetVecClient auto-reset)
+                if (lane >= H_RNGP_LO && lane <= H_RNGD_HI) v = gh[lane];
+                if (lane == H_SPARE) v = gh[lane] + 1;
+                gh[lane] = v;
+            } else {
             long long seed = p.seeds ? p.seeds[gi] : gi;
             unsigned long long sp = ((unsigned long long)seed ^ 0x5DEECE66DULL) & MASK48;
             unsigned long long sc = ((unsigned long long)(seed ^ 0x5851F42D4C957F2DLL) ^ 0x5DEECE66DULL) & MASK48;
@@ -89,6 +94,7 @@ DEV void reset_kernel_body(const ResetParams &p, int tid, int nthreads, int bid,
             if (lane == H_RNGD_LO) v = (int32_t)(uint32_t)sd;
             if (lane == H_RNGD_HI) v = (int32_t)(uint32_t)(sd >> 32);
             gh[lane] = v;
+            }
         }
         for (int k = 0; k < p.uw; k++)
             for (int i = lane; i < n; i += 32) gu[k * p.cap + i] = iu[k * p.cap + i];
@@ -178,6 +184,7 @@ struct mrts_batch {
     SmemLayout L;
     struct Plan { int wpc = 2, grid = 3; size_t smem = 0; } plan[N_KERNELS]; // per kernel: warps (games in flight) per CTA, CTAs, shared memory
     int max_range = 0, auto_reset = 0, scripted = 0, uw = MRTS_UNIT_WORDS_CORE;
+    int sequential_issue = 0; int32_t *info_out = nullptr; uint32_t tm[6] = {0, 0, 0, 0, 0, 0};
     void *obs_out[2] = {nullptr, nullptr}; int obs_dtype = 0; // device buffers mrts_batch_step writes post-step observations to
     long long launches = 0;
 };
@@ -200,7 +207,7 @@ static int launch_step(mrts_batch *b, StepParams &p) {
     int kernel = KERNEL_GENERIC;
     auto rb_or_passive = [](int pol) { return pol == MRTS_POLICY_RANDOM_BIASED || pol == MRTS_POLICY_PASSIVE; };
     if (p.mode == MODE_ROLLOUT) kernel = KERNEL_ROLLOUT;
-    else if (p.mode == MODE_GAME && p.conflict == MRTS_CANCEL_BOTH && rb_or_passive(p.policy[0]) && rb_or_passive(p.policy[1]))
+    else if (p.mode == MODE_GAME && p.conflict == MRTS_CANCEL_BOTH && rb_or_passive(p.policy[0]) && rb_or_passive(p.policy[1]) && !p.info_out && !p.sequential_issue)
         kernel = (p.obs_out[0] || p.obs_out[1]) ? KERNEL_FAST_OBS : KERNEL_FAST;
     const mrts_batch::Plan &pl = b->plan[kernel];
     int threads = pl.wpc * 32;
@@ -345,6 +352,14 @@ int mrts_batch_create(const mrts_utt *u, const mrts_map *const *maps, int n_maps
     auto b = std::unique_ptr<mrts_batch, void (*)(mrts_batch *)>(new mrts_batch, mrts_batch_destroy);
     b->utt = u->h; b->W = W; b->H = H; b->cap = cap; b->n_maps = n_maps; b->n = n_games; b->flags = flags; b->device = device;
     b->max_range = u->h.maxAttackRange();
+    for (size_t t = 0; t < u->h.types.size() && t < 32; t++) { // the reward functions identify unit types by name (src/ai/reward/*.java)
+        const std::string &nm = u->h.types[t].name; uint32_t bit = 1u << t;
+        if (nm == "Worker") { b->tm[0] |= bit; b->tm[4] |= bit; }
+        if (nm == "Barracks" || nm == "Base") b->tm[1] |= bit;
+        if (nm == "Light" || nm == "Heavy" || nm == "Ranged") { b->tm[2] |= bit; b->tm[4] |= bit; }
+        if (nm == "Base") b->tm[3] |= bit;
+        if (nm == "Resource") b->tm[5] |= bit;
+    }
     // scripted batches keep the pathfinding scratch in shared memory while a game's whole region stays small enough for
     // several games per SM; larger maps move it to a per-warp global scratch (L1/L2 resident)
     b->scripted = (flags & MRTS_FLAG_SCRIPTED_AI) ? 1 : 0;
@@ -411,7 +426,7 @@ int64_t mrts_batch_launch_count(const mrts_batch *b) { return b ? b->launches : 
 int mrts_batch_num_planes(const mrts_batch *b) { return b ? ((b->flags & MRTS_FLAG_PARTIAL_OBS) ? 8 : 6) : MRTS_E_ARG; }
 int mrts_batch_mask_width(const mrts_batch *b) { if (!b) return MRTS_E_ARG; int R = 2 * b->max_range + 1; return 1 + 6 + 16 + (int)b->utt.types.size() + R * R; }
 
-static int do_reset(mrts_batch *b, const uint8_t *mask, const int64_t *seeds, int on_device) {
+static int do_reset(mrts_batch *b, const uint8_t *mask, const int64_t *seeds, int on_device, int keep_rng = 0) {
     if (!b) return fail(MRTS_E_ARG, "null batch");
     if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
     const long long *d_seeds = (const long long *)seeds; const uint8_t *d_mask = mask;
@@ -421,7 +436,7 @@ static int do_reset(mrts_batch *b, const uint8_t *mask, const int64_t *seeds, in
         if (seeds) { if (dev_h2d(b->d_tmp, seeds, sb, b->stream)) return fail(MRTS_E_CUDA, dev_errstr()); d_seeds = (const long long *)b->d_tmp; }
         if (mask) { if (dev_h2d((char *)b->d_tmp + sb, mask, mb, b->stream)) return fail(MRTS_E_CUDA, dev_errstr()); d_mask = (const uint8_t *)b->d_tmp + sb; }
     }
-    ResetParams p{b->d_hdr, b->d_units, b->d_maps, d_seeds, d_mask, b->n, b->n_maps, b->map_words, b->cap, b->L.pcw, b->uw};
+    ResetParams p{b->d_hdr, b->d_units, b->d_maps, d_seeds, d_mask, b->n, b->n_maps, b->map_words, b->cap, b->L.pcw, b->uw, keep_rng};
     b->launches++;
     if (!mask) { if (dev_zero(b->d_stats, 8 * sizeof(unsigned long long), b->stream)) return fail(MRTS_E_CUDA, dev_errstr()); }
     b->staged[0].valid = b->staged[1].valid = false;
@@ -439,6 +454,11 @@ int mrts_batch_reset(mrts_batch *b, const int64_t *seeds, int on_device) { retur
 int mrts_batch_reset_masked(mrts_batch *b, const uint8_t *mask, const int64_t *seeds, int on_device) {
     if (!mask) return fail(MRTS_E_ARG, "mrts_batch_reset_masked: mask is required");
     return do_reset(b, mask, seeds, on_device);
+}
+
+int mrts_batch_restart_masked(mrts_batch *b, const uint8_t *mask, int on_device) {
+    if (!mask) return fail(MRTS_E_ARG, "mrts_batch_restart_masked: mask is required");
+    return do_reset(b, mask, nullptr, on_device, 1);
 }
 
 int mrts_batch_set_policy(mrts_batch *b, int player, int policy, int pathfinder) {
@@ -503,6 +523,8 @@ int mrts_batch_step(mrts_batch *b, int n_cycles, int max_cycles) {
     StepParams p; memset(&p, 0, sizeof p);
     p.mode = MODE_GAME; p.n_cycles = n_cycles; p.max_cycles = max_cycles; p.safe = 1; p.auto_reset = b->auto_reset;
     for (int pl = 0; pl < 2; pl++) { p.policy[pl] = b->policy[pl]; p.pathfinder[pl] = b->pathfinder[pl]; if (b->policy[pl] == MRTS_POLICY_EXTERNAL) fill_ext(b, p, pl); b->staged[pl].valid = false; }
+    p.sequential_issue = b->sequential_issue; p.info_out = b->info_out;
+    p.tm_worker = b->tm[0]; p.tm_building = b->tm[1]; p.tm_combat = b->tm[2]; p.tm_base = b->tm[3]; p.tm_mobile = b->tm[4]; p.tm_resource = b->tm[5];
     bool fused = !(b->flags & MRTS_FLAG_PARTIAL_OBS); // partially observable batches observe in a second launch
     if (fused) { p.obs_out[0] = b->obs_out[0]; p.obs_out[1] = b->obs_out[1]; p.obs_dtype = b->obs_dtype; }
     if (launch_step(b, p)) return fail(MRTS_E_CUDA, std::string("step launch: ") + dev_errstr());
@@ -511,6 +533,9 @@ int mrts_batch_step(mrts_batch *b, int n_cycles, int max_cycles) {
             if (b->obs_out[pl]) { int rc = mrts_batch_observe(b, pl, b->obs_dtype, b->obs_out[pl], 1); if (rc) return rc; }
     return MRTS_OK;
 }
+
+int mrts_batch_set_issue_order(mrts_batch *b, int sequential) { if (!b) return fail(MRTS_E_ARG, "null batch"); b->sequential_issue = sequential ? 1 : 0; return MRTS_OK; }
+int mrts_batch_set_info_output(mrts_batch *b, int32_t *out) { if (!b) return fail(MRTS_E_ARG, "null batch"); b->info_out = out; return MRTS_OK; }
 
 int mrts_batch_set_observation_outputs(mrts_batch *b, int dtype, void *out_player0, void *out_player1) {
     if (!b || (dtype != MRTS_DTYPE_U8 && dtype != MRTS_DTYPE_I32)) return fail(MRTS_E_ARG, "mrts_batch_set_observation_outputs: bad argument");

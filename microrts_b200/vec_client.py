@@ -1,0 +1,247 @@
+"""JNIGridnetVecClient over the batched engine -- the reference's vectorised RL facade (src/tests/JNIGridnetVecClient.java)
+with the same constructor arguments, methods and return conventions, backed by libmicrorts_cuda.so instead of one Java
+GameState per environment.
+
+  JNIGridnetVecClient(num_selfplay_envs, num_envs, max_steps, rfs, micrortsPath, mapPaths, ai2s, utt, partial_obs)  :106
+  reset(players) -> Responses(observation, reward, done)                                                          :179
+  gameStep(action, players) -> Responses                                                                          :213
+  getMasks(player) -> int[envs][H][W][mask width]                                                                 :307
+  close()                                                                                                         :318
+
+Environment layout follows the reference: the first num_selfplay_envs entries are pairs (player 0 and player 1 of the same
+game, JNIGridnetClientSelfPlay), the next num_envs entries are agent-vs-bot games (JNIGridnetClient).  What differs:
+
+* ai2s are device policies, named like the reference's AI classes (microrts_b200.ai: PassiveAI, RandomBiasedAI, WorkerRush,
+  LightRush); all maps of one client must have the same size (one batch per group of environments).
+* The per-cycle order inside an environment is the reference's: self-play pairs decide sequentially (player 1's
+  PlayerAction is built on the state that already holds player 0's, JNIGridnetClientSelfPlay.java:160-170); agent-vs-bot
+  games build both PlayerActions on the pre-issue state (JNIGridnetClient.java:168-179).
+* Rewards are the reference's reward functions (microrts_b200.rewards) evaluated from per-game step facts the step kernel
+  writes (no trace objects); auto-reset keeps the terminal reward/done and forces done[0] (:272-286).
+* Partially observable observations are taken from the state after the cycle (the reference returns a view built before
+  the cycle, JNIGridnetClient.java:163-203) -- DESIGN.md, known deviations.
+"""
+import os
+
+import numpy as np
+
+from . import api as M
+
+NO_CAP = 1 << 30
+
+
+class Responses:
+    """tests.jni.Responses (observation, reward, done)."""
+
+    def __init__(self, observation, reward, done):
+        self.observation, self.reward, self.done = observation, reward, done
+
+    def set(self, observation, reward, done):
+        self.observation, self.reward, self.done = observation, reward, done
+
+
+class AISpec:
+    def __init__(self, policy, pathfinder=M.PF_ASTAR):
+        self.policy, self.pathfinder = policy, pathfinder
+
+    def key(self):
+        return (self.policy, self.pathfinder)
+
+
+class ai:
+    """Device-resident stand-ins for the reference's AI classes accepted as `ai2s` (names as in src/ai)."""
+
+    @staticmethod
+    def PassiveAI(utt=None):
+        return AISpec(M.POLICY_PASSIVE)
+
+    @staticmethod
+    def RandomBiasedAI(utt=None):
+        return AISpec(M.POLICY_RANDOM_BIASED)
+
+    @staticmethod
+    def WorkerRush(utt=None, pathfinder=M.PF_ASTAR):
+        return AISpec(M.POLICY_WORKER_RUSH, pathfinder)
+
+    @staticmethod
+    def LightRush(utt=None, pathfinder=M.PF_ASTAR):
+        return AISpec(M.POLICY_LIGHT_RUSH, pathfinder)
+
+
+def _device_array(shape, dtype, emulated):
+    """Memory the engine writes 'on device': a torch CUDA tensor, or host memory when the library is the test emulator."""
+    if emulated:
+        return np.zeros(shape, dtype=dtype)
+    import torch
+    return torch.zeros(shape, dtype=torch.int32 if dtype == np.int32 else torch.uint8, device="cuda")
+
+
+def _host(a):
+    return a if isinstance(a, np.ndarray) else a.cpu().numpy()
+
+
+class _Group:
+    """One batch: either the self-play games (both players EXTERNAL, sequential issue) or the agent-vs-bot games that share
+    one opponent policy and one agent side."""
+
+    def __init__(self, utt, maps, envs, selfplay, spec, side, partial_obs, device, emulated, seed0):
+        self.envs, self.selfplay, self.side = envs, selfplay, side
+        n = len(envs) // 2 if selfplay else len(envs)
+        self.n = n
+        same = all(m is maps[0] for m in maps)
+        scripted = spec is not None and spec.policy in (M.POLICY_WORKER_RUSH, M.POLICY_LIGHT_RUSH)
+        self.b = M.BatchedGameState(utt, maps[0] if same else maps, n, device=device, partial_obs=partial_obs, scripted_ai=scripted)
+        b = self.b
+        if selfplay:
+            b.set_policy(0, M.POLICY_EXTERNAL)
+            b.set_policy(1, M.POLICY_EXTERNAL)
+            b.set_issue_order(True)
+        else:
+            b.set_policy(side, M.POLICY_EXTERNAL)
+            b.set_policy(1 - side, spec.policy, spec.pathfinder)
+        self.seeds = np.asarray(envs[0::2] if selfplay else envs, dtype=np.int64) + seed0  # the game of environment e is seeded with seed + e
+        self.info = _device_array((n, 2, 12), np.int32, emulated)
+        b.set_info_output(self.info)
+        self.players = [0, 1] if selfplay else [side]
+        self.obs = {p: _device_array((n, b.num_planes, b.height, b.width), np.int32, emulated) for p in self.players}
+        b.set_observation_outputs(self.obs.get(0), self.obs.get(1))  # every step() leaves the new observations in self.obs
+        self.steps = np.zeros(n, dtype=np.int64)
+
+    def observe_all(self):
+        for p in self.players:
+            self.b.observe(p, np.int32, out=self.obs[p])
+
+    def observations(self):
+        self.b.sync()
+        return {p: _host(self.obs[p]) for p in self.players}
+
+
+class JNIGridnetVecClient:
+    def __init__(self, a_num_selfplayenvs, a_num_envs, a_max_steps, a_rfs, a_micrortsPath, a_mapPaths, a_ai2s, a_utt, partial_obs=False,
+                 device=0, seed=0):
+        from . import _ffi
+        assert a_num_selfplayenvs % 2 == 0, "self-play environments come in pairs"
+        self.maxSteps, self.utt, self.rfs, self.partialObs, self.mapPaths = a_max_steps, a_utt, list(a_rfs), partial_obs, list(a_mapPaths)
+        self.num_selfplay, self.num_envs = a_num_selfplayenvs, a_num_envs
+        s1 = a_num_selfplayenvs + a_num_envs
+        assert len(self.mapPaths) >= s1 and len(a_ai2s or []) >= a_num_envs
+        emulated = "emu" in os.path.basename(getattr(_ffi.lib(), "_name", "") or "")
+        cache = {}
+
+        def load(path):
+            full = os.path.join(a_micrortsPath, path) if a_micrortsPath else path
+            if full not in cache:
+                cache[full] = M.PhysicalGameState.load(full, a_utt)
+            return cache[full]
+
+        self.groups = []
+        if a_num_selfplayenvs:
+            envs = list(range(a_num_selfplayenvs))
+            maps = [load(self.mapPaths[i * 2]) for i in range(a_num_selfplayenvs // 2)]
+            self.groups.append(_Group(a_utt, maps, envs, True, None, 0, partial_obs, device, emulated, seed))
+        self._bot_specs = list(a_ai2s or [])
+        self._bot_groups = {}  # built lazily in reset(): the agent's side comes with `players`
+        self._device, self._emulated, self._seed, self._load = device, emulated, seed, load
+        b0 = self.groups[0].b if self.groups else None
+        self.observation = None
+        self.reward = np.zeros((s1, len(self.rfs)), dtype=np.float64)
+        self.done = np.zeros((s1, len(self.rfs)), dtype=bool)
+        self.responses = Responses(None, None, None)
+        self._s1 = s1
+        self._shape = None if b0 is None else (b0.num_planes, b0.height, b0.width)
+
+    # ---------------------------------------------------------------------------------------------------------------
+    def _build_bot_groups(self, players):
+        keyed = {}
+        for i in range(self.num_envs):
+            env = self.num_selfplay + i
+            spec = self._bot_specs[i]
+            keyed.setdefault((spec.key(), int(players[env])), []).append(env)
+        for (skey, side), envs in keyed.items():
+            spec = self._bot_specs[envs[0] - self.num_selfplay]
+            maps = [self._load(self.mapPaths[e]) for e in envs]
+            g = _Group(self.utt, maps, envs, False, spec, side, self.partialObs, self._device, self._emulated, self._seed)
+            self._bot_groups[(skey, side)] = g
+            self.groups.append(g)
+        b0 = self.groups[0].b
+        self._shape = (b0.num_planes, b0.height, b0.width)
+
+    def _gather_observations(self):
+        if self.observation is None:
+            self.observation = np.zeros((self._s1,) + self._shape, dtype=np.int32)
+        for g in self.groups:
+            o = g.observations()
+            if g.selfplay:
+                self.observation[g.envs[0::2]] = o[0]
+                self.observation[g.envs[1::2]] = o[1]
+            else:
+                self.observation[g.envs] = o[g.side]
+
+    def reset(self, players):
+        if self.num_envs and not self._bot_groups:
+            self._build_bot_groups(players)
+        for g in self.groups:
+            g.b.reset(g.seeds)
+            g.steps[:] = 0
+            g.observe_all()
+        self._gather_observations()
+        self.reward[:] = 0
+        self.done[:] = False
+        self.responses.set(self.observation, self.reward, self.done)
+        return self.responses
+
+    def gameStep(self, action, players):
+        action = np.ascontiguousarray(action, dtype=np.int32)
+        assert action.ndim == 3 and action.shape[0] == self._s1 and action.shape[2] == 8, "action = [envs][k][8] vector actions"
+        for g in self.groups:
+            b = g.b
+            if g.selfplay:
+                b.set_actions(0, np.ascontiguousarray(action[g.envs[0::2]]), fill_none_duration=1)
+                b.set_actions(1, np.ascontiguousarray(action[g.envs[1::2]]), fill_none_duration=1)
+            else:
+                b.set_actions(g.side, np.ascontiguousarray(action[g.envs]), fill_none_duration=1)
+            b.step(1, NO_CAP)
+        for g in self.groups:
+            b = g.b
+            res = b.results()
+            info = _host(g.info)
+            g.steps += 1
+            sides = [(0, g.envs[0::2]), (1, g.envs[1::2])] if g.selfplay else [(g.side, g.envs)]
+            for side, envs in sides:
+                for j, rf in enumerate(self.rfs):
+                    r, d = rf.compute(info[:, side], res, side)
+                    self.reward[envs, j] = r
+                    self.done[envs, j] = d
+            # auto-reset (JNIGridnetVecClient.java:244-262,272-286): terminal reward/done are kept, done[0] is forced
+            first = g.envs[0::2] if g.selfplay else g.envs
+            finished = self.done[first, 0] | (g.steps >= self.maxSteps)
+            if finished.any():
+                b.restart_masked(finished.astype(np.uint8))
+                g.steps[finished] = 0
+                for side, envs in sides:
+                    self.done[np.asarray(envs)[finished], 0] = True
+                g.observe_all()
+        self._gather_observations()
+        self.responses.set(self.observation, self.reward, self.done)
+        return self.responses
+
+    def getMasks(self, player):
+        out = None
+        for g in self.groups:
+            if g.selfplay:
+                m0, m1 = g.b.masks(0), g.b.masks(1)
+                if out is None:
+                    out = np.zeros((self._s1,) + m0.shape[1:], dtype=np.int32)
+                out[g.envs[0::2]] = m0
+                out[g.envs[1::2]] = m1
+            else:
+                m = g.b.masks(g.side)
+                if out is None:
+                    out = np.zeros((self._s1,) + m.shape[1:], dtype=np.int32)
+                out[g.envs] = m
+        return out
+
+    def close(self):
+        for g in self.groups:
+            g.b.close()
+        self.groups = []

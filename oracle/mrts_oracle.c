@@ -608,6 +608,21 @@ int o_game_issue(OGame *g, int n, const int32_t *unit_idx, const OActionV *acts,
     return r;
 }
 
+/* issue / issueSafe that hands the PlayerAction back as the call left it: issueSafe replaces illegal actions by NONE inside the
+ * caller's PlayerAction (GameState.java:347-354,386-399), which is what the reward functions later read from the TraceEntry */
+int o_game_issue_out(OGame *g, int n, const int32_t *unit_idx, OActionV *acts, int safe) {
+    OPair *pa = (OPair *)malloc(sizeof(OPair) * (n > 0 ? n : 1));
+    for (int k = 0; k < n; k++) {
+        if (unit_idx[k] < 0 || unit_idx[k] >= g->n) { g->errors |= OE_BAD_UNIT; free(pa); return -1; }
+        pa[k].unit = g->list[unit_idx[k]];
+        pa[k].act = act_from_v(&acts[k]);
+    }
+    int r = safe ? gs_issue_safe(g, n, pa) : gs_issue(g, n, pa);
+    for (int k = 0; k < n; k++) acts[k] = act_to_v(&pa[k].act);
+    free(pa);
+    return r;
+}
+
 /* UnitAction.execute, UnitAction.java:338-465 */
 static int neighbour(const OGame *g, const OUnit *u, int dir) {
     switch (dir) {

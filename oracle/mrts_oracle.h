@@ -68,6 +68,7 @@ int o_game_is_complete(const OGame *);
 int o_game_next_change_time(const OGame *);
 /* unit_idx = positions in the current unit list */
 int o_game_issue(OGame *, int n, const int32_t *unit_idx, const OActionV *acts, int safe);
+int o_game_issue_out(OGame *g, int n, const int32_t *unit_idx, OActionV *acts_inout, int safe);
 int o_unit_actions(const OGame *, int unit_idx, int none_duration, OActionV *out, int max_out);
 int o_game_free_cell(const OGame *, int x, int y);
 

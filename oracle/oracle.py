@@ -53,6 +53,7 @@ def lib():
             "o_game_units": (i, [vp, pi32]), "o_game_assignments": (i, [vp, pi32]),
             "o_game_cycle": (i, [vp]), "o_game_is_complete": (i, [vp]), "o_game_next_change_time": (i, [vp]),
             "o_game_issue": (i, [vp, i, pi32, C.POINTER(ActionV), i]),
+            "o_game_issue_out": (i, [vp, i, pi32, C.POINTER(ActionV), i]),
             "o_unit_actions": (i, [vp, i, i, C.POINTER(ActionV), i]),
             "o_game_free_cell": (i, [vp, i, i]),
             "o_ai_random_biased": (i, [vp, i, pi32, C.POINTER(ActionV)]),
@@ -194,6 +195,14 @@ class Game:
         idx = (C.c_int32 * max(n, 1))(*[p[0] for p in pairs])
         acts = (ActionV * max(n, 1))(*[ActionV(*p[1]) for p in pairs])
         return lib().o_game_issue(self.h, n, idx, acts, 1 if safe else 0)
+
+    def issue_out(self, pairs, safe=True):
+        """issue / issueSafe; returns the PlayerAction as the call left it (issueSafe turns illegal actions into NONE)."""
+        n = len(pairs)
+        idx = (C.c_int32 * max(n, 1))(*[p[0] for p in pairs])
+        acts = (ActionV * max(n, 1))(*[ActionV(*p[1]) for p in pairs])
+        lib().o_game_issue_out(self.h, n, idx, acts, 1 if safe else 0)
+        return [(idx[k], acts[k].tup()) for k in range(n)]
 
     def unit_actions(self, unit_idx, none_duration=10):
         buf = (ActionV * 4200)()
