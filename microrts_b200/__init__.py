@@ -9,5 +9,5 @@ from .api import (ACTIONS_RAW, ACTIONS_VECTOR, BatchedGameState, MicroRTSError, 
 
 __all__ = ["UnitTypeTable", "PhysicalGameState", "BatchedGameState", "UnitAction", "MicroRTSError", "ACTIONS_RAW",
            "ACTIONS_VECTOR", "POLICY_EXTERNAL", "POLICY_PASSIVE", "POLICY_RANDOM_BIASED", "POLICY_WORKER_RUSH",
-           "POLICY_LIGHT_RUSH", "PF_ASTAR", "PF_BFS", "DTYPE_U8", "DTYPE_I32", "rewards", "vec_client"]
-from . import rewards, vec_client  # noqa: E402,F401  (JNIGridnetVecClient facade + src/ai/reward functions)
+           "POLICY_LIGHT_RUSH", "PF_ASTAR", "PF_BFS", "DTYPE_U8", "DTYPE_I32", "rewards", "vec_client", "trace"]
+from . import rewards, trace, vec_client  # noqa: E402,F401  (JNIGridnetVecClient facade + src/ai/reward functions)
