@@ -34,7 +34,8 @@ public final class BatchedGameState implements AutoCloseable {
     private final Arena arena = Arena.ofConfined();
     private final SymbolLookup lib;
     private final MethodHandle lastError, uttCreate, uttDestroy, mapLoad, mapDestroy, batchCreate, batchDestroy, reset, resetMasked,
-            setPolicy, setAutoReset, setActions, issue, step, cycleTo, observe, masks, results, stats, rollout, numPlanes, maskWidth;
+            setPolicy, setAutoReset, setActions, issue, step, cycleTo, observe, masks, results, stats, rollout, numPlanes, maskWidth,
+            restartMasked, setIssueOrder, setInfoOutput, setObservationOutputs;
 
     private MemorySegment utt, map, batch;
     public final int numGames, width, height, planes, maskW;
@@ -73,6 +74,10 @@ public final class BatchedGameState implements AutoCloseable {
         rollout = h("mrts_batch_rollout", FunctionDescriptor.of(I, P, I, I, I, I, I, P, P, P, I));
         numPlanes = h("mrts_batch_num_planes", FunctionDescriptor.of(I, P));
         maskWidth = h("mrts_batch_mask_width", FunctionDescriptor.of(I, P));
+        restartMasked = h("mrts_batch_restart_masked", FunctionDescriptor.of(I, P, P, I));
+        setIssueOrder = h("mrts_batch_set_issue_order", FunctionDescriptor.of(I, P, I));
+        setInfoOutput = h("mrts_batch_set_info_output", FunctionDescriptor.of(I, P, P));
+        setObservationOutputs = h("mrts_batch_set_observation_outputs", FunctionDescriptor.of(I, P, I, P, P));
         try {
             MemorySegment out = arena.allocate(P);
             check((int) uttCreate.invoke(uttVersion, conflictPolicy, out));
@@ -113,6 +118,25 @@ public final class BatchedGameState implements AutoCloseable {
 
     /** JNIGridnetVecClient auto-reset (src/tests/JNIGridnetVecClient.java:272-286), done on the device. */
     public void setAutoReset(boolean on) throws Throwable { check((int) setAutoReset.invoke(batch, on ? 1 : 0)); }
+
+    /** Restart the games whose mask byte is set; their RNG streams keep running (JNIGridnetVecClient.java:272-286). */
+    public void restartMasked(byte[] mask) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            check((int) restartMasked.invoke(batch, a.allocateFrom(ValueLayout.JAVA_BYTE, mask), 0));
+        }
+    }
+
+    /** true: player 1's PlayerAction is built after player 0's is issued (JNIGridnetClientSelfPlay.java:160-170). */
+    public void setSequentialIssue(boolean on) throws Throwable { check((int) setIssueOrder.invoke(batch, on ? 1 : 0)); }
+
+    /**
+     * Device buffers (CUDA device pointers wrapped as MemorySegment.ofAddress) that every later step() fills: the reward
+     * functions' step facts [numGames][2][12] and the observations of player 0 / 1 [numGames][planes][height][width].
+     */
+    public void setDeviceOutputs(MemorySegment info, int dtype, MemorySegment obs0, MemorySegment obs1) throws Throwable {
+        check((int) setInfoOutput.invoke(batch, info));
+        check((int) setObservationOutputs.invoke(batch, dtype, obs0, obs1));
+    }
 
     /** Stage vector actions [numGames][maxK][8] (PlayerAction.fromVectorAction rows) for an EXTERNAL player. */
     public void setVectorActions(int player, int[] actions, int[] counts, int maxK) throws Throwable {
