@@ -129,7 +129,7 @@ struct Game {
 DEV void g_bind(Game &g, int sb, const SmemLayout &L, int W, int H, int cap, int lane, int conflict, int scripted,
                 unsigned char *astar_global) {
     g.lane = lane; g.W = W; g.H = H; g.P = W + 2; g.cap = cap; g.pcw = L.pcw; g.conflict = conflict;
-    g.uw = scripted ? MRTS_UNIT_WORDS : MRTS_UNIT_WORDS_CORE;
+    g.uw = L.uws - 1; // host-computed: 7, or 9 for scripted batches
     g.sb = sb; g.pview = 0;
     g.o_pa0 = L.pa0; g.o_pa1 = L.pa1; g.o_pslot = L.pslot; g.o_grid = L.grid; g.o_kind = L.kind; g.o_resv = L.resv;
     g.o_claim = L.claim; g.o_list = L.list;
@@ -1121,7 +1121,8 @@ DEV void rb_player(Game &g, int pl, int n, bool simul, RbCtx &c) {
 #include "scripted.cuh"
 
 // ---- loops ---------------------------------------------------------------------------------------------------------------
-struct WarpStats { unsigned long long v[8]; };
+struct WarpStats { unsigned long long v[8]; }; // lives in shared memory; only lane 0 updates it
+DEV void stat_add(WarpStats &ws, int lane, int k, unsigned long long d) { if (lane == 0) ws.v[k] += d; }
 
 DEV int run_policy(Game &g, const StepParams &p, long long gi, int player, int pn, bool first_iter) {
     switch (p.policy[player]) {
@@ -1151,7 +1152,7 @@ DEV int run_policy(Game &g, const StepParams &p, long long gi, int player, int p
 // One decision point of RandomBiasedAI players: scan, then each deciding player's pass.  Returns the earliest completion
 // time of any assignment afterwards.  simul: Game.start semantics (both lists built on the pre-issue state, issued p0 then
 // p1); otherwise NaiveMCTS.simulate semantics (player 1 decides on the state that already holds player 0's actions).
-DEV int rb_decide(Game &g, int n, int time, int polmask, bool simul, unsigned long long &decisions) {
+DEV int rb_decide(Game &g, int n, int time, int polmask, bool simul, unsigned &decisions) {
     int par0 = 0, par1 = 0, mr;
     int idle = rb_scan(g, n, par0, par1, mr) & polmask;
     if (idle) {
@@ -1180,15 +1181,15 @@ DEV int rb_decide(Game &g, int n, int time, int polmask, bool simul, unsigned lo
 // (ai/mcts/naivemcts/NaiveMCTS.java:297-308, simul = false) for RandomBiasedAI / PassiveAI players under CANCEL_BOTH:
 // decide, then cycle.  Time jumps straight to the next completion time: while no unit is idle nothing can change
 // (GameState.getNextChangeTime, GameState.java:532-546).  Returns gameover; `time` ends at the last executed cycle or tlimit.
-DEV bool play_rb(Game &g, int polmask, bool simul, int tlimit, int &time, int &winner, unsigned long long &decisions, unsigned long long &ucyc) {
+DEV bool play_rb(Game &g, int polmask, bool simul, int tlimit, int &time, int &winner, unsigned &decisions, unsigned &ucyc) {
     bool over = game_over(g, winner); // a state that is already over ends at the very next cycle()
     int n = g.hdr()[H_NUNITS];
     #pragma unroll 1
     while (time < tlimit) {
         int mrt = rb_decide(g, n, time, polmask, simul, decisions);
         int tn = time + 1; if (!over && mrt > tn) tn = mrt;
-        if (tn > tlimit) { ucyc += (unsigned long long)n * (tlimit - time); time = tlimit; break; }
-        ucyc += (unsigned long long)n * (tn - time);
+        if (tn > tlimit) { ucyc += (unsigned)(n * (tlimit - time)); time = tlimit; break; }
+        ucyc += (unsigned)(n * (tn - time));
         time = tn;
         if (cycle_execute(g, tn) > 0) over = game_over(g, winner);
         n = g.hdr()[H_NUNITS];
@@ -1205,21 +1206,21 @@ DEV void run_game_fast(Game &g, const StepParams &p, WarpStats &ws) {
     int tlimit = t0 + p.n_cycles; if (tlimit > p.max_cycles) tlimit = p.max_cycles;
     int polmask = (p.policy[0] == POL_RANDOM_BIASED ? 1 : 0) | (p.policy[1] == POL_RANDOM_BIASED ? 2 : 0);
     int winner;
-    unsigned long long decisions = 0, ucyc = 0;
+    unsigned decisions = 0, ucyc = 0; // per step and game: at most units x cycles, far below 2^32
     if (play_rb(g, polmask, true, tlimit, time, winner, decisions, ucyc)) {
         status |= ST_OVER | ST_COUNTED | ((winner + 1) << 8);
-        ws.v[STAT_FINISHED]++; if (winner == 0) ws.v[STAT_WINS0]++; else if (winner == 1) ws.v[STAT_WINS1]++; else ws.v[STAT_DRAWS]++;
+        stat_add(ws, g.lane, STAT_FINISHED, 1); if (winner == 0) stat_add(ws, g.lane, STAT_WINS0, 1); else if (winner == 1) stat_add(ws, g.lane, STAT_WINS1, 1); else stat_add(ws, g.lane, STAT_DRAWS, 1);
     }
     if (!(status & ST_COUNTED) && time >= p.max_cycles) { // hit the cycle cap: a draw (winner() == -1)
         status |= ST_COUNTED;
-        ws.v[STAT_FINISHED]++; ws.v[STAT_DRAWS]++;
+        stat_add(ws, g.lane, STAT_FINISHED, 1); stat_add(ws, g.lane, STAT_DRAWS, 1);
     }
     __syncwarp();
     if (g.lane == 0) { g.hdr()[H_TIME] = time; g.hdr()[H_STATUS] = status; }
     __syncwarp();
-    ws.v[STAT_CYCLES] += (unsigned long long)(time - t0);
-    ws.v[STAT_DECISIONS] += decisions;
-    ws.v[STAT_UNIT_CYCLES] += ucyc;
+    stat_add(ws, g.lane, STAT_CYCLES, (unsigned long long)(time - t0));
+    stat_add(ws, g.lane, STAT_DECISIONS, decisions);
+    stat_add(ws, g.lane, STAT_UNIT_CYCLES, ucyc);
 }
 
 // ---- step facts for the reward functions (src/ai/reward/*.java) ----------------------------------------------------------
@@ -1335,7 +1336,7 @@ DEVN void run_game(Game &g, const StepParams &p, long long gi, WarpStats &ws) {
         if (over) {
             if (g.lane == 0) g.hdr()[H_STATUS] = status | ST_OVER | ST_COUNTED | ((winner + 1) << 8);
             __syncwarp();
-            ws.v[STAT_FINISHED]++; if (winner == 0) ws.v[STAT_WINS0]++; else if (winner == 1) ws.v[STAT_WINS1]++; else ws.v[STAT_DRAWS]++;
+            stat_add(ws, g.lane, STAT_FINISHED, 1); if (winner == 0) stat_add(ws, g.lane, STAT_WINS0, 1); else if (winner == 1) stat_add(ws, g.lane, STAT_WINS1, 1); else stat_add(ws, g.lane, STAT_DRAWS, 1);
             break;
         }
     }
@@ -1346,11 +1347,11 @@ DEVN void run_game(Game &g, const StepParams &p, long long gi, WarpStats &ws) {
         __syncwarp();
         if (g.lane == 0) g.hdr()[H_STATUS] = status | ST_COUNTED;
         __syncwarp();
-        ws.v[STAT_FINISHED]++; ws.v[STAT_DRAWS]++;
+        stat_add(ws, g.lane, STAT_FINISHED, 1); stat_add(ws, g.lane, STAT_DRAWS, 1);
     }
-    ws.v[STAT_CYCLES] += (unsigned long long)(tend - t0);
-    ws.v[STAT_DECISIONS] += decisions;
-    ws.v[STAT_UNIT_CYCLES] += ucyc;
+    stat_add(ws, g.lane, STAT_CYCLES, (unsigned long long)(tend - t0));
+    stat_add(ws, g.lane, STAT_DECISIONS, decisions);
+    stat_add(ws, g.lane, STAT_UNIT_CYCLES, ucyc);
 }
 
 // GameState.cycle() repeated until time == target (TestTracesIntegrity.java:81-85); no policies
@@ -1658,7 +1659,7 @@ DEV void run_rollout(Game &g, const StepParams &p, long long r, WarpStats &ws) {
     }
     __syncwarp();
     int t0 = g.hdr()[H_TIME], time = t0, winner;
-    unsigned long long decisions = 0, ucyc = 0;
+    unsigned decisions = 0, ucyc = 0;
     play_rb(g, 3, false, t0 + p.depth, time, winner, decisions, ucyc);
     __syncwarp();
     if (g.lane == 0) {
@@ -1667,10 +1668,10 @@ DEV void run_rollout(Game &g, const StepParams &p, long long r, WarpStats &ws) {
         if (p.ro_eval) p.ro_eval[r] = ev;
         if (p.ro_time) p.ro_time[r] = time - t0;
     }
-    ws.v[STAT_CYCLES] += (unsigned long long)(time - t0);
-    ws.v[STAT_DECISIONS] += decisions;
-    ws.v[STAT_UNIT_CYCLES] += ucyc;
-    ws.v[STAT_FINISHED]++;
+    stat_add(ws, g.lane, STAT_CYCLES, (unsigned long long)(time - t0));
+    stat_add(ws, g.lane, STAT_DECISIONS, decisions);
+    stat_add(ws, g.lane, STAT_UNIT_CYCLES, ucyc);
+    stat_add(ws, g.lane, STAT_FINISHED, 1);
 }
 
 // Bodies of the step kernels for one thread.  Three kernels share the loop below; what differs is which entry points
@@ -1704,8 +1705,11 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
         if (lane == 0) *g.as_gen = 0;
         __syncwarp();
     }
-    WarpStats ws;
-    for (int i = 0; i < 8; i++) ws.v[i] = 0;
+    // the warp's counters live in shared memory: every lane adds the same (warp-uniform) amounts to its own view of them, so
+    // only lane 0's stores matter; 16 registers stay free for the game loop
+    WarpStats &ws = *(WarpStats *)(mrts_smem + MRTS_CONST_WORDS * 4 + warp * L.total + L.stats);
+    if (lane < 8) ws.v[lane] = 0;
+    __syncwarp();
     long long n_items = KERNEL == KERNEL_ROLLOUT ? p.n_games * p.rollouts_per_game : p.n_games;
 #pragma unroll 1
     for (long long item = (long long)bid * wpc + warp; item < n_items; item += (long long)nblocks * wpc) {
@@ -1723,7 +1727,7 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
         else if (p.mode == MODE_ISSUE_ONLY) run_issue_only(g, p, gi);
         else if (p.mode == MODE_OBSERVE) { observe_game(g, p, gi); continue; }
         else { masks_game(g, p, gi); continue; }
-        if (g.hdr()[H_ERR] != err0) ws.v[STAT_ERRORS]++;
+        if (g.hdr()[H_ERR] != err0) stat_add(ws, g.lane, STAT_ERRORS, 1);
         g_store(g, ghdr, gun);
         if (KERNEL == KERNEL_FAST_OBS || (KERNEL == KERNEL_GENERIC && p.mode == MODE_GAME)) {
             #pragma unroll 1
@@ -1733,7 +1737,6 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
                              (char *)p.obs_out[pl] + (size_t)gi * obs_bytes_per_game(g.W, g.H, 6, p.obs_dtype), lane);
         }
     }
-    if (lane == 0 && p.stats)
-        #pragma unroll 1
-        for (int i = 0; i < 8; i++) if (ws.v[i]) atomicAdd(&p.stats[i], ws.v[i]);
+    __syncwarp();
+    if (lane < 8 && p.stats && ws.v[lane]) atomicAdd(&p.stats[lane], ws.v[lane]);
 }

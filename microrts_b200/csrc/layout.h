@@ -66,7 +66,7 @@ enum { UF_RESOURCE = 1, UF_STOCKPILE = 2, UF_HARVEST = 4, UF_MOVE = 8, UF_ATTACK
 enum { GE_UNIT_OVERFLOW = 1, GE_INCONSISTENT_OLDER = 2, GE_FAILED_PRODUCE = 4, GE_CELL_OCCUPIED = 8, GE_BAD_ACTION = 16 };
 
 struct SmemLayout {
-    int hdr, units, pa0, pa1, pslot, grid, kind, resv, claim, list, astar, total; // byte offsets inside one game's region
+    int hdr, units, pa0, pa1, pslot, grid, kind, resv, claim, list, stats, astar, total; // byte offsets inside one game's region
     int pcw;                                                                     // padded-grid size in 32-bit words
     int uws;                                                                     // unit words resident in shared memory
 };
@@ -101,6 +101,7 @@ MRTS_HD SmemLayout mrts_smem_layout(int W, int H, int cap, int scripted) {
     L.resv = o; o += pcb;
     L.claim = o; o += pcb;
     L.list = o; o += capb;
+    L.stats = o; o += 64; // the warp's 8 running counters (kept out of registers)
     L.astar = o; o += scripted == 1 ? MRTS_ASTAR_BYTES(W, H) : 0; // scripted == 2: scratch in global memory
     L.total = (o + 15) & ~15;
     L.pcw = pcb / 4;
