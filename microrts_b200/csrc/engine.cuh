@@ -84,24 +84,34 @@ struct StepParams {
     int32_t *ro_time;          // [n_games * rollouts_per_game] simulated cycles
 };
 
-// The CTA's dynamic shared memory.  Every accessor below derives its address from this symbol, so the compiler knows the
-// address space (LDS/STS with 32-bit addressing) even inside functions that are not inlined.
+// The CTA's dynamic shared memory.  A game's region and the constant block are addressed through 32-bit shared-window
+// addresses that are computed once per thread and kept in registers (smem_window / smem_ptr): the compiler infers the
+// address space from the conversion, so every access is an LDS/STS with 32-bit addressing even inside functions that are
+// not inlined, and it does not re-derive the window base from the special registers at every use.
 #ifdef MRTS_EMU
 static thread_local unsigned char *mrts_smem = nullptr;
+static inline uint32_t smem_window(int byte_offset) { return (uint32_t)byte_offset; }
+static inline unsigned char *smem_ptr(uint32_t a) { return mrts_smem + a; }
 #else
 extern __shared__ __align__(16) unsigned char mrts_smem[];
+__device__ __forceinline__ uint32_t smem_window(int byte_offset) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(mrts_smem) + (uint32_t)byte_offset;
+    asm volatile("" : "+r"(a)); // opaque: stays in a register instead of being rematerialised
+    return a;
+}
+__device__ __forceinline__ unsigned char *smem_ptr(uint32_t a) { return (unsigned char *)__cvta_shared_to_generic(a); }
 #endif
 
 struct Game {
     int lane;
     int W, H, P, cap, pcw, conflict, uw; // uw: unit words mirrored in HBM (7, or 9 with scripted policies)
-    int sb;                               // byte offset of this game's region inside the CTA's shared memory
+    uint32_t sb, cb;                      // shared-window addresses of this game's region and of the CTA's constant block
     int o_pa0, o_pa1, o_pslot, o_grid, o_kind, o_resv, o_claim, o_list;
     int pview;                            // window into the pending list (policy_scripted stages desires behind the final part)
     const uint32_t *grid_tmpl;            // global: wall-padded empty grid of this game's map
     uint16_t *as_closed, *as_xy, *as_mark, *as_next, *as_head, *as_gen; // A*/BFS scratch of this warp (scripted batches only, layout.h)
 
-    MDEV unsigned char *base() const { return mrts_smem + sb; }
+    MDEV unsigned char *base() const { return smem_ptr(sb); }
     MDEV int32_t *hdr() const { return (int32_t *)base(); }
     MDEV uint32_t *uword(int k) const { return (uint32_t *)(base() + MRTS_HDR_WORDS * 4) + k * cap; }
     MDEV uint32_t *w0() const { return uword(UW_W0); }
@@ -122,18 +132,18 @@ struct Game {
     MDEV uint8_t *resv() const { return base() + o_resv; }
     MDEV uint8_t *claim() const { return base() + o_claim; }
     MDEV uint8_t *list() const { return base() + o_list; }
-    MDEV const uint32_t *utt() const { return (const uint32_t *)mrts_smem; }
-    MDEV const uint64_t *jump() const { return (const uint64_t *)(mrts_smem + MRTS_MAX_TYPES * MRTS_UTT_WORDS * 4); }
+    MDEV const uint32_t *utt() const { return (const uint32_t *)smem_ptr(cb); }
+    MDEV const uint64_t *jump() const { return (const uint64_t *)smem_ptr(cb + MRTS_MAX_TYPES * MRTS_UTT_WORDS * 4); }
 };
 
-DEV void g_bind(Game &g, int sb, const SmemLayout &L, int W, int H, int cap, int lane, int conflict, int scripted,
+DEV void g_bind(Game &g, int region, const SmemLayout &L, int W, int H, int cap, int lane, int conflict, int scripted,
                 unsigned char *astar_global) {
     g.lane = lane; g.W = W; g.H = H; g.P = W + 2; g.cap = cap; g.pcw = L.pcw; g.conflict = conflict;
     g.uw = L.uws - 1; // host-computed: 7, or 9 for scripted batches
-    g.sb = sb; g.pview = 0;
+    g.sb = smem_window(region); g.cb = smem_window(0); g.pview = 0;
     g.o_pa0 = L.pa0; g.o_pa1 = L.pa1; g.o_pslot = L.pslot; g.o_grid = L.grid; g.o_kind = L.kind; g.o_resv = L.resv;
     g.o_claim = L.claim; g.o_list = L.list;
-    { int pc = (W + 2) * (H + 2); g.as_closed = (uint16_t *)(astar_global ? astar_global : mrts_smem + sb + L.astar); g.as_xy = g.as_closed + pc;
+    { int pc = (W + 2) * (H + 2); g.as_closed = (uint16_t *)(astar_global ? astar_global : mrts_smem + region + L.astar); g.as_xy = g.as_closed + pc;
       g.as_mark = g.as_xy + pc; g.as_next = g.as_mark + pc; g.as_head = g.as_next + pc; g.as_gen = g.as_head + MRTS_ASTAR_HEADS(W, H); }
     g.grid_tmpl = nullptr;
 }
@@ -1694,8 +1704,12 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
     __syncthreads();
     const SmemLayout &L = p.L;
     int warp = tid >> 5, lane = tid & 31, wpc = nthreads >> 5;
+    int region = MRTS_CONST_WORDS * 4 + warp * L.total;
+#ifndef MRTS_EMU
+    asm volatile("" : "+r"(lane)); // keep the lane id in a register instead of re-reading the special register
+#endif
     Game g;
-    g_bind(g, MRTS_CONST_WORDS * 4 + warp * L.total, L, p.W, p.H, p.cap, lane, p.conflict, p.scripted,
+    g_bind(g, region, L, p.W, p.H, p.cap, lane, p.conflict, p.scripted,
            p.scripted == 2 ? p.astar_scratch + ((long long)bid * wpc + warp) * p.astar_stride : nullptr);
     if (KERNEL == KERNEL_GENERIC && p.scripted) { // pathfinding scratch: no stale marks, all buckets empty, generation 0
         #pragma unroll 1
@@ -1707,7 +1721,7 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
     }
     // the warp's counters live in shared memory: every lane adds the same (warp-uniform) amounts to its own view of them, so
     // only lane 0's stores matter; 16 registers stay free for the game loop
-    WarpStats &ws = *(WarpStats *)(mrts_smem + MRTS_CONST_WORDS * 4 + warp * L.total + L.stats);
+    WarpStats &ws = *(WarpStats *)(mrts_smem + region + L.stats);
     if (lane < 8) ws.v[lane] = 0;
     __syncwarp();
     long long n_items = KERNEL == KERNEL_ROLLOUT ? p.n_games * p.rollouts_per_game : p.n_games;
