@@ -832,9 +832,23 @@ DEV void execute_serial(Game &g, int s, int &ndead) {
     uint32_t A0 = g.a0()[s]; int A1 = g.a1()[s];
     uint32_t w = g.w0()[s];
     bool dead = (A0 & A0_DEAD) != 0;
-    int t = u_type(w), pl = u_pl(w), c = cell_of(g, w);
+    int c = cell_of(g, w);
     // unitActions.remove(uaa.unit) (GameState.java:563); a dead unit lost its entry (and reservation) when it died
     g.a0()[s] = (A0 & 0xF0u) | AT_IDLE | A0_NOUT; g.rdy()[s] = MRTS_NEVER;
+    if (a_type(A0) == ACT_MOVE && !dead && (unsigned)A1 < 4u) {
+        // the common case on its own short path: a live unit steps into the cell it had reserved (UnitAction.java:346-361)
+        int nc = c + doff(g, A1);
+        if (g.resv()[nc] == s + 1) g.resv()[nc] = 0;
+        if (g.grid()[nc] != 0) g.hdr()[H_ERR] |= GE_CELL_OCCUPIED;
+        else {
+            g.grid()[c] = 0; g.grid()[nc] = (uint8_t)(s + 1);
+            g.kind()[nc] = g.kind()[c]; g.kind()[c] = 0;
+            // x +- 1 or y +- 1 inside the packed word: a legal move never leaves [0, 255], so no carry crosses a field
+            g.w0()[s] = w + ((A1 & 1) ? (uint32_t)(2 - A1) << 16 : (uint32_t)(A1 - 1) << 24);
+        }
+        return;
+    }
+    int t = u_type(w), pl = u_pl(w);
     if (!dead && a_uses_cell(a_type(A0))) { int tc = target_cell(g, c, A1); if (g.resv()[tc] == s + 1) g.resv()[tc] = 0; }
     switch (a_type(A0)) {
         case ACT_MOVE:
