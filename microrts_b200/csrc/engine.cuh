@@ -838,11 +838,12 @@ DEV void execute_serial(Game &g, int s, int &ndead) {
     if (a_type(A0) == ACT_MOVE && !dead && (unsigned)A1 < 4u) {
         // the common case on its own short path: a live unit steps into the cell it had reserved (UnitAction.java:346-361)
         int nc = c + doff(g, A1);
-        if (g.resv()[nc] == s + 1) g.resv()[nc] = 0;
-        if (g.grid()[nc] != 0) g.hdr()[H_ERR] |= GE_CELL_OCCUPIED;
+        int rv = g.resv()[nc], gv = g.grid()[nc], kv = g.kind()[c]; // three independent loads, issued together
+        if (rv == s + 1) g.resv()[nc] = 0;
+        if (gv != 0) g.hdr()[H_ERR] |= GE_CELL_OCCUPIED;
         else {
             g.grid()[c] = 0; g.grid()[nc] = (uint8_t)(s + 1);
-            g.kind()[nc] = g.kind()[c]; g.kind()[c] = 0;
+            g.kind()[nc] = (uint8_t)kv; g.kind()[c] = 0;
             // x +- 1 or y +- 1 inside the packed word: a legal move never leaves [0, 255], so no carry crosses a field
             g.w0()[s] = w + ((A1 & 1) ? (uint32_t)(2 - A1) << 16 : (uint32_t)(A1 - 1) << 24);
         }
@@ -995,13 +996,13 @@ DEV int cycle_execute(Game &g, int t_new) {
     if (g.lane == 0) g.hdr()[H_TIME] = t_new;
     int n = g.hdr()[H_NUNITS];
     // this lane's ready assignment with the smallest insertion sequence (a lane owns units lane, lane + 32, ...)
-    uint32_t cs = 0xFFFFFFFFu; int ci = 0;
+    uint32_t cs = 0xFFFFFFFFu; int ci = 0, mine = 0; // mine: ready assignments this lane still has to execute
     #pragma unroll 1
     for (int i = g.lane; i < n; i += 32) {
         if (g.rdy()[i] <= t_new) {
             uint32_t A0 = g.a0()[i];
             if (a_type(A0) == ACT_NONE) { g.a0()[i] = (A0 & 0xF0u) | AT_IDLE | A0_NOUT; g.rdy()[i] = MRTS_NEVER; }
-            else { uint32_t q = g.seq()[i]; if (q < cs) { cs = q; ci = i; } }
+            else { uint32_t q = g.seq()[i]; mine++; if (q < cs) { cs = q; ci = i; } }
         }
     }
     __syncwarp();
@@ -1013,9 +1014,11 @@ DEV int cycle_execute(Game &g, int t_new) {
         if (cs == mn) { // the owner of the oldest ready assignment executes it, then looks for its next one
             execute_serial(g, ci, ndead);
             cs = 0xFFFFFFFFu;
-            #pragma unroll 1
-            for (int i = g.lane; n > 32 && i < n; i += 32) // only when lanes own several units
-                if (g.rdy()[i] <= t_new) { uint32_t q = g.seq()[i]; if (q < cs) { cs = q; ci = i; } }
+            if (--mine > 0) { // rare: this lane owns another ready unit (units lane, lane + 32, ...)
+                #pragma unroll 1
+                for (int i = g.lane; i < n; i += 32)
+                    if (g.rdy()[i] <= t_new) { uint32_t q = g.seq()[i]; if (q < cs) { cs = q; ci = i; } }
+            }
         }
         __syncwarp(); // its effects are visible to the lane that executes the next one
     }
