@@ -334,19 +334,20 @@ DEV void enumerate(const Game &g, int s, Enum &e) {
     e.w = w; e.t = u_type(w); e.pl = u_pl(w); e.c = cell_of(g, w);
     e.fl = ut_flags(g, e.t); e.range = ut_range(g, e.t);
     int myres = u_res(g.w1()[s]);
-    int free_m = 0, atk_m = 0, harv_m = 0, ret_m = 0;
+    // The four neighbours' cell-kind bytes (up, right, down, left) packed into one word and classified for all four
+    // directions at once.  Kind byte (layout.h): 0 empty, 0xFF wall, else 0x10 | owner (bits 0-1) | resource << 2 | stockpile << 3.
     const uint8_t *kind = g.kind() + e.c;
-#pragma unroll
-    for (int d = 0; d < 4; d++) { // four independent byte loads of the cell-kind map (no unit table access)
-        int kv = kind[doff(g, d)];
-        if (kv == 0) free_m |= 1 << d;
-        else if (kv != 0xFF) {
-            int npl = kv & 3;
-            if (npl != 0 && npl != e.pl) atk_m |= 1 << d;
-            if (kv & 4) harv_m |= 1 << d;
-            if ((kv & 8) && npl == e.pl) ret_m |= 1 << d;
-        }
-    }
+    uint32_t K = (uint32_t)kind[-g.P] | ((uint32_t)kind[1] << 8) | ((uint32_t)kind[g.P] << 16) | ((uint32_t)kind[-1] << 24);
+    const uint32_t LSB = 0x01010101u;
+    uint32_t unit = (K >> 4) & ~(K >> 7) & LSB;                       // occupied by a unit (walls have bit 7)
+    uint32_t fre = ~((K >> 4) | (K >> 7)) & LSB;                      // neither unit nor wall
+    uint32_t p0 = K & unit, p1 = (K >> 1) & unit;                     // owner is player 0 / player 1
+    uint32_t own = e.pl == 1 ? p0 : (e.pl == 2 ? p1 : 0u), enemy = e.pl == 1 ? p1 : (e.pl == 2 ? p0 : 0u);
+    // byte d -> bit d: the multiply gathers bits 0, 8, 16, 24 into bits 24..27
+    int free_m = (int)((fre * 0x01020408u) >> 24) & 0xF;
+    int atk_m = (int)((enemy * 0x01020408u) >> 24) & 0xF;             // an opponent's unit (Unit.java:411-423)
+    int harv_m = (int)((((K >> 2) & unit) * 0x01020408u) >> 24) & 0xF; // a resource (Unit.java:440-452)
+    int ret_m = (int)((((K >> 3) & own) * 0x01020408u) >> 24) & 0xF;   // an own stockpile (Unit.java:453-465)
     if (!(e.fl & UF_ATTACK) || e.range != 1) atk_m = 0;
     if (!(e.fl & UF_HARVEST)) { harv_m = 0; ret_m = 0; }
     else { if (myres != 0) harv_m = 0; if (!(myres > 0)) ret_m = 0; }
@@ -360,8 +361,9 @@ DEV void enumerate(const Game &g, int s, Enum &e) {
     int aff_m = 0;
     if (e.pl != 0) {
         int pres = g.hdr()[H_RES0 + e.pl - 1], np = ut_nprod(g, e.t);
+        uint32_t pc = g.utt()[e.t * 8 + 7]; // costs of the first four produced types, one byte each
         #pragma unroll 1
-        for (int k = 0; k < np; k++) if (pres >= ut_cost(g, ut_prod(g, e.t, k))) aff_m |= 1 << k;
+        for (int k = 0; k < np; k++) { int cost = k < 4 ? (int)((pc >> (8 * k)) & 0xff) : ut_cost(g, ut_prod(g, e.t, k)); if (pres >= cost) aff_m |= 1 << k; }
     }
     e.free_m = free_m; e.atk_m = atk_m; e.harv_m = harv_m; e.ret_m = ret_m; e.aff_m = aff_m;
     e.n_atk = n_atk; e.nfree = __popc(free_m); e.n_aff = __popc(aff_m);

@@ -152,6 +152,7 @@ inline void build_const_words(const UttH &u, std::vector<uint32_t> &w) {
         q[3] = (uint32_t)t.attackTime | ((uint32_t)t.harvestTime << 16);
         q[4] = (uint32_t)t.returnTime | ((uint32_t)t.produces.size() << 16);
         for (size_t k = 0; k < t.produces.size(); k++) q[5 + (k >> 2)] |= (uint32_t)t.produces[k] << ((k & 3) * 8);
+        for (size_t k = 0; k < t.produces.size() && k < 4; k++) q[7] |= (uint32_t)(u.types[t.produces[k]].cost & 0xff) << (k * 8);
     }
     // jump[d] = (A_d, C_d): s_{+2d} = A_d * s + C_d  (mod 2^48), java.util.Random's LCG
     const uint64_t A = 0x5DEECE66DULL, C = 0xBULL, M = (1ULL << 48) - 1;

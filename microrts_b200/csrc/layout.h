@@ -49,7 +49,7 @@ enum { UW_W0 = 0, UW_W1, UW_A0, UW_A1, UW_TIS, UW_SEQ, UW_ID, UW_X0, UW_X1, MRTS
 // U0: cost | hp<<8 | minDamage<<16 | maxDamage<<24
 // U1: attackRange | sightRadius<<8 | harvestAmount<<16 | flags<<24
 // U2: produceTime | moveTime<<16      U3: attackTime | harvestTime<<16     U4: returnTime | nProduces<<16
-// U5: produces[0..3] bytes            U6: produces[4..7] bytes             U7: pad
+// U5: produces[0..3] bytes            U6: produces[4..7] bytes             U7: cost of produces[0..3], one byte each
 enum { UF_RESOURCE = 1, UF_STOCKPILE = 2, UF_HARVEST = 4, UF_MOVE = 8, UF_ATTACK = 16 };
 
 #define MRTS_JUMP_ENTRIES 65 // LCG skip-ahead: entry d advances 2*d steps (d nextDouble() draws)
