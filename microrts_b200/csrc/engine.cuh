@@ -107,13 +107,14 @@ struct Game {
     int W, H, P, cap, pcw, conflict, uw; // uw: unit words mirrored in HBM (7, or 9 with scripted policies)
     uint32_t sb, cb;                      // shared-window addresses of this game's region and of the CTA's constant block
     int o_pa0, o_pa1, o_pslot, o_grid, o_kind, o_resv, o_claim, o_list;
+    int o_rdy, uoff[MRTS_UNIT_WORDS + 1]; // byte offsets of the unit word arrays inside the region (host-computed constants)
     int pview;                            // window into the pending list (policy_scripted stages desires behind the final part)
     const uint32_t *grid_tmpl;            // global: wall-padded empty grid of this game's map
     uint16_t *as_closed, *as_xy, *as_mark, *as_next, *as_head, *as_gen; // A*/BFS scratch of this warp (scripted batches only, layout.h)
 
     MDEV unsigned char *base() const { return smem_ptr(sb); }
     MDEV int32_t *hdr() const { return (int32_t *)base(); }
-    MDEV uint32_t *uword(int k) const { return (uint32_t *)(base() + MRTS_HDR_WORDS * 4) + k * cap; }
+    MDEV uint32_t *uword(int k) const { return (uint32_t *)(base() + uoff[k]); }
     MDEV uint32_t *w0() const { return uword(UW_W0); }
     MDEV uint32_t *w1() const { return uword(UW_W1); }
     MDEV uint32_t *a0() const { return uword(UW_A0); }
@@ -123,7 +124,7 @@ struct Game {
     MDEV uint32_t *uid() const { return uword(UW_ID); }
     MDEV uint32_t *x0() const { return uword(UW_X0); }
     MDEV uint32_t *x1() const { return uword(UW_X1); }
-    MDEV int32_t *rdy() const { return (int32_t *)uword(uw); } // shared memory only: completion time, MRTS_NEVER when idle
+    MDEV int32_t *rdy() const { return (int32_t *)(base() + o_rdy); } // shared memory only: completion time, MRTS_NEVER when idle
     MDEV uint32_t *pa0() const { return (uint32_t *)(base() + o_pa0) + pview; }
     MDEV int32_t *pa1() const { return (int32_t *)(base() + o_pa1) + pview; }
     MDEV uint8_t *pslot() const { return base() + o_pslot + pview; }
@@ -138,7 +139,9 @@ struct Game {
 
 DEV void g_bind(Game &g, int region, const SmemLayout &L, int W, int H, int cap, int lane, int conflict, int scripted,
                 unsigned char *astar_global) {
-    g.lane = lane; g.W = W; g.H = H; g.P = W + 2; g.cap = cap; g.pcw = L.pcw; g.conflict = conflict;
+    g.lane = lane; g.W = W; g.H = H; g.P = L.P; g.cap = cap; g.pcw = L.pcw; g.conflict = conflict;
+    for (int k = 0; k <= MRTS_UNIT_WORDS; k++) g.uoff[k] = L.uoff[k];
+    g.o_rdy = L.rdy;
     g.uw = L.uws - 1; // host-computed: 7, or 9 for scripted batches
     g.sb = smem_window(region); g.cb = smem_window(0); g.pview = 0;
     g.o_pa0 = L.pa0; g.o_pa1 = L.pa1; g.o_pslot = L.pslot; g.o_grid = L.grid; g.o_kind = L.kind; g.o_resv = L.resv;
@@ -362,8 +365,11 @@ DEV void enumerate(const Game &g, int s, Enum &e) {
     if (e.pl != 0) {
         int pres = g.hdr()[H_RES0 + e.pl - 1], np = ut_nprod(g, e.t);
         uint32_t pc = g.utt()[e.t * 8 + 7]; // costs of the first four produced types, one byte each
+        aff_m = ((pres >= (int)(pc & 0xff)) ? 1 : 0) | ((pres >= (int)((pc >> 8) & 0xff)) ? 2 : 0) | ((pres >= (int)((pc >> 16) & 0xff)) ? 4 : 0) |
+                ((pres >= (int)(pc >> 24)) ? 8 : 0);
         #pragma unroll 1
-        for (int k = 0; k < np; k++) { int cost = k < 4 ? (int)((pc >> (8 * k)) & 0xff) : ut_cost(g, ut_prod(g, e.t, k)); if (pres >= cost) aff_m |= 1 << k; }
+        for (int k = 4; k < np; k++) if (pres >= ut_cost(g, ut_prod(g, e.t, k))) aff_m |= 1 << k;
+        aff_m &= (1 << np) - 1;
     }
     e.free_m = free_m; e.atk_m = atk_m; e.harv_m = harv_m; e.ret_m = ret_m; e.aff_m = aff_m;
     e.n_atk = n_atk; e.nfree = __popc(free_m); e.n_aff = __popc(aff_m);

@@ -69,6 +69,9 @@ struct SmemLayout {
     int hdr, units, pa0, pa1, pslot, grid, kind, resv, claim, list, stats, astar, total; // byte offsets inside one game's region
     int pcw;                                                                     // padded-grid size in 32-bit words
     int uws;                                                                     // unit words resident in shared memory
+    int P;                                                                       // padded row length W + 2
+    int uoff[MRTS_UNIT_WORDS + 1];                                               // byte offset of each unit word array (RDY is word uws - 1)
+    int rdy;                                                                     // = uoff[uws - 1]
 };
 
 // Shared-memory-only per-unit word (index uw, after the words mirrored in HBM): RDY = completion time of the unit's
@@ -91,7 +94,10 @@ MRTS_HD SmemLayout mrts_smem_layout(int W, int H, int cap, int scripted) {
     int capb = (cap + 15) & ~15;
     int o = 0;
     L.uws = (scripted ? MRTS_UNIT_WORDS : MRTS_UNIT_WORDS_CORE) + 1; // X0/X1 are resident only for scripted batches; +1: RDY
+    L.P = W + 2;
     L.hdr = o; o += MRTS_HDR_WORDS * 4;
+    for (int k = 0; k <= MRTS_UNIT_WORDS; k++) L.uoff[k] = o + k * cap * 4; // host-computed so the kernels see plain constants
+    L.rdy = L.uoff[L.uws - 1];
     L.units = o; o += (L.uws * cap * 4 + 15) & ~15; // every section starts 16-byte aligned (vector fills of the cell maps)
     L.pa0 = o; o += (cap * 4 + 15) & ~15;
     L.pa1 = o; o += (cap * 4 + 15) & ~15;
