@@ -57,6 +57,7 @@ def parse():
                          "configurations of SURVEY 8(d): obs = cfg 5 (64x64 + fused observations every cycle), scripted = cfg 3 "
                          "(24x24 WorkerRush vs LightRush, A*), rollout = cfg 4 (32x32 partially observable MCTS playouts)")
     ap.add_argument("--rollouts-per-game", type=int, default=64)
+    ap.add_argument("--observer", type=int, default=0, help="rollout workload: player whose partially observable view is the root (-1: fully observable roots)")
     ap.add_argument("--unit-capacity", type=int, default=0, help="unit slots per game (0 = automatic bound; a game that needs more sets its error flag)")
     return ap.parse_args()
 
@@ -422,7 +423,7 @@ def run_secondary(args):
         b = M.BatchedGameState(utt, M.PhysicalGameState.fromXML(P.map_to_xml(maps[key]), utt), n, device=local)
         b.set_policy(0, M.POLICY_RANDOM_BIASED); b.set_policy(1, M.POLICY_RANDOM_BIASED)
         C = 100
-        name = "maps/%s.xml: %d root states/GPU (RandomBiased self-play advanced to t=0/500/1000 by thirds) x %d NaiveMCTS playouts (RandomBiasedAI both sides, depth 100) from player 0's partially observable view, SimpleSqrtEvaluationFunction3" % (key, n, args.rollouts_per_game)
+        name = "maps/%s.xml: %d root states/GPU (RandomBiased self-play advanced to t=0/500/1000 by thirds) x %d NaiveMCTS playouts (RandomBiasedAI both sides, depth 100) from %s, SimpleSqrtEvaluationFunction3" % (key, n, args.rollouts_per_game, "fully observable roots" if args.observer < 0 else "player %d's partially observable view" % args.observer)
     stream = torch.cuda.ExternalStream(_ffi.lib().mrts_batch_stream(b._h), device=torch.device("cuda", local))
 
     def barrier():
@@ -452,7 +453,7 @@ def run_secondary(args):
         L = _ffi.lib()
 
         def step():
-            rc = L.mrts_batch_rollout(b._h, args.rollouts_per_game, 100, 0, 0, 0, None, ev.data_ptr(), tm.data_ptr(), 1)
+            rc = L.mrts_batch_rollout(b._h, args.rollouts_per_game, 100, 0, 0, args.observer, None, ev.data_ptr(), tm.data_ptr(), 1)
             assert rc == 0, L.mrts_last_error()
     else:
         b.set_auto_reset(True)

@@ -64,7 +64,7 @@ enum {
     MRTS_ACTIONS_RAW = 1
 };
 
-enum { MRTS_DTYPE_U8 = 0, MRTS_DTYPE_I32 = 1 };
+enum { MRTS_DTYPE_U8 = 0, MRTS_DTYPE_I32 = 1, MRTS_DTYPE_BITS = 2 /* masks only: element j of a row is bit j & 7 of byte j >> 3 */ };
 enum {
     MRTS_FLAG_PARTIAL_OBS = 1u,
     MRTS_FLAG_SCRIPTED_AI = 2u /* reserve pathfinding scratch so WORKER_RUSH / LIGHT_RUSH policies can be selected */
@@ -207,7 +207,8 @@ int mrts_batch_num_planes(const mrts_batch *);
  * over the batch. */
 int mrts_batch_set_observation_outputs(mrts_batch *, int dtype, void *out_player0, void *out_player1);
 /* JNIGridnetClient.getMasks(player) (src/tests/JNIGridnetClient.java:210-223, UnitAction.java:711-751):
- * out = [n_games][H][W][mask_width]. */
+ * out = [n_games][H][W][mask_width]; with MRTS_DTYPE_BITS the last dimension is (mask_width + 7) / 8 bytes of packed bits
+ * (79 entries -> 10 bytes per cell: 1/32 of the int32 array the reference allocates). */
 int mrts_batch_masks(mrts_batch *, int player, int dtype, void *out, int on_device);
 int mrts_batch_mask_width(const mrts_batch *);
 

@@ -19,7 +19,7 @@ from . import _ffi
 ACTIONS_VECTOR, ACTIONS_RAW = 0, 1
 POLICY_EXTERNAL, POLICY_PASSIVE, POLICY_RANDOM_BIASED, POLICY_WORKER_RUSH, POLICY_LIGHT_RUSH = range(5)
 PF_ASTAR, PF_BFS = 0, 1
-DTYPE_U8, DTYPE_I32 = 0, 1
+DTYPE_U8, DTYPE_I32, DTYPE_BITS = 0, 1, 2
 FLAG_PARTIAL_OBS = 1
 FLAG_SCRIPTED_AI = 2
 
@@ -316,8 +316,14 @@ class BatchedGameState:
         _check(_ffi.lib().mrts_batch_set_observation_outputs(self._h, code, ptrs[0], ptrs[1]))
 
     def masks(self, player, dtype=np.int32, out=None):
-        """JNIGridnetClient.getMasks(player) for every game: [n][H][W][mask_width]."""
-        code = DTYPE_U8 if np.dtype(dtype) == np.uint8 else DTYPE_I32
+        """JNIGridnetClient.getMasks(player) for every game: [n][H][W][mask_width]; dtype="bits": [n][H][W][(mask_width+7)//8]
+        uint8 with element j in bit j & 7 of byte j >> 3 (np.unpackbits(..., bitorder="little") restores the dense form)."""
+        if isinstance(dtype, str) and dtype == "bits":
+            code = DTYPE_BITS
+            if out is None:
+                out = np.empty((self.n, self.height, self.width, (self.mask_width + 7) // 8), dtype=np.uint8)
+        else:
+            code = DTYPE_U8 if np.dtype(dtype) == np.uint8 else DTYPE_I32
         if out is None:
             out = np.empty((self.n, self.height, self.width, self.mask_width), dtype=np.uint8 if code == DTYPE_U8 else np.int32)
         p, dev, _k = _ptr(out)

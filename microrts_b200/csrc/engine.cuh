@@ -68,7 +68,7 @@ struct StepParams {
     int n_types;               // utt.getUnitTypes().size()
     // MODE_OBSERVE / MODE_MASKS
     void *out;
-    int out_dtype;             // 0 = u8, 1 = i32
+    int out_dtype;             // 0 = u8, 1 = i32, 2 = bit-packed (masks only)
     int out_player;
     int partial_obs;
     int sequential_issue;      // MODE_GAME: player 1 decides on the state that already holds player 0's actions
@@ -600,6 +600,7 @@ DEVN int decode_external(Game &g, int player, int pn, const int32_t *rows, int c
                 if (gv != 0 && gv != 0xFF) {
                     s = gv - 1;
                     uint32_t w = g.w0()[s];
+                    if (u_pl(w) == player + 1 && a_type(g.a0()[s]) == AT_IDLE && (at < 0 || at > 5)) atomicOr(&g.hdr()[H_ERR], GE_BAD_ACTION);
                     if (u_pl(w) == player + 1 && a_type(g.a0()[s]) == AT_IDLE && at >= 0 && at <= 5) {
                         cand = true;
                         A0 = (uint32_t)at | A0_NOUT;
@@ -1587,11 +1588,14 @@ DEVN void masks_game(Game &g, const StepParams &p, long long gi) {
         Enum e; enumerate(g, s, e);
         bool mv = (e.fl & UF_MOVE) != 0;
         int pr_m = e.n_aff > 0 ? e.free_m : 0, mv_m = mv ? e.free_m : 0;
-        size_t row = ((size_t)gi * g.W * g.H + (size_t)u_y(w) * g.W + u_x(w)) * K;
+        size_t cell = (size_t)gi * g.W * g.H + (size_t)u_y(w) * g.W + u_x(w), row = cell * K;
+        int MB = (K + 7) >> 3; // bit-packed row length in bytes (out_dtype 2)
         #pragma unroll 1
-        for (int j = g.lane; j < K; j += 32) {
+        for (int jb = 0; jb < K; jb += 32) {
+            int j = jb + g.lane;
             int v = 0;
-            if (j == 0) v = 1;
+            if (j >= K) v = 0;
+            else if (j == 0) v = 1;
             else if (j < 7) {
                 switch (j - 1) {
                     case ACT_NONE: v = 1; break;
@@ -1615,8 +1619,14 @@ DEVN void masks_game(Game &g, const StepParams &p, long long gi) {
                     if (gv != 0 && gv != 0xFF) v = enemy_in_range(g, w, g.w0()[gv - 1], e.range * e.range) ? 1 : 0;
                 }
             }
-            if (p.out_dtype == 0) ((uint8_t *)p.out)[row + j] = (uint8_t)v;
-            else ((int32_t *)p.out)[row + j] = v;
+            if (p.out_dtype == 2) { // bit j of the row = element j: one ballot packs 32 elements, lanes 0..3 store its bytes
+                unsigned bits = __ballot_sync(FULLM, v != 0);
+                int byte = (jb >> 3) + g.lane;
+                if (g.lane < 4 && byte < MB) ((uint8_t *)p.out)[cell * MB + byte] = (uint8_t)(bits >> (8 * g.lane));
+            } else if (j < K) {
+                if (p.out_dtype == 0) ((uint8_t *)p.out)[row + j] = (uint8_t)v;
+                else ((int32_t *)p.out)[row + j] = v;
+            }
         }
     }
 }

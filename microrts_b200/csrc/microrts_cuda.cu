@@ -587,9 +587,10 @@ int mrts_batch_rollout(mrts_batch *b, int rollouts_per_game, int depth, int eval
 }
 
 static int emit(mrts_batch *b, int mode, int player, int dtype, void *out, int on_device, size_t elems) {
-    if (!b || !out || player < 0 || player > 1 || (dtype != MRTS_DTYPE_U8 && dtype != MRTS_DTYPE_I32)) return fail(MRTS_E_ARG, "bad observation/mask argument");
+    bool bits = mode == MODE_MASKS && dtype == MRTS_DTYPE_BITS;
+    if (!b || !out || player < 0 || player > 1 || (dtype != MRTS_DTYPE_U8 && dtype != MRTS_DTYPE_I32 && !bits)) return fail(MRTS_E_ARG, "bad observation/mask argument");
     if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
-    size_t bytes = elems * (dtype == MRTS_DTYPE_U8 ? 1 : 4);
+    size_t bytes = bits ? (size_t)b->n * b->W * b->H * ((mrts_batch_mask_width(b) + 7) / 8) : elems * (dtype == MRTS_DTYPE_U8 ? 1 : 4);
     void *d_out = out;
     if (!on_device) { if (ensure_tmp(b, bytes)) return fail(MRTS_E_CUDA, std::string("staging allocation failed: ") + dev_errstr()); d_out = b->d_tmp; }
     if (mode == MODE_MASKS && dev_zero(d_out, bytes, b->stream)) return fail(MRTS_E_CUDA, dev_errstr());

@@ -166,6 +166,7 @@ def test_observations_and_masks(backend, maps, key):
             po_b = bpo.observe(player, np.uint8)
             mk = b.masks(player, np.int32)
             mk_b = b.masks(player, np.uint8)
+            mk_bits = b.masks(player, "bits")
             assert obs_i.shape == (n, 6, maps[key]["h"], maps[key]["w"]) and po.shape[1] == 8
             for g, og in enumerate(games):
                 ref = og.observe(player)
@@ -177,6 +178,8 @@ def test_observations_and_masks(backend, maps, key):
                 ref_m = og.masks(player)
                 assert (mk[g] == ref_m).all(), "masks %s chunk %d game %d player %d" % (key, c, g, player)
                 assert (mk_b[g] == ref_m.astype(np.uint8)).all()
+                assert (np.unpackbits(mk_bits[g], axis=-1, bitorder="little")[..., :ref_m.shape[-1]] == ref_m).all(), "bit-packed masks"
+
         for bb in (b, bpo):
             bb.step(37, 3000)
         for og in games:
