@@ -100,6 +100,57 @@ def cpu_baseline(map_key, seconds, threads=None):
                        "engine (oracle/), not the JVM" % (sum(games_done), sum(cycles), map_key, threads, dt))
 
 
+def cpu_baseline_secondary(wl, seconds, n_rollouts_per_root=8, threads=None):
+    """The oracle port on the host cores for the secondary workloads (bounded sample, same definition of a game-cycle)."""
+    import golden_io
+    from oracle import oracle as O
+    maps = golden_io.load_maps()
+    threads = threads or (os.cpu_count() or 1)
+    utt = O.Utt(1, 1)
+    cycles = [0] * threads
+    deadline = time.time() + seconds
+
+    def work(i):
+        seed = 1000003 * i
+        while time.time() < deadline:
+            if wl == "scripted":
+                keys = ["24x24/basesWorkers24x24"] + ["24x24/basesWorkers24x24" + c for c in "ABCDEFGHIJKL"]
+                g = O.Game(utt, maps[keys[seed % 13]])
+                a0, a1 = O.ScriptedAI(O.AI_WORKER_RUSH, 0), O.ScriptedAI(O.AI_LIGHT_RUSH, 0)
+                while time.time() < deadline:
+                    over, _ = g.run(O.AI_WORKER_RUSH, a0, O.AI_LIGHT_RUSH, a1, 100, MAX_CYCLES)
+                    if over or g.time >= MAX_CYCLES:
+                        break
+                cycles[i] += g.time
+            elif wl == "obs":
+                g = O.Game(utt, maps["GardenOfWar64x64"]); g.seed(seed)
+                while time.time() < deadline and g.time < MAX_CYCLES and not (g.gameover and g.time > 0):
+                    cycles[i] += g.run_observing(O.AI_RANDOM_BIASED, O.AI_RANDOM_BIASED, 100, MAX_CYCLES)
+            else:
+                g = O.Game(utt, maps["BWDistantResources32x32"]); g.seed(seed)
+                g.run(O.AI_RANDOM_BIASED, None, O.AI_RANDOM_BIASED, None, (seed % 3) * 500, MAX_CYCLES)
+                for k in range(n_rollouts_per_root):
+                    if time.time() >= deadline:
+                        break
+                    c = g.po_view(0) if wl == "rollout" else g.clone()
+                    c.seed(seed * 64 + k)
+                    t0 = c.time
+                    c.simulate(t0 + 100)
+                    c.evaluate(0, 0, 1)
+                    cycles[i] += c.time - t0
+            seed += 1
+
+    t0 = time.time()
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    dt = time.time() - t0
+    return dict(value=sum(cycles) / dt, unit="game-cycles/s", cores=threads, kind="port",
+                sample="%d game-cycles of the same workload on %d host threads in %.1f s; C restatement of the Java engine (oracle/), not the JVM" % (sum(cycles), threads, dt))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -525,7 +576,7 @@ def run_secondary(args):
                roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
                              peak_source="measured (MEASURED_PEAKS.json)" if peaks else "fallback", kernel=kern, bytes_formula=form,
                              mean_launch_ms=sum(kernel_ms) / max(1, len(kernel_ms))),
-               cpu_baseline=None,
+               cpu_baseline=None if args.no_cpu_baseline else cpu_baseline_secondary("rollout_fo" if (wl == "rollout" and args.observer < 0) else wl, min(args.cpu_seconds, 6.0)),
                stats=dict(wins_p0=red["wins_p0"], wins_p1=red["wins_p1"], draws=red["draws"], games_finished=red["games_finished"],
                           game_errors=red["errors"], device_time_s=dev_s, wall_time_s=tmax.item()))
     print(json.dumps(out))

@@ -1451,3 +1451,17 @@ int o_simulate(OGame *g, int time_limit) {
     free(pa);
     return gameover;
 }
+
+/* bench helper (cpu_baseline of the observation workload): the Game.start loop body followed by getVectorObservation of
+ * both players every cycle, as a vectorised-RL client does (JNIGridnetClientSelfPlay.gameStep :157-190).  Returns cycles run. */
+int o_run_game_observing(OGame *g, int kind0, OAi *ai0, int kind1, OAi *ai1, int n_cycles, int max_cycles, int32_t *scratch) {
+    int done = 0;
+    for (int it = 0; it < n_cycles && g->time < max_cycles; it++) {
+        int over = o_run_game(g, kind0, ai0, kind1, ai1, 1, max_cycles, NULL);
+        o_observe(g, 0, scratch);
+        o_observe(g, 1, scratch);
+        done++;
+        if (over) break;
+    }
+    return done;
+}

@@ -106,6 +106,7 @@ float o_evaluate(const OGame *, int fn, int maxplayer, int minplayer);
 /* Game.start: policies on the same state, issueSafe x2, cycle.  Runs until gameover, time>=max_cycles or
  * n_cycles iterations.  ai0/ai1 may be NULL with kind RANDOM_BIASED/PASSIVE.  Returns 1 if gameover. */
 int o_run_game(OGame *, int kind0, OAi *ai0, int kind1, OAi *ai1, int n_cycles, int max_cycles, int64_t *stats);
+int o_run_game_observing(OGame *g, int kind0, OAi *ai0, int kind1, OAi *ai1, int n_cycles, int max_cycles, int32_t *scratch);
 /* NaiveMCTS.simulate: RandomBiased both sides, issue() not issueSafe() */
 int o_simulate(OGame *, int time_limit);
 

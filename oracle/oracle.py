@@ -66,6 +66,7 @@ def lib():
             "o_evaluate": (C.c_float, [vp, i, i, i]),
             "o_run_game": (i, [vp, i, vp, i, vp, i, i, C.POINTER(C.c_int64)]),
             "o_simulate": (i, [vp, i]),
+            "o_run_game_observing": (i, [vp, i, vp, i, vp, i, i, pi32]),
             "o_jr_seed": (None, [C.POINTER(C.c_uint64), i64]), "o_jr_next": (C.c_int32, [C.POINTER(C.c_uint64), i]),
             "o_jr_next_int": (C.c_int32, [C.POINTER(C.c_uint64)]),
             "o_jr_next_int_bound": (C.c_int32, [C.POINTER(C.c_uint64), C.c_int32]),
@@ -255,6 +256,11 @@ class Game:
         st = (C.c_int64 * 4)() if stats is None else stats
         return bool(lib().o_run_game(self.h, kind0, ai0.h if ai0 else None, kind1, ai1.h if ai1 else None, n_cycles,
                                       max_cycles, st)), list(st)
+
+    def run_observing(self, kind0, kind1, n_cycles, max_cycles):
+        """Game.start loop + both players' observations every cycle, entirely in C (bench cpu_baseline); returns cycles run."""
+        scratch = np.zeros(6 * self.w * self.h_, dtype=np.int32)
+        return lib().o_run_game_observing(self.h, kind0, None, kind1, None, n_cycles, max_cycles, scratch.ctypes.data_as(C.POINTER(C.c_int32)))
 
     def simulate(self, time_limit):
         return bool(lib().o_simulate(self.h, time_limit))
