@@ -111,6 +111,7 @@ struct Game {
     int pview;                            // window into the pending list (policy_scripted stages desires behind the final part)
     const uint32_t *grid_tmpl;            // global: wall-padded empty grid of this game's map
     uint16_t *as_closed, *as_xy, *as_mark, *as_next, *as_head, *as_gen; // A*/BFS scratch of this warp (scripted batches only, layout.h)
+    uint32_t as_sm;                       // its shared-window address when it lives in shared memory, else 0
 
     MDEV unsigned char *base() const { return smem_ptr(sb); }
     MDEV int32_t *hdr() const { return (int32_t *)base(); }
@@ -147,7 +148,8 @@ DEV void g_bind(Game &g, int region, const SmemLayout &L, int W, int H, int cap,
     g.o_pa0 = L.pa0; g.o_pa1 = L.pa1; g.o_pslot = L.pslot; g.o_grid = L.grid; g.o_kind = L.kind; g.o_resv = L.resv;
     g.o_claim = L.claim; g.o_list = L.list;
     { int pc = (W + 2) * (H + 2); g.as_closed = (uint16_t *)(astar_global ? astar_global : mrts_smem + region + L.astar); g.as_xy = g.as_closed + pc;
-      g.as_mark = g.as_xy + pc; g.as_next = g.as_mark + pc; g.as_head = g.as_next + pc; g.as_gen = g.as_head + MRTS_ASTAR_HEADS(W, H); }
+      g.as_mark = g.as_xy + pc; g.as_next = g.as_mark + pc; g.as_head = g.as_next + pc; g.as_gen = g.as_head + MRTS_ASTAR_HEADS(W, H);
+      g.as_sm = (scripted == 1) ? smem_window(region + L.astar) : 0u; }
     g.grid_tmpl = nullptr;
 }
 

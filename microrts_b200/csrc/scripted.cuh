@@ -48,14 +48,27 @@ enum { PFF_INOC = 1, PFF_BLOCKED = 2, PFF_CLOSED = 4 };
 #define PF_NONE 0xFFFFu
 // Positions are indices into the wall-padded grid: out of bounds looks like a wall, so there are no bounds checks, and a
 // node's coordinates are kept beside it (its cost is f - heuristic), so there are no divisions.
-DEV int pf_flags(const Game &g, int pos, int gen) { int m = g.as_mark[pos]; return (m >> 3) == gen ? (m & 7) : 0; }
-DEV void pf_set(const Game &g, int pos, int gen, int flags) { g.as_mark[pos] = (uint16_t)((gen << 3) | flags); }
+// the scratch arrays of one query; built from the shared-window address when the scratch is in shared memory, so that the
+// accesses compile to LDS/STS instead of generic loads (pf_find<true>), from the global pointers otherwise
+struct PfArr { uint16_t *closed, *xy, *mark, *next, *head, *gen; const uint8_t *grid, *resv; int P; };
+template <bool SM> DEV PfArr pf_arrays(const Game &g) {
+    PfArr a;
+    if (SM) {
+        int pc = g.P * (g.H + 2);
+        a.closed = (uint16_t *)smem_ptr(g.as_sm); a.xy = a.closed + pc; a.mark = a.xy + pc; a.next = a.mark + pc; a.head = a.next + pc;
+        a.gen = a.head + MRTS_ASTAR_HEADS(g.W, g.H);
+    } else { a.closed = g.as_closed; a.xy = g.as_xy; a.mark = g.as_mark; a.next = g.as_next; a.head = g.as_head; a.gen = g.as_gen; }
+    a.grid = g.grid(); a.resv = g.resv(); a.P = g.P;
+    return a;
+}
+DEV int pf_flags(const PfArr &g, int pos, int gen) { int m = g.mark[pos]; return (m >> 3) == gen ? (m & 7) : 0; }
+DEV void pf_set(const PfArr &g, int pos, int gen, int flags) { g.mark[pos] = (uint16_t)((gen << 3) | flags); }
 // GameState.free (GameState.java:191-207) unless the cell is used by a desire already chosen this cycle (ru)
-DEV bool pf_free(const Game &g, int pc, int fl) { return !(fl & PFF_BLOCKED) && g.grid()[pc] == 0 && g.resv()[pc] == 0; }
-DEV int pf_first_step(const Game &g, int pos, int parent) {
+DEV bool pf_free(const PfArr &g, int pc, int fl) { return !(fl & PFF_BLOCKED) && g.grid[pc] == 0 && g.resv[pc] == 0; }
+DEV int pf_first_step(const PfArr &g, int pos, int parent) {
     int last = pos;
 #pragma unroll 1
-    while (parent != pos) { last = pos; pos = parent; parent = g.as_closed[pos]; }
+    while (parent != pos) { last = pos; pos = parent; parent = g.closed[pos]; }
     if (last == pos + g.P) return 2;
     if (last == pos - 1) return 3;
     if (last == pos - g.P) return 0;
@@ -66,21 +79,23 @@ DEV int iabs(int v) { return v < 0 ? -v : v; }
 
 // findPathToPositionInRange: direction of the first step of a shortest path from unit slot s to within `range` of
 // (tx, ty), or -1 (null).  ru = target cells of the desires [0, nd) in the pending list.  One lane only.
-DEVN int pf_find(Game &g, int kind, int s, int tx, int ty, int range, int nd) {
-    int gen = *g.as_gen + 1;
+template <bool SM>
+DEVN int pf_find_t(Game &g, int kind, int s, int tx, int ty, int range, int nd) {
+    const PfArr A = pf_arrays<SM>(g);
+    int gen = *A.gen + 1;
     if (gen >= 8191) { // generation numbers wrapped: forget every mark
         int pcells = g.P * (g.H + 2);
 #pragma unroll 1
-        for (int i = 0; i < pcells; i++) g.as_mark[i] = 0;
+        for (int i = 0; i < pcells; i++) A.mark[i] = 0;
         gen = 1;
     }
-    *g.as_gen = (uint16_t)gen;
+    *A.gen = (uint16_t)gen;
 #pragma unroll 1
     for (int k = 0; k < nd; k++) {
         uint32_t A0 = g.pa0()[k];
         if (a_uses_cell(a_type(A0))) {
             int pc = linear_target_cell(g, g.w0()[g.pslot()[k]], g.pa1()[k]);
-            if (pc >= 0) pf_set(g, pc, gen, pf_flags(g, pc, gen) | PFF_BLOCKED);
+            if (pc >= 0) pf_set(A, pc, gen, pf_flags(A, pc, gen) | PFF_BLOCKED);
         }
     }
     int sq = range * range;
@@ -89,73 +104,77 @@ DEVN int pf_find(Game &g, int kind, int s, int tx, int ty, int range, int nd) {
     int result = -1;
     if (kind == 0) { // A*
         int f0 = iabs(sx - tx) + iabs(sy - ty), flo = f0, fhi = f0, fcur = f0;
-        g.as_xy[start] = (uint16_t)(sx | (sy << 8)); g.as_closed[start] = (uint16_t)start;
-        pf_set(g, start, gen, pf_flags(g, start, gen) | PFF_INOC);
-        g.as_next[start] = PF_NONE; g.as_head[f0] = (uint16_t)start;
+        A.xy[start] = (uint16_t)(sx | (sy << 8)); A.closed[start] = (uint16_t)start;
+        pf_set(A, start, gen, pf_flags(A, start, gen) | PFF_INOC);
+        A.next[start] = PF_NONE; A.head[f0] = (uint16_t)start;
 #pragma unroll 1
         for (;;) {
 #pragma unroll 1
-            while (fcur <= fhi && g.as_head[fcur] == PF_NONE) fcur++;
+            while (fcur <= fhi && A.head[fcur] == PF_NONE) fcur++;
             if (fcur > fhi) break;
-            int pos = g.as_head[fcur];
-            g.as_head[fcur] = g.as_next[pos];
-            int parent = g.as_closed[pos], xy = g.as_xy[pos];
-            int fl = pf_flags(g, pos, gen);
+            int pos = A.head[fcur];
+            A.head[fcur] = A.next[pos];
+            int parent = A.closed[pos], xy = A.xy[pos];
+            int fl = pf_flags(A, pos, gen);
             if (fl & PFF_CLOSED) continue;
-            pf_set(g, pos, gen, fl | PFF_CLOSED);
+            pf_set(A, pos, gen, fl | PFF_CLOSED);
             int x = xy & 0xff, y = xy >> 8;
-            if ((x - tx) * (x - tx) + (y - ty) * (y - ty) <= sq) { result = pf_first_step(g, pos, parent); break; }
+            if ((x - tx) * (x - tx) + (y - ty) * (y - ty) <= sq) { result = pf_first_step(A, pos, parent); break; }
             int c = fcur - (iabs(x - tx) + iabs(y - ty)) + 1; // cost of the neighbours: this node's f - heuristic + 1
 #pragma unroll 1
             for (int d = 0; d < 4; d++) { // up, right, down, left
-                int np = pos + doff(g, d);
-                int nfl = pf_flags(g, np, gen);
-                if ((nfl & PFF_INOC) || !pf_free(g, np, nfl)) continue;
+                int np = pos + ((d & 1) ? 2 - d : (d - 1) * A.P);
+                int nfl = pf_flags(A, np, gen);
+                if ((nfl & PFF_INOC) || !pf_free(A, np, nfl)) continue;
                 // addToOpen :104-138
                 int nx = x + ddx(d), ny = y + ddy(d);
-                g.as_xy[np] = (uint16_t)(nx | (ny << 8));
-                g.as_closed[np] = (uint16_t)pos;
+                A.xy[np] = (uint16_t)(nx | (ny << 8));
+                A.closed[np] = (uint16_t)pos;
                 int f = iabs(nx - tx) + iabs(ny - ty) + c;
-                g.as_next[np] = g.as_head[f]; g.as_head[f] = (uint16_t)np;
+                A.next[np] = A.head[f]; A.head[f] = (uint16_t)np;
                 if (f > fhi) fhi = f;
                 if (f < fcur) fcur = f;
                 if (f < flo) flo = f;
-                pf_set(g, np, gen, nfl | PFF_INOC);
+                pf_set(A, np, gen, nfl | PFF_INOC);
             }
         }
 #pragma unroll 1
-        for (int f = flo; f <= fhi; f++) g.as_head[f] = PF_NONE; // leave every bucket empty for the next query
+        for (int f = flo; f <= fhi; f++) A.head[f] = PF_NONE; // leave every bucket empty for the next query
         return result;
     }
     // BFS: FIFO queue (positions in next[], parents in head[]); a cell is enqueued at most once, so it never wraps
-    uint16_t *qpos = g.as_next, *qpar = g.as_head;
+    uint16_t *qpos = A.next, *qpar = A.head;
     int oi = 0, orm = 0;
-    qpos[0] = (uint16_t)start; qpar[0] = (uint16_t)start; g.as_xy[start] = (uint16_t)(sx | (sy << 8));
-    pf_set(g, start, gen, pf_flags(g, start, gen) | PFF_INOC); oi = 1;
+    qpos[0] = (uint16_t)start; qpar[0] = (uint16_t)start; A.xy[start] = (uint16_t)(sx | (sy << 8));
+    pf_set(A, start, gen, pf_flags(A, start, gen) | PFF_INOC); oi = 1;
 #pragma unroll 1
     while (oi != orm) {
         int pos = qpos[orm], parent = qpar[orm];
         orm++;
-        int fl = pf_flags(g, pos, gen);
+        int fl = pf_flags(A, pos, gen);
         if (fl & PFF_CLOSED) continue;
-        pf_set(g, pos, gen, fl | PFF_CLOSED);
-        g.as_closed[pos] = (uint16_t)parent;
-        int xy = g.as_xy[pos], x = xy & 0xff, y = xy >> 8;
-        if ((x - tx) * (x - tx) + (y - ty) * (y - ty) <= sq) { result = pf_first_step(g, pos, parent); break; }
+        pf_set(A, pos, gen, fl | PFF_CLOSED);
+        A.closed[pos] = (uint16_t)parent;
+        int xy = A.xy[pos], x = xy & 0xff, y = xy >> 8;
+        if ((x - tx) * (x - tx) + (y - ty) * (y - ty) <= sq) { result = pf_first_step(A, pos, parent); break; }
 #pragma unroll 1
         for (int d = 0; d < 4; d++) {
-            int np = pos + doff(g, d);
-            int nfl = pf_flags(g, np, gen);
-            if ((nfl & PFF_INOC) || !pf_free(g, np, nfl)) continue;
-            g.as_xy[np] = (uint16_t)((x + ddx(d)) | ((y + ddy(d)) << 8));
+            int np = pos + ((d & 1) ? 2 - d : (d - 1) * A.P);
+            int nfl = pf_flags(A, np, gen);
+            if ((nfl & PFF_INOC) || !pf_free(A, np, nfl)) continue;
+            A.xy[np] = (uint16_t)((x + ddx(d)) | ((y + ddy(d)) << 8));
             qpos[oi] = (uint16_t)np; qpar[oi] = (uint16_t)pos;
             oi++;
-            pf_set(g, np, gen, nfl | PFF_INOC);
+            pf_set(A, np, gen, nfl | PFF_INOC);
         }
     }
 #pragma unroll 1
     for (int i = 0; i < oi; i++) qpar[i] = PF_NONE; // head[] doubles as the parent queue: restore the empty buckets
     return result;
+}
+
+DEV int pf_find(Game &g, int kind, int s, int tx, int ty, int range, int nd) {
+    return g.as_sm ? pf_find_t<true>(g, kind, s, tx, ty, range, nd) : pf_find_t<false>(g, kind, s, tx, ty, range, nd);
 }
 
 // ---- AbstractionLayerAI -------------------------------------------------------------------------------------------------
@@ -444,8 +463,11 @@ DEVN int policy_scripted(Game &g, int player, int kind, int pathfinder, int pn) 
                 // desires live in the tail of the pending arrays while they are collected: [cap - 1 - k] would collide with
                 // nothing, but pf_find wants them at [0, nd): policies run one after the other, so player 0's final list
                 // [0, pn) must stay intact -> stage at [pn, pn + nd) and give pf_find a window by temporarily viewing from pn
-                Game gv = g; gv.pview = g.pview + pn;
-                if (aa_execute(gv, c, best, A0, A1)) { g.pslot()[pn + nd] = (uint8_t)best; g.pa0()[pn + nd] = A0; g.pa1()[pn + nd] = A1; nd++; }
+                int pv = g.pview;
+                g.pview = pv + pn; // (shifting the window in place: copying the whole Game struct costs ~100 local-memory accesses)
+                bool got = aa_execute(g, c, best, A0, A1);
+                g.pview = pv;
+                if (got) { g.pslot()[pn + nd] = (uint8_t)best; g.pa0()[pn + nd] = A0; g.pa1()[pn + nd] = A1; nd++; }
             }
         }
         // compose desires against gs.getResourceUsage() (:93-101): pa.consistentWith(r2) with pa.r = in-flight + accepted
