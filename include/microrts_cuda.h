@@ -51,7 +51,9 @@ enum {
     MRTS_POLICY_PASSIVE = 1,       /* ai.PassiveAI: never issues anything */
     MRTS_POLICY_RANDOM_BIASED = 2, /* ai.RandomBiasedAI (src/ai/RandomBiasedAI.java:51-107) */
     MRTS_POLICY_WORKER_RUSH = 3,   /* ai.abstraction.WorkerRush (src/ai/abstraction/WorkerRush.java:63-204) */
-    MRTS_POLICY_LIGHT_RUSH = 4     /* ai.abstraction.LightRush  (src/ai/abstraction/LightRush.java:77-258) */
+    MRTS_POLICY_LIGHT_RUSH = 4,    /* ai.abstraction.LightRush  (src/ai/abstraction/LightRush.java:77-258) */
+    MRTS_POLICY_HEAVY_RUSH = 5,    /* ai.abstraction.HeavyRush  (src/ai/abstraction/HeavyRush.java: LightRush training Heavy units) */
+    MRTS_POLICY_RANGED_RUSH = 6    /* ai.abstraction.RangedRush (src/ai/abstraction/RangedRush.java: LightRush training Ranged units) */
 };
 enum { MRTS_PF_ASTAR = 0, MRTS_PF_BFS = 1 };
 

@@ -17,7 +17,7 @@ import numpy as np
 from . import _ffi
 
 ACTIONS_VECTOR, ACTIONS_RAW = 0, 1
-POLICY_EXTERNAL, POLICY_PASSIVE, POLICY_RANDOM_BIASED, POLICY_WORKER_RUSH, POLICY_LIGHT_RUSH = range(5)
+POLICY_EXTERNAL, POLICY_PASSIVE, POLICY_RANDOM_BIASED, POLICY_WORKER_RUSH, POLICY_LIGHT_RUSH, POLICY_HEAVY_RUSH, POLICY_RANGED_RUSH = range(7)
 PF_ASTAR, PF_BFS = 0, 1
 DTYPE_U8, DTYPE_I32, DTYPE_BITS = 0, 1, 2
 FLAG_PARTIAL_OBS = 1

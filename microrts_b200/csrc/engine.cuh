@@ -33,7 +33,8 @@
 #define A0_NOUT (0xFFu << 8) // "unitType == null"
 
 enum { ACT_NONE = 0, ACT_MOVE = 1, ACT_HARVEST = 2, ACT_RETURN = 3, ACT_PRODUCE = 4, ACT_ATTACK = 5 };
-enum { POL_EXTERNAL = 0, POL_PASSIVE = 1, POL_RANDOM_BIASED = 2, POL_WORKER_RUSH = 3, POL_LIGHT_RUSH = 4 };
+enum { POL_EXTERNAL = 0, POL_PASSIVE = 1, POL_RANDOM_BIASED = 2, POL_WORKER_RUSH = 3, POL_LIGHT_RUSH = 4, POL_HEAVY_RUSH = 5, POL_RANGED_RUSH = 6 };
+#define POL_IS_SCRIPTED(p) ((p) >= POL_WORKER_RUSH && (p) <= POL_RANGED_RUSH)
 enum { FMT_VECTOR = 0, FMT_RAW = 1 };
 enum { MODE_GAME = 0, MODE_CYCLE_ONLY = 1, MODE_ISSUE_ONLY = 2, MODE_OBSERVE = 3, MODE_MASKS = 4, MODE_ROLLOUT = 5 };
 enum { ST_OVER = 1, ST_COUNTED = 2 };
@@ -1176,7 +1177,9 @@ DEV int run_policy(Game &g, const StepParams &p, long long gi, int player, int p
             }
             return pn;
         case POL_WORKER_RUSH:
-        case POL_LIGHT_RUSH: {
+        case POL_LIGHT_RUSH:
+        case POL_HEAVY_RUSH:
+        case POL_RANGED_RUSH: {
             if (!p.scripted) return pn;
             int n0 = pn;
             pn = policy_scripted(g, player, p.policy[player], p.pathfinder[player], pn);
@@ -1365,7 +1368,7 @@ DEVN void run_game(Game &g, const StepParams &p, long long gi, WarpStats &ws) {
             // re-inserted later.  Replay that one call (it cannot emit actions: no own unit is idle); the rest are no-ops.
 #pragma unroll 1
             for (int pl = 0; pl < 2; pl++)
-                if (p.policy[pl] == POL_WORKER_RUSH || p.policy[pl] == POL_LIGHT_RUSH) policy_scripted(g, pl, p.policy[pl], p.pathfinder[pl], 0);
+                if (POL_IS_SCRIPTED(p.policy[pl])) policy_scripted(g, pl, p.policy[pl], p.pathfinder[pl], 0);
         }
         int nu = g.hdr()[H_NUNITS];
         if (tn > tlimit) { ucyc += (unsigned long long)nu * (tlimit - time); __syncwarp(); if (g.lane == 0) g.hdr()[H_TIME] = tlimit; __syncwarp(); break; }

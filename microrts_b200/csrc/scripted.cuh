@@ -4,6 +4,7 @@
 //   BFSPathFinding     src/ai/abstraction/pathfinding/BFSPathFinding.java:41-147
 //   AbstractionLayerAI src/ai/abstraction/AbstractionLayerAI.java:58-113 (translateActions), :143-245 (building position)
 //   WorkerRush         src/ai/abstraction/WorkerRush.java:63-204        LightRush  src/ai/abstraction/LightRush.java:77-258
+//   HeavyRush / RangedRush  src/ai/abstraction/HeavyRush.java, RangedRush.java: LightRush with Heavy / Ranged as the trained type
 //   Attack/Harvest/Build/Train.execute   src/ai/abstraction/{Attack.java:51,Harvest.java:72,Build.java:54,Train.java:48-128}
 //
 // The AI's per-unit abstract action (the value of AbstractionLayerAI.actions for that unit) lives in the unit's X0/X1
@@ -376,7 +377,8 @@ DEVN int policy_scripted(Game &g, int player, int kind, int pathfinder, int pn) 
     int out = pn;
     if (g.lane == 0) {
         int n = g.hdr()[H_NUNITS], pl = player + 1, pres = g.hdr()[H_RES0 + player];
-        bool light = kind == POL_LIGHT_RUSH;
+        bool light = kind != POL_WORKER_RUSH; // the barracks rushes: LightRush, and HeavyRush / RangedRush = the same class with the trained type swapped
+        const int UT_RUSH = kind == POL_HEAVY_RUSH ? 5 : (kind == POL_RANGED_RUSH ? 6 : UT_LIGHT); // HeavyRush.java:55, RangedRush.java:52
         // bases (WorkerRush.java:70-76,100-102; LightRush.java:83-89,123-133)
 #pragma unroll 1
         for (int i = 0; i < n; i++) {
@@ -391,7 +393,7 @@ DEVN int policy_scripted(Game &g, int player, int kind, int pathfinder, int pn) 
 #pragma unroll 1
             for (int i = 0; i < n; i++) {
                 uint32_t w = g.w0()[i];
-                if (u_type(w) == UT_BARRACKS && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE && pres >= ut_cost(g, UT_LIGHT)) aa_put(g, i, player, AA_TRAIN, UT_LIGHT, 0, 0, REF_NULL, REF_NULL);
+                if (u_type(w) == UT_BARRACKS && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE && pres >= ut_cost(g, UT_RUSH)) aa_put(g, i, player, AA_TRAIN, UT_RUSH, 0, 0, REF_NULL, REF_NULL);
             }
         }
 #pragma unroll 1

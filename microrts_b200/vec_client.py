@@ -67,6 +67,14 @@ class ai:
     def LightRush(utt=None, pathfinder=M.PF_ASTAR):
         return AISpec(M.POLICY_LIGHT_RUSH, pathfinder)
 
+    @staticmethod
+    def HeavyRush(utt=None, pathfinder=M.PF_ASTAR):
+        return AISpec(M.POLICY_HEAVY_RUSH, pathfinder)
+
+    @staticmethod
+    def RangedRush(utt=None, pathfinder=M.PF_ASTAR):
+        return AISpec(M.POLICY_RANGED_RUSH, pathfinder)
+
 
 def _device_array(shape, dtype, emulated):
     """Memory the engine writes 'on device': a torch CUDA tensor, or host memory when the library is the test emulator."""
@@ -89,7 +97,7 @@ class _Group:
         n = len(envs) // 2 if selfplay else len(envs)
         self.n = n
         same = all(m is maps[0] for m in maps)
-        scripted = spec is not None and spec.policy in (M.POLICY_WORKER_RUSH, M.POLICY_LIGHT_RUSH)
+        scripted = spec is not None and spec.policy >= M.POLICY_WORKER_RUSH
         self.b = M.BatchedGameState(utt, maps[0] if same else maps, n, device=device, partial_obs=partial_obs, scripted_ai=scripted)
         b = self.b
         if selfplay:

@@ -1161,7 +1161,10 @@ static int type_by_role_light(void) { return 4; }
 
 static int ai_get_action(OAi *ai, OGame *g, int player, OPair *out) {
     const OUtt *t = g->utt;
-    int BASE = type_by_role_base(), BARRACKS = type_by_role_barracks(), WORKER = type_by_role_worker(), LIGHT = type_by_role_light();
+    int BASE = type_by_role_base(), BARRACKS = type_by_role_barracks(), WORKER = type_by_role_worker();
+    /* the combat unit the barracks train: Light (LightRush.java:57), Heavy (HeavyRush.java:55), Ranged (RangedRush.java:52) */
+    int LIGHT = ai->kind == O_AI_HEAVY_RUSH ? 5 : (ai->kind == O_AI_RANGED_RUSH ? 6 : type_by_role_light());
+    int barracks_rush = ai->kind == O_AI_LIGHT_RUSH || ai->kind == O_AI_HEAVY_RUSH || ai->kind == O_AI_RANGED_RUSH;
     int pres = g->res[player];
     /* bases: WorkerRush.java:70-76,100-102 ; LightRush.java:83-89,123-133 */
     for (int i = 0; i < g->n; i++) {
@@ -1177,7 +1180,7 @@ static int ai_get_action(OAi *ai, OGame *g, int player, OPair *out) {
         }
     }
     /* barracks: LightRush.java:92-98,135-139 */
-    if (ai->kind == O_AI_LIGHT_RUSH) {
+    if (barracks_rush) {
         for (int i = 0; i < g->n; i++) {
             int u = g->list[i]; const OUnit *un = &g->pool[u];
             if (un->type == BARRACKS && un->player == player && find_assign(g, u) < 0) {
@@ -1210,7 +1213,7 @@ static int ai_get_action(OAi *ai, OGame *g, int player, OPair *out) {
                 resourcesUsed += t->f[BASE][OF_COST];
             }
         }
-        if (ai->kind == O_AI_LIGHT_RUSH) {
+        if (barracks_rush) {
             if (nbarracks == 0) {
                 if (pres >= t->f[BARRACKS][OF_COST] + resourcesUsed && fw < nw) {
                     int u = workers[fw++];
@@ -1415,7 +1418,9 @@ static int policy(OGame *g, int kind, OAi *ai, int player, OPair *out) {
     switch (kind) {
         case O_AI_RANDOM_BIASED: return rb_get_action(g, player, out);
         case O_AI_WORKER_RUSH:
-        case O_AI_LIGHT_RUSH: return ai_get_action(ai, g, player, out);
+        case O_AI_LIGHT_RUSH:
+        case O_AI_HEAVY_RUSH:
+        case O_AI_RANGED_RUSH: return ai_get_action(ai, g, player, out);
         default: return 0; /* PassiveAI: empty PlayerAction */
     }
 }

@@ -21,7 +21,8 @@ extern "C" {
 
 enum { O_NONE = 0, O_MOVE = 1, O_HARVEST = 2, O_RETURN = 3, O_PRODUCE = 4, O_ATTACK = 5 };
 enum { O_UP = 0, O_RIGHT = 1, O_DOWN = 2, O_LEFT = 3 };
-enum { O_AI_NONE = 0, O_AI_PASSIVE = 1, O_AI_RANDOM_BIASED = 2, O_AI_WORKER_RUSH = 3, O_AI_LIGHT_RUSH = 4 };
+enum { O_AI_NONE = 0, O_AI_PASSIVE = 1, O_AI_RANDOM_BIASED = 2, O_AI_WORKER_RUSH = 3, O_AI_LIGHT_RUSH = 4,
+       O_AI_HEAVY_RUSH = 5, O_AI_RANGED_RUSH = 6 }; /* HeavyRush.java / RangedRush.java are LightRush.java with the trained type swapped */
 enum { O_PF_ASTAR = 0, O_PF_BFS = 1 };
 
 /* unit type fields, in the order of the UTT XML attributes */

@@ -506,6 +506,9 @@ SCRIPTED = [
     ("16x16/TwoBasesBarracks16x16", "WORKER_RUSH", "WORKER_RUSH", 1),
     ("8x8/FourBasesWorkers8x8", "LIGHT_RUSH", "RANDOM_BIASED", 0),
     ("BWDistantResources32x32", "RANDOM_BIASED", "WORKER_RUSH", 0),
+    ("16x16/basesWorkers16x16", "HEAVY_RUSH", "RANGED_RUSH", 0),
+    ("8x8/basesWorkers8x8", "RANGED_RUSH", "LIGHT_RUSH", 1),
+    ("24x24/basesWorkers24x24", "RANGED_RUSH", "HEAVY_RUSH", 0),
 ]
 
 
@@ -527,7 +530,7 @@ def test_scripted_policies_vs_oracle(backend, maps, key, p0, p1, pf):
         og = O.Game(outt, maps[key])
         og.seed(int(seeds[g]))
         games.append(og)
-        ais.append([O.ScriptedAI(k, pf) if k in (O.AI_WORKER_RUSH, O.AI_LIGHT_RUSH) else None for k in kinds])
+        ais.append([O.ScriptedAI(k, pf) if k in O.SCRIPTED_AIS else None for k in kinds])
     for t in range(0, total, chunk):
         b.step(chunk, total)
         ex = b.export()

@@ -104,7 +104,7 @@ class RefBotEnv(RefEnvBase):
         self.on_restart()
 
     def on_restart(self):
-        self.bot = O.ScriptedAI(self.kind, self.pf) if self.kind in (O.AI_WORKER_RUSH, O.AI_LIGHT_RUSH) else None
+        self.bot = O.ScriptedAI(self.kind, self.pf) if self.kind in O.SCRIPTED_AIS else None
 
     def step(self, act):
         og, pl = self.og, self.side
