@@ -10,8 +10,11 @@
 // The AI's per-unit abstract action (the value of AbstractionLayerAI.actions for that unit) lives in the unit's X0/X1
 // words; the map's insertion order is the `aseq` field.  Unit references held by abstract actions (attack target,
 // harvest target/base) are slot numbers that compact_units() re-maps; 0xFF stands for "an object no longer in the unit
-// list".  The whole policy runs on one lane: it is a chain of order-dependent decisions (each desire changes what the
-// next A* may step on), and every spatial query is O(1) on the cell maps.  First correct version; not yet tuned.
+// list".  The policy is a chain of order-dependent decisions (each desire changes what the next A* may step on), so its
+// control flow is sequential -- but it is executed by the whole warp in lockstep on warp-uniform values (every lane reads
+// the same shared-memory words), which lets the inner loops use the lanes: closest-unit searches and counts are one
+// strided pass + a warp reduction, and the pathfinders evaluate the four neighbours of a node on four lanes.  State is
+// written by lane 0 (or by the lane that owns the item) followed by __syncwarp().
 #pragma once
 
 enum { AA_NONE = 0, AA_TRAIN = 1, AA_BUILD = 2, AA_HARVEST = 3, AA_ATTACK = 4 };
@@ -26,16 +29,44 @@ DEV uint32_t aa_seq(uint32_t X0, uint32_t X1) { return (X1 >> 16) | ((X0 >> 25) 
 DEV int aa_target(uint32_t X1) { return X1 & 0xff; }
 DEV int aa_base(uint32_t X1) { return (X1 >> 8) & 0xff; }
 
-// actions.put(u, aa): an existing key keeps its position in the LinkedHashMap (lane 0 only)
+// actions.put(u, aa): an existing key keeps its position in the LinkedHashMap.  Called by the whole warp; lane 0 writes.
 DEV void aa_put(Game &g, int s, int player, int kind, int type, int bx, int by, int target, int base) {
-    uint32_t oX0 = g.x0()[s], oX1 = g.x1()[s];
-    uint32_t seq;
-    if (aa_kind(oX0) != AA_NONE) seq = aa_seq(oX0, oX1);
-    else seq = (uint32_t)g.hdr()[H_ASEQ0 + player]++;
-    uint32_t X0 = (uint32_t)kind | ((uint32_t)type << 4) | ((uint32_t)(bx & 0xff) << 8) | ((uint32_t)(by & 0xff) << 16) | (bx < 0 ? (1u << 24) : 0u) |
-                  ((seq >> 16) << 25);
-    uint32_t X1 = (uint32_t)target | ((uint32_t)base << 8) | ((seq & 0xffffu) << 16);
-    g.x0()[s] = X0; g.x1()[s] = X1;
+    __syncwarp();
+    if (g.lane == 0) {
+        uint32_t oX0 = g.x0()[s], oX1 = g.x1()[s];
+        uint32_t seq;
+        if (aa_kind(oX0) != AA_NONE) seq = aa_seq(oX0, oX1);
+        else seq = (uint32_t)g.hdr()[H_ASEQ0 + player]++;
+        uint32_t X0 = (uint32_t)kind | ((uint32_t)type << 4) | ((uint32_t)(bx & 0xff) << 8) | ((uint32_t)(by & 0xff) << 16) | (bx < 0 ? (1u << 24) : 0u) |
+                      ((seq >> 16) << 25);
+        uint32_t X1 = (uint32_t)target | ((uint32_t)base << 8) | ((seq & 0xffffu) << 16);
+        g.x0()[s] = X0; g.x1()[s] = X1;
+    }
+    __syncwarp();
+}
+
+// ---- warp-wide passes over the unit table (lane l looks at units l, l + 32, ...) ---------------------------------------------
+// first unit in list order with the smallest key: key_of(i, w0[i]) returns the distance-like key, or -1 to skip the unit
+template <class F> DEV int w_argmin(const Game &g, int n, F key_of, int *min_key = nullptr) {
+    unsigned best = 0xFFFFFFFFu;
+#pragma unroll 1
+    for (int i = g.lane; i < n; i += 32) { int k = key_of(i, g.w0()[i]); if (k >= 0) { unsigned q = ((unsigned)k << 8) | (unsigned)i; if (q < best) best = q; } }
+    best = __reduce_min_sync(FULLM, best);
+    if (min_key) *min_key = best == 0xFFFFFFFFu ? 0 : (int)(best >> 8);
+    return best == 0xFFFFFFFFu ? -1 : (int)(best & 0xff);
+}
+template <class F> DEV int w_count(const Game &g, int n, F pred) {
+    int c = 0;
+#pragma unroll 1
+    for (int i = g.lane; i < n; i += 32) c += pred(i, g.w0()[i]) ? 1 : 0;
+    return __reduce_add_sync(FULLM, c);
+}
+template <class F> DEV int w_next(const Game &g, int n, int from, F pred) { // first unit after `from` satisfying pred, or -1
+    unsigned best = 0xFFFFFFFFu;
+#pragma unroll 1
+    for (int i = g.lane; i < n; i += 32) if (i > from && (unsigned)i < best && pred(i, g.w0()[i])) best = (unsigned)i;
+    best = __reduce_min_sync(FULLM, best);
+    return best == 0xFFFFFFFFu ? -1 : (int)best;
 }
 
 // ---- pathfinding ---------------------------------------------------------------------------------------------------------
@@ -79,98 +110,129 @@ DEV int pf_first_step(const PfArr &g, int pos, int parent) {
 DEV int iabs(int v) { return v < 0 ? -v : v; }
 
 // findPathToPositionInRange: direction of the first step of a shortest path from unit slot s to within `range` of
-// (tx, ty), or -1 (null).  ru = target cells of the desires [0, nd) in the pending list.  One lane only.
+// (tx, ty), or -1 (null).  ru = target cells of the desires [0, nd) in the pending list.  Called by the whole warp with
+// uniform arguments; the search state is uniform, the four neighbours of the expanded node are examined by lanes 0..3 and
+// pushed in the reference's order (up, right, down, left) by lane 0.
 template <bool SM>
 DEVN int pf_find_t(Game &g, int kind, int s, int tx, int ty, int range, int nd) {
     const PfArr A = pf_arrays<SM>(g);
+    const int lane = g.lane;
+    __syncwarp();
     int gen = *A.gen + 1;
+    __syncwarp();
     if (gen >= 8191) { // generation numbers wrapped: forget every mark
-        int pcells = g.P * (g.H + 2);
+        int pcells = A.P * (g.H + 2);
 #pragma unroll 1
-        for (int i = 0; i < pcells; i++) A.mark[i] = 0;
+        for (int i = lane; i < pcells; i += 32) A.mark[i] = 0;
         gen = 1;
     }
-    *A.gen = (uint16_t)gen;
+    if (lane == 0) *A.gen = (uint16_t)gen;
+    __syncwarp();
 #pragma unroll 1
-    for (int k = 0; k < nd; k++) {
+    for (int k = lane; k < nd; k += 32) { // desires target distinct cells, so the lanes never write the same mark
         uint32_t A0 = g.pa0()[k];
         if (a_uses_cell(a_type(A0))) {
             int pc = linear_target_cell(g, g.w0()[g.pslot()[k]], g.pa1()[k]);
-            if (pc >= 0) pf_set(A, pc, gen, pf_flags(A, pc, gen) | PFF_BLOCKED);
+            if (pc >= 0) pf_set(A, pc, gen, PFF_BLOCKED);
         }
     }
+    __syncwarp();
     int sq = range * range;
     uint32_t sw = g.w0()[s];
     int sx = u_x(sw), sy = u_y(sw), start = cell_of(g, sw);
     int result = -1;
+    const int dl = lane & 3, doffl = (dl & 1) ? 2 - dl : (dl - 1) * A.P, dxl = ddx(dl), dyl = ddy(dl); // this lane's direction
     if (kind == 0) { // A*
         int f0 = iabs(sx - tx) + iabs(sy - ty), flo = f0, fhi = f0, fcur = f0;
-        A.xy[start] = (uint16_t)(sx | (sy << 8)); A.closed[start] = (uint16_t)start;
-        pf_set(A, start, gen, pf_flags(A, start, gen) | PFF_INOC);
-        A.next[start] = PF_NONE; A.head[f0] = (uint16_t)start;
+        if (lane == 0) {
+            A.xy[start] = (uint16_t)(sx | (sy << 8)); A.closed[start] = (uint16_t)start;
+            pf_set(A, start, gen, pf_flags(A, start, gen) | PFF_INOC);
+            A.next[start] = PF_NONE; A.head[f0] = (uint16_t)start;
+        }
+        __syncwarp();
 #pragma unroll 1
         for (;;) {
+            // smallest non-empty bucket: 32 buckets per probe
 #pragma unroll 1
-            while (fcur <= fhi && A.head[fcur] == PF_NONE) fcur++;
+            while (fcur <= fhi) {
+                unsigned m = __ballot_sync(FULLM, fcur + lane <= fhi && A.head[fcur + lane] != PF_NONE);
+                if (m) { fcur += __ffs(m) - 1; break; }
+                fcur += 32;
+            }
             if (fcur > fhi) break;
             int pos = A.head[fcur];
-            A.head[fcur] = A.next[pos];
-            int parent = A.closed[pos], xy = A.xy[pos];
-            int fl = pf_flags(A, pos, gen);
-            if (fl & PFF_CLOSED) continue;
-            pf_set(A, pos, gen, fl | PFF_CLOSED);
+            int nxt = A.next[pos], parent = A.closed[pos], xy = A.xy[pos], fl = pf_flags(A, pos, gen);
+            __syncwarp(); // every lane has read the bucket head before it is popped
+            if (lane == 0) { A.head[fcur] = (uint16_t)nxt; if (!(fl & PFF_CLOSED)) pf_set(A, pos, gen, fl | PFF_CLOSED); }
+            if (fl & PFF_CLOSED) { __syncwarp(); continue; }
             int x = xy & 0xff, y = xy >> 8;
-            if ((x - tx) * (x - tx) + (y - ty) * (y - ty) <= sq) { result = pf_first_step(A, pos, parent); break; }
+            if ((x - tx) * (x - tx) + (y - ty) * (y - ty) <= sq) { __syncwarp(); result = pf_first_step(A, pos, parent); break; }
             int c = fcur - (iabs(x - tx) + iabs(y - ty)) + 1; // cost of the neighbours: this node's f - heuristic + 1
-#pragma unroll 1
-            for (int d = 0; d < 4; d++) { // up, right, down, left
-                int np = pos + ((d & 1) ? 2 - d : (d - 1) * A.P);
+            // lanes 0..3: one neighbour each (addToOpen :104-138)
+            int np = pos + doffl, nx = x + dxl, ny = y + dyl, f = 0;
+            bool ok = false;
+            if (lane < 4) {
                 int nfl = pf_flags(A, np, gen);
-                if ((nfl & PFF_INOC) || !pf_free(A, np, nfl)) continue;
-                // addToOpen :104-138
-                int nx = x + ddx(d), ny = y + ddy(d);
-                A.xy[np] = (uint16_t)(nx | (ny << 8));
-                A.closed[np] = (uint16_t)pos;
-                int f = iabs(nx - tx) + iabs(ny - ty) + c;
-                A.next[np] = A.head[f]; A.head[f] = (uint16_t)np;
-                if (f > fhi) fhi = f;
-                if (f < fcur) fcur = f;
-                if (f < flo) flo = f;
-                pf_set(A, np, gen, nfl | PFF_INOC);
+                ok = !(nfl & PFF_INOC) && pf_free(A, np, nfl);
+                if (ok) {
+                    A.xy[np] = (uint16_t)(nx | (ny << 8)); A.closed[np] = (uint16_t)pos;
+                    f = iabs(nx - tx) + iabs(ny - ty) + c;
+                    pf_set(A, np, gen, nfl | PFF_INOC);
+                }
             }
-        }
+            unsigned okm = __ballot_sync(FULLM, ok);
 #pragma unroll 1
-        for (int f = flo; f <= fhi; f++) A.head[f] = PF_NONE; // leave every bucket empty for the next query
+            for (unsigned mm = okm; mm; mm &= mm - 1) { // pushes in direction order: a later one lands on top of its bucket
+                int d = __ffs(mm) - 1;
+                int npd = __shfl_sync(FULLM, np, d), fd = __shfl_sync(FULLM, f, d);
+                if (lane == 0) { A.next[npd] = A.head[fd]; A.head[fd] = (uint16_t)npd; }
+                if (fd > fhi) fhi = fd;
+                if (fd < fcur) fcur = fd;
+                if (fd < flo) flo = fd;
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int f = flo + lane; f <= fhi; f += 32) A.head[f] = PF_NONE; // leave every bucket empty for the next query
+        __syncwarp();
         return result;
     }
     // BFS: FIFO queue (positions in next[], parents in head[]); a cell is enqueued at most once, so it never wraps
     uint16_t *qpos = A.next, *qpar = A.head;
-    int oi = 0, orm = 0;
-    qpos[0] = (uint16_t)start; qpar[0] = (uint16_t)start; A.xy[start] = (uint16_t)(sx | (sy << 8));
-    pf_set(A, start, gen, pf_flags(A, start, gen) | PFF_INOC); oi = 1;
+    int oi = 1, orm = 0;
+    if (lane == 0) {
+        qpos[0] = (uint16_t)start; qpar[0] = (uint16_t)start; A.xy[start] = (uint16_t)(sx | (sy << 8));
+        pf_set(A, start, gen, pf_flags(A, start, gen) | PFF_INOC);
+    }
+    __syncwarp();
 #pragma unroll 1
     while (oi != orm) {
         int pos = qpos[orm], parent = qpar[orm];
         orm++;
-        int fl = pf_flags(A, pos, gen);
+        int fl = pf_flags(A, pos, gen), xy = A.xy[pos];
+        __syncwarp();
         if (fl & PFF_CLOSED) continue;
-        pf_set(A, pos, gen, fl | PFF_CLOSED);
-        A.closed[pos] = (uint16_t)parent;
-        int xy = A.xy[pos], x = xy & 0xff, y = xy >> 8;
-        if ((x - tx) * (x - tx) + (y - ty) * (y - ty) <= sq) { result = pf_first_step(A, pos, parent); break; }
-#pragma unroll 1
-        for (int d = 0; d < 4; d++) {
-            int np = pos + ((d & 1) ? 2 - d : (d - 1) * A.P);
+        if (lane == 0) { pf_set(A, pos, gen, fl | PFF_CLOSED); A.closed[pos] = (uint16_t)parent; }
+        int x = xy & 0xff, y = xy >> 8;
+        if ((x - tx) * (x - tx) + (y - ty) * (y - ty) <= sq) { __syncwarp(); result = pf_first_step(A, pos, parent); break; }
+        int np = pos + doffl;
+        bool ok = false;
+        if (lane < 4) {
             int nfl = pf_flags(A, np, gen);
-            if ((nfl & PFF_INOC) || !pf_free(A, np, nfl)) continue;
-            A.xy[np] = (uint16_t)((x + ddx(d)) | ((y + ddy(d)) << 8));
-            qpos[oi] = (uint16_t)np; qpar[oi] = (uint16_t)pos;
-            oi++;
-            pf_set(A, np, gen, nfl | PFF_INOC);
+            ok = !(nfl & PFF_INOC) && pf_free(A, np, nfl);
+            if (ok) { A.xy[np] = (uint16_t)((x + dxl) | ((y + dyl) << 8)); pf_set(A, np, gen, nfl | PFF_INOC); }
         }
+        unsigned okm = __ballot_sync(FULLM, ok);
+        int slot = oi + __popc(okm & ((1u << lane) - 1)); // queue order = direction order
+        if (ok) { qpos[slot] = (uint16_t)np; qpar[slot] = (uint16_t)pos; }
+        oi += __popc(okm);
+        __syncwarp();
     }
+    __syncwarp();
 #pragma unroll 1
-    for (int i = 0; i < oi; i++) qpar[i] = PF_NONE; // head[] doubles as the parent queue: restore the empty buckets
+    for (int i = lane; i < oi; i += 32) qpar[i] = PF_NONE; // head[] doubles as the parent queue: restore the empty buckets
+    __syncwarp();
     return result;
 }
 
@@ -203,22 +265,20 @@ DEV bool mk_move(const Game &g, const ScriptCtx &c, int s, int dir, uint32_t &A0
     return true;
 }
 
-// Train.score (Train.java:98-126)
+// Train.score (Train.java:98-126): minus the Manhattan distance to the closest resource (harvesters) / enemy unit (others)
 DEV int train_score(const Game &g, int x, int y, int type, int pl) {
-    int n = g.hdr()[H_NUNITS], distance = 0; bool first = true;
+    int n = g.hdr()[H_NUNITS], distance = 0;
     bool harvester = (ut_flags(g, type) & UF_HARVEST) != 0;
-#pragma unroll 1
-    for (int i = 0; i < n; i++) {
-        uint32_t w = g.w0()[i];
+    w_argmin(g, n, [&](int, uint32_t w) {
         bool ok = harvester ? (ut_flags(g, u_type(w)) & UF_RESOURCE) != 0 : (u_pl(w) != 0 && u_pl(w) != pl);
-        if (ok) { int d = iabs(u_x(w) - x) + iabs(u_y(w) - y); if (first || d < distance) { distance = d; first = false; } }
-    }
+        return ok ? iabs(u_x(w) - x) + iabs(u_y(w) - y) : -1;
+    }, &distance);
     return -distance;
 }
 
 DEV bool cell_gs_free(const Game &g, int pc) { return g.grid()[pc] == 0 && g.resv()[pc] == 0; }
 
-// AbstractAction.execute for slot s; returns true and (A0, A1) if it yields a unit action
+// AbstractAction.execute for slot s; returns true and (A0, A1) if it yields a unit action.  Whole warp, uniform.
 DEVN bool aa_execute(Game &g, const ScriptCtx &c, int s, uint32_t &A0, int &A1) {
     uint32_t X0 = g.x0()[s], X1 = g.x1()[s], w = g.w0()[s];
     int x = u_x(w), y = u_y(w), t = u_type(w);
@@ -264,7 +324,9 @@ DEVN bool aa_execute(Game &g, const ScriptCtx &c, int s, uint32_t &A0, int &A1) 
                 int nc = pc + doff(g, d);
                 if (cell_gs_free(g, nc)) { int sc = train_score(g, x + ddx(d), y + ddy(d), type, pl); if (sc > best || best_dir == -1) { best = sc; best_dir = d; } }
             }
-            g.x0()[s] = X0 | 8u; // completed = true
+            __syncwarp();
+            if (g.lane == 0) g.x0()[s] = X0 | 8u; // completed = true
+            __syncwarp();
             if (best_dir != -1) { A0 = ACT_PRODUCE | ((uint32_t)type << 8); A1 = best_dir; return unit_action_allowed(g, c, s, A0, A1); }
             return false;
         }
@@ -313,31 +375,19 @@ DEVN int find_building_position(const Game &g, const int *reserved, int nres, in
 }
 
 DEV void script_melee(Game &g, int s, int player) { // meleeUnitBehavior (WorkerRush.java:105-121, LightRush.java:141-159)
-    int n = g.hdr()[H_NUNITS], closest = -1, cd = 0;
+    int n = g.hdr()[H_NUNITS];
     uint32_t w = g.w0()[s];
-#pragma unroll 1
-    for (int i = 0; i < n; i++) {
-        uint32_t ow = g.w0()[i];
-        if (u_pl(ow) != 0 && u_pl(ow) != player + 1) { int d = iabs(u_x(ow) - u_x(w)) + iabs(u_y(ow) - u_y(w)); if (closest < 0 || d < cd) { closest = i; cd = d; } }
-    }
+    int closest = w_argmin(g, n, [&](int, uint32_t ow) { return (u_pl(ow) != 0 && u_pl(ow) != player + 1) ? iabs(u_x(ow) - u_x(w)) + iabs(u_y(ow) - u_y(w)) : -1; });
     if (closest >= 0) aa_put(g, s, player, AA_ATTACK, 0, 0, 0, closest + 1, REF_NULL);
 }
 
 // harvest part of workersBehavior (WorkerRush.java:148-199, LightRush.java:203-252); true if the worker is still free
 DEV bool script_harvest(Game &g, int s, int player) {
-    int n = g.hdr()[H_NUNITS], cbase = -1, cres = -1, cd = 0;
+    int n = g.hdr()[H_NUNITS];
     uint32_t w = g.w0()[s];
-#pragma unroll 1
-    for (int i = 0; i < n; i++) {
-        uint32_t ow = g.w0()[i];
-        if (ut_flags(g, u_type(ow)) & UF_RESOURCE) { int d = iabs(u_x(ow) - u_x(w)) + iabs(u_y(ow) - u_y(w)); if (cres < 0 || d < cd) { cres = i; cd = d; } }
-    }
-    cd = 0;
-#pragma unroll 1
-    for (int i = 0; i < n; i++) {
-        uint32_t ow = g.w0()[i];
-        if ((ut_flags(g, u_type(ow)) & UF_STOCKPILE) && u_pl(ow) == player + 1) { int d = iabs(u_x(ow) - u_x(w)) + iabs(u_y(ow) - u_y(w)); if (cbase < 0 || d < cd) { cbase = i; cd = d; } }
-    }
+    int cres = w_argmin(g, n, [&](int, uint32_t ow) { return (ut_flags(g, u_type(ow)) & UF_RESOURCE) ? iabs(u_x(ow) - u_x(w)) + iabs(u_y(ow) - u_y(w)) : -1; });
+    int cbase = w_argmin(g, n, [&](int, uint32_t ow) {
+        return ((ut_flags(g, u_type(ow)) & UF_STOCKPILE) && u_pl(ow) == player + 1) ? iabs(u_x(ow) - u_x(w)) + iabs(u_y(ow) - u_y(w)) : -1; });
     uint32_t X0 = g.x0()[s], X1 = g.x1()[s];
     bool is_h = aa_kind(X0) == AA_HARVEST;
     if (u_res(g.w1()[s]) > 0) {
@@ -374,77 +424,72 @@ DEV void script_build_if_not(Game &g, int s, int player, int type, int *reserved
 DEVN int policy_scripted(Game &g, int player, int kind, int pathfinder, int pn) {
     int par0, par1;
     reserved_resources(g, par0, par1);
-    int out = pn;
+    __syncwarp();
+    const int n = g.hdr()[H_NUNITS], pl = player + 1, pres = g.hdr()[H_RES0 + player];
+    const bool light = kind != POL_WORKER_RUSH; // the barracks rushes: LightRush, and HeavyRush / RangedRush = the same class with the trained type swapped
+    const int UT_RUSH = kind == POL_HEAVY_RUSH ? 5 : (kind == POL_RANGED_RUSH ? 6 : UT_LIGHT); // HeavyRush.java:55, RangedRush.java:52
+    auto own_harvester = [&](int, uint32_t w) { return u_pl(w) == pl && (ut_flags(g, u_type(w)) & UF_HARVEST) != 0; };
+    // bases (WorkerRush.java:70-76,100-102; LightRush.java:83-89,123-133)
+#pragma unroll 1
+    for (int i = 0; i < n; i++) {
+        uint32_t w = g.w0()[i];
+        if (u_type(w) == UT_BASE && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE) {
+            bool train = pres >= ut_cost(g, UT_WORKER);
+            if (light && train) train = w_count(g, n, [&](int, uint32_t ow) { return u_type(ow) == UT_WORKER && u_pl(ow) == pl; }) < 1;
+            if (train) aa_put(g, i, player, AA_TRAIN, UT_WORKER, 0, 0, REF_NULL, REF_NULL);
+        }
+    }
+    if (light) { // barracks (LightRush.java:92-98,135-139)
+#pragma unroll 1
+        for (int i = 0; i < n; i++) {
+            uint32_t w = g.w0()[i];
+            if (u_type(w) == UT_BARRACKS && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE && pres >= ut_cost(g, UT_RUSH)) aa_put(g, i, player, AA_TRAIN, UT_RUSH, 0, 0, REF_NULL, REF_NULL);
+        }
+    }
+#pragma unroll 1
+    for (int i = 0; i < n; i++) { // melee units
+        uint32_t w = g.w0()[i];
+        int fl = ut_flags(g, u_type(w));
+        if ((fl & UF_ATTACK) && !(fl & UF_HARVEST) && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE) script_melee(g, i, player);
+    }
+    // workers: all own harvesters, busy ones too, in list order
+    int nbases = w_count(g, n, [&](int, uint32_t w) { return u_pl(w) == pl && u_type(w) == UT_BASE; });
+    int nbarracks = w_count(g, n, [&](int, uint32_t w) { return u_pl(w) == pl && u_type(w) == UT_BARRACKS; });
+    int nworkers = w_count(g, n, own_harvester);
+    if (nworkers > 0) {
+        int reserved[4], nres = 0, used = 0, taken = 0; // `taken` workers were removed from the front of freeWorkers
+        int wi = -1;                                     // cursor over own harvesters in list order
+        if (nbases == 0 && taken < nworkers) {
+            if (pres >= ut_cost(g, UT_BASE) + used) { wi = w_next(g, n, wi, own_harvester); taken++; script_build_if_not(g, wi, player, UT_BASE, reserved, nres); used += ut_cost(g, UT_BASE); }
+        }
+        if (light) {
+            if (nbarracks == 0 && pres >= ut_cost(g, UT_BARRACKS) + used && taken < nworkers) {
+                wi = w_next(g, n, wi, own_harvester); taken++; script_build_if_not(g, wi, player, UT_BARRACKS, reserved, nres); used += ut_cost(g, UT_BARRACKS);
+            }
+            // harvest with every remaining worker; those that cannot, attack -- in a second pass, as the reference does
+            uint32_t still[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 1
+            for (int i = w_next(g, n, wi, own_harvester); i >= 0; i = w_next(g, n, i, own_harvester)) if (script_harvest(g, i, player)) still[i >> 5] |= 1u << (i & 31);
+#pragma unroll 1
+            for (int i = w_next(g, n, wi, own_harvester); i >= 0; i = w_next(g, n, i, own_harvester)) if (still[i >> 5] & (1u << (i & 31))) script_melee(g, i, player);
+        } else {
+            // WorkerRush.java:146-202: one harvester, the rest attack; a harvester that stays free is appended at the END
+            int hw = -1;
+            if (taken < nworkers) { hw = w_next(g, n, wi, own_harvester); wi = hw; taken++; }
+            bool hw_free = hw >= 0 && script_harvest(g, hw, player);
+#pragma unroll 1
+            for (int i = w_next(g, n, wi, own_harvester); i >= 0; i = w_next(g, n, i, own_harvester)) script_melee(g, i, player);
+            if (hw_free) script_melee(g, hw, player);
+        }
+    }
+    // ---- translateActions (AbstractionLayerAI.java:58-113): abstract actions in insertion order --------------------
+    ScriptCtx c; c.player = player; c.pf = pathfinder; c.par0 = par0; c.par1 = par1; c.nd = 0;
+    int nd = 0;
+    // this player's map entries in insertion order: lane 0 collects the slots with an insertion sort by sequence number (slot
+    // order is nearly insertion order already)
+    int ne = 0;
+    __syncwarp();
     if (g.lane == 0) {
-        int n = g.hdr()[H_NUNITS], pl = player + 1, pres = g.hdr()[H_RES0 + player];
-        bool light = kind != POL_WORKER_RUSH; // the barracks rushes: LightRush, and HeavyRush / RangedRush = the same class with the trained type swapped
-        const int UT_RUSH = kind == POL_HEAVY_RUSH ? 5 : (kind == POL_RANGED_RUSH ? 6 : UT_LIGHT); // HeavyRush.java:55, RangedRush.java:52
-        // bases (WorkerRush.java:70-76,100-102; LightRush.java:83-89,123-133)
-#pragma unroll 1
-        for (int i = 0; i < n; i++) {
-            uint32_t w = g.w0()[i];
-            if (u_type(w) == UT_BASE && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE) {
-                bool train = pres >= ut_cost(g, UT_WORKER);
-                if (light && train) { int nw = 0; for (int j = 0; j < n; j++) nw += (u_type(g.w0()[j]) == UT_WORKER && u_pl(g.w0()[j]) == pl) ? 1 : 0; train = nw < 1; }
-                if (train) aa_put(g, i, player, AA_TRAIN, UT_WORKER, 0, 0, REF_NULL, REF_NULL);
-            }
-        }
-        if (light) { // barracks (LightRush.java:92-98,135-139)
-#pragma unroll 1
-            for (int i = 0; i < n; i++) {
-                uint32_t w = g.w0()[i];
-                if (u_type(w) == UT_BARRACKS && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE && pres >= ut_cost(g, UT_RUSH)) aa_put(g, i, player, AA_TRAIN, UT_RUSH, 0, 0, REF_NULL, REF_NULL);
-            }
-        }
-#pragma unroll 1
-        for (int i = 0; i < n; i++) { // melee units
-            uint32_t w = g.w0()[i];
-            int fl = ut_flags(g, u_type(w));
-            if ((fl & UF_ATTACK) && !(fl & UF_HARVEST) && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE) script_melee(g, i, player);
-        }
-        // workers: all own harvesters, busy ones too, in list order
-        int nbases = 0, nbarracks = 0, nworkers = 0;
-#pragma unroll 1
-        for (int i = 0; i < n; i++) {
-            uint32_t w = g.w0()[i];
-            if (u_pl(w) != pl) continue;
-            if (u_type(w) == UT_BASE) nbases++;
-            if (u_type(w) == UT_BARRACKS) nbarracks++;
-            if (ut_flags(g, u_type(w)) & UF_HARVEST) nworkers++;
-        }
-        if (nworkers > 0) {
-            int reserved[4], nres = 0, used = 0, taken = 0; // `taken` workers were removed from the front of freeWorkers
-            int wi = -1;                                     // cursor over own harvesters in list order
-            auto next_worker = [&](int from) { for (int i = from + 1; i < n; i++) { uint32_t w = g.w0()[i]; if (u_pl(w) == pl && (ut_flags(g, u_type(w)) & UF_HARVEST)) return i; } return -1; };
-            if (nbases == 0 && taken < nworkers) {
-                if (pres >= ut_cost(g, UT_BASE) + used) { wi = next_worker(wi); taken++; script_build_if_not(g, wi, player, UT_BASE, reserved, nres); used += ut_cost(g, UT_BASE); }
-            }
-            if (light) {
-                if (nbarracks == 0 && pres >= ut_cost(g, UT_BARRACKS) + used && taken < nworkers) {
-                    wi = next_worker(wi); taken++; script_build_if_not(g, wi, player, UT_BARRACKS, reserved, nres); used += ut_cost(g, UT_BARRACKS);
-                }
-                // harvest with every remaining worker; those that cannot, attack -- in a second pass, as the reference does
-                uint32_t still[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll 1
-                for (int i = next_worker(wi); i >= 0; i = next_worker(i)) if (script_harvest(g, i, player)) still[i >> 5] |= 1u << (i & 31);
-#pragma unroll 1
-                for (int i = next_worker(wi); i >= 0; i = next_worker(i)) if (still[i >> 5] & (1u << (i & 31))) script_melee(g, i, player);
-            } else {
-                // WorkerRush.java:146-202: one harvester, the rest attack; a harvester that stays free is appended at the END
-                int hw = -1;
-                if (taken < nworkers) { hw = next_worker(wi); wi = hw; taken++; }
-                bool hw_free = hw >= 0 && script_harvest(g, hw, player);
-#pragma unroll 1
-                for (int i = next_worker(wi); i >= 0; i = next_worker(i)) script_melee(g, i, player);
-                if (hw_free) script_melee(g, hw, player);
-            }
-        }
-        // ---- translateActions (AbstractionLayerAI.java:58-113): abstract actions in insertion order --------------------
-        ScriptCtx c; c.player = player; c.pf = pathfinder; c.par0 = par0; c.par1 = par1; c.nd = 0;
-        int nd = 0;                 // desires are staged at pending[pn + ...]; pf_find reads ru from pending[0, nd) so stage at 0-based scratch
-        // this player's map entries in insertion order: collect the slots, then an insertion sort by sequence number (slot
-        // order is nearly insertion order already)
-        int ne = 0;
 #pragma unroll 1
         for (int i = 0; i < n; i++) {
             uint32_t X0 = g.x0()[i];
@@ -455,23 +500,37 @@ DEVN int policy_scripted(Game &g, int player, int kind, int pathfinder, int pn) 
             while (j > 0) { int o = g.list()[j - 1]; if (aa_seq(g.x0()[o], g.x1()[o]) <= q) break; g.list()[j] = (uint8_t)o; j--; }
             g.list()[j] = (uint8_t)i;
         }
+    }
+    __syncwarp();
+    ne = __shfl_sync(FULLM, ne, 0);
 #pragma unroll 1
-        for (int r = 0; r < ne; r++) {
-            int best = g.list()[r];
-            if (aa_completed(g, best)) { g.x0()[best] &= ~7u; continue; } // toDelete (a dead unit's entry vanished with its slot)
-            if (a_type(g.a0()[best]) == AT_IDLE) {
-                uint32_t A0; int A1;
-                c.nd = nd;
-                // desires live in the tail of the pending arrays while they are collected: [cap - 1 - k] would collide with
-                // nothing, but pf_find wants them at [0, nd): policies run one after the other, so player 0's final list
-                // [0, pn) must stay intact -> stage at [pn, pn + nd) and give pf_find a window by temporarily viewing from pn
-                int pv = g.pview;
-                g.pview = pv + pn; // (shifting the window in place: copying the whole Game struct costs ~100 local-memory accesses)
-                bool got = aa_execute(g, c, best, A0, A1);
-                g.pview = pv;
-                if (got) { g.pslot()[pn + nd] = (uint8_t)best; g.pa0()[pn + nd] = A0; g.pa1()[pn + nd] = A1; nd++; }
-            }
+    for (int r = 0; r < ne; r++) {
+        int best = g.list()[r];
+        if (aa_completed(g, best)) { // toDelete (a dead unit's entry vanished with its slot)
+            __syncwarp();
+            if (g.lane == 0) g.x0()[best] &= ~7u;
+            __syncwarp();
+            continue;
         }
+        if (a_type(g.a0()[best]) == AT_IDLE) {
+            uint32_t A0; int A1;
+            c.nd = nd;
+            // Desires are staged behind the part of the pending list that is already final ([0, pn): player 0's list when this is
+            // player 1) and pf_find reads them as [0, nd) through a shifted window.
+            int pv = g.pview;
+            g.pview = pv + pn;
+            bool got = aa_execute(g, c, best, A0, A1);
+            g.pview = pv;
+            __syncwarp();
+            if (got) {
+                if (g.lane == 0) { g.pslot()[pn + nd] = (uint8_t)best; g.pa0()[pn + nd] = A0; g.pa1()[pn + nd] = A1; }
+                nd++;
+            }
+            __syncwarp();
+        }
+    }
+    int out = pn;
+    if (g.lane == 0) {
         // compose desires against gs.getResourceUsage() (:93-101): pa.consistentWith(r2) with pa.r = in-flight + accepted
         int acc0 = par0, acc1 = par1, m = pn;
 #pragma unroll 1
