@@ -4,6 +4,8 @@ Every test here needs a device (`-m gpu`).  `MRTS_EMU=1` runs them against the e
 The bar is bit-exact: unit list (order, type, owner, position, resources, hit points, ids), player resources, time,
 winner, and the in-flight assignments (action, issue time, insertion order).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -538,4 +540,44 @@ def test_scripted_policies_vs_oracle(backend, maps, key, p0, p1, pf):
             if not (og.gameover and og.time > 0):
                 og.run(kinds[0], ais[g][0], kinds[1], ais[g][1], chunk, total)
             P.assert_same_state(ex, g, og, "%s %s/%s t=%d" % (key, p0, p1, t + chunk))
+    b.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# wide differential: thousands of complete games, final state against the oracle (rare paths: more than 32 units per
+# game, cross-chunk arbitration, cancel-both pairs, deaths with pending actions)
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("key,n_cuda", [("8x8/basesWorkers8x8", 4096), ("16x16/basesWorkers16x16", 2048), ("8x8/FourBasesWorkers8x8", 1024)])
+def test_wide_differential_full_games(backend, maps, key, n_cuda):
+    import threading
+    n = 6 if backend == "emu" else n_cuda
+    total = 600 if backend == "emu" else 3000
+    utt, outt = M.UnitTypeTable(1, 1), O.Utt(1, 1)
+    b = M.BatchedGameState(utt, make_pgs(maps[key], utt), n)
+    seeds = np.arange(n, dtype=np.int64) * 3 + 17
+    b.reset(seeds)
+    b.set_policy(0, M.POLICY_RANDOM_BIASED)
+    b.set_policy(1, M.POLICY_RANDOM_BIASED)
+    b.step(total, total)
+    ex = b.export()
+    games = [None] * n
+    nthreads = min(16, os.cpu_count() or 1)
+
+    def work(t):
+        for g in range(t, n, nthreads):
+            og = O.Game(outt, maps[key])
+            og.seed(int(seeds[g]))
+            og.run(O.AI_RANDOM_BIASED, None, O.AI_RANDOM_BIASED, None, total, total)
+            games[g] = og
+
+    ts = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    big = 0
+    for g, og in enumerate(games):
+        P.assert_same_state(ex, g, og, "%s wide game %d" % (key, g))
+        big += og.n_units > 32
+    assert (b.results()[:, 3] == 0).all()
+    if backend != "emu" and key.startswith("16x16"):
+        assert big > 100, "the batch should contain many games with more than 32 live units"
     b.close()
