@@ -135,7 +135,7 @@ DEV void observe_kernel_body(const ObsParams &p, int tid, int nthreads, int bid,
 
 #ifndef MRTS_EMU
 #ifndef MRTS_MIN_BLOCKS
-#define MRTS_MIN_BLOCKS 6
+#define MRTS_MIN_BLOCKS 7
 #endif
 // k_step_fast: Game.start loop with RandomBiasedAI / PassiveAI under CANCEL_BOTH (the benchmark path); k_rollout:
 // NaiveMCTS.simulate + evaluation; k_step: every other mode.  All three are persistent, one warp per game at a time.
