@@ -1008,49 +1008,48 @@ DEV int cycle_execute(Game &g, int t_new) {
     if (g.lane == 0) g.hdr()[H_TIME] = t_new;
     int n = g.hdr()[H_NUNITS];
     // this lane's ready assignment with the smallest insertion sequence (a lane owns units lane, lane + 32, ...)
-    uint32_t cs = 0xFFFFFFFFu, cA0 = 0; int ci = 0, mine = 0; // mine: ready assignments this lane still has to execute
+    uint32_t cs = 0xFFFFFFFFu; int ci = 0, mine = 0; // mine: ready assignments this lane still has to execute
     #pragma unroll 1
     for (int i = g.lane; i < n; i += 32) {
         if (g.rdy()[i] <= t_new) {
             uint32_t A0 = g.a0()[i];
             if (a_type(A0) == ACT_NONE) { g.a0()[i] = (A0 & 0xF0u) | AT_IDLE | A0_NOUT; g.rdy()[i] = MRTS_NEVER; }
-            else { uint32_t q = g.seq()[i]; mine++; if (q < cs) { cs = q; ci = i; cA0 = A0; } }
+            else { uint32_t q = g.seq()[i]; mine++; if (q < cs) { cs = q; ci = i; } }
         }
     }
-    // Common case: everything that is ready is a well-formed MOVE -- a live unit stepping into the empty cell that it alone
-    // has reserved.  Such moves touch disjoint cells and nothing else, so their order does not matter (an occupied or
-    // doubly targeted cell, any other action type, or two ready units on one lane take the ordered path below) and every
-    // owner lane executes its own at once.
-    {
-        bool par_ok = mine == 0;
-        uint32_t w = 0; int A1 = 0, c = 0, nc = 0, kv = 0;
-        if (mine == 1 && a_type(cA0) == ACT_MOVE && !(cA0 & A0_DEAD)) {
-            A1 = g.a1()[ci]; w = g.w0()[ci];
-            if ((unsigned)A1 < 4u) {
-                c = cell_of(g, w); nc = c + doff(g, A1);
-                int rv = g.resv()[nc], gv = g.grid()[nc]; kv = g.kind()[c];
-                par_ok = rv == ci + 1 && gv == 0;
-            }
-        }
-        if (__ballot_sync(FULLM, !par_ok) == 0) { // (the ballot also orders every lane's loads before the stores)
-            if (mine == 1) {
-                g.a0()[ci] = (cA0 & 0xF0u) | AT_IDLE | A0_NOUT; g.rdy()[ci] = MRTS_NEVER;
-                g.resv()[nc] = 0;
-                g.grid()[c] = 0; g.grid()[nc] = (uint8_t)(ci + 1);
-                g.kind()[nc] = (uint8_t)kv; g.kind()[c] = 0;
-                g.w0()[ci] = w + ((A1 & 1) ? (uint32_t)(2 - A1) << 16 : (uint32_t)(A1 - 1) << 24);
-            }
-            __syncwarp();
-            return 0;
-        }
-    }
-    __syncwarp();
+    // The ready assignments execute in insertion-sequence order, but a run of well-formed MOVEs -- a live unit stepping
+    // into the empty cell that it alone has reserved -- touches disjoint cells and nothing else, so the MOVEs of a run
+    // commute.  Each round: every owner lane re-examines its candidate on the current state; all well-formed MOVEs older
+    // than the oldest other assignment execute at once, then that assignment executes alone (it may kill, deplete, produce
+    // or be a MOVE that is not well-formed).  A cycle of MOVEs only -- the common case -- takes one round.
     int ndead = 0;
     #pragma unroll 1
     for (;;) {
-        uint32_t mn = __reduce_min_sync(FULLM, cs);
-        if (mn == 0xFFFFFFFFu) break;
-        if (cs == mn) { // the owner of the oldest ready assignment executes it, then looks for its next one
+        bool is_par = false;
+        uint32_t w = 0, A0 = 0; int A1 = 0, c = 0, nc = 0, kv = 0;
+        if (cs != 0xFFFFFFFFu && mine == 1) {
+            A0 = g.a0()[ci];
+            if (a_type(A0) == ACT_MOVE && !(A0 & A0_DEAD)) {
+                A1 = g.a1()[ci]; w = g.w0()[ci];
+                if ((unsigned)A1 < 4u) {
+                    c = cell_of(g, w); nc = c + doff(g, A1);
+                    int rv = g.resv()[nc], gv = g.grid()[nc]; kv = g.kind()[c];
+                    is_par = rv == ci + 1 && gv == 0;
+                }
+            }
+        }
+        uint32_t s_np = __reduce_min_sync(FULLM, is_par ? 0xFFFFFFFFu : cs); // oldest assignment that must execute alone
+        if (is_par && cs < s_np) { // (the reduction also orders every lane's loads before these stores)
+            g.a0()[ci] = (A0 & 0xF0u) | AT_IDLE | A0_NOUT; g.rdy()[ci] = MRTS_NEVER;
+            g.resv()[nc] = 0;
+            g.grid()[c] = 0; g.grid()[nc] = (uint8_t)(ci + 1);
+            g.kind()[nc] = (uint8_t)kv; g.kind()[c] = 0;
+            g.w0()[ci] = w + ((A1 & 1) ? (uint32_t)(2 - A1) << 16 : (uint32_t)(A1 - 1) << 24);
+            cs = 0xFFFFFFFFu; mine = 0;
+        }
+        __syncwarp();
+        if (s_np == 0xFFFFFFFFu) break; // nothing had to execute alone: the round took everything that was left
+        if (cs == s_np) { // the owner of the oldest remaining assignment executes it, then looks for its next one
             execute_serial(g, ci, ndead);
             cs = 0xFFFFFFFFu;
             if (--mine > 0) { // rare: this lane owns another ready unit (units lane, lane + 32, ...)
@@ -1059,7 +1058,7 @@ DEV int cycle_execute(Game &g, int t_new) {
                     if (g.rdy()[i] <= t_new) { uint32_t q = g.seq()[i]; if (q < cs) { cs = q; ci = i; } }
             }
         }
-        __syncwarp(); // its effects are visible to the lane that executes the next one
+        __syncwarp(); // its effects are visible to the lanes of the next round
     }
     ndead = __ballot_sync(FULLM, ndead > 0) ? 1 : 0;
     if (ndead) compact_units(g);
