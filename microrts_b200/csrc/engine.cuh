@@ -1114,16 +1114,22 @@ DEV bool rb_accept(const Game &g, int pl, unsigned m, bool cand, int tcell, int 
     }
     unsigned same = __match_any_sync(FULLM, (cand && tcell >= 0) ? tcell : -1 - g.lane);
     unsigned below = (1u << g.lane) - 1;
-    if (__ballot_sync(FULLM, cand && cost != 0) == 0) {
-        // No candidate costs resources: the resource half of consistentWith is the same for every lane, and verdicts only
-        // interact when two lanes want the same cell (the first in list order wins; if it is blocked, so are the others).
-        bool over = (c.par0 > 0 && c.par0 > g.hdr()[H_RES0]) || (c.par1 > 0 && c.par1 > g.hdr()[H_RES1]);
-        return cand && !over && !blocked && !(tcell >= 0 && (same & below));
-    }
-    bool mine = false;
-    unsigned acc = 0; // accepted lanes so far
+    // While no candidate that costs resources is involved, the resource half of consistentWith is the same for every lane
+    // (`over`), and verdicts only interact when two lanes want the same cell: the first in list order wins, and if it is
+    // blocked or over, so are the others.
+    int res0 = g.hdr()[H_RES0], res1 = g.hdr()[H_RES1];
+    bool over = (c.par0 > 0 && c.par0 > res0) || (c.par1 > 0 && c.par1 > res1);
+    unsigned costly = __ballot_sync(FULLM, cand && cost != 0);
+    if (costly == 0) return cand && !over && !blocked && !(tcell >= 0 && (same & below));
+    // Candidates that cost resources change the accumulated usage, so the span from the first to the last of them is
+    // decided one candidate at a time; the lanes before the span see the initial usage, the lanes after it the final one,
+    // and both are decided in parallel as above.
+    int firstc = __ffs(costly) - 1, lastc = 31 - __clz(costly);
+    bool mine = cand && g.lane < firstc && !over && !blocked && !(tcell >= 0 && (same & below));
+    unsigned acc = __ballot_sync(FULLM, mine); // accepted lanes so far
+    unsigned span = m & (0xFFFFFFFFu << firstc) & (lastc == 31 ? 0xFFFFFFFFu : ((2u << lastc) - 1));
     #pragma unroll 1
-    for (unsigned mm = m; mm; mm &= mm - 1) {
+    for (unsigned mm = span; mm; mm &= mm - 1) {
         int j = __ffs(mm) - 1;
         int co = __shfl_sync(FULLM, cost, j);
         unsigned sj = __shfl_sync(FULLM, same, j);
@@ -1132,6 +1138,11 @@ DEV bool rb_accept(const Game &g, int pl, unsigned m, bool cand, int tcell, int 
         if (ok && !res_consistent_cand_vs_acc(g, pl, co, c.par0, c.par1)) ok = false;
         if (ok) { if (pl == 1) c.par0 += co; else c.par1 += co; acc |= 1u << j; }
         if (g.lane == j) mine = ok;
+    }
+    if (g.lane > lastc) {
+        over = (c.par0 > 0 && c.par0 > res0) || (c.par1 > 0 && c.par1 > res1);
+        unsigned after = below & ~((2u << lastc) - 1); // earlier lanes behind the span
+        mine = cand && !over && !blocked && !(tcell >= 0 && ((same & acc) || (same & after)));
     }
     return mine;
 }

@@ -167,6 +167,7 @@ inline void syncthreads(int line) { yield_wait(2, line, 0); }
 #define __syncthreads() emu::syncthreads(__LINE__)
 #define __popc(x) __builtin_popcount((unsigned)(x))
 #define __ffs(x) __builtin_ffs((int)(x))
+#define __clz(x) ((x) ? __builtin_clz((unsigned)(x)) : 32)
 #define __dmul_rn(a, b) ((double)(a) * (double)(b))
 struct uint4 { unsigned x, y, z, w; };
 struct int4 { int x, y, z, w; };
