@@ -135,17 +135,23 @@ DEV void observe_kernel_body(const ObsParams &p, int tid, int nthreads, int bid,
 
 #ifndef MRTS_EMU
 #ifndef MRTS_MIN_BLOCKS
-#define MRTS_MIN_BLOCKS 7
+#define MRTS_MIN_BLOCKS 7     // k_step_fast: 72 registers, 28 warps per SM on the 16x16 configuration
+#endif
+#ifndef MRTS_MIN_BLOCKS_OBS
+#define MRTS_MIN_BLOCKS_OBS 4 // the observation variant runs on large maps, where shared memory bounds the occupancy anyway
+#endif
+#ifndef MRTS_MIN_BLOCKS_ROLLOUT
+#define MRTS_MIN_BLOCKS_ROLLOUT 5
 #endif
 // k_step_fast: Game.start loop with RandomBiasedAI / PassiveAI under CANCEL_BOTH (the benchmark path); k_rollout:
 // NaiveMCTS.simulate + evaluation; k_step: every other mode.  All three are persistent, one warp per game at a time.
 __global__ void __launch_bounds__(MRTS_WARPS_PER_CTA * 32, MRTS_MIN_BLOCKS) k_step_fast(StepParams p) {
     step_kernel_body<KERNEL_FAST>(p, mrts_smem, threadIdx.x, blockDim.x, blockIdx.x, gridDim.x);
 }
-__global__ void __launch_bounds__(MRTS_WARPS_PER_CTA * 32, MRTS_MIN_BLOCKS) k_step_fast_obs(StepParams p) {
+__global__ void __launch_bounds__(MRTS_WARPS_PER_CTA * 32, MRTS_MIN_BLOCKS_OBS) k_step_fast_obs(StepParams p) {
     step_kernel_body<KERNEL_FAST_OBS>(p, mrts_smem, threadIdx.x, blockDim.x, blockIdx.x, gridDim.x);
 }
-__global__ void __launch_bounds__(MRTS_WARPS_PER_CTA * 32, MRTS_MIN_BLOCKS) k_rollout(StepParams p) {
+__global__ void __launch_bounds__(MRTS_WARPS_PER_CTA * 32, MRTS_MIN_BLOCKS_ROLLOUT) k_rollout(StepParams p) {
     step_kernel_body<KERNEL_ROLLOUT>(p, mrts_smem, threadIdx.x, blockDim.x, blockIdx.x, gridDim.x);
 }
 __global__ void __launch_bounds__(MRTS_WARPS_PER_CTA * 32, 3) k_step(StepParams p) {
