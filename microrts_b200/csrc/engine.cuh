@@ -1079,24 +1079,37 @@ struct RbCtx {
     bool cancelled;    // lane-local: this lane's action was cancelled against the other player's (claim map needs clearing)
 };
 
-// Scan the unit table once: which players have an idle unit (bit 0 / bit 1), the in-flight PRODUCE costs per player
-// (GameState.getResourceUsage, GameState.java:652-664) and the lane-local minimum completion time of in-flight actions.
-DEV int rb_scan(const Game &g, int n, int &par0, int &par1, int &mr) {
+// Scan the unit table once: the idle units of each player compacted in list order (player 0's slots into list(), player
+// 1's into the pslot area; cnt0 / cnt1 of them), the in-flight PRODUCE costs per player (GameState.getResourceUsage,
+// GameState.java:652-664) and the lane-local minimum completion time of in-flight actions.  Returns bit 0 / bit 1: player
+// 0 / 1 has an idle unit.
+DEV int rb_scan(const Game &g, int n, int &par0, int &par1, int &mr, int &cnt0, int &cnt1) {
     int a = 0, b = 0;
-    bool i0 = false, i1 = false;
+    uint8_t *list0 = g.list(), *list1 = g.base() + g.o_pslot;
+    unsigned below = (1u << g.lane) - 1;
+    cnt0 = cnt1 = 0;
     mr = MRTS_NEVER;
     #pragma unroll 1
-    for (int i = g.lane; i < n; i += 32) {
-        uint32_t A0 = g.a0()[i];
-        int at = a_type(A0), pl = u_pl(g.w0()[i]), r = g.rdy()[i];
-        if (at == (int)AT_IDLE) { i0 |= pl == 1; i1 |= pl == 2; }
-        else {
-            if (r < mr) mr = r;
-            if (at == ACT_PRODUCE) { int c = ut_cost(g, a_utype(A0)); if (pl == 1) a += c; else b += c; }
+    for (int base = 0; base < n; base += 32) {
+        int i = base + g.lane;
+        bool i0 = false, i1 = false;
+        if (i < n) {
+            uint32_t A0 = g.a0()[i];
+            int at = a_type(A0), pl = u_pl(g.w0()[i]), r = g.rdy()[i];
+            if (at == (int)AT_IDLE) { i0 = pl == 1; i1 = pl == 2; }
+            else {
+                if (r < mr) mr = r;
+                if (at == ACT_PRODUCE) { int c = ut_cost(g, a_utype(A0)); if (pl == 1) a += c; else b += c; }
+            }
         }
+        unsigned m0 = __ballot_sync(FULLM, i0), m1 = __ballot_sync(FULLM, i1);
+        if (i0) list0[cnt0 + __popc(m0 & below)] = (uint8_t)i;
+        if (i1) list1[cnt1 + __popc(m1 & below)] = (uint8_t)i;
+        cnt0 += __popc(m0); cnt1 += __popc(m1);
     }
-    int idle = (__ballot_sync(FULLM, i0) ? 1 : 0) | (__ballot_sync(FULLM, i1) ? 2 : 0);
+    int idle = (cnt0 ? 1 : 0) | (cnt1 ? 2 : 0);
     if (idle) { par0 = __reduce_add_sync(FULLM, a); par1 = __reduce_add_sync(FULLM, b); }
+    __syncwarp();
     return idle;
 }
 
@@ -1147,15 +1160,16 @@ DEV bool rb_accept(const Game &g, int pl, unsigned m, bool cand, int tcell, int 
     return mine;
 }
 
-// One player's getAction + issue.  pl = owner code (1 = player 0, 2 = player 1).
-DEV void rb_player(Game &g, int pl, int n, bool simul, RbCtx &c) {
+// One player's getAction + issue.  pl = owner code (1 = player 0, 2 = player 1); its idle units are the `cnt` slots of
+// `list` (unit-list order), 32 per pass.
+DEV void rb_player(Game &g, int pl, const uint8_t *list, int cnt, bool simul, RbCtx &c) {
     #pragma unroll 1
-    for (int base = 0; base < n; base += 32) {
-        int i = base + g.lane;
-        bool idle = i < n && u_pl(g.w0()[i]) == pl && a_type(g.a0()[i]) == (int)AT_IDLE;
-        unsigned m = __ballot_sync(FULLM, idle);
-        if (m == 0) continue;
-        int k = c.k + __popc(m & ((1u << g.lane) - 1));
+    for (int kb = 0; kb < cnt; kb += 32) {
+        int left = cnt - kb;
+        unsigned m = left >= 32 ? 0xFFFFFFFFu : ((1u << left) - 1);
+        bool idle = (m >> g.lane) & 1;
+        int i = idle ? list[kb + g.lane] : 0;
+        int k = c.k + g.lane;
         uint32_t A0 = ACT_NONE | A0_NOUT; int A1 = 10, tcell = -1, cost = 0, t = 0;
         if (idle) {
             Enum e; enumerate(g, i, e);
@@ -1231,17 +1245,17 @@ DEV int run_policy(Game &g, const StepParams &p, long long gi, int player, int p
 // time of any assignment afterwards.  simul: Game.start semantics (both lists built on the pre-issue state, issued p0 then
 // p1); otherwise NaiveMCTS.simulate semantics (player 1 decides on the state that already holds player 0's actions).
 DEV int rb_decide(Game &g, int n, int time, int polmask, bool simul, unsigned &decisions) {
-    int par0 = 0, par1 = 0, mr;
-    int idle = rb_scan(g, n, par0, par1, mr) & polmask;
+    int par0 = 0, par1 = 0, mr, cnt0, cnt1;
+    int idle = rb_scan(g, n, par0, par1, mr, cnt0, cnt1) & polmask;
     if (idle) {
         RbCtx c;
         c.time = time; c.seq_base = (uint32_t)g.hdr()[H_NEXTSEQ]; c.s0 = hdr_rng(g, H_RNGP_LO); c.k = 0; c.minr = mr; c.cancelled = false;
         #pragma unroll 1
         for (int pl = 1; pl <= 2; pl++) {
             if (!(idle & pl)) continue;
-            if (!simul && pl == 2 && (idle & 1)) { int mr2; rb_scan(g, n, par0, par1, mr2); } // player 0's new PRODUCEs are in flight now
+            if (!simul && pl == 2 && (idle & 1)) { int mr2, x0; rb_scan(g, n, par0, par1, mr2, x0, cnt1); } // player 0's new PRODUCEs are in flight now
             c.par0 = par0; c.par1 = par1;
-            rb_player(g, pl, n, simul, c);
+            rb_player(g, pl, pl == 1 ? g.list() : g.base() + g.o_pslot, pl == 1 ? cnt0 : cnt1, simul, c);
         }
         mr = c.minr;
         if (__ballot_sync(FULLM, c.cancelled)) {
