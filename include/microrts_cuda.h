@@ -53,9 +53,13 @@ enum {
     MRTS_POLICY_WORKER_RUSH = 3,   /* ai.abstraction.WorkerRush (src/ai/abstraction/WorkerRush.java:63-204) */
     MRTS_POLICY_LIGHT_RUSH = 4,    /* ai.abstraction.LightRush  (src/ai/abstraction/LightRush.java:77-258) */
     MRTS_POLICY_HEAVY_RUSH = 5,    /* ai.abstraction.HeavyRush  (src/ai/abstraction/HeavyRush.java: LightRush training Heavy units) */
-    MRTS_POLICY_RANGED_RUSH = 6    /* ai.abstraction.RangedRush (src/ai/abstraction/RangedRush.java: LightRush training Ranged units) */
+    MRTS_POLICY_RANGED_RUSH = 6,   /* ai.abstraction.RangedRush (src/ai/abstraction/RangedRush.java: LightRush training Ranged units) */
+    MRTS_POLICY_WORKER_DEFENSE = 7, /* ai.abstraction.WorkerDefense (src/ai/abstraction/WorkerDefense.java:74-209) */
+    MRTS_POLICY_LIGHT_DEFENSE = 8,  /* ai.abstraction.LightDefense  (src/ai/abstraction/LightDefense.java:78-247) */
+    MRTS_POLICY_HEAVY_DEFENSE = 9,  /* ai.abstraction.HeavyDefense  (src/ai/abstraction/HeavyDefense.java: LightDefense training Heavy units) */
+    MRTS_POLICY_RANGED_DEFENSE = 10 /* ai.abstraction.RangedDefense (src/ai/abstraction/RangedDefense.java: LightDefense training Ranged units) */
 };
-enum { MRTS_PF_ASTAR = 0, MRTS_PF_BFS = 1 };
+enum { MRTS_PF_ASTAR = 0, MRTS_PF_BFS = 1, MRTS_PF_GREEDY = 2 /* ai.abstraction.pathfinding.GreedyPathFinding */ };
 
 /* Action row formats (8 int32 per row). */
 enum {

@@ -17,8 +17,9 @@ import numpy as np
 from . import _ffi
 
 ACTIONS_VECTOR, ACTIONS_RAW = 0, 1
-POLICY_EXTERNAL, POLICY_PASSIVE, POLICY_RANDOM_BIASED, POLICY_WORKER_RUSH, POLICY_LIGHT_RUSH, POLICY_HEAVY_RUSH, POLICY_RANGED_RUSH = range(7)
-PF_ASTAR, PF_BFS = 0, 1
+(POLICY_EXTERNAL, POLICY_PASSIVE, POLICY_RANDOM_BIASED, POLICY_WORKER_RUSH, POLICY_LIGHT_RUSH, POLICY_HEAVY_RUSH, POLICY_RANGED_RUSH,
+ POLICY_WORKER_DEFENSE, POLICY_LIGHT_DEFENSE, POLICY_HEAVY_DEFENSE, POLICY_RANGED_DEFENSE) = range(11)
+PF_ASTAR, PF_BFS, PF_GREEDY = 0, 1, 2
 DTYPE_U8, DTYPE_I32, DTYPE_BITS = 0, 1, 2
 FLAG_PARTIAL_OBS = 1
 FLAG_SCRIPTED_AI = 2

@@ -33,8 +33,10 @@
 #define A0_NOUT (0xFFu << 8) // "unitType == null"
 
 enum { ACT_NONE = 0, ACT_MOVE = 1, ACT_HARVEST = 2, ACT_RETURN = 3, ACT_PRODUCE = 4, ACT_ATTACK = 5 };
-enum { POL_EXTERNAL = 0, POL_PASSIVE = 1, POL_RANDOM_BIASED = 2, POL_WORKER_RUSH = 3, POL_LIGHT_RUSH = 4, POL_HEAVY_RUSH = 5, POL_RANGED_RUSH = 6 };
-#define POL_IS_SCRIPTED(p) ((p) >= POL_WORKER_RUSH && (p) <= POL_RANGED_RUSH)
+enum { POL_EXTERNAL = 0, POL_PASSIVE = 1, POL_RANDOM_BIASED = 2, POL_WORKER_RUSH = 3, POL_LIGHT_RUSH = 4, POL_HEAVY_RUSH = 5, POL_RANGED_RUSH = 6,
+       POL_WORKER_DEFENSE = 7, POL_LIGHT_DEFENSE = 8, POL_HEAVY_DEFENSE = 9, POL_RANGED_DEFENSE = 10 };
+#define POL_IS_SCRIPTED(p) ((p) >= POL_WORKER_RUSH && (p) <= POL_RANGED_DEFENSE)
+#define POL_IS_DEFENSE(p) ((p) >= POL_WORKER_DEFENSE && (p) <= POL_RANGED_DEFENSE)
 enum { FMT_VECTOR = 0, FMT_RAW = 1 };
 enum { MODE_GAME = 0, MODE_CYCLE_ONLY = 1, MODE_ISSUE_ONLY = 2, MODE_OBSERVE = 3, MODE_MASKS = 4, MODE_ROLLOUT = 5 };
 enum { ST_OVER = 1, ST_COUNTED = 2 };
@@ -1227,10 +1229,8 @@ DEV int run_policy(Game &g, const StepParams &p, long long gi, int player, int p
                 if (p.safe) legality_pass(g, n0, pn);
             }
             return pn;
-        case POL_WORKER_RUSH:
-        case POL_LIGHT_RUSH:
-        case POL_HEAVY_RUSH:
-        case POL_RANGED_RUSH: {
+        case POL_WORKER_RUSH: case POL_LIGHT_RUSH: case POL_HEAVY_RUSH: case POL_RANGED_RUSH:
+        case POL_WORKER_DEFENSE: case POL_LIGHT_DEFENSE: case POL_HEAVY_DEFENSE: case POL_RANGED_DEFENSE: {
             if (!p.scripted) return pn;
             int n0 = pn;
             pn = policy_scripted(g, player, p.policy[player], p.pathfinder[player], pn);

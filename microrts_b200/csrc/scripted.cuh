@@ -5,6 +5,9 @@
 //   AbstractionLayerAI src/ai/abstraction/AbstractionLayerAI.java:58-113 (translateActions), :143-245 (building position)
 //   WorkerRush         src/ai/abstraction/WorkerRush.java:63-204        LightRush  src/ai/abstraction/LightRush.java:77-258
 //   HeavyRush / RangedRush  src/ai/abstraction/HeavyRush.java, RangedRush.java: LightRush with Heavy / Ranged as the trained type
+//   WorkerDefense      src/ai/abstraction/WorkerDefense.java:74-209     LightDefense  src/ai/abstraction/LightDefense.java:78-247
+//   HeavyDefense / RangedDefense  the same class as LightDefense with the trained type swapped
+//   GreedyPathFinding  src/ai/abstraction/pathfinding/GreedyPathFinding.java:53-84
 //   Attack/Harvest/Build/Train.execute   src/ai/abstraction/{Attack.java:51,Harvest.java:72,Build.java:54,Train.java:48-128}
 //
 // The AI's per-unit abstract action (the value of AbstractionLayerAI.actions for that unit) lives in the unit's X0/X1
@@ -236,7 +239,34 @@ DEVN int pf_find_t(Game &g, int kind, int s, int tx, int ty, int range, int nd) 
     return result;
 }
 
+// GreedyPathFinding.findPathToPositionInRange (GreedyPathFinding.java:53-84): the free neighbour with the smallest squared
+// distance to the target -- the first free direction is always taken, a later one only if strictly closer.  "Already in
+// range" compares the SQUARED distance with the unsquared range (:66), as the reference does.  Lanes 0..3 look at one
+// neighbour each; the choice is made on warp-uniform values.
+DEV int pf_greedy(Game &g, int s, int tx, int ty, int range, int nd) {
+    uint32_t sw = g.w0()[s];
+    int sx = u_x(sw), sy = u_y(sw), start = cell_of(g, sw);
+    if ((tx - sx) * (tx - sx) + (ty - sy) * (ty - sy) <= range) return -1;
+    int dl = g.lane & 3, np = start + doff(g, dl);
+    bool fre = g.grid()[np] == 0 && g.resv()[np] == 0;
+#pragma unroll 1
+    for (int k = 0; k < nd && fre; k++) { // ru.getPositionsUsed(): the target cells of the desires chosen so far
+        uint32_t A0 = g.pa0()[k];
+        if (a_uses_cell(a_type(A0)) && linear_target_cell(g, g.w0()[g.pslot()[k]], g.pa1()[k]) == np) fre = false;
+    }
+    int x = sx + ddx(dl), y = sy + ddy(dl);
+    int d = fre ? (tx - x) * (tx - x) + (ty - y) * (ty - y) : -1;
+    int dir = -1, min_d = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int di = __shfl_sync(FULLM, d, i);
+        if (di >= 0 && (dir == -1 || di < min_d)) { min_d = di; dir = i; }
+    }
+    return dir;
+}
+
 DEV int pf_find(Game &g, int kind, int s, int tx, int ty, int range, int nd) {
+    if (kind == 2) return pf_greedy(g, s, tx, ty, range, nd);
     return g.as_sm ? pf_find_t<true>(g, kind, s, tx, ty, range, nd) : pf_find_t<false>(g, kind, s, tx, ty, range, nd);
 }
 
@@ -374,15 +404,28 @@ DEVN int find_building_position(const Game &g, const int *reserved, int nres, in
     return -1;
 }
 
-DEV void script_melee(Game &g, int s, int player) { // meleeUnitBehavior (WorkerRush.java:105-121, LightRush.java:141-159)
+// meleeUnitBehavior.  The rushes attack the closest enemy (WorkerRush.java:105-121, LightRush.java:141-159).  The defenses
+// (WorkerDefense.java:117-146, LightDefense.java:142-165) do so only while that enemy, or the own base -- the LAST own base
+// of the unit list, distance 0 without one -- is closer than height/2; otherwise they put an Attack with a null target,
+// which translateActions finds completed and deletes (so the unit's next entry goes to the end of the map).
+DEV void script_melee(Game &g, int s, int player, bool defense) {
     int n = g.hdr()[H_NUNITS];
     uint32_t w = g.w0()[s];
-    int closest = w_argmin(g, n, [&](int, uint32_t ow) { return (u_pl(ow) != 0 && u_pl(ow) != player + 1) ? iabs(u_x(ow) - u_x(w)) + iabs(u_y(ow) - u_y(w)) : -1; });
+    int cd = 0;
+    int closest = w_argmin(g, n, [&](int, uint32_t ow) { return (u_pl(ow) != 0 && u_pl(ow) != player + 1) ? iabs(u_x(ow) - u_x(w)) + iabs(u_y(ow) - u_y(w)) : -1; }, &cd);
+    if (defense) {
+        int last = w_argmin(g, n, [&](int i, uint32_t ow) { return (u_pl(ow) == player + 1 && u_type(ow) == 1 /* baseType */) ? 255 - i : -1; });
+        int mybase = 0;
+        if (last >= 0) { uint32_t bw = g.w0()[last]; mybase = iabs(u_x(bw) - u_x(w)) + iabs(u_y(bw) - u_y(w)); }
+        if (closest >= 0 && (cd < g.H / 2 || mybase < g.H / 2)) aa_put(g, s, player, AA_ATTACK, 0, 0, 0, closest + 1, REF_NULL);
+        else aa_put(g, s, player, AA_ATTACK, 0, 0, 0, REF_NULL, REF_NULL);
+        return;
+    }
     if (closest >= 0) aa_put(g, s, player, AA_ATTACK, 0, 0, 0, closest + 1, REF_NULL);
 }
 
 // harvest part of workersBehavior (WorkerRush.java:148-199, LightRush.java:203-252); true if the worker is still free
-DEV bool script_harvest(Game &g, int s, int player) {
+DEV bool script_harvest(Game &g, int s, int player, bool defense) {
     int n = g.hdr()[H_NUNITS];
     uint32_t w = g.w0()[s];
     int cres = w_argmin(g, n, [&](int, uint32_t ow) { return (ut_flags(g, u_type(ow)) & UF_RESOURCE) ? iabs(u_x(ow) - u_x(w)) + iabs(u_y(ow) - u_y(w)) : -1; });
@@ -390,6 +433,11 @@ DEV bool script_harvest(Game &g, int s, int player) {
         return ((ut_flags(g, u_type(ow)) & UF_STOCKPILE) && u_pl(ow) == player + 1) ? iabs(u_x(ow) - u_x(w)) + iabs(u_y(ow) - u_y(w)) : -1; });
     uint32_t X0 = g.x0()[s], X1 = g.x1()[s];
     bool is_h = aa_kind(X0) == AA_HARVEST;
+    if (defense) { // WorkerDefense.java:197-209, LightDefense.java:236-244: no special case for a worker carrying resources,
+        // and a worker that cannot harvest is never sent to attack
+        if (cres >= 0 && cbase >= 0 && (!is_h || aa_target(X1) != cres + 1 || aa_base(X1) != cbase + 1)) aa_put(g, s, player, AA_HARVEST, 0, 0, 0, cres + 1, cbase + 1);
+        return false;
+    }
     if (u_res(g.w1()[s]) > 0) {
         if (cbase >= 0) {
             if (!is_h || aa_base(X1) != cbase + 1) aa_put(g, s, player, AA_HARVEST, 0, 0, 0, REF_NULL, cbase + 1);
@@ -426,8 +474,10 @@ DEVN int policy_scripted(Game &g, int player, int kind, int pathfinder, int pn) 
     reserved_resources(g, par0, par1);
     __syncwarp();
     const int n = g.hdr()[H_NUNITS], pl = player + 1, pres = g.hdr()[H_RES0 + player];
-    const bool light = kind != POL_WORKER_RUSH; // the barracks rushes: LightRush, and HeavyRush / RangedRush = the same class with the trained type swapped
-    const int UT_RUSH = kind == POL_HEAVY_RUSH ? 5 : (kind == POL_RANGED_RUSH ? 6 : UT_LIGHT); // HeavyRush.java:55, RangedRush.java:52
+    // the barracks scripts: LightRush / LightDefense, and Heavy* / Ranged* = the same classes with the trained type swapped;
+    // the defenses share their rush's skeleton and differ in script_melee / script_harvest
+    const bool light = kind != POL_WORKER_RUSH && kind != POL_WORKER_DEFENSE, defense = POL_IS_DEFENSE(kind);
+    const int UT_RUSH = (kind == POL_HEAVY_RUSH || kind == POL_HEAVY_DEFENSE) ? 5 : ((kind == POL_RANGED_RUSH || kind == POL_RANGED_DEFENSE) ? 6 : UT_LIGHT); // HeavyRush.java:55, RangedRush.java:52
     auto own_harvester = [&](int, uint32_t w) { return u_pl(w) == pl && (ut_flags(g, u_type(w)) & UF_HARVEST) != 0; };
     // bases (WorkerRush.java:70-76,100-102; LightRush.java:83-89,123-133)
 #pragma unroll 1
@@ -450,7 +500,7 @@ DEVN int policy_scripted(Game &g, int player, int kind, int pathfinder, int pn) 
     for (int i = 0; i < n; i++) { // melee units
         uint32_t w = g.w0()[i];
         int fl = ut_flags(g, u_type(w));
-        if ((fl & UF_ATTACK) && !(fl & UF_HARVEST) && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE) script_melee(g, i, player);
+        if ((fl & UF_ATTACK) && !(fl & UF_HARVEST) && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE) script_melee(g, i, player, defense);
     }
     // workers: all own harvesters, busy ones too, in list order
     int nbases = w_count(g, n, [&](int, uint32_t w) { return u_pl(w) == pl && u_type(w) == UT_BASE; });
@@ -469,17 +519,17 @@ DEVN int policy_scripted(Game &g, int player, int kind, int pathfinder, int pn) 
             // harvest with every remaining worker; those that cannot, attack -- in a second pass, as the reference does
             uint32_t still[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll 1
-            for (int i = w_next(g, n, wi, own_harvester); i >= 0; i = w_next(g, n, i, own_harvester)) if (script_harvest(g, i, player)) still[i >> 5] |= 1u << (i & 31);
+            for (int i = w_next(g, n, wi, own_harvester); i >= 0; i = w_next(g, n, i, own_harvester)) if (script_harvest(g, i, player, defense)) still[i >> 5] |= 1u << (i & 31);
 #pragma unroll 1
-            for (int i = w_next(g, n, wi, own_harvester); i >= 0; i = w_next(g, n, i, own_harvester)) if (still[i >> 5] & (1u << (i & 31))) script_melee(g, i, player);
+            for (int i = w_next(g, n, wi, own_harvester); i >= 0; i = w_next(g, n, i, own_harvester)) if (still[i >> 5] & (1u << (i & 31))) script_melee(g, i, player, defense);
         } else {
             // WorkerRush.java:146-202: one harvester, the rest attack; a harvester that stays free is appended at the END
             int hw = -1;
             if (taken < nworkers) { hw = w_next(g, n, wi, own_harvester); wi = hw; taken++; }
-            bool hw_free = hw >= 0 && script_harvest(g, hw, player);
+            bool hw_free = hw >= 0 && script_harvest(g, hw, player, defense);
 #pragma unroll 1
-            for (int i = w_next(g, n, wi, own_harvester); i >= 0; i = w_next(g, n, i, own_harvester)) script_melee(g, i, player);
-            if (hw_free) script_melee(g, hw, player);
+            for (int i = w_next(g, n, wi, own_harvester); i >= 0; i = w_next(g, n, i, own_harvester)) script_melee(g, i, player, defense);
+            if (hw_free) script_melee(g, hw, player, defense);
         }
     }
     // ---- translateActions (AbstractionLayerAI.java:58-113): abstract actions in insertion order --------------------

@@ -75,6 +75,22 @@ class ai:
     def RangedRush(utt=None, pathfinder=M.PF_ASTAR):
         return AISpec(M.POLICY_RANGED_RUSH, pathfinder)
 
+    @staticmethod
+    def WorkerDefense(utt=None, pathfinder=M.PF_ASTAR):
+        return AISpec(M.POLICY_WORKER_DEFENSE, pathfinder)
+
+    @staticmethod
+    def LightDefense(utt=None, pathfinder=M.PF_ASTAR):
+        return AISpec(M.POLICY_LIGHT_DEFENSE, pathfinder)
+
+    @staticmethod
+    def HeavyDefense(utt=None, pathfinder=M.PF_ASTAR):
+        return AISpec(M.POLICY_HEAVY_DEFENSE, pathfinder)
+
+    @staticmethod
+    def RangedDefense(utt=None, pathfinder=M.PF_ASTAR):
+        return AISpec(M.POLICY_RANGED_DEFENSE, pathfinder)
+
 
 def _device_array(shape, dtype, emulated):
     """Memory the engine writes 'on device': a torch CUDA tensor, or host memory when the library is the test emulator."""

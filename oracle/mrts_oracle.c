@@ -848,8 +848,29 @@ static int decode_first_step(const OPf *p, int pos, int parent, int w) {
     return -1;
 }
 
+/* GreedyPathFinding.findPathToPositionInRange, GreedyPathFinding.java:53-84: the free neighbour closest (Euclidean^2) to the
+ * target; the first free direction is always taken, a later one only if strictly closer; "already in range" compares the
+ * SQUARED distance with the unsquared range (:66), as the reference does */
+static int pf_greedy(const OGame *g, int start, int targetpos, int range, const ORu *ru) {
+    int w = g->w, h = g->h;
+    const OUnit *s = &g->pool[start];
+    int x1 = s->x, y1 = s->y, x2 = targetpos % w, y2 = targetpos / w;
+    int min_d = (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1), direction = -1;
+    if (min_d <= range) return -1;
+    for (int i = 0; i < 4; i++) {
+        int x = x1 + DX[i], y = y1 + DY[i];
+        if (x >= 0 && x < w && y >= 0 && y < h && gs_free(g, x, y)) {
+            if (ru && ru_contains(ru, x + y * w)) continue;
+            int d = (x2 - x) * (x2 - x) + (y2 - y) * (y2 - y);
+            if (direction == -1 || d < min_d) { min_d = d; direction = i; }
+        }
+    }
+    return direction;
+}
+
 static int pf_find(const OGame *g, int kind, int start, int targetpos, int range, const ORu *ru) {
     int w = g->w, h = g->h, n = w * h;
+    if (kind == O_PF_GREEDY) return pf_greedy(g, start, targetpos, range, ru);
     OPf p; pf_alloc(&p, n);
     memset(p.free_, -1, n);
     for (int i = 0; i < n; i++) { p.closed[i] = -1; p.inoc[i] = 0; }
@@ -1110,15 +1131,28 @@ static void build_if_not_already(OAi *ai, const OGame *g, int u, int type, int d
 }
 
 /* WorkerRush/LightRush.meleeUnitBehavior (WorkerRush.java:105-121, LightRush.java:141-159) */
+static int is_defense(int kind) { return kind >= O_AI_WORKER_DEFENSE && kind <= O_AI_RANGED_DEFENSE; }
+
+/* meleeUnitBehavior: the rushes attack the closest enemy (WorkerRush.java:105-121, LightRush.java:141-159); the defenses do
+ * so only while the enemy or the own base (the LAST own base of the unit list; 0 without one) is closer than height/2, and
+ * otherwise put an Attack with a null target, which translateActions deletes as completed
+ * (WorkerDefense.java:117-146, LightDefense.java:142-165) */
 static void melee_behavior(OAi *ai, const OGame *g, int u, int player) {
-    int closest = -1, cd = 0;
+    int closest = -1, cd = 0, mybase = 0;
     const OUnit *me = &g->pool[u];
     for (int i = 0; i < g->n; i++) {
         const OUnit *o = &g->pool[g->list[i]];
         if (o->player >= 0 && o->player != player) {
             int d = abs(o->x - me->x) + abs(o->y - me->y);
             if (closest < 0 || d < cd) { closest = g->list[i]; cd = d; }
+        } else if (o->player == player && o->type == 1 /* baseType */) {
+            mybase = abs(o->x - me->x) + abs(o->y - me->y);
         }
+    }
+    if (is_defense(ai->kind)) {
+        if (closest >= 0 && (cd < g->h / 2 || mybase < g->h / 2)) ai_attack(ai, u, closest);
+        else ai_attack(ai, u, -1);
+        return;
     }
     if (closest >= 0) ai_attack(ai, u, closest);
 }
@@ -1138,6 +1172,13 @@ static int harvest_behavior(OAi *ai, const OGame *g, int u, int player) {
     }
     int still_free = 1;
     OAbs *aa = ai_get(ai, u);
+    if (is_defense(ai->kind)) { /* WorkerDefense.java:197-209, LightDefense.java:236-244: no carrying-resources special case */
+        if (cres >= 0 && cbase >= 0) {
+            if (aa && aa->kind == AA_HARVEST) { if (aa->target != cres || aa->base != cbase) ai_harvest(ai, u, cres, cbase); }
+            else ai_harvest(ai, u, cres, cbase);
+        }
+        return 0; /* the defenses never send a worker that cannot harvest to attack */
+    }
     if (me->res > 0) {
         if (cbase >= 0) {
             if (aa && aa->kind == AA_HARVEST) { if (aa->base != cbase) ai_harvest(ai, u, -1, cbase); }
@@ -1163,14 +1204,16 @@ static int ai_get_action(OAi *ai, OGame *g, int player, OPair *out) {
     const OUtt *t = g->utt;
     int BASE = type_by_role_base(), BARRACKS = type_by_role_barracks(), WORKER = type_by_role_worker();
     /* the combat unit the barracks train: Light (LightRush.java:57), Heavy (HeavyRush.java:55), Ranged (RangedRush.java:52) */
-    int LIGHT = ai->kind == O_AI_HEAVY_RUSH ? 5 : (ai->kind == O_AI_RANGED_RUSH ? 6 : type_by_role_light());
-    int barracks_rush = ai->kind == O_AI_LIGHT_RUSH || ai->kind == O_AI_HEAVY_RUSH || ai->kind == O_AI_RANGED_RUSH;
+    /* the defenses: WorkerDefense.java = WorkerRush's skeleton, {Light,Heavy,Ranged}Defense.java = LightRush's, with the melee and
+     * harvest rules swapped (melee_behavior / harvest_behavior) */
+    int LIGHT = (ai->kind == O_AI_HEAVY_RUSH || ai->kind == O_AI_HEAVY_DEFENSE) ? 5 : ((ai->kind == O_AI_RANGED_RUSH || ai->kind == O_AI_RANGED_DEFENSE) ? 6 : type_by_role_light());
+    int barracks_rush = ai->kind != O_AI_WORKER_RUSH && ai->kind != O_AI_WORKER_DEFENSE;
     int pres = g->res[player];
     /* bases: WorkerRush.java:70-76,100-102 ; LightRush.java:83-89,123-133 */
     for (int i = 0; i < g->n; i++) {
         int u = g->list[i]; const OUnit *un = &g->pool[u];
         if (un->type == BASE && un->player == player && find_assign(g, u) < 0) {
-            if (ai->kind == O_AI_WORKER_RUSH) {
+            if (!barracks_rush) {
                 if (pres >= t->f[WORKER][OF_COST]) ai_train(ai, u, WORKER);
             } else {
                 int nworkers = 0;
@@ -1420,7 +1463,9 @@ static int policy(OGame *g, int kind, OAi *ai, int player, OPair *out) {
         case O_AI_WORKER_RUSH:
         case O_AI_LIGHT_RUSH:
         case O_AI_HEAVY_RUSH:
-        case O_AI_RANGED_RUSH: return ai_get_action(ai, g, player, out);
+        case O_AI_RANGED_RUSH:
+        case O_AI_WORKER_DEFENSE: case O_AI_LIGHT_DEFENSE: case O_AI_HEAVY_DEFENSE:
+        case O_AI_RANGED_DEFENSE: return ai_get_action(ai, g, player, out);
         default: return 0; /* PassiveAI: empty PlayerAction */
     }
 }

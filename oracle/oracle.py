@@ -14,9 +14,11 @@ _LIB = None
 
 TYPE_NAMES = ["Resource", "Base", "Barracks", "Worker", "Light", "Heavy", "Ranged"]
 NONE, MOVE, HARVEST, RETURN, PRODUCE, ATTACK = range(6)
-AI_NONE, AI_PASSIVE, AI_RANDOM_BIASED, AI_WORKER_RUSH, AI_LIGHT_RUSH, AI_HEAVY_RUSH, AI_RANGED_RUSH = range(7)
-SCRIPTED_AIS = (AI_WORKER_RUSH, AI_LIGHT_RUSH, AI_HEAVY_RUSH, AI_RANGED_RUSH)
-PF_ASTAR, PF_BFS = 0, 1
+(AI_NONE, AI_PASSIVE, AI_RANDOM_BIASED, AI_WORKER_RUSH, AI_LIGHT_RUSH, AI_HEAVY_RUSH, AI_RANGED_RUSH,
+ AI_WORKER_DEFENSE, AI_LIGHT_DEFENSE, AI_HEAVY_DEFENSE, AI_RANGED_DEFENSE) = range(11)
+SCRIPTED_AIS = (AI_WORKER_RUSH, AI_LIGHT_RUSH, AI_HEAVY_RUSH, AI_RANGED_RUSH,
+                AI_WORKER_DEFENSE, AI_LIGHT_DEFENSE, AI_HEAVY_DEFENSE, AI_RANGED_DEFENSE)
+PF_ASTAR, PF_BFS, PF_GREEDY = 0, 1, 2
 
 
 def build(force=False):

@@ -511,6 +511,16 @@ SCRIPTED = [
     ("16x16/basesWorkers16x16", "HEAVY_RUSH", "RANGED_RUSH", 0),
     ("8x8/basesWorkers8x8", "RANGED_RUSH", "LIGHT_RUSH", 1),
     ("24x24/basesWorkers24x24", "RANGED_RUSH", "HEAVY_RUSH", 0),
+    # the defenses (WorkerDefense / LightDefense / HeavyDefense / RangedDefense) and GreedyPathFinding (pathfinder 2)
+    ("8x8/basesWorkers8x8", "WORKER_DEFENSE", "WORKER_RUSH", 0),
+    ("16x16/basesWorkers16x16", "LIGHT_RUSH", "LIGHT_DEFENSE", 0),
+    ("16x16/basesWorkers16x16", "HEAVY_DEFENSE", "RANGED_DEFENSE", 1),
+    ("24x24/basesWorkers24x24", "RANGED_DEFENSE", "WORKER_DEFENSE", 0),
+    ("8x8/FourBasesWorkers8x8", "LIGHT_DEFENSE", "RANDOM_BIASED", 0),
+    ("16x16/TwoBasesBarracks16x16", "RANDOM_BIASED", "HEAVY_DEFENSE", 2),
+    ("16x16/basesWorkers16x16", "WORKER_RUSH", "LIGHT_RUSH", 2),
+    ("8x8/basesWorkers8x8", "RANGED_RUSH", "WORKER_DEFENSE", 2),
+    ("BWDistantResources32x32", "LIGHT_RUSH", "RANGED_RUSH", 2),
 ]
 
 
