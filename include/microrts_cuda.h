@@ -57,7 +57,11 @@ enum {
     MRTS_POLICY_WORKER_DEFENSE = 7, /* ai.abstraction.WorkerDefense (src/ai/abstraction/WorkerDefense.java:74-209) */
     MRTS_POLICY_LIGHT_DEFENSE = 8,  /* ai.abstraction.LightDefense  (src/ai/abstraction/LightDefense.java:78-247) */
     MRTS_POLICY_HEAVY_DEFENSE = 9,  /* ai.abstraction.HeavyDefense  (src/ai/abstraction/HeavyDefense.java: LightDefense training Heavy units) */
-    MRTS_POLICY_RANGED_DEFENSE = 10 /* ai.abstraction.RangedDefense (src/ai/abstraction/RangedDefense.java: LightDefense training Ranged units) */
+    MRTS_POLICY_RANGED_DEFENSE = 10, /* ai.abstraction.RangedDefense (src/ai/abstraction/RangedDefense.java: LightDefense training Ranged units) */
+    /* src/ai/abstraction/partialobservability/PO{Worker,Light,Heavy,Ranged}Rush.java: the rush, whose idle combat units walk to
+       the nearest cell outside their player's sight when no enemy is visible (MRTS_FLAG_PO_POLICIES batches; without the flag
+       they behave as the plain rushes, as the reference classes do on a fully observable GameState) */
+    MRTS_POLICY_PO_WORKER_RUSH = 11, MRTS_POLICY_PO_LIGHT_RUSH = 12, MRTS_POLICY_PO_HEAVY_RUSH = 13, MRTS_POLICY_PO_RANGED_RUSH = 14
 };
 enum { MRTS_PF_ASTAR = 0, MRTS_PF_BFS = 1, MRTS_PF_GREEDY = 2 /* ai.abstraction.pathfinding.GreedyPathFinding */ };
 
@@ -73,7 +77,9 @@ enum {
 enum { MRTS_DTYPE_U8 = 0, MRTS_DTYPE_I32 = 1, MRTS_DTYPE_BITS = 2 /* masks only: element j of a row is bit j & 7 of byte j >> 3 */ };
 enum {
     MRTS_FLAG_PARTIAL_OBS = 1u,
-    MRTS_FLAG_SCRIPTED_AI = 2u /* reserve pathfinding scratch so WORKER_RUSH / LIGHT_RUSH policies can be selected */
+    MRTS_FLAG_SCRIPTED_AI = 2u, /* reserve pathfinding scratch so WORKER_RUSH / LIGHT_RUSH policies can be selected */
+    MRTS_FLAG_PO_POLICIES = 4u  /* Game(partiallyObservable = true), src/rts/Game.java:129-134: each device policy decides on its
+                                   player's PartiallyObservableGameState view; the lists go through issueSafe on the real state */
 };
 enum { MRTS_EVAL_SIMPLE_SQRT3 = 0, MRTS_EVAL_SIMPLE = 1 };
 

@@ -18,11 +18,13 @@ from . import _ffi
 
 ACTIONS_VECTOR, ACTIONS_RAW = 0, 1
 (POLICY_EXTERNAL, POLICY_PASSIVE, POLICY_RANDOM_BIASED, POLICY_WORKER_RUSH, POLICY_LIGHT_RUSH, POLICY_HEAVY_RUSH, POLICY_RANGED_RUSH,
- POLICY_WORKER_DEFENSE, POLICY_LIGHT_DEFENSE, POLICY_HEAVY_DEFENSE, POLICY_RANGED_DEFENSE) = range(11)
+ POLICY_WORKER_DEFENSE, POLICY_LIGHT_DEFENSE, POLICY_HEAVY_DEFENSE, POLICY_RANGED_DEFENSE,
+ POLICY_PO_WORKER_RUSH, POLICY_PO_LIGHT_RUSH, POLICY_PO_HEAVY_RUSH, POLICY_PO_RANGED_RUSH) = range(15)
 PF_ASTAR, PF_BFS, PF_GREEDY = 0, 1, 2
 DTYPE_U8, DTYPE_I32, DTYPE_BITS = 0, 1, 2
 FLAG_PARTIAL_OBS = 1
 FLAG_SCRIPTED_AI = 2
+FLAG_PO_POLICIES = 4
 
 
 class MicroRTSError(RuntimeError):
@@ -171,13 +173,14 @@ def _ptr(a):
 class BatchedGameState:
     """n independent GameState objects stepped in lockstep on one GPU (rts.cuda.BatchedGameState)."""
 
-    def __init__(self, utt, pgs, n_games, device=0, partial_obs=False, unit_capacity=0, scripted_ai=False):
+    def __init__(self, utt, pgs, n_games, device=0, partial_obs=False, unit_capacity=0, scripted_ai=False, po_policies=False):
+        """po_policies: Game(partiallyObservable=true) -- device policies decide on their player's PartiallyObservableGameState view."""
         maps = list(pgs) if isinstance(pgs, (list, tuple)) else [pgs]
         self.utt, self.maps, self.n = utt, maps, int(n_games)
         arr = (C.c_void_p * len(maps))(*[m._h for m in maps])
         h = C.c_void_p()
         _check(_ffi.lib().mrts_batch_create(utt._h, arr, len(maps), self.n, device,
-                                            (FLAG_PARTIAL_OBS if partial_obs else 0) | (FLAG_SCRIPTED_AI if scripted_ai else 0),
+                                            (FLAG_PARTIAL_OBS if partial_obs else 0) | (FLAG_SCRIPTED_AI if scripted_ai else 0) | (FLAG_PO_POLICIES if po_policies else 0),
                                             unit_capacity, C.byref(h)))
         self._h = h
         self.width, self.height = maps[0].getWidth(), maps[0].getHeight()

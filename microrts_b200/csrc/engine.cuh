@@ -34,8 +34,10 @@
 
 enum { ACT_NONE = 0, ACT_MOVE = 1, ACT_HARVEST = 2, ACT_RETURN = 3, ACT_PRODUCE = 4, ACT_ATTACK = 5 };
 enum { POL_EXTERNAL = 0, POL_PASSIVE = 1, POL_RANDOM_BIASED = 2, POL_WORKER_RUSH = 3, POL_LIGHT_RUSH = 4, POL_HEAVY_RUSH = 5, POL_RANGED_RUSH = 6,
-       POL_WORKER_DEFENSE = 7, POL_LIGHT_DEFENSE = 8, POL_HEAVY_DEFENSE = 9, POL_RANGED_DEFENSE = 10 };
-#define POL_IS_SCRIPTED(p) ((p) >= POL_WORKER_RUSH && (p) <= POL_RANGED_DEFENSE)
+       POL_WORKER_DEFENSE = 7, POL_LIGHT_DEFENSE = 8, POL_HEAVY_DEFENSE = 9, POL_RANGED_DEFENSE = 10,
+       POL_PO_WORKER_RUSH = 11, POL_PO_LIGHT_RUSH = 12, POL_PO_HEAVY_RUSH = 13, POL_PO_RANGED_RUSH = 14 };
+#define POL_IS_SCRIPTED(p) ((p) >= POL_WORKER_RUSH && (p) <= POL_PO_RANGED_RUSH)
+#define POL_IS_PO_RUSH(p) ((p) >= POL_PO_WORKER_RUSH && (p) <= POL_PO_RANGED_RUSH)
 #define POL_IS_DEFENSE(p) ((p) >= POL_WORKER_DEFENSE && (p) <= POL_RANGED_DEFENSE)
 enum { FMT_VECTOR = 0, FMT_RAW = 1 };
 enum { MODE_GAME = 0, MODE_CYCLE_ONLY = 1, MODE_ISSUE_ONLY = 2, MODE_OBSERVE = 3, MODE_MASKS = 4, MODE_ROLLOUT = 5 };
@@ -74,6 +76,7 @@ struct StepParams {
     int out_dtype;             // 0 = u8, 1 = i32, 2 = bit-packed (masks only)
     int out_player;
     int partial_obs;
+    int po_policies;           // MRTS_FLAG_PO_POLICIES: device policies decide on their player's partially observable view
     int sequential_issue;      // MODE_GAME: player 1 decides on the state that already holds player 0's actions
                                // (JNIGridnetClientSelfPlay.gameStep) instead of both deciding on the pre-issue state (Game.start)
     int32_t *info_out;         // MODE_GAME: [n_games][2][MRTS_INFO_WORDS] per-player step facts for the reward functions (or NULL)
@@ -110,6 +113,8 @@ struct Game {
     int W, H, P, cap, pcw, conflict, uw; // uw: unit words mirrored in HBM (7, or 9 with scripted policies)
     uint32_t sb, cb;                      // shared-window addresses of this game's region and of the CTA's constant block
     int o_pa0, o_pa1, o_pslot, o_grid, o_kind, o_resv, o_claim, o_list;
+    int o_povis, o_pohid;                 // MRTS_FLAG_PO_POLICIES batches only (layout.h)
+    bool po_view;                         // the unit table currently shows one player's partially observable view (po_hide)
     int o_rdy, uoff[MRTS_UNIT_WORDS + 1]; // byte offsets of the unit word arrays inside the region (host-computed constants)
     int pview;                            // window into the pending list (policy_scripted stages desires behind the final part)
     const uint32_t *grid_tmpl;            // global: wall-padded empty grid of this game's map
@@ -137,6 +142,8 @@ struct Game {
     MDEV uint8_t *resv() const { return base() + o_resv; }
     MDEV uint8_t *claim() const { return base() + o_claim; }
     MDEV uint8_t *list() const { return base() + o_list; }
+    MDEV uint8_t *vis() const { return base() + o_povis; }
+    MDEV uint32_t *hid() const { return (uint32_t *)(base() + o_pohid); }
     MDEV const uint32_t *utt() const { return (const uint32_t *)smem_ptr(cb); }
     MDEV const uint64_t *jump() const { return (const uint64_t *)smem_ptr(cb + MRTS_MAX_TYPES * MRTS_UTT_WORDS * 4); }
 };
@@ -149,7 +156,7 @@ DEV void g_bind(Game &g, int region, const SmemLayout &L, int W, int H, int cap,
     g.uw = L.uws - 1; // host-computed: 7, or 9 for scripted batches
     g.sb = smem_window(region); g.cb = smem_window(0); g.pview = 0;
     g.o_pa0 = L.pa0; g.o_pa1 = L.pa1; g.o_pslot = L.pslot; g.o_grid = L.grid; g.o_kind = L.kind; g.o_resv = L.resv;
-    g.o_claim = L.claim; g.o_list = L.list;
+    g.o_claim = L.claim; g.o_list = L.list; g.o_povis = L.povis; g.o_pohid = L.pohid; g.po_view = false;
     { int pc = (W + 2) * (H + 2); g.as_closed = (uint16_t *)(astar_global ? astar_global : mrts_smem + region + L.astar); g.as_xy = g.as_closed + pc;
       g.as_mark = g.as_xy + pc; g.as_next = g.as_mark + pc; g.as_head = g.as_next + pc; g.as_gen = g.as_head + MRTS_ASTAR_HEADS(W, H);
       g.as_sm = (scripted == 1) ? smem_window(region + L.astar) : 0u; }
@@ -159,6 +166,8 @@ DEV void g_bind(Game &g, int region, const SmemLayout &L, int W, int H, int cap,
 // ---- small accessors -------------------------------------------------------------------------------------------------
 DEV int u_type(uint32_t w) { return w & 0xff; }
 DEV int u_pl(uint32_t w) { return (w >> 8) & 0xff; } // 0 neutral, 1 = player 0, 2 = player 1
+#define HIDDEN_TYPE 7 // po_hide: a unit hidden from the deciding player's view shows as a neutral unit of this unused type
+DEV bool w_hidden(uint32_t w) { return (w & 0xffffu) == (uint32_t)HIDDEN_TYPE; }
 DEV int u_x(uint32_t w) { return (w >> 16) & 0xff; }
 DEV int u_y(uint32_t w) { return w >> 24; }
 DEV int cell_of(const Game &g, uint32_t w) { return (u_y(w) + 1) * g.P + u_x(w) + 1; }
@@ -461,7 +470,7 @@ DEV void reserved_resources(const Game &g, int &r0, int &r1) {
     #pragma unroll 1
     for (int i = g.lane; i < n; i += 32) {
         uint32_t A0 = g.a0()[i];
-        if (a_type(A0) == ACT_PRODUCE) { int c = ut_cost(g, a_utype(A0)); if (u_pl(g.w0()[i]) == 1) a += c; else b += c; }
+        if (a_type(A0) == ACT_PRODUCE) { int c = ut_cost(g, a_utype(A0)), pl = u_pl(g.w0()[i]); if (pl == 1) a += c; else if (pl == 2) b += c; } // pl 0: hidden by po_hide
     }
     r0 = __reduce_add_sync(FULLM, a); r1 = __reduce_add_sync(FULLM, b);
 }
@@ -1216,9 +1225,70 @@ DEV void rb_player(Game &g, int pl, const uint8_t *list, int cnt, bool simul, Rb
 struct WarpStats { unsigned long long v[8]; }; // lives in shared memory; only lane 0 updates it
 DEV void stat_add(WarpStats &ws, int lane, int k, unsigned long long d) { if (lane == 0) ws.v[k] += d; }
 
+// ---- PartiallyObservableGameState(gs, player) as seen by a device policy (PartiallyObservableGameState.java:35-71) --------
+// MRTS_FLAG_PO_POLICIES batches (Game with partiallyObservable = true, Game.java:129-134).  Instead of building a filtered
+// copy, the units the player cannot see are hidden in place for the duration of its getAction: their W0 word is parked in
+// hid[] and replaced by a neutral unit of the unused type 7 (no flags, so no predicate of any policy matches it), and their
+// cell and the cell their in-flight MOVE/PRODUCE reserves are cleared from the grid / kind / resv maps (removeUnit also drops
+// the unit's assignment from the view).  vis[] keeps the player's sight map for the PO rushes' exploration.  Slots do not
+// move, so the policy's list and abstract actions refer to the real state; po_unhide restores everything.
+DEV void stamp_sight(Game &g, uint8_t *map, uint32_t w);
+DEVN void po_hide(Game &g, int observer) {
+    int n = g.hdr()[H_NUNITS];
+    __syncwarp();
+#pragma unroll 1
+    for (int i = g.lane; i < g.pcw; i += 32) ((uint32_t *)g.vis())[i] = 0;
+    __syncwarp();
+#pragma unroll 1
+    for (int i = 0; i < n; i++) { uint32_t w = g.w0()[i]; if (u_pl(w) == observer + 1) stamp_sight(g, g.vis(), w); }
+    __syncwarp();
+#pragma unroll 1
+    for (int i = g.lane; i < n; i += 32) {
+        uint32_t w = g.w0()[i];
+        int c = cell_of(g, w);
+        bool hide = u_pl(w) != observer + 1 && !g.vis()[c];
+        g.hid()[i] = hide ? (w | 0x8000u) : 0u; // bit 15 marks the entry: a resource at (0, 0) is the all-zero word
+        if (hide) {
+            g.w0()[i] = (uint32_t)HIDDEN_TYPE | (w & 0xffff0000u);
+            g.grid()[c] = 0; g.kind()[c] = 0;
+            uint32_t A0 = g.a0()[i];
+            if (a_uses_cell(a_type(A0))) { int tc = target_cell(g, c, g.a1()[i]); if (g.resv()[tc] == (uint8_t)(i + 1)) g.resv()[tc] = 0; }
+        }
+    }
+    g.po_view = true;
+    __syncwarp();
+}
+DEVN void po_unhide(Game &g) {
+    int n = g.hdr()[H_NUNITS];
+    __syncwarp();
+#pragma unroll 1
+    for (int i = g.lane; i < n; i += 32) {
+        uint32_t w = g.hid()[i];
+        if (w == 0u) continue;
+        w &= ~0x8000u;
+        int c = cell_of(g, w);
+        g.w0()[i] = w;
+        g.grid()[c] = (uint8_t)(i + 1); g.kind()[c] = (uint8_t)kind_of(g, w);
+        uint32_t A0 = g.a0()[i];
+        if (a_uses_cell(a_type(A0))) { int tc = target_cell(g, c, g.a1()[i]); if (g.resv()[tc] == 0) g.resv()[tc] = (uint8_t)(i + 1); }
+    }
+    g.po_view = false;
+    __syncwarp();
+}
+
 DEV int run_policy(Game &g, const StepParams &p, long long gi, int player, int pn, bool first_iter) {
-    switch (p.policy[player]) {
-        case POL_RANDOM_BIASED: return policy_random_biased(g, player, pn);
+    const int pol = p.policy[player];
+    const bool po = p.po_policies && (pol == POL_RANDOM_BIASED || POL_IS_SCRIPTED(pol)); // the policy sees its PO view
+    switch (pol) {
+        case POL_RANDOM_BIASED: {
+            if (!po) return policy_random_biased(g, player, pn);
+            int n0 = pn;
+            po_hide(g, player);
+            pn = policy_random_biased(g, player, pn);
+            po_unhide(g);
+            legality_pass(g, n0, pn); // issueSafe on the real state (Game.java:136-137): a move into a cell a hidden unit holds becomes NONE
+            return pn;
+        }
         case POL_EXTERNAL:
             if (first_iter && p.ext_actions[player]) {
                 int cnt = p.ext_counts[player] ? p.ext_counts[player][gi] : p.ext_maxk[player];
@@ -1230,10 +1300,13 @@ DEV int run_policy(Game &g, const StepParams &p, long long gi, int player, int p
             }
             return pn;
         case POL_WORKER_RUSH: case POL_LIGHT_RUSH: case POL_HEAVY_RUSH: case POL_RANGED_RUSH:
-        case POL_WORKER_DEFENSE: case POL_LIGHT_DEFENSE: case POL_HEAVY_DEFENSE: case POL_RANGED_DEFENSE: {
+        case POL_WORKER_DEFENSE: case POL_LIGHT_DEFENSE: case POL_HEAVY_DEFENSE: case POL_RANGED_DEFENSE:
+        case POL_PO_WORKER_RUSH: case POL_PO_LIGHT_RUSH: case POL_PO_HEAVY_RUSH: case POL_PO_RANGED_RUSH: {
             if (!p.scripted) return pn;
             int n0 = pn;
-            pn = policy_scripted(g, player, p.policy[player], p.pathfinder[player], pn);
+            if (po) po_hide(g, player);
+            pn = policy_scripted(g, player, pol, p.pathfinder[player], pn);
+            if (po) po_unhide(g);
             legality_pass(g, n0, pn); // the list goes through issueSafe (Game.java:136-137), which may replace desires by NONE
             return pn;
         }
@@ -1394,7 +1467,8 @@ DEVN void run_game(Game &g, const StepParams &p, long long gi, WarpStats &ws) {
     bool first = true;
     if (io) { info_distance(g, p, 0, io, true); info_distance(g, p, 1, io + MRTS_INFO_WORDS, true); }
     // device policies emit self-consistent lists; under CANCEL_BOTH they can be issued in parallel (issue_policy_lists)
-    bool fast_issue = p.conflict == 1 && p.policy[0] != POL_EXTERNAL && p.policy[1] != POL_EXTERNAL;
+    // (not under MRTS_FLAG_PO_POLICIES: a list built on a partial view may collide with a hidden unit's reservation)
+    bool fast_issue = p.conflict == 1 && p.policy[0] != POL_EXTERNAL && p.policy[1] != POL_EXTERNAL && !p.po_policies;
     unsigned long long decisions = 0, ucyc = 0;
     #pragma unroll 1
     for (;;) {
@@ -1419,7 +1493,11 @@ DEVN void run_game(Game &g, const StepParams &p, long long gi, WarpStats &ws) {
             // re-inserted later.  Replay that one call (it cannot emit actions: no own unit is idle); the rest are no-ops.
 #pragma unroll 1
             for (int pl = 0; pl < 2; pl++)
-                if (POL_IS_SCRIPTED(p.policy[pl])) policy_scripted(g, pl, p.policy[pl], p.pathfinder[pl], 0);
+                if (POL_IS_SCRIPTED(p.policy[pl])) {
+                    if (p.po_policies) po_hide(g, pl);
+                    policy_scripted(g, pl, p.policy[pl], p.pathfinder[pl], 0);
+                    if (p.po_policies) po_unhide(g);
+                }
         }
         int nu = g.hdr()[H_NUNITS];
         if (tn > tlimit) { ucyc += (unsigned long long)nu * (tlimit - time); __syncwarp(); if (g.lane == 0) g.hdr()[H_TIME] = tlimit; __syncwarp(); break; }

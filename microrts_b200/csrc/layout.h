@@ -67,6 +67,7 @@ enum { GE_UNIT_OVERFLOW = 1, GE_INCONSISTENT_OLDER = 2, GE_FAILED_PRODUCE = 4, G
 
 struct SmemLayout {
     int hdr, units, pa0, pa1, pslot, grid, kind, resv, claim, list, stats, astar, total; // byte offsets inside one game's region
+    int povis, pohid;                                                            // MRTS_FLAG_PO_POLICIES: sight map of the deciding player, unit words of the units hidden from it
     int pcw;                                                                     // padded-grid size in 32-bit words
     int uws;                                                                     // unit words resident in shared memory
     int P;                                                                       // padded row length W + 2
@@ -87,7 +88,7 @@ struct SmemLayout {
 // LIFO bucket per f value), generation counter.  Owned by the warp, not the game: it is initialised once per launch.
 #define MRTS_ASTAR_HEADS(W, H) ((W) * (H) + (W) + (H) + 2)
 #define MRTS_ASTAR_BYTES(W, H) ((8 * ((W) + 2) * ((H) + 2) + 2 * MRTS_ASTAR_HEADS(W, H) + 4 + 15) & ~15)
-MRTS_HD SmemLayout mrts_smem_layout(int W, int H, int cap, int scripted) {
+MRTS_HD SmemLayout mrts_smem_layout(int W, int H, int cap, int scripted, int po_policies = 0) {
     SmemLayout L;
     int pc = (W + 2) * (H + 2);
     int pcb = (pc + 15) & ~15;
@@ -108,6 +109,8 @@ MRTS_HD SmemLayout mrts_smem_layout(int W, int H, int cap, int scripted) {
     L.claim = o; o += pcb;
     L.list = o; o += capb;
     L.stats = o; o += 64; // the warp's 8 running counters (kept out of registers)
+    L.povis = o; o += po_policies ? pcb : 0;
+    L.pohid = o; o += po_policies ? ((cap * 4 + 15) & ~15) : 0;
     L.astar = o; o += scripted == 1 ? MRTS_ASTAR_BYTES(W, H) : 0; // scripted == 2: scratch in global memory
     L.total = (o + 15) & ~15;
     L.pcw = pcb / 4;

@@ -209,11 +209,12 @@ static int launch_step(mrts_batch *b, StepParams &p) {
     p.conflict = b->utt.conflict; p.max_range = b->max_range; p.n_types = (int)b->utt.types.size();
     p.partial_obs = (b->flags & MRTS_FLAG_PARTIAL_OBS) ? 1 : 0; p.scripted = b->scripted; p.uw = b->uw;
     p.astar_scratch = b->d_astar; p.astar_stride = b->astar_stride;
+    p.po_policies = (b->flags & MRTS_FLAG_PO_POLICIES) ? 1 : 0;
     // kernel selection: the specialised kernels cover exactly the cases their loops implement
     int kernel = KERNEL_GENERIC;
     auto rb_or_passive = [](int pol) { return pol == MRTS_POLICY_RANDOM_BIASED || pol == MRTS_POLICY_PASSIVE; };
     if (p.mode == MODE_ROLLOUT) kernel = KERNEL_ROLLOUT;
-    else if (p.mode == MODE_GAME && p.conflict == MRTS_CANCEL_BOTH && rb_or_passive(p.policy[0]) && rb_or_passive(p.policy[1]) && !p.info_out && !p.sequential_issue)
+    else if (p.mode == MODE_GAME && p.conflict == MRTS_CANCEL_BOTH && rb_or_passive(p.policy[0]) && rb_or_passive(p.policy[1]) && !p.info_out && !p.sequential_issue && !p.po_policies)
         kernel = (p.obs_out[0] || p.obs_out[1]) ? KERNEL_FAST_OBS : KERNEL_FAST;
     const mrts_batch::Plan &pl = b->plan[kernel];
     int threads = pl.wpc * 32;
@@ -369,9 +370,11 @@ int mrts_batch_create(const mrts_utt *u, const mrts_map *const *maps, int n_maps
     // scripted batches keep the pathfinding scratch in shared memory while a game's whole region stays small enough for
     // several games per SM; larger maps move it to a per-warp global scratch (L1/L2 resident)
     b->scripted = (flags & MRTS_FLAG_SCRIPTED_AI) ? 1 : 0;
-    if (b->scripted && mrts_smem_layout(W, H, cap, 1).total > 48 * 1024) b->scripted = 2;
+    const int po_pol = (flags & MRTS_FLAG_PO_POLICIES) ? 1 : 0;
+    if (po_pol && u->h.types.size() >= MRTS_MAX_TYPES) return fail(MRTS_E_LIMIT, "MRTS_FLAG_PO_POLICIES needs a unit type table with at most 7 types (type 7 marks hidden units)");
+    if (b->scripted && mrts_smem_layout(W, H, cap, 1, po_pol).total > 48 * 1024) b->scripted = 2;
     b->uw = b->scripted ? MRTS_UNIT_WORDS : MRTS_UNIT_WORDS_CORE;
-    b->L = mrts_smem_layout(W, H, cap, b->scripted);
+    b->L = mrts_smem_layout(W, H, cap, b->scripted, po_pol);
     b->map_words = mrts_map_blob_words(W, H, cap);
     if (dev_select(device)) return fail(MRTS_E_CUDA, std::string("cannot select CUDA device: ") + dev_errstr());
 #ifndef MRTS_EMU
@@ -469,7 +472,7 @@ int mrts_batch_restart_masked(mrts_batch *b, const uint8_t *mask, int on_device)
 
 int mrts_batch_set_policy(mrts_batch *b, int player, int policy, int pathfinder) {
     if (!b || player < 0 || player > 1) return fail(MRTS_E_ARG, "mrts_batch_set_policy: bad argument");
-    if (policy < MRTS_POLICY_EXTERNAL || policy > MRTS_POLICY_RANGED_DEFENSE) return fail(MRTS_E_ARG, "mrts_batch_set_policy: unknown policy");
+    if (policy < MRTS_POLICY_EXTERNAL || policy > MRTS_POLICY_PO_RANGED_RUSH) return fail(MRTS_E_ARG, "mrts_batch_set_policy: unknown policy");
     if (policy >= MRTS_POLICY_WORKER_RUSH && !b->scripted)
         return fail(MRTS_E_STATE, "scripted policies need a batch created with MRTS_FLAG_SCRIPTED_AI");
     if (pathfinder < MRTS_PF_ASTAR || pathfinder > MRTS_PF_GREEDY) return fail(MRTS_E_ARG, "unknown pathfinder");

@@ -8,6 +8,7 @@
 //   WorkerDefense      src/ai/abstraction/WorkerDefense.java:74-209     LightDefense  src/ai/abstraction/LightDefense.java:78-247
 //   HeavyDefense / RangedDefense  the same class as LightDefense with the trained type swapped
 //   GreedyPathFinding  src/ai/abstraction/pathfinding/GreedyPathFinding.java:53-84
+//   POWorkerRush / POLightRush / POHeavyRush / PORangedRush  src/ai/abstraction/partialobservability/*.java:42-78 (exploration) + Move.java
 //   Attack/Harvest/Build/Train.execute   src/ai/abstraction/{Attack.java:51,Harvest.java:72,Build.java:54,Train.java:48-128}
 //
 // The AI's per-unit abstract action (the value of AbstractionLayerAI.actions for that unit) lives in the unit's X0/X1
@@ -20,7 +21,7 @@
 // written by lane 0 (or by the lane that owns the item) followed by __syncwarp().
 #pragma once
 
-enum { AA_NONE = 0, AA_TRAIN = 1, AA_BUILD = 2, AA_HARVEST = 3, AA_ATTACK = 4 };
+enum { AA_NONE = 0, AA_TRAIN = 1, AA_BUILD = 2, AA_HARVEST = 3, AA_ATTACK = 4, AA_MOVE = 5 /* Move.java: walk to (bx, by) */ };
 #define REF_NULL 0u
 #define REF_DEAD 0xFFu
 
@@ -246,7 +247,7 @@ DEVN int pf_find_t(Game &g, int kind, int s, int tx, int ty, int range, int nd) 
 DEV int pf_greedy(Game &g, int s, int tx, int ty, int range, int nd) {
     uint32_t sw = g.w0()[s];
     int sx = u_x(sw), sy = u_y(sw), start = cell_of(g, sw);
-    if ((tx - sx) * (tx - sx) + (ty - sy) * (ty - sy) <= range) return -1;
+    if (range >= 0 && (tx - sx) * (tx - sx) + (ty - sy) * (ty - sy) <= range) return -1; // range < 0: findPath (:16-47) has no such test
     int dl = g.lane & 3, np = start + doff(g, dl);
     bool fre = g.grid()[np] == 0 && g.resv()[np] == 0;
 #pragma unroll 1
@@ -265,8 +266,10 @@ DEV int pf_greedy(Game &g, int s, int tx, int ty, int range, int nd) {
     return dir;
 }
 
+// range < 0: PathFinding.findPath (A* and BFS: findPathToPositionInRange with range 0)
 DEV int pf_find(Game &g, int kind, int s, int tx, int ty, int range, int nd) {
     if (kind == 2) return pf_greedy(g, s, tx, ty, range, nd);
+    if (range < 0) range = 0;
     return g.as_sm ? pf_find_t<true>(g, kind, s, tx, ty, range, nd) : pf_find_t<false>(g, kind, s, tx, ty, range, nd);
 }
 
@@ -347,6 +350,11 @@ DEVN bool aa_execute(Game &g, const ScriptCtx &c, int s, uint32_t &A0, int &A1) 
             A0 = ACT_PRODUCE | ((uint32_t)aa_type(X0) << 8); A1 = d;
             return unit_action_allowed(g, c, s, A0, A1);
         }
+        case AA_MOVE: { // Move.java:49-55
+            int dir = pf_find(g, c.pf, s, aa_bx(X0), aa_by(X0), -1, c.nd);
+            if (mk_move(g, c, s, dir, A0, A1) && unit_action_allowed(g, c, s, A0, A1)) return true;
+            return false;
+        }
         case AA_TRAIN: { // Train.java:48-95
             int pc = cell_of(g, w), type = aa_type(X0), best_dir = -1, best = -1, pl = u_pl(w);
 #pragma unroll 1
@@ -364,7 +372,9 @@ DEVN bool aa_execute(Game &g, const ScriptCtx &c, int s, uint32_t &A0, int &A1) 
     return false;
 }
 
-DEV bool ref_alive(int r) { return r != (int)REF_NULL && r != (int)REF_DEAD; }
+// is the referenced unit in the unit list of the state the policy looks at?  (a unit hidden from a partially observable
+// view is not: PartiallyObservableGameState removes it from its copy of the list)
+DEV bool ref_alive(const Game &g, int r) { return r != (int)REF_NULL && r != (int)REF_DEAD && !(g.po_view && w_hidden(g.w0()[r - 1])); }
 
 // AbstractAction.completed
 DEV bool aa_completed(const Game &g, int s) {
@@ -372,8 +382,9 @@ DEV bool aa_completed(const Game &g, int s) {
     switch (aa_kind(X0)) {
         case AA_TRAIN: return (X0 & 8u) != 0;
         case AA_BUILD: { int bx = aa_bx(X0), by = aa_by(X0); if (bx < 0 || bx >= g.W || by >= g.H) return false; int gv = g.grid()[(by + 1) * g.P + bx + 1]; return gv != 0 && gv != 0xFF; }
-        case AA_HARVEST: return u_res(g.w1()[s]) > 0 ? !ref_alive(aa_base(X1)) : !ref_alive(aa_target(X1));
-        case AA_ATTACK: return !ref_alive(aa_target(X1));
+        case AA_HARVEST: return u_res(g.w1()[s]) > 0 ? !ref_alive(g, aa_base(X1)) : !ref_alive(g, aa_target(X1));
+        case AA_ATTACK: return !ref_alive(g, aa_target(X1));
+        case AA_MOVE: { uint32_t w = g.w0()[s]; return u_x(w) == aa_bx(X0) && u_y(w) == aa_by(X0); } // Move.java:29-31
     }
     return true;
 }
@@ -408,7 +419,7 @@ DEVN int find_building_position(const Game &g, const int *reserved, int nres, in
 // (WorkerDefense.java:117-146, LightDefense.java:142-165) do so only while that enemy, or the own base -- the LAST own base
 // of the unit list, distance 0 without one -- is closer than height/2; otherwise they put an Attack with a null target,
 // which translateActions finds completed and deletes (so the unit's next entry goes to the end of the map).
-DEV void script_melee(Game &g, int s, int player, bool defense) {
+DEV void script_melee(Game &g, int s, int player, bool defense, bool explore = false) {
     int n = g.hdr()[H_NUNITS];
     uint32_t w = g.w0()[s];
     int cd = 0;
@@ -422,6 +433,19 @@ DEV void script_melee(Game &g, int s, int player, bool defense) {
         return;
     }
     if (closest >= 0) aa_put(g, s, player, AA_ATTACK, 0, 0, 0, closest + 1, REF_NULL);
+    else if (explore) {
+        // PO*Rush.meleeUnitBehavior (POLightRush.java:56-77): no enemy in view, so walk to the nearest cell (squared distance,
+        // first minimum in row-major order) that none of the player's units can see
+        int ux = u_x(w), uy = u_y(w), cells = g.W * g.H;
+        unsigned best = 0xFFFFFFFFu;
+#pragma unroll 1
+        for (int q = g.lane; q < cells; q += 32) {
+            int y = q / g.W, x = q - y * g.W;
+            if (!g.vis()[(y + 1) * g.P + x + 1]) { unsigned k = ((unsigned)((ux - x) * (ux - x) + (uy - y) * (uy - y)) << 14) | (unsigned)q; if (k < best) best = k; }
+        }
+        best = __reduce_min_sync(FULLM, best);
+        if (best != 0xFFFFFFFFu) { int q = (int)(best & 0x3FFFu), y = q / g.W; aa_put(g, s, player, AA_MOVE, 0, q - y * g.W, y, REF_NULL, REF_NULL); }
+    }
 }
 
 // harvest part of workersBehavior (WorkerRush.java:148-199, LightRush.java:203-252); true if the worker is still free
@@ -470,6 +494,10 @@ DEV void script_build_if_not(Game &g, int s, int player, int type, int *reserved
 // WorkerRush.getAction / LightRush.getAction followed by translateActions; appends to the pending list from pn.
 // Lane 0 does the work; returns the new pending count (uniform).
 DEVN int policy_scripted(Game &g, int player, int kind, int pathfinder, int pn) {
+    // the PO rushes are their rush plus exploration, which only a partially observable view triggers (`gs instanceof
+    // PartiallyObservableGameState`, POLightRush.java:57)
+    const bool explore = POL_IS_PO_RUSH(kind) && g.po_view;
+    if (POL_IS_PO_RUSH(kind)) kind = kind - POL_PO_WORKER_RUSH + POL_WORKER_RUSH;
     int par0, par1;
     reserved_resources(g, par0, par1);
     __syncwarp();
@@ -500,7 +528,7 @@ DEVN int policy_scripted(Game &g, int player, int kind, int pathfinder, int pn) 
     for (int i = 0; i < n; i++) { // melee units
         uint32_t w = g.w0()[i];
         int fl = ut_flags(g, u_type(w));
-        if ((fl & UF_ATTACK) && !(fl & UF_HARVEST) && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE) script_melee(g, i, player, defense);
+        if ((fl & UF_ATTACK) && !(fl & UF_HARVEST) && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE) script_melee(g, i, player, defense, explore);
     }
     // workers: all own harvesters, busy ones too, in list order
     int nbases = w_count(g, n, [&](int, uint32_t w) { return u_pl(w) == pl && u_type(w) == UT_BASE; });
@@ -521,15 +549,15 @@ DEVN int policy_scripted(Game &g, int player, int kind, int pathfinder, int pn) 
 #pragma unroll 1
             for (int i = w_next(g, n, wi, own_harvester); i >= 0; i = w_next(g, n, i, own_harvester)) if (script_harvest(g, i, player, defense)) still[i >> 5] |= 1u << (i & 31);
 #pragma unroll 1
-            for (int i = w_next(g, n, wi, own_harvester); i >= 0; i = w_next(g, n, i, own_harvester)) if (still[i >> 5] & (1u << (i & 31))) script_melee(g, i, player, defense);
+            for (int i = w_next(g, n, wi, own_harvester); i >= 0; i = w_next(g, n, i, own_harvester)) if (still[i >> 5] & (1u << (i & 31))) script_melee(g, i, player, defense, explore);
         } else {
             // WorkerRush.java:146-202: one harvester, the rest attack; a harvester that stays free is appended at the END
             int hw = -1;
             if (taken < nworkers) { hw = w_next(g, n, wi, own_harvester); wi = hw; taken++; }
             bool hw_free = hw >= 0 && script_harvest(g, hw, player, defense);
 #pragma unroll 1
-            for (int i = w_next(g, n, wi, own_harvester); i >= 0; i = w_next(g, n, i, own_harvester)) script_melee(g, i, player, defense);
-            if (hw_free) script_melee(g, hw, player, defense);
+            for (int i = w_next(g, n, wi, own_harvester); i >= 0; i = w_next(g, n, i, own_harvester)) script_melee(g, i, player, defense, explore);
+            if (hw_free) script_melee(g, hw, player, defense, explore);
         }
     }
     // ---- translateActions (AbstractionLayerAI.java:58-113): abstract actions in insertion order --------------------

@@ -76,6 +76,22 @@ class ai:
         return AISpec(M.POLICY_RANGED_RUSH, pathfinder)
 
     @staticmethod
+    def POWorkerRush(utt=None, pathfinder=M.PF_ASTAR):
+        return AISpec(M.POLICY_PO_WORKER_RUSH, pathfinder)
+
+    @staticmethod
+    def POLightRush(utt=None, pathfinder=M.PF_ASTAR):
+        return AISpec(M.POLICY_PO_LIGHT_RUSH, pathfinder)
+
+    @staticmethod
+    def POHeavyRush(utt=None, pathfinder=M.PF_ASTAR):
+        return AISpec(M.POLICY_PO_HEAVY_RUSH, pathfinder)
+
+    @staticmethod
+    def PORangedRush(utt=None, pathfinder=M.PF_ASTAR):
+        return AISpec(M.POLICY_PO_RANGED_RUSH, pathfinder)
+
+    @staticmethod
     def WorkerDefense(utt=None, pathfinder=M.PF_ASTAR):
         return AISpec(M.POLICY_WORKER_DEFENSE, pathfinder)
 

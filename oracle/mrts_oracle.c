@@ -179,6 +179,7 @@ struct OGame {
     OJRandom rng_conflict; /* GameState.r               (GameState.java:37) */
     OJRandom rng_damage;   /* UnitAction.r              (UnitAction.java:24) */
     int errors;
+    int po_observer;       /* 1 + the observer when this is a PartiallyObservableGameState view (o_po_view), else 0 */
 };
 
 enum { OE_ADD_OCCUPIED = 1, OE_MIXED_OWNERS = 2, OE_BAD_UNIT = 4, OE_INCONSISTENT_OLDER = 8, OE_FAILED_PRODUCE = 16,
@@ -856,7 +857,7 @@ static int pf_greedy(const OGame *g, int start, int targetpos, int range, const 
     const OUnit *s = &g->pool[start];
     int x1 = s->x, y1 = s->y, x2 = targetpos % w, y2 = targetpos / w;
     int min_d = (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1), direction = -1;
-    if (min_d <= range) return -1;
+    if (range >= 0 && min_d <= range) return -1; /* range < 0: findPath (:16-47), which has no such test */
     for (int i = 0; i < 4; i++) {
         int x = x1 + DX[i], y = y1 + DY[i];
         if (x >= 0 && x < w && y >= 0 && y < h && gs_free(g, x, y)) {
@@ -871,6 +872,7 @@ static int pf_greedy(const OGame *g, int start, int targetpos, int range, const 
 static int pf_find(const OGame *g, int kind, int start, int targetpos, int range, const ORu *ru) {
     int w = g->w, h = g->h, n = w * h;
     if (kind == O_PF_GREEDY) return pf_greedy(g, start, targetpos, range, ru);
+    if (range < 0) range = 0; /* AStarPathFinding.findPath :43-45, BFSPathFinding.findPath :33-35 */
     OPf p; pf_alloc(&p, n);
     memset(p.free_, -1, n);
     for (int i = 0; i < n; i++) { p.closed[i] = -1; p.inoc[i] = 0; }
@@ -930,7 +932,7 @@ int o_pathfind(const OGame *g, int kind, int unit_idx, int targetpos, int range,
  *   ai/abstraction/AbstractionLayerAI.java:58-113,143-245 ; WorkerRush.java:63-204 ; LightRush.java:77-258 ;
  *   Attack.java:51 ; Harvest.java:72 ; Build.java:54 ; Train.java:48-128
  * ---------------------------------------------------------------------------------------------- */
-enum { AA_TRAIN = 1, AA_BUILD, AA_HARVEST, AA_ATTACK };
+enum { AA_TRAIN = 1, AA_BUILD, AA_HARVEST, AA_ATTACK, AA_MOVE /* Move.java */ };
 typedef struct {
     int unit; int kind;
     int type;          /* train / build */
@@ -939,7 +941,7 @@ typedef struct {
     int completed;     /* train */
 } OAbs;
 
-struct OAi { int kind; int pf; OAbs *a; int n, cap; };
+struct OAi { int kind; int pf; OAbs *a; int n, cap; int po_rush; };
 
 OAi *o_ai_create(int kind, int pathfinder) {
     OAi *ai = (OAi *)calloc(1, sizeof(OAi));
@@ -960,6 +962,7 @@ static void ai_train(OAi *ai, int u, int type) { OAbs v = {u, AA_TRAIN, type, 0,
 static void ai_build(OAi *ai, int u, int type, int x, int y) { OAbs v = {u, AA_BUILD, type, x, y, -1, -1, 0}; ai_put(ai, v); }
 static void ai_harvest(OAi *ai, int u, int target, int base) { OAbs v = {u, AA_HARVEST, -1, 0, 0, target, base, 0}; ai_put(ai, v); }
 static void ai_attack(OAi *ai, int u, int target) { OAbs v = {u, AA_ATTACK, -1, 0, 0, target, -1, 0}; ai_put(ai, v); }
+static void ai_move(OAi *ai, int u, int x, int y) { OAbs v = {u, AA_MOVE, -1, x, y, -1, -1, 0}; ai_put(ai, v); }
 
 static int in_list(const OGame *g, int u) { return u >= 0 && list_index_of(g, u) >= 0; }
 
@@ -971,6 +974,7 @@ static int aa_completed(const OAbs *aa, const OGame *g) {
             if (g->pool[aa->unit].res > 0) return !in_list(g, aa->base);
             return !in_list(g, aa->target);
         case AA_ATTACK: return !in_list(g, aa->target);                       /* Attack.java:30-33 */
+        case AA_MOVE: return g->pool[aa->unit].x == aa->x && g->pool[aa->unit].y == aa->y; /* Move.java:29-31 */
     }
     return 1;
 }
@@ -1001,6 +1005,11 @@ static int aa_execute(OAi *ai, OAbs *aa, OGame *g, const ORu *ru, OAct *out) {
             if (d <= range) { *out = mk_act(O_ATTACK, -1, t->x, t->y, -1); return 1; }
             OAct mv;
             if (mk_move(&mv, pf_find(g, ai->pf, aa->unit, t->x + t->y * w, range, ru)) && is_unit_action_allowed(g, aa->unit, &mv)) { *out = mv; return 1; }
+            return 0;
+        }
+        case AA_MOVE: { /* Move.java:49-55: pf.findPath */
+            OAct mv;
+            if (mk_move(&mv, pf_find(g, ai->pf, aa->unit, aa->x + aa->y * w, -1, ru)) && is_unit_action_allowed(g, aa->unit, &mv)) { *out = mv; return 1; }
             return 0;
         }
         case AA_HARVEST: { /* Harvest.java:72-113 */
@@ -1132,6 +1141,19 @@ static void build_if_not_already(OAi *ai, const OGame *g, int u, int type, int d
 
 /* WorkerRush/LightRush.meleeUnitBehavior (WorkerRush.java:105-121, LightRush.java:141-159) */
 static int is_defense(int kind) { return kind >= O_AI_WORKER_DEFENSE && kind <= O_AI_RANGED_DEFENSE; }
+static int is_po_rush(int kind) { return kind >= O_AI_PO_WORKER_RUSH && kind <= O_AI_PO_RANGED_RUSH; }
+/* PartiallyObservableGameState.observable :61-71 */
+static int po_observable(const OGame *g, int x, int y) {
+    int observer = g->po_observer - 1;
+    for (int i = 0; i < g->n; i++) {
+        const OUnit *u = &g->pool[g->list[i]];
+        if (u->player == observer) {
+            int d = (u->x - x) * (u->x - x) + (u->y - y) * (u->y - y), sr = g->utt->f[u->type][OF_SIGHT];
+            if (d <= sr * sr) return 1;
+        }
+    }
+    return 0;
+}
 
 /* meleeUnitBehavior: the rushes attack the closest enemy (WorkerRush.java:105-121, LightRush.java:141-159); the defenses do
  * so only while the enemy or the own base (the LAST own base of the unit list; 0 without one) is closer than height/2, and
@@ -1154,7 +1176,18 @@ static void melee_behavior(OAi *ai, const OGame *g, int u, int player) {
         else ai_attack(ai, u, -1);
         return;
     }
-    if (closest >= 0) ai_attack(ai, u, closest);
+    if (closest >= 0) { ai_attack(ai, u, closest); return; }
+    if (ai->po_rush && g->po_observer) {
+        /* PO*Rush.meleeUnitBehavior, partialobservability/POLightRush.java:56-77: explore the nearest non-observable cell */
+        int cx = 0, cy = 0, best = -1;
+        for (int i = 0; i < g->h; i++)
+            for (int j = 0; j < g->w; j++)
+                if (!po_observable(g, j, i)) {
+                    int d = (me->x - j) * (me->x - j) + (me->y - i) * (me->y - i);
+                    if (best == -1 || d < best) { cx = j; cy = i; best = d; }
+                }
+        if (best != -1) ai_move(ai, u, cx, cy);
+    }
 }
 
 /* harvest part shared by WorkerRush.workersBehavior :148-199 and LightRush.workersBehavior :203-252; returns 1 if still free */
@@ -1200,7 +1233,18 @@ static int type_by_role_barracks(void) { return 2; }
 static int type_by_role_worker(void) { return 3; }
 static int type_by_role_light(void) { return 4; }
 
+static int ai_get_action_k(OAi *ai, OGame *g, int player, OPair *out);
 static int ai_get_action(OAi *ai, OGame *g, int player, OPair *out) {
+    /* PO{Worker,Light,Heavy,Ranged}Rush extend their rush and override meleeUnitBehavior only (melee_behavior looks at the
+     * original kind through ai->po_rush) */
+    if (!is_po_rush(ai->kind)) return ai_get_action_k(ai, g, player, out);
+    int k = ai->kind;
+    ai->po_rush = 1; ai->kind = k - O_AI_PO_WORKER_RUSH + O_AI_WORKER_RUSH;
+    int n = ai_get_action_k(ai, g, player, out);
+    ai->kind = k; ai->po_rush = 0;
+    return n;
+}
+static int ai_get_action_k(OAi *ai, OGame *g, int player, OPair *out) {
     const OUtt *t = g->utt;
     int BASE = type_by_role_base(), BARRACKS = type_by_role_barracks(), WORKER = type_by_role_worker();
     /* the combat unit the barracks train: Light (LightRush.java:57), Heavy (HeavyRush.java:55), Ranged (RangedRush.java:52) */
@@ -1421,6 +1465,7 @@ OGame *o_po_view(const OGame *s, int observer) {
     }
     for (int i = 0; i < nd; i++) remove_unit(g, del[i]);
     free(del);
+    g->po_observer = observer + 1;
     return g;
 }
 
@@ -1465,7 +1510,9 @@ static int policy(OGame *g, int kind, OAi *ai, int player, OPair *out) {
         case O_AI_HEAVY_RUSH:
         case O_AI_RANGED_RUSH:
         case O_AI_WORKER_DEFENSE: case O_AI_LIGHT_DEFENSE: case O_AI_HEAVY_DEFENSE:
-        case O_AI_RANGED_DEFENSE: return ai_get_action(ai, g, player, out);
+        case O_AI_RANGED_DEFENSE:
+        case O_AI_PO_WORKER_RUSH: case O_AI_PO_LIGHT_RUSH: case O_AI_PO_HEAVY_RUSH:
+        case O_AI_PO_RANGED_RUSH: return ai_get_action(ai, g, player, out);
         default: return 0; /* PassiveAI: empty PlayerAction */
     }
 }
@@ -1481,6 +1528,32 @@ int o_run_game(OGame *g, int kind0, OAi *ai0, int kind1, OAi *ai1, int n_cycles,
         gs_issue_safe(g, n1, p1);
         gameover = o_game_cycle(g);
         if (stats) { stats[0] += 1; stats[1] += n0 + n1; stats[2] += g->n; }
+    }
+    free(p0); free(p1);
+    return gameover;
+}
+
+/* Game.start with partiallyObservable = true (Game.java:129-140): each AI decides on new PartiallyObservableGameState(gs, p);
+ * the lists are issued with issueSafe on the real state.  The view is a copy with the same unit handles, so the pairs and
+ * the AIs' abstract actions refer to the real game; the policy RNG (a static in the reference) is carried back. */
+static int policy_po(OGame *g, int kind, OAi *ai, int player, OPair *out) {
+    if (kind != O_AI_RANDOM_BIASED && !(kind >= O_AI_WORKER_RUSH && kind <= O_AI_PO_RANGED_RUSH)) return policy(g, kind, ai, player, out);
+    OGame *v = o_po_view(g, player);
+    int n = policy(v, kind, ai, player, out);
+    g->rng_policy = v->rng_policy;
+    o_game_free(v);
+    return n;
+}
+int o_run_game_po(OGame *g, int kind0, OAi *ai0, int kind1, OAi *ai1, int n_cycles, int max_cycles) {
+    int gameover = o_game_gameover(g) && g->time > 0;
+    OPair *p0 = NULL, *p1 = NULL; int cap = 0;
+    for (int it = 0; it < n_cycles && !gameover && g->time < max_cycles; it++) {
+        if (g->n + 8 > cap) { cap = g->n * 2 + 64; p0 = (OPair *)realloc(p0, sizeof(OPair) * cap); p1 = (OPair *)realloc(p1, sizeof(OPair) * cap); }
+        int n0 = policy_po(g, kind0, ai0, 0, p0);
+        int n1 = policy_po(g, kind1, ai1, 1, p1);
+        gs_issue_safe(g, n0, p0);
+        gs_issue_safe(g, n1, p1);
+        gameover = o_game_cycle(g);
     }
     free(p0); free(p1);
     return gameover;

@@ -23,7 +23,8 @@ enum { O_NONE = 0, O_MOVE = 1, O_HARVEST = 2, O_RETURN = 3, O_PRODUCE = 4, O_ATT
 enum { O_UP = 0, O_RIGHT = 1, O_DOWN = 2, O_LEFT = 3 };
 enum { O_AI_NONE = 0, O_AI_PASSIVE = 1, O_AI_RANDOM_BIASED = 2, O_AI_WORKER_RUSH = 3, O_AI_LIGHT_RUSH = 4,
        O_AI_HEAVY_RUSH = 5, O_AI_RANGED_RUSH = 6, /* HeavyRush.java / RangedRush.java are LightRush.java with the trained type swapped */
-       O_AI_WORKER_DEFENSE = 7, O_AI_LIGHT_DEFENSE = 8, O_AI_HEAVY_DEFENSE = 9, O_AI_RANGED_DEFENSE = 10 }; /* ai/abstraction/{Worker,Light,Heavy,Ranged}Defense.java */
+       O_AI_WORKER_DEFENSE = 7, O_AI_LIGHT_DEFENSE = 8, O_AI_HEAVY_DEFENSE = 9, O_AI_RANGED_DEFENSE = 10,
+       O_AI_PO_WORKER_RUSH = 11, O_AI_PO_LIGHT_RUSH = 12, O_AI_PO_HEAVY_RUSH = 13, O_AI_PO_RANGED_RUSH = 14 /* ai/abstraction/partialobservability/ */ }; /* ai/abstraction/{Worker,Light,Heavy,Ranged}Defense.java */
 enum { O_PF_ASTAR = 0, O_PF_BFS = 1, O_PF_GREEDY = 2 };
 
 /* unit type fields, in the order of the UTT XML attributes */
@@ -108,6 +109,7 @@ float o_evaluate(const OGame *, int fn, int maxplayer, int minplayer);
 /* Game.start: policies on the same state, issueSafe x2, cycle.  Runs until gameover, time>=max_cycles or
  * n_cycles iterations.  ai0/ai1 may be NULL with kind RANDOM_BIASED/PASSIVE.  Returns 1 if gameover. */
 int o_run_game(OGame *, int kind0, OAi *ai0, int kind1, OAi *ai1, int n_cycles, int max_cycles, int64_t *stats);
+int o_run_game_po(OGame *, int kind0, OAi *ai0, int kind1, OAi *ai1, int n_cycles, int max_cycles); /* Game(partiallyObservable) */
 int o_run_game_observing(OGame *g, int kind0, OAi *ai0, int kind1, OAi *ai1, int n_cycles, int max_cycles, int32_t *scratch);
 /* NaiveMCTS.simulate: RandomBiased both sides, issue() not issueSafe() */
 int o_simulate(OGame *, int time_limit);

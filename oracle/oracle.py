@@ -15,9 +15,9 @@ _LIB = None
 TYPE_NAMES = ["Resource", "Base", "Barracks", "Worker", "Light", "Heavy", "Ranged"]
 NONE, MOVE, HARVEST, RETURN, PRODUCE, ATTACK = range(6)
 (AI_NONE, AI_PASSIVE, AI_RANDOM_BIASED, AI_WORKER_RUSH, AI_LIGHT_RUSH, AI_HEAVY_RUSH, AI_RANGED_RUSH,
- AI_WORKER_DEFENSE, AI_LIGHT_DEFENSE, AI_HEAVY_DEFENSE, AI_RANGED_DEFENSE) = range(11)
-SCRIPTED_AIS = (AI_WORKER_RUSH, AI_LIGHT_RUSH, AI_HEAVY_RUSH, AI_RANGED_RUSH,
-                AI_WORKER_DEFENSE, AI_LIGHT_DEFENSE, AI_HEAVY_DEFENSE, AI_RANGED_DEFENSE)
+ AI_WORKER_DEFENSE, AI_LIGHT_DEFENSE, AI_HEAVY_DEFENSE, AI_RANGED_DEFENSE,
+ AI_PO_WORKER_RUSH, AI_PO_LIGHT_RUSH, AI_PO_HEAVY_RUSH, AI_PO_RANGED_RUSH) = range(15)
+SCRIPTED_AIS = tuple(range(AI_WORKER_RUSH, AI_PO_RANGED_RUSH + 1))
 PF_ASTAR, PF_BFS, PF_GREEDY = 0, 1, 2
 
 
@@ -70,6 +70,7 @@ def lib():
             "o_run_game": (i, [vp, i, vp, i, vp, i, i, C.POINTER(C.c_int64)]),
             "o_simulate": (i, [vp, i]),
             "o_run_game_observing": (i, [vp, i, vp, i, vp, i, i, pi32]),
+            "o_run_game_po": (i, [vp, i, vp, i, vp, i, i]),
             "o_jr_seed": (None, [C.POINTER(C.c_uint64), i64]), "o_jr_next": (C.c_int32, [C.POINTER(C.c_uint64), i]),
             "o_jr_next_int": (C.c_int32, [C.POINTER(C.c_uint64)]),
             "o_jr_next_int_bound": (C.c_int32, [C.POINTER(C.c_uint64), C.c_int32]),
@@ -254,6 +255,10 @@ class Game:
 
     def evaluate(self, fn, maxplayer, minplayer):
         return float(lib().o_evaluate(self.h, fn, maxplayer, minplayer))
+
+    def run_po(self, kind0, ai0, kind1, ai1, n_cycles, max_cycles):
+        """Game.start with partiallyObservable = true: each AI decides on its PartiallyObservableGameState view."""
+        return bool(lib().o_run_game_po(self.h, kind0, ai0.h if ai0 else None, kind1, ai1.h if ai1 else None, n_cycles, max_cycles))
 
     def run(self, kind0, ai0, kind1, ai1, n_cycles, max_cycles, stats=None):
         st = (C.c_int64 * 4)() if stats is None else stats

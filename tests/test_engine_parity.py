@@ -554,6 +554,52 @@ def test_scripted_policies_vs_oracle(backend, maps, key, p0, p1, pf):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# Game(partiallyObservable = true), rts/Game.java:129-140: every device policy decides on its player's
+# PartiallyObservableGameState view (units out of sight hidden, their reservations unknown), issueSafe on the real state;
+# PO*Rush explore when they see no enemy (ai/abstraction/partialobservability/*.java)
+# ------------------------------------------------------------------------------------------------------------------
+PO_GAMES = [
+    ("16x16/basesWorkers16x16", "PO_LIGHT_RUSH", "PO_WORKER_RUSH", 0),
+    ("24x24/basesWorkers24x24", "PO_WORKER_RUSH", "PO_HEAVY_RUSH", 0),
+    ("BWDistantResources32x32", "PO_RANGED_RUSH", "PO_LIGHT_RUSH", 0),
+    ("16x16/basesWorkers16x16", "PO_HEAVY_RUSH", "LIGHT_DEFENSE", 1),
+    ("8x8/basesWorkers8x8", "RANDOM_BIASED", "PO_WORKER_RUSH", 0),
+    ("16x16/basesWorkers16x16", "RANDOM_BIASED", "RANDOM_BIASED", 0),
+    ("16x16/TwoBasesBarracks16x16", "PO_LIGHT_RUSH", "RANDOM_BIASED", 2),
+    ("24x24/basesWorkers24x24", "LIGHT_RUSH", "WORKER_RUSH", 0),
+]
+
+
+@pytest.mark.parametrize("key,p0,p1,pf", PO_GAMES)
+def test_partially_observable_games_vs_oracle(backend, maps, key, p0, p1, pf):
+    n = 2 if backend == "emu" else 8
+    total = 600 if backend == "emu" else 3000
+    chunk = 25
+    utt, outt = M.UnitTypeTable(1, 1), O.Utt(1, 1)
+    b = M.BatchedGameState(utt, make_pgs(maps[key], utt), n, scripted_ai=True, po_policies=True)
+    seeds = np.arange(n, dtype=np.int64) + 23
+    b.reset(seeds)
+    kinds = []
+    for pl, name in enumerate((p0, p1)):
+        b.set_policy(pl, getattr(M, "POLICY_" + name), pf)
+        kinds.append(getattr(O, "AI_" + name))
+    games, ais = [], []
+    for g in range(n):
+        og = O.Game(outt, maps[key])
+        og.seed(int(seeds[g]))
+        games.append(og)
+        ais.append([O.ScriptedAI(k, pf) if k in O.SCRIPTED_AIS else None for k in kinds])
+    for t in range(0, total, chunk):
+        b.step(chunk, total)
+        ex = b.export()
+        for g, og in enumerate(games):
+            if not (og.gameover and og.time > 0):
+                og.run_po(kinds[0], ais[g][0], kinds[1], ais[g][1], chunk, total)
+            P.assert_same_state(ex, g, og, "PO %s %s/%s t=%d" % (key, p0, p1, t + chunk))
+    b.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # wide differential: thousands of complete games, final state against the oracle (rare paths: more than 32 units per
 # game, cross-chunk arbitration, cancel-both pairs, deaths with pending actions)
 # ------------------------------------------------------------------------------------------------------------------
