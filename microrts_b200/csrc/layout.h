@@ -88,7 +88,9 @@ struct SmemLayout {
 // LIFO bucket per f value), generation counter.  Owned by the warp, not the game: it is initialised once per launch.
 #define MRTS_ASTAR_HEADS(W, H) ((W) * (H) + (W) + (H) + 2)
 #define MRTS_ASTAR_BYTES(W, H) ((8 * ((W) + 2) * ((H) + 2) + 2 * MRTS_ASTAR_HEADS(W, H) + 4 + 15) & ~15)
-MRTS_HD SmemLayout mrts_smem_layout(int W, int H, int cap, int scripted, int po_policies = 0) {
+// pending = 0: the layout of the specialised kernels (fast game loop, rollouts), which fuse policy and issue and never
+// stage a pending action list -- 8 bytes per unit slot less, which is what lets one more CTA fit per SM on small maps
+MRTS_HD SmemLayout mrts_smem_layout(int W, int H, int cap, int scripted, int po_policies = 0, int pending = 1) {
     SmemLayout L;
     int pc = (W + 2) * (H + 2);
     int pcb = (pc + 15) & ~15;
@@ -100,8 +102,8 @@ MRTS_HD SmemLayout mrts_smem_layout(int W, int H, int cap, int scripted, int po_
     for (int k = 0; k <= MRTS_UNIT_WORDS; k++) L.uoff[k] = o + k * cap * 4; // host-computed so the kernels see plain constants
     L.rdy = L.uoff[L.uws - 1];
     L.units = o; o += (L.uws * cap * 4 + 15) & ~15; // every section starts 16-byte aligned (vector fills of the cell maps)
-    L.pa0 = o; o += (cap * 4 + 15) & ~15;
-    L.pa1 = o; o += (cap * 4 + 15) & ~15;
+    L.pa0 = o; o += pending ? ((cap * 4 + 15) & ~15) : 0;
+    L.pa1 = o; o += pending ? ((cap * 4 + 15) & ~15) : 0;
     L.pslot = o; o += capb;
     L.grid = o; o += pcb;
     L.kind = o; o += pcb;

@@ -135,7 +135,7 @@ DEV void observe_kernel_body(const ObsParams &p, int tid, int nthreads, int bid,
 
 #ifndef MRTS_EMU
 #ifndef MRTS_MIN_BLOCKS
-#define MRTS_MIN_BLOCKS 7     // k_step_fast: 72 registers, 28 warps per SM on the 16x16 configuration
+#define MRTS_MIN_BLOCKS 7     // k_step_fast: 72 registers, 28 warps per SM on the 16x16 configuration (8 CTAs at 64 registers spill: measured 3% slower)
 #endif
 #ifndef MRTS_MIN_BLOCKS_OBS
 #define MRTS_MIN_BLOCKS_OBS 4 // the observation variant runs on large maps, where shared memory bounds the occupancy anyway
@@ -187,7 +187,7 @@ struct mrts_batch {
     unsigned char *d_astar = nullptr; long long astar_stride = 0; // pathfinding scratch of large-map scripted batches
     Staged staged[2];
     stream_t stream = nullptr;
-    SmemLayout L;
+    SmemLayout L, Lfast; // generic kernel / specialised kernels (no pending lists, layout.h)
     struct Plan { int wpc = 2, grid = 3; size_t smem = 0; } plan[N_KERNELS]; // per kernel: warps (games in flight) per CTA, CTAs, shared memory
     int max_range = 0, auto_reset = 0, scripted = 0, uw = MRTS_UNIT_WORDS_CORE;
     int sequential_issue = 0; int32_t *info_out = nullptr; uint32_t tm[6] = {0, 0, 0, 0, 0, 0};
@@ -205,7 +205,7 @@ static int ensure_tmp(mrts_batch *b, size_t bytes) {
 
 static int launch_step(mrts_batch *b, StepParams &p) {
     p.hdr = b->d_hdr; p.units = b->d_units; p.maps = b->d_maps; p.cst = b->d_cst; p.stats = b->d_stats;
-    p.n_games = b->n; p.n_maps = b->n_maps; p.map_words = b->map_words; p.W = b->W; p.H = b->H; p.cap = b->cap; p.L = b->L;
+    p.n_games = b->n; p.n_maps = b->n_maps; p.map_words = b->map_words; p.W = b->W; p.H = b->H; p.cap = b->cap;
     p.conflict = b->utt.conflict; p.max_range = b->max_range; p.n_types = (int)b->utt.types.size();
     p.partial_obs = (b->flags & MRTS_FLAG_PARTIAL_OBS) ? 1 : 0; p.scripted = b->scripted; p.uw = b->uw;
     p.astar_scratch = b->d_astar; p.astar_stride = b->astar_stride;
@@ -217,6 +217,7 @@ static int launch_step(mrts_batch *b, StepParams &p) {
     else if (p.mode == MODE_GAME && p.conflict == MRTS_CANCEL_BOTH && rb_or_passive(p.policy[0]) && rb_or_passive(p.policy[1]) && !p.info_out && !p.sequential_issue && !p.po_policies)
         kernel = (p.obs_out[0] || p.obs_out[1]) ? KERNEL_FAST_OBS : KERNEL_FAST;
     const mrts_batch::Plan &pl = b->plan[kernel];
+    p.L = kernel == KERNEL_GENERIC ? b->L : b->Lfast;
     int threads = pl.wpc * 32;
     long long items = p.mode == MODE_ROLLOUT ? b->n * p.rollouts_per_game : b->n;
     long long need = (items + pl.wpc - 1) / pl.wpc;
@@ -375,6 +376,7 @@ int mrts_batch_create(const mrts_utt *u, const mrts_map *const *maps, int n_maps
     if (b->scripted && mrts_smem_layout(W, H, cap, 1, po_pol).total > 48 * 1024) b->scripted = 2;
     b->uw = b->scripted ? MRTS_UNIT_WORDS : MRTS_UNIT_WORDS_CORE;
     b->L = mrts_smem_layout(W, H, cap, b->scripted, po_pol);
+    b->Lfast = mrts_smem_layout(W, H, cap, b->scripted ? 2 : 0, 0, 0); // same unit words, no pathfinding scratch, no pending lists
     b->map_words = mrts_map_blob_words(W, H, cap);
     if (dev_select(device)) return fail(MRTS_E_CUDA, std::string("cannot select CUDA device: ") + dev_errstr());
 #ifndef MRTS_EMU
@@ -389,7 +391,8 @@ int mrts_batch_create(const mrts_utt *u, const mrts_map *const *maps, int n_maps
             ck(cudaFuncSetAttribute(kernels[kk], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)))
             return fail(MRTS_E_CUDA, std::string("cudaFuncSetAttribute: ") + dev_errstr());
         for (int wpc = MRTS_WARPS_PER_CTA; wpc >= 1; wpc--) {
-            size_t sm = MRTS_CONST_WORDS * 4 + (size_t)wpc * b->L.total;
+            const int region = kk == KERNEL_GENERIC ? b->L.total : b->Lfast.total;
+            size_t sm = MRTS_CONST_WORDS * 4 + (size_t)wpc * region;
             if (sm > (size_t)prop.sharedMemPerBlockOptin) continue;
             int per_sm = 0;
             if (ck(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernels[kk], wpc * 32, sm))) return fail(MRTS_E_CUDA, std::string("occupancy query: ") + dev_errstr());
@@ -397,12 +400,12 @@ int mrts_batch_create(const mrts_utt *u, const mrts_map *const *maps, int n_maps
         }
         if (!best_wpc) return fail(MRTS_E_LIMIT, "map too large for the shared-memory resident engine");
         b->plan[kk].wpc = best_wpc;
-        b->plan[kk].smem = MRTS_CONST_WORDS * 4 + (size_t)best_wpc * b->L.total;
+        b->plan[kk].smem = MRTS_CONST_WORDS * 4 + (size_t)best_wpc * (kk == KERNEL_GENERIC ? b->L.total : b->Lfast.total);
         b->plan[kk].grid = best_blocks * prop.multiProcessorCount;
     }
     if (ck(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking))) return fail(MRTS_E_CUDA, std::string("cudaStreamCreate: ") + dev_errstr());
 #else
-    for (int kk = 0; kk < N_KERNELS; kk++) { b->plan[kk].wpc = 2; b->plan[kk].smem = MRTS_CONST_WORDS * 4 + (size_t)2 * b->L.total; b->plan[kk].grid = 3; }
+    for (int kk = 0; kk < N_KERNELS; kk++) { b->plan[kk].wpc = 2; b->plan[kk].smem = MRTS_CONST_WORDS * 4 + (size_t)2 * (kk == KERNEL_GENERIC ? b->L.total : b->Lfast.total); b->plan[kk].grid = 3; }
 #endif
     if (b->scripted == 2) {
         b->astar_stride = ((long long)MRTS_ASTAR_BYTES(W, H) + 255) & ~255LL;
