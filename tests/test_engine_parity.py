@@ -637,3 +637,55 @@ def test_wide_differential_full_games(backend, maps, key, n_cuda):
     if backend != "emu" and key.startswith("16x16"):
         assert big > 100, "the batch should contain many games with more than 32 live units"
     b.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# every map of the reference (maps/**/*.xml as packed in tests/golden): RandomBiasedAI self-play on the fast kernel, and one
+# of eight policy / pathfinder / observability combinations on the generic kernel (rotating over the maps), state for state
+# against the oracle
+# ------------------------------------------------------------------------------------------------------------------
+MAP_SWEEP_COMBOS = [
+    # policy 0, policy 1, pathfinder, partially observable game
+    ("WORKER_DEFENSE", "LIGHT_RUSH", 0, False),
+    ("RANGED_RUSH", "HEAVY_DEFENSE", 1, False),
+    ("PO_LIGHT_RUSH", "PO_WORKER_RUSH", 0, True),
+    ("LIGHT_DEFENSE", "RANDOM_BIASED", 2, False),
+    ("PO_RANGED_RUSH", "RANDOM_BIASED", 1, True),
+    ("WORKER_RUSH", "RANGED_DEFENSE", 0, False),
+    ("RANDOM_BIASED", "RANDOM_BIASED", 0, True),
+    ("PO_HEAVY_RUSH", "LIGHT_DEFENSE", 2, True),
+]
+
+
+@pytest.mark.parametrize("part", range(4))
+def test_every_reference_map(backend, maps, part):
+    keys = sorted(maps.keys())
+    todo = list(enumerate(keys))[part::4]
+    if backend == "emu":
+        todo = todo[::12]
+    n, total = (1, 100) if backend == "emu" else (4, 1500)
+    utt, outt = M.UnitTypeTable(1, 1), O.Utt(1, 1)
+    for idx, key in todo:
+        big = maps[key]["w"] * maps[key]["h"] > 64 * 64
+        for scripted in (False, True):
+            if scripted:
+                p0, p1, pf, po = MAP_SWEEP_COMBOS[idx % len(MAP_SWEEP_COMBOS)]
+                cyc = min(total, 500 if big else 1000)  # pathfinding on the 128x128 maps: keep the oracle side short
+            else:
+                p0, p1, pf, po = "RANDOM_BIASED", "RANDOM_BIASED", 0, False
+                cyc = total
+            b = M.BatchedGameState(utt, make_pgs(maps[key], utt), n, scripted_ai=scripted, po_policies=po)
+            seeds = np.arange(n, dtype=np.int64) * 7 + 5
+            b.reset(seeds)
+            kinds = [getattr(O, "AI_" + p0), getattr(O, "AI_" + p1)]
+            b.set_policy(0, getattr(M, "POLICY_" + p0), pf)
+            b.set_policy(1, getattr(M, "POLICY_" + p1), pf)
+            b.step(cyc, cyc)
+            ex = b.export()
+            for g in range(n if not scripted else min(n, 2)):
+                og = O.Game(outt, maps[key])
+                og.seed(int(seeds[g]))
+                ais = [O.ScriptedAI(k, pf) if k in O.SCRIPTED_AIS else None for k in kinds]
+                (og.run_po if po else og.run)(kinds[0], ais[0], kinds[1], ais[1], cyc, cyc)
+                P.assert_same_state(ex, g, og, "%s %s/%s pf=%d po=%s" % (key, p0, p1, pf, po))
+            b.close()
