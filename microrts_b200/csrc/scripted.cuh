@@ -419,7 +419,7 @@ DEVN int find_building_position(const Game &g, const int *reserved, int nres, in
 // (WorkerDefense.java:117-146, LightDefense.java:142-165) do so only while that enemy, or the own base -- the LAST own base
 // of the unit list, distance 0 without one -- is closer than height/2; otherwise they put an Attack with a null target,
 // which translateActions finds completed and deletes (so the unit's next entry goes to the end of the map).
-DEV void script_melee(Game &g, int s, int player, bool defense, bool explore = false) {
+DEV void script_melee(Game &g, int s, int player, bool defense, bool explore = false, bool always = false) {
     int n = g.hdr()[H_NUNITS];
     uint32_t w = g.w0()[s];
     int cd = 0;
@@ -428,7 +428,7 @@ DEV void script_melee(Game &g, int s, int player, bool defense, bool explore = f
         int last = w_argmin(g, n, [&](int i, uint32_t ow) { return (u_pl(ow) == player + 1 && u_type(ow) == 1 /* baseType */) ? 255 - i : -1; });
         int mybase = 0;
         if (last >= 0) { uint32_t bw = g.w0()[last]; mybase = iabs(u_x(bw) - u_x(w)) + iabs(u_y(bw) - u_y(w)); }
-        if (closest >= 0 && (cd < g.H / 2 || mybase < g.H / 2)) aa_put(g, s, player, AA_ATTACK, 0, 0, 0, closest + 1, REF_NULL);
+        if (closest >= 0 && (always || cd < g.H / 2 || mybase < g.H / 2)) aa_put(g, s, player, AA_ATTACK, 0, 0, 0, closest + 1, REF_NULL); // always: WorkerRushPlusPlus.java:136-142
         else aa_put(g, s, player, AA_ATTACK, 0, 0, 0, REF_NULL, REF_NULL);
         return;
     }
@@ -504,7 +504,7 @@ DEVN int policy_scripted(Game &g, int player, int kind, int pathfinder, int pn) 
     const int n = g.hdr()[H_NUNITS], pl = player + 1, pres = g.hdr()[H_RES0 + player];
     // the barracks scripts: LightRush / LightDefense, and Heavy* / Ranged* = the same classes with the trained type swapped;
     // the defenses share their rush's skeleton and differ in script_melee / script_harvest
-    const bool light = kind != POL_WORKER_RUSH && kind != POL_WORKER_DEFENSE, defense = POL_IS_DEFENSE(kind);
+    const bool light = kind != POL_WORKER_RUSH && kind != POL_WORKER_DEFENSE && kind != POL_WORKER_RUSH_PP, defense = POL_IS_DEFENSE(kind), always = kind == POL_WORKER_RUSH_PP;
     const int UT_RUSH = (kind == POL_HEAVY_RUSH || kind == POL_HEAVY_DEFENSE) ? 5 : ((kind == POL_RANGED_RUSH || kind == POL_RANGED_DEFENSE) ? 6 : UT_LIGHT); // HeavyRush.java:55, RangedRush.java:52
     auto own_harvester = [&](int, uint32_t w) { return u_pl(w) == pl && (ut_flags(g, u_type(w)) & UF_HARVEST) != 0; };
     // bases (WorkerRush.java:70-76,100-102; LightRush.java:83-89,123-133)
@@ -528,7 +528,7 @@ DEVN int policy_scripted(Game &g, int player, int kind, int pathfinder, int pn) 
     for (int i = 0; i < n; i++) { // melee units
         uint32_t w = g.w0()[i];
         int fl = ut_flags(g, u_type(w));
-        if ((fl & UF_ATTACK) && !(fl & UF_HARVEST) && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE) script_melee(g, i, player, defense, explore);
+        if ((fl & UF_ATTACK) && !(fl & UF_HARVEST) && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE) script_melee(g, i, player, defense, explore, always);
     }
     // workers: all own harvesters, busy ones too, in list order
     int nbases = w_count(g, n, [&](int, uint32_t w) { return u_pl(w) == pl && u_type(w) == UT_BASE; });
@@ -549,15 +549,15 @@ DEVN int policy_scripted(Game &g, int player, int kind, int pathfinder, int pn) 
 #pragma unroll 1
             for (int i = w_next(g, n, wi, own_harvester); i >= 0; i = w_next(g, n, i, own_harvester)) if (script_harvest(g, i, player, defense)) still[i >> 5] |= 1u << (i & 31);
 #pragma unroll 1
-            for (int i = w_next(g, n, wi, own_harvester); i >= 0; i = w_next(g, n, i, own_harvester)) if (still[i >> 5] & (1u << (i & 31))) script_melee(g, i, player, defense, explore);
+            for (int i = w_next(g, n, wi, own_harvester); i >= 0; i = w_next(g, n, i, own_harvester)) if (still[i >> 5] & (1u << (i & 31))) script_melee(g, i, player, defense, explore, always);
         } else {
             // WorkerRush.java:146-202: one harvester, the rest attack; a harvester that stays free is appended at the END
             int hw = -1;
             if (taken < nworkers) { hw = w_next(g, n, wi, own_harvester); wi = hw; taken++; }
             bool hw_free = hw >= 0 && script_harvest(g, hw, player, defense);
 #pragma unroll 1
-            for (int i = w_next(g, n, wi, own_harvester); i >= 0; i = w_next(g, n, i, own_harvester)) script_melee(g, i, player, defense, explore);
-            if (hw_free) script_melee(g, hw, player, defense, explore);
+            for (int i = w_next(g, n, wi, own_harvester); i >= 0; i = w_next(g, n, i, own_harvester)) script_melee(g, i, player, defense, explore, always);
+            if (hw_free) script_melee(g, hw, player, defense, explore, always);
         }
     }
     // ---- translateActions (AbstractionLayerAI.java:58-113): abstract actions in insertion order --------------------

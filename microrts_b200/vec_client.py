@@ -92,6 +92,10 @@ class ai:
         return AISpec(M.POLICY_PO_RANGED_RUSH, pathfinder)
 
     @staticmethod
+    def WorkerRushPlusPlus(utt=None, pathfinder=M.PF_ASTAR):
+        return AISpec(M.POLICY_WORKER_RUSH_PP, pathfinder)
+
+    @staticmethod
     def WorkerDefense(utt=None, pathfinder=M.PF_ASTAR):
         return AISpec(M.POLICY_WORKER_DEFENSE, pathfinder)
 

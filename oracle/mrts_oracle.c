@@ -1140,7 +1140,8 @@ static void build_if_not_already(OAi *ai, const OGame *g, int u, int type, int d
 }
 
 /* WorkerRush/LightRush.meleeUnitBehavior (WorkerRush.java:105-121, LightRush.java:141-159) */
-static int is_defense(int kind) { return kind >= O_AI_WORKER_DEFENSE && kind <= O_AI_RANGED_DEFENSE; }
+/* WorkerRushPlusPlus.java is WorkerDefense.java whose melee units always attack (:116-143; its `resourse` flag never changes) */
+static int is_defense(int kind) { return (kind >= O_AI_WORKER_DEFENSE && kind <= O_AI_RANGED_DEFENSE) || kind == O_AI_WORKER_RUSH_PP; }
 static int is_po_rush(int kind) { return kind >= O_AI_PO_WORKER_RUSH && kind <= O_AI_PO_RANGED_RUSH; }
 /* PartiallyObservableGameState.observable :61-71 */
 static int po_observable(const OGame *g, int x, int y) {
@@ -1172,7 +1173,7 @@ static void melee_behavior(OAi *ai, const OGame *g, int u, int player) {
         }
     }
     if (is_defense(ai->kind)) {
-        if (closest >= 0 && (cd < g->h / 2 || mybase < g->h / 2)) ai_attack(ai, u, closest);
+        if (closest >= 0 && (ai->kind == O_AI_WORKER_RUSH_PP || cd < g->h / 2 || mybase < g->h / 2)) ai_attack(ai, u, closest);
         else ai_attack(ai, u, -1);
         return;
     }
@@ -1251,7 +1252,7 @@ static int ai_get_action_k(OAi *ai, OGame *g, int player, OPair *out) {
     /* the defenses: WorkerDefense.java = WorkerRush's skeleton, {Light,Heavy,Ranged}Defense.java = LightRush's, with the melee and
      * harvest rules swapped (melee_behavior / harvest_behavior) */
     int LIGHT = (ai->kind == O_AI_HEAVY_RUSH || ai->kind == O_AI_HEAVY_DEFENSE) ? 5 : ((ai->kind == O_AI_RANGED_RUSH || ai->kind == O_AI_RANGED_DEFENSE) ? 6 : type_by_role_light());
-    int barracks_rush = ai->kind != O_AI_WORKER_RUSH && ai->kind != O_AI_WORKER_DEFENSE;
+    int barracks_rush = ai->kind != O_AI_WORKER_RUSH && ai->kind != O_AI_WORKER_DEFENSE && ai->kind != O_AI_WORKER_RUSH_PP;
     int pres = g->res[player];
     /* bases: WorkerRush.java:70-76,100-102 ; LightRush.java:83-89,123-133 */
     for (int i = 0; i < g->n; i++) {
@@ -1512,7 +1513,8 @@ static int policy(OGame *g, int kind, OAi *ai, int player, OPair *out) {
         case O_AI_WORKER_DEFENSE: case O_AI_LIGHT_DEFENSE: case O_AI_HEAVY_DEFENSE:
         case O_AI_RANGED_DEFENSE:
         case O_AI_PO_WORKER_RUSH: case O_AI_PO_LIGHT_RUSH: case O_AI_PO_HEAVY_RUSH:
-        case O_AI_PO_RANGED_RUSH: return ai_get_action(ai, g, player, out);
+        case O_AI_PO_RANGED_RUSH:
+        case O_AI_WORKER_RUSH_PP: return ai_get_action(ai, g, player, out);
         default: return 0; /* PassiveAI: empty PlayerAction */
     }
 }
@@ -1537,7 +1539,7 @@ int o_run_game(OGame *g, int kind0, OAi *ai0, int kind1, OAi *ai1, int n_cycles,
  * the lists are issued with issueSafe on the real state.  The view is a copy with the same unit handles, so the pairs and
  * the AIs' abstract actions refer to the real game; the policy RNG (a static in the reference) is carried back. */
 static int policy_po(OGame *g, int kind, OAi *ai, int player, OPair *out) {
-    if (kind != O_AI_RANDOM_BIASED && !(kind >= O_AI_WORKER_RUSH && kind <= O_AI_PO_RANGED_RUSH)) return policy(g, kind, ai, player, out);
+    if (kind != O_AI_RANDOM_BIASED && !(kind >= O_AI_WORKER_RUSH && kind <= O_AI_WORKER_RUSH_PP)) return policy(g, kind, ai, player, out);
     OGame *v = o_po_view(g, player);
     int n = policy(v, kind, ai, player, out);
     g->rng_policy = v->rng_policy;

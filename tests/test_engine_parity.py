@@ -521,6 +521,8 @@ SCRIPTED = [
     ("16x16/basesWorkers16x16", "WORKER_RUSH", "LIGHT_RUSH", 2),
     ("8x8/basesWorkers8x8", "RANGED_RUSH", "WORKER_DEFENSE", 2),
     ("BWDistantResources32x32", "LIGHT_RUSH", "RANGED_RUSH", 2),
+    ("16x16/basesWorkers16x16", "WORKER_RUSH_PP", "LIGHT_RUSH", 0),
+    ("8x8/basesWorkers8x8", "WORKER_DEFENSE", "WORKER_RUSH_PP", 1),
 ]
 
 
@@ -654,6 +656,7 @@ MAP_SWEEP_COMBOS = [
     ("WORKER_RUSH", "RANGED_DEFENSE", 0, False),
     ("RANDOM_BIASED", "RANDOM_BIASED", 0, True),
     ("PO_HEAVY_RUSH", "LIGHT_DEFENSE", 2, True),
+    ("WORKER_RUSH_PP", "HEAVY_RUSH", 0, False),
 ]
 
 
