@@ -1276,42 +1276,39 @@ DEVN void po_unhide(Game &g) {
     __syncwarp();
 }
 
+// a device policy of a MRTS_FLAG_PO_POLICIES batch: decide on the player's view, then issueSafe on the real state (Game.java:
+// 129-137): a move into a cell a hidden unit holds becomes NONE.  One out-of-line copy, away from the common path.
+DEVN int run_policy_po(Game &g, const StepParams &p, int player, int pn) {
+    const int pol = p.policy[player], n0 = pn;
+    po_hide(g, player);
+    if (pol == POL_RANDOM_BIASED) pn = policy_random_biased(g, player, pn);
+    else if (p.scripted) pn = policy_scripted(g, player, pol, p.pathfinder[player], pn);
+    po_unhide(g);
+    legality_pass(g, n0, pn);
+    return pn;
+}
+
 DEV int run_policy(Game &g, const StepParams &p, long long gi, int player, int pn, bool first_iter) {
     const int pol = p.policy[player];
-    const bool po = p.po_policies && (pol == POL_RANDOM_BIASED || POL_IS_SCRIPTED(pol)); // the policy sees its PO view
-    switch (pol) {
-        case POL_RANDOM_BIASED: {
-            if (!po) return policy_random_biased(g, player, pn);
+    if (p.po_policies && (pol == POL_RANDOM_BIASED || POL_IS_SCRIPTED(pol))) return run_policy_po(g, p, player, pn);
+    if (pol == POL_RANDOM_BIASED) return policy_random_biased(g, player, pn);
+    if (pol == POL_EXTERNAL) {
+        if (first_iter && p.ext_actions[player]) {
+            int cnt = p.ext_counts[player] ? p.ext_counts[player][gi] : p.ext_maxk[player];
+            if (cnt > p.ext_maxk[player]) cnt = p.ext_maxk[player];
             int n0 = pn;
-            po_hide(g, player);
-            pn = policy_random_biased(g, player, pn);
-            po_unhide(g);
-            legality_pass(g, n0, pn); // issueSafe on the real state (Game.java:136-137): a move into a cell a hidden unit holds becomes NONE
-            return pn;
+            pn = decode_external(g, player, pn, p.ext_actions[player] + gi * (long long)p.ext_maxk[player] * 8, cnt,
+                                 p.ext_format[player], p.ext_fill[player], 2 * p.max_range + 1);
+            if (p.safe) legality_pass(g, n0, pn);
         }
-        case POL_EXTERNAL:
-            if (first_iter && p.ext_actions[player]) {
-                int cnt = p.ext_counts[player] ? p.ext_counts[player][gi] : p.ext_maxk[player];
-                if (cnt > p.ext_maxk[player]) cnt = p.ext_maxk[player];
-                int n0 = pn;
-                pn = decode_external(g, player, pn, p.ext_actions[player] + gi * (long long)p.ext_maxk[player] * 8, cnt,
-                                     p.ext_format[player], p.ext_fill[player], 2 * p.max_range + 1);
-                if (p.safe) legality_pass(g, n0, pn);
-            }
-            return pn;
-        case POL_WORKER_RUSH: case POL_LIGHT_RUSH: case POL_HEAVY_RUSH: case POL_RANGED_RUSH:
-        case POL_WORKER_DEFENSE: case POL_LIGHT_DEFENSE: case POL_HEAVY_DEFENSE: case POL_RANGED_DEFENSE:
-        case POL_PO_WORKER_RUSH: case POL_PO_LIGHT_RUSH: case POL_PO_HEAVY_RUSH: case POL_PO_RANGED_RUSH: case POL_WORKER_RUSH_PP: {
-            if (!p.scripted) return pn;
-            int n0 = pn;
-            if (po) po_hide(g, player);
-            pn = policy_scripted(g, player, pol, p.pathfinder[player], pn);
-            if (po) po_unhide(g);
-            legality_pass(g, n0, pn); // the list goes through issueSafe (Game.java:136-137), which may replace desires by NONE
-            return pn;
-        }
-        default: return pn; // PASSIVE
+        return pn;
     }
+    if (POL_IS_SCRIPTED(pol) && p.scripted) {
+        int n0 = pn;
+        pn = policy_scripted(g, player, pol, p.pathfinder[player], pn);
+        legality_pass(g, n0, pn); // the list goes through issueSafe (Game.java:136-137), which may replace desires by NONE
+    }
+    return pn; // PASSIVE
 }
 
 // One decision point of RandomBiasedAI players: scan, then each deciding player's pass.  Returns the earliest completion

@@ -65,6 +65,17 @@ template <class F> DEV int w_count(const Game &g, int n, F pred) {
     for (int i = g.lane; i < n; i += 32) c += pred(i, g.w0()[i]) ? 1 : 0;
     return __reduce_add_sync(FULLM, c);
 }
+// visit the units satisfying pred in list order: the lanes test 32 units at a time, the warp then walks the set bits (body
+// is warp-uniform and must not change what pred reads)
+template <class P, class F> DEV void w_for_each(const Game &g, int n, P pred, F body) {
+#pragma unroll 1
+    for (int base = 0; base < n; base += 32) {
+        int i = base + g.lane;
+        unsigned mask = __ballot_sync(FULLM, i < n && pred(i, g.w0()[i]));
+#pragma unroll 1
+        while (mask) { int b = __ffs(mask) - 1; mask &= mask - 1; body(base + b); }
+    }
+}
 template <class F> DEV int w_next(const Game &g, int n, int from, F pred) { // first unit after `from` satisfying pred, or -1
     unsigned best = 0xFFFFFFFFu;
 #pragma unroll 1
@@ -244,7 +255,7 @@ DEVN int pf_find_t(Game &g, int kind, int s, int tx, int ty, int range, int nd) 
 // distance to the target -- the first free direction is always taken, a later one only if strictly closer.  "Already in
 // range" compares the SQUARED distance with the unsquared range (:66), as the reference does.  Lanes 0..3 look at one
 // neighbour each; the choice is made on warp-uniform values.
-DEV int pf_greedy(Game &g, int s, int tx, int ty, int range, int nd) {
+DEVN int pf_greedy(Game &g, int s, int tx, int ty, int range, int nd) {
     uint32_t sw = g.w0()[s];
     int sx = u_x(sw), sy = u_y(sw), start = cell_of(g, sw);
     if (range >= 0 && (tx - sx) * (tx - sx) + (ty - sy) * (ty - sy) <= range) return -1; // range < 0: findPath (:16-47) has no such test
@@ -419,7 +430,9 @@ DEVN int find_building_position(const Game &g, const int *reserved, int nres, in
 // (WorkerDefense.java:117-146, LightDefense.java:142-165) do so only while that enemy, or the own base -- the LAST own base
 // of the unit list, distance 0 without one -- is closer than height/2; otherwise they put an Attack with a null target,
 // which translateActions finds completed and deletes (so the unit's next entry goes to the end of the map).
-DEV void script_melee(Game &g, int s, int player, bool defense, bool explore = false, bool always = false) {
+// (the defense and exploration variants are kept out of line: the generic kernel is instruction-cache bound, and the rushes
+// of the benchmark configuration never run them)
+DEVN void script_melee_special(Game &g, int s, int player, bool defense, bool explore, bool always) {
     int n = g.hdr()[H_NUNITS];
     uint32_t w = g.w0()[s];
     int cd = 0;
@@ -446,6 +459,13 @@ DEV void script_melee(Game &g, int s, int player, bool defense, bool explore = f
         best = __reduce_min_sync(FULLM, best);
         if (best != 0xFFFFFFFFu) { int q = (int)(best & 0x3FFFu), y = q / g.W; aa_put(g, s, player, AA_MOVE, 0, q - y * g.W, y, REF_NULL, REF_NULL); }
     }
+}
+DEV void script_melee(Game &g, int s, int player, bool defense, bool explore = false, bool always = false) {
+    if (defense || explore) { script_melee_special(g, s, player, defense, explore, always); return; }
+    int n = g.hdr()[H_NUNITS];
+    uint32_t w = g.w0()[s];
+    int closest = w_argmin(g, n, [&](int, uint32_t ow) { return (u_pl(ow) != 0 && u_pl(ow) != player + 1) ? iabs(u_x(ow) - u_x(w)) + iabs(u_y(ow) - u_y(w)) : -1; });
+    if (closest >= 0) aa_put(g, s, player, AA_ATTACK, 0, 0, 0, closest + 1, REF_NULL);
 }
 
 // harvest part of workersBehavior (WorkerRush.java:148-199, LightRush.java:203-252); true if the worker is still free
@@ -508,28 +528,20 @@ DEVN int policy_scripted(Game &g, int player, int kind, int pathfinder, int pn) 
     const int UT_RUSH = (kind == POL_HEAVY_RUSH || kind == POL_HEAVY_DEFENSE) ? 5 : ((kind == POL_RANGED_RUSH || kind == POL_RANGED_DEFENSE) ? 6 : UT_LIGHT); // HeavyRush.java:55, RangedRush.java:52
     auto own_harvester = [&](int, uint32_t w) { return u_pl(w) == pl && (ut_flags(g, u_type(w)) & UF_HARVEST) != 0; };
     // bases (WorkerRush.java:70-76,100-102; LightRush.java:83-89,123-133)
-#pragma unroll 1
-    for (int i = 0; i < n; i++) {
-        uint32_t w = g.w0()[i];
-        if (u_type(w) == UT_BASE && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE) {
-            bool train = pres >= ut_cost(g, UT_WORKER);
-            if (light && train) train = w_count(g, n, [&](int, uint32_t ow) { return u_type(ow) == UT_WORKER && u_pl(ow) == pl; }) < 1;
-            if (train) aa_put(g, i, player, AA_TRAIN, UT_WORKER, 0, 0, REF_NULL, REF_NULL);
-        }
-    }
+    w_for_each(g, n, [&](int i, uint32_t w) { return u_type(w) == UT_BASE && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE; }, [&](int i) {
+        bool train = pres >= ut_cost(g, UT_WORKER);
+        if (light && train) train = w_count(g, n, [&](int, uint32_t ow) { return u_type(ow) == UT_WORKER && u_pl(ow) == pl; }) < 1;
+        if (train) aa_put(g, i, player, AA_TRAIN, UT_WORKER, 0, 0, REF_NULL, REF_NULL);
+    });
     if (light) { // barracks (LightRush.java:92-98,135-139)
-#pragma unroll 1
-        for (int i = 0; i < n; i++) {
-            uint32_t w = g.w0()[i];
-            if (u_type(w) == UT_BARRACKS && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE && pres >= ut_cost(g, UT_RUSH)) aa_put(g, i, player, AA_TRAIN, UT_RUSH, 0, 0, REF_NULL, REF_NULL);
-        }
+        if (pres >= ut_cost(g, UT_RUSH))
+            w_for_each(g, n, [&](int i, uint32_t w) { return u_type(w) == UT_BARRACKS && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE; },
+                       [&](int i) { aa_put(g, i, player, AA_TRAIN, UT_RUSH, 0, 0, REF_NULL, REF_NULL); });
     }
-#pragma unroll 1
-    for (int i = 0; i < n; i++) { // melee units
-        uint32_t w = g.w0()[i];
+    w_for_each(g, n, [&](int i, uint32_t w) { // melee units
         int fl = ut_flags(g, u_type(w));
-        if ((fl & UF_ATTACK) && !(fl & UF_HARVEST) && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE) script_melee(g, i, player, defense, explore, always);
-    }
+        return (fl & UF_ATTACK) && !(fl & UF_HARVEST) && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE;
+    }, [&](int i) { script_melee(g, i, player, defense, explore, always); });
     // workers: all own harvesters, busy ones too, in list order
     int nbases = w_count(g, n, [&](int, uint32_t w) { return u_pl(w) == pl && u_type(w) == UT_BASE; });
     int nbarracks = w_count(g, n, [&](int, uint32_t w) { return u_pl(w) == pl && u_type(w) == UT_BARRACKS; });
@@ -567,20 +579,27 @@ DEVN int policy_scripted(Game &g, int player, int kind, int pathfinder, int pn) 
     // order is nearly insertion order already)
     int ne = 0;
     __syncwarp();
-    if (g.lane == 0) {
 #pragma unroll 1
-        for (int i = 0; i < n; i++) {
-            uint32_t X0 = g.x0()[i];
-            if (aa_kind(X0) == AA_NONE || u_pl(g.w0()[i]) != pl) continue;
-            uint32_t q = aa_seq(X0, g.x1()[i]);
-            int j = ne++;
+    for (int base = 0; base < n; base += 32) { // the entries' slots, compacted in slot order by all lanes ...
+        int i = base + g.lane;
+        bool has = i < n && aa_kind(g.x0()[i]) != AA_NONE && u_pl(g.w0()[i]) == pl;
+        unsigned m = __ballot_sync(FULLM, has);
+        if (has) g.list()[ne + __popc(m & ((1u << g.lane) - 1))] = (uint8_t)i;
+        ne += __popc(m);
+    }
+    __syncwarp();
+    if (g.lane == 0) { // ... then put into insertion order
+#pragma unroll 1
+        for (int k = 1; k < ne; k++) {
+            int i = g.list()[k];
+            uint32_t q = aa_seq(g.x0()[i], g.x1()[i]);
+            int j = k;
 #pragma unroll 1
             while (j > 0) { int o = g.list()[j - 1]; if (aa_seq(g.x0()[o], g.x1()[o]) <= q) break; g.list()[j] = (uint8_t)o; j--; }
             g.list()[j] = (uint8_t)i;
         }
     }
     __syncwarp();
-    ne = __shfl_sync(FULLM, ne, 0);
 #pragma unroll 1
     for (int r = 0; r < ne; r++) {
         int best = g.list()[r];
