@@ -692,3 +692,60 @@ def test_every_reference_map(backend, maps, part):
                 (og.run_po if po else og.run)(kinds[0], ais[0], kinds[1], ais[1], cyc, cyc)
                 P.assert_same_state(ex, g, og, "%s %s/%s pf=%d po=%s" % (key, p0, p1, pf, po))
             b.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# wide differential for the scripted policies: they are deterministic, so each runs against RandomBiasedAI opponents
+# with hundreds of different seeds (complete games, final state against the oracle); half of the combinations as
+# partially observable games
+# ------------------------------------------------------------------------------------------------------------------
+WIDE_SCRIPTED = [
+    # map, scripted policy, its side, pathfinder, partially observable
+    ("16x16/basesWorkers16x16", "LIGHT_RUSH", 0, 0, False),
+    ("16x16/basesWorkers16x16", "WORKER_RUSH", 1, 1, False),
+    ("8x8/basesWorkers8x8", "RANGED_RUSH", 0, 2, False),
+    ("16x16/TwoBasesBarracks16x16", "HEAVY_DEFENSE", 1, 0, False),
+    ("8x8/FourBasesWorkers8x8", "WORKER_DEFENSE", 0, 0, False),
+    ("16x16/basesWorkers16x16", "WORKER_RUSH_PP", 1, 0, False),
+    ("16x16/basesWorkers16x16", "PO_LIGHT_RUSH", 1, 0, True),
+    ("8x8/basesWorkers8x8", "PO_WORKER_RUSH", 0, 1, True),
+    ("16x16/basesWorkers16x16", "PO_RANGED_RUSH", 0, 2, True),
+    ("24x24/basesWorkers24x24", "LIGHT_DEFENSE", 1, 0, True),
+    ("16x16/basesWorkers16x16", "RANDOM_BIASED", 0, 0, True),
+]
+
+
+@pytest.mark.parametrize("key,pol,side,pf,po", WIDE_SCRIPTED)
+def test_wide_differential_scripted(backend, maps, key, pol, side, pf, po):
+    import threading
+    n = 3 if backend == "emu" else 2048
+    total = 400 if backend == "emu" else 3000
+    utt, outt = M.UnitTypeTable(1, 1), O.Utt(1, 1)
+    b = M.BatchedGameState(utt, make_pgs(maps[key], utt), n, scripted_ai=True, po_policies=po)
+    seeds = np.arange(n, dtype=np.int64) * 5 + 101
+    b.reset(seeds)
+    names = ["RANDOM_BIASED", "RANDOM_BIASED"]
+    names[side] = pol
+    kinds = [getattr(O, "AI_" + nm) for nm in names]
+    for pl in range(2):
+        b.set_policy(pl, getattr(M, "POLICY_" + names[pl]), pf)
+    b.step(total, total)
+    ex = b.export()
+    games = [None] * n
+    nthreads = min(16, os.cpu_count() or 1)
+
+    def work(t):
+        for g in range(t, n, nthreads):
+            og = O.Game(outt, maps[key])
+            og.seed(int(seeds[g]))
+            ais = [O.ScriptedAI(k, pf) if k in O.SCRIPTED_AIS else None for k in kinds]
+            (og.run_po if po else og.run)(kinds[0], ais[0], kinds[1], ais[1], total, total)
+            games[g] = og
+
+    ts = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for g, og in enumerate(games):
+        P.assert_same_state(ex, g, og, "%s wide %s side %d pf %d po %s game %d" % (key, pol, side, pf, po, g))
+    assert (b.results()[:, 3] == 0).all()
+    b.close()

@@ -26,4 +26,13 @@ for key in ("8x8/basesWorkers8x8", "GardenOfWar64x64"):
     s.step(300, 3000); s.sync(); s.close()               # scripted: A* scratch in shared / global memory
 po = M.BatchedGameState(utt, pgs("8x8/basesWorkers8x8"), 8, partial_obs=True)
 po.set_policy(0, M.POLICY_RANDOM_BIASED); po.set_policy(1, M.POLICY_RANDOM_BIASED); po.step(200, 3000); po.observe(1); po.sync(); po.close()
+# partially observable games (po_hide / po_unhide, exploration), the defenses, GreedyPathFinding
+for key, p0, p1, pf in (("16x16/basesWorkers16x16", M.POLICY_PO_LIGHT_RUSH, M.POLICY_PO_WORKER_RUSH, M.PF_ASTAR),
+                        ("8x8/basesWorkers8x8", M.POLICY_RANDOM_BIASED, M.POLICY_PO_RANGED_RUSH, M.PF_GREEDY),
+                        ("GardenOfWar64x64", M.POLICY_PO_HEAVY_RUSH, M.POLICY_LIGHT_DEFENSE, M.PF_BFS)):
+    s = M.BatchedGameState(utt, pgs(key), 6, scripted_ai=True, po_policies=True)
+    s.set_policy(0, p0, pf); s.set_policy(1, p1, pf)
+    s.step(400, 3000); s.sync(); s.close()
+s = M.BatchedGameState(utt, pgs("16x16/basesWorkers16x16"), 6, scripted_ai=True)
+s.set_policy(0, M.POLICY_WORKER_DEFENSE, M.PF_GREEDY); s.set_policy(1, M.POLICY_WORKER_RUSH_PP); s.step(600, 3000); s.sync(); s.close()
 print("sanitize case done")
