@@ -154,7 +154,10 @@ __global__ void __launch_bounds__(MRTS_WARPS_PER_CTA * 32, MRTS_MIN_BLOCKS_OBS) 
 __global__ void __launch_bounds__(MRTS_WARPS_PER_CTA * 32, MRTS_MIN_BLOCKS_ROLLOUT) k_rollout(StepParams p) {
     step_kernel_body<KERNEL_ROLLOUT>(p, mrts_smem, threadIdx.x, blockDim.x, blockIdx.x, gridDim.x);
 }
-__global__ void __launch_bounds__(MRTS_WARPS_PER_CTA * 32, 3) k_step(StepParams p) {
+#ifndef MRTS_MIN_BLOCKS_GENERIC
+#define MRTS_MIN_BLOCKS_GENERIC 3
+#endif
+__global__ void __launch_bounds__(MRTS_WARPS_PER_CTA * 32, MRTS_MIN_BLOCKS_GENERIC) k_step(StepParams p) {
     step_kernel_body<KERNEL_GENERIC>(p, mrts_smem, threadIdx.x, blockDim.x, blockIdx.x, gridDim.x);
 }
 __global__ void __launch_bounds__(256) k_observe(ObsParams p) { observe_kernel_body(p, threadIdx.x, blockDim.x, blockIdx.x, gridDim.x); }

@@ -650,17 +650,26 @@ DEVN int policy_scripted(Game &g, int player, int kind, int pathfinder, int pn) 
             uint32_t A0 = g.pa0()[q];
             if (a_uses_cell(a_type(A0))) g.claim()[target_cell(g, cell_of(g, g.w0()[g.pslot()[q]]), g.pa1()[q])] = 0;
         }
-        // PlayerAction.fillWithNones(gs, player, 10) (PlayerAction.java:217-235)
-#pragma unroll 1
-        for (int i = 0; i < n; i++) {
-            if (u_pl(g.w0()[i]) != pl || a_type(g.a0()[i]) != AT_IDLE) continue;
-            bool found = false;
-            for (int q = pn; q < m; q++) found |= g.pslot()[q] == i;
-            if (!found) { g.pslot()[m] = (uint8_t)i; g.pa0()[m] = ACT_NONE | A0_NOUT; g.pa1()[m] = 10; m++; }
-        }
         out = m;
     }
     __syncwarp();
     out = __shfl_sync(FULLM, out, 0);
+    { // PlayerAction.fillWithNones(gs, player, 10) (PlayerAction.java:217-235): the player's idle units without an action, in
+      // unit-list order; all lanes test 32 units at a time and append by ballot
+        const int m0 = out;
+#pragma unroll 1
+        for (int base = 0; base < n; base += 32) {
+            int i = base + g.lane;
+            bool need = i < n && u_pl(g.w0()[i]) == pl && a_type(g.a0()[i]) == AT_IDLE;
+            if (need) {
+#pragma unroll 1
+                for (int q = pn; q < m0; q++) if (g.pslot()[q] == i) { need = false; break; }
+            }
+            unsigned mk = __ballot_sync(FULLM, need);
+            if (need) { int q = out + __popc(mk & ((1u << g.lane) - 1)); g.pslot()[q] = (uint8_t)i; g.pa0()[q] = ACT_NONE | A0_NOUT; g.pa1()[q] = 10; }
+            out += __popc(mk);
+        }
+    }
+    __syncwarp();
     return out;
 }
