@@ -36,13 +36,18 @@ MAX_CYCLES = 3000
 
 
 def workload_string(args):
-    return "maps/%s.xml x %d games/GPU, RandomBiasedAI self-play (Game.start loop), UTT v1 CANCEL_BOTH, %d-cycle cap" % (
-        args.map, args.games, MAX_CYCLES)
+    return "maps/%s.xml x %d games/GPU, RandomBiasedAI self-play (Game.start loop), UTT v%d CANCEL_BOTH, %d-cycle cap" % (
+        args.map, args.games, args.utt_version, MAX_CYCLES)
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--with-masks", action="store_true",
+                    help="obs workload: also emit both players' bit-packed action masks every step (the masks variant of SURVEY 8d cfg 5)")
+    ap.add_argument("--utt-version", type=int, default=1, choices=[1, 2, 3],
+                    help="selfplay workload: UnitTypeTable version (1 = VERSION_ORIGINAL, the headline; 2 = VERSION_ORIGINAL_FINETUNED, "
+                         "the secondary variant of SURVEY 8d; 3 = VERSION_NON_DETERMINISTIC)")
     ap.add_argument("--steps", type=int, default=150)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -66,12 +71,12 @@ def parse():
 # ----------------------------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle port on the host cores (bench.py's cpu_baseline leg may execute oracle/)
 # ----------------------------------------------------------------------------------------------------------------------
-def cpu_baseline(map_key, seconds, threads=None):
+def cpu_baseline(map_key, seconds, threads=None, utt_version=1):
     import golden_io
     from oracle import oracle as O
     maps = golden_io.load_maps()
     threads = threads or (os.cpu_count() or 1)
-    utt = O.Utt(1, 1)
+    utt = O.Utt(utt_version, 1)
     cycles = [0] * threads
     games_done = [0] * threads
     deadline = time.time() + seconds
@@ -158,12 +163,12 @@ def run_reference(args):
         return
     t_per_step = max(0.25, min(20.0, 90.0 / max(1, args.steps + args.warmup)))  # the whole arm ends within about two minutes
     for _ in range(args.warmup):
-        cpu_baseline(args.map, min(1.0, t_per_step))
+        cpu_baseline(args.map, min(1.0, t_per_step), utt_version=args.utt_version)
     vals = []
     t0 = time.time()
     last = None
     for _ in range(args.steps):
-        last = cpu_baseline(args.map, t_per_step)
+        last = cpu_baseline(args.map, t_per_step, utt_version=args.utt_version)
         vals.append(last["value"])
     dt = time.time() - t0
     v = sum(vals) / len(vals)
@@ -274,7 +279,7 @@ def run_ours(args):
     import microrts_b200 as M
     import parity as P
     maps = golden_io.load_maps()
-    utt = M.UnitTypeTable(1, 1)
+    utt = M.UnitTypeTable(args.utt_version, 1)
     pgs = M.PhysicalGameState.fromXML(P.map_to_xml(maps[args.map]), utt)
     n, C = args.games, args.cycles_per_step
     b = M.BatchedGameState(utt, pgs, n, device=local)
@@ -437,7 +442,7 @@ def run_ours(args):
 
     cpu = None
     if not args.no_cpu_baseline:
-        cpu = cpu_baseline(args.map, args.cpu_seconds)
+        cpu = cpu_baseline(args.map, args.cpu_seconds, utt_version=args.utt_version)
 
     out = dict(metric="game_cycles_per_sec", value=value, unit="game-cycles/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                ms_per_step=1000.0 * wall_max / max(1, args.steps), higher_is_better=True, scaling="weak", vs_baseline=None,
@@ -487,6 +492,10 @@ def run_secondary(args):
         b.set_observation_outputs(obs[0], obs[1])
         C = args.cycles_per_step if args.cycles_per_step != 100 else 1
         name = "maps/%s.xml x %d games/GPU, RandomBiasedAI self-play, %d cycle(s) per step, 6-plane uint8 observations of BOTH players written every step (fused)" % (key, n, C)
+        if args.with_masks:
+            mbytes = (b.mask_width + 7) // 8
+            msk = [torch.empty((n, b.height, b.width, mbytes), dtype=torch.uint8, device="cuda") for _ in range(2)]
+            name += " + both players' bit-packed action masks (%d bits = %d bytes per cell)" % (b.mask_width, mbytes)
     elif wl == "scripted":
         keys = ["24x24/basesWorkers24x24"] + ["24x24/basesWorkers24x24" + c for c in "ABCDEFGHIJKL"]
         pgs = [M.PhysicalGameState.fromXML(P.map_to_xml(maps[k]), utt) for k in keys]
@@ -536,6 +545,8 @@ def run_secondary(args):
 
         def step():
             b.step(C, MAX_CYCLES)
+            if wl == "obs" and args.with_masks:
+                b.masks(0, "bits", out=msk[0]); b.masks(1, "bits", out=msk[1])
 
     t_pre = time.perf_counter()
     while time.perf_counter() - t_pre < args.prewarm_seconds:
@@ -583,6 +594,9 @@ def run_secondary(args):
         # B_state per game-cycle + B_obs = P*C*H*W bytes per emitted observation set (one per step)
         bytes_total = cycles * state_bytes + args.steps * n * 2 * 6 * b.height * b.width
         kern, form = "k_step_fast", "cycles*2*(32+24*U) + steps*games*2*6*H*W (uint8 planes of both players)"
+        if args.with_masks:
+            bytes_total += args.steps * n * 2 * b.height * b.width * ((b.mask_width + 7) // 8)
+            kern, form = "k_step_fast + k_step(masks)", form + " + steps*games*2*H*W*10 (bit-packed masks)"
     elif wl == "scripted":
         bytes_total = cycles * (state_bytes + 16.0 * mean_units)
         kern, form = "k_step", "cycles*(2*(32+24*U) + 2*8*U)"
