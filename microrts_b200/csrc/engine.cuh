@@ -1136,7 +1136,7 @@ DEV bool rb_accept(const Game &g, int pl, unsigned m, bool cand, int tcell, int 
         if (ev != 0) blocked = !(simul && g.tis()[ev - 1] == c.time && u_pl(g.w0()[ev - 1]) != pl);
         if (g.claim()[tcell] & pl) blocked = true; // this player's earlier choice of the cell was cancelled at issue (see rb_player)
     }
-    unsigned same = __match_any_sync(FULLM, (cand && tcell >= 0) ? tcell : -1 - g.lane);
+    unsigned same = __match_any_sync(FULLM, (cand && tcell >= 0) ? tcell : -1 - g.lane); // (skipping it when fewer than two lanes have a cell was measured slower)
     unsigned below = (1u << g.lane) - 1;
     // While no candidate that costs resources is involved, the resource half of consistentWith is the same for every lane
     // (`over`), and verdicts only interact when two lanes want the same cell: the first in list order wins, and if it is
@@ -1858,8 +1858,20 @@ DEV void run_rollout(Game &g, const StepParams &p, long long r, WarpStats &ws) {
 //   KERNEL_GENERIC everything else (external actions, scripted policies, other conflict policies, cycle-only,
 //                  issue-only, observations, masks)
 enum { KERNEL_FAST = 0, KERNEL_ROLLOUT = 1, KERNEL_GENERIC = 2, KERNEL_FAST_OBS = 3, N_KERNELS = 4 };
+// Copies of the specialised kernels compiled for one map size and unit capacity (step_kernel_body<KERNEL, W, H, CAP>): the
+// reference's small standard maps with the capacity mrts_batch_create derives for their basesWorkers layouts.
+// X(kernel, W, H, capacity, minimum resident CTAs per SM)
+#define MRTS_FIXED_VARIANTS(X) \
+    X(KERNEL_FAST, 16, 16, 128, MRTS_MIN_BLOCKS) \
+    X(KERNEL_FAST, 8, 8, 64, MRTS_MIN_BLOCKS) \
+    X(KERNEL_ROLLOUT, 16, 16, 128, MRTS_MIN_BLOCKS_ROLLOUT) \
+    X(KERNEL_ROLLOUT, 8, 8, 64, MRTS_MIN_BLOCKS_ROLLOUT) \
+    X(KERNEL_ROLLOUT, 32, 32, 254, MRTS_MIN_BLOCKS_ROLLOUT)
 
-template <int KERNEL>
+// FW, FH, FCAP > 0: a copy of the kernel for one fixed map size and unit capacity (a batch without scripted-policy words): the
+// shared-memory layout, the padded row length and the capacity are compile-time constants there, so the offset arithmetic of
+// every accessor folds into immediates
+template <int KERNEL, int FW = 0, int FH = 0, int FCAP = 0>
 DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int nthreads, int bid, int nblocks) {
 #ifdef MRTS_EMU
     mrts_smem = smem;
@@ -1868,14 +1880,17 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
     #pragma unroll 1
     for (int i = tid; i < MRTS_CONST_WORDS; i += nthreads) cst[i] = p.cst[i];
     __syncthreads();
-    const SmemLayout &L = p.L;
+    constexpr bool FIXED = FW > 0;
+    constexpr SmemLayout LC = mrts_smem_layout(FIXED ? FW : 8, FIXED ? FH : 8, FIXED ? FCAP : 32, 0, 0, 0);
+    const SmemLayout &L = FIXED ? LC : p.L;
+    const int pW = FIXED ? FW : p.W, pH = FIXED ? FH : p.H, pcap = FIXED ? FCAP : p.cap, puw = FIXED ? MRTS_UNIT_WORDS_CORE : p.uw;
     int warp = tid >> 5, lane = tid & 31, wpc = nthreads >> 5;
     int region = MRTS_CONST_WORDS * 4 + warp * L.total;
 #ifndef MRTS_EMU
     asm volatile("" : "+r"(lane)); // keep the lane id in a register instead of re-reading the special register
 #endif
     Game g;
-    g_bind(g, region, L, p.W, p.H, p.cap, lane, p.conflict, p.scripted,
+    g_bind(g, region, L, pW, pH, pcap, lane, p.conflict, p.scripted,
            p.scripted == 2 ? p.astar_scratch + ((long long)bid * wpc + warp) * p.astar_stride : nullptr);
     if (KERNEL == KERNEL_GENERIC && p.scripted) { // pathfinding scratch: no stale marks, all buckets empty, generation 0
         #pragma unroll 1
@@ -1897,7 +1912,7 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
         const uint32_t *blob = p.maps + (size_t)(gi % p.n_maps) * p.map_words;
         g.grid_tmpl = blob;
         int32_t *ghdr = p.hdr + gi * MRTS_HDR_WORDS;
-        uint32_t *gun = p.units + gi * (long long)p.uw * p.cap;
+        uint32_t *gun = p.units + gi * (long long)puw * pcap;
         g_load(g, ghdr, gun, KERNEL != KERNEL_ROLLOUT && p.mode == MODE_GAME && p.auto_reset, p.max_cycles);
         if (KERNEL == KERNEL_ROLLOUT) { run_rollout(g, p, item, ws); continue; } // the batch itself is not modified
         int err0 = g.hdr()[H_ERR];

@@ -8,8 +8,10 @@
 
 #if defined(__CUDACC__)
 #define MRTS_HD __host__ __device__ inline
+#define MRTS_HDC __host__ __device__ constexpr inline
 #else
 #define MRTS_HD static inline
+#define MRTS_HDC static constexpr inline
 #endif
 
 #define MRTS_HDR_WORDS 20
@@ -90,8 +92,8 @@ struct SmemLayout {
 #define MRTS_ASTAR_BYTES(W, H) ((8 * ((W) + 2) * ((H) + 2) + 2 * MRTS_ASTAR_HEADS(W, H) + 4 + 15) & ~15)
 // pending = 0: the layout of the specialised kernels (fast game loop, rollouts), which fuse policy and issue and never
 // stage a pending action list -- 8 bytes per unit slot less, which is what lets one more CTA fit per SM on small maps
-MRTS_HD SmemLayout mrts_smem_layout(int W, int H, int cap, int scripted, int po_policies = 0, int pending = 1) {
-    SmemLayout L;
+MRTS_HDC SmemLayout mrts_smem_layout(int W, int H, int cap, int scripted, int po_policies = 0, int pending = 1) {
+    SmemLayout L{};
     int pc = (W + 2) * (H + 2);
     int pcb = (pc + 15) & ~15;
     int capb = (cap + 15) & ~15;

@@ -148,6 +148,11 @@ DEV void observe_kernel_body(const ObsParams &p, int tid, int nthreads, int bid,
 __global__ void __launch_bounds__(MRTS_WARPS_PER_CTA * 32, MRTS_MIN_BLOCKS) k_step_fast(StepParams p) {
     step_kernel_body<KERNEL_FAST>(p, mrts_smem, threadIdx.x, blockDim.x, blockIdx.x, gridDim.x);
 }
+// the fixed-size copies (engine.cuh: MRTS_FIXED_VARIANTS)
+template <int KERNEL, int W, int H, int CAP, int MINB>
+__global__ void __launch_bounds__(MRTS_WARPS_PER_CTA * 32, MINB) k_fixed(StepParams p) {
+    step_kernel_body<KERNEL, W, H, CAP>(p, mrts_smem, threadIdx.x, blockDim.x, blockIdx.x, gridDim.x);
+}
 __global__ void __launch_bounds__(MRTS_WARPS_PER_CTA * 32, MRTS_MIN_BLOCKS_OBS) k_step_fast_obs(StepParams p) {
     step_kernel_body<KERNEL_FAST_OBS>(p, mrts_smem, threadIdx.x, blockDim.x, blockIdx.x, gridDim.x);
 }
@@ -178,6 +183,23 @@ struct Staged { // external actions staged on the device
     bool valid = false, own = true;
 };
 
+// one fixed-size copy: which kernel it stands in for, for which map size / capacity, and how to launch it
+struct FixedVariant {
+    int kernel, W, H, cap;
+#ifdef MRTS_EMU
+    void (*body)(const StepParams &, unsigned char *, int, int, int, int);
+#else
+    const void *fn;
+#endif
+};
+#ifdef MRTS_EMU
+#define MRTS_FV_ENTRY(K, W, H, C, MINB) {K, W, H, C, &step_kernel_body<K, W, H, C>},
+#else
+#define MRTS_FV_ENTRY(K, W, H, C, MINB) {K, W, H, C, (const void *)k_fixed<K, W, H, C, MINB>},
+#endif
+static const FixedVariant g_fixed[] = {MRTS_FIXED_VARIANTS(MRTS_FV_ENTRY)};
+static const int N_FIXED = (int)(sizeof(g_fixed) / sizeof(g_fixed[0]));
+
 struct mrts_batch {
     UttH utt;
     int W = 0, H = 0, cap = 0, n_maps = 0, map_words = 0, device = 0;
@@ -192,6 +214,7 @@ struct mrts_batch {
     stream_t stream = nullptr;
     SmemLayout L, Lfast; // generic kernel / specialised kernels (no pending lists, layout.h)
     struct Plan { int wpc = 2, grid = 3; size_t smem = 0; } plan[N_KERNELS]; // per kernel: warps (games in flight) per CTA, CTAs, shared memory
+    Plan fixed_plan[N_KERNELS]; int fixed_of[N_KERNELS] = {-1, -1, -1, -1}; // the fixed-size copy that replaces kernel k for this batch, or -1
     int max_range = 0, auto_reset = 0, scripted = 0, uw = MRTS_UNIT_WORDS_CORE;
     int sequential_issue = 0; int32_t *info_out = nullptr; uint32_t tm[6] = {0, 0, 0, 0, 0, 0};
     void *obs_out[2] = {nullptr, nullptr}; int obs_dtype = 0; // device buffers mrts_batch_step writes post-step observations to
@@ -219,7 +242,8 @@ static int launch_step(mrts_batch *b, StepParams &p) {
     if (p.mode == MODE_ROLLOUT) kernel = KERNEL_ROLLOUT;
     else if (p.mode == MODE_GAME && p.conflict == MRTS_CANCEL_BOTH && rb_or_passive(p.policy[0]) && rb_or_passive(p.policy[1]) && !p.info_out && !p.sequential_issue && !p.po_policies)
         kernel = (p.obs_out[0] || p.obs_out[1]) ? KERNEL_FAST_OBS : KERNEL_FAST;
-    const mrts_batch::Plan &pl = b->plan[kernel];
+    const int fv = b->fixed_of[kernel];
+    const mrts_batch::Plan &pl = fv >= 0 ? b->fixed_plan[kernel] : b->plan[kernel];
     p.L = kernel == KERNEL_GENERIC ? b->L : b->Lfast;
     int threads = pl.wpc * 32;
     long long items = p.mode == MODE_ROLLOUT ? b->n * p.rollouts_per_game : b->n;
@@ -228,14 +252,16 @@ static int launch_step(mrts_batch *b, StepParams &p) {
     b->launches++;
 #ifdef MRTS_EMU
     StepParams pc = p;
-    emu::launch(grid, threads, pl.smem, [pc, threads, grid, kernel](unsigned char *sm, int tid, int bid) {
-        if (kernel == KERNEL_FAST) step_kernel_body<KERNEL_FAST>(pc, sm, tid, threads, bid, grid);
+    emu::launch(grid, threads, pl.smem, [pc, threads, grid, kernel, fv](unsigned char *sm, int tid, int bid) {
+        if (fv >= 0) g_fixed[fv].body(pc, sm, tid, threads, bid, grid);
+        else if (kernel == KERNEL_FAST) step_kernel_body<KERNEL_FAST>(pc, sm, tid, threads, bid, grid);
         else if (kernel == KERNEL_FAST_OBS) step_kernel_body<KERNEL_FAST_OBS>(pc, sm, tid, threads, bid, grid);
         else if (kernel == KERNEL_ROLLOUT) step_kernel_body<KERNEL_ROLLOUT>(pc, sm, tid, threads, bid, grid);
         else step_kernel_body<KERNEL_GENERIC>(pc, sm, tid, threads, bid, grid);
     });
     return 0;
 #else
+    if (fv >= 0) { void *args[] = {&p}; return ck(cudaLaunchKernel(g_fixed[fv].fn, dim3(grid), dim3(threads), args, pl.smem, b->stream)); }
     if (kernel == KERNEL_FAST) k_step_fast<<<grid, threads, pl.smem, b->stream>>>(p);
     else if (kernel == KERNEL_FAST_OBS) k_step_fast_obs<<<grid, threads, pl.smem, b->stream>>>(p);
     else if (kernel == KERNEL_ROLLOUT) k_rollout<<<grid, threads, pl.smem, b->stream>>>(p);
@@ -388,27 +414,42 @@ int mrts_batch_create(const mrts_utt *u, const mrts_map *const *maps, int n_maps
     // Per kernel: as many games in flight per SM as shared memory and registers allow (large maps need fewer, fatter
     // CTAs); grid = resident CTAs per SM x SMs (persistent kernel).
     const void *kernels[N_KERNELS] = {(const void *)k_step_fast, (const void *)k_rollout, (const void *)k_step, (const void *)k_step_fast_obs};
-    for (int kk = 0; kk < N_KERNELS; kk++) {
+    auto make_plan = [&](const void *fn, int region, mrts_batch::Plan &out) -> int {
         int best_wpc = 0, best_warps = 0, best_blocks = 0;
-        if (ck(cudaFuncSetAttribute(kernels[kk], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin)) ||
-            ck(cudaFuncSetAttribute(kernels[kk], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)))
+        if (ck(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin)) ||
+            ck(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)))
             return fail(MRTS_E_CUDA, std::string("cudaFuncSetAttribute: ") + dev_errstr());
         for (int wpc = MRTS_WARPS_PER_CTA; wpc >= 1; wpc--) {
-            const int region = kk == KERNEL_GENERIC ? b->L.total : b->Lfast.total;
             size_t sm = MRTS_CONST_WORDS * 4 + (size_t)wpc * region;
             if (sm > (size_t)prop.sharedMemPerBlockOptin) continue;
             int per_sm = 0;
-            if (ck(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernels[kk], wpc * 32, sm))) return fail(MRTS_E_CUDA, std::string("occupancy query: ") + dev_errstr());
+            if (ck(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, wpc * 32, sm))) return fail(MRTS_E_CUDA, std::string("occupancy query: ") + dev_errstr());
             if (per_sm * wpc > best_warps) { best_warps = per_sm * wpc; best_wpc = wpc; best_blocks = per_sm; }
         }
         if (!best_wpc) return fail(MRTS_E_LIMIT, "map too large for the shared-memory resident engine");
-        b->plan[kk].wpc = best_wpc;
-        b->plan[kk].smem = MRTS_CONST_WORDS * 4 + (size_t)best_wpc * (kk == KERNEL_GENERIC ? b->L.total : b->Lfast.total);
-        b->plan[kk].grid = best_blocks * prop.multiProcessorCount;
+        out.wpc = best_wpc;
+        out.smem = MRTS_CONST_WORDS * 4 + (size_t)best_wpc * region;
+        out.grid = best_blocks * prop.multiProcessorCount;
+        return 0;
+    };
+    for (int kk = 0; kk < N_KERNELS; kk++) {
+        int rc = make_plan(kernels[kk], kk == KERNEL_GENERIC ? b->L.total : b->Lfast.total, b->plan[kk]);
+        if (rc) return rc;
     }
+#ifndef MRTS_NO_FIXED
+    // a fixed-size copy stands in when the batch has exactly its map size and capacity and no scripted-policy unit words
+    for (int v = 0; v < N_FIXED; v++)
+        if (g_fixed[v].W == W && g_fixed[v].H == H && g_fixed[v].cap == cap && !b->scripted) {
+            int rc = make_plan(g_fixed[v].fn, b->Lfast.total, b->fixed_plan[g_fixed[v].kernel]);
+            if (rc) return rc;
+            b->fixed_of[g_fixed[v].kernel] = v;
+        }
+#endif
     if (ck(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking))) return fail(MRTS_E_CUDA, std::string("cudaStreamCreate: ") + dev_errstr());
 #else
     for (int kk = 0; kk < N_KERNELS; kk++) { b->plan[kk].wpc = 2; b->plan[kk].smem = MRTS_CONST_WORDS * 4 + (size_t)2 * (kk == KERNEL_GENERIC ? b->L.total : b->Lfast.total); b->plan[kk].grid = 3; }
+    for (int v = 0; v < N_FIXED; v++)
+        if (g_fixed[v].W == W && g_fixed[v].H == H && g_fixed[v].cap == cap && !b->scripted) { b->fixed_plan[g_fixed[v].kernel] = b->plan[g_fixed[v].kernel]; b->fixed_of[g_fixed[v].kernel] = v; }
 #endif
     if (b->scripted == 2) {
         b->astar_stride = ((long long)MRTS_ASTAR_BYTES(W, H) + 255) & ~255LL;
