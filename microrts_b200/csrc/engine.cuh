@@ -22,9 +22,9 @@
 #define DEV __device__ __forceinline__
 #define MDEV __device__ __forceinline__
 #ifdef MRTS_INLINE_ALL
-#define DEVN __device__ __forceinline__
+#define DEVN static __device__ __forceinline__
 #else
-#define DEVN __device__ __noinline__
+#define DEVN static __device__ __noinline__ // static: the engine is compiled into more than one translation unit (fixed_24x24.cu)
 #endif
 #endif
 
@@ -108,14 +108,31 @@ __device__ __forceinline__ uint32_t smem_window(int byte_offset) {
 __device__ __forceinline__ unsigned char *smem_ptr(uint32_t a) { return (unsigned char *)__cvta_shared_to_generic(a); }
 #endif
 
+// MRTS_TU_FIXED: this whole translation unit is compiled for ONE layout (map MRTS_TU_W x MRTS_TU_H, MRTS_TU_CAP unit slots,
+// scripted-policy words and pathfinding scratch in shared memory; fixed_24x24.cu).  The layout fields of Game are then static
+// constants, so they fold into immediates even inside the out-of-line functions of the generic kernel, which otherwise
+// reload them from the Game object in local memory at every access.
+#ifdef MRTS_TU_FIXED
+#define MRTS_TU_LAYOUT mrts_smem_layout(MRTS_TU_W, MRTS_TU_H, MRTS_TU_CAP, 1, 0, 1)
+#endif
 struct Game {
     int lane;
+#ifdef MRTS_TU_FIXED
+    static constexpr int W = MRTS_TU_W, H = MRTS_TU_H, P = MRTS_TU_W + 2, cap = MRTS_TU_CAP, pcw = MRTS_TU_LAYOUT.pcw, uw = MRTS_TU_LAYOUT.uws - 1;
+    static constexpr int o_pa0 = MRTS_TU_LAYOUT.pa0, o_pa1 = MRTS_TU_LAYOUT.pa1, o_pslot = MRTS_TU_LAYOUT.pslot, o_grid = MRTS_TU_LAYOUT.grid,
+                         o_kind = MRTS_TU_LAYOUT.kind, o_resv = MRTS_TU_LAYOUT.resv, o_claim = MRTS_TU_LAYOUT.claim, o_list = MRTS_TU_LAYOUT.list,
+                         o_povis = MRTS_TU_LAYOUT.povis, o_pohid = MRTS_TU_LAYOUT.pohid, o_rdy = MRTS_TU_LAYOUT.rdy, o_units = MRTS_TU_LAYOUT.uoff[0];
+    int conflict;
+    MDEV static constexpr int uoffset(int k) { return o_units + k * cap * 4; }
+#else
     int W, H, P, cap, pcw, conflict, uw; // uw: unit words mirrored in HBM (7, or 9 with scripted policies)
-    uint32_t sb, cb;                      // shared-window addresses of this game's region and of the CTA's constant block
     int o_pa0, o_pa1, o_pslot, o_grid, o_kind, o_resv, o_claim, o_list;
     int o_povis, o_pohid;                 // MRTS_FLAG_PO_POLICIES batches only (layout.h)
-    bool po_view;                         // the unit table currently shows one player's partially observable view (po_hide)
     int o_rdy, uoff[MRTS_UNIT_WORDS + 1]; // byte offsets of the unit word arrays inside the region (host-computed constants)
+    MDEV int uoffset(int k) const { return uoff[k]; }
+#endif
+    uint32_t sb, cb;                      // shared-window addresses of this game's region and of the CTA's constant block
+    bool po_view;                         // the unit table currently shows one player's partially observable view (po_hide)
     int pview;                            // window into the pending list (policy_scripted stages desires behind the final part)
     const uint32_t *grid_tmpl;            // global: wall-padded empty grid of this game's map
     uint16_t *as_closed, *as_xy, *as_mark, *as_next, *as_head, *as_gen; // A*/BFS scratch of this warp (scripted batches only, layout.h)
@@ -123,7 +140,7 @@ struct Game {
 
     MDEV unsigned char *base() const { return smem_ptr(sb); }
     MDEV int32_t *hdr() const { return (int32_t *)base(); }
-    MDEV uint32_t *uword(int k) const { return (uint32_t *)(base() + uoff[k]); }
+    MDEV uint32_t *uword(int k) const { return (uint32_t *)(base() + uoffset(k)); }
     MDEV uint32_t *w0() const { return uword(UW_W0); }
     MDEV uint32_t *w1() const { return uword(UW_W1); }
     MDEV uint32_t *a0() const { return uword(UW_A0); }
@@ -150,13 +167,16 @@ struct Game {
 
 DEV void g_bind(Game &g, int region, const SmemLayout &L, int W, int H, int cap, int lane, int conflict, int scripted,
                 unsigned char *astar_global) {
-    g.lane = lane; g.W = W; g.H = H; g.P = L.P; g.cap = cap; g.pcw = L.pcw; g.conflict = conflict;
+    g.lane = lane; g.conflict = conflict;
+#ifndef MRTS_TU_FIXED
+    g.W = W; g.H = H; g.P = L.P; g.cap = cap; g.pcw = L.pcw;
     for (int k = 0; k <= MRTS_UNIT_WORDS; k++) g.uoff[k] = L.uoff[k];
     g.o_rdy = L.rdy;
     g.uw = L.uws - 1; // host-computed: 7, or 9 for scripted batches
-    g.sb = smem_window(region); g.cb = smem_window(0); g.pview = 0;
     g.o_pa0 = L.pa0; g.o_pa1 = L.pa1; g.o_pslot = L.pslot; g.o_grid = L.grid; g.o_kind = L.kind; g.o_resv = L.resv;
-    g.o_claim = L.claim; g.o_list = L.list; g.o_povis = L.povis; g.o_pohid = L.pohid; g.po_view = false;
+    g.o_claim = L.claim; g.o_list = L.list; g.o_povis = L.povis; g.o_pohid = L.pohid;
+#endif
+    g.sb = smem_window(region); g.cb = smem_window(0); g.pview = 0; g.po_view = false;
     { int pc = (W + 2) * (H + 2); g.as_closed = (uint16_t *)(astar_global ? astar_global : mrts_smem + region + L.astar); g.as_xy = g.as_closed + pc;
       g.as_mark = g.as_xy + pc; g.as_next = g.as_mark + pc; g.as_head = g.as_next + pc; g.as_gen = g.as_head + MRTS_ASTAR_HEADS(W, H);
       g.as_sm = (scripted == 1) ? smem_window(region + L.astar) : 0u; }

@@ -198,6 +198,10 @@ struct FixedVariant {
 #define MRTS_FV_ENTRY(K, W, H, C, MINB) {K, W, H, C, (const void *)k_fixed<K, W, H, C, MINB>},
 #endif
 static const FixedVariant g_fixed[] = {MRTS_FIXED_VARIANTS(MRTS_FV_ENTRY)};
+#ifndef MRTS_EMU
+// the generic kernel compiled for one layout in its own translation unit (fixed_24x24.cu)
+extern "C" __attribute__((visibility("hidden"))) const void *mrts_fixed_generic_24x24(int *W, int *H, int *cap); // library-internal
+#endif
 static const int N_FIXED = (int)(sizeof(g_fixed) / sizeof(g_fixed[0]));
 
 struct mrts_batch {
@@ -215,6 +219,7 @@ struct mrts_batch {
     SmemLayout L, Lfast; // generic kernel / specialised kernels (no pending lists, layout.h)
     struct Plan { int wpc = 2, grid = 3; size_t smem = 0; } plan[N_KERNELS]; // per kernel: warps (games in flight) per CTA, CTAs, shared memory
     Plan fixed_plan[N_KERNELS]; int fixed_of[N_KERNELS] = {-1, -1, -1, -1}; // the fixed-size copy that replaces kernel k for this batch, or -1
+    const void *generic_fixed_fn = nullptr; // fixed_24x24.cu's kernel when the batch has its layout (plan in fixed_plan[KERNEL_GENERIC])
     int max_range = 0, auto_reset = 0, scripted = 0, uw = MRTS_UNIT_WORDS_CORE;
     int sequential_issue = 0; int32_t *info_out = nullptr; uint32_t tm[6] = {0, 0, 0, 0, 0, 0};
     void *obs_out[2] = {nullptr, nullptr}; int obs_dtype = 0; // device buffers mrts_batch_step writes post-step observations to
@@ -243,7 +248,8 @@ static int launch_step(mrts_batch *b, StepParams &p) {
     else if (p.mode == MODE_GAME && p.conflict == MRTS_CANCEL_BOTH && rb_or_passive(p.policy[0]) && rb_or_passive(p.policy[1]) && !p.info_out && !p.sequential_issue && !p.po_policies)
         kernel = (p.obs_out[0] || p.obs_out[1]) ? KERNEL_FAST_OBS : KERNEL_FAST;
     const int fv = b->fixed_of[kernel];
-    const mrts_batch::Plan &pl = fv >= 0 ? b->fixed_plan[kernel] : b->plan[kernel];
+    const bool gfx = kernel == KERNEL_GENERIC && b->generic_fixed_fn;
+    const mrts_batch::Plan &pl = (fv >= 0 || gfx) ? b->fixed_plan[kernel] : b->plan[kernel];
     p.L = kernel == KERNEL_GENERIC ? b->L : b->Lfast;
     int threads = pl.wpc * 32;
     long long items = p.mode == MODE_ROLLOUT ? b->n * p.rollouts_per_game : b->n;
@@ -261,7 +267,7 @@ static int launch_step(mrts_batch *b, StepParams &p) {
     });
     return 0;
 #else
-    if (fv >= 0) { void *args[] = {&p}; return ck(cudaLaunchKernel(g_fixed[fv].fn, dim3(grid), dim3(threads), args, pl.smem, b->stream)); }
+    if (fv >= 0 || gfx) { void *args[] = {&p}; return ck(cudaLaunchKernel(gfx ? b->generic_fixed_fn : g_fixed[fv].fn, dim3(grid), dim3(threads), args, pl.smem, b->stream)); }
     if (kernel == KERNEL_FAST) k_step_fast<<<grid, threads, pl.smem, b->stream>>>(p);
     else if (kernel == KERNEL_FAST_OBS) k_step_fast_obs<<<grid, threads, pl.smem, b->stream>>>(p);
     else if (kernel == KERNEL_ROLLOUT) k_rollout<<<grid, threads, pl.smem, b->stream>>>(p);
@@ -444,6 +450,15 @@ int mrts_batch_create(const mrts_utt *u, const mrts_map *const *maps, int n_maps
             if (rc) return rc;
             b->fixed_of[g_fixed[v].kernel] = v;
         }
+    {
+        int fw = 0, fh = 0, fcap = 0;
+        const void *fn = mrts_fixed_generic_24x24(&fw, &fh, &fcap);
+        if (fw == W && fh == H && fcap == cap && b->scripted == 1 && !po_pol) {
+            int rc = make_plan(fn, b->L.total, b->fixed_plan[KERNEL_GENERIC]);
+            if (rc) return rc;
+            b->generic_fixed_fn = fn;
+        }
+    }
 #endif
     if (ck(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking))) return fail(MRTS_E_CUDA, std::string("cudaStreamCreate: ") + dev_errstr());
 #else
