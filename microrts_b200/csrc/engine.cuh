@@ -24,7 +24,7 @@
 #ifdef MRTS_INLINE_ALL
 #define DEVN static __device__ __forceinline__
 #else
-#define DEVN static __device__ __noinline__ // static: the engine is compiled into more than one translation unit (fixed_24x24.cu)
+#define DEVN static __device__ __noinline__ // static: the engine is compiled into more than one translation unit (fixed_<W>x<H>.cu)
 #endif
 #endif
 
@@ -109,7 +109,7 @@ __device__ __forceinline__ unsigned char *smem_ptr(uint32_t a) { return (unsigne
 #endif
 
 // MRTS_TU_FIXED: this whole translation unit is compiled for ONE layout (map MRTS_TU_W x MRTS_TU_H, MRTS_TU_CAP unit slots,
-// scripted-policy words and pathfinding scratch in shared memory; fixed_24x24.cu).  The layout fields of Game are then static
+// scripted-policy words and pathfinding scratch in shared memory; fixed_generic.inc).  The layout fields of Game are then static
 // constants, so they fold into immediates even inside the out-of-line functions of the generic kernel, which otherwise
 // reload them from the Game object in local memory at every access.
 #ifdef MRTS_TU_FIXED

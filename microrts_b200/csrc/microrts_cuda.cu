@@ -199,8 +199,11 @@ struct FixedVariant {
 #endif
 static const FixedVariant g_fixed[] = {MRTS_FIXED_VARIANTS(MRTS_FV_ENTRY)};
 #ifndef MRTS_EMU
-// the generic kernel compiled for one layout in its own translation unit (fixed_24x24.cu)
-extern "C" __attribute__((visibility("hidden"))) const void *mrts_fixed_generic_24x24(int *W, int *H, int *cap); // library-internal
+// the generic kernel compiled for one layout each in translation units of their own (fixed_<W>x<H>.cu, fixed_generic.inc)
+typedef const void *(*fixed_generic_getter)(int *W, int *H, int *cap);
+#define MRTS_FG_DECL(name) extern "C" __attribute__((visibility("hidden"))) const void *mrts_fixed_generic_##name(int *W, int *H, int *cap);
+MRTS_FG_DECL(24x24) MRTS_FG_DECL(16x16) MRTS_FG_DECL(8x8)
+static const fixed_generic_getter g_fixed_generic[] = {mrts_fixed_generic_24x24, mrts_fixed_generic_16x16, mrts_fixed_generic_8x8};
 #endif
 static const int N_FIXED = (int)(sizeof(g_fixed) / sizeof(g_fixed[0]));
 
@@ -219,7 +222,7 @@ struct mrts_batch {
     SmemLayout L, Lfast; // generic kernel / specialised kernels (no pending lists, layout.h)
     struct Plan { int wpc = 2, grid = 3; size_t smem = 0; } plan[N_KERNELS]; // per kernel: warps (games in flight) per CTA, CTAs, shared memory
     Plan fixed_plan[N_KERNELS]; int fixed_of[N_KERNELS] = {-1, -1, -1, -1}; // the fixed-size copy that replaces kernel k for this batch, or -1
-    const void *generic_fixed_fn = nullptr; // fixed_24x24.cu's kernel when the batch has its layout (plan in fixed_plan[KERNEL_GENERIC])
+    const void *generic_fixed_fn = nullptr; // a fixed_<W>x<H>.cu kernel when the batch has its layout (plan in fixed_plan[KERNEL_GENERIC])
     int max_range = 0, auto_reset = 0, scripted = 0, uw = MRTS_UNIT_WORDS_CORE;
     int sequential_issue = 0; int32_t *info_out = nullptr; uint32_t tm[6] = {0, 0, 0, 0, 0, 0};
     void *obs_out[2] = {nullptr, nullptr}; int obs_dtype = 0; // device buffers mrts_batch_step writes post-step observations to
@@ -450,9 +453,9 @@ int mrts_batch_create(const mrts_utt *u, const mrts_map *const *maps, int n_maps
             if (rc) return rc;
             b->fixed_of[g_fixed[v].kernel] = v;
         }
-    {
+    for (fixed_generic_getter get : g_fixed_generic) {
         int fw = 0, fh = 0, fcap = 0;
-        const void *fn = mrts_fixed_generic_24x24(&fw, &fh, &fcap);
+        const void *fn = get(&fw, &fh, &fcap);
         if (fw == W && fh == H && fcap == cap && b->scripted == 1 && !po_pol) {
             int rc = make_plan(fn, b->L.total, b->fixed_plan[KERNEL_GENERIC]);
             if (rc) return rc;
