@@ -1150,13 +1150,15 @@ DEV int rb_scan(const Game &g, int n, int &par0, int &par1, int &mr, int &cnt0, 
 // player's action of this same cycle does not block -- that player's list was built on the same state (Game.java:134-137)
 // and GameState.issue will find the pair inconsistent (handled by the caller).
 DEV bool rb_accept(const Game &g, int pl, unsigned m, bool cand, int tcell, int cost, bool simul, RbCtx &c) {
+    // lanes that want the same cell.  MATCH.ANY has a long latency: it is issued first so that the shared-memory loads below run
+    // under it (skipping it when fewer than two lanes have a cell was measured slower)
+    unsigned same = __match_any_sync(FULLM, (cand && tcell >= 0) ? tcell : -1 - g.lane);
     bool blocked = false;
     if (cand && tcell >= 0) {
         int ev = g.resv()[tcell];
         if (ev != 0) blocked = !(simul && g.tis()[ev - 1] == c.time && u_pl(g.w0()[ev - 1]) != pl);
         if (g.claim()[tcell] & pl) blocked = true; // this player's earlier choice of the cell was cancelled at issue (see rb_player)
     }
-    unsigned same = __match_any_sync(FULLM, (cand && tcell >= 0) ? tcell : -1 - g.lane); // (skipping it when fewer than two lanes have a cell was measured slower)
     unsigned below = (1u << g.lane) - 1;
     // While no candidate that costs resources is involved, the resource half of consistentWith is the same for every lane
     // (`over`), and verdicts only interact when two lanes want the same cell: the first in list order wins, and if it is
