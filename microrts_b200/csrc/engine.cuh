@@ -1734,6 +1734,20 @@ DEVN void observe_game(Game &g, const StepParams &p, long long gi) {
 DEVN void masks_game(Game &g, const StepParams &p, long long gi) {
     int n = g.hdr()[H_NUNITS], player = p.out_player;
     int R = 2 * p.max_range + 1, ctr = R / 2, nT = p.n_types, K = 1 + 6 + 16 + nT + R * R;
+    { // The game's whole mask block is zero-filled here (16-byte stores when it is aligned), then the rows of the player's idle
+      // units are written over it: the warp barrier orders the two writes and the second one merges in L2, as in obs_emit.
+        size_t per_game = (size_t)g.W * g.H * (p.out_dtype == 2 ? (size_t)((K + 7) >> 3) : (size_t)K * (p.out_dtype == 0 ? 1 : 4));
+        char *o = (char *)p.out + (size_t)gi * per_game;
+        if ((per_game & 15) == 0 && (((size_t)p.out) & 15) == 0) {
+            uint4 z; z.x = z.y = z.z = z.w = 0;
+            #pragma unroll 4
+            for (size_t q = g.lane; q < (per_game >> 4); q += 32) ((uint4 *)o)[q] = z;
+        } else {
+            #pragma unroll 1
+            for (size_t q = g.lane; q < per_game; q += 32) o[q] = 0;
+        }
+        __syncwarp();
+    }
     #pragma unroll 1
     for (int s = 0; s < n; s++) {
         uint32_t w = g.w0()[s];

@@ -667,7 +667,6 @@ static int emit(mrts_batch *b, int mode, int player, int dtype, void *out, int o
     size_t bytes = bits ? (size_t)b->n * b->W * b->H * ((mrts_batch_mask_width(b) + 7) / 8) : elems * (dtype == MRTS_DTYPE_U8 ? 1 : 4);
     void *d_out = out;
     if (!on_device) { if (ensure_tmp(b, bytes)) return fail(MRTS_E_CUDA, std::string("staging allocation failed: ") + dev_errstr()); d_out = b->d_tmp; }
-    if (mode == MODE_MASKS && dev_zero(d_out, bytes, b->stream)) return fail(MRTS_E_CUDA, dev_errstr());
     if (mode == MODE_OBSERVE && !(b->flags & MRTS_FLAG_PARTIAL_OBS)) {
         if (launch_observe(b, player, dtype, d_out)) return fail(MRTS_E_CUDA, std::string("launch: ") + dev_errstr());
     } else {
