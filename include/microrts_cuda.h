@@ -197,6 +197,14 @@ int mrts_batch_step(mrts_batch *, int n_cycles, int max_cycles);
  * (or by n_cycles when t_target is NULL). TestTracesIntegrity.java:81-85 */
 int mrts_batch_cycle_to(mrts_batch *, const int32_t *t_target, int n_cycles, int on_device);
 
+/* PathFinding.findPathToPositionInRange(start, targetpos, range, gs, null) for one unit per game
+ * (src/ai/abstraction/pathfinding/PathFinding.java:17-24; AStarPathFinding.java:52-79, BFSPathFinding.java:41-147,
+ * GreedyPathFinding.java:53-84): queries = [n_games][3] {cell of the start unit (x + y*W), target position (x + y*W), range};
+ * range < 0 asks for PathFinding.findPath.  out_dir[g] = direction of the returned MOVE (0 up, 1 right, 2 down, 3 left) or -1
+ * for null (no path, already in range, no unit on the cell).  The batch must own pathfinding scratch (MRTS_FLAG_SCRIPTED_AI);
+ * it is not modified. */
+int mrts_batch_pathfind(mrts_batch *, int pathfinder, const int32_t *queries, int32_t *out_dir, int on_device);
+
 /* NaiveMCTS.simulate + evaluate (src/ai/mcts/naivemcts/NaiveMCTS.java:195-223,297-308): for every game g and every
  * k < rollouts_per_game, clone the game's state (gs2 = leaf.gs.clone(), from observer's PartiallyObservableGameState
  * when observer >= 0, src/rts/PartiallyObservableGameState.java:35-79), play RandomBiasedAI vs itself with issue() until

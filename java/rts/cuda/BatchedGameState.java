@@ -39,7 +39,7 @@ public final class BatchedGameState implements AutoCloseable {
     private final Arena arena = Arena.ofConfined();
     private final SymbolLookup lib;
     private final MethodHandle lastError, uttCreate, uttDestroy, mapLoad, mapDestroy, batchCreate, batchDestroy, reset, resetMasked,
-            setPolicy, setAutoReset, setActions, issue, step, cycleTo, observe, masks, results, stats, rollout, numPlanes, maskWidth,
+            setPolicy, setAutoReset, setActions, issue, step, cycleTo, observe, masks, results, stats, rollout, pathfind, numPlanes, maskWidth,
             restartMasked, setIssueOrder, setInfoOutput, setObservationOutputs;
 
     private MemorySegment utt, map, batch;
@@ -77,6 +77,7 @@ public final class BatchedGameState implements AutoCloseable {
         results = h("mrts_batch_results", FunctionDescriptor.of(I, P, P, I));
         stats = h("mrts_batch_stats", FunctionDescriptor.of(I, P, P));
         rollout = h("mrts_batch_rollout", FunctionDescriptor.of(I, P, I, I, I, I, I, P, P, P, I));
+        pathfind = h("mrts_batch_pathfind", FunctionDescriptor.of(I, P, I, P, P, I));
         numPlanes = h("mrts_batch_num_planes", FunctionDescriptor.of(I, P));
         maskWidth = h("mrts_batch_mask_width", FunctionDescriptor.of(I, P));
         restartMasked = h("mrts_batch_restart_masked", FunctionDescriptor.of(I, P, P, I));
@@ -211,6 +212,19 @@ public final class BatchedGameState implements AutoCloseable {
                     seeds == null ? MemorySegment.NULL : a.allocateFrom(L, seeds), ev, tm, 0));
             if (outTime != null) MemorySegment.copy(tm, I, 0, outTime, 0, outTime.length);
             return ev.toArray(ValueLayout.JAVA_FLOAT);
+        }
+    }
+
+    /**
+     * PathFinding.findPathToPositionInRange(start, targetpos, range, gs, null) for one unit per game
+     * (src/ai/abstraction/pathfinding/PathFinding.java:17-24): queries = {cell of the unit, target position, range} per game,
+     * pathfinder = PF_ASTAR / PF_BFS / PF_GREEDY.  Returns the direction of the MOVE per game, -1 for null.
+     */
+    public int[] findPath(int pathfinder, int[] queries) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment out = a.allocate(I, numGames);
+            check((int) pathfind.invoke(batch, pathfinder, a.allocateFrom(I, queries), out, 0));
+            return out.toArray(I);
         }
     }
 

@@ -282,6 +282,14 @@ class BatchedGameState:
         p, dev, _k = _ptr(t)
         _check(_ffi.lib().mrts_batch_cycle_to(self._h, p, 0, dev))
 
+    def find_path(self, pathfinder, unit_cells, target_positions, ranges):
+        """PathFinding.findPathToPositionInRange for one unit per game: the unit on cell unit_cells[g] (x + y*W) towards
+        target_positions[g] within ranges[g] (range < 0: findPath).  Returns the MOVE direction per game, -1 for null."""
+        q = np.ascontiguousarray(np.stack([np.broadcast_to(np.asarray(a, dtype=np.int32), (self.n,)) for a in (unit_cells, target_positions, ranges)], axis=1))
+        out = np.empty(self.n, dtype=np.int32)
+        _check(_ffi.lib().mrts_batch_pathfind(self._h, pathfinder, q.ctypes.data, out.ctypes.data, 0))
+        return out
+
     def rollout(self, depth=100, rollouts_per_game=1, eval_fn=0, maxplayer=0, observer=-1, seeds=None):
         """NaiveMCTS.simulate + evaluation for every game (the batch is not modified).
         Returns (evaluation[float32], simulated_cycles[int32]) of shape [n, rollouts_per_game]; the reference's discounted

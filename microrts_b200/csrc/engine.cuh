@@ -40,7 +40,7 @@ enum { POL_EXTERNAL = 0, POL_PASSIVE = 1, POL_RANDOM_BIASED = 2, POL_WORKER_RUSH
 #define POL_IS_PO_RUSH(p) ((p) >= POL_PO_WORKER_RUSH && (p) <= POL_PO_RANGED_RUSH)
 #define POL_IS_DEFENSE(p) (((p) >= POL_WORKER_DEFENSE && (p) <= POL_RANGED_DEFENSE) || (p) == POL_WORKER_RUSH_PP) // WorkerRushPlusPlus.java = WorkerDefense.java whose melee units always attack
 enum { FMT_VECTOR = 0, FMT_RAW = 1 };
-enum { MODE_GAME = 0, MODE_CYCLE_ONLY = 1, MODE_ISSUE_ONLY = 2, MODE_OBSERVE = 3, MODE_MASKS = 4, MODE_ROLLOUT = 5 };
+enum { MODE_GAME = 0, MODE_CYCLE_ONLY = 1, MODE_ISSUE_ONLY = 2, MODE_OBSERVE = 3, MODE_MASKS = 4, MODE_ROLLOUT = 5, MODE_PATHFIND = 6 };
 enum { ST_OVER = 1, ST_COUNTED = 2 };
 enum { STAT_WINS0 = 0, STAT_WINS1, STAT_DRAWS, STAT_FINISHED, STAT_CYCLES, STAT_DECISIONS, STAT_UNIT_CYCLES, STAT_ERRORS };
 
@@ -71,6 +71,10 @@ struct StepParams {
     int ext_maxk[2], ext_format[2], ext_fill[2];
     int max_range;             // UnitTypeTable.getMaxAttackRange()
     int n_types;               // utt.getUnitTypes().size()
+    // MODE_PATHFIND: one query per game -- {cell of the unit (x + y*W), target position (x + y*W), range} -> direction or -1
+    const int32_t *pf_query;   // [n_games][3]
+    int32_t *pf_out;           // [n_games]
+    int pf_kind;
     // MODE_OBSERVE / MODE_MASKS
     void *out;
     int out_dtype;             // 0 = u8, 1 = i32, 2 = bit-packed (masks only)
@@ -1543,6 +1547,20 @@ DEVN void run_game(Game &g, const StepParams &p, long long gi, WarpStats &ws) {
     stat_add(ws, g.lane, STAT_UNIT_CYCLES, ucyc);
 }
 
+// PathFinding.findPathToPositionInRange(start, targetpos, range, gs, null) as an operator (AStarPathFinding.java:52-79,
+// BFSPathFinding.java:41-147, GreedyPathFinding.java:53-84): the unit standing on the query's cell, the game's current
+// state, no extra resource usage.  -1 = null (no path, already in range, or no unit on the cell); range < 0 = findPath.
+DEVN void pathfind_game(Game &g, const StepParams &p, long long gi) {
+    const int32_t *q = p.pf_query + gi * 3;
+    int cell = q[0], target = q[1], range = q[2], dir = -1;
+    if (p.scripted && cell >= 0 && cell < g.W * g.H && target >= 0 && target < g.W * g.H) {
+        int gv = g.grid()[(cell / g.W + 1) * g.P + cell % g.W + 1];
+        if (gv != 0 && gv != 0xFF) dir = pf_find(g, p.pf_kind, gv - 1, target % g.W, target / g.W, range, 0);
+    }
+    __syncwarp();
+    if (g.lane == 0) p.pf_out[gi] = dir;
+}
+
 // GameState.cycle() repeated until time == target (TestTracesIntegrity.java:81-85); no policies
 DEVN void run_cycles_only(Game &g, int target) {
     int winner;
@@ -1957,6 +1975,7 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
         else if (p.mode == MODE_CYCLE_ONLY) run_cycles_only(g, p.t_target ? p.t_target[gi] : g.hdr()[H_TIME] + p.n_cycles);
         else if (p.mode == MODE_ISSUE_ONLY) run_issue_only(g, p, gi);
         else if (p.mode == MODE_OBSERVE) { observe_game(g, p, gi); continue; }
+        else if (p.mode == MODE_PATHFIND) { pathfind_game(g, p, gi); continue; }
         else { masks_game(g, p, gi); continue; }
         if (g.hdr()[H_ERR] != err0) stat_add(ws, g.lane, STAT_ERRORS, 1);
         g_store(g, ghdr, gun);

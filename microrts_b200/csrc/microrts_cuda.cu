@@ -635,6 +635,24 @@ int mrts_batch_cycle_to(mrts_batch *b, const int32_t *t_target, int n_cycles, in
     return MRTS_OK;
 }
 
+int mrts_batch_pathfind(mrts_batch *b, int pathfinder, const int32_t *queries, int32_t *out_dir, int on_device) {
+    if (!b || !queries || !out_dir) return fail(MRTS_E_ARG, "mrts_batch_pathfind: null argument");
+    if (pathfinder < MRTS_PF_ASTAR || pathfinder > MRTS_PF_GREEDY) return fail(MRTS_E_ARG, "unknown pathfinder");
+    if (!b->scripted) return fail(MRTS_E_STATE, "pathfinding needs a batch created with MRTS_FLAG_SCRIPTED_AI (it owns the search scratch)");
+    if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
+    StepParams p; memset(&p, 0, sizeof p);
+    p.mode = MODE_PATHFIND; p.pf_kind = pathfinder;
+    size_t qb = (size_t)b->n * 12, ob = (size_t)b->n * 4;
+    if (on_device) { p.pf_query = queries; p.pf_out = out_dir; }
+    else {
+        if (ensure_tmp(b, qb + ob) || dev_h2d(b->d_tmp, queries, qb, b->stream)) return fail(MRTS_E_CUDA, dev_errstr());
+        p.pf_query = (const int32_t *)b->d_tmp; p.pf_out = (int32_t *)((char *)b->d_tmp + qb);
+    }
+    if (launch_step(b, p)) return fail(MRTS_E_CUDA, std::string("pathfind launch: ") + dev_errstr());
+    if (!on_device && dev_d2h(out_dir, p.pf_out, ob, b->stream)) return fail(MRTS_E_CUDA, dev_errstr());
+    return MRTS_OK;
+}
+
 int mrts_batch_rollout(mrts_batch *b, int rollouts_per_game, int depth, int eval_fn, int maxplayer, int observer, const int64_t *seeds,
                        float *out_eval, int32_t *out_time, int on_device) {
     if (!b || rollouts_per_game < 1 || depth < 0 || maxplayer < 0 || maxplayer > 1 || observer > 1 || (eval_fn != 0 && eval_fn != 1))

@@ -547,7 +547,7 @@ DEVN int policy_scripted(Game &g, int player, int kind, int pathfinder, int pn) 
     int nbarracks = w_count(g, n, [&](int, uint32_t w) { return u_pl(w) == pl && u_type(w) == UT_BARRACKS; });
     int nworkers = w_count(g, n, own_harvester);
     if (nworkers > 0) {
-        int reserved[4], nres = 0, used = 0, taken = 0; // `taken` workers were removed from the front of freeWorkers
+        int reserved[4] = {0, 0, 0, 0}, nres = 0, used = 0, taken = 0; // `taken` workers were removed from the front of freeWorkers
         int wi = -1;                                     // cursor over own harvesters in list order
         if (nbases == 0 && taken < nworkers) {
             if (pres >= ut_cost(g, UT_BASE) + used) { wi = w_next(g, n, wi, own_harvester); taken++; script_build_if_not(g, wi, player, UT_BASE, reserved, nres); used += ut_cost(g, UT_BASE); }

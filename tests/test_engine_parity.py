@@ -749,3 +749,51 @@ def test_wide_differential_scripted(backend, maps, key, pol, side, pf, po):
         P.assert_same_state(ex, g, og, "%s wide %s side %d pf %d po %s game %d" % (key, pol, side, pf, po, g))
     assert (b.results()[:, 3] == 0).all()
     b.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# PathFinding as an operator (mrts_batch_pathfind): the reference's test/microrts/TestPathfinding.java draws random
+# destinations on random maps and compares two A* implementations; here the device's A*, BFS and greedy pathfinders answer
+# random (unit, destination, range) queries on mid-game states and must return the oracle's first move
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("key", ["8x8/basesWorkers8x8", "16x16/basesWorkers16x16", "BWDistantResources32x32", "24x24/basesWorkers24x24", "GardenOfWar64x64"])
+def test_pathfinding_operator(backend, maps, key):
+    n = 4 if backend == "emu" else 256
+    rounds = 2 if backend == "emu" else 6
+    utt, outt = M.UnitTypeTable(1, 1), O.Utt(1, 1)
+    b = M.BatchedGameState(utt, make_pgs(maps[key], utt), n, scripted_ai=True)
+    seeds = np.arange(n, dtype=np.int64) + 900
+    b.reset(seeds)
+    b.set_policy(0, M.POLICY_RANDOM_BIASED)
+    b.set_policy(1, M.POLICY_RANDOM_BIASED)
+    games = []
+    for g in range(n):
+        og = O.Game(outt, maps[key])
+        og.seed(int(seeds[g]))
+        games.append(og)
+    W, H = b.width, b.height
+    rng = np.random.default_rng(7)
+    for r in range(rounds):
+        b.step(60, 3000)
+        for og in games:
+            og.run(O.AI_RANDOM_BIASED, None, O.AI_RANDOM_BIASED, None, 60, 3000)
+        ex = b.export()
+        idx = np.zeros(n, dtype=np.int64); cells = np.zeros(n, dtype=np.int32)
+        for g in range(n):
+            h, u, a = P.export_game(ex, g)
+            idx[g] = rng.integers(0, len(u))
+            cells[g] = u[idx[g], 2] + u[idx[g], 3] * W
+        targets = rng.integers(0, W * H, size=n).astype(np.int32)
+        # every other target next to some unit, so that short and blocked paths are common
+        for g in range(0, n, 2):
+            h, u, a = P.export_game(ex, g)
+            j = rng.integers(0, len(u))
+            targets[g] = int(u[j, 2]) + int(u[j, 3]) * W
+        ranges = rng.choice(np.array([-1, 1, 1, 2, 3], dtype=np.int32), size=n)
+        for pf in (M.PF_ASTAR, M.PF_BFS, M.PF_GREEDY):
+            got = b.find_path(pf, cells, targets, ranges)
+            for g, og in enumerate(games):
+                want = og.pathfind(pf, int(idx[g]), int(targets[g]), int(ranges[g]))
+                assert got[g] == want, "%s round %d game %d pf %d unit %d -> %d range %d: device %d oracle %d" % (
+                    key, r, g, pf, idx[g], targets[g], ranges[g], got[g], want)
+    b.close()
