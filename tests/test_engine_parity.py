@@ -273,16 +273,28 @@ def random_vector_actions(rng, og, player, w, h, max_k):
     return rows[:max_k]
 
 
-@pytest.mark.parametrize("key", ["8x8/basesWorkers8x8", "16x16/basesWorkers16x16"])
-def test_external_vector_actions(backend, maps, key):
+EXTERNAL_CASES = [("8x8/basesWorkers8x8", 1, 1), ("16x16/basesWorkers16x16", 1, 1),
+                  # every unit type, walls, other UnitTypeTable versions and conflict policies
+                  ("melee14x12Mixed18", 2, 1), ("BWDistantResources32x32", 3, 1), ("8x8/FourBasesWorkers8x8", 1, 2),
+                  ("16x16/TwoBasesBarracks16x16", 1, 3), ("12x12/complexBasesWorkers12x12", 3, 2), ("16x16/melee16x16Mixed12", 2, 3)]
+
+
+@pytest.mark.parametrize("key,version,conflict", EXTERNAL_CASES)
+def test_external_vector_actions(backend, maps, key, version, conflict):
     n = 3 if backend == "emu" else 32
     total = 250 if backend == "emu" else 1200
     w, h = maps[key]["w"], maps[key]["h"]
-    utt, outt = M.UnitTypeTable(1, 1), O.Utt(1, 1)
+    utt, outt = M.UnitTypeTable(version, conflict), O.Utt(version, conflict)
     b = M.BatchedGameState(utt, make_pgs(maps[key], utt), n)
+    seeds = np.arange(n, dtype=np.int64) + 5  # random damage (v3) and CANCEL_RANDOM draw from the per-game streams
+    b.reset(seeds)
     b.set_policy(0, M.POLICY_EXTERNAL)
     b.set_policy(1, M.POLICY_EXTERNAL)
-    games = [O.Game(outt, maps[key]) for _ in range(n)]
+    games = []
+    for g in range(n):
+        og = O.Game(outt, maps[key])
+        og.seed(int(seeds[g]))
+        games.append(og)
     rng = np.random.default_rng(7)
     max_k = 24
     for t in range(total):
