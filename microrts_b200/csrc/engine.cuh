@@ -50,6 +50,10 @@ struct StepParams {
     const uint32_t *maps;      // n_maps blobs (layout.h: mrts_map_blob_words)
     const uint32_t *cst;       // MRTS_CONST_WORDS: unit type table + LCG jump table
     unsigned long long *stats; // [8]
+    int32_t *results_out;      // MODE_GAME: [n_games][4] {time, winner, gameover, error bits} of the state each game is left in (or NULL)
+    unsigned long long *work_counter; // [2]: items handed out beyond each warp's first one; warps that have left the launch.
+                                      // Both are zero between launches: the last warp to leave resets them (no memset per launch,
+                                      // which would queue behind other streams' copies)
     long long n_games;
     int n_maps, map_words;
     int W, H, cap;
@@ -1922,6 +1926,15 @@ enum { KERNEL_FAST = 0, KERNEL_ROLLOUT = 1, KERNEL_GENERIC = 2, KERNEL_FAST_OBS 
     X(KERNEL_ROLLOUT, 8, 8, 64, MRTS_MIN_BLOCKS_ROLLOUT) \
     X(KERNEL_ROLLOUT, 32, 32, 254, MRTS_MIN_BLOCKS_ROLLOUT)
 
+// the warp's next work item: the global counter hands out the items behind every warp's static first one
+DEV long long next_item(const StepParams &p, int lane, long long first_dynamic) {
+    unsigned long long k = 0;
+    __syncwarp();
+    if (lane == 0) k = atomicAdd(p.work_counter, 1ULL);
+    k = __shfl_sync(FULLM, k, 0);
+    return first_dynamic + (long long)k;
+}
+
 // FW, FH, FCAP > 0: a copy of the kernel for one fixed map size and unit capacity (a batch without scripted-policy words): the
 // shared-memory layout, the padded row length and the capacity are compile-time constants there, so the offset arithmetic of
 // every accessor folds into immediates
@@ -1960,8 +1973,10 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
     if (lane < 8) ws.v[lane] = 0;
     __syncwarp();
     long long n_items = KERNEL == KERNEL_ROLLOUT ? p.n_games * p.rollouts_per_game : p.n_games;
+    // A warp's first item is static; the next ones come from a global counter, so a warp that drew cheap games (or rollouts
+    // that ended early) takes more of them and the launch has no long tail of a few unlucky warps.
 #pragma unroll 1
-    for (long long item = (long long)bid * wpc + warp; item < n_items; item += (long long)nblocks * wpc) {
+    for (long long item = (long long)bid * wpc + warp; item < n_items; item = next_item(p, lane, (long long)nblocks * wpc)) {
         long long gi = KERNEL == KERNEL_ROLLOUT ? item / p.rollouts_per_game : item;
         const uint32_t *blob = p.maps + (size_t)(gi % p.n_maps) * p.map_words;
         g.grid_tmpl = blob;
@@ -1979,6 +1994,20 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
         else { masks_game(g, p, gi); continue; }
         if (g.hdr()[H_ERR] != err0) stat_add(ws, g.lane, STAT_ERRORS, 1);
         g_store(g, ghdr, gun);
+        if (p.mode == MODE_GAME && p.results_out) {
+            // what mrts_batch_results reports (winner() / gameover(), PhysicalGameState.java:334-387), written here so that the
+            // host can fetch it with a plain copy: a results kernel would have to wait for SM slots behind whatever persistent
+            // kernel another batch has running
+            int n = g.hdr()[H_NUNITS], c0 = 0, c1 = 0;
+            #pragma unroll 1
+            for (int i = lane; i < n; i += 32) { int pl = u_pl(g.w0()[i]); c0 += pl == 1; c1 += pl == 2; }
+            c0 = __reduce_add_sync(FULLM, c0); c1 = __reduce_add_sync(FULLM, c1);
+            if (lane == 0) {
+                int4 r;
+                r.x = g.hdr()[H_TIME]; r.y = (c0 > 0 && c1 == 0) ? 0 : ((c1 > 0 && c0 == 0) ? 1 : -1); r.z = (c0 == 0 || c1 == 0) ? 1 : 0; r.w = g.hdr()[H_ERR];
+                ((int4 *)p.results_out)[gi] = r;
+            }
+        }
         if (KERNEL == KERNEL_FAST_OBS || (KERNEL == KERNEL_GENERIC && p.mode == MODE_GAME)) {
             #pragma unroll 1
             for (int pl = 0; pl < 2; pl++)
@@ -1989,4 +2018,8 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
     }
     __syncwarp();
     if (lane < 8 && p.stats && ws.v[lane]) atomicAdd(&p.stats[lane], ws.v[lane]);
+    if (lane == 0) { // no warp draws an item after it got here, so the last one to arrive can reset the counters
+        unsigned long long left = atomicAdd(p.work_counter + 1, 1ULL);
+        if (left + 1 == (unsigned long long)nblocks * wpc) { p.work_counter[0] = 0; p.work_counter[1] = 0; }
+    }
 }

@@ -215,6 +215,7 @@ struct mrts_batch {
     int policy[2] = {MRTS_POLICY_PASSIVE, MRTS_POLICY_PASSIVE}, pathfinder[2] = {0, 0};
     int32_t *d_hdr = nullptr; uint32_t *d_units = nullptr; uint32_t *d_maps = nullptr; uint32_t *d_cst = nullptr;
     unsigned long long *d_stats = nullptr;
+    int32_t *d_results = nullptr; bool results_fresh = false; // [n][4] written by the last mrts_batch_step; stale after any other change of state
     void *d_tmp = nullptr; size_t tmp_bytes = 0; // staging for host arguments
     unsigned char *d_astar = nullptr; long long astar_stride = 0; // pathfinding scratch of large-map scripted batches
     Staged staged[2];
@@ -239,6 +240,7 @@ static int ensure_tmp(mrts_batch *b, size_t bytes) {
 
 static int launch_step(mrts_batch *b, StepParams &p) {
     p.hdr = b->d_hdr; p.units = b->d_units; p.maps = b->d_maps; p.cst = b->d_cst; p.stats = b->d_stats;
+    p.work_counter = b->d_stats + 8; // games are handed out dynamically; every launch leaves the two counters at zero (step_kernel_body)
     p.n_games = b->n; p.n_maps = b->n_maps; p.map_words = b->map_words; p.W = b->W; p.H = b->H; p.cap = b->cap;
     p.conflict = b->utt.conflict; p.max_range = b->max_range; p.n_types = (int)b->utt.types.size();
     p.partial_obs = (b->flags & MRTS_FLAG_PARTIAL_OBS) ? 1 : 0; p.scripted = b->scripted; p.uw = b->uw;
@@ -372,7 +374,7 @@ void mrts_map_destroy(mrts_map *m) { delete m; }
 void mrts_batch_destroy(mrts_batch *b) {
     if (!b) return;
     dev_select(b->device);
-    dev_free(b->d_hdr); dev_free(b->d_units); dev_free(b->d_maps); dev_free(b->d_cst); dev_free(b->d_stats); dev_free(b->d_tmp); dev_free(b->d_astar);
+    dev_free(b->d_hdr); dev_free(b->d_units); dev_free(b->d_maps); dev_free(b->d_cst); dev_free(b->d_stats); dev_free(b->d_results); dev_free(b->d_tmp); dev_free(b->d_astar);
     for (auto &s : b->staged) { dev_free(s.actions); dev_free(s.counts); }
 #ifndef MRTS_EMU
     if (b->stream) cudaStreamDestroy(b->stream);
@@ -476,13 +478,13 @@ int mrts_batch_create(const mrts_utt *u, const mrts_map *const *maps, int n_maps
     size_t hdr_bytes = (size_t)n_games * MRTS_HDR_WORDS * 4, unit_bytes = (size_t)n_games * b->uw * cap * 4;
     if (dev_alloc((void **)&b->d_hdr, hdr_bytes) || dev_alloc((void **)&b->d_units, unit_bytes) ||
         dev_alloc((void **)&b->d_maps, (size_t)n_maps * b->map_words * 4) || dev_alloc((void **)&b->d_cst, MRTS_CONST_WORDS * 4) ||
-        dev_alloc((void **)&b->d_stats, 8 * sizeof(unsigned long long)))
+        dev_alloc((void **)&b->d_stats, 10 * sizeof(unsigned long long)) || dev_alloc((void **)&b->d_results, (size_t)n_games * 16)) // 8 counters + the launches' work and exit counters
         return fail(MRTS_E_CUDA, std::string("device allocation failed: ") + dev_errstr());
     std::vector<uint32_t> blob, all;
     for (int i = 0; i < n_maps; i++) { build_map_blob(maps[i]->h, cap, blob); all.insert(all.end(), blob.begin(), blob.end()); }
     std::vector<uint32_t> cst; build_const_words(u->h, cst);
     if (dev_h2d(b->d_maps, all.data(), all.size() * 4, b->stream) || dev_h2d(b->d_cst, cst.data(), cst.size() * 4, b->stream) ||
-        dev_zero(b->d_stats, 8 * sizeof(unsigned long long), b->stream) || dev_zero(b->d_units, unit_bytes, b->stream) || dev_sync(b->stream))
+        dev_zero(b->d_stats, 10 * sizeof(unsigned long long), b->stream) || dev_zero(b->d_units, unit_bytes, b->stream) || dev_sync(b->stream))
         return fail(MRTS_E_CUDA, std::string("device upload failed: ") + dev_errstr());
     mrts_batch *raw = b.release();
     int rc = mrts_batch_reset(raw, nullptr, 0);
@@ -501,6 +503,7 @@ int mrts_batch_num_planes(const mrts_batch *b) { return b ? ((b->flags & MRTS_FL
 int mrts_batch_mask_width(const mrts_batch *b) { if (!b) return MRTS_E_ARG; int R = 2 * b->max_range + 1; return 1 + 6 + 16 + (int)b->utt.types.size() + R * R; }
 
 static int do_reset(mrts_batch *b, const uint8_t *mask, const int64_t *seeds, int on_device, int keep_rng = 0) {
+    if (b) b->results_fresh = false;
     if (!b) return fail(MRTS_E_ARG, "null batch");
     if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
     const long long *d_seeds = (const long long *)seeds; const uint8_t *d_mask = mask;
@@ -581,6 +584,7 @@ static void fill_ext(mrts_batch *b, StepParams &p, int pl) {
 }
 
 int mrts_batch_issue(mrts_batch *b, int player, int format, const int32_t *actions, const int32_t *counts, int max_k, int fill_none_duration, int safe, int on_device) {
+    if (b) b->results_fresh = false;
     int rc = stage_actions(b, player, format, actions, counts, max_k, fill_none_duration, on_device);
     if (rc) return rc;
     StepParams p; memset(&p, 0, sizeof p);
@@ -601,7 +605,9 @@ int mrts_batch_step(mrts_batch *b, int n_cycles, int max_cycles) {
     p.tm_worker = b->tm[0]; p.tm_building = b->tm[1]; p.tm_combat = b->tm[2]; p.tm_base = b->tm[3]; p.tm_mobile = b->tm[4]; p.tm_resource = b->tm[5];
     bool fused = !(b->flags & MRTS_FLAG_PARTIAL_OBS); // partially observable batches observe in a second launch
     if (fused) { p.obs_out[0] = b->obs_out[0]; p.obs_out[1] = b->obs_out[1]; p.obs_dtype = b->obs_dtype; }
+    p.results_out = b->d_results;
     if (launch_step(b, p)) return fail(MRTS_E_CUDA, std::string("step launch: ") + dev_errstr());
+    b->results_fresh = true;
     if (!fused)
         for (int pl = 0; pl < 2; pl++)
             if (b->obs_out[pl]) { int rc = mrts_batch_observe(b, pl, b->obs_dtype, b->obs_out[pl], 1); if (rc) return rc; }
@@ -619,6 +625,7 @@ int mrts_batch_set_observation_outputs(mrts_batch *b, int dtype, void *out_playe
 }
 
 int mrts_batch_cycle_to(mrts_batch *b, const int32_t *t_target, int n_cycles, int on_device) {
+    if (b) b->results_fresh = false;
     if (!b) return fail(MRTS_E_ARG, "null batch");
     if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
     StepParams p; memset(&p, 0, sizeof p);
@@ -707,6 +714,10 @@ int mrts_batch_masks(mrts_batch *b, int player, int dtype, void *out, int on_dev
 int mrts_batch_results(mrts_batch *b, int32_t *out, int on_device) {
     if (!b || !out) return fail(MRTS_E_ARG, "mrts_batch_results: null argument");
     if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
+    if (b->results_fresh) { // the last step left them in d_results: a copy, no kernel
+        if (on_device ? dev_d2d(out, b->d_results, (size_t)b->n * 16, b->stream) : dev_d2h(out, b->d_results, (size_t)b->n * 16, b->stream)) return fail(MRTS_E_CUDA, dev_errstr());
+        return MRTS_OK;
+    }
     int32_t *d_out = out;
     if (!on_device) { if (ensure_tmp(b, (size_t)b->n * 16)) return fail(MRTS_E_CUDA, dev_errstr()); d_out = (int32_t *)b->d_tmp; }
     ResultParams p{b->d_hdr, b->d_units, d_out, b->n, b->cap, b->uw};
@@ -777,6 +788,7 @@ int mrts_batch_export(mrts_batch *b, int64_t first, int64_t count, mrts_state_ho
 }
 
 int mrts_batch_import(mrts_batch *b, int64_t first, int64_t count, const mrts_state_host *in) {
+    if (b) b->results_fresh = false;
     if (!b || !in || !in->header || !in->units || first < 0 || count < 0 || first + count > b->n) return fail(MRTS_E_ARG, "mrts_batch_import: bad argument");
     if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
     int cap = b->cap;
