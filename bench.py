@@ -438,7 +438,7 @@ def run_ours(args):
     roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
                     peak_source=peak_src, kernel="k_step_fast", bytes_per_game_cycle=bytes_per_cycle,
                     mean_launch_ms=sum(kernel_ms) / max(1, len(kernel_ms)),
-                    note="state-only stepping is instruction-issue bound, not HBM-bound (SURVEY 8d; profiles/r1f_*): the state stays in shared memory for the whole step, so DRAM traffic is far below the algorithmic bytes; frac is reported as the metric demands. The HBM-bound path is --workload obs")
+                    note="achieved = SURVEY 8(d) algorithmic bytes (state read + written once per game-cycle) / kernel time. The kernel keeps a game in shared memory for all cycles of a launch, so the bytes it really moves (`traffic`, ncu) are ~70x fewer and frac can exceed 1: state-only stepping is instruction-issue bound, not HBM-bound (profiles/r1v_*: issue slots 78 % busy). The HBM-bound path is --workload obs")
 
     cpu = None
     if not args.no_cpu_baseline:

@@ -1,3 +1,6 @@
+#!/usr/bin/env python3
+"""Where the time of bench.py's e2e loop goes: per step, host time spent submitting (reset_masked + step), waiting in results()
+and in the numpy bookkeeping, with the batch split into 2 or more parts.  usage: python tools/e2e_diag.py [parts]"""
 import os, sys, time
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
 import numpy as np, torch
