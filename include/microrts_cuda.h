@@ -197,6 +197,11 @@ int mrts_batch_step(mrts_batch *, int n_cycles, int max_cycles);
  * (or by n_cycles when t_target is NULL). TestTracesIntegrity.java:81-85 */
 int mrts_batch_cycle_to(mrts_batch *, const int32_t *t_target, int n_cycles, int on_device);
 
+/* EvaluationFunction.evaluate(maxplayer, 1 - maxplayer, gs) of every game's current state (src/ai/evaluation/
+ * EvaluationFunction.java; eval_fn 0 = SimpleSqrtEvaluationFunction3.java:24-44, 1 = SimpleEvaluationFunction.java:21-36), of
+ * observer's PartiallyObservableGameState view when observer >= 0.  out_eval = [n_games] float.  The batch is not modified. */
+int mrts_batch_evaluate(mrts_batch *, int eval_fn, int maxplayer, int observer, float *out_eval, int on_device);
+
 /* PathFinding.findPathToPositionInRange(start, targetpos, range, gs, null) for one unit per game
  * (src/ai/abstraction/pathfinding/PathFinding.java:17-24; AStarPathFinding.java:52-79, BFSPathFinding.java:41-147,
  * GreedyPathFinding.java:53-84): queries = [n_games][3] {cell of the start unit (x + y*W), target position (x + y*W), range};

@@ -39,7 +39,7 @@ public final class BatchedGameState implements AutoCloseable {
     private final Arena arena = Arena.ofConfined();
     private final SymbolLookup lib;
     private final MethodHandle lastError, uttCreate, uttDestroy, mapLoad, mapDestroy, batchCreate, batchDestroy, reset, resetMasked,
-            setPolicy, setAutoReset, setActions, issue, step, cycleTo, observe, masks, results, stats, rollout, pathfind, numPlanes, maskWidth,
+            setPolicy, setAutoReset, setActions, issue, step, cycleTo, observe, masks, results, stats, rollout, pathfind, evaluate, numPlanes, maskWidth,
             restartMasked, setIssueOrder, setInfoOutput, setObservationOutputs;
 
     private MemorySegment utt, map, batch;
@@ -78,6 +78,7 @@ public final class BatchedGameState implements AutoCloseable {
         stats = h("mrts_batch_stats", FunctionDescriptor.of(I, P, P));
         rollout = h("mrts_batch_rollout", FunctionDescriptor.of(I, P, I, I, I, I, I, P, P, P, I));
         pathfind = h("mrts_batch_pathfind", FunctionDescriptor.of(I, P, I, P, P, I));
+        evaluate = h("mrts_batch_evaluate", FunctionDescriptor.of(I, P, I, I, I, P, I));
         numPlanes = h("mrts_batch_num_planes", FunctionDescriptor.of(I, P));
         maskWidth = h("mrts_batch_mask_width", FunctionDescriptor.of(I, P));
         restartMasked = h("mrts_batch_restart_masked", FunctionDescriptor.of(I, P, P, I));
@@ -212,6 +213,15 @@ public final class BatchedGameState implements AutoCloseable {
                     seeds == null ? MemorySegment.NULL : a.allocateFrom(L, seeds), ev, tm, 0));
             if (outTime != null) MemorySegment.copy(tm, I, 0, outTime, 0, outTime.length);
             return ev.toArray(ValueLayout.JAVA_FLOAT);
+        }
+    }
+
+    /** EvaluationFunction.evaluate(maxplayer, 1 - maxplayer, gs) of every game (evalFn 0 = SimpleSqrtEvaluationFunction3, 1 = SimpleEvaluationFunction). */
+    public float[] evaluate(int evalFn, int maxplayer, int observer) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment out = a.allocate(ValueLayout.JAVA_FLOAT, numGames);
+            check((int) evaluate.invoke(batch, evalFn, maxplayer, observer, out, 0));
+            return out.toArray(ValueLayout.JAVA_FLOAT);
         }
     }
 

@@ -41,7 +41,7 @@ def bind(L):
         "mrts_batch_set_issue_order": (i, [vp, i]), "mrts_batch_set_info_output": (i, [vp, vp]), "mrts_batch_restart_masked": (i, [vp, vp, i]), "mrts_batch_cycle_to": (i, [vp, vp, i, i]),
         "mrts_batch_rollout": (i, [vp, i, i, i, i, i, vp, vp, vp, i]),
         "mrts_batch_observe": (i, [vp, i, i, vp, i]), "mrts_batch_num_planes": (i, [vp]),
-        "mrts_batch_pathfind": (i, [vp, i, vp, vp, i]),
+        "mrts_batch_pathfind": (i, [vp, i, vp, vp, i]), "mrts_batch_evaluate": (i, [vp, i, i, i, vp, i]),
         "mrts_batch_masks": (i, [vp, i, i, vp, i]), "mrts_batch_mask_width": (i, [vp]),
         "mrts_batch_export": (i, [vp, i64, i64, C.POINTER(StateHost)]),
         "mrts_batch_import": (i, [vp, i64, i64, C.POINTER(StateHost)]),

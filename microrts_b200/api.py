@@ -282,6 +282,13 @@ class BatchedGameState:
         p, dev, _k = _ptr(t)
         _check(_ffi.lib().mrts_batch_cycle_to(self._h, p, 0, dev))
 
+    def evaluate(self, eval_fn=0, maxplayer=0, observer=-1):
+        """EvaluationFunction.evaluate(maxplayer, 1 - maxplayer, gs) of every game's current state (0 = SimpleSqrtEvaluationFunction3,
+        1 = SimpleEvaluationFunction); observer >= 0: of that player's partially observable view."""
+        out = np.empty(self.n, dtype=np.float32)
+        _check(_ffi.lib().mrts_batch_evaluate(self._h, eval_fn, maxplayer, observer, out.ctypes.data, 0))
+        return out
+
     def find_path(self, pathfinder, unit_cells, target_positions, ranges):
         """PathFinding.findPathToPositionInRange for one unit per game: the unit on cell unit_cells[g] (x + y*W) towards
         target_positions[g] within ranges[g] (range < 0: findPath).  Returns the MOVE direction per game, -1 for null."""

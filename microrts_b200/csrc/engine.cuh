@@ -1894,7 +1894,7 @@ DEV void run_rollout(Game &g, const StepParams &p, long long r, WarpStats &ws) {
     __syncwarp();
     int t0 = g.hdr()[H_TIME], time = t0, winner;
     unsigned decisions = 0, ucyc = 0;
-    play_rb(g, 3, false, t0 + p.depth, time, winner, decisions, ucyc);
+    if (p.depth >= 0) play_rb(g, 3, false, t0 + p.depth, time, winner, decisions, ucyc); // depth < 0: mrts_batch_evaluate, no playout
     __syncwarp();
     if (g.lane == 0) {
         g.hdr()[H_TIME] = time;

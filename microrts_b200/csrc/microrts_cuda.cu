@@ -642,6 +642,18 @@ int mrts_batch_cycle_to(mrts_batch *b, const int32_t *t_target, int n_cycles, in
     return MRTS_OK;
 }
 
+int mrts_batch_evaluate(mrts_batch *b, int eval_fn, int maxplayer, int observer, float *out_eval, int on_device) {
+    if (!b || !out_eval || maxplayer < 0 || maxplayer > 1 || observer > 1 || (eval_fn != 0 && eval_fn != 1)) return fail(MRTS_E_ARG, "mrts_batch_evaluate: bad argument");
+    if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
+    StepParams p; memset(&p, 0, sizeof p);
+    p.mode = MODE_ROLLOUT; p.rollouts_per_game = 1; p.depth = -1; p.eval_fn = eval_fn; p.maxplayer = maxplayer; p.observer = observer < 0 ? -1 : observer;
+    if (on_device) p.ro_eval = out_eval;
+    else { if (ensure_tmp(b, (size_t)b->n * 4)) return fail(MRTS_E_CUDA, dev_errstr()); p.ro_eval = (float *)b->d_tmp; }
+    if (launch_step(b, p)) return fail(MRTS_E_CUDA, std::string("evaluate launch: ") + dev_errstr());
+    if (!on_device && dev_d2h(out_eval, p.ro_eval, (size_t)b->n * 4, b->stream)) return fail(MRTS_E_CUDA, dev_errstr());
+    return MRTS_OK;
+}
+
 int mrts_batch_pathfind(mrts_batch *b, int pathfinder, const int32_t *queries, int32_t *out_dir, int on_device) {
     if (!b || !queries || !out_dir) return fail(MRTS_E_ARG, "mrts_batch_pathfind: null argument");
     if (pathfinder < MRTS_PF_ASTAR || pathfinder > MRTS_PF_GREEDY) return fail(MRTS_E_ARG, "unknown pathfinder");

@@ -809,3 +809,34 @@ def test_pathfinding_operator(backend, maps, key):
                 assert got[g] == want, "%s round %d game %d pf %d unit %d -> %d range %d: device %d oracle %d" % (
                     key, r, g, pf, idx[g], targets[g], ranges[g], got[g], want)
     b.close()
+
+
+def test_evaluation_operator(backend, maps):
+    """EvaluationFunction.evaluate as an operator (mrts_batch_evaluate): both evaluation functions, both players, fully
+    observable and from each player's partially observable view, on mid-game states; float32 results must be identical."""
+    key = "16x16/basesWorkers16x16"
+    n = 4 if backend == "emu" else 128
+    utt, outt = M.UnitTypeTable(1, 1), O.Utt(1, 1)
+    b = M.BatchedGameState(utt, make_pgs(maps[key], utt), n)
+    seeds = np.arange(n, dtype=np.int64) + 31
+    b.reset(seeds)
+    b.set_policy(0, M.POLICY_RANDOM_BIASED)
+    b.set_policy(1, M.POLICY_RANDOM_BIASED)
+    games = []
+    for g in range(n):
+        og = O.Game(outt, maps[key])
+        og.seed(int(seeds[g]))
+        games.append(og)
+    for r in range(3):
+        b.step(250, 3000)
+        for og in games:
+            og.run(O.AI_RANDOM_BIASED, None, O.AI_RANDOM_BIASED, None, 250, 3000)
+        for fn in (0, 1):
+            for maxp in (0, 1):
+                for observer in (-1, 0, 1):
+                    got = b.evaluate(fn, maxp, observer)
+                    for g, og in enumerate(games):
+                        view = og if observer < 0 else og.po_view(observer)
+                        want = np.float32(view.evaluate(fn, maxp, 1 - maxp))
+                        assert got[g] == want, "round %d fn %d maxplayer %d observer %d game %d: %r != %r" % (r, fn, maxp, observer, g, got[g], want)
+    b.close()
