@@ -45,7 +45,7 @@ enum { ST_OVER = 1, ST_COUNTED = 2 };
 enum { STAT_WINS0 = 0, STAT_WINS1, STAT_DRAWS, STAT_FINISHED, STAT_CYCLES, STAT_DECISIONS, STAT_UNIT_CYCLES, STAT_ERRORS };
 
 struct StepParams {
-    int32_t *hdr;              // [n_games][16]
+    int32_t *hdr;              // [n_games][MRTS_HDR_WORDS]
     uint32_t *units;           // [n_games][7][cap]
     const uint32_t *maps;      // n_maps blobs (layout.h: mrts_map_blob_words)
     const uint32_t *cst;       // MRTS_CONST_WORDS: unit type table + LCG jump table

@@ -1,6 +1,6 @@
 // layout.h -- data layout shared by the device engine and the host C-ABI.
 //
-// One game = a 16-word header + MRTS_UNIT_WORDS struct-of-arrays over `cap` unit slots, both in HBM and (while a
+// One game = a 20-word header (MRTS_HDR_WORDS) + MRTS_UNIT_WORDS struct-of-arrays over `cap` unit slots, both in HBM and (while a
 // warp owns the game) in shared memory.  Unit slot order IS the reference's PhysicalGameState.units list order
 // (src/rts/PhysicalGameState.java:54); assignment (LinkedHashMap) order is carried by a per-unit sequence number.
 #pragma once
