@@ -1927,12 +1927,16 @@ enum { KERNEL_FAST = 0, KERNEL_ROLLOUT = 1, KERNEL_GENERIC = 2, KERNEL_FAST_OBS 
     X(KERNEL_ROLLOUT, 32, 32, 254, MRTS_MIN_BLOCKS_ROLLOUT)
 
 // the warp's next work item: the global counter hands out the items behind every warp's static first one
-DEV long long next_item(const StepParams &p, int lane, long long first_dynamic) {
+// (CHUNK items per draw: rollouts from a partially observable root can be a handful of cycles long, and one atomic per
+// rollout on a single address would become the limit)
+template <int CHUNK>
+DEV long long next_item(const StepParams &p, int lane, long long first_dynamic, long long cur) {
+    if (CHUNK > 1 && cur >= first_dynamic && ((cur - first_dynamic + 1) % CHUNK) != 0) return cur + 1; // still inside the drawn chunk
     unsigned long long k = 0;
     __syncwarp();
     if (lane == 0) k = atomicAdd(p.work_counter, 1ULL);
     k = __shfl_sync(FULLM, k, 0);
-    return first_dynamic + (long long)k;
+    return first_dynamic + (long long)k * CHUNK;
 }
 
 // FW, FH, FCAP > 0: a copy of the kernel for one fixed map size and unit capacity (a batch without scripted-policy words): the
@@ -1976,7 +1980,7 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
     // A warp's first item is static; the next ones come from a global counter, so a warp that drew cheap games (or rollouts
     // that ended early) takes more of them and the launch has no long tail of a few unlucky warps.
 #pragma unroll 1
-    for (long long item = (long long)bid * wpc + warp; item < n_items; item = next_item(p, lane, (long long)nblocks * wpc)) {
+    for (long long item = (long long)bid * wpc + warp; item < n_items; item = next_item<KERNEL == KERNEL_ROLLOUT ? 8 : 1>(p, lane, (long long)nblocks * wpc, item)) {
         long long gi = KERNEL == KERNEL_ROLLOUT ? item / p.rollouts_per_game : item;
         const uint32_t *blob = p.maps + (size_t)(gi % p.n_maps) * p.map_words;
         g.grid_tmpl = blob;
