@@ -607,12 +607,18 @@ def run_secondary(args):
         kern, form = "k_rollout", "rollouts*(32+24*U0+8)"
         extra = dict(rollouts_per_s=rollouts / tmax.item(), mean_rollout_cycles=cycles / max(1, rollouts), root_units=root_units)
     achieved = bytes_total / dev_s / 1e9
+    obs_traffic = None  # dram bytes of one launch from the committed ncu capture, for the configuration it was taken on
+    if wl == "obs" and not args.with_masks and n == 65536 and C == 1:
+        try:
+            obs_traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_step_fast_obs_dram_bytes_per_launch")
+        except Exception:
+            pass
     out = dict(metric="game_cycles_per_sec", value=red["cycles"] / tmax.item(), unit="game-cycles/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                ms_per_step=1000.0 * tmax.item() / max(1, args.steps), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="int32", data="synthetic",
                config=dict(workload=name, games_per_gpu=n, cycles_per_step=C, max_cycles=MAX_CYCLES, mean_live_units=mean_units,
                            l2="state + outputs larger than L2, no flush", unit_capacity=b.cap, **extra),
                clocks=clk, e2e=None, gpu_launches=launches,
-               roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
+               roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=obs_traffic,
                              peak_source="measured (MEASURED_PEAKS.json)" if peaks else "fallback", kernel=kern, bytes_formula=form,
                              mean_launch_ms=sum(kernel_ms) / max(1, len(kernel_ms))),
                cpu_baseline=None if args.no_cpu_baseline else cpu_baseline_secondary("rollout_fo" if (wl == "rollout" and args.observer < 0) else wl, min(args.cpu_seconds, 6.0)),
