@@ -1320,7 +1320,9 @@ DEVN int run_policy_po(Game &g, const StepParams &p, int player, int pn) {
 
 DEV int run_policy(Game &g, const StepParams &p, long long gi, int player, int pn, bool first_iter) {
     const int pol = p.policy[player];
+#ifndef MRTS_TU_RUSH_ONLY
     if (p.po_policies && (pol == POL_RANDOM_BIASED || POL_IS_SCRIPTED(pol))) return run_policy_po(g, p, player, pn);
+#endif
     if (pol == POL_RANDOM_BIASED) return policy_random_biased(g, player, pn);
     if (pol == POL_EXTERNAL) {
         if (first_iter && p.ext_actions[player]) {
@@ -1521,9 +1523,13 @@ DEVN void run_game(Game &g, const StepParams &p, long long gi, WarpStats &ws) {
 #pragma unroll 1
             for (int pl = 0; pl < 2; pl++)
                 if (POL_IS_SCRIPTED(p.policy[pl])) {
+#ifndef MRTS_TU_RUSH_ONLY
                     if (p.po_policies) po_hide(g, pl);
+#endif
                     policy_scripted(g, pl, p.policy[pl], p.pathfinder[pl], 0);
+#ifndef MRTS_TU_RUSH_ONLY
                     if (p.po_policies) po_unhide(g);
+#endif
                 }
         }
         int nu = g.hdr()[H_NUNITS];

@@ -200,10 +200,11 @@ struct FixedVariant {
 static const FixedVariant g_fixed[] = {MRTS_FIXED_VARIANTS(MRTS_FV_ENTRY)};
 #ifndef MRTS_EMU
 // the generic kernel compiled for one layout each in translation units of their own (fixed_<W>x<H>.cu, fixed_generic.inc)
-typedef const void *(*fixed_generic_getter)(int *W, int *H, int *cap);
-#define MRTS_FG_DECL(name) extern "C" __attribute__((visibility("hidden"))) const void *mrts_fixed_generic_##name(int *W, int *H, int *cap);
-MRTS_FG_DECL(24x24) MRTS_FG_DECL(16x16) MRTS_FG_DECL(8x8)
-static const fixed_generic_getter g_fixed_generic[] = {mrts_fixed_generic_24x24, mrts_fixed_generic_16x16, mrts_fixed_generic_8x8};
+typedef const void *(*fixed_generic_getter)(int *W, int *H, int *cap, int *rush_only);
+#define MRTS_FG_DECL(name) extern "C" __attribute__((visibility("hidden"))) const void *mrts_fixed_generic_##name(int *W, int *H, int *cap, int *rush_only);
+MRTS_FG_DECL(24x24) MRTS_FG_DECL(16x16) MRTS_FG_DECL(8x8) MRTS_FG_DECL(24x24_rush) MRTS_FG_DECL(16x16_rush)
+static const fixed_generic_getter g_fixed_generic[] = {mrts_fixed_generic_24x24, mrts_fixed_generic_16x16, mrts_fixed_generic_8x8,
+                                                        mrts_fixed_generic_24x24_rush, mrts_fixed_generic_16x16_rush};
 #endif
 static const int N_FIXED = (int)(sizeof(g_fixed) / sizeof(g_fixed[0]));
 
@@ -224,6 +225,7 @@ struct mrts_batch {
     struct Plan { int wpc = 2, grid = 3; size_t smem = 0; } plan[N_KERNELS]; // per kernel: warps (games in flight) per CTA, CTAs, shared memory
     Plan fixed_plan[N_KERNELS]; int fixed_of[N_KERNELS] = {-1, -1, -1, -1}; // the fixed-size copy that replaces kernel k for this batch, or -1
     const void *generic_fixed_fn = nullptr; // a fixed_<W>x<H>.cu kernel when the batch has its layout (plan in fixed_plan[KERNEL_GENERIC])
+    const void *generic_rush_fn = nullptr; Plan rush_plan; // its rush-only copy (fixed_<W>x<H>_rush.cu), for steps whose policies allow it
     int max_range = 0, auto_reset = 0, scripted = 0, uw = MRTS_UNIT_WORDS_CORE;
     int sequential_issue = 0; int32_t *info_out = nullptr; uint32_t tm[6] = {0, 0, 0, 0, 0, 0};
     void *obs_out[2] = {nullptr, nullptr}; int obs_dtype = 0; // device buffers mrts_batch_step writes post-step observations to
@@ -254,7 +256,10 @@ static int launch_step(mrts_batch *b, StepParams &p) {
         kernel = (p.obs_out[0] || p.obs_out[1]) ? KERNEL_FAST_OBS : KERNEL_FAST;
     const int fv = b->fixed_of[kernel];
     const bool gfx = kernel == KERNEL_GENERIC && b->generic_fixed_fn;
-    const mrts_batch::Plan &pl = (fv >= 0 || gfx) ? b->fixed_plan[kernel] : b->plan[kernel];
+    // the rush-only copy: a game step in which neither player runs a defense, WorkerRushPlusPlus or a PO rush
+    auto plain = [](int pol) { return pol <= MRTS_POLICY_RANGED_RUSH; };
+    const bool rush = gfx && b->generic_rush_fn && p.mode == MODE_GAME && plain(p.policy[0]) && plain(p.policy[1]);
+    const mrts_batch::Plan &pl = rush ? b->rush_plan : ((fv >= 0 || gfx) ? b->fixed_plan[kernel] : b->plan[kernel]);
     p.L = kernel == KERNEL_GENERIC ? b->L : b->Lfast;
     int threads = pl.wpc * 32;
     long long items = p.mode == MODE_ROLLOUT ? b->n * p.rollouts_per_game : b->n;
@@ -272,7 +277,7 @@ static int launch_step(mrts_batch *b, StepParams &p) {
     });
     return 0;
 #else
-    if (fv >= 0 || gfx) { void *args[] = {&p}; return ck(cudaLaunchKernel(gfx ? b->generic_fixed_fn : g_fixed[fv].fn, dim3(grid), dim3(threads), args, pl.smem, b->stream)); }
+    if (fv >= 0 || gfx) { void *args[] = {&p}; return ck(cudaLaunchKernel(rush ? b->generic_rush_fn : (gfx ? b->generic_fixed_fn : g_fixed[fv].fn), dim3(grid), dim3(threads), args, pl.smem, b->stream)); }
     if (kernel == KERNEL_FAST) k_step_fast<<<grid, threads, pl.smem, b->stream>>>(p);
     else if (kernel == KERNEL_FAST_OBS) k_step_fast_obs<<<grid, threads, pl.smem, b->stream>>>(p);
     else if (kernel == KERNEL_ROLLOUT) k_rollout<<<grid, threads, pl.smem, b->stream>>>(p);
@@ -456,12 +461,12 @@ int mrts_batch_create(const mrts_utt *u, const mrts_map *const *maps, int n_maps
             b->fixed_of[g_fixed[v].kernel] = v;
         }
     for (fixed_generic_getter get : g_fixed_generic) {
-        int fw = 0, fh = 0, fcap = 0;
-        const void *fn = get(&fw, &fh, &fcap);
+        int fw = 0, fh = 0, fcap = 0, rush_only = 0;
+        const void *fn = get(&fw, &fh, &fcap, &rush_only);
         if (fw == W && fh == H && fcap == cap && b->scripted == 1 && !po_pol) {
-            int rc = make_plan(fn, b->L.total, b->fixed_plan[KERNEL_GENERIC]);
+            int rc = make_plan(fn, b->L.total, rush_only ? b->rush_plan : b->fixed_plan[KERNEL_GENERIC]);
             if (rc) return rc;
-            b->generic_fixed_fn = fn;
+            (rush_only ? b->generic_rush_fn : b->generic_fixed_fn) = fn;
         }
     }
 #endif

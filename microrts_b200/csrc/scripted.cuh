@@ -516,15 +516,23 @@ DEV void script_build_if_not(Game &g, int s, int player, int type, int *reserved
 DEVN int policy_scripted(Game &g, int player, int kind, int pathfinder, int pn) {
     // the PO rushes are their rush plus exploration, which only a partially observable view triggers (`gs instanceof
     // PartiallyObservableGameState`, POLightRush.java:57)
+#ifdef MRTS_TU_RUSH_ONLY
+    const bool explore = false;
+#else
     const bool explore = POL_IS_PO_RUSH(kind) && g.po_view;
     if (POL_IS_PO_RUSH(kind)) kind = kind - POL_PO_WORKER_RUSH + POL_WORKER_RUSH;
+#endif
     int par0, par1;
     reserved_resources(g, par0, par1);
     __syncwarp();
     const int n = g.hdr()[H_NUNITS], pl = player + 1, pres = g.hdr()[H_RES0 + player];
     // the barracks scripts: LightRush / LightDefense, and Heavy* / Ranged* = the same classes with the trained type swapped;
     // the defenses share their rush's skeleton and differ in script_melee / script_harvest
+#ifdef MRTS_TU_RUSH_ONLY
+    const bool light = kind != POL_WORKER_RUSH, defense = false, always = false;
+#else
     const bool light = kind != POL_WORKER_RUSH && kind != POL_WORKER_DEFENSE && kind != POL_WORKER_RUSH_PP, defense = POL_IS_DEFENSE(kind), always = kind == POL_WORKER_RUSH_PP;
+#endif
     const int UT_RUSH = (kind == POL_HEAVY_RUSH || kind == POL_HEAVY_DEFENSE) ? 5 : ((kind == POL_RANGED_RUSH || kind == POL_RANGED_DEFENSE) ? 6 : UT_LIGHT); // HeavyRush.java:55, RangedRush.java:52
     auto own_harvester = [&](int, uint32_t w) { return u_pl(w) == pl && (ut_flags(g, u_type(w)) & UF_HARVEST) != 0; };
     // bases (WorkerRush.java:70-76,100-102; LightRush.java:83-89,123-133)
