@@ -56,6 +56,15 @@ public final class BatchedGameState implements AutoCloseable {
      */
     public BatchedGameState(Path libraryPath, int uttVersion, int conflictPolicy, String mapPath, int numGames, int device,
                             boolean partialObs) {
+        this(libraryPath, uttVersion, conflictPolicy, mapPath, numGames, device, partialObs ? FLAG_PARTIAL_OBS : 0);
+    }
+
+    /**
+     * @param flags FLAG_PARTIAL_OBS (8-plane observations), FLAG_SCRIPTED_AI (the scripted POLICY_* and findPath need it),
+     *              FLAG_PO_POLICIES (Game with partiallyObservable = true: device policies decide on their player's view)
+     */
+    public BatchedGameState(Path libraryPath, int uttVersion, int conflictPolicy, String mapPath, int numGames, int device,
+                            int flags) {
         lib = SymbolLookup.libraryLookup(libraryPath, arena);
         lastError = h("mrts_last_error", FunctionDescriptor.of(P));
         uttCreate = h("mrts_utt_create", FunctionDescriptor.of(I, I, I, P));
@@ -93,7 +102,7 @@ public final class BatchedGameState implements AutoCloseable {
             map = out.get(P, 0);
             MemorySegment maps = arena.allocate(P);
             maps.set(P, 0, map);
-            check((int) batchCreate.invoke(utt, maps, 1, (long) numGames, device, partialObs ? 1 : 0, 0, out));
+            check((int) batchCreate.invoke(utt, maps, 1, (long) numGames, device, flags, 0, out));
             batch = out.get(P, 0);
             this.numGames = numGames;
             this.planes = (int) numPlanes.invoke(batch);
