@@ -8,6 +8,11 @@
 // Lanes work on different units (enumeration, sampling, legality) and arbitrate order-dependent effects with
 // ballot / shuffle / redux; effects that the reference applies sequentially are replayed in the same order.
 //
+// Kernels (step_kernel_body at the end of the file): persistent grids; a warp takes its first game statically and the next ones
+// from a global counter.  The hot kernels exist in three forms: with the layout as kernel parameters, as fixed-size template
+// copies (MRTS_FIXED_VARIANTS) and, for the generic kernel, as whole translation units compiled for one layout
+// (MRTS_TU_FIXED, fixed_generic.inc) -- in the last two the shared-memory offsets are compile-time constants.
+//
 // Each function cites the reference code it restates (paths under the reference checkout, src/...).
 // The file is also compiled for the host by tests/emu (MRTS_EMU) where warp primitives are emulated with
 // coroutines; that build is test tooling only and is never linked into libmicrorts_cuda.so.
