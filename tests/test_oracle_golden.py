@@ -84,3 +84,94 @@ def test_regenerate_lightrush_traces(traces, maps):
         last = np.array(ents[-1]["units"], dtype=np.int32).reshape(-1, 6)
         assert (g.units()[:, :6] == last).all()
     assert n == 140
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# hand-derived known answers for the parts of the oracle the reference holds no golden data for (worked out on paper from
+# the cited Java: GreedyPathFinding.java:53-84, PartiallyObservableGameState.java:35-71, WorkerDefense.java:117-146,
+# POLightRush.java:42-78).  They keep the checker itself honest on CPU; the device is compared with it in the gpu tests.
+# ------------------------------------------------------------------------------------------------------------------
+def _tiny_map(units, w=8, h=8, walls=()):
+    terrain = ["0"] * (w * h)
+    for x, y in walls:
+        terrain[x + y * w] = "1"
+    return {"w": w, "h": h, "players": [[0, 5], [1, 5]], "terrain": "".join(terrain),
+            "units": [[t, 100 + i, p, x, y, r, hp] for i, (t, p, x, y, r, hp) in enumerate(units)]}
+
+
+def test_greedy_pathfinder_known_answers():
+    utt = O.Utt(1, 1)
+    # a worker at (1,1), target (5,1): RIGHT is the free neighbour closest to the target
+    g = O.Game(utt, _tiny_map([("Worker", 0, 1, 1, 0, 1), ("Base", 1, 6, 6, 0, 10)]))
+    assert g.pathfind(O.PF_GREEDY, 0, 5 + 1 * 8, 1) == 1
+    # a wall on the right: UP (1,0) and DOWN (1,2) tie at squared distance 17, LEFT is farther; the first in direction order wins
+    g = O.Game(utt, _tiny_map([("Worker", 0, 1, 1, 0, 1), ("Base", 1, 6, 6, 0, 10)], walls=[(2, 1)]))
+    assert g.pathfind(O.PF_GREEDY, 0, 5 + 1 * 8, 1) == 0
+    # "already in range" compares the SQUARED distance with the unsquared range (GreedyPathFinding.java:66): at squared distance 4
+    # a range of 3 returns null although 2 <= 3 would also, and a range of 1 does not (distance 2 > 1)
+    g = O.Game(utt, _tiny_map([("Worker", 0, 1, 1, 0, 1), ("Base", 1, 6, 6, 0, 10)]))
+    assert g.pathfind(O.PF_GREEDY, 0, 3 + 1 * 8, 4) == -1
+    assert g.pathfind(O.PF_GREEDY, 0, 3 + 1 * 8, 1) == 1
+    # boxed in by units and the map edge: null
+    g = O.Game(utt, _tiny_map([("Worker", 0, 0, 0, 0, 1), ("Worker", 0, 1, 0, 0, 1), ("Worker", 0, 0, 1, 0, 1), ("Base", 1, 6, 6, 0, 10)]))
+    assert g.pathfind(O.PF_GREEDY, 0, 5 + 5 * 8, 1) == -1
+    # A* and BFS agree with the obvious first step around a wall segment
+    g = O.Game(utt, _tiny_map([("Worker", 0, 1, 1, 0, 1), ("Base", 1, 6, 6, 0, 10)], walls=[(2, 0), (2, 1), (2, 2)]))
+    assert g.pathfind(O.PF_ASTAR, 0, 4 + 1 * 8, 0) == g.pathfind(O.PF_BFS, 0, 4 + 1 * 8, 0) == 2  # down, around the wall's lower end
+
+
+def test_partially_observable_view_known_answers():
+    utt = O.Utt(1, 1)
+    # worker sight radius 3, base 5 (UnitTypeTable.java): player 0 has a worker at (1,1) only
+    units = [("Worker", 0, 1, 1, 0, 1), ("Resource", -1, 4, 1, 20, 1), ("Resource", -1, 5, 1, 20, 1), ("Worker", 1, 3, 3, 0, 1), ("Base", 1, 6, 6, 0, 10)]
+    g = O.Game(utt, _tiny_map(units))
+    v = g.po_view(0)
+    seen = {(int(u[2]), int(u[3])) for u in v.units()}
+    # (4,1): dx=3 -> 9 <= 9 visible; (5,1): 16 > 9 hidden; (3,3): 4+4=8 visible; (6,6): hidden; own unit always there
+    assert seen == {(1, 1), (4, 1), (3, 3)}
+    v1 = g.po_view(1)
+    seen1 = {(int(u[2]), int(u[3])) for u in v1.units()}
+    # player 1: worker (3,3) radius 3 and base (6,6) radius 5: (1,1): 8 <= 9 from the worker; (4,1): 1+4=5; (5,1): 4+4=8
+    assert seen1 == {(1, 1), (4, 1), (5, 1), (3, 3), (6, 6)}
+
+
+def _action_of(pairs, unit_idx):
+    for u, a in pairs:
+        if u == unit_idx:
+            return a
+    return None
+
+
+def test_defense_and_po_rush_known_answers():
+    utt = O.Utt(1, 1)
+    # 8x8 map (height / 2 = 4).  Player 0: base (0,0), a Light at (1,0) [distance to base 1 < 4].  Enemy worker far away at (7,7).
+    near_base = [("Base", 0, 0, 0, 0, 10), ("Light", 0, 1, 0, 0, 4), ("Worker", 1, 7, 7, 0, 1), ("Base", 1, 6, 7, 0, 10)]
+    g = O.Game(utt, _tiny_map(near_base))
+    ai = O.ScriptedAI(O.AI_LIGHT_DEFENSE)
+    act = _action_of(ai.get_action(g, 0), 1)
+    assert act is not None and act[0] == O.MOVE            # close to its base: it goes after the closest enemy (LightDefense.java:157-159)
+    # the same Light far from its base (6,0) [distance 6] and far from every enemy (closest: (7,7), distance 8): Attack(null),
+    # deleted by translateActions, so fillWithNones gives it NONE(10) (LightDefense.java:160-163, PlayerAction.java:217-235)
+    far = [("Base", 0, 0, 0, 0, 10), ("Light", 0, 6, 0, 0, 4), ("Worker", 1, 7, 7, 0, 1), ("Base", 1, 6, 7, 0, 10)]
+    g = O.Game(utt, _tiny_map(far))
+    ai = O.ScriptedAI(O.AI_LIGHT_DEFENSE)
+    act = _action_of(ai.get_action(g, 0), 1)
+    assert act is not None and act[0] == O.NONE and act[1] == 10
+    # WorkerRushPlusPlus attacks regardless of the distances (WorkerRushPlusPlus.java:136-138)
+    ai = O.ScriptedAI(O.AI_WORKER_RUSH_PP)
+    act = _action_of(ai.get_action(O.Game(utt, _tiny_map(far)), 0), 1)
+    assert act is not None and act[0] == O.MOVE
+    # POLightRush on player 0's view of a 16x16 map: no enemy in sight, so the Light at (2,2) explores towards the nearest cell
+    # nobody sees.  Sight: base (0,0) radius 5, Light radius 2 -> the first non-observable cell in row-major order with the
+    # smallest squared distance to (2,2) is (4,4)?  (dx,dy)=(2,2): 8 > 4 for the Light; from the base 16+16=32 > 25 -> unseen,
+    # distance 8; closer candidates: (2,5)/(5,2): distance 9; (3,4): base 9+16=25 seen; (4,3) seen -> target (4,4): move DOWN
+    # or RIGHT first; A* expands ... the move must at least be a MOVE towards larger x or y.
+    units = [("Base", 0, 0, 0, 0, 10), ("Light", 0, 2, 2, 0, 4), ("Base", 1, 15, 15, 0, 10)]
+    g = O.Game(utt, _tiny_map(units, 16, 16))
+    ai = O.ScriptedAI(O.AI_PO_LIGHT_RUSH)
+    act = _action_of(ai.get_action(g.po_view(0), 0), 1)
+    assert act is not None and act[0] == O.MOVE and act[1] in (1, 2)
+    # on the fully observable state the same class attacks instead (POLightRush.java:52-54)
+    ai = O.ScriptedAI(O.AI_PO_LIGHT_RUSH)
+    act = _action_of(ai.get_action(g, 0), 1)
+    assert act is not None and act[0] == O.MOVE
