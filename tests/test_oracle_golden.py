@@ -175,3 +175,41 @@ def test_defense_and_po_rush_known_answers():
     ai = O.ScriptedAI(O.AI_PO_LIGHT_RUSH)
     act = _action_of(ai.get_action(g, 0), 1)
     assert act is not None and act[0] == O.MOVE
+
+
+def test_observation_and_mask_known_answers(maps):
+    """GameState.getVectorObservation (GameState.java:922-968) and JNIGridnetClient.getMasks / UnitAction.getValidActionArray
+    (UnitAction.java:711-751) of the initial state of maps/8x8/basesWorkers8x8.xml, written out by hand."""
+    utt = O.Utt(1, 1)
+    g = O.Game(utt, maps["8x8/basesWorkers8x8"])
+    # units: Resource (0,0) and (7,7) with 20 resources and 1 hp; Base p0 (2,1) hp 10; Base p1 (5,6); Worker p0 (1,1); Worker p1 (6,6)
+    for player in (0, 1):
+        o = g.observe(player)
+        want = np.zeros((6, 8, 8), dtype=np.int32)
+        for (x, y, hp, res, owner, tid) in ((0, 0, 1, 20, -1, 0), (7, 7, 1, 20, -1, 0), (2, 1, 10, 0, 0, 1), (5, 6, 10, 0, 1, 1), (1, 1, 1, 0, 0, 3), (6, 6, 1, 0, 1, 3)):
+            want[0, y, x] = hp
+            want[1, y, x] = res
+            if owner >= 0:
+                want[2, y, x] = (owner + player) % 2 + 1  # 1 = the observing player's own unit, 2 = the opponent's
+            want[3, y, x] = tid + 1
+        assert (o == want).all()                          # no action in flight (plane 4), no walls (plane 5)
+    m = g.masks(0)
+    assert m.shape == (8, 8, 1 + 6 + 16 + 7 + 49)
+    # worker (1,1) of player 0, 5 resources: up (1,0), down (1,2) and left (0,1) are free, the base is on the right; the resource at
+    # (0,0) is diagonal (no harvest); it can afford a Barracks (5) but not a Base (10)
+    w = np.zeros(79, dtype=np.int32)
+    w[0] = 1
+    w[1 + O.NONE] = w[1 + O.MOVE] = w[1 + O.PRODUCE] = 1
+    w[7 + 0] = w[7 + 2] = w[7 + 3] = 1                    # move directions
+    w[19 + 0] = w[19 + 2] = w[19 + 3] = 1                 # produce directions
+    w[23 + 2] = 1                                         # produce type: Barracks (ID 2)
+    assert (m[1, 1] == w).all()
+    # base (2,1): trains a Worker (cost 1) into (2,0), (3,1) or (2,2); the worker stands on its left
+    b = np.zeros(79, dtype=np.int32)
+    b[0] = 1
+    b[1 + O.NONE] = b[1 + O.PRODUCE] = 1
+    b[19 + 0] = b[19 + 1] = b[19 + 2] = 1
+    b[23 + 3] = 1
+    assert (m[1, 2] == b).all()
+    mask_cells = {(y, x) for y in range(8) for x in range(8) if m[y, x].any()}
+    assert mask_cells == {(1, 1), (1, 2)}                 # only player 0's idle units carry a mask
