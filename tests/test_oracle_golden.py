@@ -213,3 +213,20 @@ def test_observation_and_mask_known_answers(maps):
     assert (m[1, 2] == b).all()
     mask_cells = {(y, x) for y in range(8) for x in range(8) if m[y, x].any()}
     assert mask_cells == {(1, 1), (1, 2)}                 # only player 0's idle units carry a mask
+
+
+def test_evaluation_known_answers():
+    """SimpleSqrtEvaluationFunction3.java:24-44 (hp / maxhp is an INTEGER division inside the sqrt) and
+    SimpleEvaluationFunction.java:21-36, on a position small enough to add up by hand."""
+    utt = O.Utt(1, 1)
+    # player 0: base (hp 10/10), worker carrying 1 resource; player 1: base with 4 of 10 hit points; 5 resources each
+    g = O.Game(utt, _tiny_map([("Base", 0, 1, 1, 0, 10), ("Worker", 0, 2, 2, 1, 1), ("Base", 1, 6, 6, 0, 4)]))
+    # Sqrt3: s0 = 5*20 + (1*10 + 40*1*sqrt(1/1)) + 40*10*sqrt(10/10) = 550 ; s1 = 5*20 + 40*10*sqrt(4/10 = 0) = 100
+    want = np.float32(2 * np.float32(550) / np.float32(650)) - np.float32(1)
+    assert np.float32(g.evaluate(0, 0, 1)) == np.float32(want)
+    assert np.float32(g.evaluate(0, 1, 0)) == np.float32(np.float32(2 * np.float32(100) / np.float32(650)) - np.float32(1))
+    # Simple: s0 = 100 + 10 + 40*1*1/1 + 40*10*10/10 = 550 ; s1 = 100 + 40*10*4/10 = 260
+    assert g.evaluate(1, 0, 1) == 290.0 and g.evaluate(1, 1, 0) == -290.0
+    # a player without units scores 0 in Sqrt3 (:41-43), so the other side's evaluation is 2*s/(s+0) - 1 = 1
+    g = O.Game(utt, _tiny_map([("Base", 0, 1, 1, 0, 10)]))
+    assert g.evaluate(0, 0, 1) == 1.0 and g.evaluate(0, 1, 0) == -1.0
