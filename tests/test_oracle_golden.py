@@ -230,3 +230,31 @@ def test_evaluation_known_answers():
     # a player without units scores 0 in Sqrt3 (:41-43), so the other side's evaluation is 2*s/(s+0) - 1 = 1
     g = O.Game(utt, _tiny_map([("Base", 0, 1, 1, 0, 10)]))
     assert g.evaluate(0, 0, 1) == 1.0 and g.evaluate(0, 1, 0) == -1.0
+
+
+def test_vector_action_known_answers(maps):
+    """PlayerAction.fromVectorAction (PlayerAction.java:384-417) + UnitAction.fromVectorAction (UnitAction.java:675-709) on the
+    initial state of maps/8x8/basesWorkers8x8.xml: rows are [cell, type, moveDir, harvestDir, returnDir, produceDir, produceType,
+    attackIdx]; rows that name an empty cell, the opponent's unit or a cell already used by an earlier row are dropped."""
+    utt = O.Utt(1, 1)
+    g = O.Game(utt, maps["8x8/basesWorkers8x8"])
+    rows = np.array([
+        [1 + 1 * 8, O.MOVE, 2, 0, 0, 0, 0, 0],      # worker (1,1): move DOWN (to (1,2))
+        [2 + 1 * 8, O.PRODUCE, 0, 0, 0, 2, 3, 0],   # base (2,1): produce a Worker (type 3) DOWN (to (2,2))
+        [6 + 6 * 8, O.MOVE, 0, 0, 0, 0, 0, 0],      # the opponent's worker: ignored
+        [3 + 3 * 8, O.MOVE, 1, 0, 0, 0, 0, 0],      # empty cell: ignored
+    ], dtype=np.int32)
+    pa = g.from_vector_action(0, rows, fill_none=1)
+    # unit-list indices: 4 = worker p0, 2 = base p0; action = (type, parameter, x, y, unit type)
+    assert pa == [(4, (O.MOVE, 2, 0, 0, -1)), (2, (O.PRODUCE, 2, 0, 0, 3))]
+    # two rows whose actions target the same cell: the second is inconsistent with the resource usage built so far and is dropped
+    rows = np.array([[2 + 1 * 8, O.PRODUCE, 0, 0, 0, 3, 3, 0],   # base (2,1) produces LEFT?  (1,1) is the worker's cell -- still a position
+                     [1 + 1 * 8, O.MOVE, 1, 0, 0, 0, 0, 0]], dtype=np.int32)
+    pa = g.from_vector_action(0, rows, fill_none=1)
+    assert pa[0] == (2, (O.PRODUCE, 3, 0, 0, 3))
+    # an attack index is relative to the unit on a (2a+1)^2 window, a = the largest attack range of the table (3 -> 7x7):
+    # index 3 + 2*7 = 17 is (dx, dy) = (0, -1)
+    rows = np.array([[1 + 1 * 8, O.ATTACK, 0, 0, 0, 0, 0, 17]], dtype=np.int32)
+    pa = g.from_vector_action(0, rows, fill_none=1)
+    # the base was not addressed: JNIAI.getAction fills it with NONE of duration 1 (ai/jni/JNIAI.java:53)
+    assert pa == [(4, (O.ATTACK, -1, 1, 0, -1)), (2, (O.NONE, 1, 0, 0, -1))]
