@@ -258,3 +258,46 @@ def test_vector_action_known_answers(maps):
     pa = g.from_vector_action(0, rows, fill_none=1)
     # the base was not addressed: JNIAI.getAction fills it with NONE of duration 1 (ai/jni/JNIAI.java:53)
     assert pa == [(4, (O.ATTACK, -1, 1, 0, -1)), (2, (O.NONE, 1, 0, 0, -1))]
+
+
+class _JavaRandom:
+    """java.util.Random as the Java SE specification defines it (48-bit LCG), written independently of the oracle."""
+    def __init__(self, seed):
+        self.s = (seed ^ 0x5DEECE66D) & ((1 << 48) - 1)
+
+    def next(self, bits):
+        self.s = (self.s * 0x5DEECE66D + 0xB) & ((1 << 48) - 1)
+        return self.s >> (48 - bits)
+
+    def next_double(self):
+        return ((self.next(26) << 27) + self.next(27)) * (1.0 / (1 << 53))
+
+
+def test_random_biased_known_answer(maps):
+    """RandomBiasedAI.getAction (RandomBiasedAI.java:51-107) + Sampler.weighted (Sampler.java:116-137) for player 0 on the initial
+    state of maps/8x8/basesWorkers8x8.xml with util.Sampler.generator = new Random(42), action lists written out by hand from
+    Unit.getUnitActions (Unit.java:382-522)."""
+    r = _JavaRandom(42)
+    d1, d2 = r.next_double(), r.next_double()
+    assert d1 == 0.7275636800328681                      # the known answer of the Java SE specification
+    # base (2,1), 5 resources: Worker (cost 1) up / right / down (the worker is on its left), then NONE: four actions of weight 1
+    base_list = [(O.PRODUCE, 0, 3), (O.PRODUCE, 1, 3), (O.PRODUCE, 2, 3), (O.NONE, 10, -1)]
+    # worker (1,1): Base (10) is too expensive; Barracks (5) up / down / left (the base is on its right); move up / down / left; NONE
+    worker_list = [(O.PRODUCE, 0, 2), (O.PRODUCE, 2, 2), (O.PRODUCE, 3, 2), (O.MOVE, 0, -1), (O.MOVE, 2, -1), (O.MOVE, 3, -1), (O.NONE, 10, -1)]
+
+    def weighted(draw, n):  # all weights are 1 here: first i with i + 1 >= draw * n
+        tmp, acc = draw * n, 0.0
+        for i in range(n):
+            acc += 1.0
+            if acc >= tmp:
+                return i
+        return n - 1
+
+    b = base_list[weighted(d1, len(base_list))]
+    w = worker_list[weighted(d2, len(worker_list))]
+    g = O.Game(O.Utt(1, 1), maps["8x8/basesWorkers8x8"])
+    g.seed(42)
+    pa = g.random_biased(0)
+    # units are visited in unit-list order: the base (index 2) before the worker (index 4); the two choices use different cells
+    assert pa == [(2, (b[0], b[1], 0, 0, b[2])), (4, (w[0], w[1], 0, 0, w[2]))]
+    assert b == (O.PRODUCE, 2, 3) and w[0] in (O.MOVE, O.PRODUCE)   # 0.7275.. * 4 = 2.91 -> third action: a Worker below the base
