@@ -301,3 +301,41 @@ def test_random_biased_known_answer(maps):
     # units are visited in unit-list order: the base (index 2) before the worker (index 4); the two choices use different cells
     assert pa == [(2, (b[0], b[1], 0, 0, b[2])), (4, (w[0], w[1], 0, 0, w[2]))]
     assert b == (O.PRODUCE, 2, 3) and w[0] in (O.MOVE, O.PRODUCE)   # 0.7275.. * 4 = 2.91 -> third action: a Worker below the base
+
+
+def test_issue_conflict_known_answers():
+    """GameState.issue (GameState.java:249-328) and issueSafe (:338-408) on positions small enough to follow by hand: two units that
+    choose the same cell in the same cycle, under each move-conflict strategy, and an illegal action."""
+    # a Light of player 0 at (1,1) (move time 8) and a Worker of player 1 at (3,1) (move time 10) both step into (2,1)
+    units = [("Light", 0, 1, 1, 0, 4), ("Worker", 1, 3, 1, 0, 1), ("Base", 0, 0, 7, 0, 10), ("Base", 1, 7, 7, 0, 10)]
+    move_right, move_left = (O.MOVE, 1, 0, 0, -1), (O.MOVE, 3, 0, 0, -1)
+    # CANCEL_BOTH (1): both become NONE of duration min(8, 10) (:276-278, :289-296)
+    g = O.Game(O.Utt(1, 1), _tiny_map(units))
+    g.issue([(0, move_right)]); g.issue([(1, move_left)])
+    a = g.assignments()
+    assert a[0, :3].tolist() == [1, O.NONE, 8] and a[1, :3].tolist() == [1, O.NONE, 8]
+    # CANCEL_ALTERNATING (3): the counter starts even, so the NEW action is the one cancelled (:283-286); the old MOVE stays
+    g = O.Game(O.Utt(1, 3), _tiny_map(units))
+    g.issue([(0, move_right)]); g.issue([(1, move_left)])
+    a = g.assignments()
+    assert a[0, :3].tolist() == [1, O.MOVE, 1] and a[1, :3].tolist() == [1, O.NONE, 8]
+    # ... and the next conflict cancels the OLD one
+    units2 = units + [("Light", 0, 1, 4, 0, 4), ("Worker", 1, 3, 4, 0, 1)]
+    g = O.Game(O.Utt(1, 3), _tiny_map(units2))
+    g.issue([(0, move_right), (4, move_right)]); g.issue([(1, move_left), (5, move_left)])
+    a = g.assignments()
+    assert a[0, :3].tolist() == [1, O.MOVE, 1] and a[1, :3].tolist() == [1, O.NONE, 8]
+    assert a[4, :3].tolist() == [1, O.NONE, 8] and a[5, :3].tolist() == [1, O.MOVE, 3]
+    # after 8 cycles the surviving MOVE of the Light has executed
+    g = O.Game(O.Utt(1, 3), _tiny_map(units))
+    g.issue([(0, move_right)]); g.issue([(1, move_left)])
+    for _ in range(8):
+        g.cycle()
+    u = g.units()
+    assert (int(u[0, 2]), int(u[0, 3])) == (2, 1) and (int(u[1, 2]), int(u[1, 3])) == (3, 1)
+    # issueSafe: an action that is not among the unit's legal actions is replaced by NONE with the action's own duration (:352-366):
+    # the base cannot move
+    g = O.Game(O.Utt(1, 1), _tiny_map(units))
+    g.issue([(2, (O.MOVE, 0, 0, 0, -1))], safe=True)
+    a = g.assignments()
+    assert a[2, 0] == 1 and a[2, 1] == O.NONE
