@@ -339,3 +339,38 @@ def test_issue_conflict_known_answers():
     g.issue([(2, (O.MOVE, 0, 0, 0, -1))], safe=True)
     a = g.assignments()
     assert a[2, 0] == 1 and a[2, 1] == O.NONE
+
+
+def test_execute_known_answers():
+    """UnitAction.execute (UnitAction.java:338-465) and ETA (:307-329) followed by hand with the VERSION_ORIGINAL numbers of
+    UnitTypeTable.java (worker: harvest 20, return = move time 10, attack 5, produced in 50; harvest amount 1; Light: 2 damage)."""
+    utt = O.Utt(1, 1)
+    # resource (0,0) with 20, worker p0 (1,0), base p0 (2,0); an enemy base far away keeps the game alive
+    g = O.Game(utt, _tiny_map([("Resource", -1, 0, 0, 20, 1), ("Worker", 0, 1, 0, 0, 1), ("Base", 0, 2, 0, 0, 10), ("Base", 1, 7, 7, 0, 10)]))
+    g.issue([(1, (O.HARVEST, 3, 0, 0, -1))])                 # harvest LEFT
+    for _ in range(19):
+        g.cycle()
+    assert int(g.units()[1, 4]) == 0                         # not yet: ETA 20
+    g.cycle()
+    u = g.units()
+    assert int(u[0, 4]) == 19 and int(u[1, 4]) == 1          # the resource lost one unit, the worker carries it
+    g.issue([(1, (O.RETURN, 1, 0, 0, -1))])                  # return RIGHT to the base: ETA = move time 10 (:316-318)
+    for _ in range(10):
+        g.cycle()
+    assert [g.resources(0), g.resources(1)] == [6, 5] and int(g.units()[1, 4]) == 0
+    # the base trains a Worker DOWN: the cost leaves the player when the action EXECUTES, 50 cycles later (:404-418), and the new unit
+    # joins the END of the unit list
+    g.issue([(2, (O.PRODUCE, 2, 0, 0, 3))])
+    for _ in range(49):
+        g.cycle()
+    assert [g.resources(0), g.resources(1)] == [6, 5] and g.n_units == 4
+    g.cycle()
+    u = g.units()
+    assert [g.resources(0), g.resources(1)] == [5, 5] and g.n_units == 5 and u[4, :4].tolist() == [3, 0, 2, 1]
+    # a Light (2 damage) attacks the adjacent enemy Worker (1 hp): after attackTime 5 the worker is gone, and with it the assignment it had
+    g = O.Game(utt, _tiny_map([("Light", 0, 1, 1, 0, 4), ("Worker", 1, 2, 1, 0, 1), ("Base", 0, 0, 7, 0, 10), ("Base", 1, 7, 7, 0, 10)]))
+    g.issue([(0, (O.ATTACK, -1, 2, 1, -1))]); g.issue([(1, (O.MOVE, 1, 0, 0, -1))])
+    for _ in range(5):
+        g.cycle()
+    u = g.units()
+    assert g.n_units == 3 and [int(t) for t in u[:, 0]] == [4, 1, 1] and g.assignments()[:, 0].tolist() == [0, 0, 0]
