@@ -138,3 +138,19 @@ def test_initial_observation_and_masks(backend, maps):
     assert (m[1, 2] == bs).all()
     assert {(y, x) for y in range(8) for x in range(8) if m[y, x].any()} == {(1, 1), (1, 2)}
     b.close()
+
+
+@pytest.mark.parametrize("pf,moves", [(0, (3, 2)), (1, (0, 1))])
+def test_worker_rush_first_decision(backend, maps, pf, moves):
+    """see test_oracle_golden.test_worker_rush_first_decision_known_answer: the bases train a Worker up / down, the workers step
+    towards their resource -- LEFT / DOWN with A*, UP / RIGHT with BFS."""
+    utt = M.UnitTypeTable(1, 1)
+    b = M.BatchedGameState(utt, M.PhysicalGameState.fromXML(P.map_to_xml(maps["8x8/basesWorkers8x8"]), utt), 2, scripted_ai=True)
+    b.reset(np.zeros(2, dtype=np.int64))
+    b.set_policy(0, M.POLICY_WORKER_RUSH, pf)
+    b.set_policy(1, M.POLICY_WORKER_RUSH, pf)
+    b.step(1, 3000)
+    h, u, a = state(b)
+    assert a[2, [0, 1, 4]].tolist() == [PRODUCE, 0, 3] and a[3, [0, 1, 4]].tolist() == [PRODUCE, 2, 3]
+    assert a[4, :2].tolist() == [MOVE, moves[0]] and a[5, :2].tolist() == [MOVE, moves[1]]
+    b.close()

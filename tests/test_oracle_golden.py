@@ -374,3 +374,16 @@ def test_execute_known_answers():
         g.cycle()
     u = g.units()
     assert g.n_units == 3 and [int(t) for t in u[:, 0]] == [4, 1, 1] and g.assignments()[:, 0].tolist() == [0, 0, 0]
+
+
+def test_worker_rush_first_decision_known_answer(maps):
+    """WorkerRush.getAction (WorkerRush.java:63-204) on the initial state of maps/8x8/basesWorkers8x8.xml, by hand:
+    the base trains a Worker into the free neighbour closest to a resource (Train.java:48-128: up (2,0), distance 2, beats right and
+    down at 4); the worker becomes the harvester and A* to a cell adjacent to the resource at (0,0) expands up (1,0), down, left
+    (0,1) and pops the NEWEST node of the smallest f first (AStarPathFinding.java:104-138) -- (0,1), already adjacent: first move LEFT.
+    BFS pops the oldest, (1,0): UP.  Player 1 is the mirror image: train DOWN (5,7), move DOWN (A*) / RIGHT (BFS)."""
+    g = O.Game(O.Utt(1, 1), maps["8x8/basesWorkers8x8"])
+    assert O.ScriptedAI(O.AI_WORKER_RUSH, O.PF_ASTAR).get_action(g, 0) == [(2, (O.PRODUCE, 0, 0, 0, 3)), (4, (O.MOVE, 3, 0, 0, -1))]
+    assert O.ScriptedAI(O.AI_WORKER_RUSH, O.PF_BFS).get_action(g, 0) == [(2, (O.PRODUCE, 0, 0, 0, 3)), (4, (O.MOVE, 0, 0, 0, -1))]
+    assert O.ScriptedAI(O.AI_WORKER_RUSH, O.PF_ASTAR).get_action(g, 1) == [(3, (O.PRODUCE, 2, 0, 0, 3)), (5, (O.MOVE, 2, 0, 0, -1))]
+    assert O.ScriptedAI(O.AI_WORKER_RUSH, O.PF_BFS).get_action(g, 1) == [(3, (O.PRODUCE, 2, 0, 0, 3)), (5, (O.MOVE, 1, 0, 0, -1))]
