@@ -154,3 +154,12 @@ def test_worker_rush_first_decision(backend, maps, pf, moves):
     assert a[2, [0, 1, 4]].tolist() == [PRODUCE, 0, 3] and a[3, [0, 1, 4]].tolist() == [PRODUCE, 2, 3]
     assert a[4, :2].tolist() == [MOVE, moves[0]] and a[5, :2].tolist() == [MOVE, moves[1]]
     b.close()
+
+
+def test_partially_observable_observation(backend, maps):
+    from test_oracle_golden import _po_expectations
+    utt = M.UnitTypeTable(1, 1)
+    b = M.BatchedGameState(utt, M.PhysicalGameState.fromXML(P.map_to_xml(maps["8x8/basesWorkers8x8"]), utt), 2, partial_obs=True)
+    b.reset(np.zeros(2, dtype=np.int64))
+    _po_expectations(b.observe(0)[0])
+    b.close()

@@ -387,3 +387,23 @@ def test_worker_rush_first_decision_known_answer(maps):
     assert O.ScriptedAI(O.AI_WORKER_RUSH, O.PF_BFS).get_action(g, 0) == [(2, (O.PRODUCE, 0, 0, 0, 3)), (4, (O.MOVE, 0, 0, 0, -1))]
     assert O.ScriptedAI(O.AI_WORKER_RUSH, O.PF_ASTAR).get_action(g, 1) == [(3, (O.PRODUCE, 2, 0, 0, 3)), (5, (O.MOVE, 2, 0, 0, -1))]
     assert O.ScriptedAI(O.AI_WORKER_RUSH, O.PF_BFS).get_action(g, 1) == [(3, (O.PRODUCE, 2, 0, 0, 3)), (5, (O.MOVE, 1, 0, 0, -1))]
+
+
+def _po_expectations(o):
+    """player 0's 8-plane observation of the initial state of maps/8x8/basesWorkers8x8.xml (PartiallyObservableGameState.java:82-179):
+    its base (2,1) sees 5 cells far, its worker (1,1) 3; nothing of player 1 is in sight, nor the resource at (7,7)."""
+    assert o.shape == (8, 8, 8)
+    assert o[3, 1, 2] == 2 and o[3, 1, 1] == 4 and o[3, 0, 0] == 1       # own base, own worker, the near resource (type + 1)
+    assert o[3, 6, 5] == 0 and o[3, 6, 6] == 0 and o[3, 7, 7] == 0       # the enemy base and worker and the far resource are hidden
+    assert o[0, 6, 5] == 0 and o[1, 7, 7] == 0 and o[2, 6, 6] == 0
+    vis = o[6]
+    assert vis[1, 7] == 1 and vis[2, 7] == 0      # (7,1): dx = 5 from the base, 25 <= 25; (7,2): 26
+    assert vis[6, 2] == 1 and vis[7, 2] == 0      # (2,6): dy = 5; (2,7): 6
+    assert vis[4, 6] == 1 and vis[5, 6] == 0      # (6,4): 16 + 9 = 25; (6,5): 16 + 16 = 32
+    assert vis[0, 0] == 1 and vis[7, 7] == 0
+    assert not o[7].any()                         # no enemy unit is visible, so nothing is known about what the opponent sees
+
+
+def test_partially_observable_observation_known_answers(maps):
+    g = O.Game(O.Utt(1, 1), maps["8x8/basesWorkers8x8"])
+    _po_expectations(g.po_view(0).observe(0, po=True))
