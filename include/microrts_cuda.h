@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MRTS_ABI_VERSION 1
+#define MRTS_ABI_VERSION 2
 
 enum {
     MRTS_OK = 0,
@@ -75,6 +75,8 @@ enum {
     MRTS_ACTIONS_RAW = 1
 };
 
+/* MRTS_DTYPE_U8 keeps the low 8 bits of every value: hit points and resources above 255 (custom unit type tables, large resource
+ * piles) wrap; use MRTS_DTYPE_I32 when the map or table can exceed that */
 enum { MRTS_DTYPE_U8 = 0, MRTS_DTYPE_I32 = 1, MRTS_DTYPE_BITS = 2 /* masks only: element j of a row is bit j & 7 of byte j >> 3 */ };
 enum {
     MRTS_FLAG_PARTIAL_OBS = 1u,
@@ -156,6 +158,13 @@ int mrts_batch_reset_masked(mrts_batch *, const uint8_t *mask, const int64_t *se
 /* restart the masked games from their map like mrts_batch_reset_masked, but keep their RNG streams running (the reference's
  * Random objects are static and survive JNIGridnetVecClient's resets, src/tests/JNIGridnetVecClient.java:272-286) */
 int mrts_batch_restart_masked(mrts_batch *, const uint8_t *mask, int on_device);
+
+/* GameState.clone() (src/rts/GameState.java:582-604; NaiveMCTS clones the leaf's state before every playout, NaiveMCTS.java:
+ * 201) for many games at once: game g of dst becomes a copy of game src_index[g] of src (src_index NULL: game g), for the games
+ * whose mask byte is non-zero (mask NULL: all).  Both batches must share map size, unit capacity, flags' unit words and device.
+ * The counters of dst (mrts_batch_stats) are not changed. */
+int mrts_batch_copy_games(mrts_batch *dst, const mrts_batch *src, const int64_t *src_index /* [dst games] or NULL */,
+                          const uint8_t *mask /* [dst games] or NULL */, int on_device);
 
 int mrts_batch_set_policy(mrts_batch *, int player, int policy, int pathfinder);
 /* Order of the two players inside one mrts_batch_step cycle.  0 (default): both PlayerActions are built on the pre-issue
@@ -256,6 +265,26 @@ int mrts_batch_results(mrts_batch *, int32_t *out /* [n_games][4] */, int on_dev
 
 /* counters since the last reset: {wins_p0, wins_p1, draws, games_finished, cycles, decisions, unit_cycles, errors} */
 int mrts_batch_stats(mrts_batch *, int64_t out[8]);
+/* Symbol of the step kernel the batch launched last (which of the specialised / fixed-layout copies ran), for benchmark reports. */
+const char *mrts_batch_last_kernel(const mrts_batch *);
+/* Bytes of game state and outputs the batch's kernels have read from (out[0]) and written to (out[1]) global memory since the last
+ * full reset: headers + live unit words per load / store, observation planes, masks, results.  What the roofline's "real traffic"
+ * figure is checked against (map templates, a few KB per map and L2 resident, are not counted). */
+int mrts_batch_io_bytes(mrts_batch *, int64_t out[2]);
+
+/* The run's single collective: the eight counters summed over every rank's batch with one ncclAllReduce(int64,
+ * sum) on the batch's stream; every rank receives the totals.  comm NULL = mrts_batch_stats.  The reference has no counterpart
+ * (it is single-process); a multi-GPU host -- rts.cuda.BatchedGameState with one thread or process per GPU -- creates the
+ * communicator once: one rank calls mrts_nccl_unique_id and hands the 128 bytes to the others (a Java array between threads, a file or
+ * socket between processes), then every rank calls mrts_nccl_comm_create (collective).  mrts_nccl_comm_wrap adopts an existing
+ * ncclComm_t.  NCCL is resolved with dlopen("libnccl.so.2") at the first call: single-GPU users need no NCCL at all. */
+#define MRTS_NCCL_UNIQUE_ID_BYTES 128
+typedef struct mrts_comm mrts_comm;
+int mrts_nccl_unique_id(uint8_t out[MRTS_NCCL_UNIQUE_ID_BYTES]);
+int mrts_nccl_comm_create(const uint8_t id[MRTS_NCCL_UNIQUE_ID_BYTES], int n_ranks, int rank, int device, mrts_comm **out);
+int mrts_nccl_comm_wrap(void *nccl_comm /* ncclComm_t */, int device, mrts_comm **out);
+void mrts_nccl_comm_destroy(mrts_comm *);
+int mrts_batch_stats_allreduce(mrts_batch *, int64_t out[8], mrts_comm *comm_or_null);
 /* number of kernels this batch has launched so far */
 int64_t mrts_batch_launch_count(const mrts_batch *);
 

@@ -34,6 +34,7 @@ def bind(L):
         "mrts_batch_num_games": (i64, [vp]), "mrts_batch_unit_capacity": (i, [vp]), "mrts_batch_device": (i, [vp]),
         "mrts_batch_stream": (vp, [vp]), "mrts_batch_sync": (i, [vp]),
         "mrts_batch_reset": (i, [vp, vp, i]), "mrts_batch_reset_masked": (i, [vp, vp, vp, i]),
+        "mrts_batch_copy_games": (i, [vp, vp, vp, vp, i]),
         "mrts_batch_set_policy": (i, [vp, i, i, i]), "mrts_batch_set_auto_reset": (i, [vp, i]),
         "mrts_batch_set_actions": (i, [vp, i, i, vp, vp, i, i, i]),
         "mrts_batch_issue": (i, [vp, i, i, vp, vp, i, i, i, i]),
@@ -46,7 +47,9 @@ def bind(L):
         "mrts_batch_export": (i, [vp, i64, i64, C.POINTER(StateHost)]),
         "mrts_batch_import": (i, [vp, i64, i64, C.POINTER(StateHost)]),
         "mrts_batch_results": (i, [vp, vp, i]), "mrts_batch_stats": (i, [vp, vp]),
-        "mrts_batch_launch_count": (i64, [vp]),
+        "mrts_batch_launch_count": (i64, [vp]), "mrts_batch_last_kernel": (C.c_char_p, [vp]), "mrts_batch_io_bytes": (i, [vp, vp]),
+        "mrts_nccl_unique_id": (i, [vp]), "mrts_nccl_comm_create": (i, [vp, i, i, i, pvp]), "mrts_nccl_comm_wrap": (i, [vp, i, pvp]),
+        "mrts_nccl_comm_destroy": (None, [vp]), "mrts_batch_stats_allreduce": (i, [vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)  # AttributeError here means the library does not export a declared symbol

@@ -213,6 +213,15 @@ class BatchedGameState:
         assert s is None or dm == ds
         _check(_ffi.lib().mrts_batch_reset_masked(self._h, pm, ps, dm))
 
+    def copy_games(self, src, src_index=None, mask=None):
+        """GameState.clone() batched: game g becomes a copy of src's game src_index[g] (default g) where mask[g] (default all)."""
+        idx = None if src_index is None else (np.ascontiguousarray(src_index, dtype=np.int64) if isinstance(src_index, (list, np.ndarray)) else src_index)
+        m = None if mask is None else (np.ascontiguousarray(mask, dtype=np.uint8) if isinstance(mask, (list, np.ndarray)) else mask)
+        pi, di, _k1 = _ptr(idx)
+        pm, dm, _k2 = _ptr(m)
+        assert idx is None or m is None or di == dm
+        _check(_ffi.lib().mrts_batch_copy_games(self._h, src._h, pi, pm, di if idx is not None else dm))
+
     def set_policy(self, player, policy, pathfinder=PF_ASTAR):
         _check(_ffi.lib().mrts_batch_set_policy(self._h, player, policy, pathfinder))
 
@@ -254,14 +263,16 @@ class BatchedGameState:
         """Stage one PlayerAction per game ([n][max_k][8] rows) for the next step() of an EXTERNAL player."""
         a, c, k = self._actions(actions, counts)
         pa, da, _k1 = _ptr(a)
-        pc, _dc, _k2 = _ptr(c)
+        pc, dc, _k2 = _ptr(c)
+        assert c is None or a is None or dc == da, "actions and counts must both be host arrays or both device tensors"
         _check(_ffi.lib().mrts_batch_set_actions(self._h, player, fmt, pa, pc, k, fill_none_duration, da))
 
     def issue(self, player, actions, counts=None, fmt=ACTIONS_RAW, safe=False, fill_none_duration=-1):
         """GameState.issue(pa) (GameState.java:249-328) for every game; issueSafe when safe=True."""
         a, c, k = self._actions(actions, counts)
         pa, da, _k1 = _ptr(a)
-        pc, _dc, _k2 = _ptr(c)
+        pc, dc, _k2 = _ptr(c)
+        assert c is None or a is None or dc == da, "actions and counts must both be host arrays or both device tensors"
         _check(_ffi.lib().mrts_batch_issue(self._h, player, fmt, pa, pc, k, fill_none_duration, 1 if safe else 0, da))
 
     def issueSafe(self, player, actions, counts=None, fmt=ACTIONS_RAW, fill_none_duration=-1):
@@ -361,6 +372,16 @@ class BatchedGameState:
         out = np.zeros(8, dtype=np.int64)
         _check(_ffi.lib().mrts_batch_stats(self._h, out.ctypes.data))
         return dict(zip(["wins_p0", "wins_p1", "draws", "games_finished", "cycles", "decisions", "unit_cycles", "errors"], out.tolist()))
+
+    def io_bytes(self):
+        """(bytes read, bytes written) of game state and outputs by the batch's kernels since the last full reset."""
+        out = np.zeros(2, dtype=np.int64)
+        _check(_ffi.lib().mrts_batch_io_bytes(self._h, out.ctypes.data))
+        return int(out[0]), int(out[1])
+
+    @property
+    def last_kernel(self):
+        return _ffi.lib().mrts_batch_last_kernel(self._h).decode()
 
     @property
     def launch_count(self):

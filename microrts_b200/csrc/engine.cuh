@@ -47,7 +47,9 @@ enum { POL_EXTERNAL = 0, POL_PASSIVE = 1, POL_RANDOM_BIASED = 2, POL_WORKER_RUSH
 enum { FMT_VECTOR = 0, FMT_RAW = 1 };
 enum { MODE_GAME = 0, MODE_CYCLE_ONLY = 1, MODE_ISSUE_ONLY = 2, MODE_OBSERVE = 3, MODE_MASKS = 4, MODE_ROLLOUT = 5, MODE_PATHFIND = 6 };
 enum { ST_OVER = 1, ST_COUNTED = 2 };
-enum { STAT_WINS0 = 0, STAT_WINS1, STAT_DRAWS, STAT_FINISHED, STAT_CYCLES, STAT_DECISIONS, STAT_UNIT_CYCLES, STAT_ERRORS };
+enum { STAT_WINS0 = 0, STAT_WINS1, STAT_DRAWS, STAT_FINISHED, STAT_CYCLES, STAT_DECISIONS, STAT_UNIT_CYCLES, STAT_ERRORS,
+       STAT_IO_READ, STAT_IO_WRITE, N_WARP_STATS }; // the last two: bytes of game state / outputs the step kernels read from and wrote to global memory (mrts_batch_io_bytes)
+#define MRTS_STATS_IO_SLOT 18 // where they live in the batch's counter array: behind the 8 counters, 2 work counters and 8 words of all-reduce scratch
 
 struct StepParams {
     int32_t *hdr;              // [n_games][MRTS_HDR_WORDS]
@@ -604,6 +606,17 @@ DEVN int policy_random_biased(Game &g, int player, int pn) {
 DEVN int decode_external(Game &g, int player, int pn, const int32_t *rows, int count, int format, int fill, int maxR) {
     int cells = g.W * g.H;
     int start = pn;
+    // The pending list holds `cap` entries for both players together.  A player's list without duplicate rows never exceeds its
+    // unit count; rows addressing the same idle unit twice are all accepted (as PlayerAction.fromVectorAction does), so the
+    // first list is cut where it would eat the room of the other player's units, the second at the capacity: rows beyond that are
+    // dropped and the game is flagged GE_BAD_ACTION.
+    int limit = g.cap;
+    if (start == 0) {
+        int n = g.hdr()[H_NUNITS], opp = 0;
+        #pragma unroll 1
+        for (int i = g.lane; i < n; i += 32) opp += u_pl(g.w0()[i]) == 2 - player ? 1 : 0;
+        limit -= __reduce_add_sync(FULLM, opp);
+    }
     if (format == FMT_RAW) {
         #pragma unroll 1
         for (int kb = 0; kb < count; kb += 32) {
@@ -626,8 +639,9 @@ DEVN int decode_external(Game &g, int player, int pn, const int32_t *rows, int c
             }
             unsigned m = __ballot_sync(FULLM, ok);
             if (k < count && !ok) atomicOr(&g.hdr()[H_ERR], GE_BAD_ACTION);
-            if (ok) { int q = pn + __popc(m & ((1u << g.lane) - 1)); g.pslot()[q] = (uint8_t)s; g.pa0()[q] = A0; g.pa1()[q] = A1; }
+            if (ok) { int q = pn + __popc(m & ((1u << g.lane) - 1)); if (q < limit) { g.pslot()[q] = (uint8_t)s; g.pa0()[q] = A0; g.pa1()[q] = A1; } }
             pn += __popc(m);
+            if (pn > limit) { pn = limit; if (g.lane == 0) atomicOr(&g.hdr()[H_ERR], GE_BAD_ACTION); } // the pending list holds `cap` entries: rows beyond it (duplicates) are dropped and flagged
         }
         __syncwarp();
         return pn;
@@ -672,8 +686,9 @@ DEVN int decode_external(Game &g, int player, int pn, const int32_t *rows, int c
         int cnt = count - kb; if (cnt > 32) cnt = 32;
         bool ok = accept_in_order(g, player, cnt, tcell, cost, cand, par0, par1);
         unsigned m = __ballot_sync(FULLM, ok);
-        if (ok) { int q = pn + __popc(m & ((1u << g.lane) - 1)); g.pslot()[q] = (uint8_t)s; g.pa0()[q] = A0; g.pa1()[q] = A1; }
+        if (ok) { int q = pn + __popc(m & ((1u << g.lane) - 1)); if (q < limit) { g.pslot()[q] = (uint8_t)s; g.pa0()[q] = A0; g.pa1()[q] = A1; } }
         pn += __popc(m);
+        if (pn > limit) { pn = limit; if (g.lane == 0) atomicOr(&g.hdr()[H_ERR], GE_BAD_ACTION); }
         __syncwarp();
     }
     // drop this player's tentative claims (they only model PlayerAction.r while the action list is being built)
@@ -695,8 +710,9 @@ DEVN int decode_external(Game &g, int player, int pn, const int32_t *rows, int c
             bool idle = i < n && u_pl(g.w0()[i]) == player + 1 && a_type(g.a0()[i]) == AT_IDLE;
             if (idle) for (int q = start; q < pn; q++) if (g.pslot()[q] == i) { idle = false; break; }
             unsigned m = __ballot_sync(FULLM, idle);
-            if (idle) { int q = pn + __popc(m & ((1u << g.lane) - 1)); g.pslot()[q] = (uint8_t)i; g.pa0()[q] = ACT_NONE | A0_NOUT; g.pa1()[q] = fill; }
+            if (idle) { int q = pn + __popc(m & ((1u << g.lane) - 1)); if (q < limit) { g.pslot()[q] = (uint8_t)i; g.pa0()[q] = ACT_NONE | A0_NOUT; g.pa1()[q] = fill; } }
             pn += __popc(m);
+            if (pn > limit) { pn = limit; if (g.lane == 0) atomicOr(&g.hdr()[H_ERR], GE_BAD_ACTION); }
             __syncwarp();
         }
     }
@@ -1257,7 +1273,7 @@ DEV void rb_player(Game &g, int pl, const uint8_t *list, int cnt, bool simul, Rb
 #include "scripted.cuh"
 
 // ---- loops ---------------------------------------------------------------------------------------------------------------
-struct WarpStats { unsigned long long v[8]; }; // lives in shared memory; only lane 0 updates it
+struct WarpStats { unsigned long long v[N_WARP_STATS]; }; // lives in shared memory; only lane 0 updates it
 DEV void stat_add(WarpStats &ws, int lane, int k, unsigned long long d) { if (lane == 0) ws.v[k] += d; }
 
 // ---- PartiallyObservableGameState(gs, player) as seen by a device policy (PartiallyObservableGameState.java:35-71) --------
@@ -1674,6 +1690,7 @@ DEV void obs_emit(const uint32_t *w0, const uint32_t *w1, const uint32_t *a0, in
     __syncwarp();
 }
 DEV size_t obs_bytes_per_game(int W, int H, int C, int dtype) { return (size_t)C * W * H * (dtype == 0 ? 1 : 4); }
+DEV size_t mask_bytes_per_game(int W, int H, int K, int dtype) { return (size_t)W * H * (dtype == 2 ? (size_t)((K + 7) >> 3) : (size_t)K * (dtype == 0 ? 1 : 4)); }
 // the map blob's terrain plane (layout.h)
 DEV const uint8_t *map_terrain(const uint32_t *blob, int W, int H, int cap) { return (const uint8_t *)(blob + mrts_map_terrain_offset_words(W, H, cap)); }
 
@@ -1985,7 +2002,7 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
     // the warp's counters live in shared memory: every lane adds the same (warp-uniform) amounts to its own view of them, so
     // only lane 0's stores matter; 16 registers stay free for the game loop
     WarpStats &ws = *(WarpStats *)(mrts_smem + region + L.stats);
-    if (lane < 8) ws.v[lane] = 0;
+    if (lane < N_WARP_STATS) ws.v[lane] = 0;
     __syncwarp();
     long long n_items = KERNEL == KERNEL_ROLLOUT ? p.n_games * p.rollouts_per_game : p.n_games;
     // A warp's first item is static; the next ones come from a global counter, so a warp that drew cheap games (or rollouts
@@ -1998,17 +2015,19 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
         int32_t *ghdr = p.hdr + gi * MRTS_HDR_WORDS;
         uint32_t *gun = p.units + gi * (long long)puw * pcap;
         g_load(g, ghdr, gun, KERNEL != KERNEL_ROLLOUT && p.mode == MODE_GAME && p.auto_reset, p.max_cycles);
-        if (KERNEL == KERNEL_ROLLOUT) { run_rollout(g, p, item, ws); continue; } // the batch itself is not modified
+        stat_add(ws, lane, STAT_IO_READ, (unsigned long long)(MRTS_HDR_WORDS * 4 + puw * 4 * g.hdr()[H_NUNITS]));
+        if (KERNEL == KERNEL_ROLLOUT) { run_rollout(g, p, item, ws); stat_add(ws, lane, STAT_IO_WRITE, 8); continue; } // the batch itself is not modified
         int err0 = g.hdr()[H_ERR];
         if (KERNEL == KERNEL_FAST || KERNEL == KERNEL_FAST_OBS) run_game_fast(g, p, ws);
         else if (p.mode == MODE_GAME) run_game(g, p, gi, ws);
         else if (p.mode == MODE_CYCLE_ONLY) run_cycles_only(g, p.t_target ? p.t_target[gi] : g.hdr()[H_TIME] + p.n_cycles);
         else if (p.mode == MODE_ISSUE_ONLY) run_issue_only(g, p, gi);
-        else if (p.mode == MODE_OBSERVE) { observe_game(g, p, gi); continue; }
+        else if (p.mode == MODE_OBSERVE) { observe_game(g, p, gi); stat_add(ws, lane, STAT_IO_WRITE, obs_bytes_per_game(g.W, g.H, p.partial_obs ? 8 : 6, p.out_dtype)); continue; }
         else if (p.mode == MODE_PATHFIND) { pathfind_game(g, p, gi); continue; }
-        else { masks_game(g, p, gi); continue; }
+        else { masks_game(g, p, gi); stat_add(ws, lane, STAT_IO_WRITE, mask_bytes_per_game(g.W, g.H, 1 + 6 + 16 + p.n_types + (2 * p.max_range + 1) * (2 * p.max_range + 1), p.out_dtype)); continue; }
         if (g.hdr()[H_ERR] != err0) stat_add(ws, g.lane, STAT_ERRORS, 1);
         g_store(g, ghdr, gun);
+        stat_add(ws, lane, STAT_IO_WRITE, (unsigned long long)(MRTS_HDR_WORDS * 4 + puw * 4 * g.hdr()[H_NUNITS] + (p.mode == MODE_GAME && p.results_out ? 16 : 0)));
         if (p.mode == MODE_GAME && p.results_out) {
             // what mrts_batch_results reports (winner() / gameover(), PhysicalGameState.java:334-387), written here so that the
             // host can fetch it with a plain copy: a results kernel would have to wait for SM slots behind whatever persistent
@@ -2026,13 +2045,15 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
         if (KERNEL == KERNEL_FAST_OBS || (KERNEL == KERNEL_GENERIC && p.mode == MODE_GAME)) {
             #pragma unroll 1
             for (int pl = 0; pl < 2; pl++)
-                if (p.obs_out[pl])
+                if (p.obs_out[pl]) {
+                    stat_add(ws, lane, STAT_IO_WRITE, obs_bytes_per_game(g.W, g.H, 6, p.obs_dtype));
                     obs_emit(g.w0(), g.w1(), g.a0(), g.hdr()[H_NUNITS], g.W, g.H, map_terrain(blob, g.W, g.H, g.cap), pl, p.obs_dtype,
                              (char *)p.obs_out[pl] + (size_t)gi * obs_bytes_per_game(g.W, g.H, 6, p.obs_dtype), lane);
+                }
         }
     }
     __syncwarp();
-    if (lane < 8 && p.stats && ws.v[lane]) atomicAdd(&p.stats[lane], ws.v[lane]);
+    if (lane < N_WARP_STATS && p.stats && ws.v[lane]) atomicAdd(&p.stats[lane < 8 ? lane : lane - 8 + MRTS_STATS_IO_SLOT], ws.v[lane]);
     if (lane == 0) { // no warp draws an item after it got here, so the last one to arrive can reset the counters
         unsigned long long left = atomicAdd(p.work_counter + 1, 1ULL);
         if (left + 1 == (unsigned long long)nblocks * wpc) { p.work_counter[0] = 0; p.work_counter[1] = 0; }

@@ -263,6 +263,7 @@ inline bool map_check(const MapH &m, const UttH &utt, std::string &err) {
         if (u.type < 0 || u.type >= (int)utt.types.size()) { err = "unit with unknown type"; return false; }
         if (u.x < 0 || u.y < 0 || u.x >= m.w || u.y >= m.h) { err = "unit outside the map"; return false; }
         if (u.player < -1 || u.player > 1) { err = "unit owner must be -1, 0 or 1"; return false; }
+        if (u.x + u.y * m.w < (int)m.terrain.size() && m.terrain[u.x + u.y * m.w]) { err = "unit placed on a wall cell: (" + std::to_string(u.x) + ", " + std::to_string(u.y) + ")"; return false; } // the occupancy grid holds one byte per cell: wall OR unit
         if (occ[u.x + u.y * m.w]) { err = "PhysicalGameState.addUnit: added two units in position: (" + std::to_string(u.x) + ", " + std::to_string(u.y) + ")"; return false; }
         if (u.res < -32768 || u.res > 32767 || u.hp < -32768 || u.hp > 32767) { err = "unit resources/hitpoints out of range"; return false; }
         occ[u.x + u.y * m.w] = 1;

@@ -112,7 +112,7 @@ MRTS_HDC SmemLayout mrts_smem_layout(int W, int H, int cap, int scripted, int po
     L.resv = o; o += pcb;
     L.claim = o; o += pcb;
     L.list = o; o += capb;
-    L.stats = o; o += 64; // the warp's 8 running counters (kept out of registers)
+    L.stats = o; o += 80; // the warp's 10 running counters (kept out of registers)
     L.povis = o; o += po_policies ? pcb : 0;
     L.pohid = o; o += po_policies ? ((cap * 4 + 15) & ~15) : 0;
     L.astar = o; o += scripted == 1 ? MRTS_ASTAR_BYTES(W, H) : 0; // scripted == 2: scratch in global memory

@@ -14,6 +14,7 @@
 #include "cuda_shim.h"
 #else
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #endif
 
 #include "engine.cuh"
@@ -116,6 +117,29 @@ DEV void results_kernel_body(const ResultParams &p, long long gi) {
     o[3] = h[H_ERR];
 }
 
+struct CopyParams {
+    int32_t *dhdr; uint32_t *dunits; const int32_t *shdr; const uint32_t *sunits;
+    const long long *src_index; const uint8_t *mask;
+    long long n_dst, n_src; int cap, uw;
+};
+// GameState.clone() (GameState.java:582-604) for many games at once: game g of the destination batch becomes a copy of game
+// src_index[g] (or g) of the source batch, where mask[g] != 0 (or everywhere); one warp per game
+DEV void copy_kernel_body(const CopyParams &p, int tid, int nthreads, int bid, int nblocks) {
+    int warp = tid >> 5, lane = tid & 31, wpc = nthreads >> 5;
+    for (long long gi = (long long)bid * wpc + warp; gi < p.n_dst; gi += (long long)nblocks * wpc) {
+        if (p.mask && !p.mask[gi]) continue;
+        long long si = p.src_index ? p.src_index[gi] : gi;
+        if (si < 0 || si >= p.n_src) continue;
+        const int32_t *sh = p.shdr + si * MRTS_HDR_WORDS;
+        const uint32_t *su = p.sunits + si * (long long)p.uw * p.cap;
+        uint32_t *du = p.dunits + gi * (long long)p.uw * p.cap;
+        if (lane < MRTS_HDR_WORDS) p.dhdr[gi * MRTS_HDR_WORDS + lane] = sh[lane];
+        int n = sh[H_NUNITS];
+        for (int k = 0; k < p.uw; k++)
+            for (int i = lane; i < n; i += 32) du[k * p.cap + i] = su[k * p.cap + i];
+    }
+}
+
 struct ObsParams {
     const int32_t *hdr; const uint32_t *units; const uint32_t *maps; void *out;
     long long n_games; int n_maps, map_words, W, H, cap, uw, player, dtype;
@@ -166,6 +190,7 @@ __global__ void __launch_bounds__(MRTS_WARPS_PER_CTA * 32, MRTS_MIN_BLOCKS_GENER
     step_kernel_body<KERNEL_GENERIC>(p, mrts_smem, threadIdx.x, blockDim.x, blockIdx.x, gridDim.x);
 }
 __global__ void __launch_bounds__(256) k_observe(ObsParams p) { observe_kernel_body(p, threadIdx.x, blockDim.x, blockIdx.x, gridDim.x); }
+__global__ void __launch_bounds__(128) k_copy_games(CopyParams p) { copy_kernel_body(p, threadIdx.x, blockDim.x, blockIdx.x, gridDim.x); }
 __global__ void __launch_bounds__(128) k_reset(ResetParams p) { reset_kernel_body(p, threadIdx.x, blockDim.x, blockIdx.x, gridDim.x); }
 __global__ void __launch_bounds__(128) k_results(ResultParams p) { results_kernel_body(p, (long long)blockIdx.x * blockDim.x + threadIdx.x); }
 #endif
@@ -230,6 +255,8 @@ struct mrts_batch {
     int sequential_issue = 0; int32_t *info_out = nullptr; uint32_t tm[6] = {0, 0, 0, 0, 0, 0};
     void *obs_out[2] = {nullptr, nullptr}; int obs_dtype = 0; // device buffers mrts_batch_step writes post-step observations to
     long long launches = 0;
+    long long host_io[2] = {0, 0}; // bytes moved by the kernels that carry no counters (k_observe), added to mrts_batch_io_bytes
+    char last_kernel[64] = "";     // symbol of the most recent step-kernel launch (mrts_batch_last_kernel)
 };
 
 static int ensure_tmp(mrts_batch *b, size_t bytes) {
@@ -266,6 +293,13 @@ static int launch_step(mrts_batch *b, StepParams &p) {
     long long need = (items + pl.wpc - 1) / pl.wpc;
     int grid = (int)std::min<long long>(pl.grid, std::max<long long>(need, 1));
     b->launches++;
+    {
+        static const char *names[N_KERNELS] = {"k_step_fast", "k_rollout", "k_step", "k_step_fast_obs"};
+        if (rush) snprintf(b->last_kernel, sizeof b->last_kernel, "k_step_fixed_%dx%d_rush", b->W, b->H);
+        else if (gfx) snprintf(b->last_kernel, sizeof b->last_kernel, "k_step_fixed_%dx%d", b->W, b->H);
+        else if (fv >= 0) snprintf(b->last_kernel, sizeof b->last_kernel, "k_fixed<%s,%d,%d,%d>", names[kernel], b->W, b->H, b->cap);
+        else snprintf(b->last_kernel, sizeof b->last_kernel, "%s", names[kernel]);
+    }
 #ifdef MRTS_EMU
     StepParams pc = p;
     emu::launch(grid, threads, pl.smem, [pc, threads, grid, kernel, fv](unsigned char *sm, int tid, int bid) {
@@ -289,6 +323,7 @@ static int launch_step(mrts_batch *b, StepParams &p) {
 static int launch_observe(mrts_batch *b, int player, int dtype, void *d_out) {
     ObsParams p{b->d_hdr, b->d_units, b->d_maps, d_out, b->n, b->n_maps, b->map_words, b->W, b->H, b->cap, b->uw, player, dtype};
     b->launches++;
+    b->host_io[1] += (long long)b->n * 6 * b->W * b->H * (dtype == MRTS_DTYPE_U8 ? 1 : 4); // (its reads, 12 bytes per live unit, are not counted)
 #ifdef MRTS_EMU
     emu::launch(2, 64, 0, [p](unsigned char *, int tid, int bid) { observe_kernel_body(p, tid, 64, bid, 2); });
     return 0;
@@ -391,6 +426,15 @@ int mrts_batch_create(const mrts_utt *u, const mrts_map *const *maps, int n_maps
     if (!u || !maps || n_maps < 1 || n_games < 1 || !out) return fail(MRTS_E_ARG, "mrts_batch_create: bad argument");
     std::string err;
     if (!utt_check_limits(u->h, err)) return fail(MRTS_E_LIMIT, err);
+    if (!maps[0]) return fail(MRTS_E_ARG, "mrts_batch_create: null map handle");
+    if (flags & MRTS_FLAG_SCRIPTED_AI) {
+        // the scripted policies address the standard unit types by id (scripted.cuh: UT_BASE ...); the reference looks them up by
+        // name (utt.getUnitType("Worker"), WorkerRush.java:52-55), so a table that orders or names them differently is refused
+        static const char *std_names[] = {"Resource", "Base", "Barracks", "Worker", "Light", "Heavy", "Ranged"};
+        for (size_t t = 0; t < 7; t++)
+            if (t >= u->h.types.size() || u->h.types[t].name != std_names[t])
+                return fail(MRTS_E_STATE, std::string("MRTS_FLAG_SCRIPTED_AI needs the standard unit types at ids 0..6 (Resource, Base, Barracks, Worker, Light, Heavy, Ranged); type ") + std::to_string(t) + " differs");
+    }
     int W = maps[0]->h.w, H = maps[0]->h.h, bound = 0;
     for (int i = 0; i < n_maps; i++) {
         if (!maps[i] || maps[i]->h.w != W || maps[i]->h.h != H) return fail(MRTS_E_ARG, "mrts_batch_create: all maps of a batch must have the same size");
@@ -483,13 +527,13 @@ int mrts_batch_create(const mrts_utt *u, const mrts_map *const *maps, int n_maps
     size_t hdr_bytes = (size_t)n_games * MRTS_HDR_WORDS * 4, unit_bytes = (size_t)n_games * b->uw * cap * 4;
     if (dev_alloc((void **)&b->d_hdr, hdr_bytes) || dev_alloc((void **)&b->d_units, unit_bytes) ||
         dev_alloc((void **)&b->d_maps, (size_t)n_maps * b->map_words * 4) || dev_alloc((void **)&b->d_cst, MRTS_CONST_WORDS * 4) ||
-        dev_alloc((void **)&b->d_stats, 10 * sizeof(unsigned long long)) || dev_alloc((void **)&b->d_results, (size_t)n_games * 16)) // 8 counters + the launches' work and exit counters
+        dev_alloc((void **)&b->d_stats, 20 * sizeof(unsigned long long)) || dev_alloc((void **)&b->d_results, (size_t)n_games * 16)) // 8 counters + the launches' work and exit counters + 8 words of all-reduce scratch + 2 global-memory byte counters
         return fail(MRTS_E_CUDA, std::string("device allocation failed: ") + dev_errstr());
     std::vector<uint32_t> blob, all;
     for (int i = 0; i < n_maps; i++) { build_map_blob(maps[i]->h, cap, blob); all.insert(all.end(), blob.begin(), blob.end()); }
     std::vector<uint32_t> cst; build_const_words(u->h, cst);
     if (dev_h2d(b->d_maps, all.data(), all.size() * 4, b->stream) || dev_h2d(b->d_cst, cst.data(), cst.size() * 4, b->stream) ||
-        dev_zero(b->d_stats, 10 * sizeof(unsigned long long), b->stream) || dev_zero(b->d_units, unit_bytes, b->stream) || dev_sync(b->stream))
+        dev_zero(b->d_stats, 20 * sizeof(unsigned long long), b->stream) || dev_zero(b->d_units, unit_bytes, b->stream) || dev_sync(b->stream))
         return fail(MRTS_E_CUDA, std::string("device upload failed: ") + dev_errstr());
     mrts_batch *raw = b.release();
     int rc = mrts_batch_reset(raw, nullptr, 0);
@@ -504,6 +548,14 @@ int mrts_batch_device(const mrts_batch *b) { return b ? b->device : MRTS_E_ARG; 
 void *mrts_batch_stream(const mrts_batch *b) { return b ? (void *)b->stream : nullptr; }
 int mrts_batch_sync(mrts_batch *b) { if (!b) return MRTS_E_ARG; if (dev_sync(b->stream)) return fail(MRTS_E_CUDA, std::string("stream sync: ") + dev_errstr()); return MRTS_OK; }
 int64_t mrts_batch_launch_count(const mrts_batch *b) { return b ? b->launches : 0; }
+const char *mrts_batch_last_kernel(const mrts_batch *b) { return b ? b->last_kernel : ""; }
+int mrts_batch_io_bytes(mrts_batch *b, int64_t out[2]) {
+    if (!b || !out) return fail(MRTS_E_ARG, "mrts_batch_io_bytes: null argument");
+    if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
+    if (dev_d2h(out, b->d_stats + MRTS_STATS_IO_SLOT, 2 * sizeof(int64_t), b->stream)) return fail(MRTS_E_CUDA, dev_errstr());
+    out[0] += b->host_io[0]; out[1] += b->host_io[1];
+    return MRTS_OK;
+}
 int mrts_batch_num_planes(const mrts_batch *b) { return b ? ((b->flags & MRTS_FLAG_PARTIAL_OBS) ? 8 : 6) : MRTS_E_ARG; }
 int mrts_batch_mask_width(const mrts_batch *b) { if (!b) return MRTS_E_ARG; int R = 2 * b->max_range + 1; return 1 + 6 + 16 + (int)b->utt.types.size() + R * R; }
 
@@ -520,7 +572,7 @@ static int do_reset(mrts_batch *b, const uint8_t *mask, const int64_t *seeds, in
     }
     ResetParams p{b->d_hdr, b->d_units, b->d_maps, d_seeds, d_mask, b->n, b->n_maps, b->map_words, b->cap, b->L.pcw, b->uw, keep_rng};
     b->launches++;
-    if (!mask) { if (dev_zero(b->d_stats, 8 * sizeof(unsigned long long), b->stream)) return fail(MRTS_E_CUDA, dev_errstr()); }
+    if (!mask) { if (dev_zero(b->d_stats, 8 * sizeof(unsigned long long), b->stream) || dev_zero(b->d_stats + MRTS_STATS_IO_SLOT, 2 * sizeof(unsigned long long), b->stream)) return fail(MRTS_E_CUDA, dev_errstr()); }
     b->staged[0].valid = b->staged[1].valid = false;
 #ifdef MRTS_EMU
     emu::launch(2, 128, 0, [p](unsigned char *, int tid, int bid) { reset_kernel_body(p, tid, 128, bid, 2); });
@@ -541,6 +593,34 @@ int mrts_batch_reset_masked(mrts_batch *b, const uint8_t *mask, const int64_t *s
 int mrts_batch_restart_masked(mrts_batch *b, const uint8_t *mask, int on_device) {
     if (!mask) return fail(MRTS_E_ARG, "mrts_batch_restart_masked: mask is required");
     return do_reset(b, mask, nullptr, on_device, 1);
+}
+
+int mrts_batch_copy_games(mrts_batch *dst, const mrts_batch *src, const int64_t *src_index, const uint8_t *mask, int on_device) {
+    if (!dst || !src) return fail(MRTS_E_ARG, "mrts_batch_copy_games: null batch");
+    if (dst->W != src->W || dst->H != src->H || dst->cap != src->cap || dst->uw != src->uw || dst->device != src->device)
+        return fail(MRTS_E_ARG, "mrts_batch_copy_games: the batches must have the same map size, unit capacity, unit words and device");
+    if (!src_index && dst->n > src->n) return fail(MRTS_E_ARG, "mrts_batch_copy_games: without src_index the source must hold at least as many games");
+    if (dev_select(dst->device)) return fail(MRTS_E_CUDA, dev_errstr());
+    dst->results_fresh = false;
+    const long long *d_idx = (const long long *)src_index; const uint8_t *d_mask = mask;
+    if (!on_device && (src_index || mask)) {
+        size_t ib = src_index ? (size_t)dst->n * 8 : 0, mb = mask ? (size_t)dst->n : 0;
+        if (ensure_tmp(dst, ib + mb)) return fail(MRTS_E_CUDA, std::string("staging allocation failed: ") + dev_errstr());
+        if (src_index) { if (dev_h2d(dst->d_tmp, src_index, ib, dst->stream)) return fail(MRTS_E_CUDA, dev_errstr()); d_idx = (const long long *)dst->d_tmp; }
+        if (mask) { if (dev_h2d((char *)dst->d_tmp + ib, mask, mb, dst->stream)) return fail(MRTS_E_CUDA, dev_errstr()); d_mask = (const uint8_t *)dst->d_tmp + ib; }
+    }
+    if (dev_sync(src->stream)) return fail(MRTS_E_CUDA, dev_errstr()); // the source's pending work is finished before its state is read on dst's stream
+    CopyParams p{dst->d_hdr, dst->d_units, src->d_hdr, src->d_units, d_idx, d_mask, dst->n, src->n, dst->cap, dst->uw};
+    dst->launches++;
+#ifdef MRTS_EMU
+    emu::launch(2, 128, 0, [p](unsigned char *, int tid, int bid) { copy_kernel_body(p, tid, 128, bid, 2); });
+#else
+    int grid = (int)std::min<long long>((dst->n + 3) / 4, 148 * 16);
+    k_copy_games<<<grid, 128, 0, dst->stream>>>(p);
+    if (ck(cudaGetLastError())) return fail(MRTS_E_CUDA, std::string("copy launch: ") + dev_errstr());
+    if (!on_device && (src_index || mask)) if (dev_sync(dst->stream)) return fail(MRTS_E_CUDA, dev_errstr()); // staging buffer reuse
+#endif
+    return MRTS_OK;
 }
 
 int mrts_batch_set_policy(mrts_batch *b, int player, int policy, int pathfinder) {
@@ -708,6 +788,7 @@ static int emit(mrts_batch *b, int mode, int player, int dtype, void *out, int o
     if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
     size_t bytes = bits ? (size_t)b->n * b->W * b->H * ((mrts_batch_mask_width(b) + 7) / 8) : elems * (dtype == MRTS_DTYPE_U8 ? 1 : 4);
     void *d_out = out;
+    if (on_device && (((uintptr_t)out) & 15)) return fail(MRTS_E_ARG, "on-device observation/mask buffers must be 16-byte aligned (the planes are written with 16-byte stores)");
     if (!on_device) { if (ensure_tmp(b, bytes)) return fail(MRTS_E_CUDA, std::string("staging allocation failed: ") + dev_errstr()); d_out = b->d_tmp; }
     if (mode == MODE_OBSERVE && !(b->flags & MRTS_FLAG_PARTIAL_OBS)) {
         if (launch_observe(b, player, dtype, d_out)) return fail(MRTS_E_CUDA, std::string("launch: ") + dev_errstr());
@@ -753,6 +834,103 @@ int mrts_batch_stats(mrts_batch *b, int64_t out[8]) {
     if (!b || !out) return fail(MRTS_E_ARG, "mrts_batch_stats: null argument");
     if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
     if (dev_d2h(out, b->d_stats, 8 * sizeof(int64_t), b->stream)) return fail(MRTS_E_CUDA, dev_errstr());
+    return MRTS_OK;
+}
+
+// ---- the run's single collective: all-reduce (sum) of the eight counters over NCCL --------------------------------
+// NCCL is resolved at run time (dlopen) so that the library neither links a second copy next to the one a host process may
+// already carry nor needs NCCL at all for single-GPU use.  Types per nccl.h (2.x ABI): ncclUniqueId = 128 bytes, ncclComm_t opaque,
+// ncclInt64 = 4, ncclSum = 0, ncclSuccess = 0.
+struct mrts_comm { void *comm = nullptr; int n_ranks = 1, rank = 0, device = 0; bool owned = true; };
+#ifndef MRTS_EMU
+namespace {
+struct NcclApi {
+    struct Uid { char b[128]; }; // ncclUniqueId, passed by value
+    void *h = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, Uid, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+int nccl_load() {
+    if (g_nccl.h) return 0;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD); // the copy the host process already loaded, if any
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return -1;
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
+    g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce) return -1;
+    g_nccl.h = h;
+    return 0;
+}
+std::string nccl_err(int rc) { return g_nccl.GetErrorString ? std::string(g_nccl.GetErrorString(rc)) : ("NCCL error " + std::to_string(rc)); }
+}
+#endif
+
+int mrts_nccl_unique_id(uint8_t out[MRTS_NCCL_UNIQUE_ID_BYTES]) {
+    if (!out) return fail(MRTS_E_ARG, "mrts_nccl_unique_id: null argument");
+#ifdef MRTS_EMU
+    memset(out, 0, MRTS_NCCL_UNIQUE_ID_BYTES); return MRTS_OK;
+#else
+    if (nccl_load()) return fail(MRTS_E_STATE, "libnccl.so.2 cannot be loaded");
+    int rc = g_nccl.GetUniqueId(out);
+    if (rc) return fail(MRTS_E_CUDA, "ncclGetUniqueId: " + nccl_err(rc));
+    return MRTS_OK;
+#endif
+}
+
+int mrts_nccl_comm_create(const uint8_t id[MRTS_NCCL_UNIQUE_ID_BYTES], int n_ranks, int rank, int device, mrts_comm **out) {
+    if (!id || !out || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(MRTS_E_ARG, "mrts_nccl_comm_create: bad argument");
+    auto c = std::make_unique<mrts_comm>();
+    c->n_ranks = n_ranks; c->rank = rank; c->device = device;
+#ifndef MRTS_EMU
+    if (nccl_load()) return fail(MRTS_E_STATE, "libnccl.so.2 cannot be loaded");
+    if (dev_select(device)) return fail(MRTS_E_CUDA, std::string("cannot select CUDA device: ") + dev_errstr());
+    NcclApi::Uid uid; memcpy(uid.b, id, sizeof uid.b);
+    int rc = g_nccl.CommInitRank(&c->comm, n_ranks, uid, rank);
+    if (rc) return fail(MRTS_E_CUDA, "ncclCommInitRank: " + nccl_err(rc));
+#endif
+    *out = c.release();
+    return MRTS_OK;
+}
+
+int mrts_nccl_comm_wrap(void *nccl_comm, int device, mrts_comm **out) {
+    if (!nccl_comm || !out) return fail(MRTS_E_ARG, "mrts_nccl_comm_wrap: null argument");
+#ifndef MRTS_EMU
+    if (nccl_load()) return fail(MRTS_E_STATE, "libnccl.so.2 cannot be loaded");
+#endif
+    auto *c = new mrts_comm; c->comm = nccl_comm; c->device = device; c->owned = false; c->n_ranks = 0;
+    *out = c;
+    return MRTS_OK;
+}
+
+void mrts_nccl_comm_destroy(mrts_comm *c) {
+    if (!c) return;
+#ifndef MRTS_EMU
+    if (c->owned && c->comm && g_nccl.CommDestroy) { cudaSetDevice(c->device); g_nccl.CommDestroy(c->comm); }
+#endif
+    delete c;
+}
+
+int mrts_batch_stats_allreduce(mrts_batch *b, int64_t out[8], mrts_comm *comm) {
+    if (!comm) return mrts_batch_stats(b, out);
+    if (!b || !out) return fail(MRTS_E_ARG, "mrts_batch_stats_allreduce: null argument");
+    if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
+    unsigned long long *scratch = b->d_stats + 10;
+    if (dev_d2d(scratch, b->d_stats, 8 * sizeof(int64_t), b->stream)) return fail(MRTS_E_CUDA, dev_errstr());
+#ifndef MRTS_EMU
+    if (comm->comm) { // one ncclAllReduce of 8 int64 on the batch's stream: nothing to fuse with, the counters are final when it runs
+        int rc = g_nccl.AllReduce(scratch, scratch, 8, /* ncclInt64 */ 4, /* ncclSum */ 0, comm->comm, b->stream);
+        if (rc) return fail(MRTS_E_CUDA, "ncclAllReduce: " + nccl_err(rc));
+    }
+#endif
+    if (dev_d2h(out, scratch, 8 * sizeof(int64_t), b->stream)) return fail(MRTS_E_CUDA, dev_errstr());
     return MRTS_OK;
 }
 

@@ -31,7 +31,7 @@ def main():
     b.set_policy(0, M.POLICY_RANDOM_BIASED)
     b.set_policy(1, M.POLICY_RANDOM_BIASED)
     b.step(cycles, cycles)
-    total = sharding.reduce_stats(b.stats())
+    total = sharding.reduce_stats_host(b.stats())
     res = b.results()
     gathered = [None] * world
     dist.all_gather_object(gathered, (first, res.tolist()))

@@ -12,7 +12,7 @@ Outputs (committed):
 The packs carry parsed *data* only (unit tuples, action tuples); no reference source text.
 Usage: python tests/golden/make_golden.py [/root/reference]
 """
-import gzip, io, json, os, struct, sys, zipfile
+import gzip, io, json, os, shutil, struct, sys, zipfile
 import xml.etree.ElementTree as ET
 
 REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
@@ -47,6 +47,8 @@ def build_maps():
             maps[key] = parse_pgs(e)
     with gzip.GzipFile(os.path.join(OUT, "maps.pack.gz"), "wb", mtime=0) as g:
         g.write(json.dumps(maps, sort_keys=True, separators=(",", ":")).encode())
+    # the same pack ships with the package (microrts_b200/maps.py: standard_map) so that bench.py needs nothing under tests/
+    shutil.copyfile(os.path.join(OUT, "maps.pack.gz"), os.path.join(OUT, "..", "..", "microrts_b200", "data", "maps.pack.gz"))
     print("maps:", len(maps))
     return maps
 

@@ -6,17 +6,7 @@ from oracle import oracle as O
 TYPE_NAMES = O.TYPE_NAMES
 
 
-def map_to_xml(m):
-    """Serialise a golden map dict in the reference's map format (PhysicalGameState.toxml layout)."""
-    s = ['<rts.PhysicalGameState width="%d" height="%d">' % (m["w"], m["h"]), "  <terrain>%s</terrain>" % m["terrain"], "  <players>"]
-    for pid, res in m["players"]:
-        s.append('    <rts.Player ID="%d" resources="%d">\n    </rts.Player>' % (pid, res))
-    s.append("  </players>\n  <units>")
-    for (tn, uid, pl, x, y, res, hp) in m["units"]:
-        s.append('    <rts.units.Unit type="%s" ID="%d" player="%d" x="%d" y="%d" resources="%d" hitpoints="%d" >\n    </rts.units.Unit>'
-                 % (tn, uid, pl, x, y, res, hp))
-    s.append("  </units>\n</rts.PhysicalGameState>")
-    return "\n".join(s) + "\n"
+from microrts_b200.maps import map_to_xml  # noqa: E402,F401  (the map text format lives in the package)
 
 
 def export_game(ex, g):

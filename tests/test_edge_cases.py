@@ -152,3 +152,43 @@ def test_rollouts_ragged_roots_and_zero_depth(backend, maps):
     for k in ("header", "units", "actions", "rng"):
         assert (before[k] == after[k]).all()
     b.close()
+
+
+def test_duplicate_rows_cannot_overflow_the_pending_list(backend, maps):
+    """max_k == unit capacity rows that all address the same idle unit (NONE actions are always accepted, as
+    PlayerAction.fromVectorAction does): the pending list must not spill into the neighbouring shared-memory arrays.  The
+    flooded games are flagged MRTS_GE_BAD_ACTION and stay well-formed; a game of the same batch with ordinary rows still equals
+    the oracle."""
+    key = "8x8/basesWorkers8x8"
+    m = maps[key]
+    utt, b = make(maps, key, 4)
+    outt = O.Utt(1, 1)
+    cap = b.cap
+    b.set_policy(0, M.POLICY_EXTERNAL)
+    b.set_policy(1, M.POLICY_EXTERNAL)
+    cells = [[u[3] + u[4] * m["w"] for u in m["units"] if u[0] == "Worker" and u[2] == pl][0] for pl in (0, 1)]
+    rows = [np.zeros((4, cap, 8), dtype=np.int32) for _ in range(2)]
+    counts = [np.zeros(4, dtype=np.int32) for _ in range(2)]
+    for pl in (0, 1):
+        rows[pl][:, :, 0] = cells[pl]                  # every row: NONE for the player's worker
+        counts[pl][:] = [cap, cap, 1, 3]               # games 0, 1 flooded; game 2 one row; game 3 three duplicates
+    for pl in (0, 1):
+        b.set_actions(pl, rows[pl], counts[pl], M.ACTIONS_VECTOR, fill_none_duration=1)
+    b.step(1, 3000)
+    ex = b.export()
+    assert (ex["header"][:2, 6] & 16).all(), "flooded games are flagged"
+    assert (ex["header"][2:, 6] == 0).all()
+    for g in range(4):
+        hdr, units, acts = P.export_game(ex, g)
+        assert hdr[0] == 1 and hdr[3] == len(m["units"])
+        assert not units[units[:, 1] < 0, 7].any(), "a neutral unit was given an assignment"
+        exp = np.array([[P.TYPE_NAMES.index(u[0]), u[2], u[3], u[4], u[5], u[6]] for u in m["units"]], dtype=np.int32)
+        assert (units[:, :6] == exp).all(), "unit table damaged"
+    for g, k in ((2, 1), (3, 3)):
+        og = O.Game(outt, m)
+        pas = [og.from_vector_action(pl, rows[pl][g, :k], fill_none=1) for pl in (0, 1)]
+        og.issue(pas[0], True); og.issue(pas[1], True); og.cycle()
+        P.assert_same_state(ex, g, og, "duplicate rows game %d" % g)
+    b.step(5, 3000)  # and the batch keeps stepping
+    assert (b.export()["header"][:, 0] == 6).all()
+    b.close()
