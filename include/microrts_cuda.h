@@ -137,7 +137,7 @@ void mrts_map_destroy(mrts_map *);
 
 /* ---- batch of n_games GameState objects on one device: new GameState(pgs, utt), GameState.java:62-65 ----
  * Game g starts from maps[g % n_maps]; all maps must share width and height. unit_capacity 0 = automatic
- * (initial units + total resources, rounded up; at most 254). */
+ * (initial units + total resources, rounded up; at most 252; a given capacity is rounded up to a multiple of 4). */
 int mrts_batch_create(const mrts_utt *, const mrts_map *const *maps, int n_maps, int64_t n_games, int device,
                       uint32_t flags, int unit_capacity, mrts_batch **out);
 void mrts_batch_destroy(mrts_batch *);

@@ -324,21 +324,43 @@ DEV void g_rebuild(Game &g, bool with_rdy) {
     }
     __syncwarp();
 }
+// 16-byte asynchronous copies global -> shared (LDGSTS): a lane moves four unit slots of one word array per instruction and all of
+// a game's copies are in flight together, so loading a game costs one memory round trip instead of one per word array.
+#ifdef MRTS_EMU
+DEV void cp_async16(void *smem_dst, const void *gsrc) { memcpy(smem_dst, gsrc, 16); }
+DEV void cp_async_wait_all() {}
+#else
+DEV void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+DEV void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+#endif
+// unit words [0, uw) of slots [0, n) from `src` ([uw][cap] words, 16-byte aligned: cap is a multiple of 4) into the game's table;
+// slots up to the next multiple of 4 come along (never read: every pass over the table stops at nUnits)
+DEV void load_unit_words(Game &g, const uint32_t *src, int n) {
+    uint32_t *su = g.w0();
+    #pragma unroll 1
+    for (int i = g.lane * 4; i < n; i += 128)
+        #pragma unroll
+        for (int k = 0; k < MRTS_UNIT_WORDS; k++) if (k < g.uw) cp_async16(su + k * g.cap + i, src + k * g.cap + i);
+}
 // Load the game from HBM; when `restart_if_over` and the game ended in an earlier step (game over, or time >= max_cycles),
 // start it again from the map's initial state instead (the blob's init header/units): the three RNG streams keep running,
 // as the reference's static Random objects do across games, and H_SPARE counts episodes.
+// The first 128 unit slots are requested together with the header (before the unit count is known): one round trip for almost
+// every game; only games with more live units, or restarted ones, pay a second.
 DEV void g_load(Game &g, const int32_t *ghdr, const uint32_t *gun, bool restart_if_over, int max_cycles) {
     __syncwarp();
     int32_t v = 0;
     if (g.lane < MRTS_HDR_WORDS) v = ghdr[g.lane];
+    const int spec = g.cap < 128 ? g.cap : 128; // speculative part
+    load_unit_words(g, gun, spec);
     bool restart = false;
     if (restart_if_over) {
         int st = __shfl_sync(FULLM, v, H_STATUS), tm = __shfl_sync(FULLM, v, H_TIME);
         restart = (st & ST_OVER) || tm >= max_cycles;
     }
-    const uint32_t *src = gun;
     if (restart) {
-        src = g.grid_tmpl + g.pcw + MRTS_HDR_WORDS;
         if (g.lane < MRTS_HDR_WORDS) {
             int32_t iv = ((const int32_t *)(g.grid_tmpl + g.pcw))[g.lane];
             if (g.lane == H_SPARE) iv = v + 1;
@@ -347,11 +369,18 @@ DEV void g_load(Game &g, const int32_t *ghdr, const uint32_t *gun, bool restart_
     }
     if (g.lane < MRTS_HDR_WORDS) g.hdr()[g.lane] = v;
     int n = __shfl_sync(FULLM, v, H_NUNITS);
-    uint32_t *su = g.w0();
-    #pragma unroll 1
-    for (int k = 0; k < g.uw; k++)
+    if (restart) {
+        cp_async_wait_all(); // the speculative copies have landed before the same words are requested from the map
+        __syncwarp();
+        load_unit_words(g, g.grid_tmpl + g.pcw + MRTS_HDR_WORDS, n);
+    } else if (n > spec) {
+        uint32_t *su = g.w0();
         #pragma unroll 1
-        for (int i = g.lane; i < n; i += 32) su[k * g.cap + i] = src[k * g.cap + i];
+        for (int i = spec + g.lane * 4; i < n; i += 128)
+            #pragma unroll
+            for (int k = 0; k < MRTS_UNIT_WORDS; k++) if (k < g.uw) cp_async16(su + k * g.cap + i, gun + k * g.cap + i);
+    }
+    cp_async_wait_all();
     g_rebuild(g, true);
 }
 DEV void g_store(Game &g, int32_t *ghdr, uint32_t *gun) {
@@ -360,9 +389,9 @@ DEV void g_store(Game &g, int32_t *ghdr, uint32_t *gun) {
     int n = g.hdr()[H_NUNITS];
     const uint32_t *su = g.w0();
     #pragma unroll 1
-    for (int k = 0; k < g.uw; k++)
-        #pragma unroll 1
-        for (int i = g.lane; i < n; i += 32) gun[k * g.cap + i] = su[k * g.cap + i];
+    for (int i = g.lane * 4; i < n; i += 128) // 16 bytes (four slots of one word array) per lane and store
+        #pragma unroll
+        for (int k = 0; k < MRTS_UNIT_WORDS; k++) if (k < g.uw) *(uint4 *)(gun + k * g.cap + i) = *(const uint4 *)(su + k * g.cap + i);
     __syncwarp();
 }
 
@@ -1952,7 +1981,7 @@ enum { KERNEL_FAST = 0, KERNEL_ROLLOUT = 1, KERNEL_GENERIC = 2, KERNEL_FAST_OBS 
     X(KERNEL_FAST, 8, 8, 64, MRTS_MIN_BLOCKS) \
     X(KERNEL_ROLLOUT, 16, 16, 128, MRTS_MIN_BLOCKS_ROLLOUT) \
     X(KERNEL_ROLLOUT, 8, 8, 64, MRTS_MIN_BLOCKS_ROLLOUT) \
-    X(KERNEL_ROLLOUT, 32, 32, 254, MRTS_MIN_BLOCKS_ROLLOUT)
+    X(KERNEL_ROLLOUT, 32, 32, 252, MRTS_MIN_BLOCKS_ROLLOUT)
 
 // the warp's next work item: the global counter hands out the items behind every warp's static first one
 // (CHUNK items per draw: rollouts from a partially observable root can be a handful of cycles long, and one atomic per

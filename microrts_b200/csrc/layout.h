@@ -61,7 +61,7 @@ enum { UF_RESOURCE = 1, UF_STOCKPILE = 2, UF_HARVEST = 4, UF_MOVE = 8, UF_ATTACK
 #define MRTS_CONST_WORDS (MRTS_ETA_OFFSET + MRTS_MAX_TYPES * 4) // utt words + jump table (u64 pairs) + ETA table
 
 #define MRTS_INFO_WORDS 12 // per player and game: step facts for the reward functions (engine.cuh: info_count / info_distance)
-#define MRTS_MAX_CAP 254
+#define MRTS_MAX_CAP 252 // slot ids are bytes (0 empty, 0xFF wall); a multiple of 4 so that every unit word array starts 16-byte aligned (vector loads / stores)
 #define MRTS_WARPS_PER_CTA 4
 
 // engine error bits == MRTS_GE_* of the public header

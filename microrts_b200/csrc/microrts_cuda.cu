@@ -442,8 +442,8 @@ int mrts_batch_create(const mrts_utt *u, const mrts_map *const *maps, int n_maps
         bound = std::max(bound, map_unit_bound(maps[i]->h));
         bound = std::max(bound, (int)maps[i]->h.units.size());
     }
-    int cap = unit_capacity > 0 ? unit_capacity : std::min(MRTS_MAX_CAP, (bound + 31) & ~31);
-    if (cap > MRTS_MAX_CAP) return fail(MRTS_E_LIMIT, "unit capacity above 254");
+    int cap = unit_capacity > 0 ? ((unit_capacity + 3) & ~3) : std::min(MRTS_MAX_CAP, (bound + 31) & ~31); // multiple of 4: 16-byte aligned unit word arrays
+    if (cap > MRTS_MAX_CAP) return fail(MRTS_E_LIMIT, "unit capacity above 252");
     for (int i = 0; i < n_maps; i++) if ((int)maps[i]->h.units.size() > cap) return fail(MRTS_E_LIMIT, "map has more initial units than the unit capacity");
     if (cap < 32) cap = 32;
     auto b = std::unique_ptr<mrts_batch, void (*)(mrts_batch *)>(new mrts_batch, mrts_batch_destroy);
