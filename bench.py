@@ -707,7 +707,7 @@ def run_rollout(ctx, n, steps, warmup, prewarm, cpu_seconds):
 
 def run_vec(ctx, n_envs, steps, warmup, prewarm, cpu_seconds):
     from microrts_b200 import vec_bench
-    return vec_bench.run(ctx, n_envs, steps, warmup, prewarm, cpu_seconds, cpu_baseline)
+    return vec_bench.run(ctx, n_envs, steps, warmup, prewarm, cpu_seconds, cpu_baseline, timed_window, roofline)
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -195,6 +195,10 @@ int mrts_batch_set_actions(mrts_batch *, int player, int format, const int32_t *
                            int max_k, int fill_none_duration, int on_device);
 
 /* GameState.issueSafe(pa) / GameState.issue(pa) right now (GameState.java:338-408 / 249-328), no cycle. */
+/* Both players' PlayerActions of every game from ONE array in that same environment order: row block 2g = player 0 of game g, row
+ * block 2g + 1 = player 1 ([2 * n_games][max_k][8], every game max_k rows).  One host -> device copy; async != 0 returns without
+ * waiting for it (the host array, ideally pinned, must stay untouched until the batch is synchronised). */
+int mrts_batch_set_actions_interleaved(mrts_batch *, int format, const int32_t *actions, int max_k, int fill_none_duration, int on_device, int async);
 int mrts_batch_issue(mrts_batch *, int player, int format, const int32_t *actions, const int32_t *counts,
                      int max_k, int fill_none_duration, int safe, int on_device);
 
@@ -241,6 +245,22 @@ int mrts_batch_num_planes(const mrts_batch *);
  * (src/tests/JNIGridnetVecClient.java:213-297) -- from the state that is already in shared memory, without a second pass
  * over the batch. */
 int mrts_batch_set_observation_outputs(mrts_batch *, int dtype, void *out_player0, void *out_player1);
+/* The same for the action masks (JNIGridnetClient.getMasks, src/tests/JNIGridnetClient.java:210-223; UnitAction.getValidActionArray,
+ * src/rts/UnitAction.java:711-751): every later mrts_batch_step also writes the bit-packed masks of the state it leaves behind,
+ * [n_games][H][W][(mask width + 7) / 8] bytes per player (element j of a cell in bit j & 7 of byte j >> 3, as MRTS_DTYPE_BITS of
+ * mrts_batch_masks), into 16-byte aligned device buffers; NULL disables a player.  One launch then carries the step, both
+ * observations and both masks. */
+int mrts_batch_set_mask_outputs(mrts_batch *, void *out_player0, void *out_player1);
+/* JNIGridnetVecClient.gameStep's auto-reset (src/tests/JNIGridnetVecClient.java:244-262,272-286) inside the step launch: after the
+ * cycle, a game whose environment is done -- done_mode 1: the game is over (WinLossRewardFunction first); 2: no Resource unit holds
+ * resources (ResourceGatherRewardFunction first); 3: never by state -- or that has taken max_steps steps since its last reset, is
+ * restarted from its map before the fused observations / masks are written (the RNG streams keep running).  The step's results and
+ * reward facts stay the terminal ones; bit 1 of results[g][2] reports the restart.  done_mode 0 switches it off (the default). */
+int mrts_batch_set_vec_autoreset(mrts_batch *, int done_mode, int max_steps);
+/* Game g's fused outputs (observations, masks) are written at game slot g * game_stride of their buffers (default 1).  With stride 2,
+ * out_player0 = base and out_player1 = base + one game's bytes, the two players of game g land next to each other: the environment
+ * order of JNIGridnetVecClient's self-play pairs (src/tests/JNIGridnetVecClient.java:226-236, environment 2g = player 0 of game g). */
+int mrts_batch_set_output_stride(mrts_batch *, int game_stride);
 /* JNIGridnetClient.getMasks(player) (src/tests/JNIGridnetClient.java:210-223, UnitAction.java:711-751):
  * out = [n_games][H][W][mask_width]; with MRTS_DTYPE_BITS the last dimension is (mask_width + 7) / 8 bytes of packed bits
  * (79 entries -> 10 bytes per cell: 1/32 of the int32 array the reference allocates). */

@@ -345,6 +345,48 @@ class BatchedGameState:
         self._obs_keepalive = (out0, out1)
         _check(_ffi.lib().mrts_batch_set_observation_outputs(self._h, code, ptrs[0], ptrs[1]))
 
+    def set_output_layout(self, obs, masks=None, interleaved=False, side=0):
+        """Fused outputs in environment order (JNIGridnetVecClient): obs = [E][C][H][W] and masks = [E][H][W][(mask_width + 7) // 8]
+        device arrays.  interleaved: E = 2n, environment 2g is player 0 of game g and 2g + 1 player 1 (self-play pairs); otherwise
+        E = n and the arrays hold player `side` only."""
+        code = DTYPE_U8 if "uint8" in str(obs.dtype) else DTYPE_I32
+        E = 2 * self.n if interleaved else self.n
+        assert tuple(obs.shape) == (E, self.num_planes, self.height, self.width)
+        opg = self.num_planes * self.height * self.width * (1 if code == DTYPE_U8 else 4)
+        base = _ptr(obs)[0]
+        ptrs = [base, base + opg] if interleaved else [base if side == 0 else None, base if side == 1 else None]
+        mptrs = [None, None]
+        if masks is not None:
+            mb = (self.mask_width + 7) // 8
+            assert tuple(masks.shape) == (E, self.height, self.width, mb) and "uint8" in str(masks.dtype)
+            mbase = _ptr(masks)[0]
+            mptrs = [mbase, mbase + self.height * self.width * mb] if interleaved else [mbase if side == 0 else None, mbase if side == 1 else None]
+        self._obs_keepalive, self._mask_keepalive = obs, masks
+        L = _ffi.lib()
+        _check(L.mrts_batch_set_output_stride(self._h, 2 if interleaved else 1))
+        _check(L.mrts_batch_set_observation_outputs(self._h, code, ptrs[0], ptrs[1]))
+        _check(L.mrts_batch_set_mask_outputs(self._h, mptrs[0], mptrs[1]))
+
+    def set_vec_autoreset(self, done_mode, max_steps):
+        """JNIGridnetVecClient's auto-reset inside the step launch (mrts_batch_set_vec_autoreset)."""
+        _check(_ffi.lib().mrts_batch_set_vec_autoreset(self._h, done_mode, max_steps))
+
+    def set_actions_interleaved(self, actions, fmt=ACTIONS_VECTOR, fill_none_duration=1, async_copy=False):
+        """Both players' rows of every game from one [2n][max_k][8] array in self-play environment order (2g = player 0 of game g)."""
+        if isinstance(actions, (list, np.ndarray)):
+            actions = np.ascontiguousarray(actions, dtype=np.int32)
+        assert actions.shape[0] == 2 * self.n and actions.shape[2] == 8
+        pa, da, _k = _ptr(actions)
+        _check(_ffi.lib().mrts_batch_set_actions_interleaved(self._h, fmt, pa, int(actions.shape[1]), fill_none_duration, da, 1 if async_copy else 0))
+
+    def set_mask_outputs(self, out0=None, out1=None):
+        """Fused emission of the bit-packed action masks: every later step() also writes getMasks(0) / (1) of the state it leaves
+        behind into out0 / out1 ([n][H][W][(mask_width + 7) // 8] uint8 device tensors; None disables a player)."""
+        for o in (out0, out1):
+            assert o is None or (tuple(o.shape) == (self.n, self.height, self.width, (self.mask_width + 7) // 8) and "uint8" in str(o.dtype))
+        self._mask_keepalive = (out0, out1)
+        _check(_ffi.lib().mrts_batch_set_mask_outputs(self._h, _ptr(out0)[0] if out0 is not None else None, _ptr(out1)[0] if out1 is not None else None))
+
     def masks(self, player, dtype=np.int32, out=None):
         """JNIGridnetClient.getMasks(player) for every game: [n][H][W][mask_width]; dtype="bits": [n][H][W][(mask_width+7)//8]
         uint8 with element j in bit j & 7 of byte j >> 3 (np.unpackbits(..., bitorder="little") restores the dense form)."""

@@ -80,6 +80,11 @@ struct StepParams {
     const int32_t *ext_actions[2]; // [n_games][max_k][8]
     const int32_t *ext_counts[2];  // [n_games]
     int ext_maxk[2], ext_format[2], ext_fill[2];
+    long long ext_stride[2];   // int32 elements between consecutive games' rows (max_k * 8, or twice that for an interleaved array)
+    int vec_reset;             // MODE_GAME, JNIGridnetVecClient.gameStep's auto-reset inside the launch: 0 off; 1 restart when the game is over; 2 when no
+                               // Resource unit holds resources any more; 3 never on the state -- always also after vec_max_steps steps
+    int vec_max_steps;
+    int out_stride;            // fused outputs (obs_out, mask_out): game g is written at game slot g * out_stride of the buffers
     int max_range;             // UnitTypeTable.getMaxAttackRange()
     int n_types;               // utt.getUnitTypes().size()
     // MODE_PATHFIND: one query per game -- {cell of the unit (x + y*W), target position (x + y*W), range} -> direction or -1
@@ -98,6 +103,8 @@ struct StepParams {
     uint32_t tm_worker, tm_building, tm_combat, tm_base, tm_mobile, tm_resource; // unit type id bit masks, resolved by name on the host
     void *obs_out[2];          // MODE_GAME: when set, the post-step observation of player 0 / 1 is written here ([n][6][H][W])
     int obs_dtype;
+    void *mask_out[2];         // MODE_GAME: when set, the post-step bit-packed action masks of player 0 / 1 ([n][H][W][(K+7)/8] bytes)
+    int zero_bytes;            // KERNEL_FAST_OBS: size of the CTA's block of zeros behind the warps' regions (source of the bulk stores), or 0
     // MODE_ROLLOUT: item r = game r / rollouts_per_game
     int rollouts_per_game, depth, eval_fn, maxplayer, observer;
     const long long *ro_seeds; // [n_games * rollouts_per_game] or NULL (seed = r)
@@ -1379,7 +1386,7 @@ DEV int run_policy(Game &g, const StepParams &p, long long gi, int player, int p
             int cnt = p.ext_counts[player] ? p.ext_counts[player][gi] : p.ext_maxk[player];
             if (cnt > p.ext_maxk[player]) cnt = p.ext_maxk[player];
             int n0 = pn;
-            pn = decode_external(g, player, pn, p.ext_actions[player] + gi * (long long)p.ext_maxk[player] * 8, cnt,
+            pn = decode_external(g, player, pn, p.ext_actions[player] + gi * p.ext_stride[player], cnt,
                                  p.ext_format[player], p.ext_fill[player], 2 * p.max_range + 1);
             if (p.safe) legality_pass(g, n0, pn);
         }
@@ -1644,7 +1651,7 @@ DEVN void run_issue_only(Game &g, const StepParams &p, long long gi) {
     int pl = p.issue_player;
     int cnt = p.ext_counts[pl] ? p.ext_counts[pl][gi] : p.ext_maxk[pl];
     if (cnt > p.ext_maxk[pl]) cnt = p.ext_maxk[pl];
-    int pn = decode_external(g, pl, 0, p.ext_actions[pl] + gi * (long long)p.ext_maxk[pl] * 8, cnt, p.ext_format[pl],
+    int pn = decode_external(g, pl, 0, p.ext_actions[pl] + gi * p.ext_stride[pl], cnt, p.ext_format[pl],
                              p.ext_fill[pl], 2 * p.max_range + 1);
     if (p.safe) legality_pass(g, 0, pn);
     issue_pending(g, 0, pn);
@@ -1656,18 +1663,43 @@ DEVN void run_issue_only(Game &g, const StepParams &p, long long gi) {
 // the map's terrain plane for plane 5) and the units' five values are then scattered over them: the warp barrier orders
 // the two writes and the second one merges in L2, so DRAM sees each output byte once.  w0/w1/a0 point at the unit table
 // (shared memory inside the step kernels, HBM in k_observe).
+// ---- bulk stores shared -> global (cp.async.bulk, the 1-D TMA path): one instruction by one lane moves up to 4 KB ----------------
+// The fused step + observation kernel writes the planes' and masks' zeros from a block of zeros in shared memory this way: almost
+// every output byte is a zero, so the LSU only sees the few values scattered over them afterwards.
+#ifdef MRTS_EMU
+DEV void bulk_zero(uint32_t, int, void *dst, size_t bytes) { memset(dst, 0, bytes); }
+DEV void bulk_wait_all() {}
+#else
+// lane 0 only: dst 16-byte aligned, bytes a multiple of 16; zsm = shared-window address of zbytes zeros
+DEV void bulk_zero(uint32_t zsm, int zbytes, void *dst, size_t bytes) {
+    char *d = (char *)dst;
+    #pragma unroll 1
+    for (size_t o = 0; o < bytes; o += (size_t)zbytes) {
+        uint32_t sz = bytes - o < (size_t)zbytes ? (uint32_t)(bytes - o) : (uint32_t)zbytes;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(d + o), "r"(zsm), "r"(sz) : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// every bulk store of this thread has been performed: later stores to the same bytes land on top of them
+DEV void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+#endif
+
+// prezeroed: planes 0-4 were zeroed by bulk stores issued by lane 0 earlier; they are waited for before the units are scattered
 DEV void obs_emit(const uint32_t *w0, const uint32_t *w1, const uint32_t *a0, int n, int W, int H, const uint8_t *terrain, int player,
-                  int dtype, void *out, int lane) {
+                  int dtype, void *out, int lane, bool prezeroed = false) {
     int cells = W * H;
     if (dtype == 0) {
         uint8_t *o = (uint8_t *)out;
         if ((cells & 15) == 0) {
             int nq = cells >> 4;
             uint4 z; z.x = z.y = z.z = z.w = 0;
-            #pragma unroll 4
-            for (int q = lane; q < 5 * nq; q += 32) ((uint4 *)o)[q] = z;
+            if (!prezeroed) {
+                #pragma unroll 4
+                for (int q = lane; q < 5 * nq; q += 32) ((uint4 *)o)[q] = z;
+            }
             #pragma unroll 2
             for (int q = lane; q < nq; q += 32) ((uint4 *)(o + 5 * cells))[q] = ((const uint4 *)terrain)[q];
+            if (prezeroed && lane == 0) bulk_wait_all();
         } else {
             #pragma unroll 1
             for (int q = lane; q < 5 * cells; q += 32) o[q] = 0;
@@ -1877,6 +1909,63 @@ DEVN void masks_game(Game &g, const StepParams &p, long long gi) {
     }
 }
 
+// The same masks, bit-packed, written by the step kernels for the state they leave behind (mrts_batch_set_mask_outputs): one lane
+// per idle unit builds the unit's whole row (K <= 128 bits) in registers from the category masks of enumerate().  The game's block
+// is zeroed first (16-byte stores, or bulk stores issued earlier when `prezeroed`).
+DEV void masks_emit_bits(const Game &g, const StepParams &p, int player, void *out, bool prezeroed) {
+    const int n = g.hdr()[H_NUNITS], R = 2 * p.max_range + 1, ctr = R / 2, nT = p.n_types, K = 1 + 6 + 16 + nT + R * R, MB = (K + 7) >> 3;
+    const size_t per_game = (size_t)g.W * g.H * MB;
+    uint8_t *o = (uint8_t *)out;
+    if (!prezeroed) {
+        if ((per_game & 15) == 0) {
+            uint4 z; z.x = z.y = z.z = z.w = 0;
+            #pragma unroll 4
+            for (size_t q = g.lane; q < (per_game >> 4); q += 32) ((uint4 *)o)[q] = z;
+        } else {
+            #pragma unroll 1
+            for (size_t q = g.lane; q < per_game; q += 32) o[q] = 0;
+        }
+    } else if (g.lane == 0) bulk_wait_all();
+    __syncwarp();
+    #pragma unroll 1
+    for (int s = g.lane; s < n; s += 32) {
+        uint32_t w = g.w0()[s];
+        if (u_pl(w) != player + 1 || a_type(g.a0()[s]) != AT_IDLE) continue;
+        Enum e; enumerate(g, s, e);
+        const int mv_m = (e.fl & UF_MOVE) ? e.free_m : 0, pr_m = e.n_aff > 0 ? e.free_m : 0;
+        unsigned long long lo = 3ull /* the unit can act; NONE */ | (mv_m ? 4ull : 0) | (e.harv_m ? 8ull : 0) | (e.ret_m ? 16ull : 0) | (pr_m ? 32ull : 0) |
+                                (e.n_atk > 0 ? 64ull : 0) | ((unsigned long long)mv_m << 7) | ((unsigned long long)e.harv_m << 11) |
+                                ((unsigned long long)e.ret_m << 15) | ((unsigned long long)pr_m << 19), hi = 0;
+        if (e.nfree > 0) {
+            int np = ut_nprod(g, e.t);
+            #pragma unroll 1
+            for (int k = 0; k < np; k++) if ((e.aff_m >> k) & 1) lo |= 1ull << (23 + ut_prod(g, e.t, k));
+        }
+        if (e.fl & UF_ATTACK) {
+            const int base = 23 + nT;
+            if (e.range == 1) {
+                #pragma unroll
+                for (int d = 0; d < 4; d++)
+                    if ((e.atk_m >> d) & 1) { int j = base + (ddy(d) + ctr) * R + ddx(d) + ctr; if (j < 64) lo |= 1ull << j; else hi |= 1ull << (j - 64); }
+            } else {
+                const int sq = e.range * e.range;
+                #pragma unroll 1
+                for (int i = 0; i < n; i++) {
+                    uint32_t ow = g.w0()[i];
+                    if (enemy_in_range(g, w, ow, sq)) {
+                        int j = base + (u_y(ow) - u_y(w) + ctr) * R + (u_x(ow) - u_x(w)) + ctr;
+                        if (j < 64) lo |= 1ull << j; else hi |= 1ull << (j - 64);
+                    }
+                }
+            }
+        }
+        uint8_t *row = o + ((size_t)u_y(w) * g.W + u_x(w)) * MB;
+        #pragma unroll 1
+        for (int b = 0; b < MB; b++) row[b] = (uint8_t)((b < 8 ? lo >> (8 * b) : hi >> (8 * (b - 8))) & 0xff);
+    }
+    __syncwarp();
+}
+
 // ---- NaiveMCTS playout (ai/mcts/naivemcts/NaiveMCTS.java:195-223,297-308) -----------------------------------------------
 // PartiallyObservableGameState(gs, observer) (rts/PartiallyObservableGameState.java:35-71): drop every unit that is not
 // the observer's and lies outside the sight radius of all observer units (with its assignment).
@@ -2030,6 +2119,18 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
     }
     // the warp's counters live in shared memory: every lane adds the same (warp-uniform) amounts to its own view of them, so
     // only lane 0's stores matter; 16 registers stay free for the game loop
+    // KERNEL_FAST_OBS: the CTA's block of zeros behind the warps' regions (never written again) feeds the bulk stores
+    uint32_t zsm = 0;
+    if (KERNEL == KERNEL_FAST_OBS && p.zero_bytes > 0) {
+        unsigned char *zb = mrts_smem + MRTS_CONST_WORDS * 4 + wpc * L.total;
+        #pragma unroll 1
+        for (int i = tid; i < p.zero_bytes / 16; i += nthreads) { uint4 z; z.x = z.y = z.z = z.w = 0; ((uint4 *)zb)[i] = z; }
+#ifndef MRTS_EMU
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the zeros are visible to the async proxy that reads them
+#endif
+        __syncthreads();
+        zsm = smem_window(MRTS_CONST_WORDS * 4 + wpc * L.total);
+    }
     WarpStats &ws = *(WarpStats *)(mrts_smem + region + L.stats);
     if (lane < N_WARP_STATS) ws.v[lane] = 0;
     __syncwarp();
@@ -2047,6 +2148,20 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
         stat_add(ws, lane, STAT_IO_READ, (unsigned long long)(MRTS_HDR_WORDS * 4 + puw * 4 * g.hdr()[H_NUNITS]));
         if (KERNEL == KERNEL_ROLLOUT) { run_rollout(g, p, item, ws); stat_add(ws, lane, STAT_IO_WRITE, 8); continue; } // the batch itself is not modified
         int err0 = g.hdr()[H_ERR];
+        // outputs of the state this step leaves behind: their zeros (planes 0-4 of each observation, the whole mask block) leave
+        // now through bulk stores, under the game's cycle(s); the values are scattered over them once they have landed
+        const int cells = pW * pH;
+        const size_t obs_pg = obs_bytes_per_game(pW, pH, 6, p.obs_dtype);
+        const size_t mask_pg = mask_bytes_per_game(pW, pH, 1 + 6 + 16 + p.n_types + (2 * p.max_range + 1) * (2 * p.max_range + 1), 2);
+        const bool obs_bulk = KERNEL == KERNEL_FAST_OBS && zsm != 0 && p.obs_dtype == 0 && ((5 * cells) & 15) == 0 && (obs_pg & 15) == 0;
+        const bool mask_bulk = KERNEL == KERNEL_FAST_OBS && zsm != 0 && (mask_pg & 15) == 0;
+        if (KERNEL == KERNEL_FAST_OBS && lane == 0) {
+            #pragma unroll 1
+            for (int pl = 0; pl < 2; pl++) {
+                if (obs_bulk && p.obs_out[pl]) bulk_zero(zsm, p.zero_bytes, (char *)p.obs_out[pl] + (size_t)gi * p.out_stride * obs_pg, (size_t)5 * cells);
+                if (mask_bulk && p.mask_out[pl]) bulk_zero(zsm, p.zero_bytes, (char *)p.mask_out[pl] + (size_t)gi * p.out_stride * mask_pg, mask_pg);
+            }
+        }
         if (KERNEL == KERNEL_FAST || KERNEL == KERNEL_FAST_OBS) run_game_fast(g, p, ws);
         else if (p.mode == MODE_GAME) run_game(g, p, gi, ws);
         else if (p.mode == MODE_CYCLE_ONLY) run_cycles_only(g, p.t_target ? p.t_target[gi] : g.hdr()[H_TIME] + p.n_cycles);
@@ -2055,8 +2170,6 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
         else if (p.mode == MODE_PATHFIND) { pathfind_game(g, p, gi); continue; }
         else { masks_game(g, p, gi); stat_add(ws, lane, STAT_IO_WRITE, mask_bytes_per_game(g.W, g.H, 1 + 6 + 16 + p.n_types + (2 * p.max_range + 1) * (2 * p.max_range + 1), p.out_dtype)); continue; }
         if (g.hdr()[H_ERR] != err0) stat_add(ws, g.lane, STAT_ERRORS, 1);
-        g_store(g, ghdr, gun);
-        stat_add(ws, lane, STAT_IO_WRITE, (unsigned long long)(MRTS_HDR_WORDS * 4 + puw * 4 * g.hdr()[H_NUNITS] + (p.mode == MODE_GAME && p.results_out ? 16 : 0)));
         if (p.mode == MODE_GAME && p.results_out) {
             // what mrts_batch_results reports (winner() / gameover(), PhysicalGameState.java:334-387), written here so that the
             // host can fetch it with a plain copy: a results kernel would have to wait for SM slots behind whatever persistent
@@ -2065,19 +2178,46 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
             #pragma unroll 1
             for (int i = lane; i < n; i += 32) { int pl = u_pl(g.w0()[i]); c0 += pl == 1; c1 += pl == 2; }
             c0 = __reduce_add_sync(FULLM, c0); c1 = __reduce_add_sync(FULLM, c1);
-            if (lane == 0) {
-                int4 r;
-                r.x = g.hdr()[H_TIME]; r.y = (c0 > 0 && c1 == 0) ? 0 : ((c1 > 0 && c0 == 0) ? 1 : -1); r.z = (c0 == 0 || c1 == 0) ? 1 : 0; r.w = g.hdr()[H_ERR];
-                ((int4 *)p.results_out)[gi] = r;
+            int4 r;
+            r.x = g.hdr()[H_TIME]; r.y = (c0 > 0 && c1 == 0) ? 0 : ((c1 > 0 && c0 == 0) ? 1 : -1); r.z = (c0 == 0 || c1 == 0) ? 1 : 0; r.w = g.hdr()[H_ERR];
+            if (KERNEL == KERNEL_GENERIC && p.vec_reset) {
+                // JNIGridnetVecClient.gameStep (src/tests/JNIGridnetVecClient.java:244-262,272-286): an environment whose first reward
+                // function reports done, or that has run max_steps steps, is reset inside the same gameStep -- the step's results and
+                // reward facts are the terminal ones, the observation (and masks) returned are the restarted game's.  The static
+                // Random objects keep running; bit 1 of results[2] tells the host that the game restarted.
+                int steps = g.hdr()[H_ENVSTEPS] + 1;
+                bool resleft = p.info_out ? p.info_out[gi * (2 * MRTS_INFO_WORDS) + 10] != 0 : true;
+                bool done0 = p.vec_reset == 1 ? r.z != 0 : (p.vec_reset == 2 ? !resleft : false);
+                bool restart = done0 || steps >= p.vec_max_steps;
+                __syncwarp();
+                if (restart) {
+                    r.z |= 2;
+                    const int32_t *ih = (const int32_t *)(blob + L.pcw);
+                    if (lane < MRTS_HDR_WORDS && !(lane >= H_RNGP_LO && lane <= H_RNGD_HI)) g.hdr()[lane] = lane == H_SPARE ? g.hdr()[lane] + 1 : ih[lane];
+                    __syncwarp();
+                    load_unit_words(g, blob + L.pcw + MRTS_HDR_WORDS, g.hdr()[H_NUNITS]);
+                    cp_async_wait_all();
+                    g_rebuild(g, true);
+                } else if (lane == 0) g.hdr()[H_ENVSTEPS] = steps;
+                __syncwarp();
             }
+            if (lane == 0) ((int4 *)p.results_out)[gi] = r;
         }
+        g_store(g, ghdr, gun);
+        stat_add(ws, lane, STAT_IO_WRITE, (unsigned long long)(MRTS_HDR_WORDS * 4 + puw * 4 * g.hdr()[H_NUNITS] + (p.mode == MODE_GAME && p.results_out ? 16 : 0)));
         if (KERNEL == KERNEL_FAST_OBS || (KERNEL == KERNEL_GENERIC && p.mode == MODE_GAME)) {
             #pragma unroll 1
             for (int pl = 0; pl < 2; pl++)
                 if (p.obs_out[pl]) {
-                    stat_add(ws, lane, STAT_IO_WRITE, obs_bytes_per_game(g.W, g.H, 6, p.obs_dtype));
+                    stat_add(ws, lane, STAT_IO_WRITE, obs_pg);
                     obs_emit(g.w0(), g.w1(), g.a0(), g.hdr()[H_NUNITS], g.W, g.H, map_terrain(blob, g.W, g.H, g.cap), pl, p.obs_dtype,
-                             (char *)p.obs_out[pl] + (size_t)gi * obs_bytes_per_game(g.W, g.H, 6, p.obs_dtype), lane);
+                             (char *)p.obs_out[pl] + (size_t)gi * p.out_stride * obs_pg, lane, obs_bulk);
+                }
+            #pragma unroll 1
+            for (int pl = 0; pl < 2; pl++)
+                if (p.mask_out[pl]) {
+                    stat_add(ws, lane, STAT_IO_WRITE, mask_pg);
+                    masks_emit_bits(g, p, pl, (char *)p.mask_out[pl] + (size_t)gi * p.out_stride * mask_pg, mask_bulk);
                 }
         }
     }

@@ -31,7 +31,8 @@ enum {
     H_SPARE = 15,   // episode counter (auto-reset)
     H_ASEQ0 = 16,   // next insertion sequence of player 0's AbstractionLayerAI.actions map
     H_ASEQ1 = 17,
-    H_RSV0 = 18, H_RSV1 = 19
+    H_ENVSTEPS = 18, // steps since the environment's last reset (JNIGridnetVecClient.envSteps; in-kernel auto-reset only)
+    H_RSV1 = 19
 };
 
 // per-unit words

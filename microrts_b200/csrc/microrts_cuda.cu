@@ -202,10 +202,12 @@ struct mrts_utt { UttH h; };
 struct mrts_map { MapH h; };
 
 struct Staged { // external actions staged on the device
-    int32_t *actions = nullptr, *counts = nullptr;
+    int32_t *actions = nullptr, *counts = nullptr; // buffers this player owns
+    const int32_t *rows = nullptr;                 // what the next step reads: `actions`, or the other player's buffer (interleaved staging)
     size_t cap_rows = 0;
     int max_k = 0, format = 0, fill = -1;
-    bool valid = false, own = true;
+    long long stride = 0;                          // int32 elements between consecutive games' rows
+    bool valid = false, has_counts = false;
 };
 
 // one fixed-size copy: which kernel it stands in for, for which map size / capacity, and how to launch it
@@ -254,6 +256,10 @@ struct mrts_batch {
     int max_range = 0, auto_reset = 0, scripted = 0, uw = MRTS_UNIT_WORDS_CORE;
     int sequential_issue = 0; int32_t *info_out = nullptr; uint32_t tm[6] = {0, 0, 0, 0, 0, 0};
     void *obs_out[2] = {nullptr, nullptr}; int obs_dtype = 0; // device buffers mrts_batch_step writes post-step observations to
+    void *mask_out[2] = {nullptr, nullptr};                   // ... and the post-step bit-packed action masks
+    int zero_bytes = 0;                                       // block of zeros per CTA of k_step_fast_obs (source of its bulk stores)
+    int vec_reset = 0, vec_max_steps = 0;                     // in-kernel auto-reset of the JNIGridnetVecClient flow (mrts_batch_set_vec_autoreset)
+    int out_stride = 1;                                       // game g's fused outputs go to game slot g * out_stride (mrts_batch_set_output_stride)
     long long launches = 0;
     long long host_io[2] = {0, 0}; // bytes moved by the kernels that carry no counters (k_observe), added to mrts_batch_io_bytes
     char last_kernel[64] = "";     // symbol of the most recent step-kernel launch (mrts_batch_last_kernel)
@@ -279,8 +285,9 @@ static int launch_step(mrts_batch *b, StepParams &p) {
     int kernel = KERNEL_GENERIC;
     auto rb_or_passive = [](int pol) { return pol == MRTS_POLICY_RANDOM_BIASED || pol == MRTS_POLICY_PASSIVE; };
     if (p.mode == MODE_ROLLOUT) kernel = KERNEL_ROLLOUT;
-    else if (p.mode == MODE_GAME && p.conflict == MRTS_CANCEL_BOTH && rb_or_passive(p.policy[0]) && rb_or_passive(p.policy[1]) && !p.info_out && !p.sequential_issue && !p.po_policies)
-        kernel = (p.obs_out[0] || p.obs_out[1]) ? KERNEL_FAST_OBS : KERNEL_FAST;
+    else if (p.mode == MODE_GAME && p.conflict == MRTS_CANCEL_BOTH && rb_or_passive(p.policy[0]) && rb_or_passive(p.policy[1]) && !p.info_out && !p.sequential_issue && !p.po_policies && !p.vec_reset)
+        kernel = (p.obs_out[0] || p.obs_out[1] || p.mask_out[0] || p.mask_out[1]) ? KERNEL_FAST_OBS : KERNEL_FAST;
+    p.zero_bytes = kernel == KERNEL_FAST_OBS ? b->zero_bytes : 0;
     const int fv = b->fixed_of[kernel];
     const bool gfx = kernel == KERNEL_GENERIC && b->generic_fixed_fn;
     // the rush-only copy: a game step in which neither player runs a defense, WorkerRushPlusPlus or a PO rush
@@ -444,7 +451,7 @@ int mrts_batch_create(const mrts_utt *u, const mrts_map *const *maps, int n_maps
     }
     int cap = unit_capacity > 0 ? ((unit_capacity + 3) & ~3) : std::min(MRTS_MAX_CAP, (bound + 31) & ~31); // multiple of 4: 16-byte aligned unit word arrays
     if (cap > MRTS_MAX_CAP) return fail(MRTS_E_LIMIT, "unit capacity above 252");
-    for (int i = 0; i < n_maps; i++) if ((int)maps[i]->h.units.size() > cap) return fail(MRTS_E_LIMIT, "map has more initial units than the unit capacity");
+    for (int i = 0; i < n_maps; i++) if ((int)maps[i]->h.units.size() > (unit_capacity > 0 ? unit_capacity : cap)) return fail(MRTS_E_LIMIT, "map has more initial units than the unit capacity");
     if (cap < 32) cap = 32;
     auto b = std::unique_ptr<mrts_batch, void (*)(mrts_batch *)>(new mrts_batch, mrts_batch_destroy);
     b->utt = u->h; b->W = W; b->H = H; b->cap = cap; b->n_maps = n_maps; b->n = n_games; b->flags = flags; b->device = device;
@@ -474,13 +481,13 @@ int mrts_batch_create(const mrts_utt *u, const mrts_map *const *maps, int n_maps
     // Per kernel: as many games in flight per SM as shared memory and registers allow (large maps need fewer, fatter
     // CTAs); grid = resident CTAs per SM x SMs (persistent kernel).
     const void *kernels[N_KERNELS] = {(const void *)k_step_fast, (const void *)k_rollout, (const void *)k_step, (const void *)k_step_fast_obs};
-    auto make_plan = [&](const void *fn, int region, mrts_batch::Plan &out) -> int {
+    auto make_plan = [&](const void *fn, int region, mrts_batch::Plan &out, int extra = 0) -> int {
         int best_wpc = 0, best_warps = 0, best_blocks = 0;
         if (ck(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin)) ||
             ck(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)))
             return fail(MRTS_E_CUDA, std::string("cudaFuncSetAttribute: ") + dev_errstr());
         for (int wpc = MRTS_WARPS_PER_CTA; wpc >= 1; wpc--) {
-            size_t sm = MRTS_CONST_WORDS * 4 + (size_t)wpc * region;
+            size_t sm = MRTS_CONST_WORDS * 4 + (size_t)wpc * region + extra;
             if (sm > (size_t)prop.sharedMemPerBlockOptin) continue;
             int per_sm = 0;
             if (ck(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, wpc * 32, sm))) return fail(MRTS_E_CUDA, std::string("occupancy query: ") + dev_errstr());
@@ -488,12 +495,14 @@ int mrts_batch_create(const mrts_utt *u, const mrts_map *const *maps, int n_maps
         }
         if (!best_wpc) return fail(MRTS_E_LIMIT, "map too large for the shared-memory resident engine");
         out.wpc = best_wpc;
-        out.smem = MRTS_CONST_WORDS * 4 + (size_t)best_wpc * region;
+        out.smem = MRTS_CONST_WORDS * 4 + (size_t)best_wpc * region + extra;
         out.grid = best_blocks * prop.multiProcessorCount;
         return 0;
     };
+    // the fused step + observation kernel keeps one block of zeros per CTA: the source of the bulk stores that zero its outputs
+    { int z5 = (5 * W * H) & ~15; b->zero_bytes = z5 >= 256 ? std::min(4096, z5) : 0; }
     for (int kk = 0; kk < N_KERNELS; kk++) {
-        int rc = make_plan(kernels[kk], kk == KERNEL_GENERIC ? b->L.total : b->Lfast.total, b->plan[kk]);
+        int rc = make_plan(kernels[kk], kk == KERNEL_GENERIC ? b->L.total : b->Lfast.total, b->plan[kk], kk == KERNEL_FAST_OBS ? b->zero_bytes : 0);
         if (rc) return rc;
     }
 #ifndef MRTS_NO_FIXED
@@ -650,12 +659,34 @@ static int stage_actions(mrts_batch *b, int player, int format, const int32_t *a
     size_t ab = (size_t)b->n * max_k * 8 * 4;
     if (ab) { if (on_device ? dev_d2d(s.actions, actions, ab, b->stream) : dev_h2d(s.actions, actions, ab, b->stream)) return fail(MRTS_E_CUDA, dev_errstr()); }
     if (counts) { if (on_device ? dev_d2d(s.counts, counts, (size_t)b->n * 4, b->stream) : dev_h2d(s.counts, counts, (size_t)b->n * 4, b->stream)) return fail(MRTS_E_CUDA, dev_errstr()); }
-    else {
-        std::vector<int32_t> c((size_t)b->n, max_k);
-        if (dev_h2d(s.counts, c.data(), c.size() * 4, b->stream) || dev_sync(b->stream)) return fail(MRTS_E_CUDA, dev_errstr());
-    }
+    s.has_counts = counts != nullptr; // without counts every game has max_k rows (the kernels take the count from max_k)
     if (!on_device && dev_sync(b->stream)) return fail(MRTS_E_CUDA, dev_errstr()); // caller may reuse its host buffers
-    s.max_k = max_k; s.format = format; s.fill = fill; s.valid = true;
+    s.max_k = max_k; s.format = format; s.fill = fill; s.valid = true; s.rows = s.actions; s.stride = (long long)max_k * 8;
+    return MRTS_OK;
+}
+
+// Both players' PlayerActions of every game in ONE array laid out like JNIGridnetVecClient's self-play environments
+// (src/tests/JNIGridnetVecClient.java:226-236): row block 2g is player 0 of game g, row block 2g + 1 is player 1.  One host -> device
+// copy; with `async` the call returns without waiting for it (the host array must stay untouched until the batch is synchronised).
+int mrts_batch_set_actions_interleaved(mrts_batch *b, int format, const int32_t *actions, int max_k, int fill_none_duration, int on_device, int async) {
+    if (!b || max_k < 1 || !actions) return fail(MRTS_E_ARG, "bad action arguments");
+    if (format != MRTS_ACTIONS_VECTOR && format != MRTS_ACTIONS_RAW) return fail(MRTS_E_ARG, "unknown action format");
+    if (max_k > b->cap) return fail(MRTS_E_ARG, "max_k exceeds the unit capacity of the batch");
+    if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
+    Staged &s = b->staged[0];
+    size_t rows = (size_t)b->n * 2 * (size_t)max_k;
+    if (rows > s.cap_rows || !s.counts) {
+        dev_free(s.actions); dev_free(s.counts); s.actions = nullptr; s.counts = nullptr; s.cap_rows = 0;
+        if (dev_alloc((void **)&s.actions, rows * 8 * 4) || dev_alloc((void **)&s.counts, (size_t)b->n * 4)) return fail(MRTS_E_CUDA, std::string("staging allocation failed: ") + dev_errstr());
+        s.cap_rows = rows;
+    }
+    if (on_device ? dev_d2d(s.actions, actions, rows * 32, b->stream) : dev_h2d(s.actions, actions, rows * 32, b->stream)) return fail(MRTS_E_CUDA, dev_errstr());
+    if (!on_device && !async && dev_sync(b->stream)) return fail(MRTS_E_CUDA, dev_errstr());
+    for (int pl = 0; pl < 2; pl++) {
+        Staged &t = b->staged[pl];
+        t.rows = s.actions + (size_t)pl * max_k * 8; t.stride = (long long)max_k * 16; t.max_k = max_k; t.format = format; t.fill = fill_none_duration;
+        t.has_counts = false; t.valid = true;
+    }
     return MRTS_OK;
 }
 
@@ -665,7 +696,7 @@ int mrts_batch_set_actions(mrts_batch *b, int player, int format, const int32_t 
 
 static void fill_ext(mrts_batch *b, StepParams &p, int pl) {
     Staged &s = b->staged[pl];
-    if (s.valid) { p.ext_actions[pl] = s.actions; p.ext_counts[pl] = s.counts; p.ext_maxk[pl] = s.max_k; p.ext_format[pl] = s.format; p.ext_fill[pl] = s.fill; }
+    if (s.valid) { p.ext_actions[pl] = s.rows; p.ext_counts[pl] = s.has_counts ? s.counts : nullptr; p.ext_maxk[pl] = s.max_k; p.ext_format[pl] = s.format; p.ext_fill[pl] = s.fill; p.ext_stride[pl] = s.stride; }
 }
 
 int mrts_batch_issue(mrts_batch *b, int player, int format, const int32_t *actions, const int32_t *counts, int max_k, int fill_none_duration, int safe, int on_device) {
@@ -690,6 +721,8 @@ int mrts_batch_step(mrts_batch *b, int n_cycles, int max_cycles) {
     p.tm_worker = b->tm[0]; p.tm_building = b->tm[1]; p.tm_combat = b->tm[2]; p.tm_base = b->tm[3]; p.tm_mobile = b->tm[4]; p.tm_resource = b->tm[5];
     bool fused = !(b->flags & MRTS_FLAG_PARTIAL_OBS); // partially observable batches observe in a second launch
     if (fused) { p.obs_out[0] = b->obs_out[0]; p.obs_out[1] = b->obs_out[1]; p.obs_dtype = b->obs_dtype; }
+    p.out_stride = b->out_stride; p.vec_reset = b->vec_reset; p.vec_max_steps = b->vec_max_steps;
+    p.mask_out[0] = b->mask_out[0]; p.mask_out[1] = b->mask_out[1]; // masks are of the full state (JNIGridnetClient.getMasks uses gs), fused in every batch
     p.results_out = b->d_results;
     if (launch_step(b, p)) return fail(MRTS_E_CUDA, std::string("step launch: ") + dev_errstr());
     b->results_fresh = true;
@@ -706,6 +739,27 @@ int mrts_batch_set_observation_outputs(mrts_batch *b, int dtype, void *out_playe
     if (!b || (dtype != MRTS_DTYPE_U8 && dtype != MRTS_DTYPE_I32)) return fail(MRTS_E_ARG, "mrts_batch_set_observation_outputs: bad argument");
     if ((((uintptr_t)out_player0) | ((uintptr_t)out_player1)) & 15) return fail(MRTS_E_ARG, "observation buffers must be 16-byte aligned");
     b->obs_out[0] = out_player0; b->obs_out[1] = out_player1; b->obs_dtype = dtype;
+    return MRTS_OK;
+}
+
+int mrts_batch_set_vec_autoreset(mrts_batch *b, int done_mode, int max_steps) {
+    if (!b || done_mode < 0 || done_mode > 3 || (done_mode && max_steps < 1)) return fail(MRTS_E_ARG, "mrts_batch_set_vec_autoreset: bad argument");
+    if (done_mode && (b->flags & MRTS_FLAG_PARTIAL_OBS)) return fail(MRTS_E_STATE, "in-kernel auto-reset needs fused observations (not a MRTS_FLAG_PARTIAL_OBS batch)");
+    b->vec_reset = done_mode; b->vec_max_steps = max_steps;
+    return MRTS_OK;
+}
+
+int mrts_batch_set_output_stride(mrts_batch *b, int game_stride) {
+    if (!b || game_stride < 1) return fail(MRTS_E_ARG, "mrts_batch_set_output_stride: bad argument");
+    b->out_stride = game_stride;
+    return MRTS_OK;
+}
+
+int mrts_batch_set_mask_outputs(mrts_batch *b, void *out_player0, void *out_player1) {
+    if (!b) return fail(MRTS_E_ARG, "null batch");
+    if ((((uintptr_t)out_player0) | ((uintptr_t)out_player1)) & 15) return fail(MRTS_E_ARG, "mask buffers must be 16-byte aligned");
+    if (mrts_batch_mask_width(b) > 128) return fail(MRTS_E_LIMIT, "fused masks hold at most 128 elements per cell (unit type table with a very long attack range): use mrts_batch_masks");
+    b->mask_out[0] = out_player0; b->mask_out[1] = out_player1;
     return MRTS_OK;
 }
 

@@ -20,6 +20,10 @@ game, JNIGridnetClientSelfPlay), the next num_envs entries are agent-vs-bot game
   writes (no trace objects); auto-reset keeps the terminal reward/done and forces done[0] (:272-286).
 * Partially observable observations are taken from the state after the cycle (the reference returns a view built before
   the cycle, JNIGridnetClient.java:163-203) -- DESIGN.md, known deviations.
+* One kernel launch per gameStep and group: decode of the vector actions, issueSafe of both players, cycle, reward facts, the
+  auto-reset of finished environments (mrts_batch_set_vec_autoreset) and the observations (optionally the bit-packed masks) of every
+  environment, written in environment order.  Host arrays are pinned and reused; `compact=True` returns uint8 observations and keeps
+  the masks bit-packed (getMasksPacked) -- 4 KB instead of 87 KB per 16x16 environment and step across PCIe.
 """
 import os
 
@@ -120,18 +124,28 @@ def _device_array(shape, dtype, emulated):
     return torch.zeros(shape, dtype=torch.int32 if dtype == np.int32 else torch.uint8, device="cuda")
 
 
+def _host_array(shape, dtype, emulated):
+    """Pinned host memory (a numpy view of a pinned torch tensor) that device results are copied into asynchronously."""
+    if emulated:
+        return np.zeros(shape, dtype=dtype), None
+    import torch
+    t = torch.zeros(shape, dtype={np.int32: torch.int32, np.uint8: torch.uint8}[dtype]).pin_memory()
+    return t.numpy(), t
+
+
 def _host(a):
     return a if isinstance(a, np.ndarray) else a.cpu().numpy()
 
 
 class _Group:
     """One batch: either the self-play games (both players EXTERNAL, sequential issue) or the agent-vs-bot games that share
-    one opponent policy and one agent side."""
+    one opponent policy and one agent side.  Its environments are envs[0], envs[1], ... of the client; self-play environments come
+    in pairs (player 0, player 1 of one game) and the group's output arrays are laid out in that environment order."""
 
-    def __init__(self, utt, maps, envs, selfplay, spec, side, partial_obs, device, emulated, seed0):
-        self.envs, self.selfplay, self.side = envs, selfplay, side
+    def __init__(self, utt, maps, envs, selfplay, spec, side, partial_obs, device, emulated, seed0, rfs, max_steps, compact, fused_masks):
+        self.envs, self.selfplay, self.side, self.emulated = np.asarray(envs), selfplay, side, emulated
         n = len(envs) // 2 if selfplay else len(envs)
-        self.n = n
+        self.n, self.E = n, len(envs)
         same = all(m is maps[0] for m in maps)
         scripted = spec is not None and spec.policy >= M.POLICY_WORKER_RUSH
         self.b = M.BatchedGameState(utt, maps[0] if same else maps, n, device=device, partial_obs=partial_obs, scripted_ai=scripted)
@@ -147,10 +161,81 @@ class _Group:
         self.info = _device_array((n, 2, 12), np.int32, emulated)
         b.set_info_output(self.info)
         self.players = [0, 1] if selfplay else [side]
-        self.obs = {p: _device_array((n, b.num_planes, b.height, b.width), np.int32, emulated) for p in self.players}
-        b.set_observation_outputs(self.obs.get(0), self.obs.get(1))  # every step() leaves the new observations in self.obs
+        self.contiguous = bool((np.diff(self.envs) == 1).all()) if len(envs) > 1 else True
+        done_mode = getattr(rfs[0], "DONE_MODE", None) if rfs else 3
+        # fast path: fused outputs in environment order + auto-reset inside the step launch
+        self.fast = (not partial_obs) and done_mode is not None
+        self.obs_dtype = np.uint8 if compact else np.int32
+        self.fused_masks = bool(fused_masks) and self.fast
+        shape = (b.num_planes, b.height, b.width)
+        if self.fast:
+            self.obs_dev = _device_array((self.E,) + shape, self.obs_dtype, emulated)
+            self.obs_host, self._obs_pin = _host_array((self.E,) + shape, self.obs_dtype, emulated)
+            self.mask_dev = self.mask_host = self._mask_pin = None
+            if self.fused_masks:
+                mshape = (self.E, b.height, b.width, (b.mask_width + 7) // 8)
+                self.mask_dev = _device_array(mshape, np.uint8, emulated)
+                self.mask_host, self._mask_pin = _host_array(mshape, np.uint8, emulated)
+            b.set_output_layout(self.obs_dev, self.mask_dev, interleaved=selfplay, side=side)
+            b.set_vec_autoreset(done_mode, max_steps)
+            self.res_dev = _device_array((n, 4), np.int32, emulated)
+            self.res_host, self._res_pin = _host_array((n, 4), np.int32, emulated)
+            self.info_host, self._info_pin = _host_array((n, 2, 12), np.int32, emulated)
+            self._stream = None
+            if not emulated:
+                import torch
+                from . import _ffi
+                self._stream = torch.cuda.ExternalStream(_ffi.lib().mrts_batch_stream(b._h), device=torch.device("cuda", device))
+        else:
+            self.obs = {p: _device_array((n,) + shape, np.int32, emulated) for p in self.players}
+            b.set_observation_outputs(self.obs.get(0), self.obs.get(1))  # every step() leaves the new observations in self.obs
         self.steps = np.zeros(n, dtype=np.int64)
 
+    # -- fast path -------------------------------------------------------------------------------------------------------
+    def stage_and_step(self, action):
+        """Actions in (one host -> device copy), one step launch, results / reward facts / observations (/ masks) out -- all queued on the
+        batch's stream without waiting."""
+        b = self.b
+        block = action[self.envs[0]:self.envs[-1] + 1] if self.contiguous else np.ascontiguousarray(action[self.envs])
+        if self.selfplay:
+            b.set_actions_interleaved(block, fill_none_duration=1, async_copy=True)
+        else:
+            b.set_actions(self.side, block, fill_none_duration=1)
+        b.step(1, NO_CAP)
+        self._block_keepalive = block
+        if self.emulated:
+            b.results(self.res_host)
+            self.info_host[...] = self.info
+            self.obs_host[...] = self.obs_dev
+            if self.fused_masks:
+                self.mask_host[...] = self.mask_dev
+            return
+        import torch
+        b.results(self.res_dev)  # a device -> device copy of what the step kernel left
+        with torch.cuda.stream(self._stream):
+            self._res_pin.copy_(self.res_dev, non_blocking=True)
+            self._info_pin.copy_(self.info, non_blocking=True)
+            self._obs_pin.copy_(self.obs_dev, non_blocking=True)
+            if self.fused_masks:
+                self._mask_pin.copy_(self.mask_dev, non_blocking=True)
+
+    def download_observations(self):
+        """After a reset: observations (and masks) of the current state."""
+        b = self.b
+        for p in self.players:
+            o = b.observe(p, self.obs_dtype)  # host array [n][C][H][W]
+            if self.selfplay:
+                self.obs_host[p::2] = o
+            else:
+                self.obs_host[...] = o
+            if self.fused_masks:
+                mk = b.masks(p, "bits")
+                if self.selfplay:
+                    self.mask_host[p::2] = mk
+                else:
+                    self.mask_host[...] = mk
+
+    # -- host-driven path (partially observable batches, custom reward classes) --------------------------------------------
     def observe_all(self):
         for p in self.players:
             self.b.observe(p, np.int32, out=self.obs[p])
@@ -162,30 +247,34 @@ class _Group:
 
 class JNIGridnetVecClient:
     def __init__(self, a_num_selfplayenvs, a_num_envs, a_max_steps, a_rfs, a_micrortsPath, a_mapPaths, a_ai2s, a_utt, partial_obs=False,
-                 device=0, seed=0):
+                 device=0, seed=0, compact=False, fused_masks=None):
         from . import _ffi
         assert a_num_selfplayenvs % 2 == 0, "self-play environments come in pairs"
         self.maxSteps, self.utt, self.rfs, self.partialObs, self.mapPaths = a_max_steps, a_utt, list(a_rfs), partial_obs, list(a_mapPaths)
         self.num_selfplay, self.num_envs = a_num_selfplayenvs, a_num_envs
+        self.compact = bool(compact)
+        self.fused_masks = self.compact if fused_masks is None else bool(fused_masks)
         s1 = a_num_selfplayenvs + a_num_envs
         assert len(self.mapPaths) >= s1 and len(a_ai2s or []) >= a_num_envs
         emulated = "emu" in os.path.basename(getattr(_ffi.lib(), "_name", "") or "")
         cache = {}
 
         def load(path):
+            if isinstance(path, M.PhysicalGameState):
+                return path
             full = os.path.join(a_micrortsPath, path) if a_micrortsPath else path
             if full not in cache:
                 cache[full] = M.PhysicalGameState.load(full, a_utt)
             return cache[full]
 
+        self._device, self._emulated, self._seed, self._load = device, emulated, seed, load
         self.groups = []
         if a_num_selfplayenvs:
             envs = list(range(a_num_selfplayenvs))
             maps = [load(self.mapPaths[i * 2]) for i in range(a_num_selfplayenvs // 2)]
-            self.groups.append(_Group(a_utt, maps, envs, True, None, 0, partial_obs, device, emulated, seed))
+            self.groups.append(self._make_group(maps, envs, True, None, 0))
         self._bot_specs = list(a_ai2s or [])
         self._bot_groups = {}  # built lazily in reset(): the agent's side comes with `players`
-        self._device, self._emulated, self._seed, self._load = device, emulated, seed, load
         b0 = self.groups[0].b if self.groups else None
         self.observation = None
         self.reward = np.zeros((s1, len(self.rfs)), dtype=np.float64)
@@ -193,6 +282,11 @@ class JNIGridnetVecClient:
         self.responses = Responses(None, None, None)
         self._s1 = s1
         self._shape = None if b0 is None else (b0.num_planes, b0.height, b0.width)
+        self._packed = None
+
+    def _make_group(self, maps, envs, selfplay, spec, side):
+        return _Group(self.utt, maps, envs, selfplay, spec, side, self.partialObs, self._device, self._emulated, self._seed, self.rfs,
+                      self.maxSteps, self.compact, self.fused_masks)
 
     # ---------------------------------------------------------------------------------------------------------------
     def _build_bot_groups(self, players):
@@ -204,16 +298,33 @@ class JNIGridnetVecClient:
         for (skey, side), envs in keyed.items():
             spec = self._bot_specs[envs[0] - self.num_selfplay]
             maps = [self._load(self.mapPaths[e]) for e in envs]
-            g = _Group(self.utt, maps, envs, False, spec, side, self.partialObs, self._device, self._emulated, self._seed)
+            g = self._make_group(maps, envs, False, spec, side)
             self._bot_groups[(skey, side)] = g
             self.groups.append(g)
         b0 = self.groups[0].b
         self._shape = (b0.num_planes, b0.height, b0.width)
 
+    def _single(self):
+        """The one group that covers every environment in order, if there is one: the client's arrays are then that group's."""
+        g = self.groups[0] if len(self.groups) == 1 else None
+        return g if g is not None and g.fast and g.E == self._s1 and g.contiguous else None
+
     def _gather_observations(self):
+        one = self._single()
+        if one is not None:
+            self.observation = one.obs_host
+            self._packed = one.mask_host
+            return
         if self.observation is None:
-            self.observation = np.zeros((self._s1,) + self._shape, dtype=np.int32)
+            self.observation = np.zeros((self._s1,) + self._shape, dtype=np.uint8 if self.compact else np.int32)
         for g in self.groups:
+            if g.fast:
+                self.observation[g.envs] = g.obs_host
+                if g.fused_masks:
+                    if self._packed is None:
+                        self._packed = np.zeros((self._s1,) + g.mask_host.shape[1:], dtype=np.uint8)
+                    self._packed[g.envs] = g.mask_host
+                continue
             o = g.observations()
             if g.selfplay:
                 self.observation[g.envs[0::2]] = o[0]
@@ -227,7 +338,10 @@ class JNIGridnetVecClient:
         for g in self.groups:
             g.b.reset(g.seeds)
             g.steps[:] = 0
-            g.observe_all()
+            if g.fast:
+                g.download_observations()
+            else:
+                g.observe_all()
         self._gather_observations()
         self.reward[:] = 0
         self.done[:] = False
@@ -235,9 +349,13 @@ class JNIGridnetVecClient:
         return self.responses
 
     def gameStep(self, action, players):
-        action = np.ascontiguousarray(action, dtype=np.int32)
+        if not isinstance(action, np.ndarray) or action.dtype != np.int32 or not action.flags["C_CONTIGUOUS"]:
+            action = np.ascontiguousarray(action, dtype=np.int32)
         assert action.ndim == 3 and action.shape[0] == self._s1 and action.shape[2] == 8, "action = [envs][k][8] vector actions"
         for g in self.groups:
+            if g.fast:
+                g.stage_and_step(action)
+                continue
             b = g.b
             if g.selfplay:
                 b.set_actions(0, np.ascontiguousarray(action[g.envs[0::2]]), fill_none_duration=1)
@@ -247,8 +365,11 @@ class JNIGridnetVecClient:
             b.step(1, NO_CAP)
         for g in self.groups:
             b = g.b
-            res = b.results()
-            info = _host(g.info)
+            if g.fast:
+                b.sync()
+                res, info = g.res_host, g.info_host
+            else:
+                res, info = b.results(), _host(g.info)
             g.steps += 1
             sides = [(0, g.envs[0::2]), (1, g.envs[1::2])] if g.selfplay else [(g.side, g.envs)]
             for side, envs in sides:
@@ -257,6 +378,12 @@ class JNIGridnetVecClient:
                     self.reward[envs, j] = r
                     self.done[envs, j] = d
             # auto-reset (JNIGridnetVecClient.java:244-262,272-286): terminal reward/done are kept, done[0] is forced
+            if g.fast:
+                finished = (res[:, 2] & 2) != 0  # the step kernel restarted these games before it wrote their observations
+                if finished.any():
+                    for side, envs in sides:
+                        self.done[np.asarray(envs)[finished], 0] = True
+                continue
             first = g.envs[0::2] if g.selfplay else g.envs
             finished = self.done[first, 0] | (g.steps >= self.maxSteps)
             if finished.any():
@@ -284,6 +411,12 @@ class JNIGridnetVecClient:
                     out = np.zeros((self._s1,) + m.shape[1:], dtype=np.int32)
                 out[g.envs] = m
         return out
+
+    def getMasksPacked(self):
+        """The masks of getMasks bit-packed, [envs][H][W][(mask width + 7) // 8] uint8 (element j of a cell in bit j & 7 of byte j >> 3),
+        as the last reset / gameStep left them -- needs fused_masks (implied by compact=True): they arrive with the observations."""
+        assert self.fused_masks and self._packed is not None, "construct the client with fused_masks=True (or compact=True)"
+        return self._packed
 
     def close(self):
         for g in self.groups:

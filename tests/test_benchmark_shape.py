@@ -68,13 +68,21 @@ def test_cfg5_fused_observations_and_masks_64x64(backend, maps, dtype):
     b.set_observation_outputs(o0, o1)
     mb = (b.mask_width + 7) // 8
     assert b.mask_width == 79
+    # the configuration bench.py --workload obs --with-masks launches: one kernel per step writes both observations and both masks
+    f0, f1 = _device_buffer(backend, (n, m["h"], m["w"], mb), np.uint8), _device_buffer(backend, (n, m["h"], m["w"], mb), np.uint8)
+    b.set_mask_outputs(f0, f1)
     mask_games = list(range(n)) if backend == "emu" else list(range(0, n, 4))
     for it in range(steps):
         b.step(1, 3000)
         b.sync()
         a = [_to_numpy(o0), _to_numpy(o1)]
         check_masks = it % 10 == 0 or it == steps - 1
+        launches = b.launch_count
         mk_bits = [b.masks(pl, "bits") for pl in (0, 1)]
+        fused = [_to_numpy(f0), _to_numpy(f1)]
+        for pl in (0, 1):
+            assert (fused[pl] == mk_bits[pl]).all(), "fused masks differ from mrts_batch_masks at step %d player %d" % (it, pl)
+        assert b.launch_count == launches + 2
         mk_dense = [b.masks(pl, np.uint8) for pl in (0, 1)] if check_masks else None
         for g, og in enumerate(games):
             if not (og.gameover and og.time > 0):

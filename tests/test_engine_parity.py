@@ -219,6 +219,10 @@ def test_fused_step_observations(backend, maps, key, dtype, external):
     shape = (n, 6, m["h"], m["w"])
     o0, o1 = _device_buffer(backend, shape, dtype), _device_buffer(backend, shape, dtype)
     b.set_observation_outputs(o0, o1)
+    # ... and the fused bit-packed action masks (mrts_batch_set_mask_outputs)
+    mshape = (n, m["h"], m["w"], (b.mask_width + 7) // 8)
+    k0, k1 = _device_buffer(backend, mshape, np.uint8), _device_buffer(backend, mshape, np.uint8)
+    b.set_mask_outputs(k0, k1)
     games = []
     for g in range(n):
         og = O.Game(outt, m)
@@ -228,10 +232,15 @@ def test_fused_step_observations(backend, maps, key, dtype, external):
         b.step(23, 3000)
         b.sync()
         a0, a1 = _to_numpy(o0), _to_numpy(o1)
+        mk = [_to_numpy(k0), _to_numpy(k1)]
         for g, og in enumerate(games):
             og.run(O.AI_RANDOM_BIASED, None, O.AI_PASSIVE if external else O.AI_RANDOM_BIASED, None, 23, 3000)
             assert (a0[g] == og.observe(0).astype(dtype)).all(), (key, it, g)
             assert (a1[g] == og.observe(1).astype(dtype)).all(), (key, it, g)
+            for pl in (0, 1):
+                ref_m = og.masks(pl)
+                assert (np.unpackbits(mk[pl][g], axis=-1, bitorder="little")[..., :ref_m.shape[-1]] == ref_m).all(), "fused masks %s it %d game %d player %d" % (key, it, g, pl)
+    b.set_mask_outputs(None, None)
     # player 1 only, then disabled: untouched buffers stay untouched
     b.set_observation_outputs(None, o1)
     before = _to_numpy(o0).copy()

@@ -141,11 +141,13 @@ def random_actions(rng, og, player, w, h, k):
     return rows
 
 
-@pytest.mark.parametrize("key,n_sp,bots,max_steps", [
-    ("8x8/basesWorkers8x8", 4, ["RandomBiasedAI", "PassiveAI", "WorkerRush"], 60),
-    ("16x16/basesWorkers16x16", 2, ["LightRush", "RandomBiasedAI"], 150),
+@pytest.mark.parametrize("key,n_sp,bots,max_steps,compact", [
+    ("8x8/basesWorkers8x8", 4, ["RandomBiasedAI", "PassiveAI", "WorkerRush"], 60, False),
+    ("16x16/basesWorkers16x16", 2, ["LightRush", "RandomBiasedAI"], 150, False),
+    ("8x8/basesWorkers8x8", 6, [], 45, True),                        # one self-play group: the client's arrays are the group's pinned arrays
+    ("16x16/basesWorkers16x16", 2, ["WorkerRush", "PassiveAI"], 80, True),
 ])
-def test_vec_client_matches_reference_flow(backend, maps, tmp_path, key, n_sp, bots, max_steps):
+def test_vec_client_matches_reference_flow(backend, maps, tmp_path, key, n_sp, bots, max_steps, compact):
     m = maps[key]
     path = tmp_path / "map.xml"
     path.write_text(P.map_to_xml(m))
@@ -156,7 +158,7 @@ def test_vec_client_matches_reference_flow(backend, maps, tmp_path, key, n_sp, b
     specs = [getattr(ai, b)(utt) for b in bots]
     kinds = {"RandomBiasedAI": O.AI_RANDOM_BIASED, "PassiveAI": O.AI_PASSIVE, "WorkerRush": O.AI_WORKER_RUSH, "LightRush": O.AI_LIGHT_RUSH}
     seed = 123
-    vc = JNIGridnetVecClient(n_sp, n_envs, max_steps, rfs, "", [str(path)] * s1, specs, utt, partial_obs=False, seed=seed)
+    vc = JNIGridnetVecClient(n_sp, n_envs, max_steps, rfs, "", [str(path)] * s1, specs, utt, partial_obs=False, seed=seed, compact=compact)
     players = [0] * s1
     resp = vc.reset(players)
     ref_sp = [RefSelfPlay(outt, m, seed + 2 * i) for i in range(n_sp // 2)]
@@ -165,6 +167,10 @@ def test_vec_client_matches_reference_flow(backend, maps, tmp_path, key, n_sp, b
 
     def check_obs_masks(ctx):
         mk = vc.getMasks(0)
+        if compact:  # uint8 observations; the bit-packed masks that came with them equal the dense ones
+            assert resp.observation.dtype == np.uint8
+            packed = vc.getMasksPacked()
+            assert (np.unpackbits(packed, axis=-1, bitorder="little")[..., :mk.shape[-1]] == mk).all(), (ctx, "packed masks")
         for i, e in enumerate(ref_sp):
             for pl in (0, 1):
                 assert (resp.observation[2 * i + pl] == e.og.observe(pl)).all(), (ctx, "obs selfplay", i, pl)
