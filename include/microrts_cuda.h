@@ -19,6 +19,7 @@
  */
 #ifndef MICRORTS_CUDA_H
 #define MICRORTS_CUDA_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -283,6 +284,9 @@ int mrts_batch_import(mrts_batch *, int64_t first, int64_t count, const mrts_sta
 /* light per-game result: out[g] = {time, winner(-1 none), gameover, error bits} */
 int mrts_batch_results(mrts_batch *, int32_t *out /* [n_games][4] */, int on_device);
 
+/* Queue a device -> host copy behind the batch's pending work on its stream and return at once (mrts_batch_sync waits): how a host
+ * fetches the fused outputs (observations, masks, reward facts) into its own -- ideally pinned -- arrays without a second stream. */
+int mrts_batch_copy_to_host(mrts_batch *, void *host_dst, const void *device_src, size_t bytes);
 /* counters since the last reset: {wins_p0, wins_p1, draws, games_finished, cycles, decisions, unit_cycles, errors} */
 int mrts_batch_stats(mrts_batch *, int64_t out[8]);
 /* Symbol of the step kernel the batch launched last (which of the specialised / fixed-layout copies ran), for benchmark reports. */

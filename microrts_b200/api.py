@@ -410,6 +410,12 @@ class BatchedGameState:
         _check(_ffi.lib().mrts_batch_results(self._h, p, dev))
         return out
 
+    def copy_to_host(self, host, dev):
+        """Queue an asynchronous device -> host copy of `dev` (device tensor) into `host` (numpy array, ideally pinned) on the batch's
+        stream; sync() waits for it."""
+        assert host.nbytes == dev.numel() * dev.element_size() if hasattr(dev, "numel") else host.nbytes == dev.nbytes
+        _check(_ffi.lib().mrts_batch_copy_to_host(self._h, host.ctypes.data, _ptr(dev)[0], host.nbytes))
+
     def stats(self):
         out = np.zeros(8, dtype=np.int64)
         _check(_ffi.lib().mrts_batch_stats(self._h, out.ctypes.data))

@@ -1377,6 +1377,14 @@ DEVN int run_policy_po(Game &g, const StepParams &p, int player, int pn) {
 
 DEV int run_policy(Game &g, const StepParams &p, long long gi, int player, int pn, bool first_iter) {
     const int pol = p.policy[player];
+#ifdef MRTS_TU_RUSH_ONLY
+    { // the lean copy: both players run a scripted rush with A* (microrts_cuda.cu launches it for nothing else)
+        int n0 = pn;
+        pn = policy_scripted(g, player, pol, 0, pn);
+        legality_pass(g, n0, pn);
+        return pn;
+    }
+#endif
 #ifndef MRTS_TU_RUSH_ONLY
     if (p.po_policies && (pol == POL_RANDOM_BIASED || POL_IS_SCRIPTED(pol))) return run_policy_po(g, p, player, pn);
 #endif
@@ -1543,7 +1551,11 @@ DEVN void info_distance(Game &g, const StepParams &p, int player, int32_t *o, bo
 // Game.start loop body (rts/Game.java:126-140) with exact skipping of cycles in which nothing can happen.
 DEVN void run_game(Game &g, const StepParams &p, long long gi, WarpStats &ws) {
     int status = g.hdr()[H_STATUS];
+#ifdef MRTS_TU_RUSH_ONLY
+    int32_t *const io = nullptr; // the lean copy carries no reward facts, no sequential issue and no general issue()
+#else
     int32_t *io = p.info_out ? p.info_out + gi * (2 * MRTS_INFO_WORDS) : nullptr;
+#endif
     if (io) { if (g.lane < 2 * MRTS_INFO_WORDS) io[g.lane] = 0; __syncwarp(); }
     if (status & ST_OVER) return;
     int t0 = g.hdr()[H_TIME];
@@ -1554,7 +1566,12 @@ DEVN void run_game(Game &g, const StepParams &p, long long gi, WarpStats &ws) {
     if (io) { info_distance(g, p, 0, io, true); info_distance(g, p, 1, io + MRTS_INFO_WORDS, true); }
     // device policies emit self-consistent lists; under CANCEL_BOTH they can be issued in parallel (issue_policy_lists)
     // (not under MRTS_FLAG_PO_POLICIES: a list built on a partial view may collide with a hidden unit's reservation)
-    bool fast_issue = p.conflict == 1 && p.policy[0] != POL_EXTERNAL && p.policy[1] != POL_EXTERNAL && !p.po_policies;
+#ifdef MRTS_TU_RUSH_ONLY
+    const bool fast_issue = true, seq_issue = false;
+#else
+    const bool fast_issue = p.conflict == 1 && p.policy[0] != POL_EXTERNAL && p.policy[1] != POL_EXTERNAL && !p.po_policies;
+    const bool seq_issue = p.sequential_issue != 0;
+#endif
     unsigned long long decisions = 0, ucyc = 0;
     #pragma unroll 1
     for (;;) {
@@ -1562,17 +1579,21 @@ DEVN void run_game(Game &g, const StepParams &p, long long gi, WarpStats &ws) {
         if (time >= tlimit) break;
         int pn0 = run_policy(g, p, gi, 0, 0, first);
         if (io) info_count(g, p, 0, 0, pn0, io);
-        if (p.sequential_issue) issue_pending(g, 0, pn0);
+        if (seq_issue) issue_pending(g, 0, pn0);
         int pn1 = run_policy(g, p, gi, 1, pn0, first);
         if (io) info_count(g, p, 1, pn0, pn1, io + MRTS_INFO_WORDS);
         first = false;
-        if (p.sequential_issue) issue_pending(g, pn0, pn1);
+        if (seq_issue) issue_pending(g, pn0, pn1);
         else if (fast_issue) issue_policy_lists(g, pn0, pn1);
         else { issue_pending(g, 0, pn0); issue_pending(g, pn0, pn1); }
         decisions += pn1;
         int mrt = min_ready_time(g);
         int tn = time + 1; if (!over && mrt > tn) tn = mrt;
+#ifdef MRTS_TU_RUSH_ONLY
+        if (tn > time + 1) {
+#else
         if (tn > time + 1 && p.scripted) {
+#endif
             // Cycles time+1 .. tn-1 are skipped because nothing can change in them, but the reference still calls getAction
             // in each.  For the scripted AIs the FIRST of those calls is not a no-op: translateActions drops the entries that
             // completed while being executed in this cycle (Train), which decides their position in the map when they are
@@ -2098,6 +2119,11 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
     for (int i = tid; i < MRTS_CONST_WORDS; i += nthreads) cst[i] = p.cst[i];
     __syncthreads();
     constexpr bool FIXED = FW > 0;
+#ifdef MRTS_TU_RUSH_ONLY
+    constexpr bool LEAN = true; // MODE_GAME with scripted rushes only: no other mode, no fused outputs, no in-kernel environment reset
+#else
+    constexpr bool LEAN = false;
+#endif
     constexpr SmemLayout LC = mrts_smem_layout(FIXED ? FW : 8, FIXED ? FH : 8, FIXED ? FCAP : 32, 0, 0, 0);
     const SmemLayout &L = FIXED ? LC : p.L;
     const int pW = FIXED ? FW : p.W, pH = FIXED ? FH : p.H, pcap = FIXED ? FCAP : p.cap, puw = FIXED ? MRTS_UNIT_WORDS_CORE : p.uw;
@@ -2109,7 +2135,7 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
     Game g;
     g_bind(g, region, L, pW, pH, pcap, lane, p.conflict, p.scripted,
            p.scripted == 2 ? p.astar_scratch + ((long long)bid * wpc + warp) * p.astar_stride : nullptr);
-    if (KERNEL == KERNEL_GENERIC && p.scripted) { // pathfinding scratch: no stale marks, all buckets empty, generation 0
+    if (KERNEL == KERNEL_GENERIC && (LEAN || p.scripted)) { // pathfinding scratch: no stale marks, all buckets empty, generation 0
         #pragma unroll 1
         for (int i = lane; i < (p.W + 2) * (p.H + 2); i += 32) g.as_mark[i] = 0;
         #pragma unroll 1
@@ -2144,7 +2170,7 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
         g.grid_tmpl = blob;
         int32_t *ghdr = p.hdr + gi * MRTS_HDR_WORDS;
         uint32_t *gun = p.units + gi * (long long)puw * pcap;
-        g_load(g, ghdr, gun, KERNEL != KERNEL_ROLLOUT && p.mode == MODE_GAME && p.auto_reset, p.max_cycles);
+        g_load(g, ghdr, gun, KERNEL != KERNEL_ROLLOUT && (LEAN || p.mode == MODE_GAME) && p.auto_reset, p.max_cycles);
         stat_add(ws, lane, STAT_IO_READ, (unsigned long long)(MRTS_HDR_WORDS * 4 + puw * 4 * g.hdr()[H_NUNITS]));
         if (KERNEL == KERNEL_ROLLOUT) { run_rollout(g, p, item, ws); stat_add(ws, lane, STAT_IO_WRITE, 8); continue; } // the batch itself is not modified
         int err0 = g.hdr()[H_ERR];
@@ -2163,14 +2189,14 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
             }
         }
         if (KERNEL == KERNEL_FAST || KERNEL == KERNEL_FAST_OBS) run_game_fast(g, p, ws);
-        else if (p.mode == MODE_GAME) run_game(g, p, gi, ws);
+        else if (LEAN || p.mode == MODE_GAME) run_game(g, p, gi, ws);
         else if (p.mode == MODE_CYCLE_ONLY) run_cycles_only(g, p.t_target ? p.t_target[gi] : g.hdr()[H_TIME] + p.n_cycles);
         else if (p.mode == MODE_ISSUE_ONLY) run_issue_only(g, p, gi);
         else if (p.mode == MODE_OBSERVE) { observe_game(g, p, gi); stat_add(ws, lane, STAT_IO_WRITE, obs_bytes_per_game(g.W, g.H, p.partial_obs ? 8 : 6, p.out_dtype)); continue; }
         else if (p.mode == MODE_PATHFIND) { pathfind_game(g, p, gi); continue; }
         else { masks_game(g, p, gi); stat_add(ws, lane, STAT_IO_WRITE, mask_bytes_per_game(g.W, g.H, 1 + 6 + 16 + p.n_types + (2 * p.max_range + 1) * (2 * p.max_range + 1), p.out_dtype)); continue; }
         if (g.hdr()[H_ERR] != err0) stat_add(ws, g.lane, STAT_ERRORS, 1);
-        if (p.mode == MODE_GAME && p.results_out) {
+        if ((LEAN || p.mode == MODE_GAME) && p.results_out) {
             // what mrts_batch_results reports (winner() / gameover(), PhysicalGameState.java:334-387), written here so that the
             // host can fetch it with a plain copy: a results kernel would have to wait for SM slots behind whatever persistent
             // kernel another batch has running
@@ -2180,7 +2206,7 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
             c0 = __reduce_add_sync(FULLM, c0); c1 = __reduce_add_sync(FULLM, c1);
             int4 r;
             r.x = g.hdr()[H_TIME]; r.y = (c0 > 0 && c1 == 0) ? 0 : ((c1 > 0 && c0 == 0) ? 1 : -1); r.z = (c0 == 0 || c1 == 0) ? 1 : 0; r.w = g.hdr()[H_ERR];
-            if (KERNEL == KERNEL_GENERIC && p.vec_reset) {
+            if (!LEAN && KERNEL == KERNEL_GENERIC && p.vec_reset) {
                 // JNIGridnetVecClient.gameStep (src/tests/JNIGridnetVecClient.java:244-262,272-286): an environment whose first reward
                 // function reports done, or that has run max_steps steps, is reset inside the same gameStep -- the step's results and
                 // reward facts are the terminal ones, the observation (and masks) returned are the restarted game's.  The static
@@ -2205,7 +2231,7 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
         }
         g_store(g, ghdr, gun);
         stat_add(ws, lane, STAT_IO_WRITE, (unsigned long long)(MRTS_HDR_WORDS * 4 + puw * 4 * g.hdr()[H_NUNITS] + (p.mode == MODE_GAME && p.results_out ? 16 : 0)));
-        if (KERNEL == KERNEL_FAST_OBS || (KERNEL == KERNEL_GENERIC && p.mode == MODE_GAME)) {
+        if (KERNEL == KERNEL_FAST_OBS || (!LEAN && KERNEL == KERNEL_GENERIC && p.mode == MODE_GAME)) {
             #pragma unroll 1
             for (int pl = 0; pl < 2; pl++)
                 if (p.obs_out[pl]) {

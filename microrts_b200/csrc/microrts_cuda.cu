@@ -291,8 +291,11 @@ static int launch_step(mrts_batch *b, StepParams &p) {
     const int fv = b->fixed_of[kernel];
     const bool gfx = kernel == KERNEL_GENERIC && b->generic_fixed_fn;
     // the rush-only copy: a game step in which neither player runs a defense, WorkerRushPlusPlus or a PO rush
-    auto plain = [](int pol) { return pol <= MRTS_POLICY_RANGED_RUSH; };
-    const bool rush = gfx && b->generic_rush_fn && p.mode == MODE_GAME && plain(p.policy[0]) && plain(p.policy[1]);
+    // the lean rush-only copy: a game step in which both players run a scripted rush with A* under CANCEL_BOTH, nothing else asked for
+    auto is_rush = [](int pol) { return pol >= MRTS_POLICY_WORKER_RUSH && pol <= MRTS_POLICY_RANGED_RUSH; };
+    const bool rush = gfx && b->generic_rush_fn && p.mode == MODE_GAME && is_rush(p.policy[0]) && is_rush(p.policy[1]) &&
+                      p.pathfinder[0] == MRTS_PF_ASTAR && p.pathfinder[1] == MRTS_PF_ASTAR && p.conflict == MRTS_CANCEL_BOTH && !p.info_out &&
+                      !p.sequential_issue && !p.vec_reset && !p.obs_out[0] && !p.obs_out[1] && !p.mask_out[0] && !p.mask_out[1];
     const mrts_batch::Plan &pl = rush ? b->rush_plan : ((fv >= 0 || gfx) ? b->fixed_plan[kernel] : b->plan[kernel]);
     p.L = kernel == KERNEL_GENERIC ? b->L : b->Lfast;
     int threads = pl.wpc * 32;
@@ -881,6 +884,17 @@ int mrts_batch_results(mrts_batch *b, int32_t *out, int on_device) {
     if (ck(cudaGetLastError())) return fail(MRTS_E_CUDA, std::string("results launch: ") + dev_errstr());
 #endif
     if (!on_device && dev_d2h(out, d_out, (size_t)b->n * 16, b->stream)) return fail(MRTS_E_CUDA, dev_errstr());
+    return MRTS_OK;
+}
+
+int mrts_batch_copy_to_host(mrts_batch *b, void *host_dst, const void *device_src, size_t bytes) {
+    if (!b || !host_dst || !device_src) return fail(MRTS_E_ARG, "mrts_batch_copy_to_host: null argument");
+    if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
+#ifdef MRTS_EMU
+    memcpy(host_dst, device_src, bytes);
+#else
+    if (ck(cudaMemcpyAsync(host_dst, device_src, bytes, cudaMemcpyDeviceToHost, b->stream))) return fail(MRTS_E_CUDA, dev_errstr());
+#endif
     return MRTS_OK;
 }
 

@@ -128,8 +128,9 @@ DEV int iabs(int v) { return v < 0 ? -v : v; }
 // (tx, ty), or -1 (null).  ru = target cells of the desires [0, nd) in the pending list.  Called by the whole warp with
 // uniform arguments; the search state is uniform, the four neighbours of the expanded node are examined by lanes 0..3 and
 // pushed in the reference's order (up, right, down, left) by lane 0.
-template <bool SM>
+template <bool SM, int KIND = -1> // KIND >= 0: the search kind as a compile-time constant (the other one is not compiled in)
 DEVN int pf_find_t(Game &g, int kind, int s, int tx, int ty, int range, int nd) {
+    if (KIND >= 0) kind = KIND;
     const PfArr A = pf_arrays<SM>(g);
     const int lane = g.lane;
     __syncwarp();
@@ -279,6 +280,9 @@ DEVN int pf_greedy(Game &g, int s, int tx, int ty, int range, int nd) {
 
 // range < 0: PathFinding.findPath (A* and BFS: findPathToPositionInRange with range 0)
 DEV int pf_find(Game &g, int kind, int s, int tx, int ty, int range, int nd) {
+#ifdef MRTS_TU_RUSH_ONLY
+    return pf_find_t<true, 0>(g, 0, s, tx, ty, range < 0 ? 0 : range, nd); // the lean copy: A*, scratch in shared memory
+#endif
     if (kind == 2) return pf_greedy(g, s, tx, ty, range, nd);
     if (range < 0) range = 0;
     return g.as_sm ? pf_find_t<true>(g, kind, s, tx, ty, range, nd) : pf_find_t<false>(g, kind, s, tx, ty, range, nd);

@@ -181,11 +181,6 @@ class _Group:
             self.res_dev = _device_array((n, 4), np.int32, emulated)
             self.res_host, self._res_pin = _host_array((n, 4), np.int32, emulated)
             self.info_host, self._info_pin = _host_array((n, 2, 12), np.int32, emulated)
-            self._stream = None
-            if not emulated:
-                import torch
-                from . import _ffi
-                self._stream = torch.cuda.ExternalStream(_ffi.lib().mrts_batch_stream(b._h), device=torch.device("cuda", device))
         else:
             self.obs = {p: _device_array((n,) + shape, np.int32, emulated) for p in self.players}
             b.set_observation_outputs(self.obs.get(0), self.obs.get(1))  # every step() leaves the new observations in self.obs
@@ -210,14 +205,12 @@ class _Group:
             if self.fused_masks:
                 self.mask_host[...] = self.mask_dev
             return
-        import torch
         b.results(self.res_dev)  # a device -> device copy of what the step kernel left
-        with torch.cuda.stream(self._stream):
-            self._res_pin.copy_(self.res_dev, non_blocking=True)
-            self._info_pin.copy_(self.info, non_blocking=True)
-            self._obs_pin.copy_(self.obs_dev, non_blocking=True)
-            if self.fused_masks:
-                self._mask_pin.copy_(self.mask_dev, non_blocking=True)
+        b.copy_to_host(self.res_host, self.res_dev)  # all queued on the batch's own stream (mrts_batch_copy_to_host); sync() waits
+        b.copy_to_host(self.info_host, self.info)
+        b.copy_to_host(self.obs_host, self.obs_dev)
+        if self.fused_masks:
+            b.copy_to_host(self.mask_host, self.mask_dev)
 
     def download_observations(self):
         """After a reset: observations (and masks) of the current state."""

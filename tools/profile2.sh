@@ -3,7 +3,7 @@
 # 1. the bench command without ncu (must exit 0; its JSON line gives the game-cycles per launch)  2. the launch list
 # 3. one `--set full` capture of the (SKIP+1)-th launch matching REGEX  4. summaries: gpurun_out/LABEL_KEY_ncu_full.txt and an
 #    entry KEY in gpurun_out/traffic_LABEL.json (tools/ncu_summary.py)
-L=$1; K=$2; RX=$3; SKIP=$4; GAMES=$5; shift 6
+L=$1; K=$2; RX=$3; SKIP=$4; GAMES=$5; shift 5; [ "$1" = "--" ] && shift
 CMD="python bench.py --no-cpu-baseline --no-e2e --no-secondary --prewarm-seconds 0 $*"
 O=gpurun_out/${L}_${K}
 $CMD > ${O}_plain.log 2> ${O}_plain.err || { echo "plain run failed ($K)"; tail -5 ${O}_plain.err; exit 1; }
