@@ -281,6 +281,22 @@ typedef struct {
 } mrts_state_host;
 int mrts_batch_export(mrts_batch *, int64_t first, int64_t count, mrts_state_host *out);
 int mrts_batch_import(mrts_batch *, int64_t first, int64_t count, const mrts_state_host *in);
+/* Unit.getUnitActions (src/rts/units/Unit.java:382-522) of every idle unit of `player`, as ORDERED lists -- the order
+ * RandomBiasedAI samples from and PlayerActionGenerator enumerates (src/rts/PlayerActionGenerator.java:56-106) -- together with what the
+ * generator's constructor derives from the state (the resource usage of the assignments in flight, GameState.java:652-664):
+ *   out_hdr[g][8]       choices; resources used by player 0, 1; resources of player 0, 1; positions used; time;
+ *                       bit 0 gameover | (winner + 1) << 1 | bit 3 / bit 4: player 0 / 1 has a unit without an assignment
+ *   out_positions[g][]  (unit capacity entries) linear positions x + y * W reserved by in-flight MOVE / PRODUCE, unit-list order
+ *   out_choices[g][c]   {unit slot, Unit.ID, type | x << 8 | y << 16 | (owner + 1) << 24, number of actions} for the c-th idle unit in
+ *                       unit-list order (at most max_choices are written; out_hdr[g][0] is the full count)
+ *   out_lists[g][c][k]  the k-th action of that unit: type | (direction + 1) << 4 | x << 8 | y << 16 | (unit type + 1) << 24
+ *                       (x, y: the attacked cell; a NONE action lasts none_duration; lists longer than max_actions are cut)
+ * GameState.getPlayerActions / PlayerActionGenerator stay host-side on top of this (microrts_b200/csrc/player_actions.hpp). */
+int mrts_batch_unit_actions(mrts_batch *, int player, int none_duration, int max_choices, int max_actions, int32_t *out_hdr,
+                            int32_t *out_positions, int32_t *out_choices, int32_t *out_lists, int on_device);
+/* cycle() while the game is not over and neither player has a unit without an assignment -- the loop at the head of every MCTS node
+ * (src/ai/mcts/naivemcts/NaiveMCTSNode.java:48-53) */
+int mrts_batch_cycle_to_decision(mrts_batch *);
 /* light per-game result: out[g] = {time, winner(-1 none), gameover, error bits} */
 int mrts_batch_results(mrts_batch *, int32_t *out /* [n_games][4] */, int on_device);
 

@@ -47,7 +47,8 @@ def bind(L):
         "mrts_batch_masks": (i, [vp, i, i, vp, i]), "mrts_batch_mask_width": (i, [vp]),
         "mrts_batch_export": (i, [vp, i64, i64, C.POINTER(StateHost)]),
         "mrts_batch_import": (i, [vp, i64, i64, C.POINTER(StateHost)]),
-        "mrts_batch_results": (i, [vp, vp, i]), "mrts_batch_copy_to_host": (i, [vp, vp, vp, C.c_size_t]), "mrts_batch_stats": (i, [vp, vp]),
+        "mrts_batch_results": (i, [vp, vp, i]), "mrts_batch_cycle_to_decision": (i, [vp]),
+        "mrts_batch_unit_actions": (i, [vp, i, i, i, i, vp, vp, vp, vp, i]), "mrts_batch_copy_to_host": (i, [vp, vp, vp, C.c_size_t]), "mrts_batch_stats": (i, [vp, vp]),
         "mrts_batch_launch_count": (i64, [vp]), "mrts_batch_last_kernel": (C.c_char_p, [vp]), "mrts_batch_io_bytes": (i, [vp, vp]),
         "mrts_nccl_unique_id": (i, [vp]), "mrts_nccl_comm_create": (i, [vp, i, i, i, pvp]), "mrts_nccl_comm_wrap": (i, [vp, i, pvp]),
         "mrts_nccl_comm_destroy": (None, [vp]), "mrts_batch_stats_allreduce": (i, [vp, vp, vp]),

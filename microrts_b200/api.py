@@ -293,6 +293,37 @@ class BatchedGameState:
         p, dev, _k = _ptr(t)
         _check(_ffi.lib().mrts_batch_cycle_to(self._h, p, 0, dev))
 
+    def cycle_to_decision(self):
+        """cycle() until the game is over or some player has a unit without an assignment (the loop at the head of an MCTS node)."""
+        _check(_ffi.lib().mrts_batch_cycle_to_decision(self._h))
+
+    def unit_actions(self, player, none_duration=10, max_choices=None, max_actions=64):
+        """Unit.getUnitActions of every idle unit of `player`, ordered (mrts_batch_unit_actions).  Returns per game a dict
+        {time, gameover, winner, can_act: (p0, p1), resources, resources_used, positions_used, choices: [(slot, id, type, x, y, [actions])]}
+        with actions as (type, parameter, x, y, unit type) tuples like the oracle's (parameter = direction, or the duration of NONE)."""
+        K = max_choices or self.cap
+        hdr = np.zeros((self.n, 8), dtype=np.int32)
+        pos = np.zeros((self.n, self.cap), dtype=np.int32)
+        ch = np.zeros((self.n, K, 4), dtype=np.int32)
+        ls = np.zeros((self.n, K, max_actions), dtype=np.int32)
+        _check(_ffi.lib().mrts_batch_unit_actions(self._h, player, none_duration, K, max_actions, hdr.ctypes.data, pos.ctypes.data, ch.ctypes.data, ls.ctypes.data, 0))
+        out = []
+        for g in range(self.n):
+            h = hdr[g]
+            choices = []
+            for c in range(min(int(h[0]), K)):
+                slot, uid, packed, cnt = [int(v) for v in ch[g, c]]
+                acts = []
+                for k in range(min(cnt, max_actions)):
+                    v = int(ls[g, c, k]) & 0xffffffff
+                    at, d, x, y, ut = v & 15, ((v >> 4) & 15) - 1, (v >> 8) & 255, (v >> 16) & 255, ((v >> 24) & 255) - 1
+                    acts.append((at, none_duration if at == 0 else d, x, y, ut))
+                choices.append((slot, uid, packed & 255, (packed >> 8) & 255, (packed >> 16) & 255, acts))
+            out.append(dict(time=int(h[6]), gameover=bool(h[7] & 1), winner=((int(h[7]) >> 1) & 3) - 1, can_act=(bool(h[7] & 8), bool(h[7] & 16)),
+                            resources=(int(h[3]), int(h[4])), resources_used=(int(h[1]), int(h[2])), positions_used=[int(v) for v in pos[g, :int(h[5])]],
+                            choices=choices))
+        return out
+
     def evaluate(self, eval_fn=0, maxplayer=0, observer=-1):
         """EvaluationFunction.evaluate(maxplayer, 1 - maxplayer, gs) of every game's current state (0 = SimpleSqrtEvaluationFunction3,
         1 = SimpleEvaluationFunction); observer >= 0: of that player's partially observable view."""

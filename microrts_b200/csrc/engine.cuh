@@ -45,7 +45,8 @@ enum { POL_EXTERNAL = 0, POL_PASSIVE = 1, POL_RANDOM_BIASED = 2, POL_WORKER_RUSH
 #define POL_IS_PO_RUSH(p) ((p) >= POL_PO_WORKER_RUSH && (p) <= POL_PO_RANGED_RUSH)
 #define POL_IS_DEFENSE(p) (((p) >= POL_WORKER_DEFENSE && (p) <= POL_RANGED_DEFENSE) || (p) == POL_WORKER_RUSH_PP) // WorkerRushPlusPlus.java = WorkerDefense.java whose melee units always attack
 enum { FMT_VECTOR = 0, FMT_RAW = 1 };
-enum { MODE_GAME = 0, MODE_CYCLE_ONLY = 1, MODE_ISSUE_ONLY = 2, MODE_OBSERVE = 3, MODE_MASKS = 4, MODE_ROLLOUT = 5, MODE_PATHFIND = 6 };
+enum { MODE_GAME = 0, MODE_CYCLE_ONLY = 1, MODE_ISSUE_ONLY = 2, MODE_OBSERVE = 3, MODE_MASKS = 4, MODE_ROLLOUT = 5, MODE_PATHFIND = 6,
+       MODE_UNIT_ACTIONS = 7, MODE_CYCLE_DECISION = 8 };
 enum { ST_OVER = 1, ST_COUNTED = 2 };
 enum { STAT_WINS0 = 0, STAT_WINS1, STAT_DRAWS, STAT_FINISHED, STAT_CYCLES, STAT_DECISIONS, STAT_UNIT_CYCLES, STAT_ERRORS,
        STAT_IO_READ, STAT_IO_WRITE, N_WARP_STATS }; // the last two: bytes of game state / outputs the step kernels read from and wrote to global memory (mrts_batch_io_bytes)
@@ -91,6 +92,9 @@ struct StepParams {
     const int32_t *pf_query;   // [n_games][3]
     int32_t *pf_out;           // [n_games]
     int pf_kind;
+    // MODE_UNIT_ACTIONS: the ordered legal action lists of out_player's idle units + the state's resource usage (mrts_batch_unit_actions)
+    int32_t *ua_hdr, *ua_pos, *ua_choice, *ua_list; // [n][8], [n][cap], [n][K][4], [n][K][ua_max_actions] with K = ua_max_choices
+    int ua_max_choices, ua_max_actions, ua_none_duration;
     // MODE_OBSERVE / MODE_MASKS
     void *out;
     int out_dtype;             // 0 = u8, 1 = i32, 2 = bit-packed (masks only)
@@ -302,20 +306,34 @@ DEV int kind_of(const Game &g, uint32_t w) { // the cell-kind byte of a unit (la
 }
 // Rebuild the cell maps from the unit table: grid (slot+1), kind, resv (in-flight MOVE/PRODUCE targets); claim cleared.
 // with_rdy: also recompute the completion times (after a load; compaction carries them along instead).
-DEV void g_rebuild(Game &g, bool with_rdy) {
-    __syncwarp();
-    { // 16 bytes per lane and iteration; the template loads of several iterations are in flight together
-        uint4 z; z.x = z.y = z.z = z.w = 0;
-        int nq = g.pcw >> 2;
-        #pragma unroll 4
-        for (int i = g.lane; i < nq; i += 32) {
-            uint4 t = ((const uint4 *)g.grid_tmpl)[i];
-            ((uint4 *)g.grid())[i] = t;
-            ((uint4 *)g.kind())[i] = t;
-            ((uint4 *)g.resv())[i] = z;
-            ((uint4 *)g.claim())[i] = z;
-        }
+// 16-byte asynchronous copies global -> shared (LDGSTS): a lane moves four unit slots of one word array per instruction and all of
+// a game's copies are in flight together, so loading a game costs one memory round trip instead of one per word array.
+#ifdef MRTS_EMU
+DEV void cp_async16(void *smem_dst, const void *gsrc) { memcpy(smem_dst, gsrc, 16); }
+DEV void cp_async_wait_all() {}
+#else
+DEV void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+DEV void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+#endif
+// the wall-padded empty grid of the game's map into grid[] and kind[] (asynchronous 16-byte copies: all in flight together, and
+// together with the unit words when a game is loaded), zeros into resv[] and claim[]
+DEV void g_template(Game &g) {
+    uint4 z; z.x = z.y = z.z = z.w = 0;
+    int nq = g.pcw >> 2;
+    #pragma unroll 2
+    for (int i = g.lane; i < nq; i += 32) {
+        cp_async16((uint4 *)g.grid() + i, (const uint4 *)g.grid_tmpl + i);
+        cp_async16((uint4 *)g.kind() + i, (const uint4 *)g.grid_tmpl + i);
+        ((uint4 *)g.resv())[i] = z;
+        ((uint4 *)g.claim())[i] = z;
     }
+}
+DEV void g_rebuild(Game &g, bool with_rdy, bool template_pending = false) {
+    __syncwarp();
+    if (!template_pending) g_template(g);
+    cp_async_wait_all();
     __syncwarp();
     int n = g.hdr()[H_NUNITS];
     #pragma unroll 1
@@ -331,17 +349,6 @@ DEV void g_rebuild(Game &g, bool with_rdy) {
     }
     __syncwarp();
 }
-// 16-byte asynchronous copies global -> shared (LDGSTS): a lane moves four unit slots of one word array per instruction and all of
-// a game's copies are in flight together, so loading a game costs one memory round trip instead of one per word array.
-#ifdef MRTS_EMU
-DEV void cp_async16(void *smem_dst, const void *gsrc) { memcpy(smem_dst, gsrc, 16); }
-DEV void cp_async_wait_all() {}
-#else
-DEV void cp_async16(void *smem_dst, const void *gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-DEV void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
-#endif
 // unit words [0, uw) of slots [0, n) from `src` ([uw][cap] words, 16-byte aligned: cap is a multiple of 4) into the game's table;
 // slots up to the next multiple of 4 come along (never read: every pass over the table stops at nUnits)
 DEV void load_unit_words(Game &g, const uint32_t *src, int n) {
@@ -362,6 +369,7 @@ DEV void g_load(Game &g, const int32_t *ghdr, const uint32_t *gun, bool restart_
     if (g.lane < MRTS_HDR_WORDS) v = ghdr[g.lane];
     const int spec = g.cap < 128 ? g.cap : 128; // speculative part
     load_unit_words(g, gun, spec);
+    g_template(g); // the cell maps' template travels with them
     bool restart = false;
     if (restart_if_over) {
         int st = __shfl_sync(FULLM, v, H_STATUS), tm = __shfl_sync(FULLM, v, H_TIME);
@@ -387,8 +395,7 @@ DEV void g_load(Game &g, const int32_t *ghdr, const uint32_t *gun, bool restart_
             #pragma unroll
             for (int k = 0; k < MRTS_UNIT_WORDS; k++) if (k < g.uw) cp_async16(su + k * g.cap + i, gun + k * g.cap + i);
     }
-    cp_async_wait_all();
-    g_rebuild(g, true);
+    g_rebuild(g, true, true); // waits for every copy above
 }
 DEV void g_store(Game &g, int32_t *ghdr, uint32_t *gun) {
     __syncwarp();
@@ -1667,6 +1674,87 @@ DEVN void run_cycles_only(Game &g, int target) {
     }
 }
 
+// NaiveMCTSNode's constructor loop (ai/mcts/naivemcts/NaiveMCTSNode.java:48-53): cycle() while the game is not over and neither player
+// has a unit without an assignment (GameState.canExecuteAnyAction, GameState.java:416-423)
+DEVN void run_cycles_to_decision(Game &g) {
+    int winner;
+    #pragma unroll 1
+    for (;;) {
+        bool over = game_over(g, winner);
+        int n = g.hdr()[H_NUNITS], idle = 0;
+        #pragma unroll 1
+        for (int i = g.lane; i < n; i += 32) idle |= (u_pl(g.w0()[i]) != 0 && a_type(g.a0()[i]) == (int)AT_IDLE) ? 1 : 0;
+        idle = __ballot_sync(FULLM, idle) != 0;
+        __syncwarp();
+        if (g.lane == 0) { int st = g.hdr()[H_STATUS] & ~(ST_OVER | 0x300); if (over) st |= ST_OVER | ((winner + 1) << 8); g.hdr()[H_STATUS] = st; }
+        __syncwarp();
+        if (over || idle) break;
+        int time = g.hdr()[H_TIME], mrt = min_ready_time(g);
+        cycle_execute_ni(g, mrt > time + 1 && mrt != MRTS_NEVER ? mrt : time + 1);
+    }
+}
+
+// Unit.getUnitActions (units/Unit.java:382-522) for every idle unit of out_player, as ordered lists (the order RandomBiasedAI samples
+// from and PlayerActionGenerator enumerates, rts/PlayerActionGenerator.java:56-106), plus what the generator's constructor derives
+// from the state: the resource usage of the assignments in flight (GameState.getResourceUsage, GameState.java:652-664).
+//   hdr[8]    : choices, resources used by player 0 / 1, resources of player 0 / 1, positions used, time, bit 0 gameover | (winner + 1) << 1 |
+//               bit 3 / 4: player 0 / 1 can execute an action
+//   pos[]     : the linear positions x + y * W reserved by in-flight MOVE / PRODUCE assignments, unit-list order
+//   choice[][4]: unit slot, Unit.ID, type | x << 8 | y << 16 | owner << 24, number of actions (the full count even when the list is cut)
+//   list[][]  : action type | (direction + 1) << 4 | x << 8 | y << 16 | (unit type + 1) << 24   (x, y: attack target; NONE lasts none_duration)
+DEVN void unit_actions_game(Game &g, const StepParams &p, long long gi) {
+    const int n = g.hdr()[H_NUNITS], player = p.out_player, K = p.ua_max_choices, MA = p.ua_max_actions;
+    int32_t *hd = p.ua_hdr + gi * 8, *pos = p.ua_pos + gi * (long long)g.cap, *ch = p.ua_choice + gi * (long long)K * 4, *ls = p.ua_list + gi * (long long)K * MA;
+    int ru0, ru1, winner, nc = 0, np = 0, can = 0;
+    reserved_resources(g, ru0, ru1);
+    bool over = game_over(g, winner);
+    const unsigned below = (1u << g.lane) - 1;
+    #pragma unroll 1
+    for (int base = 0; base < n; base += 32) {
+        int i = base + g.lane;
+        bool idle = false, uses = false, mine = false; uint32_t w = 0, A0 = 0; int A1 = 0;
+        if (i < n) {
+            w = g.w0()[i]; A0 = g.a0()[i]; A1 = g.a1()[i];
+            idle = a_type(A0) == (int)AT_IDLE && u_pl(w) != 0;
+            mine = idle && u_pl(w) == player + 1;
+            uses = a_uses_cell(a_type(A0));
+        }
+        can |= (__ballot_sync(FULLM, idle && u_pl(w) == 1) ? 1 : 0) | (__ballot_sync(FULLM, idle && u_pl(w) == 2) ? 2 : 0);
+        unsigned mu = __ballot_sync(FULLM, uses), mm = __ballot_sync(FULLM, mine);
+        if (uses) { // UnitAction.resourceUsage: linear arithmetic on x + y * W (UnitAction.java:255-270)
+            int q = np + __popc(mu & below), lin = u_x(w) + u_y(w) * g.W;
+            if ((unsigned)A1 < 4u) lin += (A1 == 0 ? -g.W : (A1 == 1 ? 1 : (A1 == 2 ? g.W : -1)));
+            if (q < g.cap) pos[q] = lin;
+        }
+        np += __popc(mu);
+        if (mine) {
+            int c = nc + __popc(mm & below);
+            if (c < K) {
+                Enum e; enumerate(g, i, e);
+                int cnt = e.nb + e.nfree * (e.n_aff + ((e.fl & UF_MOVE) ? 1 : 0)) + 1;
+                ch[c * 4] = i; ch[c * 4 + 1] = (int32_t)g.uid()[i]; ch[c * 4 + 2] = (int32_t)(u_type(w) | (u_x(w) << 8) | (u_y(w) << 16) | (u_pl(w) << 24)); ch[c * 4 + 3] = cnt;
+                #pragma unroll 1
+                for (int k = 0; k < cnt && k < MA; k++) {
+                    uint32_t P0; int P1, tc, cost;
+                    pick_action(g, e, k, p.ua_none_duration, P0, P1, tc, cost);
+                    int at = a_type(P0);
+                    uint32_t v = (uint32_t)at;
+                    if (at >= ACT_MOVE && at <= ACT_PRODUCE) v |= (uint32_t)(P1 + 1) << 4;
+                    if (at == ACT_ATTACK) v |= ((P0 >> 16) & 0xffu) << 8 | (P0 >> 24) << 16;
+                    if (at == ACT_PRODUCE) v |= (a_utype(P0) + 1u) << 24;
+                    ls[c * MA + k] = (int32_t)v;
+                }
+            }
+        }
+        nc += __popc(mm);
+    }
+    __syncwarp();
+    if (g.lane == 0) {
+        hd[0] = nc; hd[1] = ru0; hd[2] = ru1; hd[3] = g.hdr()[H_RES0]; hd[4] = g.hdr()[H_RES1]; hd[5] = np; hd[6] = g.hdr()[H_TIME];
+        hd[7] = (over ? 1 : 0) | ((winner + 1) << 1) | (can << 3);
+    }
+}
+
 // issueSafe / issue of one staged PlayerAction, no cycle
 DEVN void run_issue_only(Game &g, const StepParams &p, long long gi) {
     int pl = p.issue_player;
@@ -1718,8 +1806,14 @@ DEV void obs_emit(const uint32_t *w0, const uint32_t *w1, const uint32_t *a0, in
                 #pragma unroll 4
                 for (int q = lane; q < 5 * nq; q += 32) ((uint4 *)o)[q] = z;
             }
-            #pragma unroll 2
-            for (int q = lane; q < nq; q += 32) ((uint4 *)(o + 5 * cells))[q] = ((const uint4 *)terrain)[q];
+            #pragma unroll 1
+            for (int q0 = lane; q0 < nq; q0 += 256) { // the terrain plane: eight 16-byte loads in flight per lane, then the stores
+                uint4 t[8];
+                #pragma unroll
+                for (int j = 0; j < 8; j++) if (q0 + j * 32 < nq) t[j] = ((const uint4 *)terrain)[q0 + j * 32];
+                #pragma unroll
+                for (int j = 0; j < 8; j++) if (q0 + j * 32 < nq) ((uint4 *)(o + 5 * cells))[q0 + j * 32] = t[j];
+            }
             if (prezeroed && lane == 0) bulk_wait_all();
         } else {
             #pragma unroll 1
@@ -2194,6 +2288,8 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
         else if (p.mode == MODE_ISSUE_ONLY) run_issue_only(g, p, gi);
         else if (p.mode == MODE_OBSERVE) { observe_game(g, p, gi); stat_add(ws, lane, STAT_IO_WRITE, obs_bytes_per_game(g.W, g.H, p.partial_obs ? 8 : 6, p.out_dtype)); continue; }
         else if (p.mode == MODE_PATHFIND) { pathfind_game(g, p, gi); continue; }
+        else if (p.mode == MODE_UNIT_ACTIONS) { unit_actions_game(g, p, gi); continue; }
+        else if (p.mode == MODE_CYCLE_DECISION) run_cycles_to_decision(g);
         else { masks_game(g, p, gi); stat_add(ws, lane, STAT_IO_WRITE, mask_bytes_per_game(g.W, g.H, 1 + 6 + 16 + p.n_types + (2 * p.max_range + 1) * (2 * p.max_range + 1), p.out_dtype)); continue; }
         if (g.hdr()[H_ERR] != err0) stat_add(ws, g.lane, STAT_ERRORS, 1);
         if ((LEAN || p.mode == MODE_GAME) && p.results_out) {

@@ -784,6 +784,38 @@ int mrts_batch_cycle_to(mrts_batch *b, const int32_t *t_target, int n_cycles, in
     return MRTS_OK;
 }
 
+int mrts_batch_cycle_to_decision(mrts_batch *b) {
+    if (b) b->results_fresh = false;
+    if (!b) return fail(MRTS_E_ARG, "null batch");
+    if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
+    StepParams p; memset(&p, 0, sizeof p);
+    p.mode = MODE_CYCLE_DECISION;
+    if (launch_step(b, p)) return fail(MRTS_E_CUDA, std::string("cycle launch: ") + dev_errstr());
+    return MRTS_OK;
+}
+
+int mrts_batch_unit_actions(mrts_batch *b, int player, int none_duration, int max_choices, int max_actions, int32_t *out_hdr, int32_t *out_positions,
+                            int32_t *out_choices, int32_t *out_lists, int on_device) {
+    if (!b || player < 0 || player > 1 || max_choices < 1 || max_actions < 1 || !out_hdr || !out_positions || !out_choices || !out_lists)
+        return fail(MRTS_E_ARG, "mrts_batch_unit_actions: bad argument");
+    if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
+    size_t nh = (size_t)b->n * 8, np = (size_t)b->n * b->cap, nc = (size_t)b->n * max_choices * 4, nl = (size_t)b->n * max_choices * max_actions;
+    StepParams p; memset(&p, 0, sizeof p);
+    p.mode = MODE_UNIT_ACTIONS; p.out_player = player; p.ua_none_duration = none_duration; p.ua_max_choices = max_choices; p.ua_max_actions = max_actions;
+    if (on_device) { p.ua_hdr = out_hdr; p.ua_pos = out_positions; p.ua_choice = out_choices; p.ua_list = out_lists; }
+    else {
+        if (ensure_tmp(b, (nh + np + nc + nl) * 4)) return fail(MRTS_E_CUDA, std::string("staging allocation failed: ") + dev_errstr());
+        int32_t *t = (int32_t *)b->d_tmp;
+        p.ua_hdr = t; p.ua_pos = t + nh; p.ua_choice = t + nh + np; p.ua_list = t + nh + np + nc;
+    }
+    if (launch_step(b, p)) return fail(MRTS_E_CUDA, std::string("unit actions launch: ") + dev_errstr());
+    if (!on_device) {
+        if (dev_d2h(out_hdr, p.ua_hdr, nh * 4, b->stream) || dev_d2h(out_positions, p.ua_pos, np * 4, b->stream) ||
+            dev_d2h(out_choices, p.ua_choice, nc * 4, b->stream) || dev_d2h(out_lists, p.ua_list, nl * 4, b->stream)) return fail(MRTS_E_CUDA, dev_errstr());
+    }
+    return MRTS_OK;
+}
+
 int mrts_batch_evaluate(mrts_batch *b, int eval_fn, int maxplayer, int observer, float *out_eval, int on_device) {
     if (!b || !out_eval || maxplayer < 0 || maxplayer > 1 || observer > 1 || (eval_fn != 0 && eval_fn != 1)) return fail(MRTS_E_ARG, "mrts_batch_evaluate: bad argument");
     if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());

@@ -849,3 +849,62 @@ def test_evaluation_operator(backend, maps):
                         want = np.float32(view.evaluate(fn, maxp, 1 - maxp))
                         assert got[g] == want, "round %d fn %d maxplayer %d observer %d game %d: %r != %r" % (r, fn, maxp, observer, g, got[g], want)
     b.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# ordered unit action lists (Unit.getUnitActions) and the node loop of the MCTS searches, against the oracle
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("key,version", [("8x8/basesWorkers8x8", 1), ("16x16/basesWorkers16x16", 2), ("melee14x12Mixed18", 1), ("BWDistantResources32x32", 3)])
+def test_unit_action_lists_and_cycle_to_decision(backend, maps, key, version):
+    n = 3 if backend == "emu" else 16
+    rounds = 5 if backend == "emu" else 14
+    utt, outt = M.UnitTypeTable(version, 1), O.Utt(version, 1)
+    m = maps[key]
+    b = M.BatchedGameState(utt, make_pgs(m, utt), n)
+    seeds = np.arange(n, dtype=np.int64) * 31 + 2
+    b.reset(seeds)
+    b.set_policy(0, M.POLICY_RANDOM_BIASED)
+    b.set_policy(1, M.POLICY_RANDOM_BIASED)
+    games = []
+    for g in range(n):
+        og = O.Game(outt, m)
+        og.seed(int(seeds[g]))
+        games.append(og)
+    cost = [outt.field(t, 0) for t in range(7)]
+    for r in range(rounds):
+        for player in (0, 1):
+            ua = b.unit_actions(player, none_duration=10 if r % 2 == 0 else 7)
+            for g, og in enumerate(games):
+                units, asg = og.units(), og.assignments()
+                d = ua[g]
+                assert d["time"] == og.time and d["gameover"] == og.gameover and d["winner"] == og.winner
+                idle = [i for i in range(len(units)) if units[i][1] == player and not asg[i][0]]
+                assert [c[0] for c in d["choices"]] == idle, (key, r, g, player)
+                for (slot, uid, ty, x, y, acts) in d["choices"]:
+                    assert (ty, x, y) == (units[slot][0], units[slot][2], units[slot][3]) and uid == units[slot][6]
+                    ref = og.unit_actions(slot, 10 if r % 2 == 0 else 7)
+                    norm = [(t, p, (ax if t == O.ATTACK else 0), (ay if t == O.ATTACK else 0), (ut if t == O.PRODUCE else -1)) for (t, p, ax, ay, ut) in ref]
+                    got = [(t, (p if t != O.ATTACK else -1), ax, ay, ut) for (t, p, ax, ay, ut) in acts]
+                    norm = [(t, (p if t != O.ATTACK else -1), ax, ay, ut) for (t, p, ax, ay, ut) in norm]
+                    assert got == norm, "unit actions %s round %d game %d unit %d\ndev=%s\nref=%s" % (key, r, g, slot, got, norm)
+                used, res_used = [], [0, 0]
+                for i in range(len(units)):
+                    if asg[i][0] and asg[i][1] in (O.MOVE, O.PRODUCE):
+                        pos = units[i][2] + units[i][3] * m["w"] + {0: -m["w"], 1: 1, 2: m["w"], 3: -1}.get(int(asg[i][2]), 0)
+                        used.append(int(pos))
+                        if asg[i][1] == O.PRODUCE:
+                            res_used[units[i][1]] += cost[asg[i][5]]
+                assert d["positions_used"] == used and list(d["resources_used"]) == res_used
+                assert d["resources"] == (og.resources(0), og.resources(1))
+                assert d["can_act"] == tuple(any(units[i][1] == pl and not asg[i][0] for i in range(len(units))) for pl in (0, 1))
+        # both players act, then the node loop: cycle until somebody can act again
+        b.step(1, 3000)
+        b.cycle_to_decision()
+        ex = b.export()
+        for g, og in enumerate(games):
+            if not (og.gameover and og.time > 0):
+                og.run(O.AI_RANDOM_BIASED, None, O.AI_RANDOM_BIASED, None, 1, 3000)
+            while og.winner == -1 and not og.gameover and og.is_complete():
+                og.cycle()
+            P.assert_same_state(ex, g, og, "cycle_to_decision %s round %d" % (key, r))
+    b.close()
