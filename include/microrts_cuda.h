@@ -297,6 +297,48 @@ int mrts_batch_unit_actions(mrts_batch *, int player, int none_duration, int max
 /* cycle() while the game is not over and neither player has a unit without an assignment -- the loop at the head of every MCTS node
  * (src/ai/mcts/naivemcts/NaiveMCTSNode.java:48-53) */
 int mrts_batch_cycle_to_decision(mrts_batch *);
+/* ---- host side of the search AIs, over the calls above -------------------------------------------------------------------------
+ * GameState.getPlayerActions(player) (src/rts/GameState.java:493-524, PlayerAction.cartesianProduct src/rts/PlayerAction.java:180-195)
+ * of one game, in the reference's order: PlayerAction i = out_counts[i] RAW rows at out_rows[i][..][8] ({cell, type, parameter, x, y,
+ * unit type, 0, 0}: what mrts_batch_issue takes).  At most max_player_actions are written; *out_total is the full count. */
+int mrts_batch_player_actions(mrts_batch *, int64_t game, int player, int32_t *out_rows /* [max_player_actions][max_k][8] */,
+                              int32_t *out_counts, int64_t max_player_actions, int max_k, int64_t *out_total);
+/* rts.PlayerActionGenerator (src/rts/PlayerActionGenerator.java:56-252) for one game and player.  The reference's static / unseeded
+ * generators become a java.util.Random state the caller owns (mrts_java_random_seed(seed) = the state of new Random(seed)). */
+typedef struct mrts_pag mrts_pag;
+#define MRTS_PAG_DONE (-100) /* mrts_pag_next: getNextAction returned null (every PlayerAction has been generated) */
+int mrts_pag_create(mrts_batch *, int64_t game, int player, int none_duration, mrts_pag **out); /* MRTS_E_STATE: no unit can act */
+void mrts_pag_destroy(mrts_pag *);
+int64_t mrts_pag_size(const mrts_pag *);       /* getSize(): product of the list sizes, capped at Long.MAX_VALUE */
+int64_t mrts_pag_generated(const mrts_pag *);  /* getGenerated() */
+int mrts_pag_num_choices(const mrts_pag *);
+int mrts_pag_next(mrts_pag *, int32_t *rows /* [max_k][8] RAW */, int max_k);   /* getNextAction(-1): number of rows, or MRTS_PAG_DONE */
+int mrts_pag_random(mrts_pag *, int64_t *rng_state, int32_t *rows, int max_k);  /* getRandom() */
+int mrts_pag_randomize_order(mrts_pag *, int64_t *rng_state);                   /* randomizeOrder() */
+int64_t mrts_java_random_seed(int64_t seed);
+
+/* ai.mcts.naivemcts.NaiveMCTS (src/ai/mcts/naivemcts/NaiveMCTS.java:140-158,195-262; NaiveMCTSNode.java) for every game of `roots` at once:
+ * search t looks for `player`'s best PlayerAction in game t.  The trees live on the host; node states, cloneIssue, the nodes' cycle
+ * loops, the move generators' lists and the playouts (RandomBiasedAI both sides, `lookahead` cycles, eval_fn) run on the device for all
+ * searches in lockstep.  Search t's generators are seeded from seeds[t] (the reference's are unseeded statics). */
+typedef struct mrts_mcts mrts_mcts;
+typedef struct {
+    int lookahead;          /* MAXSIMULATIONTIME (100) */
+    int max_depth;          /* MAX_TREE_DEPTH (10) */
+    float epsilon_l, epsilon_g, epsilon_0; /* 0.3, 0.0, 0.4 */
+    int global_strategy;    /* 0 = E_GREEDY, 1 = UCB1 */
+    int force_exploration;  /* forceExplorationOfNonSampledActions */
+    int eval_fn;            /* 0 = SimpleSqrtEvaluationFunction3, 1 = SimpleEvaluationFunction */
+} mrts_mcts_params;
+int mrts_mcts_create(mrts_batch *roots, int player, const mrts_mcts_params *, int max_nodes_per_tree, const int64_t *seeds, mrts_mcts **out);
+int mrts_mcts_iterate(mrts_mcts *, int n_iterations);  /* NaiveMCTS.iteration n times per search */
+int mrts_mcts_num_nodes(const mrts_mcts *, int64_t tree);
+int mrts_mcts_root(const mrts_mcts *, int64_t tree, int32_t *root_visits, double *root_accum, int32_t *child_visits, double *child_accum, int max_children);
+int mrts_mcts_best_actions(const mrts_mcts *, int32_t *out_rows /* [n_games][max_k][8] RAW */, int32_t *out_counts, int max_k); /* getBestActionSoFar */
+void mrts_mcts_destroy(mrts_mcts *);
+/* game s of src becomes game dst_index[s] of dst (entries < 0 are skipped): the scatter form of mrts_batch_copy_games */
+int mrts_batch_scatter_games(mrts_batch *dst, const mrts_batch *src, const int64_t *dst_index /* [src games] */, int on_device);
+
 /* light per-game result: out[g] = {time, winner(-1 none), gameover, error bits} */
 int mrts_batch_results(mrts_batch *, int32_t *out /* [n_games][4] */, int on_device);
 

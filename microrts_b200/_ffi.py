@@ -17,6 +17,11 @@ class StateHost(C.Structure):
                 ("rng", C.POINTER(C.c_int64))]
 
 
+class MctsParams(C.Structure):
+    _fields_ = [("lookahead", C.c_int), ("max_depth", C.c_int), ("epsilon_l", C.c_float), ("epsilon_g", C.c_float), ("epsilon_0", C.c_float),
+                ("global_strategy", C.c_int), ("force_exploration", C.c_int), ("eval_fn", C.c_int)]
+
+
 def bind(L):
     vp, i, i64, u32 = C.c_void_p, C.c_int, C.c_int64, C.c_uint32
     pvp = C.POINTER(C.c_void_p)
@@ -49,6 +54,14 @@ def bind(L):
         "mrts_batch_import": (i, [vp, i64, i64, C.POINTER(StateHost)]),
         "mrts_batch_results": (i, [vp, vp, i]), "mrts_batch_cycle_to_decision": (i, [vp]),
         "mrts_batch_unit_actions": (i, [vp, i, i, i, i, vp, vp, vp, vp, i]), "mrts_batch_copy_to_host": (i, [vp, vp, vp, C.c_size_t]), "mrts_batch_stats": (i, [vp, vp]),
+        "mrts_batch_scatter_games": (i, [vp, vp, vp, i]),
+        "mrts_batch_player_actions": (i, [vp, i64, i, vp, vp, i64, i, C.POINTER(C.c_int64)]),
+        "mrts_pag_create": (i, [vp, i64, i, i, pvp]), "mrts_pag_destroy": (None, [vp]), "mrts_pag_size": (i64, [vp]), "mrts_pag_generated": (i64, [vp]),
+        "mrts_pag_num_choices": (i, [vp]), "mrts_pag_next": (i, [vp, vp, i]), "mrts_pag_random": (i, [vp, C.POINTER(C.c_int64), vp, i]),
+        "mrts_pag_randomize_order": (i, [vp, C.POINTER(C.c_int64)]), "mrts_java_random_seed": (i64, [i64]),
+        "mrts_mcts_create": (i, [vp, i, C.POINTER(MctsParams), i, vp, pvp]), "mrts_mcts_iterate": (i, [vp, i]), "mrts_mcts_num_nodes": (i, [vp, i64]),
+        "mrts_mcts_root": (i, [vp, i64, C.POINTER(C.c_int32), C.POINTER(C.c_double), vp, vp, i]), "mrts_mcts_best_actions": (i, [vp, vp, vp, i]),
+        "mrts_mcts_destroy": (None, [vp]),
         "mrts_batch_launch_count": (i64, [vp]), "mrts_batch_last_kernel": (C.c_char_p, [vp]), "mrts_batch_io_bytes": (i, [vp, vp]),
         "mrts_nccl_unique_id": (i, [vp]), "mrts_nccl_comm_create": (i, [vp, i, i, i, pvp]), "mrts_nccl_comm_wrap": (i, [vp, i, pvp]),
         "mrts_nccl_comm_destroy": (None, [vp]), "mrts_batch_stats_allreduce": (i, [vp, vp, vp]),

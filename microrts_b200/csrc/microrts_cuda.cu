@@ -19,6 +19,7 @@
 
 #include "engine.cuh"
 #include "host_model.hpp"
+#include "mcts.hpp"
 
 using namespace mrts;
 
@@ -121,14 +122,19 @@ struct CopyParams {
     int32_t *dhdr; uint32_t *dunits; const int32_t *shdr; const uint32_t *sunits;
     const long long *src_index; const uint8_t *mask;
     long long n_dst, n_src; int cap, uw;
+    const long long *dst_index; // scatter form: source game s goes to destination game dst_index[s] (< 0: skipped); src_index / mask unused
 };
 // GameState.clone() (GameState.java:582-604) for many games at once: game g of the destination batch becomes a copy of game
 // src_index[g] (or g) of the source batch, where mask[g] != 0 (or everywhere); one warp per game
 DEV void copy_kernel_body(const CopyParams &p, int tid, int nthreads, int bid, int nblocks) {
     int warp = tid >> 5, lane = tid & 31, wpc = nthreads >> 5;
-    for (long long gi = (long long)bid * wpc + warp; gi < p.n_dst; gi += (long long)nblocks * wpc) {
-        if (p.mask && !p.mask[gi]) continue;
-        long long si = p.src_index ? p.src_index[gi] : gi;
+    for (long long it = (long long)bid * wpc + warp; it < (p.dst_index ? p.n_src : p.n_dst); it += (long long)nblocks * wpc) {
+        long long gi = it, si = it;
+        if (p.dst_index) { gi = p.dst_index[it]; if (gi < 0 || gi >= p.n_dst) continue; }
+        else {
+            if (p.mask && !p.mask[gi]) continue;
+            si = p.src_index ? p.src_index[gi] : gi;
+        }
         if (si < 0 || si >= p.n_src) continue;
         const int32_t *sh = p.shdr + si * MRTS_HDR_WORDS;
         const uint32_t *su = p.sunits + si * (long long)p.uw * p.cap;
@@ -237,6 +243,7 @@ static const int N_FIXED = (int)(sizeof(g_fixed) / sizeof(g_fixed[0]));
 
 struct mrts_batch {
     UttH utt;
+    std::vector<MapH> maps_h; // the maps the batch was created from (a search clones the configuration for its node pool)
     int W = 0, H = 0, cap = 0, n_maps = 0, map_words = 0, device = 0;
     long long n = 0;
     uint32_t flags = 0;
@@ -459,6 +466,7 @@ int mrts_batch_create(const mrts_utt *u, const mrts_map *const *maps, int n_maps
     auto b = std::unique_ptr<mrts_batch, void (*)(mrts_batch *)>(new mrts_batch, mrts_batch_destroy);
     b->utt = u->h; b->W = W; b->H = H; b->cap = cap; b->n_maps = n_maps; b->n = n_games; b->flags = flags; b->device = device;
     b->max_range = u->h.maxAttackRange();
+    for (int i = 0; i < n_maps; i++) b->maps_h.push_back(maps[i]->h);
     for (size_t t = 0; t < u->h.types.size() && t < 32; t++) { // the reward functions identify unit types by name (src/ai/reward/*.java)
         const std::string &nm = u->h.types[t].name; uint32_t bit = 1u << t;
         if (nm == "Worker") { b->tm[0] |= bit; b->tm[4] |= bit; }
@@ -622,7 +630,7 @@ int mrts_batch_copy_games(mrts_batch *dst, const mrts_batch *src, const int64_t 
         if (mask) { if (dev_h2d((char *)dst->d_tmp + ib, mask, mb, dst->stream)) return fail(MRTS_E_CUDA, dev_errstr()); d_mask = (const uint8_t *)dst->d_tmp + ib; }
     }
     if (dev_sync(src->stream)) return fail(MRTS_E_CUDA, dev_errstr()); // the source's pending work is finished before its state is read on dst's stream
-    CopyParams p{dst->d_hdr, dst->d_units, src->d_hdr, src->d_units, d_idx, d_mask, dst->n, src->n, dst->cap, dst->uw};
+    CopyParams p{dst->d_hdr, dst->d_units, src->d_hdr, src->d_units, d_idx, d_mask, dst->n, src->n, dst->cap, dst->uw, nullptr};
     dst->launches++;
 #ifdef MRTS_EMU
     emu::launch(2, 128, 0, [p](unsigned char *, int tid, int bid) { copy_kernel_body(p, tid, 128, bid, 2); });
@@ -631,6 +639,31 @@ int mrts_batch_copy_games(mrts_batch *dst, const mrts_batch *src, const int64_t 
     k_copy_games<<<grid, 128, 0, dst->stream>>>(p);
     if (ck(cudaGetLastError())) return fail(MRTS_E_CUDA, std::string("copy launch: ") + dev_errstr());
     if (!on_device && (src_index || mask)) if (dev_sync(dst->stream)) return fail(MRTS_E_CUDA, dev_errstr()); // staging buffer reuse
+#endif
+    return MRTS_OK;
+}
+
+int mrts_batch_scatter_games(mrts_batch *dst, const mrts_batch *src, const int64_t *dst_index, int on_device) {
+    if (!dst || !src || !dst_index) return fail(MRTS_E_ARG, "mrts_batch_scatter_games: null argument");
+    if (dst->W != src->W || dst->H != src->H || dst->cap != src->cap || dst->uw != src->uw || dst->device != src->device)
+        return fail(MRTS_E_ARG, "mrts_batch_scatter_games: the batches must have the same map size, unit capacity, unit words and device");
+    if (dev_select(dst->device)) return fail(MRTS_E_CUDA, dev_errstr());
+    dst->results_fresh = false;
+    const long long *d_idx = (const long long *)dst_index;
+    if (!on_device) {
+        if (ensure_tmp(dst, (size_t)src->n * 8) || dev_h2d(dst->d_tmp, dst_index, (size_t)src->n * 8, dst->stream)) return fail(MRTS_E_CUDA, dev_errstr());
+        d_idx = (const long long *)dst->d_tmp;
+    }
+    if (dev_sync(src->stream)) return fail(MRTS_E_CUDA, dev_errstr());
+    CopyParams p{dst->d_hdr, dst->d_units, src->d_hdr, src->d_units, nullptr, nullptr, dst->n, src->n, dst->cap, dst->uw, d_idx};
+    dst->launches++;
+#ifdef MRTS_EMU
+    emu::launch(2, 128, 0, [p](unsigned char *, int tid, int bid) { copy_kernel_body(p, tid, 128, bid, 2); });
+#else
+    int grid = (int)std::min<long long>((src->n + 3) / 4, 148 * 16);
+    k_copy_games<<<grid, 128, 0, dst->stream>>>(p);
+    if (ck(cudaGetLastError())) return fail(MRTS_E_CUDA, std::string("copy launch: ") + dev_errstr());
+    if (!on_device && dev_sync(dst->stream)) return fail(MRTS_E_CUDA, dev_errstr());
 #endif
     return MRTS_OK;
 }
@@ -1125,6 +1158,228 @@ int mrts_batch_import(mrts_batch *b, int64_t first, int64_t count, const mrts_st
     if (count && (dev_h2d(b->d_hdr + first * MRTS_HDR_WORDS, hdr.data(), hdr.size() * 4, b->stream) ||
                   dev_h2d(b->d_units + first * (long long)b->uw * cap, un.data(), un.size() * 4, b->stream) || dev_sync(b->stream)))
         return fail(MRTS_E_CUDA, dev_errstr());
+    return MRTS_OK;
+}
+
+// ---- host half of getPlayerActions / PlayerActionGenerator (player_actions.hpp) ----------------------------------------------
+static int fetch_views(mrts_batch *b, int player, int none_duration, int64_t first, int64_t count, std::vector<HView> &out) {
+    // unit action lists of games [first, first + count) of the batch as host views (the kernel runs over the whole batch)
+    const int K = b->cap, MA = 64;
+    std::vector<int32_t> hdr((size_t)b->n * 8), pos((size_t)b->n * b->cap), ch((size_t)b->n * K * 4), ls((size_t)b->n * K * MA);
+    int rc = mrts_batch_unit_actions(b, player, none_duration, K, MA, hdr.data(), pos.data(), ch.data(), ls.data(), 0);
+    if (rc) return rc;
+    out.resize((size_t)count);
+    for (int64_t g = 0; g < count; g++) {
+        int64_t gi = first + g;
+        if (!decode_view(&hdr[gi * 8], &pos[gi * b->cap], &ch[gi * K * 4], &ls[gi * (size_t)K * MA], K, MA, b->W, none_duration, out[g]))
+            return fail(MRTS_E_LIMIT, "a unit has more than 64 legal actions");
+    }
+    return MRTS_OK;
+}
+
+struct mrts_pag { PlayerActionGenerator g; };
+
+int mrts_pag_create(mrts_batch *b, int64_t game, int player, int none_duration, mrts_pag **out) {
+    if (!b || !out || game < 0 || game >= b->n || player < 0 || player > 1) return fail(MRTS_E_ARG, "mrts_pag_create: bad argument");
+    std::vector<HView> v;
+    int rc = fetch_views(b, player, none_duration, game, 1, v);
+    if (rc) return rc;
+    auto p = std::make_unique<mrts_pag>();
+    if (!p->g.init(v[0], b->utt)) return fail(MRTS_E_STATE, "Move generator created with no units that can execute actions");
+    *out = p.release();
+    return MRTS_OK;
+}
+void mrts_pag_destroy(mrts_pag *p) { delete p; }
+int64_t mrts_pag_size(const mrts_pag *p) { return p ? p->g.size : MRTS_E_ARG; }
+int64_t mrts_pag_generated(const mrts_pag *p) { return p ? p->g.generated : MRTS_E_ARG; }
+int mrts_pag_num_choices(const mrts_pag *p) { return p ? (int)p->g.view.choices.size() : MRTS_E_ARG; }
+static int rows_out(const HView &v, const HPlayerAction &pa, int32_t *rows, int max_k) {
+    if ((int)pa.size() > max_k) return fail(MRTS_E_ARG, "max_k is smaller than the PlayerAction");
+    for (size_t k = 0; k < pa.size(); k++) raw_row(v, pa[k], rows + k * 8);
+    return (int)pa.size();
+}
+int mrts_pag_next(mrts_pag *p, int32_t *rows, int max_k) {
+    if (!p || !rows) return fail(MRTS_E_ARG, "mrts_pag_next: null argument");
+    HPlayerAction pa;
+    if (!p->g.next(pa)) return MRTS_PAG_DONE;
+    return rows_out(p->g.view, pa, rows, max_k);
+}
+int mrts_pag_random(mrts_pag *p, int64_t *rng_state, int32_t *rows, int max_k) {
+    if (!p || !rows || !rng_state) return fail(MRTS_E_ARG, "mrts_pag_random: null argument");
+    JavaRandom r; r.s = (uint64_t)*rng_state;
+    HPlayerAction pa; p->g.random(r, pa);
+    *rng_state = (int64_t)r.s;
+    return rows_out(p->g.view, pa, rows, max_k);
+}
+int mrts_pag_randomize_order(mrts_pag *p, int64_t *rng_state) {
+    if (!p || !rng_state) return fail(MRTS_E_ARG, "mrts_pag_randomize_order: null argument");
+    JavaRandom r; r.s = (uint64_t)*rng_state;
+    p->g.randomize_order(r);
+    *rng_state = (int64_t)r.s;
+    return MRTS_OK;
+}
+int64_t mrts_java_random_seed(int64_t seed) { return (int64_t)jr_scramble(seed); }
+
+int mrts_batch_player_actions(mrts_batch *b, int64_t game, int player, int32_t *out_rows, int32_t *out_counts, int64_t max_player_actions, int max_k, int64_t *out_total) {
+    if (!b || !out_total || game < 0 || game >= b->n || player < 0 || player > 1 || max_player_actions < 0 || (max_player_actions && (!out_rows || !out_counts)))
+        return fail(MRTS_E_ARG, "mrts_batch_player_actions: bad argument");
+    std::vector<HView> v;
+    int rc = fetch_views(b, player, 10, game, 1, v);
+    if (rc) return rc;
+    std::vector<HPlayerAction> l;
+    *out_total = player_actions(v[0], b->utt, l, max_player_actions);
+    for (size_t i = 0; i < l.size(); i++) {
+        int n = rows_out(v[0], l[i], out_rows + i * (size_t)max_k * 8, max_k);
+        if (n < 0) return n;
+        out_counts[i] = n;
+    }
+    return MRTS_OK;
+}
+
+// ---- NaiveMCTS over the batch (mcts.hpp) -----------------------------------------------------------------------------------
+struct mrts_mcts {
+    NaiveMctsHost H;
+    mrts_batch *pool = nullptr, *work = nullptr;
+    int T = 0, Tpad = 0, max_nodes = 0;
+    std::vector<int64_t> idx; std::vector<uint8_t> mask; std::vector<int32_t> rows, counts; std::vector<float> ev; std::vector<int32_t> tm; std::vector<int64_t> seeds;
+    int64_t slot(int t, int node) const { return (int64_t)node * Tpad + t; }
+};
+void mrts_mcts_destroy(mrts_mcts *m) { if (!m) return; mrts_batch_destroy(m->pool); mrts_batch_destroy(m->work); delete m; }
+
+// node constructor for the work batch's games selected by `which`: the cycle loop, then the move generator's lists; attaches the nodes
+static int mcts_finish_nodes(mrts_mcts *m, const std::vector<uint8_t> &which, bool roots) {
+    int rc = mrts_batch_cycle_to_decision(m->work);
+    if (rc) return rc;
+    std::vector<HView> v[2];
+    for (int pl = 0; pl < 2; pl++) { rc = fetch_views(m->work, pl, 10, 0, m->T, v[pl]); if (rc) return rc; }
+    const int maxp = m->H.player, minp = 1 - maxp;
+    for (int t = 0; t < m->T; t++) {
+        if (!which[t]) continue;
+        MTree &tr = m->H.trees[t];
+        const HView &a = v[maxp][t];
+        int type = -1; const HView *view = nullptr;
+        if (a.winner != -1 || a.gameover) type = -1;
+        else if (a.can[maxp]) { type = 0; view = &v[maxp][t]; }
+        else if (a.can[minp]) { type = 1; view = &v[minp][t]; }
+        if (roots) {
+            MNode nn; nn.type = type; nn.time = a.time;
+            if (view) { nn.has_gen = true; nn.view = *view; for (const HChoice &c : view->choices) { nn.ate_accum.emplace_back(c.acts.size(), 0.0); nn.ate_visits.emplace_back(c.acts.size(), 0); } }
+            tr.nodes.clear(); tr.nodes.push_back(std::move(nn)); tr.root_time = a.time;
+            m->idx[t] = m->slot(t, 0);
+        } else {
+            int id = m->H.attach_new_node(tr, type, a.time, view);
+            m->idx[t] = m->slot(t, id);
+        }
+    }
+    for (int t = 0; t < m->T; t++) if (!which[t]) m->idx[t] = -1;
+    return mrts_batch_scatter_games(m->pool, m->work, m->idx.data(), 0);
+}
+
+int mrts_mcts_create(mrts_batch *roots, int player, const mrts_mcts_params *prm, int max_nodes_per_tree, const int64_t *seeds, mrts_mcts **out) {
+    if (!roots || !prm || !out || player < 0 || player > 1 || max_nodes_per_tree < 2) return fail(MRTS_E_ARG, "mrts_mcts_create: bad argument");
+    if (roots->utt.conflict != MRTS_CANCEL_BOTH) return fail(MRTS_E_STATE, "the rollout kernel implements CANCEL_BOTH only");
+    if (roots->scripted || (roots->flags & (MRTS_FLAG_PARTIAL_OBS | MRTS_FLAG_PO_POLICIES))) return fail(MRTS_E_STATE, "searches run on plain batches (no scripted-policy words, fully observable)");
+    auto m = std::unique_ptr<mrts_mcts, void (*)(mrts_mcts *)>(new mrts_mcts, mrts_mcts_destroy);
+    const int T = (int)roots->n, nm = roots->n_maps;
+    m->T = T; m->Tpad = (T + nm - 1) / nm * nm; m->max_nodes = max_nodes_per_tree;
+    m->H.P.lookahead = prm->lookahead; m->H.P.max_depth = prm->max_depth; m->H.P.e_l = prm->epsilon_l; m->H.P.e_g = prm->epsilon_g; m->H.P.e_0 = prm->epsilon_0;
+    m->H.P.strategy = prm->global_strategy; m->H.P.fensa = prm->force_exploration; m->H.P.eval_fn = prm->eval_fn;
+    m->H.player = player; m->H.utt = roots->utt;
+    mrts_utt u; u.h = roots->utt;
+    std::vector<mrts_map> mh(nm); std::vector<const mrts_map *> mp(nm);
+    for (int i = 0; i < nm; i++) { mh[i].h = roots->maps_h[i]; mp[i] = &mh[i]; }
+    int rc = mrts_batch_create(&u, mp.data(), nm, (int64_t)m->Tpad * max_nodes_per_tree, roots->device, 0, roots->cap, &m->pool);
+    if (rc) return rc;
+    rc = mrts_batch_create(&u, mp.data(), nm, T, roots->device, 0, roots->cap, &m->work);
+    if (rc) return rc;
+    m->H.trees.resize(T);
+    for (int t = 0; t < T; t++) {
+        MTree &tr = m->H.trees[t];
+        tr.seed = seeds ? seeds[t] : t; tr.r = JavaRandom(tr.seed); tr.sampler = JavaRandom(tr.seed ^ 0x2545F4914F6CDD1DLL);
+    }
+    m->idx.assign(T, -1); m->mask.assign(T, 0); m->counts.assign(T, 0); m->ev.assign(T, 0); m->tm.assign(T, 0); m->seeds.assign(T, 0);
+    rc = mrts_batch_copy_games(m->work, roots, nullptr, nullptr, 0); // startNewComputation(player, gs.clone())
+    if (rc) return rc;
+    rc = mcts_finish_nodes(m.get(), std::vector<uint8_t>(T, 1), true);
+    if (rc) return rc;
+    *out = m.release();
+    return MRTS_OK;
+}
+
+int mrts_mcts_iterate(mrts_mcts *m, int n_iterations) {
+    if (!m || n_iterations < 0) return fail(MRTS_E_ARG, "mrts_mcts_iterate: bad argument");
+    const int T = m->T;
+    for (int it = 0; it < n_iterations; it++) {
+        // 1. selectLeaf on the host for every search; a search either lands on an existing node or asks for a new one
+        int max_k = 1, creating = 0;
+        for (int t = 0; t < T; t++) {
+            MTree &tr = m->H.trees[t];
+            tr.creating = false; tr.leaf = -1;
+            m->H.select_leaf(tr, 0);
+            if (tr.creating) {
+                if ((int)tr.nodes.size() >= m->max_nodes) return fail(MRTS_E_LIMIT, "a search tree outgrew max_nodes_per_tree");
+                creating++; max_k = std::max(max_k, (int)tr.new_pa.size());
+            }
+        }
+        // 2. the new nodes: clone the parent's state, issue the sampled PlayerAction (gs.cloneIssue), run the node's constructor
+        if (creating) {
+            std::vector<uint8_t> which(T, 0);
+            for (int t = 0; t < T; t++) { MTree &tr = m->H.trees[t]; which[t] = tr.creating; m->idx[t] = tr.creating ? m->slot(t, tr.new_parent) : 0; }
+            int rc = mrts_batch_copy_games(m->work, m->pool, m->idx.data(), which.data(), 0);
+            if (rc) return rc;
+            for (int pl = 0; pl < 2; pl++) { // the acting player of a node: the searching player at max nodes, the opponent at min nodes
+                m->rows.assign((size_t)T * max_k * 8, 0); m->counts.assign(T, 0);
+                bool any = false;
+                for (int t = 0; t < T; t++) {
+                    MTree &tr = m->H.trees[t];
+                    if (!tr.creating) continue;
+                    const MNode &par = tr.nodes[tr.new_parent];
+                    if ((par.type == 0 ? m->H.player : 1 - m->H.player) != pl) continue;
+                    any = true; m->counts[t] = (int32_t)tr.new_pa.size();
+                    for (size_t k = 0; k < tr.new_pa.size(); k++) raw_row(par.view, tr.new_pa[k], &m->rows[((size_t)t * max_k + k) * 8]);
+                }
+                if (any) { rc = mrts_batch_issue(m->work, pl, MRTS_ACTIONS_RAW, m->rows.data(), m->counts.data(), max_k, -1, 0, 0); if (rc) return rc; }
+            }
+            rc = mcts_finish_nodes(m, which, false);
+            if (rc) return rc;
+        }
+        // 3. one playout per search from its leaf (simulate + evaluate on the device)
+        for (int t = 0; t < T; t++) { MTree &tr = m->H.trees[t]; m->idx[t] = m->slot(t, tr.leaf); m->seeds[t] = tr.seed * 1000003LL + tr.runs; }
+        int rc = mrts_batch_copy_games(m->work, m->pool, m->idx.data(), nullptr, 0);
+        if (rc) return rc;
+        rc = mrts_batch_rollout(m->work, 1, m->H.P.lookahead, m->H.P.eval_fn, m->H.player, -1, m->seeds.data(), m->ev.data(), m->tm.data(), 0);
+        if (rc) return rc;
+        // 4. propagateEvaluation
+        for (int t = 0; t < T; t++) {
+            MTree &tr = m->H.trees[t];
+            int time = tr.nodes[tr.leaf].time + m->tm[t] - tr.root_time;
+            double evaluation = (double)m->ev[t] * std::pow(0.99, time / 10.0);
+            m->H.propagate(tr, tr.leaf, evaluation);
+            tr.runs++;
+        }
+    }
+    return MRTS_OK;
+}
+
+int mrts_mcts_num_nodes(const mrts_mcts *m, int64_t tree) { return (m && tree >= 0 && tree < m->T) ? (int)m->H.trees[tree].nodes.size() : MRTS_E_ARG; }
+int mrts_mcts_root(const mrts_mcts *m, int64_t tree, int32_t *root_visits, double *root_accum, int32_t *child_visits, double *child_accum, int max_children) {
+    if (!m || tree < 0 || tree >= m->T || !root_visits || !root_accum) return fail(MRTS_E_ARG, "mrts_mcts_root: bad argument");
+    const MTree &tr = m->H.trees[tree]; const MNode &root = tr.nodes[0];
+    *root_visits = root.visits; *root_accum = root.accum;
+    for (int i = 0; i < (int)root.children.size() && i < max_children; i++) { child_visits[i] = tr.nodes[root.children[i]].visits; child_accum[i] = tr.nodes[root.children[i]].accum; }
+    return (int)root.children.size();
+}
+int mrts_mcts_best_actions(const mrts_mcts *m, int32_t *out_rows, int32_t *out_counts, int max_k) {
+    if (!m || !out_rows || !out_counts || max_k < 1) return fail(MRTS_E_ARG, "mrts_mcts_best_actions: bad argument");
+    for (int t = 0; t < m->T; t++) {
+        const MTree &tr = m->H.trees[t];
+        int best = m->H.most_visited(tr);
+        out_counts[t] = 0;
+        if (best < 0) continue; // no children: the empty PlayerAction
+        int n = rows_out(tr.nodes[0].view, tr.nodes[0].pas[best], out_rows + (size_t)t * max_k * 8, max_k);
+        if (n < 0) return n;
+        out_counts[t] = n;
+    }
     return MRTS_OK;
 }
 

@@ -1590,3 +1590,402 @@ int o_run_game_observing(OGame *g, int kind0, OAi *ai0, int kind1, OAi *ai1, int
     }
     return done;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * PlayerActionGenerator (rts/PlayerActionGenerator.java) and GameState.getPlayerActions (GameState.java:493-524)
+ * PARITY UNPINNED: the reference holds no golden data for them; the restatement follows the cited lines.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct { int unit; int n; OAct *l; } OChoice;
+struct OPag {
+    OGame *g; /* borrowed */
+    ORu base_ru;
+    int nc; OChoice *c;
+    int64_t size, generated;
+    int *sizes, *cur;
+    int more;
+};
+
+/* PlayerActionGenerator(GameState, pID, noneDuration), PlayerActionGenerator.java:56-106; NULL = "created with no units that can execute actions" */
+OPag *o_pag_create(OGame *g, int player, int none_duration) {
+    OPag *p = (OPag *)calloc(1, sizeof(OPag));
+    p->g = g; ru_init(&p->base_ru); gs_resource_usage(g, &p->base_ru);
+    p->size = 1; p->more = 1;
+    p->c = (OChoice *)calloc((size_t)g->n + 1, sizeof(OChoice));
+    OAct *tmp = (OAct *)malloc(sizeof(OAct) * MAX_UA);
+    for (int i = 0; i < g->n; i++) {
+        int u = g->list[i];
+        if (g->pool[u].player == player && find_assign(g, u) < 0) {
+            int n = unit_actions(g, u, none_duration, tmp, MAX_UA);
+            OChoice *c = &p->c[p->nc++];
+            c->unit = u; c->n = n; c->l = (OAct *)malloc(sizeof(OAct) * (size_t)n); memcpy(c->l, tmp, sizeof(OAct) * (size_t)n);
+            if (INT64_MAX / p->size <= (int64_t)n) p->size = INT64_MAX; else p->size *= (int64_t)n;
+        }
+    }
+    free(tmp);
+    if (p->nc == 0) { ru_free(&p->base_ru); free(p->c); free(p); return NULL; }
+    p->sizes = (int *)malloc(sizeof(int) * (size_t)p->nc); p->cur = (int *)calloc((size_t)p->nc, sizeof(int));
+    for (int i = 0; i < p->nc; i++) p->sizes[i] = p->c[i].n;
+    return p;
+}
+void o_pag_free(OPag *p) {
+    if (!p) return;
+    for (int i = 0; i < p->nc; i++) free(p->c[i].l);
+    ru_free(&p->base_ru); free(p->c); free(p->sizes); free(p->cur); free(p);
+}
+int64_t o_pag_size(const OPag *p) { return p->size; }
+int64_t o_pag_generated(const OPag *p) { return p->generated; }
+int o_pag_n_choices(const OPag *p) { return p->nc; }
+
+static void ru_clone(ORu *dst, const ORu *src) { ru_init(dst); for (int i = 0; i < src->npos; i++) ru_add_pos(dst, src->pos[i]); dst->res[0] = src->res[0]; dst->res[1] = src->res[1]; }
+
+/* incrementCurrentChoice, PlayerActionGenerator.java:128-140 */
+static void pag_increment(OPag *p, int start) {
+    for (int i = 0; i < start; i++) p->cur[i] = 0;
+    p->cur[start]++;
+    if (p->cur[start] >= p->sizes[start]) {
+        if (start < p->nc - 1) pag_increment(p, start + 1); else p->more = 0;
+    }
+}
+/* getNextAction, PlayerActionGenerator.java:148-195 (no cut-off time): pairs in the order they are added (last choice first);
+ * returns the number of pairs, or -1 when the generator is exhausted */
+int o_pag_next(OPag *p, int32_t *unit_idx, OActionV *acts) {
+    OGame *g = p->g;
+    while (p->more) {
+        int consistent = 1, n = 0;
+        ORu r; ru_clone(&r, &p->base_ru);
+        int i = p->nc;
+        while (i > 0) {
+            i--;
+            OChoice *c = &p->c[i];
+            OAct *ua = &c->l[p->cur[i]];
+            const ORu1 *r2 = act_ru(ua, g, c->unit);
+            if (ru_consistent_with_ru1(&r, r2, g)) { ru_merge1(&r, r2); unit_idx[n] = list_index_of(g, c->unit); acts[n] = act_to_v(ua); n++; }
+            else { consistent = 0; break; }
+        }
+        ru_free(&r);
+        pag_increment(p, i);
+        if (consistent) { p->generated++; return n; }
+    }
+    return -1;
+}
+/* randomizeOrder, PlayerActionGenerator.java:114-121 with the given Random in place of the static one */
+void o_pag_randomize_order(OPag *p, OJRandom *r) {
+    for (int i = 0; i < p->nc; i++) {
+        OChoice *c = &p->c[i];
+        int m = c->n;
+        OAct *tmp = (OAct *)malloc(sizeof(OAct) * (size_t)m); memcpy(tmp, c->l, sizeof(OAct) * (size_t)m);
+        for (int k = 0; k < c->n; k++) {
+            int j = o_jr_next_int_bound(r, m);
+            c->l[k] = tmp[j];
+            memmove(&tmp[j], &tmp[j + 1], sizeof(OAct) * (size_t)(m - j - 1)); m--;
+        }
+        free(tmp);
+    }
+}
+/* getRandom, PlayerActionGenerator.java:201-222 with the given Random in place of `new Random()` */
+int o_pag_random(OPag *p, OJRandom *r, int32_t *unit_idx, OActionV *acts) {
+    OGame *g = p->g;
+    ORu ru; ru_clone(&ru, &p->base_ru);
+    int n = 0;
+    for (int i = 0; i < p->nc; i++) {
+        OChoice *c = &p->c[i];
+        int m = c->n;
+        OAct *l = (OAct *)malloc(sizeof(OAct) * (size_t)m); memcpy(l, c->l, sizeof(OAct) * (size_t)m);
+        int consistent = 0;
+        do {
+            int j = o_jr_next_int_bound(r, m);
+            OAct ua = l[j];
+            memmove(&l[j], &l[j + 1], sizeof(OAct) * (size_t)(m - j - 1)); m--;
+            const ORu1 *r2 = act_ru(&ua, g, c->unit);
+            if (ru_consistent_with_ru1(&ru, r2, g)) { ru_merge1(&ru, r2); unit_idx[n] = list_index_of(g, c->unit); acts[n] = act_to_v(&ua); n++; consistent = 1; }
+        } while (!consistent);
+        free(l);
+    }
+    ru_free(&ru);
+    return n;
+}
+
+/* GameState.getPlayerActions, GameState.java:493-524 + PlayerAction.cartesianProduct, PlayerAction.java:180-195.
+ * out: per PlayerAction {n, n x (unit list index, type, param, x, y, utype)}; returns the number of PlayerActions (writes while they fit) */
+int64_t o_player_actions(OGame *g, int player, int32_t *out, int64_t max_ints) {
+    typedef struct { ORu r; int n; OPair *a; } PA;
+    int64_t nl = 1, cap = 16;
+    PA *l = (PA *)malloc(sizeof(PA) * (size_t)cap);
+    ru_init(&l[0].r); gs_resource_usage(g, &l[0].r); l[0].n = 0; l[0].a = NULL;
+    OAct *tmp = (OAct *)malloc(sizeof(OAct) * MAX_UA);
+    for (int i = 0; i < g->n; i++) {
+        int u = g->list[i];
+        if (g->pool[u].player != player || find_assign(g, u) >= 0) continue;
+        int na = unit_actions(g, u, 10, tmp, MAX_UA);
+        int64_t n2 = 0, cap2 = nl * 2 + 16;
+        PA *l2 = (PA *)malloc(sizeof(PA) * (size_t)cap2);
+        for (int64_t k = 0; k < nl; k++) {
+            for (int a = 0; a < na; a++) {
+                const ORu1 *r2 = act_ru(&tmp[a], g, u);
+                if (!ru_consistent_with_ru1(&l[k].r, r2, g)) continue;
+                if (n2 == cap2) { cap2 *= 2; l2 = (PA *)realloc(l2, sizeof(PA) * (size_t)cap2); }
+                PA *q = &l2[n2++];
+                ru_clone(&q->r, &l[k].r); ru_merge1(&q->r, r2);
+                q->n = l[k].n + 1; q->a = (OPair *)malloc(sizeof(OPair) * (size_t)q->n);
+                if (l[k].n) memcpy(q->a, l[k].a, sizeof(OPair) * (size_t)l[k].n);
+                q->a[q->n - 1].unit = u; q->a[q->n - 1].act = tmp[a];
+            }
+        }
+        for (int64_t k = 0; k < nl; k++) { ru_free(&l[k].r); free(l[k].a); }
+        free(l); l = l2; nl = n2;
+    }
+    free(tmp);
+    int64_t w = 0;
+    for (int64_t k = 0; k < nl; k++) {
+        if (w + 1 + 6 * (int64_t)l[k].n <= max_ints) {
+            out[w++] = l[k].n;
+            for (int j = 0; j < l[k].n; j++) {
+                out[w++] = list_index_of(g, l[k].a[j].unit); out[w++] = l[k].a[j].act.type; out[w++] = l[k].a[j].act.param;
+                out[w++] = l[k].a[j].act.x; out[w++] = l[k].a[j].act.y; out[w++] = l[k].a[j].act.utype;
+            }
+        }
+        ru_free(&l[k].r); free(l[k].a);
+    }
+    free(l);
+    return nl;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * NaiveMCTS (ai/mcts/naivemcts/NaiveMCTS.java, NaiveMCTSNode.java, ai/mcts/MCTSNode.java), RandomBiasedAI playouts,
+ * SimpleSqrtEvaluationFunction3 / SimpleEvaluationFunction.  The reference draws from two unseeded static generators (MCTSNode.r
+ * and util.Sampler.generator, the latter shared with the playout policy) and cannot be replayed; here a search owns a seeded
+ * MCTSNode.r stream and a seeded Sampler stream for the tree, and playout k of the search is seeded with seed * 1000003 + k.
+ * PARITY UNPINNED (no golden data in the reference).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ONode {
+    int type;            /* 0 max, 1 min, -1 game over */
+    struct ONode *parent;
+    OGame *gs;
+    int depth;
+    double accum; int visits;
+    int nch, chcap; struct ONode **children;
+    int **codes;         /* per child: the code vector (one action index per choice) == the BigInteger action code */
+    OPair **pas; int *pan; /* per child: the PlayerAction in the order it was built */
+    OPag *gen;           /* moveGenerator; its choices are the unit action table */
+    double **ate_accum; int **ate_visits;
+} ONode;
+struct OMcts {
+    ONode *tree; OGame *start; int player;
+    int lookahead, max_depth, strategy, fensa, eval_fn;
+    float e_l, e_g, e_0;
+    OJRandom r, sampler;
+    int64_t seed; int64_t runs;
+    double bound;
+};
+
+static float jr_next_float(OJRandom *r) { return o_jr_next(r, 24) / (float)(1 << 24); }
+
+static ONode *node_new(OMcts *m, OGame *gs /* owned */, ONode *parent) {
+    ONode *nd = (ONode *)calloc(1, sizeof(ONode));
+    nd->parent = parent; nd->gs = gs; nd->depth = parent ? parent->depth + 1 : 0;
+    int maxp = m->player, minp = 1 - m->player;
+    while (o_game_winner(gs) == -1 && !o_game_gameover(gs) && !can_execute_any(gs, maxp) && !can_execute_any(gs, minp)) o_game_cycle(gs);
+    if (o_game_winner(gs) != -1 || o_game_gameover(gs)) nd->type = -1;
+    else if (can_execute_any(gs, maxp)) { nd->type = 0; nd->gen = o_pag_create(gs, maxp, 10); }
+    else if (can_execute_any(gs, minp)) { nd->type = 1; nd->gen = o_pag_create(gs, minp, 10); }
+    else nd->type = -1;
+    if (nd->gen) {
+        nd->ate_accum = (double **)malloc(sizeof(double *) * (size_t)nd->gen->nc); nd->ate_visits = (int **)malloc(sizeof(int *) * (size_t)nd->gen->nc);
+        for (int i = 0; i < nd->gen->nc; i++) { nd->ate_accum[i] = (double *)calloc((size_t)nd->gen->c[i].n, sizeof(double)); nd->ate_visits[i] = (int *)calloc((size_t)nd->gen->c[i].n, sizeof(int)); }
+    }
+    return nd;
+}
+static void node_free(ONode *nd) {
+    if (!nd) return;
+    for (int i = 0; i < nd->nch; i++) { node_free(nd->children[i]); free(nd->codes[i]); free(nd->pas[i]); }
+    if (nd->gen) { for (int i = 0; i < nd->gen->nc; i++) { free(nd->ate_accum[i]); free(nd->ate_visits[i]); } free(nd->ate_accum); free(nd->ate_visits); }
+    o_pag_free(nd->gen); o_game_free(nd->gs);
+    free(nd->children); free(nd->codes); free(nd->pas); free(nd->pan); free(nd);
+}
+
+/* Sampler.weighted(double[]), util/Sampler.java:116-137 on the search's Sampler stream */
+static int sampler_weighted(OMcts *m, const double *dist, int n) {
+    double total = 0, accum = 0, tmp;
+    for (int i = 0; i < n; i++) total += dist[i];
+    if (total == 0) return o_jr_next_int_bound(&m->sampler, n);
+    tmp = o_jr_next_double(&m->sampler) * total;
+    for (int i = 0; i < n; i++) { accum += dist[i]; if (accum >= tmp) return i; }
+    return n - 1; /* Java: throws */
+}
+
+static ONode *select_leaf(OMcts *m, ONode *nd);
+
+/* selectFromAlreadySampledEpsilonGreedy, NaiveMCTSNode.java:136-162 */
+static ONode *select_egreedy(OMcts *m, ONode *nd) {
+    if (jr_next_float(&m->r) >= m->e_g) {
+        ONode *best = NULL;
+        for (int i = 0; i < nd->nch; i++) {
+            ONode *c = nd->children[i];
+            if (nd->type == 0) { if (!best || (c->accum / c->visits) > (best->accum / best->visits)) best = c; }
+            else { if (!best || (c->accum / c->visits) < (best->accum / best->visits)) best = c; }
+        }
+        return best;
+    }
+    return nd->children[o_jr_next_int_bound(&m->r, nd->nch)];
+}
+/* selectFromAlreadySampledUCB1, NaiveMCTSNode.java:165-188 (C = 0.05) */
+static ONode *select_ucb1(OMcts *m, ONode *nd) {
+    ONode *best = NULL; double bestScore = 0; const float C = 0.05f;
+    for (int i = 0; i < nd->nch; i++) {
+        ONode *c = nd->children[i];
+        double exploitation = ((double)c->accum) / c->visits;
+        double exploration = sqrt(log((double)nd->visits) / c->visits);
+        if (nd->type == 0) exploitation = (m->bound + exploitation) / (2 * m->bound);
+        else exploitation = (m->bound - exploitation) / (2 * m->bound);
+        double tmp = C * exploitation + exploration;
+        if (!best || tmp > bestScore) { best = c; bestScore = tmp; }
+    }
+    return best;
+}
+
+/* selectLeafUsingLocalMABs, NaiveMCTSNode.java:191-330 */
+static ONode *select_local(OMcts *m, ONode *nd) {
+    OPag *gen = nd->gen; OGame *gs = nd->gs;
+    int nc = gen->nc;
+    double **dists = (double **)malloc(sizeof(double *) * (size_t)nc);
+    int *not_sampled = (int *)malloc(sizeof(int) * (size_t)nc), nns = 0;
+    for (int e = 0; e < nc; e++) {
+        int na = gen->c[e].n;
+        double *dist = (double *)malloc(sizeof(double) * (size_t)na);
+        int bestIdx = -1, visits = 0; double bestEval = 0;
+        const double *acc = nd->ate_accum[e]; const int *vc = nd->ate_visits[e];
+        for (int i = 0; i < na; i++) {
+            if (nd->type == 0) {
+                if (bestIdx == -1 || (visits != 0 && vc[i] == 0) || (visits != 0 && (acc[i] / vc[i]) > bestEval)) {
+                    bestIdx = i; bestEval = vc[i] > 0 ? acc[i] / vc[i] : 0; visits = vc[i];
+                }
+            } else {
+                if (bestIdx == -1 || (visits != 0 && vc[i] == 0) || (visits != 0 && (acc[i] / vc[i]) < bestEval)) {
+                    bestIdx = i; bestEval = vc[i] > 0 ? acc[i] / vc[i] : 0; visits = vc[i];
+                }
+            }
+            dist[i] = m->e_l / na; /* float arithmetic, widened */
+        }
+        if (vc[bestIdx] != 0) dist[bestIdx] = (1 - m->e_l) + (m->e_l / na);
+        else if (m->fensa) { for (int j = 0; j < na; j++) if (vc[j] > 0) dist[j] = 0; }
+        not_sampled[nns++] = e;
+        dists[e] = dist;
+    }
+    ORu ru; ru_init(&ru); gs_resource_usage(gs, &ru);
+    OPair *pa = (OPair *)malloc(sizeof(OPair) * (size_t)nc); int npa = 0;
+    int *code_v = (int *)calloc((size_t)nc, sizeof(int));
+    while (nns > 0) {
+        int k = o_jr_next_int_bound(&m->r, nns);
+        int i = not_sampled[k];
+        memmove(&not_sampled[k], &not_sampled[k + 1], sizeof(int) * (size_t)(nns - k - 1)); nns--;
+        OChoice *c = &gen->c[i];
+        const double *distribution = dists[i];
+        int code = sampler_weighted(m, distribution, c->n);
+        OAct *ua = &c->l[code];
+        const ORu1 *r2 = act_ru(ua, gs, c->unit);
+        if (!ru_consistent_with_ru1(&ru, r2, gs)) {
+            int nl = c->n;
+            double *dl = (double *)malloc(sizeof(double) * (size_t)nl); int *outs = (int *)malloc(sizeof(int) * (size_t)nl);
+            for (int j = 0; j < nl; j++) { dl[j] = distribution[j]; outs[j] = j; }
+            do {
+                int idx = 0; while (outs[idx] != code) idx++;
+                memmove(&dl[idx], &dl[idx + 1], sizeof(double) * (size_t)(nl - idx - 1));
+                memmove(&outs[idx], &outs[idx + 1], sizeof(int) * (size_t)(nl - idx - 1)); nl--;
+                /* Sampler.weighted(List<Double>, List<?>), util/Sampler.java:141-161 */
+                double total = 0, accum = 0, tmp;
+                for (int j = 0; j < nl; j++) total += dl[j];
+                if (total == 0) code = outs[o_jr_next_int_bound(&m->sampler, nl)];
+                else { tmp = o_jr_next_double(&m->sampler) * total; code = outs[nl - 1]; for (int j = 0; j < nl; j++) { accum += dl[j]; if (accum >= tmp) { code = outs[j]; break; } } }
+                ua = &c->l[code];
+                r2 = act_ru(ua, gs, c->unit);
+            } while (!ru_consistent_with_ru1(&ru, r2, gs));
+            free(dl); free(outs);
+        }
+        ru_merge1(&ru, r2);
+        pa[npa].unit = c->unit; pa[npa].act = *ua; npa++;
+        code_v[i] = code;
+    }
+    ru_free(&ru);
+    for (int e = 0; e < nc; e++) free(dists[e]);
+    free(dists); free(not_sampled);
+    for (int ch = 0; ch < nd->nch; ch++)
+        if (memcmp(nd->codes[ch], code_v, sizeof(int) * (size_t)nc) == 0) { free(code_v); free(pa); return select_leaf(m, nd->children[ch]); }
+    /* new child: gs.cloneIssue(pa2), then the node's own loop */
+    OGame *gs2 = o_game_clone(gs);
+    OPair *keep = (OPair *)malloc(sizeof(OPair) * (size_t)(npa ? npa : 1)); /* `actions.add(pa2)`: the PlayerAction as it was built */
+    memcpy(keep, pa, sizeof(OPair) * (size_t)npa);
+    gs_issue(gs2, npa, pa);
+    if (nd->nch == nd->chcap) {
+        nd->chcap = nd->chcap ? nd->chcap * 2 : 8;
+        nd->children = (ONode **)realloc(nd->children, sizeof(ONode *) * (size_t)nd->chcap); nd->codes = (int **)realloc(nd->codes, sizeof(int *) * (size_t)nd->chcap);
+        nd->pas = (OPair **)realloc(nd->pas, sizeof(OPair *) * (size_t)nd->chcap); nd->pan = (int *)realloc(nd->pan, sizeof(int) * (size_t)nd->chcap);
+    }
+    ONode *node = node_new(m, gs2, nd);
+    nd->children[nd->nch] = node; nd->codes[nd->nch] = code_v; nd->pas[nd->nch] = keep; nd->pan[nd->nch] = npa; nd->nch++;
+    free(pa);
+    return node;
+}
+
+/* selectLeaf, NaiveMCTSNode.java:108-133 */
+static ONode *select_leaf(OMcts *m, ONode *nd) {
+    if (!nd->gen) return nd;
+    if (nd->depth >= m->max_depth) return nd;
+    if (nd->nch > 0 && jr_next_float(&m->r) >= m->e_0) {
+        ONode *sel = m->strategy == 0 ? select_egreedy(m, nd) : select_ucb1(m, nd);
+        return select_leaf(m, sel);
+    }
+    return select_local(m, nd);
+}
+
+/* propagateEvaluation, NaiveMCTSNode.java:341-368 */
+static void propagate(ONode *nd, double evaluation, ONode *child) {
+    nd->accum += evaluation; nd->visits++;
+    if (child) {
+        int idx = 0; while (nd->children[idx] != child) idx++;
+        const int *code = nd->codes[idx];
+        for (int i = 0; i < nd->gen->nc; i++) { nd->ate_accum[i][code[i]] += evaluation; nd->ate_visits[i][code[i]]++; }
+    }
+    if (nd->parent) propagate(nd->parent, evaluation, nd);
+}
+
+OMcts *o_mcts_create(const OGame *g, int player, int lookahead, int max_depth, float e_l, float e_g, float e_0, int strategy, int fensa, int eval_fn, int64_t seed) {
+    OMcts *m = (OMcts *)calloc(1, sizeof(OMcts));
+    m->player = player; m->lookahead = lookahead; m->max_depth = max_depth; m->e_l = e_l; m->e_g = e_g; m->e_0 = e_0; m->strategy = strategy; m->fensa = fensa;
+    m->eval_fn = eval_fn; m->seed = seed; m->bound = 1.0;
+    o_jr_seed(&m->r, seed); o_jr_seed(&m->sampler, seed ^ 0x2545F4914F6CDD1DLL);
+    m->tree = node_new(m, o_game_clone(g), NULL); /* startNewComputation(player, gs.clone()): tree = new NaiveMCTSNode(..., gs, ...) */
+    m->start = o_game_clone(m->tree->gs);         /* gs_to_start_from = gs: the same object, i.e. after the root's own cycle loop */
+    return m;
+}
+void o_mcts_free(OMcts *m) { if (!m) return; node_free(m->tree); o_game_free(m->start); free(m); }
+
+/* NaiveMCTS.iteration, NaiveMCTS.java:195-223, n times */
+void o_mcts_iterate(OMcts *m, int n) {
+    for (int it = 0; it < n; it++) {
+        ONode *leaf = select_leaf(m, m->tree);
+        OGame *gs2 = o_game_clone(leaf->gs);
+        o_game_seed(gs2, m->seed * 1000003LL + m->runs);
+        o_simulate(gs2, gs2->time + m->lookahead);
+        int time = gs2->time - m->start->time;
+        double evaluation = o_evaluate(gs2, m->eval_fn, m->player, 1 - m->player) * pow(0.99, time / 10.0);
+        o_game_free(gs2);
+        propagate(leaf, evaluation, NULL);
+        m->runs++;
+    }
+}
+/* root statistics: out_visits/out_accum per child (creation order); returns the number of children */
+int o_mcts_root(const OMcts *m, int *root_visits, double *root_accum, int *out_visits, double *out_accum, int max_children) {
+    *root_visits = m->tree->visits; *root_accum = m->tree->accum;
+    for (int i = 0; i < m->tree->nch && i < max_children; i++) { out_visits[i] = m->tree->children[i]->visits; out_accum[i] = m->tree->children[i]->accum; }
+    return m->tree->nch;
+}
+int o_mcts_n_nodes_rec(const ONode *nd) { int c = 1; for (int i = 0; i < nd->nch; i++) c += o_mcts_n_nodes_rec(nd->children[i]); return c; }
+int o_mcts_n_nodes(const OMcts *m) { return o_mcts_n_nodes_rec(m->tree); }
+/* getBestActionSoFar / getMostVisitedActionIdx, NaiveMCTS.java:226-262: pairs of the most visited child (first maximum); -1 = no children */
+int o_mcts_best_action(const OMcts *m, int32_t *unit_idx, OActionV *acts) {
+    const ONode *t = m->tree; int best = -1;
+    for (int i = 0; i < t->nch; i++) if (best == -1 || t->children[i]->visits > t->children[best]->visits) best = i;
+    if (best < 0) return -1;
+    for (int k = 0; k < t->pan[best]; k++) { unit_idx[k] = list_index_of(t->gs, t->pas[best][k].unit); acts[k] = act_to_v(&t->pas[best][k].act); }
+    return t->pan[best];
+}

@@ -115,6 +115,27 @@ int o_run_game_observing(OGame *g, int kind0, OAi *ai0, int kind1, OAi *ai1, int
 /* NaiveMCTS.simulate: RandomBiased both sides, issue() not issueSafe() */
 int o_simulate(OGame *, int time_limit);
 
+/* PlayerActionGenerator / GameState.getPlayerActions (parity unpinned) */
+typedef struct OPag OPag;
+OPag *o_pag_create(OGame *, int player, int none_duration); /* the game must outlive the generator; NULL: no unit can act */
+void o_pag_free(OPag *);
+int64_t o_pag_size(const OPag *);
+int64_t o_pag_generated(const OPag *);
+int o_pag_n_choices(const OPag *);
+int o_pag_next(OPag *, int32_t *unit_idx, OActionV *acts);
+void o_pag_randomize_order(OPag *, OJRandom *);
+int o_pag_random(OPag *, OJRandom *, int32_t *unit_idx, OActionV *acts);
+int64_t o_player_actions(OGame *, int player, int32_t *out, int64_t max_ints);
+
+/* NaiveMCTS with seeded generators (parity unpinned) */
+typedef struct OMcts OMcts;
+OMcts *o_mcts_create(const OGame *, int player, int lookahead, int max_depth, float e_l, float e_g, float e_0, int strategy, int fensa, int eval_fn, int64_t seed);
+void o_mcts_free(OMcts *);
+void o_mcts_iterate(OMcts *, int n);
+int o_mcts_root(const OMcts *, int *root_visits, double *root_accum, int *out_visits, double *out_accum, int max_children);
+int o_mcts_n_nodes(const OMcts *);
+int o_mcts_best_action(const OMcts *, int32_t *unit_idx, OActionV *acts);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,6 +71,12 @@ def lib():
             "o_simulate": (i, [vp, i]),
             "o_run_game_observing": (i, [vp, i, vp, i, vp, i, i, pi32]),
             "o_run_game_po": (i, [vp, i, vp, i, vp, i, i]),
+            "o_pag_create": (vp, [vp, i, i]), "o_pag_free": (None, [vp]), "o_pag_size": (i64, [vp]), "o_pag_generated": (i64, [vp]), "o_pag_n_choices": (i, [vp]),
+            "o_pag_next": (i, [vp, pi32, C.POINTER(ActionV)]), "o_pag_randomize_order": (None, [vp, C.POINTER(C.c_uint64)]),
+            "o_pag_random": (i, [vp, C.POINTER(C.c_uint64), pi32, C.POINTER(ActionV)]), "o_player_actions": (i64, [vp, i, pi32, i64]),
+            "o_mcts_create": (vp, [vp, i, i, i, C.c_float, C.c_float, C.c_float, i, i, i, i64]), "o_mcts_free": (None, [vp]), "o_mcts_iterate": (None, [vp, i]),
+            "o_mcts_root": (i, [vp, pi32, C.POINTER(C.c_double), pi32, C.POINTER(C.c_double), i]), "o_mcts_n_nodes": (i, [vp]),
+            "o_mcts_best_action": (i, [vp, pi32, C.POINTER(ActionV)]),
             "o_jr_seed": (None, [C.POINTER(C.c_uint64), i64]), "o_jr_next": (C.c_int32, [C.POINTER(C.c_uint64), i]),
             "o_jr_next_int": (C.c_int32, [C.POINTER(C.c_uint64)]),
             "o_jr_next_int_bound": (C.c_int32, [C.POINTER(C.c_uint64), C.c_int32]),
@@ -287,3 +293,79 @@ class ScriptedAI:
 
     def get_action(self, game, player):
         return game._pairs(lib().o_ai_get_action, self.h, game.h, player)
+
+
+class Pag:
+    """PlayerActionGenerator of the oracle (the game must stay alive while the generator is used)."""
+
+    def __init__(self, game, player, none_duration=10):
+        self.game = game
+        self.h = lib().o_pag_create(game.h, player, none_duration)
+        assert self.h, "no unit can act"
+
+    def __del__(self):
+        try:
+            lib().o_pag_free(self.h)
+        except Exception:
+            pass
+
+    size = property(lambda self: lib().o_pag_size(self.h))
+    generated = property(lambda self: lib().o_pag_generated(self.h))
+
+    def _out(self, fn, *args):
+        cap = self.game.n_units + 8
+        idx = (C.c_int32 * cap)()
+        acts = (ActionV * cap)()
+        n = fn(self.h, *args, idx, acts)
+        return None if n < 0 else [(idx[k], acts[k].tup()) for k in range(n)]
+
+    def next(self):
+        return self._out(lib().o_pag_next)
+
+    def random(self, rng):
+        return self._out(lib().o_pag_random, C.byref(rng.s))
+
+    def randomize_order(self, rng):
+        lib().o_pag_randomize_order(self.h, C.byref(rng.s))
+
+
+def player_actions(game, player, max_ints=4000000):
+    """GameState.getPlayerActions: (list of [(unit index, action tuple)], total count)."""
+    buf = np.zeros(max_ints, dtype=np.int32)
+    total = lib().o_player_actions(game.h, player, buf.ctypes.data_as(C.POINTER(C.c_int32)), max_ints)
+    out, w = [], 0
+    while len(out) < total and w < max_ints and (w + 1 + 6 * int(buf[w])) <= max_ints:
+        n = int(buf[w]); w += 1
+        out.append([(int(buf[w + 6 * j]), tuple(int(v) for v in buf[w + 6 * j + 1:w + 6 * j + 6])) for j in range(n)])
+        w += 6 * n
+    return out, total
+
+
+class Mcts:
+    def __init__(self, game, player, seed, lookahead=100, max_depth=10, e_l=0.3, e_g=0.0, e_0=0.4, strategy=0, fensa=True, eval_fn=0):
+        self.game = game
+        self.h = lib().o_mcts_create(game.h, player, lookahead, max_depth, e_l, e_g, e_0, strategy, 1 if fensa else 0, eval_fn, seed)
+
+    def __del__(self):
+        try:
+            lib().o_mcts_free(self.h)
+        except Exception:
+            pass
+
+    def iterate(self, n):
+        lib().o_mcts_iterate(self.h, n)
+
+    def root(self, max_children=4096):
+        rv, ra = C.c_int32(0), C.c_double(0)
+        cv, ca = (C.c_int32 * max_children)(), (C.c_double * max_children)()
+        n = lib().o_mcts_root(self.h, C.byref(rv), C.byref(ra), cv, ca, max_children)
+        return rv.value, ra.value, np.array(cv[:n], dtype=np.int32), np.array(ca[:n], dtype=np.float64)
+
+    n_nodes = property(lambda self: lib().o_mcts_n_nodes(self.h))
+
+    def best_action(self):
+        cap = self.game.n_units + 8
+        idx = (C.c_int32 * cap)()
+        acts = (ActionV * cap)()
+        n = lib().o_mcts_best_action(self.h, idx, acts)
+        return None if n < 0 else [(idx[k], acts[k].tup()) for k in range(n)]

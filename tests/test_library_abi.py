@@ -27,7 +27,7 @@ def test_exports_every_declared_symbol(lib):
     raw = ctypes.CDLL(os.path.join(ROOT, "microrts_b200", "libmicrorts_cuda.so"))
     missing = [n for n in sorted(names) if not hasattr(raw, n)]
     assert not missing, missing
-    assert lib.mrts_abi_version() == 1
+    assert lib.mrts_abi_version() == 2
 
 
 def test_no_oracle_or_cpu_path_in_product():
