@@ -1163,17 +1163,37 @@ int mrts_batch_import(mrts_batch *b, int64_t first, int64_t count, const mrts_st
 
 // ---- host half of getPlayerActions / PlayerActionGenerator (player_actions.hpp) ----------------------------------------------
 static int fetch_views(mrts_batch *b, int player, int none_duration, int64_t first, int64_t count, std::vector<HView> &out) {
-    // unit action lists of games [first, first + count) of the batch as host views (the kernel runs over the whole batch)
+    // unit action lists of games [first, first + count) of the batch as host views.  The kernel runs over the whole batch into device
+    // staging; the headers come back first, and of the (sparse) choice / list / position arrays only the leading part any game uses
     const int K = b->cap, MA = 64;
-    std::vector<int32_t> hdr((size_t)b->n * 8), pos((size_t)b->n * b->cap), ch((size_t)b->n * K * 4), ls((size_t)b->n * K * MA);
-    int rc = mrts_batch_unit_actions(b, player, none_duration, K, MA, hdr.data(), pos.data(), ch.data(), ls.data(), 0);
+    const size_t nh = (size_t)b->n * 8, np = (size_t)b->n * b->cap, nc = (size_t)b->n * K * 4, nl = (size_t)b->n * K * MA;
+    if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
+    if (ensure_tmp(b, (nh + np + nc + nl) * 4)) return fail(MRTS_E_CUDA, std::string("staging allocation failed: ") + dev_errstr());
+    int32_t *t = (int32_t *)b->d_tmp, *d_hdr = t, *d_pos = t + nh, *d_ch = t + nh + np, *d_ls = t + nh + np + nc;
+    int rc = mrts_batch_unit_actions(b, player, none_duration, K, MA, d_hdr, d_pos, d_ch, d_ls, 1);
     if (rc) return rc;
-    out.resize((size_t)count);
+    std::vector<int32_t> hdr((size_t)count * 8);
+    if (dev_d2h(hdr.data(), d_hdr + first * 8, hdr.size() * 4, b->stream)) return fail(MRTS_E_CUDA, dev_errstr());
+    int kmax = 1, pmax = 1;
+    for (int64_t g = 0; g < count; g++) { kmax = std::max(kmax, std::min(hdr[g * 8], K)); pmax = std::max(pmax, std::min(hdr[g * 8 + 5], b->cap)); }
+    std::vector<int32_t> pos((size_t)count * pmax), ch((size_t)count * kmax * 4), ls((size_t)count * kmax * MA);
+#ifdef MRTS_EMU
     for (int64_t g = 0; g < count; g++) {
-        int64_t gi = first + g;
-        if (!decode_view(&hdr[gi * 8], &pos[gi * b->cap], &ch[gi * K * 4], &ls[gi * (size_t)K * MA], K, MA, b->W, none_duration, out[g]))
-            return fail(MRTS_E_LIMIT, "a unit has more than 64 legal actions");
+        memcpy(&pos[g * pmax], d_pos + (first + g) * b->cap, (size_t)pmax * 4);
+        memcpy(&ch[g * kmax * 4], d_ch + (first + g) * K * 4, (size_t)kmax * 16);
+        memcpy(&ls[g * (size_t)kmax * MA], d_ls + (first + g) * (size_t)K * MA, (size_t)kmax * MA * 4);
     }
+#else
+    if (ck(cudaMemcpy2DAsync(pos.data(), (size_t)pmax * 4, d_pos + first * b->cap, (size_t)b->cap * 4, (size_t)pmax * 4, (size_t)count, cudaMemcpyDeviceToHost, b->stream)) ||
+        ck(cudaMemcpy2DAsync(ch.data(), (size_t)kmax * 16, d_ch + first * K * 4, (size_t)K * 16, (size_t)kmax * 16, (size_t)count, cudaMemcpyDeviceToHost, b->stream)) ||
+        ck(cudaMemcpy2DAsync(ls.data(), (size_t)kmax * MA * 4, d_ls + first * (size_t)K * MA, (size_t)K * MA * 4, (size_t)kmax * MA * 4, (size_t)count, cudaMemcpyDeviceToHost, b->stream)) ||
+        dev_sync(b->stream))
+        return fail(MRTS_E_CUDA, dev_errstr());
+#endif
+    out.resize((size_t)count);
+    for (int64_t g = 0; g < count; g++)
+        if (!decode_view(&hdr[g * 8], &pos[g * pmax], &ch[g * kmax * 4], &ls[g * (size_t)kmax * MA], kmax, MA, b->W, none_duration, out[g]))
+            return fail(MRTS_E_LIMIT, "a unit has more than 64 legal actions");
     return MRTS_OK;
 }
 
