@@ -77,6 +77,8 @@ struct StepParams {
     int uw;                    // unit words per slot in HBM and shared memory: 7, or 9 (X0/X1) for scripted batches
     unsigned char *astar_scratch; // scripted == 2: [grid * warps per CTA][astar_stride] bytes
     long long astar_stride;
+    unsigned char *ff_cache;      // MRTS_PF_FLOODFILL: [n_games][2][ff_stride] bytes (scripted.cuh: pf_floodfill), or null
+    long long ff_stride;
     int auto_reset;            // MODE_GAME: restart finished games from their map at the start of the step
     const int32_t *ext_actions[2]; // [n_games][max_k][8]
     const int32_t *ext_counts[2];  // [n_games]
@@ -163,6 +165,8 @@ struct Game {
     const uint32_t *grid_tmpl;            // global: wall-padded empty grid of this game's map
     uint16_t *as_closed, *as_xy, *as_mark, *as_next, *as_head, *as_gen; // A*/BFS scratch of this warp (scripted batches only, layout.h)
     uint32_t as_sm;                       // its shared-window address when it lives in shared memory, else 0
+    unsigned char *ff_cache;              // FloodFillPathFinding: this game's two per-player distance-map caches in HBM (or null)
+    long long ff_stride;                  // bytes per player
 
     MDEV unsigned char *base() const { return smem_ptr(sb); }
     MDEV int32_t *hdr() const { return (int32_t *)base(); }
@@ -206,7 +210,7 @@ DEV void g_bind(Game &g, int region, const SmemLayout &L, int W, int H, int cap,
     { int pc = (W + 2) * (H + 2); g.as_closed = (uint16_t *)(astar_global ? astar_global : mrts_smem + region + L.astar); g.as_xy = g.as_closed + pc;
       g.as_mark = g.as_xy + pc; g.as_next = g.as_mark + pc; g.as_head = g.as_next + pc; g.as_gen = g.as_head + MRTS_ASTAR_HEADS(W, H);
       g.as_sm = (scripted == 1) ? smem_window(region + L.astar) : 0u; }
-    g.grid_tmpl = nullptr;
+    g.grid_tmpl = nullptr; g.ff_cache = nullptr; g.ff_stride = 0;
 }
 
 // ---- small accessors -------------------------------------------------------------------------------------------------
@@ -2257,11 +2261,29 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
     long long n_items = KERNEL == KERNEL_ROLLOUT ? p.n_games * p.rollouts_per_game : p.n_games;
     // A warp's first item is static; the next ones come from a global counter, so a warp that drew cheap games (or rollouts
     // that ended early) takes more of them and the launch has no long tail of a few unlucky warps.
+    // Short steps (the one-cycle steps of the observation-emitting and RL paths) are bound by the latency of a game's first loads from
+    // HBM: such a launch draws the warp's NEXT game at the start of the current one and asks L2 for its header and first unit words,
+    // which then arrive while the current game is being stepped.
+    const bool ahead = (KERNEL == KERNEL_FAST_OBS || KERNEL == KERNEL_GENERIC) && !LEAN && p.mode == MODE_GAME && p.n_cycles <= 4;
+    long long drawn = -1;
 #pragma unroll 1
-    for (long long item = (long long)bid * wpc + warp; item < n_items; item = next_item<KERNEL == KERNEL_ROLLOUT ? 8 : 1>(p, lane, (long long)nblocks * wpc, item)) {
+    for (long long item = (long long)bid * wpc + warp; item < n_items;
+         item = ahead ? drawn : next_item<KERNEL == KERNEL_ROLLOUT ? 8 : 1>(p, lane, (long long)nblocks * wpc, item)) {
+        if (ahead) {
+            drawn = next_item<1>(p, lane, (long long)nblocks * wpc, item);
+            if (drawn < n_items) {
+#ifndef MRTS_EMU
+                const char *nh = (const char *)(p.hdr + drawn * MRTS_HDR_WORDS), *nu = (const char *)(p.units + drawn * (long long)puw * pcap);
+                if (lane < 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(nh + lane * 64));                 // 80 bytes: one or two lines
+                else if (lane < 2 + 2 * puw) { int k = (lane - 2) >> 1, half = (lane - 2) & 1;                     // the first 64 slots of every word array
+                    if (half * 32 < pcap) asm volatile("prefetch.global.L2 [%0];" ::"l"(nu + ((size_t)k * pcap + half * 32) * 4)); }
+#endif
+            }
+        }
         long long gi = KERNEL == KERNEL_ROLLOUT ? item / p.rollouts_per_game : item;
         const uint32_t *blob = p.maps + (size_t)(gi % p.n_maps) * p.map_words;
         g.grid_tmpl = blob;
+        if (KERNEL == KERNEL_GENERIC && !LEAN) { g.ff_cache = p.ff_cache ? p.ff_cache + (size_t)gi * 2 * p.ff_stride : nullptr; g.ff_stride = p.ff_stride; }
         int32_t *ghdr = p.hdr + gi * MRTS_HDR_WORDS;
         uint32_t *gun = p.units + gi * (long long)puw * pcap;
         g_load(g, ghdr, gun, KERNEL != KERNEL_ROLLOUT && (LEAN || p.mode == MODE_GAME) && p.auto_reset, p.max_cycles);

@@ -253,6 +253,7 @@ struct mrts_batch {
     int32_t *d_results = nullptr; bool results_fresh = false; // [n][4] written by the last mrts_batch_step; stale after any other change of state
     void *d_tmp = nullptr; size_t tmp_bytes = 0; // staging for host arguments
     unsigned char *d_astar = nullptr; long long astar_stride = 0; // pathfinding scratch of large-map scripted batches
+    unsigned char *d_ff = nullptr; long long ff_stride = 0;       // FloodFillPathFinding caches, allocated when a player asks for that pathfinder
     Staged staged[2];
     stream_t stream = nullptr;
     SmemLayout L, Lfast; // generic kernel / specialised kernels (no pending lists, layout.h)
@@ -286,7 +287,7 @@ static int launch_step(mrts_batch *b, StepParams &p) {
     p.n_games = b->n; p.n_maps = b->n_maps; p.map_words = b->map_words; p.W = b->W; p.H = b->H; p.cap = b->cap;
     p.conflict = b->utt.conflict; p.max_range = b->max_range; p.n_types = (int)b->utt.types.size();
     p.partial_obs = (b->flags & MRTS_FLAG_PARTIAL_OBS) ? 1 : 0; p.scripted = b->scripted; p.uw = b->uw;
-    p.astar_scratch = b->d_astar; p.astar_stride = b->astar_stride;
+    p.astar_scratch = b->d_astar; p.astar_stride = b->astar_stride; p.ff_cache = b->d_ff; p.ff_stride = b->ff_stride;
     p.po_policies = (b->flags & MRTS_FLAG_PO_POLICIES) ? 1 : 0;
     // kernel selection: the specialised kernels cover exactly the cases their loops implement
     int kernel = KERNEL_GENERIC;
@@ -431,7 +432,7 @@ void mrts_map_destroy(mrts_map *m) { delete m; }
 void mrts_batch_destroy(mrts_batch *b) {
     if (!b) return;
     dev_select(b->device);
-    dev_free(b->d_hdr); dev_free(b->d_units); dev_free(b->d_maps); dev_free(b->d_cst); dev_free(b->d_stats); dev_free(b->d_results); dev_free(b->d_tmp); dev_free(b->d_astar);
+    dev_free(b->d_hdr); dev_free(b->d_units); dev_free(b->d_maps); dev_free(b->d_cst); dev_free(b->d_stats); dev_free(b->d_results); dev_free(b->d_tmp); dev_free(b->d_astar); dev_free(b->d_ff);
     for (auto &s : b->staged) { dev_free(s.actions); dev_free(s.counts); }
 #ifndef MRTS_EMU
     if (b->stream) cudaStreamDestroy(b->stream);
@@ -673,7 +674,15 @@ int mrts_batch_set_policy(mrts_batch *b, int player, int policy, int pathfinder)
     if (policy < MRTS_POLICY_EXTERNAL || policy > MRTS_POLICY_WORKER_RUSH_PP) return fail(MRTS_E_ARG, "mrts_batch_set_policy: unknown policy");
     if (policy >= MRTS_POLICY_WORKER_RUSH && !b->scripted)
         return fail(MRTS_E_STATE, "scripted policies need a batch created with MRTS_FLAG_SCRIPTED_AI");
-    if (pathfinder < MRTS_PF_ASTAR || pathfinder > MRTS_PF_GREEDY) return fail(MRTS_E_ARG, "unknown pathfinder");
+    if (pathfinder < MRTS_PF_ASTAR || pathfinder > MRTS_PF_FLOODFILL) return fail(MRTS_E_ARG, "unknown pathfinder");
+    if (pathfinder == MRTS_PF_FLOODFILL && !b->d_ff) {
+        // one cache per game and player: last frame + a valid bit and a W*H map of u16 distances per target position (scripted.cuh)
+        long long cells = (long long)b->W * b->H, words = 1 + (cells + 31) / 32; words += words & 1;
+        b->ff_stride = words * 4 + cells * cells * 2; b->ff_stride = (b->ff_stride + 15) & ~15LL;
+        unsigned long long total = (unsigned long long)b->n * 2ULL * (unsigned long long)b->ff_stride;
+        if (total > (64ULL << 30)) return fail(MRTS_E_LIMIT, "FloodFillPathFinding keeps one distance map per target cell, game and player: this batch would need more than 64 GB");
+        if (dev_select(b->device) || dev_alloc((void **)&b->d_ff, (size_t)total) || dev_zero(b->d_ff, (size_t)total, b->stream)) { b->d_ff = nullptr; return fail(MRTS_E_CUDA, std::string("FloodFill cache allocation failed: ") + dev_errstr()); }
+    }
     b->policy[player] = policy; b->pathfinder[player] = pathfinder;
     return MRTS_OK;
 }
@@ -863,7 +872,7 @@ int mrts_batch_evaluate(mrts_batch *b, int eval_fn, int maxplayer, int observer,
 
 int mrts_batch_pathfind(mrts_batch *b, int pathfinder, const int32_t *queries, int32_t *out_dir, int on_device) {
     if (!b || !queries || !out_dir) return fail(MRTS_E_ARG, "mrts_batch_pathfind: null argument");
-    if (pathfinder < MRTS_PF_ASTAR || pathfinder > MRTS_PF_GREEDY) return fail(MRTS_E_ARG, "unknown pathfinder");
+    if (pathfinder < MRTS_PF_ASTAR || pathfinder > MRTS_PF_GREEDY) return fail(MRTS_E_ARG, "unknown pathfinder (FloodFillPathFinding is stateful: it only runs inside a scripted policy)");
     if (!b->scripted) return fail(MRTS_E_STATE, "pathfinding needs a batch created with MRTS_FLAG_SCRIPTED_AI (it owns the search scratch)");
     if (dev_select(b->device)) return fail(MRTS_E_CUDA, dev_errstr());
     StepParams p; memset(&p, 0, sizeof p);

@@ -278,12 +278,111 @@ DEVN int pf_greedy(Game &g, int s, int tx, int ty, int range, int nd) {
     return dir;
 }
 
+// FloodFillPathFinding.findPathToPositionInRange (FloodFillPathFinding.java:168-213) with its per-instance cache of distance maps
+// (:17, one int[w][h] per target position, kept across cycles and queried again as long as the step it suggests is free).  The
+// instance is the AI's: a game carries one cache per player in HBM -- [last frame, valid bits per target position, W*H maps of W*H
+// u16 distances (0xFFFF = Integer.MAX_VALUE)] -- allocated when a player's pathfinder is set to MRTS_PF_FLOODFILL.
+// doFloodFill (:47-107): breadth first from the TARGET over cells that are free (gs.getAllFree: no wall, no unit, not the target of an
+// in-flight MOVE / PRODUCE) and not used by this cycle's earlier desires; neighbours in the order left, up, right, down; it stops after
+// the node whose neighbourhood contains the start cell.  getAction (:139-166): the neighbour of the start with the smallest distance,
+// first minimum in the order left, up, right, down.
+#ifndef MRTS_TU_RUSH_ONLY
+DEV int ff_get_action(const Game &g, const uint16_t *dist, int x, int y) {
+    const int W = g.W, H = g.H;
+    int d0 = x > 0 ? dist[(x - 1) + y * W] : 0xFFFF, d1 = y > 0 ? dist[x + (y - 1) * W] : 0xFFFF;
+    int d2 = x + 1 < W ? dist[(x + 1) + y * W] : 0xFFFF, d3 = y + 1 < H ? dist[x + (y + 1) * W] : 0xFFFF;
+    int index = 0, mn = d0;
+    if (d1 < mn) { index = 1; mn = d1; }
+    if (d2 < mn) { index = 2; mn = d2; }
+    if (d3 < mn) { index = 3; mn = d3; }
+    if (mn == 0xFFFF) return -1;
+    return index == 0 ? 3 : index - 1; // left, up, right, down -> DIRECTION_LEFT (3), UP (0), RIGHT (1), DOWN (2)
+}
+DEVN int pf_floodfill(Game &g, int player, int s, int tx, int ty, int range, int nd) {
+    const PfArr A = g.as_sm ? pf_arrays<true>(g) : pf_arrays<false>(g);
+    const int lane = g.lane, W = g.W, H = g.H, cells = W * H;
+    uint32_t sw = g.w0()[s];
+    const int sx = u_x(sw), sy = u_y(sw);
+    if (range < 0) range = 0;
+    if ((sx - tx) * (sx - tx) + (sy - ty) * (sy - ty) <= range * range) return -1; // already there
+    if (!g.ff_cache) return -1;
+    int32_t *hdr = (int32_t *)(g.ff_cache + (size_t)player * g.ff_stride);       // [0] lastFrame, [1..] valid bits
+    uint32_t *valid = (uint32_t *)(hdr + 1);
+    uint16_t *maps = (uint16_t *)(hdr + 1 + ((cells + 31) >> 5) + (((cells + 31) >> 5) & 1 ? 0 : 1)); // 8-byte aligned start
+    const int time = g.hdr()[H_TIME], target = tx + ty * W;
+    __syncwarp();
+    if (time < hdr[0]) { // a new game: cache.clear()
+        __syncwarp();
+        for (int i = lane; i < ((cells + 31) >> 5); i += 32) valid[i] = 0;
+    }
+    __syncwarp();
+    if (lane == 0) hdr[0] = time;
+    // initFree: the cells used by the desires chosen so far this cycle
+    int gen = *A.gen + 1;
+    __syncwarp();
+    if (gen >= 8191) { int pcells = A.P * (H + 2); for (int i = lane; i < pcells; i += 32) A.mark[i] = 0; gen = 1; }
+    if (lane == 0) *A.gen = (uint16_t)gen;
+    __syncwarp();
+    for (int k = lane; k < nd; k += 32) {
+        uint32_t A0 = g.pa0()[k];
+        if (a_uses_cell(a_type(A0))) { int pc = linear_target_cell(g, g.w0()[g.pslot()[k]], g.pa1()[k]); if (pc >= 0) pf_set(A, pc, gen, PFF_BLOCKED); }
+    }
+    __syncwarp();
+    uint16_t *dist = maps + (size_t)target * cells;
+    bool cached = (valid[target >> 5] >> (target & 31)) & 1;
+    __syncwarp();
+    if (cached) {
+        int dir = ff_get_action(g, dist, sx, sy);
+        if (dir >= 0) {
+            int pc = cell_of(g, sw) + doff(g, dir);
+            bool ok = !(pf_flags(A, pc, gen) & PFF_BLOCKED) && g.grid()[pc] == 0 && g.resv()[pc] == 0; // free[][] and gs.free()
+            if (ok) return dir;
+        }
+        // the suggested step is taken, or there is no step: cache.remove(targetpos) and compute again
+    }
+    // calculateDistances (:108-126)
+    __syncwarp();
+    for (int i = lane; i < cells; i += 32) dist[i] = 0xFFFF;
+    __syncwarp();
+    uint16_t *q = A.next; // the fringe: linear positions x + y * W
+    int qn = 1, index = 0;
+    if (lane == 0) { dist[target] = 0; q[0] = (uint16_t)target; }
+    __syncwarp();
+    const int dl = lane & 3; // this lane's neighbour: 0 left, 1 up, 2 right, 3 down
+    const int ddxl = dl == 0 ? -1 : (dl == 2 ? 1 : 0), ddyl = dl == 1 ? -1 : (dl == 3 ? 1 : 0);
+#pragma unroll 1
+    while (index < qn) {
+        int cur = q[index], x = cur % W, y = cur / W, dcur = dist[cur];
+        int nx = x + ddxl, ny = y + ddyl;
+        bool inb = nx >= 0 && ny >= 0 && nx < W && ny < H, ok = false, hit = false;
+        if (lane < 4) {
+            hit = nx == sx && ny == sy;
+            if (inb) {
+                int pc = (ny + 1) * A.P + nx + 1;
+                ok = dist[nx + ny * W] == 0xFFFF && !(pf_flags(A, pc, gen) & PFF_BLOCKED) && g.grid()[pc] == 0 && g.resv()[pc] == 0;
+            }
+        }
+        unsigned okm = __ballot_sync(FULLM, ok), hitm = __ballot_sync(FULLM, hit);
+        if (ok) { int slot = qn + __popc(okm & ((1u << lane) - 1)); dist[nx + ny * W] = (uint16_t)(dcur + 1); q[slot] = (uint16_t)(nx + ny * W); }
+        qn += __popc(okm);
+        __syncwarp();
+        if (hitm) break;
+        index++;
+    }
+    __syncwarp();
+    if (lane == 0) valid[target >> 5] |= 1u << (target & 31);
+    __syncwarp();
+    return ff_get_action(g, dist, sx, sy);
+}
+#endif
+
 // range < 0: PathFinding.findPath (A* and BFS: findPathToPositionInRange with range 0)
 DEV int pf_find(Game &g, int kind, int s, int tx, int ty, int range, int nd) {
 #ifdef MRTS_TU_RUSH_ONLY
     return pf_find_t<true, 0>(g, 0, s, tx, ty, range < 0 ? 0 : range, nd); // the lean copy: A*, scratch in shared memory
 #endif
     if (kind == 2) return pf_greedy(g, s, tx, ty, range, nd);
+    if (kind == 3) return pf_floodfill(g, u_pl(g.w0()[s]) == 2 ? 1 : 0, s, tx, ty, range, nd);
     if (range < 0) range = 0;
     return g.as_sm ? pf_find_t<true>(g, kind, s, tx, ty, range, nd) : pf_find_t<false>(g, kind, s, tx, ty, range, nd);
 }

@@ -919,6 +919,91 @@ static int pf_find(const OGame *g, int kind, int start, int targetpos, int range
     return result;
 }
 
+/* FloodFillPathFinding, ai/abstraction/pathfinding/FloodFillPathFinding.java (whole file): an instance keeps `cache`, a map from target
+ * position to a distance array, and `lastFrame`.  PARITY UNPINNED (no golden data in the reference). */
+typedef struct { int w, h; int **cache; /* [w*h] -> int[w*h] (distances[x][y] at x*h + y) or NULL */ int last_frame; } OFf;
+static OFf *ff_new(void) { OFf *f = (OFf *)calloc(1, sizeof(OFf)); f->last_frame = -1; return f; }
+static void ff_clear(OFf *f) { if (f->cache) for (int i = 0; i < f->w * f->h; i++) { free(f->cache[i]); f->cache[i] = NULL; } }
+static void ff_free(OFf *f) { if (!f) return; ff_clear(f); free(f->cache); free(f); }
+/* getAction :139-166 */
+static int ff_get_action(const OFf *f, const int *distances, int x, int y) {
+    int w = f->w, h = f->h;
+#define FF_B(X, Y) ((X) >= 0 && (Y) >= 0 && (X) < w && (Y) < h)
+    int dists[4] = {FF_B(x - 1, y) ? distances[(x - 1) * h + y] : INT32_MAX, FF_B(x, y - 1) ? distances[x * h + y - 1] : INT32_MAX,
+                    FF_B(x + 1, y) ? distances[(x + 1) * h + y] : INT32_MAX, FF_B(x, y + 1) ? distances[x * h + y + 1] : INT32_MAX};
+    int index = 0, min = dists[0];
+    for (int i = 1; i < 4; i++) if (dists[i] < min) { index = i; min = dists[i]; }
+    if (min == INT32_MAX) return -1;
+    switch (index) { case 0: return O_LEFT; case 1: return O_UP; case 2: return O_RIGHT; default: return O_DOWN; }
+}
+/* GameState.getAllFree :215-229 over PhysicalGameState.getAllFree :512-525 */
+static void gs_all_free(const OGame *g, uint8_t *fr /* [x*h + y] */) {
+    int w = g->w, h = g->h;
+    for (int x = 0; x < w; x++) for (int y = 0; y < h; y++) fr[x * h + y] = terrain_at(g, x, y) == 0;
+    for (int i = 0; i < g->n; i++) { const OUnit *u = &g->pool[g->list[i]]; fr[u->x * h + u->y] = 0; }
+    for (int i = 0; i < g->na; i++) {
+        const OAssign *a = &g->asg[i];
+        if (a->act.type == O_MOVE || a->act.type == O_PRODUCE) {
+            const OUnit *u = &g->pool[a->unit];
+            int d = a->act.param, x = u->x + (d == O_RIGHT) - (d == O_LEFT), y = u->y + (d == O_DOWN) - (d == O_UP);
+            if (d >= 0 && d < 4 && x >= 0 && y >= 0 && x < w && y < h) fr[x * h + y] = 0; /* (the reference would throw outside the map) */
+        }
+    }
+}
+static int pf_floodfill(OFf *f, const OGame *g, int start, int targetpos, int range, const ORu *ru) {
+    const OUnit *s = &g->pool[start];
+    int w = g->w, h = g->h;
+    if (range < 0) range = 0; /* findPath :38-40 */
+    if (f->w != w || f->h != h) { ff_clear(f); free(f->cache); f->w = w; f->h = h; f->cache = (int **)calloc((size_t)w * h, sizeof(int *)); }
+    int x = targetpos % w, y = targetpos / w;
+    if ((s->x - x) * (s->x - x) + (s->y - y) * (s->y - y) <= range * range) return -1; /* already there */
+    if (g->time < f->last_frame) ff_clear(f); /* new game */
+    f->last_frame = g->time;
+    uint8_t *fre = (uint8_t *)malloc((size_t)w * h); memset(fre, 1, (size_t)w * h); /* initFree :127-138 */
+    if (ru) for (int i = 0; i < ru->npos; i++) { int q = ru->pos[i]; if (q >= 0 && q < w * h) fre[(q % w) * h + q / w] = 0; }
+    int result;
+    if (f->cache[targetpos]) {
+        int action = ff_get_action(f, f->cache[targetpos], s->x, s->y);
+        int ok = 0;
+        if (action >= 0) {
+            int px = s->x + DX[action], py = s->y + DY[action];
+            ok = fre[px * h + py] && gs_free(g, px, py);
+        }
+        if (ok) { free(fre); return action; }
+        free(f->cache[targetpos]); f->cache[targetpos] = NULL; /* cache.remove(targetpos) */
+    }
+    /* calculateDistances :108-126 (ALT_THRESHOLD = 0: the alternative path finder is unreachable past the range test above) */
+    int *distances = (int *)malloc(sizeof(int) * (size_t)w * h);
+    for (int i = 0; i < w * h; i++) distances[i] = INT32_MAX;
+    distances[x * h + y] = 0;
+    { /* doFloodFill :47-107 */
+        uint8_t *gsFree = (uint8_t *)malloc((size_t)w * h); gs_all_free(g, gsFree);
+        int *fx = (int *)malloc(sizeof(int) * ((size_t)w * h + 8)), *fy = (int *)malloc(sizeof(int) * ((size_t)w * h + 8));
+        int nf = 1, index = 0, reached = 0, finalX = s->x, finalY = s->y;
+        fx[0] = x; fy[0] = y;
+        static const int NX[4] = {-1, 0, 1, 0}, NY[4] = {0, -1, 0, 1}; /* left, up, right, down */
+        while (index < nf) {
+            int cx = fx[index], cy = fy[index];
+            for (int k = 0; k < 4; k++) {
+                int nx = cx + NX[k], ny = cy + NY[k];
+                if (nx == finalX && ny == finalY) reached = 1;
+                if (FF_B(nx, ny) && distances[nx * h + ny] == INT32_MAX && fre[nx * h + ny] && gsFree[nx * h + ny]) {
+                    distances[nx * h + ny] = distances[cx * h + cy] + 1;
+                    fx[nf] = nx; fy[nf] = ny; nf++;
+                }
+            }
+            if (reached) break;
+            index++;
+        }
+        free(gsFree); free(fx); free(fy);
+    }
+#undef FF_B
+    f->cache[targetpos] = distances;
+    result = ff_get_action(f, distances, s->x, s->y);
+    free(fre);
+    return result;
+}
+
 int o_pathfind(const OGame *g, int kind, int unit_idx, int targetpos, int range, int n_ru, const int32_t *ru_pos) {
     ORu r; ru_init(&r);
     for (int i = 0; i < n_ru; i++) ru_add_pos(&r, ru_pos[i]);
@@ -941,7 +1026,11 @@ typedef struct {
     int completed;     /* train */
 } OAbs;
 
-struct OAi { int kind; int pf; OAbs *a; int n, cap; int po_rush; };
+struct OAi { int kind; int pf; OAbs *a; int n, cap; int po_rush; OFf *ff; /* the instance's FloodFillPathFinding, pf == 3 */ };
+static int ai_pf(OAi *ai, const OGame *g, int start, int targetpos, int range, const ORu *ru) {
+    if (ai->pf == 3) { if (!ai->ff) ai->ff = ff_new(); return pf_floodfill(ai->ff, g, start, targetpos, range, ru); }
+    return pf_find(g, ai->pf, start, targetpos, range, ru);
+}
 
 OAi *o_ai_create(int kind, int pathfinder) {
     OAi *ai = (OAi *)calloc(1, sizeof(OAi));
@@ -949,7 +1038,7 @@ OAi *o_ai_create(int kind, int pathfinder) {
     return ai;
 }
 OAi *o_ai_clone(const OAi *s) { return o_ai_create(s->kind, s->pf); } /* AI.clone(): fresh instance, empty actions map */
-void o_ai_free(OAi *ai) { if (ai) { free(ai->a); free(ai); } }
+void o_ai_free(OAi *ai) { if (ai) { ff_free(ai->ff); free(ai->a); free(ai); } }
 
 static OAbs *ai_get(OAi *ai, int u) { for (int i = 0; i < ai->n; i++) if (ai->a[i].unit == u) return &ai->a[i]; return NULL; }
 static void ai_put(OAi *ai, OAbs v) { /* LinkedHashMap.put: existing key keeps its slot */
@@ -1004,12 +1093,12 @@ static int aa_execute(OAi *ai, OAbs *aa, OGame *g, const ORu *ru, OAct *out) {
             int range = g->utt->f[unit->type][OF_RANGE];
             if (d <= range) { *out = mk_act(O_ATTACK, -1, t->x, t->y, -1); return 1; }
             OAct mv;
-            if (mk_move(&mv, pf_find(g, ai->pf, aa->unit, t->x + t->y * w, range, ru)) && is_unit_action_allowed(g, aa->unit, &mv)) { *out = mv; return 1; }
+            if (mk_move(&mv, ai_pf(ai, g, aa->unit, t->x + t->y * w, range, ru)) && is_unit_action_allowed(g, aa->unit, &mv)) { *out = mv; return 1; }
             return 0;
         }
         case AA_MOVE: { /* Move.java:49-55: pf.findPath */
             OAct mv;
-            if (mk_move(&mv, pf_find(g, ai->pf, aa->unit, aa->x + aa->y * w, -1, ru)) && is_unit_action_allowed(g, aa->unit, &mv)) { *out = mv; return 1; }
+            if (mk_move(&mv, ai_pf(ai, g, aa->unit, aa->x + aa->y * w, -1, ru)) && is_unit_action_allowed(g, aa->unit, &mv)) { *out = mv; return 1; }
             return 0;
         }
         case AA_HARVEST: { /* Harvest.java:72-113 */
@@ -1018,7 +1107,7 @@ static int aa_execute(OAi *ai, OAbs *aa, OGame *g, const ORu *ru, OAct *out) {
             if (other < 0) return 0;
             const OUnit *t = &g->pool[other];
             OAct mv;
-            if (mk_move(&mv, pf_find(g, ai->pf, aa->unit, t->x + t->y * w, 1, ru))) {
+            if (mk_move(&mv, ai_pf(ai, g, aa->unit, t->x + t->y * w, 1, ru))) {
                 if (is_unit_action_allowed(g, aa->unit, &mv)) { *out = mv; return 1; }
                 return 0;
             }
@@ -1030,7 +1119,7 @@ static int aa_execute(OAi *ai, OAbs *aa, OGame *g, const ORu *ru, OAct *out) {
         }
         case AA_BUILD: { /* Build.java:54-77 */
             OAct mv;
-            if (mk_move(&mv, pf_find(g, ai->pf, aa->unit, aa->x + aa->y * w, 1, ru))) {
+            if (mk_move(&mv, ai_pf(ai, g, aa->unit, aa->x + aa->y * w, 1, ru))) {
                 if (is_unit_action_allowed(g, aa->unit, &mv)) { *out = mv; return 1; }
                 return 0;
             }

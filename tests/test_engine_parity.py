@@ -544,6 +544,12 @@ SCRIPTED = [
     ("BWDistantResources32x32", "LIGHT_RUSH", "RANGED_RUSH", 2),
     ("16x16/basesWorkers16x16", "WORKER_RUSH_PP", "LIGHT_RUSH", 0),
     ("8x8/basesWorkers8x8", "WORKER_DEFENSE", "WORKER_RUSH_PP", 1),
+    # FloodFillPathFinding (pathfinder 3): distance maps cached per target position in each AI instance across cycles
+    ("8x8/basesWorkers8x8", "WORKER_RUSH", "LIGHT_RUSH", 3),
+    ("16x16/basesWorkers16x16", "LIGHT_RUSH", "WORKER_RUSH", 3),
+    ("16x16/TwoBasesBarracks16x16", "RANGED_RUSH", "HEAVY_RUSH", 3),
+    ("24x24/basesWorkers24x24", "WORKER_RUSH", "LIGHT_DEFENSE", 3),
+    ("BWDistantResources32x32", "LIGHT_RUSH", "WORKER_RUSH", 3),
 ]
 
 
