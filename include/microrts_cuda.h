@@ -262,7 +262,7 @@ int mrts_batch_set_vec_autoreset(mrts_batch *, int done_mode, int max_steps);
 /* Game g's fused outputs (observations, masks) are written at game slot g * game_stride of their buffers (default 1).  With stride 2,
  * out_player0 = base and out_player1 = base + one game's bytes, the two players of game g land next to each other: the environment
  * order of JNIGridnetVecClient's self-play pairs (src/tests/JNIGridnetVecClient.java:226-236, environment 2g = player 0 of game g). */
-int mrts_batch_set_output_stride(mrts_batch *, int game_stride);
+int mrts_batch_set_output_stride(mrts_batch *, int game_stride); /* mrts_batch_masks with on_device != 0 follows it too */
 /* JNIGridnetClient.getMasks(player) (src/tests/JNIGridnetClient.java:210-223, UnitAction.java:711-751):
  * out = [n_games][H][W][mask_width]; with MRTS_DTYPE_BITS the last dimension is (mask_width + 7) / 8 bytes of packed bits
  * (79 entries -> 10 bytes per cell: 1/32 of the int32 array the reference allocates). */

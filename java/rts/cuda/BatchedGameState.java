@@ -26,10 +26,11 @@ public final class BatchedGameState implements AutoCloseable {
             POLICY_HEAVY_RUSH = 5, POLICY_RANGED_RUSH = 6, POLICY_WORKER_DEFENSE = 7, POLICY_LIGHT_DEFENSE = 8, POLICY_HEAVY_DEFENSE = 9,
             POLICY_RANGED_DEFENSE = 10, POLICY_PO_WORKER_RUSH = 11, POLICY_PO_LIGHT_RUSH = 12, POLICY_PO_HEAVY_RUSH = 13,
             POLICY_PO_RANGED_RUSH = 14, POLICY_WORKER_RUSH_PP = 15;   // MRTS_POLICY_* of include/microrts_cuda.h
-    public static final int PF_ASTAR = 0, PF_BFS = 1, PF_GREEDY = 2;    // ai.abstraction.pathfinding.{AStar,BFS,Greedy}PathFinding
+    public static final int PF_ASTAR = 0, PF_BFS = 1, PF_GREEDY = 2, PF_FLOODFILL = 3; // ai.abstraction.pathfinding.{AStar,BFS,Greedy,FloodFill}PathFinding
     public static final int FLAG_PARTIAL_OBS = 1, FLAG_SCRIPTED_AI = 2, FLAG_PO_POLICIES = 4; // MRTS_FLAG_*
     public static final int ACTIONS_VECTOR = 0, ACTIONS_RAW = 1;
-    public static final int DTYPE_U8 = 0, DTYPE_I32 = 1;
+    public static final int DTYPE_U8 = 0, DTYPE_I32 = 1, DTYPE_BITS = 2;
+    public static final int NCCL_UNIQUE_ID_BYTES = 128, PAG_DONE = -100;
 
     private static final Linker LINKER = Linker.nativeLinker();
     private static final ValueLayout.OfInt I = ValueLayout.JAVA_INT;
@@ -40,7 +41,9 @@ public final class BatchedGameState implements AutoCloseable {
     private final SymbolLookup lib;
     private final MethodHandle lastError, uttCreate, uttDestroy, mapLoad, mapDestroy, batchCreate, batchDestroy, reset, resetMasked,
             setPolicy, setAutoReset, setActions, issue, step, cycleTo, observe, masks, results, stats, rollout, pathfind, evaluate, numPlanes, maskWidth,
-            restartMasked, setIssueOrder, setInfoOutput, setObservationOutputs;
+            restartMasked, setIssueOrder, setInfoOutput, setObservationOutputs, setMaskOutputs, setOutputStride, setVecAutoreset, setActionsInterleaved,
+            copyGames, scatterGames, copyToHost, sync, unitActions, cycleToDecision, playerActions, statsAllreduce, ncclUniqueId, ncclCommCreate, ncclCommDestroy,
+            mctsCreate, mctsIterate, mctsRoot, mctsBestActions, mctsDestroy, pagCreate, pagNext, pagSize, pagDestroy;
 
     private MemorySegment utt, map, batch;
     public final int numGames, width, height, planes, maskW;
@@ -94,6 +97,30 @@ public final class BatchedGameState implements AutoCloseable {
         setIssueOrder = h("mrts_batch_set_issue_order", FunctionDescriptor.of(I, P, I));
         setInfoOutput = h("mrts_batch_set_info_output", FunctionDescriptor.of(I, P, P));
         setObservationOutputs = h("mrts_batch_set_observation_outputs", FunctionDescriptor.of(I, P, I, P, P));
+        setMaskOutputs = h("mrts_batch_set_mask_outputs", FunctionDescriptor.of(I, P, P, P));
+        setOutputStride = h("mrts_batch_set_output_stride", FunctionDescriptor.of(I, P, I));
+        setVecAutoreset = h("mrts_batch_set_vec_autoreset", FunctionDescriptor.of(I, P, I, I));
+        setActionsInterleaved = h("mrts_batch_set_actions_interleaved", FunctionDescriptor.of(I, P, I, P, I, I, I, I));
+        copyGames = h("mrts_batch_copy_games", FunctionDescriptor.of(I, P, P, P, P, I));
+        scatterGames = h("mrts_batch_scatter_games", FunctionDescriptor.of(I, P, P, P, I));
+        copyToHost = h("mrts_batch_copy_to_host", FunctionDescriptor.of(I, P, P, P, L));
+        sync = h("mrts_batch_sync", FunctionDescriptor.of(I, P));
+        unitActions = h("mrts_batch_unit_actions", FunctionDescriptor.of(I, P, I, I, I, I, P, P, P, P, I));
+        cycleToDecision = h("mrts_batch_cycle_to_decision", FunctionDescriptor.of(I, P));
+        playerActions = h("mrts_batch_player_actions", FunctionDescriptor.of(I, P, L, I, P, P, L, I, P));
+        statsAllreduce = h("mrts_batch_stats_allreduce", FunctionDescriptor.of(I, P, P, P));
+        ncclUniqueId = h("mrts_nccl_unique_id", FunctionDescriptor.of(I, P));
+        ncclCommCreate = h("mrts_nccl_comm_create", FunctionDescriptor.of(I, P, I, I, I, P));
+        ncclCommDestroy = h("mrts_nccl_comm_destroy", FunctionDescriptor.ofVoid(P));
+        mctsCreate = h("mrts_mcts_create", FunctionDescriptor.of(I, P, I, P, I, P, P));
+        mctsIterate = h("mrts_mcts_iterate", FunctionDescriptor.of(I, P, I));
+        mctsRoot = h("mrts_mcts_root", FunctionDescriptor.of(I, P, L, P, P, P, P, I));
+        mctsBestActions = h("mrts_mcts_best_actions", FunctionDescriptor.of(I, P, P, P, I));
+        mctsDestroy = h("mrts_mcts_destroy", FunctionDescriptor.ofVoid(P));
+        pagCreate = h("mrts_pag_create", FunctionDescriptor.of(I, P, L, I, I, P));
+        pagNext = h("mrts_pag_next", FunctionDescriptor.of(I, P, P, I));
+        pagSize = h("mrts_pag_size", FunctionDescriptor.of(L, P));
+        pagDestroy = h("mrts_pag_destroy", FunctionDescriptor.ofVoid(P));
         try {
             MemorySegment out = arena.allocate(P);
             check((int) uttCreate.invoke(uttVersion, conflictPolicy, out));
@@ -245,6 +272,97 @@ public final class BatchedGameState implements AutoCloseable {
             check((int) pathfind.invoke(batch, pathfinder, a.allocateFrom(I, queries), out, 0));
             return out.toArray(I);
         }
+    }
+
+    // ---- the vectorised RL flow in one launch per gameStep (tests.CudaGridnetVecClient drives these) ---------------------------------
+    /** Fused outputs in JNIGridnetVecClient's environment order: obs = [2 * numGames][planes][h][w] device memory, environment 2g = player 0 of game g. */
+    public void setInterleavedOutputs(int dtype, MemorySegment obs, long obsBytesPerEnv, MemorySegment masks, long maskBytesPerEnv) throws Throwable {
+        check((int) setOutputStride.invoke(batch, 2));
+        check((int) setObservationOutputs.invoke(batch, dtype, obs, obs.asSlice(obsBytesPerEnv)));
+        check((int) setMaskOutputs.invoke(batch, masks, masks.equals(MemorySegment.NULL) ? MemorySegment.NULL : masks.asSlice(maskBytesPerEnv)));
+    }
+
+    /** JNIGridnetVecClient's auto-reset inside the step launch: doneMode 1 game over, 2 resources exhausted, 3 never; always after maxSteps. */
+    public void setVecAutoreset(int doneMode, int maxSteps) throws Throwable { check((int) setVecAutoreset.invoke(batch, doneMode, maxSteps)); }
+
+    /** Both players' vector actions of every game from one [2 * numGames][maxK][8] array in environment order (off-heap, ideally pinned). */
+    public void setActionsInterleaved(MemorySegment actions, int maxK, boolean async) throws Throwable {
+        check((int) setActionsInterleaved.invoke(batch, ACTIONS_VECTOR, actions, maxK, 1, 0, async ? 1 : 0));
+    }
+
+    /** Queue a device -> host copy behind the step on the batch's stream; sync() waits. */
+    public void copyToHost(MemorySegment host, MemorySegment device, long bytes) throws Throwable { check((int) copyToHost.invoke(batch, host, device, bytes)); }
+
+    public void sync() throws Throwable { check((int) sync.invoke(batch)); }
+
+    /** gs.clone() for many games at once: game g becomes a copy of src's game srcIndex[g] (null: g). */
+    public void copyGames(BatchedGameState src, long[] srcIndex) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            check((int) copyGames.invoke(batch, src.batch, srcIndex == null ? MemorySegment.NULL : a.allocateFrom(L, srcIndex), MemorySegment.NULL, 0));
+        }
+    }
+
+    /** cycle() until the game is over or somebody can act (the loop at the head of NaiveMCTSNode). */
+    public void cycleToDecision() throws Throwable { check((int) cycleToDecision.invoke(batch)); }
+
+    /** GameState.getPlayerActions(player) of one game as RAW rows; returns the number of PlayerActions. */
+    public long getPlayerActions(long game, int player, int[] outRows, int[] outCounts, int maxK) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment rows = a.allocate(I, outRows.length), counts = a.allocate(I, outCounts.length), total = a.allocate(L);
+            check((int) playerActions.invoke(batch, game, player, rows, counts, (long) outCounts.length, maxK, total));
+            MemorySegment.copy(rows, I, 0, outRows, 0, outRows.length);
+            MemorySegment.copy(counts, I, 0, outCounts, 0, outCounts.length);
+            return total.get(L, 0);
+        }
+    }
+
+    /**
+     * One NaiveMCTS search per game (src/ai/mcts/naivemcts/NaiveMCTS.java): `iterations` playouts each, then getBestActionSoFar as RAW rows
+     * [numGames][maxK][8] + counts -- issue them with issueSafe(player, rows, counts, maxK).
+     */
+    public int[] naiveMcts(int player, int iterations, int lookahead, int maxDepth, float eL, float eG, float e0, long[] seeds, int[] outCounts, int maxK) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment prm = a.allocate(32);
+            prm.set(I, 0, lookahead); prm.set(I, 4, maxDepth); prm.set(ValueLayout.JAVA_FLOAT, 8, eL); prm.set(ValueLayout.JAVA_FLOAT, 12, eG);
+            prm.set(ValueLayout.JAVA_FLOAT, 16, e0); prm.set(I, 20, 0); prm.set(I, 24, 1); prm.set(I, 28, 0);
+            MemorySegment out = a.allocate(P);
+            check((int) mctsCreate.invoke(batch, player, prm, iterations + 2, seeds == null ? MemorySegment.NULL : a.allocateFrom(L, seeds), out));
+            MemorySegment m = out.get(P, 0);
+            try {
+                check((int) mctsIterate.invoke(m, iterations));
+                MemorySegment rows = a.allocate(I, (long) numGames * maxK * 8), counts = a.allocate(I, numGames);
+                check((int) mctsBestActions.invoke(m, rows, counts, maxK));
+                MemorySegment.copy(counts, I, 0, outCounts, 0, numGames);
+                return rows.toArray(I);
+            } finally {
+                mctsDestroy.invoke(m);
+            }
+        }
+    }
+
+    /** The run's one collective: the eight counters summed over every rank's batch (ncclAllReduce inside the library). */
+    public long[] statsAllReduce(MemorySegment comm) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment seg = a.allocate(L, 8);
+            check((int) statsAllreduce.invoke(batch, seg, comm));
+            return seg.toArray(L);
+        }
+    }
+
+    /** Rank 0 of a multi-GPU host calls this and hands the 128 bytes to the other ranks (threads: an array; processes: a file or socket). */
+    public byte[] ncclUniqueId() throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment id = a.allocate(NCCL_UNIQUE_ID_BYTES);
+            check((int) ncclUniqueId.invoke(id));
+            return id.toArray(ValueLayout.JAVA_BYTE);
+        }
+    }
+
+    /** Collective over all ranks: the communicator statsAllReduce takes. */
+    public MemorySegment ncclCommCreate(byte[] uniqueId, int nRanks, int rank, int device) throws Throwable {
+        MemorySegment out = arena.allocate(P);
+        check((int) ncclCommCreate.invoke(arena.allocateFrom(ValueLayout.JAVA_BYTE, uniqueId), nRanks, rank, device, out));
+        return out.get(P, 0);
     }
 
     @Override

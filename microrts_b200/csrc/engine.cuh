@@ -1967,7 +1967,7 @@ DEVN void masks_game(Game &g, const StepParams &p, long long gi) {
     { // The game's whole mask block is zero-filled here (16-byte stores when it is aligned), then the rows of the player's idle
       // units are written over it: the warp barrier orders the two writes and the second one merges in L2, as in obs_emit.
         size_t per_game = (size_t)g.W * g.H * (p.out_dtype == 2 ? (size_t)((K + 7) >> 3) : (size_t)K * (p.out_dtype == 0 ? 1 : 4));
-        char *o = (char *)p.out + (size_t)gi * per_game;
+        char *o = (char *)p.out + (size_t)gi * (p.out_stride > 1 ? p.out_stride : 1) * per_game;
         if ((per_game & 15) == 0 && (((size_t)p.out) & 15) == 0) {
             uint4 z; z.x = z.y = z.z = z.w = 0;
             #pragma unroll 4
@@ -1985,7 +1985,7 @@ DEVN void masks_game(Game &g, const StepParams &p, long long gi) {
         Enum e; enumerate(g, s, e);
         bool mv = (e.fl & UF_MOVE) != 0;
         int pr_m = e.n_aff > 0 ? e.free_m : 0, mv_m = mv ? e.free_m : 0;
-        size_t cell = (size_t)gi * g.W * g.H + (size_t)u_y(w) * g.W + u_x(w), row = cell * K;
+        size_t cell = (size_t)gi * (p.out_stride > 1 ? p.out_stride : 1) * g.W * g.H + (size_t)u_y(w) * g.W + u_x(w), row = cell * K;
         int MB = (K + 7) >> 3; // bit-packed row length in bytes (out_dtype 2)
         #pragma unroll 1
         for (int jb = 0; jb < K; jb += 32) {

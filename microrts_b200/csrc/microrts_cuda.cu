@@ -926,6 +926,7 @@ static int emit(mrts_batch *b, int mode, int player, int dtype, void *out, int o
     } else {
         StepParams p; memset(&p, 0, sizeof p);
         p.mode = mode; p.out = d_out; p.out_dtype = dtype; p.out_player = player;
+        if (mode == MODE_MASKS && on_device) p.out_stride = b->out_stride; // on-device mask outputs follow mrts_batch_set_output_stride (environment order)
         if (launch_step(b, p)) return fail(MRTS_E_CUDA, std::string("launch: ") + dev_errstr());
     }
     if (!on_device && dev_d2h(out, d_out, bytes, b->stream)) return fail(MRTS_E_CUDA, dev_errstr());

@@ -380,11 +380,12 @@ DEVN int pf_floodfill(Game &g, int player, int s, int tx, int ty, int range, int
 DEV int pf_find(Game &g, int kind, int s, int tx, int ty, int range, int nd) {
 #ifdef MRTS_TU_RUSH_ONLY
     return pf_find_t<true, 0>(g, 0, s, tx, ty, range < 0 ? 0 : range, nd); // the lean copy: A*, scratch in shared memory
-#endif
+#else
     if (kind == 2) return pf_greedy(g, s, tx, ty, range, nd);
     if (kind == 3) return pf_floodfill(g, u_pl(g.w0()[s]) == 2 ? 1 : 0, s, tx, ty, range, nd);
     if (range < 0) range = 0;
     return g.as_sm ? pf_find_t<true>(g, kind, s, tx, ty, range, nd) : pf_find_t<false>(g, kind, s, tx, ty, range, nd);
+#endif
 }
 
 // ---- AbstractionLayerAI -------------------------------------------------------------------------------------------------

@@ -390,6 +390,22 @@ class JNIGridnetVecClient:
         return self.responses
 
     def getMasks(self, player):
+        one = self._single()
+        if one is not None and one.selfplay and not self._emulated:
+            # dense int32 masks written by the device straight in environment order into a reused device array, one copy into a reused
+            # pinned array (the reference's getMasks also returns buffers it owns)
+            g, b = one, one.b
+            if getattr(g, "dense_dev", None) is None:
+                shape = (g.E, b.height, b.width, b.mask_width)
+                g.dense_dev = _device_array(shape, np.int32, False)
+                g.dense_host, g._dense_pin = _host_array(shape, np.int32, False)
+            per_env = b.height * b.width * b.mask_width
+            flat = g.dense_dev.view(-1)
+            b.masks(0, np.int32, out=flat[0:])           # player 0 -> environments 0, 2, 4, ... (output stride 2)
+            b.masks(1, np.int32, out=flat[per_env:])     # player 1 -> environments 1, 3, 5, ...
+            b.copy_to_host(g.dense_host, g.dense_dev)
+            b.sync()
+            return g.dense_host
         out = None
         for g in self.groups:
             if g.selfplay:

@@ -1004,6 +1004,17 @@ static int pf_floodfill(OFf *f, const OGame *g, int start, int targetpos, int ra
     return result;
 }
 
+/* a FloodFillPathFinding instance of its own (known-answer tests): the cache lives as long as the handle */
+void *o_ff_create(void) { return ff_new(); }
+void o_ff_free(void *f) { ff_free((OFf *)f); }
+int o_ff_find(void *f, const OGame *g, int unit_idx, int targetpos, int range, int n_ru, const int32_t *ru_pos) {
+    ORu r; ru_init(&r);
+    for (int i = 0; i < n_ru; i++) ru_add_pos(&r, ru_pos[i]);
+    int d = pf_floodfill((OFf *)f, g, g->list[unit_idx], targetpos, range, &r);
+    ru_free(&r);
+    return d;
+}
+
 int o_pathfind(const OGame *g, int kind, int unit_idx, int targetpos, int range, int n_ru, const int32_t *ru_pos) {
     ORu r; ru_init(&r);
     for (int i = 0; i < n_ru; i++) ru_add_pos(&r, ru_pos[i]);

@@ -97,6 +97,11 @@ int o_from_vector_action(OGame *, int player, int n, const int32_t *vec /*[n][8]
 /* returns direction 0..3 or -1 (null) */
 int o_pathfind(const OGame *, int kind, int unit_idx, int targetpos, int range, int n_ru, const int32_t *ru_pos);
 
+/* a FloodFillPathFinding instance (stateful: its cache of distance maps persists across calls) */
+void *o_ff_create(void);
+void o_ff_free(void *);
+int o_ff_find(void *ff, const OGame *, int unit_idx, int targetpos, int range, int n_ru, const int32_t *ru_pos);
+
 /* observations / masks */
 void o_observe(const OGame *, int player, int32_t *out /*[6][h][w]*/);
 void o_observe_po(const OGame *po_view, int player, int32_t *out /*[8][h][w]*/);

@@ -64,6 +64,7 @@ def lib():
             "o_ai_get_action": (i, [vp, vp, i, pi32, C.POINTER(ActionV)]),
             "o_from_vector_action": (i, [vp, i, i, pi32, i, pi32, C.POINTER(ActionV)]),
             "o_pathfind": (i, [vp, i, i, i, i, i, pi32]),
+            "o_ff_create": (vp, []), "o_ff_free": (None, [vp]), "o_ff_find": (i, [vp, vp, i, i, i, i, pi32]),
             "o_observe": (None, [vp, i, pi32]), "o_observe_po": (None, [vp, i, pi32]), "o_masks": (None, [vp, i, pi32]),
             "o_po_view": (vp, [vp, i]),
             "o_evaluate": (C.c_float, [vp, i, i, i]),
@@ -369,3 +370,20 @@ class Mcts:
         acts = (ActionV * cap)()
         n = lib().o_mcts_best_action(self.h, idx, acts)
         return None if n < 0 else [(idx[k], acts[k].tup()) for k in range(n)]
+
+
+class FloodFill:
+    """One FloodFillPathFinding instance of the oracle (its distance-map cache persists across find() calls)."""
+
+    def __init__(self):
+        self.h = lib().o_ff_create()
+
+    def __del__(self):
+        try:
+            lib().o_ff_free(self.h)
+        except Exception:
+            pass
+
+    def find(self, game, unit_idx, targetpos, rng, ru=()):
+        a = (C.c_int32 * max(1, len(ru)))(*ru)
+        return lib().o_ff_find(self.h, game.h, unit_idx, targetpos, rng, len(ru), a)

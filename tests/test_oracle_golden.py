@@ -120,6 +120,30 @@ def test_greedy_pathfinder_known_answers():
     assert g.pathfind(O.PF_ASTAR, 0, 4 + 1 * 8, 0) == g.pathfind(O.PF_BFS, 0, 4 + 1 * 8, 0) == 2  # down, around the wall's lower end
 
 
+def test_floodfill_pathfinder_known_answers():
+    """FloodFillPathFinding.java:47-107,139-213 by hand on an empty 8x8 map."""
+    utt = O.Utt(1, 1)
+    ff = O.FloodFill()
+    target = 5 + 1 * 8
+    # worker at (1,1), target (5,1): the flood from the target reaches (2,1) at distance 3 and stops after expanding it (its
+    # neighbourhood holds the start), so (1,0) and (1,2) (distance 5) are never labelled: RIGHT
+    g = O.Game(utt, _tiny_map([("Worker", 0, 1, 1, 0, 1), ("Base", 1, 6, 6, 0, 10)]))
+    assert ff.find(g, 0, target, 1) == 1
+    # already within range 1 of the target: null, and nothing is cached
+    g2 = O.Game(utt, _tiny_map([("Worker", 0, 4, 1, 0, 1), ("Base", 1, 6, 6, 0, 10)]))
+    assert ff.find(g2, 0, target, 1) == -1
+    # same instance, same target, but (2,1) is now occupied: the cached map still says RIGHT, the cell is not free, so the map is
+    # dropped and recomputed around the blocker; (1,0) and (1,2) are both labelled 5 before either is expanded -> first minimum in
+    # the order left, up, right, down = UP
+    g3 = O.Game(utt, _tiny_map([("Worker", 0, 1, 1, 0, 1), ("Worker", 0, 2, 1, 0, 1), ("Base", 1, 6, 6, 0, 10)]))
+    assert ff.find(g3, 0, target, 1) == 0
+    # a fresh instance with (1,0) reserved by an earlier desire of the same cycle (ru): DOWN
+    assert O.FloodFill().find(g3, 0, target, 1, ru=[1 + 0 * 8]) == 2
+    # the stale map is reused as long as the step it suggests is free: the instance that computed "UP" for g3 answers UP for the
+    # unblocked map g as well (a fresh instance says RIGHT)
+    assert ff.find(g, 0, target, 1) == 0 and O.FloodFill().find(g, 0, target, 1) == 1
+
+
 def test_partially_observable_view_known_answers():
     utt = O.Utt(1, 1)
     # worker sight radius 3, base 5 (UnitTypeTable.java): player 0 has a worker at (1,1) only
