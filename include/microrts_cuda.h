@@ -318,7 +318,7 @@ int mrts_pag_random(mrts_pag *, int64_t *rng_state, int32_t *rows, int max_k);  
 int mrts_pag_randomize_order(mrts_pag *, int64_t *rng_state);                   /* randomizeOrder() */
 int64_t mrts_java_random_seed(int64_t seed);
 
-/* ai.mcts.naivemcts.NaiveMCTS (src/ai/mcts/naivemcts/NaiveMCTS.java:140-158,195-262; NaiveMCTSNode.java) for every game of `roots` at once:
+/* ai.mcts.naivemcts.NaiveMCTS (src/ai/mcts/naivemcts/NaiveMCTS.java:140-158,195-262; NaiveMCTSNode.java) or ai.mcts.uct.UCT for every game of `roots` at once:
  * search t looks for `player`'s best PlayerAction in game t.  The trees live on the host; node states, cloneIssue, the nodes' cycle
  * loops, the move generators' lists and the playouts (RandomBiasedAI both sides, `lookahead` cycles, eval_fn) run on the device for all
  * searches in lockstep.  Search t's generators are seeded from seeds[t] (the reference's are unseeded statics). */
@@ -330,6 +330,8 @@ typedef struct {
     int global_strategy;    /* 0 = E_GREEDY, 1 = UCB1 */
     int force_exploration;  /* forceExplorationOfNonSampledActions */
     int eval_fn;            /* 0 = SimpleSqrtEvaluationFunction3, 1 = SimpleEvaluationFunction */
+    int algorithm;          /* 0 = NaiveMCTS; 1 = UCT (src/ai/mcts/uct/UCT.java:103-199, UCTNode.java: every node's shuffled PlayerActionGenerator
+                             * is exhausted before UCB1 (C = 0.05) picks among the children; the epsilons and the strategy are unused) */
 } mrts_mcts_params;
 int mrts_mcts_create(mrts_batch *roots, int player, const mrts_mcts_params *, int max_nodes_per_tree, const int64_t *seeds, mrts_mcts **out);
 int mrts_mcts_iterate(mrts_mcts *, int n_iterations);  /* NaiveMCTS.iteration n times per search */

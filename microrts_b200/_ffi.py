@@ -19,7 +19,7 @@ class StateHost(C.Structure):
 
 class MctsParams(C.Structure):
     _fields_ = [("lookahead", C.c_int), ("max_depth", C.c_int), ("epsilon_l", C.c_float), ("epsilon_g", C.c_float), ("epsilon_0", C.c_float),
-                ("global_strategy", C.c_int), ("force_exploration", C.c_int), ("eval_fn", C.c_int)]
+                ("global_strategy", C.c_int), ("force_exploration", C.c_int), ("eval_fn", C.c_int), ("algorithm", C.c_int)]
 
 
 def bind(L):

@@ -4,6 +4,8 @@
 //   NaiveMCTSNode (constructor, selectLeaf, selectFromAlreadySampled*, selectLeafUsingLocalMABs, propagateEvaluation)
 //                                                                    src/ai/mcts/naivemcts/NaiveMCTSNode.java:39-105,108-188,191-330,341-368
 //   Sampler.weighted                                                 src/util/Sampler.java:116-137,141-161
+//   UCT.startNewComputation / monteCarloRun / getBestActionSoFar     src/ai/mcts/uct/UCT.java:103-110,140-168,171-199
+//   UCTNode (constructor, UCTSelectLeaf, childValue)                 src/ai/mcts/uct/UCTNode.java:37-68,70-109,112-125
 // The trees (visit counts, the local multi-armed bandits, the children maps) live on the host; every game-rule operation runs on
 // the device for all searches at once: a node's state is a game of a pool batch; creating a node is clone (mrts_batch_copy_games) +
 // issue of the sampled PlayerAction + the node's cycle loop (mrts_batch_cycle_to_decision) + its move generator's lists
@@ -31,6 +33,8 @@ struct MNode {
     std::vector<HPlayerAction> pas;                 // per child: the PlayerAction in the order it was sampled
     std::map<std::vector<int>, int> children_map;
     std::vector<std::vector<double>> ate_accum; std::vector<std::vector<int>> ate_visits; // unitActionTable
+    // UCT: the node's move generator (shuffled at construction), UCTNode.hasMoreActions and the float accumulator of UCTNode
+    PlayerActionGenerator gen; bool has_more = true; float accum_f = 0;
 };
 
 struct MTree {
@@ -45,6 +49,7 @@ struct MTree {
 class NaiveMctsHost {
   public:
     MctsParams P; int player = 0; UttH utt; double bound = 1.0;
+    int algorithm = 0; // 0 = NaiveMCTS, 1 = UCT
     std::vector<MTree> trees;
 
     int sampler_weighted(MTree &t, const std::vector<double> &dist) {
@@ -139,22 +144,60 @@ class NaiveMctsHost {
             return;
         }
     }
-    // the node created for the iteration in flight: `type` and `view` come from the device
+    // UCTSelectLeaf
+    void select_leaf_uct(MTree &t, int ni) {
+        for (;;) {
+            MNode &nd = t.nodes[ni];
+            if (nd.depth >= P.max_depth) { t.leaf = ni; return; }
+            if (nd.has_more) {
+                if (!nd.has_gen) { t.leaf = ni; return; }
+                HPlayerAction pa;
+                if (nd.gen.next(pa)) { t.creating = true; t.new_parent = ni; t.new_pa = pa; t.new_code.clear(); t.leaf = -1; return; }
+                nd.has_more = false;
+            }
+            int best = -1; double best_score = 0; const float C = 0.05f; const float fbound = 1.0f;
+            for (int ci : nd.children) {
+                MNode &c = t.nodes[ci];
+                double exploitation = ((double)c.accum_f) / c.visits, exploration = std::sqrt(std::log((double)nd.visits) / c.visits);
+                exploitation = nd.type == 0 ? (fbound + exploitation) / (2 * fbound) : (fbound - exploitation) / (2 * fbound);
+                double tmp = C * exploitation + exploration;
+                if (best < 0 || tmp > best_score) { best = ci; best_score = tmp; }
+            }
+            if (best < 0) { t.leaf = ni; return; }
+            ni = best;
+        }
+    }
+    // what a node's constructor derives from its (already cycled) state: `type` and `view` come from the device
+    void init_node(MTree &t, MNode &nn, int type, int time, const HView *view) {
+        nn.type = type; nn.time = time;
+        if (!view) return;
+        nn.has_gen = true; nn.view = *view;
+        if (algorithm == 0) {
+            for (const HChoice &c : view->choices) { nn.ate_accum.emplace_back(c.acts.size(), 0.0); nn.ate_visits.emplace_back(c.acts.size(), 0); }
+        } else {
+            nn.gen.init(*view, utt);
+            nn.gen.randomize_order(t.r); // moveGenerator.randomizeOrder()
+            nn.view = nn.gen.view;       // the rows of a sampled PlayerAction index the shuffled lists
+        }
+    }
+    // the node created for the iteration in flight
     int attach_new_node(MTree &t, int type, int time, const HView *view) {
         MNode nn;
-        nn.parent = t.new_parent; nn.depth = t.nodes[t.new_parent].depth + 1; nn.type = type; nn.time = time;
-        if (view) {
-            nn.has_gen = true; nn.view = *view;
-            for (const HChoice &c : view->choices) { nn.ate_accum.emplace_back(c.acts.size(), 0.0); nn.ate_visits.emplace_back(c.acts.size(), 0); }
-        }
+        nn.parent = t.new_parent; nn.depth = t.nodes[t.new_parent].depth + 1;
+        init_node(t, nn, type, time, view);
         int id = (int)t.nodes.size();
         t.nodes.push_back(std::move(nn));
         MNode &par = t.nodes[t.new_parent];
-        par.children.push_back(id); par.codes.push_back(t.new_code); par.pas.push_back(t.new_pa); par.children_map[t.new_code] = id;
+        par.children.push_back(id); par.codes.push_back(t.new_code); par.pas.push_back(t.new_pa);
+        if (algorithm == 0) par.children_map[t.new_code] = id;
         t.leaf = id; t.creating = false;
         return id;
     }
     void propagate(MTree &t, int ni, double evaluation) {
+        if (algorithm == 1) { // UCT.monteCarloRun: float accumulators up the parents
+            while (ni >= 0) { MNode &nd = t.nodes[ni]; nd.accum_f += evaluation; nd.accum = nd.accum_f; nd.visits++; ni = nd.parent; }
+            return;
+        }
         int child = -1;
         while (ni >= 0) {
             MNode &nd = t.nodes[ni];
@@ -169,7 +212,12 @@ class NaiveMctsHost {
     }
     int most_visited(const MTree &t) const {
         const MNode &root = t.nodes[0]; int best = -1;
-        for (int i = 0; i < (int)root.children.size(); i++) if (best == -1 || t.nodes[root.children[i]].visits > t.nodes[root.children[best]].visits) best = i;
+        for (int i = 0; i < (int)root.children.size(); i++) {
+            const MNode &c = t.nodes[root.children[i]];
+            if (best == -1) { best = i; continue; }
+            const MNode &b = t.nodes[root.children[best]];
+            if (c.visits > b.visits || (algorithm == 1 && c.visits == b.visits && c.accum_f > b.accum_f)) best = i; // UCT breaks ties by evaluation
+        }
         return best;
     }
 };

@@ -1292,8 +1292,8 @@ static int mcts_finish_nodes(mrts_mcts *m, const std::vector<uint8_t> &which, bo
         else if (a.can[maxp]) { type = 0; view = &v[maxp][t]; }
         else if (a.can[minp]) { type = 1; view = &v[minp][t]; }
         if (roots) {
-            MNode nn; nn.type = type; nn.time = a.time;
-            if (view) { nn.has_gen = true; nn.view = *view; for (const HChoice &c : view->choices) { nn.ate_accum.emplace_back(c.acts.size(), 0.0); nn.ate_visits.emplace_back(c.acts.size(), 0); } }
+            MNode nn;
+            m->H.init_node(tr, nn, type, a.time, view);
             tr.nodes.clear(); tr.nodes.push_back(std::move(nn)); tr.root_time = a.time;
             m->idx[t] = m->slot(t, 0);
         } else {
@@ -1314,6 +1314,7 @@ int mrts_mcts_create(mrts_batch *roots, int player, const mrts_mcts_params *prm,
     m->T = T; m->Tpad = (T + nm - 1) / nm * nm; m->max_nodes = max_nodes_per_tree;
     m->H.P.lookahead = prm->lookahead; m->H.P.max_depth = prm->max_depth; m->H.P.e_l = prm->epsilon_l; m->H.P.e_g = prm->epsilon_g; m->H.P.e_0 = prm->epsilon_0;
     m->H.P.strategy = prm->global_strategy; m->H.P.fensa = prm->force_exploration; m->H.P.eval_fn = prm->eval_fn;
+    m->H.algorithm = prm->algorithm ? 1 : 0;
     m->H.player = player; m->H.utt = roots->utt;
     mrts_utt u; u.h = roots->utt;
     std::vector<mrts_map> mh(nm); std::vector<const mrts_map *> mp(nm);
@@ -1345,7 +1346,7 @@ int mrts_mcts_iterate(mrts_mcts *m, int n_iterations) {
         for (int t = 0; t < T; t++) {
             MTree &tr = m->H.trees[t];
             tr.creating = false; tr.leaf = -1;
-            m->H.select_leaf(tr, 0);
+            if (m->H.algorithm == 0) m->H.select_leaf(tr, 0); else m->H.select_leaf_uct(tr, 0);
             if (tr.creating) {
                 if ((int)tr.nodes.size() >= m->max_nodes) return fail(MRTS_E_LIMIT, "a search tree outgrew max_nodes_per_tree");
                 creating++; max_k = std::max(max_k, (int)tr.new_pa.size());

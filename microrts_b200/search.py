@@ -74,8 +74,8 @@ class NaiveMCTS:
     """One NaiveMCTS search per game of `roots` (the searching player's move in each), advanced in lockstep."""
 
     def __init__(self, roots, player, seeds=None, lookahead=100, max_depth=10, epsilon_l=0.3, epsilon_g=0.0, epsilon_0=0.4, global_strategy=0,
-                 force_exploration=True, eval_fn=0, max_nodes_per_tree=1001):
-        prm = _ffi.MctsParams(lookahead, max_depth, epsilon_l, epsilon_g, epsilon_0, global_strategy, 1 if force_exploration else 0, eval_fn)
+                 force_exploration=True, eval_fn=0, max_nodes_per_tree=1001, algorithm=0):
+        prm = _ffi.MctsParams(lookahead, max_depth, epsilon_l, epsilon_g, epsilon_0, global_strategy, 1 if force_exploration else 0, eval_fn, algorithm)
         s = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.int64)
         assert s is None or len(s) == roots.n
         h = C.c_void_p()
@@ -112,3 +112,10 @@ class NaiveMCTS:
         counts = np.zeros(self.n, dtype=np.int32)
         _check(_ffi.lib().mrts_mcts_best_actions(self._h, rows.ctypes.data, counts.ctypes.data, self._max_k))
         return rows, counts
+
+
+class UCT(NaiveMCTS):
+    """ai.mcts.uct.UCT (src/ai/mcts/uct/UCT.java, UCTNode.java), one search per game: the same lockstep machinery with UCTSelectLeaf."""
+
+    def __init__(self, roots, player, seeds=None, lookahead=100, max_depth=10, eval_fn=0, max_nodes_per_tree=1001):
+        super().__init__(roots, player, seeds=seeds, lookahead=lookahead, max_depth=max_depth, eval_fn=eval_fn, max_nodes_per_tree=max_nodes_per_tree, algorithm=1)

@@ -2089,3 +2089,117 @@ int o_mcts_best_action(const OMcts *m, int32_t *unit_idx, OActionV *acts) {
     for (int k = 0; k < t->pan[best]; k++) { unit_idx[k] = list_index_of(t->gs, t->pas[best][k].unit); acts[k] = act_to_v(&t->pas[best][k].act); }
     return t->pan[best];
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * UCT (ai/mcts/uct/UCT.java:103-175, UCTNode.java:37-125) with RandomBiasedAI playouts.  As for NaiveMCTS the reference's generators
+ * are unseeded statics (PlayerActionGenerator.r shuffles every node's move generator); here a search owns one seeded stream for the
+ * shuffles and playout k is seeded with seed * 1000003 + k.  PARITY UNPINNED.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct OUNode {
+    int type; struct OUNode *parent; OGame *gs; int depth;
+    int has_more; OPag *gen;
+    int nch, chcap; struct OUNode **children; OPair **pas; int *pan;
+    float accum; int visits;
+} OUNode;
+struct OUct { OUNode *tree; int start_time; int player, lookahead, max_depth, eval_fn; float bound; OJRandom r; int64_t seed, runs; };
+
+static OUNode *unode_new(OUct *m, OGame *gs, OUNode *parent) {
+    OUNode *nd = (OUNode *)calloc(1, sizeof(OUNode));
+    nd->parent = parent; nd->gs = gs; nd->depth = parent ? parent->depth + 1 : 0; nd->has_more = 1;
+    int maxp = m->player, minp = 1 - m->player;
+    while (o_game_winner(gs) == -1 && !o_game_gameover(gs) && !can_execute_any(gs, maxp) && !can_execute_any(gs, minp)) o_game_cycle(gs);
+    if (o_game_winner(gs) != -1 || o_game_gameover(gs)) nd->type = -1;
+    else if (can_execute_any(gs, maxp)) { nd->type = 0; nd->gen = o_pag_create(gs, maxp, 10); o_pag_randomize_order(nd->gen, &m->r); }
+    else if (can_execute_any(gs, minp)) { nd->type = 1; nd->gen = o_pag_create(gs, minp, 10); o_pag_randomize_order(nd->gen, &m->r); }
+    else nd->type = -1;
+    return nd;
+}
+static void unode_free(OUNode *nd) {
+    if (!nd) return;
+    for (int i = 0; i < nd->nch; i++) { unode_free(nd->children[i]); free(nd->pas[i]); }
+    o_pag_free(nd->gen); o_game_free(nd->gs); free(nd->children); free(nd->pas); free(nd->pan); free(nd);
+}
+/* childValue, UCTNode.java:112-125 (C = 0.05; evaluation_bound is a float) */
+static double uct_child_value(const OUct *m, const OUNode *nd, const OUNode *c) {
+    const float C = 0.05f;
+    double exploitation = ((double)c->accum) / c->visits;
+    double exploration = sqrt(log((double)nd->visits) / c->visits);
+    if (nd->type == 0) exploitation = (m->bound + exploitation) / (2 * m->bound);
+    else exploitation = (m->bound - exploitation) / (2 * m->bound);
+    return C * exploitation + exploration;
+}
+/* UCTSelectLeaf, UCTNode.java:70-109 */
+static OUNode *uct_select_leaf(OUct *m, OUNode *nd) {
+    if (nd->depth >= m->max_depth) return nd;
+    if (nd->has_more) {
+        if (!nd->gen) return nd;
+        int32_t *idx = (int32_t *)malloc(sizeof(int32_t) * (size_t)(nd->gs->n + 8));
+        OActionV *acts = (OActionV *)malloc(sizeof(OActionV) * (size_t)(nd->gs->n + 8));
+        int n = o_pag_next(nd->gen, idx, acts);
+        if (n >= 0) {
+            OPair *pa = (OPair *)malloc(sizeof(OPair) * (size_t)(n ? n : 1)), *keep = (OPair *)malloc(sizeof(OPair) * (size_t)(n ? n : 1));
+            for (int k = 0; k < n; k++) { pa[k].unit = nd->gs->list[idx[k]]; pa[k].act = act_from_v(&acts[k]); keep[k] = pa[k]; }
+            OGame *gs2 = o_game_clone(nd->gs);
+            gs_issue(gs2, n, pa);
+            free(pa); free(idx); free(acts);
+            if (nd->nch == nd->chcap) {
+                nd->chcap = nd->chcap ? nd->chcap * 2 : 8;
+                nd->children = (OUNode **)realloc(nd->children, sizeof(OUNode *) * (size_t)nd->chcap);
+                nd->pas = (OPair **)realloc(nd->pas, sizeof(OPair *) * (size_t)nd->chcap); nd->pan = (int *)realloc(nd->pan, sizeof(int) * (size_t)nd->chcap);
+            }
+            OUNode *node = unode_new(m, gs2, nd);
+            nd->children[nd->nch] = node; nd->pas[nd->nch] = keep; nd->pan[nd->nch] = n; nd->nch++;
+            return node;
+        }
+        free(idx); free(acts);
+        nd->has_more = 0;
+    }
+    double best_score = 0; OUNode *best = NULL;
+    for (int i = 0; i < nd->nch; i++) {
+        double tmp = uct_child_value(m, nd, nd->children[i]);
+        if (!best || tmp > best_score) { best = nd->children[i]; best_score = tmp; }
+    }
+    if (!best) return nd;
+    return uct_select_leaf(m, best);
+}
+OUct *o_uct_create(const OGame *g, int player, int lookahead, int max_depth, int eval_fn, int64_t seed) {
+    OUct *m = (OUct *)calloc(1, sizeof(OUct));
+    m->player = player; m->lookahead = lookahead; m->max_depth = max_depth; m->eval_fn = eval_fn; m->seed = seed; m->bound = 1.0f;
+    o_jr_seed(&m->r, seed);
+    m->tree = unode_new(m, o_game_clone(g), NULL);
+    m->start_time = m->tree->gs->time; /* gs_to_start_from is the root's own state object */
+    return m;
+}
+void o_uct_free(OUct *m) { if (!m) return; unode_free(m->tree); free(m); }
+/* monteCarloRun, UCT.java:140-168, n times */
+void o_uct_iterate(OUct *m, int n) {
+    for (int it = 0; it < n; it++) {
+        OUNode *leaf = uct_select_leaf(m, m->tree);
+        OGame *gs2 = o_game_clone(leaf->gs);
+        o_game_seed(gs2, m->seed * 1000003LL + m->runs);
+        o_simulate(gs2, gs2->time + m->lookahead);
+        int time = gs2->time - m->start_time;
+        double evaluation = o_evaluate(gs2, m->eval_fn, m->player, 1 - m->player) * pow(0.99, time / 10.0);
+        o_game_free(gs2);
+        while (leaf) { leaf->accum += evaluation; /* float += double */ leaf->visits++; leaf = leaf->parent; }
+        m->runs++;
+    }
+}
+int o_uct_root(const OUct *m, int *root_visits, float *root_accum, int *out_visits, float *out_accum, int max_children) {
+    *root_visits = m->tree->visits; *root_accum = m->tree->accum;
+    for (int i = 0; i < m->tree->nch && i < max_children; i++) { out_visits[i] = m->tree->children[i]->visits; out_accum[i] = m->tree->children[i]->accum; }
+    return m->tree->nch;
+}
+static int uct_count(const OUNode *nd) { int c = 1; for (int i = 0; i < nd->nch; i++) c += uct_count(nd->children[i]); return c; }
+int o_uct_n_nodes(const OUct *m) { return uct_count(m->tree); }
+/* getBestActionSoFar, UCT.java:171-199: most visited child, ties by accumulated evaluation */
+int o_uct_best_action(const OUct *m, int32_t *unit_idx, OActionV *acts) {
+    const OUNode *t = m->tree; int best = -1;
+    for (int i = 0; i < t->nch; i++) {
+        const OUNode *c = t->children[i];
+        if (best == -1 || c->visits > t->children[best]->visits || (c->visits == t->children[best]->visits && c->accum > t->children[best]->accum)) best = i;
+    }
+    if (best < 0) return -1;
+    for (int k = 0; k < t->pan[best]; k++) { unit_idx[k] = list_index_of(t->gs, t->pas[best][k].unit); acts[k] = act_to_v(&t->pas[best][k].act); }
+    return t->pan[best];
+}

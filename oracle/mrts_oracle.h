@@ -141,6 +141,15 @@ int o_mcts_root(const OMcts *, int *root_visits, double *root_accum, int *out_vi
 int o_mcts_n_nodes(const OMcts *);
 int o_mcts_best_action(const OMcts *, int32_t *unit_idx, OActionV *acts);
 
+/* UCT with seeded generators (parity unpinned) */
+typedef struct OUct OUct;
+OUct *o_uct_create(const OGame *, int player, int lookahead, int max_depth, int eval_fn, int64_t seed);
+void o_uct_free(OUct *);
+void o_uct_iterate(OUct *, int n);
+int o_uct_root(const OUct *, int *root_visits, float *root_accum, int *out_visits, float *out_accum, int max_children);
+int o_uct_n_nodes(const OUct *);
+int o_uct_best_action(const OUct *, int32_t *unit_idx, OActionV *acts);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,9 @@ def lib():
             "o_mcts_create": (vp, [vp, i, i, i, C.c_float, C.c_float, C.c_float, i, i, i, i64]), "o_mcts_free": (None, [vp]), "o_mcts_iterate": (None, [vp, i]),
             "o_mcts_root": (i, [vp, pi32, C.POINTER(C.c_double), pi32, C.POINTER(C.c_double), i]), "o_mcts_n_nodes": (i, [vp]),
             "o_mcts_best_action": (i, [vp, pi32, C.POINTER(ActionV)]),
+            "o_uct_create": (vp, [vp, i, i, i, i, i64]), "o_uct_free": (None, [vp]), "o_uct_iterate": (None, [vp, i]),
+            "o_uct_root": (i, [vp, pi32, C.POINTER(C.c_float), pi32, C.POINTER(C.c_float), i]), "o_uct_n_nodes": (i, [vp]),
+            "o_uct_best_action": (i, [vp, pi32, C.POINTER(ActionV)]),
             "o_jr_seed": (None, [C.POINTER(C.c_uint64), i64]), "o_jr_next": (C.c_int32, [C.POINTER(C.c_uint64), i]),
             "o_jr_next_int": (C.c_int32, [C.POINTER(C.c_uint64)]),
             "o_jr_next_int_bound": (C.c_int32, [C.POINTER(C.c_uint64), C.c_int32]),
@@ -387,3 +390,33 @@ class FloodFill:
     def find(self, game, unit_idx, targetpos, rng, ru=()):
         a = (C.c_int32 * max(1, len(ru)))(*ru)
         return lib().o_ff_find(self.h, game.h, unit_idx, targetpos, rng, len(ru), a)
+
+
+class Uct:
+    def __init__(self, game, player, seed, lookahead=100, max_depth=10, eval_fn=0):
+        self.game = game
+        self.h = lib().o_uct_create(game.h, player, lookahead, max_depth, eval_fn, seed)
+
+    def __del__(self):
+        try:
+            lib().o_uct_free(self.h)
+        except Exception:
+            pass
+
+    def iterate(self, n):
+        lib().o_uct_iterate(self.h, n)
+
+    def root(self, max_children=4096):
+        rv, ra = C.c_int32(0), C.c_float(0)
+        cv, ca = (C.c_int32 * max_children)(), (C.c_float * max_children)()
+        n = lib().o_uct_root(self.h, C.byref(rv), C.byref(ra), cv, ca, max_children)
+        return rv.value, float(ra.value), np.array(cv[:n], dtype=np.int32), np.array(ca[:n], dtype=np.float64)
+
+    n_nodes = property(lambda self: lib().o_uct_n_nodes(self.h))
+
+    def best_action(self):
+        cap = self.game.n_units + 8
+        idx = (C.c_int32 * cap)()
+        acts = (ActionV * cap)()
+        n = lib().o_uct_best_action(self.h, idx, acts)
+        return None if n < 0 else [(idx[k], acts[k].tup()) for k in range(n)]

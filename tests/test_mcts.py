@@ -134,3 +134,32 @@ def test_naive_mcts_trees_equal_the_oracle(backend, maps, key, player, strategy,
         assert (before[k] == after[k]).all(), "the search modified the root batch"
     search.close()
     b.close()
+
+
+@pytest.mark.parametrize("key,player", [("8x8/basesWorkers8x8", 0), ("16x16/basesWorkers16x16", 1)])
+def test_uct_trees_equal_the_oracle(backend, maps, key, player):
+    """ai.mcts.uct.UCT: every node's shuffled move generator is exhausted before UCB1 chooses among its children."""
+    n = 3 if backend == "emu" else 10
+    iters = 40 if backend == "emu" else 250
+    utt, b, games = advanced_games(backend, maps, key, n, warm=[0] + [31 * g + 7 for g in range(1, n)])
+    seeds = np.arange(n, dtype=np.int64) * 11 + 3
+    search = S.UCT(b, player, seeds=seeds, lookahead=100, max_depth=10, max_nodes_per_tree=iters + 2)
+    refs = [O.Uct(og, player, int(seeds[g]), 100, 10, 0) for g, og in enumerate(games)]
+    done = 0
+    for chunk in (1, 9, iters - 10):
+        search.iterate(chunk)
+        done += chunk
+        for g, ref in enumerate(refs):
+            ref.iterate(chunk)
+            rv, ra, cv, ca = search.root(g)
+            orv, ora, ocv, oca = ref.root()
+            assert rv == orv == done and search.num_nodes(g) == ref.n_nodes, (key, g, done, search.num_nodes(g), ref.n_nodes)
+            assert (cv == ocv).all() and (ca == oca).all() and ra == ora, "tree %d after %d iterations\nvisits %s\noracle %s" % (g, done, cv, ocv)
+    rows, counts = search.best_actions()
+    w = maps[key]["w"]
+    for g, ref in enumerate(refs):
+        best = ref.best_action()
+        exp = [] if best is None else rows_of(best, games[g].units(), w)
+        assert rows[g, :counts[g]].tolist() == exp, (key, g)
+    search.close()
+    b.close()
