@@ -163,7 +163,7 @@ struct Game {
     bool po_view;                         // the unit table currently shows one player's partially observable view (po_hide)
     int pview;                            // window into the pending list (policy_scripted stages desires behind the final part)
     const uint32_t *grid_tmpl;            // global: wall-padded empty grid of this game's map
-    uint16_t *as_closed, *as_xy, *as_mark, *as_next, *as_head, *as_gen; // A*/BFS scratch of this warp (scripted batches only, layout.h)
+    uint16_t *as_mark, *as_next, *as_head, *as_gen; // A*/BFS scratch of this warp (scripted batches only, layout.h)
     uint32_t as_sm;                       // its shared-window address when it lives in shared memory, else 0
     unsigned char *ff_cache;              // FloodFillPathFinding: this game's two per-player distance-map caches in HBM (or null)
     long long ff_stride;                  // bytes per player
@@ -207,8 +207,8 @@ DEV void g_bind(Game &g, int region, const SmemLayout &L, int W, int H, int cap,
     g.o_claim = L.claim; g.o_list = L.list; g.o_povis = L.povis; g.o_pohid = L.pohid;
 #endif
     g.sb = smem_window(region); g.cb = smem_window(0); g.pview = 0; g.po_view = false;
-    { int pc = (W + 2) * (H + 2); g.as_closed = (uint16_t *)(astar_global ? astar_global : mrts_smem + region + L.astar); g.as_xy = g.as_closed + pc;
-      g.as_mark = g.as_xy + pc; g.as_next = g.as_mark + pc; g.as_head = g.as_next + pc; g.as_gen = g.as_head + MRTS_ASTAR_HEADS(W, H);
+    { int pc = (W + 2) * (H + 2); g.as_mark = (uint16_t *)(astar_global ? astar_global : mrts_smem + region + L.astar);
+      g.as_next = g.as_mark + pc; g.as_head = g.as_next + pc; g.as_gen = g.as_head + MRTS_ASTAR_HEADS(W, H);
       g.as_sm = (scripted == 1) ? smem_window(region + L.astar) : 0u; }
     g.grid_tmpl = nullptr; g.ff_cache = nullptr; g.ff_stride = 0;
 }

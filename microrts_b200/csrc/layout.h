@@ -86,11 +86,12 @@ struct SmemLayout {
 // isStockpile<<3 | 0x10 -- what Unit.getUnitActions needs to know about a neighbouring cell, without touching the unit.
 #define CK_UNIT 0x10
 
-// A* / BFS scratch of one warp (scripted policies only), all u16; PC = padded cells (W+2)*(H+2): parent[PC], xy[PC]
-// (x | y << 8), mark[PC] (query generation << 3 | flags), next[PC] (bucket chains / BFS queue), head[W*H + W + H + 2] (one
-// LIFO bucket per f value), generation counter.  Owned by the warp, not the game: it is initialised once per launch.
+// A* / BFS / flood-fill scratch of one warp (scripted policies only), all u16; PC = padded cells (W+2)*(H+2): mark[PC] (query
+// generation << 5 | direction the node was reached by << 3 | flags), next[PC] (bucket chains / FIFO queue), head[W*H + W + H + 2]
+// (one LIFO bucket per f value), generation counter.  A node's parent is its cell minus the direction's offset and its
+// coordinates follow from its index, so neither is stored.  Owned by the warp, not the game: it is initialised once per launch.
 #define MRTS_ASTAR_HEADS(W, H) ((W) * (H) + (W) + (H) + 2)
-#define MRTS_ASTAR_BYTES(W, H) ((8 * ((W) + 2) * ((H) + 2) + 2 * MRTS_ASTAR_HEADS(W, H) + 4 + 15) & ~15)
+#define MRTS_ASTAR_BYTES(W, H) ((4 * ((W) + 2) * ((H) + 2) + 2 * MRTS_ASTAR_HEADS(W, H) + 4 + 15) & ~15)
 // pending = 0: the layout of the specialised kernels (fast game loop, rollouts), which fuse policy and issue and never
 // stage a pending action list -- 8 bytes per unit slot less, which is what lets one more CTA fit per SM on small maps
 MRTS_HDC SmemLayout mrts_smem_layout(int W, int H, int cap, int scripted, int po_policies = 0, int pending = 1) {

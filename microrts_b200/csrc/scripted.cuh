@@ -93,41 +93,42 @@ template <class F> DEV int w_next(const Game &g, int n, int from, F pred) { // f
 // instead of being cleared for every query.
 enum { PFF_INOC = 1, PFF_BLOCKED = 2, PFF_CLOSED = 4 };
 #define PF_NONE 0xFFFFu
-// Positions are indices into the wall-padded grid: out of bounds looks like a wall, so there are no bounds checks, and a
-// node's coordinates are kept beside it (its cost is f - heuristic), so there are no divisions.
+#define PF_GEN_LIMIT 2047 // generation numbers have 11 bits of the mark word
+// Positions are indices into the wall-padded grid: out of bounds looks like a wall, so there are no bounds checks.  A node's
+// coordinates follow from its index (a division by the padded row length: a constant in the fixed-layout kernels), its cost is
+// f - heuristic, and its parent is the cell it was reached from: index minus the offset of the direction kept in its mark word.
 // the scratch arrays of one query; built from the shared-window address when the scratch is in shared memory, so that the
 // accesses compile to LDS/STS instead of generic loads (pf_find<true>), from the global pointers otherwise
-struct PfArr { uint16_t *closed, *xy, *mark, *next, *head, *gen; const uint8_t *grid, *resv; int P; };
+struct PfArr { uint16_t *mark, *next, *head, *gen; const uint8_t *grid, *resv; int P; };
 template <bool SM> DEV PfArr pf_arrays(const Game &g) {
     PfArr a;
     if (SM) {
         int pc = g.P * (g.H + 2);
-        a.closed = (uint16_t *)smem_ptr(g.as_sm); a.xy = a.closed + pc; a.mark = a.xy + pc; a.next = a.mark + pc; a.head = a.next + pc;
+        a.mark = (uint16_t *)smem_ptr(g.as_sm); a.next = a.mark + pc; a.head = a.next + pc;
         a.gen = a.head + MRTS_ASTAR_HEADS(g.W, g.H);
-    } else { a.closed = g.as_closed; a.xy = g.as_xy; a.mark = g.as_mark; a.next = g.as_next; a.head = g.as_head; a.gen = g.as_gen; }
+    } else { a.mark = g.as_mark; a.next = g.as_next; a.head = g.as_head; a.gen = g.as_gen; }
     a.grid = g.grid(); a.resv = g.resv(); a.P = g.P;
     return a;
 }
-DEV int pf_flags(const PfArr &g, int pos, int gen) { int m = g.mark[pos]; return (m >> 3) == gen ? (m & 7) : 0; }
-DEV void pf_set(const PfArr &g, int pos, int gen, int flags) { g.mark[pos] = (uint16_t)((gen << 3) | flags); }
+DEV int pf_flags(const PfArr &g, int pos, int gen) { int m = g.mark[pos]; return (m >> 5) == gen ? (m & 7) : 0; }
+DEV void pf_set(const PfArr &g, int pos, int gen, int flags, int dir = 0) { g.mark[pos] = (uint16_t)((gen << 5) | (dir << 3) | flags); }
+DEV int pf_off(const PfArr &g, int d) { return (d & 1) ? 2 - d : (d - 1) * g.P; } // up -P, right +1, down +P, left -1
 // GameState.free (GameState.java:191-207) unless the cell is used by a desire already chosen this cycle (ru)
 DEV bool pf_free(const PfArr &g, int pc, int fl) { return !(fl & PFF_BLOCKED) && g.grid[pc] == 0 && g.resv[pc] == 0; }
-DEV int pf_first_step(const PfArr &g, int pos, int parent) {
-    int last = pos;
+// the first step of the path that ends in `pos`: walk the parent links back to the start
+DEV int pf_first_step(const PfArr &g, int pos, int start) {
+    int d = -1;
 #pragma unroll 1
-    while (parent != pos) { last = pos; pos = parent; parent = g.closed[pos]; }
-    if (last == pos + g.P) return 2;
-    if (last == pos - 1) return 3;
-    if (last == pos - g.P) return 0;
-    if (last == pos + 1) return 1;
-    return -1;
+    while (pos != start) { d = (g.mark[pos] >> 3) & 3; pos -= pf_off(g, d); }
+    return d;
 }
 DEV int iabs(int v) { return v < 0 ? -v : v; }
 
 // findPathToPositionInRange: direction of the first step of a shortest path from unit slot s to within `range` of
 // (tx, ty), or -1 (null).  ru = target cells of the desires [0, nd) in the pending list.  Called by the whole warp with
 // uniform arguments; the search state is uniform, the four neighbours of the expanded node are examined by lanes 0..3 and
-// pushed in the reference's order (up, right, down, left) by lane 0.
+// pushed in the reference's order (up, right, down, left): lanes that push into the same bucket chain themselves in that order
+// (a later direction lands on top), all at once.
 template <bool SM, int KIND = -1> // KIND >= 0: the search kind as a compile-time constant (the other one is not compiled in)
 DEVN int pf_find_t(Game &g, int kind, int s, int tx, int ty, int range, int nd) {
     if (KIND >= 0) kind = KIND;
@@ -136,7 +137,7 @@ DEVN int pf_find_t(Game &g, int kind, int s, int tx, int ty, int range, int nd) 
     __syncwarp();
     int gen = *A.gen + 1;
     __syncwarp();
-    if (gen >= 8191) { // generation numbers wrapped: forget every mark
+    if (gen >= PF_GEN_LIMIT) { // generation numbers wrapped: forget every mark
         int pcells = A.P * (g.H + 2);
 #pragma unroll 1
         for (int i = lane; i < pcells; i += 32) A.mark[i] = 0;
@@ -158,10 +159,10 @@ DEVN int pf_find_t(Game &g, int kind, int s, int tx, int ty, int range, int nd) 
     int sx = u_x(sw), sy = u_y(sw), start = cell_of(g, sw);
     int result = -1;
     const int dl = lane & 3, doffl = (dl & 1) ? 2 - dl : (dl - 1) * A.P, dxl = ddx(dl), dyl = ddy(dl); // this lane's direction
+    const unsigned below = (1u << lane) - 1;
     if (kind == 0) { // A*
         int f0 = iabs(sx - tx) + iabs(sy - ty), flo = f0, fhi = f0, fcur = f0;
         if (lane == 0) {
-            A.xy[start] = (uint16_t)(sx | (sy << 8)); A.closed[start] = (uint16_t)start;
             pf_set(A, start, gen, pf_flags(A, start, gen) | PFF_INOC);
             A.next[start] = PF_NONE; A.head[f0] = (uint16_t)start;
         }
@@ -177,34 +178,37 @@ DEVN int pf_find_t(Game &g, int kind, int s, int tx, int ty, int range, int nd) 
             }
             if (fcur > fhi) break;
             int pos = A.head[fcur];
-            int nxt = A.next[pos], parent = A.closed[pos], xy = A.xy[pos], fl = pf_flags(A, pos, gen);
+            int nxt = A.next[pos], mk = A.mark[pos], fl = (mk >> 5) == gen ? (mk & 7) : 0;
             __syncwarp(); // every lane has read the bucket head before it is popped
-            if (lane == 0) { A.head[fcur] = (uint16_t)nxt; if (!(fl & PFF_CLOSED)) pf_set(A, pos, gen, fl | PFF_CLOSED); }
+            if (lane == 0) { A.head[fcur] = (uint16_t)nxt; if (!(fl & PFF_CLOSED)) A.mark[pos] = (uint16_t)(mk | PFF_CLOSED); }
             if (fl & PFF_CLOSED) { __syncwarp(); continue; }
-            int x = xy & 0xff, y = xy >> 8;
-            if ((x - tx) * (x - tx) + (y - ty) * (y - ty) <= sq) { __syncwarp(); result = pf_first_step(A, pos, parent); break; }
+            int y = pos / A.P, x = pos - y * A.P - 1; y -= 1;
+            if ((x - tx) * (x - tx) + (y - ty) * (y - ty) <= sq) { __syncwarp(); result = pf_first_step(A, pos, start); break; }
             int c = fcur - (iabs(x - tx) + iabs(y - ty)) + 1; // cost of the neighbours: this node's f - heuristic + 1
             // lanes 0..3: one neighbour each (addToOpen :104-138)
-            int np = pos + doffl, nx = x + dxl, ny = y + dyl, f = 0;
+            int np = pos + doffl, f = -1 - lane;
             bool ok = false;
             if (lane < 4) {
                 int nfl = pf_flags(A, np, gen);
                 ok = !(nfl & PFF_INOC) && pf_free(A, np, nfl);
-                if (ok) {
-                    A.xy[np] = (uint16_t)(nx | (ny << 8)); A.closed[np] = (uint16_t)pos;
-                    f = iabs(nx - tx) + iabs(ny - ty) + c;
-                    pf_set(A, np, gen, nfl | PFF_INOC);
-                }
+                if (ok) { f = iabs(x + dxl - tx) + iabs(y + dyl - ty) + c; pf_set(A, np, gen, nfl | PFF_INOC, dl); }
             }
+            // the lanes that push into the same bucket (a neighbour's f is this node's or two more): chained in direction order
             unsigned okm = __ballot_sync(FULLM, ok);
-#pragma unroll 1
-            for (unsigned mm = okm; mm; mm &= mm - 1) { // pushes in direction order: a later one lands on top of its bucket
-                int d = __ffs(mm) - 1;
-                int npd = __shfl_sync(FULLM, np, d), fd = __shfl_sync(FULLM, f, d);
-                if (lane == 0) { A.next[npd] = A.head[fd]; A.head[fd] = (uint16_t)npd; }
-                if (fd > fhi) fhi = fd;
-                if (fd < fcur) fcur = fd;
-                if (fd < flo) flo = fd;
+            if (okm) {
+                int fa = __shfl_sync(FULLM, f, __ffs(okm) - 1);
+                unsigned ma = __ballot_sync(FULLM, ok && f == fa), mb = okm & ~ma; // with a Manhattan heuristic f is this node's or two more
+                int fb = mb ? __shfl_sync(FULLM, f, __ffs(mb) - 1) : fa;
+                unsigned same = f == fa ? ma : mb;
+                int prev = (same & below) ? 31 - __clz(same & below) : -1;
+                int prev_np = __shfl_sync(FULLM, np, prev < 0 ? 0 : prev);
+                if (ok) A.next[np] = prev >= 0 ? (uint16_t)prev_np : A.head[f];
+                __syncwarp(); // every chain start has read its bucket head before the heads move
+                if (ok && !(same & ~below & ~(1u << lane))) A.head[f] = (uint16_t)np; // the last lane of a bucket's chain is its new head
+                int fmax = fa > fb ? fa : fb, fmin = fa < fb ? fa : fb;
+                if (fmax > fhi) fhi = fmax;
+                if (fmin < fcur) fcur = fmin;
+                if (fmin < flo) flo = fmin;
             }
             __syncwarp();
         }
@@ -214,40 +218,35 @@ DEVN int pf_find_t(Game &g, int kind, int s, int tx, int ty, int range, int nd) 
         __syncwarp();
         return result;
     }
-    // BFS: FIFO queue (positions in next[], parents in head[]); a cell is enqueued at most once, so it never wraps
-    uint16_t *qpos = A.next, *qpar = A.head;
+    // BFS: FIFO queue of positions in next[]; a cell is enqueued at most once (so it never wraps) and remembers the direction it
+    // was reached by
+    uint16_t *qpos = A.next;
     int oi = 1, orm = 0;
-    if (lane == 0) {
-        qpos[0] = (uint16_t)start; qpar[0] = (uint16_t)start; A.xy[start] = (uint16_t)(sx | (sy << 8));
-        pf_set(A, start, gen, pf_flags(A, start, gen) | PFF_INOC);
-    }
+    if (lane == 0) { qpos[0] = (uint16_t)start; pf_set(A, start, gen, pf_flags(A, start, gen) | PFF_INOC); }
     __syncwarp();
 #pragma unroll 1
     while (oi != orm) {
-        int pos = qpos[orm], parent = qpar[orm];
+        int pos = qpos[orm];
         orm++;
-        int fl = pf_flags(A, pos, gen), xy = A.xy[pos];
+        int mk = A.mark[pos], fl = (mk >> 5) == gen ? (mk & 7) : 0;
         __syncwarp();
         if (fl & PFF_CLOSED) continue;
-        if (lane == 0) { pf_set(A, pos, gen, fl | PFF_CLOSED); A.closed[pos] = (uint16_t)parent; }
-        int x = xy & 0xff, y = xy >> 8;
-        if ((x - tx) * (x - tx) + (y - ty) * (y - ty) <= sq) { __syncwarp(); result = pf_first_step(A, pos, parent); break; }
+        if (lane == 0) A.mark[pos] = (uint16_t)(mk | PFF_CLOSED);
+        int y = pos / A.P, x = pos - y * A.P - 1; y -= 1;
+        if ((x - tx) * (x - tx) + (y - ty) * (y - ty) <= sq) { __syncwarp(); result = pf_first_step(A, pos, start); break; }
         int np = pos + doffl;
         bool ok = false;
         if (lane < 4) {
             int nfl = pf_flags(A, np, gen);
             ok = !(nfl & PFF_INOC) && pf_free(A, np, nfl);
-            if (ok) { A.xy[np] = (uint16_t)((x + dxl) | ((y + dyl) << 8)); pf_set(A, np, gen, nfl | PFF_INOC); }
+            if (ok) pf_set(A, np, gen, nfl | PFF_INOC, dl);
         }
         unsigned okm = __ballot_sync(FULLM, ok);
-        int slot = oi + __popc(okm & ((1u << lane) - 1)); // queue order = direction order
-        if (ok) { qpos[slot] = (uint16_t)np; qpar[slot] = (uint16_t)pos; }
+        int slot = oi + __popc(okm & below); // queue order = direction order
+        if (ok) qpos[slot] = (uint16_t)np;
         oi += __popc(okm);
         __syncwarp();
     }
-    __syncwarp();
-#pragma unroll 1
-    for (int i = lane; i < oi; i += 32) qpar[i] = PF_NONE; // head[] doubles as the parent queue: restore the empty buckets
     __syncwarp();
     return result;
 }
@@ -320,7 +319,7 @@ DEVN int pf_floodfill(Game &g, int player, int s, int tx, int ty, int range, int
     // initFree: the cells used by the desires chosen so far this cycle
     int gen = *A.gen + 1;
     __syncwarp();
-    if (gen >= 8191) { int pcells = A.P * (H + 2); for (int i = lane; i < pcells; i += 32) A.mark[i] = 0; gen = 1; }
+    if (gen >= PF_GEN_LIMIT) { int pcells = A.P * (H + 2); for (int i = lane; i < pcells; i += 32) A.mark[i] = 0; gen = 1; }
     if (lane == 0) *A.gen = (uint16_t)gen;
     __syncwarp();
     for (int k = lane; k < nd; k += 32) {
