@@ -111,6 +111,7 @@ struct StepParams {
     int obs_dtype;
     void *mask_out[2];         // MODE_GAME: when set, the post-step bit-packed action masks of player 0 / 1 ([n][H][W][(K+7)/8] bytes)
     int zero_bytes;            // KERNEL_FAST_OBS: size of the CTA's block of zeros behind the warps' regions (source of the bulk stores), or 0
+    int terr_bytes, tmpl_bytes; // ... followed by the map's terrain plane (source of plane 5's bulk store) and its wall-padded grid template (single-map batches)
     // MODE_ROLLOUT: item r = game r / rollouts_per_game
     int rollouts_per_game, depth, eval_fn, maxplayer, observer;
     const long long *ro_seeds; // [n_games * rollouts_per_game] or NULL (seed = r)
@@ -151,8 +152,10 @@ struct Game {
                          o_kind = MRTS_TU_LAYOUT.kind, o_resv = MRTS_TU_LAYOUT.resv, o_claim = MRTS_TU_LAYOUT.claim, o_list = MRTS_TU_LAYOUT.list,
                          o_povis = MRTS_TU_LAYOUT.povis, o_pohid = MRTS_TU_LAYOUT.pohid, o_rdy = MRTS_TU_LAYOUT.rdy, o_units = MRTS_TU_LAYOUT.uoff[0];
     int conflict;
+    static constexpr bool slim = false;
     MDEV static constexpr int uoffset(int k) { return o_units + k * cap * 4; }
 #else
+    bool slim;                            // no kind / claim maps (layout.h: the fused step + observation kernel)
     int W, H, P, cap, pcw, conflict, uw; // uw: unit words mirrored in HBM (7, or 9 with scripted policies)
     int o_pa0, o_pa1, o_pslot, o_grid, o_kind, o_resv, o_claim, o_list;
     int o_povis, o_pohid;                 // MRTS_FLAG_PO_POLICIES batches only (layout.h)
@@ -165,6 +168,7 @@ struct Game {
     const uint32_t *grid_tmpl;            // global: wall-padded empty grid of this game's map
     uint16_t *as_mark, *as_next, *as_head, *as_gen; // A*/BFS scratch of this warp (scripted batches only, layout.h)
     uint32_t as_sm;                       // its shared-window address when it lives in shared memory, else 0
+    const uint4 *tmpl_sm;                 // the CTA's copy of the wall-padded empty grid in shared memory (fused step + observation kernel), or null
     unsigned char *ff_cache;              // FloodFillPathFinding: this game's two per-player distance-map caches in HBM (or null)
     long long ff_stride;                  // bytes per player
 
@@ -196,9 +200,10 @@ struct Game {
 };
 
 DEV void g_bind(Game &g, int region, const SmemLayout &L, int W, int H, int cap, int lane, int conflict, int scripted,
-                unsigned char *astar_global) {
+                unsigned char *astar_global, bool slim = false) {
     g.lane = lane; g.conflict = conflict;
 #ifndef MRTS_TU_FIXED
+    g.slim = slim;
     g.W = W; g.H = H; g.P = L.P; g.cap = cap; g.pcw = L.pcw;
     for (int k = 0; k <= MRTS_UNIT_WORDS; k++) g.uoff[k] = L.uoff[k];
     g.o_rdy = L.rdy;
@@ -210,7 +215,7 @@ DEV void g_bind(Game &g, int region, const SmemLayout &L, int W, int H, int cap,
     { int pc = (W + 2) * (H + 2); g.as_mark = (uint16_t *)(astar_global ? astar_global : mrts_smem + region + L.astar);
       g.as_next = g.as_mark + pc; g.as_head = g.as_next + pc; g.as_gen = g.as_head + MRTS_ASTAR_HEADS(W, H);
       g.as_sm = (scripted == 1) ? smem_window(region + L.astar) : 0u; }
-    g.grid_tmpl = nullptr; g.ff_cache = nullptr; g.ff_stride = 0;
+    g.grid_tmpl = nullptr; g.ff_cache = nullptr; g.ff_stride = 0; g.tmpl_sm = nullptr;
 }
 
 // ---- small accessors -------------------------------------------------------------------------------------------------
@@ -326,12 +331,24 @@ DEV void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.
 DEV void g_template(Game &g) {
     uint4 z; z.x = z.y = z.z = z.w = 0;
     int nq = g.pcw >> 2;
+    if (g.tmpl_sm) { // the CTA keeps the template in shared memory: no L2 traffic per game
+        #pragma unroll 2
+        for (int i = g.lane; i < nq; i += 32) {
+            uint4 t = g.tmpl_sm[i];
+            ((uint4 *)g.grid())[i] = t;
+            ((uint4 *)g.resv())[i] = z;
+            if (!g.slim) { ((uint4 *)g.kind())[i] = t; ((uint4 *)g.claim())[i] = z; }
+        }
+        return;
+    }
     #pragma unroll 2
     for (int i = g.lane; i < nq; i += 32) {
         cp_async16((uint4 *)g.grid() + i, (const uint4 *)g.grid_tmpl + i);
-        cp_async16((uint4 *)g.kind() + i, (const uint4 *)g.grid_tmpl + i);
         ((uint4 *)g.resv())[i] = z;
-        ((uint4 *)g.claim())[i] = z;
+        if (!g.slim) {
+            cp_async16((uint4 *)g.kind() + i, (const uint4 *)g.grid_tmpl + i);
+            ((uint4 *)g.claim())[i] = z;
+        }
     }
 }
 DEV void g_rebuild(Game &g, bool with_rdy, bool template_pending = false) {
@@ -345,7 +362,7 @@ DEV void g_rebuild(Game &g, bool with_rdy, bool template_pending = false) {
         uint32_t w = g.w0()[i];
         int c = cell_of(g, w);
         g.grid()[c] = (uint8_t)(i + 1);
-        g.kind()[c] = (uint8_t)kind_of(g, w);
+        if (!g.slim) g.kind()[c] = (uint8_t)kind_of(g, w);
         uint32_t A0 = g.a0()[i];
         int A1 = g.a1()[i];
         if (a_uses_cell(a_type(A0))) g.resv()[target_cell(g, c, A1)] = (uint8_t)(i + 1);
@@ -435,8 +452,17 @@ DEV void enumerate(const Game &g, int s, Enum &e) {
     int myres = u_res(g.w1()[s]);
     // The four neighbours' cell-kind bytes (up, right, down, left) packed into one word and classified for all four
     // directions at once.  Kind byte (layout.h): 0 empty, 0xFF wall, else 0x10 | owner (bits 0-1) | resource << 2 | stockpile << 3.
-    const uint8_t *kind = g.kind() + e.c;
-    uint32_t K = (uint32_t)kind[-g.P] | ((uint32_t)kind[1] << 8) | ((uint32_t)kind[g.P] << 16) | ((uint32_t)kind[-1] << 24);
+    uint32_t K;
+    if (!g.slim) {
+        const uint8_t *kind = g.kind() + e.c;
+        K = (uint32_t)kind[-g.P] | ((uint32_t)kind[1] << 8) | ((uint32_t)kind[g.P] << 16) | ((uint32_t)kind[-1] << 24);
+    } else { // no kind map: the occupant's kind through grid[] and the unit table
+        const uint8_t *gr = g.grid() + e.c;
+        int g0 = gr[-g.P], g1 = gr[1], g2 = gr[g.P], g3 = gr[-1];
+        uint32_t k0 = (g0 == 0 || g0 == 0xFF) ? (uint32_t)g0 : (uint32_t)kind_of(g, g.w0()[g0 - 1]), k1 = (g1 == 0 || g1 == 0xFF) ? (uint32_t)g1 : (uint32_t)kind_of(g, g.w0()[g1 - 1]);
+        uint32_t k2 = (g2 == 0 || g2 == 0xFF) ? (uint32_t)g2 : (uint32_t)kind_of(g, g.w0()[g2 - 1]), k3 = (g3 == 0 || g3 == 0xFF) ? (uint32_t)g3 : (uint32_t)kind_of(g, g.w0()[g3 - 1]);
+        K = k0 | (k1 << 8) | (k2 << 16) | (k3 << 24);
+    }
     const uint32_t LSB = 0x01010101u;
     uint32_t unit = (K >> 4) & ~(K >> 7) & LSB;                       // occupied by a unit (walls have bit 7)
     uint32_t fre = ~((K >> 4) | (K >> 7)) & LSB;                      // neither unit nor wall
@@ -934,7 +960,7 @@ DEVN void issue_policy_lists(Game &g, int pn0, int pn1) {
 DEV void kill_unit(Game &g, int v) { // GameState.removeUnit (GameState.java:79-82); lane 0 only
     uint32_t vw = g.w0()[v]; uint32_t V0 = g.a0()[v];
     int vc = cell_of(g, vw);
-    g.grid()[vc] = 0; g.kind()[vc] = 0;
+    g.grid()[vc] = 0; if (!g.slim) g.kind()[vc] = 0;
     if (a_uses_cell(a_type(V0))) { int tc = target_cell(g, vc, g.a1()[v]); if (g.resv()[tc] == v + 1) g.resv()[tc] = 0; }
     g.a0()[v] = V0 | A0_DEAD; // keeps its action words: a ready action of a dead unit still executes this cycle
 }
@@ -957,12 +983,12 @@ DEV void execute_serial(Game &g, int s, int &ndead) {
     if (a_type(A0) == ACT_MOVE && !dead && (unsigned)A1 < 4u) {
         // the common case on its own short path: a live unit steps into the cell it had reserved (UnitAction.java:346-361)
         int nc = c + doff(g, A1);
-        int rv = g.resv()[nc], gv = g.grid()[nc], kv = g.kind()[c]; // three independent loads, issued together
+        int rv = g.resv()[nc], gv = g.grid()[nc], kv = g.slim ? 0 : g.kind()[c]; // three independent loads, issued together
         if (rv == s + 1) g.resv()[nc] = 0;
         if (gv != 0) g.hdr()[H_ERR] |= GE_CELL_OCCUPIED;
         else {
             g.grid()[c] = 0; g.grid()[nc] = (uint8_t)(s + 1);
-            g.kind()[nc] = (uint8_t)kv; g.kind()[c] = 0;
+            if (!g.slim) { g.kind()[nc] = (uint8_t)kv; g.kind()[c] = 0; }
             // x +- 1 or y +- 1 inside the packed word: a legal move never leaves [0, 255], so no carry crosses a field
             g.w0()[s] = w + ((A1 & 1) ? (uint32_t)(2 - A1) << 16 : (uint32_t)(A1 - 1) << 24);
         }
@@ -977,7 +1003,7 @@ DEV void execute_serial(Game &g, int s, int &ndead) {
                 if (g.grid()[nc] != 0) g.hdr()[H_ERR] |= GE_CELL_OCCUPIED;
                 else {
                     g.grid()[c] = 0; g.grid()[nc] = (uint8_t)(s + 1);
-                    g.kind()[nc] = g.kind()[c]; g.kind()[c] = 0;
+                    if (!g.slim) { g.kind()[nc] = g.kind()[c]; g.kind()[c] = 0; }
                     g.w0()[s] = (w & 0xffffu) | ((uint32_t)(u_x(w) + ddx(A1)) << 16) | ((uint32_t)(u_y(w) + ddy(A1)) << 24);
                 }
             }
@@ -1039,7 +1065,7 @@ DEV void execute_serial(Game &g, int s, int &ndead) {
                         g.w1()[n] = mk_w1(ut_hp(g, ut), 0);
                         g.a0()[n] = AT_IDLE | A0_NOUT; g.a1()[n] = 0; g.tis()[n] = 0; g.seq()[n] = 0; g.uid()[n] = (uint32_t)id;
                         if (g.uw > MRTS_UNIT_WORDS_CORE) { g.x0()[n] = 0; g.x1()[n] = 0; }
-                        g.grid()[nc] = (uint8_t)(n + 1); g.kind()[nc] = (uint8_t)kind_of(g, g.w0()[n]); g.rdy()[n] = MRTS_NEVER;
+                        g.grid()[nc] = (uint8_t)(n + 1); if (!g.slim) g.kind()[nc] = (uint8_t)kind_of(g, g.w0()[n]); g.rdy()[n] = MRTS_NEVER;
                         g.hdr()[H_NUNITS] = n + 1;
                         g.hdr()[H_RES0 + pl - 1] = pres - cost;
                     }
@@ -1140,7 +1166,7 @@ DEV int cycle_execute(Game &g, int t_new) {
                 A1 = g.a1()[ci]; w = g.w0()[ci];
                 if ((unsigned)A1 < 4u) {
                     c = cell_of(g, w); nc = c + doff(g, A1);
-                    int rv = g.resv()[nc], gv = g.grid()[nc]; kv = g.kind()[c];
+                    int rv = g.resv()[nc], gv = g.grid()[nc]; kv = g.slim ? 0 : g.kind()[c];
                     is_par = rv == ci + 1 && gv == 0;
                 }
             }
@@ -1150,7 +1176,7 @@ DEV int cycle_execute(Game &g, int t_new) {
             g.a0()[ci] = (A0 & 0xF0u) | AT_IDLE | A0_NOUT; g.rdy()[ci] = MRTS_NEVER;
             g.resv()[nc] = 0;
             g.grid()[c] = 0; g.grid()[nc] = (uint8_t)(ci + 1);
-            g.kind()[nc] = (uint8_t)kv; g.kind()[c] = 0;
+            if (!g.slim) { g.kind()[nc] = (uint8_t)kv; g.kind()[c] = 0; }
             g.w0()[ci] = w + ((A1 & 1) ? (uint32_t)(2 - A1) << 16 : (uint32_t)(A1 - 1) << 24);
             cs = 0xFFFFFFFFu; mine = 0;
         }
@@ -1232,8 +1258,9 @@ DEV bool rb_accept(const Game &g, int pl, unsigned m, bool cand, int tcell, int 
     bool blocked = false;
     if (cand && tcell >= 0) {
         int ev = g.resv()[tcell];
-        if (ev != 0) blocked = !(simul && g.tis()[ev - 1] == c.time && u_pl(g.w0()[ev - 1]) != pl);
-        if (g.claim()[tcell] & pl) blocked = true; // this player's earlier choice of the cell was cancelled at issue (see rb_player)
+        if (g.slim && ev > MRTS_MAX_CAP) blocked = true; // (slim layout) the claim of a cancelled pair, coded into resv[]: see rb_player
+        else if (ev != 0) blocked = !(simul && g.tis()[ev - 1] == c.time && u_pl(g.w0()[ev - 1]) != pl);
+        if (!g.slim && (g.claim()[tcell] & pl)) blocked = true; // this player's earlier choice of the cell was cancelled at issue (see rb_player)
     }
     unsigned below = (1u << g.lane) - 1;
     // While no candidate that costs resources is involved, the resource half of consistentWith is the same for every lane
@@ -1304,7 +1331,10 @@ DEV void rb_player(Game &g, int pl, const uint8_t *list, int cnt, bool simul, Rb
                     g.a0()[es] = (E0 & 0xF0u) | ACT_NONE | A0_NOUT; g.a1()[es] = eta; g.rdy()[es] = c.time + eta;
                     g.resv()[tcell] = 0;
                     // the cell stays part of this player's PlayerAction.r: a later unit of the same list must not choose it
-                    g.claim()[tcell] |= (uint8_t)pl; c.cancelled = true;
+                    // (only the second player's pass can cancel, so in the slim layout one code in resv[] is enough: no slot is
+                    // numbered above MRTS_MAX_CAP)
+                    if (g.slim) g.resv()[tcell] = (uint8_t)(MRTS_MAX_CAP + 1); else g.claim()[tcell] |= (uint8_t)pl;
+                    c.cancelled = true;
                     A0 = ACT_NONE | A0_NOUT; A1 = eta;
                 } else g.resv()[tcell] = (uint8_t)(i + 1);
             }
@@ -1437,8 +1467,18 @@ DEV int rb_decide(Game &g, int n, int time, int polmask, bool simul, unsigned &d
         }
         mr = c.minr;
         if (__ballot_sync(FULLM, c.cancelled)) {
-            #pragma unroll 1
-            for (int i = g.lane; i < g.pcw; i += 32) ((uint32_t *)g.claim())[i] = 0;
+            if (!g.slim) {
+                #pragma unroll 1
+                for (int i = g.lane; i < g.pcw; i += 32) ((uint32_t *)g.claim())[i] = 0;
+            } else { // drop the claim codes from resv[] (0xFF never occurs there: a wall is never a target)
+                #pragma unroll 1
+                for (int i = g.lane; i < g.pcw; i += 32) {
+                    uint32_t v = ((uint32_t *)g.resv())[i], hit = 0;
+                    #pragma unroll
+                    for (int b = 0; b < 4; b++) if (((v >> (8 * b)) & 0xff) > (uint32_t)MRTS_MAX_CAP) hit |= 0xffu << (8 * b);
+                    if (hit) ((uint32_t *)g.resv())[i] = v & ~hit;
+                }
+            }
         }
         if (g.lane == 0) { g.hdr()[H_NEXTSEQ] = (int32_t)(c.seq_base + c.k); hdr_set_rng(g, H_RNGP_LO, lcg_jump(g, c.s0, c.k)); }
         __syncwarp();
@@ -1781,6 +1821,7 @@ DEVN void run_issue_only(Game &g, const StepParams &p, long long gi) {
 // every output byte is a zero, so the LSU only sees the few values scattered over them afterwards.
 #ifdef MRTS_EMU
 DEV void bulk_zero(uint32_t, int, void *dst, size_t bytes) { memset(dst, 0, bytes); }
+DEV void bulk_copy(uint32_t, void *, uint32_t) {}
 DEV void bulk_wait_all() {}
 #else
 // lane 0 only: dst 16-byte aligned, bytes a multiple of 16; zsm = shared-window address of zbytes zeros
@@ -1793,13 +1834,17 @@ DEV void bulk_zero(uint32_t zsm, int zbytes, void *dst, size_t bytes) {
     }
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+DEV void bulk_copy(uint32_t src_sm, void *dst, uint32_t bytes) { // lane 0 only; joins the bulk group the next bulk_zero commits, or commit below
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_sm), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 // every bulk store of this thread has been performed: later stores to the same bytes land on top of them
 DEV void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 #endif
 
 // prezeroed: planes 0-4 were zeroed by bulk stores issued by lane 0 earlier; they are waited for before the units are scattered
 DEV void obs_emit(const uint32_t *w0, const uint32_t *w1, const uint32_t *a0, int n, int W, int H, const uint8_t *terrain, int player,
-                  int dtype, void *out, int lane, bool prezeroed = false) {
+                  int dtype, void *out, int lane, bool prezeroed = false, bool terrain_done = false) {
     int cells = W * H;
     if (dtype == 0) {
         uint8_t *o = (uint8_t *)out;
@@ -1811,7 +1856,7 @@ DEV void obs_emit(const uint32_t *w0, const uint32_t *w1, const uint32_t *a0, in
                 for (int q = lane; q < 5 * nq; q += 32) ((uint4 *)o)[q] = z;
             }
             #pragma unroll 1
-            for (int q0 = lane; q0 < nq; q0 += 256) { // the terrain plane: eight 16-byte loads in flight per lane, then the stores
+            for (int q0 = lane; q0 < (terrain_done ? 0 : nq); q0 += 256) { // the terrain plane: eight 16-byte loads in flight per lane, then the stores
                 uint4 t[8];
                 #pragma unroll
                 for (int j = 0; j < 8; j++) if (q0 + j * 32 < nq) t[j] = ((const uint4 *)terrain)[q0 + j * 32];
@@ -2232,7 +2277,7 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
 #endif
     Game g;
     g_bind(g, region, L, pW, pH, pcap, lane, p.conflict, p.scripted,
-           p.scripted == 2 ? p.astar_scratch + ((long long)bid * wpc + warp) * p.astar_stride : nullptr);
+           p.scripted == 2 ? p.astar_scratch + ((long long)bid * wpc + warp) * p.astar_stride : nullptr, KERNEL == KERNEL_FAST_OBS);
     if (KERNEL == KERNEL_GENERIC && (LEAN || p.scripted)) { // pathfinding scratch: no stale marks, all buckets empty, generation 0
         #pragma unroll 1
         for (int i = lane; i < (p.W + 2) * (p.H + 2); i += 32) g.as_mark[i] = 0;
@@ -2254,6 +2299,21 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
 #endif
         __syncthreads();
         zsm = smem_window(MRTS_CONST_WORDS * 4 + wpc * L.total);
+    }
+    uint32_t tsm = 0; // the terrain plane and the grid template of the batch's one map, staged once per CTA
+    if (KERNEL == KERNEL_FAST_OBS && (p.terr_bytes > 0 || p.tmpl_bytes > 0)) {
+        unsigned char *tb = mrts_smem + MRTS_CONST_WORDS * 4 + wpc * L.total + p.zero_bytes;
+        const uint4 *ter = (const uint4 *)map_terrain(p.maps, pW, pH, pcap);
+        #pragma unroll 1
+        for (int i = tid; i < p.terr_bytes / 16; i += nthreads) ((uint4 *)tb)[i] = ter[i];
+        #pragma unroll 1
+        for (int i = tid; i < p.tmpl_bytes / 16; i += nthreads) ((uint4 *)(tb + p.terr_bytes))[i] = ((const uint4 *)p.maps)[i];
+#ifndef MRTS_EMU
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+        __syncthreads();
+        if (p.terr_bytes > 0) tsm = smem_window(MRTS_CONST_WORDS * 4 + wpc * L.total + p.zero_bytes);
+        if (p.tmpl_bytes > 0) g.tmpl_sm = (const uint4 *)(tb + p.terr_bytes);
     }
     WarpStats &ws = *(WarpStats *)(mrts_smem + region + L.stats);
     if (lane < N_WARP_STATS) ws.v[lane] = 0;
@@ -2300,10 +2360,16 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
         if (KERNEL == KERNEL_FAST_OBS && lane == 0) {
             #pragma unroll 1
             for (int pl = 0; pl < 2; pl++) {
-                if (obs_bulk && p.obs_out[pl]) bulk_zero(zsm, p.zero_bytes, (char *)p.obs_out[pl] + (size_t)gi * p.out_stride * obs_pg, (size_t)5 * cells);
+                if (obs_bulk && p.obs_out[pl]) {
+                    bulk_zero(zsm, p.zero_bytes, (char *)p.obs_out[pl] + (size_t)gi * p.out_stride * obs_pg, (size_t)5 * cells);
+                    if (tsm) bulk_copy(tsm, (char *)p.obs_out[pl] + (size_t)gi * p.out_stride * obs_pg + (size_t)5 * cells, (uint32_t)cells); // plane 5 never changes
+                }
                 if (mask_bulk && p.mask_out[pl]) bulk_zero(zsm, p.zero_bytes, (char *)p.mask_out[pl] + (size_t)gi * p.out_stride * mask_pg, mask_pg);
             }
         }
+#ifdef MRTS_DBG_NO_GAME // (profiling experiments only: build_variants/, never the shipped library)
+        if (KERNEL == KERNEL_FAST_OBS) {} else
+#endif
         if (KERNEL == KERNEL_FAST || KERNEL == KERNEL_FAST_OBS) run_game_fast(g, p, ws);
         else if (LEAN || p.mode == MODE_GAME) run_game(g, p, gi, ws);
         else if (p.mode == MODE_CYCLE_ONLY) run_cycles_only(g, p.t_target ? p.t_target[gi] : g.hdr()[H_TIME] + p.n_cycles);
@@ -2349,13 +2415,16 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
         }
         g_store(g, ghdr, gun);
         stat_add(ws, lane, STAT_IO_WRITE, (unsigned long long)(MRTS_HDR_WORDS * 4 + puw * 4 * g.hdr()[H_NUNITS] + (p.mode == MODE_GAME && p.results_out ? 16 : 0)));
+#ifdef MRTS_DBG_NO_EMIT
+        if (KERNEL == KERNEL_FAST_OBS) { if (lane == 0) bulk_wait_all(); } else
+#endif
         if (KERNEL == KERNEL_FAST_OBS || (!LEAN && KERNEL == KERNEL_GENERIC && p.mode == MODE_GAME)) {
             #pragma unroll 1
             for (int pl = 0; pl < 2; pl++)
                 if (p.obs_out[pl]) {
                     stat_add(ws, lane, STAT_IO_WRITE, obs_pg);
                     obs_emit(g.w0(), g.w1(), g.a0(), g.hdr()[H_NUNITS], g.W, g.H, map_terrain(blob, g.W, g.H, g.cap), pl, p.obs_dtype,
-                             (char *)p.obs_out[pl] + (size_t)gi * p.out_stride * obs_pg, lane, obs_bulk);
+                             (char *)p.obs_out[pl] + (size_t)gi * p.out_stride * obs_pg, lane, obs_bulk, obs_bulk && tsm != 0);
                 }
             #pragma unroll 1
             for (int pl = 0; pl < 2; pl++)

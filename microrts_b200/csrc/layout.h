@@ -94,7 +94,10 @@ struct SmemLayout {
 #define MRTS_ASTAR_BYTES(W, H) ((4 * ((W) + 2) * ((H) + 2) + 2 * MRTS_ASTAR_HEADS(W, H) + 4 + 15) & ~15)
 // pending = 0: the layout of the specialised kernels (fast game loop, rollouts), which fuse policy and issue and never
 // stage a pending action list -- 8 bytes per unit slot less, which is what lets one more CTA fit per SM on small maps
-MRTS_HDC SmemLayout mrts_smem_layout(int W, int H, int cap, int scripted, int po_policies = 0, int pending = 1) {
+// slim = 1: the layout of the fused step + observation kernel, which runs on large maps where the cell maps bound the occupancy: no
+// kind map (a neighbour's kind is looked up through grid[] and the unit table) and no claim map (the few cells a cancelled pair
+// leaves claimed are coded into resv[]) -- half the map bytes, 12 instead of 8 games in flight per SM on a 64x64 map
+MRTS_HDC SmemLayout mrts_smem_layout(int W, int H, int cap, int scripted, int po_policies = 0, int pending = 1, int slim = 0) {
     SmemLayout L{};
     int pc = (W + 2) * (H + 2);
     int pcb = (pc + 15) & ~15;
@@ -110,9 +113,9 @@ MRTS_HDC SmemLayout mrts_smem_layout(int W, int H, int cap, int scripted, int po
     L.pa1 = o; o += pending ? ((cap * 4 + 15) & ~15) : 0;
     L.pslot = o; o += capb;
     L.grid = o; o += pcb;
-    L.kind = o; o += pcb;
+    L.kind = o; o += slim ? 0 : pcb;
     L.resv = o; o += pcb;
-    L.claim = o; o += pcb;
+    L.claim = o; o += slim ? 0 : pcb;
     L.list = o; o += capb;
     L.stats = o; o += 80; // the warp's 10 running counters (kept out of registers)
     L.povis = o; o += po_policies ? pcb : 0;

@@ -256,7 +256,7 @@ struct mrts_batch {
     unsigned char *d_ff = nullptr; long long ff_stride = 0;       // FloodFillPathFinding caches, allocated when a player asks for that pathfinder
     Staged staged[2];
     stream_t stream = nullptr;
-    SmemLayout L, Lfast; // generic kernel / specialised kernels (no pending lists, layout.h)
+    SmemLayout L, Lfast, Lslim; // generic kernel / specialised kernels (no pending lists, layout.h) / the fused step + observation kernel (no kind and claim maps either)
     struct Plan { int wpc = 2, grid = 3; size_t smem = 0; } plan[N_KERNELS]; // per kernel: warps (games in flight) per CTA, CTAs, shared memory
     Plan fixed_plan[N_KERNELS]; int fixed_of[N_KERNELS] = {-1, -1, -1, -1}; // the fixed-size copy that replaces kernel k for this batch, or -1
     const void *generic_fixed_fn = nullptr; // a fixed_<W>x<H>.cu kernel when the batch has its layout (plan in fixed_plan[KERNEL_GENERIC])
@@ -266,6 +266,7 @@ struct mrts_batch {
     void *obs_out[2] = {nullptr, nullptr}; int obs_dtype = 0; // device buffers mrts_batch_step writes post-step observations to
     void *mask_out[2] = {nullptr, nullptr};                   // ... and the post-step bit-packed action masks
     int zero_bytes = 0;                                       // block of zeros per CTA of k_step_fast_obs (source of its bulk stores)
+    int terr_bytes = 0, tmpl_bytes = 0;                       // ... and its staged terrain plane / grid template (single-map batches)
     int vec_reset = 0, vec_max_steps = 0;                     // in-kernel auto-reset of the JNIGridnetVecClient flow (mrts_batch_set_vec_autoreset)
     int out_stride = 1;                                       // game g's fused outputs go to game slot g * out_stride (mrts_batch_set_output_stride)
     long long launches = 0;
@@ -296,6 +297,7 @@ static int launch_step(mrts_batch *b, StepParams &p) {
     else if (p.mode == MODE_GAME && p.conflict == MRTS_CANCEL_BOTH && rb_or_passive(p.policy[0]) && rb_or_passive(p.policy[1]) && !p.info_out && !p.sequential_issue && !p.po_policies && !p.vec_reset)
         kernel = (p.obs_out[0] || p.obs_out[1] || p.mask_out[0] || p.mask_out[1]) ? KERNEL_FAST_OBS : KERNEL_FAST;
     p.zero_bytes = kernel == KERNEL_FAST_OBS ? b->zero_bytes : 0;
+    p.terr_bytes = kernel == KERNEL_FAST_OBS ? b->terr_bytes : 0; p.tmpl_bytes = kernel == KERNEL_FAST_OBS ? b->tmpl_bytes : 0;
     const int fv = b->fixed_of[kernel];
     const bool gfx = kernel == KERNEL_GENERIC && b->generic_fixed_fn;
     // the rush-only copy: a game step in which neither player runs a defense, WorkerRushPlusPlus or a PO rush
@@ -305,7 +307,7 @@ static int launch_step(mrts_batch *b, StepParams &p) {
                       p.pathfinder[0] == MRTS_PF_ASTAR && p.pathfinder[1] == MRTS_PF_ASTAR && p.conflict == MRTS_CANCEL_BOTH && !p.info_out &&
                       !p.sequential_issue && !p.vec_reset && !p.obs_out[0] && !p.obs_out[1] && !p.mask_out[0] && !p.mask_out[1];
     const mrts_batch::Plan &pl = rush ? b->rush_plan : ((fv >= 0 || gfx) ? b->fixed_plan[kernel] : b->plan[kernel]);
-    p.L = kernel == KERNEL_GENERIC ? b->L : b->Lfast;
+    p.L = kernel == KERNEL_GENERIC ? b->L : (kernel == KERNEL_FAST_OBS ? b->Lslim : b->Lfast);
     int threads = pl.wpc * 32;
     long long items = p.mode == MODE_ROLLOUT ? b->n * p.rollouts_per_game : b->n;
     long long need = (items + pl.wpc - 1) / pl.wpc;
@@ -331,7 +333,15 @@ static int launch_step(mrts_batch *b, StepParams &p) {
 #else
     if (fv >= 0 || gfx) { void *args[] = {&p}; return ck(cudaLaunchKernel(rush ? b->generic_rush_fn : (gfx ? b->generic_fixed_fn : g_fixed[fv].fn), dim3(grid), dim3(threads), args, pl.smem, b->stream)); }
     if (kernel == KERNEL_FAST) k_step_fast<<<grid, threads, pl.smem, b->stream>>>(p);
-    else if (kernel == KERNEL_FAST_OBS) k_step_fast_obs<<<grid, threads, pl.smem, b->stream>>>(p);
+    else if (kernel == KERNEL_FAST_OBS) {
+        // With the action masks as well a game writes 128 KB (64x64): measured, ONE resident CTA (four games) per SM then moves more
+        // bytes per second than two (5.9 against 4.9 TB/s) -- fewer write streams in flight at once.  The kernel's shared memory
+        // request is padded so that no second CTA fits.  MRTS_DBG_OBS_CTAS overrides the cap (profiling experiments).
+        size_t sm = pl.smem; int gr = grid, cap_ctas = (p.mask_out[0] || p.mask_out[1]) && b->W * b->H >= 1024 ? 1 : 0;
+        if (const char *e = getenv("MRTS_DBG_OBS_CTAS")) cap_ctas = atoi(e);
+        if (cap_ctas > 0) { sm = std::max(sm, (size_t)(233472 / (cap_ctas + 1) - 1024 + 16) & ~(size_t)15); gr = std::min(grid, cap_ctas * 148); }
+        k_step_fast_obs<<<gr, threads, sm, b->stream>>>(p);
+    }
     else if (kernel == KERNEL_ROLLOUT) k_rollout<<<grid, threads, pl.smem, b->stream>>>(p);
     else k_step<<<grid, threads, pl.smem, b->stream>>>(p);
     return ck(cudaGetLastError());
@@ -485,6 +495,7 @@ int mrts_batch_create(const mrts_utt *u, const mrts_map *const *maps, int n_maps
     b->uw = b->scripted ? MRTS_UNIT_WORDS : MRTS_UNIT_WORDS_CORE;
     b->L = mrts_smem_layout(W, H, cap, b->scripted, po_pol);
     b->Lfast = mrts_smem_layout(W, H, cap, b->scripted ? 2 : 0, 0, 0); // same unit words, no pathfinding scratch, no pending lists
+    b->Lslim = mrts_smem_layout(W, H, cap, b->scripted ? 2 : 0, 0, 0, 1);
     b->map_words = mrts_map_blob_words(W, H, cap);
     if (dev_select(device)) return fail(MRTS_E_CUDA, std::string("cannot select CUDA device: ") + dev_errstr());
 #ifndef MRTS_EMU
@@ -512,9 +523,15 @@ int mrts_batch_create(const mrts_utt *u, const mrts_map *const *maps, int n_maps
         return 0;
     };
     // the fused step + observation kernel keeps one block of zeros per CTA: the source of the bulk stores that zero its outputs
-    { int z5 = (5 * W * H) & ~15; b->zero_bytes = z5 >= 256 ? std::min(4096, z5) : 0; }
+    // (measured on config 5: two CTAs of four games per SM with 20 KB bulk stores beat three CTAs with 4 KB ones -- the write streams of
+    // too many games in flight get in each other's way -- so the kernel spends shared memory on large sources instead of on occupancy)
+    { int z5 = (5 * W * H) & ~15; b->zero_bytes = z5 >= 256 ? std::min(32768, z5) : 0; }
+    if (n_maps == 1 && b->zero_bytes) {
+        b->tmpl_bytes = b->Lslim.pcw * 4;
+        if (((W * H) & 15) == 0 && W * H <= 16384) b->terr_bytes = W * H;
+    }
     for (int kk = 0; kk < N_KERNELS; kk++) {
-        int rc = make_plan(kernels[kk], kk == KERNEL_GENERIC ? b->L.total : b->Lfast.total, b->plan[kk], kk == KERNEL_FAST_OBS ? b->zero_bytes : 0);
+        int rc = make_plan(kernels[kk], kk == KERNEL_GENERIC ? b->L.total : (kk == KERNEL_FAST_OBS ? b->Lslim.total : b->Lfast.total), b->plan[kk], kk == KERNEL_FAST_OBS ? b->zero_bytes + b->terr_bytes + b->tmpl_bytes : 0);
         if (rc) return rc;
     }
 #ifndef MRTS_NO_FIXED
@@ -537,7 +554,7 @@ int mrts_batch_create(const mrts_utt *u, const mrts_map *const *maps, int n_maps
 #endif
     if (ck(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking))) return fail(MRTS_E_CUDA, std::string("cudaStreamCreate: ") + dev_errstr());
 #else
-    for (int kk = 0; kk < N_KERNELS; kk++) { b->plan[kk].wpc = 2; b->plan[kk].smem = MRTS_CONST_WORDS * 4 + (size_t)2 * (kk == KERNEL_GENERIC ? b->L.total : b->Lfast.total); b->plan[kk].grid = 3; }
+    for (int kk = 0; kk < N_KERNELS; kk++) { b->plan[kk].wpc = 2; b->plan[kk].smem = MRTS_CONST_WORDS * 4 + (size_t)2 * (kk == KERNEL_GENERIC ? b->L.total : (kk == KERNEL_FAST_OBS ? b->Lslim.total : b->Lfast.total)) + (kk == KERNEL_FAST_OBS ? b->zero_bytes : 0); b->plan[kk].grid = 3; }
     for (int v = 0; v < N_FIXED; v++)
         if (g_fixed[v].W == W && g_fixed[v].H == H && g_fixed[v].cap == cap && !b->scripted) { b->fixed_plan[g_fixed[v].kernel] = b->plan[g_fixed[v].kernel]; b->fixed_of[g_fixed[v].kernel] = v; }
 #endif

@@ -914,3 +914,43 @@ def test_unit_action_lists_and_cycle_to_decision(backend, maps, key, version):
                 og.cycle()
             P.assert_same_state(ex, g, og, "cycle_to_decision %s round %d" % (key, r))
     b.close()
+
+
+@pytest.mark.parametrize("key,sizes,cycles,chunk", [("8x8/basesWorkers8x8", (6, 128), (3000, 3000), 53), ("8x8/FourBasesWorkers8x8", (4, 48), (1500, 3000), 7),
+                                                     ("16x16/basesWorkers16x16", (3, 64), (900, 3000), 1), ("melee14x12Mixed18", (2, 32), (500, 2000), 10)])
+def test_selfplay_through_the_observation_kernel(backend, maps, key, sizes, cycles, chunk):
+    """Whole games through the fused step + observation kernel, whose shared-memory layout has no kind and no claim map
+    (layout.h, slim): neighbour kinds come from grid[] + the unit table and the claims of cancelled pairs are coded into resv[].
+    Small maps make same-cell conflicts between the two players frequent.  States, RNG streams and the final planes equal the oracle."""
+    n = sizes[0] if backend == "emu" else sizes[1]
+    total = cycles[0] if backend == "emu" else cycles[1]
+    utt, outt = M.UnitTypeTable(1, 1), O.Utt(1, 1)
+    m = maps[key]
+    b = M.BatchedGameState(utt, make_pgs(m, utt), n)
+    seeds = np.arange(n, dtype=np.int64) * 977 + 31
+    b.reset(seeds)
+    b.set_policy(0, M.POLICY_RANDOM_BIASED)
+    b.set_policy(1, M.POLICY_RANDOM_BIASED)
+    shape = (n, 6, m["h"], m["w"])
+    o0, o1 = _device_buffer(backend, shape, np.uint8), _device_buffer(backend, shape, np.uint8)
+    b.set_observation_outputs(o0, o1)
+    games = []
+    for g in range(n):
+        og = O.Game(outt, m)
+        og.seed(int(seeds[g]))
+        games.append(og)
+    every = max(1, 200 // chunk)
+    for it, t in enumerate(range(0, total, chunk)):
+        b.step(chunk, total)
+        assert b.last_kernel == "k_step_fast_obs"
+        for og in games:
+            if not (og.gameover and og.time > 0):
+                og.run(O.AI_RANDOM_BIASED, None, O.AI_RANDOM_BIASED, None, chunk, total)
+        if it % every == 0 or t + chunk >= total:
+            ex = b.export()
+            a0, a1 = _to_numpy(o0), _to_numpy(o1)
+            for g, og in enumerate(games):
+                P.assert_same_state(ex, g, og, "%s obs kernel t=%d" % (key, t + chunk))
+                assert [int(v) for v in ex["rng"][g]] == [og.rng_state(k) for k in range(3)]
+                assert (a0[g] == og.observe(0).astype(np.uint8)).all() and (a1[g] == og.observe(1).astype(np.uint8)).all()
+    b.close()
