@@ -2321,25 +2321,8 @@ DEV void step_kernel_body(const StepParams &p, unsigned char *smem, int tid, int
     long long n_items = KERNEL == KERNEL_ROLLOUT ? p.n_games * p.rollouts_per_game : p.n_games;
     // A warp's first item is static; the next ones come from a global counter, so a warp that drew cheap games (or rollouts
     // that ended early) takes more of them and the launch has no long tail of a few unlucky warps.
-    // Short steps (the one-cycle steps of the observation-emitting and RL paths) are bound by the latency of a game's first loads from
-    // HBM: such a launch draws the warp's NEXT game at the start of the current one and asks L2 for its header and first unit words,
-    // which then arrive while the current game is being stepped.
-    const bool ahead = (KERNEL == KERNEL_FAST_OBS || KERNEL == KERNEL_GENERIC) && !LEAN && p.mode == MODE_GAME && p.n_cycles <= 4;
-    long long drawn = -1;
 #pragma unroll 1
-    for (long long item = (long long)bid * wpc + warp; item < n_items;
-         item = ahead ? drawn : next_item<KERNEL == KERNEL_ROLLOUT ? 8 : 1>(p, lane, (long long)nblocks * wpc, item)) {
-        if (ahead) {
-            drawn = next_item<1>(p, lane, (long long)nblocks * wpc, item);
-            if (drawn < n_items) {
-#ifndef MRTS_EMU
-                const char *nh = (const char *)(p.hdr + drawn * MRTS_HDR_WORDS), *nu = (const char *)(p.units + drawn * (long long)puw * pcap);
-                if (lane < 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(nh + lane * 64));                 // 80 bytes: one or two lines
-                else if (lane < 2 + 2 * puw) { int k = (lane - 2) >> 1, half = (lane - 2) & 1;                     // the first 64 slots of every word array
-                    if (half * 32 < pcap) asm volatile("prefetch.global.L2 [%0];" ::"l"(nu + ((size_t)k * pcap + half * 32) * 4)); }
-#endif
-            }
-        }
+    for (long long item = (long long)bid * wpc + warp; item < n_items; item = next_item<KERNEL == KERNEL_ROLLOUT ? 8 : 1>(p, lane, (long long)nblocks * wpc, item)) {
         long long gi = KERNEL == KERNEL_ROLLOUT ? item / p.rollouts_per_game : item;
         const uint32_t *blob = p.maps + (size_t)(gi % p.n_maps) * p.map_words;
         g.grid_tmpl = blob;
