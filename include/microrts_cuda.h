@@ -201,6 +201,9 @@ int mrts_batch_set_actions(mrts_batch *, int player, int format, const int32_t *
  * block 2g + 1 = player 1 ([2 * n_games][max_k][8], every game max_k rows).  One host -> device copy; async != 0 returns without
  * waiting for it (the host array, ideally pinned, must stay untouched until the batch is synchronised). */
 int mrts_batch_set_actions_interleaved(mrts_batch *, int format, const int32_t *actions, int max_k, int fill_none_duration, int on_device, int async);
+/* ... followed by the one-cycle step: JNIGridnetVecClient.gameStep of the self-play environments as ONE call (no cycle cap; the
+ * environments' step limit is mrts_batch_set_vec_autoreset's) */
+int mrts_batch_vec_step(mrts_batch *, const int32_t *actions /* [2 * n_games][max_k][8] */, int max_k, int on_device, int async);
 int mrts_batch_issue(mrts_batch *, int player, int format, const int32_t *actions, const int32_t *counts,
                      int max_k, int fill_none_duration, int safe, int on_device);
 

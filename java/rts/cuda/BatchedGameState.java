@@ -42,7 +42,7 @@ public final class BatchedGameState implements AutoCloseable {
     private final MethodHandle lastError, uttCreate, uttDestroy, mapLoad, mapDestroy, batchCreate, batchDestroy, reset, resetMasked,
             setPolicy, setAutoReset, setActions, issue, step, cycleTo, observe, masks, results, stats, rollout, pathfind, evaluate, numPlanes, maskWidth,
             restartMasked, setIssueOrder, setInfoOutput, setObservationOutputs, setMaskOutputs, setOutputStride, setVecAutoreset, setActionsInterleaved,
-            copyGames, scatterGames, copyToHost, sync, unitActions, cycleToDecision, playerActions, statsAllreduce, ncclUniqueId, ncclCommCreate, ncclCommDestroy,
+            vecStep, copyGames, scatterGames, copyToHost, sync, unitActions, cycleToDecision, playerActions, statsAllreduce, ncclUniqueId, ncclCommCreate, ncclCommDestroy,
             mctsCreate, mctsIterate, mctsRoot, mctsBestActions, mctsDestroy, pagCreate, pagNext, pagSize, pagDestroy;
 
     private MemorySegment utt, map, batch;
@@ -101,6 +101,7 @@ public final class BatchedGameState implements AutoCloseable {
         setOutputStride = h("mrts_batch_set_output_stride", FunctionDescriptor.of(I, P, I));
         setVecAutoreset = h("mrts_batch_set_vec_autoreset", FunctionDescriptor.of(I, P, I, I));
         setActionsInterleaved = h("mrts_batch_set_actions_interleaved", FunctionDescriptor.of(I, P, I, P, I, I, I, I));
+        vecStep = h("mrts_batch_vec_step", FunctionDescriptor.of(I, P, P, I, I, I));
         copyGames = h("mrts_batch_copy_games", FunctionDescriptor.of(I, P, P, P, P, I));
         scatterGames = h("mrts_batch_scatter_games", FunctionDescriptor.of(I, P, P, P, I));
         copyToHost = h("mrts_batch_copy_to_host", FunctionDescriptor.of(I, P, P, P, L));
@@ -289,6 +290,9 @@ public final class BatchedGameState implements AutoCloseable {
     public void setActionsInterleaved(MemorySegment actions, int maxK, boolean async) throws Throwable {
         check((int) setActionsInterleaved.invoke(batch, ACTIONS_VECTOR, actions, maxK, 1, 0, async ? 1 : 0));
     }
+
+    /** setActionsInterleaved + step(1) in one native call: JNIGridnetVecClient.gameStep of the self-play environments. */
+    public void vecStep(MemorySegment actions, int maxK, boolean async) throws Throwable { check((int) vecStep.invoke(batch, actions, maxK, 0, async ? 1 : 0)); }
 
     /** Queue a device -> host copy behind the step on the batch's stream; sync() waits. */
     public void copyToHost(MemorySegment host, MemorySegment device, long bytes) throws Throwable { check((int) copyToHost.invoke(batch, host, device, bytes)); }

@@ -44,7 +44,7 @@ def bind(L):
         "mrts_batch_set_actions": (i, [vp, i, i, vp, vp, i, i, i]),
         "mrts_batch_issue": (i, [vp, i, i, vp, vp, i, i, i, i]),
         "mrts_batch_step": (i, [vp, i, i]), "mrts_batch_set_observation_outputs": (i, [vp, i, vp, vp]), "mrts_batch_set_mask_outputs": (i, [vp, vp, vp]), "mrts_batch_set_output_stride": (i, [vp, i]), "mrts_batch_set_vec_autoreset": (i, [vp, i, i]),
-        "mrts_batch_set_actions_interleaved": (i, [vp, i, vp, i, i, i, i]),
+        "mrts_batch_set_actions_interleaved": (i, [vp, i, vp, i, i, i, i]), "mrts_batch_vec_step": (i, [vp, vp, i, i, i]),
         "mrts_batch_set_issue_order": (i, [vp, i]), "mrts_batch_set_info_output": (i, [vp, vp]), "mrts_batch_restart_masked": (i, [vp, vp, i]), "mrts_batch_cycle_to": (i, [vp, vp, i, i]),
         "mrts_batch_rollout": (i, [vp, i, i, i, i, i, vp, vp, vp, i]),
         "mrts_batch_observe": (i, [vp, i, i, vp, i]), "mrts_batch_num_planes": (i, [vp]),

@@ -410,6 +410,11 @@ class BatchedGameState:
         pa, da, _k = _ptr(actions)
         _check(_ffi.lib().mrts_batch_set_actions_interleaved(self._h, fmt, pa, int(actions.shape[1]), fill_none_duration, da, 1 if async_copy else 0))
 
+    def vec_step(self, actions, async_copy=True):
+        """set_actions_interleaved + step(1) in one library call (JNIGridnetVecClient.gameStep of self-play environments)."""
+        pa, da, _k = _ptr(actions)
+        _check(_ffi.lib().mrts_batch_vec_step(self._h, pa, int(actions.shape[1]), da, 1 if async_copy else 0))
+
     def set_mask_outputs(self, out0=None, out1=None):
         """Fused emission of the bit-packed action masks: every later step() also writes getMasks(0) / (1) of the state it leaves
         behind into out0 / out1 ([n][H][W][(mask_width + 7) // 8] uint8 device tensors; None disables a player)."""

@@ -794,6 +794,14 @@ int mrts_batch_step(mrts_batch *b, int n_cycles, int max_cycles) {
     return MRTS_OK;
 }
 
+// JNIGridnetVecClient.gameStep for the self-play environments in one call: both players' vector actions in environment order, then the
+// one-cycle step (src/tests/JNIGridnetVecClient.java:226-236)
+int mrts_batch_vec_step(mrts_batch *b, const int32_t *actions, int max_k, int on_device, int async) {
+    int rc = mrts_batch_set_actions_interleaved(b, MRTS_ACTIONS_VECTOR, actions, max_k, 1, on_device, async);
+    if (rc) return rc;
+    return mrts_batch_step(b, 1, 0x3fffffff);
+}
+
 int mrts_batch_set_issue_order(mrts_batch *b, int sequential) { if (!b) return fail(MRTS_E_ARG, "null batch"); b->sequential_issue = sequential ? 1 : 0; return MRTS_OK; }
 int mrts_batch_set_info_output(mrts_batch *b, int32_t *out) { if (!b) return fail(MRTS_E_ARG, "null batch"); b->info_out = out; return MRTS_OK; }
 

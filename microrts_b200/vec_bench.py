@@ -60,8 +60,7 @@ def run(ctx, n_envs, steps, warmup, prewarm, cpu_seconds, cpu_baseline, timed_wi
     it = [0]
 
     def dev_step():
-        b.set_actions_interleaved(dev_pool[it[0] % len(dev_pool)], fill_none_duration=1)
-        b.step(1, 1 << 30)
+        b.vec_step(dev_pool[it[0] % len(dev_pool)])
         it[0] += 1
     w = timed_window(ctx, b, dev_step, steps, warmup, prewarm)
     d = w["stats"]

@@ -193,10 +193,10 @@ class _Group:
         b = self.b
         block = action[self.envs[0]:self.envs[-1] + 1] if self.contiguous else np.ascontiguousarray(action[self.envs])
         if self.selfplay:
-            b.set_actions_interleaved(block, fill_none_duration=1, async_copy=True)
+            b.vec_step(block, async_copy=True)   # actions in + the one-cycle step: one library call
         else:
             b.set_actions(self.side, block, fill_none_duration=1)
-        b.step(1, NO_CAP)
+            b.step(1, NO_CAP)
         self._block_keepalive = block
         if self.emulated:
             b.results(self.res_host)
