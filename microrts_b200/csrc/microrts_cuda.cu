@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #ifdef MRTS_EMU
@@ -360,6 +361,21 @@ static int launch_observe(mrts_batch *b, int player, int dtype, void *d_out) {
     k_observe<<<grid, 256, 0, b->stream>>>(p);
     return ck(cudaGetLastError());
 #endif
+}
+
+// the searches are independent: their host work (tree descent, back-propagation, decoding of the device's lists) is spread over the
+// host's cores
+template <class F> static void parallel_for(int n, F fn) {
+    int nt = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+    if (n < 128 || nt < 2) { for (int i = 0; i < n; i++) fn(i); return; }
+    std::vector<std::thread> th;
+    int chunk = (n + nt - 1) / nt;
+    for (int t = 0; t < nt; t++) {
+        int lo = t * chunk, hi = std::min(n, lo + chunk);
+        if (lo >= hi) break;
+        th.emplace_back([lo, hi, &fn]() { for (int i = lo; i < hi; i++) fn(i); });
+    }
+    for (auto &x : th) x.join();
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1226,9 +1242,11 @@ static int fetch_views(mrts_batch *b, int player, int none_duration, int64_t fir
         return fail(MRTS_E_CUDA, dev_errstr());
 #endif
     out.resize((size_t)count);
-    for (int64_t g = 0; g < count; g++)
-        if (!decode_view(&hdr[g * 8], &pos[g * pmax], &ch[g * kmax * 4], &ls[g * (size_t)kmax * MA], kmax, MA, b->W, none_duration, out[g]))
-            return fail(MRTS_E_LIMIT, "a unit has more than 64 legal actions");
+    std::vector<uint8_t> bad((size_t)count, 0);
+    parallel_for((int)count, [&](int g) {
+        if (!decode_view(&hdr[(size_t)g * 8], &pos[(size_t)g * pmax], &ch[(size_t)g * kmax * 4], &ls[(size_t)g * kmax * MA], kmax, MA, b->W, none_duration, out[g])) bad[g] = 1;
+    });
+    for (int64_t g = 0; g < count; g++) if (bad[g]) return fail(MRTS_E_LIMIT, "a unit has more than 64 legal actions");
     return MRTS_OK;
 }
 
@@ -1308,8 +1326,8 @@ static int mcts_finish_nodes(mrts_mcts *m, const std::vector<uint8_t> &which, bo
     std::vector<HView> v[2];
     for (int pl = 0; pl < 2; pl++) { rc = fetch_views(m->work, pl, 10, 0, m->T, v[pl]); if (rc) return rc; }
     const int maxp = m->H.player, minp = 1 - maxp;
-    for (int t = 0; t < m->T; t++) {
-        if (!which[t]) continue;
+    parallel_for(m->T, [&](int t) {
+        if (!which[t]) return;
         MTree &tr = m->H.trees[t];
         const HView &a = v[maxp][t];
         int type = -1; const HView *view = nullptr;
@@ -1325,7 +1343,7 @@ static int mcts_finish_nodes(mrts_mcts *m, const std::vector<uint8_t> &which, bo
             int id = m->H.attach_new_node(tr, type, a.time, view);
             m->idx[t] = m->slot(t, id);
         }
-    }
+    });
     for (int t = 0; t < m->T; t++) if (!which[t]) m->idx[t] = -1;
     return mrts_batch_scatter_games(m->pool, m->work, m->idx.data(), 0);
 }
@@ -1368,10 +1386,13 @@ int mrts_mcts_iterate(mrts_mcts *m, int n_iterations) {
     for (int it = 0; it < n_iterations; it++) {
         // 1. selectLeaf on the host for every search; a search either lands on an existing node or asks for a new one
         int max_k = 1, creating = 0;
-        for (int t = 0; t < T; t++) {
+        parallel_for(T, [m](int t) {
             MTree &tr = m->H.trees[t];
             tr.creating = false; tr.leaf = -1;
             if (m->H.algorithm == 0) m->H.select_leaf(tr, 0); else m->H.select_leaf_uct(tr, 0);
+        });
+        for (int t = 0; t < T; t++) {
+            MTree &tr = m->H.trees[t];
             if (tr.creating) {
                 if ((int)tr.nodes.size() >= m->max_nodes) return fail(MRTS_E_LIMIT, "a search tree outgrew max_nodes_per_tree");
                 creating++; max_k = std::max(max_k, (int)tr.new_pa.size());
@@ -1406,13 +1427,13 @@ int mrts_mcts_iterate(mrts_mcts *m, int n_iterations) {
         rc = mrts_batch_rollout(m->work, 1, m->H.P.lookahead, m->H.P.eval_fn, m->H.player, -1, m->seeds.data(), m->ev.data(), m->tm.data(), 0);
         if (rc) return rc;
         // 4. propagateEvaluation
-        for (int t = 0; t < T; t++) {
+        parallel_for(T, [m](int t) {
             MTree &tr = m->H.trees[t];
             int time = tr.nodes[tr.leaf].time + m->tm[t] - tr.root_time;
             double evaluation = (double)m->ev[t] * std::pow(0.99, time / 10.0);
             m->H.propagate(tr, tr.leaf, evaluation);
             tr.runs++;
-        }
+        });
     }
     return MRTS_OK;
 }

@@ -202,3 +202,58 @@ def test_cfg4_contact_root_rollouts(backend, maps):
         assert len(have) * R >= 768 and total_cycles / (len(have) * R) > 10, "contact roots play on instead of ending at the first cycle"
     play.close()
     roots.close()
+
+
+def test_cfg5_full_size_fused_outputs_equal_the_standalone_kernels(backend, maps):
+    """65 536 games of GardenOfWar64x64 exactly as bench.py --workload obs --with-masks launches them: after every one-cycle step the
+    planes and masks the fused kernel wrote (bulk stores + scattered values) equal, for EVERY game, what the standalone observation
+    kernel and the mask mode of the generic kernel write from the same state (plain stores, independent code paths), and a sample of
+    games equals the oracle.  Size-independent check of the store ordering (zeros before values) under full load."""
+    if backend == "emu":
+        pytest.skip("full-size batch runs on the GPU only")
+    import torch
+    key, n = "GardenOfWar64x64", 65536
+    m = maps[key]
+    utt, outt = M.UnitTypeTable(1, 1), O.Utt(1, 1)
+    b = M.BatchedGameState(utt, M.maps.standard_map(key, utt), n)
+    seeds = np.arange(n, dtype=np.int64) + 77
+    b.reset(seeds)
+    b.set_policy(0, M.POLICY_RANDOM_BIASED)
+    b.set_policy(1, M.POLICY_RANDOM_BIASED)
+    b.step(400, 3000)  # into the mid-game, without outputs
+    mb = (b.mask_width + 7) // 8
+    obs = [torch.full((n, 6, 64, 64), 0x55, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    msk = [torch.full((n, 64, 64, mb), 0x55, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    ref_o = torch.empty((n, 6, 64, 64), dtype=torch.uint8, device="cuda")
+    ref_m = torch.empty((n, 64, 64, mb), dtype=torch.uint8, device="cuda")
+    b.set_observation_outputs(obs[0], obs[1])
+    b.set_mask_outputs(msk[0], msk[1])
+    sample = list(range(0, 24)) + [4095, 32768, 65535]
+    games = []
+    for g in sample:
+        og = O.Game(outt, m)
+        og.seed(int(seeds[g]))
+        og.run(O.AI_RANDOM_BIASED, None, O.AI_RANDOM_BIASED, None, 400, 3000)
+        games.append(og)
+    terrain = torch.tensor([int(c) for c in m["terrain"]], dtype=torch.uint8, device="cuda").reshape(64, 64)
+    for it in range(6):
+        b.step(1, 3000)
+        assert b.last_kernel == "k_step_fast_obs"
+        b.sync()
+        for pl in (0, 1):
+            b.observe(pl, np.uint8, out=ref_o)
+            b.sync()
+            assert torch.equal(obs[pl], ref_o), "fused planes of player %d differ from k_observe at step %d" % (pl, it)
+            assert bool((obs[pl][:, 5] == terrain).all())
+            b.masks(pl, "bits", out=ref_m)
+            b.sync()
+            assert torch.equal(msk[pl], ref_m), "fused masks of player %d differ from the mask kernel at step %d" % (pl, it)
+        for og in games:
+            og.run(O.AI_RANDOM_BIASED, None, O.AI_RANDOM_BIASED, None, 1, 3000)
+        for pl in (0, 1):
+            o_h, m_h = obs[pl][sample].cpu().numpy(), msk[pl][sample].cpu().numpy()
+            for k, og in enumerate(games):
+                assert (o_h[k] == og.observe(pl).astype(np.uint8)).all(), (it, sample[k], pl)
+                assert (np.unpackbits(m_h[k], axis=-1, bitorder="little")[..., :79] == og.masks(pl)).all(), (it, sample[k], pl)
+    assert (b.results()[:, 3] == 0).all()
+    b.close()

@@ -163,3 +163,23 @@ def test_uct_trees_equal_the_oracle(backend, maps, key, player):
         assert rows[g, :counts[g]].tolist() == exp, (key, g)
     search.close()
     b.close()
+
+
+def test_many_searches_in_lockstep(backend, maps):
+    """160 searches at once (the host side of the searches runs on several threads above 128): a sample of the trees equals the oracle."""
+    key, n, iters = "8x8/basesWorkers8x8", 160, (6 if backend == "emu" else 60)
+    utt, base, games4 = advanced_games(backend, maps, key, 4, warm=[0, 40, 90, 150])
+    b = M.BatchedGameState(utt, M.maps.standard_map(key, utt), n)
+    b.copy_games(base, src_index=np.arange(n, dtype=np.int64) % 4)
+    seeds = np.arange(n, dtype=np.int64) * 3 + 1000
+    search = S.NaiveMCTS(b, 0, seeds=seeds, max_nodes_per_tree=iters + 2)
+    search.iterate(iters)
+    for g in (0, 1, 2, 3, 77, 130, 159):
+        ref = O.Mcts(games4[g % 4], 0, int(seeds[g]))
+        ref.iterate(iters)
+        rv, ra, cv, ca = search.root(g)
+        orv, ora, ocv, oca = ref.root()
+        assert rv == orv == iters and search.num_nodes(g) == ref.n_nodes and (cv == ocv).all() and (ca == oca).all() and ra == ora, g
+    search.close()
+    b.close()
+    base.close()
