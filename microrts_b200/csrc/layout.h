@@ -32,7 +32,7 @@ enum {
     H_ASEQ0 = 16,   // next insertion sequence of player 0's AbstractionLayerAI.actions map
     H_ASEQ1 = 17,
     H_ENVSTEPS = 18, // steps since the environment's last reset (JNIGridnetVecClient.envSteps; in-kernel auto-reset only)
-    H_RSV1 = 19
+    H_AIFLAGS = 19  // bit p: player p's CRush_V1.buildingRacks field (cRush/CRush_V1.java:64)
 };
 
 // per-unit words

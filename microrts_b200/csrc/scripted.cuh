@@ -21,7 +21,8 @@
 // written by lane 0 (or by the lane that owns the item) followed by __syncwarp().
 #pragma once
 
-enum { AA_NONE = 0, AA_TRAIN = 1, AA_BUILD = 2, AA_HARVEST = 3, AA_ATTACK = 4, AA_MOVE = 5 /* Move.java: walk to (bx, by) */ };
+enum { AA_NONE = 0, AA_TRAIN = 1, AA_BUILD = 2, AA_HARVEST = 3, AA_ATTACK = 4, AA_MOVE = 5 /* Move.java: walk to (bx, by) */,
+       AA_RANGED_ATTACK = 6 /* cRush/RangedAttack.java: target + the closest own barracks in the base field */ };
 #define REF_NULL 0u
 #define REF_DEAD 0xFFu
 
@@ -438,6 +439,24 @@ DEVN bool aa_execute(Game &g, const ScriptCtx &c, int s, uint32_t &A0, int &A1) 
             if (mk_move(g, c, s, dir, A0, A1) && unit_action_allowed(g, c, s, A0, A1)) return true;
             return false;
         }
+#ifndef MRTS_TU_RUSH_ONLY
+        case AA_RANGED_ATTACK: { // cRush/RangedAttack.java:58-87: step back towards the barracks while a slower enemy is well inside
+            // the range, shoot when in range, approach otherwise (the square roots compare like their integer squares)
+            uint32_t tw = g.w0()[aa_target(X1) - 1];
+            int dx = u_x(tw) - x, dy = u_y(tw) - y, range = ut_range(g, t), d2 = dx * dx + dy * dy, rd2 = 0;
+            const int racks = aa_base(X1);
+            uint32_t rw = 0;
+            if (racks != (int)REF_NULL) { rw = g.w0()[racks - 1]; int rdx = u_x(rw) - x, rdy = u_y(rw) - y; rd2 = rdx * rdx + rdy * rdy; }
+            const uint16_t *eta = (const uint16_t *)(g.utt() + MRTS_ETA_OFFSET);
+            int dir;
+            if (range >= 1 && d2 <= (range - 1) * (range - 1) && rd2 > 4 && eta[t * 8 + ACT_MOVE] < eta[u_type(tw) * 8 + ACT_MOVE])
+                dir = pf_find(g, c.pf, s, u_x(rw), u_y(rw), range, c.nd);
+            else if (d2 <= range * range) { A0 = ACT_ATTACK | A0_NOUT | ((uint32_t)u_x(tw) << 16) | ((uint32_t)u_y(tw) << 24); A1 = -1; return true; }
+            else dir = pf_find(g, c.pf, s, u_x(tw), u_y(tw), range, c.nd);
+            if (mk_move(g, c, s, dir, A0, A1) && unit_action_allowed(g, c, s, A0, A1)) return true;
+            return false;
+        }
+#endif
         case AA_HARVEST: { // Harvest.java:72-113
             bool empty = u_res(g.w1()[s]) == 0;
             int other = empty ? aa_target(X1) : aa_base(X1);
@@ -497,7 +516,7 @@ DEV bool aa_completed(const Game &g, int s) {
         case AA_TRAIN: return (X0 & 8u) != 0;
         case AA_BUILD: { int bx = aa_bx(X0), by = aa_by(X0); if (bx < 0 || bx >= g.W || by >= g.H) return false; int gv = g.grid()[(by + 1) * g.P + bx + 1]; return gv != 0 && gv != 0xFF; }
         case AA_HARVEST: return u_res(g.w1()[s]) > 0 ? !ref_alive(g, aa_base(X1)) : !ref_alive(g, aa_target(X1));
-        case AA_ATTACK: return !ref_alive(g, aa_target(X1));
+        case AA_ATTACK: case AA_RANGED_ATTACK: return !ref_alive(g, aa_target(X1)); // Attack.java:30-33, RangedAttack.java:36-39
         case AA_MOVE: { uint32_t w = g.w0()[s]; return u_x(w) == aa_bx(X0) && u_y(w) == aa_by(X0); } // Move.java:29-31
     }
     return true;
@@ -614,76 +633,10 @@ DEV void script_build_if_not(Game &g, int s, int player, int type, int *reserved
 #define UT_WORKER 3
 #define UT_LIGHT 4
 
-// WorkerRush.getAction / LightRush.getAction followed by translateActions; appends to the pending list from pn.
-// Lane 0 does the work; returns the new pending count (uniform).
-DEVN int policy_scripted(Game &g, int player, int kind, int pathfinder, int pn) {
-    // the PO rushes are their rush plus exploration, which only a partially observable view triggers (`gs instanceof
-    // PartiallyObservableGameState`, POLightRush.java:57)
-#ifdef MRTS_TU_RUSH_ONLY
-    const bool explore = false;
-#else
-    const bool explore = POL_IS_PO_RUSH(kind) && g.po_view;
-    if (POL_IS_PO_RUSH(kind)) kind = kind - POL_PO_WORKER_RUSH + POL_WORKER_RUSH;
-#endif
-    int par0, par1;
-    reserved_resources(g, par0, par1);
-    __syncwarp();
+// translateActions (AbstractionLayerAI.java:58-113): the player's abstract actions in insertion order become desires, the
+// desires a player action (appended to the pending list from pn; returns the new pending count, uniform)
+DEV int translate_actions(Game &g, int player, int pathfinder, int par0, int par1, int pn) {
     const int n = g.hdr()[H_NUNITS], pl = player + 1, pres = g.hdr()[H_RES0 + player];
-    // the barracks scripts: LightRush / LightDefense, and Heavy* / Ranged* = the same classes with the trained type swapped;
-    // the defenses share their rush's skeleton and differ in script_melee / script_harvest
-#ifdef MRTS_TU_RUSH_ONLY
-    const bool light = kind != POL_WORKER_RUSH, defense = false, always = false;
-#else
-    const bool light = kind != POL_WORKER_RUSH && kind != POL_WORKER_DEFENSE && kind != POL_WORKER_RUSH_PP, defense = POL_IS_DEFENSE(kind), always = kind == POL_WORKER_RUSH_PP;
-#endif
-    const int UT_RUSH = (kind == POL_HEAVY_RUSH || kind == POL_HEAVY_DEFENSE) ? 5 : ((kind == POL_RANGED_RUSH || kind == POL_RANGED_DEFENSE) ? 6 : UT_LIGHT); // HeavyRush.java:55, RangedRush.java:52
-    auto own_harvester = [&](int, uint32_t w) { return u_pl(w) == pl && (ut_flags(g, u_type(w)) & UF_HARVEST) != 0; };
-    // bases (WorkerRush.java:70-76,100-102; LightRush.java:83-89,123-133)
-    w_for_each(g, n, [&](int i, uint32_t w) { return u_type(w) == UT_BASE && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE; }, [&](int i) {
-        bool train = pres >= ut_cost(g, UT_WORKER);
-        if (light && train) train = w_count(g, n, [&](int, uint32_t ow) { return u_type(ow) == UT_WORKER && u_pl(ow) == pl; }) < 1;
-        if (train) aa_put(g, i, player, AA_TRAIN, UT_WORKER, 0, 0, REF_NULL, REF_NULL);
-    });
-    if (light) { // barracks (LightRush.java:92-98,135-139)
-        if (pres >= ut_cost(g, UT_RUSH))
-            w_for_each(g, n, [&](int i, uint32_t w) { return u_type(w) == UT_BARRACKS && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE; },
-                       [&](int i) { aa_put(g, i, player, AA_TRAIN, UT_RUSH, 0, 0, REF_NULL, REF_NULL); });
-    }
-    w_for_each(g, n, [&](int i, uint32_t w) { // melee units
-        int fl = ut_flags(g, u_type(w));
-        return (fl & UF_ATTACK) && !(fl & UF_HARVEST) && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE;
-    }, [&](int i) { script_melee(g, i, player, defense, explore, always); });
-    // workers: all own harvesters, busy ones too, in list order
-    int nbases = w_count(g, n, [&](int, uint32_t w) { return u_pl(w) == pl && u_type(w) == UT_BASE; });
-    int nbarracks = w_count(g, n, [&](int, uint32_t w) { return u_pl(w) == pl && u_type(w) == UT_BARRACKS; });
-    int nworkers = w_count(g, n, own_harvester);
-    if (nworkers > 0) {
-        int reserved[4] = {0, 0, 0, 0}, nres = 0, used = 0, taken = 0; // `taken` workers were removed from the front of freeWorkers
-        int wi = -1;                                     // cursor over own harvesters in list order
-        if (nbases == 0 && taken < nworkers) {
-            if (pres >= ut_cost(g, UT_BASE) + used) { wi = w_next(g, n, wi, own_harvester); taken++; script_build_if_not(g, wi, player, UT_BASE, reserved, nres); used += ut_cost(g, UT_BASE); }
-        }
-        if (light) {
-            if (nbarracks == 0 && pres >= ut_cost(g, UT_BARRACKS) + used && taken < nworkers) {
-                wi = w_next(g, n, wi, own_harvester); taken++; script_build_if_not(g, wi, player, UT_BARRACKS, reserved, nres); used += ut_cost(g, UT_BARRACKS);
-            }
-            // harvest with every remaining worker; those that cannot, attack -- in a second pass, as the reference does
-            uint32_t still[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll 1
-            for (int i = w_next(g, n, wi, own_harvester); i >= 0; i = w_next(g, n, i, own_harvester)) if (script_harvest(g, i, player, defense)) still[i >> 5] |= 1u << (i & 31);
-#pragma unroll 1
-            for (int i = w_next(g, n, wi, own_harvester); i >= 0; i = w_next(g, n, i, own_harvester)) if (still[i >> 5] & (1u << (i & 31))) script_melee(g, i, player, defense, explore, always);
-        } else {
-            // WorkerRush.java:146-202: one harvester, the rest attack; a harvester that stays free is appended at the END
-            int hw = -1;
-            if (taken < nworkers) { hw = w_next(g, n, wi, own_harvester); wi = hw; taken++; }
-            bool hw_free = hw >= 0 && script_harvest(g, hw, player, defense);
-#pragma unroll 1
-            for (int i = w_next(g, n, wi, own_harvester); i >= 0; i = w_next(g, n, i, own_harvester)) script_melee(g, i, player, defense, explore, always);
-            if (hw_free) script_melee(g, hw, player, defense, explore, always);
-        }
-    }
-    // ---- translateActions (AbstractionLayerAI.java:58-113): abstract actions in insertion order --------------------
     ScriptCtx c; c.player = player; c.pf = pathfinder; c.par0 = par0; c.par1 = par1; c.nd = 0;
     int nd = 0;
     // this player's map entries in insertion order: lane 0 collects the slots with an insertion sort by sequence number (slot
@@ -783,4 +736,163 @@ DEVN int policy_scripted(Game &g, int player, int kind, int pathfinder, int pn) 
     }
     __syncwarp();
     return out;
+}
+
+#ifndef MRTS_TU_RUSH_ONLY
+// CRush_V1.rangedUnitBehavior (cRush/CRush_V1.java:194-220): closest enemy and closest own barracks in ONE pass over the unit
+// list that shares its running distance between the two searches -- order-dependent, so every lane walks the list
+DEVN void script_crush_ranged(Game &g, int s, int player) {
+    const int n = g.hdr()[H_NUNITS], pl = player + 1;
+    const uint32_t w = g.w0()[s];
+    int enemy = -1, racks = -1, cd = 0;
+#pragma unroll 1
+    for (int i = 0; i < n; i++) {
+        uint32_t ow = g.w0()[i];
+        bool en = u_pl(ow) != 0 && u_pl(ow) != pl, rk = u_type(ow) == UT_BARRACKS && u_pl(ow) == pl;
+        if (en || rk) {
+            int d = iabs(u_x(ow) - u_x(w)) + iabs(u_y(ow) - u_y(w));
+            if (en && (enemy < 0 || d < cd)) { enemy = i; cd = d; }
+            if (rk && (racks < 0 || d < cd)) { racks = i; cd = d; }
+        }
+    }
+    if (enemy >= 0) aa_put(g, s, player, AA_RANGED_ATTACK, 0, 0, 0, enemy + 1, racks < 0 ? (int)REF_NULL : racks + 1);
+}
+
+// CRush_V1.getAction (cRush/CRush_V1.java:68-131) followed by translateActions.  On maps of at most 144 cells: a worker rush
+// that keeps one harvester per base (rushWorkersBehavior :329-416, rushBaseBehavior :324-326).  On larger maps: nbases + 1
+// harvesters, one barracks training Ranged units (workersBehavior :222-321, baseBehavior :133-168, barracksBehavior :170-174),
+// every other worker fights.  The AI's `buildingRacks` field is a bit of header word H_AIFLAGS; `resourcesUsed` is written
+// and read within one getAction.
+DEVN int policy_crush(Game &g, int player, int pathfinder, int pn) {
+    int par0, par1;
+    reserved_resources(g, par0, par1);
+    __syncwarp();
+    const int n = g.hdr()[H_NUNITS], pl = player + 1, pres = g.hdr()[H_RES0 + player];
+    const int UT_RANGED = 6;
+    const bool rush = g.W * g.H <= 144;
+    auto own_harvester = [&](int, uint32_t w) { return u_pl(w) == pl && (ut_flags(g, u_type(w)) & UF_HARVEST) != 0; };
+    const int nbases = w_count(g, n, [&](int, uint32_t w) { return u_pl(w) == pl && u_type(w) == UT_BASE; });
+    const int nbarracks = w_count(g, n, [&](int, uint32_t w) { return u_pl(w) == pl && u_type(w) == UT_BARRACKS; });
+    const int nworkers = w_count(g, n, [&](int, uint32_t w) { return u_pl(w) == pl && u_type(w) == UT_WORKER; });
+    const int nw = w_count(g, n, own_harvester);
+    bool building = ((g.hdr()[H_AIFLAGS] >> player) & 1) != 0;
+    const bool was_building = building;
+    int resources_used = 0;
+    if (nw > 0) {
+        // freeWorkers = the first nfree own harvesters of the unit list (minus the `taken` builders), battleWorkers = the rest
+        const int keep = rush ? nbases : nbases + 1;
+        const int nfree = (rush && pres == 0) ? 0 : (nw > keep ? keep : nw);
+        int reserved[4] = {0, 0, 0, 0}, nres = 0, taken = 0, wi = -1;
+        if (nbases == 0 && taken < nfree && pres >= ut_cost(g, UT_BASE)) { wi = w_next(g, n, wi, own_harvester); taken++; script_build_if_not(g, wi, player, UT_BASE, reserved, nres); }
+        if (!rush) {
+            if (nbarracks == 0 && taken < nfree && nworkers > 1 && pres >= ut_cost(g, UT_BARRACKS)) {
+                wi = w_next(g, n, wi, own_harvester); taken++; script_build_if_not(g, wi, player, UT_BARRACKS, reserved, nres);
+                resources_used += ut_cost(g, UT_BARRACKS);
+                building = true;
+            } else resources_used = ut_cost(g, UT_BARRACKS) * nbarracks;
+            if (nbarracks > 1) building = true;
+        }
+        int ord = 0;
+#pragma unroll 1
+        for (int i = w_next(g, n, -1, own_harvester); i >= 0; i = w_next(g, n, i, own_harvester), ord++) if (ord >= nfree) script_melee(g, i, player, false);
+        ord = 0;
+#pragma unroll 1
+        for (int i = w_next(g, n, -1, own_harvester); i >= 0 && ord < nfree; i = w_next(g, n, i, own_harvester), ord++) if (ord >= taken) script_harvest(g, i, player, true);
+    }
+    if (building != was_building) { __syncwarp(); if (g.lane == 0) g.hdr()[H_AIFLAGS] |= 1 << player; __syncwarp(); }
+    w_for_each(g, n, [&](int i, uint32_t w) { return u_type(w) == UT_BASE && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE; }, [&](int i) {
+        bool train;
+        if (rush) train = pres >= ut_cost(g, UT_WORKER);
+        else {
+            train = nworkers < nbases + 1 && pres >= ut_cost(g, UT_WORKER);
+            int resources = pres;
+            if (resources_used != ut_cost(g, UT_BARRACKS) * nbarracks) resources -= ut_cost(g, UT_BARRACKS); // "buffers the resources that are being used for barracks"
+            if (building && resources >= ut_cost(g, UT_WORKER) + ut_cost(g, UT_RANGED)) train = true;
+        }
+        if (train) aa_put(g, i, player, AA_TRAIN, UT_WORKER, 0, 0, REF_NULL, REF_NULL);
+    });
+    if (pres >= ut_cost(g, UT_RANGED))
+        w_for_each(g, n, [&](int i, uint32_t w) { return u_type(w) == UT_BARRACKS && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE; },
+                   [&](int i) { aa_put(g, i, player, AA_TRAIN, UT_RANGED, 0, 0, REF_NULL, REF_NULL); });
+    w_for_each(g, n, [&](int i, uint32_t w) {
+        int fl = ut_flags(g, u_type(w));
+        return (fl & UF_ATTACK) && !(fl & UF_HARVEST) && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE;
+    }, [&](int i) { if (u_type(g.w0()[i]) == UT_RANGED) script_crush_ranged(g, i, player); else script_melee(g, i, player, false); });
+    return translate_actions(g, player, pathfinder, par0, par1, pn);
+}
+#endif
+
+// WorkerRush.getAction / LightRush.getAction followed by translateActions; appends to the pending list from pn.
+// Lane 0 does the work; returns the new pending count (uniform).
+DEVN int policy_scripted(Game &g, int player, int kind, int pathfinder, int pn) {
+    // the PO rushes are their rush plus exploration, which only a partially observable view triggers (`gs instanceof
+    // PartiallyObservableGameState`, POLightRush.java:57)
+#ifdef MRTS_TU_RUSH_ONLY
+    const bool explore = false;
+#else
+    const bool explore = POL_IS_PO_RUSH(kind) && g.po_view;
+    if (POL_IS_PO_RUSH(kind)) kind = kind - POL_PO_WORKER_RUSH + POL_WORKER_RUSH;
+#endif
+#ifndef MRTS_TU_RUSH_ONLY
+    if (kind == POL_CRUSH_V1) return policy_crush(g, player, pathfinder, pn);
+#endif
+    int par0, par1;
+    reserved_resources(g, par0, par1);
+    __syncwarp();
+    const int n = g.hdr()[H_NUNITS], pl = player + 1, pres = g.hdr()[H_RES0 + player];
+    // the barracks scripts: LightRush / LightDefense, and Heavy* / Ranged* = the same classes with the trained type swapped;
+    // the defenses share their rush's skeleton and differ in script_melee / script_harvest
+#ifdef MRTS_TU_RUSH_ONLY
+    const bool light = kind != POL_WORKER_RUSH, defense = false, always = false;
+#else
+    const bool light = kind != POL_WORKER_RUSH && kind != POL_WORKER_DEFENSE && kind != POL_WORKER_RUSH_PP, defense = POL_IS_DEFENSE(kind), always = kind == POL_WORKER_RUSH_PP;
+#endif
+    const int UT_RUSH = (kind == POL_HEAVY_RUSH || kind == POL_HEAVY_DEFENSE) ? 5 : ((kind == POL_RANGED_RUSH || kind == POL_RANGED_DEFENSE) ? 6 : UT_LIGHT); // HeavyRush.java:55, RangedRush.java:52
+    auto own_harvester = [&](int, uint32_t w) { return u_pl(w) == pl && (ut_flags(g, u_type(w)) & UF_HARVEST) != 0; };
+    // bases (WorkerRush.java:70-76,100-102; LightRush.java:83-89,123-133)
+    w_for_each(g, n, [&](int i, uint32_t w) { return u_type(w) == UT_BASE && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE; }, [&](int i) {
+        bool train = pres >= ut_cost(g, UT_WORKER);
+        if (light && train) train = w_count(g, n, [&](int, uint32_t ow) { return u_type(ow) == UT_WORKER && u_pl(ow) == pl; }) < 1;
+        if (train) aa_put(g, i, player, AA_TRAIN, UT_WORKER, 0, 0, REF_NULL, REF_NULL);
+    });
+    if (light) { // barracks (LightRush.java:92-98,135-139)
+        if (pres >= ut_cost(g, UT_RUSH))
+            w_for_each(g, n, [&](int i, uint32_t w) { return u_type(w) == UT_BARRACKS && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE; },
+                       [&](int i) { aa_put(g, i, player, AA_TRAIN, UT_RUSH, 0, 0, REF_NULL, REF_NULL); });
+    }
+    w_for_each(g, n, [&](int i, uint32_t w) { // melee units
+        int fl = ut_flags(g, u_type(w));
+        return (fl & UF_ATTACK) && !(fl & UF_HARVEST) && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE;
+    }, [&](int i) { script_melee(g, i, player, defense, explore, always); });
+    // workers: all own harvesters, busy ones too, in list order
+    int nbases = w_count(g, n, [&](int, uint32_t w) { return u_pl(w) == pl && u_type(w) == UT_BASE; });
+    int nbarracks = w_count(g, n, [&](int, uint32_t w) { return u_pl(w) == pl && u_type(w) == UT_BARRACKS; });
+    int nworkers = w_count(g, n, own_harvester);
+    if (nworkers > 0) {
+        int reserved[4] = {0, 0, 0, 0}, nres = 0, used = 0, taken = 0; // `taken` workers were removed from the front of freeWorkers
+        int wi = -1;                                     // cursor over own harvesters in list order
+        if (nbases == 0 && taken < nworkers) {
+            if (pres >= ut_cost(g, UT_BASE) + used) { wi = w_next(g, n, wi, own_harvester); taken++; script_build_if_not(g, wi, player, UT_BASE, reserved, nres); used += ut_cost(g, UT_BASE); }
+        }
+        if (light) {
+            if (nbarracks == 0 && pres >= ut_cost(g, UT_BARRACKS) + used && taken < nworkers) {
+                wi = w_next(g, n, wi, own_harvester); taken++; script_build_if_not(g, wi, player, UT_BARRACKS, reserved, nres); used += ut_cost(g, UT_BARRACKS);
+            }
+            // harvest with every remaining worker; those that cannot, attack -- in a second pass, as the reference does
+            uint32_t still[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 1
+            for (int i = w_next(g, n, wi, own_harvester); i >= 0; i = w_next(g, n, i, own_harvester)) if (script_harvest(g, i, player, defense)) still[i >> 5] |= 1u << (i & 31);
+#pragma unroll 1
+            for (int i = w_next(g, n, wi, own_harvester); i >= 0; i = w_next(g, n, i, own_harvester)) if (still[i >> 5] & (1u << (i & 31))) script_melee(g, i, player, defense, explore, always);
+        } else {
+            // WorkerRush.java:146-202: one harvester, the rest attack; a harvester that stays free is appended at the END
+            int hw = -1;
+            if (taken < nworkers) { hw = w_next(g, n, wi, own_harvester); wi = hw; taken++; }
+            bool hw_free = hw >= 0 && script_harvest(g, hw, player, defense);
+#pragma unroll 1
+            for (int i = w_next(g, n, wi, own_harvester); i >= 0; i = w_next(g, n, i, own_harvester)) script_melee(g, i, player, defense, explore, always);
+            if (hw_free) script_melee(g, hw, player, defense, explore, always);
+        }
+    }
+    return translate_actions(g, player, pathfinder, par0, par1, pn);
 }

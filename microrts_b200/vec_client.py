@@ -100,6 +100,10 @@ class ai:
         return AISpec(M.POLICY_WORKER_RUSH_PP, pathfinder)
 
     @staticmethod
+    def CRush_V1(utt=None, pathfinder=M.PF_ASTAR):
+        return AISpec(M.POLICY_CRUSH_V1, pathfinder)
+
+    @staticmethod
     def WorkerDefense(utt=None, pathfinder=M.PF_ASTAR):
         return AISpec(M.POLICY_WORKER_DEFENSE, pathfinder)
 

@@ -1028,7 +1028,7 @@ int o_pathfind(const OGame *g, int kind, int unit_idx, int targetpos, int range,
  *   ai/abstraction/AbstractionLayerAI.java:58-113,143-245 ; WorkerRush.java:63-204 ; LightRush.java:77-258 ;
  *   Attack.java:51 ; Harvest.java:72 ; Build.java:54 ; Train.java:48-128
  * ---------------------------------------------------------------------------------------------- */
-enum { AA_TRAIN = 1, AA_BUILD, AA_HARVEST, AA_ATTACK, AA_MOVE /* Move.java */ };
+enum { AA_TRAIN = 1, AA_BUILD, AA_HARVEST, AA_ATTACK, AA_MOVE /* Move.java */, AA_RANGED_ATTACK /* cRush/RangedAttack.java: target + base = racks */ };
 typedef struct {
     int unit; int kind;
     int type;          /* train / build */
@@ -1037,7 +1037,8 @@ typedef struct {
     int completed;     /* train */
 } OAbs;
 
-struct OAi { int kind; int pf; OAbs *a; int n, cap; int po_rush; OFf *ff; /* the instance's FloodFillPathFinding, pf == 3 */ };
+struct OAi { int kind; int pf; OAbs *a; int n, cap; int po_rush; OFf *ff; /* the instance's FloodFillPathFinding, pf == 3 */
+             int building_racks, resources_used; /* CRush_V1.java:64-65 */ };
 static int ai_pf(OAi *ai, const OGame *g, int start, int targetpos, int range, const ORu *ru) {
     if (ai->pf == 3) { if (!ai->ff) ai->ff = ff_new(); return pf_floodfill(ai->ff, g, start, targetpos, range, ru); }
     return pf_find(g, ai->pf, start, targetpos, range, ru);
@@ -1063,6 +1064,7 @@ static void ai_build(OAi *ai, int u, int type, int x, int y) { OAbs v = {u, AA_B
 static void ai_harvest(OAi *ai, int u, int target, int base) { OAbs v = {u, AA_HARVEST, -1, 0, 0, target, base, 0}; ai_put(ai, v); }
 static void ai_attack(OAi *ai, int u, int target) { OAbs v = {u, AA_ATTACK, -1, 0, 0, target, -1, 0}; ai_put(ai, v); }
 static void ai_move(OAi *ai, int u, int x, int y) { OAbs v = {u, AA_MOVE, -1, x, y, -1, -1, 0}; ai_put(ai, v); }
+static void ai_ranged_attack(OAi *ai, int u, int target, int racks) { OAbs v = {u, AA_RANGED_ATTACK, -1, 0, 0, target, racks, 0}; ai_put(ai, v); } /* CRush_V1.java:419-421 */
 
 static int in_list(const OGame *g, int u) { return u >= 0 && list_index_of(g, u) >= 0; }
 
@@ -1074,6 +1076,7 @@ static int aa_completed(const OAbs *aa, const OGame *g) {
             if (g->pool[aa->unit].res > 0) return !in_list(g, aa->base);
             return !in_list(g, aa->target);
         case AA_ATTACK: return !in_list(g, aa->target);                       /* Attack.java:30-33 */
+        case AA_RANGED_ATTACK: return !in_list(g, aa->target);                /* RangedAttack.java:36-39 */
         case AA_MOVE: return g->pool[aa->unit].x == aa->x && g->pool[aa->unit].y == aa->y; /* Move.java:29-31 */
     }
     return 1;
@@ -1104,6 +1107,24 @@ static int aa_execute(OAi *ai, OAbs *aa, OGame *g, const ORu *ru, OAct *out) {
             int range = g->utt->f[unit->type][OF_RANGE];
             if (d <= range) { *out = mk_act(O_ATTACK, -1, t->x, t->y, -1); return 1; }
             OAct mv;
+            if (mk_move(&mv, ai_pf(ai, g, aa->unit, t->x + t->y * w, range, ru)) && is_unit_action_allowed(g, aa->unit, &mv)) { *out = mv; return 1; }
+            return 0;
+        }
+        case AA_RANGED_ATTACK: { /* cRush/RangedAttack.java:58-87: step back towards the barracks while a slower enemy is well
+                                  * inside the range, shoot when in range, approach otherwise */
+            const OUnit *t = &g->pool[aa->target];
+            int range = g->utt->f[unit->type][OF_RANGE];
+            double rd = 0.0;
+            if (aa->base >= 0) { const OUnit *r = &g->pool[aa->base]; int rdx = r->x - unit->x, rdy = r->y - unit->y; rd = sqrt((double)(rdx * rdx + rdy * rdy)); }
+            int dx = t->x - unit->x, dy = t->y - unit->y;
+            double d = sqrt((double)(dx * dx + dy * dy));
+            OAct mv;
+            if (d <= range - 1 && rd > 2 && g->utt->f[unit->type][OF_MOVE_T] < g->utt->f[t->type][OF_MOVE_T]) {
+                const OUnit *r = &g->pool[aa->base];
+                if (mk_move(&mv, ai_pf(ai, g, aa->unit, r->x + r->y * w, range, ru)) && is_unit_action_allowed(g, aa->unit, &mv)) { *out = mv; return 1; }
+                return 0;
+            }
+            if (d <= range) { *out = mk_act(O_ATTACK, -1, t->x, t->y, -1); return 1; }
             if (mk_move(&mv, ai_pf(ai, g, aa->unit, t->x + t->y * w, range, ru)) && is_unit_action_allowed(g, aa->unit, &mv)) { *out = mv; return 1; }
             return 0;
         }
@@ -1306,7 +1327,7 @@ static int harvest_behavior(OAi *ai, const OGame *g, int u, int player) {
     }
     int still_free = 1;
     OAbs *aa = ai_get(ai, u);
-    if (is_defense(ai->kind)) { /* WorkerDefense.java:197-209, LightDefense.java:236-244: no carrying-resources special case */
+    if (is_defense(ai->kind) || ai->kind == O_AI_CRUSH_V1) { /* WorkerDefense.java:197-209, LightDefense.java:236-244, CRush_V1.java:291-320: no carrying-resources special case */
         if (cres >= 0 && cbase >= 0) {
             if (aa && aa->kind == AA_HARVEST) { if (aa->target != cres || aa->base != cbase) ai_harvest(ai, u, cres, cbase); }
             else ai_harvest(ai, u, cres, cbase);
@@ -1335,9 +1356,11 @@ static int type_by_role_worker(void) { return 3; }
 static int type_by_role_light(void) { return 4; }
 
 static int ai_get_action_k(OAi *ai, OGame *g, int player, OPair *out);
+static int ai_get_action_crush(OAi *ai, OGame *g, int player, OPair *out);
 static int ai_get_action(OAi *ai, OGame *g, int player, OPair *out) {
     /* PO{Worker,Light,Heavy,Ranged}Rush extend their rush and override meleeUnitBehavior only (melee_behavior looks at the
      * original kind through ai->po_rush) */
+    if (ai->kind == O_AI_CRUSH_V1) return ai_get_action_crush(ai, g, player, out);
     if (!is_po_rush(ai->kind)) return ai_get_action_k(ai, g, player, out);
     int k = ai->kind;
     ai->po_rush = 1; ai->kind = k - O_AI_PO_WORKER_RUSH + O_AI_WORKER_RUSH;
@@ -1425,6 +1448,103 @@ static int ai_get_action_k(OAi *ai, OGame *g, int player, OPair *out) {
         }
     }
     free(workers);
+    return ai_translate(ai, g, player, out);
+}
+
+
+/* ------------------------------------------------------------------------------------------------
+ * CRush_V1 (ai/abstraction/cRush/CRush_V1.java:68-421): on maps of at most 144 cells a worker rush that keeps one harvester
+ * per base; on larger maps nbases + 1 harvesters, one barracks, ranged units that step back from slower enemies
+ * (RangedAttack.java), and every other worker fights.
+ * ---------------------------------------------------------------------------------------------- */
+static void crush_ranged_behavior(OAi *ai, const OGame *g, int u, int player) { /* :194-220: ONE running distance for both searches */
+    const OUnit *me = &g->pool[u];
+    int enemy = -1, racks = -1, cd = 0;
+    for (int i = 0; i < g->n; i++) {
+        const OUnit *o = &g->pool[g->list[i]];
+        if (o->player >= 0 && o->player != player) {
+            int d = abs(o->x - me->x) + abs(o->y - me->y);
+            if (enemy < 0 || d < cd) { enemy = g->list[i]; cd = d; }
+        }
+        if (o->type == type_by_role_barracks() && o->player == player) {
+            int d = abs(o->x - me->x) + abs(o->y - me->y);
+            if (racks < 0 || d < cd) { racks = g->list[i]; cd = d; }
+        }
+    }
+    if (enemy >= 0) ai_ranged_attack(ai, u, enemy, racks);
+}
+
+/* workersBehavior :222-321 (rush == 0) and rushWorkersBehavior :329-416 (rush == 1) */
+static void crush_workers(OAi *ai, const OGame *g, int player, const int *workers, int nw, int rush) {
+    const OUtt *t = g->utt;
+    int BASE = type_by_role_base(), BARRACKS = type_by_role_barracks(), WORKER = type_by_role_worker();
+    int nbases = 0, nbarracks = 0, nworkers = 0, pres = g->res[player];
+    ai->resources_used = 0;
+    for (int i = 0; i < g->n; i++) {
+        const OUnit *o = &g->pool[g->list[i]];
+        if (o->player != player) continue;
+        if (o->type == BASE) nbases++;
+        if (o->type == BARRACKS) nbarracks++;
+        if (o->type == WORKER) nworkers++;
+    }
+    /* freeWorkers = workers[f0, f1), battleWorkers = workers[b0, nw) */
+    int f0 = 0, f1, b0;
+    int keep = rush ? nbases : nbases + 1;
+    if (rush && pres == 0) { f1 = 0; b0 = 0; }
+    else if (nw > keep) { f1 = keep; b0 = keep; }
+    else { f1 = nw; b0 = nw; }
+    if (nw == 0) return; /* `workers.isEmpty()`: the list only loses elements when more than `keep` remain */
+    int reserved[8], nres = 0;
+    if (nbases == 0 && f0 < f1) {
+        if (pres >= t->f[BASE][OF_COST]) { int u = workers[f0++]; build_if_not_already(ai, g, u, BASE, g->pool[u].x, g->pool[u].y, reserved, &nres); }
+    }
+    if (!rush) {
+        if (nbarracks == 0 && f0 < f1 && nworkers > 1 && pres >= t->f[BARRACKS][OF_COST]) {
+            int u = workers[f0++];
+            build_if_not_already(ai, g, u, BARRACKS, g->pool[u].x, g->pool[u].y, reserved, &nres);
+            ai->resources_used += t->f[BARRACKS][OF_COST];
+            ai->building_racks = 1;
+        } else ai->resources_used = t->f[BARRACKS][OF_COST] * nbarracks;
+        if (nbarracks > 1) ai->building_racks = 1;
+    }
+    for (int i = b0; i < nw; i++) melee_behavior(ai, g, workers[i], player);
+    for (int i = f0; i < f1; i++) harvest_behavior(ai, g, workers[i], player);
+}
+
+static int ai_get_action_crush(OAi *ai, OGame *g, int player, OPair *out) {
+    const OUtt *t = g->utt;
+    int BASE = type_by_role_base(), BARRACKS = type_by_role_barracks(), WORKER = type_by_role_worker(), RANGED = 6;
+    int rush = g->w * g->h <= 144, pres = g->res[player];
+    int *workers = (int *)malloc(sizeof(int) * (g->n + 1)); int nw = 0;
+    for (int i = 0; i < g->n; i++) { int u = g->list[i]; const OUnit *un = &g->pool[u]; if ((t->flags[un->type] & OFL_HARVEST) && un->player == player) workers[nw++] = u; }
+    crush_workers(ai, g, player, workers, nw, rush);
+    free(workers);
+    for (int i = 0; i < g->n; i++) { /* bases: rushBaseBehavior :324-326, baseBehavior :133-168 */
+        int u = g->list[i]; const OUnit *un = &g->pool[u];
+        if (!(un->type == BASE && un->player == player && find_assign(g, u) < 0)) continue;
+        if (rush) { if (pres >= t->f[WORKER][OF_COST]) ai_train(ai, u, WORKER); continue; }
+        int nbases = 0, nbarracks = 0, nworkers = 0, resources = pres;
+        for (int j = 0; j < g->n; j++) {
+            const OUnit *o = &g->pool[g->list[j]];
+            if (o->player != player) continue;
+            if (o->type == WORKER) nworkers++;
+            if (o->type == BARRACKS) nbarracks++;
+            if (o->type == BASE) nbases++;
+        }
+        if (nworkers < nbases + 1 && pres >= t->f[WORKER][OF_COST]) ai_train(ai, u, WORKER);
+        if (ai->resources_used != t->f[BARRACKS][OF_COST] * nbarracks) resources -= t->f[BARRACKS][OF_COST];
+        if (ai->building_racks && resources >= t->f[WORKER][OF_COST] + t->f[RANGED][OF_COST]) ai_train(ai, u, WORKER);
+    }
+    for (int i = 0; i < g->n; i++) { /* barracks :170-174 */
+        int u = g->list[i]; const OUnit *un = &g->pool[u];
+        if (un->type == BARRACKS && un->player == player && find_assign(g, u) < 0 && pres >= t->f[RANGED][OF_COST]) ai_train(ai, u, RANGED);
+    }
+    for (int i = 0; i < g->n; i++) { /* melee and ranged units :117-128 */
+        int u = g->list[i]; const OUnit *un = &g->pool[u];
+        if ((t->flags[un->type] & OFL_ATTACK) && !(t->flags[un->type] & OFL_HARVEST) && un->player == player && find_assign(g, u) < 0) {
+            if (un->type == RANGED) crush_ranged_behavior(ai, g, u, player); else melee_behavior(ai, g, u, player);
+        }
+    }
     return ai_translate(ai, g, player, out);
 }
 
@@ -1614,7 +1734,7 @@ static int policy(OGame *g, int kind, OAi *ai, int player, OPair *out) {
         case O_AI_RANGED_DEFENSE:
         case O_AI_PO_WORKER_RUSH: case O_AI_PO_LIGHT_RUSH: case O_AI_PO_HEAVY_RUSH:
         case O_AI_PO_RANGED_RUSH:
-        case O_AI_WORKER_RUSH_PP: return ai_get_action(ai, g, player, out);
+        case O_AI_WORKER_RUSH_PP: case O_AI_CRUSH_V1: return ai_get_action(ai, g, player, out);
         default: return 0; /* PassiveAI: empty PlayerAction */
     }
 }
@@ -1639,7 +1759,7 @@ int o_run_game(OGame *g, int kind0, OAi *ai0, int kind1, OAi *ai1, int n_cycles,
  * the lists are issued with issueSafe on the real state.  The view is a copy with the same unit handles, so the pairs and
  * the AIs' abstract actions refer to the real game; the policy RNG (a static in the reference) is carried back. */
 static int policy_po(OGame *g, int kind, OAi *ai, int player, OPair *out) {
-    if (kind != O_AI_RANDOM_BIASED && !(kind >= O_AI_WORKER_RUSH && kind <= O_AI_WORKER_RUSH_PP)) return policy(g, kind, ai, player, out);
+    if (kind != O_AI_RANDOM_BIASED && !(kind >= O_AI_WORKER_RUSH && kind <= O_AI_CRUSH_V1)) return policy(g, kind, ai, player, out);
     OGame *v = o_po_view(g, player);
     int n = policy(v, kind, ai, player, out);
     g->rng_policy = v->rng_policy;

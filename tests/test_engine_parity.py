@@ -550,6 +550,16 @@ SCRIPTED = [
     ("16x16/TwoBasesBarracks16x16", "RANGED_RUSH", "HEAVY_RUSH", 3),
     ("24x24/basesWorkers24x24", "WORKER_RUSH", "LIGHT_DEFENSE", 3),
     ("BWDistantResources32x32", "LIGHT_RUSH", "WORKER_RUSH", 3),
+    # CRush_V1 (ai/abstraction/cRush): worker rush on maps of at most 144 cells, barracks + kiting ranged units (RangedAttack)
+    # on larger ones; Heavy units are the slower enemies its ranged units step back from
+    ("8x8/basesWorkers8x8", "CRUSH_V1", "WORKER_RUSH", 0),
+    ("8x8/FourBasesWorkers8x8", "LIGHT_RUSH", "CRUSH_V1", 0),
+    ("16x16/basesWorkers16x16", "CRUSH_V1", "HEAVY_RUSH", 0),
+    ("16x16/basesWorkers16x16", "LIGHT_RUSH", "CRUSH_V1", 1),
+    ("16x16/TwoBasesBarracks16x16", "CRUSH_V1", "CRUSH_V1", 0),
+    ("24x24/basesWorkers24x24", "HEAVY_RUSH", "CRUSH_V1", 0),
+    ("BWDistantResources32x32", "CRUSH_V1", "HEAVY_DEFENSE", 3),
+    ("16x16/basesWorkers16x16", "RANDOM_BIASED", "CRUSH_V1", 2),
 ]
 
 
@@ -684,6 +694,8 @@ MAP_SWEEP_COMBOS = [
     ("RANDOM_BIASED", "RANDOM_BIASED", 0, True),
     ("PO_HEAVY_RUSH", "LIGHT_DEFENSE", 2, True),
     ("WORKER_RUSH_PP", "HEAVY_RUSH", 0, False),
+    ("CRUSH_V1", "HEAVY_RUSH", 0, False),
+    ("RANDOM_BIASED", "CRUSH_V1", 0, True),
 ]
 
 
@@ -739,6 +751,9 @@ WIDE_SCRIPTED = [
     ("16x16/basesWorkers16x16", "PO_RANGED_RUSH", 0, 2, True),
     ("24x24/basesWorkers24x24", "LIGHT_DEFENSE", 1, 0, True),
     ("16x16/basesWorkers16x16", "RANDOM_BIASED", 0, 0, True),
+    ("16x16/basesWorkers16x16", "CRUSH_V1", 0, 0, False),
+    ("8x8/basesWorkers8x8", "CRUSH_V1", 1, 0, False),
+    ("24x24/basesWorkers24x24", "CRUSH_V1", 1, 0, True),
 ]
 
 

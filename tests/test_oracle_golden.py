@@ -201,6 +201,60 @@ def test_defense_and_po_rush_known_answers():
     assert act is not None and act[0] == O.MOVE
 
 
+def test_crush_v1_known_answers():
+    """cRush/CRush_V1.java + RangedAttack.java, decided by hand on tiny 16x16 states (more than 144 cells: the barracks
+    variant).  Type table version 1: Ranged range 3 / move time 10, Heavy move time 12, Light move time 8."""
+    utt = O.Utt(1, 1)
+    # -- RangedAttack.execute (:58-87).  Ranged at (8,8), own barracks at (0,2): sqrt(64+36) > 2.
+    # a Heavy two cells below: d = 2 <= range - 1 and 10 < 12 -> it walks towards the barracks (up or left), away from the Heavy
+    racks = [("Base", 0, 0, 0, 0, 10), ("Barracks", 0, 0, 2, 0, 4), ("Ranged", 0, 8, 8, 0, 1), ("Heavy", 1, 8, 10, 0, 4), ("Base", 1, 15, 15, 0, 10)]
+    act = _action_of(O.ScriptedAI(O.AI_CRUSH_V1).get_action(O.Game(utt, _tiny_map(racks, 16, 16)), 0), 2)
+    assert act is not None and act[0] == O.MOVE and act[1] in (0, 3)
+    # a Light in the same place is not slower (8 < 10): d <= range -> shoot it
+    light = [u if u[0] != "Heavy" else ("Light", 1, 8, 10, 0, 4) for u in racks]
+    act = _action_of(O.ScriptedAI(O.AI_CRUSH_V1).get_action(O.Game(utt, _tiny_map(light, 16, 16)), 0), 2)
+    assert act is not None and act[0] == O.ATTACK and (act[2], act[3]) == (8, 10)
+    # the Heavy at distance 3 = range: not "well inside" (3 > range - 1) -> shoot
+    edge = [u if u[0] != "Heavy" else ("Heavy", 1, 8, 11, 0, 4) for u in racks]
+    act = _action_of(O.ScriptedAI(O.AI_CRUSH_V1).get_action(O.Game(utt, _tiny_map(edge, 16, 16)), 0), 2)
+    assert act is not None and act[0] == O.ATTACK and (act[2], act[3]) == (8, 11)
+    # without a barracks (racks == null, rd = 0) it shoots the adjacent Heavy as well
+    none = [u for u in racks if u[0] != "Barracks"]
+    act = _action_of(O.ScriptedAI(O.AI_CRUSH_V1).get_action(O.Game(utt, _tiny_map(none, 16, 16)), 0), 1)
+    assert act is not None and act[0] == O.ATTACK
+    # -- rangedUnitBehavior (:194-220) shares ONE running distance between "closest enemy" and "closest barracks": Heavy A at
+    # distance 2 comes first, then the barracks (always accepted as the first one) sets the distance to 14, and Heavy B at
+    # distance 5, listed later, is now "closer" and becomes the target: 5 > range -> the unit walks DOWN towards B instead of
+    # stepping back from A
+    shared = [("Base", 0, 0, 0, 0, 10), ("Ranged", 0, 8, 8, 0, 1), ("Heavy", 1, 8, 6, 0, 4), ("Barracks", 0, 0, 2, 0, 4), ("Heavy", 1, 8, 13, 0, 4), ("Base", 1, 15, 15, 0, 10)]
+    act = _action_of(O.ScriptedAI(O.AI_CRUSH_V1).get_action(O.Game(utt, _tiny_map(shared, 16, 16)), 0), 1)
+    assert act is not None and act[0] == O.MOVE and act[1] == 2
+    # -- workersBehavior / baseBehavior (:222-321, :133-168): base (2,2), three workers, 5 resources, no barracks.  nbases + 1 = 2
+    # workers stay free: the first is sent to build the barracks (nworkers > 1, 5 >= 5) at the first free cell of the ring around
+    # it, (0,1): a diagonal neighbour of (1,2), so it moves up or left; the second harvests from (0,4): it walks (down or left);
+    # the third is a battle worker and walks towards the enemy.  The base: 3 workers >= nbases + 1; resourcesUsed = 5 != 5 * 0
+    # barracks -> 5 - 5 = 0 resources left for "worker + ranged" -> nothing to do: NONE(10)
+    eco = [("Base", 0, 2, 2, 0, 10), ("Worker", 0, 1, 2, 0, 1), ("Worker", 0, 1, 3, 0, 1), ("Worker", 0, 3, 3, 0, 1), ("Resource", -1, 0, 4, 20, 1),
+           ("Base", 1, 13, 13, 0, 10), ("Worker", 1, 12, 12, 0, 1)]
+    m = _tiny_map(eco, 16, 16)
+    pa = O.ScriptedAI(O.AI_CRUSH_V1).get_action(O.Game(utt, m), 0)
+    assert _action_of(pa, 0)[0] == O.NONE and _action_of(pa, 0)[1] == 10
+    assert _action_of(pa, 1)[0] == O.MOVE and _action_of(pa, 1)[1] in (0, 3)
+    assert _action_of(pa, 2)[0] == O.MOVE and _action_of(pa, 2)[1] in (2, 3)
+    assert _action_of(pa, 3)[0] == O.MOVE and _action_of(pa, 3)[1] in (1, 2)
+    # with 8 resources the base sees 8 - 5 = 3 >= worker (1) + ranged (2) and, buildingRacks being set, trains a worker
+    m8 = dict(m, players=[[0, 8], [1, 5]])
+    pa = O.ScriptedAI(O.AI_CRUSH_V1).get_action(O.Game(utt, m8), 0)
+    assert _action_of(pa, 0)[0] == O.PRODUCE and _action_of(pa, 0)[4] == 3
+    # -- on a map of at most 144 cells the same state is a worker rush (:329-416): one harvester per base, the other two fight
+    # (no barracks is ever planned), and the base trains workers whenever it can pay for one
+    pa = O.ScriptedAI(O.AI_CRUSH_V1).get_action(O.Game(utt, _tiny_map([u if u[1] != 1 else (u[0], 1, u[2] - 4, u[3] - 4, u[4], u[5]) for u in eco], 12, 12)), 0)
+    assert _action_of(pa, 0)[0] == O.PRODUCE and _action_of(pa, 0)[4] == 3
+    assert _action_of(pa, 1)[0] == O.MOVE and _action_of(pa, 1)[1] in (2, 3)      # the harvester (first worker) heads for (0,4)
+    assert _action_of(pa, 2)[0] == O.MOVE and _action_of(pa, 2)[1] in (1, 2)      # battle workers walk towards the enemy
+    assert _action_of(pa, 3)[0] == O.MOVE and _action_of(pa, 3)[1] in (1, 2)
+
+
 def test_observation_and_mask_known_answers(maps):
     """GameState.getVectorObservation (GameState.java:922-968) and JNIGridnetClient.getMasks / UnitAction.getValidActionArray
     (UnitAction.java:711-751) of the initial state of maps/8x8/basesWorkers8x8.xml, written out by hand."""
