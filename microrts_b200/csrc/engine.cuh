@@ -41,8 +41,8 @@ enum { ACT_NONE = 0, ACT_MOVE = 1, ACT_HARVEST = 2, ACT_RETURN = 3, ACT_PRODUCE 
 enum { POL_EXTERNAL = 0, POL_PASSIVE = 1, POL_RANDOM_BIASED = 2, POL_WORKER_RUSH = 3, POL_LIGHT_RUSH = 4, POL_HEAVY_RUSH = 5, POL_RANGED_RUSH = 6,
        POL_WORKER_DEFENSE = 7, POL_LIGHT_DEFENSE = 8, POL_HEAVY_DEFENSE = 9, POL_RANGED_DEFENSE = 10,
        POL_PO_WORKER_RUSH = 11, POL_PO_LIGHT_RUSH = 12, POL_PO_HEAVY_RUSH = 13, POL_PO_RANGED_RUSH = 14, POL_WORKER_RUSH_PP = 15,
-       POL_CRUSH_V1 = 16 /* ai.abstraction.cRush.CRush_V1 */ };
-#define POL_IS_SCRIPTED(p) ((p) >= POL_WORKER_RUSH && (p) <= POL_CRUSH_V1)
+       POL_CRUSH_V1 = 16, POL_CRUSH_V2 = 17 /* ai.abstraction.cRush.CRush_V1, CRush_V2 */ };
+#define POL_IS_SCRIPTED(p) ((p) >= POL_WORKER_RUSH && (p) <= POL_CRUSH_V2)
 #define POL_IS_PO_RUSH(p) ((p) >= POL_PO_WORKER_RUSH && (p) <= POL_PO_RANGED_RUSH)
 #define POL_IS_DEFENSE(p) (((p) >= POL_WORKER_DEFENSE && (p) <= POL_RANGED_DEFENSE) || (p) == POL_WORKER_RUSH_PP) // WorkerRushPlusPlus.java = WorkerDefense.java whose melee units always attack
 enum { FMT_VECTOR = 0, FMT_RAW = 1 };
@@ -1103,6 +1103,9 @@ DEV void compact_units(Game &g) {
         uint32_t X1 = g.x1()[i];
         uint32_t t = X1 & 0xff, b = (X1 >> 8) & 0xff;
         if (t != 0 && t != 0xFF) { t = g.list()[t - 1]; if (t == 0) t = 0xFF; }
+#ifndef MRTS_TU_RUSH_ONLY
+        if ((g.x0()[i] & 7u) == 7u) { g.x1()[i] = (X1 & 0xffffff00u) | t; continue; } // AA_TACTIC (scripted.cuh): the base field is a coordinate
+#endif
         if (b != 0 && b != 0xFF) { b = g.list()[b - 1]; if (b == 0) b = 0xFF; }
         g.x1()[i] = (X1 & 0xffff0000u) | (b << 8) | t;
     }

@@ -22,7 +22,16 @@
 #pragma once
 
 enum { AA_NONE = 0, AA_TRAIN = 1, AA_BUILD = 2, AA_HARVEST = 3, AA_ATTACK = 4, AA_MOVE = 5 /* Move.java: walk to (bx, by) */,
-       AA_RANGED_ATTACK = 6 /* cRush/RangedAttack.java: target + the closest own barracks in the base field */ };
+       AA_RANGED_ATTACK = 6 /* cRush/RangedAttack.java: target + the closest own barracks in the base field */,
+       AA_TACTIC = 7 /* cRush/CRanged_Tactic.java: target + the POSITIONS of `home` and `enemyBase` (bases never move, and the
+                        reference keeps using a destroyed base's last position); x == 0xFF stands for null */ };
+// type ids by name, as the reference looks them up (utt.getUnitType("Worker") ...): standard tables use these ids
+#define UT_BASE 1
+#define UT_BARRACKS 2
+#define UT_WORKER 3
+#define UT_LIGHT 4
+#define UT_HEAVY 5
+#define UT_RANGED 6
 #define REF_NULL 0u
 #define REF_DEAD 0xFFu
 
@@ -30,7 +39,13 @@ DEV int aa_kind(uint32_t X0) { return X0 & 7; }
 DEV int aa_type(uint32_t X0) { return (X0 >> 4) & 0xF; }
 DEV int aa_bx(uint32_t X0) { return (X0 & (1u << 24)) ? -1 : (int)((X0 >> 8) & 0xff); }
 DEV int aa_by(uint32_t X0) { return (X0 >> 16) & 0xff; }
-DEV uint32_t aa_seq(uint32_t X0, uint32_t X1) { return (X1 >> 16) | ((X0 >> 25) << 16); }
+DEV uint32_t aa_seq(uint32_t X0, uint32_t X1) { return (X1 >> 16) | ((X0 >> 27) << 16); } // 21 bits
+// AA_TACTIC: X0 = kind | hy[4:0] << 3 | ex << 8 | ey << 16 | hy[7:5] << 24 | seq, X1 = target | hx << 8 | seq (hx is NOT a unit
+// reference: compact_units leaves the base field of this kind alone)
+DEV int aa_thx(uint32_t X1) { return (X1 >> 8) & 0xff; }
+DEV int aa_thy(uint32_t X0) { return (int)(((X0 >> 3) & 0x1f) | (((X0 >> 24) & 7) << 5)); }
+DEV int aa_tex(uint32_t X0) { return (X0 >> 8) & 0xff; }
+DEV int aa_tey(uint32_t X0) { return (X0 >> 16) & 0xff; }
 DEV int aa_target(uint32_t X1) { return X1 & 0xff; }
 DEV int aa_base(uint32_t X1) { return (X1 >> 8) & 0xff; }
 
@@ -43,7 +58,9 @@ DEV void aa_put(Game &g, int s, int player, int kind, int type, int bx, int by, 
         if (aa_kind(oX0) != AA_NONE) seq = aa_seq(oX0, oX1);
         else seq = (uint32_t)g.hdr()[H_ASEQ0 + player]++;
         uint32_t X0 = (uint32_t)kind | ((uint32_t)type << 4) | ((uint32_t)(bx & 0xff) << 8) | ((uint32_t)(by & 0xff) << 16) | (bx < 0 ? (1u << 24) : 0u) |
-                      ((seq >> 16) << 25);
+                      (((seq >> 16) & 0x1fu) << 27);
+        if (kind == AA_TACTIC) // type = home y, base = home x, (bx, by) = enemy base
+            X0 = (uint32_t)kind | ((uint32_t)(type & 0x1f) << 3) | ((uint32_t)(bx & 0xff) << 8) | ((uint32_t)(by & 0xff) << 16) | ((uint32_t)((type >> 5) & 7) << 24) | (((seq >> 16) & 0x1fu) << 27);
         uint32_t X1 = (uint32_t)target | ((uint32_t)base << 8) | ((seq & 0xffffu) << 16);
         g.x0()[s] = X0; g.x1()[s] = X1;
     }
@@ -303,6 +320,7 @@ DEVN int pf_floodfill(Game &g, int player, int s, int tx, int ty, int range, int
     const int lane = g.lane, W = g.W, H = g.H, cells = W * H;
     uint32_t sw = g.w0()[s];
     const int sx = u_x(sw), sy = u_y(sw);
+    if (tx < 0 || ty < 0 || tx >= W || ty >= H) return -1; // the reference indexes its distance array with the target (an exception off the map): null
     if (range < 0) range = 0;
     if ((sx - tx) * (sx - tx) + (sy - ty) * (sy - ty) <= range * range) return -1; // already there
     if (!g.ff_cache) return -1;
@@ -426,6 +444,75 @@ DEV int train_score(const Game &g, int x, int y, int type, int pl) {
 
 DEV bool cell_gs_free(const Game &g, int pc) { return g.grid()[pc] == 0 && g.resv()[pc] == 0; }
 
+
+#ifndef MRTS_TU_RUSH_ONLY
+// findPathToPositionInRange with the target as the reference passes it, a LINEAR position x + y * width that the pathfinders split
+// again with Java's % and / (a column off the map aliases into the neighbouring row, a negative position keeps a negative x)
+DEV int pf_find_lin(Game &g, int kind, int s, int pos, int range, int nd) {
+    return pf_find(g, kind, s, pos % g.W, pos / g.W, range, nd);
+}
+// PhysicalGameState.getUnitAt: the unit's slot, or -1 (null) for a free cell, a wall or a position off the map; |x|, |y| at most one off
+DEV int unit_at(const Game &g, int x, int y) { int v = g.grid()[(y + 1) * g.P + x + 1]; return (v == 0 || v == 0xFF) ? -1 : v - 1; }
+
+// cRush/CRanged_Tactic.java:77-307 (execute, squareMove).  Distances are square roots of integers compared with each other or
+// with integers: their squares are compared instead.  Whole warp, uniform.
+DEVN bool tactic_execute(Game &g, const ScriptCtx &c, int s, uint32_t &A0, int &A1) {
+    const uint32_t X0 = g.x0()[s], X1 = g.x1()[s], w = g.w0()[s], tw = g.w0()[aa_target(X1) - 1];
+    const int n = g.hdr()[H_NUNITS], W = g.W;
+    const int x = u_x(w), y = u_y(w), t = u_type(w), pl = u_pl(w), tx = u_x(tw), ty = u_y(tw);
+    int hx = aa_thx(X1), hy = aa_thy(X0), ex = aa_tex(X0), ey = aa_tey(X0);
+    if (hx == 0xFF) { hx = x; hy = y; }   // home == null: the unit itself (:84-86)
+    if (ex == 0xFF) { ex = tx; ey = ty; } // enemyBase == null: the target (:88-90)
+    const int range = ut_range(g, t);
+    const int rd2 = (hx - x) * (hx - x) + (hy - y) * (hy - y), d2 = (tx - x) * (tx - x) + (ty - y) * (ty - y);
+    // `u2.getPlayer() != p.getID()`: neutral units count as well, only their types never match
+    const int n_enemy_bases = w_count(g, n, [&](int, uint32_t ow) { return u_pl(ow) != pl && u_type(ow) == UT_BASE; });
+    const int enemy_attack_units = w_count(g, n, [&](int, uint32_t ow) { int ot = u_type(ow); return u_pl(ow) != pl && (ot == UT_RANGED || ot == UT_HEAVY || ot == UT_LIGHT); });
+    const int enemy_workers = w_count(g, n, [&](int, uint32_t ow) { return u_pl(ow) != pl && u_type(ow) == UT_WORKER; });
+    const int cutoff = (g.W * g.H > 3000) ? 15000 : 5000;
+    const bool time_to_attack = ((enemy_workers < 2 * n_enemy_bases || n_enemy_bases == 0) && enemy_attack_units == 0) || g.hdr()[H_TIME] > cutoff;
+    // nearestRangedAlly(enemyBase) :367-389: the first own Ranged unit with the smallest distance to the enemy base
+    const int ally = w_argmin(g, n, [&](int, uint32_t ow) { return (u_pl(ow) == pl && u_type(ow) == UT_RANGED) ? (u_x(ow) - ex) * (u_x(ow) - ex) + (u_y(ow) - ey) * (u_y(ow) - ey) : -1; });
+    int ax = 0, ay = 0, ad2 = 0;
+    if (ally >= 0) { uint32_t aw = g.w0()[ally]; ax = u_x(aw); ay = u_y(aw); ad2 = (tx - ax) * (tx - ax) + (ty - ay) * (ty - ay); }
+    const int tpos = tx + ty * W;
+    int dir = -1;
+    if (d2 <= range * range) { A0 = ACT_ATTACK | A0_NOUT | ((uint32_t)tx << 16) | ((uint32_t)ty << 24); A1 = -1; return true; } // :152, :179
+    if (t == UT_WORKER) { // :149-176
+        if (time_to_attack || ally < 0) dir = pf_find_lin(g, c.pf, s, tpos, range, c.nd);
+        else {
+            dir = pf_find_lin(g, c.pf, s, d2 > ad2 ? tpos : ax + ay * W, range, c.nd);
+            if (dir < 0) dir = pf_find_lin(g, c.pf, s, (ax - 1) + ay * W, range + 1, c.nd);
+            if (dir < 0) dir = pf_find_lin(g, c.pf, s, tpos, range, c.nd);
+        }
+    } else if (ally < 0 || ally == s) { // the unit leads :182-194
+        if (time_to_attack && u_type(tw) == UT_BASE) dir = pf_find_lin(g, c.pf, s, tpos, range, c.nd);
+        else if (rd2 < 25 || (ex - x) * (ex - x) + (ey - y) * (ey - y) > (ex - hx) * (ex - hx) + (ey - hy) * (ey - hy)) dir = pf_find_lin(g, c.pf, s, ex + ey * W, range, c.nd);
+    } else if (time_to_attack) { // :195-216 (d > range here, so of RangedAttack's three cases only the approach is left)
+        dir = pf_find_lin(g, c.pf, s, tpos, range, c.nd);
+    } else { // line up next to the leading ranged unit :218-268, squareMove :290-343
+        auto eb2 = [&](int px, int py) { return (ex - px) * (ex - px) + (ey - py) * (ey - py); };
+        const int sgn = eb2(ax, ay + 1) > eb2(ax, ay) ? 1 : -1; // below / right of the leader, or above / left
+#pragma unroll 1
+        for (;;) {
+            int a = unit_at(g, ax, ay + sgn), b = unit_at(g, ax + sgn, ay + sgn), cc = unit_at(g, ax + sgn, ay);
+            bool found = true;
+            if (a >= 0 && a != s && b >= 0 && b != s && cc >= 0 && cc != s) { uint32_t cw = g.w0()[cc]; ax = u_x(cw); ay = u_y(cw); found = false; }
+            a = unit_at(g, ax, ay + sgn); b = unit_at(g, ax + sgn, ay + sgn); cc = unit_at(g, ax + sgn, ay);
+            if (found || a < 0 || b < 0 || cc < 0) break;
+        }
+        const int sg = eb2(ax, ay + 1) > eb2(ax, ay) ? 1 : -1; // squareMove decides again, around the unit it was handed
+        const int a = unit_at(g, ax, ay + sg), b = unit_at(g, ax + sg, ay + sg), cc = unit_at(g, ax + sg, ay);
+        if (s == a || s == b || s == cc) return false;
+        // pf.findPath = range 0.  The reference computes all six paths and uses one: only that one is searched here
+        if (a < 0) dir = pf_find_lin(g, c.pf, s, ax + (ay + sg) * W, -1, c.nd);
+        else if (cc < 0) dir = pf_find_lin(g, c.pf, s, (ax + sg) + ay * W, -1, c.nd);
+        else if (b < 0) dir = pf_find_lin(g, c.pf, s, (ax + sg) + (ay + sg) * W, -1, c.nd);
+    }
+    return mk_move(g, c, s, dir, A0, A1) && unit_action_allowed(g, c, s, A0, A1);
+}
+#endif
+
 // AbstractAction.execute for slot s; returns true and (A0, A1) if it yields a unit action.  Whole warp, uniform.
 DEVN bool aa_execute(Game &g, const ScriptCtx &c, int s, uint32_t &A0, int &A1) {
     uint32_t X0 = g.x0()[s], X1 = g.x1()[s], w = g.w0()[s];
@@ -440,6 +527,7 @@ DEVN bool aa_execute(Game &g, const ScriptCtx &c, int s, uint32_t &A0, int &A1) 
             return false;
         }
 #ifndef MRTS_TU_RUSH_ONLY
+        case AA_TACTIC: return tactic_execute(g, c, s, A0, A1);
         case AA_RANGED_ATTACK: { // cRush/RangedAttack.java:58-87: step back towards the barracks while a slower enemy is well inside
             // the range, shoot when in range, approach otherwise (the square roots compare like their integer squares)
             uint32_t tw = g.w0()[aa_target(X1) - 1];
@@ -516,7 +604,7 @@ DEV bool aa_completed(const Game &g, int s) {
         case AA_TRAIN: return (X0 & 8u) != 0;
         case AA_BUILD: { int bx = aa_bx(X0), by = aa_by(X0); if (bx < 0 || bx >= g.W || by >= g.H) return false; int gv = g.grid()[(by + 1) * g.P + bx + 1]; return gv != 0 && gv != 0xFF; }
         case AA_HARVEST: return u_res(g.w1()[s]) > 0 ? !ref_alive(g, aa_base(X1)) : !ref_alive(g, aa_target(X1));
-        case AA_ATTACK: case AA_RANGED_ATTACK: return !ref_alive(g, aa_target(X1)); // Attack.java:30-33, RangedAttack.java:36-39
+        case AA_ATTACK: case AA_RANGED_ATTACK: case AA_TACTIC: return !ref_alive(g, aa_target(X1)); // Attack.java:30-33, RangedAttack.java:36-39
         case AA_MOVE: { uint32_t w = g.w0()[s]; return u_x(w) == aa_bx(X0) && u_y(w) == aa_by(X0); } // Move.java:29-31
     }
     return true;
@@ -627,11 +715,6 @@ DEV void script_build_if_not(Game &g, int s, int player, int type, int *reserved
     }
 }
 
-// type ids by name, as the reference looks them up (utt.getUnitType("Worker") ...): standard tables use these ids
-#define UT_BASE 1
-#define UT_BARRACKS 2
-#define UT_WORKER 3
-#define UT_LIGHT 4
 
 // translateActions (AbstractionLayerAI.java:58-113): the player's abstract actions in insertion order become desires, the
 // desires a player action (appended to the pending list from pn; returns the new pending count, uniform)
@@ -758,23 +841,81 @@ DEVN void script_crush_ranged(Game &g, int s, int player) {
     if (enemy >= 0) aa_put(g, s, player, AA_RANGED_ATTACK, 0, 0, 0, enemy + 1, racks < 0 ? (int)REF_NULL : racks + 1);
 }
 
+// CRush_V2.meleeUnitBehavior (cRush/CRush_V2.java:174-219) / rangedUnitBehavior (:221-264): closest enemy, own barracks, own base
+// and enemy base in one pass with one shared running distance (an enemy base is tested twice: as an enemy, then as a base).
+// Before cycle 400 and on small maps everything but the Ranged units simply attacks; otherwise CRanged_Tactic.
+DEVN void script_crush2_combat(Game &g, int s, int player, bool ranged, bool rush) {
+    const int n = g.hdr()[H_NUNITS], pl = player + 1;
+    const uint32_t w = g.w0()[s];
+    int enemy = -1, racks = -1, base = -1, ebase = -1, cd = 0;
+#pragma unroll 1
+    for (int i = 0; i < n; i++) {
+        uint32_t ow = g.w0()[i];
+        int op = u_pl(ow), ot = u_type(ow);
+        bool en = op != 0 && op != pl, own_b = op == pl && (ot == UT_BASE || ot == UT_BARRACKS), eb = ot == UT_BASE && op != pl;
+        if (en || own_b || eb) {
+            int d = iabs(u_x(ow) - u_x(w)) + iabs(u_y(ow) - u_y(w));
+            if (en && (enemy < 0 || d < cd)) { enemy = i; cd = d; }
+            if (own_b && ot == UT_BARRACKS && (racks < 0 || d < cd)) { racks = i; cd = d; }
+            if (own_b && ot == UT_BASE && (base < 0 || d < cd)) { base = i; cd = d; }
+            if (eb && (ebase < 0 || d < cd)) { ebase = i; cd = d; }
+        }
+    }
+    if (enemy < 0) return;
+    if (!ranged && (g.hdr()[H_TIME] < 400 || rush)) { aa_put(g, s, player, AA_ATTACK, 0, 0, 0, enemy + 1, REF_NULL); return; }
+    int hx = 0xFF, hy = 0, ex = 0xFF, ey = 0;
+    if (base >= 0) { uint32_t bw = g.w0()[base]; hx = u_x(bw); hy = u_y(bw); }
+    if (ebase >= 0) { uint32_t bw = g.w0()[ebase]; ex = u_x(bw); ey = u_y(bw); }
+    aa_put(g, s, player, AA_TACTIC, hy, ex, ey, enemy + 1, hx);
+}
+
+// CRush_V2.workersBehavior :335-383: a free worker leaves a resource alone that lies closer to the enemy base than to its own
+// base (distance() is 0.0 when either end is null: without an enemy base nobody harvests)
+DEVN void script_crush2_harvest(Game &g, int s, int player) {
+    const int n = g.hdr()[H_NUNITS], pl = player + 1;
+    const uint32_t w = g.w0()[s];
+    int cres = -1, ebase = -1, cd = 0;
+#pragma unroll 1
+    for (int i = 0; i < n; i++) {
+        uint32_t ow = g.w0()[i];
+        bool rs = (ut_flags(g, u_type(ow)) & UF_RESOURCE) != 0, eb = u_type(ow) == UT_BASE && u_pl(ow) != pl;
+        if (rs || eb) {
+            int d = iabs(u_x(ow) - u_x(w)) + iabs(u_y(ow) - u_y(w));
+            if (rs && (cres < 0 || d < cd)) { cres = i; cd = d; }
+            if (eb && (ebase < 0 || d < cd)) { ebase = i; cd = d; }
+        }
+    }
+    int cbase = w_argmin(g, n, [&](int, uint32_t ow) {
+        return ((ut_flags(g, u_type(ow)) & UF_STOCKPILE) && u_pl(ow) == pl) ? iabs(u_x(ow) - u_x(w)) + iabs(u_y(ow) - u_y(w)) : -1; });
+    if (cres < 0) return;
+    const uint32_t rw = g.w0()[cres];
+    int de = 0, db = 0;
+    if (ebase >= 0) { uint32_t bw = g.w0()[ebase]; de = (u_x(bw) - u_x(rw)) * (u_x(bw) - u_x(rw)) + (u_y(bw) - u_y(rw)) * (u_y(bw) - u_y(rw)); }
+    if (cbase >= 0) { uint32_t bw = g.w0()[cbase]; db = (u_x(bw) - u_x(rw)) * (u_x(bw) - u_x(rw)) + (u_y(bw) - u_y(rw)) * (u_y(bw) - u_y(rw)); }
+    if (de < db || cbase < 0) return;
+    uint32_t X0 = g.x0()[s], X1 = g.x1()[s];
+    if (!(aa_kind(X0) == AA_HARVEST) || aa_target(X1) != cres + 1 || aa_base(X1) != cbase + 1) aa_put(g, s, player, AA_HARVEST, 0, 0, 0, cres + 1, cbase + 1);
+}
+
 // CRush_V1.getAction (cRush/CRush_V1.java:68-131) followed by translateActions.  On maps of at most 144 cells: a worker rush
 // that keeps one harvester per base (rushWorkersBehavior :329-416, rushBaseBehavior :324-326).  On larger maps: nbases + 1
 // harvesters, one barracks training Ranged units (workersBehavior :222-321, baseBehavior :133-168, barracksBehavior :170-174),
 // every other worker fights.  The AI's `buildingRacks` field is a bit of header word H_AIFLAGS; `resourcesUsed` is written
 // and read within one getAction.
-DEVN int policy_crush(Game &g, int player, int pathfinder, int pn) {
+// v2: CRush_V2.java -- the base also trains a worker when there are more than 6 Ranged units (:154), combat units follow
+// CRanged_Tactic, free workers weigh resources against the enemy base.
+DEVN int policy_crush(Game &g, int player, int pathfinder, int pn, bool v2) {
     int par0, par1;
     reserved_resources(g, par0, par1);
     __syncwarp();
     const int n = g.hdr()[H_NUNITS], pl = player + 1, pres = g.hdr()[H_RES0 + player];
-    const int UT_RANGED = 6;
     const bool rush = g.W * g.H <= 144;
     auto own_harvester = [&](int, uint32_t w) { return u_pl(w) == pl && (ut_flags(g, u_type(w)) & UF_HARVEST) != 0; };
     const int nbases = w_count(g, n, [&](int, uint32_t w) { return u_pl(w) == pl && u_type(w) == UT_BASE; });
     const int nbarracks = w_count(g, n, [&](int, uint32_t w) { return u_pl(w) == pl && u_type(w) == UT_BARRACKS; });
     const int nworkers = w_count(g, n, [&](int, uint32_t w) { return u_pl(w) == pl && u_type(w) == UT_WORKER; });
     const int nw = w_count(g, n, own_harvester);
+    const int nranged = v2 ? w_count(g, n, [&](int, uint32_t w) { return u_pl(w) == pl && u_type(w) == UT_RANGED; }) : 0;
     bool building = ((g.hdr()[H_AIFLAGS] >> player) & 1) != 0;
     const bool was_building = building;
     int resources_used = 0;
@@ -794,17 +935,19 @@ DEVN int policy_crush(Game &g, int player, int pathfinder, int pn) {
         }
         int ord = 0;
 #pragma unroll 1
-        for (int i = w_next(g, n, -1, own_harvester); i >= 0; i = w_next(g, n, i, own_harvester), ord++) if (ord >= nfree) script_melee(g, i, player, false);
+        for (int i = w_next(g, n, -1, own_harvester); i >= 0; i = w_next(g, n, i, own_harvester), ord++)
+            if (ord >= nfree) { if (v2) script_crush2_combat(g, i, player, false, rush); else script_melee(g, i, player, false); }
         ord = 0;
 #pragma unroll 1
-        for (int i = w_next(g, n, -1, own_harvester); i >= 0 && ord < nfree; i = w_next(g, n, i, own_harvester), ord++) if (ord >= taken) script_harvest(g, i, player, true);
+        for (int i = w_next(g, n, -1, own_harvester); i >= 0 && ord < nfree; i = w_next(g, n, i, own_harvester), ord++)
+            if (ord >= taken) { if (v2 && !rush) script_crush2_harvest(g, i, player); else script_harvest(g, i, player, true); }
     }
     if (building != was_building) { __syncwarp(); if (g.lane == 0) g.hdr()[H_AIFLAGS] |= 1 << player; __syncwarp(); }
     w_for_each(g, n, [&](int i, uint32_t w) { return u_type(w) == UT_BASE && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE; }, [&](int i) {
         bool train;
         if (rush) train = pres >= ut_cost(g, UT_WORKER);
         else {
-            train = nworkers < nbases + 1 && pres >= ut_cost(g, UT_WORKER);
+            train = (nworkers < nbases + 1 && pres >= ut_cost(g, UT_WORKER)) || (v2 && nranged > 6);
             int resources = pres;
             if (resources_used != ut_cost(g, UT_BARRACKS) * nbarracks) resources -= ut_cost(g, UT_BARRACKS); // "buffers the resources that are being used for barracks"
             if (building && resources >= ut_cost(g, UT_WORKER) + ut_cost(g, UT_RANGED)) train = true;
@@ -817,7 +960,12 @@ DEVN int policy_crush(Game &g, int player, int pathfinder, int pn) {
     w_for_each(g, n, [&](int i, uint32_t w) {
         int fl = ut_flags(g, u_type(w));
         return (fl & UF_ATTACK) && !(fl & UF_HARVEST) && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE;
-    }, [&](int i) { if (u_type(g.w0()[i]) == UT_RANGED) script_crush_ranged(g, i, player); else script_melee(g, i, player, false); });
+    }, [&](int i) {
+        const bool ranged = u_type(g.w0()[i]) == UT_RANGED;
+        if (v2) script_crush2_combat(g, i, player, ranged, rush);
+        else if (ranged) script_crush_ranged(g, i, player);
+        else script_melee(g, i, player, false);
+    });
     return translate_actions(g, player, pathfinder, par0, par1, pn);
 }
 #endif
@@ -834,7 +982,7 @@ DEVN int policy_scripted(Game &g, int player, int kind, int pathfinder, int pn) 
     if (POL_IS_PO_RUSH(kind)) kind = kind - POL_PO_WORKER_RUSH + POL_WORKER_RUSH;
 #endif
 #ifndef MRTS_TU_RUSH_ONLY
-    if (kind == POL_CRUSH_V1) return policy_crush(g, player, pathfinder, pn);
+    if (kind == POL_CRUSH_V1 || kind == POL_CRUSH_V2) return policy_crush(g, player, pathfinder, pn, kind == POL_CRUSH_V2);
 #endif
     int par0, par1;
     reserved_resources(g, par0, par1);

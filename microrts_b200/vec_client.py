@@ -104,6 +104,10 @@ class ai:
         return AISpec(M.POLICY_CRUSH_V1, pathfinder)
 
     @staticmethod
+    def CRush_V2(utt=None, pathfinder=M.PF_ASTAR):
+        return AISpec(M.POLICY_CRUSH_V2, pathfinder)
+
+    @staticmethod
     def WorkerDefense(utt=None, pathfinder=M.PF_ASTAR):
         return AISpec(M.POLICY_WORKER_DEFENSE, pathfinder)
 

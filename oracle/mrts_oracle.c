@@ -953,6 +953,7 @@ static void gs_all_free(const OGame *g, uint8_t *fr /* [x*h + y] */) {
 static int pf_floodfill(OFf *f, const OGame *g, int start, int targetpos, int range, const ORu *ru) {
     const OUnit *s = &g->pool[start];
     int w = g->w, h = g->h;
+    if (targetpos < 0 || targetpos >= w * h) return -1; /* the reference indexes distances[x][y] with the target (an exception off the map): null */
     if (range < 0) range = 0; /* findPath :38-40 */
     if (f->w != w || f->h != h) { ff_clear(f); free(f->cache); f->w = w; f->h = h; f->cache = (int **)calloc((size_t)w * h, sizeof(int *)); }
     int x = targetpos % w, y = targetpos / w;
@@ -1028,7 +1029,8 @@ int o_pathfind(const OGame *g, int kind, int unit_idx, int targetpos, int range,
  *   ai/abstraction/AbstractionLayerAI.java:58-113,143-245 ; WorkerRush.java:63-204 ; LightRush.java:77-258 ;
  *   Attack.java:51 ; Harvest.java:72 ; Build.java:54 ; Train.java:48-128
  * ---------------------------------------------------------------------------------------------- */
-enum { AA_TRAIN = 1, AA_BUILD, AA_HARVEST, AA_ATTACK, AA_MOVE /* Move.java */, AA_RANGED_ATTACK /* cRush/RangedAttack.java: target + base = racks */ };
+enum { AA_TRAIN = 1, AA_BUILD, AA_HARVEST, AA_ATTACK, AA_MOVE /* Move.java */, AA_RANGED_ATTACK /* cRush/RangedAttack.java: target + base = racks */,
+       AA_TACTIC /* cRush/CRanged_Tactic.java: target, base = home, x = enemyBase (-1: null) */ };
 typedef struct {
     int unit; int kind;
     int type;          /* train / build */
@@ -1064,7 +1066,14 @@ static void ai_build(OAi *ai, int u, int type, int x, int y) { OAbs v = {u, AA_B
 static void ai_harvest(OAi *ai, int u, int target, int base) { OAbs v = {u, AA_HARVEST, -1, 0, 0, target, base, 0}; ai_put(ai, v); }
 static void ai_attack(OAi *ai, int u, int target) { OAbs v = {u, AA_ATTACK, -1, 0, 0, target, -1, 0}; ai_put(ai, v); }
 static void ai_move(OAi *ai, int u, int x, int y) { OAbs v = {u, AA_MOVE, -1, x, y, -1, -1, 0}; ai_put(ai, v); }
+static void ai_tactic(OAi *ai, int u, int target, int home, int eb) { OAbs v = {u, AA_TACTIC, -1, eb, 0, target, home, 0}; ai_put(ai, v); } /* CRush_V2.java:477-479 */
 static void ai_ranged_attack(OAi *ai, int u, int target, int racks) { OAbs v = {u, AA_RANGED_ATTACK, -1, 0, 0, target, racks, 0}; ai_put(ai, v); } /* CRush_V1.java:419-421 */
+
+/* unit types by name, as the reference looks them up (utt.getUnitType("Worker") ...): the ids of the standard tables */
+static int type_by_role_base(void) { return 1; }
+static int type_by_role_barracks(void) { return 2; }
+static int type_by_role_worker(void) { return 3; }
+static int type_by_role_light(void) { return 4; }
 
 static int in_list(const OGame *g, int u) { return u >= 0 && list_index_of(g, u) >= 0; }
 
@@ -1077,6 +1086,7 @@ static int aa_completed(const OAbs *aa, const OGame *g) {
             return !in_list(g, aa->target);
         case AA_ATTACK: return !in_list(g, aa->target);                       /* Attack.java:30-33 */
         case AA_RANGED_ATTACK: return !in_list(g, aa->target);                /* RangedAttack.java:36-39 */
+        case AA_TACTIC: return !in_list(g, aa->target);                       /* CRanged_Tactic.java:59-62 */
         case AA_MOVE: return g->pool[aa->unit].x == aa->x && g->pool[aa->unit].y == aa->y; /* Move.java:29-31 */
     }
     return 1;
@@ -1093,6 +1103,98 @@ static int train_score(const OGame *g, int x, int y, int type, int player) {
         if (ok) { int d = abs(u->x - x) + abs(u->y - y); if (first || d < distance) { distance = d; first = 0; } }
     }
     return -distance;
+}
+
+
+/* cRush/CRanged_Tactic.java:77-307.  Distances are square roots of integers that are only compared with each other or with
+ * integers, so their squares are compared instead. */
+static int d2_units(const OUnit *a, const OUnit *b) { int dx = b->x - a->x, dy = b->y - a->y; return dx * dx + dy * dy; }
+static int tactic_unit_at(const OGame *g, int x, int y) { /* PhysicalGameState.getUnitAt: null off the map */
+    if (x < 0 || y < 0 || x >= g->w || y >= g->h) return -1;
+    return unit_at(g, x, y);
+}
+static int tactic_allowed(OGame *g, int unit, int dir, OAct *out) {
+    OAct mv;
+    if (mk_move(&mv, dir) && is_unit_action_allowed(g, unit, &mv)) { *out = mv; return 1; }
+    return 0;
+}
+static int tactic_execute(OAi *ai, OAbs *aa, OGame *g, const ORu *ru, OAct *out) {
+    const OUtt *t = g->utt;
+    const int WORKER = type_by_role_worker(), BASE = type_by_role_base(), LIGHT = type_by_role_light(), HEAVY = 5, RANGED = 6;
+    const int w = g->w, u = aa->unit;
+    const OUnit *unit = &g->pool[u], *target = &g->pool[aa->target];
+    const int player = unit->player;
+    const OUnit *home = aa->base >= 0 ? &g->pool[aa->base] : unit;            /* :84-86 */
+    const OUnit *eb = aa->x >= 0 ? &g->pool[aa->x] : target;                  /* :88-90 */
+    const int range = t->f[unit->type][OF_RANGE];
+    const int rd2 = d2_units(unit, home), d2 = d2_units(unit, target);
+    int n_enemy_bases = 0, enemy_attack_units = 0, enemy_workers = 0;
+    const int cutoff = (g->w * g->h > 3000) ? 15000 : 5000;
+    for (int i = 0; i < g->n; i++) { /* `player != p.getID()`: neutral units count as well, only their types never match */
+        const OUnit *o = &g->pool[g->list[i]];
+        if (o->player == player) continue;
+        if (o->type == BASE) n_enemy_bases++;
+        if (o->type == RANGED || o->type == HEAVY || o->type == LIGHT) enemy_attack_units++;
+        if (o->type == WORKER) enemy_workers++;
+    }
+    int time_to_attack = ((enemy_workers < 2 * n_enemy_bases || n_enemy_bases == 0) && enemy_attack_units == 0) || g->time > cutoff;
+    /* nearestRangedAlly(enemyBase) :367-389: first own Ranged unit with the smallest distance to the enemy base */
+    int ally = -1, best = -1;
+    for (int i = 0; i < g->n; i++) {
+        const OUnit *o = &g->pool[g->list[i]];
+        if (o->player == player && o->type == RANGED) { int dd = d2_units(o, eb); if (best == -1 || dd < best) { best = dd; ally = g->list[i]; } }
+    }
+    const int ad2 = ally >= 0 ? d2_units(&g->pool[ally], target) : 0;
+    const int tpos = target->x + target->y * w;
+    if (unit->type == WORKER) { /* :149-176 */
+        if (d2 <= range * range) { *out = mk_act(O_ATTACK, -1, target->x, target->y, -1); return 1; }
+        int dir;
+        if (time_to_attack) dir = ai_pf(ai, g, u, tpos, range, ru);
+        else if (ally >= 0) {
+            const OUnit *al = &g->pool[ally];
+            if (d2 > ad2) dir = ai_pf(ai, g, u, tpos, range, ru);
+            else dir = ai_pf(ai, g, u, al->x + al->y * w, range, ru);
+            if (dir < 0) dir = ai_pf(ai, g, u, (al->x - 1) + al->y * w, range + 1, ru);
+            if (dir < 0) dir = ai_pf(ai, g, u, tpos, range, ru);
+        } else dir = ai_pf(ai, g, u, tpos, range, ru);
+        return tactic_allowed(g, u, dir, out);
+    }
+    if (d2 <= range * range) { *out = mk_act(O_ATTACK, -1, target->x, target->y, -1); return 1; } /* :179-181 */
+    if (ally < 0 || ally == u) { /* the unit leads: :182-194 */
+        int dir = -1;
+        if (time_to_attack && target->type == BASE) dir = ai_pf(ai, g, u, tpos, range, ru);
+        else if (rd2 < 25 || d2_units(unit, eb) > d2_units(home, eb)) dir = ai_pf(ai, g, u, eb->x + eb->y * w, range, ru);
+        return tactic_allowed(g, u, dir, out);
+    }
+    if (time_to_attack) { /* :195-216 */
+        if (range >= 1 && d2 <= (range - 1) * (range - 1) && rd2 > 4 && t->f[unit->type][OF_MOVE_T] < t->f[target->type][OF_MOVE_T])
+            return tactic_allowed(g, u, ai_pf(ai, g, u, home->x + home->y * w, range, ru), out);
+        if (d2 <= range * range) { *out = mk_act(O_ATTACK, -1, target->x, target->y, -1); return 1; }
+        return tactic_allowed(g, u, ai_pf(ai, g, u, tpos, range, ru), out);
+    }
+    /* line up next to the leading ranged unit :218-268, squareMove :290-343 */
+    int ax = g->pool[ally].x, ay = g->pool[ally].y;
+#define D2XY(X, Y) (((eb->x) - (X)) * ((eb->x) - (X)) + ((eb->y) - (Y)) * ((eb->y) - (Y)))
+    int sgn = D2XY(ax, ay + 1) > D2XY(ax, ay) ? 1 : -1; /* down / right of the leader, or up / left */
+    for (;;) {
+        int a = tactic_unit_at(g, ax, ay + sgn), b = tactic_unit_at(g, ax + sgn, ay + sgn), c = tactic_unit_at(g, ax + sgn, ay);
+        int found = 0;
+        if (a >= 0 && a != u && b >= 0 && b != u && c >= 0 && c != u) { ax = g->pool[c].x; ay = g->pool[c].y; } else found = 1;
+        a = tactic_unit_at(g, ax, ay + sgn); b = tactic_unit_at(g, ax + sgn, ay + sgn); c = tactic_unit_at(g, ax + sgn, ay);
+        if (a < 0 || b < 0 || c < 0) found = 1;
+        if (found) break;
+    }
+    {
+        int sg = D2XY(ax, ay + 1) > D2XY(ax, ay) ? 1 : -1; /* squareMove decides again, around the unit it was handed */
+        int a = tactic_unit_at(g, ax, ay + sg), b = tactic_unit_at(g, ax + sg, ay + sg), c = tactic_unit_at(g, ax + sg, ay);
+        if (u == a || u == b || u == c) return 0;
+        int dir = -1; /* pf.findPath = range 0; linear positions, as the reference computes them (a column off the map aliases) */
+        if (a < 0) dir = ai_pf(ai, g, u, ax + (ay + sg) * w, -1, ru);
+        else if (c < 0) dir = ai_pf(ai, g, u, (ax + sg) + ay * w, -1, ru);
+        else if (b < 0) dir = ai_pf(ai, g, u, (ax + sg) + (ay + sg) * w, -1, ru);
+        return tactic_allowed(g, u, dir, out);
+    }
+#undef D2XY
 }
 
 /* returns 1 and fills *out if the abstract action yields a unit action, 0 for null */
@@ -1128,6 +1230,7 @@ static int aa_execute(OAi *ai, OAbs *aa, OGame *g, const ORu *ru, OAct *out) {
             if (mk_move(&mv, ai_pf(ai, g, aa->unit, t->x + t->y * w, range, ru)) && is_unit_action_allowed(g, aa->unit, &mv)) { *out = mv; return 1; }
             return 0;
         }
+        case AA_TACTIC: return tactic_execute(ai, aa, g, ru, out);
         case AA_MOVE: { /* Move.java:49-55: pf.findPath */
             OAct mv;
             if (mk_move(&mv, ai_pf(ai, g, aa->unit, aa->x + aa->y * w, -1, ru)) && is_unit_action_allowed(g, aa->unit, &mv)) { *out = mv; return 1; }
@@ -1327,7 +1430,7 @@ static int harvest_behavior(OAi *ai, const OGame *g, int u, int player) {
     }
     int still_free = 1;
     OAbs *aa = ai_get(ai, u);
-    if (is_defense(ai->kind) || ai->kind == O_AI_CRUSH_V1) { /* WorkerDefense.java:197-209, LightDefense.java:236-244, CRush_V1.java:291-320: no carrying-resources special case */
+    if (is_defense(ai->kind) || ai->kind == O_AI_CRUSH_V1 || ai->kind == O_AI_CRUSH_V2) { /* WorkerDefense.java:197-209, LightDefense.java:236-244, CRush_V1.java:291-320: no carrying-resources special case */
         if (cres >= 0 && cbase >= 0) {
             if (aa && aa->kind == AA_HARVEST) { if (aa->target != cres || aa->base != cbase) ai_harvest(ai, u, cres, cbase); }
             else ai_harvest(ai, u, cres, cbase);
@@ -1350,17 +1453,13 @@ static int harvest_behavior(OAi *ai, const OGame *g, int u, int player) {
     return still_free;
 }
 
-static int type_by_role_base(void) { return 1; }
-static int type_by_role_barracks(void) { return 2; }
-static int type_by_role_worker(void) { return 3; }
-static int type_by_role_light(void) { return 4; }
 
 static int ai_get_action_k(OAi *ai, OGame *g, int player, OPair *out);
 static int ai_get_action_crush(OAi *ai, OGame *g, int player, OPair *out);
 static int ai_get_action(OAi *ai, OGame *g, int player, OPair *out) {
     /* PO{Worker,Light,Heavy,Ranged}Rush extend their rush and override meleeUnitBehavior only (melee_behavior looks at the
      * original kind through ai->po_rush) */
-    if (ai->kind == O_AI_CRUSH_V1) return ai_get_action_crush(ai, g, player, out);
+    if (ai->kind == O_AI_CRUSH_V1 || ai->kind == O_AI_CRUSH_V2) return ai_get_action_crush(ai, g, player, out);
     if (!is_po_rush(ai->kind)) return ai_get_action_k(ai, g, player, out);
     int k = ai->kind;
     ai->po_rush = 1; ai->kind = k - O_AI_PO_WORKER_RUSH + O_AI_WORKER_RUSH;
@@ -1474,6 +1573,49 @@ static void crush_ranged_behavior(OAi *ai, const OGame *g, int u, int player) { 
     if (enemy >= 0) ai_ranged_attack(ai, u, enemy, racks);
 }
 
+/* CRush_V2.meleeUnitBehavior :174-219 / rangedUnitBehavior :221-264: closest enemy, own barracks, own base and enemy base in one
+ * pass with one shared running distance (an enemy base is tested twice: as an enemy, then as a base) */
+static void crush2_combat_behavior(OAi *ai, const OGame *g, int u, int player, int ranged, int rush) {
+    const OUnit *me = &g->pool[u];
+    int enemy = -1, racks = -1, base = -1, ebase = -1, cd = 0;
+    for (int i = 0; i < g->n; i++) {
+        const OUnit *o = &g->pool[g->list[i]];
+        int d = abs(o->x - me->x) + abs(o->y - me->y);
+        if (o->player >= 0 && o->player != player && (enemy < 0 || d < cd)) { enemy = g->list[i]; cd = d; }
+        if (o->type == type_by_role_barracks() && o->player == player && (racks < 0 || d < cd)) { racks = g->list[i]; cd = d; }
+        if (o->type == type_by_role_base() && o->player == player && (base < 0 || d < cd)) { base = g->list[i]; cd = d; }
+        if (o->type == type_by_role_base() && o->player != player && (ebase < 0 || d < cd)) { ebase = g->list[i]; cd = d; }
+    }
+    if (enemy < 0) return;
+    if (!ranged && (g->time < 400 || rush)) ai_attack(ai, u, enemy);
+    else ai_tactic(ai, u, enemy, base, ebase);
+}
+
+/* CRush_V2.workersBehavior :335-383: the harvesters leave a resource alone that lies closer to the enemy base than to their own */
+static void crush2_harvest(OAi *ai, const OGame *g, int u, int player) {
+    const OUnit *me = &g->pool[u];
+    int cbase = -1, cres = -1, ebase = -1, cd = 0;
+    for (int i = 0; i < g->n; i++) {
+        const OUnit *o = &g->pool[g->list[i]];
+        int d = abs(o->x - me->x) + abs(o->y - me->y);
+        if ((g->utt->flags[o->type] & OFL_RESOURCE) && (cres < 0 || d < cd)) { cres = g->list[i]; cd = d; }
+        if (o->type == type_by_role_base() && o->player != player && (ebase < 0 || d < cd)) { ebase = g->list[i]; cd = d; }
+    }
+    cd = 0;
+    for (int i = 0; i < g->n; i++) {
+        const OUnit *o = &g->pool[g->list[i]];
+        if ((g->utt->flags[o->type] & OFL_STOCKPILE) && o->player == player) { int d = abs(o->x - me->x) + abs(o->y - me->y); if (cbase < 0 || d < cd) { cbase = g->list[i]; cd = d; } }
+    }
+    if (cres < 0) return;
+    /* distance(a, b) is 0.0 when either is null (:482-485) */
+    int de = ebase >= 0 ? d2_units(&g->pool[cres], &g->pool[ebase]) : 0, db = cbase >= 0 ? d2_units(&g->pool[cres], &g->pool[cbase]) : 0;
+    if (de < db) return;
+    if (cbase < 0) return;
+    OAbs *aa = ai_get(ai, u);
+    if (aa && aa->kind == AA_HARVEST) { if (aa->target != cres || aa->base != cbase) ai_harvest(ai, u, cres, cbase); }
+    else ai_harvest(ai, u, cres, cbase);
+}
+
 /* workersBehavior :222-321 (rush == 0) and rushWorkersBehavior :329-416 (rush == 1) */
 static void crush_workers(OAi *ai, const OGame *g, int player, const int *workers, int nw, int rush) {
     const OUtt *t = g->utt;
@@ -1507,14 +1649,16 @@ static void crush_workers(OAi *ai, const OGame *g, int player, const int *worker
         } else ai->resources_used = t->f[BARRACKS][OF_COST] * nbarracks;
         if (nbarracks > 1) ai->building_racks = 1;
     }
-    for (int i = b0; i < nw; i++) melee_behavior(ai, g, workers[i], player);
-    for (int i = f0; i < f1; i++) harvest_behavior(ai, g, workers[i], player);
+    const int v2 = ai->kind == O_AI_CRUSH_V2;
+    for (int i = b0; i < nw; i++) { if (v2) crush2_combat_behavior(ai, g, workers[i], player, 0, rush); else melee_behavior(ai, g, workers[i], player); }
+    for (int i = f0; i < f1; i++) { if (v2 && !rush) crush2_harvest(ai, g, workers[i], player); else harvest_behavior(ai, g, workers[i], player); }
 }
 
 static int ai_get_action_crush(OAi *ai, OGame *g, int player, OPair *out) {
     const OUtt *t = g->utt;
     int BASE = type_by_role_base(), BARRACKS = type_by_role_barracks(), WORKER = type_by_role_worker(), RANGED = 6;
     int rush = g->w * g->h <= 144, pres = g->res[player];
+    const int v2 = ai->kind == O_AI_CRUSH_V2;
     int *workers = (int *)malloc(sizeof(int) * (g->n + 1)); int nw = 0;
     for (int i = 0; i < g->n; i++) { int u = g->list[i]; const OUnit *un = &g->pool[u]; if ((t->flags[un->type] & OFL_HARVEST) && un->player == player) workers[nw++] = u; }
     crush_workers(ai, g, player, workers, nw, rush);
@@ -1523,15 +1667,16 @@ static int ai_get_action_crush(OAi *ai, OGame *g, int player, OPair *out) {
         int u = g->list[i]; const OUnit *un = &g->pool[u];
         if (!(un->type == BASE && un->player == player && find_assign(g, u) < 0)) continue;
         if (rush) { if (pres >= t->f[WORKER][OF_COST]) ai_train(ai, u, WORKER); continue; }
-        int nbases = 0, nbarracks = 0, nworkers = 0, resources = pres;
+        int nbases = 0, nbarracks = 0, nworkers = 0, nranged = 0, resources = pres;
         for (int j = 0; j < g->n; j++) {
             const OUnit *o = &g->pool[g->list[j]];
             if (o->player != player) continue;
+            if (o->type == RANGED) nranged++;
             if (o->type == WORKER) nworkers++;
             if (o->type == BARRACKS) nbarracks++;
             if (o->type == BASE) nbases++;
         }
-        if (nworkers < nbases + 1 && pres >= t->f[WORKER][OF_COST]) ai_train(ai, u, WORKER);
+        if ((nworkers < nbases + 1 && pres >= t->f[WORKER][OF_COST]) || (v2 && nranged > 6)) ai_train(ai, u, WORKER); /* CRush_V2.java:154 */
         if (ai->resources_used != t->f[BARRACKS][OF_COST] * nbarracks) resources -= t->f[BARRACKS][OF_COST];
         if (ai->building_racks && resources >= t->f[WORKER][OF_COST] + t->f[RANGED][OF_COST]) ai_train(ai, u, WORKER);
     }
@@ -1542,7 +1687,8 @@ static int ai_get_action_crush(OAi *ai, OGame *g, int player, OPair *out) {
     for (int i = 0; i < g->n; i++) { /* melee and ranged units :117-128 */
         int u = g->list[i]; const OUnit *un = &g->pool[u];
         if ((t->flags[un->type] & OFL_ATTACK) && !(t->flags[un->type] & OFL_HARVEST) && un->player == player && find_assign(g, u) < 0) {
-            if (un->type == RANGED) crush_ranged_behavior(ai, g, u, player); else melee_behavior(ai, g, u, player);
+            if (v2) crush2_combat_behavior(ai, g, u, player, un->type == RANGED, rush);
+            else if (un->type == RANGED) crush_ranged_behavior(ai, g, u, player); else melee_behavior(ai, g, u, player);
         }
     }
     return ai_translate(ai, g, player, out);
@@ -1734,7 +1880,7 @@ static int policy(OGame *g, int kind, OAi *ai, int player, OPair *out) {
         case O_AI_RANGED_DEFENSE:
         case O_AI_PO_WORKER_RUSH: case O_AI_PO_LIGHT_RUSH: case O_AI_PO_HEAVY_RUSH:
         case O_AI_PO_RANGED_RUSH:
-        case O_AI_WORKER_RUSH_PP: case O_AI_CRUSH_V1: return ai_get_action(ai, g, player, out);
+        case O_AI_WORKER_RUSH_PP: case O_AI_CRUSH_V1: case O_AI_CRUSH_V2: return ai_get_action(ai, g, player, out);
         default: return 0; /* PassiveAI: empty PlayerAction */
     }
 }
@@ -1759,7 +1905,7 @@ int o_run_game(OGame *g, int kind0, OAi *ai0, int kind1, OAi *ai1, int n_cycles,
  * the lists are issued with issueSafe on the real state.  The view is a copy with the same unit handles, so the pairs and
  * the AIs' abstract actions refer to the real game; the policy RNG (a static in the reference) is carried back. */
 static int policy_po(OGame *g, int kind, OAi *ai, int player, OPair *out) {
-    if (kind != O_AI_RANDOM_BIASED && !(kind >= O_AI_WORKER_RUSH && kind <= O_AI_CRUSH_V1)) return policy(g, kind, ai, player, out);
+    if (kind != O_AI_RANDOM_BIASED && !(kind >= O_AI_WORKER_RUSH && kind <= O_AI_CRUSH_V2)) return policy(g, kind, ai, player, out);
     OGame *v = o_po_view(g, player);
     int n = policy(v, kind, ai, player, out);
     g->rng_policy = v->rng_policy;

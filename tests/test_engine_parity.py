@@ -560,6 +560,17 @@ SCRIPTED = [
     ("24x24/basesWorkers24x24", "HEAVY_RUSH", "CRUSH_V1", 0),
     ("BWDistantResources32x32", "CRUSH_V1", "HEAVY_DEFENSE", 3),
     ("16x16/basesWorkers16x16", "RANDOM_BIASED", "CRUSH_V1", 2),
+    # CRush_V2: CRush_V1 whose combat units follow CRanged_Tactic from cycle 400 on (formation behind the leading Ranged unit,
+    # attack when the enemy has nothing but workers left) -- long games
+    ("8x8/basesWorkers8x8", "WORKER_RUSH", "CRUSH_V2", 0),
+    ("16x16/basesWorkers16x16", "CRUSH_V2", "LIGHT_RUSH", 0),
+    ("16x16/basesWorkers16x16", "HEAVY_RUSH", "CRUSH_V2", 0),
+    ("16x16/basesWorkers16x16", "CRUSH_V2", "CRUSH_V2", 1),
+    ("16x16/TwoBasesBarracks16x16", "CRUSH_V2", "RANDOM_BIASED", 0),
+    ("24x24/basesWorkers24x24", "CRUSH_V2", "HEAVY_RUSH", 0),
+    ("24x24/basesWorkers24x24", "CRUSH_V1", "CRUSH_V2", 0),
+    ("BWDistantResources32x32", "RANGED_RUSH", "CRUSH_V2", 3),
+    ("16x16/basesWorkers16x16", "CRUSH_V2", "LIGHT_DEFENSE", 2),
 ]
 
 
@@ -696,6 +707,8 @@ MAP_SWEEP_COMBOS = [
     ("WORKER_RUSH_PP", "HEAVY_RUSH", 0, False),
     ("CRUSH_V1", "HEAVY_RUSH", 0, False),
     ("RANDOM_BIASED", "CRUSH_V1", 0, True),
+    ("CRUSH_V2", "LIGHT_RUSH", 0, False),
+    ("CRUSH_V2", "RANDOM_BIASED", 3, False),
 ]
 
 
@@ -754,6 +767,8 @@ WIDE_SCRIPTED = [
     ("16x16/basesWorkers16x16", "CRUSH_V1", 0, 0, False),
     ("8x8/basesWorkers8x8", "CRUSH_V1", 1, 0, False),
     ("24x24/basesWorkers24x24", "CRUSH_V1", 1, 0, True),
+    ("16x16/basesWorkers16x16", "CRUSH_V2", 1, 0, False),
+    ("16x16/TwoBasesBarracks16x16", "CRUSH_V2", 0, 1, True),
 ]
 
 

@@ -255,6 +255,60 @@ def test_crush_v1_known_answers():
     assert _action_of(pa, 3)[0] == O.MOVE and _action_of(pa, 3)[1] in (1, 2)
 
 
+def test_crush_v2_known_answers():
+    """cRush/CRush_V2.java + CRanged_Tactic.java, decided by hand on 16x16 states (Ranged: range 3, sight 3)."""
+    utt = O.Utt(1, 1)
+
+    def decide(units, unit_idx, cycles=0, player=0):
+        g = O.Game(utt, _tiny_map(units, 16, 16))
+        for _ in range(cycles):
+            g.cycle()
+        return _action_of(O.ScriptedAI(O.AI_CRUSH_V2).get_action(g, player), unit_idx)
+
+    # enemy: a base and two workers -> not "time to attack" (2 workers >= 2 * 1 bases)
+    enemy = [("Base", 1, 15, 15, 0, 10), ("Worker", 1, 12, 8, 0, 1), ("Worker", 1, 14, 14, 0, 1)]
+    # the only Ranged unit leads.  Far from home (distance^2 128 >= 25) and closer to the enemy base (98) than home is (450): it
+    # waits (move == null -> NONE(10), :186-193) ...
+    act = decide([("Base", 0, 0, 0, 0, 10), ("Ranged", 0, 8, 8, 0, 1)] + enemy, 1)
+    assert act[0] == O.NONE and act[1] == 10
+    # ... close to home (8 < 25) it heads for the enemy base
+    act = decide([("Base", 0, 0, 0, 0, 10), ("Ranged", 0, 2, 2, 0, 1)] + enemy, 1)
+    assert act[0] == O.MOVE and act[1] in (1, 2)
+    # a target within range is shot whatever the role (:179-181)
+    act = decide([("Base", 0, 0, 0, 0, 10), ("Ranged", 0, 10, 8, 0, 1)] + enemy, 1)
+    assert act[0] == O.ATTACK and (act[2], act[3]) == (12, 8)
+    # a second Ranged unit follows the one nearest to the enemy base, (8,8).  The cell below the leader is closer to the enemy base
+    # (85 < 98), so the formation grows up / left: first the cell above the leader, (8,7) -- the follower at (4,4) walks right or down
+    two = [("Base", 0, 0, 0, 0, 10), ("Ranged", 0, 8, 8, 0, 1), ("Ranged", 0, 4, 4, 0, 1)] + enemy
+    act = decide(two, 2)
+    assert act[0] == O.MOVE and act[1] in (1, 2)
+    # standing on (8,7) it is in formation: null -> NONE(10) (:326-328)
+    act = decide([u if u[2:4] != (4, 4) else ("Ranged", 0, 8, 7, 0, 1) for u in two], 2)
+    assert act[0] == O.NONE and act[1] == 10
+    # with (8,7) taken by another unit the next free cell is the one on the left, (7,8): the follower at (5,8) walks right
+    act = decide(two[:2] + [("Ranged", 0, 5, 8, 0, 1), ("Worker", 0, 8, 7, 0, 1)] + enemy, 2)
+    assert act[0] == O.MOVE and act[1] == 1
+    # one enemy worker left for one base and no combat unit: time to attack, the follower goes after its target (the worker at (12,8))
+    act = decide([("Base", 0, 0, 0, 0, 10), ("Ranged", 0, 8, 8, 0, 1), ("Ranged", 0, 4, 8, 0, 1), ("Base", 1, 15, 15, 0, 10), ("Worker", 1, 12, 8, 0, 1)], 2)
+    assert act[0] == O.MOVE and act[1] == 1
+    # before cycle 400 a Light unit simply attacks (:213-214); from cycle 400 on it follows the tactic like a Ranged unit -- the
+    # leader is the Ranged unit (8,8), and the Light at (8,5) is already where a follower belongs?  No: (8,7) is free, so it walks
+    # down towards it
+    light = [("Base", 0, 0, 0, 0, 10), ("Ranged", 0, 8, 8, 0, 1), ("Light", 0, 8, 5, 0, 4)] + enemy
+    act = decide(light, 2)
+    assert act[0] == O.MOVE and act[1] in (1, 2)           # Attack: A* towards the worker at (12,8)
+    act = decide(light, 2, cycles=400)
+    assert act[0] == O.MOVE and act[1] == 2                # formation: down to (8,7)
+    # free workers (:335-383): the closest resource (1,4) lies nearer to the own base (0,0) than to the enemy base -> harvest;
+    # a resource next to the enemy base instead is left alone, and without an enemy base nobody harvests at all
+    eco = [("Base", 0, 0, 0, 0, 10), ("Worker", 0, 1, 1, 0, 1), ("Resource", -1, 1, 4, 20, 1)] + enemy
+    assert decide(eco, 1)[0] == O.MOVE
+    far = [("Base", 0, 0, 0, 0, 10), ("Worker", 0, 1, 1, 0, 1), ("Resource", -1, 13, 13, 20, 1)] + enemy
+    assert decide(far, 1)[0] == O.NONE
+    nobase = [("Base", 0, 0, 0, 0, 10), ("Worker", 0, 1, 1, 0, 1), ("Resource", -1, 1, 4, 20, 1), ("Worker", 1, 12, 8, 0, 1)]
+    assert decide(nobase, 1)[0] == O.NONE
+
+
 def test_observation_and_mask_known_answers(maps):
     """GameState.getVectorObservation (GameState.java:922-968) and JNIGridnetClient.getMasks / UnitAction.getValidActionArray
     (UnitAction.java:711-751) of the initial state of maps/8x8/basesWorkers8x8.xml, written out by hand."""
