@@ -65,7 +65,8 @@ enum {
     MRTS_POLICY_PO_WORKER_RUSH = 11, MRTS_POLICY_PO_LIGHT_RUSH = 12, MRTS_POLICY_PO_HEAVY_RUSH = 13, MRTS_POLICY_PO_RANGED_RUSH = 14,
     MRTS_POLICY_WORKER_RUSH_PP = 15, /* ai.abstraction.WorkerRushPlusPlus (src/ai/abstraction/WorkerRushPlusPlus.java:74-207) */
     MRTS_POLICY_CRUSH_V1 = 16, /* ai.abstraction.cRush.CRush_V1 (src/ai/abstraction/cRush/CRush_V1.java:68-421, RangedAttack.java:58-87) */
-    MRTS_POLICY_CRUSH_V2 = 17 /* ai.abstraction.cRush.CRush_V2 (src/ai/abstraction/cRush/CRush_V2.java:69-479, CRanged_Tactic.java:77-389) */
+    MRTS_POLICY_CRUSH_V2 = 17, /* ai.abstraction.cRush.CRush_V2 (src/ai/abstraction/cRush/CRush_V2.java:69-479, CRanged_Tactic.java:77-389) */
+    MRTS_POLICY_EMR_DETERMINISTICO = 18 /* ai.abstraction.EMRDeterministico (src/ai/abstraction/EMRDeterministico.java:74-358) */
 };
 enum { MRTS_PF_ASTAR = 0, MRTS_PF_BFS = 1, MRTS_PF_GREEDY = 2 /* ai.abstraction.pathfinding.GreedyPathFinding */,
        MRTS_PF_FLOODFILL = 3 /* ai.abstraction.pathfinding.FloodFillPathFinding: keeps its cache of distance maps per game and player in HBM */ };

@@ -25,7 +25,7 @@ public final class BatchedGameState implements AutoCloseable {
     public static final int POLICY_EXTERNAL = 0, POLICY_PASSIVE = 1, POLICY_RANDOM_BIASED = 2, POLICY_WORKER_RUSH = 3, POLICY_LIGHT_RUSH = 4,
             POLICY_HEAVY_RUSH = 5, POLICY_RANGED_RUSH = 6, POLICY_WORKER_DEFENSE = 7, POLICY_LIGHT_DEFENSE = 8, POLICY_HEAVY_DEFENSE = 9,
             POLICY_RANGED_DEFENSE = 10, POLICY_PO_WORKER_RUSH = 11, POLICY_PO_LIGHT_RUSH = 12, POLICY_PO_HEAVY_RUSH = 13,
-            POLICY_PO_RANGED_RUSH = 14, POLICY_WORKER_RUSH_PP = 15, POLICY_CRUSH_V1 = 16, POLICY_CRUSH_V2 = 17;   // MRTS_POLICY_* of include/microrts_cuda.h
+            POLICY_PO_RANGED_RUSH = 14, POLICY_WORKER_RUSH_PP = 15, POLICY_CRUSH_V1 = 16, POLICY_CRUSH_V2 = 17, POLICY_EMR_DETERMINISTICO = 18;   // MRTS_POLICY_* of include/microrts_cuda.h
     public static final int PF_ASTAR = 0, PF_BFS = 1, PF_GREEDY = 2, PF_FLOODFILL = 3; // ai.abstraction.pathfinding.{AStar,BFS,Greedy,FloodFill}PathFinding
     public static final int FLAG_PARTIAL_OBS = 1, FLAG_SCRIPTED_AI = 2, FLAG_PO_POLICIES = 4; // MRTS_FLAG_*
     public static final int ACTIONS_VECTOR = 0, ACTIONS_RAW = 1;

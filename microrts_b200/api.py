@@ -19,7 +19,7 @@ from . import _ffi
 ACTIONS_VECTOR, ACTIONS_RAW = 0, 1
 (POLICY_EXTERNAL, POLICY_PASSIVE, POLICY_RANDOM_BIASED, POLICY_WORKER_RUSH, POLICY_LIGHT_RUSH, POLICY_HEAVY_RUSH, POLICY_RANGED_RUSH,
  POLICY_WORKER_DEFENSE, POLICY_LIGHT_DEFENSE, POLICY_HEAVY_DEFENSE, POLICY_RANGED_DEFENSE,
- POLICY_PO_WORKER_RUSH, POLICY_PO_LIGHT_RUSH, POLICY_PO_HEAVY_RUSH, POLICY_PO_RANGED_RUSH, POLICY_WORKER_RUSH_PP, POLICY_CRUSH_V1, POLICY_CRUSH_V2) = range(18)
+ POLICY_PO_WORKER_RUSH, POLICY_PO_LIGHT_RUSH, POLICY_PO_HEAVY_RUSH, POLICY_PO_RANGED_RUSH, POLICY_WORKER_RUSH_PP, POLICY_CRUSH_V1, POLICY_CRUSH_V2, POLICY_EMR_DETERMINISTICO) = range(19)
 PF_ASTAR, PF_BFS, PF_GREEDY, PF_FLOODFILL = 0, 1, 2, 3
 DTYPE_U8, DTYPE_I32, DTYPE_BITS = 0, 1, 2
 FLAG_PARTIAL_OBS = 1

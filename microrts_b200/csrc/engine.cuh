@@ -41,8 +41,8 @@ enum { ACT_NONE = 0, ACT_MOVE = 1, ACT_HARVEST = 2, ACT_RETURN = 3, ACT_PRODUCE 
 enum { POL_EXTERNAL = 0, POL_PASSIVE = 1, POL_RANDOM_BIASED = 2, POL_WORKER_RUSH = 3, POL_LIGHT_RUSH = 4, POL_HEAVY_RUSH = 5, POL_RANGED_RUSH = 6,
        POL_WORKER_DEFENSE = 7, POL_LIGHT_DEFENSE = 8, POL_HEAVY_DEFENSE = 9, POL_RANGED_DEFENSE = 10,
        POL_PO_WORKER_RUSH = 11, POL_PO_LIGHT_RUSH = 12, POL_PO_HEAVY_RUSH = 13, POL_PO_RANGED_RUSH = 14, POL_WORKER_RUSH_PP = 15,
-       POL_CRUSH_V1 = 16, POL_CRUSH_V2 = 17 /* ai.abstraction.cRush.CRush_V1, CRush_V2 */ };
-#define POL_IS_SCRIPTED(p) ((p) >= POL_WORKER_RUSH && (p) <= POL_CRUSH_V2)
+       POL_CRUSH_V1 = 16, POL_CRUSH_V2 = 17 /* ai.abstraction.cRush.CRush_V1, CRush_V2 */, POL_EMR_DETERMINISTICO = 18 };
+#define POL_IS_SCRIPTED(p) ((p) >= POL_WORKER_RUSH && (p) <= POL_EMR_DETERMINISTICO)
 #define POL_IS_PO_RUSH(p) ((p) >= POL_PO_WORKER_RUSH && (p) <= POL_PO_RANGED_RUSH)
 #define POL_IS_DEFENSE(p) (((p) >= POL_WORKER_DEFENSE && (p) <= POL_RANGED_DEFENSE) || (p) == POL_WORKER_RUSH_PP) // WorkerRushPlusPlus.java = WorkerDefense.java whose melee units always attack
 enum { FMT_VECTOR = 0, FMT_RAW = 1 };

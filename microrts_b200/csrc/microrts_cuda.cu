@@ -704,7 +704,7 @@ int mrts_batch_scatter_games(mrts_batch *dst, const mrts_batch *src, const int64
 
 int mrts_batch_set_policy(mrts_batch *b, int player, int policy, int pathfinder) {
     if (!b || player < 0 || player > 1) return fail(MRTS_E_ARG, "mrts_batch_set_policy: bad argument");
-    if (policy < MRTS_POLICY_EXTERNAL || policy > MRTS_POLICY_CRUSH_V2) return fail(MRTS_E_ARG, "mrts_batch_set_policy: unknown policy");
+    if (policy < MRTS_POLICY_EXTERNAL || policy > MRTS_POLICY_EMR_DETERMINISTICO) return fail(MRTS_E_ARG, "mrts_batch_set_policy: unknown policy");
     if (policy >= MRTS_POLICY_WORKER_RUSH && !b->scripted)
         return fail(MRTS_E_STATE, "scripted policies need a batch created with MRTS_FLAG_SCRIPTED_AI");
     if (pathfinder < MRTS_PF_ASTAR || pathfinder > MRTS_PF_FLOODFILL) return fail(MRTS_E_ARG, "unknown pathfinder");

@@ -704,11 +704,13 @@ DEV bool script_harvest(Game &g, int s, int player, bool defense) {
     return true;
 }
 
-DEV void script_build_if_not(Game &g, int s, int player, int type, int *reserved, int &nres) { // buildIfNotAlreadyBuilding :231-245
+// desired position: the builder's own cell unless (dX, dY) is given
+DEV void script_build_if_not(Game &g, int s, int player, int type, int *reserved, int &nres, int dX = -1000, int dY = 0) { // buildIfNotAlreadyBuilding :231-245
     uint32_t X0 = g.x0()[s];
     if (!(aa_kind(X0) == AA_BUILD && aa_type(X0) == type)) {
         uint32_t w = g.w0()[s];
-        int pos = find_building_position(g, reserved, nres, u_x(w), u_y(w));
+        if (dX == -1000) { dX = u_x(w); dY = u_y(w); }
+        int pos = find_building_position(g, reserved, nres, dX, dY);
         int bx = pos < 0 ? -1 : pos % g.W, by = pos < 0 ? 0 : pos / g.W; // Java: -1 % w == -1, -1 / w == 0
         aa_put(g, s, player, AA_BUILD, type, bx, by, REF_NULL, REF_NULL);
         if (nres < 4) reserved[nres++] = pos;
@@ -968,6 +970,63 @@ DEVN int policy_crush(Game &g, int player, int pathfinder, int pn, bool v2) {
     });
     return translate_actions(g, player, pathfinder, par0, par1, pn);
 }
+// EMRDeterministico.getAction (ai/abstraction/EMRDeterministico.java:74-358) followed by translateActions: workers until 4 (6 per
+// base once there is a barracks), barracks training Light, Ranged, Heavy in turn, further barracks and bases as resources allow,
+// every combat unit attacks the closest enemy.
+DEVN int policy_emr(Game &g, int player, int pathfinder, int pn) {
+    int par0, par1;
+    reserved_resources(g, par0, par1);
+    __syncwarp();
+    const int n = g.hdr()[H_NUNITS], pl = player + 1, pres = g.hdr()[H_RES0 + player];
+    auto count_type = [&](int type) { return w_count(g, n, [&](int, uint32_t w) { return u_pl(w) == pl && u_type(w) == type; }); };
+    const int nworkers = count_type(UT_WORKER), nbases = count_type(UT_BASE), nbarracks = count_type(UT_BARRACKS);
+    const int narmy = count_type(UT_LIGHT) + count_type(UT_RANGED) + count_type(UT_HEAVY);
+    w_for_each(g, n, [&](int i, uint32_t w) { return u_type(w) == UT_BASE && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE; }, [&](int i) { // :133-162
+        if (nworkers < (nbarracks == 0 ? 4 : 6 * nbases) && pres >= ut_cost(g, UT_WORKER)) aa_put(g, i, player, AA_TRAIN, UT_WORKER, 0, 0, REF_NULL, REF_NULL);
+    });
+    w_for_each(g, n, [&](int i, uint32_t w) { return u_type(w) == UT_BARRACKS && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE; }, [&](int i) { // :164-194
+        const int turn = narmy % 3, type = turn == 0 ? UT_LIGHT : (turn == 1 ? UT_RANGED : UT_HEAVY);
+        if (pres >= ut_cost(g, type)) aa_put(g, i, player, AA_TRAIN, type, 0, 0, REF_NULL, REF_NULL);
+    });
+    // workers :213-284: every own Worker that can harvest, busy or not, in list order
+    auto own_worker = [&](int, uint32_t w) { return u_pl(w) == pl && u_type(w) == UT_WORKER && (ut_flags(g, UT_WORKER) & UF_HARVEST) != 0; };
+    const int nw = w_count(g, n, own_worker);
+    if (nw > 0) {
+        int reserved[4] = {0, 0, 0, 0}, nres = 0, used = 0, taken = 0, wi = -1;
+        if (nbases == 0 && taken < nw && pres >= ut_cost(g, UT_BASE) + used) {
+            wi = w_next(g, n, wi, own_worker); taken++; script_build_if_not(g, wi, player, UT_BASE, reserved, nres); used += ut_cost(g, UT_BASE);
+        }
+        if ((nbarracks == 0 || narmy > 2) && taken < nw && pres >= ut_cost(g, UT_BARRACKS) + used) { // the first barracks, or one more
+            wi = w_next(g, n, wi, own_worker); taken++; script_build_if_not(g, wi, player, UT_BARRACKS, reserved, nres); used += ut_cost(g, UT_BARRACKS);
+        }
+        if (nbarracks != 0) {
+            // otherResourcePoint :287-311: the resources farther than 10 (in x or in y) from every own base, as a HashSet<Unit>; its
+            // first element -- Unit.hashCode() = (int) ID, spread h ^ (h >>> 16) over 16 slots (doubled while size > 0.75 * slots),
+            // slots walked upwards, each in insertion order -- is where the next base goes
+            auto other = [&](int, uint32_t w) {
+                if (!(ut_flags(g, u_type(w)) & UF_RESOURCE)) return false;
+                bool mine = false;
+                for (int j = 0; j < n; j++) { uint32_t bw = g.w0()[j]; mine |= u_type(bw) == UT_BASE && u_pl(bw) == pl && iabs(u_x(w) - u_x(bw)) <= 10 && iabs(u_y(w) - u_y(bw)) <= 10; }
+                return !mine;
+            };
+            const int no = w_count(g, n, other);
+            if (no > 0 && taken < nw && pres >= ut_cost(g, UT_BASE) + used) {
+                int cap = 16;
+                while (no * 4 > cap * 3) cap *= 2;
+                const int first = w_argmin(g, n, [&](int i, uint32_t w) { uint32_t h = g.uid()[i]; h ^= h >> 16; return other(i, w) ? (int)(h & (uint32_t)(cap - 1)) : -1; });
+                const uint32_t rw = g.w0()[first];
+                wi = w_next(g, n, wi, own_worker); taken++; script_build_if_not(g, wi, player, UT_BASE, reserved, nres, u_x(rw) + 1, u_y(rw) + 1); used += ut_cost(g, UT_BASE);
+            }
+        }
+#pragma unroll 1
+        for (int i = w_next(g, n, wi, own_worker); i >= 0; i = w_next(g, n, i, own_worker)) script_harvest(g, i, player, true); // harvestWorkers :325-358
+    }
+    w_for_each(g, n, [&](int i, uint32_t w) { // :196-211
+        int fl = ut_flags(g, u_type(w));
+        return (fl & UF_ATTACK) && !(fl & UF_HARVEST) && u_pl(w) == pl && a_type(g.a0()[i]) == AT_IDLE;
+    }, [&](int i) { script_melee(g, i, player, false); });
+    return translate_actions(g, player, pathfinder, par0, par1, pn);
+}
 #endif
 
 // WorkerRush.getAction / LightRush.getAction followed by translateActions; appends to the pending list from pn.
@@ -982,6 +1041,7 @@ DEVN int policy_scripted(Game &g, int player, int kind, int pathfinder, int pn) 
     if (POL_IS_PO_RUSH(kind)) kind = kind - POL_PO_WORKER_RUSH + POL_WORKER_RUSH;
 #endif
 #ifndef MRTS_TU_RUSH_ONLY
+    if (kind == POL_EMR_DETERMINISTICO) return policy_emr(g, player, pathfinder, pn);
     if (kind == POL_CRUSH_V1 || kind == POL_CRUSH_V2) return policy_crush(g, player, pathfinder, pn, kind == POL_CRUSH_V2);
 #endif
     int par0, par1;

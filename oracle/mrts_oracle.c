@@ -1430,7 +1430,7 @@ static int harvest_behavior(OAi *ai, const OGame *g, int u, int player) {
     }
     int still_free = 1;
     OAbs *aa = ai_get(ai, u);
-    if (is_defense(ai->kind) || ai->kind == O_AI_CRUSH_V1 || ai->kind == O_AI_CRUSH_V2) { /* WorkerDefense.java:197-209, LightDefense.java:236-244, CRush_V1.java:291-320: no carrying-resources special case */
+    if (is_defense(ai->kind) || ai->kind == O_AI_CRUSH_V1 || ai->kind == O_AI_CRUSH_V2 || ai->kind == O_AI_EMR_DETERMINISTICO) { /* WorkerDefense.java:197-209, LightDefense.java:236-244, CRush_V1.java:291-320: no carrying-resources special case */
         if (cres >= 0 && cbase >= 0) {
             if (aa && aa->kind == AA_HARVEST) { if (aa->target != cres || aa->base != cbase) ai_harvest(ai, u, cres, cbase); }
             else ai_harvest(ai, u, cres, cbase);
@@ -1456,9 +1456,11 @@ static int harvest_behavior(OAi *ai, const OGame *g, int u, int player) {
 
 static int ai_get_action_k(OAi *ai, OGame *g, int player, OPair *out);
 static int ai_get_action_crush(OAi *ai, OGame *g, int player, OPair *out);
+static int ai_get_action_emr(OAi *ai, OGame *g, int player, OPair *out);
 static int ai_get_action(OAi *ai, OGame *g, int player, OPair *out) {
     /* PO{Worker,Light,Heavy,Ranged}Rush extend their rush and override meleeUnitBehavior only (melee_behavior looks at the
      * original kind through ai->po_rush) */
+    if (ai->kind == O_AI_EMR_DETERMINISTICO) return ai_get_action_emr(ai, g, player, out);
     if (ai->kind == O_AI_CRUSH_V1 || ai->kind == O_AI_CRUSH_V2) return ai_get_action_crush(ai, g, player, out);
     if (!is_po_rush(ai->kind)) return ai_get_action_k(ai, g, player, out);
     int k = ai->kind;
@@ -1694,6 +1696,101 @@ static int ai_get_action_crush(OAi *ai, OGame *g, int player, OPair *out) {
     return ai_translate(ai, g, player, out);
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * EMRDeterministico (ai/abstraction/EMRDeterministico.java:74-358): workers until 4 (6 per base once there is a barracks),
+ * barracks training Light, Ranged, Heavy in turn, further barracks and bases as resources allow, every combat unit attacks
+ * the closest enemy.  Deterministic (its Random is never used); the one subtle point is otherResourcePoint (:287-311), which
+ * returns the resources in HashSet order.
+ * ---------------------------------------------------------------------------------------------- */
+/* first element of a java.util.HashSet<Unit> filled in list order: Unit.hashCode() = (int) ID (Unit.java:548-550), HashMap
+ * spreads h ^ (h >>> 16) over a power-of-two table (16 slots, doubled while size > 0.75 * slots), iteration walks the slots
+ * upwards and each slot in insertion order */
+static int hashset_first(const OGame *g, const int *units, int n) {
+    int cap = 16;
+    while (n * 4 > cap * 3) cap *= 2;
+    int best = -1; uint32_t best_slot = 0;
+    for (int i = 0; i < n; i++) {
+        uint32_t h = (uint32_t)g->pool[units[i]].id;
+        h ^= h >> 16;
+        uint32_t slot = h & (uint32_t)(cap - 1);
+        if (best < 0 || slot < best_slot) { best = units[i]; best_slot = slot; }
+    }
+    return best;
+}
+
+static int ai_get_action_emr(OAi *ai, OGame *g, int player, OPair *out) {
+    const OUtt *t = g->utt;
+    const int BASE = type_by_role_base(), BARRACKS = type_by_role_barracks(), WORKER = type_by_role_worker(), LIGHT = type_by_role_light(), HEAVY = 5, RANGED = 6;
+    const int pres = g->res[player];
+    int nworkers = 0, nbases = 0, nbarracks = 0, nlight = 0, nranged = 0, nheavy = 0;
+    for (int i = 0; i < g->n; i++) {
+        const OUnit *o = &g->pool[g->list[i]];
+        if (o->player != player) continue;
+        if (o->type == WORKER) nworkers++;
+        if (o->type == BASE) nbases++;
+        if (o->type == BARRACKS) nbarracks++;
+        if (o->type == LIGHT) nlight++;
+        if (o->type == RANGED) nranged++;
+        if (o->type == HEAVY) nheavy++;
+    }
+    for (int i = 0; i < g->n; i++) { /* bases :133-162 */
+        int u = g->list[i]; const OUnit *un = &g->pool[u];
+        if (!(un->type == BASE && un->player == player && find_assign(g, u) < 0)) continue;
+        int limit = nbarracks == 0 ? 4 : 6 * nbases;
+        if (nworkers < limit && pres >= t->f[WORKER][OF_COST]) ai_train(ai, u, WORKER);
+    }
+    for (int i = 0; i < g->n; i++) { /* barracks :164-194 */
+        int u = g->list[i]; const OUnit *un = &g->pool[u];
+        if (!(un->type == BARRACKS && un->player == player && find_assign(g, u) < 0)) continue;
+        int sum = nlight + nheavy + nranged;
+        if (sum % 3 == 0 && pres >= t->f[LIGHT][OF_COST]) ai_train(ai, u, LIGHT);
+        else if (sum % 3 == 1 && pres >= t->f[RANGED][OF_COST]) ai_train(ai, u, RANGED);
+        else if (sum % 3 == 2 && pres >= t->f[HEAVY][OF_COST]) ai_train(ai, u, HEAVY);
+    }
+    /* workers :213-284: every own Worker that can harvest, busy or not */
+    int *workers = (int *)malloc(sizeof(int) * (g->n + 1)); int nw = 0;
+    for (int i = 0; i < g->n; i++) { int u = g->list[i]; const OUnit *un = &g->pool[u]; if ((t->flags[un->type] & OFL_HARVEST) && un->player == player && un->type == WORKER) workers[nw++] = u; }
+    if (nw > 0) {
+        int narmy = nlight + nranged + nheavy, used = 0, fw = 0, reserved[8], nres = 0;
+        if (nbases == 0 && fw < nw && pres >= t->f[BASE][OF_COST] + used) {
+            int u = workers[fw++]; build_if_not_already(ai, g, u, BASE, g->pool[u].x, g->pool[u].y, reserved, &nres); used += t->f[BASE][OF_COST];
+        }
+        if (nbarracks == 0 && fw < nw) {
+            if (pres >= t->f[BARRACKS][OF_COST] + used) { int u = workers[fw++]; build_if_not_already(ai, g, u, BARRACKS, g->pool[u].x, g->pool[u].y, reserved, &nres); used += t->f[BARRACKS][OF_COST]; }
+        } else if (nbarracks > 0 && fw < nw && narmy > 2) {
+            if (pres >= t->f[BARRACKS][OF_COST] + used) { int u = workers[fw++]; build_if_not_already(ai, g, u, BARRACKS, g->pool[u].x, g->pool[u].y, reserved, &nres); used += t->f[BARRACKS][OF_COST]; }
+        }
+        if (nbarracks != 0) {
+            /* otherResourcePoint :287-311: the resources farther than 10 (in x or in y) from every own base */
+            int *other = (int *)malloc(sizeof(int) * (g->n + 1)); int no = 0;
+            for (int i = 0; i < g->n; i++) {
+                const OUnit *r = &g->pool[g->list[i]];
+                if (!(t->flags[r->type] & OFL_RESOURCE)) continue;
+                int mine = 0;
+                for (int j = 0; j < g->n; j++) {
+                    const OUnit *b = &g->pool[g->list[j]];
+                    if (b->type == BASE && b->player == player && abs(r->x - b->x) <= 10 && abs(r->y - b->y) <= 10) mine = 1;
+                }
+                if (!mine) other[no++] = g->list[i];
+            }
+            if (no > 0 && fw < nw && pres >= t->f[BASE][OF_COST] + used) {
+                const OUnit *r = &g->pool[hashset_first(g, other, no)];
+                int u = workers[fw++];
+                build_if_not_already(ai, g, u, BASE, r->x + 1, r->y + 1, reserved, &nres);
+                used += t->f[BASE][OF_COST];
+            }
+            free(other);
+        }
+        for (int i = fw; i < nw; i++) harvest_behavior(ai, g, workers[i], player); /* harvestWorkers :325-358 */
+    }
+    free(workers);
+    for (int i = 0; i < g->n; i++) { /* combat units :196-211 */
+        int u = g->list[i]; const OUnit *un = &g->pool[u];
+        if ((t->flags[un->type] & OFL_ATTACK) && !(t->flags[un->type] & OFL_HARVEST) && un->player == player && find_assign(g, u) < 0) melee_behavior(ai, g, u, player);
+    }
+    return ai_translate(ai, g, player, out);
+}
+
 int o_ai_get_action(OAi *ai, OGame *g, int player, int32_t *unit_idx, OActionV *acts) {
     OPair *pa = (OPair *)malloc(sizeof(OPair) * (g->n + 1));
     int n = ai_get_action(ai, g, player, pa);
@@ -1880,7 +1977,7 @@ static int policy(OGame *g, int kind, OAi *ai, int player, OPair *out) {
         case O_AI_RANGED_DEFENSE:
         case O_AI_PO_WORKER_RUSH: case O_AI_PO_LIGHT_RUSH: case O_AI_PO_HEAVY_RUSH:
         case O_AI_PO_RANGED_RUSH:
-        case O_AI_WORKER_RUSH_PP: case O_AI_CRUSH_V1: case O_AI_CRUSH_V2: return ai_get_action(ai, g, player, out);
+        case O_AI_WORKER_RUSH_PP: case O_AI_CRUSH_V1: case O_AI_CRUSH_V2: case O_AI_EMR_DETERMINISTICO: return ai_get_action(ai, g, player, out);
         default: return 0; /* PassiveAI: empty PlayerAction */
     }
 }
@@ -1905,7 +2002,7 @@ int o_run_game(OGame *g, int kind0, OAi *ai0, int kind1, OAi *ai1, int n_cycles,
  * the lists are issued with issueSafe on the real state.  The view is a copy with the same unit handles, so the pairs and
  * the AIs' abstract actions refer to the real game; the policy RNG (a static in the reference) is carried back. */
 static int policy_po(OGame *g, int kind, OAi *ai, int player, OPair *out) {
-    if (kind != O_AI_RANDOM_BIASED && !(kind >= O_AI_WORKER_RUSH && kind <= O_AI_CRUSH_V2)) return policy(g, kind, ai, player, out);
+    if (kind != O_AI_RANDOM_BIASED && !(kind >= O_AI_WORKER_RUSH && kind <= O_AI_EMR_DETERMINISTICO)) return policy(g, kind, ai, player, out);
     OGame *v = o_po_view(g, player);
     int n = policy(v, kind, ai, player, out);
     g->rng_policy = v->rng_policy;

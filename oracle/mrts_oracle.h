@@ -26,7 +26,8 @@ enum { O_AI_NONE = 0, O_AI_PASSIVE = 1, O_AI_RANDOM_BIASED = 2, O_AI_WORKER_RUSH
        O_AI_WORKER_DEFENSE = 7, O_AI_LIGHT_DEFENSE = 8, O_AI_HEAVY_DEFENSE = 9, O_AI_RANGED_DEFENSE = 10,
        O_AI_PO_WORKER_RUSH = 11, O_AI_PO_LIGHT_RUSH = 12, O_AI_PO_HEAVY_RUSH = 13, O_AI_PO_RANGED_RUSH = 14, /* ai/abstraction/partialobservability/ */
        O_AI_WORKER_RUSH_PP = 15 /* ai/abstraction/WorkerRushPlusPlus.java */,
-       O_AI_CRUSH_V1 = 16, O_AI_CRUSH_V2 = 17 /* ai/abstraction/cRush/CRush_V1.java, CRush_V2.java + CRanged_Tactic.java */ }; /* ai/abstraction/{Worker,Light,Heavy,Ranged}Defense.java */
+       O_AI_CRUSH_V1 = 16, O_AI_CRUSH_V2 = 17, /* ai/abstraction/cRush/CRush_V1.java, CRush_V2.java + CRanged_Tactic.java */
+       O_AI_EMR_DETERMINISTICO = 18 /* ai/abstraction/EMRDeterministico.java */ }; /* ai/abstraction/{Worker,Light,Heavy,Ranged}Defense.java */
 enum { O_PF_ASTAR = 0, O_PF_BFS = 1, O_PF_GREEDY = 2 };
 
 /* unit type fields, in the order of the UTT XML attributes */

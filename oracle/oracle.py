@@ -16,8 +16,8 @@ TYPE_NAMES = ["Resource", "Base", "Barracks", "Worker", "Light", "Heavy", "Range
 NONE, MOVE, HARVEST, RETURN, PRODUCE, ATTACK = range(6)
 (AI_NONE, AI_PASSIVE, AI_RANDOM_BIASED, AI_WORKER_RUSH, AI_LIGHT_RUSH, AI_HEAVY_RUSH, AI_RANGED_RUSH,
  AI_WORKER_DEFENSE, AI_LIGHT_DEFENSE, AI_HEAVY_DEFENSE, AI_RANGED_DEFENSE,
- AI_PO_WORKER_RUSH, AI_PO_LIGHT_RUSH, AI_PO_HEAVY_RUSH, AI_PO_RANGED_RUSH, AI_WORKER_RUSH_PP, AI_CRUSH_V1, AI_CRUSH_V2) = range(18)
-SCRIPTED_AIS = tuple(range(AI_WORKER_RUSH, AI_CRUSH_V2 + 1))
+ AI_PO_WORKER_RUSH, AI_PO_LIGHT_RUSH, AI_PO_HEAVY_RUSH, AI_PO_RANGED_RUSH, AI_WORKER_RUSH_PP, AI_CRUSH_V1, AI_CRUSH_V2, AI_EMR_DETERMINISTICO) = range(19)
+SCRIPTED_AIS = tuple(range(AI_WORKER_RUSH, AI_EMR_DETERMINISTICO + 1))
 PF_ASTAR, PF_BFS, PF_GREEDY, PF_FLOODFILL = 0, 1, 2, 3
 
 

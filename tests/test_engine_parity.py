@@ -571,6 +571,14 @@ SCRIPTED = [
     ("24x24/basesWorkers24x24", "CRUSH_V1", "CRUSH_V2", 0),
     ("BWDistantResources32x32", "RANGED_RUSH", "CRUSH_V2", 3),
     ("16x16/basesWorkers16x16", "CRUSH_V2", "LIGHT_DEFENSE", 2),
+    # EMRDeterministico: economy first (up to 6 workers per base, more barracks and bases), Light / Ranged / Heavy in turn
+    ("8x8/basesWorkers8x8", "EMR_DETERMINISTICO", "WORKER_RUSH", 0),
+    ("16x16/basesWorkers16x16", "LIGHT_RUSH", "EMR_DETERMINISTICO", 0),
+    ("24x24/basesWorkers24x24", "EMR_DETERMINISTICO", "HEAVY_RUSH", 1),
+    ("BWDistantResources32x32", "EMR_DETERMINISTICO", "EMR_DETERMINISTICO", 0),
+    ("BWDistantResources32x32", "PASSIVE", "EMR_DETERMINISTICO", 0),
+    ("16x16/TwoBasesBarracks16x16", "EMR_DETERMINISTICO", "CRUSH_V2", 0),
+    ("16x16/basesWorkers16x16", "EMR_DETERMINISTICO", "RANGED_DEFENSE", 3),
 ]
 
 
@@ -601,6 +609,33 @@ def test_scripted_policies_vs_oracle(backend, maps, key, p0, p1, pf):
                 og.run(kinds[0], ais[g][0], kinds[1], ais[g][1], chunk, total)
             P.assert_same_state(ex, g, og, "%s %s/%s t=%d" % (key, p0, p1, t + chunk))
     b.close()
+
+
+def test_emr_second_base_hashset_order_on_device(backend):
+    """EMRDeterministico builds its second base next to the first element of a HashSet<Unit> of far resources
+    (EMRDeterministico.java:264-311): hash order of the unit IDs, not list order.  Custom map of tests/test_oracle_golden.py
+    (IDs 104 and 112: the resource listed last comes first), against the oracle and against the hand-derived outcome."""
+    from test_oracle_golden import EMR_SECOND_BASE, _tiny_map
+    mapd = dict(_tiny_map(EMR_SECOND_BASE, 16, 16), players=[[0, 15], [1, 5]])
+    utt, outt = M.UnitTypeTable(1, 1), O.Utt(1, 1)
+    for opp in ("PASSIVE", "WORKER_RUSH"):
+        b = M.BatchedGameState(utt, make_pgs(mapd, utt), 4, scripted_ai=True)
+        b.reset(np.arange(4, dtype=np.int64) + 3)
+        b.set_policy(0, M.POLICY_EMR_DETERMINISTICO, 0)
+        b.set_policy(1, getattr(M, "POLICY_" + opp), 0)
+        og = O.Game(outt, mapd)
+        og.seed(3)
+        k1 = getattr(O, "AI_" + opp)
+        a0, a1 = O.ScriptedAI(O.AI_EMR_DETERMINISTICO, 0), (O.ScriptedAI(k1, 0) if k1 in O.SCRIPTED_AIS else None)
+        for t in range(0, 800, 40):
+            b.step(40, 3000)
+            if not (og.gameover and og.time > 0):
+                og.run(O.AI_EMR_DETERMINISTICO, a0, k1, a1, 40, 3000)
+            P.assert_same_state(b.export(), 0, og, "EMR second base vs %s t=%d" % (opp, t + 40))
+            if opp == "PASSIVE" and t + 40 == 400:
+                bases = sorted((int(u[2]), int(u[3])) for u in og.units() if u[0] == 1 and u[1] == 0)
+                assert len(bases) >= 2 and all(q == (1, 1) or q[1] >= 12 for q in bases), bases
+        b.close()
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -709,6 +744,7 @@ MAP_SWEEP_COMBOS = [
     ("RANDOM_BIASED", "CRUSH_V1", 0, True),
     ("CRUSH_V2", "LIGHT_RUSH", 0, False),
     ("CRUSH_V2", "RANDOM_BIASED", 3, False),
+    ("EMR_DETERMINISTICO", "WORKER_RUSH", 0, False),
 ]
 
 
@@ -769,6 +805,8 @@ WIDE_SCRIPTED = [
     ("24x24/basesWorkers24x24", "CRUSH_V1", 1, 0, True),
     ("16x16/basesWorkers16x16", "CRUSH_V2", 1, 0, False),
     ("16x16/TwoBasesBarracks16x16", "CRUSH_V2", 0, 1, True),
+    ("16x16/basesWorkers16x16", "EMR_DETERMINISTICO", 0, 0, False),
+    ("BWDistantResources32x32", "EMR_DETERMINISTICO", 1, 0, True),
 ]
 
 

@@ -309,6 +309,39 @@ def test_crush_v2_known_answers():
     assert decide(nobase, 1)[0] == O.NONE
 
 
+EMR_SECOND_BASE = [("Base", 0, 1, 1, 0, 10), ("Barracks", 0, 3, 1, 0, 4), ("Worker", 0, 10, 8, 0, 1), ("Resource", -1, 0, 0, 20, 1),
+                   ("Resource", -1, 13, 8, 20, 1),                                            # ID 104: hash slot 104 & 15 = 8
+                   ("Base", 1, 15, 15, 0, 10), ("Worker", 1, 14, 15, 0, 1), ("Worker", 1, 13, 15, 0, 1), ("Worker", 1, 12, 15, 0, 1),
+                   ("Worker", 1, 11, 15, 0, 1), ("Worker", 1, 10, 15, 0, 1), ("Worker", 1, 9, 15, 0, 1),
+                   ("Resource", -1, 9, 13, 20, 1)]                                            # ID 112: hash slot 0
+
+
+def test_emr_deterministico_known_answers():
+    """EMRDeterministico.java: the second base goes next to the FIRST ELEMENT OF A HashSet<Unit> of far resources (:264-276,
+    :287-311).  Unit.hashCode() is the ID, so with IDs 104 and 112 in a 16-slot table the resource listed LAST (slot 0) comes
+    first: desired position (10,14); the ring of radius 1 around it starts with its top row y = 13, x = 9..11, where (9,13) holds
+    the resource and (10,13) is free.  The worker at (10,8) walks straight down; for the other resource, (13,8), it would walk
+    right."""
+    utt = O.Utt(1, 1)
+    m = dict(_tiny_map(EMR_SECOND_BASE, 16, 16), players=[[0, 15], [1, 5]])
+    pa = O.ScriptedAI(O.AI_EMR_DETERMINISTICO).get_action(O.Game(utt, m), 0)
+    act = _action_of(pa, 2)
+    assert act[0] == O.MOVE and act[1] == 2
+    # the base trains a worker (1 < 6 workers), the barracks a Light (0 army units: turn 0)
+    assert _action_of(pa, 0)[0] == O.PRODUCE and _action_of(pa, 0)[4] == 3
+    assert _action_of(pa, 1)[0] == O.PRODUCE and _action_of(pa, 1)[4] == 4
+    # with too few resources for a base (10) nothing is built and the worker harvests from the closest resource, (13,8): right
+    poor = dict(m, players=[[0, 7], [1, 5]])
+    act = _action_of(O.ScriptedAI(O.AI_EMR_DETERMINISTICO).get_action(O.Game(utt, poor), 0), 2)
+    assert act[0] == O.MOVE and act[1] == 1
+    # play it: the new base appears in the lower part of the map, next to resource 112, not next to 104
+    g = O.Game(utt, m)
+    ai = O.ScriptedAI(O.AI_EMR_DETERMINISTICO)
+    g.run(O.AI_EMR_DETERMINISTICO, ai, O.AI_PASSIVE, None, 400, 3000)
+    bases = sorted((int(u[2]), int(u[3])) for u in g.units() if u[0] == 1 and u[1] == 0)
+    assert (1, 1) in bases and len(bases) >= 2 and all(b == (1, 1) or b[1] >= 12 for b in bases), bases
+
+
 def test_observation_and_mask_known_answers(maps):
     """GameState.getVectorObservation (GameState.java:922-968) and JNIGridnetClient.getMasks / UnitAction.getValidActionArray
     (UnitAction.java:711-751) of the initial state of maps/8x8/basesWorkers8x8.xml, written out by hand."""
