@@ -10,6 +10,9 @@
 //   GreedyPathFinding  src/ai/abstraction/pathfinding/GreedyPathFinding.java:53-84
 //   POWorkerRush / POLightRush / POHeavyRush / PORangedRush  src/ai/abstraction/partialobservability/*.java:42-78 (exploration) + Move.java
 //   Attack/Harvest/Build/Train.execute   src/ai/abstraction/{Attack.java:51,Harvest.java:72,Build.java:54,Train.java:48-128}
+//   FloodFillPathFinding  src/ai/abstraction/pathfinding/FloodFillPathFinding.java:47-213
+//   CRush_V1 / CRush_V2   src/ai/abstraction/cRush/CRush_V1.java:68-421, CRush_V2.java:69-479, RangedAttack.java:58-87, CRanged_Tactic.java:77-389
+//   EMRDeterministico     src/ai/abstraction/EMRDeterministico.java:74-358
 //
 // The AI's per-unit abstract action (the value of AbstractionLayerAI.actions for that unit) lives in the unit's X0/X1
 // words; the map's insertion order is the `aseq` field.  Unit references held by abstract actions (attack target,
