@@ -1,14 +1,17 @@
 #!/usr/bin/env python3
-"""Small pass over every kernel of the library, sized for compute-sanitizer (memcheck / racecheck / synccheck):
+"""Small pass over every kernel of the library, sized for a memory checker.
 
-    compute-sanitizer --tool memcheck  python tools/sanitize.py
-    compute-sanitizer --tool racecheck python tools/sanitize.py
-    compute-sanitizer --tool synccheck python tools/sanitize.py
+On a GPU box with compute-sanitizer available:
+    compute-sanitizer --tool memcheck|racecheck|synccheck python tools/sanitize.py
+(compute-sanitizer is closed on the pool this repository is developed on.)  Without one, the same kernel sources run on the warp
+emulator (tests/emu) built with AddressSanitizer + UndefinedBehaviorSanitizer -- every "device" buffer is a heap block there:
+    LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.so)" ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0 \
+        MRTS_EMU=1 MRTS_EMU_ASAN=1 python tools/sanitize.py          # or: ... python -m pytest tests -m gpu
 
 Each section launches one kernel kind (fast self-play, fixed-layout copies, the generic scripted kernel with every policy family and
 pathfinder, the lean rush kernel, partially observable policies, rollouts, observation / mask / evaluation / pathfinding operators,
 the fused step + observation kernel with masks, the JNIGridnetVecClient step with in-kernel reset, game copies, the host searches).
-Prints the kernels launched; the sanitizer's own summary follows."""
+Prints the kernels launched; the checker's own report follows."""
 import os
 import sys
 
