@@ -163,3 +163,76 @@ def test_partially_observable_observation(backend, maps):
     b.reset(np.zeros(2, dtype=np.int64))
     _po_expectations(b.observe(0)[0])
     b.close()
+
+
+def _first_decision(units, policy, cycles=0, players=None, w=16, h=16):
+    """the assignments one cycle after `policy` (player 0, A*) decided on the given state; player 1 is passive"""
+    utt = M.UnitTypeTable(1, 1)
+    mapd = tiny_map(units, w, h)
+    if players is not None:
+        mapd["players"] = players
+    b = M.BatchedGameState(utt, M.PhysicalGameState.fromXML(P.map_to_xml(mapd), utt), 2, scripted_ai=True)
+    b.reset(np.zeros(2, dtype=np.int64))
+    b.set_policy(0, policy, M.PF_ASTAR)
+    b.set_policy(1, M.POLICY_PASSIVE)
+    if cycles:
+        b.cycle(cycles)
+    b.step(1, 3000)
+    a = state(b)[2]
+    b.close()
+    return a
+
+
+def test_crush_and_emr_decisions(backend):
+    """The hand-derived answers of tests/test_oracle_golden.py (test_crush_v1_known_answers, test_crush_v2_known_answers,
+    test_emr_deterministico_known_answers) asked of the device: cRush/CRush_V1.java + RangedAttack.java, CRush_V2.java +
+    CRanged_Tactic.java, EMRDeterministico.java."""
+    from test_oracle_golden import EMR_SECOND_BASE
+    # CRush_V1 / RangedAttack: step back from a slower enemy well inside the range, shoot a faster one, shoot at the edge of the range
+    racks = [("Base", 0, 0, 0, 0, 10), ("Barracks", 0, 0, 2, 0, 4), ("Ranged", 0, 8, 8, 0, 1), ("Heavy", 1, 8, 10, 0, 4), ("Base", 1, 15, 15, 0, 10)]
+    a = _first_decision(racks, M.POLICY_CRUSH_V1)
+    assert a[2, 0] == MOVE and a[2, 1] in (0, 3)
+    a = _first_decision([u if u[0] != "Heavy" else ("Light", 1, 8, 10, 0, 4) for u in racks], M.POLICY_CRUSH_V1)
+    assert a[2, 0] == ATTACK and a[2, 2:4].tolist() == [8, 10]
+    a = _first_decision([u if u[0] != "Heavy" else ("Heavy", 1, 8, 11, 0, 4) for u in racks], M.POLICY_CRUSH_V1)
+    assert a[2, 0] == ATTACK and a[2, 2:4].tolist() == [8, 11]
+    # one running distance for "closest enemy" and "closest barracks": the Heavy listed after the barracks becomes the target
+    shared = [("Base", 0, 0, 0, 0, 10), ("Ranged", 0, 8, 8, 0, 1), ("Heavy", 1, 8, 6, 0, 4), ("Barracks", 0, 0, 2, 0, 4), ("Heavy", 1, 8, 13, 0, 4), ("Base", 1, 15, 15, 0, 10)]
+    a = _first_decision(shared, M.POLICY_CRUSH_V1)
+    assert a[1, :2].tolist() == [MOVE, 2]
+    # economy: 5 resources go to the barracks (base idle: NONE 10), 8 leave enough for "worker + ranged"
+    eco = [("Base", 0, 2, 2, 0, 10), ("Worker", 0, 1, 2, 0, 1), ("Worker", 0, 1, 3, 0, 1), ("Worker", 0, 3, 3, 0, 1), ("Resource", -1, 0, 4, 20, 1),
+           ("Base", 1, 13, 13, 0, 10), ("Worker", 1, 12, 12, 0, 1)]
+    a = _first_decision(eco, M.POLICY_CRUSH_V1)
+    assert a[0, :2].tolist() == [NONE, 10] and a[1, 0] == MOVE and a[1, 1] in (0, 3) and a[2, 0] == MOVE and a[3, 0] == MOVE and a[3, 1] in (1, 2)
+    a = _first_decision(eco, M.POLICY_CRUSH_V1, players=[[0, 8], [1, 5]])
+    assert a[0, [0, 4]].tolist() == [PRODUCE, 3]
+    # CRush_V2 / CRanged_Tactic: the leader waits far from home, a follower lines up above the leader, stands still once there
+    enemy = [("Base", 1, 15, 15, 0, 10), ("Worker", 1, 12, 8, 0, 1), ("Worker", 1, 14, 14, 0, 1)]
+    a = _first_decision([("Base", 0, 0, 0, 0, 10), ("Ranged", 0, 8, 8, 0, 1)] + enemy, M.POLICY_CRUSH_V2)
+    assert a[1, :2].tolist() == [NONE, 10]
+    a = _first_decision([("Base", 0, 0, 0, 0, 10), ("Ranged", 0, 2, 2, 0, 1)] + enemy, M.POLICY_CRUSH_V2)
+    assert a[1, 0] == MOVE and a[1, 1] in (1, 2)
+    two = [("Base", 0, 0, 0, 0, 10), ("Ranged", 0, 8, 8, 0, 1), ("Ranged", 0, 4, 4, 0, 1)] + enemy
+    a = _first_decision(two, M.POLICY_CRUSH_V2)
+    assert a[2, 0] == MOVE and a[2, 1] in (1, 2)
+    a = _first_decision([u if u[2:4] != (4, 4) else ("Ranged", 0, 8, 7, 0, 1) for u in two], M.POLICY_CRUSH_V2)
+    assert a[2, :2].tolist() == [NONE, 10]
+    a = _first_decision(two[:2] + [("Ranged", 0, 5, 8, 0, 1), ("Worker", 0, 8, 7, 0, 1)] + enemy, M.POLICY_CRUSH_V2)
+    assert a[2, :2].tolist() == [MOVE, 1]
+    # a Light attacks before cycle 400 and lines up behind the leading Ranged unit afterwards
+    light = [("Base", 0, 0, 0, 0, 10), ("Ranged", 0, 8, 8, 0, 1), ("Light", 0, 8, 5, 0, 4)] + enemy
+    a = _first_decision(light, M.POLICY_CRUSH_V2)
+    assert a[2, 0] == MOVE and a[2, 1] in (1, 2)
+    a = _first_decision(light, M.POLICY_CRUSH_V2, cycles=400)
+    assert a[2, :2].tolist() == [MOVE, 2]
+    # free workers leave a resource next to the enemy base alone
+    a = _first_decision([("Base", 0, 0, 0, 0, 10), ("Worker", 0, 1, 1, 0, 1), ("Resource", -1, 1, 4, 20, 1)] + enemy, M.POLICY_CRUSH_V2)
+    assert a[1, 0] == MOVE
+    a = _first_decision([("Base", 0, 0, 0, 0, 10), ("Worker", 0, 1, 1, 0, 1), ("Resource", -1, 13, 13, 20, 1)] + enemy, M.POLICY_CRUSH_V2)
+    assert a[1, 0] == NONE
+    # EMRDeterministico: the second base goes next to the far resource that comes first in HashSet order (ID 112, listed last)
+    a = _first_decision(EMR_SECOND_BASE, M.POLICY_EMR_DETERMINISTICO, players=[[0, 15], [1, 5]])
+    assert a[2, :2].tolist() == [MOVE, 2] and a[0, [0, 4]].tolist() == [PRODUCE, 3] and a[1, [0, 4]].tolist() == [PRODUCE, 4]
+    a = _first_decision(EMR_SECOND_BASE, M.POLICY_EMR_DETERMINISTICO, players=[[0, 7], [1, 5]])
+    assert a[2, :2].tolist() == [MOVE, 1]
