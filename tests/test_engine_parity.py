@@ -16,6 +16,10 @@ from oracle import oracle as O
 pytestmark = pytest.mark.gpu
 
 
+# MRTS_SEED_OFFSET shifts the seeds of every randomized differential test: a soak run repeats the suite with other games
+SOAK = int(os.environ.get("MRTS_SEED_OFFSET", "0"))
+
+
 def make_pgs(mapd, utt):
     return M.PhysicalGameState.fromXML(P.map_to_xml(mapd), utt)
 
@@ -90,7 +94,7 @@ def run_selfplay(backend, maps, key, sizes, cycles, chunk, version=1, conflict=1
     total = cycles[0] if backend == "emu" else cycles[1]
     utt, outt = M.UnitTypeTable(version, conflict), O.Utt(version, conflict)
     b = M.BatchedGameState(utt, make_pgs(maps[key], utt), n)
-    seeds = np.arange(n, dtype=np.int64) * 7919 + seed0
+    seeds = np.arange(n, dtype=np.int64) * 7919 + seed0 + SOAK
     b.reset(seeds)
     b.set_policy(0, M.POLICY_RANDOM_BIASED)
     b.set_policy(1, M.POLICY_RANDOM_BIASED)
@@ -150,7 +154,7 @@ def test_observations_and_masks(backend, maps, key):
     pgs = make_pgs(maps[key], utt)
     b = M.BatchedGameState(utt, pgs, n)
     bpo = M.BatchedGameState(utt, pgs, n, partial_obs=True)
-    seeds = np.arange(n, dtype=np.int64) + 5
+    seeds = np.arange(n, dtype=np.int64) + 5 + SOAK
     games = []
     for bb in (b, bpo):
         bb.reset(seeds)
@@ -212,7 +216,7 @@ def test_fused_step_observations(backend, maps, key, dtype, external):
     utt, outt = M.UnitTypeTable(1, 1), O.Utt(1, 1)
     m = maps[key]
     b = M.BatchedGameState(utt, make_pgs(m, utt), n)
-    seeds = np.arange(n, dtype=np.int64) + 77
+    seeds = np.arange(n, dtype=np.int64) + 77 + SOAK
     b.reset(seeds)
     b.set_policy(0, M.POLICY_RANDOM_BIASED)
     b.set_policy(1, M.POLICY_EXTERNAL if external else M.POLICY_RANDOM_BIASED)
@@ -295,7 +299,7 @@ def test_external_vector_actions(backend, maps, key, version, conflict):
     w, h = maps[key]["w"], maps[key]["h"]
     utt, outt = M.UnitTypeTable(version, conflict), O.Utt(version, conflict)
     b = M.BatchedGameState(utt, make_pgs(maps[key], utt), n)
-    seeds = np.arange(n, dtype=np.int64) + 5  # random damage (v3) and CANCEL_RANDOM draw from the per-game streams
+    seeds = np.arange(n, dtype=np.int64) + 5 + SOAK  # random damage (v3) and CANCEL_RANDOM draw from the per-game streams
     b.reset(seeds)
     b.set_policy(0, M.POLICY_EXTERNAL)
     b.set_policy(1, M.POLICY_EXTERNAL)
@@ -338,7 +342,7 @@ def test_auto_reset_and_masked_reset(backend, maps):
     cap = 400  # short cap so that episodes roll over
     utt, outt = M.UnitTypeTable(1, 1), O.Utt(1, 1)
     b = M.BatchedGameState(utt, make_pgs(maps[key], utt), n)
-    seeds = np.arange(n, dtype=np.int64) + 77
+    seeds = np.arange(n, dtype=np.int64) + 77 + SOAK
     b.reset(seeds)
     b.set_policy(0, M.POLICY_RANDOM_BIASED)
     b.set_policy(1, M.POLICY_RANDOM_BIASED)
@@ -408,7 +412,7 @@ def test_full_size_batch_properties(backend, maps):
     key, n = "16x16/basesWorkers16x16", 65536
     utt, outt = M.UnitTypeTable(1, 1), O.Utt(1, 1)
     pgs = make_pgs(maps[key], utt)
-    seeds = np.arange(n, dtype=np.int64)
+    seeds = np.arange(n, dtype=np.int64) + SOAK
     b = M.BatchedGameState(utt, pgs, n)
     b.set_policy(0, M.POLICY_RANDOM_BIASED)
     b.set_policy(1, M.POLICY_RANDOM_BIASED)
@@ -454,7 +458,7 @@ def test_rollouts(backend, maps, key, observer):
     depth = 100
     utt, outt = M.UnitTypeTable(1, 1), O.Utt(1, 1)
     b = M.BatchedGameState(utt, make_pgs(maps[key], utt), n)
-    seeds = np.arange(n, dtype=np.int64) + 3
+    seeds = np.arange(n, dtype=np.int64) + 3 + SOAK
     b.reset(seeds)
     b.set_policy(0, M.POLICY_RANDOM_BIASED)
     b.set_policy(1, M.POLICY_RANDOM_BIASED)
@@ -589,7 +593,7 @@ def test_scripted_policies_vs_oracle(backend, maps, key, p0, p1, pf):
     chunk = 25
     utt, outt = M.UnitTypeTable(1, 1), O.Utt(1, 1)
     b = M.BatchedGameState(utt, make_pgs(maps[key], utt), n, scripted_ai=True)
-    seeds = np.arange(n, dtype=np.int64) + 11
+    seeds = np.arange(n, dtype=np.int64) + 11 + SOAK
     b.reset(seeds)
     kinds = []
     for pl, name in enumerate((p0, p1)):
@@ -662,7 +666,7 @@ def test_partially_observable_games_vs_oracle(backend, maps, key, p0, p1, pf):
     chunk = 25
     utt, outt = M.UnitTypeTable(1, 1), O.Utt(1, 1)
     b = M.BatchedGameState(utt, make_pgs(maps[key], utt), n, scripted_ai=True, po_policies=True)
-    seeds = np.arange(n, dtype=np.int64) + 23
+    seeds = np.arange(n, dtype=np.int64) + 23 + SOAK
     b.reset(seeds)
     kinds = []
     for pl, name in enumerate((p0, p1)):
@@ -695,7 +699,7 @@ def test_wide_differential_full_games(backend, maps, key, n_cuda):
     total = 600 if backend == "emu" else 3000
     utt, outt = M.UnitTypeTable(1, 1), O.Utt(1, 1)
     b = M.BatchedGameState(utt, make_pgs(maps[key], utt), n)
-    seeds = np.arange(n, dtype=np.int64) * 3 + 17
+    seeds = np.arange(n, dtype=np.int64) * 3 + 17 + SOAK
     b.reset(seeds)
     b.set_policy(0, M.POLICY_RANDOM_BIASED)
     b.set_policy(1, M.POLICY_RANDOM_BIASED)
@@ -766,7 +770,7 @@ def test_every_reference_map(backend, maps, part):
                 p0, p1, pf, po = "RANDOM_BIASED", "RANDOM_BIASED", 0, False
                 cyc = total
             b = M.BatchedGameState(utt, make_pgs(maps[key], utt), n, scripted_ai=scripted, po_policies=po)
-            seeds = np.arange(n, dtype=np.int64) * 7 + 5
+            seeds = np.arange(n, dtype=np.int64) * 7 + 5 + SOAK
             b.reset(seeds)
             kinds = [getattr(O, "AI_" + p0), getattr(O, "AI_" + p1)]
             b.set_policy(0, getattr(M, "POLICY_" + p0), pf)
@@ -817,7 +821,7 @@ def test_wide_differential_scripted(backend, maps, key, pol, side, pf, po):
     total = 400 if backend == "emu" else 3000
     utt, outt = M.UnitTypeTable(1, 1), O.Utt(1, 1)
     b = M.BatchedGameState(utt, make_pgs(maps[key], utt), n, scripted_ai=True, po_policies=po)
-    seeds = np.arange(n, dtype=np.int64) * 5 + 101
+    seeds = np.arange(n, dtype=np.int64) * 5 + 101 + SOAK
     b.reset(seeds)
     names = ["RANDOM_BIASED", "RANDOM_BIASED"]
     names[side] = pol
@@ -857,7 +861,7 @@ def test_pathfinding_operator(backend, maps, key):
     rounds = 2 if backend == "emu" else 6
     utt, outt = M.UnitTypeTable(1, 1), O.Utt(1, 1)
     b = M.BatchedGameState(utt, make_pgs(maps[key], utt), n, scripted_ai=True)
-    seeds = np.arange(n, dtype=np.int64) + 900
+    seeds = np.arange(n, dtype=np.int64) + 900 + SOAK
     b.reset(seeds)
     b.set_policy(0, M.POLICY_RANDOM_BIASED)
     b.set_policy(1, M.POLICY_RANDOM_BIASED)
@@ -901,7 +905,7 @@ def test_evaluation_operator(backend, maps):
     n = 4 if backend == "emu" else 128
     utt, outt = M.UnitTypeTable(1, 1), O.Utt(1, 1)
     b = M.BatchedGameState(utt, make_pgs(maps[key], utt), n)
-    seeds = np.arange(n, dtype=np.int64) + 31
+    seeds = np.arange(n, dtype=np.int64) + 31 + SOAK
     b.reset(seeds)
     b.set_policy(0, M.POLICY_RANDOM_BIASED)
     b.set_policy(1, M.POLICY_RANDOM_BIASED)
@@ -935,7 +939,7 @@ def test_unit_action_lists_and_cycle_to_decision(backend, maps, key, version):
     utt, outt = M.UnitTypeTable(version, 1), O.Utt(version, 1)
     m = maps[key]
     b = M.BatchedGameState(utt, make_pgs(m, utt), n)
-    seeds = np.arange(n, dtype=np.int64) * 31 + 2
+    seeds = np.arange(n, dtype=np.int64) * 31 + 2 + SOAK
     b.reset(seeds)
     b.set_policy(0, M.POLICY_RANDOM_BIASED)
     b.set_policy(1, M.POLICY_RANDOM_BIASED)
@@ -995,7 +999,7 @@ def test_selfplay_through_the_observation_kernel(backend, maps, key, sizes, cycl
     utt, outt = M.UnitTypeTable(1, 1), O.Utt(1, 1)
     m = maps[key]
     b = M.BatchedGameState(utt, make_pgs(m, utt), n)
-    seeds = np.arange(n, dtype=np.int64) * 977 + 31
+    seeds = np.arange(n, dtype=np.int64) * 977 + 31 + SOAK
     b.reset(seeds)
     b.set_policy(0, M.POLICY_RANDOM_BIASED)
     b.set_policy(1, M.POLICY_RANDOM_BIASED)
