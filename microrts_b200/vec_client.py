@@ -156,7 +156,11 @@ class _Group:
         self.n, self.E = n, len(envs)
         same = all(m is maps[0] for m in maps)
         scripted = spec is not None and spec.policy >= M.POLICY_WORKER_RUSH
-        self.b = M.BatchedGameState(utt, maps[0] if same else maps, n, device=device, partial_obs=partial_obs, scripted_ai=scripted)
+        # partial_obs: the opponent decides on ITS PartiallyObservableGameState, as ai2.getAction(1 - player, player2gs) does
+        # (JNIGridnetClient.java:164-172); RandomBiasedAI and the scripted AIs are device policies, so the batch hides the state from them
+        po_pol = bool(partial_obs) and not selfplay and spec is not None and spec.policy >= M.POLICY_RANDOM_BIASED
+        self.b = M.BatchedGameState(utt, maps[0] if same else maps, n, device=device, partial_obs=partial_obs, scripted_ai=scripted or po_pol,
+                                    po_policies=po_pol)
         b = self.b
         if selfplay:
             b.set_policy(0, M.POLICY_EXTERNAL)

@@ -97,10 +97,17 @@ class RefSelfPlay(RefEnvBase):
         return [ref_rewards(pl, pre, pas, og) for pl in (0, 1)]
 
 
+def view_pairs_to_game(view, og, pairs):
+    """unit indices of a PartiallyObservableGameState's list -> indices of the real state's list (same units, found by position)"""
+    vu, gu = view.units(), og.units()
+    at = {(int(u[2]), int(u[3])): i for i, u in enumerate(gu)}
+    return [(at[(int(vu[i][2]), int(vu[i][3]))], a) for i, a in pairs]
+
+
 class RefBotEnv(RefEnvBase):
-    def __init__(self, outt, mapd, seed, kind, pf, side):
+    def __init__(self, outt, mapd, seed, kind, pf, side, partial=False):
         super().__init__(outt, mapd, seed)
-        self.kind, self.pf, self.side = kind, pf, side
+        self.kind, self.pf, self.side, self.partial = kind, pf, side, partial
         self.on_restart()
 
     def on_restart(self):
@@ -109,13 +116,26 @@ class RefBotEnv(RefEnvBase):
     def step(self, act):
         og, pl = self.og, self.side
         pre = [tuple(u) for u in og.units()]
-        pa1 = og.from_vector_action(pl, act, fill_none=1)
-        if self.kind == O.AI_RANDOM_BIASED:
-            pa2 = og.random_biased(1 - pl)
-        elif self.bot is not None:
-            pa2 = self.bot.get_action(og, 1 - pl)
+        if self.partial:
+            # JNIGridnetClient.gameStep :163-172: both players decide on their PartiallyObservableGameState, issueSafe on the real state
+            v1, v2 = og.po_view(pl), og.po_view(1 - pl)
+            pa1 = view_pairs_to_game(v1, og, v1.from_vector_action(pl, act, fill_none=1))
+            if self.kind == O.AI_RANDOM_BIASED:
+                pa2 = view_pairs_to_game(v2, og, v2.random_biased(1 - pl))
+                for k in range(3):  # RandomBiasedAI's generator is not part of the view
+                    og.set_rng_state(k, v2.rng_state(k))
+            elif self.bot is not None:
+                pa2 = view_pairs_to_game(v2, og, self.bot.get_action(v2, 1 - pl))
+            else:
+                pa2 = []
         else:
-            pa2 = []
+            pa1 = og.from_vector_action(pl, act, fill_none=1)
+            if self.kind == O.AI_RANDOM_BIASED:
+                pa2 = og.random_biased(1 - pl)
+            elif self.bot is not None:
+                pa2 = self.bot.get_action(og, 1 - pl)
+            else:
+                pa2 = []
         pas = [None, None]
         pas[pl] = og.issue_out(pa1, safe=True)
         pas[1 - pl] = og.issue_out(pa2, safe=True)
@@ -141,13 +161,17 @@ def random_actions(rng, og, player, w, h, k):
     return rows
 
 
-@pytest.mark.parametrize("key,n_sp,bots,max_steps,compact", [
-    ("8x8/basesWorkers8x8", 4, ["RandomBiasedAI", "PassiveAI", "WorkerRush"], 60, False),
-    ("16x16/basesWorkers16x16", 2, ["LightRush", "RandomBiasedAI"], 150, False),
-    ("8x8/basesWorkers8x8", 6, [], 45, True),                        # one self-play group: the client's arrays are the group's pinned arrays
-    ("16x16/basesWorkers16x16", 2, ["WorkerRush", "PassiveAI"], 80, True),
+@pytest.mark.parametrize("key,n_sp,bots,max_steps,compact,partial", [
+    ("8x8/basesWorkers8x8", 4, ["RandomBiasedAI", "PassiveAI", "WorkerRush"], 60, False, False),
+    ("16x16/basesWorkers16x16", 2, ["LightRush", "RandomBiasedAI"], 150, False, False),
+    ("8x8/basesWorkers8x8", 6, [], 45, True, False),                 # one self-play group: the client's arrays are the group's pinned arrays
+    ("16x16/basesWorkers16x16", 2, ["WorkerRush", "PassiveAI"], 80, True, False),
+    # partial_obs = true: 8-plane observations of the agent's view, the opponent decides on ITS view.  (The reference hands out the
+    # view object built BEFORE the cycle -- stale unit list, live units; here the observation is of the state after the cycle:
+    # DESIGN.md section 8, deviation 2.)
+    ("16x16/basesWorkers16x16", 2, ["LightRush", "RandomBiasedAI", "WorkerRush"], 200, False, True),
 ])
-def test_vec_client_matches_reference_flow(backend, maps, tmp_path, key, n_sp, bots, max_steps, compact):
+def test_vec_client_matches_reference_flow(backend, maps, tmp_path, key, n_sp, bots, max_steps, compact, partial):
     m = maps[key]
     path = tmp_path / "map.xml"
     path.write_text(P.map_to_xml(m))
@@ -158,12 +182,15 @@ def test_vec_client_matches_reference_flow(backend, maps, tmp_path, key, n_sp, b
     specs = [getattr(ai, b)(utt) for b in bots]
     kinds = {"RandomBiasedAI": O.AI_RANDOM_BIASED, "PassiveAI": O.AI_PASSIVE, "WorkerRush": O.AI_WORKER_RUSH, "LightRush": O.AI_LIGHT_RUSH}
     seed = 123
-    vc = JNIGridnetVecClient(n_sp, n_envs, max_steps, rfs, "", [str(path)] * s1, specs, utt, partial_obs=False, seed=seed, compact=compact)
+    vc = JNIGridnetVecClient(n_sp, n_envs, max_steps, rfs, "", [str(path)] * s1, specs, utt, partial_obs=partial, seed=seed, compact=compact)
     players = [0] * s1
     resp = vc.reset(players)
     ref_sp = [RefSelfPlay(outt, m, seed + 2 * i) for i in range(n_sp // 2)]
-    ref_bot = [RefBotEnv(outt, m, seed + n_sp + i, kinds[b], 0, 0) for i, b in enumerate(bots)]
+    ref_bot = [RefBotEnv(outt, m, seed + n_sp + i, kinds[b], 0, 0, partial) for i, b in enumerate(bots)]
     steps = np.zeros(s1, dtype=int)
+
+    def ref_obs(og, pl):
+        return og.po_view(pl).observe(pl, po=True) if partial else og.observe(pl)
 
     def check_obs_masks(ctx):
         mk = vc.getMasks(0)
@@ -173,10 +200,10 @@ def test_vec_client_matches_reference_flow(backend, maps, tmp_path, key, n_sp, b
             assert (np.unpackbits(packed, axis=-1, bitorder="little")[..., :mk.shape[-1]] == mk).all(), (ctx, "packed masks")
         for i, e in enumerate(ref_sp):
             for pl in (0, 1):
-                assert (resp.observation[2 * i + pl] == e.og.observe(pl)).all(), (ctx, "obs selfplay", i, pl)
+                assert (resp.observation[2 * i + pl] == ref_obs(e.og, pl)).all(), (ctx, "obs selfplay", i, pl)
                 assert (mk[2 * i + pl] == e.og.masks(pl)).all(), (ctx, "masks selfplay", i, pl)
         for i, e in enumerate(ref_bot):
-            assert (resp.observation[n_sp + i] == e.og.observe(0)).all(), (ctx, "obs bot", i)
+            assert (resp.observation[n_sp + i] == ref_obs(e.og, 0)).all(), (ctx, "obs bot", i)
             assert (mk[n_sp + i] == e.og.masks(0)).all(), (ctx, "masks bot", i)
 
     check_obs_masks("reset")
@@ -215,6 +242,6 @@ def test_vec_client_matches_reference_flow(backend, maps, tmp_path, key, n_sp, b
             check_obs_masks("step %d" % t)
         else:
             for i, e in enumerate(ref_sp):
-                assert (resp.observation[2 * i] == e.og.observe(0)).all(), ("obs", t, i)
+                assert (resp.observation[2 * i] == ref_obs(e.og, 0)).all(), ("obs", t, i)
     assert n_resets > 0 or backend == "emu"
     vc.close()
