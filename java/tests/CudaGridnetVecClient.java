@@ -23,7 +23,9 @@ import tests.JNIGridnetVecClient.Responses;
  *
  * NOT COMPILED in the build container of this repository (no JDK there); the Python mirror microrts_b200/vec_client.py is the
  * tested implementation of exactly this flow.  Device memory comes from the caller (cudaMalloc through any CUDA binding): obsDev,
- * infoDev, resDev.  Only num_envs == 0 (self-play) is shown; agent-vs-bot environments add setPolicy(1 - side, POLICY_*).
+ * infoDev, resDev.  Only num_envs == 0 (self-play) is shown; agent-vs-bot environments add setPolicy(1 - side, POLICY_*)
+ * on a batch created with FLAG_SCRIPTED_AI (plus FLAG_PO_POLICIES when partial_obs: the opponent then decides on its own view, as
+ * ai2.getAction(1 - player, player2gs) does in JNIGridnetClient.gameStep).
  */
 public class CudaGridnetVecClient {
     final BatchedGameState gs;
