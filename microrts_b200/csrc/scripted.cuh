@@ -191,14 +191,17 @@ DEVN int pf_find_t(Game &g, int kind, int s, int tx, int ty, int range, int nd) 
 #pragma unroll 1
         for (;;) {
             // smallest non-empty bucket: 32 buckets per probe
+            int pos = A.head[fcur]; // the search mostly runs along one f value: look at the current bucket first
+            if (pos == PF_NONE) {
 #pragma unroll 1
-            while (fcur <= fhi) {
-                unsigned m = __ballot_sync(FULLM, fcur + lane <= fhi && A.head[fcur + lane] != PF_NONE);
-                if (m) { fcur += __ffs(m) - 1; break; }
-                fcur += 32;
+                while (fcur <= fhi) {
+                    unsigned m = __ballot_sync(FULLM, fcur + lane <= fhi && A.head[fcur + lane] != PF_NONE);
+                    if (m) { fcur += __ffs(m) - 1; break; }
+                    fcur += 32;
+                }
+                if (fcur > fhi) break;
+                pos = A.head[fcur];
             }
-            if (fcur > fhi) break;
-            int pos = A.head[fcur];
             int nxt = A.next[pos], mk = A.mark[pos], fl = (mk >> 5) == gen ? (mk & 7) : 0;
             __syncwarp(); // every lane has read the bucket head before it is popped
             if (lane == 0) { A.head[fcur] = (uint16_t)nxt; if (!(fl & PFF_CLOSED)) A.mark[pos] = (uint16_t)(mk | PFF_CLOSED); }
