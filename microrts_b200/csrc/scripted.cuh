@@ -182,7 +182,8 @@ DEVN int pf_find_t(Game &g, int kind, int s, int tx, int ty, int range, int nd) 
     const int dl = lane & 3, doffl = (dl & 1) ? 2 - dl : (dl - 1) * A.P, dxl = ddx(dl), dyl = ddy(dl); // this lane's direction
     const unsigned below = (1u << lane) - 1;
     if (kind == 0) { // A*
-        int f0 = iabs(sx - tx) + iabs(sy - ty), flo = f0, fhi = f0, fcur = f0;
+        const int f0 = iabs(sx - tx) + iabs(sy - ty); // f never falls below the start's
+        int fhi = f0, fcur = f0;
         if (lane == 0) {
             pf_set(A, start, gen, pf_flags(A, start, gen) | PFF_INOC);
             A.next[start] = PF_NONE; A.head[f0] = (uint16_t)start;
@@ -217,28 +218,24 @@ DEVN int pf_find_t(Game &g, int kind, int s, int tx, int ty, int range, int nd) 
                 ok = !(nfl & PFF_INOC) && pf_free(A, np, nfl);
                 if (ok) { f = iabs(x + dxl - tx) + iabs(y + dyl - ty) + c; pf_set(A, np, gen, nfl | PFF_INOC, dl); }
             }
-            // the lanes that push into the same bucket (a neighbour's f is this node's or two more): chained in direction order
+            // the lanes that push into the same bucket are chained in direction order.  The Manhattan heuristic is consistent: a neighbour's f
+            // is this node's (one step closer) or two more (one step farther), so there are at most two buckets, both known
             unsigned okm = __ballot_sync(FULLM, ok);
             if (okm) {
-                int fa = __shfl_sync(FULLM, f, __ffs(okm) - 1);
-                unsigned ma = __ballot_sync(FULLM, ok && f == fa), mb = okm & ~ma; // with a Manhattan heuristic f is this node's or two more
-                int fb = mb ? __shfl_sync(FULLM, f, __ffs(mb) - 1) : fa;
-                unsigned same = f == fa ? ma : mb;
+                unsigned m0 = __ballot_sync(FULLM, ok && f == fcur), m2 = okm & ~m0;
+                unsigned same = f == fcur ? m0 : m2;
                 int prev = (same & below) ? 31 - __clz(same & below) : -1;
                 int prev_np = __shfl_sync(FULLM, np, prev < 0 ? 0 : prev);
                 if (ok) A.next[np] = prev >= 0 ? (uint16_t)prev_np : A.head[f];
                 __syncwarp(); // every chain start has read its bucket head before the heads move
                 if (ok && !(same & ~below & ~(1u << lane))) A.head[f] = (uint16_t)np; // the last lane of a bucket's chain is its new head
-                int fmax = fa > fb ? fa : fb, fmin = fa < fb ? fa : fb;
-                if (fmax > fhi) fhi = fmax;
-                if (fmin < fcur) fcur = fmin;
-                if (fmin < flo) flo = fmin;
+                if (m2 && fcur + 2 > fhi) fhi = fcur + 2;
             }
             __syncwarp();
         }
         __syncwarp();
 #pragma unroll 1
-        for (int f = flo + lane; f <= fhi; f += 32) A.head[f] = PF_NONE; // leave every bucket empty for the next query
+        for (int f = f0 + lane; f <= fhi; f += 32) A.head[f] = PF_NONE; // leave every bucket empty for the next query
         __syncwarp();
         return result;
     }
