@@ -195,18 +195,17 @@ DEVN int pf_find_t(Game &g, int kind, int s, int tx, int ty, int range, int nd) 
             int pos = A.head[fcur]; // the search mostly runs along one f value: look at the current bucket first
             if (pos == PF_NONE) {
 #pragma unroll 1
-                while (fcur <= fhi) {
-                    unsigned m = __ballot_sync(FULLM, fcur + lane <= fhi && A.head[fcur + lane] != PF_NONE);
-                    if (m) { fcur += __ffs(m) - 1; break; }
-                    fcur += 32;
+                while (fcur <= fhi) { // every f has the parity of the start's: 32 candidate buckets per probe, two apart
+                    unsigned m = __ballot_sync(FULLM, fcur + 2 * lane <= fhi && A.head[fcur + 2 * lane] != PF_NONE);
+                    if (m) { fcur += 2 * (__ffs(m) - 1); break; }
+                    fcur += 64;
                 }
                 if (fcur > fhi) break;
                 pos = A.head[fcur];
             }
-            int nxt = A.next[pos], mk = A.mark[pos], fl = (mk >> 5) == gen ? (mk & 7) : 0;
+            int nxt = A.next[pos];
             __syncwarp(); // every lane has read the bucket head before it is popped
-            if (lane == 0) { A.head[fcur] = (uint16_t)nxt; if (!(fl & PFF_CLOSED)) A.mark[pos] = (uint16_t)(mk | PFF_CLOSED); }
-            if (fl & PFF_CLOSED) { __syncwarp(); continue; }
+            if (lane == 0) A.head[fcur] = (uint16_t)nxt; // (a cell enters `open` once, so it is popped once: no closed test needed)
             int y = pos / A.P, x = pos - y * A.P - 1; y -= 1;
             if ((x - tx) * (x - tx) + (y - ty) * (y - ty) <= sq) { __syncwarp(); result = pf_first_step(A, pos, start); break; }
             int c = fcur - (iabs(x - tx) + iabs(y - ty)) + 1; // cost of the neighbours: this node's f - heuristic + 1
