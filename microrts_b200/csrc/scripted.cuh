@@ -206,16 +206,16 @@ DEVN int pf_find_t(Game &g, int kind, int s, int tx, int ty, int range, int nd) 
             int nxt = A.next[pos];
             __syncwarp(); // every lane has read the bucket head before it is popped
             if (lane == 0) A.head[fcur] = (uint16_t)nxt; // (a cell enters `open` once, so it is popped once: no closed test needed)
-            int y = pos / A.P, x = pos - y * A.P - 1; y -= 1;
-            if ((x - tx) * (x - tx) + (y - ty) * (y - ty) <= sq) { __syncwarp(); result = pf_first_step(A, pos, start); break; }
-            int c = fcur - (iabs(x - tx) + iabs(y - ty)) + 1; // cost of the neighbours: this node's f - heuristic + 1
-            // lanes 0..3: one neighbour each (addToOpen :104-138)
-            int np = pos + doffl, f = -1 - lane;
+            int y = pos / A.P, hx = pos - y * A.P - 1 - tx, hy = y - 1 - ty; // offset from the target
+            if (hx * hx + hy * hy <= sq) { __syncwarp(); result = pf_first_step(A, pos, start); break; }
+            // lanes 0..3: one neighbour each (addToOpen :104-138).  A step away from the target (or sideways past it) costs two more in f,
+            // a step towards it leaves f as it is: f = heuristic + cost never needs the two terms themselves
+            int np = pos + doffl, f = fcur + ((dxl * hx + dyl * hy >= 0) ? 2 : 0);
             bool ok = false;
             if (lane < 4) {
                 int nfl = pf_flags(A, np, gen);
                 ok = !(nfl & PFF_INOC) && pf_free(A, np, nfl);
-                if (ok) { f = iabs(x + dxl - tx) + iabs(y + dyl - ty) + c; pf_set(A, np, gen, nfl | PFF_INOC, dl); }
+                if (ok) pf_set(A, np, gen, nfl | PFF_INOC, dl);
             }
             // the lanes that push into the same bucket are chained in direction order.  The Manhattan heuristic is consistent: a neighbour's f
             // is this node's (one step closer) or two more (one step farther), so there are at most two buckets, both known
