@@ -110,14 +110,17 @@ template <class F> DEV int w_next(const Game &g, int n, int from, F pred) { // f
 // node of equal f, and pops from the end (AStarPathFinding.java:104-138,175-295): the node with the smallest f comes out
 // first and, among equal f, the NEWEST one.  That is exactly one LIFO stack per f value, so the open list here is a bucket
 // queue (head[f] -> chain through next[]): O(1) push and pop, same expansion order.  A node enters `open` at most once
-// (inOpenOrClosed), so its parent can be stored when it is pushed.  Per-cell state carries the query's generation number
-// instead of being cleared for every query.
+// (inOpenOrClosed) and so is popped once; what the caller wants of the path -- its first step -- is stored when the node is
+// pushed (A*: the first step of the path that reached it, handed down from its parent; BFS: the direction it was reached by,
+// walked back at the end).  A neighbour's f is the expanded node's (a step towards the target) or two more (away from it), the
+// heuristic being consistent: every f has the parity of the start's and never falls below it.  Per-cell state carries the query's
+// generation number instead of being cleared for every query.
 enum { PFF_INOC = 1, PFF_BLOCKED = 2, PFF_CLOSED = 4 };
 #define PF_NONE 0xFFFFu
 #define PF_GEN_LIMIT 2047 // generation numbers have 11 bits of the mark word
 // Positions are indices into the wall-padded grid: out of bounds looks like a wall, so there are no bounds checks.  A node's
-// coordinates follow from its index (a division by the padded row length: a constant in the fixed-layout kernels), its cost is
-// f - heuristic, and its parent is the cell it was reached from: index minus the offset of the direction kept in its mark word.
+// coordinates follow from its index (a division by the padded row length: a constant in the fixed-layout kernels); neither its
+// cost nor its parent is stored.
 // the scratch arrays of one query; built from the shared-window address when the scratch is in shared memory, so that the
 // accesses compile to LDS/STS instead of generic loads (pf_find<true>), from the global pointers otherwise
 struct PfArr { uint16_t *mark, *next, *head, *gen; const uint8_t *grid, *resv; int P; };
@@ -203,11 +206,11 @@ DEVN int pf_find_t(Game &g, int kind, int s, int tx, int ty, int range, int nd) 
                 if (fcur > fhi) break;
                 pos = A.head[fcur];
             }
-            int nxt = A.next[pos];
+            int nxt = A.next[pos], fs = (A.mark[pos] >> 3) & 3; // fs: the first step of the path that reached pos (travels with the marks)
             __syncwarp(); // every lane has read the bucket head before it is popped
             if (lane == 0) A.head[fcur] = (uint16_t)nxt; // (a cell enters `open` once, so it is popped once: no closed test needed)
             int y = pos / A.P, hx = pos - y * A.P - 1 - tx, hy = y - 1 - ty; // offset from the target
-            if (hx * hx + hy * hy <= sq) { __syncwarp(); result = pf_first_step(A, pos, start); break; }
+            if (hx * hx + hy * hy <= sq) { result = pos == start ? -1 : fs; break; }
             // lanes 0..3: one neighbour each (addToOpen :104-138).  A step away from the target (or sideways past it) costs two more in f,
             // a step towards it leaves f as it is: f = heuristic + cost never needs the two terms themselves
             int np = pos + doffl, f = fcur + ((dxl * hx + dyl * hy >= 0) ? 2 : 0);
@@ -215,7 +218,7 @@ DEVN int pf_find_t(Game &g, int kind, int s, int tx, int ty, int range, int nd) 
             if (lane < 4) {
                 int nfl = pf_flags(A, np, gen);
                 ok = !(nfl & PFF_INOC) && pf_free(A, np, nfl);
-                if (ok) pf_set(A, np, gen, nfl | PFF_INOC, dl);
+                if (ok) pf_set(A, np, gen, nfl | PFF_INOC, pos == start ? dl : fs);
             }
             // the lanes that push into the same bucket are chained in direction order.  The Manhattan heuristic is consistent: a neighbour's f
             // is this node's (one step closer) or two more (one step farther), so there are at most two buckets, both known
