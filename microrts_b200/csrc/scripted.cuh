@@ -1094,16 +1094,31 @@ DEVN int policy_scripted(Game &g, int player, int kind, int pathfinder, int pn) 
             // harvest with every remaining worker; those that cannot, attack -- in a second pass, as the reference does
             uint32_t still[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll 1
-            for (int i = w_next(g, n, wi, own_harvester); i >= 0; i = w_next(g, n, i, own_harvester)) if (script_harvest(g, i, player, defense)) still[i >> 5] |= 1u << (i & 31);
+            for (int base = 0; base < n; base += 32) { // (one ballot per 32 units instead of a search per worker)
+                int i = base + g.lane;
+                unsigned mask = __ballot_sync(FULLM, i < n && i > wi && own_harvester(i, g.w0()[i])), st = 0;
 #pragma unroll 1
-            for (int i = w_next(g, n, wi, own_harvester); i >= 0; i = w_next(g, n, i, own_harvester)) if (still[i >> 5] & (1u << (i & 31))) script_melee(g, i, player, defense, explore, always);
+                while (mask) { int b = __ffs(mask) - 1; mask &= mask - 1; if (script_harvest(g, base + b, player, defense)) st |= 1u << b; }
+                still[base >> 5] = st;
+            }
+#pragma unroll 1
+            for (int base = 0; base < n; base += 32) {
+                unsigned mask = still[base >> 5];
+#pragma unroll 1
+                while (mask) { int b = __ffs(mask) - 1; mask &= mask - 1; script_melee(g, base + b, player, defense, explore, always); }
+            }
         } else {
             // WorkerRush.java:146-202: one harvester, the rest attack; a harvester that stays free is appended at the END
             int hw = -1;
             if (taken < nworkers) { hw = w_next(g, n, wi, own_harvester); wi = hw; taken++; }
             bool hw_free = hw >= 0 && script_harvest(g, hw, player, defense);
 #pragma unroll 1
-            for (int i = w_next(g, n, wi, own_harvester); i >= 0; i = w_next(g, n, i, own_harvester)) script_melee(g, i, player, defense, explore, always);
+            for (int base = 0; base < n; base += 32) {
+                int i = base + g.lane;
+                unsigned mask = __ballot_sync(FULLM, i < n && i > wi && own_harvester(i, g.w0()[i]));
+#pragma unroll 1
+                while (mask) { int b = __ffs(mask) - 1; mask &= mask - 1; script_melee(g, base + b, player, defense, explore, always); }
+            }
             if (hw_free) script_melee(g, hw, player, defense, explore, always);
         }
     }
