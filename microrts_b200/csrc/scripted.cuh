@@ -729,20 +729,25 @@ DEV int translate_actions(Game &g, int player, int pathfinder, int par0, int par
     const int n = g.hdr()[H_NUNITS], pl = player + 1, pres = g.hdr()[H_RES0 + player];
     ScriptCtx c; c.player = player; c.pf = pathfinder; c.par0 = par0; c.par1 = par1; c.nd = 0;
     int nd = 0;
-    // this player's map entries in insertion order: lane 0 collects the slots with an insertion sort by sequence number (slot
-    // order is nearly insertion order already)
+    // The reference walks the player's map entries in insertion order: a completed entry is dropped, an entry of an idle unit is
+    // executed.  completed() reads nothing an execute() changes (the Train flag belongs to the executed entry itself), so all
+    // entries are tested at once, one per lane, and the completed ones dropped on the spot; only the few entries left to EXECUTE
+    // are put into insertion order (an insertion sort by sequence number on lane 0: slot order is nearly that order already).
     int ne = 0;
     __syncwarp();
 #pragma unroll 1
-    for (int base = 0; base < n; base += 32) { // the entries' slots, compacted in slot order by all lanes ...
+    for (int base = 0; base < n; base += 32) {
         int i = base + g.lane;
         bool has = i < n && aa_kind(g.x0()[i]) != AA_NONE && u_pl(g.w0()[i]) == pl;
-        unsigned m = __ballot_sync(FULLM, has);
-        if (has) g.list()[ne + __popc(m & ((1u << g.lane) - 1))] = (uint8_t)i;
+        bool comp = has && aa_completed(g, i);
+        if (comp) g.x0()[i] &= ~7u; // toDelete (a dead unit's entry vanished with its slot)
+        bool run = has && !comp && a_type(g.a0()[i]) == AT_IDLE;
+        unsigned m = __ballot_sync(FULLM, run);
+        if (run) g.list()[ne + __popc(m & ((1u << g.lane) - 1))] = (uint8_t)i;
         ne += __popc(m);
     }
     __syncwarp();
-    if (g.lane == 0) { // ... then put into insertion order
+    if (g.lane == 0) {
 #pragma unroll 1
         for (int k = 1; k < ne; k++) {
             int i = g.list()[k];
@@ -757,28 +762,20 @@ DEV int translate_actions(Game &g, int player, int pathfinder, int par0, int par
 #pragma unroll 1
     for (int r = 0; r < ne; r++) {
         int best = g.list()[r];
-        if (aa_completed(g, best)) { // toDelete (a dead unit's entry vanished with its slot)
-            __syncwarp();
-            if (g.lane == 0) g.x0()[best] &= ~7u;
-            __syncwarp();
-            continue;
+        uint32_t A0; int A1;
+        c.nd = nd;
+        // Desires are staged behind the part of the pending list that is already final ([0, pn): player 0's list when this is
+        // player 1) and pf_find reads them as [0, nd) through a shifted window.
+        int pv = g.pview;
+        g.pview = pv + pn;
+        bool got = aa_execute(g, c, best, A0, A1);
+        g.pview = pv;
+        __syncwarp();
+        if (got) {
+            if (g.lane == 0) { g.pslot()[pn + nd] = (uint8_t)best; g.pa0()[pn + nd] = A0; g.pa1()[pn + nd] = A1; }
+            nd++;
         }
-        if (a_type(g.a0()[best]) == AT_IDLE) {
-            uint32_t A0; int A1;
-            c.nd = nd;
-            // Desires are staged behind the part of the pending list that is already final ([0, pn): player 0's list when this is
-            // player 1) and pf_find reads them as [0, nd) through a shifted window.
-            int pv = g.pview;
-            g.pview = pv + pn;
-            bool got = aa_execute(g, c, best, A0, A1);
-            g.pview = pv;
-            __syncwarp();
-            if (got) {
-                if (g.lane == 0) { g.pslot()[pn + nd] = (uint8_t)best; g.pa0()[pn + nd] = A0; g.pa1()[pn + nd] = A1; }
-                nd++;
-            }
-            __syncwarp();
-        }
+        __syncwarp();
     }
     int out = pn;
     if (g.lane == 0) {
