@@ -546,9 +546,16 @@ DEV int sample_index(double draw, int nb, int total) {
 
 // Unit.canExecuteAction (units/Unit.java:531-534): is (A0,A1) in getUnitActions(u, ETA)?  NONE is always legal.
 DEV bool action_is_legal(const Game &g, int s, uint32_t A0, int A1) {
-    Enum e; enumerate(g, s, e);
     int at = a_type(A0);
     bool dir_ok = (unsigned)A1 < 4u;
+    if (at == ACT_NONE) return true;
+    if (at == ACT_MOVE && !g.slim) { // the common cases without the full enumeration: the target cell's kind byte decides a MOVE
+        if (!dir_ok) return false;
+        uint32_t w = g.w0()[s];
+        int k = g.kind()[cell_of(g, w) + doff(g, A1)];
+        return (ut_flags(g, u_type(w)) & UF_MOVE) && !((k >> 4) & 1) && !((k >> 7) & 1); // neither unit nor wall, as enumerate's free_m
+    }
+    Enum e; enumerate(g, s, e);
     switch (at) {
         case ACT_NONE: return true;
         case ACT_MOVE: return dir_ok && (e.fl & UF_MOVE) && ((e.free_m >> A1) & 1);
