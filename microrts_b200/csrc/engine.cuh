@@ -555,6 +555,16 @@ DEV bool action_is_legal(const Game &g, int s, uint32_t A0, int A1) {
         int k = g.kind()[cell_of(g, w) + doff(g, A1)];
         return (ut_flags(g, u_type(w)) & UF_MOVE) && !((k >> 4) & 1) && !((k >> 7) & 1); // neither unit nor wall, as enumerate's free_m
     }
+    if (at == ACT_ATTACK) { // the attacked cell holds an enemy within range (the enumeration would walk the whole unit list for a ranged unit)
+        uint32_t w = g.w0()[s];
+        int t = u_type(w), range = ut_range(g, t);
+        if (!(ut_flags(g, t) & UF_ATTACK)) return false;
+        int ax = (A0 >> 16) & 0xff, ay = A0 >> 24;
+        if (ax >= g.W || ay >= g.H) return false;
+        int gv = g.grid()[(ay + 1) * g.P + ax + 1];
+        if (gv == 0 || gv == 0xFF) return false;
+        return enemy_in_range(g, w, g.w0()[gv - 1], range * range);
+    }
     Enum e; enumerate(g, s, e);
     switch (at) {
         case ACT_NONE: return true;
