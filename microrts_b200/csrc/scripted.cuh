@@ -400,13 +400,23 @@ DEVN int pf_floodfill(Game &g, int player, int s, int tx, int ty, int range, int
 #endif
 
 // range < 0: PathFinding.findPath (A* and BFS: findPathToPositionInRange with range 0)
+// (A* and BFS pop the start first and stop there when it is within range: null.  Harvesters next to their resource or base ask
+// exactly that, half of their queries, so it is answered before the search is set up.)
+DEV bool pf_start_in_range(const Game &g, int s, int tx, int ty, int range) {
+    uint32_t sw = g.w0()[s];
+    int dx = u_x(sw) - tx, dy = u_y(sw) - ty;
+    return dx * dx + dy * dy <= range * range;
+}
 DEV int pf_find(Game &g, int kind, int s, int tx, int ty, int range, int nd) {
 #ifdef MRTS_TU_RUSH_ONLY
-    return pf_find_t<true, 0>(g, 0, s, tx, ty, range < 0 ? 0 : range, nd); // the lean copy: A*, scratch in shared memory
+    if (range < 0) range = 0;
+    if (pf_start_in_range(g, s, tx, ty, range)) return -1;
+    return pf_find_t<true, 0>(g, 0, s, tx, ty, range, nd); // the lean copy: A*, scratch in shared memory
 #else
     if (kind == 2) return pf_greedy(g, s, tx, ty, range, nd);
     if (kind == 3) return pf_floodfill(g, u_pl(g.w0()[s]) == 2 ? 1 : 0, s, tx, ty, range, nd);
     if (range < 0) range = 0;
+    if (pf_start_in_range(g, s, tx, ty, range)) return -1;
     return g.as_sm ? pf_find_t<true>(g, kind, s, tx, ty, range, nd) : pf_find_t<false>(g, kind, s, tx, ty, range, nd);
 #endif
 }
